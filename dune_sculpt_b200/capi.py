@@ -1,0 +1,453 @@
+"""ctypes bindings of the two native libraries (no torch types cross this boundary).
+
+libdune_sculpt_cuda.so  -- the C ABI of include/dune_sculpt_cuda.h (CUDA kernels, sm_100a)
+libdune_sculpt_host.so  -- the reference-named host entry points of include/dune_pbvh.h
+
+Loading never needs a GPU; creating a device context does and fails loudly without one.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .meshgen import Mesh
+
+_LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+
+DSC_NUM_STAGES = 8
+
+# tools / presets / flags (include/dune_sculpt_cuda.h)
+TOOL_DRAW, TOOL_SMOOTH, TOOL_INFLATE, TOOL_GRAB, TOOL_CLAY_STRIPS = 1, 2, 4, 5, 18
+CURVE_CUSTOM, CURVE_SMOOTH, CURVE_SPHERE, CURVE_ROOT, CURVE_SHARP, CURVE_LIN = 0, 1, 2, 3, 4, 5
+CURVE_POW4, CURVE_INVSQUARE, CURVE_CONSTANT, CURVE_SMOOTHER = 6, 7, 8, 9
+DIR_AREA, DIR_VIEW, DIR_X, DIR_Y, DIR_Z = 0, 1, 2, 3, 4
+DAB_FRONTFACE, DAB_PLANE_TRIM, DAB_FIRST_STEP, DAB_NO_NORMALS, DAB_NO_BOUNDS = 1, 2, 4, 8, 16
+PBVH_Leaf, PBVH_UpdateNormals, PBVH_UpdateBB, PBVH_UpdateOriginalBB = 1, 2, 4, 8
+PBVH_FullyHidden, PBVH_FullyMasked = 1 << 10, 1 << 11
+
+
+class DscDab(C.Structure):
+    _fields_ = [
+        ("tool", C.c_int), ("curve_preset", C.c_int), ("flags", C.c_int), ("sculpt_plane", C.c_int),
+        ("location", C.c_float * 3), ("radius", C.c_float), ("view_normal", C.c_float * 3),
+        ("bstrength", C.c_float), ("scale", C.c_float * 3), ("hardness", C.c_float),
+        ("normal_radius_factor", C.c_float), ("plane_offset", C.c_float), ("plane_trim", C.c_float),
+        ("tip_roundness", C.c_float), ("grab_delta", C.c_float * 3), ("radius_scale", C.c_float),
+    ]
+
+
+class DscStrokeStats(C.Structure):
+    _fields_ = [("vertex_dabs", C.c_int64), ("node_hits", C.c_int64), ("moved_verts", C.c_int64),
+                ("dabs", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+class BB(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3)]
+
+
+class PBVHNode(C.Structure):
+    _fields_ = [
+        ("vb", BB), ("orig_vb", BB), ("children_offset", C.c_int), ("prim_indices", c_int_p),
+        ("totprim", C.c_uint), ("vert_indices", c_int_p), ("uniq_verts", C.c_uint), ("face_verts", C.c_uint),
+        ("face_vert_indices", c_int_p), ("flag", C.c_uint),
+    ]
+
+
+class PBVH(C.Structure):
+    _fields_ = [
+        ("nodes", C.POINTER(PBVHNode)), ("node_mem_count", C.c_int), ("totnode", C.c_int),
+        ("prim_indices", c_int_p), ("totprim", C.c_int), ("totvert", C.c_int), ("leaf_limit", C.c_int),
+        ("vert_normals", c_float_p), ("verts", C.c_void_p), ("mpoly", C.c_void_p), ("mloop", C.c_void_p),
+        ("looptri", C.c_void_p), ("totpoly", C.c_int), ("totloop", C.c_int), ("vmask", c_float_p),
+        ("vert_bitmap", C.POINTER(C.c_uint)), ("deformed", C.c_bool), ("owns_normals", C.c_bool),
+        ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
+        ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
+    ]
+
+
+MVERT = np.dtype([("co", np.float32, 3), ("flag", np.int8), ("bweight", np.int8), ("_pad", np.int8, 2)])
+MPOLY = np.dtype([("loopstart", np.int32), ("totloop", np.int32), ("mat_nr", np.int16), ("flag", np.int8), ("_pad", np.int8)])
+MLOOP = np.dtype([("v", np.uint32), ("e", np.uint32)])
+MLOOPTRI = np.dtype([("tri", np.uint32, 3), ("poly", np.uint32)])
+
+SEARCH_CB = C.CFUNCTYPE(C.c_bool, C.POINTER(PBVHNode), C.c_void_p)
+
+
+class SculptSearchSphereData(C.Structure):
+    _fields_ = [("center", c_float_p), ("radius_squared", C.c_float), ("original", C.c_bool),
+                ("ignore_fully_ineffective", C.c_bool)]
+
+
+# every symbol include/dune_sculpt_cuda.h declares (checked by tests/test_abi.py)
+CUDA_SYMBOLS = [
+    "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
+    "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
+    "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
+    "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
+    "dsc_download_co", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
+    "dsc_download_node_flags", "dsc_download_touched", "dsc_upload_co", "dsc_synchronize", "dsc_timer_start",
+    "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
+]
+HOST_SYMBOLS = [
+    "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
+    "DUNE_pbvh_mesh_sizes_set", "DUNE_pbvh_mask_layer_set", "DUNE_pbvh_vert_normals_set", "DUNE_pbvh_leaf_limit_set",
+    "DUNE_pbvh_device_attach", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
+    "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
+    "BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_hidden_get", "BKE_pbvh_node_fully_masked_set",
+    "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
+    "BKE_pbvh_node_get_original_BB", "BKE_pbvh_update_normals", "BKE_pbvh_update_bounds", "BKE_pbvh_vert_coords_alloc",
+    "BKE_pbvh_vert_coords_apply", "BKE_pbvh_get_verts", "BKE_pbvh_get_vert_normals", "DUNE_sculpt_brush_strength",
+    "DUNE_sculpt_dab_defaults", "DUNE_sculpt_stroke_begin", "DUNE_sculpt_dab", "DUNE_sculpt_stroke_end",
+    "DUNE_sculpt_automask_boundary_edges", "DUNE_sculpt_automask_topology", "MEM_freeN",
+]
+
+_cuda = None
+_host = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def _load(name):
+    path = os.path.join(_LIB_DIR, name)
+    if not os.path.exists(path):
+        raise NativeLibraryMissing(
+            "%s is not built: run `python -m dune_sculpt_b200.build` (nvcc, sm_100a). There is no fallback path." % path)
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+def cuda_lib():
+    global _cuda
+    if _cuda is None:
+        L = _load("libdune_sculpt_cuda.so")
+        L.dsc_last_error.restype = C.c_char_p
+        L.dsc_last_error.argtypes = [C.c_void_p]
+        L.dsc_stage_name.restype = C.c_char_p
+        L.dsc_stream.restype = C.c_void_p
+        L.dsc_stream.argtypes = [C.c_void_p]
+        L.dsc_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.dsc_ctx_destroy.argtypes = [C.c_void_p]
+        L.dsc_ctx_destroy.restype = None
+        for fn in ("dsc_recalc_normals", "dsc_stroke_end", "dsc_update_normals", "dsc_synchronize", "dsc_timer_start"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.dsc_stroke_begin.argtypes = [C.c_void_p, c_float_p]
+        L.dsc_dab.argtypes = [C.c_void_p, C.POINTER(DscDab)]
+        L.dsc_gather_readback.argtypes = [C.c_void_p, c_int_p, C.c_int, c_int_p]
+        L.dsc_search_sphere.argtypes = [C.c_void_p, c_float_p, C.c_float, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p]
+        L.dsc_last_area.argtypes = [C.c_void_p, c_float_p, c_float_p]
+        L.dsc_debug_capture.argtypes = [C.c_void_p, C.c_int]
+        L.dsc_last_moved.argtypes = [C.c_void_p, c_int_p, C.c_int, c_int_p]
+        L.dsc_stroke_stats.argtypes = [C.c_void_p, C.POINTER(DscStrokeStats)]
+        L.dsc_update_bounds.argtypes = [C.c_void_p, C.c_int]
+        L.dsc_node_mark_update.argtypes = [C.c_void_p, C.c_int]
+        L.dsc_node_flag_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        for fn in ("dsc_download_co", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_upload_co",
+                   "dsc_set_custom_curve", "dsc_set_mask"):
+            getattr(L, fn).argtypes = [C.c_void_p, c_float_p]
+        L.dsc_download_node_bb.argtypes = [C.c_void_p, c_float_p, c_float_p]
+        L.dsc_download_node_flags.argtypes = [C.c_void_p, c_int_p]
+        L.dsc_download_touched.argtypes = [C.c_void_p, c_ubyte_p]
+        L.dsc_timer_stop.argtypes = [C.c_void_p, c_float_p]
+        L.dsc_stage_timing.argtypes = [C.c_void_p, C.c_int]
+        L.dsc_stage_times.argtypes = [C.c_void_p, c_float_p, c_int_p]
+        _cuda = L
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        cuda_lib()
+        L = _load("libdune_sculpt_host.so")
+        L.BKE_pbvh_new.restype = C.POINTER(PBVH)
+        L.BKE_pbvh_free.argtypes = [C.POINTER(PBVH)]
+        L.BKE_pbvh_free.restype = None
+        L.BKE_mesh_recalc_looptri.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.BKE_mesh_recalc_looptri.restype = None
+        L.BKE_pbvh_build_mesh.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.BKE_pbvh_build_mesh.restype = None
+        L.DUNE_pbvh_mesh_sizes_set.argtypes = [C.POINTER(PBVH), C.c_int, C.c_int]
+        L.DUNE_pbvh_mask_layer_set.argtypes = [C.POINTER(PBVH), c_float_p]
+        L.DUNE_pbvh_vert_normals_set.argtypes = [C.POINTER(PBVH), c_float_p]
+        L.DUNE_pbvh_leaf_limit_set.argtypes = [C.POINTER(PBVH), C.c_int]
+        L.DUNE_pbvh_device_attach.argtypes = [C.POINTER(PBVH), C.c_int]
+        L.DUNE_pbvh_device_detach.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_device_sync_to_host.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_device_error.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_device_error.restype = C.c_char_p
+        L.BKE_pbvh_search_gather.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.POINTER(C.POINTER(PBVHNode))), c_int_p]
+        L.BKE_pbvh_search_gather.restype = None
+        L.BKE_pbvh_update_normals.argtypes = [C.POINTER(PBVH), C.c_void_p]
+        L.BKE_pbvh_update_normals.restype = None
+        L.BKE_pbvh_update_bounds.argtypes = [C.POINTER(PBVH), C.c_int]
+        L.BKE_pbvh_update_bounds.restype = None
+        L.BKE_pbvh_node_mark_update.argtypes = [C.POINTER(PBVHNode)]
+        L.BKE_pbvh_node_mark_update.restype = None
+        L.BKE_pbvh_vert_coords_alloc.argtypes = [C.POINTER(PBVH)]
+        L.BKE_pbvh_vert_coords_alloc.restype = c_float_p
+        L.BKE_pbvh_vert_coords_apply.argtypes = [C.POINTER(PBVH), c_float_p, C.c_int]
+        L.BKE_pbvh_vert_coords_apply.restype = None
+        L.BKE_pbvh_get_verts.argtypes = [C.POINTER(PBVH)]
+        L.BKE_pbvh_get_verts.restype = C.c_void_p
+        L.BKE_pbvh_get_vert_normals.argtypes = [C.POINTER(PBVH)]
+        L.BKE_pbvh_get_vert_normals.restype = c_float_p
+        L.MEM_freeN.argtypes = [C.c_void_p]
+        L.MEM_freeN.restype = None
+        L.DUNE_sculpt_brush_strength.argtypes = [C.c_int, C.c_float, C.c_float, C.c_bool, C.c_bool, C.c_float, C.c_float]
+        L.DUNE_sculpt_brush_strength.restype = C.c_float
+        L.DUNE_sculpt_dab_defaults.argtypes = [C.POINTER(DscDab), C.c_int]
+        L.DUNE_sculpt_dab_defaults.restype = None
+        L.DUNE_sculpt_stroke_begin.argtypes = [C.POINTER(PBVH), c_float_p]
+        L.DUNE_sculpt_dab.argtypes = [C.POINTER(PBVH), C.POINTER(DscDab)]
+        L.DUNE_sculpt_stroke_end.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_sculpt_automask_boundary_edges.argtypes = [C.POINTER(PBVH), C.c_int, c_float_p]
+        L.DUNE_sculpt_automask_boundary_edges.restype = None
+        L.DUNE_sculpt_automask_topology.argtypes = [C.POINTER(PBVH), C.c_int, c_float_p, C.c_float, c_float_p]
+        L.DUNE_sculpt_automask_topology.restype = None
+        _host = L
+    return _host
+
+
+def fptr(a):
+    return a.ctypes.data_as(c_float_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+def make_dab(tool, location, radius, **kw):
+    """Dab descriptor with the Brush defaults (types/types_brush_defaults.h) for `tool`."""
+    d = DscDab()
+    host_lib().DUNE_sculpt_dab_defaults(C.byref(d), int(tool))
+    d.location[:] = [float(x) for x in location]
+    d.radius = float(radius)
+    for k, v in kw.items():
+        if k in ("view_normal", "scale", "grab_delta"):
+            getattr(d, k)[:] = [float(x) for x in v]
+        elif k in ("flags", "curve_preset", "sculpt_plane"):
+            setattr(d, k, int(v))
+        else:
+            setattr(d, k, float(v))
+    return d
+
+
+class SculptSession:
+    """A mesh + its PBVH through the reference-named host API, optionally attached to a device."""
+
+    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None):
+        H = host_lib()
+        self.H = H
+        self.mesh = mesh
+        self.mvert = np.zeros(mesh.totvert, dtype=MVERT)
+        self.mvert["co"] = mesh.co
+        self.mpoly = np.zeros(mesh.totpoly, dtype=MPOLY)
+        self.mpoly["loopstart"] = mesh.poly_start
+        self.mpoly["totloop"] = mesh.poly_len
+        self.mloop = np.zeros(mesh.totloop, dtype=MLOOP)
+        self.mloop["v"] = mesh.loop_v.astype(np.uint32)
+        self.tottri = int(H.BKE_mesh_poly_to_tri_count(mesh.totpoly, mesh.totloop))
+        self.looptri = np.zeros(max(self.tottri, 1), dtype=MLOOPTRI)
+        H.BKE_mesh_recalc_looptri(self.mloop.ctypes.data, self.mpoly.ctypes.data, self.mvert.ctypes.data, mesh.totloop,
+                                  mesh.totpoly, self.looptri.ctypes.data)
+        self.mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.float32)
+        self.vnors = None if no is None else np.ascontiguousarray(no, dtype=np.float32)
+        self.pbvh = H.BKE_pbvh_new()
+        H.DUNE_pbvh_mesh_sizes_set(self.pbvh, mesh.totpoly, mesh.totloop)
+        if leaf_limit:
+            H.DUNE_pbvh_leaf_limit_set(self.pbvh, int(leaf_limit))
+        if self.mask is not None:
+            H.DUNE_pbvh_mask_layer_set(self.pbvh, fptr(self.mask))
+        if self.vnors is not None:
+            H.DUNE_pbvh_vert_normals_set(self.pbvh, fptr(self.vnors))
+        H.BKE_pbvh_build_mesh(self.pbvh, None, self.mpoly.ctypes.data, self.mloop.ctypes.data, self.mvert.ctypes.data,
+                              mesh.totvert, None, None, None, self.looptri.ctypes.data, self.tottri)
+        self.ctx = None
+        if device is not None:
+            self.attach(device)
+
+    # ---- host-side structure -------------------------------------------------------------
+    @property
+    def totnode(self):
+        return int(self.pbvh.contents.totnode)
+
+    def node_arrays(self):
+        p = self.pbvh.contents
+        n = p.totnode
+        out = {k: np.zeros(n, dtype=np.int32) for k in ("children_offset", "flag", "prim_offset", "totprim", "uniq_verts", "face_verts")}
+        out["vb"] = np.zeros((n, 6), dtype=np.float32)
+        out["orig_vb"] = np.zeros((n, 6), dtype=np.float32)
+        base = C.addressof(p.prim_indices.contents) if p.totprim else 0
+        for i in range(n):
+            nd = p.nodes[i]
+            out["vb"][i, :3] = nd.vb.bmin[:]
+            out["vb"][i, 3:] = nd.vb.bmax[:]
+            out["orig_vb"][i, :3] = nd.orig_vb.bmin[:]
+            out["orig_vb"][i, 3:] = nd.orig_vb.bmax[:]
+            out["children_offset"][i] = nd.children_offset
+            out["flag"][i] = nd.flag
+            if nd.flag & PBVH_Leaf:
+                out["prim_offset"][i] = (C.addressof(nd.prim_indices.contents) - base) // 4
+                out["totprim"][i] = nd.totprim
+                out["uniq_verts"][i] = nd.uniq_verts
+                out["face_verts"][i] = nd.face_verts
+        return out
+
+    def prim_indices(self):
+        p = self.pbvh.contents
+        return np.ctypeslib.as_array(p.prim_indices, shape=(p.totprim,)).copy()
+
+    def node_vert_indices(self, i):
+        nd = self.pbvh.contents.nodes[i]
+        return np.ctypeslib.as_array(nd.vert_indices, shape=(nd.uniq_verts + nd.face_verts,)).copy()
+
+    def node_face_vert_indices(self, i):
+        nd = self.pbvh.contents.nodes[i]
+        return np.ctypeslib.as_array(nd.face_vert_indices, shape=(nd.totprim * 3,)).copy().reshape(-1, 3)
+
+    def neighbor_tables(self):
+        p = self.pbvh.contents
+        v = p.totvert
+        off = np.ctypeslib.as_array(p.nb_offsets, shape=(v + 1,)).copy()
+        idx = np.ctypeslib.as_array(p.nb_indices, shape=(int(off[-1]),)).copy()
+        bnd = np.ctypeslib.as_array(p.boundary, shape=(v,)).copy()
+        return off, idx, bnd
+
+    # ---- device ----------------------------------------------------------------------------
+    def _chk(self, r):
+        if r != 0:
+            msg = self.H.DUNE_pbvh_device_error(self.pbvh)
+            raise DeviceError("dune_sculpt_cuda error %d: %s" % (r, (msg or b"").decode()))
+
+    def attach(self, device=0):
+        self._chk(self.H.DUNE_pbvh_device_attach(self.pbvh, int(device)))
+        self.ctx = C.c_void_p(self.pbvh.contents.device)
+        self.D = cuda_lib()
+
+    def stroke_begin(self, automask=None):
+        a = None if automask is None else np.ascontiguousarray(automask, dtype=np.float32)
+        self._chk(self.H.DUNE_sculpt_stroke_begin(self.pbvh, None if a is None else fptr(a)))
+
+    def dab(self, d):
+        self._chk(self.H.DUNE_sculpt_dab(self.pbvh, C.byref(d)))
+
+    def stroke_end(self):
+        self._chk(self.H.DUNE_sculpt_stroke_end(self.pbvh))
+
+    def hits(self):
+        n = C.c_int(0)
+        buf = np.zeros(max(self.totnode, 1), dtype=np.int32)
+        self._chk(self.D.dsc_gather_readback(self.ctx, iptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def search_sphere(self, center, radius_sq, original=False, ignore=True):
+        c = np.asarray(center, dtype=np.float32)
+        n = C.c_int(0)
+        buf = np.zeros(max(self.totnode, 1), dtype=np.int32)
+        self._chk(self.D.dsc_search_sphere(self.ctx, fptr(c), C.c_float(radius_sq), int(original), int(ignore), iptr(buf),
+                                           buf.size, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def capture(self, on=True):
+        self._chk(self.D.dsc_debug_capture(self.ctx, int(on)))
+
+    def moved(self):
+        n = C.c_int(0)
+        buf = np.zeros(self.mesh.totvert, dtype=np.int32)
+        self._chk(self.D.dsc_last_moved(self.ctx, iptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def last_area(self):
+        no = np.zeros(3, dtype=np.float32)
+        co = np.zeros(3, dtype=np.float32)
+        self._chk(self.D.dsc_last_area(self.ctx, fptr(no), fptr(co)))
+        return no, co
+
+    def _dl3(self, fn):
+        out = np.zeros((self.mesh.totvert, 3), dtype=np.float32)
+        self._chk(getattr(self.D, fn)(self.ctx, fptr(out)))
+        return out
+
+    def co(self):
+        return self._dl3("dsc_download_co")
+
+    def no(self):
+        return self._dl3("dsc_download_no")
+
+    def orig_co(self):
+        return self._dl3("dsc_download_orig_co")
+
+    def orig_no(self):
+        return self._dl3("dsc_download_orig_no")
+
+    def node_bb(self):
+        bb = np.zeros((self.totnode, 6), dtype=np.float32)
+        obb = np.zeros((self.totnode, 6), dtype=np.float32)
+        self._chk(self.D.dsc_download_node_bb(self.ctx, fptr(bb), fptr(obb)))
+        return bb, obb
+
+    def node_flags(self):
+        f = np.zeros(self.totnode, dtype=np.int32)
+        self._chk(self.D.dsc_download_node_flags(self.ctx, iptr(f)))
+        return f
+
+    def touched(self):
+        t = np.zeros(self.totnode, dtype=np.uint8)
+        self._chk(self.D.dsc_download_touched(self.ctx, t.ctypes.data_as(c_ubyte_p)))
+        return np.nonzero(t)[0].astype(np.int32)
+
+    def stats(self):
+        s = DscStrokeStats()
+        self._chk(self.D.dsc_stroke_stats(self.ctx, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in DscStrokeStats._fields_}
+
+    def set_node_flag(self, node, flag, on=True):
+        self._chk(self.D.dsc_node_flag_set(self.ctx, int(node), int(flag), int(on)))
+
+    def set_custom_curve(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        assert t.size == 257
+        self._chk(self.D.dsc_set_custom_curve(self.ctx, fptr(t)))
+
+    def synchronize(self):
+        self._chk(self.D.dsc_synchronize(self.ctx))
+
+    def timer_start(self):
+        self._chk(self.D.dsc_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._chk(self.D.dsc_timer_stop(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def stage_timing(self, on):
+        self._chk(self.D.dsc_stage_timing(self.ctx, int(on)))
+
+    def stage_times(self):
+        ms = (C.c_float * DSC_NUM_STAGES)()
+        ln = (C.c_int * DSC_NUM_STAGES)()
+        self._chk(self.D.dsc_stage_times(self.ctx, ms, ln))
+        return {self.D.dsc_stage_name(i).decode(): (float(ms[i]), int(ln[i])) for i in range(DSC_NUM_STAGES)}
+
+    def close(self):
+        if self.pbvh is not None:
+            self.H.BKE_pbvh_free(self.pbvh)
+            self.pbvh = None
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,887 @@
+/* Host C side of the B200 sculpt-stroke path: the reference's PBVH entry points (see
+ * include/dune_pbvh.h) over libdune_sculpt_cuda.  The PBVH topology is built here on the host --
+ * it is a once-per-session step and fixes the parity-critical ownership and
+ * ordering -- with the split rule, leaf limit and first-touch vertex ownership of
+ * kernel/intern/pbvh.c:2070-2514; everything per-dab runs on the device.
+ */
+#include "../../include/dune_pbvh.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define LEAF_LIMIT 10000 /* pbvh.c:1950 */
+
+#ifdef DUNE_PBVH_OWN_MEM
+void *MEM_mallocN(size_t len, const char *str)
+{
+  (void)str;
+  return malloc(len ? len : 1);
+}
+void *MEM_callocN(size_t len, const char *str)
+{
+  (void)str;
+  return calloc(len ? len : 1, 1);
+}
+void MEM_freeN(void *vmemh) { free(vmemh); }
+#endif
+
+/* ------------------------------------------------------------------------------------ mesh */
+
+int BKE_mesh_poly_to_tri_count(int totpoly, int totloop) { return totloop - 2 * totpoly; }
+
+static bool quad_needs_flip(const float a[3], const float b[3], const float c[3], const float d[3])
+{
+  /* lib/intern/math_geom.cc:5362-5378: diagonal a-c is degenerate when b and d lie on its same side */
+  float ab[3], ac[3], ad[3];
+  for (int i = 0; i < 3; i++) {
+    ab[i] = b[i] - a[i];
+    ac[i] = c[i] - a[i];
+    ad[i] = d[i] - a[i];
+  }
+  const float n1[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+  const float n2[3] = {ad[1] * ac[2] - ad[2] * ac[1], ad[2] * ac[0] - ad[0] * ac[2], ad[0] * ac[1] - ad[1] * ac[0]};
+  return (n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2]) > 0.0f;
+}
+
+void BKE_mesh_recalc_looptri(const MLoop *mloop, const MPoly *mpoly, const MVert *mvert, int totloop, int totpoly,
+                             MLoopTri *mlooptri)
+{
+  (void)totloop;
+  MLoopTri *out = mlooptri;
+  for (int p = 0; p < totpoly; p++) {
+    const unsigned ls = (unsigned)mpoly[p].loopstart;
+    const int n = mpoly[p].totloop;
+    if (n == 4) {
+      /* mesh_tessellate.c:429-447 */
+      out[0].tri[0] = ls; out[0].tri[1] = ls + 1; out[0].tri[2] = ls + 2; out[0].poly = (unsigned)p;
+      out[1].tri[0] = ls; out[1].tri[1] = ls + 2; out[1].tri[2] = ls + 3; out[1].poly = (unsigned)p;
+      if (quad_needs_flip(mvert[mloop[ls].v].co, mvert[mloop[ls + 1].v].co, mvert[mloop[ls + 2].v].co,
+                          mvert[mloop[ls + 3].v].co)) {
+        out[0].tri[2] = out[1].tri[2];
+        out[1].tri[0] = out[0].tri[1];
+      }
+      out += 2;
+    }
+    else {
+      /* triangle, or fan for n-gons (the reference runs polyfill there; no config uses n-gons) */
+      for (int k = 1; k + 1 < n; k++, out++) {
+        out->tri[0] = ls; out->tri[1] = ls + (unsigned)k; out->tri[2] = ls + (unsigned)k + 1; out->poly = (unsigned)p;
+      }
+    }
+  }
+}
+
+/* ----------------------------------------------------------------------------------- build */
+
+typedef struct PrimBox {
+  float lo[3], hi[3], mid[3];
+} PrimBox;
+
+typedef struct BuildJob {
+  int node, offset, count;
+  bool root_cb;
+} BuildJob;
+
+static inline float minf(float a, float b) { return (a < b) ? a : b; }
+static inline float maxf(float a, float b) { return (a > b) ? a : b; }
+
+static void bb_clear(BB *bb)
+{
+  for (int i = 0; i < 3; i++) {
+    bb->bmin[i] = FLT_MAX;
+    bb->bmax[i] = -FLT_MAX;
+  }
+}
+
+static void ensure_nodes(PBVH *pbvh, int totnode)
+{
+  /* growth policy of pbvh.c:2134-2145 (capacity only; indices are what matter) */
+  if (totnode > pbvh->node_mem_count) {
+    int cap = pbvh->node_mem_count + pbvh->node_mem_count / 3;
+    if (cap < totnode) cap = totnode;
+    PBVHNode *nn = calloc((size_t)cap, sizeof(PBVHNode));
+    if (pbvh->nodes) {
+      memcpy(nn, pbvh->nodes, sizeof(PBVHNode) * (size_t)pbvh->totnode);
+      free(pbvh->nodes);
+    }
+    pbvh->nodes = nn;
+    pbvh->node_mem_count = cap;
+  }
+  pbvh->totnode = totnode;
+}
+
+static void node_box_from_prims(PBVH *pbvh, PBVHNode *node, const PrimBox *pb, int offset, int count)
+{
+  /* pbvh.c:2240-2247 */
+  bb_clear(&node->vb);
+  for (int i = offset + count - 1; i >= offset; i--) {
+    const PrimBox *b = &pb[pbvh->prim_indices[i]];
+    for (int k = 0; k < 3; k++) {
+      node->vb.bmin[k] = minf(node->vb.bmin[k], b->lo[k]);
+      node->vb.bmax[k] = maxf(node->vb.bmax[k], b->hi[k]);
+    }
+  }
+  node->orig_vb = node->vb;
+}
+
+static void leaf_collect_verts(PBVH *pbvh, PBVHNode *node, int node_index, int *stamp, int *local)
+{
+  /* pbvh.c:2149-2238: a vertex belongs ("unique") to the first leaf, in build order, that uses
+   * it; later leaves list it after their unique verts.  Within a leaf, order = first use. */
+  const int totface = (int)node->totprim;
+  int(*fvi)[3] = malloc(sizeof(int[3]) * (size_t)(totface ? totface : 1));
+  unsigned uniq = 0, shared = 0;
+  for (int i = 0; i < totface; i++) {
+    const MLoopTri *lt = &pbvh->looptri[node->prim_indices[i]];
+    for (int j = 0; j < 3; j++) {
+      const int v = (int)pbvh->mloop[lt->tri[j]].v;
+      if (stamp[v] != node_index) {
+        stamp[v] = node_index;
+        if (!(pbvh->vert_bitmap[v >> 5] & (1u << (v & 31)))) {
+          pbvh->vert_bitmap[v >> 5] |= 1u << (v & 31);
+          local[v] = (int)uniq++;
+        }
+        else {
+          local[v] = ~(int)(shared++);
+        }
+      }
+      fvi[i][j] = local[v];
+    }
+  }
+  int *vi = calloc((size_t)(uniq + shared ? uniq + shared : 1), sizeof(int));
+  for (int i = 0; i < totface; i++) {
+    const MLoopTri *lt = &pbvh->looptri[node->prim_indices[i]];
+    for (int j = 0; j < 3; j++) {
+      int ndx = fvi[i][j];
+      if (ndx < 0) {
+        ndx = -ndx + (int)uniq - 1;
+        fvi[i][j] = ndx;
+      }
+      vi[ndx] = (int)pbvh->mloop[lt->tri[j]].v;
+    }
+  }
+  node->uniq_verts = uniq;
+  node->face_verts = shared;
+  node->vert_indices = vi;
+  node->face_vert_indices = (const int(*)[3])fvi;
+  node->flag |= PBVH_RebuildDrawBuffers | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw;
+}
+
+static int split_by_centroid(int *prims, int lo, int hi, int axis, float mid, const PrimBox *pb)
+{
+  /* Hoare partition on centroid < mid (pbvh.c:2070-2088); returns first index of the right part */
+  int i = lo, j = hi;
+  for (;;) {
+    while (pb[prims[i]].mid[axis] < mid) i++;
+    while (mid < pb[prims[j]].mid[axis]) j--;
+    if (!(i < j)) return i;
+    const int t = prims[i];
+    prims[i] = prims[j];
+    prims[j] = t;
+    i++;
+  }
+}
+
+PBVH *BKE_pbvh_new(void)
+{
+  PBVH *pbvh = calloc(1, sizeof(PBVH));
+  pbvh->leaf_limit = LEAF_LIMIT;
+  return pbvh;
+}
+
+void DUNE_pbvh_mesh_sizes_set(PBVH *pbvh, int totpoly, int totloop)
+{
+  pbvh->totpoly = totpoly;
+  pbvh->totloop = totloop;
+}
+void DUNE_pbvh_mask_layer_set(PBVH *pbvh, float *vmask) { pbvh->vmask = vmask; }
+void DUNE_pbvh_vert_normals_set(PBVH *pbvh, float (*vert_normals)[3])
+{
+  if (pbvh->owns_normals) free(pbvh->vert_normals);
+  pbvh->vert_normals = vert_normals;
+  pbvh->owns_normals = false;
+}
+void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit) { pbvh->leaf_limit = leaf_limit > 0 ? leaf_limit : LEAF_LIMIT; }
+
+void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, const MLoop *mloop, MVert *verts,
+                         int totvert, struct CustomData *vdata, struct CustomData *ldata, struct CustomData *pdata,
+                         const MLoopTri *looptri, int looptri_num)
+{
+  (void)mesh; (void)vdata; (void)ldata; (void)pdata;
+  pbvh->mpoly = mpoly;
+  pbvh->mloop = mloop;
+  pbvh->looptri = looptri;
+  pbvh->verts = verts;
+  pbvh->totvert = totvert;
+  if (!pbvh->vert_normals) {
+    pbvh->vert_normals = calloc((size_t)(totvert ? totvert : 1), sizeof(float[3]));
+    pbvh->owns_normals = true;
+  }
+  pbvh->vert_bitmap = calloc((size_t)totvert / 32 + 1, sizeof(unsigned));
+  if (pbvh->leaf_limit <= 0) pbvh->leaf_limit = LEAF_LIMIT;
+  if (!looptri_num) return;
+
+  /* per-looptri box and centroid (pbvh.c:2490-2504) */
+  PrimBox *pb = malloc(sizeof(PrimBox) * (size_t)looptri_num);
+  BB cb;
+  bb_clear(&cb);
+  for (int i = 0; i < looptri_num; i++) {
+    PrimBox *b = &pb[i];
+    for (int k = 0; k < 3; k++) {
+      b->lo[k] = FLT_MAX;
+      b->hi[k] = -FLT_MAX;
+    }
+    for (int j = 0; j < 3; j++) {
+      const float *co = verts[mloop[looptri[i].tri[j]].v].co;
+      for (int k = 0; k < 3; k++) {
+        b->lo[k] = minf(b->lo[k], co[k]);
+        b->hi[k] = maxf(b->hi[k], co[k]);
+      }
+    }
+    for (int k = 0; k < 3; k++) {
+      b->mid[k] = (b->lo[k] + b->hi[k]) * 0.5f;
+      cb.bmin[k] = minf(cb.bmin[k], b->mid[k]);
+      cb.bmax[k] = maxf(cb.bmax[k], b->mid[k]);
+    }
+  }
+
+  pbvh->totprim = looptri_num;
+  pbvh->prim_indices = malloc(sizeof(int) * (size_t)looptri_num);
+  for (int i = 0; i < looptri_num; i++) pbvh->prim_indices[i] = i;
+  pbvh->node_mem_count = 0;
+  pbvh->totnode = 0;
+  ensure_nodes(pbvh, 100);
+  pbvh->totnode = 1;
+
+  int *stamp = malloc(sizeof(int) * (size_t)totvert);
+  int *local = malloc(sizeof(int) * (size_t)totvert);
+  for (int i = 0; i < totvert; i++) stamp[i] = -1;
+
+  /* pre-order walk, left subtree first: node numbering and vertex ownership then come out as in
+   * the recursive build_sub (pbvh.c:2372-2425) */
+  int cap = 128, top = 0;
+  BuildJob *stack = malloc(sizeof(BuildJob) * (size_t)cap);
+  stack[top++] = (BuildJob){0, 0, looptri_num, true};
+  while (top) {
+    const BuildJob job = stack[--top];
+    if (job.count <= pbvh->leaf_limit) {
+      PBVHNode *node = &pbvh->nodes[job.node];
+      node->flag |= PBVH_Leaf;
+      node->prim_indices = pbvh->prim_indices + job.offset;
+      node->totprim = (unsigned)job.count;
+      node_box_from_prims(pbvh, node, pb, job.offset, job.count);
+      leaf_collect_verts(pbvh, node, job.node, stamp, local);
+      continue;
+    }
+    const int child = pbvh->totnode;
+    ensure_nodes(pbvh, pbvh->totnode + 2);
+    PBVHNode *node = &pbvh->nodes[job.node];
+    node->children_offset = child;
+    node_box_from_prims(pbvh, node, pb, job.offset, job.count);
+    BB c;
+    if (job.root_cb) {
+      c = cb;
+    }
+    else {
+      bb_clear(&c);
+      for (int i = job.offset + job.count - 1; i >= job.offset; i--) {
+        const float *mid = pb[pbvh->prim_indices[i]].mid;
+        for (int k = 0; k < 3; k++) {
+          c.bmin[k] = minf(c.bmin[k], mid[k]);
+          c.bmax[k] = maxf(c.bmax[k], mid[k]);
+        }
+      }
+    }
+    /* widest centroid extent (pbvh.c:1995-2016), split at the midpoint (pbvh.c:2402-2410) */
+    const float dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
+    int axis;
+    if (dx > dy) axis = (dx > dz) ? 0 : 2;
+    else axis = (dy > dz) ? 1 : 2;
+    const int end = split_by_centroid(pbvh->prim_indices, job.offset, job.offset + job.count - 1, axis,
+                                      (c.bmax[axis] + c.bmin[axis]) * 0.5f, pb);
+    if (top + 2 > cap) {
+      cap *= 2;
+      stack = realloc(stack, sizeof(BuildJob) * (size_t)cap);
+    }
+    stack[top++] = (BuildJob){child + 1, end, job.offset + job.count - end, false};
+    stack[top++] = (BuildJob){child, job.offset, end - job.offset, false};
+  }
+  free(stack);
+  free(stamp);
+  free(local);
+  free(pb);
+  memset(pbvh->vert_bitmap, 0, sizeof(unsigned) * ((size_t)totvert / 32 + 1)); /* pbvh.c:2512-2513 */
+}
+
+void BKE_pbvh_free(PBVH *pbvh)
+{
+  if (!pbvh) return;
+  DUNE_pbvh_device_detach(pbvh);
+  for (int i = 0; i < pbvh->totnode; i++) {
+    PBVHNode *node = &pbvh->nodes[i];
+    if (node->flag & PBVH_Leaf) {
+      free((void *)node->vert_indices);
+      free((void *)node->face_vert_indices);
+    }
+  }
+  if (pbvh->deformed) free(pbvh->verts); /* pbvh.c:2597-2603 */
+  if (pbvh->owns_normals) free(pbvh->vert_normals);
+  free(pbvh->nodes);
+  free(pbvh->prim_indices);
+  free(pbvh->vert_bitmap);
+  free(pbvh->nb_offsets);
+  free(pbvh->nb_indices);
+  free(pbvh->boundary);
+  free(pbvh);
+}
+
+/* ------------------------------------------------------------------------- session tables */
+
+/* vertex -> poly map, count / prefix / fill (kernel/intern/mesh_mapping.c:182-229), then the
+ * neighbour list of the sculpt neighbour iterator: per incident poly the previous and next corner
+ * (kernel/intern/mesh.c:1566-1589), first occurrence kept.  An edge seen from one poly only makes
+ * both its verts boundary verts. */
+static void build_neighbor_tables(PBVH *pbvh)
+{
+  const int V = pbvh->totvert, P = pbvh->totpoly, Lp = pbvh->totloop;
+  int *pm_off = calloc((size_t)V + 1, sizeof(int));
+  int *pm_idx = malloc(sizeof(int) * (size_t)(Lp ? Lp : 1));
+  for (int p = 0; p < P; p++) {
+    for (int j = 0; j < pbvh->mpoly[p].totloop; j++) pm_off[pbvh->mloop[pbvh->mpoly[p].loopstart + j].v + 1]++;
+  }
+  for (int v = 0; v < V; v++) pm_off[v + 1] += pm_off[v];
+  int *fill = calloc((size_t)V + 1, sizeof(int));
+  for (int p = 0; p < P; p++) {
+    for (int j = 0; j < pbvh->mpoly[p].totloop; j++) {
+      const int v = (int)pbvh->mloop[pbvh->mpoly[p].loopstart + j].v;
+      pm_idx[pm_off[v] + fill[v]++] = p;
+    }
+  }
+  free(fill);
+
+  pbvh->nb_offsets = malloc(sizeof(int) * ((size_t)V + 1));
+  pbvh->nb_indices = malloc(sizeof(int) * (size_t)(2 * Lp + 1));
+  pbvh->boundary = calloc((size_t)V + 1, 1);
+  int *uses = malloc(sizeof(int) * (size_t)(2 * Lp + 1));
+  int n = 0;
+  for (int v = 0; v < V; v++) {
+    const int first = n;
+    pbvh->nb_offsets[v] = n;
+    for (int k = pm_off[v]; k < pm_off[v + 1]; k++) {
+      const MPoly *mp = &pbvh->mpoly[pm_idx[k]];
+      const MLoop *ml = &pbvh->mloop[mp->loopstart];
+      int corner = -1;
+      for (int j = 0; j < mp->totloop; j++) {
+        if ((int)ml[j].v == v) {
+          corner = j;
+          break;
+        }
+      }
+      if (corner < 0) continue;
+      const int adj[2] = {(int)ml[(corner + mp->totloop - 1) % mp->totloop].v, (int)ml[(corner + 1) % mp->totloop].v};
+      for (int j = 0; j < 2; j++) {
+        if (adj[j] == v) continue;
+        int at = -1;
+        for (int q = first; q < n; q++) {
+          if (pbvh->nb_indices[q] == adj[j]) {
+            at = q;
+            break;
+          }
+        }
+        if (at < 0) {
+          pbvh->nb_indices[n] = adj[j];
+          uses[n++] = 1;
+        }
+        else {
+          uses[at]++;
+        }
+      }
+    }
+    for (int q = first; q < n; q++) {
+      if (uses[q] < 2) {
+        pbvh->boundary[v] = 1;
+        pbvh->boundary[pbvh->nb_indices[q]] = 1;
+      }
+    }
+  }
+  pbvh->nb_offsets[V] = n;
+  free(uses);
+  free(pm_off);
+  free(pm_idx);
+}
+
+/* -------------------------------------------------------------------------- device hooks */
+
+static char g_attach_error[512];
+
+const char *DUNE_pbvh_device_error(const PBVH *pbvh)
+{
+  if (pbvh && pbvh->device) return dsc_last_error(pbvh->device);
+  return g_attach_error[0] ? g_attach_error : dsc_last_error(NULL);
+}
+
+int DUNE_pbvh_device_attach(PBVH *pbvh, int device)
+{
+  g_attach_error[0] = 0;
+  if (!pbvh || !pbvh->nodes) return DSC_ERR_INVALID;
+  if (pbvh->device) return DSC_OK;
+  if (pbvh->totpoly <= 0 || pbvh->totloop <= 0) {
+    snprintf(g_attach_error, sizeof(g_attach_error), "DUNE_pbvh_mesh_sizes_set() was not called");
+    return DSC_ERR_STATE;
+  }
+  DscContext *ctx = NULL;
+  int r = dsc_ctx_create(device, &ctx);
+  if (r != DSC_OK) {
+    snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(NULL));
+    return r;
+  }
+  if (!pbvh->nb_offsets) build_neighbor_tables(pbvh);
+
+  const int V = pbvh->totvert, T = pbvh->totprim, N = pbvh->totnode;
+  float *co = malloc(sizeof(float[3]) * (size_t)V);
+  for (int v = 0; v < V; v++) memcpy(co + 3 * (size_t)v, pbvh->verts[v].co, sizeof(float[3]));
+  int *poly_start = malloc(sizeof(int) * (size_t)pbvh->totpoly), *poly_len = malloc(sizeof(int) * (size_t)pbvh->totpoly);
+  for (int p = 0; p < pbvh->totpoly; p++) {
+    poly_start[p] = pbvh->mpoly[p].loopstart;
+    poly_len[p] = pbvh->mpoly[p].totloop;
+  }
+  int *loop_v = malloc(sizeof(int) * (size_t)pbvh->totloop);
+  for (int l = 0; l < pbvh->totloop; l++) loop_v[l] = (int)pbvh->mloop[l].v;
+  int *tri_vert = malloc(sizeof(int[3]) * (size_t)T), *tri_poly = malloc(sizeof(int) * (size_t)T);
+  for (int t = 0; t < T; t++) {
+    for (int j = 0; j < 3; j++) tri_vert[3 * (size_t)t + j] = (int)pbvh->mloop[pbvh->looptri[t].tri[j]].v;
+    tri_poly[t] = (int)pbvh->looptri[t].poly;
+  }
+  /* normals: use the host's if they are populated, else let the device compute them */
+  bool have_no = false;
+  for (int v = 0; v < V && !have_no; v++) {
+    have_no = pbvh->vert_normals[v][0] != 0.0f || pbvh->vert_normals[v][1] != 0.0f || pbvh->vert_normals[v][2] != 0.0f;
+  }
+  DscMeshDesc me = {0};
+  me.totvert = V;
+  me.co = co;
+  me.no = have_no ? (const float *)pbvh->vert_normals : NULL;
+  me.mask = pbvh->vmask;
+  me.totpoly = pbvh->totpoly;
+  me.totloop = pbvh->totloop;
+  me.poly_loopstart = poly_start;
+  me.poly_totloop = poly_len;
+  me.loop_vert = loop_v;
+  me.tottri = T;
+  me.tri_vert = tri_vert;
+  me.tri_poly = tri_poly;
+  me.nb_offsets = pbvh->nb_offsets;
+  me.nb_indices = pbvh->nb_indices;
+  me.boundary = pbvh->boundary;
+  r = dsc_mesh_upload(ctx, &me);
+
+  float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
+  int *child = malloc(sizeof(int) * (size_t)N), *flag = malloc(sizeof(int) * (size_t)N);
+  int *prim_off = malloc(sizeof(int) * (size_t)N), *totprim = malloc(sizeof(int) * (size_t)N);
+  int *uniq = malloc(sizeof(int) * (size_t)N), *face = malloc(sizeof(int) * (size_t)N), *vert_off = malloc(sizeof(int) * (size_t)N);
+  size_t totvi = 0;
+  for (int n = 0; n < N; n++) {
+    const PBVHNode *node = &pbvh->nodes[n];
+    memcpy(bb + 6 * (size_t)n, &node->vb, sizeof(float[6]));
+    memcpy(obb + 6 * (size_t)n, &node->orig_vb, sizeof(float[6]));
+    child[n] = node->children_offset;
+    flag[n] = (int)node->flag;
+    const bool leaf = (node->flag & PBVH_Leaf) != 0;
+    prim_off[n] = leaf ? (int)(node->prim_indices - pbvh->prim_indices) : 0;
+    totprim[n] = leaf ? (int)node->totprim : 0;
+    uniq[n] = leaf ? (int)node->uniq_verts : 0;
+    face[n] = leaf ? (int)node->face_verts : 0;
+    vert_off[n] = (int)totvi;
+    if (leaf) totvi += node->uniq_verts + node->face_verts;
+  }
+  int *vert_indices = malloc(sizeof(int) * (totvi ? totvi : 1));
+  for (int n = 0; n < N; n++) {
+    const PBVHNode *node = &pbvh->nodes[n];
+    if (node->flag & PBVH_Leaf) {
+      memcpy(vert_indices + vert_off[n], node->vert_indices, sizeof(int) * (node->uniq_verts + node->face_verts));
+    }
+  }
+  DscPbvhDesc pd = {0};
+  pd.totnode = N;
+  pd.node_bb = bb;
+  pd.node_orig_bb = obb;
+  pd.children_offset = child;
+  pd.flag = flag;
+  pd.prim_offset = prim_off;
+  pd.totprim = totprim;
+  pd.prim_indices = pbvh->prim_indices;
+  pd.uniq_verts = uniq;
+  pd.face_verts = face;
+  pd.vert_offset = vert_off;
+  pd.vert_indices = vert_indices;
+  if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
+
+  free(co); free(poly_start); free(poly_len); free(loop_v); free(tri_vert); free(tri_poly);
+  free(bb); free(obb); free(child); free(flag); free(prim_off); free(totprim); free(uniq); free(face);
+  free(vert_off); free(vert_indices);
+  if (r != DSC_OK) {
+    snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(ctx));
+    dsc_ctx_destroy(ctx);
+    return r;
+  }
+  pbvh->device = ctx;
+  pbvh->device_dirty = !have_no; /* device computed the normals */
+  return DSC_OK;
+}
+
+void DUNE_pbvh_device_detach(PBVH *pbvh)
+{
+  if (pbvh && pbvh->device) {
+    dsc_ctx_destroy(pbvh->device);
+    pbvh->device = NULL;
+  }
+}
+
+int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
+{
+  if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
+  if (!pbvh->device_dirty) return DSC_OK;
+  const int V = pbvh->totvert, N = pbvh->totnode;
+  float *co = malloc(sizeof(float[3]) * (size_t)V);
+  int r = dsc_download_co(pbvh->device, co);
+  if (r == DSC_OK) {
+    if (!pbvh->deformed) {
+      /* first write: take a private copy like BKE_pbvh_vert_coords_apply (pbvh.c:4714-4725) */
+      MVert *dup = malloc(sizeof(MVert) * (size_t)V);
+      memcpy(dup, pbvh->verts, sizeof(MVert) * (size_t)V);
+      pbvh->verts = dup;
+      pbvh->deformed = true;
+    }
+    for (int v = 0; v < V; v++) memcpy(pbvh->verts[v].co, co + 3 * (size_t)v, sizeof(float[3]));
+    r = dsc_download_no(pbvh->device, (float *)pbvh->vert_normals);
+  }
+  free(co);
+  if (r != DSC_OK) return r;
+  float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
+  int *flag = malloc(sizeof(int) * (size_t)N);
+  r = dsc_download_node_bb(pbvh->device, bb, obb);
+  if (r == DSC_OK) r = dsc_download_node_flags(pbvh->device, flag);
+  if (r == DSC_OK) {
+    for (int n = 0; n < N; n++) {
+      memcpy(&pbvh->nodes[n].vb, bb + 6 * (size_t)n, sizeof(float[6]));
+      memcpy(&pbvh->nodes[n].orig_vb, obb + 6 * (size_t)n, sizeof(float[6]));
+      pbvh->nodes[n].flag = (unsigned)flag[n];
+    }
+    pbvh->device_dirty = false;
+  }
+  free(bb); free(obb); free(flag);
+  return r;
+}
+
+/* ------------------------------------------------------------------------------ traversal */
+
+bool SCULPT_search_sphere_cb(PBVHNode *node, void *data_v)
+{
+  const SculptSearchSphereData *data = data_v;
+  if (data->ignore_fully_ineffective) {
+    if (BKE_pbvh_node_fully_hidden_get(node)) return false;
+    if (BKE_pbvh_node_fully_masked_get(node)) return false;
+  }
+  const BB *bb = data->original ? &node->orig_vb : &node->vb;
+  float t[3];
+  for (int i = 0; i < 3; i++) {
+    float nearest = data->center[i];
+    if (bb->bmin[i] > data->center[i]) nearest = bb->bmin[i];
+    else if (bb->bmax[i] < data->center[i]) nearest = bb->bmax[i];
+    t[i] = data->center[i] - nearest;
+  }
+  return (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) < data->radius_squared;
+}
+
+void BKE_pbvh_search_gather(PBVH *pbvh, BKE_pbvh_SearchCallback scb, void *search_data, PBVHNode ***r_array, int *r_tot)
+{
+  *r_array = NULL;
+  *r_tot = 0;
+  if (!pbvh->nodes) return;
+  if (pbvh->device && scb == SCULPT_search_sphere_cb) {
+    /* device path: flat leaf test + ordered compaction, then node indices -> pointers */
+    const SculptSearchSphereData *d = search_data;
+    int *idx = malloc(sizeof(int) * (size_t)pbvh->totnode);
+    int tot = 0;
+    if (dsc_search_sphere(pbvh->device, d->center, d->radius_squared, d->original, d->ignore_fully_ineffective, idx,
+                          pbvh->totnode, &tot) == DSC_OK &&
+        tot > 0) {
+      PBVHNode **array = MEM_mallocN(sizeof(PBVHNode *) * (size_t)tot, __func__);
+      for (int i = 0; i < tot; i++) array[i] = &pbvh->nodes[idx[i]];
+      *r_array = array;
+      *r_tot = tot;
+    }
+    free(idx);
+    return;
+  }
+  /* host path for arbitrary callbacks: stack DFS, children left first (pbvh.c:2664-2705) */
+  if (pbvh->device) DUNE_pbvh_device_sync_to_host(pbvh);
+  int cap = 64, top = 0, tot = 0, space = 0;
+  int *stack = malloc(sizeof(int) * (size_t)cap);
+  PBVHNode **array = NULL;
+  stack[top++] = 0;
+  while (top) {
+    PBVHNode *node = &pbvh->nodes[stack[--top]];
+    if (scb && !scb(node, search_data)) continue;
+    if (node->flag & PBVH_Leaf) {
+      if (tot == space) {
+        space = tot ? space * 2 : 32;
+        PBVHNode **na = MEM_callocN(sizeof(PBVHNode *) * (size_t)space, __func__);
+        if (array) {
+          memcpy(na, array, sizeof(PBVHNode *) * (size_t)tot);
+          MEM_freeN(array);
+        }
+        array = na;
+      }
+      array[tot++] = node;
+      continue;
+    }
+    if (top + 2 > cap) {
+      cap *= 2;
+      stack = realloc(stack, sizeof(int) * (size_t)cap);
+    }
+    stack[top++] = node->children_offset + 1;
+    stack[top++] = node->children_offset;
+  }
+  free(stack);
+  *r_array = array;
+  *r_tot = tot;
+}
+
+/* ---------------------------------------------------------------------------- node access */
+
+void BKE_pbvh_node_mark_update(PBVHNode *node)
+{
+  node->flag |= PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw;
+}
+void BKE_pbvh_vert_mark_update(PBVH *pbvh, int index) { pbvh->vert_bitmap[index >> 5] |= 1u << (index & 31); }
+void BKE_pbvh_node_fully_hidden_set(PBVHNode *node, int fully_hidden)
+{
+  if (fully_hidden) node->flag |= PBVH_FullyHidden;
+  else node->flag &= ~(unsigned)PBVH_FullyHidden;
+}
+bool BKE_pbvh_node_fully_hidden_get(PBVHNode *node) { return (node->flag & PBVH_Leaf) && (node->flag & PBVH_FullyHidden); }
+void BKE_pbvh_node_fully_masked_set(PBVHNode *node, int fully_masked)
+{
+  if (fully_masked) node->flag |= PBVH_FullyMasked;
+  else node->flag &= ~(unsigned)PBVH_FullyMasked;
+}
+bool BKE_pbvh_node_fully_masked_get(PBVHNode *node) { return (node->flag & PBVH_Leaf) && (node->flag & PBVH_FullyMasked); }
+void BKE_pbvh_node_get_verts(PBVH *pbvh, PBVHNode *node, const int **r_vert_indices, MVert **r_verts)
+{
+  if (r_vert_indices) *r_vert_indices = node->vert_indices;
+  if (r_verts) *r_verts = pbvh->verts;
+}
+void BKE_pbvh_node_num_verts(PBVH *pbvh, PBVHNode *node, int *r_uniquevert, int *r_totvert)
+{
+  (void)pbvh;
+  if (r_totvert) *r_totvert = (int)(node->uniq_verts + node->face_verts);
+  if (r_uniquevert) *r_uniquevert = (int)node->uniq_verts;
+}
+void BKE_pbvh_node_get_BB(PBVHNode *node, float bb_min[3], float bb_max[3])
+{
+  memcpy(bb_min, node->vb.bmin, sizeof(float[3]));
+  memcpy(bb_max, node->vb.bmax, sizeof(float[3]));
+}
+void BKE_pbvh_node_get_original_BB(PBVHNode *node, float bb_min[3], float bb_max[3])
+{
+  memcpy(bb_min, node->orig_vb.bmin, sizeof(float[3]));
+  memcpy(bb_max, node->orig_vb.bmax, sizeof(float[3]));
+}
+
+/* -------------------------------------------------------------------------------- updates */
+
+/* Host-side marks made since the last device call are pushed down first, then the device runs the
+ * stage, then the host copies are refreshed lazily (device_dirty). */
+static void push_host_marks(PBVH *pbvh)
+{
+  for (int n = 0; n < pbvh->totnode; n++) {
+    PBVHNode *node = &pbvh->nodes[n];
+    if ((node->flag & PBVH_Leaf) && (node->flag & (PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB))) {
+      dsc_node_flag_set(pbvh->device, n, (int)(node->flag & (PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB)), 1);
+    }
+  }
+}
+
+void BKE_pbvh_update_normals(PBVH *pbvh, struct SubdivCCG *subdiv_ccg)
+{
+  (void)subdiv_ccg;
+  if (!pbvh->device) return; /* no CPU fallback: without a device the PBVH is a plain container */
+  if (!pbvh->device_dirty) push_host_marks(pbvh);
+  dsc_update_normals(pbvh->device);
+  pbvh->device_dirty = true;
+}
+
+void BKE_pbvh_update_bounds(PBVH *pbvh, int flag)
+{
+  if (!pbvh->nodes || !pbvh->device) return;
+  if (!pbvh->device_dirty) push_host_marks(pbvh);
+  dsc_update_bounds(pbvh->device, flag);
+  pbvh->device_dirty = true;
+}
+
+/* ----------------------------------------------------------------------------------- sync */
+
+float (*BKE_pbvh_vert_coords_alloc(PBVH *pbvh))[3]
+{
+  if (!pbvh->verts) return NULL;
+  float(*vertCos)[3] = MEM_callocN(3 * (size_t)pbvh->totvert * sizeof(float), "BKE_pbvh_get_vertCoords");
+  if (pbvh->device && pbvh->device_dirty) {
+    dsc_download_co(pbvh->device, (float *)vertCos);
+  }
+  else {
+    for (int a = 0; a < pbvh->totvert; a++) memcpy(vertCos[a], pbvh->verts[a].co, sizeof(float[3]));
+  }
+  return vertCos;
+}
+
+void BKE_pbvh_vert_coords_apply(PBVH *pbvh, const float (*vertCos)[3], const int totvert)
+{
+  if (totvert != pbvh->totvert || !pbvh->verts) return;
+  if (!pbvh->deformed) {
+    MVert *dup = malloc(sizeof(MVert) * (size_t)totvert);
+    memcpy(dup, pbvh->verts, sizeof(MVert) * (size_t)totvert);
+    pbvh->verts = dup;
+    pbvh->deformed = true;
+  }
+  for (int a = 0; a < totvert; a++) memcpy(pbvh->verts[a].co, vertCos[a], sizeof(float[3]));
+  if (pbvh->device) {
+    dsc_upload_co(pbvh->device, (const float *)vertCos);
+    pbvh->device_dirty = true;
+  }
+}
+
+MVert *BKE_pbvh_get_verts(const PBVH *pbvh)
+{
+  if (pbvh->device && pbvh->device_dirty) DUNE_pbvh_device_sync_to_host((PBVH *)pbvh);
+  return pbvh->verts;
+}
+const float (*BKE_pbvh_get_vert_normals(const PBVH *pbvh))[3]
+{
+  if (pbvh->device && pbvh->device_dirty) DUNE_pbvh_device_sync_to_host((PBVH *)pbvh);
+  return (const float(*)[3])pbvh->vert_normals;
+}
+
+/* ----------------------------------------------------------------------------- stroke side */
+
+float DUNE_sculpt_brush_strength(int sculpt_tool, float root_alpha, float pressure, bool dir_in, bool invert, float overlap,
+                                 float feather)
+{
+  /* alpha is squared; direction from BRUSH_DIR_IN and the invert modifier */
+  const float alpha = root_alpha * root_alpha;
+  const float flip = (dir_in ? -1.0f : 1.0f) * (invert ? -1.0f : 1.0f);
+  switch (sculpt_tool) {
+    case DSC_TOOL_DRAW:
+      return alpha * flip * pressure * overlap * feather;
+    case DSC_TOOL_CLAY_STRIPS:
+      return alpha * flip * powf(pressure, 1.5f) * overlap * feather * 0.3f;
+    case DSC_TOOL_INFLATE:
+      return ((flip > 0.0f) ? 0.250f : 0.125f) * alpha * flip * pressure * overlap * feather;
+    case DSC_TOOL_SMOOTH:
+      return flip * alpha * pressure * feather;
+    case DSC_TOOL_GRAB:
+      return root_alpha * feather;
+  }
+  return 0.0f;
+}
+
+void DUNE_sculpt_dab_defaults(DscDab *dab, int sculpt_tool)
+{
+  memset(dab, 0, sizeof(*dab));
+  dab->tool = sculpt_tool;
+  dab->curve_preset = DSC_CURVE_SMOOTH;
+  dab->sculpt_plane = DSC_DIR_AREA;         /* types_brush_defaults.h:28 */
+  dab->normal_radius_factor = 0.5f;         /* :23 */
+  dab->plane_offset = 0.0f;                 /* :34 */
+  dab->plane_trim = 0.5f;                   /* :35 */
+  dab->hardness = 0.0f;                     /* :83 */
+  dab->tip_roundness = 0.0f;
+  dab->scale[0] = dab->scale[1] = dab->scale[2] = 1.0f;
+  dab->view_normal[2] = 1.0f;
+  dab->radius = 1.0f;
+  dab->radius_scale = 1.0f;
+  dab->bstrength = DUNE_sculpt_brush_strength(sculpt_tool, 1.0f /* :20 */, 1.0f, false, false, 1.0f, 1.0f);
+}
+
+int DUNE_sculpt_stroke_begin(PBVH *pbvh, const float *automask)
+{
+  if (!pbvh->device) return DSC_ERR_STATE;
+  int r = dsc_stroke_begin(pbvh->device, automask);
+  if (r == DSC_OK) pbvh->in_stroke = true;
+  return r;
+}
+int DUNE_sculpt_dab(PBVH *pbvh, const DscDab *dab)
+{
+  if (!pbvh->device) return DSC_ERR_STATE;
+  pbvh->device_dirty = true;
+  return dsc_dab(pbvh->device, dab);
+}
+int DUNE_sculpt_stroke_end(PBVH *pbvh)
+{
+  if (!pbvh->device) return DSC_ERR_STATE;
+  int r = dsc_stroke_end(pbvh->device);
+  pbvh->in_stroke = false;
+  if (r != DSC_OK) return r;
+  return DUNE_pbvh_device_sync_to_host(pbvh);
+}
+
+void DUNE_sculpt_automask_boundary_edges(const PBVH *pbvh, int propagation_steps, float *r_factor)
+{
+  const int V = pbvh->totvert;
+  if (!pbvh->nb_offsets) build_neighbor_tables((PBVH *)pbvh);
+  int *dist = malloc(sizeof(int) * (size_t)(V ? V : 1));
+  for (int i = 0; i < V; i++) {
+    dist[i] = pbvh->boundary[i] ? 0 : -1;
+    r_factor[i] = 1.0f;
+  }
+  for (int it = 0; it < propagation_steps; it++) {
+    for (int i = 0; i < V; i++) {
+      if (dist[i] != -1) continue;
+      for (int q = pbvh->nb_offsets[i]; q < pbvh->nb_offsets[i + 1]; q++) {
+        if (dist[pbvh->nb_indices[q]] == it) dist[i] = it + 1;
+      }
+    }
+  }
+  for (int i = 0; i < V; i++) {
+    if (dist[i] == -1) continue;
+    const float p = 1.0f - ((float)dist[i] / (float)propagation_steps);
+    r_factor[i] *= (1.0f - p * p);
+  }
+  free(dist);
+}
+
+void DUNE_sculpt_automask_topology(const PBVH *pbvh, int seed_vert, const float location[3], float radius, float *r_factor)
+{
+  const int V = pbvh->totvert;
+  if (!pbvh->nb_offsets) build_neighbor_tables((PBVH *)pbvh);
+  for (int i = 0; i < V; i++) r_factor[i] = 0.0f;
+  if (seed_vert < 0 || seed_vert >= V) return;
+  int *queue = malloc(sizeof(int) * (size_t)V);
+  unsigned char *seen = calloc((size_t)V, 1);
+  int head = 0, tail = 0;
+  queue[tail++] = seed_vert;
+  seen[seed_vert] = 1;
+  r_factor[seed_vert] = 1.0f;
+  const float rsq = radius * radius;
+  while (head < tail) {
+    const int v = queue[head++];
+    for (int q = pbvh->nb_offsets[v]; q < pbvh->nb_offsets[v + 1]; q++) {
+      const int u = pbvh->nb_indices[q];
+      if (seen[u]) continue;
+      seen[u] = 1;
+      r_factor[u] = 1.0f;
+      bool go_on = true;
+      if (radius > 0.0f) {
+        const float *co = pbvh->verts[u].co;
+        const float dx = co[0] - location[0], dy = co[1] - location[1], dz = co[2] - location[2];
+        go_on = (dx * dx + dy * dy + dz * dz) <= rsq;
+      }
+      if (go_on) queue[tail++] = u;
+    }
+  }
+  free(queue);
+  free(seen);
+}

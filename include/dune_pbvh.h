@@ -1,0 +1,211 @@
+/* Host side (C) of the B200 sculpt-stroke path: the reference's own PBVH entry points, kept by name
+ * and argument meaning, backed by the device-resident mesh of libdune_sculpt_cuda.
+ *
+ * In the reference these functions live in source/dune/kernel/intern/pbvh.c (second copy, lines
+ * 1913-4986) and their declarations in the absent BKE_pbvh.h; a maintainer keeps their pbvh.c and
+ * adds the DUNE_pbvh_device_* hooks shown in INTEGRATION.md.  This stand-alone build of the same
+ * interface is what the parity tests and bench.py drive.  Citations are relative to
+ * /root/reference/source/dune/ .
+ *
+ * Ownership follows the reference: arrays handed back through out-params are MEM_mallocN'd here
+ * and freed by the caller with MEM_freeN (pbvh.c:2750, paint_hide.c:371-373); a gather that finds
+ * nothing returns NULL, 0 (pbvh.c:2760-2766).  Outside the reference tree MEM_* map to malloc/free.
+ */
+#ifndef DUNE_PBVH_H
+#define DUNE_PBVH_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include "dune_sculpt_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef MEM_mallocN
+#  define DUNE_PBVH_OWN_MEM 1
+void *MEM_mallocN(size_t len, const char *str);
+void *MEM_callocN(size_t len, const char *str);
+void MEM_freeN(void *vmemh);
+#  define MEM_SAFE_FREE(v) \
+    do { \
+      if (v) { \
+        MEM_freeN((void *)(v)); \
+        (v) = NULL; \
+      } \
+    } while (0)
+#endif
+
+/* types/types_meshdata.h:13-17, 50-57, 69-74, 178-181 */
+typedef struct MVert {
+  float co[3];
+  char flag, bweight;
+  char _pad[2];
+} MVert;
+typedef struct MPoly {
+  int loopstart;
+  int totloop;
+  short mat_nr;
+  char flag, _pad;
+} MPoly;
+typedef struct MLoop {
+  unsigned int v;
+  unsigned int e;
+} MLoop;
+typedef struct MLoopTri {
+  unsigned int tri[3];
+  unsigned int poly;
+} MLoopTri;
+
+struct Mesh;       /* opaque here */
+struct CustomData; /* opaque here */
+struct SubdivCCG;
+
+/* kernel/intern/pbvh_intern.h:4-7 */
+typedef struct BB {
+  float bmin[3], bmax[3];
+} BB;
+
+/* PBVHNodeFlags: values of the absent public header (names used at pbvh.c:3643-3726) */
+typedef enum {
+  PBVH_Leaf = 1 << 0,
+  PBVH_UpdateNormals = 1 << 1,
+  PBVH_UpdateBB = 1 << 2,
+  PBVH_UpdateOriginalBB = 1 << 3,
+  PBVH_UpdateDrawBuffers = 1 << 4,
+  PBVH_UpdateRedraw = 1 << 5,
+  PBVH_UpdateMask = 1 << 6,
+  PBVH_UpdateVisibility = 1 << 8,
+  PBVH_RebuildDrawBuffers = 1 << 9,
+  PBVH_FullyHidden = 1 << 10,
+  PBVH_FullyMasked = 1 << 11,
+  PBVH_FullyUnmasked = 1 << 12,
+  PBVH_UpdateColor = 1 << 14,
+} PBVHNodeFlags;
+
+/* kernel/intern/pbvh_intern.h:15-90, the fields on this path */
+typedef struct PBVHNode {
+  BB vb;
+  BB orig_vb;
+  int children_offset;
+  int *prim_indices;
+  unsigned int totprim;
+  const int *vert_indices;
+  unsigned int uniq_verts, face_verts;
+  const int (*face_vert_indices)[3];
+  unsigned int flag;
+} PBVHNode;
+
+/* kernel/intern/pbvh_intern.h:98-162, the fields on this path */
+typedef struct PBVH {
+  PBVHNode *nodes;
+  int node_mem_count, totnode;
+  int *prim_indices;
+  int totprim;
+  int totvert;
+  int leaf_limit;
+  float (*vert_normals)[3];
+  MVert *verts;
+  const MPoly *mpoly;
+  const MLoop *mloop;
+  const MLoopTri *looptri;
+  int totpoly, totloop;
+  float *vmask; /* CD_PAINT_MASK layer (pbvh.c:4894) or NULL */
+  unsigned int *vert_bitmap;
+  bool deformed;
+  bool owns_normals;
+
+  /* device side */
+  DscContext *device;
+  bool device_dirty; /* the device holds newer positions / normals / boxes than the host arrays */
+  bool in_stroke;
+  /* session tables (kernel/intern/paint.c:1685-1688 pmap, boundary info) */
+  int *nb_offsets, *nb_indices;
+  unsigned char *boundary;
+} PBVH;
+
+typedef bool (*BKE_pbvh_SearchCallback)(PBVHNode *node, void *data);
+
+/* ---- mesh helpers ---- */
+/* kernel/intern/mesh_tessellate.c:665 BKE_mesh_recalc_looptri (tri / quad rule :420-447) */
+int BKE_mesh_poly_to_tri_count(int totpoly, int totloop);
+void BKE_mesh_recalc_looptri(const MLoop *mloop, const MPoly *mpoly, const MVert *mvert, int totloop, int totpoly,
+                             MLoopTri *mlooptri);
+
+/* ---- build / free: pbvh.c:2563-2620, 2452-2514 ---- */
+PBVH *BKE_pbvh_new(void);
+void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, const MLoop *mloop, MVert *verts,
+                         int totvert, struct CustomData *vdata, struct CustomData *ldata, struct CustomData *pdata,
+                         const MLoopTri *looptri, int looptri_num);
+void BKE_pbvh_free(PBVH *pbvh);
+/* not in the reference: sizes and layers the reference pulls out of Mesh / CustomData */
+void DUNE_pbvh_mesh_sizes_set(PBVH *pbvh, int totpoly, int totloop);
+void DUNE_pbvh_mask_layer_set(PBVH *pbvh, float *vmask);
+void DUNE_pbvh_vert_normals_set(PBVH *pbvh, float (*vert_normals)[3]);
+void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit);
+
+/* ---- device hooks (new) ---- */
+int DUNE_pbvh_device_attach(PBVH *pbvh, int device);
+void DUNE_pbvh_device_detach(PBVH *pbvh);
+/* bring host arrays (verts, normals, node boxes, flags) up to date with the device */
+int DUNE_pbvh_device_sync_to_host(PBVH *pbvh);
+const char *DUNE_pbvh_device_error(const PBVH *pbvh);
+
+/* ---- traversal: pbvh.c:2736-2767 ---- */
+void BKE_pbvh_search_gather(PBVH *pbvh, BKE_pbvh_SearchCallback scb, void *search_data, PBVHNode ***r_array,
+                            int *r_tot);
+
+/* The sphere search callback of the stroke operator (absent from the reference).
+ * When passed to BKE_pbvh_search_gather on a device-attached PBVH the test runs on the device. */
+typedef struct SculptSearchSphereData {
+  const float *center;
+  float radius_squared;
+  bool original;
+  bool ignore_fully_ineffective;
+} SculptSearchSphereData;
+bool SCULPT_search_sphere_cb(PBVHNode *node, void *data_v);
+
+/* ---- node / vertex access: pbvh.c:3641-3840 ---- */
+void BKE_pbvh_node_mark_update(PBVHNode *node);
+void BKE_pbvh_vert_mark_update(PBVH *pbvh, int index);
+void BKE_pbvh_node_fully_hidden_set(PBVHNode *node, int fully_hidden);
+bool BKE_pbvh_node_fully_hidden_get(PBVHNode *node);
+void BKE_pbvh_node_fully_masked_set(PBVHNode *node, int fully_masked);
+bool BKE_pbvh_node_fully_masked_get(PBVHNode *node);
+void BKE_pbvh_node_get_verts(PBVH *pbvh, PBVHNode *node, const int **r_vert_indices, MVert **r_verts);
+void BKE_pbvh_node_num_verts(PBVH *pbvh, PBVHNode *node, int *r_uniquevert, int *r_totvert);
+void BKE_pbvh_node_get_BB(PBVHNode *node, float bb_min[3], float bb_max[3]);
+void BKE_pbvh_node_get_original_BB(PBVHNode *node, float bb_min[3], float bb_max[3]);
+
+/* ---- updates: pbvh.c:4559-4587, 3319-3339 ---- */
+void BKE_pbvh_update_normals(PBVH *pbvh, struct SubdivCCG *subdiv_ccg);
+void BKE_pbvh_update_bounds(PBVH *pbvh, int flag);
+
+/* ---- sync: pbvh.c:4689-4749, 4961-4971 ---- */
+float (*BKE_pbvh_vert_coords_alloc(PBVH *pbvh))[3];
+void BKE_pbvh_vert_coords_apply(PBVH *pbvh, const float (*vertCos)[3], int totvert);
+MVert *BKE_pbvh_get_verts(const PBVH *pbvh);
+const float (*BKE_pbvh_get_vert_normals(const PBVH *pbvh))[3];
+
+/* ---- stroke driver (the missing sculpt.c side) ---- */
+/* brush_strength(): SURVEY.md row a14.  alpha is Brush.alpha (types/types_brush.h:194), dir_in is
+ * BRUSH_DIR_IN (types_brush_enums.h:347), invert the Ctrl modifier */
+float DUNE_sculpt_brush_strength(int sculpt_tool, float alpha, float pressure, bool dir_in, bool invert,
+                                 float overlap, float feather);
+/* Brush defaults (types/types_brush_defaults.h:9-91) into a dab descriptor */
+void DUNE_sculpt_dab_defaults(DscDab *dab, int sculpt_tool);
+int DUNE_sculpt_stroke_begin(PBVH *pbvh, const float *automask);
+int DUNE_sculpt_dab(PBVH *pbvh, const DscDab *dab);
+int DUNE_sculpt_stroke_end(PBVH *pbvh);
+
+/* automasking factors computed at stroke start:
+ * boundary-edge propagation (automasking_boundary_edges_propagation_steps, types_brush.h:288) and
+ * topology flood fill from a seed vertex inside `radius` of `location` */
+void DUNE_sculpt_automask_boundary_edges(const PBVH *pbvh, int propagation_steps, float *r_factor);
+void DUNE_sculpt_automask_topology(const PBVH *pbvh, int seed_vert, const float location[3], float radius,
+                                   float *r_factor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,207 @@
+/* libdune_sculpt_cuda -- C ABI of the B200 sculpt-stroke path.
+ *
+ * Plain C, POD only, caller-allocated outputs.  These are the entry points the reference's host C
+ * code (kernel/intern/pbvh.c, kernel/intern/paint.c and the stroke operator) binds to; each one
+ * names the reference interface it sits behind.  Citations are relative to
+ * /root/reference/source/dune/ ; "pbvh.c" = kernel/intern/pbvh.c second copy (lines 1913-4986).
+ * See INTEGRATION.md for the call sites a maintainer adds.
+ *
+ * Threading: one DscContext per PBVH, driven from one host thread (the reference calls the PBVH
+ * API from the main thread only, pbvh.c:4953-4959).  All device work is queued on the context's
+ * stream; dsc_dab() returns without waiting.  Functions that hand data back synchronise.
+ *
+ * Errors: every function returns DSC_OK (0) or a negative DscStatus; dsc_last_error() gives text.
+ * There is no CPU fallback: without a usable device dsc_ctx_create() fails.
+ */
+#ifndef DUNE_SCULPT_CUDA_H
+#define DUNE_SCULPT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct DscContext DscContext;
+
+typedef enum DscStatus {
+  DSC_OK = 0,
+  DSC_ERR_NO_DEVICE = -1,
+  DSC_ERR_CUDA = -2,
+  DSC_ERR_INVALID = -3,
+  DSC_ERR_STATE = -4,
+  DSC_ERR_UNSUPPORTED = -5,
+  DSC_ERR_NCCL = -6,
+} DscStatus;
+
+/* PBVHNodeFlags (names at pbvh.c:3643-3726; values of the absent public header) */
+enum {
+  DSC_PBVH_Leaf = 1 << 0,
+  DSC_PBVH_UpdateNormals = 1 << 1,
+  DSC_PBVH_UpdateBB = 1 << 2,
+  DSC_PBVH_UpdateOriginalBB = 1 << 3,
+  DSC_PBVH_UpdateDrawBuffers = 1 << 4,
+  DSC_PBVH_UpdateRedraw = 1 << 5,
+  DSC_PBVH_UpdateMask = 1 << 6,
+  DSC_PBVH_UpdateVisibility = 1 << 8,
+  DSC_PBVH_RebuildDrawBuffers = 1 << 9,
+  DSC_PBVH_FullyHidden = 1 << 10,
+  DSC_PBVH_FullyMasked = 1 << 11,
+  DSC_PBVH_FullyUnmasked = 1 << 12,
+  DSC_PBVH_UpdateColor = 1 << 14,
+};
+
+/* Brush.sculpt_tool, types/types_brush_enums.h:410-443 */
+enum { DSC_TOOL_DRAW = 1, DSC_TOOL_SMOOTH = 2, DSC_TOOL_INFLATE = 4, DSC_TOOL_GRAB = 5, DSC_TOOL_CLAY_STRIPS = 18 };
+/* Brush.curve_preset, types/types_brush_enums.h:176-187 */
+enum {
+  DSC_CURVE_CUSTOM = 0, DSC_CURVE_SMOOTH = 1, DSC_CURVE_SPHERE = 2, DSC_CURVE_ROOT = 3, DSC_CURVE_SHARP = 4,
+  DSC_CURVE_LIN = 5, DSC_CURVE_POW4 = 6, DSC_CURVE_INVSQUARE = 7, DSC_CURVE_CONSTANT = 8, DSC_CURVE_SMOOTHER = 9,
+};
+/* Brush.sculpt_plane, types/types_brush_enums.h:580-586 */
+enum { DSC_DIR_AREA = 0, DSC_DIR_VIEW = 1, DSC_DIR_X = 2, DSC_DIR_Y = 3, DSC_DIR_Z = 4 };
+
+enum {
+  DSC_DAB_FRONTFACE = 1 << 0,  /* BRUSH_FRONTFACE, types_brush_enums.h:365 */
+  DSC_DAB_PLANE_TRIM = 1 << 1, /* BRUSH_PLANE_TRIM, types_brush_enums.h:364 */
+  DSC_DAB_FIRST_STEP = 1 << 2, /* first dab of the stroke */
+  DSC_DAB_NO_NORMALS = 1 << 3, /* do not run the BKE_pbvh_update_normals stage for this dab */
+  DSC_DAB_NO_BOUNDS = 1 << 4,  /* do not run the BKE_pbvh_update_bounds stage for this dab */
+};
+
+/* Mesh arrays, original vertex order.  Replaces the borrowed pointers BKE_pbvh_build_mesh stores
+ * (pbvh.c:2467-2480: mpoly, mloop, verts, vert_normals, looptri, CD_PAINT_MASK pbvh.c:4894) and
+ * the session tables of sculpt_update_object (kernel/intern/paint.c:1685-1688, pmap). */
+typedef struct DscMeshDesc {
+  int totvert;
+  const float *co;   /* [totvert][3], MVert.co (types/types_meshdata.h:13-17) */
+  const float *no;   /* [totvert][3] vert_normals, or NULL: computed on the device */
+  const float *mask; /* [totvert] CD_PAINT_MASK, or NULL */
+  int totpoly, totloop;
+  const int *poly_loopstart; /* MPoly.loopstart */
+  const int *poly_totloop;   /* MPoly.totloop */
+  const int *loop_vert;      /* MLoop.v */
+  int tottri;
+  const int *tri_vert; /* [tottri][3] mloop[MLoopTri.tri[j]].v (pbvh.c:2951-2956) */
+  const int *tri_poly; /* [tottri] MLoopTri.poly */
+  /* vertex -> edge-neighbour CSR in the order the neighbour iterator lists them (smooth brush);
+   * NULL if the smooth brush is not used */
+  const int *nb_offsets; /* [totvert + 1] */
+  const int *nb_indices;
+  const unsigned char *boundary; /* [totvert] boundary-vertex flags, or NULL */
+} DscMeshDesc;
+
+/* The built PBVH, flattened.  Replaces PBVH.nodes / PBVHNode (kernel/intern/pbvh_intern.h:15-162). */
+typedef struct DscPbvhDesc {
+  int totnode;
+  const float *node_bb;      /* [totnode][6] PBVHNode.vb (bmin, bmax) */
+  const float *node_orig_bb; /* [totnode][6] PBVHNode.orig_vb */
+  const int *children_offset; /* [totnode], inner nodes */
+  const int *flag;            /* [totnode] PBVHNodeFlags */
+  const int *prim_offset;     /* [totnode] leaf: PBVHNode.prim_indices - PBVH.prim_indices */
+  const int *totprim;         /* [totnode] */
+  const int *prim_indices;    /* [tottri] PBVH.prim_indices */
+  const int *uniq_verts;      /* [totnode] */
+  const int *face_verts;      /* [totnode] */
+  const int *vert_offset;     /* [totnode] leaf: start of its vert_indices in the array below */
+  const int *vert_indices;    /* concatenated PBVHNode.vert_indices, unique verts first */
+} DscPbvhDesc;
+
+/* One dab.  Host fills it from Brush / StrokeCache; bstrength is the brush_strength() scalar. */
+typedef struct DscDab {
+  int tool;
+  int curve_preset;
+  int flags;
+  int sculpt_plane;
+  float location[3];
+  float radius;
+  float view_normal[3];
+  float bstrength;
+  float scale[3];
+  float hardness;
+  float normal_radius_factor;
+  float plane_offset;
+  float plane_trim;
+  float tip_roundness;
+  float grab_delta[3];
+  float radius_scale;
+} DscDab;
+
+/* Counters of the running stroke (device-side, read back on demand). */
+typedef struct DscStrokeStats {
+  int64_t vertex_dabs;  /* sum over dabs of uniq_verts of the gathered leaves */
+  int64_t node_hits;    /* sum over dabs of the number of gathered leaves */
+  int64_t moved_verts;  /* sum over dabs of vertices the brush displaced */
+  int64_t dabs;
+  int64_t kernel_launches; /* kernels launched by this context since stroke begin */
+} DscStrokeStats;
+
+/* --- context ---------------------------------------------------------------------------- */
+int dsc_ctx_create(int device, DscContext **r_ctx);
+void dsc_ctx_destroy(DscContext *ctx);
+const char *dsc_last_error(const DscContext *ctx); /* ctx may be NULL: last create error */
+int dsc_abi_version(void);
+
+/* --- session start: behind BKE_pbvh_build_mesh (pbvh.c:2452-2514) ------------------------- */
+int dsc_mesh_upload(DscContext *ctx, const DscMeshDesc *mesh);
+int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pbvh);
+/* vertex normals of the whole mesh from the current positions (all vertices dirty, all leaves
+ * flagged): what BKE_pbvh_vert_coords_apply triggers (pbvh.c:4739-4747) */
+int dsc_recalc_normals(DscContext *ctx);
+int dsc_set_custom_curve(DscContext *ctx, const float *table257); /* colortools.c:942-965 LUT */
+int dsc_set_mask(DscContext *ctx, const float *mask /* [totvert] or NULL */);
+/* PBVHNode.flag bits a host pass owns (FullyHidden / FullyMasked, pbvh.c:3678-3710) */
+int dsc_node_flag_set(DscContext *ctx, int node, int flag, int on);
+
+/* --- stroke: behind the stroke operator's per-dab sequence --------------- */
+int dsc_stroke_begin(DscContext *ctx, const float *automask /* [totvert] or NULL */);
+/* gather -> undo snapshot + mark -> brush -> normals -> bounds, queued on the stream */
+int dsc_dab(DscContext *ctx, const DscDab *dab);
+/* BKE_pbvh_search_gather result of the last dab (pbvh.c:2736-2767): node indices in traversal
+ * order.  r_nodes may be NULL to get the count only.  Synchronises. */
+int dsc_gather_readback(DscContext *ctx, int *r_nodes, int capacity, int *r_tot);
+/* stand-alone BKE_pbvh_search_gather with the sphere callback (no marking) */
+int dsc_search_sphere(DscContext *ctx, const float center[3], float radius_sq, int original,
+                      int ignore_fully_ineffective, int *r_nodes, int capacity, int *r_tot);
+/* area normal / centre the last dab used (zero normal if the tool did not need one) */
+int dsc_last_area(DscContext *ctx, float r_no[3], float r_co[3]);
+/* vertices the last dab marked (BKE_pbvh_vert_mark_update, pbvh.c:3729), ascending vertex index;
+ * only recorded while dsc_debug_capture(ctx, 1) is on */
+int dsc_debug_capture(DscContext *ctx, int on);
+int dsc_last_moved(DscContext *ctx, int *r_verts, int capacity, int *r_tot);
+int dsc_stroke_stats(DscContext *ctx, DscStrokeStats *r_stats);
+/* flushes PBVH_UpdateOriginalBB (pbvh.c:3298-3314) and closes the stroke */
+int dsc_stroke_end(DscContext *ctx);
+
+/* --- the PBVH update entry points on their own ------------------------------------------- */
+int dsc_update_normals(DscContext *ctx);         /* BKE_pbvh_update_normals, pbvh.c:4559 */
+int dsc_update_bounds(DscContext *ctx, int flag); /* BKE_pbvh_update_bounds, pbvh.c:3319 */
+int dsc_node_mark_update(DscContext *ctx, int node); /* BKE_pbvh_node_mark_update, pbvh.c:3641 */
+
+/* --- sync: behind BKE_pbvh_vert_coords_alloc/apply, get_verts, get_vert_normals
+ *     (pbvh.c:4689-4749, 4961-4971) and the undo push (paint_hide.c:78) --------------------- */
+int dsc_download_co(DscContext *ctx, float *r_co /* [totvert][3] */);
+int dsc_download_no(DscContext *ctx, float *r_no /* [totvert][3] */);
+int dsc_download_orig_co(DscContext *ctx, float *r_co /* [totvert][3] */);
+int dsc_download_orig_no(DscContext *ctx, float *r_no /* [totvert][3] */);
+int dsc_download_node_bb(DscContext *ctx, float *r_bb /* [totnode][6] */, float *r_orig_bb /* or NULL */);
+int dsc_download_node_flags(DscContext *ctx, int *r_flags /* [totnode] */);
+/* undo-node membership of the running / last stroke: r_touched[node] = 1 */
+int dsc_download_touched(DscContext *ctx, unsigned char *r_touched /* [totnode] */);
+int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_coords_apply */
+int dsc_synchronize(DscContext *ctx);
+
+/* --- timing helpers (CUDA events on the context's stream) --------------------------------- */
+int dsc_timer_start(DscContext *ctx);
+int dsc_timer_stop(DscContext *ctx, float *r_ms); /* synchronises */
+void *dsc_stream(DscContext *ctx);                /* cudaStream_t */
+/* per-stage device time of the dabs since the last reset; stage names via dsc_stage_name() */
+#define DSC_NUM_STAGES 8
+int dsc_stage_timing(DscContext *ctx, int enable);
+int dsc_stage_times(DscContext *ctx, float r_ms[DSC_NUM_STAGES], int r_launches[DSC_NUM_STAGES]);
+const char *dsc_stage_name(int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

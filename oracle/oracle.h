@@ -1,0 +1,149 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+ *
+ * CPU restatement (plain C11) of the reference's sculpt-stroke hot path, used only as the checker
+ * by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing
+ * in the product path (dune_sculpt_b200/, include/) may include, link or call this.
+ *
+ * "Parity unpinned": the reference (/root/reference) ships no test, golden vector or fixture for
+ * PBVH / sculpt / normals, cannot be compiled here (pbvh.c is two concatenated
+ * copies, its public header is absent) and has no source for the brush layer.
+ * The PBVH parts below follow source/dune/kernel/intern/pbvh.c line by line in behaviour (each
+ * function cites the lines); the brush parts (marked DAGGER) restate the upstream project's
+ * published behaviour and are the specification by decision.
+ *
+ * All paths cited are relative to /root/reference/source/dune/ .  "pbvh.c" is
+ * kernel/intern/pbvh.c, second (complete) copy, lines 1913-4986.
+ */
+#ifndef DUNE_ORACLE_H
+#define DUNE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* PBVHNodeFlags: names used at pbvh.c:3643-3726; numeric values from the (absent) public header,
+ * upstream values, SURVEY.md section 8a row a8. */
+enum {
+  OR_PBVH_Leaf = 1 << 0,
+  OR_PBVH_UpdateNormals = 1 << 1,
+  OR_PBVH_UpdateBB = 1 << 2,
+  OR_PBVH_UpdateOriginalBB = 1 << 3,
+  OR_PBVH_UpdateDrawBuffers = 1 << 4,
+  OR_PBVH_UpdateRedraw = 1 << 5,
+  OR_PBVH_UpdateMask = 1 << 6,
+  OR_PBVH_UpdateVisibility = 1 << 8,
+  OR_PBVH_RebuildDrawBuffers = 1 << 9,
+  OR_PBVH_FullyHidden = 1 << 10,
+  OR_PBVH_FullyMasked = 1 << 11,
+  OR_PBVH_FullyUnmasked = 1 << 12,
+  OR_PBVH_UpdateColor = 1 << 14,
+};
+
+/* eBrushSculptTool, types/types_brush_enums.h:410-443 */
+enum { OR_TOOL_DRAW = 1, OR_TOOL_SMOOTH = 2, OR_TOOL_INFLATE = 4, OR_TOOL_GRAB = 5, OR_TOOL_CLAY_STRIPS = 18 };
+/* eBrushCurvePreset, types/types_brush_enums.h:176-187 */
+enum {
+  OR_CURVE_CUSTOM = 0, OR_CURVE_SMOOTH = 1, OR_CURVE_SPHERE = 2, OR_CURVE_ROOT = 3, OR_CURVE_SHARP = 4,
+  OR_CURVE_LIN = 5, OR_CURVE_POW4 = 6, OR_CURVE_INVSQUARE = 7, OR_CURVE_CONSTANT = 8, OR_CURVE_SMOOTHER = 9,
+};
+/* sculpt_plane, types/types_brush_enums.h:580-586 */
+enum { OR_DIR_AREA = 0, OR_DIR_VIEW = 1, OR_DIR_X = 2, OR_DIR_Y = 3, OR_DIR_Z = 4 };
+
+enum {
+  OR_DAB_FRONTFACE = 1 << 0,  /* BRUSH_FRONTFACE, types_brush_enums.h:365 */
+  OR_DAB_PLANE_TRIM = 1 << 1, /* BRUSH_PLANE_TRIM, types_brush_enums.h:364 */
+  OR_DAB_FIRST_STEP = 1 << 2, /* first dab of the stroke (clay strips skips it) */
+  OR_DAB_NO_NORMALS = 1 << 3, /* skip BKE_pbvh_update_normals after the dab */
+  OR_DAB_NO_BOUNDS = 1 << 4,  /* skip BKE_pbvh_update_bounds after the dab */
+};
+
+typedef struct OrBB {
+  float bmin[3], bmax[3];
+} OrBB;
+
+/* One dab.  Field meaning follows SURVEY.md section 8a rows a11-a20. */
+typedef struct OrDab {
+  int tool;
+  int curve_preset;
+  int flags;
+  int sculpt_plane;
+  float location[3];
+  float radius;
+  float view_normal[3];
+  float bstrength; /* signed, brush_strength() result, row a14 */
+  float scale[3];
+  float hardness;
+  float normal_radius_factor;
+  float plane_offset;
+  float plane_trim;
+  float tip_roundness;
+  float grab_delta[3];
+  float radius_scale; /* gather radius multiplier, 1.0 normally */
+} OrDab;
+
+typedef struct OrPbvh OrPbvh;
+
+/* ---- mesh helpers (oracle_mesh.c) ---- */
+int or_looptri_count(int totpoly, const int *poly_len);
+void or_looptri_calc(int totpoly, const int *poly_start, const int *poly_len, const int *loop_v,
+                     const float (*co)[3], int (*r_tri_loop)[3], int *r_tri_poly);
+void or_vert_poly_map(int totvert, int totpoly, const int *poly_start, const int *poly_len,
+                      const int *loop_v, int *r_off /* V+1 */, int *r_idx /* totloop */);
+/* returns number of neighbour entries written; r_idx must hold 2*totloop ints */
+int or_vert_neighbors(int totvert, int totpoly, const int *poly_start, const int *poly_len,
+                      const int *loop_v, int *r_off /* V+1 */, int *r_idx, unsigned char *r_boundary /* V */);
+
+/* ---- PBVH (oracle_pbvh.c) ---- */
+OrPbvh *or_pbvh_build_mesh(int totvert, const float (*co)[3], const float (*no)[3], const float *mask,
+                           int totpoly, const int *poly_start, const int *poly_len, int totloop,
+                           const int *loop_v, int leaf_limit /* 0 = LEAF_LIMIT */);
+void or_pbvh_free(OrPbvh *p);
+int or_pbvh_totnode(const OrPbvh *p);
+int or_pbvh_tottri(const OrPbvh *p);
+int or_pbvh_totvert(const OrPbvh *p);
+/* flat export: arrays sized totnode */
+void or_pbvh_nodes(const OrPbvh *p, OrBB *vb, OrBB *orig_vb, int *children_offset, int *flag,
+                   int *prim_offset, int *totprim, int *uniq_verts, int *face_verts);
+const int *or_pbvh_prim_indices(const OrPbvh *p);
+const int *or_pbvh_node_vert_indices(const OrPbvh *p, int node);
+const int *or_pbvh_node_face_vert_indices(const OrPbvh *p, int node);
+const int *or_pbvh_tri_verts(const OrPbvh *p); /* [T][3] vertex indices */
+const int *or_pbvh_tri_poly(const OrPbvh *p);
+float *or_pbvh_co(OrPbvh *p);
+float *or_pbvh_no(OrPbvh *p);
+float *or_pbvh_orig_co(OrPbvh *p);
+float *or_pbvh_orig_no(OrPbvh *p);
+void or_pbvh_node_set_flag(OrPbvh *p, int node, int flag, int on);
+
+/* BKE_pbvh_search_gather with the sphere callback; returns count, node indices in r_nodes */
+int or_gather_sphere(OrPbvh *p, const float center[3], float radius_sq, int original,
+                     int ignore_fully_ineffective, int *r_nodes);
+/* BKE_pbvh_search_gather(update_search_cb, flag) */
+int or_gather_flag(OrPbvh *p, int flag, int *r_nodes);
+void or_vert_mark_update(OrPbvh *p, int v);
+void or_node_mark_update(OrPbvh *p, int node);
+void or_update_normals(OrPbvh *p);
+void or_update_bounds(OrPbvh *p, int flag);
+/* full-mesh vertex normals the way the accumulate pass would produce them with every vertex dirty */
+void or_recalc_all_normals(OrPbvh *p);
+void or_set_threads(int n);
+
+/* ---- sculpt session (oracle_sculpt.c) ---- */
+void or_stroke_begin(OrPbvh *p, const float *automask /* V or NULL */);
+void or_stroke_end(OrPbvh *p);
+void or_set_custom_curve(OrPbvh *p, const float *table257);
+int or_dab(OrPbvh *p, const OrDab *d);
+/* results of the last dab */
+int or_last_hits(const OrPbvh *p, int *r_nodes);         /* gathered leaves, gather order */
+int or_last_moved(const OrPbvh *p, int *r_verts);        /* vertices marked update, iteration order */
+void or_last_area(const OrPbvh *p, float r_no[3], float r_co[3]);
+int or_touched_nodes(const OrPbvh *p, int *r_nodes);     /* undo-node membership, ascending node index */
+int64_t or_stroke_vertex_dabs(const OrPbvh *p);          /* sum of uniq_verts over hit leaves */
+float or_brush_curve_strength(const OrPbvh *p, int preset, float final_len, float radius);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

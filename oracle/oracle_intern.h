@@ -1,0 +1,62 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.h).  Internal structs. */
+#ifndef DUNE_ORACLE_INTERN_H
+#define DUNE_ORACLE_INTERN_H
+
+#include "oracle.h"
+
+/* kernel/intern/pbvh_intern.h:4-11 */
+typedef struct OrBBC {
+  float bmin[3], bmax[3], bcentroid[3];
+} OrBBC;
+
+/* kernel/intern/pbvh_intern.h:15-90 (fields on the path only) */
+typedef struct OrNode {
+  OrBB vb, orig_vb;
+  int children_offset;
+  int prim_offset; /* prim_indices = pbvh->prim_indices + prim_offset */
+  int totprim;
+  int *vert_indices;
+  int uniq_verts, face_verts;
+  int (*face_vert_indices)[3];
+  unsigned flag;
+} OrNode;
+
+/* kernel/intern/pbvh_intern.h:98-162 plus the sculpt-session state the brushes need */
+struct OrPbvh {
+  OrNode *nodes;
+  int node_mem_count, totnode;
+  int *prim_indices;
+  int totprim, totvert, leaf_limit;
+
+  float (*co)[3];  /* MVert.co */
+  float (*no)[3];  /* vert_normals */
+  float *mask;     /* CD_PAINT_MASK or NULL */
+  int totpoly, totloop;
+  int *poly_start, *poly_len, *loop_v;
+  int (*tri_loop)[3]; /* MLoopTri.tri */
+  int (*tri_v)[3];    /* mloop[tri].v resolved */
+  int *tri_poly;
+  unsigned char *vert_bitmap; /* one byte per vertex */
+
+  /* sculpt session DAGGER */
+  int *nb_off, *nb_idx; /* vertex neighbours, reference order */
+  unsigned char *boundary;
+  float *automask;
+  float (*orig_co)[3], (*orig_no)[3];
+  unsigned char *touched; /* per node: undo node pushed this stroke */
+  float curve_table[257];
+  int has_curve_table;
+
+  int *last_hits, last_tothit;
+  int *last_moved, last_totmoved;
+  float last_area_no[3], last_area_co[3];
+  int64_t vertex_dabs;
+  float (*scratch)[3];      /* Jacobi buffer for smooth, indexed by vertex */
+  unsigned char *iter_flag; /* smooth: vertex moved in this iteration */
+  int *moved_stamp;         /* dab serial at which the vertex was last listed in last_moved */
+  int dab_serial;
+};
+
+extern int or_threads;
+
+#endif

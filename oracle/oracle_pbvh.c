@@ -1,0 +1,699 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ * PBVH build / traversal / normals / bounds restated from kernel/intern/pbvh.c. */
+#include "oracle_intern.h"
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#  include <omp.h>
+#endif
+
+#define LEAF_LIMIT 10000 /* pbvh.c:1950 */
+
+int or_threads = 1;
+void or_set_threads(int n)
+{
+  or_threads = n < 1 ? 1 : n;
+#ifdef _OPENMP
+  omp_set_num_threads(or_threads);
+#endif
+}
+
+static inline float min_ff(float a, float b) { return (a < b) ? a : b; }
+static inline float max_ff(float a, float b) { return (a > b) ? a : b; }
+
+/* pbvh.c:1973-1993 */
+static void BB_reset(OrBB *bb)
+{
+  bb->bmin[0] = bb->bmin[1] = bb->bmin[2] = FLT_MAX;
+  bb->bmax[0] = bb->bmax[1] = bb->bmax[2] = -FLT_MAX;
+}
+static void BB_expand(OrBB *bb, const float co[3])
+{
+  for (int i = 0; i < 3; i++) {
+    bb->bmin[i] = min_ff(bb->bmin[i], co[i]);
+    bb->bmax[i] = max_ff(bb->bmax[i], co[i]);
+  }
+}
+static void BB_expand_with_bb(OrBB *bb, const OrBB *bb2)
+{
+  for (int i = 0; i < 3; i++) {
+    bb->bmin[i] = min_ff(bb->bmin[i], bb2->bmin[i]);
+    bb->bmax[i] = max_ff(bb->bmax[i], bb2->bmax[i]);
+  }
+}
+/* pbvh.c:1995-2016 */
+static int BB_widest_axis(const OrBB *bb)
+{
+  float dim[3];
+  for (int i = 0; i < 3; i++) {
+    dim[i] = bb->bmax[i] - bb->bmin[i];
+  }
+  if (dim[0] > dim[1]) {
+    return (dim[0] > dim[2]) ? 0 : 2;
+  }
+  return (dim[1] > dim[2]) ? 1 : 2;
+}
+
+/* pbvh.c:2026-2046 update_node_vb (leaf: PBVH_ITER_ALL over unique + shared verts) */
+static void update_node_vb(OrPbvh *p, OrNode *node)
+{
+  OrBB vb;
+  BB_reset(&vb);
+  if (node->flag & OR_PBVH_Leaf) {
+    const int tot = node->uniq_verts + node->face_verts;
+    for (int i = 0; i < tot; i++) {
+      BB_expand(&vb, p->co[node->vert_indices[i]]);
+    }
+  }
+  else {
+    BB_expand_with_bb(&vb, &p->nodes[node->children_offset].vb);
+    BB_expand_with_bb(&vb, &p->nodes[node->children_offset + 1].vb);
+  }
+  node->vb = vb;
+}
+
+/* pbvh.c:2070-2088 */
+static int partition_indices(int *prim_indices, int lo, int hi, int axis, float mid, const OrBBC *prim_bbc)
+{
+  int i = lo, j = hi;
+  for (;;) {
+    for (; prim_bbc[prim_indices[i]].bcentroid[axis] < mid; i++) {
+    }
+    for (; mid < prim_bbc[prim_indices[j]].bcentroid[axis]; j--) {
+    }
+    if (!(i < j)) {
+      return i;
+    }
+    int t = prim_indices[i];
+    prim_indices[i] = prim_indices[j];
+    prim_indices[j] = t;
+    i++;
+  }
+}
+
+/* pbvh.c:2134-2145 */
+static void pbvh_grow_nodes(OrPbvh *p, int totnode)
+{
+  if (totnode > p->node_mem_count) {
+    int old = p->node_mem_count;
+    p->node_mem_count = p->node_mem_count + (p->node_mem_count / 3);
+    if (p->node_mem_count < totnode) {
+      p->node_mem_count = totnode;
+    }
+    p->nodes = realloc(p->nodes, sizeof(OrNode) * (size_t)p->node_mem_count);
+    memset(p->nodes + old, 0, sizeof(OrNode) * (size_t)(p->node_mem_count - old));
+  }
+  p->totnode = totnode;
+}
+
+/* pbvh.c:2149-2171 map_insert_vert.  The GHash is replaced by a stamp array with the same
+ * key -> value semantics (value >= 0: unique slot, value < 0: ~shared slot). */
+typedef struct LeafMap {
+  int *stamp, *value;
+} LeafMap;
+
+static int map_insert_vert(OrPbvh *p, LeafMap *map, int node_index, int *face_verts, int *uniq_verts, int vertex)
+{
+  if (map->stamp[vertex] != node_index) {
+    int value_i;
+    map->stamp[vertex] = node_index;
+    if (p->vert_bitmap[vertex] == 0) {
+      p->vert_bitmap[vertex] = 1;
+      value_i = *uniq_verts;
+      (*uniq_verts)++;
+    }
+    else {
+      value_i = ~(*face_verts);
+      (*face_verts)++;
+    }
+    map->value[vertex] = value_i;
+    return value_i;
+  }
+  return map->value[vertex];
+}
+
+/* pbvh.c:2174-2238 build_mesh_leaf_node */
+static void build_mesh_leaf_node(OrPbvh *p, LeafMap *map, int node_index)
+{
+  OrNode *node = &p->nodes[node_index];
+  node->uniq_verts = node->face_verts = 0;
+  const int totface = node->totprim;
+  const int *prims = p->prim_indices + node->prim_offset;
+
+  int(*fvi)[3] = malloc(sizeof(int[3]) * (size_t)totface);
+  node->face_vert_indices = fvi;
+  for (int i = 0; i < totface; i++) {
+    const int *vt = p->tri_v[prims[i]];
+    for (int j = 0; j < 3; j++) {
+      fvi[i][j] = map_insert_vert(p, map, node_index, &node->face_verts, &node->uniq_verts, vt[j]);
+    }
+  }
+  int *vert_indices = calloc((size_t)(node->uniq_verts + node->face_verts), sizeof(int));
+  node->vert_indices = vert_indices;
+  /* Build the vertex list, unique verts first (pbvh.c:2210-2231): every key lands at the slot its
+   * value names, so the iteration order of the hash does not matter. */
+  for (int i = 0; i < totface; i++) {
+    const int *vt = p->tri_v[prims[i]];
+    for (int j = 0; j < 3; j++) {
+      int ndx = fvi[i][j];
+      if (ndx < 0) {
+        ndx = -ndx + node->uniq_verts - 1;
+        fvi[i][j] = ndx;
+      }
+      vert_indices[ndx] = vt[j];
+    }
+  }
+  node->flag |= OR_PBVH_RebuildDrawBuffers | OR_PBVH_UpdateDrawBuffers | OR_PBVH_UpdateRedraw; /* pbvh.c:3663 */
+}
+
+/* pbvh.c:2240-2247 */
+static void update_vb(OrPbvh *p, OrNode *node, const OrBBC *prim_bbc, int offset, int count)
+{
+  BB_reset(&node->vb);
+  for (int i = offset + count - 1; i >= offset; i--) {
+    BB_expand_with_bb(&node->vb, (const OrBB *)(&prim_bbc[p->prim_indices[i]]));
+  }
+  node->orig_vb = node->vb;
+}
+
+/* pbvh.c:2309-2325 */
+static void build_leaf(OrPbvh *p, LeafMap *map, int node_index, const OrBBC *prim_bbc, int offset, int count)
+{
+  p->nodes[node_index].flag |= OR_PBVH_Leaf;
+  p->nodes[node_index].prim_offset = offset;
+  p->nodes[node_index].totprim = count;
+  update_vb(p, &p->nodes[node_index], prim_bbc, offset, count);
+  build_mesh_leaf_node(p, map, node_index);
+}
+
+/* pbvh.c:2372-2425 build_sub (single material: leaf_needs_material_split is always false) */
+static void build_sub(OrPbvh *p, LeafMap *map, int node_index, OrBB *cb, const OrBBC *prim_bbc, int offset, int count)
+{
+  int end;
+  OrBB cb_backing;
+
+  const int below_leaf_limit = count <= p->leaf_limit;
+  if (below_leaf_limit) {
+    build_leaf(p, map, node_index, prim_bbc, offset, count);
+    return;
+  }
+
+  p->nodes[node_index].children_offset = p->totnode;
+  pbvh_grow_nodes(p, p->totnode + 2);
+
+  update_vb(p, &p->nodes[node_index], prim_bbc, offset, count);
+
+  if (!cb) {
+    cb = &cb_backing;
+    BB_reset(cb);
+    for (int i = offset + count - 1; i >= offset; i--) {
+      BB_expand(cb, prim_bbc[p->prim_indices[i]].bcentroid);
+    }
+  }
+  const int axis = BB_widest_axis(cb);
+  end = partition_indices(p->prim_indices, offset, offset + count - 1, axis,
+                          (cb->bmax[axis] + cb->bmin[axis]) * 0.5f, prim_bbc);
+
+  build_sub(p, map, p->nodes[node_index].children_offset, NULL, prim_bbc, offset, end - offset);
+  build_sub(p, map, p->nodes[node_index].children_offset + 1, NULL, prim_bbc, end, offset + count - end);
+}
+
+/* pbvh.c:2452-2514 BKE_pbvh_build_mesh (+ pbvh_build 2427-2450) */
+OrPbvh *or_pbvh_build_mesh(int totvert, const float (*co)[3], const float (*no)[3], const float *mask,
+                           int totpoly, const int *poly_start, const int *poly_len, int totloop,
+                           const int *loop_v, int leaf_limit)
+{
+  OrPbvh *p = calloc(1, sizeof(OrPbvh));
+  p->totvert = totvert;
+  p->totpoly = totpoly;
+  p->totloop = totloop;
+  p->leaf_limit = leaf_limit > 0 ? leaf_limit : LEAF_LIMIT;
+  p->co = malloc(sizeof(float[3]) * (size_t)totvert);
+  memcpy(p->co, co, sizeof(float[3]) * (size_t)totvert);
+  p->no = calloc((size_t)totvert, sizeof(float[3]));
+  if (no) {
+    memcpy(p->no, no, sizeof(float[3]) * (size_t)totvert);
+  }
+  if (mask) {
+    p->mask = malloc(sizeof(float) * (size_t)totvert);
+    memcpy(p->mask, mask, sizeof(float) * (size_t)totvert);
+  }
+  p->poly_start = malloc(sizeof(int) * (size_t)totpoly);
+  p->poly_len = malloc(sizeof(int) * (size_t)totpoly);
+  p->loop_v = malloc(sizeof(int) * (size_t)totloop);
+  memcpy(p->poly_start, poly_start, sizeof(int) * (size_t)totpoly);
+  memcpy(p->poly_len, poly_len, sizeof(int) * (size_t)totpoly);
+  memcpy(p->loop_v, loop_v, sizeof(int) * (size_t)totloop);
+
+  const int looptri_num = or_looptri_count(totpoly, poly_len);
+  p->tri_loop = malloc(sizeof(int[3]) * (size_t)(looptri_num > 0 ? looptri_num : 1));
+  p->tri_v = malloc(sizeof(int[3]) * (size_t)(looptri_num > 0 ? looptri_num : 1));
+  p->tri_poly = malloc(sizeof(int) * (size_t)(looptri_num > 0 ? looptri_num : 1));
+  or_looptri_calc(totpoly, poly_start, poly_len, loop_v, (const float(*)[3])p->co, p->tri_loop, p->tri_poly);
+  for (int i = 0; i < looptri_num; i++) {
+    for (int j = 0; j < 3; j++) {
+      p->tri_v[i][j] = loop_v[p->tri_loop[i][j]];
+    }
+  }
+  p->vert_bitmap = calloc((size_t)totvert + 1, 1);
+
+  OrBB cb;
+  BB_reset(&cb);
+  OrBBC *prim_bbc = malloc(sizeof(OrBBC) * (size_t)(looptri_num > 0 ? looptri_num : 1));
+  for (int i = 0; i < looptri_num; i++) {
+    OrBBC *bbc = prim_bbc + i;
+    BB_reset((OrBB *)bbc);
+    for (int j = 0; j < 3; j++) {
+      BB_expand((OrBB *)bbc, p->co[p->tri_v[i][j]]);
+    }
+    for (int k = 0; k < 3; k++) { /* pbvh.c:2018-2023 */
+      bbc->bcentroid[k] = (bbc->bmin[k] + bbc->bmax[k]) * 0.5f;
+    }
+    BB_expand(&cb, bbc->bcentroid);
+  }
+
+  if (looptri_num) {
+    p->totprim = looptri_num;
+    p->prim_indices = malloc(sizeof(int) * (size_t)looptri_num);
+    for (int i = 0; i < looptri_num; i++) {
+      p->prim_indices[i] = i;
+    }
+    p->node_mem_count = 100;
+    p->nodes = calloc((size_t)p->node_mem_count, sizeof(OrNode));
+    p->totnode = 1;
+    LeafMap map;
+    map.stamp = malloc(sizeof(int) * (size_t)totvert);
+    map.value = malloc(sizeof(int) * (size_t)totvert);
+    for (int i = 0; i < totvert; i++) {
+      map.stamp[i] = -1;
+    }
+    build_sub(p, &map, 0, &cb, prim_bbc, 0, looptri_num);
+    free(map.stamp);
+    free(map.value);
+  }
+  free(prim_bbc);
+  memset(p->vert_bitmap, 0, (size_t)totvert); /* pbvh.c:2512-2513 */
+
+  /* sculpt-session side tables (kernel/intern/paint.c:1685-1688 builds pmap at session start) */
+  p->nb_off = malloc(sizeof(int) * ((size_t)totvert + 1));
+  p->nb_idx = malloc(sizeof(int) * (size_t)(2 * totloop + 1));
+  p->boundary = malloc((size_t)totvert + 1);
+  or_vert_neighbors(totvert, totpoly, poly_start, poly_len, loop_v, p->nb_off, p->nb_idx, p->boundary);
+  p->orig_co = calloc((size_t)totvert, sizeof(float[3]));
+  p->orig_no = calloc((size_t)totvert, sizeof(float[3]));
+  p->touched = calloc((size_t)p->totnode + 1, 1);
+  p->last_hits = malloc(sizeof(int) * (size_t)(p->totnode + 1));
+  p->last_moved = malloc(sizeof(int) * ((size_t)totvert + 1));
+  p->scratch = malloc(sizeof(float[3]) * ((size_t)totvert + 1));
+  p->iter_flag = calloc((size_t)totvert + 1, 1);
+  p->moved_stamp = calloc((size_t)totvert + 1, sizeof(int));
+  return p;
+}
+
+/* pbvh.c:2570-2620 */
+void or_pbvh_free(OrPbvh *p)
+{
+  if (!p) {
+    return;
+  }
+  for (int i = 0; i < p->totnode; i++) {
+    if (p->nodes[i].flag & OR_PBVH_Leaf) {
+      free(p->nodes[i].vert_indices);
+      free(p->nodes[i].face_vert_indices);
+    }
+  }
+  free(p->nodes); free(p->prim_indices); free(p->co); free(p->no); free(p->mask);
+  free(p->poly_start); free(p->poly_len); free(p->loop_v); free(p->tri_loop); free(p->tri_v);
+  free(p->tri_poly); free(p->vert_bitmap); free(p->nb_off); free(p->nb_idx); free(p->boundary);
+  free(p->automask); free(p->orig_co); free(p->orig_no); free(p->touched); free(p->last_hits);
+  free(p->last_moved); free(p->scratch); free(p->iter_flag); free(p->moved_stamp);
+  free(p);
+}
+
+int or_pbvh_totnode(const OrPbvh *p) { return p->totnode; }
+int or_pbvh_tottri(const OrPbvh *p) { return p->totprim; }
+int or_pbvh_totvert(const OrPbvh *p) { return p->totvert; }
+const int *or_pbvh_prim_indices(const OrPbvh *p) { return p->prim_indices; }
+const int *or_pbvh_node_vert_indices(const OrPbvh *p, int n) { return p->nodes[n].vert_indices; }
+const int *or_pbvh_node_face_vert_indices(const OrPbvh *p, int n) { return (const int *)p->nodes[n].face_vert_indices; }
+const int *or_pbvh_tri_verts(const OrPbvh *p) { return (const int *)p->tri_v; }
+const int *or_pbvh_tri_poly(const OrPbvh *p) { return p->tri_poly; }
+float *or_pbvh_co(OrPbvh *p) { return (float *)p->co; }
+float *or_pbvh_no(OrPbvh *p) { return (float *)p->no; }
+float *or_pbvh_orig_co(OrPbvh *p) { return (float *)p->orig_co; }
+float *or_pbvh_orig_no(OrPbvh *p) { return (float *)p->orig_no; }
+
+void or_pbvh_nodes(const OrPbvh *p, OrBB *vb, OrBB *orig_vb, int *children_offset, int *flag,
+                   int *prim_offset, int *totprim, int *uniq_verts, int *face_verts)
+{
+  for (int i = 0; i < p->totnode; i++) {
+    const OrNode *n = &p->nodes[i];
+    if (vb) vb[i] = n->vb;
+    if (orig_vb) orig_vb[i] = n->orig_vb;
+    if (children_offset) children_offset[i] = n->children_offset;
+    if (flag) flag[i] = (int)n->flag;
+    if (prim_offset) prim_offset[i] = n->prim_offset;
+    if (totprim) totprim[i] = n->totprim;
+    if (uniq_verts) uniq_verts[i] = n->uniq_verts;
+    if (face_verts) face_verts[i] = n->face_verts;
+  }
+}
+
+void or_pbvh_node_set_flag(OrPbvh *p, int node, int flag, int on)
+{
+  if (on) {
+    p->nodes[node].flag |= (unsigned)flag;
+  }
+  else {
+    p->nodes[node].flag &= ~(unsigned)flag;
+  }
+}
+
+/* ---- traversal: pbvh.c:2622-2705 (pbvh_iter_begin / pbvh_stack_push / pbvh_iter_next) ---- */
+typedef int (*OrSearchCb)(OrPbvh *p, OrNode *node, void *data);
+
+typedef struct OrStackItem {
+  int node;
+  int revisiting;
+} OrStackItem;
+
+static int search_gather(OrPbvh *p, OrSearchCb scb, void *data, int *r_nodes)
+{
+  /* pbvh.c:2736-2767 BKE_pbvh_search_gather: leaves in pbvh_iter_next order */
+  int tot = 0;
+  if (p->totnode == 0) {
+    return 0;
+  }
+  int space = 100, size = 0;
+  OrStackItem *stack = malloc(sizeof(OrStackItem) * (size_t)space);
+  stack[size].node = 0;
+  stack[size].revisiting = 0;
+  size++;
+  while (size) {
+    size--;
+    const int ni = stack[size].node;
+    const int revisiting = stack[size].revisiting;
+    OrNode *node = &p->nodes[ni];
+    if (revisiting) {
+      continue; /* inner node handed back to the caller, which only keeps leaves (pbvh.c:2746) */
+    }
+    if (scb && !scb(p, node, data)) {
+      continue;
+    }
+    if (node->flag & OR_PBVH_Leaf) {
+      r_nodes[tot++] = ni;
+      continue;
+    }
+    if (size + 3 > space) {
+      space *= 2;
+      stack = realloc(stack, sizeof(OrStackItem) * (size_t)space);
+    }
+    stack[size].node = ni; stack[size].revisiting = 1; size++;
+    stack[size].node = node->children_offset + 1; stack[size].revisiting = 0; size++;
+    stack[size].node = node->children_offset; stack[size].revisiting = 0; size++;
+  }
+  free(stack);
+  return tot;
+}
+
+/* DAGGER sphere search callback; AABB accessors pbvh.c:3830-3840,
+ * fully hidden / masked pbvh.c:3690-3710 */
+typedef struct SphereData {
+  const float *center;
+  float radius_squared;
+  int original, ignore_fully_ineffective;
+} SphereData;
+
+static int search_sphere_cb(OrPbvh *p, OrNode *node, void *data_v)
+{
+  (void)p;
+  const SphereData *data = data_v;
+  const float *center = data->center;
+  float nearest[3], t[3];
+  if (data->ignore_fully_ineffective) {
+    if ((node->flag & OR_PBVH_Leaf) && (node->flag & OR_PBVH_FullyHidden)) {
+      return 0;
+    }
+    if ((node->flag & OR_PBVH_Leaf) && (node->flag & OR_PBVH_FullyMasked)) {
+      return 0;
+    }
+  }
+  const OrBB *bb = data->original ? &node->orig_vb : &node->vb;
+  for (int i = 0; i < 3; i++) {
+    if (bb->bmin[i] > center[i]) {
+      nearest[i] = bb->bmin[i];
+    }
+    else if (bb->bmax[i] < center[i]) {
+      nearest[i] = bb->bmax[i];
+    }
+    else {
+      nearest[i] = center[i];
+    }
+  }
+  t[0] = center[0] - nearest[0];
+  t[1] = center[1] - nearest[1];
+  t[2] = center[2] - nearest[2];
+  return (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) < data->radius_squared;
+}
+
+int or_gather_sphere(OrPbvh *p, const float center[3], float radius_sq, int original,
+                     int ignore_fully_ineffective, int *r_nodes)
+{
+  SphereData d = {center, radius_sq, original, ignore_fully_ineffective};
+  return search_gather(p, search_sphere_cb, &d, r_nodes);
+}
+
+/* pbvh.c:2891-2900 update_search_cb */
+static int update_search_cb(OrPbvh *p, OrNode *node, void *data_v)
+{
+  (void)p;
+  const int flag = *(int *)data_v;
+  if (node->flag & OR_PBVH_Leaf) {
+    return (node->flag & (unsigned)flag) != 0;
+  }
+  return 1;
+}
+
+int or_gather_flag(OrPbvh *p, int flag, int *r_nodes)
+{
+  return search_gather(p, update_search_cb, &flag, r_nodes);
+}
+
+/* pbvh.c:3641-3645, 3729-3733 */
+void or_node_mark_update(OrPbvh *p, int node)
+{
+  p->nodes[node].flag |= OR_PBVH_UpdateNormals | OR_PBVH_UpdateBB | OR_PBVH_UpdateOriginalBB |
+                         OR_PBVH_UpdateDrawBuffers | OR_PBVH_UpdateRedraw;
+}
+void or_vert_mark_update(OrPbvh *p, int v) { p->vert_bitmap[v] = 1; }
+
+/* lib/intern/math_vector_inline.c:1165-1181 normalize_v3 */
+static float normalize_v3(float n[3])
+{
+  float d = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+  if (d > 1.0e-35f) {
+    d = sqrtf(d);
+    const float f = 1.0f / d;
+    n[0] = n[0] * f;
+    n[1] = n[1] * f;
+    n[2] = n[2] * f;
+  }
+  else {
+    n[0] = n[1] = n[2] = 0.0f;
+    d = 0.0f;
+  }
+  return d;
+}
+
+/* kernel/intern/mesh_evaluate.c:39-86 BKE_mesh_calc_poly_normal;
+ * lib/intern/math_geom.cc:31-69 normal_tri_v3 / normal_quad_v3;
+ * lib/intern/math_vector_inline.c:961-966 add_newell_cross_v3_v3v3 */
+static void calc_poly_normal(const OrPbvh *p, int poly, float r_no[3])
+{
+  const int ls = p->poly_start[poly], n = p->poly_len[poly];
+  const int *lv = p->loop_v + ls;
+  if (n > 4) {
+    const float *v_prev = p->co[lv[n - 1]];
+    r_no[0] = r_no[1] = r_no[2] = 0.0f;
+    for (int i = 0; i < n; i++) {
+      const float *v_curr = p->co[lv[i]];
+      r_no[0] += (v_prev[1] - v_curr[1]) * (v_prev[2] + v_curr[2]);
+      r_no[1] += (v_prev[2] - v_curr[2]) * (v_prev[0] + v_curr[0]);
+      r_no[2] += (v_prev[0] - v_curr[0]) * (v_prev[1] + v_curr[1]);
+      v_prev = v_curr;
+    }
+    if (normalize_v3(r_no) == 0.0f) {
+      r_no[2] = 1.0f;
+    }
+  }
+  else if (n == 3) {
+    const float *v1 = p->co[lv[0]], *v2 = p->co[lv[1]], *v3 = p->co[lv[2]];
+    float n1[3], n2[3];
+    n1[0] = v1[0] - v2[0]; n2[0] = v2[0] - v3[0];
+    n1[1] = v1[1] - v2[1]; n2[1] = v2[1] - v3[1];
+    n1[2] = v1[2] - v2[2]; n2[2] = v2[2] - v3[2];
+    r_no[0] = n1[1] * n2[2] - n1[2] * n2[1];
+    r_no[1] = n1[2] * n2[0] - n1[0] * n2[2];
+    r_no[2] = n1[0] * n2[1] - n1[1] * n2[0];
+    normalize_v3(r_no);
+  }
+  else if (n == 4) {
+    const float *v1 = p->co[lv[0]], *v2 = p->co[lv[1]], *v3 = p->co[lv[2]], *v4 = p->co[lv[3]];
+    float n1[3], n2[3];
+    n1[0] = v1[0] - v3[0]; n1[1] = v1[1] - v3[1]; n1[2] = v1[2] - v3[2];
+    n2[0] = v2[0] - v4[0]; n2[1] = v2[1] - v4[1]; n2[2] = v2[2] - v4[2];
+    r_no[0] = n1[1] * n2[2] - n1[2] * n2[1];
+    r_no[1] = n1[2] * n2[0] - n1[0] * n2[2];
+    r_no[2] = n1[0] * n2[1] - n1[1] * n2[0];
+    normalize_v3(r_no);
+  }
+  else {
+    r_no[0] = 0.0f; r_no[1] = 0.0f; r_no[2] = 1.0f;
+  }
+}
+
+/* pbvh.c:2912-3036 pbvh_faces_update_normals: clear / accumulate / store over flagged nodes.
+ * One thread: the accumulation order is nodes in gather order, looptris in node order -- for one
+ * vertex that is ascending position in prim_indices.  Threads > 1: float atomics as the
+ * reference (pbvh.c:2970-2976), order not defined. */
+static void faces_update_normals(OrPbvh *p, const int *nodes, int totnode)
+{
+  const int par = (or_threads > 1 && totnode > 1); /* pbvh.c:4953-4959 */
+#pragma omp parallel for schedule(dynamic) if (par)
+  for (int n = 0; n < totnode; n++) {
+    OrNode *node = &p->nodes[nodes[n]];
+    if (node->flag & OR_PBVH_UpdateNormals) {
+      for (int i = 0; i < node->uniq_verts; i++) {
+        const int v = node->vert_indices[i];
+        if (p->vert_bitmap[v]) {
+          p->no[v][0] = p->no[v][1] = p->no[v][2] = 0.0f;
+        }
+      }
+    }
+  }
+#pragma omp parallel for schedule(dynamic) if (par)
+  for (int n = 0; n < totnode; n++) {
+    OrNode *node = &p->nodes[nodes[n]];
+    if (node->flag & OR_PBVH_UpdateNormals) {
+      int mpoly_prev = -1;
+      float fn[3] = {0, 0, 0};
+      const int *faces = p->prim_indices + node->prim_offset;
+      for (int i = 0; i < node->totprim; i++) {
+        const int t = faces[i];
+        const int *vtri = p->tri_v[t];
+        if (p->tri_poly[t] != mpoly_prev) {
+          calc_poly_normal(p, p->tri_poly[t], fn);
+          mpoly_prev = p->tri_poly[t];
+        }
+        for (int j = 3; j--;) {
+          const int v = vtri[j];
+          if (p->vert_bitmap[v]) {
+            for (int k = 3; k--;) {
+              if (par) {
+#pragma omp atomic
+                p->no[v][k] += fn[k];
+              }
+              else {
+                p->no[v][k] += fn[k];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma omp parallel for schedule(dynamic) if (par)
+  for (int n = 0; n < totnode; n++) {
+    OrNode *node = &p->nodes[nodes[n]];
+    if (node->flag & OR_PBVH_UpdateNormals) {
+      for (int i = 0; i < node->uniq_verts; i++) {
+        const int v = node->vert_indices[i];
+        if (p->vert_bitmap[v]) {
+          normalize_v3(p->no[v]);
+          p->vert_bitmap[v] = 0;
+        }
+      }
+      node->flag &= ~(unsigned)OR_PBVH_UpdateNormals;
+    }
+  }
+}
+
+/* pbvh.c:4559-4587 BKE_pbvh_update_normals (PBVH_FACES branch) */
+void or_update_normals(OrPbvh *p)
+{
+  int *nodes = malloc(sizeof(int) * (size_t)(p->totnode + 1));
+  const int totnode = or_gather_flag(p, OR_PBVH_UpdateNormals, nodes);
+  if (totnode > 0) {
+    faces_update_normals(p, nodes, totnode);
+  }
+  free(nodes);
+}
+
+void or_recalc_all_normals(OrPbvh *p)
+{
+  for (int i = 0; i < p->totnode; i++) {
+    if (p->nodes[i].flag & OR_PBVH_Leaf) {
+      p->nodes[i].flag |= OR_PBVH_UpdateNormals;
+    }
+  }
+  memset(p->vert_bitmap, 1, (size_t)p->totvert);
+  or_update_normals(p);
+}
+
+/* pbvh.c:3287-3317 pbvh_flush_bb */
+static int pbvh_flush_bb(OrPbvh *p, OrNode *node, int flag)
+{
+  int update = 0;
+  if (node->flag & OR_PBVH_Leaf) {
+    if (flag & OR_PBVH_UpdateBB) {
+      update |= (int)(node->flag & OR_PBVH_UpdateBB);
+      node->flag &= ~(unsigned)OR_PBVH_UpdateBB;
+    }
+    if (flag & OR_PBVH_UpdateOriginalBB) {
+      update |= (int)(node->flag & OR_PBVH_UpdateOriginalBB);
+      node->flag &= ~(unsigned)OR_PBVH_UpdateOriginalBB;
+    }
+    return update;
+  }
+  update |= pbvh_flush_bb(p, p->nodes + node->children_offset, flag);
+  update |= pbvh_flush_bb(p, p->nodes + node->children_offset + 1, flag);
+  if (update & OR_PBVH_UpdateBB) {
+    update_node_vb(p, node);
+  }
+  if (update & OR_PBVH_UpdateOriginalBB) {
+    node->orig_vb = node->vb;
+  }
+  return update;
+}
+
+/* pbvh.c:3319-3339 BKE_pbvh_update_bounds (+ 3124-3160 pbvh_update_BB_redraw) */
+void or_update_bounds(OrPbvh *p, int flag)
+{
+  if (!p->nodes) {
+    return;
+  }
+  int *nodes = malloc(sizeof(int) * (size_t)(p->totnode + 1));
+  const int totnode = or_gather_flag(p, flag, nodes);
+  if (flag & (OR_PBVH_UpdateBB | OR_PBVH_UpdateOriginalBB | OR_PBVH_UpdateRedraw)) {
+    const int par = (or_threads > 1 && totnode > 1);
+#pragma omp parallel for schedule(dynamic) if (par)
+    for (int n = 0; n < totnode; n++) {
+      OrNode *node = &p->nodes[nodes[n]];
+      if ((flag & OR_PBVH_UpdateBB) && (node->flag & OR_PBVH_UpdateBB)) {
+        update_node_vb(p, node);
+      }
+      if ((flag & OR_PBVH_UpdateOriginalBB) && (node->flag & OR_PBVH_UpdateOriginalBB)) {
+        node->orig_vb = node->vb;
+      }
+      if ((flag & OR_PBVH_UpdateRedraw) && (node->flag & OR_PBVH_UpdateRedraw)) {
+        node->flag &= ~(unsigned)OR_PBVH_UpdateRedraw;
+      }
+    }
+  }
+  if (flag & (OR_PBVH_UpdateBB | OR_PBVH_UpdateOriginalBB)) {
+    pbvh_flush_bb(p, p->nodes, flag);
+  }
+  free(nodes);
+}

@@ -1,0 +1,230 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.h).  TEST INFRASTRUCTURE: only tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs may import this."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+
+
+class OrBB(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3)]
+
+
+class OrDab(C.Structure):
+    _fields_ = [
+        ("tool", C.c_int), ("curve_preset", C.c_int), ("flags", C.c_int), ("sculpt_plane", C.c_int),
+        ("location", C.c_float * 3), ("radius", C.c_float), ("view_normal", C.c_float * 3),
+        ("bstrength", C.c_float), ("scale", C.c_float * 3), ("hardness", C.c_float),
+        ("normal_radius_factor", C.c_float), ("plane_offset", C.c_float), ("plane_trim", C.c_float),
+        ("tip_roundness", C.c_float), ("grab_delta", C.c_float * 3), ("radius_scale", C.c_float),
+    ]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "build", "liboracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        L.or_pbvh_build_mesh.restype = C.c_void_p
+        L.or_pbvh_build_mesh.argtypes = [C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p, C.c_int,
+                                         c_int_p, C.c_int]
+        L.or_pbvh_free.argtypes = [C.c_void_p]
+        for fn in ("or_pbvh_totnode", "or_pbvh_tottri", "or_pbvh_totvert"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.or_pbvh_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [c_int_p] * 6
+        for fn in ("or_pbvh_prim_indices", "or_pbvh_tri_verts", "or_pbvh_tri_poly"):
+            getattr(L, fn).restype = c_int_p
+            getattr(L, fn).argtypes = [C.c_void_p]
+        for fn in ("or_pbvh_node_vert_indices", "or_pbvh_node_face_vert_indices"):
+            getattr(L, fn).restype = c_int_p
+            getattr(L, fn).argtypes = [C.c_void_p, C.c_int]
+        for fn in ("or_pbvh_co", "or_pbvh_no", "or_pbvh_orig_co", "or_pbvh_orig_no"):
+            getattr(L, fn).restype = c_float_p
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.or_pbvh_node_set_flag.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.or_gather_sphere.argtypes = [C.c_void_p, c_float_p, C.c_float, C.c_int, C.c_int, c_int_p]
+        L.or_gather_flag.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.or_vert_mark_update.argtypes = [C.c_void_p, C.c_int]
+        L.or_node_mark_update.argtypes = [C.c_void_p, C.c_int]
+        L.or_update_normals.argtypes = [C.c_void_p]
+        L.or_update_bounds.argtypes = [C.c_void_p, C.c_int]
+        L.or_recalc_all_normals.argtypes = [C.c_void_p]
+        L.or_set_threads.argtypes = [C.c_int]
+        L.or_stroke_begin.argtypes = [C.c_void_p, c_float_p]
+        L.or_stroke_end.argtypes = [C.c_void_p]
+        L.or_set_custom_curve.argtypes = [C.c_void_p, c_float_p]
+        L.or_dab.argtypes = [C.c_void_p, C.POINTER(OrDab)]
+        L.or_last_hits.argtypes = [C.c_void_p, c_int_p]
+        L.or_last_moved.argtypes = [C.c_void_p, c_int_p]
+        L.or_last_area.argtypes = [C.c_void_p, c_float_p, c_float_p]
+        L.or_touched_nodes.argtypes = [C.c_void_p, c_int_p]
+        L.or_stroke_vertex_dabs.argtypes = [C.c_void_p]
+        L.or_stroke_vertex_dabs.restype = C.c_int64
+        L.or_brush_curve_strength.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.or_brush_curve_strength.restype = C.c_float
+        L.or_looptri_count.argtypes = [C.c_int, c_int_p]
+        L.or_looptri_calc.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p]
+        L.or_vert_neighbors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def fptr(a):
+    return a.ctypes.data_as(c_float_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def dab_from(d):
+    """copy a product DscDab (same field layout by design of the dab descriptor) into an OrDab"""
+    o = OrDab()
+    C.memmove(C.byref(o), C.byref(d), C.sizeof(OrDab))
+    return o
+
+
+class Oracle:
+    def __init__(self, mesh, mask=None, no=None, leaf_limit=0, threads=1):
+        L = lib()
+        self.L = L
+        self.mesh = mesh
+        co = np.ascontiguousarray(mesh.co, dtype=np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.float32)
+        n = None if no is None else np.ascontiguousarray(no, dtype=np.float32)
+        L.or_set_threads(int(threads))
+        self.p = C.c_void_p(L.or_pbvh_build_mesh(mesh.totvert, fptr(co), None if n is None else fptr(n),
+                                                 None if m is None else fptr(m), mesh.totpoly, iptr(mesh.poly_start),
+                                                 iptr(mesh.poly_len), mesh.totloop, iptr(mesh.loop_v), int(leaf_limit)))
+        self.totnode = L.or_pbvh_totnode(self.p)
+        self.tottri = L.or_pbvh_tottri(self.p)
+        self.totvert = mesh.totvert
+        if no is None:
+            L.or_recalc_all_normals(self.p)
+
+    def set_threads(self, n):
+        self.L.or_set_threads(int(n))
+
+    def node_arrays(self):
+        n = self.totnode
+        vb = np.zeros((n, 6), dtype=np.float32)
+        ovb = np.zeros((n, 6), dtype=np.float32)
+        out = {k: np.zeros(n, dtype=np.int32) for k in ("children_offset", "flag", "prim_offset", "totprim", "uniq_verts", "face_verts")}
+        self.L.or_pbvh_nodes(self.p, vb.ctypes.data, ovb.ctypes.data, iptr(out["children_offset"]), iptr(out["flag"]),
+                             iptr(out["prim_offset"]), iptr(out["totprim"]), iptr(out["uniq_verts"]), iptr(out["face_verts"]))
+        out["vb"] = vb
+        out["orig_vb"] = ovb
+        return out
+
+    def prim_indices(self):
+        return np.ctypeslib.as_array(self.L.or_pbvh_prim_indices(self.p), shape=(self.tottri,)).copy()
+
+    def tri_verts(self):
+        return np.ctypeslib.as_array(self.L.or_pbvh_tri_verts(self.p), shape=(self.tottri * 3,)).copy().reshape(-1, 3)
+
+    def tri_poly(self):
+        return np.ctypeslib.as_array(self.L.or_pbvh_tri_poly(self.p), shape=(self.tottri,)).copy()
+
+    def node_vert_indices(self, i, count):
+        return np.ctypeslib.as_array(self.L.or_pbvh_node_vert_indices(self.p, i), shape=(count,)).copy()
+
+    def node_face_vert_indices(self, i, totprim):
+        return np.ctypeslib.as_array(self.L.or_pbvh_node_face_vert_indices(self.p, i), shape=(totprim * 3,)).copy().reshape(-1, 3)
+
+    def _v3(self, fn):
+        return np.ctypeslib.as_array(getattr(self.L, fn)(self.p), shape=(self.totvert * 3,)).copy().reshape(-1, 3)
+
+    def co(self):
+        return self._v3("or_pbvh_co")
+
+    def no(self):
+        return self._v3("or_pbvh_no")
+
+    def orig_co(self):
+        return self._v3("or_pbvh_orig_co")
+
+    def orig_no(self):
+        return self._v3("or_pbvh_orig_no")
+
+    def set_co(self, co):
+        a = np.ctypeslib.as_array(self.L.or_pbvh_co(self.p), shape=(self.totvert * 3,))
+        a[:] = np.ascontiguousarray(co, dtype=np.float32).reshape(-1)
+
+    def set_node_flag(self, node, flag, on=True):
+        self.L.or_pbvh_node_set_flag(self.p, int(node), int(flag), int(on))
+
+    def gather_sphere(self, center, radius_sq, original=False, ignore=True):
+        c = np.asarray(center, dtype=np.float32)
+        buf = np.zeros(self.totnode + 1, dtype=np.int32)
+        n = self.L.or_gather_sphere(self.p, fptr(c), C.c_float(radius_sq), int(original), int(ignore), iptr(buf))
+        return buf[:n].copy()
+
+    def stroke_begin(self, automask=None):
+        a = None if automask is None else np.ascontiguousarray(automask, dtype=np.float32)
+        self.L.or_stroke_begin(self.p, None if a is None else fptr(a))
+
+    def stroke_end(self):
+        self.L.or_stroke_end(self.p)
+
+    def set_custom_curve(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        self.L.or_set_custom_curve(self.p, fptr(t))
+
+    def dab(self, d):
+        o = d if isinstance(d, OrDab) else dab_from(d)
+        r = self.L.or_dab(self.p, C.byref(o))
+        assert r >= 0, "oracle does not implement tool %d" % o.tool
+        return r
+
+    def hits(self):
+        buf = np.zeros(self.totnode + 1, dtype=np.int32)
+        n = self.L.or_last_hits(self.p, iptr(buf))
+        return buf[:n].copy()
+
+    def moved(self):
+        buf = np.zeros(self.totvert + 1, dtype=np.int32)
+        n = self.L.or_last_moved(self.p, iptr(buf))
+        return buf[:n].copy()
+
+    def last_area(self):
+        no = np.zeros(3, dtype=np.float32)
+        co = np.zeros(3, dtype=np.float32)
+        self.L.or_last_area(self.p, fptr(no), fptr(co))
+        return no, co
+
+    def touched(self):
+        buf = np.zeros(self.totnode + 1, dtype=np.int32)
+        n = self.L.or_touched_nodes(self.p, iptr(buf))
+        return buf[:n].copy()
+
+    def vertex_dabs(self):
+        return int(self.L.or_stroke_vertex_dabs(self.p))
+
+    def update_normals(self):
+        self.L.or_update_normals(self.p)
+
+    def update_bounds(self, flag):
+        self.L.or_update_bounds(self.p, int(flag))
+
+    def curve_strength(self, preset, p, length):
+        return float(self.L.or_brush_curve_strength(self.p, int(preset), C.c_float(p), C.c_float(length)))
+
+    def close(self):
+        if self.p is not None:
+            self.L.or_pbvh_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
