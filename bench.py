@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Headline benchmark of the sculpt-stroke hot path (BASELINE.json: vertex-dabs/sec and ms/dab,
+% of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid 4096]
+
+N = 1 workload (config.workload): C3 -- draw brush + normal recompute + BB refit on the 16,777,216-
+vertex height-field grid, radius sweep 1-50 % of the bounding-box diagonal, 32 dabs per radius.
+One *step* = one pass of the whole 224-dab stroke script.  `value` = vertex-dabs / second with the
+mesh resident in HBM (CUDA events around the K strokes); `e2e` = the same strokes driven through
+the reference-named host API with host buffers: per dab the descriptor goes host->device, at stroke
+end positions, normals, node boxes and flags come back device->host, all inside the timed region.
+
+Prints ONE JSON line on rank 0.  --impl reference times the CPU oracle (OpenMP, all host threads)
+on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vertex_dabs_per_sec"
+UNIT = "vertex-dabs/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args):
+    from dune_sculpt_b200 import meshgen, stroke
+    t0 = time.time()
+    mesh = meshgen.grid(args.grid)
+    diag = mesh.bbox_diag()
+    dabs = stroke.c3_radius_sweep(diag, dabs_per_radius=args.dabs_per_radius)
+    log("[bench] mesh grid %d^2: V=%d polys=%d diag=%.4f, %d dabs/stroke (%.1fs)" %
+        (args.grid, mesh.totvert, mesh.totpoly, diag, len(dabs), time.time() - t0))
+    return mesh, diag, dabs
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle (a port -- the reference itself does not compile here) with
+    OpenMP over hit nodes, the decomposition the reference uses (lib/intern/task_range.cc:89-127)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dune_sculpt_b200 import build as b
+    b.build_oracle()
+    from oracle_py import Oracle
+    mesh, diag, dabs = build_workload(args)
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    orc = Oracle(mesh, threads=cores)
+    log("[bench] oracle PBVH build %.1fs, %d nodes, %d threads" % (time.time() - t0, orc.totnode, cores))
+    # bounded sample: `sample_per_radius` dabs of every radius of the sweep per step
+    per = args.dabs_per_radius
+    nrad = len(dabs) // per
+    sample = [dabs[r * per + k] for r in range(nrad) for k in range(args.cpu_sample_per_radius)]
+    orc.stroke_begin()
+    for _ in range(args.warmup_ref):
+        for d in sample[:2]:
+            orc.dab(d)
+    vd0 = orc.vertex_dabs()
+    t0 = time.perf_counter()
+    for _ in range(args.steps_ref):
+        for d in sample:
+            orc.dab(d)
+    dt = time.perf_counter() - t0
+    vd = orc.vertex_dabs() - vd0
+    orc.stroke_end()
+    value = vd / dt
+    sample_desc = "%d dabs per radius x %d radii of the C3 sweep per step (%d dabs), %d steps" % (
+        args.cpu_sample_per_radius, nrad, len(sample), args.steps_ref)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps_ref,
+        "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps_ref, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, mesh, len(dabs)),
+        "ms_per_dab": 1e3 * dt / (args.steps_ref * len(sample)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, mesh, ndabs):
+    return {"workload": "C3 draw+normals+BB radius sweep 1-50%% bbox diag, grid %d^2 (V=%d), %d dabs/stroke" %
+                        (args.grid, mesh.totvert, ndabs),
+            "verts": mesh.totvert, "dabs_per_step": ndabs, "brush": "draw, SMOOTH falloff, area-normal direction",
+            "l2": "inputs larger than L2 (resident mesh arrays > 2 GB; every stroke sweeps all of them)"}
+
+
+def analysis_pass(ses, dabs, na):
+    """One untimed stroke with a sync after every dab: per-dab U/A/T/M and per-stage device times,
+    for the roofline object."""
+    from dune_sculpt_b200 import stroke, capi
+    uniq, face, totprim = na["uniq_verts"].astype(np.int64), na["face_verts"].astype(np.int64), na["totprim"].astype(np.int64)
+    ninner = int((na["flag"] & 1 == 0).sum())
+    ses.stage_timing(True)
+    ses.stroke_begin()
+    moved_prev = 0
+    touched = np.zeros(ses.totnode, dtype=bool)
+    tot = {"U": 0, "A": 0, "T": 0, "M": 0, "first_A": 0, "hits": 0}
+    stage_bytes = {"gather": 0, "area_normal": 0, "brush": 0, "normals": 0, "leaf_bb": 0, "bb_flush": 0}
+    nleaf = int((na["flag"] & 1).sum())
+    for d in dabs:
+        ses.dab(d)
+        h = ses.hits()
+        st = ses.stats()
+        M = st["moved_verts"] - moved_prev
+        moved_prev = st["moved_verts"]
+        U = int(uniq[h].sum())
+        A = U + int(face[h].sum())
+        T = int(totprim[h].sum())
+        new = h[~touched[h]]
+        touched[h] = True
+        first_A = int(uniq[new].sum() + face[new].sum())
+        tot["U"] += U; tot["A"] += A; tot["T"] += T; tot["M"] += M; tot["first_A"] += first_A; tot["hits"] += h.size
+        stage_bytes["gather"] += 48 * nleaf
+        stage_bytes["area_normal"] += U * 12 + M * 12
+        stage_bytes["brush"] += U * 12 + M * 12 + first_A * 24
+        stage_bytes["normals"] += T * 12 + A * 12 + M * 12
+        stage_bytes["leaf_bb"] += 0 * A + 24 * h.size  # position gather is counted once, under normals
+        stage_bytes["bb_flush"] += 72 * ninner
+    ses.stroke_end()
+    times = ses.stage_times()
+    ses.stage_timing(False)
+    return tot, stage_bytes, times
+
+
+def run_ours(args, rank, world):
+    from dune_sculpt_b200 import build as b
+    b.build_cuda()
+    b.build_host()
+    from dune_sculpt_b200 import capi
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    mesh, diag, dabs = build_workload(args)
+    t0 = time.time()
+    ses = capi.SculptSession(mesh, device=local_rank)  # fails loudly without a device / the .so
+    na = ses.node_arrays()
+    log("[bench] host PBVH build + device upload %.1fs, %d nodes (%d leaves)" %
+        (time.time() - t0, ses.totnode, int((na["flag"] & 1).sum())))
+    D, ctx = ses.D, ses.ctx
+    import ctypes as C
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def device_stroke():
+        ses._chk(D.dsc_stroke_begin(ctx, None))
+        for d in dabs:
+            ses._chk(D.dsc_dab(ctx, C.byref(d)))
+        ses._chk(D.dsc_stroke_end(ctx))
+
+    # ---- device-resident timing: `value`
+    for _ in range(args.warmup):
+        device_stroke()
+    ses.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    vd = 0
+    launches = 0
+    ses.timer_start()
+    for _ in range(args.steps):
+        device_stroke()
+        st = ses.stats()  # small D2H of the counters, once per stroke
+        vd += st["vertex_dabs"]
+        launches += st["kernel_launches"]
+    ms = ses.timer_stop()
+    clocks = sampler.stop()
+    barrier()
+
+    # ---- end-to-end timing through the host API: `e2e`
+    H = ses.H
+    h2d = len(dabs) * C.sizeof(capi.DscDab)
+    d2h = mesh.totvert * 24 + ses.totnode * (48 + 4) + 8
+    for _ in range(1):
+        ses.stroke_begin(); [ses.dab(d) for d in dabs]; ses.stroke_end()
+    ses.synchronize()
+    barrier()
+    vd_e = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ses.stroke_begin()
+        for d in dabs:
+            ses.dab(d)
+        vd_e += ses.stats()["vertex_dabs"]
+        ses.stroke_end()  # flush + download co / no / boxes / flags into the host PBVH
+    ses.synchronize()
+    dt_e = time.perf_counter() - t0
+    barrier()
+
+    # ---- max over ranks
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms, dt_e], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([float(vd), float(vd_e), float(launches)], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        ms, dt_e = float(t[0]), float(t[1])
+        vd, vd_e, launches = int(s[0]), int(s[1]), int(s[2])
+
+    # ---- roofline of the dominant kernel (untimed analysis stroke, CUDA events per stage)
+    tot, stage_bytes, times = analysis_pass(ses, dabs, na)
+    peak, peak_src = measured_peaks()
+    dom = max((k for k in stage_bytes), key=lambda k: times[k][0])
+    dom_ms, dom_launches = times[dom]
+    achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    total_bytes = sum(stage_bytes.values())
+    total_ms = sum(v[0] for v in times.values())
+    stages = {k: {"ms": round(times[k][0], 4), "launches": times[k][1], "alg_bytes": int(stage_bytes.get(k, 0)),
+                  "gbs": round(stage_bytes.get(k, 0) / (times[k][0] * 1e-3) / 1e9, 1) if times[k][0] > 0 else None}
+              for k in times}
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": int(stage_bytes[dom] / max(dom_launches, 1)),
+                "whole_path": {"achieved": round(total_bytes / (total_ms * 1e-3) / 1e9, 1) if total_ms > 0 else None,
+                               "frac": round(total_bytes / (total_ms * 1e-3) / 1e9 / peak, 4) if total_ms > 0 else None,
+                               "frac_of_8TBs_nominal": round(total_bytes / (total_ms * 1e-3) / 1e9 / 8000.0, 4) if total_ms > 0 else None,
+                               "bytes_per_vertex_dab": round(total_bytes / max(tot["U"], 1), 2)},
+                "stages": stages}
+
+    if rank != 0:
+        ses.close()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, OpenMP, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, mesh, dabs)
+
+    ndabs = len(dabs) * args.steps
+    out = {
+        "metric": METRIC, "value": vd / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh, len(dabs)),
+        "ms_per_dab": ms / ndabs, "vertex_dabs_per_step": vd // args.steps,
+        "e2e": {"value": vd_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * dt_e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+    ses.close()
+
+
+def cpu_baseline(args, mesh, dabs):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dune_sculpt_b200 import build as b
+    b.build_oracle()
+    from oracle_py import Oracle
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    orc = Oracle(mesh, threads=cores)
+    log("[bench] cpu_baseline: oracle PBVH build %.1fs" % (time.time() - t0))
+    per = args.dabs_per_radius
+    nrad = len(dabs) // per
+    sample = [dabs[r * per + k] for r in range(nrad) for k in range(args.cpu_sample_per_radius)]
+    orc.stroke_begin()
+    orc.dab(sample[0])
+    vd0 = orc.vertex_dabs()
+    t0 = time.perf_counter()
+    for d in sample:
+        orc.dab(d)
+    dt = time.perf_counter() - t0
+    vd = orc.vertex_dabs() - vd0
+    orc.close()
+    return {"value": vd / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d dabs per radius x %d radii of the same sweep (%d dabs, %.1f s), OpenMP over hit nodes" %
+                      (args.cpu_sample_per_radius, nrad, len(sample), dt),
+            "ms_per_dab": 1e3 * dt / len(sample)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=4096)
+    ap.add_argument("--dabs-per-radius", type=int, default=32)
+    ap.add_argument("--cpu-sample-per-radius", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # the CPU arm's steps are bounded samples: cap them so the run ends within minutes
+    args.steps_ref = max(1, min(args.steps, 3))
+    args.warmup_ref = max(0, min(args.warmup, 1))
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl")
+    run_ours(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,7 @@ struct DscContext {
   int *d_slot_of = nullptr;
   float *d_mask = nullptr, *d_automask = nullptr, *d_curve = nullptr;
   float *d_stage3 = nullptr; /* [totvert][3] export/import staging */
+  unsigned *d_capture = nullptr;
   int *d_list = nullptr, *d_count = nullptr;
   DevMesh m;
   DabState *h_state = nullptr; /* pinned */
@@ -319,7 +320,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     m.mask = ctx->d_mask;
   }
   if ((r = dev_zero(ctx, &m.dirty, (size_t)ctx->nwords)) || (r = dev_zero(ctx, &m.iter_moved, (size_t)ctx->nwords)) ||
-      (r = dev_zero(ctx, &m.capture, (size_t)ctx->nwords)))
+      (r = dev_zero(ctx, &ctx->d_capture, (size_t)ctx->nwords)))
     return r;
   if ((r = dev_upload(ctx, &ctx->d_slot_of, ctx->slot_of))) return r;
   if ((r = dev_alloc(ctx, &ctx->d_stage3, (size_t)3 * V))) return r;
@@ -634,6 +635,7 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
   DevMesh &m = ctx->m;
   cudaStream_t st = ctx->stream;
 
+  if (ctx->capture) CU(cudaMemsetAsync(ctx->d_capture, 0, sizeof(unsigned) * (size_t)ctx->nwords, st));
   /* 1. gather + undo membership + node marks */
   {
     StageScope s(ctx, ST_GATHER);
@@ -683,9 +685,6 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     StageScope s(ctx, ST_BRUSH);
     k_brush<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d);
     LAUNCH_CHECK();
-  }
-  if (ctx->capture) {
-    CU(cudaMemcpyAsync(m.capture, m.dirty, sizeof(unsigned) * (size_t)ctx->nwords, cudaMemcpyDeviceToDevice, st));
   }
   /* 4. normals, 5. bounds */
   int clear = 0, r;
@@ -753,6 +752,7 @@ int dsc_debug_capture(DscContext *ctx, int on)
 {
   if (!ctx) return DSC_ERR_INVALID;
   ctx->capture = on != 0;
+  ctx->m.capture = ctx->capture ? ctx->d_capture : nullptr;
   return DSC_OK;
 }
 
@@ -761,7 +761,7 @@ int dsc_last_moved(DscContext *ctx, int *r_verts, int capacity, int *r_tot)
   NEED_PBVH();
   if (!ctx->capture) return fail(ctx, DSC_ERR_STATE, "dsc_debug_capture(ctx, 1) first");
   CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), ctx->stream));
-  k_export_bits<<<ctx->grid, 256, 0, ctx->stream>>>(ctx->d_count, ctx->d_list, ctx->m.capture, ctx->d_slot_of, ctx->totvert);
+  k_export_bits<<<ctx->grid, 256, 0, ctx->stream>>>(ctx->d_count, ctx->d_list, ctx->d_capture, ctx->d_slot_of, ctx->totvert);
   LAUNCH_CHECK();
   int tot = 0;
   CU(cudaMemcpyAsync(&tot, ctx->d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -47,7 +47,7 @@ struct DevMesh {
   const float *mask, *automask;
   unsigned *dirty;      /* PBVH.vert_bitmap, one bit per slot */
   unsigned *iter_moved; /* smooth: moved in this iteration */
-  unsigned *capture;    /* debug: copy of the dirty bits after the brush stage */
+  unsigned *capture;    /* debug: verts the current dab marked (NULL when capture is off) */
   const unsigned char *boundary;
   const unsigned *nb_off;
   const int *nb_idx;
@@ -286,6 +286,9 @@ __global__ void __launch_bounds__(1024) k_gather(DevMesh m, float cx, float cy, 
     if (lane == 0 && vd) atomicAdd(&s_vd, vd);
     __syncthreads();
     if (tid == 0) {
+      /* what dsc_last_area reports when the tool samples no plane: zero normal, brush location */
+      m.st->area_no[0] = m.st->area_no[1] = m.st->area_no[2] = 0.0f;
+      m.st->area_co[0] = cx; m.st->area_co[1] = cy; m.st->area_co[2] = cz;
       m.st->hit_count = s_base;
       m.st->vd_total += s_vd;
       m.st->hits_total += (unsigned long long)s_base;
@@ -573,6 +576,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d)
       const unsigned bal = __ballot_sync(0xffffffffu, moved);
       if (bal && lane == 0) {
         m.dirty[s >> 5] |= bal;
+        if (m.capture) m.capture[s >> 5] |= bal;
         moved_cnt += __popc(bal);
       }
     }
@@ -657,6 +661,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, 
         m.iter_moved[s >> 5] = bal;
         if (bal) {
           m.dirty[s >> 5] |= bal;
+          if (m.capture) m.capture[s >> 5] |= bal;
           moved_cnt += __popc(bal);
         }
       }

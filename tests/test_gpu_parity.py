@@ -1,0 +1,260 @@
+"""CUDA path vs CPU oracle on identical meshes and stroke scripts (the parity tests proper).
+Every test goes through the reference-named host API and the C ABI; nothing here touches torch."""
+import numpy as np
+import pytest
+
+from dune_sculpt_b200 import capi, meshgen, stroke
+from parity import run_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _line_dabs(tool, p0, p1, radius, n, **kw):
+    pts = stroke.line_points(p0, p1, radius, count=n)
+    bs = stroke._strength(tool, kw.pop("alpha", 0.6), invert=kw.pop("invert", False))
+    out = []
+    prev = None
+    for i, p in enumerate(pts):
+        k = dict(kw)
+        k.setdefault("view_normal", (0, 0, 1))
+        k["flags"] = k.get("flags", 0) | (capi.DAB_FIRST_STEP if i == 0 else 0)
+        if tool == capi.TOOL_CLAY_STRIPS:
+            k["grab_delta"] = (0, 0, 0) if prev is None else (p - prev)
+        out.append(capi.make_dab(tool, p, radius, bstrength=bs, **k))
+        prev = p
+    return out
+
+
+@pytest.mark.parametrize("preset", [capi.CURVE_SMOOTH, capi.CURVE_SPHERE, capi.CURVE_ROOT, capi.CURVE_SHARP,
+                                    capi.CURVE_LIN, capi.CURVE_POW4, capi.CURVE_INVSQUARE, capi.CURVE_CONSTANT,
+                                    capi.CURVE_SMOOTHER])
+def test_draw_presets_small_grid(preset):
+    m = meshgen.grid(129)
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.6, -0.3, 0.0), (0.6, 0.4, 0.0), 0.3, 12, curve_preset=preset)
+    r = run_parity(m, dabs, leaf_limit=300)
+    assert r["moved"] > 0
+
+
+def test_draw_custom_curve_and_hardness():
+    m = meshgen.grid(129)
+    t = np.linspace(0.0, 1.0, 257, dtype=np.float32)
+    table = (1.0 - t) ** 1.7
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.6, -0.3, 0.0), (0.6, 0.4, 0.0), 0.3, 10, curve_preset=capi.CURVE_CUSTOM,
+                      hardness=0.35)
+    run_parity(m, dabs, leaf_limit=300, curve=table)
+
+
+@pytest.mark.parametrize("plane", [capi.DIR_AREA, capi.DIR_VIEW, capi.DIR_X, capi.DIR_Z])
+def test_draw_sculpt_plane(plane):
+    m = meshgen.cube(5)
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.7, 0.1, 1.0), (0.7, -0.2, 1.0), 0.35, 10, sculpt_plane=plane,
+                      view_normal=(0.1, 0.2, 0.97))
+    run_parity(m, dabs, leaf_limit=150)
+
+
+def test_draw_frontface_mask_automask_invert():
+    m = meshgen.icosphere(24)
+    mask = meshgen.low_freq_mask(m, seed=3)
+    rng = np.random.default_rng(5)
+    automask = rng.uniform(0.0, 1.0, size=m.totvert).astype(np.float32)
+    dabs = _line_dabs(capi.TOOL_DRAW, (0.0, -0.5, 0.86), (0.3, 0.5, 0.81), 0.4, 10, flags=capi.DAB_FRONTFACE,
+                      view_normal=(0.0, 0.0, 1.0), invert=True)
+    run_parity(m, dabs, mask=mask, automask=automask, leaf_limit=120)
+
+
+def test_inflate_icosphere():
+    m = meshgen.icosphere(20, noise=0.002)
+    dabs = _line_dabs(capi.TOOL_INFLATE, (0.0, 0.0, 1.0), (0.8, 0.0, 0.6), 0.35, 12)
+    run_parity(m, dabs, leaf_limit=100)
+
+
+def test_inflate_closed_form():
+    # sphere + inflate with CONSTANT falloff: |co| grows by fade * r * bstrength along the (radial) normal
+    m = meshgen.icosphere(16)
+    d = capi.make_dab(capi.TOOL_INFLATE, (0, 0, 1), 0.5, curve_preset=capi.CURVE_CONSTANT, bstrength=0.2)
+    r = run_parity(m, [d], leaf_limit=100)
+    before = np.linalg.norm(m.co.astype(np.float64), axis=1)
+    after = np.linalg.norm(r["co"].astype(np.float64), axis=1)
+    inside = np.linalg.norm(m.co - np.array([0, 0, 1], np.float32), axis=1) <= 0.5
+    assert np.allclose((after - before)[inside], 0.2 * 0.5, atol=2e-3)  # vertex normal ~ radial on a coarse sphere
+    assert np.array_equal(r["co"][~inside], m.co[~inside])
+
+
+def test_draw_closed_form_flat_grid():
+    # flat grid + draw along +Z with CONSTANT falloff => exact dz = radius * bstrength
+    m = meshgen.grid(65, height=0.0)
+    d = capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.4, curve_preset=capi.CURVE_CONSTANT, sculpt_plane=capi.DIR_Z,
+                      bstrength=0.25)
+    r = run_parity(m, [d], leaf_limit=100)
+    inside = (m.co[:, 0] ** 2 + m.co[:, 1] ** 2) <= np.float32(0.4) ** 2
+    assert np.array_equal(r["co"][inside, 2], np.full(inside.sum(), np.float32(0.4) * np.float32(0.25), np.float32))
+    assert np.array_equal(r["co"][~inside], m.co[~inside])
+
+
+def test_grab_uses_original_boxes_and_coords():
+    m = meshgen.grid(97)
+    loc = (0.1, -0.2, 0.0)
+    bs = stroke._strength(capi.TOOL_GRAB, 0.8)
+    dabs = [capi.make_dab(capi.TOOL_GRAB, loc, 0.35, bstrength=bs, grab_delta=np.array([0.2, 0.1, 0.5]) * (i + 1) / 10,
+                          flags=capi.DAB_FIRST_STEP if i == 0 else 0) for i in range(10)]
+    run_parity(m, dabs, leaf_limit=200)
+
+
+@pytest.mark.parametrize("invert", [False, True])
+def test_clay_strips(invert):
+    m = meshgen.grid(129)
+    dabs = _line_dabs(capi.TOOL_CLAY_STRIPS, (-0.6, -0.3, 0.0), (0.6, 0.4, 0.0), 0.3, 14, flags=capi.DAB_PLANE_TRIM,
+                      tip_roundness=0.18, invert=invert, alpha=1.0)
+    r = run_parity(m, dabs, leaf_limit=300)
+    assert r["moved"] > 0
+
+
+def test_clay_strips_view_plane_with_mask():
+    m = meshgen.grid(129)
+    mask = meshgen.low_freq_mask(m, seed=9)
+    dabs = _line_dabs(capi.TOOL_CLAY_STRIPS, (-0.5, 0.3, 0.0), (0.5, -0.4, 0.0), 0.25, 12, sculpt_plane=capi.DIR_VIEW,
+                      plane_offset=0.1, alpha=1.0)
+    run_parity(m, dabs, mask=mask, leaf_limit=300)
+
+
+@pytest.mark.parametrize("alpha", [0.3, 0.75, 1.0])
+def test_smooth_icosphere(alpha):
+    m = meshgen.icosphere(24, noise=0.004)
+    dabs = stroke.c2_smooth_stroke(dabs=12, radius=0.45, alpha=alpha)
+    r = run_parity(m, dabs, leaf_limit=120)
+    assert r["moved"] > 0
+
+
+def test_smooth_grid_boundary_rules():
+    # open mesh: boundary verts average boundary neighbours only, corners stay
+    m = meshgen.grid(65)
+    dabs = _line_dabs(capi.TOOL_SMOOTH, (-0.9, -0.9, 0.0), (0.9, -0.8, 0.0), 0.4, 8, alpha=1.0)
+    r = run_parity(m, dabs, leaf_limit=150)
+    assert np.array_equal(r["co"][0], m.co[0])  # corner vertex has two neighbours
+
+
+def test_fully_masked_and_hidden_nodes_are_skipped():
+    m = meshgen.grid(97)
+
+    def pre(orc, ses):
+        na = orc.node_arrays()
+        leaves = np.nonzero(na["flag"] & 1)[0]
+        for k, n in enumerate(leaves[::3]):
+            f = capi.PBVH_FullyMasked if k % 2 else capi.PBVH_FullyHidden
+            orc.set_node_flag(int(n), f, True)
+            ses.set_node_flag(int(n), f, True)
+
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.6, -0.3, 0.0), (0.6, 0.4, 0.0), 0.3, 8)
+    run_parity(m, dabs, leaf_limit=200, pre=pre)
+
+
+def test_skip_normals_and_bounds_flags_persist():
+    m = meshgen.grid(97)
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.6, -0.3, 0.0), (0.6, 0.4, 0.0), 0.3, 9)
+    for i, d in enumerate(dabs):
+        if i % 3 != 2:
+            d.flags |= capi.DAB_NO_NORMALS
+        if i % 2 == 0:
+            d.flags |= capi.DAB_NO_BOUNDS
+    run_parity(m, dabs, leaf_limit=200)
+
+
+def test_triangle_mesh_default_leaf_limit_single_leaf():
+    m = meshgen.icosphere(10)  # 2000 tris: the whole mesh is one leaf
+    dabs = _line_dabs(capi.TOOL_DRAW, (0.0, 0.0, 1.0), (0.5, 0.2, 0.8), 0.5, 5, view_normal=(0, 0, 1))
+    run_parity(m, dabs)
+
+
+def test_search_gather_through_host_api():
+    """BKE_pbvh_search_gather(SCULPT_search_sphere_cb) on a device-attached PBVH == oracle DFS"""
+    import ctypes as C
+    from oracle_py import Oracle
+    m = meshgen.cube(5)
+    orc = Oracle(m, leaf_limit=100)
+    ses = capi.SculptSession(m, leaf_limit=100, device=0)
+    H = capi.host_lib()
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        c = rng.uniform(-1.2, 1.2, size=3).astype(np.float32)
+        rsq = float(rng.uniform(0.01, 1.5))
+        for original in (False, True):
+            data = capi.SculptSearchSphereData(capi.fptr(c), rsq, original, True)
+            arr = C.POINTER(C.POINTER(capi.PBVHNode))()
+            tot = C.c_int(0)
+            H.BKE_pbvh_search_gather(ses.pbvh, C.cast(H.SCULPT_search_sphere_cb, C.c_void_p), C.byref(data),
+                                     C.byref(arr), C.byref(tot))
+            base = C.addressof(ses.pbvh.contents.nodes.contents)
+            got = [(C.addressof(arr[i].contents) - base) // C.sizeof(capi.PBVHNode) for i in range(tot.value)]
+            if tot.value:
+                H.MEM_freeN(arr)
+            else:
+                assert not arr  # NULL, 0 when nothing is found (pbvh.c:2760-2766)
+            assert got == list(orc.gather_sphere(c, rsq, original))
+    ses.close()
+    orc.close()
+
+
+def test_vert_coords_apply_roundtrip():
+    """BKE_pbvh_vert_coords_apply -> device normals + boxes == oracle recompute"""
+    from oracle_py import Oracle
+    m = meshgen.grid(65)
+    ses = capi.SculptSession(m, leaf_limit=150, device=0)
+    rng = np.random.default_rng(4)
+    co = m.co.copy()
+    sel = rng.uniform(size=m.totvert) < 0.3
+    co[sel] += rng.normal(scale=0.01, size=(int(sel.sum()), 3)).astype(np.float32)
+    H = capi.host_lib()
+    H.BKE_pbvh_vert_coords_apply(ses.pbvh, capi.fptr(co), m.totvert)
+    m2 = meshgen.Mesh(co, m.poly_start, m.poly_len, m.loop_v)
+    # oracle: same topology (built from the ORIGINAL coordinates), new coordinates, everything dirty
+    orc = Oracle(m, leaf_limit=150)
+    orc.set_co(co)
+    orc.L.or_recalc_all_normals(orc.p)
+    for n in np.nonzero(orc.node_arrays()["flag"] & 1)[0]:
+        orc.L.or_node_mark_update(orc.p, int(n))
+    orc.update_bounds(capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB)
+    assert np.array_equal(ses.co(), co)
+    # verts that did not move keep their old normal on the device (only changed verts are marked,
+    # pbvh.c:4731-4736) unless a neighbour moved -- compare the moved ones
+    no_g, no_o = ses.no(), orc.no()
+    assert np.array_equal(no_g[sel], no_o[sel])
+    bb, obb = ses.node_bb()
+    na = orc.node_arrays()
+    assert np.array_equal(bb, na["vb"]) and np.array_equal(obb, na["orig_vb"])
+    out = H.BKE_pbvh_vert_coords_alloc(ses.pbvh)
+    back = np.ctypeslib.as_array(out, shape=(m.totvert * 3,)).reshape(-1, 3).copy()
+    H.MEM_freeN(out)
+    assert np.array_equal(back, co)
+    assert m2.totvert == m.totvert
+    ses.close()
+    orc.close()
+
+
+def test_c1_cube_draw_stroke_full_size():
+    """config C1: 393,218-vertex cube, 100-dab draw stroke, default leaf limit"""
+    m = meshgen.cube(8)
+    assert m.totvert == 393218
+    r = run_parity(m, stroke.c1_draw_stroke(), check_every=5)
+    assert r["moved"] > 0
+
+
+def test_c2_icosphere_smooth_stroke_reduced():
+    """config C2 at f=158 (249,642 verts), 40 dabs: same script shape, oracle-sized"""
+    m = meshgen.icosphere(158, noise=0.002)
+    r = run_parity(m, stroke.c2_smooth_stroke(dabs=40), check_every=4)
+    assert r["moved"] > 0
+
+
+def test_c4_tools_reduced_grid():
+    """config C4 on a 512^2 grid: each tool with mask and automask"""
+    m = meshgen.grid(512)
+    mask = meshgen.low_freq_mask(m)
+    diag = m.bbox_diag()
+    for tool in (capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_CLAY_STRIPS, capi.TOOL_GRAB):
+        ses = capi.SculptSession(m, leaf_limit=0)
+        auto = np.zeros(m.totvert, dtype=np.float32)
+        capi.host_lib().DUNE_sculpt_automask_boundary_edges(ses.pbvh, 1, capi.fptr(auto))
+        ses.close()
+        dabs = stroke.c4_tool_stroke(tool, diag, dabs=12)
+        r = run_parity(m, dabs, mask=mask, automask=auto, check_every=3)
+        assert r["moved"] > 0, tool
