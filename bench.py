@@ -163,15 +163,18 @@ def workload_config(args, mesh, ndabs):
 def analysis_pass(ses, dabs, na):
     """One untimed stroke with a sync after every dab: per-dab U/A/T/M and per-stage device times,
     for the roofline object."""
-    from dune_sculpt_b200 import stroke, capi
     uniq, face, totprim = na["uniq_verts"].astype(np.int64), na["face_verts"].astype(np.int64), na["totprim"].astype(np.int64)
-    ninner = int((na["flag"] & 1 == 0).sum())
+    n = ses.totnode
+    parent = np.full(n, -1, dtype=np.int64)
+    inner = np.nonzero((na["flag"] & 1) == 0)[0]
+    parent[na["children_offset"][inner]] = inner
+    parent[na["children_offset"][inner] + 1] = inner
     ses.stage_timing(True)
     ses.stroke_begin()
     moved_prev = 0
-    touched = np.zeros(ses.totnode, dtype=bool)
+    touched = np.zeros(n, dtype=bool)
     tot = {"U": 0, "A": 0, "T": 0, "M": 0, "first_A": 0, "hits": 0}
-    stage_bytes = {"gather": 0, "area_normal": 0, "brush": 0, "normals": 0, "leaf_bb": 0, "bb_flush": 0}
+    stage_bytes = {"gather": 0, "area_normal": 0, "brush": 0, "normals_bb": 0, "bb_refit": 0}
     nleaf = int((na["flag"] & 1).sum())
     for d in dabs:
         ses.dab(d)
@@ -185,13 +188,22 @@ def analysis_pass(ses, dabs, na):
         new = h[~touched[h]]
         touched[h] = True
         first_A = int(uniq[new].sum() + face[new].sum())
+        anc = 0
+        f = np.unique(parent[h])
+        f = f[f >= 0]
+        seen = np.zeros(n, dtype=bool)
+        while f.size:
+            f = f[~seen[f]]
+            seen[f] = True
+            anc += f.size
+            f = np.unique(parent[f])
+            f = f[f >= 0]
         tot["U"] += U; tot["A"] += A; tot["T"] += T; tot["M"] += M; tot["first_A"] += first_A; tot["hits"] += h.size
         stage_bytes["gather"] += 48 * nleaf
         stage_bytes["area_normal"] += U * 12 + M * 12
         stage_bytes["brush"] += U * 12 + M * 12 + first_A * 24
-        stage_bytes["normals"] += T * 12 + A * 12 + M * 12
-        stage_bytes["leaf_bb"] += 0 * A + 24 * h.size  # position gather is counted once, under normals
-        stage_bytes["bb_flush"] += 72 * ninner
+        stage_bytes["normals_bb"] += T * 12 + A * 12 + M * 12 + 24 * h.size
+        stage_bytes["bb_refit"] += 72 * anc
     ses.stroke_end()
     times = ses.stage_times()
     ses.stage_timing(False)

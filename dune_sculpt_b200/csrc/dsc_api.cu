@@ -7,15 +7,17 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #define DSC_ABI_VERSION 1
+#define DSC_SMEM_BUDGET (216 * 1024) /* dynamic shared memory a leaf may ask of k_normals_bb_smem */
 
 static thread_local std::string g_create_error;
 
 enum { ST_GATHER, ST_AREA, ST_BRUSH, ST_SMOOTH, ST_NORMALS, ST_LEAFBB, ST_FLUSH, ST_OTHER };
 static const char *k_stage_names[DSC_NUM_STAGES] = {"gather", "area_normal", "brush", "smooth",
-                                                    "normals", "leaf_bb", "bb_flush", "other"};
+                                                    "normals_bb", "leaf_bb", "bb_refit", "other"};
 
 struct StageEvent {
   int stage;
@@ -25,7 +27,10 @@ struct StageEvent {
 struct DscContext {
   int device = 0;
   int num_sms = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  /* the dab pipeline */
+  cudaStream_t stream2 = nullptr; /* bottom-up box refit, overlapped with the next dab */
+  cudaEvent_t ev_fork = nullptr, ev_bb = nullptr, ev_refit[DSC_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  bool side_busy = false; /* something was queued on stream2 since the last join */
   std::string error;
   std::vector<void *> allocs;
 
@@ -37,16 +42,26 @@ struct DscContext {
   std::vector<unsigned char> h_boundary;
   bool has_no = false, has_mask = false, has_nb = false;
 
-  std::vector<int> slot_of;   /* vertex -> slot */
-  std::vector<int> leaf_node; /* leaf -> node */
+  std::vector<int> slot_of;     /* vertex -> slot */
+  std::vector<int> leaf_node;   /* leaf (= device id) -> host node index */
+  std::vector<int> dev_of_node; /* host node index -> device node id */
+  std::vector<int> node_of_dev;
+  bool stale_flags = false; /* leaves may carry update flags from an earlier dab or from the host */
+  bool any_slow_leaf = false;
+  size_t nb_smem = 0; /* dynamic shared memory of k_normals_bb_smem */
+  int nb_grid = 148;
+  long long dab_index = 0;
+  int last_slot = 0;
+
   int *d_slot_of = nullptr;
   float *d_mask = nullptr, *d_automask = nullptr, *d_curve = nullptr;
   float *d_stage3 = nullptr; /* [totvert][3] export/import staging */
   unsigned *d_capture = nullptr;
   int *d_list = nullptr, *d_count = nullptr;
   DevMesh m;
-  DabState *h_state = nullptr; /* pinned */
-  int *h_list = nullptr;       /* pinned, nleaf ints */
+  DabState *h_state = nullptr;   /* pinned */
+  StrokeTotals *h_tot = nullptr; /* pinned */
+  int *h_list = nullptr;         /* pinned, nleaf ints */
 
   bool capture = false;
   bool stage_timing = false;
@@ -91,6 +106,13 @@ template<typename T> static int dev_upload(DscContext *ctx, T **p, const std::ve
   if (!v.empty()) CU(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   return DSC_OK;
 }
+template<typename T, typename U> static int dev_upload_c(DscContext *ctx, const T **p, const std::vector<U> &v)
+{
+  U *d = nullptr;
+  int r = dev_upload(ctx, &d, v);
+  *p = reinterpret_cast<const T *>(d);
+  return r;
+}
 template<typename T> static int dev_zero(DscContext *ctx, T **p, size_t n)
 {
   int r = dev_alloc(ctx, p, n);
@@ -103,25 +125,44 @@ template<typename T> static int dev_zero(DscContext *ctx, T **p, size_t n)
 struct StageScope {
   DscContext *ctx;
   int stage;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  StageScope(DscContext *c, int s) : ctx(c), stage(s)
+  StageScope(DscContext *c, int s, cudaStream_t stream = nullptr) : ctx(c), stage(s), st(stream ? stream : c->stream)
   {
     ctx->launches++;
     ctx->stage_launches[stage]++;
     if (ctx->stage_timing) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, ctx->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~StageScope()
   {
     if (ctx->stage_timing) {
-      cudaEventRecord(b, ctx->stream);
+      cudaEventRecord(b, st);
       ctx->events.push_back({stage, a, b});
     }
   }
 };
+
+/* the main stream waits for everything queued on the side stream */
+static int join_side(DscContext *ctx)
+{
+  if (ctx->side_busy) {
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream2));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
+    ctx->side_busy = false;
+  }
+  return DSC_OK;
+}
+static int sync_all(DscContext *ctx)
+{
+  CU(cudaStreamSynchronize(ctx->stream2));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->side_busy = false;
+  return DSC_OK;
+}
 
 extern "C" {
 
@@ -157,9 +198,15 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
   ctx->num_sms = prop.multiProcessorCount;
   ctx->grid = ctx->num_sms * 8;
   memset(&ctx->m, 0, sizeof(ctx->m));
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->t0) != cudaSuccess || cudaEventCreate(&ctx->t1) != cudaSuccess ||
-      cudaMallocHost((void **)&ctx->h_state, sizeof(DabState)) != cudaSuccess) {
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_bb, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreate(&ctx->t0) == cudaSuccess && cudaEventCreate(&ctx->t1) == cudaSuccess &&
+            cudaMallocHost((void **)&ctx->h_state, sizeof(DabState)) == cudaSuccess &&
+            cudaMallocHost((void **)&ctx->h_tot, sizeof(StrokeTotals)) == cudaSuccess;
+  for (int i = 0; ok && i < DSC_SLOTS; i++) ok = cudaEventCreateWithFlags(&ctx->ev_refit[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     fail(nullptr, DSC_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return DSC_ERR_CUDA;
@@ -172,6 +219,7 @@ void dsc_ctx_destroy(DscContext *ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->allocs) cudaFree(p);
   for (auto &ev : ctx->events) {
@@ -179,9 +227,14 @@ void dsc_ctx_destroy(DscContext *ctx)
     cudaEventDestroy(ev.b);
   }
   if (ctx->h_state) cudaFreeHost(ctx->h_state);
+  if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
   if (ctx->h_list) cudaFreeHost(ctx->h_list);
   cudaEventDestroy(ctx->t0);
   cudaEventDestroy(ctx->t1);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_bb);
+  for (int i = 0; i < DSC_SLOTS; i++) cudaEventDestroy(ctx->ev_refit[i]);
+  cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -233,6 +286,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   const int V = ctx->totvert, T = ctx->tottri, N = pb->totnode;
   ctx->totnode = N;
   DevMesh &m = ctx->m;
+  int r;
 
   /* leaves in traversal order = ascending prim offset */
   std::vector<int> leaves;
@@ -243,9 +297,9 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   const int L = (int)leaves.size();
   ctx->leaf_node = leaves;
 
-  /* slots */
+  /* slots: each leaf's unique verts are one 128-byte aligned run */
   ctx->slot_of.assign(V, -1);
-  std::vector<int> leaf_ubeg(L), leaf_ucnt(L), leaf_sbeg(L), leaf_scnt(L), leaf_pbeg(L), leaf_pcnt(L);
+  std::vector<int> leaf_ubeg(L), leaf_ucnt(L), leaf_scnt(L), leaf_pbeg(L), leaf_pcnt(L);
   long long cur = 0;
   int expect_prim = 0;
   for (int l = 0; l < L; l++) {
@@ -253,6 +307,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     cur = (cur + 31) & ~31ll;
     leaf_ubeg[l] = (int)cur;
     leaf_ucnt[l] = pb->uniq_verts[n];
+    leaf_scnt[l] = pb->face_verts[n];
     leaf_pbeg[l] = pb->prim_offset[n];
     leaf_pcnt[l] = pb->totprim[n];
     if (leaf_pbeg[l] != expect_prim) return fail(ctx, DSC_ERR_INVALID, "leaf prim ranges do not tile prim_indices");
@@ -267,31 +322,13 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     if (cur > 0x7fffff00ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 slots");
   }
   if (expect_prim != T) return fail(ctx, DSC_ERR_INVALID, "leaves hold %d looptris, mesh has %d", expect_prim, T);
+  cur = (cur + 31) & ~31ll;
   for (int v = 0; v < V; v++) {
-    if (ctx->slot_of[v] < 0) { /* loose vertex: not in any face; park it after the leaves */
-      ctx->slot_of[v] = (int)cur++;
-    }
+    if (ctx->slot_of[v] < 0) ctx->slot_of[v] = (int)cur++; /* loose vertex: in no face; parked after the leaves */
   }
-  const int VP = (int)((cur + 31) & ~31ll);
+  const int VP = (int)((cur + 31) & ~31ll) + 32;
   ctx->vpad = VP;
   ctx->nwords = VP / 32;
-
-  std::vector<int> shared;
-  for (int l = 0; l < L; l++) {
-    const int n = leaves[l];
-    const int *vi = pb->vert_indices + pb->vert_offset[n];
-    leaf_sbeg[l] = (int)shared.size();
-    leaf_scnt[l] = pb->face_verts[n];
-    for (int i = 0; i < pb->face_verts[n]; i++) shared.push_back(ctx->slot_of[vi[pb->uniq_verts[n] + i]]);
-  }
-  std::vector<int> chunk_leaf, chunk_beg, chunk_cnt;
-  for (int l = 0; l < L; l++) {
-    for (int off = 0; off < leaf_ucnt[l]; off += DSC_CHUNK) {
-      chunk_leaf.push_back(l);
-      chunk_beg.push_back(leaf_ubeg[l] + off);
-      chunk_cnt.push_back(std::min(DSC_CHUNK, leaf_ucnt[l] - off));
-    }
-  }
 
   /* per-slot vertex data */
   auto to_slots = [&](const std::vector<float> &src, int comp, int stride) {
@@ -299,7 +336,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     for (int v = 0; v < V; v++) out[ctx->slot_of[v]] = src[(size_t)stride * v + comp];
     return out;
   };
-  int r;
   for (int k = 0; k < 3; k++) {
     float **dst = (k == 0) ? &m.cx : (k == 1) ? &m.cy : &m.cz;
     if ((r = dev_upload(ctx, dst, to_slots(ctx->h_co, k, 3)))) return r;
@@ -308,6 +344,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       if ((r = dev_upload(ctx, dn, to_slots(ctx->h_no, k, 3)))) return r;
     }
     else if ((r = dev_zero(ctx, dn, (size_t)VP))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
   }
   if ((r = dev_zero(ctx, &m.ox, (size_t)VP)) || (r = dev_zero(ctx, &m.oy, (size_t)VP)) || (r = dev_zero(ctx, &m.oz, (size_t)VP)) ||
       (r = dev_zero(ctx, &m.onx, (size_t)VP)) || (r = dev_zero(ctx, &m.ony, (size_t)VP)) || (r = dev_zero(ctx, &m.onz, (size_t)VP)))
@@ -343,27 +380,187 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       for (int q = ctx->h_nb_off[v]; q < ctx->h_nb_off[v + 1]; q++) idx[n++] = ctx->slot_of[ctx->h_nb_idx[q]];
     }
     off[VP] = n;
-    unsigned *d_off;
-    int *d_idx;
-    unsigned char *d_b;
-    if ((r = dev_upload(ctx, &d_off, off)) || (r = dev_upload(ctx, &d_idx, idx)) || (r = dev_upload(ctx, &d_b, bnd))) return r;
-    m.nb_off = d_off;
-    m.nb_idx = d_idx;
-    m.boundary = d_b;
+    if ((r = dev_upload_c(ctx, &m.nb_off, off)) || (r = dev_upload_c(ctx, &m.nb_idx, idx)) || (r = dev_upload_c(ctx, &m.boundary, bnd)))
+      return r;
+    CU(cudaStreamSynchronize(ctx->stream));
   }
 
-  /* looptris by position: poly verts as slots, owning leaf; vertex -> looptri CSR */
+  /* looptris by position; vertex -> looptri CSR; per-leaf local tables of the shared-memory normals kernel */
+  std::vector<int> leaf_sbeg(L), leaf_xcnt(L, 0), leaf_ebeg(L), leaf_eown(L), leaf_ehalo(L), leaf_hbeg(L), leaf_nbeg(L), leaf_ncnt(L, 0);
+  std::vector<unsigned char> leaf_fast(L, 1);
   {
-    std::vector<int> pv[4];
-    for (int k = 0; k < 4; k++) pv[k].assign((size_t)std::max(T, 1), -1);
     std::vector<int> tri_leaf((size_t)std::max(T, 1), 0);
-    std::vector<int> ngon_id(ctx->totpoly, -1), poly_off(1, 0), poly_slots;
     std::vector<unsigned> deg((size_t)VP + 1, 0);
     for (int l = 0; l < L; l++) {
       for (int pos = leaf_pbeg[l]; pos < leaf_pbeg[l] + leaf_pcnt[l]; pos++) {
         const int t = pb->prim_indices[pos];
         if (t < 0 || t >= T) return fail(ctx, DSC_ERR_INVALID, "prim_indices[%d] out of range", pos);
         tri_leaf[pos] = l;
+        for (int k = 0; k < 3; k++) deg[ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + k]]]++;
+      }
+    }
+    std::vector<unsigned> vt_off((size_t)VP + 1, 0);
+    for (int s = 0; s < VP; s++) vt_off[s + 1] = vt_off[s] + deg[s];
+    std::vector<unsigned> vt_idx((size_t)std::max<unsigned>(vt_off[VP], 1u));
+    std::fill(deg.begin(), deg.end(), 0u);
+    for (int pos = 0; pos < T; pos++) {
+      const int t = pb->prim_indices[pos];
+      /* the reference adds the face normal for corner j = 2, 1, 0 (pbvh.c:2966); a vertex that is
+       * listed twice in one looptri gets it twice -- same here, order within a looptri is moot */
+      for (int k = 0; k < 3; k++) {
+        const int s = ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + k]];
+        vt_idx[vt_off[s] + deg[s]++] = (unsigned)pos;
+      }
+    }
+    std::vector<unsigned>().swap(deg);
+
+    /* ---- local tables ---- */
+    std::vector<int> stage;           /* per leaf: shared slots, then extra slots */
+    std::vector<unsigned short> e_pv; /* 4 per entry */
+    std::vector<unsigned char> e_halo_nb; /* per halo entry: index into the leaf's neighbour list */
+    std::vector<int> nb_leaf;             /* concatenated neighbour-leaf lists */
+    std::vector<unsigned> v2_goff((size_t)VP / 32 + 1, 0);
+    std::vector<unsigned short> v2_idx;
+    v2_idx.reserve(vt_idx.size() + vt_idx.size() / 8);
+    std::vector<unsigned short> col; /* entries of the current group, [vertex][row] */
+    std::vector<int> coln;
+    std::vector<int> lstamp((size_t)VP, -1), lidx((size_t)VP, 0);
+    std::vector<int> pstamp((size_t)std::max(ctx->totpoly, 1), -1), pentry((size_t)std::max(ctx->totpoly, 1), 0);
+    std::vector<int> tri_entry;
+    std::unordered_map<unsigned long long, int> halo;
+    int next_group_to_fill = 0;
+    size_t max_smem = 0;
+    for (int l = 0; l < L; l++) {
+      const int n = leaves[l];
+      const int ub = leaf_ubeg[l], U = leaf_ucnt[l], S = leaf_scnt[l];
+      const int pbeg = leaf_pbeg[l], pend = pbeg + leaf_pcnt[l];
+      const int *vi = pb->vert_indices + pb->vert_offset[n];
+      leaf_sbeg[l] = (int)stage.size();
+      for (int i = 0; i < U; i++) {
+        lstamp[ub + i] = l;
+        lidx[ub + i] = i;
+      }
+      int nloc = U;
+      for (int i = 0; i < S; i++) {
+        const int s = ctx->slot_of[vi[U + i]];
+        lstamp[s] = l;
+        lidx[s] = nloc++;
+        stage.push_back(s);
+      }
+      bool ok = true;
+      int ne = 0;
+      leaf_ebeg[l] = (int)(e_pv.size() / 4);
+      leaf_hbeg[l] = (int)e_halo_nb.size();
+      leaf_nbeg[l] = (int)nb_leaf.size();
+      auto add_entry = [&](int p) -> int {
+        const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
+        unsigned short loc[4] = {0, 0, 0, 0xffff};
+        if (len == 3 || len == 4) {
+          for (int k = 0; k < len; k++) {
+            const int s = ctx->slot_of[ctx->h_loop_v[ls + k]];
+            if (lstamp[s] != l) {
+              lstamp[s] = l;
+              lidx[s] = nloc++;
+              stage.push_back(s);
+              leaf_xcnt[l]++;
+            }
+            loc[k] = (unsigned short)std::min(lidx[s], 0xfffe);
+            if (lidx[s] > 0xfffe) ok = false;
+          }
+        }
+        else {
+          ok = false; /* n-gon: this leaf takes the general path */
+        }
+        e_pv.insert(e_pv.end(), loc, loc + 4);
+        return ne++;
+      };
+      tri_entry.assign((size_t)(pend - pbeg), 0);
+      for (int pos = pbeg; pos < pend; pos++) {
+        const int p = ctx->h_tri_poly[pb->prim_indices[pos]];
+        if (pstamp[p] != l) {
+          pstamp[p] = l;
+          pentry[p] = add_entry(p);
+        }
+        tri_entry[pos - pbeg] = pentry[p];
+      }
+      leaf_eown[l] = ne;
+      halo.clear();
+      const int G0 = ub / 32, ng = (U + 31) / 32;
+      for (; next_group_to_fill < G0; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
+      for (int g = 0; g < ng; g++) {
+        const int i0 = g * 32, cntv = std::min(32, U - i0);
+        coln.assign(32, 0);
+        int width = 0;
+        for (int i = 0; i < cntv; i++) width = std::max(width, (int)(vt_off[ub + i0 + i + 1] - vt_off[ub + i0 + i]));
+        col.assign((size_t)32 * std::max(width, 1), (unsigned short)0xffff);
+        for (int i = 0; i < cntv; i++) {
+          const int s = ub + i0 + i;
+          for (unsigned q = vt_off[s]; q < vt_off[s + 1]; q++) {
+            const int pos = (int)vt_idx[q];
+            int e;
+            if (pos >= pbeg && pos < pend) {
+              e = tri_entry[pos - pbeg];
+            }
+            else {
+              const int p = ctx->h_tri_poly[pb->prim_indices[pos]];
+              const int ol = tri_leaf[pos];
+              const unsigned long long key = ((unsigned long long)(unsigned)p << 32) | (unsigned)ol;
+              auto it = halo.find(key);
+              if (it == halo.end()) {
+                e = add_entry(p);
+                int k = 0;
+                for (; k < leaf_ncnt[l]; k++) {
+                  if (nb_leaf[leaf_nbeg[l] + k] == ol) break;
+                }
+                if (k == leaf_ncnt[l]) {
+                  nb_leaf.push_back(ol);
+                  leaf_ncnt[l]++;
+                }
+                if (k > 255) ok = false;
+                e_halo_nb.push_back((unsigned char)std::min(k, 255));
+                halo.emplace(key, e);
+              }
+              else {
+                e = it->second;
+              }
+            }
+            if (e >= 0xffff) ok = false;
+            col[(size_t)coln[i] * 32 + i] = (unsigned short)std::min(e, 0xfffe);
+            coln[i]++;
+          }
+        }
+        v2_goff[G0 + g] = (unsigned)v2_idx.size();
+        v2_idx.insert(v2_idx.end(), col.begin(), col.begin() + (size_t)32 * width);
+      }
+      next_group_to_fill = G0 + ng;
+      leaf_ehalo[l] = ne - leaf_eown[l];
+      const size_t bytes = dsc_nb_smem_bytes(nloc, ne, ng, leaf_ncnt[l]);
+      if (!ok || bytes > DSC_SMEM_BUDGET) {
+        leaf_fast[l] = 0;
+        ctx->any_slow_leaf = true;
+      }
+      else {
+        max_smem = std::max(max_smem, bytes);
+      }
+    }
+    for (; next_group_to_fill <= VP / 32; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
+    if (v2_idx.empty()) v2_idx.push_back(0xffff);
+    ctx->nb_smem = std::max<size_t>(max_smem, 1024);
+
+    if ((r = dev_upload_c(ctx, &m.stage_slots, stage)) || (r = dev_upload_c(ctx, &m.e_pv, e_pv)) ||
+        (r = dev_upload_c(ctx, &m.e_halo_nb, e_halo_nb)) || (r = dev_upload_c(ctx, &m.nb_leaf, nb_leaf)) ||
+        (r = dev_upload_c(ctx, &m.v2_goff, v2_goff)) || (r = dev_upload_c(ctx, &m.v2_idx, v2_idx)) ||
+        (r = dev_upload_c(ctx, &m.leaf_fast, leaf_fast)))
+      return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+
+    if (ctx->any_slow_leaf) {
+      /* general path tables: poly verts as slots per looptri position, n-gon lists */
+      std::vector<int> pv[4];
+      for (int k = 0; k < 4; k++) pv[k].assign((size_t)std::max(T, 1), -1);
+      std::vector<int> ngon_id((size_t)std::max(ctx->totpoly, 1), -1), poly_off(1, 0), poly_slots;
+      for (int pos = 0; pos < T; pos++) {
+        const int t = pb->prim_indices[pos];
         const int p = ctx->h_tri_poly[t];
         const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
         if (len == 3 || len == 4) {
@@ -382,104 +579,118 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         else {
           return fail(ctx, DSC_ERR_UNSUPPORTED, "poly %d has %d corners", p, len);
         }
-        for (int k = 0; k < 3; k++) deg[ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + k]]]++;
       }
+      if ((r = dev_upload_c(ctx, &m.pv0, pv[0])) || (r = dev_upload_c(ctx, &m.pv1, pv[1])) || (r = dev_upload_c(ctx, &m.pv2, pv[2])) ||
+          (r = dev_upload_c(ctx, &m.pv3, pv[3])) || (r = dev_upload_c(ctx, &m.tri_leaf, tri_leaf)) ||
+          (r = dev_upload_c(ctx, &m.poly_off, poly_off)) || (r = dev_upload_c(ctx, &m.poly_slots, poly_slots)) ||
+          (r = dev_upload_c(ctx, &m.vt_off, vt_off)) || (r = dev_upload_c(ctx, &m.vt_idx, vt_idx)))
+        return r;
+      CU(cudaStreamSynchronize(ctx->stream));
     }
-    std::vector<unsigned> vt_off((size_t)VP + 1, 0);
-    for (int s = 0; s < VP; s++) vt_off[s + 1] = vt_off[s] + deg[s];
-    std::vector<unsigned> vt_idx((size_t)std::max<unsigned>(vt_off[VP], 1u));
-    std::fill(deg.begin(), deg.end(), 0u);
-    for (int pos = 0; pos < T; pos++) {
-      const int t = pb->prim_indices[pos];
-      /* the reference adds the face normal for corner j = 2, 1, 0 (pbvh.c:2966); a vertex that is
-       * listed twice in one looptri gets it twice -- same here, order within a looptri is moot */
-      for (int k = 0; k < 3; k++) {
-        const int s = ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + k]];
-        vt_idx[vt_off[s] + deg[s]++] = (unsigned)pos;
-      }
-    }
-    int *d_pv[4], *d_tl, *d_po, *d_ps;
-    unsigned *d_vo, *d_vi;
-    for (int k = 0; k < 4; k++) {
-      if ((r = dev_upload(ctx, &d_pv[k], pv[k]))) return r;
-    }
-    if ((r = dev_upload(ctx, &d_tl, tri_leaf)) || (r = dev_upload(ctx, &d_po, poly_off)) || (r = dev_upload(ctx, &d_ps, poly_slots)) ||
-        (r = dev_upload(ctx, &d_vo, vt_off)) || (r = dev_upload(ctx, &d_vi, vt_idx)))
+  }
+
+  /* leaves */
+  {
+    if ((r = dev_upload_c(ctx, &m.leaf_ubeg, leaf_ubeg)) || (r = dev_upload_c(ctx, &m.leaf_ucnt, leaf_ucnt)) ||
+        (r = dev_upload_c(ctx, &m.leaf_sbeg, leaf_sbeg)) || (r = dev_upload_c(ctx, &m.leaf_scnt, leaf_scnt)) ||
+        (r = dev_upload_c(ctx, &m.leaf_pbeg, leaf_pbeg)) || (r = dev_upload_c(ctx, &m.leaf_pcnt, leaf_pcnt)) ||
+        (r = dev_upload_c(ctx, &m.leaf_xcnt, leaf_xcnt)) || (r = dev_upload_c(ctx, &m.leaf_ebeg, leaf_ebeg)) ||
+        (r = dev_upload_c(ctx, &m.leaf_eown, leaf_eown)) || (r = dev_upload_c(ctx, &m.leaf_ehalo, leaf_ehalo)) ||
+        (r = dev_upload_c(ctx, &m.leaf_hbeg, leaf_hbeg)) || (r = dev_upload_c(ctx, &m.leaf_nbeg, leaf_nbeg)) ||
+        (r = dev_upload_c(ctx, &m.leaf_ncnt, leaf_ncnt)))
       return r;
-    m.pv0 = d_pv[0]; m.pv1 = d_pv[1]; m.pv2 = d_pv[2]; m.pv3 = d_pv[3];
-    m.tri_leaf = d_tl; m.poly_off = d_po; m.poly_slots = d_ps; m.vt_off = d_vo; m.vt_idx = d_vi;
-    CU(cudaStreamSynchronize(ctx->stream)); /* host vectors die here */
-  }
-
-  /* leaves, chunks */
-  {
-    int *d;
-    if ((r = dev_upload(ctx, &d, leaves))) return r; m.leaf_node = d;
-    if ((r = dev_upload(ctx, &d, leaf_ubeg))) return r; m.leaf_ubeg = d;
-    if ((r = dev_upload(ctx, &d, leaf_ucnt))) return r; m.leaf_ucnt = d;
-    if ((r = dev_upload(ctx, &d, leaf_sbeg))) return r; m.leaf_sbeg = d;
-    if ((r = dev_upload(ctx, &d, leaf_scnt))) return r; m.leaf_scnt = d;
-    if ((r = dev_upload(ctx, &d, leaf_pbeg))) return r; m.leaf_pbeg = d;
-    if ((r = dev_upload(ctx, &d, leaf_pcnt))) return r; m.leaf_pcnt = d;
-    if ((r = dev_upload(ctx, &d, shared))) return r; m.shared_slots = d;
-    if ((r = dev_upload(ctx, &d, chunk_leaf))) return r; m.chunk_leaf = d;
-    if ((r = dev_upload(ctx, &d, chunk_beg))) return r; m.chunk_beg = d;
-    if ((r = dev_upload(ctx, &d, chunk_cnt))) return r; m.chunk_cnt = d;
     m.nleaf = L;
-    m.nchunk = (int)chunk_leaf.size();
+    int max_u = 1;
+    for (int l = 0; l < L; l++) max_u = std::max(max_u, leaf_ucnt[l]);
+    m.max_chunks = (max_u + DSC_CHUNK - 1) / DSC_CHUNK;
     if ((r = dev_zero(ctx, &m.leaf_state, (size_t)L))) return r;
-    if ((r = dev_zero(ctx, &m.hit_list, (size_t)L)) || (r = dev_zero(ctx, &m.search_list, (size_t)L))) return r;
+    if ((r = dev_zero(ctx, &m.hit_list, (size_t)L * DSC_SLOTS)) || (r = dev_zero(ctx, &m.area_list, (size_t)L * DSC_SLOTS)) ||
+        (r = dev_zero(ctx, &m.search_list, (size_t)L)) || (r = dev_zero(ctx, &m.flag_list, (size_t)L)))
+      return r;
     CU(cudaMallocHost((void **)&ctx->h_list, sizeof(int) * (size_t)std::max(L, 1)));
+    CU(cudaStreamSynchronize(ctx->stream));
   }
 
-  /* nodes: SoA boxes, flags, children, parents, inner nodes by depth */
+  /* nodes in device numbering: leaves [0, L) in traversal order, then the inner nodes breadth-first */
   {
-    std::vector<float> bb((size_t)6 * N), obb((size_t)6 * N);
-    std::vector<int> flag(N), child(N), parent(N, -1), depth(N, 0);
+    std::vector<int> hflag(N), hchild(N);
     for (int n = 0; n < N; n++) {
-      for (int k = 0; k < 6; k++) {
-        bb[(size_t)k * N + n] = pb->node_bb[(size_t)6 * n + k];
-        obb[(size_t)k * N + n] = pb->node_orig_bb[(size_t)6 * n + k];
-      }
-      flag[n] = pb->flag[n];
-      child[n] = pb->children_offset[n];
+      hflag[n] = pb->flag[n];
+      hchild[n] = pb->children_offset[n];
     }
-    std::vector<int> order(1, 0);
-    int maxdepth = 0;
+    ctx->dev_of_node.assign(N, -1);
+    ctx->node_of_dev.assign(N, -1);
+    for (int l = 0; l < L; l++) {
+      ctx->dev_of_node[leaves[l]] = l;
+      ctx->node_of_dev[l] = leaves[l];
+    }
+    std::vector<int> order(1, 0), depth(N, 0);
+    int next = L, maxdepth = 0;
     for (size_t i = 0; i < order.size(); i++) {
       const int n = order[i];
-      if (flag[n] & DSC_PBVH_Leaf) continue;
-      const int c = child[n];
+      if (hflag[n] & DSC_PBVH_Leaf) continue;
+      ctx->dev_of_node[n] = next;
+      ctx->node_of_dev[next] = n;
+      next++;
+      const int c = hchild[n];
       if (c <= 0 || c + 1 >= N) return fail(ctx, DSC_ERR_INVALID, "node %d has bad children_offset %d", n, c);
       for (int k = 0; k < 2; k++) {
-        parent[c + k] = n;
         depth[c + k] = depth[n] + 1;
         maxdepth = std::max(maxdepth, depth[c + k]);
         order.push_back(c + k);
+      }
+    }
+    if (next != N || (int)order.size() != N) return fail(ctx, DSC_ERR_INVALID, "PBVH is not a tree over %d nodes", N);
+    std::vector<float> bb((size_t)6 * N), obb((size_t)6 * N);
+    std::vector<int> flag(N), child0(N, -1), child1(N, -1);
+    std::vector<int4> topo(N, make_int4(-1, 0, -1, 0));
+    for (int n = 0; n < N; n++) {
+      const int dn = ctx->dev_of_node[n];
+      for (int k = 0; k < 6; k++) {
+        bb[(size_t)k * N + dn] = pb->node_bb[(size_t)6 * n + k];
+        obb[(size_t)k * N + dn] = pb->node_orig_bb[(size_t)6 * n + k];
+      }
+      flag[dn] = hflag[n];
+      if (!(hflag[n] & DSC_PBVH_Leaf)) {
+        child0[dn] = ctx->dev_of_node[hchild[n]];
+        child1[dn] = ctx->dev_of_node[hchild[n] + 1];
+      }
+    }
+    for (int dn = 0; dn < N; dn++) {
+      if (child0[dn] >= 0) {
+        topo[child0[dn]] = make_int4(dn, 1, child1[dn], 0);
+        topo[child1[dn]] = make_int4(dn, 2, child0[dn], 0);
       }
     }
     std::vector<int> level_off(maxdepth + 2, 0), level_nodes;
     for (int dpt = 0; dpt <= maxdepth; dpt++) {
       level_off[dpt] = (int)level_nodes.size();
       for (int n : order) {
-        if (!(flag[n] & DSC_PBVH_Leaf) && depth[n] == dpt) level_nodes.push_back(n);
+        if (!(hflag[n] & DSC_PBVH_Leaf) && depth[n] == dpt) level_nodes.push_back(ctx->dev_of_node[n]);
       }
     }
     level_off[maxdepth + 1] = (int)level_nodes.size();
     m.nlevel = maxdepth + 1;
-    int *d;
     if ((r = dev_upload(ctx, &m.bb, bb)) || (r = dev_upload(ctx, &m.obb, obb)) || (r = dev_upload(ctx, &m.node_flag, flag))) return r;
-    if ((r = dev_upload(ctx, &d, child))) return r; m.node_child = d;
-    if ((r = dev_upload(ctx, &d, parent))) return r; m.node_parent = d;
-    if ((r = dev_upload(ctx, &d, level_off))) return r; m.level_off = d;
-    if ((r = dev_upload(ctx, &d, level_nodes))) return r; m.level_nodes = d;
-    if ((r = dev_zero(ctx, &m.node_mark, (size_t)N))) return r;
+    if ((r = dev_upload_c(ctx, &m.topo, topo)) || (r = dev_upload_c(ctx, &m.child0, child0)) ||
+        (r = dev_upload_c(ctx, &m.child1, child1)) || (r = dev_upload_c(ctx, &m.level_off, level_off)) ||
+        (r = dev_upload_c(ctx, &m.level_nodes, level_nodes)))
+      return r;
+    if ((r = dev_zero(ctx, &m.node_mark, (size_t)N)) || (r = dev_zero(ctx, &m.pending, (size_t)N)) ||
+        (r = dev_zero(ctx, &m.arrived, (size_t)N)))
+      return r;
     m.totnode = N;
     CU(cudaStreamSynchronize(ctx->stream));
   }
-  if ((r = dev_zero(ctx, &m.st, 1))) return r;
+  if ((r = dev_zero(ctx, &m.st, DSC_SLOTS)) || (r = dev_zero(ctx, &m.tot, 1))) return r;
   if ((r = dev_zero(ctx, &ctx->d_curve, 257))) return r;
   CU(cudaStreamSynchronize(ctx->stream));
+
+  /* launch shape of the shared-memory normals kernel */
+  CU(cudaFuncSetAttribute(k_normals_bb_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
+  int occ = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_bb_smem, NB_BLOCK, ctx->nb_smem));
+  ctx->nb_grid = ctx->num_sms * std::max(occ, 1);
 
   /* the host staging copies are no longer needed */
   std::vector<float>().swap(ctx->h_co);
@@ -503,33 +714,71 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
 
 #define LAUNCH_CHECK() CU(cudaGetLastError())
 
-static int run_normals(DscContext *ctx)
+/* which leaf list a stage walks: the hit list of a dab, or -- when leaves may carry flags from
+ * elsewhere -- the list k_collect_flagged builds */
+struct LeafList {
+  const int *list;
+  const int *count;
+};
+static LeafList hit_list(DscContext *ctx, int slot)
 {
-  StageScope s(ctx, ST_NORMALS);
-  k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m);
+  return {ctx->m.hit_list + (size_t)slot * ctx->m.nleaf, &ctx->m.st[slot].hit_count};
+}
+static LeafList flag_list(DscContext *ctx) { return {ctx->m.flag_list, &ctx->m.tot->flag_count}; }
+
+static int run_collect(DscContext *ctx, int flags)
+{
+  StageScope s(ctx, ST_OTHER);
+  k_collect_flagged<<<1, 1024, 0, ctx->stream>>>(ctx->m, flags);
   LAUNCH_CHECK();
   return DSC_OK;
 }
-static int run_bounds(DscContext *ctx, int clear_mask)
+/* normals and/or leaf boxes of the listed leaves (mode: NB_NORMALS | NB_BOUNDS) */
+static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode)
 {
   {
-    StageScope s(ctx, ST_LEAFBB);
-    k_leaf_bb<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m);
+    StageScope s(ctx, ST_NORMALS);
+    k_normals_bb_smem<<<ctx->nb_grid, NB_BLOCK, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.list, ll.count, mode);
     LAUNCH_CHECK();
   }
-  {
-    StageScope s(ctx, ST_FLUSH);
-    k_flush<<<1, 1024, 0, ctx->stream>>>(ctx->m, clear_mask);
-    LAUNCH_CHECK();
+  if (ctx->any_slow_leaf) {
+    if (mode & NB_NORMALS) {
+      StageScope s(ctx, ST_NORMALS);
+      k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1);
+      LAUNCH_CHECK();
+    }
+    if (mode & NB_BOUNDS) {
+      StageScope s(ctx, ST_LEAFBB);
+      k_leaf_bb<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1);
+      LAUNCH_CHECK();
+    }
   }
   return DSC_OK;
 }
-static int run_flush_only(DscContext *ctx, int clear_mask)
+static int run_clear(DscContext *ctx, LeafList ll, int clear_mask)
+{
+  StageScope s(ctx, ST_OTHER);
+  k_clear_flags<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, clear_mask);
+  LAUNCH_CHECK();
+  return DSC_OK;
+}
+static int run_flush_full(DscContext *ctx)
 {
   StageScope s(ctx, ST_FLUSH);
-  k_flush<<<1, 1024, 0, ctx->stream>>>(ctx->m, clear_mask);
+  k_flush<<<1, 1024, 0, ctx->stream>>>(ctx->m);
   LAUNCH_CHECK();
   return DSC_OK;
+}
+/* flagged leaves -> normals / boxes -> whole-tree flush -> clear: every non-dab entry point */
+static int run_flagged(DscContext *ctx, int want)
+{
+  int r;
+  if ((r = join_side(ctx))) return r;
+  if ((r = run_collect(ctx, want))) return r;
+  const int mode = ((want & F_UpdateNormals) ? NB_NORMALS : 0) | ((want & F_UpdateBB) ? NB_BOUNDS : 0);
+  if ((r = run_normals_bounds(ctx, flag_list(ctx), mode))) return r;
+  if ((want & F_UpdateBB) && (r = run_flush_full(ctx))) return r;
+  return run_clear(ctx, flag_list(ctx), want);
 }
 
 int dsc_recalc_normals(DscContext *ctx)
@@ -541,9 +790,7 @@ int dsc_recalc_normals(DscContext *ctx)
     k_mark_all<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->m, F_UpdateNormals, 1, ctx->nwords);
     LAUNCH_CHECK();
   }
-  int r = run_normals(ctx);
-  if (r) return r;
-  return run_flush_only(ctx, F_UpdateNormals);
+  return run_flagged(ctx, F_UpdateNormals);
 }
 
 int dsc_set_custom_curve(DscContext *ctx, const float *table257)
@@ -586,10 +833,13 @@ int dsc_node_flag_set(DscContext *ctx, int node, int flag, int on)
   NEED_PBVH();
   if (node < 0 || node >= ctx->totnode) return fail(ctx, DSC_ERR_INVALID, "node %d out of range", node);
   int f = 0;
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(&f, ctx->m.node_flag + node, sizeof(int), cudaMemcpyDeviceToHost));
+  const int dn = ctx->dev_of_node[node];
+  int r = sync_all(ctx);
+  if (r) return r;
+  CU(cudaMemcpy(&f, ctx->m.node_flag + dn, sizeof(int), cudaMemcpyDeviceToHost));
   f = on ? (f | flag) : (f & ~flag);
-  CU(cudaMemcpy(ctx->m.node_flag + node, &f, sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->m.node_flag + dn, &f, sizeof(int), cudaMemcpyHostToDevice));
+  if (on && (flag & (F_UpdateNormals | F_UpdateBB))) ctx->stale_flags = true;
   return DSC_OK;
 }
 
@@ -603,17 +853,21 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
 {
   NEED_PBVH();
   if (ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "stroke already open");
+  int r = join_side(ctx);
+  if (r) return r;
   if (automask) {
-    int r = upload_per_vertex(ctx, ctx->d_automask, automask);
-    if (r) return r;
+    if ((r = upload_per_vertex(ctx, ctx->d_automask, automask))) return r;
     ctx->m.automask = ctx->d_automask;
   }
   else {
     ctx->m.automask = nullptr;
   }
   CU(cudaMemsetAsync(ctx->m.leaf_state, 0, sizeof(unsigned) * (size_t)std::max(ctx->m.nleaf, 1), ctx->stream));
-  CU(cudaMemsetAsync(ctx->m.st, 0, sizeof(DabState), ctx->stream));
+  CU(cudaMemsetAsync(ctx->m.st, 0, sizeof(DabState) * DSC_SLOTS, ctx->stream));
+  CU(cudaMemsetAsync(ctx->m.tot, 0, sizeof(StrokeTotals), ctx->stream));
   ctx->launches = 0;
+  ctx->dab_index = 0;
+  ctx->last_slot = 0;
   ctx->in_stroke = true;
   return DSC_OK;
 }
@@ -634,21 +888,40 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
   memcpy(&d, dab, sizeof(d));
   DevMesh &m = ctx->m;
   cudaStream_t st = ctx->stream;
-
+  const int slot = (int)(ctx->dab_index & (DSC_SLOTS - 1));
+  const LeafList hits = hit_list(ctx, slot);
+  const bool do_normals = !(dab->flags & DSC_DAB_NO_NORMALS), do_bounds = !(dab->flags & DSC_DAB_NO_BOUNDS);
+  /* the stages below walk the hit list unless some leaf may still carry flags of an earlier dab */
+  const bool use_hits = !ctx->stale_flags;
+  int r;
   if (ctx->capture) CU(cudaMemsetAsync(ctx->d_capture, 0, sizeof(unsigned) * (size_t)ctx->nwords, st));
-  /* 1. gather + undo membership + node marks */
+
+  /* 1. gather + undo membership + node marks.  It recycles the ring slot the refit of three dabs ago read. */
+  CU(cudaStreamWaitEvent(st, ctx->ev_refit[(slot + 1) & (DSC_SLOTS - 1)], 0));
   {
     StageScope s(ctx, ST_GATHER);
     const float rs = dab->radius * dab->radius_scale;
-    k_gather<<<1, 1024, 0, st>>>(m, dab->location[0], dab->location[1], dab->location[2], rs * rs,
-                                 tool == DSC_TOOL_GRAB ? 1 : 0, 1, 1);
+    float ar = sqrtf(dab->radius * dab->radius); /* radius of the normal-sampling sphere, same float steps as k_area */
+    ar *= dab->normal_radius_factor;
+    k_gather<<<(m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st>>>(m, slot, dab->location[0], dab->location[1],
+                                                                          dab->location[2], rs * rs, ar * ar,
+                                                                          tool == DSC_TOOL_GRAB ? 1 : 0, 1, 1);
     LAUNCH_CHECK();
+  }
+  if (do_bounds && use_hits) {
+    /* side stream: tag the ancestors of the hit leaves for the bottom-up refit while the brush runs */
+    CU(cudaEventRecord(ctx->ev_fork, st));
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    StageScope s(ctx, ST_FLUSH, ctx->stream2);
+    k_tag_ancestors<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, hits.list, hits.count);
+    LAUNCH_CHECK();
+    ctx->side_busy = true;
   }
   /* 2.-3. brush */
   if (tool == DSC_TOOL_SMOOTH) {
     {
       StageScope s(ctx, ST_SMOOTH);
-      k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m);
+      k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
       LAUNCH_CHECK();
     }
     const int max_iterations = 4;
@@ -665,12 +938,12 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
       if (it == count && count > 0 && strength == 0.0f) break;
       {
         StageScope s(ctx, ST_SMOOTH);
-        k_smooth_a<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, strength);
+        k_smooth_a<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot, strength);
         LAUNCH_CHECK();
       }
       {
         StageScope s(ctx, ST_SMOOTH);
-        k_smooth_b<<<ctx->grid, DSC_BLOCK, 0, st>>>(m);
+        k_smooth_b<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
         LAUNCH_CHECK();
       }
     }
@@ -679,40 +952,59 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     const bool needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS;
     if (needs_area) {
       StageScope s(ctx, ST_AREA);
-      k_area<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, tool == DSC_TOOL_CLAY_STRIPS ? 1 : 0);
+      k_area<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot, tool == DSC_TOOL_CLAY_STRIPS ? 1 : 0);
       LAUNCH_CHECK();
     }
     StageScope s(ctx, ST_BRUSH);
-    k_brush<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d);
+    k_brush<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot);
     LAUNCH_CHECK();
   }
   /* 4. normals, 5. bounds */
-  int clear = 0, r;
-  if (!(dab->flags & DSC_DAB_NO_NORMALS)) {
-    if ((r = run_normals(ctx))) return r;
-    clear |= F_UpdateNormals;
+  if (use_hits) {
+    const int mode = (do_normals ? NB_NORMALS : 0) | (do_bounds ? NB_BOUNDS : 0);
+    if (mode) {
+      if ((r = run_normals_bounds(ctx, hits, mode))) return r;
+    }
+    if (do_bounds) {
+      /* side stream: carry the refreshed leaf boxes up the tree; overlaps the next dab */
+      CU(cudaEventRecord(ctx->ev_bb, st));
+      CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_bb, 0));
+      {
+        StageScope s(ctx, ST_FLUSH, ctx->stream2);
+        k_refit<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, hits.list, hits.count);
+        LAUNCH_CHECK();
+      }
+      CU(cudaEventRecord(ctx->ev_refit[slot], ctx->stream2));
+      ctx->side_busy = true;
+    }
+    if (mode) {
+      if ((r = run_clear(ctx, hits, (do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0)))) return r;
+    }
+    if (!do_normals || !do_bounds) ctx->stale_flags = true;
   }
-  if (!(dab->flags & DSC_DAB_NO_BOUNDS)) {
-    if ((r = run_bounds(ctx, clear | F_UpdateBB))) return r;
+  else {
+    const int want = (do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0);
+    if (want && (r = run_flagged(ctx, want))) return r;
+    if (do_normals && do_bounds) ctx->stale_flags = false;
   }
-  else if (clear) {
-    if ((r = run_flush_only(ctx, clear))) return r;
-  }
+  ctx->last_slot = slot;
+  ctx->dab_index++;
   return DSC_OK;
 }
 
-static int read_list(DscContext *ctx, const int *d_list, const int *d_count_field, int *r_nodes, int capacity, int *r_tot)
+static int read_list(DscContext *ctx, const int *d_list, const int *d_count, int *r_nodes, int capacity, int *r_tot)
 {
   int tot = 0;
-  CU(cudaMemcpyAsync(&ctx->h_state->hit_count, d_count_field, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  tot = ctx->h_state->hit_count;
+  int r = sync_all(ctx);
+  if (r) return r;
+  CU(cudaMemcpy(&tot, d_count, sizeof(int), cudaMemcpyDeviceToHost));
   if (r_tot) *r_tot = tot;
   if (r_nodes && tot > 0) {
     if (capacity < tot) return fail(ctx, DSC_ERR_INVALID, "capacity %d < %d gathered nodes", capacity, tot);
-    CU(cudaMemcpyAsync(ctx->h_list, d_list, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < tot; i++) r_nodes[i] = ctx->leaf_node[ctx->h_list[i]];
+    CU(cudaMemcpy(ctx->h_list, d_list, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost));
+    /* leaf ids are traversal ranks: ascending id = the order BKE_pbvh_search_gather emits */
+    std::sort(ctx->h_list, ctx->h_list + tot);
+    for (int i = 0; i < tot; i++) r_nodes[i] = ctx->node_of_dev[ctx->h_list[i]];
   }
   return DSC_OK;
 }
@@ -720,27 +1012,32 @@ static int read_list(DscContext *ctx, const int *d_list, const int *d_count_fiel
 int dsc_gather_readback(DscContext *ctx, int *r_nodes, int capacity, int *r_tot)
 {
   NEED_PBVH();
-  return read_list(ctx, ctx->m.hit_list, &ctx->m.st->hit_count, r_nodes, capacity, r_tot);
+  const LeafList ll = hit_list(ctx, ctx->last_slot);
+  return read_list(ctx, ll.list, ll.count, r_nodes, capacity, r_tot);
 }
 
 int dsc_search_sphere(DscContext *ctx, const float center[3], float radius_sq, int original, int ignore_fully_ineffective,
                       int *r_nodes, int capacity, int *r_tot)
 {
   NEED_PBVH();
+  int r = join_side(ctx);
+  if (r) return r;
+  CU(cudaMemsetAsync(&ctx->m.tot->search_count, 0, sizeof(int), ctx->stream));
   {
     StageScope s(ctx, ST_GATHER);
-    k_gather<<<1, 1024, 0, ctx->stream>>>(ctx->m, center[0], center[1], center[2], radius_sq, original ? 1 : 0,
-                                          ignore_fully_ineffective ? 1 : 0, 0);
+    k_gather<<<(ctx->m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, ctx->stream>>>(
+        ctx->m, 0, center[0], center[1], center[2], radius_sq, 0.0f, original ? 1 : 0, ignore_fully_ineffective ? 1 : 0, 0);
     LAUNCH_CHECK();
   }
-  return read_list(ctx, ctx->m.search_list, &ctx->m.st->search_count, r_nodes, capacity, r_tot);
+  return read_list(ctx, ctx->m.search_list, &ctx->m.tot->search_count, r_nodes, capacity, r_tot);
 }
 
 int dsc_last_area(DscContext *ctx, float r_no[3], float r_co[3])
 {
   NEED_PBVH();
-  CU(cudaMemcpyAsync(ctx->h_state, ctx->m.st, sizeof(DabState), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = sync_all(ctx);
+  if (r) return r;
+  CU(cudaMemcpy(ctx->h_state, ctx->m.st + ctx->last_slot, sizeof(DabState), cudaMemcpyDeviceToHost));
   for (int k = 0; k < 3; k++) {
     if (r_no) r_no[k] = ctx->h_state->area_no[k];
     if (r_co) r_co[k] = ctx->h_state->area_co[k];
@@ -779,12 +1076,12 @@ int dsc_stroke_stats(DscContext *ctx, DscStrokeStats *r)
 {
   NEED_PBVH();
   if (!r) return fail(ctx, DSC_ERR_INVALID, "r_stats is NULL");
-  CU(cudaMemcpyAsync(ctx->h_state, ctx->m.st, sizeof(DabState), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_tot, ctx->m.tot, sizeof(StrokeTotals), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  r->vertex_dabs = (int64_t)ctx->h_state->vd_total;
-  r->node_hits = (int64_t)ctx->h_state->hits_total;
-  r->moved_verts = (int64_t)ctx->h_state->moved_total;
-  r->dabs = (int64_t)ctx->h_state->dabs;
+  r->vertex_dabs = (int64_t)ctx->h_tot->vd_total;
+  r->node_hits = (int64_t)ctx->h_tot->hits_total;
+  r->moved_verts = (int64_t)ctx->h_tot->moved_total;
+  r->dabs = (int64_t)ctx->h_tot->dabs;
   r->kernel_launches = ctx->launches;
   return DSC_OK;
 }
@@ -792,13 +1089,13 @@ int dsc_stroke_stats(DscContext *ctx, DscStrokeStats *r)
 int dsc_update_normals(DscContext *ctx)
 {
   NEED_PBVH();
-  int r = run_normals(ctx);
-  if (r) return r;
-  return run_flush_only(ctx, F_UpdateNormals);
+  return run_flagged(ctx, F_UpdateNormals);
 }
 
 static int run_orig_flush(DscContext *ctx)
 {
+  int r = join_side(ctx);
+  if (r) return r;
   StageScope s(ctx, ST_OTHER);
   k_orig_leaves<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream>>>(ctx->m);
   LAUNCH_CHECK();
@@ -813,7 +1110,7 @@ int dsc_update_bounds(DscContext *ctx, int flag)
   NEED_PBVH();
   int r;
   if (flag & DSC_PBVH_UpdateBB) {
-    if ((r = run_bounds(ctx, F_UpdateBB))) return r;
+    if ((r = run_flagged(ctx, F_UpdateBB))) return r;
   }
   if (flag & DSC_PBVH_UpdateOriginalBB) {
     if ((r = run_orig_flush(ctx))) return r;
@@ -828,8 +1125,7 @@ int dsc_stroke_end(DscContext *ctx)
   int r = run_orig_flush(ctx);
   if (r) return r;
   ctx->in_stroke = false;
-  CU(cudaStreamSynchronize(ctx->stream));
-  return DSC_OK;
+  return sync_all(ctx);
 }
 
 static int export3(DscContext *ctx, float *out, const float *ax, const float *ay, const float *az)
@@ -868,13 +1164,15 @@ int dsc_download_node_bb(DscContext *ctx, float *r_bb, float *r_orig_bb)
   NEED_PBVH();
   const int N = ctx->totnode;
   std::vector<float> tmp((size_t)6 * N);
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = sync_all(ctx);
+  if (r) return r;
   for (int pass = 0; pass < 2; pass++) {
     float *out = pass ? r_orig_bb : r_bb;
     if (!out) continue;
     CU(cudaMemcpy(tmp.data(), pass ? ctx->m.obb : ctx->m.bb, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int n = 0; n < N; n++) {
-      for (int k = 0; k < 6; k++) out[(size_t)6 * n + k] = tmp[(size_t)k * N + n];
+      const int dn = ctx->dev_of_node[n];
+      for (int k = 0; k < 6; k++) out[(size_t)6 * n + k] = tmp[(size_t)k * N + dn];
     }
   }
   return DSC_OK;
@@ -883,8 +1181,11 @@ int dsc_download_node_bb(DscContext *ctx, float *r_bb, float *r_orig_bb)
 int dsc_download_node_flags(DscContext *ctx, int *r_flags)
 {
   NEED_PBVH();
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(r_flags, ctx->m.node_flag, sizeof(int) * (size_t)ctx->totnode, cudaMemcpyDeviceToHost));
+  std::vector<int> tmp((size_t)ctx->totnode);
+  int r = sync_all(ctx);
+  if (r) return r;
+  CU(cudaMemcpy(tmp.data(), ctx->m.node_flag, sizeof(int) * (size_t)ctx->totnode, cudaMemcpyDeviceToHost));
+  for (int n = 0; n < ctx->totnode; n++) r_flags[n] = tmp[ctx->dev_of_node[n]];
   return DSC_OK;
 }
 
@@ -893,7 +1194,8 @@ int dsc_download_touched(DscContext *ctx, unsigned char *r_touched)
   NEED_PBVH();
   const int L = ctx->m.nleaf;
   std::vector<unsigned> st((size_t)std::max(L, 1));
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = sync_all(ctx);
+  if (r) return r;
   CU(cudaMemcpy(st.data(), ctx->m.leaf_state, sizeof(unsigned) * (size_t)L, cudaMemcpyDeviceToHost));
   memset(r_touched, 0, (size_t)ctx->totnode);
   for (int l = 0; l < L; l++) {
@@ -906,6 +1208,8 @@ int dsc_upload_co(DscContext *ctx, const float *co)
 {
   NEED_PBVH();
   if (!co) return fail(ctx, DSC_ERR_INVALID, "co is NULL");
+  int r = join_side(ctx);
+  if (r) return r;
   CU(cudaMemcpyAsync(ctx->d_stage3, co, sizeof(float) * 3 * (size_t)ctx->totvert, cudaMemcpyHostToDevice, ctx->stream));
   k_import3<<<ctx->grid, 256, 0, ctx->stream>>>(ctx->d_stage3, ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->d_slot_of, ctx->m.dirty,
                                                 ctx->totvert);
@@ -915,31 +1219,31 @@ int dsc_upload_co(DscContext *ctx, const float *co)
   k_mark_all<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->m, F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw,
                                                        0, ctx->nwords);
   LAUNCH_CHECK();
-  int r = run_normals(ctx);
-  if (r) return r;
-  if ((r = run_bounds(ctx, F_UpdateNormals | F_UpdateBB))) return r;
+  if ((r = run_flagged(ctx, F_UpdateNormals | F_UpdateBB))) return r;
   if ((r = run_orig_flush(ctx))) return r;
-  CU(cudaStreamSynchronize(ctx->stream));
-  return DSC_OK;
+  return sync_all(ctx);
 }
 
 int dsc_synchronize(DscContext *ctx)
 {
   if (!ctx) return DSC_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaStreamSynchronize(ctx->stream));
-  return DSC_OK;
+  return sync_all(ctx);
 }
 
 int dsc_timer_start(DscContext *ctx)
 {
   if (!ctx) return DSC_ERR_INVALID;
+  int r = join_side(ctx);
+  if (r) return r;
   CU(cudaEventRecord(ctx->t0, ctx->stream));
   return DSC_OK;
 }
 int dsc_timer_stop(DscContext *ctx, float *r_ms)
 {
   if (!ctx) return DSC_ERR_INVALID;
+  int r = join_side(ctx); /* the timed region ends when the side stream has drained too */
+  if (r) return r;
   CU(cudaEventRecord(ctx->t1, ctx->stream));
   CU(cudaEventSynchronize(ctx->t1));
   float ms = 0.0f;
@@ -951,7 +1255,8 @@ int dsc_timer_stop(DscContext *ctx, float *r_ms)
 int dsc_stage_timing(DscContext *ctx, int enable)
 {
   if (!ctx) return DSC_ERR_INVALID;
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = sync_all(ctx);
+  if (r) return r;
   for (auto &ev : ctx->events) {
     cudaEventDestroy(ev.a);
     cudaEventDestroy(ev.b);
@@ -968,7 +1273,8 @@ int dsc_stage_timing(DscContext *ctx, int enable)
 int dsc_stage_times(DscContext *ctx, float r_ms[DSC_NUM_STAGES], int r_launches[DSC_NUM_STAGES])
 {
   if (!ctx) return DSC_ERR_INVALID;
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = sync_all(ctx);
+  if (r) return r;
   for (auto &ev : ctx->events) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) ctx->stage_ms[ev.stage] += ms;

@@ -18,7 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define DSC_CHUNK 1024        /* slots per work item, multiple of 32 */
+#define DSC_CHUNK 1024        /* slots per work item = DSC_BLOCK threads x 4 slots */
 #define DSC_BLOCK 256
 #define DSC_LEAF_HIT 1u
 #define DSC_LEAF_FIRST 2u
@@ -29,14 +29,24 @@ enum {
   F_UpdateDrawBuffers = 1 << 4, F_UpdateRedraw = 1 << 5, F_FullyHidden = 1 << 10, F_FullyMasked = 1 << 11,
 };
 
+#define DSC_SLOTS 4 /* per-dab state ring: dab i uses slot i & 3 (the side stream may lag two dabs) */
+
 struct DabState {
-  int hit_count;
-  int search_count;
-  unsigned long long vd_total, hits_total, moved_total, dabs;
+  int hit_count;  /* leaves gathered by the dab (hit list of this slot) */
+  int area_count; /* hit leaves that also reach the normal-sampling sphere (area list of this slot) */
+  int pad0, pad1;
   long long acc[16]; /* nos[2][3], cos[2][3], count_no[2], count_co[2] */
   float area_no[3], area_co[3];
 };
 
+struct StrokeTotals {
+  unsigned long long vd_total, hits_total, moved_total, dabs;
+  int search_count; /* leaves found by the last stand-alone search (search_list) */
+  int flag_count;   /* leaves collected by k_collect_flagged (flag_list) */
+};
+
+/* Nodes are renumbered on the device: ids [0, nleaf) are the leaves in traversal order, ids
+ * [nleaf, totnode) the inner nodes, root first (breadth-first).  The host translates. */
 struct DevMesh {
   /* per slot */
   float *cx, *cy, *cz;    /* MVert.co */
@@ -51,31 +61,47 @@ struct DevMesh {
   const unsigned char *boundary;
   const unsigned *nb_off;
   const int *nb_idx;
+  /* general normals path (any poly size / leaf size); NULL when every leaf takes the smem path */
   const unsigned *vt_off; /* slot -> incident looptri positions, ascending */
   const unsigned *vt_idx;
   /* per looptri position: slots of the verts of its poly; [3] = -1 triangle, <= -2 n-gon id */
   const int *pv0, *pv1, *pv2, *pv3;
   const int *poly_off, *poly_slots; /* n-gons only */
-  const int *tri_leaf;              /* leaf (traversal index) holding the looptri position */
-  /* leaves, traversal order */
+  const int *tri_leaf;              /* leaf holding the looptri position */
+  /* smem normals path: per leaf a local vertex list (unique | shared | extra) and local poly
+   * entries (own | halo); per unique vert the entries of its looptris in ascending position */
+  const unsigned char *leaf_fast;
+  const int *leaf_xcnt;             /* extra staged verts after the shared ones */
+  const int *leaf_ebeg, *leaf_eown, *leaf_ehalo, *leaf_hbeg;
+  const ushort4 *e_pv;              /* local vertex indices of the entry's poly, w = 0xffff: triangle */
+  const unsigned char *e_halo_nb;   /* halo entry -> index into the leaf's neighbour-leaf list */
+  const int *leaf_nbeg, *leaf_ncnt; /* neighbour leaves (owners of halo looptris) */
+  const int *nb_leaf;
+  /* vertex -> entry lists, sliced ELL: per group of 32 slots `width` rows of 32 entries, row j =
+   * the j-th looptri (ascending position) of each of the 32 verts, 0xffff = none */
+  const unsigned *v2_goff;          /* [slots / 32 + 1], in entries */
+  const unsigned short *v2_idx;
+  /* leaves */
   int nleaf;
-  const int *leaf_node, *leaf_ubeg, *leaf_ucnt, *leaf_sbeg, *leaf_scnt, *leaf_pbeg, *leaf_pcnt;
-  const int *shared_slots;
+  int max_chunks; /* ceil(max uniq_verts / DSC_CHUNK) */
+  const int *leaf_ubeg, *leaf_ucnt, *leaf_sbeg, *leaf_scnt, *leaf_pbeg, *leaf_pcnt;
+  const int *stage_slots; /* per leaf: slots of its shared verts, then of its extra verts */
   unsigned *leaf_state;
-  /* work items */
-  int nchunk;
-  const int *chunk_leaf, *chunk_beg, *chunk_cnt;
-  /* nodes */
+  /* nodes, device numbering */
   int totnode;
   float *bb, *obb; /* [6][totnode] */
   int *node_flag;
-  const int *node_child, *node_parent;
+  const int4 *topo; /* x parent (-1 root), y side bit of this node in its parent (1 / 2), z sibling */
+  const int *child0, *child1;
+  int *pending, *arrived; /* bottom-up refit: which children will arrive / have arrived */
   int *node_mark;
   int nlevel;
   const int *level_off, *level_nodes; /* inner nodes by depth, root first */
   /* per-dab state */
-  DabState *st;
-  int *hit_list, *search_list;
+  DabState *st;       /* [DSC_SLOTS] */
+  StrokeTotals *tot;
+  int *hit_list, *area_list; /* [DSC_SLOTS][nleaf] */
+  int *search_list, *flag_list;
   const float *curve; /* 257-entry LUT or NULL */
 };
 
@@ -151,7 +177,8 @@ __device__ __forceinline__ float dsc_strength_factor(const DevMesh &m, const Dab
     final_len = d.radius;
   }
   else {
-    q = (q - d.hardness) / (1.0f - d.hardness);
+    /* (q - 0) / (1 - 0) is q exactly: skip the IEEE divide when there is no hardness */
+    if (d.hardness != 0.0f) q = (q - d.hardness) / (1.0f - d.hardness);
     final_len = q * d.radius;
   }
   avg *= dsc_curve_strength(m, d.curve_preset, final_len, d.radius);
@@ -207,104 +234,193 @@ __device__ __forceinline__ void dsc_poly_normal(const DevMesh &m, unsigned pos, 
 }
 
 /* ------------------------------------------------------------------------------ K1 gather */
-/* One CTA.  Flat leaf test in traversal order + order-preserving ballot compaction.  A leaf passes
- * BKE_pbvh_search_gather's DFS iff it passes the callback itself, because every inner AABB is the
- * union of its children (pbvh.c:2040-2043) and the sphere test is monotone in the box.
- * mark != 0: also does the per-node part of the dab: undo-node membership (first touch) and
- * BKE_pbvh_node_mark_update (pbvh.c:3641-3645). */
-__global__ void __launch_bounds__(1024) k_gather(DevMesh m, float cx, float cy, float cz, float radius_sq,
-                                                 int original, int ignore_ineffective, int mark)
+/* One thread per leaf, any number of CTAs.  A leaf passes BKE_pbvh_search_gather's DFS iff it
+ * passes the callback itself, because every inner AABB is the union of its children
+ * (pbvh.c:2040-2043) and the sphere test is monotone in the box -- so the tree walk collapses to a
+ * flat test.  Hits are appended with one warp-aggregated atomic; leaf ids ARE traversal ranks, so
+ * the host gets BKE_pbvh_search_gather's order back by sorting the ids it reads.
+ * mark != 0 is the dab: undo-node membership (first touch), BKE_pbvh_node_mark_update
+ * (pbvh.c:3641-3645), the sub-list of leaves that reach the (smaller) normal-sampling sphere, and
+ * the reset of the next slot of the per-dab state ring. */
+__global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float cx, float cy, float cz, float radius_sq,
+                                                      float area_radius_sq, int original, int ignore_ineffective, int mark)
 {
-  __shared__ int warp_cnt[32];
-  __shared__ int s_base;
-  __shared__ unsigned long long s_vd;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (mark && tid < 16) m.st->acc[tid] = 0;
-  if (tid == 0) {
-    s_base = 0;
-    s_vd = 0ull;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int l = blockIdx.x * DSC_BLOCK + tid;
+  DabState *st = m.st + slot;
+  if (mark && blockIdx.x == 0) {
+    DabState *nx = m.st + ((slot + 1) & (DSC_SLOTS - 1));
+    if (tid < 16) nx->acc[tid] = 0;
+    if (tid == 16) nx->hit_count = 0;
+    if (tid == 17) nx->area_count = 0;
+    if (tid == 18) {
+      /* what dsc_last_area reports when the tool samples no plane: zero normal, brush location */
+      st->area_no[0] = st->area_no[1] = st->area_no[2] = 0.0f;
+      st->area_co[0] = cx; st->area_co[1] = cy; st->area_co[2] = cz;
+      m.tot->dabs += 1ull;
+    }
+  }
+  bool hit = false, ahit = false;
+  int flag = 0;
+  unsigned lst = 0;
+  if (l < m.nleaf) {
+    const float *bbs = original ? m.obb : m.bb;
+    const int tn = m.totnode;
+    flag = m.node_flag[l];
+    if (mark) lst = m.leaf_state[l];
+    const float c[3] = {cx, cy, cz};
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float bmin = bbs[i * tn + l], bmax = bbs[(3 + i) * tn + l];
+      float nearest;
+      if (bmin > c[i]) nearest = bmin;
+      else if (bmax < c[i]) nearest = bmax;
+      else nearest = c[i];
+      t[i] = c[i] - nearest;
+    }
+    const float dist = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    const bool skip = ignore_ineffective && (flag & (F_FullyHidden | F_FullyMasked));
+    hit = !skip && (dist < radius_sq);
+    ahit = hit && mark && (dist <= area_radius_sq);
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, hit);
+  if (bal) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(mark ? &st->hit_count : &m.tot->search_count, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) (mark ? m.hit_list + (size_t)slot * m.nleaf : m.search_list)[base + __popc(bal & ((1u << lane) - 1u))] = l;
+  }
+  if (!mark) return;
+  const unsigned abal = __ballot_sync(0xffffffffu, ahit);
+  if (abal) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&st->area_count, __popc(abal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ahit) m.area_list[(size_t)slot * m.nleaf + base + __popc(abal & ((1u << lane) - 1u))] = l;
+  }
+  unsigned long long vd = 0;
+  if (l < m.nleaf) {
+    if (hit) {
+      m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((lst & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
+      m.node_flag[l] = flag | F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw;
+      vd = (unsigned long long)m.leaf_ucnt[l];
+    }
+    else if (lst & (DSC_LEAF_HIT | DSC_LEAF_FIRST)) {
+      m.leaf_state[l] = lst & DSC_LEAF_TOUCHED;
+    }
+  }
+  if (bal) {
+    for (int o = 16; o > 0; o >>= 1) vd += __shfl_down_sync(0xffffffffu, vd, o);
+    if (lane == 0) {
+      atomicAdd(&m.tot->vd_total, vd);
+      atomicAdd(&m.tot->hits_total, (unsigned long long)__popc(bal));
+    }
+  }
+}
+
+/* leaves carrying any of `flags` (update_search_cb, pbvh.c:2891-2900) */
+__global__ void __launch_bounds__(1024) k_collect_flagged(DevMesh m, int flags)
+{
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int l = threadIdx.x; l < m.nleaf; l += blockDim.x) {
+    if (m.node_flag[l] & flags) m.flag_list[atomicAdd(&s_cnt, 1)] = l;
   }
   __syncthreads();
-  const float *bbs = original ? m.obb : m.bb;
+  if (threadIdx.x == 0) m.tot->flag_count = s_cnt;
+}
+
+/* Bottom-up refit, pass 1: tags the ancestors of the listed leaves.  pending[p] gets bit 1 / bit 2
+ * when a leaf below its first / second child is listed.  A walker stops at the first node that
+ * already carries its bit (somebody else tagged everything above). */
+__global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, const int *list, const int *count)
+{
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 t = m.topo[list[i]];
+    while (t.x >= 0) {
+      const int4 tp = m.topo[t.x]; /* in flight together with the atomic */
+      const int old = atomicOr(&m.pending[t.x], t.y);
+      if (old & t.y) break;
+      t = tp;
+    }
+  }
+}
+
+/* Bottom-up refit, pass 2 = pbvh_flush_bb (pbvh.c:3287-3317) without a level-by-level sweep: one
+ * walker per refreshed leaf carries its box upwards; at every inner node the walker that completes
+ * the last pending child merges the sibling's box, stores the node and carries on, the other one
+ * retires.  Only nodes above a refreshed leaf are touched, as in the reference.  Runs on the side
+ * stream: nothing on the device reads inner boxes (the gather is flat), only the host does. */
+__global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, const int *list, const int *count)
+{
+  const int n = *count;
   const int tn = m.totnode;
-  int *out = mark ? m.hit_list : m.search_list;
-  unsigned long long vd = 0;
-  for (int l0 = 0; l0 < m.nleaf; l0 += 1024) {
-    const int l = l0 + tid;
-    bool hit = false;
-    int node = -1;
-    if (l < m.nleaf) {
-      node = m.leaf_node[l];
-      const int flag = m.node_flag[node];
-      const bool skip = ignore_ineffective && (flag & (F_FullyHidden | F_FullyMasked));
-      if (!skip) {
-        const float c[3] = {cx, cy, cz};
-        float t[3];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int leaf = list[i];
+    float box[6];
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-          const float bmin = bbs[i * tn + node], bmax = bbs[(3 + i) * tn + node];
-          float nearest;
-          if (bmin > c[i]) nearest = bmin;
-          else if (bmax < c[i]) nearest = bmax;
-          else nearest = c[i];
-          t[i] = c[i] - nearest;
-        }
-        hit = (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) < radius_sq;
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
+    for (int k = 0; k < 6; k++) box[k] = __ldcg(&m.bb[k * tn + leaf]);
+    int4 t = m.topo[leaf];
+    while (t.x >= 0) {
+      const int p = t.x;
+      const int4 tp = m.topo[p];
+      const int pend = m.pending[p];
+      __threadfence(); /* my box (stored below, or by the leaf kernel) is visible before I arrive */
+      const int old = atomicOr(&m.arrived[p], t.y);
+      if ((old | t.y) != pend) break; /* the sibling subtree is still on its way */
+      /* ordered after the atomic: if the sibling subtree was refreshed it arrived, fenced, before
+       * me; if not, its stored box is current */
 #pragma unroll
-    for (int w = 0; w < 32; w++) {
-      const int c = warp_cnt[w];
-      if (w < warp) before += c;
-      total += c;
-    }
-    if (hit) {
-      const int pos = s_base + before + __popc(bal & ((1u << lane) - 1u));
-      out[pos] = l;
-    }
-    if (mark && l < m.nleaf) {
-      const unsigned st = m.leaf_state[l];
-      if (hit) {
-        m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((st & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
-        m.node_flag[node] |= F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw;
-        vd += (unsigned long long)m.leaf_ucnt[l];
+      for (int k = 0; k < 3; k++) {
+        box[k] = fminf(box[k], __ldcg(&m.bb[k * tn + t.z]));
+        box[3 + k] = fmaxf(box[3 + k], __ldcg(&m.bb[(3 + k) * tn + t.z]));
       }
-      else {
-        m.leaf_state[l] = st & DSC_LEAF_TOUCHED;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) s_base += total;
-    __syncthreads();
-  }
-  if (mark) {
-    for (int o = 16; o > 0; o >>= 1) vd += __shfl_down_sync(0xffffffffu, vd, o);
-    if (lane == 0 && vd) atomicAdd(&s_vd, vd);
-    __syncthreads();
-    if (tid == 0) {
-      /* what dsc_last_area reports when the tool samples no plane: zero normal, brush location */
-      m.st->area_no[0] = m.st->area_no[1] = m.st->area_no[2] = 0.0f;
-      m.st->area_co[0] = cx; m.st->area_co[1] = cy; m.st->area_co[2] = cz;
-      m.st->hit_count = s_base;
-      m.st->vd_total += s_vd;
-      m.st->hits_total += (unsigned long long)s_base;
-      m.st->dabs += 1ull;
+#pragma unroll
+      for (int k = 0; k < 6; k++) __stcg(&m.bb[k * tn + p], box[k]);
+      m.arrived[p] = 0;
+      m.pending[p] = 0;
+      t = tp;
     }
   }
-  else if (tid == 0) {
-    m.st->search_count = s_base;
-  }
+}
+
+/* work unit u of a leaf list: (leaf, chunk) -> slot range; returns false if the chunk is empty */
+__device__ __forceinline__ bool dsc_unit(const DevMesh &m, const int *list, int u, int &leaf, int &beg, int &cnt)
+{
+  const int h = u / m.max_chunks, c = u - h * m.max_chunks;
+  leaf = list[h];
+  const int ucnt = m.leaf_ucnt[leaf];
+  const int off = c * DSC_CHUNK;
+  if (off >= ucnt) return false;
+  cnt = min(DSC_CHUNK, ucnt - off);
+  beg = m.leaf_ubeg[leaf] + off;
+  return true;
+}
+
+__device__ __forceinline__ float4 ld4(const float *p, int s) { return *reinterpret_cast<const float4 *>(p + s); }
+__device__ __forceinline__ void st4(float *p, int s, const float4 &v) { *reinterpret_cast<float4 *>(p + s) = v; }
+
+/* 4-bit per-lane flags -> one 32-bit word per 8 lanes (lane & 7 == 0 holds it) */
+__device__ __forceinline__ unsigned dsc_pack_nibbles(unsigned nib, int lane)
+{
+  unsigned w = nib << (4 * (lane & 7));
+  w |= __shfl_xor_sync(0xffffffffu, w, 1);
+  w |= __shfl_xor_sync(0xffffffffu, w, 2);
+  w |= __shfl_xor_sync(0xffffffffu, w, 4);
+  return w;
 }
 
 /* ------------------------------------------------------------------- K3a area normal / centre */
 /* SURVEY.md 8a row a15.  Unique verts of hit leaves inside radius * normal_radius_factor; two
- * buckets by the sign of dot(view_normal, no); smoothstep weight; exact int64 sums. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int use_cos)
+ * buckets by the sign of dot(view_normal, no); smoothstep weight; exact int64 sums.  Streams
+ * float4 runs of the SoA position arrays; normals are only fetched for runs with a vert inside. */
+__global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int slot, int use_cos)
 {
+  DabState *st = m.st + slot;
+  const int *alist = m.area_list + (size_t)slot * m.nleaf;
   __shared__ unsigned long long sacc[16];
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 16) sacc[tid] = 0ull;
@@ -315,23 +431,38 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int 
   long long n0x = 0, n0y = 0, n0z = 0, n1x = 0, n1y = 0, n1z = 0;
   long long c0x = 0, c0y = 0, c0z = 0, c1x = 0, c1y = 0, c1z = 0;
   long long cnt0 = 0, cnt1 = 0;
-  for (int c = blockIdx.x; c < m.nchunk; c += gridDim.x) {
-    if (!(m.leaf_state[m.chunk_leaf[c]] & DSC_LEAF_HIT)) continue;
-    const int beg = m.chunk_beg[c], cnt = m.chunk_cnt[c];
-    for (int i = tid; i < cnt; i += DSC_BLOCK) {
-      const int s = beg + i;
-      const float dx = m.cx[s] - d.loc[0], dy = m.cy[s] - d.loc[1], dz = m.cz[s] - d.loc[2];
-      const float distsq = dx * dx + dy * dy + dz * dz;
-      if (distsq > radius_sq) continue;
-      const float vx = m.nx[s], vy = m.ny[s], vz = m.nz[s];
+  const int total = st->area_count * m.max_chunks;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int leaf, beg, cnt;
+    if (!dsc_unit(m, alist, u, leaf, beg, cnt)) continue;
+    const int nvalid = cnt - 4 * tid;
+    if (nvalid <= 0) continue;
+    const int s0 = beg + 4 * tid;
+    const float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
+    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+    float dxs[4], dys[4], dzs[4], dsq[4];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      dxs[j] = xs[j] - d.loc[0]; dys[j] = ys[j] - d.loc[1]; dzs[j] = zs[j] - d.loc[2];
+      dsq[j] = dxs[j] * dxs[j] + dys[j] * dys[j] + dzs[j] * dzs[j];
+      any |= (j < nvalid) && !(dsq[j] > radius_sq);
+    }
+    if (!any) continue;
+    const float4 NX = ld4(m.nx, s0), NY = ld4(m.ny, s0), NZ = ld4(m.nz, s0);
+    const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (j >= nvalid || dsq[j] > radius_sq) continue;
+      const float vx = vxs[j], vy = vys[j], vz = vzs[j];
       const bool flip = (d.view_n[0] * vx + d.view_n[1] * vy + d.view_n[2] * vz) <= 0.0f;
-      const float q = 1.0f - (sqrtf(distsq) / test_radius);
+      const float q = 1.0f - (sqrtf(dsq[j]) / test_radius);
       const float f = dsc_clamp(3.0f * q * q - 2.0f * q * q * q, 0.0f, 1.0f);
       if (use_cos) {
         const float w = 1.0f - f;
-        const long long ax = dsc_fix32((dx * w) / test_radius);
-        const long long ay = dsc_fix32((dy * w) / test_radius);
-        const long long az = dsc_fix32((dz * w) / test_radius);
+        const long long ax = dsc_fix32((dxs[j] * w) / test_radius);
+        const long long ay = dsc_fix32((dys[j] * w) / test_radius);
+        const long long az = dsc_fix32((dzs[j] * w) / test_radius);
         if (flip) { c1x += ax; c1y += ay; c1z += az; }
         else { c0x += ax; c0y += ay; c0z += az; }
       }
@@ -349,7 +480,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int 
     if (lane == 0 && x != 0) atomicAdd(&sacc[k], (unsigned long long)x);
   }
   __syncthreads();
-  if (tid < 16 && sacc[tid] != 0ull) atomicAdd((unsigned long long *)&m.st->acc[tid], sacc[tid]);
+  if (tid < 16 && sacc[tid] != 0ull) atomicAdd((unsigned long long *)&st->acc[tid], sacc[tid]);
 }
 
 /* finalisation of the sums, same float/double steps as the CPU path */
@@ -402,202 +533,240 @@ struct BrushDerived {
   int flip, skip;
 };
 
-/* Draw / inflate / grab / clay strips over the unique verts of hit leaves (SURVEY.md 8a rows
- * a11-a19).  First touch of a leaf in the stroke snapshots co/no into orig_co/orig_no before the
- * vertex is moved (row a9).  Displaced verts get their vert_bitmap bit (pbvh.c:3729). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d)
+/* per-dab constants every CTA derives from the dab descriptor and the area sums */
+__device__ void dsc_brush_derive(DabState *st, const DabParams &d, BrushDerived &D, bool publish)
 {
+  D.skip = 0;
+  float an[3] = {0, 0, 0}, ac[3] = {d.loc[0], d.loc[1], d.loc[2]};
+  if (d.tool == 1) {
+    dsc_sculpt_normal(st, d, an);
+    for (int k = 0; k < 3; k++) {
+      float o = an[k] * d.radius;
+      o = o * d.scale[k];
+      o = o * d.bstrength;
+      D.offset[k] = o;
+    }
+  }
+  else if (d.tool == 18) {
+    D.flip = (d.bstrength < 0.0f);
+    const float radius = D.flip ? -d.radius : d.radius;
+    const float displace = radius * (0.18f + d.plane_offset);
+    D.bstrength = D.flip ? -d.bstrength : d.bstrength;
+    float area_no[3];
+    if (d.sculpt_plane == 0) {
+      dsc_area_finalize(st, d, true, an, ac);
+      area_no[0] = an[0]; area_no[1] = an[1]; area_no[2] = an[2];
+    }
+    else {
+      dsc_sculpt_normal(st, d, an);
+      dsc_area_finalize(st, d, true, area_no, ac);
+    }
+    const float area_co0[3] = {ac[0], ac[1], ac[2]};
+    if ((d.flags & 4) || (d.grab_delta[0] == 0.0f && d.grab_delta[1] == 0.0f && d.grab_delta[2] == 0.0f)) {
+      D.skip = 1;
+    }
+    float area_co[3];
+    for (int k = 0; k < 3; k++) {
+      const float t = (an[k] * d.scale[k]) * displace;
+      area_co[k] = area_co0[k] + t;
+      D.origin[k] = area_co[k] + area_no[k] * (-radius * 0.7f);
+      D.plane_no[k] = an[k];
+    }
+    float a0[3], a1[3];
+    a0[0] = area_no[1] * d.grab_delta[2] - area_no[2] * d.grab_delta[1];
+    a0[1] = area_no[2] * d.grab_delta[0] - area_no[0] * d.grab_delta[2];
+    a0[2] = area_no[0] * d.grab_delta[1] - area_no[1] * d.grab_delta[0];
+    a1[0] = area_no[1] * a0[2] - area_no[2] * a0[1];
+    a1[1] = area_no[2] * a0[0] - area_no[0] * a0[2];
+    a1[2] = area_no[0] * a0[1] - area_no[1] * a0[0];
+    float a2[3] = {area_no[0], area_no[1], area_no[2]};
+    dsc_normalize(a0[0], a0[1], a0[2]);
+    dsc_normalize(a1[0], a1[1], a1[2]);
+    dsc_normalize(a2[0], a2[1], a2[2]);
+    for (int k = 0; k < 3; k++) {
+      D.ax[0][k] = a0[k]; D.ax[1][k] = a1[k]; D.ax[2][k] = a2[k];
+    }
+    D.sc[0] = d.radius; D.sc[1] = d.radius; D.sc[2] = d.radius * 1.25f;
+    D.plane_d = -(an[0] * area_co[0] + an[1] * area_co[1] + an[2] * area_co[2]);
+    D.trim_sq = (d.radius * d.radius) * (d.plane_trim * d.plane_trim);
+    /* what the host reads back as the plane: centre before the offset */
+    ac[0] = area_co0[0]; ac[1] = area_co0[1]; ac[2] = area_co0[2];
+  }
+  if (publish) {
+    for (int k = 0; k < 3; k++) {
+      st->area_no[k] = an[k];
+      st->area_co[k] = ac[k];
+    }
+  }
+}
+
+/* one vertex of the brush loop; returns true if it was displaced (new position in x, y, z) */
+__device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabParams &d, const BrushDerived &D, int s,
+                                                 float &x, float &y, float &z, float tx, float ty, float tz, float vnx,
+                                                 float vny, float vnz, float radius_sq)
+{
+  const int tool = d.tool;
+  if (tool == 18) {
+    /* clay strips: brush-local cube test + plane */
+    const float rx = x - D.origin[0], ry = y - D.origin[1], rz = z - D.origin[2];
+    float local[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      local[k] = fabsf((rx * D.ax[k][0] + ry * D.ax[k][1] + rz * D.ax[k][2]) / D.sc[k]);
+    }
+    const float side = 1.0f;
+    if (!(local[0] <= side && local[1] <= side && local[2] <= side)) return false;
+    const float roundness = d.tip_roundness;
+    const float hardness = 1.0f - roundness;
+    const float constant_side = hardness * side;
+    const float falloff_side = roundness * side;
+    float dist;
+    const float mn = local[0] < local[1] ? local[0] : local[1];
+    const float mx = local[0] > local[1] ? local[0] : local[1];
+    if (mn > constant_side) {
+      const float ex = local[0] - constant_side, ey = local[1] - constant_side;
+      dist = sqrtf(ex * ex + ey * ey) / falloff_side;
+    }
+    else if (mx > constant_side) {
+      dist = (mx - constant_side) / falloff_side;
+    }
+    else {
+      dist = 0.0f;
+    }
+    float side_d = (x * D.plane_no[0] + y * D.plane_no[1] + z * D.plane_no[2]) + D.plane_d;
+    if (D.flip) side_d = -side_d;
+    if (!(side_d <= 0.0f)) return false;
+    const float pd = (D.plane_no[0] * x + D.plane_no[1] * y + D.plane_no[2] * z) + D.plane_d;
+    const float ix = x + D.plane_no[0] * (-pd), iy = y + D.plane_no[1] * (-pd), iz = z + D.plane_no[2] * (-pd);
+    const float vx = ix - x, vy = iy - y, vz = iz - z;
+    if ((d.flags & 2) && !((vx * vx + vy * vy + vz * vz) <= D.trim_sq)) return false;
+    const float fade = D.bstrength * dsc_strength_factor(m, d, d.radius * dist, vnx, vny, vnz, s);
+    const float px = vx * fade, py = vy * fade, pz = vz * fade;
+    x = x + px; y = y + py; z = z + pz;
+    return true;
+  }
+  /* sphere test (row a11); grab tests and offsets the stroke-start coordinates (row a19) */
+  const float dx = tx - d.loc[0], dy = ty - d.loc[1], dz = tz - d.loc[2];
+  const float distsq = dx * dx + dy * dy + dz * dz;
+  if (distsq > radius_sq) return false;
+  float fade = dsc_strength_factor(m, d, sqrtf(distsq), vnx, vny, vnz, s);
+  if (tool == 1) {
+    const float px = D.offset[0] * fade, py = D.offset[1] * fade, pz = D.offset[2] * fade;
+    x = x + px; y = y + py; z = z + pz;
+  }
+  else if (tool == 4) {
+    fade = d.bstrength * fade;
+    const float sc = fade * d.radius;
+    const float px = (vnx * sc) * d.scale[0], py = (vny * sc) * d.scale[1], pz = (vnz * sc) * d.scale[2];
+    x = x + px; y = y + py; z = z + pz;
+  }
+  else {
+    fade = d.bstrength * fade;
+    const float px = d.grab_delta[0] * fade, py = d.grab_delta[1] * fade, pz = d.grab_delta[2] * fade;
+    x = tx + px; y = ty + py; z = tz + pz;
+  }
+  return true;
+}
+
+/* Draw / inflate / grab / clay strips over the unique verts of hit leaves (SURVEY.md 8a rows
+ * a11-a19).  Each thread owns 4 consecutive slots (float4 loads / stores of the SoA arrays).
+ * First touch of a leaf in the stroke snapshots co/no into orig_co/orig_no before the vertex is
+ * moved (row a9).  Displaced verts get their vert_bitmap bit (pbvh.c:3729). */
+__global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int slot)
+{
+  DabState *st = m.st + slot;
+  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
   __shared__ BrushDerived D;
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) {
     s_moved = 0;
-    D.skip = 0;
-    float an[3] = {0, 0, 0}, ac[3] = {d.loc[0], d.loc[1], d.loc[2]};
-    if (d.tool == 1) {
-      dsc_sculpt_normal(m.st, d, an);
-      for (int k = 0; k < 3; k++) {
-        float o = an[k] * d.radius;
-        o = o * d.scale[k];
-        o = o * d.bstrength;
-        D.offset[k] = o;
-      }
-    }
-    else if (d.tool == 18) {
-      D.flip = (d.bstrength < 0.0f);
-      const float radius = D.flip ? -d.radius : d.radius;
-      const float displace = radius * (0.18f + d.plane_offset);
-      D.bstrength = D.flip ? -d.bstrength : d.bstrength;
-      float area_no[3];
-      if (d.sculpt_plane == 0) {
-        dsc_area_finalize(m.st, d, true, an, ac);
-        area_no[0] = an[0]; area_no[1] = an[1]; area_no[2] = an[2];
-      }
-      else {
-        dsc_sculpt_normal(m.st, d, an);
-        dsc_area_finalize(m.st, d, true, area_no, ac);
-      }
-      const float area_co0[3] = {ac[0], ac[1], ac[2]};
-      if ((d.flags & 4) || (d.grab_delta[0] == 0.0f && d.grab_delta[1] == 0.0f && d.grab_delta[2] == 0.0f)) {
-        D.skip = 1;
-      }
-      float area_co[3];
-      for (int k = 0; k < 3; k++) {
-        const float t = (an[k] * d.scale[k]) * displace;
-        area_co[k] = area_co0[k] + t;
-        D.origin[k] = area_co[k] + area_no[k] * (-radius * 0.7f);
-        D.plane_no[k] = an[k];
-      }
-      float a0[3], a1[3];
-      a0[0] = area_no[1] * d.grab_delta[2] - area_no[2] * d.grab_delta[1];
-      a0[1] = area_no[2] * d.grab_delta[0] - area_no[0] * d.grab_delta[2];
-      a0[2] = area_no[0] * d.grab_delta[1] - area_no[1] * d.grab_delta[0];
-      a1[0] = area_no[1] * a0[2] - area_no[2] * a0[1];
-      a1[1] = area_no[2] * a0[0] - area_no[0] * a0[2];
-      a1[2] = area_no[0] * a0[1] - area_no[1] * a0[0];
-      float a2[3] = {area_no[0], area_no[1], area_no[2]};
-      dsc_normalize(a0[0], a0[1], a0[2]);
-      dsc_normalize(a1[0], a1[1], a1[2]);
-      dsc_normalize(a2[0], a2[1], a2[2]);
-      for (int k = 0; k < 3; k++) {
-        D.ax[0][k] = a0[k]; D.ax[1][k] = a1[k]; D.ax[2][k] = a2[k];
-      }
-      D.sc[0] = d.radius; D.sc[1] = d.radius; D.sc[2] = d.radius * 1.25f;
-      D.plane_d = -(an[0] * area_co[0] + an[1] * area_co[1] + an[2] * area_co[2]);
-      D.trim_sq = (d.radius * d.radius) * (d.plane_trim * d.plane_trim);
-      /* what the host reads back as the plane: centre before the offset */
-      ac[0] = area_co0[0]; ac[1] = area_co0[1]; ac[2] = area_co0[2];
-    }
-    if (blockIdx.x == 0) {
-      for (int k = 0; k < 3; k++) {
-        m.st->area_no[k] = an[k];
-        m.st->area_co[k] = ac[k];
-      }
-    }
+    dsc_brush_derive(st, d, D, blockIdx.x == 0);
   }
   __syncthreads();
   const int tool = d.tool;
   const float radius_sq = d.radius * d.radius;
   const bool need_no = (tool == 4) || (d.flags & 1);
+  const bool use_orig = (tool == 5);
   unsigned moved_cnt = 0;
-  for (int c = blockIdx.x; c < m.nchunk; c += gridDim.x) {
-    const unsigned lst = m.leaf_state[m.chunk_leaf[c]];
-    if (!(lst & DSC_LEAF_HIT)) continue;
-    const bool first = (lst & DSC_LEAF_FIRST) != 0;
-    const int beg = m.chunk_beg[c], cnt = m.chunk_cnt[c];
-    const int cnt32 = (cnt + 31) & ~31;
-    for (int i = tid; i < cnt32; i += DSC_BLOCK) {
-      const int s = beg + i;
-      bool moved = false;
-      if (i < cnt) {
-        const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
-        float vnx = 0.0f, vny = 0.0f, vnz = 0.0f;
-        if (first) {
-          vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s];
-          m.ox[s] = x; m.oy[s] = y; m.oz[s] = z;
-          m.onx[s] = vnx; m.ony[s] = vny; m.onz[s] = vnz;
-        }
-        if (!D.skip) {
-          if (tool == 18) {
-            /* clay strips: brush-local cube test + plane */
-            const float rx = x - D.origin[0], ry = y - D.origin[1], rz = z - D.origin[2];
-            float local[3];
+  const int total = st->hit_count * m.max_chunks;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int leaf, beg, cnt;
+    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
+    const bool first = (m.leaf_state[leaf] & DSC_LEAF_FIRST) != 0;
+    const int nvalid = cnt - 4 * tid;
+    const int s0 = beg + 4 * tid;
+    unsigned nib = 0;
+    if (nvalid > 0) {
+      float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
+      float4 NX = make_float4(0, 0, 0, 0), NY = NX, NZ = NX;
+      float4 TX = X, TY = Y, TZ = Z;
+      if (first) {
+        NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0);
+        st4(m.ox, s0, X); st4(m.oy, s0, Y); st4(m.oz, s0, Z);
+        st4(m.onx, s0, NX); st4(m.ony, s0, NY); st4(m.onz, s0, NZ);
+      }
+      else if (use_orig) {
+        TX = ld4(m.ox, s0); TY = ld4(m.oy, s0); TZ = ld4(m.oz, s0);
+      }
+      if (!D.skip) {
+        float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+        const float txs[4] = {TX.x, TX.y, TX.z, TX.w}, tys[4] = {TY.x, TY.y, TY.z, TY.w}, tzs[4] = {TZ.x, TZ.y, TZ.z, TZ.w};
+        if (need_no && !first) {
+          /* only needed for verts inside; one cheap pre-test keeps the streaming case at 12 B/vert */
+          bool any = (tool == 18);
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-              local[k] = fabsf((rx * D.ax[k][0] + ry * D.ax[k][1] + rz * D.ax[k][2]) / D.sc[k]);
-            }
-            const float side = 1.0f;
-            if (local[0] <= side && local[1] <= side && local[2] <= side) {
-              const float roundness = d.tip_roundness;
-              const float hardness = 1.0f - roundness;
-              const float constant_side = hardness * side;
-              const float falloff_side = roundness * side;
-              float dist;
-              const float mn = local[0] < local[1] ? local[0] : local[1];
-              const float mx = local[0] > local[1] ? local[0] : local[1];
-              if (mn > constant_side) {
-                const float ex = local[0] - constant_side, ey = local[1] - constant_side;
-                dist = sqrtf(ex * ex + ey * ey) / falloff_side;
-              }
-              else if (mx > constant_side) {
-                dist = (mx - constant_side) / falloff_side;
-              }
-              else {
-                dist = 0.0f;
-              }
-              float side_d = (x * D.plane_no[0] + y * D.plane_no[1] + z * D.plane_no[2]) + D.plane_d;
-              if (D.flip) side_d = -side_d;
-              if (side_d <= 0.0f) {
-                const float pd = (D.plane_no[0] * x + D.plane_no[1] * y + D.plane_no[2] * z) + D.plane_d;
-                const float ix = x + D.plane_no[0] * (-pd), iy = y + D.plane_no[1] * (-pd), iz = z + D.plane_no[2] * (-pd);
-                const float vx = ix - x, vy = iy - y, vz = iz - z;
-                if (!(d.flags & 2) || ((vx * vx + vy * vy + vz * vz) <= D.trim_sq)) {
-                  if (!first && (d.flags & 1)) { vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s]; }
-                  const float fade = D.bstrength * dsc_strength_factor(m, d, d.radius * dist, vnx, vny, vnz, s);
-                  const float px = vx * fade, py = vy * fade, pz = vz * fade;
-                  m.cx[s] = x + px; m.cy[s] = y + py; m.cz[s] = z + pz;
-                  moved = true;
-                }
-              }
-            }
+          for (int j = 0; j < 4; j++) {
+            const float dx = txs[j] - d.loc[0], dy = tys[j] - d.loc[1], dz = tzs[j] - d.loc[2];
+            any |= !((dx * dx + dy * dy + dz * dz) > radius_sq);
           }
-          else {
-            /* sphere test: grab tests the stroke-start coordinates */
-            float tx = x, ty = y, tz = z;
-            if (tool == 5 && !first) { tx = m.ox[s]; ty = m.oy[s]; tz = m.oz[s]; }
-            const float dx = tx - d.loc[0], dy = ty - d.loc[1], dz = tz - d.loc[2];
-            const float distsq = dx * dx + dy * dy + dz * dz;
-            if (!(distsq > radius_sq)) {
-              if (!first && need_no) {
-                if (tool == 5) { vnx = m.onx[s]; vny = m.ony[s]; vnz = m.onz[s]; }
-                else { vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s]; }
-              }
-              float fade = dsc_strength_factor(m, d, sqrtf(distsq), vnx, vny, vnz, s);
-              if (tool == 1) {
-                const float px = D.offset[0] * fade, py = D.offset[1] * fade, pz = D.offset[2] * fade;
-                m.cx[s] = x + px; m.cy[s] = y + py; m.cz[s] = z + pz;
-              }
-              else if (tool == 4) {
-                fade = d.bstrength * fade;
-                const float sc = fade * d.radius;
-                const float px = (vnx * sc) * d.scale[0], py = (vny * sc) * d.scale[1], pz = (vnz * sc) * d.scale[2];
-                m.cx[s] = x + px; m.cy[s] = y + py; m.cz[s] = z + pz;
-              }
-              else {
-                fade = d.bstrength * fade;
-                const float px = d.grab_delta[0] * fade, py = d.grab_delta[1] * fade, pz = d.grab_delta[2] * fade;
-                m.cx[s] = tx + px; m.cy[s] = ty + py; m.cz[s] = tz + pz;
-              }
-              moved = true;
-            }
+          if (any) {
+            if (use_orig) { NX = ld4(m.onx, s0); NY = ld4(m.ony, s0); NZ = ld4(m.onz, s0); }
+            else { NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0); }
           }
         }
+        const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j < nvalid && dsc_brush_vertex(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j], vys[j],
+                                             vzs[j], radius_sq)) {
+            nib |= 1u << j;
+          }
+        }
+        if (nib) {
+          st4(m.cx, s0, make_float4(xs[0], xs[1], xs[2], xs[3]));
+          st4(m.cy, s0, make_float4(ys[0], ys[1], ys[2], ys[3]));
+          st4(m.cz, s0, make_float4(zs[0], zs[1], zs[2], zs[3]));
+        }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, moved);
-      if (bal && lane == 0) {
-        m.dirty[s >> 5] |= bal;
-        if (m.capture) m.capture[s >> 5] |= bal;
-        moved_cnt += __popc(bal);
-      }
+    }
+    const unsigned w = dsc_pack_nibbles(nib, lane);
+    if (w && (lane & 7) == 0) {
+      atomicOr(&m.dirty[s0 >> 5], w); /* fire-and-forget RED: no round trip for the old word */
+      if (m.capture) atomicOr(&m.capture[s0 >> 5], w);
+      moved_cnt += __popc(w);
     }
   }
   if (moved_cnt) atomicAdd(&s_moved, moved_cnt);
   __syncthreads();
-  if (tid == 0 && s_moved) atomicAdd(&m.st->moved_total, (unsigned long long)s_moved);
+  if (tid == 0 && s_moved) atomicAdd(&m.tot->moved_total, (unsigned long long)s_moved);
 }
 
 /* snapshot only (smooth brush: first touch, before iteration 0) */
-__global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m)
+__global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m, int slot)
 {
-  for (int c = blockIdx.x; c < m.nchunk; c += gridDim.x) {
-    const unsigned lst = m.leaf_state[m.chunk_leaf[c]];
-    if ((lst & (DSC_LEAF_HIT | DSC_LEAF_FIRST)) != (DSC_LEAF_HIT | DSC_LEAF_FIRST)) continue;
-    const int beg = m.chunk_beg[c], cnt = m.chunk_cnt[c];
-    for (int i = threadIdx.x; i < cnt; i += DSC_BLOCK) {
-      const int s = beg + i;
-      m.ox[s] = m.cx[s]; m.oy[s] = m.cy[s]; m.oz[s] = m.cz[s];
-      m.onx[s] = m.nx[s]; m.ony[s] = m.ny[s]; m.onz[s] = m.nz[s];
-    }
+  const DabState *st = m.st + slot;
+  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
+  const int tid = threadIdx.x;
+  const int total = st->hit_count * m.max_chunks;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int leaf, beg, cnt;
+    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
+    if (!(m.leaf_state[leaf] & DSC_LEAF_FIRST)) continue;
+    if (cnt - 4 * tid <= 0) continue;
+    const int s0 = beg + 4 * tid;
+    st4(m.ox, s0, ld4(m.cx, s0)); st4(m.oy, s0, ld4(m.cy, s0)); st4(m.oz, s0, ld4(m.cz, s0));
+    st4(m.onx, s0, ld4(m.nx, s0)); st4(m.ony, s0, ld4(m.ny, s0)); st4(m.onz, s0, ld4(m.nz, s0));
   }
 }
 
@@ -605,18 +774,21 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m)
 /* One Jacobi iteration, part A: new position of every unique vert of a hit leaf inside the
  * sphere = co + (neighbour average - co) * fade, into the scratch arrays (SURVEY.md 8a row a20:
  * interior verts average all edge neighbours, boundary verts only boundary neighbours, boundary
- * verts with <= 2 neighbours stay). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, float strength)
+ * verts with <= 2 neighbours stay).  The CSR gather is served by L2. */
+__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, int slot, float strength)
 {
+  const DabState *st = m.st + slot;
+  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) s_moved = 0;
   __syncthreads();
   const float radius_sq = d.radius * d.radius;
   unsigned moved_cnt = 0;
-  for (int c = blockIdx.x; c < m.nchunk; c += gridDim.x) {
-    if (!(m.leaf_state[m.chunk_leaf[c]] & DSC_LEAF_HIT)) continue;
-    const int beg = m.chunk_beg[c], cnt = m.chunk_cnt[c];
+  const int total = st->hit_count * m.max_chunks;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int leaf, beg, cnt;
+    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
     const int cnt32 = (cnt + 31) & ~31;
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
@@ -630,23 +802,23 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, 
           if (d.flags & 1) { vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s]; }
           const float fade = strength * dsc_strength_factor(m, d, sqrtf(distsq), vnx, vny, vnz, s);
           float ax = 0.0f, ay = 0.0f, az = 0.0f;
-          int total = 0;
+          int tot = 0;
           const unsigned qb = m.nb_off[s], qe = m.nb_off[s + 1];
           const int neighbor_count = (int)(qe - qb);
           const bool is_boundary = m.boundary[s] != 0;
           for (unsigned q = qb; q < qe; q++) {
-            const int u = m.nb_idx[q];
-            if (!is_boundary || m.boundary[u]) {
-              ax += m.cx[u]; ay += m.cy[u]; az += m.cz[u];
-              total++;
+            const int v = m.nb_idx[q];
+            if (!is_boundary || m.boundary[v]) {
+              ax += m.cx[v]; ay += m.cy[v]; az += m.cz[v];
+              tot++;
             }
           }
           float rx, ry, rz;
-          if ((neighbor_count <= 2 && is_boundary) || total == 0) {
+          if ((neighbor_count <= 2 && is_boundary) || tot == 0) {
             rx = x; ry = y; rz = z;
           }
           else {
-            const float f = 1.0f / (float)total;
+            const float f = 1.0f / (float)tot;
             rx = ax * f; ry = ay * f; rz = az * f;
           }
           const float vx = rx - x, vy = ry - y, vz = rz - z;
@@ -669,15 +841,18 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, 
   }
   if (moved_cnt) atomicAdd(&s_moved, moved_cnt);
   __syncthreads();
-  if (tid == 0 && s_moved) atomicAdd(&m.st->moved_total, (unsigned long long)s_moved);
+  if (tid == 0 && s_moved) atomicAdd(&m.tot->moved_total, (unsigned long long)s_moved);
 }
 
 /* part B: commit the scratch positions */
-__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m)
+__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m, int slot)
 {
-  for (int c = blockIdx.x; c < m.nchunk; c += gridDim.x) {
-    if (!(m.leaf_state[m.chunk_leaf[c]] & DSC_LEAF_HIT)) continue;
-    const int beg = m.chunk_beg[c], cnt = m.chunk_cnt[c];
+  const DabState *st = m.st + slot;
+  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
+  const int total = st->hit_count * m.max_chunks;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int leaf, beg, cnt;
+    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
     for (int i = threadIdx.x; i < cnt; i += DSC_BLOCK) {
       const int s = beg + i;
       if ((m.iter_moved[s >> 5] >> (s & 31)) & 1u) {
@@ -688,19 +863,22 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m)
 }
 
 /* ------------------------------------------------------------------------------ K5 normals */
-/* BKE_pbvh_update_normals for PBVH_FACES (pbvh.c:2912-3036): for every dirty unique vert of a
- * leaf flagged UpdateNormals, normal = normalize(sum of the poly normals of its looptris), summed
- * in ascending looptri position; then the dirty bit is cleared.  Like the reference's accumulate
- * pass, looptris of leaves that are not flagged contribute nothing (pbvh.c:2943). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m)
+/* BKE_pbvh_update_normals for PBVH_FACES (pbvh.c:2912-3036), general gather form: for every dirty
+ * unique vert of a listed (flagged) leaf, normal = normalize(sum of the poly normals of its
+ * looptris), summed in ascending looptri position; then the dirty bit is cleared.  Like the
+ * reference's accumulate pass, looptris of leaves that are not flagged contribute nothing
+ * (pbvh.c:2943).  Handles any poly size and leaf size; leaves that fit the shared-memory kernel
+ * below are skipped when skip_fast is set. */
+__global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *list, const int *count, int skip_fast)
 {
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int c = blockIdx.x; c < m.nchunk; c += gridDim.x) {
-    const int leaf = m.chunk_leaf[c];
-    const int node = m.leaf_node[leaf];
-    if (!(m.node_flag[node] & F_UpdateNormals)) continue;
+  const int total = *count * m.max_chunks;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int leaf, beg, cnt;
+    if (!dsc_unit(m, list, u, leaf, beg, cnt)) continue;
+    if (skip_fast && m.leaf_fast[leaf]) continue;
+    if (!(m.node_flag[leaf] & F_UpdateNormals)) continue;
     const unsigned pb = (unsigned)m.leaf_pbeg[leaf], pe = pb + (unsigned)m.leaf_pcnt[leaf];
-    const int beg = m.chunk_beg[c], cnt = m.chunk_cnt[c];
     const int cnt32 = (cnt + 31) & ~31;
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
@@ -712,7 +890,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m)
         for (unsigned q = qb; q < qe; q++) {
           const unsigned pos = m.vt_idx[q];
           if (pos < pb || pos >= pe) {
-            if (!(m.node_flag[m.leaf_node[m.tri_leaf[pos]]] & F_UpdateNormals)) continue;
+            if (!(m.node_flag[m.tri_leaf[pos]] & F_UpdateNormals)) continue;
           }
           float fx, fy, fz;
           dsc_poly_normal(m, pos, fx, fy, fz);
@@ -727,30 +905,243 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m)
   }
 }
 
+/* ----------------------------------------------------------- K5 + K6 fused, shared-memory form */
+#define NB_BLOCK 512
+#define NB_NORMALS 1
+#define NB_BOUNDS 2
+/* bytes of dynamic shared memory a leaf needs (host and device agree through this one formula) */
+__host__ __device__ inline size_t dsc_nb_smem_bytes(int nloc, int ne, int ng, int ncnt)
+{
+  return 12 * (size_t)((nloc + 3) & ~3) + 12 * (size_t)ne + 4 * (size_t)(2 * ng + 1 + ncnt);
+}
+/* One CTA per listed leaf.  Phase 1 stages the leaf's vertex positions in shared memory: the
+ * unique verts as a float4 stream, the shared (and extra) verts by gather -- the only gathers
+ * left on the path -- and reduces the leaf AABB over unique + shared on the way (update_node_vb,
+ * pbvh.c:2033-2041).  Phase 2 computes the normal of every poly the leaf's looptris belong to, and
+ * of the halo polys around it, once, from shared memory (BKE_mesh_calc_poly_normal).  Phase 3
+ * sums, per dirty unique vert, the normals of its looptris in ascending looptri position
+ * (pbvh.c:2933-2981 run single-threaded), normalises, stores, clears the dirty bit.
+ * Halo polys whose owning leaf is not flagged UpdateNormals contribute zero (pbvh.c:2943).
+ * Every global load of phases 2 and 3 is issued in independent batches (4 entries, 2 x 8 index
+ * rows per thread) so the HBM round trip is paid per batch, not per element.
+ * Leaves with no dirty vert only refresh their box; leaves that do not fit (leaf_fast == 0) are
+ * left to k_normals / k_leaf_bb. */
+__global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, const int *list, const int *count, int mode)
+{
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[6][NB_BLOCK / 32];
+  constexpr int NW = NB_BLOCK / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tn = m.totnode;
+  const int n = *count;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int l = list[h];
+    if (!m.leaf_fast[l]) continue;
+    const int flag = m.node_flag[l];
+    const bool do_n = (mode & NB_NORMALS) && (flag & F_UpdateNormals);
+    const bool do_b = (mode & NB_BOUNDS) && (flag & F_UpdateBB);
+    if (!do_n && !do_b) continue;
+    const int ub = m.leaf_ubeg[l], U = m.leaf_ucnt[l];
+    const int sb = m.leaf_sbeg[l], S = m.leaf_scnt[l], X = m.leaf_xcnt[l];
+    const int eb = m.leaf_ebeg[l], eown = m.leaf_eown[l], ne = eown + m.leaf_ehalo[l];
+    const int hb = m.leaf_hbeg[l], nbeg = m.leaf_nbeg[l], ncnt = m.leaf_ncnt[l];
+    const int ng = (U + 31) >> 5, G0 = ub >> 5;
+    const int nlp = (U + S + X + 3) & ~3;
+    float *px = smem, *py = smem + nlp, *pz = smem + 2 * nlp;
+    float *fx = smem + 3 * nlp, *fy = fx + ne, *fz = fx + 2 * ne;
+    unsigned *sdirty = reinterpret_cast<unsigned *>(fx + 3 * ne);
+    unsigned *sgoff = sdirty + ng;
+    unsigned *snb = sgoff + ng + 1;
+    __syncthreads(); /* the previous leaf is done with the shared arrays */
+    int anyd = 0;
+    if (do_n) {
+      for (int w = tid; w < ng; w += NB_BLOCK) {
+        const unsigned dw = m.dirty[G0 + w];
+        sdirty[w] = dw;
+        anyd |= (dw != 0u);
+      }
+      for (int w = tid; w <= ng; w += NB_BLOCK) sgoff[w] = m.v2_goff[G0 + w];
+      for (int w = tid; w < ncnt; w += NB_BLOCK) snb[w] = (unsigned)(m.node_flag[m.nb_leaf[nbeg + w]] & F_UpdateNormals);
+    }
+    anyd = __syncthreads_or(anyd);
+    if (!anyd && !do_b) continue;
+    const int nloc = U + S + (anyd ? X : 0);
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    /* phase 1: stage + box */
+    for (int i = 4 * tid; i < U; i += 4 * NB_BLOCK) {
+      const float4 A = ld4(m.cx, ub + i), B = ld4(m.cy, ub + i), C = ld4(m.cz, ub + i);
+      *reinterpret_cast<float4 *>(px + i) = A;
+      *reinterpret_cast<float4 *>(py + i) = B;
+      *reinterpret_cast<float4 *>(pz + i) = C;
+      const float xs[4] = {A.x, A.y, A.z, A.w}, ys[4] = {B.x, B.y, B.z, B.w}, zs[4] = {C.x, C.y, C.z, C.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (i + j < U) {
+          mn[0] = fminf(mn[0], xs[j]); mx[0] = fmaxf(mx[0], xs[j]);
+          mn[1] = fminf(mn[1], ys[j]); mx[1] = fmaxf(mx[1], ys[j]);
+          mn[2] = fminf(mn[2], zs[j]); mx[2] = fmaxf(mx[2], zs[j]);
+        }
+      }
+    }
+    __syncthreads(); /* the float4 tail of the unique run may overlap the first shared entries */
+    for (int i = U + tid; i < nloc; i += NB_BLOCK) {
+      const int s = m.stage_slots[sb + (i - U)];
+      const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
+      px[i] = x; py[i] = y; pz[i] = z;
+      if (i < U + S) {
+        mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+        mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+        mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+      }
+    }
+    if (do_b) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        for (int o = 16; o > 0; o >>= 1) {
+          mn[k] = fminf(mn[k], __shfl_down_sync(0xffffffffu, mn[k], o));
+          mx[k] = fmaxf(mx[k], __shfl_down_sync(0xffffffffu, mx[k], o));
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          red[k][warp] = mn[k];
+          red[3 + k][warp] = mx[k];
+        }
+      }
+    }
+    __syncthreads();
+    if (do_b && tid < 6) {
+      float v = red[tid][0];
+      for (int w = 1; w < NW; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+      m.bb[tid * tn + l] = v;
+    }
+    if (!anyd) continue;
+    /* phase 2: poly normals of the local entries, 4 in flight per thread */
+    for (int e0 = tid; e0 < ne; e0 += 4 * NB_BLOCK) {
+      ushort4 pv[4];
+      unsigned hn[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * NB_BLOCK;
+        pv[u] = make_ushort4(0, 0, 0, 0);
+        hn[u] = 0;
+        if (e < ne) {
+          pv[u] = m.e_pv[eb + e];
+          if (e >= eown) hn[u] = m.e_halo_nb[hb + (e - eown)];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * NB_BLOCK;
+        if (e >= ne) break;
+        float ox, oy, oz;
+        const ushort4 v = pv[u];
+        if (e < eown || snb[hn[u]]) {
+          if (v.w != 0xffffu) {
+            /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
+            const float n1x = px[v.x] - px[v.z], n1y = py[v.x] - py[v.z], n1z = pz[v.x] - pz[v.z];
+            const float n2x = px[v.y] - px[v.w], n2y = py[v.y] - py[v.w], n2z = pz[v.y] - pz[v.w];
+            ox = n1y * n2z - n1z * n2y;
+            oy = n1z * n2x - n1x * n2z;
+            oz = n1x * n2y - n1y * n2x;
+          }
+          else {
+            /* normal_tri_v3, lib/intern/math_geom.cc:31-49 */
+            const float bx = px[v.y], by = py[v.y], bz = pz[v.y];
+            const float n1x = px[v.x] - bx, n1y = py[v.x] - by, n1z = pz[v.x] - bz;
+            const float n2x = bx - px[v.z], n2y = by - py[v.z], n2z = bz - pz[v.z];
+            ox = n1y * n2z - n1z * n2y;
+            oy = n1z * n2x - n1x * n2z;
+            oz = n1x * n2y - n1y * n2x;
+          }
+          dsc_normalize(ox, oy, oz);
+        }
+        else {
+          ox = oy = oz = 0.0f;
+        }
+        fx[e] = ox; fy[e] = oy; fz[e] = oz;
+      }
+    }
+    __syncthreads();
+    /* phase 3: one warp per group of 32 verts, two groups (2 x 8 index rows) in flight */
+    for (int g0 = warp; g0 < ng; g0 += 2 * NW) {
+      unsigned word[2], off[2];
+      int wd[2];
+      unsigned short en[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int g = g0 + u * NW;
+        const bool ok = g < ng;
+        word[u] = ok ? sdirty[g] : 0u;
+        off[u] = ok ? sgoff[g] : 0u;
+        wd[u] = ok ? (int)((sgoff[g + 1] - off[u]) >> 5) : 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          en[u][j] = (word[u] != 0u && j < wd[u]) ? m.v2_idx[off[u] + j * 32 + lane] : (unsigned short)0xffffu;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (word[u] == 0u) continue; /* warp-uniform */
+        const int g = g0 + u * NW;
+        const int s = ub + g * 32 + lane;
+        if ((word[u] >> lane) & 1u) {
+          float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const unsigned e = en[u][j];
+            if (e != 0xffffu) {
+              sx += fx[e]; sy += fy[e]; sz += fz[e];
+            }
+          }
+          for (int j = 8; j < wd[u]; j++) {
+            const unsigned e = m.v2_idx[off[u] + j * 32 + lane];
+            if (e != 0xffffu) {
+              sx += fx[e]; sy += fy[e]; sz += fz[e];
+            }
+          }
+          dsc_normalize(sx, sy, sz);
+          m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
+        }
+        if (lane == 0) m.dirty[G0 + g] = 0u;
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------ K6 leaf BB */
-/* update_node_vb leaf branch (pbvh.c:2033-2041): min/max over ALL verts of the leaf, unique
- * (stream) and shared (gather), for leaves flagged UpdateBB. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_leaf_bb(DevMesh m)
+/* update_node_vb leaf branch (pbvh.c:2033-2041) on its own: min/max over ALL verts of a listed
+ * leaf flagged UpdateBB, unique (float4 stream) and shared (gather). */
+__global__ void __launch_bounds__(DSC_BLOCK) k_leaf_bb(DevMesh m, const int *list, const int *count, int skip_fast)
 {
   __shared__ float red[6][DSC_BLOCK / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
-  for (int l = blockIdx.x; l < m.nleaf; l += gridDim.x) {
-    const int node = m.leaf_node[l];
-    if (!(m.node_flag[node] & F_UpdateBB)) continue;
+  const int n = *count;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int l = list[h];
+    if (skip_fast && m.leaf_fast[l]) continue;
+    if (!(m.node_flag[l] & F_UpdateBB)) continue;
     float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
     float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
     const int ub = m.leaf_ubeg[l], uc = m.leaf_ucnt[l];
-    for (int i = tid; i < uc; i += DSC_BLOCK) {
-      const int s = ub + i;
-      const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
-      mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
-      mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
-      mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+    for (int i = 4 * tid; i < uc; i += 4 * DSC_BLOCK) {
+      const float4 X = ld4(m.cx, ub + i), Y = ld4(m.cy, ub + i), Z = ld4(m.cz, ub + i);
+      const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (i + j < uc) {
+          mn[0] = fminf(mn[0], xs[j]); mx[0] = fmaxf(mx[0], xs[j]);
+          mn[1] = fminf(mn[1], ys[j]); mx[1] = fmaxf(mx[1], ys[j]);
+          mn[2] = fminf(mn[2], zs[j]); mx[2] = fmaxf(mx[2], zs[j]);
+        }
+      }
     }
     const int sb = m.leaf_sbeg[l], sc = m.leaf_scnt[l];
     for (int i = tid; i < sc; i += DSC_BLOCK) {
-      const int s = m.shared_slots[sb + i];
+      const int s = m.stage_slots[sb + i];
       const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
       mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
       mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
@@ -775,23 +1166,21 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_leaf_bb(DevMesh m)
     if (tid < 6) {
       float v = red[tid][0];
       for (int w = 1; w < DSC_BLOCK / 32; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
-      m.bb[tid * tn + node] = v;
+      m.bb[tid * tn + l] = v;
     }
   }
 }
 
-/* ------------------------------------------------------------------------------ K7 BB flush */
-/* pbvh_flush_bb (pbvh.c:3287-3317), bottom-up by depth in one CTA.  Every inner node is
- * recomputed: an inner node none of whose leaves changed already equals the union of its
- * children, so the result is the reference's.  Then the leaf flags in clear_mask are dropped. */
-__global__ void __launch_bounds__(1024) k_flush(DevMesh m, int clear_mask)
+/* Whole-tree flush by depth in one CTA (session start, vert_coords_apply, stand-alone
+ * BKE_pbvh_update_bounds): every inner node = union of its children. */
+__global__ void __launch_bounds__(1024) k_flush(DevMesh m)
 {
   const int tn = m.totnode;
   for (int lev = m.nlevel - 1; lev >= 0; lev--) {
     const int b = m.level_off[lev], e = m.level_off[lev + 1];
     for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
       const int node = m.level_nodes[i];
-      const int c0 = m.node_child[node], c1 = c0 + 1;
+      const int c0 = m.child0[node], c1 = m.child1[node];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         m.bb[k * tn + node] = fminf(__ldcg(&m.bb[k * tn + c0]), __ldcg(&m.bb[k * tn + c1]));
@@ -801,12 +1190,16 @@ __global__ void __launch_bounds__(1024) k_flush(DevMesh m, int clear_mask)
     __threadfence_block();
     __syncthreads();
   }
-  if (clear_mask) {
-    for (int l = threadIdx.x; l < m.nleaf; l += blockDim.x) {
-      const int node = m.leaf_node[l];
-      const int f = m.node_flag[node];
-      if (f & clear_mask) m.node_flag[node] = f & ~clear_mask;
-    }
+}
+
+/* drops leaf flags once their stage ran (pbvh.c:3007, 3295) */
+__global__ void __launch_bounds__(DSC_BLOCK) k_clear_flags(DevMesh m, const int *list, const int *count, int clear_mask)
+{
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int l = list[i];
+    const int f = m.node_flag[l];
+    if (f & clear_mask) m.node_flag[l] = f & ~clear_mask;
   }
 }
 
@@ -816,19 +1209,18 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_orig_leaves(DevMesh m)
 {
   const int tn = m.totnode;
   for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < m.nleaf; l += gridDim.x * blockDim.x) {
-    const int node = m.leaf_node[l];
-    const int f = m.node_flag[node];
+    const int f = m.node_flag[l];
     if (!(f & F_UpdateOriginalBB)) continue;
-    m.node_flag[node] = f & ~F_UpdateOriginalBB;
-    for (int k = 0; k < 6; k++) m.obb[k * tn + node] = m.bb[k * tn + node];
-    int p = m.node_parent[node];
-    while (p >= 0 && atomicExch(&m.node_mark[p], 1) == 0) p = m.node_parent[p];
+    m.node_flag[l] = f & ~F_UpdateOriginalBB;
+    for (int k = 0; k < 6; k++) m.obb[k * tn + l] = m.bb[k * tn + l];
+    int p = m.topo[l].x;
+    while (p >= 0 && atomicExch(&m.node_mark[p], 1) == 0) p = m.topo[p].x;
   }
 }
 __global__ void __launch_bounds__(DSC_BLOCK) k_orig_inner(DevMesh m)
 {
   const int tn = m.totnode;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < tn; n += gridDim.x * blockDim.x) {
+  for (int n = m.nleaf + blockIdx.x * blockDim.x + threadIdx.x; n < tn; n += gridDim.x * blockDim.x) {
     if (m.node_mark[n]) {
       m.node_mark[n] = 0;
       for (int k = 0; k < 6; k++) m.obb[k * tn + n] = m.bb[k * tn + n];
@@ -840,7 +1232,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_orig_inner(DevMesh m)
 __global__ void k_mark_all(DevMesh m, int flags, int all_dirty, int nwords)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m.nleaf) m.node_flag[m.leaf_node[i]] |= flags;
+  if (i < m.nleaf) m.node_flag[i] |= flags;
   if (all_dirty) {
     for (int w = i; w < nwords; w += gridDim.x * blockDim.x) m.dirty[w] = 0xffffffffu;
   }
