@@ -534,6 +534,11 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       }
       next_group_to_fill = G0 + ng;
       leaf_ehalo[l] = ne - leaf_eown[l];
+      /* row padding points at the leaf's zero entry (index ne) */
+      for (size_t q = v2_goff[G0]; q < v2_idx.size(); q++) {
+        if (v2_idx[q] == 0xffff) v2_idx[q] = (unsigned short)std::min(ne, 0xffff);
+      }
+      if (ne >= 0xffff) ok = false;
       const size_t bytes = dsc_nb_smem_bytes(nloc, ne, ng, leaf_ncnt[l]);
       if (!ok || bytes > DSC_SMEM_BUDGET) {
         leaf_fast[l] = 0;

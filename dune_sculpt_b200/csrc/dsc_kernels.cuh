@@ -471,6 +471,8 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int 
       else { n0x += bx; n0y += by; n0z += bz; cnt0++; }
     }
   }
+  /* most CTAs of a small dab sampled nothing: leave before the reduction */
+  if (!__syncthreads_or((cnt0 | cnt1) != 0)) return;
   long long v[16] = {n0x, n0y, n0z, n1x, n1y, n1z, c0x, c0y, c0z, c1x, c1y, c1z, cnt0, cnt1,
                      use_cos ? cnt0 : 0, use_cos ? cnt1 : 0};
 #pragma unroll
@@ -912,24 +914,26 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *lis
 /* bytes of dynamic shared memory a leaf needs (host and device agree through this one formula) */
 __host__ __device__ inline size_t dsc_nb_smem_bytes(int nloc, int ne, int ng, int ncnt)
 {
-  return 12 * (size_t)((nloc + 3) & ~3) + 12 * (size_t)ne + 4 * (size_t)(2 * ng + 1 + ncnt);
+  return 12 * (size_t)nloc + 12 * (size_t)(ne + 1) + 4 * (size_t)(2 * ng + 1 + ncnt);
 }
-/* One CTA per listed leaf.  Phase 1 stages the leaf's vertex positions in shared memory: the
- * unique verts as a float4 stream, the shared (and extra) verts by gather -- the only gathers
- * left on the path -- and reduces the leaf AABB over unique + shared on the way (update_node_vb,
- * pbvh.c:2033-2041).  Phase 2 computes the normal of every poly the leaf's looptris belong to, and
- * of the halo polys around it, once, from shared memory (BKE_mesh_calc_poly_normal).  Phase 3
- * sums, per dirty unique vert, the normals of its looptris in ascending looptri position
- * (pbvh.c:2933-2981 run single-threaded), normalises, stores, clears the dirty bit.
- * Halo polys whose owning leaf is not flagged UpdateNormals contribute zero (pbvh.c:2943).
- * Every global load of phases 2 and 3 is issued in independent batches (4 entries, 2 x 8 index
- * rows per thread) so the HBM round trip is paid per batch, not per element.
+/* One CTA per listed leaf.  Phase 1 stages the leaf's vertex positions in shared memory (xyz
+ * interleaved): the unique verts as a unit-stride stream, the shared (and extra) verts by gather
+ * -- the only gathers left on the path -- and reduces the leaf AABB over unique + shared on the
+ * way (update_node_vb, pbvh.c:2033-2041).  Phase 2 computes the normal of every poly the leaf's
+ * looptris belong to, and of the halo polys around it, once, from shared memory
+ * (BKE_mesh_calc_poly_normal).  Phase 3 sums, per dirty unique vert, the normals of its looptris
+ * in ascending looptri position (pbvh.c:2933-2981 run single-threaded), normalises, stores, clears
+ * the dirty bit.  Halo polys whose owning leaf is not flagged UpdateNormals contribute zero
+ * (pbvh.c:2943); so does the padding of the index rows (entry `ne` is a stored zero vector; adding
+ * +0 is exact).  Global loads of phases 2 and 3 are issued in independent batches (4 entries,
+ * 2 x 8 index rows per thread) so the HBM round trip is paid per batch, not per element.
  * Leaves with no dirty vert only refresh their box; leaves that do not fit (leaf_fast == 0) are
  * left to k_normals / k_leaf_bb. */
 __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, const int *list, const int *count, int mode)
 {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[6][NB_BLOCK / 32];
+  __shared__ int s_dcount;
   constexpr int NW = NB_BLOCK / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
@@ -946,49 +950,45 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
     const int eb = m.leaf_ebeg[l], eown = m.leaf_eown[l], ne = eown + m.leaf_ehalo[l];
     const int hb = m.leaf_hbeg[l], nbeg = m.leaf_nbeg[l], ncnt = m.leaf_ncnt[l];
     const int ng = (U + 31) >> 5, G0 = ub >> 5;
-    const int nlp = (U + S + X + 3) & ~3;
-    float *px = smem, *py = smem + nlp, *pz = smem + 2 * nlp;
-    float *fx = smem + 3 * nlp, *fy = fx + ne, *fz = fx + 2 * ne;
-    unsigned *sdirty = reinterpret_cast<unsigned *>(fx + 3 * ne);
+    float *P = smem;                         /* [U + S + X][3] */
+    float *F = smem + 3 * (U + S + X);       /* [ne + 1][3], entry ne = zero */
+    unsigned *sdirty = reinterpret_cast<unsigned *>(F + 3 * (ne + 1));
     unsigned *sgoff = sdirty + ng;
     unsigned *snb = sgoff + ng + 1;
     __syncthreads(); /* the previous leaf is done with the shared arrays */
-    int anyd = 0;
+    if (tid == 0) s_dcount = 0;
+    __syncthreads();
     if (do_n) {
+      int dc = 0;
       for (int w = tid; w < ng; w += NB_BLOCK) {
         const unsigned dw = m.dirty[G0 + w];
         sdirty[w] = dw;
-        anyd |= (dw != 0u);
+        dc += __popc(dw);
       }
+      if (dc) atomicAdd(&s_dcount, dc);
       for (int w = tid; w <= ng; w += NB_BLOCK) sgoff[w] = m.v2_goff[G0 + w];
       for (int w = tid; w < ncnt; w += NB_BLOCK) snb[w] = (unsigned)(m.node_flag[m.nb_leaf[nbeg + w]] & F_UpdateNormals);
     }
-    anyd = __syncthreads_or(anyd);
+    __syncthreads();
+    const int dcount = s_dcount;
+    const bool anyd = dcount > 0;
     if (!anyd && !do_b) continue;
     const int nloc = U + S + (anyd ? X : 0);
     float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
     float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
     /* phase 1: stage + box */
-    for (int i = 4 * tid; i < U; i += 4 * NB_BLOCK) {
-      const float4 A = ld4(m.cx, ub + i), B = ld4(m.cy, ub + i), C = ld4(m.cz, ub + i);
-      *reinterpret_cast<float4 *>(px + i) = A;
-      *reinterpret_cast<float4 *>(py + i) = B;
-      *reinterpret_cast<float4 *>(pz + i) = C;
-      const float xs[4] = {A.x, A.y, A.z, A.w}, ys[4] = {B.x, B.y, B.z, B.w}, zs[4] = {C.x, C.y, C.z, C.w};
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (i + j < U) {
-          mn[0] = fminf(mn[0], xs[j]); mx[0] = fmaxf(mx[0], xs[j]);
-          mn[1] = fminf(mn[1], ys[j]); mx[1] = fmaxf(mx[1], ys[j]);
-          mn[2] = fminf(mn[2], zs[j]); mx[2] = fmaxf(mx[2], zs[j]);
-        }
-      }
+#pragma unroll 4
+    for (int i = tid; i < U; i += NB_BLOCK) {
+      const float x = m.cx[ub + i], y = m.cy[ub + i], z = m.cz[ub + i];
+      P[3 * i] = x; P[3 * i + 1] = y; P[3 * i + 2] = z;
+      mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+      mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+      mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
     }
-    __syncthreads(); /* the float4 tail of the unique run may overlap the first shared entries */
     for (int i = U + tid; i < nloc; i += NB_BLOCK) {
       const int s = m.stage_slots[sb + (i - U)];
       const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
-      px[i] = x; py[i] = y; pz[i] = z;
+      P[3 * i] = x; P[3 * i + 1] = y; P[3 * i + 2] = z;
       if (i < U + S) {
         mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
         mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
@@ -1011,6 +1011,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
         }
       }
     }
+    if (tid < 3) F[3 * ne + tid] = 0.0f;
     __syncthreads();
     if (do_b && tid < 6) {
       float v = red[tid][0];
@@ -1018,7 +1019,9 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
       m.bb[tid * tn + l] = v;
     }
     if (!anyd) continue;
-    /* phase 2: poly normals of the local entries, 4 in flight per thread */
+    /* phase 2: poly normals of the local entries, 4 in flight per thread.  When few verts of the
+     * leaf are dirty, entries that touch no dirty unique vert are skipped (nothing will read them). */
+    const bool sparse = dcount * 2 < U;
     for (int e0 = tid; e0 < ne; e0 += 4 * NB_BLOCK) {
       ushort4 pv[4];
       unsigned hn[4];
@@ -1036,22 +1039,33 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
       for (int u = 0; u < 4; u++) {
         const int e = e0 + u * NB_BLOCK;
         if (e >= ne) break;
-        float ox, oy, oz;
         const ushort4 v = pv[u];
+        if (sparse) {
+          bool need = false;
+          const unsigned li[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (li[k] < (unsigned)U) need |= ((sdirty[li[k] >> 5] >> (li[k] & 31)) & 1u) != 0u;
+          }
+          if (!need) continue;
+        }
+        float ox, oy, oz;
         if (e < eown || snb[hn[u]]) {
+          const float *a = P + 3 * v.x, *b = P + 3 * v.y, *c = P + 3 * v.z;
           if (v.w != 0xffffu) {
             /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
-            const float n1x = px[v.x] - px[v.z], n1y = py[v.x] - py[v.z], n1z = pz[v.x] - pz[v.z];
-            const float n2x = px[v.y] - px[v.w], n2y = py[v.y] - py[v.w], n2z = pz[v.y] - pz[v.w];
+            const float *dd = P + 3 * v.w;
+            const float n1x = a[0] - c[0], n1y = a[1] - c[1], n1z = a[2] - c[2];
+            const float n2x = b[0] - dd[0], n2y = b[1] - dd[1], n2z = b[2] - dd[2];
             ox = n1y * n2z - n1z * n2y;
             oy = n1z * n2x - n1x * n2z;
             oz = n1x * n2y - n1y * n2x;
           }
           else {
             /* normal_tri_v3, lib/intern/math_geom.cc:31-49 */
-            const float bx = px[v.y], by = py[v.y], bz = pz[v.y];
-            const float n1x = px[v.x] - bx, n1y = py[v.x] - by, n1z = pz[v.x] - bz;
-            const float n2x = bx - px[v.z], n2y = by - py[v.z], n2z = bz - pz[v.z];
+            const float bx = b[0], by = b[1], bz = b[2];
+            const float n1x = a[0] - bx, n1y = a[1] - by, n1z = a[2] - bz;
+            const float n2x = bx - c[0], n2y = by - c[1], n2z = bz - c[2];
             ox = n1y * n2z - n1z * n2y;
             oy = n1z * n2x - n1x * n2z;
             oz = n1x * n2y - n1y * n2x;
@@ -1061,7 +1075,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
         else {
           ox = oy = oz = 0.0f;
         }
-        fx[e] = ox; fy[e] = oy; fz[e] = oz;
+        F[3 * e] = ox; F[3 * e + 1] = oy; F[3 * e + 2] = oz;
       }
     }
     __syncthreads();
@@ -1069,7 +1083,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
     for (int g0 = warp; g0 < ng; g0 += 2 * NW) {
       unsigned word[2], off[2];
       int wd[2];
-      unsigned short en[2][8];
+      unsigned en[2][8];
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         const int g = g0 + u * NW;
@@ -1079,7 +1093,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
         wd[u] = ok ? (int)((sgoff[g + 1] - off[u]) >> 5) : 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          en[u][j] = (word[u] != 0u && j < wd[u]) ? m.v2_idx[off[u] + j * 32 + lane] : (unsigned short)0xffffu;
+          en[u][j] = (word[u] != 0u && j < wd[u]) ? (unsigned)m.v2_idx[off[u] + j * 32 + lane] : (unsigned)ne;
         }
       }
 #pragma unroll
@@ -1091,16 +1105,14 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
           float sx = 0.0f, sy = 0.0f, sz = 0.0f;
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            const unsigned e = en[u][j];
-            if (e != 0xffffu) {
-              sx += fx[e]; sy += fy[e]; sz += fz[e];
+            if (j < wd[u]) { /* warp-uniform */
+              const float *f = F + 3 * en[u][j];
+              sx += f[0]; sy += f[1]; sz += f[2];
             }
           }
           for (int j = 8; j < wd[u]; j++) {
-            const unsigned e = m.v2_idx[off[u] + j * 32 + lane];
-            if (e != 0xffffu) {
-              sx += fx[e]; sy += fy[e]; sz += fz[e];
-            }
+            const float *f = F + 3 * (unsigned)m.v2_idx[off[u] + j * 32 + lane];
+            sx += f[0]; sy += f[1]; sz += f[2];
           }
           dsc_normalize(sx, sy, sz);
           m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
