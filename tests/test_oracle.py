@@ -1,0 +1,168 @@
+"""CPU checks of the oracle itself: invariants the reference code guarantees, closed forms, and
+single-thread vs OpenMP agreement (SURVEY.md section 8c pins 1-3).  No GPU."""
+import numpy as np
+import pytest
+
+from dune_sculpt_b200 import capi, meshgen, stroke
+from oracle_py import Oracle
+
+
+def _meshes():
+    return [("grid", meshgen.grid(97), 300), ("cube", meshgen.cube(5), 150), ("ico", meshgen.icosphere(20), 111)]
+
+
+@pytest.mark.parametrize("name,mesh,ll", _meshes(), ids=[m[0] for m in _meshes()])
+def test_pbvh_invariants(name, mesh, ll):
+    o = Oracle(mesh, leaf_limit=ll)
+    na = o.node_arrays()
+    leaf = (na["flag"] & 1) != 0
+    owner = np.full(mesh.totvert, -1)
+    co = o.co()
+    prims = o.prim_indices()
+    assert np.array_equal(np.sort(prims), np.arange(o.tottri))          # prim_indices is a permutation
+    expect = 0
+    for i in np.nonzero(leaf)[0][np.argsort(na["prim_offset"][leaf])]:
+        assert na["prim_offset"][i] == expect and 0 < na["totprim"][i] <= ll  # leaves tile prim_indices, leaf limit
+        expect += na["totprim"][i]
+        vi = o.node_vert_indices(i, na["uniq_verts"][i] + na["face_verts"][i])
+        u = vi[:na["uniq_verts"][i]]
+        assert (owner[u] == -1).all()                                     # unique in exactly one leaf (pbvh.c:2157-2165)
+        owner[u] = i
+        assert len(set(vi.tolist())) == vi.size
+        assert (co[vi] >= na["vb"][i, :3] - 0).all() and (co[vi] <= na["vb"][i, 3:]).all()  # leaf box holds its verts
+        fvi = o.node_face_vert_indices(i, na["totprim"][i])
+        tv = o.tri_verts()[prims[na["prim_offset"][i]:na["prim_offset"][i] + na["totprim"][i]]]
+        assert np.array_equal(vi[fvi], tv)                                # face_vert_indices index vert_indices
+    assert expect == o.tottri and (owner >= 0).all() and na["uniq_verts"].sum() == mesh.totvert
+    for i in np.nonzero(~leaf)[0]:
+        c = na["children_offset"][i]
+        assert np.array_equal(na["vb"][i, :3], np.minimum(na["vb"][c, :3], na["vb"][c + 1, :3]))   # pbvh.c:2040-2043
+        assert np.array_equal(na["vb"][i, 3:], np.maximum(na["vb"][c, 3:], na["vb"][c + 1, 3:]))
+    ln = np.linalg.norm(o.no().astype(np.float64), axis=1)
+    assert np.all((np.abs(ln - 1.0) < 1e-6) | (ln == 0.0))
+    assert np.array_equal(na["vb"], na["orig_vb"])
+
+
+def test_gather_is_the_flat_leaf_test():
+    """the DFS of pbvh.c:2664-2705 with the sphere callback returns exactly the leaves that pass the
+    callback themselves, in ascending prim offset -- what the CUDA gather relies on"""
+    m = meshgen.cube(5)
+    o = Oracle(m, leaf_limit=100)
+    na = o.node_arrays()
+    leaves = np.nonzero(na["flag"] & 1)[0]
+    leaves = leaves[np.argsort(na["prim_offset"][leaves])]
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        c = rng.uniform(-1.3, 1.3, size=3).astype(np.float32)
+        rsq = np.float32(rng.uniform(0.0, 2.0))
+        bb = na["vb"][leaves]
+        nearest = np.clip(c[None, :], bb[:, :3], bb[:, 3:])
+        t = (c[None, :] - nearest).astype(np.float32)
+        d = (t[:, 0] * t[:, 0] + t[:, 1] * t[:, 1]) + t[:, 2] * t[:, 2]
+        assert np.array_equal(o.gather_sphere(c, float(rsq)), leaves[d < rsq])
+
+
+def test_curve_presets_known_values():
+    o = Oracle(meshgen.grid(5))
+    f = lambda preset, p: o.curve_strength(preset, np.float32((1.0 - p) * 2.0), 2.0)  # noqa: E731  p = 1 - len/r
+    for p in (0.0, 0.25, 0.5, 1.0):
+        assert f(capi.CURVE_SMOOTH, p) == pytest.approx(3 * p * p - 2 * p ** 3, abs=1e-6)
+        assert f(capi.CURVE_SMOOTHER, p) == pytest.approx(p ** 3 * (p * (6 * p - 15) + 10), abs=1e-6)
+        assert f(capi.CURVE_SPHERE, p) == pytest.approx(np.sqrt(2 * p - p * p), abs=1e-6)
+        assert f(capi.CURVE_ROOT, p) == pytest.approx(np.sqrt(p), abs=1e-6)
+        assert f(capi.CURVE_SHARP, p) == pytest.approx(p * p, abs=1e-6)
+        assert f(capi.CURVE_LIN, p) == pytest.approx(p, abs=1e-6)
+        assert f(capi.CURVE_POW4, p) == pytest.approx(p ** 4, abs=1e-6)
+        assert f(capi.CURVE_INVSQUARE, p) == pytest.approx(p * (2 - p), abs=1e-6)
+    assert f(capi.CURVE_CONSTANT, 0.3) == 1.0
+    assert o.curve_strength(capi.CURVE_CONSTANT, 2.0, 2.0) == 0.0  # p >= len -> 0
+    t = np.linspace(0, 1, 257, dtype=np.float32) ** 2
+    o.set_custom_curve(t)
+    assert f(capi.CURVE_CUSTOM, 0.5) == pytest.approx(0.25, abs=1e-4)  # LUT is indexed by 1 - p (colortools.c:942-965)
+
+
+def test_draw_closed_form():
+    m = meshgen.grid(65, height=0.0)
+    o = Oracle(m, leaf_limit=100)
+    o.stroke_begin()
+    d = capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.4, curve_preset=capi.CURVE_CONSTANT, sculpt_plane=capi.DIR_Z, bstrength=0.25)
+    o.dab(d)
+    inside = (m.co[:, 0] ** 2 + m.co[:, 1] ** 2) <= np.float32(0.4) ** 2
+    co = o.co()
+    assert np.array_equal(co[inside, 2], np.full(inside.sum(), np.float32(0.4) * np.float32(0.25), np.float32))
+    assert np.array_equal(co[~inside], m.co[~inside])
+    assert np.array_equal(np.sort(o.moved()), np.nonzero(inside)[0])
+    # area normal of a flat patch is +Z whatever the summation order
+    o2 = Oracle(m, leaf_limit=100)
+    o2.stroke_begin()
+    o2.dab(capi.make_dab(capi.TOOL_DRAW, (0.1, 0.1, 0), 0.5))
+    no, _ = o2.last_area()
+    assert no[0] == 0.0 and no[1] == 0.0 and abs(no[2] - 1.0) < 2e-7
+
+
+def test_inflate_sphere_radius_grows():
+    m = meshgen.icosphere(32)
+    o = Oracle(m, leaf_limit=500)
+    o.stroke_begin()
+    o.dab(capi.make_dab(capi.TOOL_INFLATE, (0, 0, 1), 0.4, curve_preset=capi.CURVE_CONSTANT, bstrength=0.2))
+    inside = np.linalg.norm(m.co - np.array([0, 0, 1], np.float32), axis=1) <= np.float32(0.4)
+    grow = np.linalg.norm(o.co().astype(np.float64), axis=1) - 1.0
+    assert np.allclose(grow[inside], 0.2 * 0.4, atol=5e-4) and np.all(grow[~inside] == 0.0 + (np.linalg.norm(m.co[~inside].astype(np.float64), axis=1) - 1.0))
+
+
+def test_undo_membership_and_original_boxes():
+    m = meshgen.grid(97)
+    o = Oracle(m, leaf_limit=200)
+    o.stroke_begin()
+    hit = set()
+    for d in stroke.c4_tool_stroke(capi.TOOL_DRAW, m.bbox_diag(), dabs=6):
+        o.dab(d)
+        hit |= set(o.hits().tolist())
+        na = o.node_arrays()
+        assert np.array_equal(na["orig_vb"], Oracle(m, leaf_limit=200).node_arrays()["vb"])  # orig_vb frozen during the stroke
+    assert set(o.touched().tolist()) == hit
+    oc = o.orig_co()
+    for n in hit:
+        na = o.node_arrays()
+        u = o.node_vert_indices(n, na["uniq_verts"][n])
+        assert np.array_equal(oc[u], m.co[u])  # snapshot = stroke-start coordinates
+    o.stroke_end()
+    na = o.node_arrays()
+    assert np.array_equal(na["orig_vb"], na["vb"])
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_GRAB, capi.TOOL_CLAY_STRIPS, capi.TOOL_SMOOTH])
+def test_single_thread_vs_openmp(tool):
+    """the timed OpenMP mode may differ from the deterministic mode only through the order of the
+    float atomics of the normal accumulation (pbvh.c:2970-2976)"""
+    m = meshgen.grid(129)
+    dabs = stroke.c4_tool_stroke(tool, m.bbox_diag(), dabs=8) if tool != capi.TOOL_SMOOTH else \
+        [capi.make_dab(capi.TOOL_SMOOTH, (0.1 * i - 0.3, 0.05 * i, 0.0), 0.4, bstrength=0.6) for i in range(6)]
+    res = []
+    for threads in (1, 4):
+        o = Oracle(m, leaf_limit=300, threads=threads)
+        o.stroke_begin()
+        for d in dabs:
+            o.dab(d)
+        o.stroke_end()
+        res.append((o.co(), o.no(), o.node_arrays()["vb"], o.touched()))
+        o.set_threads(1)
+    tol = 1e-5 * m.bbox_diag()
+    assert np.abs(res[0][0] - res[1][0]).max() <= tol
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-5
+    assert np.abs(res[0][2] - res[1][2]).max() <= tol
+    assert np.array_equal(res[0][3], res[1][3])
+
+
+def test_golden_fixtures():
+    """regression pins generated by tests/golden/make_golden.py FROM THE ORACLE (the reference ships
+    no vectors for this path: parity unpinned)"""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+    want = json.load(open(os.path.join(here, "golden", "oracle_strokes.json")))
+    got = make_golden.compute()
+    assert got == want
