@@ -91,11 +91,13 @@ CUDA_SYMBOLS = [
     "dsc_download_co", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
     "dsc_download_node_flags", "dsc_download_touched", "dsc_upload_co", "dsc_synchronize", "dsc_timer_start",
     "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
+    "dsc_dist_unique_id", "dsc_dist_init", "dsc_dist_partition", "dsc_dist_halo_plan", "dsc_dist_free",
+    "dsc_dist_owned_range",
 ]
 HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
     "DUNE_pbvh_mesh_sizes_set", "DUNE_pbvh_mask_layer_set", "DUNE_pbvh_vert_normals_set", "DUNE_pbvh_leaf_limit_set",
-    "DUNE_pbvh_device_attach", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
+    "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
     "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
     "BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_hidden_get", "BKE_pbvh_node_fully_masked_set",
     "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
@@ -155,6 +157,10 @@ def cuda_lib():
         L.dsc_timer_stop.argtypes = [C.c_void_p, c_float_p]
         L.dsc_stage_timing.argtypes = [C.c_void_p, C.c_int]
         L.dsc_stage_times.argtypes = [C.c_void_p, c_float_p, c_int_p]
+        L.dsc_dist_unique_id.argtypes = [C.c_char_p]
+        L.dsc_dist_owned_range.argtypes = [C.c_void_p, c_int_p]
+        L.dsc_dist_free.argtypes = [C.c_void_p]
+        L.dsc_dist_free.restype = None
         _cuda = L
     return _cuda
 
@@ -178,6 +184,7 @@ def host_lib():
         L.DUNE_pbvh_leaf_limit_set.argtypes = [C.POINTER(PBVH), C.c_int]
         L.DUNE_pbvh_device_attach.argtypes = [C.POINTER(PBVH), C.c_int]
         L.DUNE_pbvh_device_detach.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_device_attach_dist.argtypes = [C.POINTER(PBVH), C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.DUNE_pbvh_device_sync_to_host.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_error.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_error.restype = C.c_char_p
@@ -215,6 +222,28 @@ def host_lib():
     return _host
 
 
+def nccl_unique_id():
+    """rank 0 makes the NCCL id; the host broadcasts the 128 bytes to the other ranks"""
+    buf = C.create_string_buffer(128)
+    r = cuda_lib().dsc_dist_unique_id(buf)
+    if r != 0:
+        raise DeviceError("dsc_dist_unique_id: %s" % (cuda_lib().dsc_last_error(None) or b"").decode())
+    return buf.raw
+
+
+class DscMeshDesc(C.Structure):
+    _fields_ = [("totvert", C.c_int), ("co", c_float_p), ("no", c_float_p), ("mask", c_float_p), ("totpoly", C.c_int),
+                ("totloop", C.c_int), ("poly_loopstart", c_int_p), ("poly_totloop", c_int_p), ("loop_vert", c_int_p),
+                ("tottri", C.c_int), ("tri_vert", c_int_p), ("tri_poly", c_int_p), ("nb_offsets", c_int_p),
+                ("nb_indices", c_int_p), ("boundary", c_ubyte_p)]
+
+
+class DscPbvhDesc(C.Structure):
+    _fields_ = [("totnode", C.c_int), ("node_bb", c_float_p), ("node_orig_bb", c_float_p), ("children_offset", c_int_p),
+                ("flag", c_int_p), ("prim_offset", c_int_p), ("totprim", c_int_p), ("prim_indices", c_int_p),
+                ("uniq_verts", c_int_p), ("face_verts", c_int_p), ("vert_offset", c_int_p), ("vert_indices", c_int_p)]
+
+
 def fptr(a):
     return a.ctypes.data_as(c_float_p)
 
@@ -246,7 +275,8 @@ def make_dab(tool, location, radius, **kw):
 class SculptSession:
     """A mesh + its PBVH through the reference-named host API, optionally attached to a device."""
 
-    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None):
+    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None):
+        """dist = (world, rank, nccl_id_bytes) attaches this process as one rank of a partitioned PBVH"""
         H = host_lib()
         self.H = H
         self.mesh = mesh
@@ -274,6 +304,7 @@ class SculptSession:
         H.BKE_pbvh_build_mesh(self.pbvh, None, self.mpoly.ctypes.data, self.mloop.ctypes.data, self.mvert.ctypes.data,
                               mesh.totvert, None, None, None, self.looptri.ctypes.data, self.tottri)
         self.ctx = None
+        self.dist = dist
         if device is not None:
             self.attach(device)
 
@@ -324,6 +355,67 @@ class SculptSession:
         bnd = np.ctypeslib.as_array(p.boundary, shape=(v,)).copy()
         return off, idx, bnd
 
+    def descs(self, with_neighbors=True):
+        """the flattened mesh / PBVH descriptors of the C ABI, from the host-side PBVH (keeps the arrays alive)"""
+        m = self.mesh
+        na = self.node_arrays()
+        keep = {}
+        keep["tri_vert"] = np.ascontiguousarray(self.mloop["v"][self.looptri["tri"][:self.tottri]].astype(np.int32))
+        keep["tri_poly"] = np.ascontiguousarray(self.looptri["poly"][:self.tottri].astype(np.int32))
+        keep["co"] = np.ascontiguousarray(m.co)
+        me = DscMeshDesc()
+        me.totvert, me.totpoly, me.totloop, me.tottri = m.totvert, m.totpoly, m.totloop, self.tottri
+        me.co = fptr(keep["co"])
+        me.poly_loopstart, me.poly_totloop, me.loop_vert = iptr(m.poly_start), iptr(m.poly_len), iptr(m.loop_v)
+        me.tri_vert, me.tri_poly = iptr(keep["tri_vert"]), iptr(keep["tri_poly"])
+        if with_neighbors:
+            auto = np.zeros(m.totvert, np.float32)
+            self.H.DUNE_sculpt_automask_boundary_edges(self.pbvh, 1, fptr(auto))  # builds the session tables
+            off, idx, bnd = self.neighbor_tables()
+            keep["off"], keep["idx"], keep["bnd"] = off.astype(np.int32), idx.astype(np.int32), bnd
+            me.nb_offsets, me.nb_indices = iptr(keep["off"]), iptr(keep["idx"])
+            me.boundary = keep["bnd"].ctypes.data_as(c_ubyte_p)
+        leaf = (na["flag"] & PBVH_Leaf) != 0
+        cnt = np.where(leaf, na["uniq_verts"] + na["face_verts"], 0).astype(np.int64)
+        voff = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+        vi = np.zeros(max(int(cnt.sum()), 1), np.int32)
+        for i in np.nonzero(leaf)[0]:
+            vi[voff[i]:voff[i] + cnt[i]] = self.node_vert_indices(int(i))
+        keep.update(vb=np.ascontiguousarray(na["vb"]), ovb=np.ascontiguousarray(na["orig_vb"]), voff=voff, vi=vi,
+                    prims=self.prim_indices().astype(np.int32), na=na)
+        pd = DscPbvhDesc()
+        pd.totnode = self.totnode
+        pd.node_bb, pd.node_orig_bb = fptr(keep["vb"]), fptr(keep["ovb"])
+        pd.children_offset, pd.flag = iptr(na["children_offset"]), iptr(na["flag"])
+        pd.prim_offset, pd.totprim, pd.prim_indices = iptr(na["prim_offset"]), iptr(na["totprim"]), iptr(keep["prims"])
+        pd.uniq_verts, pd.face_verts = iptr(na["uniq_verts"]), iptr(na["face_verts"])
+        pd.vert_offset, pd.vert_indices = iptr(voff), iptr(vi)
+        return me, pd, keep
+
+    def partition(self, world):
+        """leaf ranges and per-node owner of the spatial partition (host only)"""
+        me, pd, keep = self.descs(with_neighbors=False)
+        rng = np.zeros(world + 1, np.int32)
+        owner = np.zeros(self.totnode, np.int32)
+        r = cuda_lib().dsc_dist_partition(C.byref(pd), int(world), iptr(rng), iptr(owner))
+        assert r == 0
+        return rng, owner
+
+    def halo_plan(self, world, rank):
+        """(send_off, send_vert, recv_off, recv_vert) of one rank, in vertex ids (host only)"""
+        me, pd, keep = self.descs(with_neighbors=True)
+        L = cuda_lib()
+        ptrs = [c_int_p() for _ in range(4)]
+        r = L.dsc_dist_halo_plan(C.byref(me), C.byref(pd), int(world), int(rank), *[C.byref(p) for p in ptrs])
+        assert r == 0
+        soff = np.ctypeslib.as_array(ptrs[0], shape=(world + 1,)).copy()
+        roff = np.ctypeslib.as_array(ptrs[2], shape=(world + 1,)).copy()
+        sv = np.ctypeslib.as_array(ptrs[1], shape=(max(int(soff[-1]), 1),)).copy()[:soff[-1]]
+        rv = np.ctypeslib.as_array(ptrs[3], shape=(max(int(roff[-1]), 1),)).copy()[:roff[-1]]
+        for p in ptrs:
+            L.dsc_dist_free(p)
+        return soff, sv, roff, rv
+
     # ---- device ----------------------------------------------------------------------------
     def _chk(self, r):
         if r != 0:
@@ -331,7 +423,11 @@ class SculptSession:
             raise DeviceError("dune_sculpt_cuda error %d: %s" % (r, (msg or b"").decode()))
 
     def attach(self, device=0):
-        self._chk(self.H.DUNE_pbvh_device_attach(self.pbvh, int(device)))
+        if self.dist is not None and self.dist[0] > 1:
+            world, rank, nid = self.dist
+            self._chk(self.H.DUNE_pbvh_device_attach_dist(self.pbvh, int(device), int(world), int(rank), nid))
+        else:
+            self._chk(self.H.DUNE_pbvh_device_attach(self.pbvh, int(device)))
         self.ctx = C.c_void_p(self.pbvh.contents.device)
         self.D = cuda_lib()
 

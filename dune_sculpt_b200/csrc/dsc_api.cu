@@ -2,6 +2,9 @@
 #include "../../include/dune_sculpt_cuda.h"
 #include "dsc_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -52,6 +55,15 @@ struct DscContext {
   int nb_grid = 148;
   long long dab_index = 0;
   int last_slot = 0;
+
+  /* multi-GPU */
+  int world = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  std::vector<int> leaf_range;            /* [world + 1] traversal-order leaf bounds */
+  std::vector<int> slot_range;            /* [world + 1] slot bounds of the owned unique-vert runs */
+  std::vector<int> send_off, recv_off;    /* [world + 1] into the index lists below */
+  int *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  float *d_send_buf = nullptr, *d_recv_buf = nullptr;
 
   int *d_slot_of = nullptr;
   float *d_mask = nullptr, *d_automask = nullptr, *d_curve = nullptr;
@@ -164,6 +176,183 @@ static int sync_all(DscContext *ctx)
   return DSC_OK;
 }
 
+
+/* ------------------------------------------------------------------------------ NCCL, loaded lazily */
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load(std::string &err)
+{
+  if (g_nccl.lib) return true;
+  /* picks up the libnccl a host process (e.g. torch) already loaded, else the system one */
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    err = std::string("dlopen(libnccl.so.2): ") + dlerror();
+    return false;
+  }
+#define NCCL_SYM(field, name) \
+  *(void **)(&g_nccl.field) = dlsym(lib, name); \
+  if (!g_nccl.field) { \
+    err = std::string("libnccl lacks ") + name; \
+    return false; \
+  }
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+  NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  NCCL_SYM(AllReduce, "ncclAllReduce");
+  NCCL_SYM(Broadcast, "ncclBroadcast");
+  NCCL_SYM(Send, "ncclSend");
+  NCCL_SYM(Recv, "ncclRecv");
+  NCCL_SYM(GroupStart, "ncclGroupStart");
+  NCCL_SYM(GroupEnd, "ncclGroupEnd");
+  NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+  g_nccl.lib = lib;
+  return true;
+}
+
+#define NC(call) \
+  do { \
+    ncclResult_t r_ = (call); \
+    if (r_ != ncclSuccess) return fail(ctx, DSC_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+/* ---- partition: contiguous runs of leaves in traversal order.  With 2^k ranks and a tree at least
+ * k deep these are the subtrees k levels below the root (a spatial cut); otherwise runs of equal
+ * weight (unique verts + looptris). ---- */
+static void plan_partition(const DscPbvhDesc *pb, int world, std::vector<int> &leaves, std::vector<int> &range)
+{
+  const int N = pb->totnode;
+  leaves.clear();
+  for (int n = 0; n < N; n++) {
+    if (pb->flag[n] & DSC_PBVH_Leaf) leaves.push_back(n);
+  }
+  std::sort(leaves.begin(), leaves.end(), [&](int a, int b) { return pb->prim_offset[a] < pb->prim_offset[b]; });
+  const int L = (int)leaves.size();
+  range.assign(world + 1, L);
+  range[0] = 0;
+  if (world <= 1) return;
+  std::vector<int> rank_of(N, -1);
+  for (int l = 0; l < L; l++) rank_of[leaves[l]] = l;
+  /* leaf span of every node: children have larger indices than their parent (pbvh.c:2387-2388) */
+  std::vector<int> lo(N, L), hi(N, -1);
+  for (int n = N - 1; n >= 0; n--) {
+    if (pb->flag[n] & DSC_PBVH_Leaf) {
+      lo[n] = hi[n] = rank_of[n];
+    }
+    else {
+      const int c = pb->children_offset[n];
+      lo[n] = std::min(lo[c], lo[c + 1]);
+      hi[n] = std::max(hi[c], hi[c + 1]);
+    }
+  }
+  bool done = false;
+  if ((world & (world - 1)) == 0) {
+    std::vector<int> front(1, 0);
+    for (int w = 1; w < world; w *= 2) {
+      std::vector<int> next;
+      for (int n : front) {
+        if (pb->flag[n] & DSC_PBVH_Leaf) next.push_back(n);
+        else {
+          next.push_back(pb->children_offset[n]);
+          next.push_back(pb->children_offset[n] + 1);
+        }
+      }
+      front.swap(next);
+    }
+    if ((int)front.size() == world) {
+      std::sort(front.begin(), front.end(), [&](int a, int b) { return lo[a] < lo[b]; });
+      for (int r = 0; r < world; r++) range[r] = lo[front[r]];
+      range[world] = L;
+      done = true;
+    }
+  }
+  if (!done) {
+    double total = 0;
+    for (int l = 0; l < L; l++) total += pb->uniq_verts[leaves[l]] + pb->totprim[leaves[l]];
+    double acc = 0;
+    int r = 1;
+    for (int l = 0; l < L && r < world; l++) {
+      acc += pb->uniq_verts[leaves[l]] + pb->totprim[leaves[l]];
+      if (acc >= total * r / world) range[r++] = l + 1;
+    }
+    for (; r < world; r++) range[r] = L;
+  }
+}
+
+/* ---- halo plan in vertex ids: need[q] = vertices rank q reads but does not own: the shared and
+ * extra verts of its leaves' polys, the verts of the halo polys around its unique verts, and (smooth)
+ * the edge neighbours of its unique verts.  triples are (reader, owner, vertex), sorted, unique. ---- */
+struct HaloTriple {
+  int reader, owner, vert;
+  bool operator<(const HaloTriple &o) const
+  {
+    return reader != o.reader ? reader < o.reader : owner != o.owner ? owner < o.owner : vert < o.vert;
+  }
+  bool operator==(const HaloTriple &o) const { return reader == o.reader && owner == o.owner && vert == o.vert; }
+};
+
+static void plan_halo(const DscMeshDesc *me, const DscPbvhDesc *pb, int world, const std::vector<int> &leaves,
+                      const std::vector<int> &range, std::vector<HaloTriple> &out)
+{
+  const int V = me->totvert, L = (int)leaves.size();
+  std::vector<int> vowner(V, -1), leaf_rank(L, 0);
+  for (int r = 0; r < world; r++) {
+    for (int l = range[r]; l < range[r + 1]; l++) leaf_rank[l] = r;
+  }
+  for (int l = 0; l < L; l++) {
+    const int n = leaves[l];
+    const int *vi = pb->vert_indices + pb->vert_offset[n];
+    for (int i = 0; i < pb->uniq_verts[n]; i++) vowner[vi[i]] = leaf_rank[l];
+  }
+  out.clear();
+  for (int l = 0; l < L; l++) {
+    const int n = leaves[l], q = leaf_rank[l];
+    for (int pos = pb->prim_offset[n]; pos < pb->prim_offset[n] + pb->totprim[n]; pos++) {
+      const int t = pb->prim_indices[pos];
+      const int p = me->tri_poly[t];
+      const int ls = me->poly_loopstart[p], len = me->poly_totloop[p];
+      /* the leaf's own polys */
+      for (int k = 0; k < len; k++) {
+        const int u = me->loop_vert[ls + k];
+        if (vowner[u] != q && vowner[u] >= 0) out.push_back({q, vowner[u], u});
+      }
+      /* this looptri is a halo looptri of the owners of its foreign verts */
+      for (int j = 0; j < 3; j++) {
+        const int v = me->tri_vert[(size_t)3 * t + j];
+        const int q2 = vowner[v];
+        if (q2 == q || q2 < 0) continue;
+        for (int k = 0; k < len; k++) {
+          const int u = me->loop_vert[ls + k];
+          if (vowner[u] != q2 && vowner[u] >= 0) out.push_back({q2, vowner[u], u});
+        }
+      }
+    }
+  }
+  if (me->nb_offsets && me->nb_indices) {
+    for (int v = 0; v < V; v++) {
+      for (int k = me->nb_offsets[v]; k < me->nb_offsets[v + 1]; k++) {
+        const int u = me->nb_indices[k];
+        if (vowner[u] != vowner[v] && vowner[u] >= 0 && vowner[v] >= 0) out.push_back({vowner[v], vowner[u], u});
+      }
+    }
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
 extern "C" {
 
 int dsc_abi_version(void) { return DSC_ABI_VERSION; }
@@ -221,6 +410,7 @@ void dsc_ctx_destroy(DscContext *ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   for (void *p : ctx->allocs) cudaFree(p);
   for (auto &ev : ctx->events) {
     cudaEventDestroy(ev.a);
@@ -240,6 +430,91 @@ void dsc_ctx_destroy(DscContext *ctx)
 }
 
 void *dsc_stream(DscContext *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int dsc_dist_unique_id(char id[DSC_NCCL_ID_BYTES])
+{
+  DscContext *ctx = nullptr;
+  std::string err;
+  if (!nccl_load(err)) return fail(nullptr, DSC_ERR_NCCL, "%s", err.c_str());
+  static_assert(sizeof(ncclUniqueId) <= DSC_NCCL_ID_BYTES, "id fits");
+  ncclUniqueId uid;
+  NC(g_nccl.GetUniqueId(&uid));
+  memset(id, 0, DSC_NCCL_ID_BYTES);
+  memcpy(id, &uid, sizeof(uid));
+  return DSC_OK;
+}
+
+int dsc_dist_init(DscContext *ctx, int world, int rank, const char id[DSC_NCCL_ID_BYTES])
+{
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return fail(ctx, DSC_ERR_INVALID, "bad world / rank");
+  if (ctx->have_pbvh) return fail(ctx, DSC_ERR_STATE, "dsc_dist_init must precede dsc_pbvh_upload");
+  ctx->world = world;
+  ctx->rank = rank;
+  if (world == 1) return DSC_OK;
+  std::string err;
+  if (!nccl_load(err)) return fail(ctx, DSC_ERR_NCCL, "%s", err.c_str());
+  CU(cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NC(g_nccl.CommInitRank(&ctx->comm, world, uid, rank));
+  return DSC_OK;
+}
+
+int dsc_dist_partition(const DscPbvhDesc *pb, int world, int *r_leaf_range, int *r_owner)
+{
+  if (!pb || world < 1) return DSC_ERR_INVALID;
+  std::vector<int> leaves, range;
+  plan_partition(pb, world, leaves, range);
+  if (r_leaf_range) memcpy(r_leaf_range, range.data(), sizeof(int) * (size_t)(world + 1));
+  if (r_owner) {
+    for (int n = 0; n < pb->totnode; n++) r_owner[n] = -1;
+    for (int r = 0; r < world; r++) {
+      for (int l = range[r]; l < range[r + 1]; l++) r_owner[leaves[l]] = r;
+    }
+  }
+  return DSC_OK;
+}
+
+int dsc_dist_halo_plan(const DscMeshDesc *me, const DscPbvhDesc *pb, int world, int rank, int **r_send_off, int **r_send_vert,
+                       int **r_recv_off, int **r_recv_vert)
+{
+  if (!me || !pb || world < 1 || rank < 0 || rank >= world) return DSC_ERR_INVALID;
+  std::vector<int> leaves, range;
+  plan_partition(pb, world, leaves, range);
+  std::vector<HaloTriple> tr;
+  plan_halo(me, pb, world, leaves, range, tr);
+  std::vector<int> soff(world + 1, 0), roff(world + 1, 0), sv, rv;
+  for (int p = 0; p < world; p++) {
+    soff[p] = (int)sv.size();
+    roff[p] = (int)rv.size();
+    for (const HaloTriple &t : tr) {
+      if (t.owner == rank && t.reader == p) sv.push_back(t.vert);
+      if (t.reader == rank && t.owner == p) rv.push_back(t.vert);
+    }
+  }
+  soff[world] = (int)sv.size();
+  roff[world] = (int)rv.size();
+  auto dup = [](const std::vector<int> &v) {
+    int *p = (int *)malloc(sizeof(int) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(int) * v.size());
+    return p;
+  };
+  if (r_send_off) *r_send_off = dup(soff);
+  if (r_send_vert) *r_send_vert = dup(sv);
+  if (r_recv_off) *r_recv_off = dup(roff);
+  if (r_recv_vert) *r_recv_vert = dup(rv);
+  return DSC_OK;
+}
+
+void dsc_dist_free(void *p) { free(p); }
+
+int dsc_dist_owned_range(DscContext *ctx, int r_range[2])
+{
+  if (!ctx || !ctx->have_pbvh) return DSC_ERR_STATE;
+  r_range[0] = ctx->m.own_lo;
+  r_range[1] = ctx->m.own_hi;
+  return DSC_OK;
+}
 
 int dsc_mesh_upload(DscContext *ctx, const DscMeshDesc *me)
 {
@@ -697,6 +972,57 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_bb_smem, NB_BLOCK, ctx->nb_smem));
   ctx->nb_grid = ctx->num_sms * std::max(occ, 1);
 
+  /* multi-GPU: owned leaf run, hit-mask ring, halo index lists */
+  m.own_lo = 0;
+  m.own_hi = L;
+  ctx->leaf_range.assign(2, 0);
+  ctx->leaf_range[1] = L;
+  if (ctx->world > 1) {
+    std::vector<int> pl;
+    plan_partition(pb, ctx->world, pl, ctx->leaf_range);
+    m.own_lo = ctx->leaf_range[ctx->rank];
+    m.own_hi = ctx->leaf_range[ctx->rank + 1];
+    ctx->slot_range.assign(ctx->world + 1, 0);
+    for (int q = 0; q <= ctx->world; q++) {
+      const int l = ctx->leaf_range[q];
+      ctx->slot_range[q] = (l < L) ? leaf_ubeg[l] : ((L ? leaf_ubeg[L - 1] + leaf_ucnt[L - 1] + 31 : 0) & ~31);
+    }
+    m.ghit_words = (L + 31) / 32 + 1;
+    if ((r = dev_zero(ctx, &m.ghit, (size_t)m.ghit_words * DSC_SLOTS))) return r;
+    DscMeshDesc me;
+    memset(&me, 0, sizeof(me));
+    me.totvert = V;
+    me.totpoly = ctx->totpoly;
+    me.totloop = ctx->totloop;
+    me.tottri = T;
+    me.poly_loopstart = ctx->h_poly_start.data();
+    me.poly_totloop = ctx->h_poly_len.data();
+    me.loop_vert = ctx->h_loop_v.data();
+    me.tri_vert = ctx->h_tri_vert.data();
+    me.tri_poly = ctx->h_tri_poly.data();
+    me.nb_offsets = ctx->has_nb ? ctx->h_nb_off.data() : nullptr;
+    me.nb_indices = ctx->has_nb ? ctx->h_nb_idx.data() : nullptr;
+    std::vector<HaloTriple> tr;
+    plan_halo(&me, pb, ctx->world, pl, ctx->leaf_range, tr);
+    std::vector<int> sidx, ridx;
+    ctx->send_off.assign(ctx->world + 1, 0);
+    ctx->recv_off.assign(ctx->world + 1, 0);
+    for (int q = 0; q < ctx->world; q++) {
+      ctx->send_off[q] = (int)sidx.size();
+      ctx->recv_off[q] = (int)ridx.size();
+      for (const HaloTriple &t : tr) {
+        if (t.owner == ctx->rank && t.reader == q) sidx.push_back(ctx->slot_of[t.vert]);
+        if (t.reader == ctx->rank && t.owner == q) ridx.push_back(ctx->slot_of[t.vert]);
+      }
+    }
+    ctx->send_off[ctx->world] = (int)sidx.size();
+    ctx->recv_off[ctx->world] = (int)ridx.size();
+    if ((r = dev_upload(ctx, &ctx->d_send_idx, sidx)) || (r = dev_upload(ctx, &ctx->d_recv_idx, ridx)) ||
+        (r = dev_alloc(ctx, &ctx->d_send_buf, 3 * sidx.size() + 1)) || (r = dev_alloc(ctx, &ctx->d_recv_buf, 3 * ridx.size() + 1)))
+      return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+
   /* the host staging copies are no longer needed */
   std::vector<float>().swap(ctx->h_co);
   std::vector<float>().swap(ctx->h_no);
@@ -739,17 +1065,17 @@ static int run_collect(DscContext *ctx, int flags)
   return DSC_OK;
 }
 /* normals and/or leaf boxes of the listed leaves (mode: NB_NORMALS | NB_BOUNDS) */
-static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode)
+static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode, const unsigned *ghit = nullptr)
 {
   {
     StageScope s(ctx, ST_NORMALS);
-    k_normals_bb_smem<<<ctx->nb_grid, NB_BLOCK, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.list, ll.count, mode);
+    k_normals_bb_smem<<<ctx->nb_grid, NB_BLOCK, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.list, ll.count, mode, ghit);
     LAUNCH_CHECK();
   }
   if (ctx->any_slow_leaf) {
     if (mode & NB_NORMALS) {
       StageScope s(ctx, ST_NORMALS);
-      k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1);
+      k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1, ghit);
       LAUNCH_CHECK();
     }
     if (mode & NB_BOUNDS) {
@@ -784,6 +1110,83 @@ static int run_flagged(DscContext *ctx, int want)
   if ((r = run_normals_bounds(ctx, flag_list(ctx), mode))) return r;
   if ((want & F_UpdateBB) && (r = run_flush_full(ctx))) return r;
   return run_clear(ctx, flag_list(ctx), want);
+}
+
+/* ---- multi-GPU steps of a dab ---- */
+/* one all-reduce pair per dab: the exact area sums and the bitmask of gathered leaves (disjoint per
+ * rank, so sum == or) */
+static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
+{
+  NC(g_nccl.GroupStart());
+  if (with_area) {
+    NC(g_nccl.AllReduce(ctx->m.st[slot].acc, ctx->m.st[slot].acc, 16, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+  }
+  unsigned *gh = ctx->m.ghit + (size_t)slot * ctx->m.ghit_words;
+  NC(g_nccl.AllReduce(gh, gh, (size_t)ctx->m.ghit_words, ncclUint32, ncclSum, ctx->comm, ctx->stream));
+  NC(g_nccl.GroupEnd());
+  ctx->launches++;
+  return DSC_OK;
+}
+/* one-ring halo: owners push the positions other ranks' leaves read */
+static int dist_halo_exchange(DscContext *ctx)
+{
+  const int W = ctx->world;
+  const int ns = ctx->send_off[W], nr = ctx->recv_off[W];
+  /* per peer the buffer holds [3][count] */
+  for (int q = 0; q < W; q++) {
+    const int n = ctx->send_off[q + 1] - ctx->send_off[q];
+    if (n) {
+      k_halo_pack<<<std::min((n + 255) / 256, ctx->num_sms * 4), 256, 0, ctx->stream>>>(
+          ctx->d_send_buf + 3 * (size_t)ctx->send_off[q], ctx->d_send_idx + ctx->send_off[q], n, ctx->m.cx, ctx->m.cy, ctx->m.cz);
+      LAUNCH_CHECK();
+      ctx->launches++;
+    }
+  }
+  if (ns || nr) {
+    NC(g_nccl.GroupStart());
+    for (int q = 0; q < W; q++) {
+      const int n = ctx->send_off[q + 1] - ctx->send_off[q], k = ctx->recv_off[q + 1] - ctx->recv_off[q];
+      if (n) NC(g_nccl.Send(ctx->d_send_buf + 3 * (size_t)ctx->send_off[q], 3 * (size_t)n, ncclFloat, q, ctx->comm, ctx->stream));
+      if (k) NC(g_nccl.Recv(ctx->d_recv_buf + 3 * (size_t)ctx->recv_off[q], 3 * (size_t)k, ncclFloat, q, ctx->comm, ctx->stream));
+    }
+    NC(g_nccl.GroupEnd());
+  }
+  for (int q = 0; q < W; q++) {
+    const int k = ctx->recv_off[q + 1] - ctx->recv_off[q];
+    if (k) {
+      k_halo_unpack<<<std::min((k + 255) / 256, ctx->num_sms * 4), 256, 0, ctx->stream>>>(
+          ctx->d_recv_buf + 3 * (size_t)ctx->recv_off[q], ctx->d_recv_idx + ctx->recv_off[q], k, ctx->m.cx, ctx->m.cy, ctx->m.cz);
+      LAUNCH_CHECK();
+      ctx->launches++;
+    }
+  }
+  return DSC_OK;
+}
+/* every rank broadcasts the runs it owns (vertex data, leaf boxes, leaf flags and stroke state), then
+ * each replica flushes the whole tree: the BB-root reduction of SURVEY.md section 8e */
+static int dist_gather_all(DscContext *ctx)
+{
+  DevMesh &m = ctx->m;
+  const int N = ctx->totnode;
+  float *vert_arrays[12] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz, m.ox, m.oy, m.oz, m.onx, m.ony, m.onz};
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < ctx->world; q++) {
+    const int s0 = ctx->slot_range[q], sn = ctx->slot_range[q + 1] - s0;
+    const int l0 = ctx->leaf_range[q], ln = ctx->leaf_range[q + 1] - l0;
+    if (sn > 0) {
+      for (int a = 0; a < 12; a++) NC(g_nccl.Broadcast(vert_arrays[a] + s0, vert_arrays[a] + s0, (size_t)sn, ncclFloat, q, ctx->comm, ctx->stream));
+    }
+    if (ln > 0) {
+      for (int k = 0; k < 6; k++) NC(g_nccl.Broadcast(m.bb + (size_t)k * N + l0, m.bb + (size_t)k * N + l0, (size_t)ln, ncclFloat, q, ctx->comm, ctx->stream));
+      NC(g_nccl.Broadcast(m.node_flag + l0, m.node_flag + l0, (size_t)ln, ncclInt32, q, ctx->comm, ctx->stream));
+      NC(g_nccl.Broadcast(m.leaf_state + l0, m.leaf_state + l0, (size_t)ln, ncclUint32, q, ctx->comm, ctx->stream));
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  StageScope s(ctx, ST_FLUSH);
+  k_flush<<<1, 1024, 0, ctx->stream>>>(ctx->m);
+  LAUNCH_CHECK();
+  return DSC_OK;
 }
 
 int dsc_recalc_normals(DscContext *ctx)
@@ -898,6 +1301,9 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
   const bool do_normals = !(dab->flags & DSC_DAB_NO_NORMALS), do_bounds = !(dab->flags & DSC_DAB_NO_BOUNDS);
   /* the stages below walk the hit list unless some leaf may still carry flags of an earlier dab */
   const bool use_hits = !ctx->stale_flags;
+  const bool dist = ctx->world > 1;
+  if (dist && (!use_hits || !do_normals || !do_bounds))
+    return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
   int r;
   if (ctx->capture) CU(cudaMemsetAsync(ctx->d_capture, 0, sizeof(unsigned) * (size_t)ctx->nwords, st));
 
@@ -913,7 +1319,7 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
                                                                           tool == DSC_TOOL_GRAB ? 1 : 0, 1, 1);
     LAUNCH_CHECK();
   }
-  if (do_bounds && use_hits) {
+  if (do_bounds && use_hits && !dist) {
     /* side stream: tag the ancestors of the hit leaves for the bottom-up refit while the brush runs */
     CU(cudaEventRecord(ctx->ev_fork, st));
     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
@@ -951,7 +1357,9 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
         k_smooth_b<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
         LAUNCH_CHECK();
       }
+      if (dist && (r = dist_halo_exchange(ctx))) return r; /* the next iteration reads the ring */
     }
+    if (dist && (r = dist_allreduce_dab(ctx, slot, false))) return r;
   }
   else {
     const bool needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS;
@@ -960,17 +1368,21 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
       k_area<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot, tool == DSC_TOOL_CLAY_STRIPS ? 1 : 0);
       LAUNCH_CHECK();
     }
-    StageScope s(ctx, ST_BRUSH);
-    k_brush<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot);
-    LAUNCH_CHECK();
+    if (dist && (r = dist_allreduce_dab(ctx, slot, needs_area))) return r;
+    {
+      StageScope s(ctx, ST_BRUSH);
+      k_brush<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot);
+      LAUNCH_CHECK();
+    }
+    if (dist && (r = dist_halo_exchange(ctx))) return r;
   }
   /* 4. normals, 5. bounds */
   if (use_hits) {
     const int mode = (do_normals ? NB_NORMALS : 0) | (do_bounds ? NB_BOUNDS : 0);
     if (mode) {
-      if ((r = run_normals_bounds(ctx, hits, mode))) return r;
+      if ((r = run_normals_bounds(ctx, hits, mode, dist ? m.ghit + (size_t)slot * m.ghit_words : nullptr))) return r;
     }
-    if (do_bounds) {
+    if (do_bounds && !dist) {
       /* side stream: carry the refreshed leaf boxes up the tree; overlaps the next dab */
       CU(cudaEventRecord(ctx->ev_bb, st));
       CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_bb, 0));
@@ -1127,7 +1539,9 @@ int dsc_stroke_end(DscContext *ctx)
 {
   NEED_PBVH();
   if (!ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "no stroke open");
-  int r = run_orig_flush(ctx);
+  int r;
+  if (ctx->world > 1 && (r = dist_gather_all(ctx))) return r;
+  r = run_orig_flush(ctx);
   if (r) return r;
   ctx->in_stroke = false;
   return sync_all(ctx);

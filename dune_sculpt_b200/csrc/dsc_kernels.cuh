@@ -97,6 +97,11 @@ struct DevMesh {
   int *node_mark;
   int nlevel;
   const int *level_off, *level_nodes; /* inner nodes by depth, root first */
+  /* multi-GPU: this rank owns leaves [own_lo, own_hi); ghit = per-dab bitmask of gathered leaves,
+   * one ring slot per dab, all-reduced across ranks (NULL on one GPU) */
+  int own_lo, own_hi;
+  unsigned *ghit;
+  int ghit_words;
   /* per-dab state */
   DabState *st;       /* [DSC_SLOTS] */
   StrokeTotals *tot;
@@ -253,6 +258,10 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
     if (tid < 16) nx->acc[tid] = 0;
     if (tid == 16) nx->hit_count = 0;
     if (tid == 17) nx->area_count = 0;
+    if (m.ghit) {
+      unsigned *nm = m.ghit + (size_t)((slot + 1) & (DSC_SLOTS - 1)) * m.ghit_words;
+      for (int w = tid; w < m.ghit_words; w += DSC_BLOCK) nm[w] = 0u;
+    }
     if (tid == 18) {
       /* what dsc_last_area reports when the tool samples no plane: zero normal, brush location */
       st->area_no[0] = st->area_no[1] = st->area_no[2] = 0.0f;
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
   bool hit = false, ahit = false;
   int flag = 0;
   unsigned lst = 0;
-  if (l < m.nleaf) {
+  if (l < m.nleaf && (!mark || (l >= m.own_lo && l < m.own_hi))) {
     const float *bbs = original ? m.obb : m.bb;
     const int tn = m.totnode;
     flag = m.node_flag[l];
@@ -292,6 +301,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
     if (hit) (mark ? m.hit_list + (size_t)slot * m.nleaf : m.search_list)[base + __popc(bal & ((1u << lane) - 1u))] = l;
   }
   if (!mark) return;
+  if (m.ghit && bal && lane == 0) m.ghit[(size_t)slot * m.ghit_words + (l >> 5)] = bal; /* l is 32-aligned here */
   const unsigned abal = __ballot_sync(0xffffffffu, ahit);
   if (abal) {
     int base = 0;
@@ -871,7 +881,15 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m, int slot)
  * reference's accumulate pass, looptris of leaves that are not flagged contribute nothing
  * (pbvh.c:2943).  Handles any poly size and leaf size; leaves that fit the shared-memory kernel
  * below are skipped when skip_fast is set. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *list, const int *count, int skip_fast)
+/* is the leaf flagged for a normals update -- here, or (multi-GPU) gathered this dab by its owner */
+__device__ __forceinline__ bool dsc_leaf_updates_normals(const DevMesh &m, const unsigned *ghit, int leaf)
+{
+  if (m.node_flag[leaf] & F_UpdateNormals) return true;
+  return ghit && ((ghit[leaf >> 5] >> (leaf & 31)) & 1u);
+}
+
+__global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *list, const int *count, int skip_fast,
+                                                       const unsigned *ghit)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const int total = *count * m.max_chunks;
@@ -892,7 +910,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *lis
         for (unsigned q = qb; q < qe; q++) {
           const unsigned pos = m.vt_idx[q];
           if (pos < pb || pos >= pe) {
-            if (!(m.node_flag[m.tri_leaf[pos]] & F_UpdateNormals)) continue;
+            if (!dsc_leaf_updates_normals(m, ghit, m.tri_leaf[pos])) continue;
           }
           float fx, fy, fz;
           dsc_poly_normal(m, pos, fx, fy, fz);
@@ -929,7 +947,8 @@ __host__ __device__ inline size_t dsc_nb_smem_bytes(int nloc, int ne, int ng, in
  * 2 x 8 index rows per thread) so the HBM round trip is paid per batch, not per element.
  * Leaves with no dirty vert only refresh their box; leaves that do not fit (leaf_fast == 0) are
  * left to k_normals / k_leaf_bb. */
-__global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, const int *list, const int *count, int mode)
+__global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, const int *list, const int *count, int mode,
+                                                                 const unsigned *ghit)
 {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[6][NB_BLOCK / 32];
@@ -967,7 +986,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
       }
       if (dc) atomicAdd(&s_dcount, dc);
       for (int w = tid; w <= ng; w += NB_BLOCK) sgoff[w] = m.v2_goff[G0 + w];
-      for (int w = tid; w < ncnt; w += NB_BLOCK) snb[w] = (unsigned)(m.node_flag[m.nb_leaf[nbeg + w]] & F_UpdateNormals);
+      for (int w = tid; w < ncnt; w += NB_BLOCK) snb[w] = dsc_leaf_updates_normals(m, ghit, m.nb_leaf[nbeg + w]) ? 1u : 0u;
     }
     __syncthreads();
     const int dcount = s_dcount;
@@ -1237,6 +1256,29 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_orig_inner(DevMesh m)
       m.node_mark[n] = 0;
       for (int k = 0; k < 6; k++) m.obb[k * tn + n] = m.bb[k * tn + n];
     }
+  }
+}
+
+/* ------------------------------------------------------------------- multi-GPU halo pack / unpack */
+/* positions of the halo slots, [3][n] in the buffer */
+__global__ void k_halo_pack(float *__restrict__ buf, const int *__restrict__ idx, int n, const float *__restrict__ ax,
+                            const float *__restrict__ ay, const float *__restrict__ az)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = idx[i];
+    buf[i] = ax[s];
+    buf[n + i] = ay[s];
+    buf[2 * n + i] = az[s];
+  }
+}
+__global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restrict__ idx, int n, float *__restrict__ ax,
+                              float *__restrict__ ay, float *__restrict__ az)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = idx[i];
+    ax[s] = buf[i];
+    ay[s] = buf[n + i];
+    az[s] = buf[2 * n + i];
   }
 }
 

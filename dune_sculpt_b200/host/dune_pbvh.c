@@ -423,7 +423,9 @@ const char *DUNE_pbvh_device_error(const PBVH *pbvh)
   return g_attach_error[0] ? g_attach_error : dsc_last_error(NULL);
 }
 
-int DUNE_pbvh_device_attach(PBVH *pbvh, int device)
+int DUNE_pbvh_device_attach(PBVH *pbvh, int device) { return DUNE_pbvh_device_attach_dist(pbvh, device, 1, 0, NULL); }
+
+int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, const char *nccl_id)
 {
   g_attach_error[0] = 0;
   if (!pbvh || !pbvh->nodes) return DSC_ERR_INVALID;
@@ -437,6 +439,14 @@ int DUNE_pbvh_device_attach(PBVH *pbvh, int device)
   if (r != DSC_OK) {
     snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(NULL));
     return r;
+  }
+  if (world > 1) {
+    r = dsc_dist_init(ctx, world, rank, nccl_id);
+    if (r != DSC_OK) {
+      snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(ctx));
+      dsc_ctx_destroy(ctx);
+      return r;
+    }
   }
   if (!pbvh->nb_offsets) build_neighbor_tables(pbvh);
 

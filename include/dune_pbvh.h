@@ -146,6 +146,8 @@ void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit);
 
 /* ---- device hooks (new) ---- */
 int DUNE_pbvh_device_attach(PBVH *pbvh, int device);
+/* one rank of a PBVH partitioned across the GPUs of one box (see dsc_dist_init) */
+int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, const char *nccl_id);
 void DUNE_pbvh_device_detach(PBVH *pbvh);
 /* bring host arrays (verts, normals, node boxes, flags) up to date with the device */
 int DUNE_pbvh_device_sync_to_host(PBVH *pbvh);

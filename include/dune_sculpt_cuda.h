@@ -191,6 +191,28 @@ int dsc_download_touched(DscContext *ctx, unsigned char *r_touched /* [totnode] 
 int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_coords_apply */
 int dsc_synchronize(DscContext *ctx);
 
+/* --- multi-GPU: one process per GPU, the PBVH partitioned spatially (contiguous runs of leaves in
+ *     traversal order = subtrees) across the ranks of one box.  Every rank holds the whole mesh and
+ *     computes the leaves it owns; NCCL carries, per dab, one small all-reduce (area-normal sums +
+ *     the bitmask of gathered leaves) and one exchange of the one-ring halo positions; at stroke
+ *     end the owned vertex runs and leaf boxes are all-gathered (the BB-root reduction) so every
+ *     replica is whole again.  Call order: dsc_ctx_create, dsc_dist_init, dsc_mesh_upload,
+ *     dsc_pbvh_upload.  Not in the reference. ------------------------- */
+#define DSC_NCCL_ID_BYTES 128
+int dsc_dist_unique_id(char id[DSC_NCCL_ID_BYTES]); /* rank 0 makes it, the host broadcasts it */
+int dsc_dist_init(DscContext *ctx, int world, int rank, const char id[DSC_NCCL_ID_BYTES]);
+/* the partition alone, no device needed: r_leaf_range[world + 1] bounds in traversal-order leaf
+ * ranks, r_owner[totnode] owning rank of each leaf node (-1 for inner nodes) */
+int dsc_dist_partition(const DscPbvhDesc *pbvh, int world, int *r_leaf_range, int *r_owner);
+/* halo plan of one rank, no device needed: for every peer the vertices this rank sends (it owns
+ * them, the peer's leaves reference them) and receives.  Arrays are malloc'd; free with
+ * dsc_dist_free.  r_send_off / r_recv_off have world + 1 entries. */
+int dsc_dist_halo_plan(const DscMeshDesc *mesh, const DscPbvhDesc *pbvh, int world, int rank, int **r_send_off,
+                       int **r_send_vert, int **r_recv_off, int **r_recv_vert);
+void dsc_dist_free(void *p);
+/* leaf nodes this rank owns: r_range[2] = first and one-past-last leaf in traversal order */
+int dsc_dist_owned_range(DscContext *ctx, int r_range[2]);
+
 /* --- timing helpers (CUDA events on the context's stream) --------------------------------- */
 int dsc_timer_start(DscContext *ctx);
 int dsc_timer_stop(DscContext *ctx, float *r_ms); /* synchronises */

@@ -1,0 +1,74 @@
+"""One rank of the multi-GPU parity check (launched by tests/test_gpu_multi.py, one process per GPU).
+Every rank holds the whole mesh, computes the leaves it owns, and after stroke end must hold exactly
+the state the single-process CPU oracle produces."""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+from dune_sculpt_b200 import capi, meshgen, stroke  # noqa: E402
+from oracle_py import Oracle  # noqa: E402
+
+
+def main():
+    world, rank, idfile, scenario = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
+    if rank == 0:
+        nid = capi.nccl_unique_id()
+        with open(idfile + ".tmp", "wb") as f:
+            f.write(nid)
+        os.replace(idfile + ".tmp", idfile)
+    else:
+        t0 = time.time()
+        while not os.path.exists(idfile):
+            time.sleep(0.05)
+            assert time.time() - t0 < 120, "no NCCL id from rank 0"
+        nid = open(idfile, "rb").read()
+    if scenario == "grid":
+        mesh, ll = meshgen.grid(257), 900
+        diag = mesh.bbox_diag()
+        dabs = []
+        for tool in (capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_CLAY_STRIPS, capi.TOOL_GRAB):
+            dabs += stroke.c4_tool_stroke(tool, diag, dabs=6, radius_pct=14.0)
+        dabs += [capi.make_dab(capi.TOOL_SMOOTH, (0.12 * i - 0.5, 0.05 * i - 0.1, 0.0), 0.45, bstrength=0.8) for i in range(6)]
+        mask = meshgen.low_freq_mask(mesh)
+    else:
+        mesh, ll = meshgen.icosphere(48, noise=0.003), 700
+        dabs = stroke.c2_smooth_stroke(dabs=8, radius=0.6) + \
+            [capi.make_dab(capi.TOOL_DRAW, p, 0.5, bstrength=0.2, view_normal=p) for p in ((0, 0, 1), (0.6, 0, 0.8), (1, 0, 0))]
+        mask = None
+    orc = Oracle(mesh, mask=mask, leaf_limit=ll)
+    ses = capi.SculptSession(mesh, mask=mask, leaf_limit=ll, device=rank, dist=(world, rank, nid))
+    rng, owner = ses.partition(world)
+    orc.stroke_begin()
+    ses.stroke_begin()
+    vd = 0
+    for i, d in enumerate(dabs):
+        orc.dab(d)
+        ses.dab(d)
+        ho = orc.hits()
+        mine = ho[owner[ho] == rank]
+        hg = ses.hits()
+        assert np.array_equal(mine, hg), "rank %d dab %d: own hit list differs (%d vs %d)" % (rank, i, mine.size, hg.size)
+    orc.stroke_end()
+    ses.stroke_end()  # all-gathers the owned runs: every replica is whole again
+    vd = ses.stats()["vertex_dabs"]
+    co_o, co_g = orc.co(), ses.co()
+    assert np.array_equal(co_o, co_g), "rank %d: positions differ (max %g)" % (rank, np.abs(co_o - co_g).max())
+    assert np.array_equal(orc.no(), ses.no()), "rank %d: normals differ" % rank
+    na = orc.node_arrays()
+    bb, obb = ses.node_bb()
+    assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: boxes differ" % rank
+    assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
+    assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
+    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d" %
+          (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs()), flush=True)
+    ses.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+"""Host logic of the multi-GPU path on the CPU, world_size 2 over gloo: the spatial partition, the
+symmetry of the halo plan, and a simulated halo exchange (what NCCL send/recv carries on the box)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dune_sculpt_b200 import capi, meshgen
+        mesh = meshgen.icosphere(24, noise=0.002)
+        ses = capi.SculptSession(mesh, leaf_limit=300)
+        rng, owner = ses.partition(world)
+        na = ses.node_arrays()
+        leaves = np.nonzero(na["flag"] & 1)[0]
+        leaves = leaves[np.argsort(na["prim_offset"][leaves])]
+        # contiguous runs in traversal order, every leaf owned exactly once
+        assert rng[0] == 0 and rng[-1] == leaves.size and np.all(np.diff(rng) > 0)
+        assert np.array_equal(owner[leaves], np.repeat(np.arange(world), np.diff(rng)))
+        soff, sv, roff, rv = ses.halo_plan(world, rank)
+        # vertex ownership: unique verts of owned leaves
+        vowner = np.full(mesh.totvert, -1)
+        for n in leaves:
+            vi = ses.node_vert_indices(int(n))
+            vowner[vi[:na["uniq_verts"][n]]] = owner[n]
+        assert (vowner >= 0).all()
+        assert np.all(vowner[sv] == rank) and np.all(vowner[rv] != rank)
+        # symmetry: what I send to p is what p expects from me (sizes first, then the ids)
+        peer = 1 - rank
+        mine = torch.tensor([int(soff[peer + 1] - soff[peer]), int(roff[peer + 1] - roff[peer])], dtype=torch.long)
+        theirs = [torch.zeros(2, dtype=torch.long) for _ in range(world)]
+        dist.all_gather(theirs, mine)
+        assert theirs[peer][1].item() == mine[0].item() and theirs[peer][0].item() == mine[1].item()
+        send_ids = torch.from_numpy(sv[soff[peer]:soff[peer + 1]].astype(np.int64))
+        recv_ids = torch.zeros(int(mine[1]), dtype=torch.long)
+        if rank == 0:
+            dist.send(send_ids, peer); dist.recv(recv_ids, peer)
+        else:
+            dist.recv(recv_ids, peer); dist.send(send_ids, peer)
+        assert np.array_equal(recv_ids.numpy(), rv[roff[peer]:roff[peer + 1]])
+        # simulated dab: each rank moves the verts it owns, then the halo exchange must make every
+        # vertex its leaves read (shared verts and smooth neighbours) current
+        truth = mesh.co.astype(np.float64) * (1.0 + 0.01 * (vowner[:, None] + 1))
+        local = mesh.co.astype(np.float64).copy()
+        local[vowner == rank] = truth[vowner == rank]
+        payload = torch.from_numpy(local[sv[soff[peer]:soff[peer + 1]]])
+        got = torch.zeros((int(mine[1]), 3), dtype=torch.float64)
+        if rank == 0:
+            dist.send(payload, peer); dist.recv(got, peer)
+        else:
+            dist.recv(got, peer); dist.send(payload, peer)
+        local[rv[roff[peer]:roff[peer + 1]]] = got.numpy()
+        off, idx, _ = ses.neighbor_tables()
+        for n in leaves[owner[leaves] == rank]:
+            vi = ses.node_vert_indices(int(n))
+            assert np.array_equal(local[vi], truth[vi])           # unique + shared verts of my leaves
+            for v in vi[:na["uniq_verts"][n]]:
+                nb = idx[off[v]:off[v + 1]]
+                assert np.array_equal(local[nb], truth[nb])       # one-ring of my unique verts
+        q.put((rank, "ok", int(sv.size), int(rv.size)))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc()), 0, 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_and_halo_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, ns, nr in sorted(res):
+        assert status == "ok", "rank %d: %s" % (rank, status)
+        assert ns > 0 and nr > 0
+
+
+def test_partition_shapes():
+    sys.path.insert(0, ROOT)
+    from dune_sculpt_b200 import capi, meshgen
+    ses = capi.SculptSession(meshgen.grid(129), leaf_limit=300)
+    for world in (1, 2, 3, 4, 8):
+        rng, owner = ses.partition(world)
+        assert rng[0] == 0 and rng[-1] == int((ses.node_arrays()["flag"] & 1).sum())
+        assert sorted(set(owner[owner >= 0].tolist())) == list(range(world))
+    # power-of-two worlds cut the tree at depth log2(world): every rank owns whole subtrees
+    rng, owner = ses.partition(4)
+    na = ses.node_arrays()
+    c = na["children_offset"]
+    depth2 = [c[c[0]], c[c[0]] + 1, c[c[0] + 1], c[c[0] + 1] + 1]
+
+    def leaves_under(n):
+        if na["flag"][n] & 1:
+            return [n]
+        return leaves_under(c[n]) + leaves_under(c[n] + 1)
+    for n in depth2:
+        assert len(set(owner[leaves_under(int(n))].tolist())) == 1
+    ses.close()
