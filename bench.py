@@ -154,8 +154,12 @@ def run_reference(args, rank):
 
 
 def workload_config(args, mesh, ndabs):
+    world = int(os.environ.get("WORLD_SIZE", 1))
     return {"workload": "C3 draw+normals+BB radius sweep 1-50%% bbox diag, grid %d^2 (V=%d), %d dabs/stroke" %
-                        (args.grid, mesh.totvert, ndabs),
+                        (args.grid, mesh.totvert, ndabs) +
+                        ("" if world == 1 else "; PBVH partitioned spatially over %d GPUs (same mesh: strong scaling), per dab one "
+                         "NCCL all-reduce (area sums + hit mask) and one one-ring halo exchange" % world),
+            "parallelism": "single GPU" if world == 1 else "pbvh-partition x%d" % world,
             "verts": mesh.totvert, "dabs_per_step": ndabs, "brush": "draw, SMOOTH falloff, area-normal direction",
             "l2": "inputs larger than L2 (resident mesh arrays > 2 GB; every stroke sweeps all of them)"}
 
@@ -218,7 +222,17 @@ def run_ours(args, rank, world):
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     mesh, diag, dabs = build_workload(args)
     t0 = time.time()
-    ses = capi.SculptSession(mesh, device=local_rank)  # fails loudly without a device / the .so
+    dist_arg = None
+    if world > 1:
+        # NCCL id of the library's own communicator: made on rank 0, broadcast through torch.distributed
+        import torch
+        import torch.distributed as dist
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda:%d" % local_rank)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        dist_arg = (world, rank, bytes(idt.cpu().numpy().tobytes()))
+    ses = capi.SculptSession(mesh, device=local_rank, dist=dist_arg)  # fails loudly without a device / the .so
     na = ses.node_arrays()
     log("[bench] host PBVH build + device upload %.1fs, %d nodes (%d leaves)" %
         (time.time() - t0, ses.totnode, int((na["flag"] & 1).sum())))
@@ -318,7 +332,8 @@ def run_ours(args, rank, world):
     ndabs = len(dabs) * args.steps
     out = {
         "metric": METRIC, "value": vd / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh, len(dabs)),
         "ms_per_dab": ms / ndabs, "vertex_dabs_per_step": vd // args.steps,
         "e2e": {"value": vd_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
