@@ -244,10 +244,11 @@ def run_ours(args, rank, world):
             import torch.distributed as dist
             dist.barrier()
 
+    dab_arr = (capi.DscDab * len(dabs))(*dabs)  # the stroke script as one C array
+
     def device_stroke():
         ses._chk(D.dsc_stroke_begin(ctx, None))
-        for d in dabs:
-            ses._chk(D.dsc_dab(ctx, C.byref(d)))
+        ses._chk(D.dsc_dabs(ctx, dab_arr, len(dabs)))
         ses._chk(D.dsc_stroke_end(ctx))
 
     # ---- device-resident timing: `value`
@@ -274,15 +275,14 @@ def run_ours(args, rank, world):
     h2d = len(dabs) * C.sizeof(capi.DscDab)
     d2h = mesh.totvert * 24 + ses.totnode * (48 + 4) + 8
     for _ in range(1):
-        ses.stroke_begin(); [ses.dab(d) for d in dabs]; ses.stroke_end()
+        ses.stroke_begin(); ses.dabs(dab_arr, len(dabs)); ses.stroke_end()
     ses.synchronize()
     barrier()
     vd_e = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ses.stroke_begin()
-        for d in dabs:
-            ses.dab(d)
+        ses.dabs(dab_arr, len(dabs))  # host descriptors cross the ABI dab by dab inside the C loop
         vd_e += ses.stats()["vertex_dabs"]
         ses.stroke_end()  # flush + download co / no / boxes / flags into the host PBVH
     ses.synchronize()

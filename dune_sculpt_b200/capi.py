@@ -65,6 +65,7 @@ class PBVH(C.Structure):
         ("looptri", C.c_void_p), ("totpoly", C.c_int), ("totloop", C.c_int), ("vmask", c_float_p),
         ("vert_bitmap", C.POINTER(C.c_uint)), ("deformed", C.c_bool), ("owns_normals", C.c_bool),
         ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
+        ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool),
         ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
     ]
 
@@ -86,9 +87,10 @@ class SculptSearchSphereData(C.Structure):
 CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
     "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
+    "dsc_dabs",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
-    "dsc_download_co", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
+    "dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
     "dsc_download_node_flags", "dsc_download_touched", "dsc_upload_co", "dsc_synchronize", "dsc_timer_start",
     "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
     "dsc_dist_unique_id", "dsc_dist_init", "dsc_dist_partition", "dsc_dist_halo_plan", "dsc_dist_free",
@@ -139,6 +141,7 @@ def cuda_lib():
             getattr(L, fn).argtypes = [C.c_void_p]
         L.dsc_stroke_begin.argtypes = [C.c_void_p, c_float_p]
         L.dsc_dab.argtypes = [C.c_void_p, C.POINTER(DscDab)]
+        L.dsc_dabs.argtypes = [C.c_void_p, C.POINTER(DscDab), C.c_int]
         L.dsc_gather_readback.argtypes = [C.c_void_p, c_int_p, C.c_int, c_int_p]
         L.dsc_search_sphere.argtypes = [C.c_void_p, c_float_p, C.c_float, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p]
         L.dsc_last_area.argtypes = [C.c_void_p, c_float_p, c_float_p]
@@ -148,7 +151,7 @@ def cuda_lib():
         L.dsc_update_bounds.argtypes = [C.c_void_p, C.c_int]
         L.dsc_node_mark_update.argtypes = [C.c_void_p, C.c_int]
         L.dsc_node_flag_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
-        for fn in ("dsc_download_co", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_upload_co",
+        for fn in ("dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_upload_co",
                    "dsc_set_custom_curve", "dsc_set_mask"):
             getattr(L, fn).argtypes = [C.c_void_p, c_float_p]
         L.dsc_download_node_bb.argtypes = [C.c_void_p, c_float_p, c_float_p]
@@ -235,7 +238,7 @@ class DscMeshDesc(C.Structure):
     _fields_ = [("totvert", C.c_int), ("co", c_float_p), ("no", c_float_p), ("mask", c_float_p), ("totpoly", C.c_int),
                 ("totloop", C.c_int), ("poly_loopstart", c_int_p), ("poly_totloop", c_int_p), ("loop_vert", c_int_p),
                 ("tottri", C.c_int), ("tri_vert", c_int_p), ("tri_poly", c_int_p), ("nb_offsets", c_int_p),
-                ("nb_indices", c_int_p), ("boundary", c_ubyte_p)]
+                ("nb_indices", c_int_p), ("boundary", c_ubyte_p), ("vert_tail", C.POINTER(C.c_uint))]
 
 
 class DscPbvhDesc(C.Structure):
@@ -437,6 +440,11 @@ class SculptSession:
 
     def dab(self, d):
         self._chk(self.H.DUNE_sculpt_dab(self.pbvh, C.byref(d)))
+
+    def dabs(self, dab_array, count):
+        """a run of dabs in one C call (dab_array: ctypes array of DscDab)"""
+        self.pbvh.contents.device_dirty = True
+        self._chk(self.D.dsc_dabs(self.ctx, dab_array, int(count)))
 
     def stroke_end(self):
         self._chk(self.H.DUNE_sculpt_stroke_end(self.pbvh))

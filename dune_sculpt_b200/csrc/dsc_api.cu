@@ -41,6 +41,8 @@ struct DscContext {
   bool have_mesh = false, have_pbvh = false, in_stroke = false;
   int totvert = 0, totpoly = 0, totloop = 0, tottri = 0, totnode = 0, vpad = 0, nwords = 0;
   std::vector<float> h_co, h_no, h_mask;
+  std::vector<unsigned> h_tail;
+  unsigned *d_tail = nullptr;
   std::vector<int> h_poly_start, h_poly_len, h_loop_v, h_tri_vert, h_tri_poly, h_nb_off, h_nb_idx;
   std::vector<unsigned char> h_boundary;
   bool has_no = false, has_mask = false, has_nb = false;
@@ -532,6 +534,7 @@ int dsc_mesh_upload(DscContext *ctx, const DscMeshDesc *me)
   if (me->no) ctx->h_no.assign(me->no, me->no + (size_t)3 * me->totvert);
   ctx->has_mask = me->mask != nullptr;
   if (me->mask) ctx->h_mask.assign(me->mask, me->mask + me->totvert);
+  if (me->vert_tail) ctx->h_tail.assign(me->vert_tail, me->vert_tail + me->totvert);
   ctx->h_poly_start.assign(me->poly_loopstart, me->poly_loopstart + me->totpoly);
   ctx->h_poly_len.assign(me->poly_totloop, me->poly_totloop + me->totpoly);
   ctx->h_loop_v.assign(me->loop_vert, me->loop_vert + me->totloop);
@@ -635,7 +638,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       (r = dev_zero(ctx, &ctx->d_capture, (size_t)ctx->nwords)))
     return r;
   if ((r = dev_upload(ctx, &ctx->d_slot_of, ctx->slot_of))) return r;
-  if ((r = dev_alloc(ctx, &ctx->d_stage3, (size_t)3 * V))) return r;
+  if ((r = dev_alloc(ctx, &ctx->d_stage3, (size_t)4 * V))) return r;
+  if (!ctx->h_tail.empty() && (r = dev_upload(ctx, &ctx->d_tail, ctx->h_tail))) return r;
   if ((r = dev_alloc(ctx, &ctx->d_list, (size_t)std::max(V, L))) || (r = dev_zero(ctx, &ctx->d_count, 1))) return r;
 
   /* smooth adjacency in slot order */
@@ -879,6 +883,11 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_upload_c(ctx, &m.leaf_hbeg, leaf_hbeg)) || (r = dev_upload_c(ctx, &m.leaf_nbeg, leaf_nbeg)) ||
         (r = dev_upload_c(ctx, &m.leaf_ncnt, leaf_ncnt)))
       return r;
+    {
+      std::vector<int4> meta((size_t)std::max(L, 1));
+      for (int l = 0; l < L; l++) meta[l] = make_int4(leaf_ubeg[l], leaf_ucnt[l], leaf_sbeg[l], leaf_scnt[l]);
+      if ((r = dev_upload_c(ctx, &m.leaf_meta, meta))) return r;
+    }
     m.nleaf = L;
     int max_u = 1;
     for (int l = 0; l < L; l++) max_u = std::max(max_u, leaf_ucnt[l]);
@@ -1027,6 +1036,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   std::vector<float>().swap(ctx->h_co);
   std::vector<float>().swap(ctx->h_no);
   std::vector<float>().swap(ctx->h_mask);
+  std::vector<unsigned>().swap(ctx->h_tail);
   std::vector<int>().swap(ctx->h_tri_vert);
   std::vector<int>().swap(ctx->h_tri_poly);
   std::vector<int>().swap(ctx->h_loop_v);
@@ -1409,6 +1419,16 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
   return DSC_OK;
 }
 
+int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
+{
+  if (count < 0 || (count > 0 && !dabs)) return fail(ctx, DSC_ERR_INVALID, "bad dab array");
+  for (int i = 0; i < count; i++) {
+    const int r = dsc_dab(ctx, dabs + i);
+    if (r) return r;
+  }
+  return DSC_OK;
+}
+
 static int read_list(DscContext *ctx, const int *d_list, const int *d_count, int *r_nodes, int capacity, int *r_tot)
 {
   int tot = 0;
@@ -1561,6 +1581,30 @@ int dsc_download_co(DscContext *ctx, float *r_co)
 {
   NEED_PBVH();
   return export3(ctx, r_co, ctx->m.cx, ctx->m.cy, ctx->m.cz);
+}
+int dsc_download_mvert(DscContext *ctx, void *r_mvert)
+{
+  NEED_PBVH();
+  if (!r_mvert) return fail(ctx, DSC_ERR_INVALID, "output pointer is NULL");
+  k_export_mvert<<<ctx->grid, 256, 0, ctx->stream>>>(reinterpret_cast<float4 *>(ctx->d_stage3), ctx->m.cx, ctx->m.cy, ctx->m.cz,
+                                                     ctx->d_slot_of, ctx->d_tail, ctx->totvert);
+  LAUNCH_CHECK();
+  CU(cudaMemcpyAsync(r_mvert, ctx->d_stage3, sizeof(float) * 4 * (size_t)ctx->totvert, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSC_OK;
+}
+int dsc_host_register(DscContext *ctx, void *ptr, size_t bytes)
+{
+  if (!ctx || !ptr) return DSC_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return DSC_OK;
+}
+int dsc_host_unregister(DscContext *ctx, void *ptr)
+{
+  if (!ctx || !ptr) return DSC_ERR_INVALID;
+  CU(cudaHostUnregister(ptr));
+  return DSC_OK;
 }
 int dsc_download_no(DscContext *ctx, float *r_no)
 {

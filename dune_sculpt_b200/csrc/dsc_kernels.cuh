@@ -85,6 +85,7 @@ struct DevMesh {
   int nleaf;
   int max_chunks; /* ceil(max uniq_verts / DSC_CHUNK) */
   const int *leaf_ubeg, *leaf_ucnt, *leaf_sbeg, *leaf_scnt, *leaf_pbeg, *leaf_pcnt;
+  const int4 *leaf_meta; /* {ubeg, ucnt, sbeg, scnt}: one load per work unit */
   const int *stage_slots; /* per leaf: slots of its shared verts, then of its extra verts */
   unsigned *leaf_state;
   /* nodes, device numbering */
@@ -402,11 +403,11 @@ __device__ __forceinline__ bool dsc_unit(const DevMesh &m, const int *list, int 
 {
   const int h = u / m.max_chunks, c = u - h * m.max_chunks;
   leaf = list[h];
-  const int ucnt = m.leaf_ucnt[leaf];
+  const int4 meta = m.leaf_meta[leaf];
   const int off = c * DSC_CHUNK;
-  if (off >= ucnt) return false;
-  cnt = min(DSC_CHUNK, ucnt - off);
-  beg = m.leaf_ubeg[leaf] + off;
+  if (off >= meta.y) return false;
+  cnt = min(DSC_CHUNK, meta.y - off);
+  beg = meta.x + off;
   return true;
 }
 
@@ -1102,7 +1103,7 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
     for (int g0 = warp; g0 < ng; g0 += 2 * NW) {
       unsigned word[2], off[2];
       int wd[2];
-      unsigned en[2][8];
+      unsigned short en[2][8];
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         const int g = g0 + u * NW;
@@ -1110,9 +1111,12 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
         word[u] = ok ? sdirty[g] : 0u;
         off[u] = ok ? sgoff[g] : 0u;
         wd[u] = ok ? (int)((sgoff[g + 1] - off[u]) >> 5) : 0;
+        const unsigned short *row = m.v2_idx + off[u] + lane;
+        const int w8 = word[u] != 0u ? min(wd[u], 8) : 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          en[u][j] = (word[u] != 0u && j < wd[u]) ? (unsigned)m.v2_idx[off[u] + j * 32 + lane] : (unsigned)ne;
+          if (j >= w8) break; /* warp-uniform */
+          en[u][j] = row[j * 32];
         }
       }
 #pragma unroll
@@ -1122,12 +1126,12 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
         const int s = ub + g * 32 + lane;
         if ((word[u] >> lane) & 1u) {
           float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+          const int w8 = min(wd[u], 8);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            if (j < wd[u]) { /* warp-uniform */
-              const float *f = F + 3 * en[u][j];
-              sx += f[0]; sy += f[1]; sz += f[2];
-            }
+            if (j >= w8) break; /* warp-uniform */
+            const float *f = F + 3 * en[u][j];
+            sx += f[0]; sy += f[1]; sz += f[2];
           }
           for (int j = 8; j < wd[u]; j++) {
             const float *f = F + 3 * (unsigned)m.v2_idx[off[u] + j * 32 + lane];
@@ -1301,6 +1305,16 @@ __global__ void k_export3(float *__restrict__ out, const float *__restrict__ ax,
     out[3 * v + 0] = ax[s];
     out[3 * v + 1] = ay[s];
     out[3 * v + 2] = az[s];
+  }
+}
+/* slot order -> MVert records {co[3], tail} in original vertex order */
+__global__ void k_export_mvert(float4 *__restrict__ out, const float *__restrict__ ax, const float *__restrict__ ay,
+                               const float *__restrict__ az, const int *__restrict__ slot_of,
+                               const unsigned *__restrict__ tail, int totvert)
+{
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < totvert; v += gridDim.x * blockDim.x) {
+    const int s = slot_of[v];
+    out[v] = make_float4(ax[s], ay[s], az[s], __uint_as_float(tail ? tail[v] : 0u));
   }
 }
 __global__ void k_import3(const float *__restrict__ in, float *__restrict__ ax, float *__restrict__ ay,

@@ -470,7 +470,10 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
   for (int v = 0; v < V && !have_no; v++) {
     have_no = pbvh->vert_normals[v][0] != 0.0f || pbvh->vert_normals[v][1] != 0.0f || pbvh->vert_normals[v][2] != 0.0f;
   }
+  unsigned int *tail = malloc(sizeof(unsigned int) * (size_t)V);
+  for (int v = 0; v < V; v++) memcpy(&tail[v], &pbvh->verts[v].flag, 4);
   DscMeshDesc me = {0};
+  me.vert_tail = tail;
   me.totvert = V;
   me.co = co;
   me.no = have_no ? (const float *)pbvh->vert_normals : NULL;
@@ -529,7 +532,7 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
   pd.vert_indices = vert_indices;
   if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
 
-  free(co); free(poly_start); free(poly_len); free(loop_v); free(tri_vert); free(tri_poly);
+  free(tail); free(co); free(poly_start); free(poly_len); free(loop_v); free(tri_vert); free(tri_poly);
   free(bb); free(obb); free(child); free(flag); free(prim_off); free(totprim); free(uniq); free(face);
   free(vert_off); free(vert_indices);
   if (r != DSC_OK) {
@@ -539,12 +542,17 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
   }
   pbvh->device = ctx;
   pbvh->device_dirty = !have_no; /* device computed the normals */
+  /* page-lock what the stroke-end sync writes: the normals array now, the private MVert copy when it is made */
+  if (dsc_host_register(ctx, pbvh->vert_normals, sizeof(float[3]) * (size_t)V) == DSC_OK) pbvh->normals_pinned = true;
   return DSC_OK;
 }
 
 void DUNE_pbvh_device_detach(PBVH *pbvh)
 {
   if (pbvh && pbvh->device) {
+    if (pbvh->normals_pinned) dsc_host_unregister(pbvh->device, pbvh->vert_normals);
+    if (pbvh->verts_pinned) dsc_host_unregister(pbvh->device, pbvh->verts);
+    pbvh->normals_pinned = pbvh->verts_pinned = false;
     dsc_ctx_destroy(pbvh->device);
     pbvh->device = NULL;
   }
@@ -555,20 +563,17 @@ int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
   if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
   if (!pbvh->device_dirty) return DSC_OK;
   const int V = pbvh->totvert, N = pbvh->totnode;
-  float *co = malloc(sizeof(float[3]) * (size_t)V);
-  int r = dsc_download_co(pbvh->device, co);
-  if (r == DSC_OK) {
-    if (!pbvh->deformed) {
-      /* first write: take a private copy like BKE_pbvh_vert_coords_apply (pbvh.c:4714-4725) */
-      MVert *dup = malloc(sizeof(MVert) * (size_t)V);
-      memcpy(dup, pbvh->verts, sizeof(MVert) * (size_t)V);
-      pbvh->verts = dup;
-      pbvh->deformed = true;
-    }
-    for (int v = 0; v < V; v++) memcpy(pbvh->verts[v].co, co + 3 * (size_t)v, sizeof(float[3]));
-    r = dsc_download_no(pbvh->device, (float *)pbvh->vert_normals);
+  if (!pbvh->deformed) {
+    /* first write: take a private copy like BKE_pbvh_vert_coords_apply (pbvh.c:4714-4725) */
+    MVert *dup = malloc(sizeof(MVert) * (size_t)V);
+    memcpy(dup, pbvh->verts, sizeof(MVert) * (size_t)V);
+    pbvh->verts = dup;
+    pbvh->deformed = true;
+    if (dsc_host_register(pbvh->device, dup, sizeof(MVert) * (size_t)V) == DSC_OK) pbvh->verts_pinned = true;
   }
-  free(co);
+  /* whole MVert records and the normals array arrive by DMA; no host-side scatter */
+  int r = dsc_download_mvert(pbvh->device, pbvh->verts);
+  if (r == DSC_OK) r = dsc_download_no(pbvh->device, (float *)pbvh->vert_normals);
   if (r != DSC_OK) return r;
   float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
   int *flag = malloc(sizeof(int) * (size_t)N);
@@ -756,6 +761,7 @@ void BKE_pbvh_vert_coords_apply(PBVH *pbvh, const float (*vertCos)[3], const int
     memcpy(dup, pbvh->verts, sizeof(MVert) * (size_t)totvert);
     pbvh->verts = dup;
     pbvh->deformed = true;
+    if (pbvh->device && dsc_host_register(pbvh->device, dup, sizeof(MVert) * (size_t)totvert) == DSC_OK) pbvh->verts_pinned = true;
   }
   for (int a = 0; a < totvert; a++) memcpy(pbvh->verts[a].co, vertCos[a], sizeof(float[3]));
   if (pbvh->device) {

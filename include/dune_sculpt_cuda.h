@@ -16,6 +16,7 @@
 #ifndef DUNE_SCULPT_CUDA_H
 #define DUNE_SCULPT_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -89,6 +90,9 @@ typedef struct DscMeshDesc {
   const int *nb_offsets; /* [totvert + 1] */
   const int *nb_indices;
   const unsigned char *boundary; /* [totvert] boundary-vertex flags, or NULL */
+  /* [totvert] the 4 bytes that follow MVert.co (flag, bweight, pad: types_meshdata.h:13-17), kept so
+   * dsc_download_mvert can hand back whole MVert records; NULL = zeros */
+  const unsigned int *vert_tail;
 } DscMeshDesc;
 
 /* The built PBVH, flattened.  Replaces PBVH.nodes / PBVHNode (kernel/intern/pbvh_intern.h:15-162). */
@@ -157,6 +161,8 @@ int dsc_node_flag_set(DscContext *ctx, int node, int flag, int on);
 int dsc_stroke_begin(DscContext *ctx, const float *automask /* [totvert] or NULL */);
 /* gather -> undo snapshot + mark -> brush -> normals -> bounds, queued on the stream */
 int dsc_dab(DscContext *ctx, const DscDab *dab);
+/* the same for a run of dabs (a whole stroke segment); nothing is waited for */
+int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count);
 /* BKE_pbvh_search_gather result of the last dab (pbvh.c:2736-2767): node indices in traversal
  * order.  r_nodes may be NULL to get the count only.  Synchronises. */
 int dsc_gather_readback(DscContext *ctx, int *r_nodes, int capacity, int *r_tot);
@@ -181,6 +187,12 @@ int dsc_node_mark_update(DscContext *ctx, int node); /* BKE_pbvh_node_mark_updat
 /* --- sync: behind BKE_pbvh_vert_coords_alloc/apply, get_verts, get_vert_normals
  *     (pbvh.c:4689-4749, 4961-4971) and the undo push (paint_hide.c:78) --------------------- */
 int dsc_download_co(DscContext *ctx, float *r_co /* [totvert][3] */);
+/* positions as complete 16-byte MVert records (BKE_pbvh_get_verts): one DMA, no host-side scatter */
+int dsc_download_mvert(DscContext *ctx, void *r_mvert /* [totvert] MVert */);
+/* page-lock / release a host array the download calls write into (cudaHostRegister); optional, it
+ * lets the stroke-end downloads run at PCIe speed */
+int dsc_host_register(DscContext *ctx, void *ptr, size_t bytes);
+int dsc_host_unregister(DscContext *ctx, void *ptr);
 int dsc_download_no(DscContext *ctx, float *r_no /* [totvert][3] */);
 int dsc_download_orig_co(DscContext *ctx, float *r_co /* [totvert][3] */);
 int dsc_download_orig_no(DscContext *ctx, float *r_no /* [totvert][3] */);
