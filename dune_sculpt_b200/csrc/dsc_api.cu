@@ -6,6 +6,8 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -575,30 +577,100 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   const int L = (int)leaves.size();
   ctx->leaf_node = leaves;
 
-  /* slots: each leaf's unique verts are one 128-byte aligned run */
+  /* slots: each leaf's unique verts are one 128-byte aligned run, cut into tiles of <= DSC_TILE
+   * slots.  Inside a leaf the order is ours to choose (the host translates through slot_of), so the
+   * verts are split by recursive coordinate bisection into spatially compact tiles and ordered in
+   * rows inside a tile: a tile's polys then reach few verts of other tiles, and those sit in runs. */
   ctx->slot_of.assign(V, -1);
-  std::vector<int> leaf_ubeg(L), leaf_ucnt(L), leaf_scnt(L), leaf_pbeg(L), leaf_pcnt(L);
+  std::vector<int> leaf_ubeg(L), leaf_ucnt(L), leaf_scnt(L), leaf_pbeg(L), leaf_pcnt(L), leaf_tile0(L + 1, 0);
+  std::vector<int2> tile_range;
+  std::vector<int> tile_leaf;
   long long cur = 0;
   int expect_prim = 0;
-  for (int l = 0; l < L; l++) {
-    const int n = leaves[l];
-    cur = (cur + 31) & ~31ll;
-    leaf_ubeg[l] = (int)cur;
-    leaf_ucnt[l] = pb->uniq_verts[n];
-    leaf_scnt[l] = pb->face_verts[n];
-    leaf_pbeg[l] = pb->prim_offset[n];
-    leaf_pcnt[l] = pb->totprim[n];
-    if (leaf_pbeg[l] != expect_prim) return fail(ctx, DSC_ERR_INVALID, "leaf prim ranges do not tile prim_indices");
-    expect_prim += leaf_pcnt[l];
-    const int *vi = pb->vert_indices + pb->vert_offset[n];
-    for (int i = 0; i < pb->uniq_verts[n]; i++) {
-      const int v = vi[i];
-      if (v < 0 || v >= V || ctx->slot_of[v] != -1) return fail(ctx, DSC_ERR_INVALID, "vertex %d is not unique in exactly one leaf", v);
-      ctx->slot_of[v] = (int)cur + i;
+  {
+    std::vector<int> ord;
+    const float *hco = ctx->h_co.data();
+    for (int l = 0; l < L; l++) {
+      const int n = leaves[l];
+      cur = (cur + 31) & ~31ll;
+      leaf_ubeg[l] = (int)cur;
+      leaf_ucnt[l] = pb->uniq_verts[n];
+      leaf_scnt[l] = pb->face_verts[n];
+      leaf_pbeg[l] = pb->prim_offset[n];
+      leaf_pcnt[l] = pb->totprim[n];
+      if (leaf_pbeg[l] != expect_prim) return fail(ctx, DSC_ERR_INVALID, "leaf prim ranges do not tile prim_indices");
+      expect_prim += leaf_pcnt[l];
+      const int *vi = pb->vert_indices + pb->vert_offset[n];
+      const int U = pb->uniq_verts[n];
+      for (int i = 0; i < U; i++) {
+        const int v = vi[i];
+        if (v < 0 || v >= V || ctx->slot_of[v] != -1) return fail(ctx, DSC_ERR_INVALID, "vertex %d is not unique in exactly one leaf", v);
+        ctx->slot_of[v] = -2; /* claimed; the slot follows */
+      }
+      ord.assign(vi, vi + U);
+      leaf_tile0[l] = (int)tile_range.size();
+      /* bisection of ord[lo, hi) into k tiles, slots from `base` */
+      struct Job { int lo, hi, k, base; };
+      std::vector<Job> jobs(1, Job{0, U, std::max(1, (U + DSC_TILE - 1) / DSC_TILE), (int)cur});
+      std::vector<int2> made;
+      while (!jobs.empty()) {
+        const Job j = jobs.back();
+        jobs.pop_back();
+        const int cnt = j.hi - j.lo;
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int i = j.lo; i < j.hi; i++) {
+          for (int k = 0; k < 3; k++) {
+            const float c = hco[(size_t)3 * ord[i] + k];
+            mn[k] = std::min(mn[k], c);
+            mx[k] = std::max(mx[k], c);
+          }
+        }
+        int ax[3] = {0, 1, 2};
+        std::sort(ax, ax + 3, [&](int a, int b) { return (mx[a] - mn[a]) > (mx[b] - mn[b]) || ((mx[a] - mn[a]) == (mx[b] - mn[b]) && a < b); });
+        if (j.k > 1) {
+          const int kl = j.k / 2;
+          long long nl = ((long long)cnt * kl + j.k - 1) / j.k;
+          nl = std::min<long long>((nl + 31) & ~31ll, std::min<long long>((long long)kl * DSC_TILE, cnt));
+          const int a = ax[0];
+          std::nth_element(ord.begin() + j.lo, ord.begin() + j.lo + nl, ord.begin() + j.hi, [&](int p, int q) {
+            const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
+            return cp < cq || (cp == cq && p < q);
+          });
+          /* right half first on the stack so tiles come out in slot order */
+          jobs.push_back(Job{j.lo + (int)nl, j.hi, j.k - kl, j.base + (int)nl});
+          jobs.push_back(Job{j.lo, j.lo + (int)nl, kl, j.base});
+          continue;
+        }
+        /* one tile: rows along the second-widest axis, ascending along the widest inside a row */
+        const int a = ax[0], b = ax[1];
+        const float ea = mx[a] - mn[a], eb2 = mx[b] - mn[b];
+        int rows = 1;
+        if (ea > 0.0f && eb2 > 0.0f) rows = std::max(1, std::min(cnt, (int)lrintf(sqrtf((float)cnt * eb2 / ea))));
+        auto row_of = [&](int v) {
+          if (rows <= 1) return 0;
+          const int rr = (int)((hco[(size_t)3 * v + b] - mn[b]) / eb2 * (float)rows);
+          return std::min(std::max(rr, 0), rows - 1);
+        };
+        std::sort(ord.begin() + j.lo, ord.begin() + j.hi, [&](int p, int q) {
+          const int rp = row_of(p), rq = row_of(q);
+          if (rp != rq) return rp < rq;
+          const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
+          return cp < cq || (cp == cq && p < q);
+        });
+        for (int i = j.lo; i < j.hi; i++) ctx->slot_of[ord[i]] = j.base + (i - j.lo);
+        made.push_back(make_int2(j.base, cnt));
+      }
+      std::sort(made.begin(), made.end(), [](const int2 &x, const int2 &y) { return x.x < y.x; });
+      for (const int2 &t : made) {
+        tile_range.push_back(t);
+        tile_leaf.push_back(l);
+      }
+      cur += U;
+      if (cur > 0x7fffff00ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 slots");
     }
-    cur += pb->uniq_verts[n];
-    if (cur > 0x7fffff00ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 slots");
+    leaf_tile0[L] = (int)tile_range.size();
   }
+  const int NT = (int)tile_range.size();
   if (expect_prim != T) return fail(ctx, DSC_ERR_INVALID, "leaves hold %d looptris, mesh has %d", expect_prim, T);
   cur = (cur + 31) & ~31ll;
   for (int v = 0; v < V; v++) {
@@ -664,8 +736,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     CU(cudaStreamSynchronize(ctx->stream));
   }
 
-  /* looptris by position; vertex -> looptri CSR; per-leaf local tables of the shared-memory normals kernel */
-  std::vector<int> leaf_sbeg(L), leaf_xcnt(L, 0), leaf_ebeg(L), leaf_eown(L), leaf_ehalo(L), leaf_hbeg(L), leaf_nbeg(L), leaf_ncnt(L, 0);
+  /* looptris by position; vertex -> looptri CSR; per-tile local tables of the shared-memory normals kernel */
+  std::vector<int> leaf_sbeg(L);
   std::vector<unsigned char> leaf_fast(L, 1);
   {
     std::vector<int> tri_leaf((size_t)std::max(T, 1), 0);
@@ -693,148 +765,212 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     }
     std::vector<unsigned>().swap(deg);
 
-    /* ---- local tables ---- */
-    std::vector<int> stage;           /* per leaf: shared slots, then extra slots */
-    std::vector<unsigned short> e_pv; /* 4 per entry */
-    std::vector<unsigned char> e_halo_nb; /* per halo entry: index into the leaf's neighbour list */
-    std::vector<int> nb_leaf;             /* concatenated neighbour-leaf lists */
+    /* ---- local tables, tile by tile ---- */
+    std::vector<int> leaf_sslots;          /* per leaf: slots of its shared verts (general path) */
+    std::vector<int> stage;                /* per tile: staged slots, box-counted ones first */
+    std::vector<unsigned short> e_pv;      /* 4 per entry */
+    std::vector<int> e_halo_leaf;          /* per other-leaf entry: that leaf */
+    std::vector<TileMeta> tmeta((size_t)std::max(NT, 1));
     std::vector<unsigned> v2_goff((size_t)VP / 32 + 1, 0);
-    std::vector<unsigned short> v2_idx;
-    v2_idx.reserve(vt_idx.size() + vt_idx.size() / 8);
-    std::vector<unsigned short> col; /* entries of the current group, [vertex][row] */
-    std::vector<int> coln;
-    std::vector<int> lstamp((size_t)VP, -1), lidx((size_t)VP, 0);
+    std::vector<unsigned> v2_idx;
+    v2_idx.reserve(vt_idx.size() / 2 + vt_idx.size() / 8);
+    std::vector<int> lstamp((size_t)VP, -1), lidx((size_t)VP, 0); /* slot -> local index in the current tile */
+    std::vector<int> sh_leaf((size_t)VP, -1), sh_done((size_t)VP, -1); /* slot is a shared vert of leaf / already box-counted */
     std::vector<int> pstamp((size_t)std::max(ctx->totpoly, 1), -1), pentry((size_t)std::max(ctx->totpoly, 1), 0);
-    std::vector<int> tri_entry;
     std::unordered_map<unsigned long long, int> halo;
+    std::vector<int> own_polys, halo_polys, halo_leaves, st_bb, st_x;
+    std::vector<unsigned> rows, raw, goff_local; /* entry ids of the current group, [row][lane]; bit 31 = other-leaf entry */
     int next_group_to_fill = 0;
     size_t max_smem = 0;
     for (int l = 0; l < L; l++) {
       const int n = leaves[l];
-      const int ub = leaf_ubeg[l], U = leaf_ucnt[l], S = leaf_scnt[l];
+      const int U_leaf = leaf_ucnt[l], S = leaf_scnt[l];
       const int pbeg = leaf_pbeg[l], pend = pbeg + leaf_pcnt[l];
       const int *vi = pb->vert_indices + pb->vert_offset[n];
-      leaf_sbeg[l] = (int)stage.size();
-      for (int i = 0; i < U; i++) {
-        lstamp[ub + i] = l;
-        lidx[ub + i] = i;
-      }
-      int nloc = U;
+      leaf_sbeg[l] = (int)leaf_sslots.size();
       for (int i = 0; i < S; i++) {
-        const int s = ctx->slot_of[vi[U + i]];
-        lstamp[s] = l;
-        lidx[s] = nloc++;
-        stage.push_back(s);
+        const int sl = ctx->slot_of[vi[U_leaf + i]];
+        leaf_sslots.push_back(sl);
+        sh_leaf[sl] = l;
       }
       bool ok = true;
-      int ne = 0;
-      leaf_ebeg[l] = (int)(e_pv.size() / 4);
-      leaf_hbeg[l] = (int)e_halo_nb.size();
-      leaf_nbeg[l] = (int)nb_leaf.size();
-      auto add_entry = [&](int p) -> int {
-        const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
-        unsigned short loc[4] = {0, 0, 0, 0xffff};
-        if (len == 3 || len == 4) {
-          for (int k = 0; k < len; k++) {
-            const int s = ctx->slot_of[ctx->h_loop_v[ls + k]];
-            if (lstamp[s] != l) {
-              lstamp[s] = l;
-              lidx[s] = nloc++;
-              stage.push_back(s);
-              leaf_xcnt[l]++;
-            }
-            loc[k] = (unsigned short)std::min(lidx[s], 0xfffe);
-            if (lidx[s] > 0xfffe) ok = false;
-          }
+      const int t_lo = leaf_tile0[l], t_hi = leaf_tile0[l + 1];
+      for (int tg = t_lo; tg < t_hi; tg++) {
+        const int ub = tile_range[tg].x, U = tile_range[tg].y;
+        TileMeta &tm = tmeta[tg];
+        tm.ubeg = ub;
+        tm.ucnt = U;
+        tm.sbeg = (int)stage.size();
+        if ((e_pv.size() / 4) & 1) e_pv.insert(e_pv.end(), 4, (unsigned short)0); /* bulk copies start 16-byte aligned */
+        tm.ebeg = (int)(e_pv.size() / 4);
+        tm.hbeg = (int)e_halo_leaf.size();
+        tm.leaf = l;
+        tm.tile0 = t_lo;
+        for (int i = 0; i < U; i++) {
+          lstamp[ub + i] = tg;
+          lidx[ub + i] = i;
         }
-        else {
-          ok = false; /* n-gon: this leaf takes the general path */
-        }
-        e_pv.insert(e_pv.end(), loc, loc + 4);
-        return ne++;
-      };
-      tri_entry.assign((size_t)(pend - pbeg), 0);
-      for (int pos = pbeg; pos < pend; pos++) {
-        const int p = ctx->h_tri_poly[pb->prim_indices[pos]];
-        if (pstamp[p] != l) {
-          pstamp[p] = l;
-          pentry[p] = add_entry(p);
-        }
-        tri_entry[pos - pbeg] = pentry[p];
-      }
-      leaf_eown[l] = ne;
-      halo.clear();
-      const int G0 = ub / 32, ng = (U + 31) / 32;
-      for (; next_group_to_fill < G0; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
-      for (int g = 0; g < ng; g++) {
-        const int i0 = g * 32, cntv = std::min(32, U - i0);
-        coln.assign(32, 0);
-        int width = 0;
-        for (int i = 0; i < cntv; i++) width = std::max(width, (int)(vt_off[ub + i0 + i + 1] - vt_off[ub + i0 + i]));
-        col.assign((size_t)32 * std::max(width, 1), (unsigned short)0xffff);
-        for (int i = 0; i < cntv; i++) {
-          const int s = ub + i0 + i;
-          for (unsigned q = vt_off[s]; q < vt_off[s + 1]; q++) {
-            const int pos = (int)vt_idx[q];
-            int e;
-            if (pos >= pbeg && pos < pend) {
-              e = tri_entry[pos - pbeg];
-            }
-            else {
+        own_polys.clear();
+        halo_polys.clear();
+        halo_leaves.clear();
+        halo.clear();
+        const int G0 = ub / 32, ng = (U + 31) / 32;
+        for (; next_group_to_fill < G0; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
+        raw.clear();
+        goff_local.assign((size_t)ng, 0u);
+        for (int g = 0; g < ng; g++) {
+          const int i0 = g * 32, cntv = std::min(32, U - i0);
+          int width = 0;
+          for (int i = 0; i < cntv; i++) width = std::max(width, (int)(vt_off[ub + i0 + i + 1] - vt_off[ub + i0 + i]));
+          const int wpairs = (width + 1) / 2;
+          rows.assign((size_t)64 * std::max(wpairs, 1), 0xffffffffu);
+          for (int i = 0; i < cntv; i++) {
+            const int sl = ub + i0 + i;
+            int r2 = 0;
+            for (unsigned q = vt_off[sl]; q < vt_off[sl + 1]; q++, r2++) {
+              const int pos = (int)vt_idx[q];
               const int p = ctx->h_tri_poly[pb->prim_indices[pos]];
-              const int ol = tri_leaf[pos];
-              const unsigned long long key = ((unsigned long long)(unsigned)p << 32) | (unsigned)ol;
-              auto it = halo.find(key);
-              if (it == halo.end()) {
-                e = add_entry(p);
-                int k = 0;
-                for (; k < leaf_ncnt[l]; k++) {
-                  if (nb_leaf[leaf_nbeg[l] + k] == ol) break;
+              unsigned e;
+              if (pos >= pbeg && pos < pend) {
+                if (pstamp[p] != tg) {
+                  pstamp[p] = tg;
+                  pentry[p] = (int)own_polys.size();
+                  own_polys.push_back(p);
                 }
-                if (k == leaf_ncnt[l]) {
-                  nb_leaf.push_back(ol);
-                  leaf_ncnt[l]++;
-                }
-                if (k > 255) ok = false;
-                e_halo_nb.push_back((unsigned char)std::min(k, 255));
-                halo.emplace(key, e);
+                e = (unsigned)pentry[p];
               }
               else {
-                e = it->second;
+                const int ol = tri_leaf[pos];
+                const unsigned long long key = ((unsigned long long)(unsigned)p << 32) | (unsigned)ol;
+                auto it = halo.find(key);
+                if (it == halo.end()) {
+                  it = halo.emplace(key, (int)halo_polys.size()).first;
+                  halo_polys.push_back(p);
+                  halo_leaves.push_back(ol);
+                }
+                e = 0x80000000u | (unsigned)it->second;
               }
+              rows[(size_t)r2 * 32 + i] = e;
             }
-            if (e >= 0xffff) ok = false;
-            col[(size_t)coln[i] * 32 + i] = (unsigned short)std::min(e, 0xfffe);
-            coln[i]++;
+          }
+          goff_local[g] = (unsigned)(raw.size() / 2);
+          for (int w = 0; w < wpairs; w++) {
+            for (int i = 0; i < 32; i++) {
+              raw.push_back(rows[(size_t)(2 * w) * 32 + i]);
+              raw.push_back(rows[(size_t)(2 * w + 1) * 32 + i]);
+            }
           }
         }
-        v2_goff[G0 + g] = (unsigned)v2_idx.size();
-        v2_idx.insert(v2_idx.end(), col.begin(), col.begin() + (size_t)32 * width);
+        next_group_to_fill = G0 + ng;
+        const int eown = (int)own_polys.size(), ehalo = (int)halo_polys.size(), ne = eown + ehalo;
+        tm.eown = eown;
+        tm.ehalo = ehalo;
+        if (ne >= 0xffff) ok = false;
+        /* pack the rows two entries to a word; other-leaf ids follow the own ones, padding -> the zero entry `ne` */
+        {
+          auto fix = [&](unsigned id) -> unsigned {
+            if (id == 0xffffffffu) return (unsigned)std::min(ne, 0xffff);
+            if (id & 0x80000000u) return (unsigned)std::min(eown + (int)(id & 0x7fffffffu), 0xfffe);
+            return (unsigned)std::min((int)id, 0xfffe);
+          };
+          const unsigned base = (unsigned)v2_idx.size();
+          for (size_t q = 0; q + 1 < raw.size(); q += 2) v2_idx.push_back(fix(raw[q]) | (fix(raw[q + 1]) << 16));
+          for (int g = 0; g < ng; g++) v2_goff[G0 + g] = base + goff_local[g];
+        }
+        /* staged verts: corners of the entries that are not unique verts of this tile */
+        st_bb.clear();
+        st_x.clear();
+        auto visit_poly = [&](int p) {
+          const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
+          if (len != 3 && len != 4) {
+            ok = false; /* n-gon: this leaf takes the general path */
+            return;
+          }
+          for (int k = 0; k < len; k++) {
+            const int sl = ctx->slot_of[ctx->h_loop_v[ls + k]];
+            if (lstamp[sl] == tg) continue;
+            lstamp[sl] = tg;
+            lidx[sl] = -1;
+            if (sh_leaf[sl] == l && sh_done[sl] != l) {
+              sh_done[sl] = l;
+              st_bb.push_back(sl);
+            }
+            else {
+              st_x.push_back(sl);
+            }
+          }
+        };
+        for (int p : own_polys) visit_poly(p);
+        for (int p : halo_polys) visit_poly(p);
+        if (tg == t_hi - 1) {
+          /* shared verts of the leaf that no tile reached through a poly of its unique verts */
+          for (int i = 0; i < S; i++) {
+            const int sl = leaf_sslots[(size_t)leaf_sbeg[l] + i];
+            if (sh_done[sl] != l) {
+              sh_done[sl] = l;
+              if (lstamp[sl] == tg && lidx[sl] == -1) {
+                /* staged here already as a plain corner: move it to the box-counted part */
+                st_x.erase(std::find(st_x.begin(), st_x.end(), sl));
+              }
+              lstamp[sl] = tg;
+              lidx[sl] = -1;
+              st_bb.push_back(sl);
+            }
+          }
+        }
+        std::sort(st_bb.begin(), st_bb.end());
+        std::sort(st_x.begin(), st_x.end());
+        int nloc = (U + 3) & ~3; /* staged verts follow the 16-byte padded unique run */
+        for (int sl : st_bb) {
+          lidx[sl] = nloc++;
+          stage.push_back(sl);
+        }
+        for (int sl : st_x) {
+          lidx[sl] = nloc++;
+          stage.push_back(sl);
+        }
+        tm.sbb = (int)st_bb.size();
+        tm.xcnt = (int)st_x.size();
+        if (nloc > 0xfffe) ok = false;
+        auto emit = [&](int p) {
+          const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
+          unsigned short loc[4] = {0, 0, 0, 0xffff};
+          if (len == 3 || len == 4) {
+            for (int k = 0; k < len; k++) loc[k] = (unsigned short)std::min(std::max(lidx[ctx->slot_of[ctx->h_loop_v[ls + k]]], 0), 0xfffe);
+          }
+          e_pv.insert(e_pv.end(), loc, loc + 4);
+        };
+        for (int p : own_polys) emit(p);
+        for (int p : halo_polys) emit(p);
+        e_halo_leaf.insert(e_halo_leaf.end(), halo_leaves.begin(), halo_leaves.end());
+        const size_t bytes = dsc_tile_smem_bytes(dsc_tile_nloc_a(U, tm.sbb, tm.xcnt), ne, (int)(raw.size() / 2), ehalo);
+        if (bytes > DSC_SMEM_BUDGET) ok = false;
+        else max_smem = std::max(max_smem, bytes);
       }
-      next_group_to_fill = G0 + ng;
-      leaf_ehalo[l] = ne - leaf_eown[l];
-      /* row padding points at the leaf's zero entry (index ne) */
-      for (size_t q = v2_goff[G0]; q < v2_idx.size(); q++) {
-        if (v2_idx[q] == 0xffff) v2_idx[q] = (unsigned short)std::min(ne, 0xffff);
-      }
-      if (ne >= 0xffff) ok = false;
-      const size_t bytes = dsc_nb_smem_bytes(nloc, ne, ng, leaf_ncnt[l]);
-      if (!ok || bytes > DSC_SMEM_BUDGET) {
+      if (!ok) {
         leaf_fast[l] = 0;
         ctx->any_slow_leaf = true;
       }
-      else {
-        max_smem = std::max(max_smem, bytes);
-      }
+      for (int tg = t_lo; tg < t_hi; tg++) tmeta[tg].ntfast = (t_hi - t_lo) | (ok ? 1 << 16 : 0);
+      if (t_hi - t_lo > 0xffff) return fail(ctx, DSC_ERR_UNSUPPORTED, "leaf %d has too many tiles", l);
     }
     for (; next_group_to_fill <= VP / 32; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
-    if (v2_idx.empty()) v2_idx.push_back(0xffff);
+    if (v2_idx.empty()) v2_idx.push_back(0u);
+    e_pv.insert(e_pv.end(), 8, (unsigned short)0); /* the last tile's bulk copy may read one entry past its own */
     ctx->nb_smem = std::max<size_t>(max_smem, 1024);
 
+    static_assert(sizeof(TileMeta) == 3 * sizeof(int4), "TileMeta is three int4");
     if ((r = dev_upload_c(ctx, &m.stage_slots, stage)) || (r = dev_upload_c(ctx, &m.e_pv, e_pv)) ||
-        (r = dev_upload_c(ctx, &m.e_halo_nb, e_halo_nb)) || (r = dev_upload_c(ctx, &m.nb_leaf, nb_leaf)) ||
+        (r = dev_upload_c(ctx, &m.e_halo_leaf, e_halo_leaf)) || (r = dev_upload_c(ctx, &m.tile_meta, tmeta)) ||
+        (r = dev_upload_c(ctx, &m.tile_range, tile_range)) || (r = dev_upload_c(ctx, &m.leaf_tile0, leaf_tile0)) ||
         (r = dev_upload_c(ctx, &m.v2_goff, v2_goff)) || (r = dev_upload_c(ctx, &m.v2_idx, v2_idx)) ||
         (r = dev_upload_c(ctx, &m.leaf_fast, leaf_fast)))
+      return r;
+    m.ntile = NT;
+    if ((r = dev_zero(ctx, &m.tile_bb, (size_t)6 * std::max(NT, 1))) || (r = dev_zero(ctx, &m.leaf_tcnt, (size_t)std::max(L, 1))) ||
+        (r = dev_zero(ctx, &m.tile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
+        (r = dev_zero(ctx, &m.atile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
+        (r = dev_zero(ctx, &m.flag_tile_list, (size_t)std::max(NT, 1))))
       return r;
     CU(cudaStreamSynchronize(ctx->stream));
 
@@ -867,7 +1003,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       if ((r = dev_upload_c(ctx, &m.pv0, pv[0])) || (r = dev_upload_c(ctx, &m.pv1, pv[1])) || (r = dev_upload_c(ctx, &m.pv2, pv[2])) ||
           (r = dev_upload_c(ctx, &m.pv3, pv[3])) || (r = dev_upload_c(ctx, &m.tri_leaf, tri_leaf)) ||
           (r = dev_upload_c(ctx, &m.poly_off, poly_off)) || (r = dev_upload_c(ctx, &m.poly_slots, poly_slots)) ||
-          (r = dev_upload_c(ctx, &m.vt_off, vt_off)) || (r = dev_upload_c(ctx, &m.vt_idx, vt_idx)))
+          (r = dev_upload_c(ctx, &m.vt_off, vt_off)) || (r = dev_upload_c(ctx, &m.vt_idx, vt_idx)) ||
+          (r = dev_upload_c(ctx, &m.leaf_sslots, leaf_sslots)))
         return r;
       CU(cudaStreamSynchronize(ctx->stream));
     }
@@ -877,17 +1014,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   {
     if ((r = dev_upload_c(ctx, &m.leaf_ubeg, leaf_ubeg)) || (r = dev_upload_c(ctx, &m.leaf_ucnt, leaf_ucnt)) ||
         (r = dev_upload_c(ctx, &m.leaf_sbeg, leaf_sbeg)) || (r = dev_upload_c(ctx, &m.leaf_scnt, leaf_scnt)) ||
-        (r = dev_upload_c(ctx, &m.leaf_pbeg, leaf_pbeg)) || (r = dev_upload_c(ctx, &m.leaf_pcnt, leaf_pcnt)) ||
-        (r = dev_upload_c(ctx, &m.leaf_xcnt, leaf_xcnt)) || (r = dev_upload_c(ctx, &m.leaf_ebeg, leaf_ebeg)) ||
-        (r = dev_upload_c(ctx, &m.leaf_eown, leaf_eown)) || (r = dev_upload_c(ctx, &m.leaf_ehalo, leaf_ehalo)) ||
-        (r = dev_upload_c(ctx, &m.leaf_hbeg, leaf_hbeg)) || (r = dev_upload_c(ctx, &m.leaf_nbeg, leaf_nbeg)) ||
-        (r = dev_upload_c(ctx, &m.leaf_ncnt, leaf_ncnt)))
+        (r = dev_upload_c(ctx, &m.leaf_pbeg, leaf_pbeg)) || (r = dev_upload_c(ctx, &m.leaf_pcnt, leaf_pcnt)))
       return r;
-    {
-      std::vector<int4> meta((size_t)std::max(L, 1));
-      for (int l = 0; l < L; l++) meta[l] = make_int4(leaf_ubeg[l], leaf_ucnt[l], leaf_sbeg[l], leaf_scnt[l]);
-      if ((r = dev_upload_c(ctx, &m.leaf_meta, meta))) return r;
-    }
     m.nleaf = L;
     int max_u = 1;
     for (int l = 0; l < L; l++) max_u = std::max(max_u, leaf_ucnt[l]);
@@ -895,6 +1023,9 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     if ((r = dev_zero(ctx, &m.leaf_state, (size_t)L))) return r;
     if ((r = dev_zero(ctx, &m.hit_list, (size_t)L * DSC_SLOTS)) || (r = dev_zero(ctx, &m.area_list, (size_t)L * DSC_SLOTS)) ||
         (r = dev_zero(ctx, &m.search_list, (size_t)L)) || (r = dev_zero(ctx, &m.flag_list, (size_t)L)))
+      return r;
+    m.ghit_words = (L + 31) / 32 + 1;
+    if ((r = dev_zero(ctx, &m.ghit, (size_t)m.ghit_words * DSC_SLOTS)) || (r = dev_zero(ctx, &m.flag_mask, (size_t)m.ghit_words)))
       return r;
     CU(cudaMallocHost((void **)&ctx->h_list, sizeof(int) * (size_t)std::max(L, 1)));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -976,9 +1107,9 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   CU(cudaStreamSynchronize(ctx->stream));
 
   /* launch shape of the shared-memory normals kernel */
-  CU(cudaFuncSetAttribute(k_normals_bb_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
+  CU(cudaFuncSetAttribute(k_normals_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
   int occ = 1;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_bb_smem, NB_BLOCK, ctx->nb_smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_tile, NT_BLOCK, ctx->nb_smem));
   ctx->nb_grid = ctx->num_sms * std::max(occ, 1);
 
   /* multi-GPU: owned leaf run, hit-mask ring, halo index lists */
@@ -996,8 +1127,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       const int l = ctx->leaf_range[q];
       ctx->slot_range[q] = (l < L) ? leaf_ubeg[l] : ((L ? leaf_ubeg[L - 1] + leaf_ucnt[L - 1] + 31 : 0) & ~31);
     }
-    m.ghit_words = (L + 31) / 32 + 1;
-    if ((r = dev_zero(ctx, &m.ghit, (size_t)m.ghit_words * DSC_SLOTS))) return r;
     DscMeshDesc me;
     memset(&me, 0, sizeof(me));
     me.totvert = V;
@@ -1060,12 +1189,21 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
 struct LeafList {
   const int *list;
   const int *count;
+  const int4 *tiles; /* the tiles of the listed leaves */
+  const int *tile_count;
+  const unsigned *mask; /* bit per leaf: updates its normals with this list */
 };
 static LeafList hit_list(DscContext *ctx, int slot)
 {
-  return {ctx->m.hit_list + (size_t)slot * ctx->m.nleaf, &ctx->m.st[slot].hit_count};
+  DevMesh &m = ctx->m;
+  return {m.hit_list + (size_t)slot * m.nleaf, &m.st[slot].hit_count, m.tile_list + (size_t)slot * m.ntile, &m.st[slot].tile_count,
+          m.ghit + (size_t)slot * m.ghit_words};
 }
-static LeafList flag_list(DscContext *ctx) { return {ctx->m.flag_list, &ctx->m.tot->flag_count}; }
+static LeafList flag_list(DscContext *ctx)
+{
+  DevMesh &m = ctx->m;
+  return {m.flag_list, &m.tot->flag_count, m.flag_tile_list, &m.tot->flag_tiles, m.flag_mask};
+}
 
 static int run_collect(DscContext *ctx, int flags)
 {
@@ -1075,17 +1213,17 @@ static int run_collect(DscContext *ctx, int flags)
   return DSC_OK;
 }
 /* normals and/or leaf boxes of the listed leaves (mode: NB_NORMALS | NB_BOUNDS) */
-static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode, const unsigned *ghit = nullptr)
+static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode)
 {
   {
     StageScope s(ctx, ST_NORMALS);
-    k_normals_bb_smem<<<ctx->nb_grid, NB_BLOCK, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.list, ll.count, mode, ghit);
+    k_normals_tile<<<ctx->nb_grid, NT_BLOCK, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.tiles, ll.tile_count, mode, ll.mask);
     LAUNCH_CHECK();
   }
   if (ctx->any_slow_leaf) {
     if (mode & NB_NORMALS) {
       StageScope s(ctx, ST_NORMALS);
-      k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1, ghit);
+      k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1, ll.mask);
       LAUNCH_CHECK();
     }
     if (mode & NB_BOUNDS) {
@@ -1324,9 +1462,15 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     const float rs = dab->radius * dab->radius_scale;
     float ar = sqrtf(dab->radius * dab->radius); /* radius of the normal-sampling sphere, same float steps as k_area */
     ar *= dab->normal_radius_factor;
+    /* flags this dab clears again before it ends are not set in the first place, unless the general
+     * path (which reads them) has work */
+    const int all_flags = F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw;
+    int set_flags = all_flags;
+    if (use_hits && !ctx->any_slow_leaf) set_flags &= ~((do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0));
+    const int ent_bits = (do_normals ? DSC_ENT_NORMALS : 0) | (do_bounds ? DSC_ENT_BOUNDS : 0);
     k_gather<<<(m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st>>>(m, slot, dab->location[0], dab->location[1],
                                                                           dab->location[2], rs * rs, ar * ar,
-                                                                          tool == DSC_TOOL_GRAB ? 1 : 0, 1, 1);
+                                                                          tool == DSC_TOOL_GRAB ? 1 : 0, 1, 1, set_flags, ent_bits);
     LAUNCH_CHECK();
   }
   if (do_bounds && use_hits && !dist) {
@@ -1381,7 +1525,12 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     if (dist && (r = dist_allreduce_dab(ctx, slot, needs_area))) return r;
     {
       StageScope s(ctx, ST_BRUSH);
-      k_brush<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot);
+      switch (tool) {
+        case DSC_TOOL_DRAW: k_brush<DSC_TOOL_DRAW><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
+        case DSC_TOOL_INFLATE: k_brush<DSC_TOOL_INFLATE><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
+        case DSC_TOOL_GRAB: k_brush<DSC_TOOL_GRAB><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
+        default: k_brush<DSC_TOOL_CLAY_STRIPS><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
+      }
       LAUNCH_CHECK();
     }
     if (dist && (r = dist_halo_exchange(ctx))) return r;
@@ -1390,7 +1539,7 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
   if (use_hits) {
     const int mode = (do_normals ? NB_NORMALS : 0) | (do_bounds ? NB_BOUNDS : 0);
     if (mode) {
-      if ((r = run_normals_bounds(ctx, hits, mode, dist ? m.ghit + (size_t)slot * m.ghit_words : nullptr))) return r;
+      if ((r = run_normals_bounds(ctx, hits, mode))) return r;
     }
     if (do_bounds && !dist) {
       /* side stream: carry the refreshed leaf boxes up the tree; overlaps the next dab */
@@ -1404,7 +1553,7 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
       CU(cudaEventRecord(ctx->ev_refit[slot], ctx->stream2));
       ctx->side_busy = true;
     }
-    if (mode) {
+    if (mode && ctx->any_slow_leaf) {
       if ((r = run_clear(ctx, hits, (do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0)))) return r;
     }
     if (!do_normals || !do_bounds) ctx->stale_flags = true;
@@ -1463,7 +1612,7 @@ int dsc_search_sphere(DscContext *ctx, const float center[3], float radius_sq, i
   {
     StageScope s(ctx, ST_GATHER);
     k_gather<<<(ctx->m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, ctx->stream>>>(
-        ctx->m, 0, center[0], center[1], center[2], radius_sq, 0.0f, original ? 1 : 0, ignore_fully_ineffective ? 1 : 0, 0);
+        ctx->m, 0, center[0], center[1], center[2], radius_sq, 0.0f, original ? 1 : 0, ignore_fully_ineffective ? 1 : 0, 0, 0, 0);
     LAUNCH_CHECK();
   }
   return read_list(ctx, ctx->m.search_list, &ctx->m.tot->search_count, r_nodes, capacity, r_tot);

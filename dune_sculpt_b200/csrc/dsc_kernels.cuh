@@ -19,6 +19,10 @@
 #include <stdint.h>
 
 #define DSC_CHUNK 1024        /* slots per work item = DSC_BLOCK threads x 4 slots */
+#define DSC_TILE 1024         /* most unique verts of a tile */
+#define DSC_ENT_FIRST 1       /* tile-list entry bits: first touch of the leaf in this stroke */
+#define DSC_ENT_NORMALS 2     /* the leaf updates its normals with this list */
+#define DSC_ENT_BOUNDS 4      /* ... its box */
 #define DSC_BLOCK 256
 #define DSC_LEAF_HIT 1u
 #define DSC_LEAF_FIRST 2u
@@ -32,9 +36,10 @@ enum {
 #define DSC_SLOTS 4 /* per-dab state ring: dab i uses slot i & 3 (the side stream may lag two dabs) */
 
 struct DabState {
-  int hit_count;  /* leaves gathered by the dab (hit list of this slot) */
-  int area_count; /* hit leaves that also reach the normal-sampling sphere (area list of this slot) */
-  int pad0, pad1;
+  int hit_count;   /* leaves gathered by the dab (hit list of this slot) */
+  int area_count;  /* hit leaves that also reach the normal-sampling sphere */
+  int tile_count;  /* tiles of the gathered leaves (tile list of this slot) */
+  int atile_count; /* tiles of the leaves that reach the normal-sampling sphere (area tile list) */
   long long acc[16]; /* nos[2][3], cos[2][3], count_no[2], count_co[2] */
   float area_no[3], area_co[3];
 };
@@ -43,6 +48,7 @@ struct StrokeTotals {
   unsigned long long vd_total, hits_total, moved_total, dabs;
   int search_count; /* leaves found by the last stand-alone search (search_list) */
   int flag_count;   /* leaves collected by k_collect_flagged (flag_list) */
+  int flag_tiles;   /* their tiles (flag_tile_list) */
 };
 
 /* Nodes are renumbered on the device: ids [0, nleaf) are the leaves in traversal order, ids
@@ -68,25 +74,31 @@ struct DevMesh {
   const int *pv0, *pv1, *pv2, *pv3;
   const int *poly_off, *poly_slots; /* n-gons only */
   const int *tri_leaf;              /* leaf holding the looptri position */
-  /* smem normals path: per leaf a local vertex list (unique | shared | extra) and local poly
-   * entries (own | halo); per unique vert the entries of its looptris in ascending position */
+  /* Tiles: every leaf's run of unique-vertex slots is cut into spatially compact runs of at most
+   * DSC_TILE slots (32-aligned); a tile is the work unit of the per-vertex kernels and of the
+   * shared-memory normals kernel.  Per tile: a local vertex list (unique | staged) and local poly
+   * entries (own leaf | other leaves); per unique vert the entries of its looptris in ascending
+   * looptri position. */
+  int ntile;
+  const int *leaf_tile0;      /* [nleaf + 1] */
+  const int2 *tile_range;     /* {first slot, unique verts} */
+  const int4 *tile_meta;      /* 3 per tile, see TileMeta */
+  const int *stage_slots;     /* per tile: slots of the staged verts (counted in the leaf box first) */
+  const ushort4 *e_pv;        /* local vertex indices of the entry's poly, w = 0xffff: triangle */
+  const int *e_halo_leaf;     /* per other-leaf entry: the leaf that holds its looptri */
+  /* vertex -> entry lists, sliced ELL: per group of 32 slots `width` row pairs of 32 words, word j
+   * of a lane = entries of its looptris 2j (low half) and 2j + 1 (high half), ascending position;
+   * padding points at the tile's zero entry */
+  const unsigned *v2_goff;    /* [slots / 32 + 1], in words */
+  const unsigned *v2_idx;
+  float *tile_bb;             /* [6][ntile] box of the tile's unique + box-counted staged verts */
+  int *leaf_tcnt;             /* tiles of the leaf whose box is done (this dab) */
   const unsigned char *leaf_fast;
-  const int *leaf_xcnt;             /* extra staged verts after the shared ones */
-  const int *leaf_ebeg, *leaf_eown, *leaf_ehalo, *leaf_hbeg;
-  const ushort4 *e_pv;              /* local vertex indices of the entry's poly, w = 0xffff: triangle */
-  const unsigned char *e_halo_nb;   /* halo entry -> index into the leaf's neighbour-leaf list */
-  const int *leaf_nbeg, *leaf_ncnt; /* neighbour leaves (owners of halo looptris) */
-  const int *nb_leaf;
-  /* vertex -> entry lists, sliced ELL: per group of 32 slots `width` rows of 32 entries, row j =
-   * the j-th looptri (ascending position) of each of the 32 verts, 0xffff = none */
-  const unsigned *v2_goff;          /* [slots / 32 + 1], in entries */
-  const unsigned short *v2_idx;
   /* leaves */
   int nleaf;
   int max_chunks; /* ceil(max uniq_verts / DSC_CHUNK) */
   const int *leaf_ubeg, *leaf_ucnt, *leaf_sbeg, *leaf_scnt, *leaf_pbeg, *leaf_pcnt;
-  const int4 *leaf_meta; /* {ubeg, ucnt, sbeg, scnt}: one load per work unit */
-  const int *stage_slots; /* per leaf: slots of its shared verts, then of its extra verts */
+  const int *leaf_sslots; /* per leaf: slots of its shared verts (general path only) */
   unsigned *leaf_state;
   /* nodes, device numbering */
   int totnode;
@@ -101,13 +113,16 @@ struct DevMesh {
   /* multi-GPU: this rank owns leaves [own_lo, own_hi); ghit = per-dab bitmask of gathered leaves,
    * one ring slot per dab, all-reduced across ranks (NULL on one GPU) */
   int own_lo, own_hi;
-  unsigned *ghit;
+  unsigned *ghit; /* [DSC_SLOTS][ghit_words] leaves gathered by the dab = leaves whose normals update */
   int ghit_words;
+  unsigned *flag_mask; /* the same for the leaf list k_collect_flagged builds */
   /* per-dab state */
   DabState *st;       /* [DSC_SLOTS] */
   StrokeTotals *tot;
   int *hit_list, *area_list; /* [DSC_SLOTS][nleaf] */
+  int4 *tile_list, *atile_list; /* [DSC_SLOTS][ntile] {tile, first slot, unique verts, DSC_ENT_* bits} */
   int *search_list, *flag_list;
+  int4 *flag_tile_list;
   const float *curve; /* 257-entry LUT or NULL */
 };
 
@@ -249,7 +264,8 @@ __device__ __forceinline__ void dsc_poly_normal(const DevMesh &m, unsigned pos, 
  * (pbvh.c:3641-3645), the sub-list of leaves that reach the (smaller) normal-sampling sphere, and
  * the reset of the next slot of the per-dab state ring. */
 __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float cx, float cy, float cz, float radius_sq,
-                                                      float area_radius_sq, int original, int ignore_ineffective, int mark)
+                                                      float area_radius_sq, int original, int ignore_ineffective, int mark,
+                                                      int set_flags, int ent_bits)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const int l = blockIdx.x * DSC_BLOCK + tid;
@@ -259,10 +275,8 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
     if (tid < 16) nx->acc[tid] = 0;
     if (tid == 16) nx->hit_count = 0;
     if (tid == 17) nx->area_count = 0;
-    if (m.ghit) {
-      unsigned *nm = m.ghit + (size_t)((slot + 1) & (DSC_SLOTS - 1)) * m.ghit_words;
-      for (int w = tid; w < m.ghit_words; w += DSC_BLOCK) nm[w] = 0u;
-    }
+    if (tid == 19) nx->tile_count = 0;
+    if (tid == 20) nx->atile_count = 0;
     if (tid == 18) {
       /* what dsc_last_area reports when the tool samples no plane: zero normal, brush location */
       st->area_no[0] = st->area_no[1] = st->area_no[2] = 0.0f;
@@ -302,7 +316,10 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
     if (hit) (mark ? m.hit_list + (size_t)slot * m.nleaf : m.search_list)[base + __popc(bal & ((1u << lane) - 1u))] = l;
   }
   if (!mark) return;
-  if (m.ghit && bal && lane == 0) m.ghit[(size_t)slot * m.ghit_words + (l >> 5)] = bal; /* l is 32-aligned here */
+  /* the bitmask of gathered leaves: every warp stores its word, so the ring slot needs no reset */
+  if (lane == 0 && (l >> 5) < m.ghit_words) m.ghit[(size_t)slot * m.ghit_words + (l >> 5)] = bal;
+  if (!hit && l < m.nleaf && (lst & (DSC_LEAF_HIT | DSC_LEAF_FIRST))) m.leaf_state[l] = lst & DSC_LEAF_TOUCHED;
+  if (!bal) return;
   const unsigned abal = __ballot_sync(0xffffffffu, ahit);
   if (abal) {
     int base = 0;
@@ -310,37 +327,71 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
     base = __shfl_sync(0xffffffffu, base, 0);
     if (ahit) m.area_list[(size_t)slot * m.nleaf + base + __popc(abal & ((1u << lane) - 1u))] = l;
   }
-  unsigned long long vd = 0;
-  if (l < m.nleaf) {
-    if (hit) {
-      m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((lst & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
-      m.node_flag[l] = flag | F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw;
-      vd = (unsigned long long)m.leaf_ucnt[l];
+  /* tile lists: the work units of the per-vertex kernels */
+  int t0 = 0, nt = 0;
+  if (hit) {
+    t0 = m.leaf_tile0[l];
+    nt = m.leaf_tile0[l + 1] - t0;
+  }
+  const int bits = ent_bits | ((lst & DSC_LEAF_TOUCHED) ? 0 : DSC_ENT_FIRST);
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1 && !abal) break;
+    const int mine = (pass == 0 || ahit) ? nt : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    else if (lst & (DSC_LEAF_HIT | DSC_LEAF_FIRST)) {
-      m.leaf_state[l] = lst & DSC_LEAF_TOUCHED;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31) base = atomicAdd(pass == 0 ? &st->tile_count : &st->atile_count, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int4 *tl = (pass == 0 ? m.tile_list : m.atile_list) + (size_t)slot * m.ntile + base + (incl - mine);
+    for (int k = 0; k < mine; k++) {
+      const int2 r = m.tile_range[t0 + k];
+      tl[k] = make_int4(t0 + k, r.x, r.y, bits);
     }
   }
-  if (bal) {
-    for (int o = 16; o > 0; o >>= 1) vd += __shfl_down_sync(0xffffffffu, vd, o);
-    if (lane == 0) {
-      atomicAdd(&m.tot->vd_total, vd);
-      atomicAdd(&m.tot->hits_total, (unsigned long long)__popc(bal));
-    }
+  unsigned long long vd = 0;
+  if (hit) {
+    m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((lst & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
+    m.node_flag[l] = flag | set_flags;
+    vd = (unsigned long long)m.leaf_ucnt[l];
+  }
+  for (int o = 16; o > 0; o >>= 1) vd += __shfl_down_sync(0xffffffffu, vd, o);
+  if (lane == 0) {
+    atomicAdd(&m.tot->vd_total, vd);
+    atomicAdd(&m.tot->hits_total, (unsigned long long)__popc(bal));
   }
 }
 
 /* leaves carrying any of `flags` (update_search_cb, pbvh.c:2891-2900) */
 __global__ void __launch_bounds__(1024) k_collect_flagged(DevMesh m, int flags)
 {
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
+  __shared__ int s_cnt, s_tiles;
+  if (threadIdx.x == 0) s_cnt = s_tiles = 0;
+  for (int w = threadIdx.x; w < m.ghit_words; w += blockDim.x) m.flag_mask[w] = 0u;
   __syncthreads();
   for (int l = threadIdx.x; l < m.nleaf; l += blockDim.x) {
-    if (m.node_flag[l] & flags) m.flag_list[atomicAdd(&s_cnt, 1)] = l;
+    const int f = m.node_flag[l] & flags;
+    if (!f) continue;
+    m.flag_list[atomicAdd(&s_cnt, 1)] = l;
+    if (f & F_UpdateNormals) atomicOr(&m.flag_mask[l >> 5], 1u << (l & 31));
+    const int bits = ((f & F_UpdateNormals) ? DSC_ENT_NORMALS : 0) | ((f & F_UpdateBB) ? DSC_ENT_BOUNDS : 0);
+    const int t0 = m.leaf_tile0[l], nt = m.leaf_tile0[l + 1] - t0;
+    const int base = atomicAdd(&s_tiles, nt);
+    for (int k = 0; k < nt; k++) {
+      const int2 r = m.tile_range[t0 + k];
+      m.flag_tile_list[base + k] = make_int4(t0 + k, r.x, r.y, bits);
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) m.tot->flag_count = s_cnt;
+  if (threadIdx.x == 0) {
+    m.tot->flag_count = s_cnt;
+    m.tot->flag_tiles = s_tiles;
+  }
 }
 
 /* Bottom-up refit, pass 1: tags the ancestors of the listed leaves.  pending[p] gets bit 1 / bit 2
@@ -398,16 +449,16 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, const int *list,
   }
 }
 
-/* work unit u of a leaf list: (leaf, chunk) -> slot range; returns false if the chunk is empty */
+/* general path: work unit u of a leaf list: (leaf, chunk) -> slot range; false if the chunk is empty */
 __device__ __forceinline__ bool dsc_unit(const DevMesh &m, const int *list, int u, int &leaf, int &beg, int &cnt)
 {
   const int h = u / m.max_chunks, c = u - h * m.max_chunks;
   leaf = list[h];
-  const int4 meta = m.leaf_meta[leaf];
+  const int ucnt = m.leaf_ucnt[leaf];
   const int off = c * DSC_CHUNK;
-  if (off >= meta.y) return false;
-  cnt = min(DSC_CHUNK, meta.y - off);
-  beg = meta.x + off;
+  if (off >= ucnt) return false;
+  cnt = min(DSC_CHUNK, ucnt - off);
+  beg = m.leaf_ubeg[leaf] + off;
   return true;
 }
 
@@ -431,7 +482,7 @@ __device__ __forceinline__ unsigned dsc_pack_nibbles(unsigned nib, int lane)
 __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int slot, int use_cos)
 {
   DabState *st = m.st + slot;
-  const int *alist = m.area_list + (size_t)slot * m.nleaf;
+  const int4 *alist = m.atile_list + (size_t)slot * m.ntile;
   __shared__ unsigned long long sacc[16];
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 16) sacc[tid] = 0ull;
@@ -442,13 +493,12 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int 
   long long n0x = 0, n0y = 0, n0z = 0, n1x = 0, n1y = 0, n1z = 0;
   long long c0x = 0, c0y = 0, c0z = 0, c1x = 0, c1y = 0, c1z = 0;
   long long cnt0 = 0, cnt1 = 0;
-  const int total = st->area_count * m.max_chunks;
+  const int total = st->atile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    int leaf, beg, cnt;
-    if (!dsc_unit(m, alist, u, leaf, beg, cnt)) continue;
-    const int nvalid = cnt - 4 * tid;
+    const int4 ent = alist[u];
+    const int nvalid = ent.z - 4 * tid;
     if (nvalid <= 0) continue;
-    const int s0 = beg + 4 * tid;
+    const int s0 = ent.y + 4 * tid;
     const float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
     const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
     float dxs[4], dys[4], dzs[4], dsq[4];
@@ -614,11 +664,12 @@ __device__ void dsc_brush_derive(DabState *st, const DabParams &d, BrushDerived 
 }
 
 /* one vertex of the brush loop; returns true if it was displaced (new position in x, y, z) */
+template<int TOOL>
 __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabParams &d, const BrushDerived &D, int s,
                                                  float &x, float &y, float &z, float tx, float ty, float tz, float vnx,
                                                  float vny, float vnz, float radius_sq)
 {
-  const int tool = d.tool;
+  constexpr int tool = TOOL;
   if (tool == 18) {
     /* clay strips: brush-local cube test + plane */
     const float rx = x - D.origin[0], ry = y - D.origin[1], rz = z - D.origin[2];
@@ -682,13 +733,14 @@ __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabPara
 }
 
 /* Draw / inflate / grab / clay strips over the unique verts of hit leaves (SURVEY.md 8a rows
- * a11-a19).  Each thread owns 4 consecutive slots (float4 loads / stores of the SoA arrays).
- * First touch of a leaf in the stroke snapshots co/no into orig_co/orig_no before the vertex is
- * moved (row a9).  Displaced verts get their vert_bitmap bit (pbvh.c:3729). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int slot)
+ * a11-a19), one instantiation per tool.  A CTA takes one tile at a time; each thread owns 4
+ * consecutive slots (float4 loads / stores of the SoA arrays).  First touch of a leaf in the stroke
+ * snapshots co/no into orig_co/orig_no before the vertex is moved (row a9).  Displaced verts get
+ * their vert_bitmap bit (pbvh.c:3729). */
+template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int slot)
 {
   DabState *st = m.st + slot;
-  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
+  const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   __shared__ BrushDerived D;
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -697,18 +749,17 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int
     dsc_brush_derive(st, d, D, blockIdx.x == 0);
   }
   __syncthreads();
-  const int tool = d.tool;
+  constexpr int tool = TOOL;
   const float radius_sq = d.radius * d.radius;
   const bool need_no = (tool == 4) || (d.flags & 1);
-  const bool use_orig = (tool == 5);
+  constexpr bool use_orig = (tool == 5);
   unsigned moved_cnt = 0;
-  const int total = st->hit_count * m.max_chunks;
+  const int total = st->tile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    int leaf, beg, cnt;
-    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
-    const bool first = (m.leaf_state[leaf] & DSC_LEAF_FIRST) != 0;
-    const int nvalid = cnt - 4 * tid;
-    const int s0 = beg + 4 * tid;
+    const int4 ent = tl[u];
+    const bool first = (ent.w & DSC_ENT_FIRST) != 0;
+    const int nvalid = ent.z - 4 * tid;
+    const int s0 = ent.y + 4 * tid;
     unsigned nib = 0;
     if (nvalid > 0) {
       float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
@@ -722,7 +773,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int
       else if (use_orig) {
         TX = ld4(m.ox, s0); TY = ld4(m.oy, s0); TZ = ld4(m.oz, s0);
       }
-      if (!D.skip) {
+      if (!(tool == 18 && D.skip)) {
         float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
         const float txs[4] = {TX.x, TX.y, TX.z, TX.w}, tys[4] = {TY.x, TY.y, TY.z, TY.w}, tzs[4] = {TZ.x, TZ.y, TZ.z, TZ.w};
         if (need_no && !first) {
@@ -741,8 +792,8 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int
         const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          if (j < nvalid && dsc_brush_vertex(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j], vys[j],
-                                             vzs[j], radius_sq)) {
+          if (j < nvalid && dsc_brush_vertex<TOOL>(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j],
+                                                   vys[j], vzs[j], radius_sq)) {
             nib |= 1u << j;
           }
         }
@@ -769,15 +820,14 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int
 __global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m, int slot)
 {
   const DabState *st = m.st + slot;
-  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
+  const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   const int tid = threadIdx.x;
-  const int total = st->hit_count * m.max_chunks;
+  const int total = st->tile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    int leaf, beg, cnt;
-    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
-    if (!(m.leaf_state[leaf] & DSC_LEAF_FIRST)) continue;
-    if (cnt - 4 * tid <= 0) continue;
-    const int s0 = beg + 4 * tid;
+    const int4 ent = tl[u];
+    if (!(ent.w & DSC_ENT_FIRST)) continue;
+    if (ent.z - 4 * tid <= 0) continue;
+    const int s0 = ent.y + 4 * tid;
     st4(m.ox, s0, ld4(m.cx, s0)); st4(m.oy, s0, ld4(m.cy, s0)); st4(m.oz, s0, ld4(m.cz, s0));
     st4(m.onx, s0, ld4(m.nx, s0)); st4(m.ony, s0, ld4(m.ny, s0)); st4(m.onz, s0, ld4(m.nz, s0));
   }
@@ -791,17 +841,17 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m, int slot)
 __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, int slot, float strength)
 {
   const DabState *st = m.st + slot;
-  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
+  const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) s_moved = 0;
   __syncthreads();
   const float radius_sq = d.radius * d.radius;
   unsigned moved_cnt = 0;
-  const int total = st->hit_count * m.max_chunks;
+  const int total = st->tile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    int leaf, beg, cnt;
-    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
+    const int4 ent = tl[u];
+    const int beg = ent.y, cnt = ent.z;
     const int cnt32 = (cnt + 31) & ~31;
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
@@ -861,11 +911,11 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, 
 __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m, int slot)
 {
   const DabState *st = m.st + slot;
-  const int *hlist = m.hit_list + (size_t)slot * m.nleaf;
-  const int total = st->hit_count * m.max_chunks;
+  const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
+  const int total = st->tile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    int leaf, beg, cnt;
-    if (!dsc_unit(m, hlist, u, leaf, beg, cnt)) continue;
+    const int4 ent = tl[u];
+    const int beg = ent.y, cnt = ent.z;
     for (int i = threadIdx.x; i < cnt; i += DSC_BLOCK) {
       const int s = beg + i;
       if ((m.iter_moved[s >> 5] >> (s & 31)) & 1u) {
@@ -927,95 +977,184 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *lis
 }
 
 /* ----------------------------------------------------------- K5 + K6 fused, shared-memory form */
-#define NB_BLOCK 512
+#define NT_BLOCK 256
 #define NB_NORMALS 1
 #define NB_BOUNDS 2
-/* bytes of dynamic shared memory a leaf needs (host and device agree through this one formula) */
-__host__ __device__ inline size_t dsc_nb_smem_bytes(int nloc, int ne, int ng, int ncnt)
+/* tile_meta: 3 x int4 per tile */
+struct TileMeta {
+  int ubeg, ucnt, sbeg, sbb;     /* unique slot run; staged verts: offset, how many count in the leaf box */
+  int xcnt, ebeg, eown, ehalo;   /* further staged verts; entries: offset (even), own-leaf, other-leaf */
+  int hbeg, leaf, tile0, ntfast; /* e_halo_leaf offset; leaf; its first tile; tile count | fast << 16 */
+};
+/* shared-memory carve of one tile (host and device agree through these formulas): positions SoA
+ * [3][nloc_a], poly normals float4 [ne + 1], poly entries ushort4 [ne_a], index words [v2w],
+ * other-leaf entry switches [ehalo] */
+__host__ __device__ inline int dsc_tile_nloc_a(int ucnt, int sbb, int xcnt) { return (((ucnt + 3) & ~3) + sbb + xcnt + 3) & ~3; }
+__host__ __device__ inline size_t dsc_tile_smem_bytes(int nloc_a, int ne, int v2w, int ehalo)
 {
-  return 12 * (size_t)nloc + 12 * (size_t)(ne + 1) + 4 * (size_t)(2 * ng + 1 + ncnt);
+  return 12 * (size_t)nloc_a + 16 * ((size_t)ne + 1) + 8 * (size_t)((ne + 1) & ~1) + 4 * (size_t)v2w + (((size_t)ehalo + 15) & ~(size_t)15);
 }
-/* One CTA per listed leaf.  Phase 1 stages the leaf's vertex positions in shared memory (xyz
- * interleaved): the unique verts as a unit-stride stream, the shared (and extra) verts by gather
- * -- the only gathers left on the path -- and reduces the leaf AABB over unique + shared on the
- * way (update_node_vb, pbvh.c:2033-2041).  Phase 2 computes the normal of every poly the leaf's
- * looptris belong to, and of the halo polys around it, once, from shared memory
- * (BKE_mesh_calc_poly_normal).  Phase 3 sums, per dirty unique vert, the normals of its looptris
- * in ascending looptri position (pbvh.c:2933-2981 run single-threaded), normalises, stores, clears
- * the dirty bit.  Halo polys whose owning leaf is not flagged UpdateNormals contribute zero
- * (pbvh.c:2943); so does the padding of the index rows (entry `ne` is a stored zero vector; adding
- * +0 is exact).  Global loads of phases 2 and 3 are issued in independent batches (4 entries,
- * 2 x 8 index rows per thread) so the HBM round trip is paid per batch, not per element.
- * Leaves with no dirty vert only refresh their box; leaves that do not fit (leaf_fast == 0) are
- * left to k_normals / k_leaf_bb. */
-__global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, const int *list, const int *count, int mode,
-                                                                 const unsigned *ghit)
+
+/* --- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier --- */
+__device__ __forceinline__ unsigned dsc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dsc_mbar_init(unsigned long long *bar, unsigned count)
 {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ float red[6][NB_BLOCK / 32];
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dsc_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(dsc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dsc_mbar_arrive(unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(dsc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dsc_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DSC_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DSC_DONE_%=;\n"
+      "bra DSC_WAIT_%=;\n"
+      "DSC_DONE_%=:\n"
+      "}\n" ::"r"(dsc_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void dsc_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dsc_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(dsc_smem_u32(bar))
+               : "memory");
+}
+
+/* One CTA per listed tile (a spatially compact run of <= DSC_TILE unique verts of one leaf), several
+ * CTAs per SM so the phases of different tiles overlap.
+ * Phase 0 reads the tile's dirty words; a tile with no dirty vert only refreshes its box.
+ * Phase 1: one thread queues TMA bulk copies of the tile's contiguous inputs -- the three position
+ * runs of its unique verts, its poly entries, its index words -- into shared memory, completing on
+ * an mbarrier; meanwhile all threads gather the staged verts (corners of the tile's polys owned by
+ * other tiles / leaves, and the leaf's shared verts assigned to it for the box: the only gathers
+ * left on the path) and arrive on the same mbarrier.  The tile box is reduced from shared memory;
+ * the last tile of a leaf to finish merges the tile boxes into the leaf box (update_node_vb,
+ * pbvh.c:2033-2041).
+ * Phase 2 computes, once, the normal of every poly incident to the tile's unique verts
+ * (BKE_mesh_calc_poly_normal), own-leaf entries always, entries of looptris held by another leaf
+ * only if that leaf updates its normals too (pbvh.c:2943).
+ * Phase 3 sums, per dirty unique vert, the normals of its looptris in ascending looptri position
+ * (pbvh.c:2933-2981 run single-threaded), normalises, stores, clears the dirty bit.  Padding of the
+ * index rows points at a stored zero vector (adding +0 is exact).
+ * Leaves that do not fit (fast == 0) are left to k_normals / k_leaf_bb. */
+__global__ void __launch_bounds__(NT_BLOCK, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
+                                                              const unsigned *upd)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ float red[6][NT_BLOCK / 32];
+  __shared__ unsigned sdirty[DSC_TILE / 32];
+  __shared__ unsigned sgoff[DSC_TILE / 32 + 1];
   __shared__ int s_dcount;
-  constexpr int NW = NB_BLOCK / 32;
+  constexpr int NW = NT_BLOCK / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
   const int n = *count;
+  if (tid == 0) dsc_mbar_init(&s_bar, NT_BLOCK);
+  unsigned parity = 0;
   for (int h = blockIdx.x; h < n; h += gridDim.x) {
-    const int l = list[h];
-    if (!m.leaf_fast[l]) continue;
-    const int flag = m.node_flag[l];
-    const bool do_n = (mode & NB_NORMALS) && (flag & F_UpdateNormals);
-    const bool do_b = (mode & NB_BOUNDS) && (flag & F_UpdateBB);
+    const int4 ent = list[h];
+    const int tile = ent.x;
+    const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
+    const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
     if (!do_n && !do_b) continue;
-    const int ub = m.leaf_ubeg[l], U = m.leaf_ucnt[l];
-    const int sb = m.leaf_sbeg[l], S = m.leaf_scnt[l], X = m.leaf_xcnt[l];
-    const int eb = m.leaf_ebeg[l], eown = m.leaf_eown[l], ne = eown + m.leaf_ehalo[l];
-    const int hb = m.leaf_hbeg[l], nbeg = m.leaf_nbeg[l], ncnt = m.leaf_ncnt[l];
+    const int4 q0 = m.tile_meta[3 * tile], q1 = m.tile_meta[3 * tile + 1], q2 = m.tile_meta[3 * tile + 2];
+    if (!(q2.w >> 16)) continue;
+    const int ub = q0.x, U = q0.y, sb = q0.z, SB = q0.w;
+    const int X = q1.x, eb = q1.y, eown = q1.z, ehalo = q1.w, ne = q1.z + q1.w;
     const int ng = (U + 31) >> 5, G0 = ub >> 5;
-    float *P = smem;                         /* [U + S + X][3] */
-    float *F = smem + 3 * (U + S + X);       /* [ne + 1][3], entry ne = zero */
-    unsigned *sdirty = reinterpret_cast<unsigned *>(F + 3 * (ne + 1));
-    unsigned *sgoff = sdirty + ng;
-    unsigned *snb = sgoff + ng + 1;
-    __syncthreads(); /* the previous leaf is done with the shared arrays */
-    if (tid == 0) s_dcount = 0;
-    __syncthreads();
-    if (do_n) {
-      int dc = 0;
-      for (int w = tid; w < ng; w += NB_BLOCK) {
-        const unsigned dw = m.dirty[G0 + w];
-        sdirty[w] = dw;
-        dc += __popc(dw);
+    const int UA = (U + 3) & ~3;
+    __syncthreads(); /* the previous tile is done with the shared arrays (and the mbarrier is initialised) */
+    /* phase 0 */
+    {
+      unsigned dw = 0u;
+      if (do_n && tid < ng) dw = m.dirty[G0 + tid];
+      if (tid < ng) sdirty[tid] = dw;
+      if (do_n && tid <= ng) sgoff[tid] = m.v2_goff[G0 + tid];
+      if (warp == 0) {
+        int c = __popc(dw);
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) s_dcount = c;
       }
-      if (dc) atomicAdd(&s_dcount, dc);
-      for (int w = tid; w <= ng; w += NB_BLOCK) sgoff[w] = m.v2_goff[G0 + w];
-      for (int w = tid; w < ncnt; w += NB_BLOCK) snb[w] = dsc_leaf_updates_normals(m, ghit, m.nb_leaf[nbeg + w]) ? 1u : 0u;
     }
     __syncthreads();
     const int dcount = s_dcount;
     const bool anyd = dcount > 0;
     if (!anyd && !do_b) continue;
-    const int nloc = U + S + (anyd ? X : 0);
+    const int nstaged = SB + (anyd ? X : 0);
+    const int nloc_a = dsc_tile_nloc_a(U, SB, X);
+    const int v2w = anyd ? (int)(sgoff[ng] - sgoff[0]) : 0;
+    float *PX = reinterpret_cast<float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
+    float4 *F = reinterpret_cast<float4 *>(PZ + nloc_a); /* [ne + 1], entry ne = zero */
+    const ushort4 *E = reinterpret_cast<const ushort4 *>(F + ne + 1);
+    const unsigned *V2 = reinterpret_cast<const unsigned *>(E + ((ne + 1) & ~1));
+    unsigned char *H = reinterpret_cast<unsigned char *>(const_cast<unsigned *>(V2) + v2w);
+    /* phase 1 */
+    if (tid == 0) {
+      const unsigned pbytes = 4u * (unsigned)UA;
+      const unsigned ebytes = anyd ? 8u * (unsigned)((ne + 1) & ~1) : 0u;
+      const unsigned vbytes = 4u * (unsigned)v2w;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      dsc_mbar_expect_tx(&s_bar, 3u * pbytes + ebytes + vbytes);
+      if (pbytes) {
+        dsc_bulk_g2s(PX, m.cx + ub, pbytes, &s_bar);
+        dsc_bulk_g2s(PY, m.cy + ub, pbytes, &s_bar);
+        dsc_bulk_g2s(PZ, m.cz + ub, pbytes, &s_bar);
+      }
+      if (ebytes) dsc_bulk_g2s(const_cast<ushort4 *>(E), m.e_pv + eb, ebytes, &s_bar);
+      if (vbytes) dsc_bulk_g2s(const_cast<unsigned *>(V2), m.v2_idx + sgoff[0], vbytes, &s_bar);
+      F[ne] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
     float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    /* phase 1: stage + box */
-#pragma unroll 4
-    for (int i = tid; i < U; i += NB_BLOCK) {
-      const float x = m.cx[ub + i], y = m.cy[ub + i], z = m.cz[ub + i];
-      P[3 * i] = x; P[3 * i + 1] = y; P[3 * i + 2] = z;
-      mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
-      mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
-      mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
-    }
-    for (int i = U + tid; i < nloc; i += NB_BLOCK) {
-      const int s = m.stage_slots[sb + (i - U)];
+    for (int i = tid; i < nstaged; i += NT_BLOCK) {
+      const int s = m.stage_slots[sb + i];
       const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
-      P[3 * i] = x; P[3 * i + 1] = y; P[3 * i + 2] = z;
-      if (i < U + S) {
+      PX[UA + i] = x; PY[UA + i] = y; PZ[UA + i] = z;
+      if (i < SB) {
         mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
         mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
         mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
       }
     }
+    if (anyd) {
+      for (int i = tid; i < ehalo; i += NT_BLOCK) {
+        const int ol = m.e_halo_leaf[q2.x + i];
+        H[i] = (unsigned char)((upd[ol >> 5] >> (ol & 31)) & 1u);
+      }
+    }
+    dsc_mbar_arrive(&s_bar);
+    dsc_mbar_wait(&s_bar, parity);
+    parity ^= 1u;
     if (do_b) {
+      /* box of the unique verts, four per thread straight from shared memory */
+      const int i0 = 4 * tid;
+      if (i0 + 3 < U) {
+        const float4 x4 = *reinterpret_cast<const float4 *>(PX + i0), y4 = *reinterpret_cast<const float4 *>(PY + i0),
+                     z4 = *reinterpret_cast<const float4 *>(PZ + i0);
+        mn[0] = fminf(fminf(mn[0], x4.x), fminf(fminf(x4.y, x4.z), x4.w));
+        mx[0] = fmaxf(fmaxf(mx[0], x4.x), fmaxf(fmaxf(x4.y, x4.z), x4.w));
+        mn[1] = fminf(fminf(mn[1], y4.x), fminf(fminf(y4.y, y4.z), y4.w));
+        mx[1] = fmaxf(fmaxf(mx[1], y4.x), fmaxf(fmaxf(y4.y, y4.z), y4.w));
+        mn[2] = fminf(fminf(mn[2], z4.x), fminf(fminf(z4.y, z4.z), z4.w));
+        mx[2] = fmaxf(fmaxf(mx[2], z4.x), fmaxf(fmaxf(z4.y, z4.z), z4.w));
+      }
+      else {
+        for (int i = i0; i < U; i++) {
+          mn[0] = fminf(mn[0], PX[i]); mx[0] = fmaxf(mx[0], PX[i]);
+          mn[1] = fminf(mn[1], PY[i]); mx[1] = fmaxf(mx[1], PY[i]);
+          mn[2] = fminf(mn[2], PZ[i]); mx[2] = fmaxf(mx[2], PZ[i]);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -1031,35 +1170,13 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
         }
       }
     }
-    if (tid < 3) F[3 * ne + tid] = 0.0f;
-    __syncthreads();
-    if (do_b && tid < 6) {
-      float v = red[tid][0];
-      for (int w = 1; w < NW; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
-      m.bb[tid * tn + l] = v;
-    }
-    if (!anyd) continue;
-    /* phase 2: poly normals of the local entries, 4 in flight per thread.  When few verts of the
-     * leaf are dirty, entries that touch no dirty unique vert are skipped (nothing will read them). */
-    const bool sparse = dcount * 2 < U;
-    for (int e0 = tid; e0 < ne; e0 += 4 * NB_BLOCK) {
-      ushort4 pv[4];
-      unsigned hn[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int e = e0 + u * NB_BLOCK;
-        pv[u] = make_ushort4(0, 0, 0, 0);
-        hn[u] = 0;
-        if (e < ne) {
-          pv[u] = m.e_pv[eb + e];
-          if (e >= eown) hn[u] = m.e_halo_nb[hb + (e - eown)];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int e = e0 + u * NB_BLOCK;
-        if (e >= ne) break;
-        const ushort4 v = pv[u];
+    /* phase 2: poly normals of the local entries.  When few verts of the tile are dirty, entries
+     * that touch no dirty unique vert are skipped (nothing will read them). */
+    if (anyd) {
+      const bool sparse = dcount * 2 < U;
+#pragma unroll 2
+      for (int e = tid; e < ne; e += NT_BLOCK) {
+        const ushort4 v = E[e];
         if (sparse) {
           bool need = false;
           const unsigned li[4] = {v.x, v.y, v.z, v.w};
@@ -1069,79 +1186,103 @@ __global__ void __launch_bounds__(NB_BLOCK, 2) k_normals_bb_smem(DevMesh m, cons
           }
           if (!need) continue;
         }
-        float ox, oy, oz;
-        if (e < eown || snb[hn[u]]) {
-          const float *a = P + 3 * v.x, *b = P + 3 * v.y, *c = P + 3 * v.z;
+        float ox = 0.0f, oy = 0.0f, oz = 0.0f;
+        if (e < eown || H[e - eown]) {
+          const float ax = PX[v.x], ay = PY[v.x], az = PZ[v.x];
+          const float bx = PX[v.y], by = PY[v.y], bz = PZ[v.y];
+          const float cx = PX[v.z], cy = PY[v.z], cz = PZ[v.z];
+          float n1x, n1y, n1z, n2x, n2y, n2z;
           if (v.w != 0xffffu) {
             /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
-            const float *dd = P + 3 * v.w;
-            const float n1x = a[0] - c[0], n1y = a[1] - c[1], n1z = a[2] - c[2];
-            const float n2x = b[0] - dd[0], n2y = b[1] - dd[1], n2z = b[2] - dd[2];
-            ox = n1y * n2z - n1z * n2y;
-            oy = n1z * n2x - n1x * n2z;
-            oz = n1x * n2y - n1y * n2x;
+            const float dx = PX[v.w], dy = PY[v.w], dz = PZ[v.w];
+            n1x = ax - cx; n1y = ay - cy; n1z = az - cz;
+            n2x = bx - dx; n2y = by - dy; n2z = bz - dz;
           }
           else {
             /* normal_tri_v3, lib/intern/math_geom.cc:31-49 */
-            const float bx = b[0], by = b[1], bz = b[2];
-            const float n1x = a[0] - bx, n1y = a[1] - by, n1z = a[2] - bz;
-            const float n2x = bx - c[0], n2y = by - c[1], n2z = bz - c[2];
-            ox = n1y * n2z - n1z * n2y;
-            oy = n1z * n2x - n1x * n2z;
-            oz = n1x * n2y - n1y * n2x;
+            n1x = ax - bx; n1y = ay - by; n1z = az - bz;
+            n2x = bx - cx; n2y = by - cy; n2z = bz - cz;
           }
+          ox = n1y * n2z - n1z * n2y;
+          oy = n1z * n2x - n1x * n2z;
+          oz = n1x * n2y - n1y * n2x;
           dsc_normalize(ox, oy, oz);
         }
-        else {
-          ox = oy = oz = 0.0f;
-        }
-        F[3 * e] = ox; F[3 * e + 1] = oy; F[3 * e + 2] = oz;
+        F[e] = make_float4(ox, oy, oz, 0.0f);
       }
     }
     __syncthreads();
-    /* phase 3: one warp per group of 32 verts, two groups (2 x 8 index rows) in flight */
-    for (int g0 = warp; g0 < ng; g0 += 2 * NW) {
-      unsigned word[2], off[2];
-      int wd[2];
-      unsigned short en[2][8];
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int g = g0 + u * NW;
-        const bool ok = g < ng;
-        word[u] = ok ? sdirty[g] : 0u;
-        off[u] = ok ? sgoff[g] : 0u;
-        wd[u] = ok ? (int)((sgoff[g + 1] - off[u]) >> 5) : 0;
-        const unsigned short *row = m.v2_idx + off[u] + lane;
-        const int w8 = word[u] != 0u ? min(wd[u], 8) : 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          if (j >= w8) break; /* warp-uniform */
-          en[u][j] = row[j * 32];
+    if (do_b && warp == 0) {
+      /* tile box; the last tile of the leaf to get here merges them into the leaf box */
+      const int leaf = q2.y;
+      float v = 0.0f;
+      if (lane < 6) {
+        v = red[lane][0];
+        for (int w = 1; w < NW; w++) v = (lane < 3) ? fminf(v, red[lane][w]) : fmaxf(v, red[lane][w]);
+      }
+      const int nt = q2.w & 0xffff;
+      if (nt == 1) {
+        if (lane < 6) {
+          m.tile_bb[lane * m.ntile + tile] = v;
+          m.bb[lane * tn + leaf] = v;
         }
       }
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (word[u] == 0u) continue; /* warp-uniform */
-        const int g = g0 + u * NW;
+      else {
+        if (lane < 6) __stcg(&m.tile_bb[lane * m.ntile + tile], v);
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          last = atomicAdd(&m.leaf_tcnt[leaf], 1) == nt - 1;
+          if (last) m.leaf_tcnt[leaf] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          if (lane < 6) {
+            for (int t = 0; t < nt; t++) {
+              const float o = __ldcg(&m.tile_bb[lane * m.ntile + q2.z + t]);
+              v = (lane < 3) ? fminf(v, o) : fmaxf(v, o);
+            }
+            m.bb[lane * tn + leaf] = v;
+          }
+        }
+      }
+    }
+    if (!anyd) continue;
+    /* phase 3: one warp per group of 32 verts */
+    const unsigned goff0 = sgoff[0];
+    for (int g = warp; g < ng; g += NW) {
+      const unsigned word = sdirty[g];
+      if (word == 0u) continue; /* warp-uniform */
+      if ((word >> lane) & 1u) {
+        const unsigned off = sgoff[g];
+        const int wd = (int)((sgoff[g + 1] - off) >> 5);
+        const unsigned *rp = V2 + (off - goff0) + lane;
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        if (wd == 3) {
+          const unsigned w0 = rp[0], w1 = rp[32], w2 = rp[64];
+          float4 f;
+          f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+          f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+          f = F[w1 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+          f = F[w1 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+          f = F[w2 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+          f = F[w2 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+        }
+        else {
+          for (int j = 0; j < wd; j++) {
+            const unsigned w0 = rp[j * 32];
+            float4 f;
+            f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+            f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+          }
+        }
+        dsc_normalize(sx, sy, sz);
         const int s = ub + g * 32 + lane;
-        if ((word[u] >> lane) & 1u) {
-          float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-          const int w8 = min(wd[u], 8);
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            if (j >= w8) break; /* warp-uniform */
-            const float *f = F + 3 * en[u][j];
-            sx += f[0]; sy += f[1]; sz += f[2];
-          }
-          for (int j = 8; j < wd[u]; j++) {
-            const float *f = F + 3 * (unsigned)m.v2_idx[off[u] + j * 32 + lane];
-            sx += f[0]; sy += f[1]; sz += f[2];
-          }
-          dsc_normalize(sx, sy, sz);
-          m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
-        }
-        if (lane == 0) m.dirty[G0 + g] = 0u;
+        m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
       }
+      if (lane == 0) m.dirty[G0 + g] = 0u;
     }
   }
 }
@@ -1176,7 +1317,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_leaf_bb(DevMesh m, const int *lis
     }
     const int sb = m.leaf_sbeg[l], sc = m.leaf_scnt[l];
     for (int i = tid; i < sc; i += DSC_BLOCK) {
-      const int s = m.stage_slots[sb + i];
+      const int s = m.leaf_sslots[sb + i];
       const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
       mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
       mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
