@@ -6,7 +6,8 @@
 
 N = 1 workload (config.workload): C3 -- draw brush + normal recompute + BB refit on the 16,777,216-
 vertex height-field grid, radius sweep 1-50 % of the bounding-box diagonal, 32 dabs per radius.
-One *step* = one pass of the whole 224-dab stroke script.  `value` = vertex-dabs / second with the
+One *step* = a device-to-device rollback of the mesh to its rest state + one pass of the whole 224-dab
+stroke script (so every step does identical work).  `value` = vertex-dabs / second with the
 mesh resident in HBM (CUDA events around the K strokes); `e2e` = the same strokes driven through
 the reference-named host API with host buffers: per dab the descriptor goes host->device, at stroke
 end positions, normals, node boxes and flags come back device->host, all inside the timed region.
@@ -161,7 +162,8 @@ def workload_config(args, mesh, ndabs):
                          "NCCL all-reduce (area sums + hit mask) and one one-ring halo exchange" % world),
             "parallelism": "single GPU" if world == 1 else "pbvh-partition x%d" % world,
             "verts": mesh.totvert, "dabs_per_step": ndabs, "brush": "draw, SMOOTH falloff, area-normal direction",
-            "l2": "inputs larger than L2 (resident mesh arrays > 2 GB; every stroke sweeps all of them)"}
+            "l2": "inputs larger than L2 (resident mesh arrays > 2 GB; every stroke sweeps all of them)",
+            "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
 
 
 def analysis_pass(ses, dabs, na):
@@ -173,6 +175,7 @@ def analysis_pass(ses, dabs, na):
     inner = np.nonzero((na["flag"] & 1) == 0)[0]
     parent[na["children_offset"][inner]] = inner
     parent[na["children_offset"][inner] + 1] = inner
+    ses.rollback()
     ses.stage_timing(True)
     ses.stroke_begin()
     moved_prev = 0
@@ -246,7 +249,12 @@ def run_ours(args, rank, world):
 
     dab_arr = (capi.DscDab * len(dabs))(*dabs)  # the stroke script as one C array
 
+    # every step starts from the same rest state: a device-to-device rollback to the checkpoint, timed as
+    # part of the step (without it the draw strokes pile up and later steps sweep a different surface)
+    ses.checkpoint()
+
     def device_stroke():
+        ses._chk(D.dsc_state_restore(ctx))
         ses._chk(D.dsc_stroke_begin(ctx, None))
         ses._chk(D.dsc_dabs(ctx, dab_arr, len(dabs)))
         ses._chk(D.dsc_stroke_end(ctx))
@@ -275,12 +283,13 @@ def run_ours(args, rank, world):
     h2d = len(dabs) * C.sizeof(capi.DscDab)
     d2h = mesh.totvert * 24 + ses.totnode * (48 + 4) + 8
     for _ in range(1):
-        ses.stroke_begin(); ses.dabs(dab_arr, len(dabs)); ses.stroke_end()
+        ses.rollback(); ses.stroke_begin(); ses.dabs(dab_arr, len(dabs)); ses.stroke_end()
     ses.synchronize()
     barrier()
     vd_e = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        ses.rollback()
         ses.stroke_begin()
         ses.dabs(dab_arr, len(dabs))  # host descriptors cross the ABI dab by dab inside the C loop
         vd_e += ses.stats()["vertex_dabs"]
@@ -300,6 +309,25 @@ def run_ours(args, rank, world):
         ms, dt_e = float(t[0]), float(t[1])
         vd, vd_e, launches = int(s[0]), int(s[1]), int(s[2])
 
+    # ---- the sweep radius by radius (untimed for `value`: one more stroke, CUDA events around each radius group)
+    per = args.dabs_per_radius
+    sweep = []
+    ses._chk(D.dsc_state_restore(ctx))
+    ses._chk(D.dsc_stroke_begin(ctx, None))
+    vd_prev = 0
+    for g in range(len(dabs) // per):
+        grp = (capi.DscDab * per)(*dabs[g * per:(g + 1) * per])
+        ses.timer_start()
+        ses._chk(D.dsc_dabs(ctx, grp, per))
+        g_ms = ses.timer_stop()
+        vd_now = ses.stats()["vertex_dabs"]
+        sweep.append({"radius_pct_diag": round(100.0 * float(dabs[g * per].radius) / diag, 2), "dabs": per,
+                      "us_per_dab": round(1e3 * g_ms / per, 2), "vertex_dabs_per_dab": (vd_now - vd_prev) // per,
+                      "gvd_per_s": round((vd_now - vd_prev) / (g_ms * 1e-3) / 1e9, 2) if g_ms > 0 else None})
+        vd_prev = vd_now
+    ses._chk(D.dsc_stroke_end(ctx))
+    ses.synchronize()
+
     # ---- roofline of the dominant kernel (untimed analysis stroke, CUDA events per stage)
     tot, stage_bytes, times = analysis_pass(ses, dabs, na)
     peak, peak_src = measured_peaks()
@@ -307,7 +335,7 @@ def run_ours(args, rank, world):
     dom_ms, dom_launches = times[dom]
     achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     total_bytes = sum(stage_bytes.values())
-    total_ms = sum(v[0] for v in times.values())
+    total_ms = ms / args.steps  # the timed strokes themselves: side-stream refit overlapped, no per-stage events
     stages = {k: {"ms": round(times[k][0], 4), "launches": times[k][1], "alg_bytes": int(stage_bytes.get(k, 0)),
                   "gbs": round(stage_bytes.get(k, 0) / (times[k][0] * 1e-3) / 1e9, 1) if times[k][0] > 0 else None}
               for k in times}
@@ -317,8 +345,9 @@ def run_ours(args, rank, world):
                 "whole_path": {"achieved": round(total_bytes / (total_ms * 1e-3) / 1e9, 1) if total_ms > 0 else None,
                                "frac": round(total_bytes / (total_ms * 1e-3) / 1e9 / peak, 4) if total_ms > 0 else None,
                                "frac_of_8TBs_nominal": round(total_bytes / (total_ms * 1e-3) / 1e9 / 8000.0, 4) if total_ms > 0 else None,
-                               "bytes_per_vertex_dab": round(total_bytes / max(tot["U"], 1), 2)},
-                "stages": stages}
+                               "bytes_per_vertex_dab": round(total_bytes / max(tot["U"], 1), 2),
+                               "how": "algorithmic bytes of one stroke / device time of one timed stroke"},
+                "stages": stages, "radius_sweep": sweep}
 
     if rank != 0:
         ses.close()

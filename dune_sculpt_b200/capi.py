@@ -87,7 +87,7 @@ class SculptSearchSphereData(C.Structure):
 CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
     "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
-    "dsc_dabs",
+    "dsc_dabs", "dsc_state_save", "dsc_state_restore",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
     "dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
@@ -100,6 +100,7 @@ HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
     "DUNE_pbvh_mesh_sizes_set", "DUNE_pbvh_mask_layer_set", "DUNE_pbvh_vert_normals_set", "DUNE_pbvh_leaf_limit_set",
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
+    "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback",
     "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
     "BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_hidden_get", "BKE_pbvh_node_fully_masked_set",
     "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
@@ -137,7 +138,8 @@ def cuda_lib():
         L.dsc_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.dsc_ctx_destroy.argtypes = [C.c_void_p]
         L.dsc_ctx_destroy.restype = None
-        for fn in ("dsc_recalc_normals", "dsc_stroke_end", "dsc_update_normals", "dsc_synchronize", "dsc_timer_start"):
+        for fn in ("dsc_recalc_normals", "dsc_stroke_end", "dsc_update_normals", "dsc_synchronize", "dsc_timer_start",
+                   "dsc_state_save", "dsc_state_restore"):
             getattr(L, fn).argtypes = [C.c_void_p]
         L.dsc_stroke_begin.argtypes = [C.c_void_p, c_float_p]
         L.dsc_dab.argtypes = [C.c_void_p, C.POINTER(DscDab)]
@@ -189,6 +191,8 @@ def host_lib():
         L.DUNE_pbvh_device_detach.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_attach_dist.argtypes = [C.POINTER(PBVH), C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.DUNE_pbvh_device_sync_to_host.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_device_checkpoint.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_device_rollback.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_error.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_error.restype = C.c_char_p
         L.BKE_pbvh_search_gather.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_void_p,
@@ -448,6 +452,14 @@ class SculptSession:
 
     def stroke_end(self):
         self._chk(self.H.DUNE_sculpt_stroke_end(self.pbvh))
+
+    def checkpoint(self):
+        """remember the resident mesh state (device-to-device)"""
+        self._chk(self.H.DUNE_pbvh_device_checkpoint(self.pbvh))
+
+    def rollback(self):
+        """back to the checkpoint (device-to-device); the host arrays follow at the next sync"""
+        self._chk(self.H.DUNE_pbvh_device_rollback(self.pbvh))
 
     def hits(self):
         n = C.c_int(0)

@@ -72,6 +72,9 @@ struct DscContext {
   int *d_slot_of = nullptr;
   float *d_mask = nullptr, *d_automask = nullptr, *d_curve = nullptr;
   float *d_stage3 = nullptr; /* [totvert][3] export/import staging */
+  float *d_save_v = nullptr, *d_save_bb = nullptr; /* dsc_state_save: co / no, node + tile boxes */
+  int *d_save_flag = nullptr;
+  bool have_save = false, save_stale_flags = false;
   unsigned *d_capture = nullptr;
   int *d_list = nullptr, *d_count = nullptr;
   DevMesh m;
@@ -932,8 +935,10 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         tm.sbb = (int)st_bb.size();
         tm.xcnt = (int)st_x.size();
         if (nloc > 0xfffe) ok = false;
+        bool allquad = true;
         auto emit = [&](int p) {
           const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
+          if (len != 4) allquad = false;
           unsigned short loc[4] = {0, 0, 0, 0xffff};
           if (len == 3 || len == 4) {
             for (int k = 0; k < len; k++) loc[k] = (unsigned short)std::min(std::max(lidx[ctx->slot_of[ctx->h_loop_v[ls + k]]], 0), 0xfffe);
@@ -943,6 +948,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         for (int p : own_polys) emit(p);
         for (int p : halo_polys) emit(p);
         e_halo_leaf.insert(e_halo_leaf.end(), halo_leaves.begin(), halo_leaves.end());
+        tm.ntfast = allquad ? 1 << 17 : 0;
         const size_t bytes = dsc_tile_smem_bytes(dsc_tile_nloc_a(U, tm.sbb, tm.xcnt), ne, (int)(raw.size() / 2), ehalo);
         if (bytes > DSC_SMEM_BUDGET) ok = false;
         else max_smem = std::max(max_smem, bytes);
@@ -951,7 +957,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         leaf_fast[l] = 0;
         ctx->any_slow_leaf = true;
       }
-      for (int tg = t_lo; tg < t_hi; tg++) tmeta[tg].ntfast = (t_hi - t_lo) | (ok ? 1 << 16 : 0);
+      for (int tg = t_lo; tg < t_hi; tg++) tmeta[tg].ntfast |= (t_hi - t_lo) | (ok ? 1 << 16 : 0); /* bit 17: all entries are quads */
       if (t_hi - t_lo > 0xffff) return fail(ctx, DSC_ERR_UNSUPPORTED, "leaf %d has too many tiles", l);
     }
     for (; next_group_to_fill <= VP / 32; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
@@ -1834,6 +1840,54 @@ int dsc_upload_co(DscContext *ctx, const float *co)
   if ((r = run_flagged(ctx, F_UpdateNormals | F_UpdateBB))) return r;
   if ((r = run_orig_flush(ctx))) return r;
   return sync_all(ctx);
+}
+
+/* Checkpoint / rollback of the resident mesh state (positions, normals, node boxes, node flags):
+ * device-to-device copies.  What an operator cancel or the undo system's restore does on the host
+ * side of the reference (the undo nodes' co / no written back, paint_hide.c:78, then
+ * BKE_pbvh_update_bounds), kept on the device so no mesh crosses PCIe. */
+int dsc_state_save(DscContext *ctx)
+{
+  NEED_PBVH();
+  if (ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "no checkpoint inside a stroke");
+  int r = join_side(ctx);
+  if (r) return r;
+  DevMesh &m = ctx->m;
+  const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode, NT = (size_t)std::max(m.ntile, 1);
+  if (!ctx->d_save_v) {
+    if ((r = dev_alloc(ctx, &ctx->d_save_v, 6 * VP)) || (r = dev_alloc(ctx, &ctx->d_save_bb, 12 * N + 6 * NT)) ||
+        (r = dev_alloc(ctx, &ctx->d_save_flag, N)))
+      return r;
+  }
+  float *src[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
+  for (int k = 0; k < 6; k++) CU(cudaMemcpyAsync(ctx->d_save_v + k * VP, src[k], VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_save_bb, m.bb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_save_bb + 6 * N, m.obb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_save_bb + 12 * N, m.tile_bb, 6 * NT * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_save_flag, m.node_flag, N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->save_stale_flags = ctx->stale_flags;
+  ctx->have_save = true;
+  return DSC_OK;
+}
+int dsc_state_restore(DscContext *ctx)
+{
+  NEED_PBVH();
+  if (ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "no rollback inside a stroke");
+  if (!ctx->have_save) return fail(ctx, DSC_ERR_STATE, "dsc_state_save first");
+  int r = join_side(ctx);
+  if (r) return r;
+  DevMesh &m = ctx->m;
+  const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode, NT = (size_t)std::max(m.ntile, 1);
+  float *dst[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
+  for (int k = 0; k < 6; k++) CU(cudaMemcpyAsync(dst[k], ctx->d_save_v + k * VP, VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(m.bb, ctx->d_save_bb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(m.obb, ctx->d_save_bb + 6 * N, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(m.tile_bb, ctx->d_save_bb + 12 * N, 6 * NT * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(m.node_flag, ctx->d_save_flag, N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemsetAsync(m.dirty, 0, sizeof(unsigned) * (size_t)ctx->nwords, ctx->stream));
+  ctx->stale_flags = ctx->save_stale_flags;
+  ctx->launches += 11;
+  return DSC_OK;
 }
 
 int dsc_synchronize(DscContext *ctx)

@@ -1046,11 +1046,66 @@ __device__ __forceinline__ void dsc_bulk_g2s(void *dst, const void *src, unsigne
  * (pbvh.c:2933-2981 run single-threaded), normalises, stores, clears the dirty bit.  Padding of the
  * index rows points at a stored zero vector (adding +0 is exact).
  * Leaves that do not fit (fast == 0) are left to k_normals / k_leaf_bb. */
+/* normal of one local poly entry from the staged positions */
+template<bool ALLQUAD>
+__device__ __forceinline__ float4 dsc_entry_normal(const float *PX, const float *PY, const float *PZ, const ushort4 v)
+{
+  const float ax = PX[v.x], ay = PY[v.x], az = PZ[v.x];
+  const float bx = PX[v.y], by = PY[v.y], bz = PZ[v.y];
+  const float cx = PX[v.z], cy = PY[v.z], cz = PZ[v.z];
+  float n1x, n1y, n1z, n2x, n2y, n2z;
+  if (ALLQUAD || v.w != 0xffffu) {
+    /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
+    const float dx = PX[v.w], dy = PY[v.w], dz = PZ[v.w];
+    n1x = ax - cx; n1y = ay - cy; n1z = az - cz;
+    n2x = bx - dx; n2y = by - dy; n2z = bz - dz;
+  }
+  else {
+    /* normal_tri_v3, lib/intern/math_geom.cc:31-49 */
+    n1x = ax - bx; n1y = ay - by; n1z = az - bz;
+    n2x = bx - cx; n2y = by - cy; n2z = bz - cz;
+  }
+  float ox = n1y * n2z - n1z * n2y;
+  float oy = n1z * n2x - n1x * n2z;
+  float oz = n1x * n2y - n1y * n2x;
+  dsc_normalize(ox, oy, oz);
+  return make_float4(ox, oy, oz, 0.0f);
+}
+
+template<bool ALLQUAD>
+__device__ __forceinline__ void dsc_tile_poly_normals(const float *PX, const float *PY, const float *PZ, const ushort4 *E,
+                                                      float4 *F, const unsigned char *H, const unsigned *sdirty, int tid,
+                                                      int U, int eown, int ne, bool sparse)
+{
+  if (!sparse) {
+#pragma unroll 2
+    for (int e = tid; e < eown; e += NT_BLOCK) F[e] = dsc_entry_normal<ALLQUAD>(PX, PY, PZ, E[e]);
+    for (int e = eown + tid; e < ne; e += NT_BLOCK) {
+      F[e] = H[e - eown] ? dsc_entry_normal<ALLQUAD>(PX, PY, PZ, E[e]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+  else {
+    /* few verts of the tile are dirty: entries that touch no dirty unique vert are skipped (nothing reads them) */
+    for (int e = tid; e < ne; e += NT_BLOCK) {
+      const ushort4 v = E[e];
+      bool need = false;
+      const unsigned li[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (li[k] < (unsigned)U) need |= ((sdirty[li[k] >> 5] >> (li[k] & 31)) & 1u) != 0u;
+      }
+      if (!need) continue;
+      F[e] = (e < eown || H[e - eown]) ? dsc_entry_normal<ALLQUAD>(PX, PY, PZ, v) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT_BLOCK, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
                                                               const unsigned *upd)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ __align__(16) int4 s_meta[3];
   __shared__ float red[6][NT_BLOCK / 32];
   __shared__ unsigned sdirty[DSC_TILE / 32];
   __shared__ unsigned sgoff[DSC_TILE / 32 + 1];
@@ -1061,35 +1116,54 @@ __global__ void __launch_bounds__(NT_BLOCK, 4) k_normals_tile(DevMesh m, const i
   const int n = *count;
   if (tid == 0) dsc_mbar_init(&s_bar, NT_BLOCK);
   unsigned parity = 0;
-  for (int h = blockIdx.x; h < n; h += gridDim.x) {
-    const int4 ent = list[h];
+  int h = blockIdx.x;
+  if (h >= n) return;
+  int4 ent = list[h];
+  /* warp 0 keeps the next tile's descriptor, dirty words and index offsets in flight (registers)
+   * while the current tile is processed */
+  int4 pf_q = make_int4(0, 0, 0, 0);
+  unsigned pf_dirty = 0u, pf_goff = 0u, pf_glast = 0u;
+  auto prefetch = [&](const int4 &e) {
+    if (warp != 0) return;
+    const int ngn = (e.z + 31) >> 5, g0n = e.y >> 5;
+    const bool dn = (mode & NB_NORMALS) && (e.w & DSC_ENT_NORMALS);
+    if (lane < 3) pf_q = m.tile_meta[3 * e.x + lane];
+    pf_dirty = (dn && lane < ngn) ? m.dirty[g0n + lane] : 0u;
+    pf_goff = (dn && lane < ngn) ? m.v2_goff[g0n + lane] : 0u;
+    pf_glast = (dn && lane == 0) ? m.v2_goff[g0n + ngn] : 0u;
+  };
+  prefetch(ent);
+  while (h < n) {
+    const int hn = h + (int)gridDim.x;
+    int4 ent_n = make_int4(0, 0, 0, 0);
+    if (hn < n) ent_n = list[hn];
     const int tile = ent.x;
+    const int ub = ent.y, U = ent.z;
+    const int ng = (U + 31) >> 5, G0 = ub >> 5;
     const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
     const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
-    if (!do_n && !do_b) continue;
-    const int4 q0 = m.tile_meta[3 * tile], q1 = m.tile_meta[3 * tile + 1], q2 = m.tile_meta[3 * tile + 2];
-    if (!(q2.w >> 16)) continue;
-    const int ub = q0.x, U = q0.y, sb = q0.z, SB = q0.w;
-    const int X = q1.x, eb = q1.y, eown = q1.z, ehalo = q1.w, ne = q1.z + q1.w;
-    const int ng = (U + 31) >> 5, G0 = ub >> 5;
-    const int UA = (U + 3) & ~3;
     __syncthreads(); /* the previous tile is done with the shared arrays (and the mbarrier is initialised) */
-    /* phase 0 */
-    {
-      unsigned dw = 0u;
-      if (do_n && tid < ng) dw = m.dirty[G0 + tid];
-      if (tid < ng) sdirty[tid] = dw;
-      if (do_n && tid <= ng) sgoff[tid] = m.v2_goff[G0 + tid];
-      if (warp == 0) {
-        int c = __popc(dw);
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) s_dcount = c;
-      }
+    /* phase 0: the prefetched words land in shared memory */
+    if (warp == 0) {
+      if (lane < 3) s_meta[lane] = pf_q;
+      sdirty[lane] = pf_dirty;
+      sgoff[lane] = pf_goff;
+      if (lane == 0) sgoff[ng] = pf_glast;
+      int c = __popc(pf_dirty);
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) s_dcount = c;
     }
     __syncthreads();
+    if (hn < n) prefetch(ent_n);
+    const int4 q0 = s_meta[0], q1 = s_meta[1], q2 = s_meta[2];
     const int dcount = s_dcount;
     const bool anyd = dcount > 0;
-    if (!anyd && !do_b) continue;
+    h = hn;
+    ent = ent_n;
+    if (!(q2.w & (1 << 16)) || !(anyd || do_b)) continue;
+    const int sb = q0.z, SB = q0.w;
+    const int X = q1.x, eb = q1.y, eown = q1.z, ehalo = q1.w, ne = q1.z + q1.w;
+    const int UA = (U + 3) & ~3;
     const int nstaged = SB + (anyd ? X : 0);
     const int nloc_a = dsc_tile_nloc_a(U, SB, X);
     const int v2w = anyd ? (int)(sgoff[ng] - sgoff[0]) : 0;
@@ -1170,46 +1244,11 @@ __global__ void __launch_bounds__(NT_BLOCK, 4) k_normals_tile(DevMesh m, const i
         }
       }
     }
-    /* phase 2: poly normals of the local entries.  When few verts of the tile are dirty, entries
-     * that touch no dirty unique vert are skipped (nothing will read them). */
+    /* phase 2: poly normals of the local entries */
     if (anyd) {
       const bool sparse = dcount * 2 < U;
-#pragma unroll 2
-      for (int e = tid; e < ne; e += NT_BLOCK) {
-        const ushort4 v = E[e];
-        if (sparse) {
-          bool need = false;
-          const unsigned li[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if (li[k] < (unsigned)U) need |= ((sdirty[li[k] >> 5] >> (li[k] & 31)) & 1u) != 0u;
-          }
-          if (!need) continue;
-        }
-        float ox = 0.0f, oy = 0.0f, oz = 0.0f;
-        if (e < eown || H[e - eown]) {
-          const float ax = PX[v.x], ay = PY[v.x], az = PZ[v.x];
-          const float bx = PX[v.y], by = PY[v.y], bz = PZ[v.y];
-          const float cx = PX[v.z], cy = PY[v.z], cz = PZ[v.z];
-          float n1x, n1y, n1z, n2x, n2y, n2z;
-          if (v.w != 0xffffu) {
-            /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
-            const float dx = PX[v.w], dy = PY[v.w], dz = PZ[v.w];
-            n1x = ax - cx; n1y = ay - cy; n1z = az - cz;
-            n2x = bx - dx; n2y = by - dy; n2z = bz - dz;
-          }
-          else {
-            /* normal_tri_v3, lib/intern/math_geom.cc:31-49 */
-            n1x = ax - bx; n1y = ay - by; n1z = az - bz;
-            n2x = bx - cx; n2y = by - cy; n2z = bz - cz;
-          }
-          ox = n1y * n2z - n1z * n2y;
-          oy = n1z * n2x - n1x * n2z;
-          oz = n1x * n2y - n1y * n2x;
-          dsc_normalize(ox, oy, oz);
-        }
-        F[e] = make_float4(ox, oy, oz, 0.0f);
-      }
+      if (q2.w & (1 << 17)) dsc_tile_poly_normals<true>(PX, PY, PZ, E, F, H, sdirty, tid, U, eown, ne, sparse);
+      else dsc_tile_poly_normals<false>(PX, PY, PZ, E, F, H, sdirty, tid, U, eown, ne, sparse);
     }
     __syncthreads();
     if (do_b && warp == 0) {

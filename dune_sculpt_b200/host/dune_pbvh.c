@@ -558,6 +558,20 @@ void DUNE_pbvh_device_detach(PBVH *pbvh)
   }
 }
 
+int DUNE_pbvh_device_checkpoint(PBVH *pbvh)
+{
+  if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
+  return dsc_state_save(pbvh->device);
+}
+
+int DUNE_pbvh_device_rollback(PBVH *pbvh)
+{
+  if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
+  const int r = dsc_state_restore(pbvh->device);
+  if (r == DSC_OK) pbvh->device_dirty = true;
+  return r;
+}
+
 int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
 {
   if (!pbvh || !pbvh->device) return DSC_ERR_STATE;

@@ -152,6 +152,9 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
 void DUNE_pbvh_device_detach(PBVH *pbvh);
 /* bring host arrays (verts, normals, node boxes, flags) up to date with the device */
 int DUNE_pbvh_device_sync_to_host(PBVH *pbvh);
+/* checkpoint / rollback of the device-resident mesh (operator cancel, undo restore): device-to-device */
+int DUNE_pbvh_device_checkpoint(PBVH *pbvh);
+int DUNE_pbvh_device_rollback(PBVH *pbvh);
 const char *DUNE_pbvh_device_error(const PBVH *pbvh);
 
 /* ---- traversal: pbvh.c:2736-2767 ---- */

@@ -201,6 +201,12 @@ int dsc_download_node_flags(DscContext *ctx, int *r_flags /* [totnode] */);
 /* undo-node membership of the running / last stroke: r_touched[node] = 1 */
 int dsc_download_touched(DscContext *ctx, unsigned char *r_touched /* [totnode] */);
 int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_coords_apply */
+/* Checkpoint / rollback of the resident mesh state (positions, normals, node boxes and flags) by
+ * device-to-device copies: what operator cancel / the undo restore do on the host side of the
+ * reference (undo nodes written back, paint_hide.c:78, then BKE_pbvh_update_bounds), without the
+ * mesh crossing PCIe.  Not inside a stroke.  Queued on the stream like a dab. */
+int dsc_state_save(DscContext *ctx);
+int dsc_state_restore(DscContext *ctx);
 int dsc_synchronize(DscContext *ctx);
 
 /* --- multi-GPU: one process per GPU, the PBVH partitioned spatially (contiguous runs of leaves in

@@ -258,3 +258,40 @@ def test_c4_tools_reduced_grid():
         dabs = stroke.c4_tool_stroke(tool, diag, dabs=12)
         r = run_parity(m, dabs, mask=mask, automask=auto, check_every=3)
         assert r["moved"] > 0, tool
+
+
+def test_c3_radius_sweep_reduced_grid():
+    """config C3 on a 768^2 grid (589,824 verts, multi-tile leaves): draw + normals + bounds per dab,
+    radius sweep 1-50 % of the diagonal, 2 dabs per radius"""
+    m = meshgen.grid(768)
+    dabs = stroke.c3_radius_sweep(m.bbox_diag(), dabs_per_radius=2)
+    r = run_parity(m, dabs, check_every=1)
+    assert r["moved"] > 0
+
+
+def test_checkpoint_rollback_repeats_the_stroke_bit_for_bit():
+    """dsc_state_save / dsc_state_restore: after a rollback the same stroke gives the same mesh
+    (what bench.py relies on to make every step identical), and the host arrays follow"""
+    m = meshgen.grid(300)
+    dabs = stroke.c3_radius_sweep(m.bbox_diag(), dabs_per_radius=2)
+    ses = capi.SculptSession(m, device=0)
+    try:
+        co0, no0 = ses.co(), ses.no()
+        bb0, obb0 = ses.node_bb()
+        ses.checkpoint()
+        outs = []
+        for _ in range(2):
+            ses.stroke_begin()
+            for d in dabs:
+                ses.dab(d)
+            ses.stroke_end()
+            outs.append((ses.co(), ses.no(), ses.node_bb(), ses.stats()["vertex_dabs"]))
+            ses.rollback()
+            assert np.array_equal(ses.co(), co0) and np.array_equal(ses.no(), no0)
+            bb, obb = ses.node_bb()
+            assert np.array_equal(bb, bb0) and np.array_equal(obb, obb0)
+        assert not np.array_equal(outs[0][0], co0)
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        assert np.array_equal(outs[0][2][0], outs[1][2][0]) and outs[0][3] == outs[1][3]
+    finally:
+        ses.close()
