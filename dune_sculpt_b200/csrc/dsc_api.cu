@@ -16,7 +16,7 @@
 #include <vector>
 
 #define DSC_ABI_VERSION 1
-#define DSC_SMEM_BUDGET (216 * 1024) /* dynamic shared memory a leaf may ask of k_normals_bb_smem */
+#define DSC_TILE_SMEM_BUDGET (96 * 1024) /* shared memory one tile may ask of k_normals_tile; heavier tiles take the general path */
 
 static thread_local std::string g_create_error;
 
@@ -34,7 +34,7 @@ struct DscContext {
   int num_sms = 148;
   cudaStream_t stream = nullptr;  /* the dab pipeline */
   cudaStream_t stream2 = nullptr; /* bottom-up box refit, overlapped with the next dab */
-  cudaEvent_t ev_fork = nullptr, ev_bb = nullptr, ev_refit[DSC_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_bb = nullptr, ev_tag = nullptr, ev_refit[DSC_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   bool side_busy = false; /* something was queued on stream2 since the last join */
   std::string error;
   std::vector<void *> allocs;
@@ -398,6 +398,7 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
             cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_bb, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_tag, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreate(&ctx->t0) == cudaSuccess && cudaEventCreate(&ctx->t1) == cudaSuccess &&
             cudaMallocHost((void **)&ctx->h_state, sizeof(DabState)) == cudaSuccess &&
             cudaMallocHost((void **)&ctx->h_tot, sizeof(StrokeTotals)) == cudaSuccess;
@@ -430,6 +431,7 @@ void dsc_ctx_destroy(DscContext *ctx)
   cudaEventDestroy(ctx->t1);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_bb);
+  cudaEventDestroy(ctx->ev_tag);
   for (int i = 0; i < DSC_SLOTS; i++) cudaEventDestroy(ctx->ev_refit[i]);
   cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
@@ -785,6 +787,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     std::vector<unsigned> rows, raw, goff_local; /* entry ids of the current group, [row][lane]; bit 31 = other-leaf entry */
     int next_group_to_fill = 0;
     size_t max_smem = 0;
+    struct TileDims { int tile, nloc_a, ne, v2w, ehalo; };
+    std::vector<TileDims> tile_dims;
     for (int l = 0; l < L; l++) {
       const int n = leaves[l];
       const int U_leaf = leaf_ucnt[l], S = leaf_scnt[l];
@@ -950,12 +954,17 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         e_halo_leaf.insert(e_halo_leaf.end(), halo_leaves.begin(), halo_leaves.end());
         tm.ntfast = allquad ? 1 << 17 : 0;
         const size_t bytes = dsc_tile_smem_bytes(dsc_tile_nloc_a(U, tm.sbb, tm.xcnt), ne, (int)(raw.size() / 2), ehalo);
-        if (bytes > DSC_SMEM_BUDGET) ok = false;
-        else max_smem = std::max(max_smem, bytes);
+        if (bytes > DSC_TILE_SMEM_BUDGET) {
+          ok = false; /* a tile this heavy would push the regions past what an SM can hold: general path */
+        }
+        else {
+          tile_dims.push_back({tg, dsc_tile_nloc_a(U, tm.sbb, tm.xcnt), ne, (int)(raw.size() / 2), ehalo});
+        }
       }
       if (!ok) {
         leaf_fast[l] = 0;
         ctx->any_slow_leaf = true;
+        while (!tile_dims.empty() && tile_dims.back().tile >= t_lo) tile_dims.pop_back();
       }
       for (int tg = t_lo; tg < t_hi; tg++) tmeta[tg].ntfast |= (t_hi - t_lo) | (ok ? 1 << 16 : 0); /* bit 17: all entries are quads */
       if (t_hi - t_lo > 0xffff) return fail(ctx, DSC_ERR_UNSUPPORTED, "leaf %d has too many tiles", l);
@@ -963,7 +972,29 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     for (; next_group_to_fill <= VP / 32; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
     if (v2_idx.empty()) v2_idx.push_back(0u);
     e_pv.insert(e_pv.end(), 8, (unsigned short)0); /* the last tile's bulk copy may read one entry past its own */
-    ctx->nb_smem = std::max<size_t>(max_smem, 1024);
+    {
+      /* every shared-memory region is sized for the largest fast tile, so it never moves between tiles */
+      int mx_nloc = 4, mx_ne = 1, mx_v2 = 32, mx_h = 16;
+      for (const TileDims &t : tile_dims) {
+        mx_nloc = std::max(mx_nloc, t.nloc_a);
+        mx_ne = std::max(mx_ne, t.ne);
+        mx_v2 = std::max(mx_v2, t.v2w);
+        mx_h = std::max(mx_h, t.ehalo);
+      }
+      m.sm_off_f = 12 * mx_nloc;
+      m.sm_off_e = m.sm_off_f + 16 * (mx_ne + 1);
+      m.sm_off_v2 = m.sm_off_e + 8 * ((mx_ne + 1) & ~1);
+      m.sm_off_h = m.sm_off_v2 + 4 * mx_v2;
+      ctx->nb_smem = (size_t)m.sm_off_h + (((size_t)mx_h + 15) & ~(size_t)15);
+      (void)max_smem;
+      if (ctx->nb_smem > 220 * 1024) {
+        /* the regions' maxima do not fit one SM together: every leaf takes the general path */
+        std::fill(leaf_fast.begin(), leaf_fast.end(), (unsigned char)0);
+        for (TileMeta &t : tmeta) t.ntfast &= ~(1 << 16);
+        ctx->any_slow_leaf = true;
+        ctx->nb_smem = 1024;
+      }
+    }
 
     static_assert(sizeof(TileMeta) == 3 * sizeof(int4), "TileMeta is three int4");
     if ((r = dev_upload_c(ctx, &m.stage_slots, stage)) || (r = dev_upload_c(ctx, &m.e_pv, e_pv)) ||
@@ -973,8 +1004,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_upload_c(ctx, &m.leaf_fast, leaf_fast)))
       return r;
     m.ntile = NT;
-    if ((r = dev_zero(ctx, &m.tile_bb, (size_t)6 * std::max(NT, 1))) || (r = dev_zero(ctx, &m.leaf_tcnt, (size_t)std::max(L, 1))) ||
-        (r = dev_zero(ctx, &m.tile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
+    if ((r = dev_zero(ctx, &m.tile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
         (r = dev_zero(ctx, &m.atile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
         (r = dev_zero(ctx, &m.flag_tile_list, (size_t)std::max(NT, 1))))
       return r;
@@ -1115,7 +1145,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   /* launch shape of the shared-memory normals kernel */
   CU(cudaFuncSetAttribute(k_normals_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
   int occ = 1;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_tile, NT_BLOCK, ctx->nb_smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_tile, NT_THREADS, ctx->nb_smem));
   ctx->nb_grid = ctx->num_sms * std::max(occ, 1);
 
   /* multi-GPU: owned leaf run, hit-mask ring, halo index lists */
@@ -1223,7 +1253,7 @@ static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode)
 {
   {
     StageScope s(ctx, ST_NORMALS);
-    k_normals_tile<<<ctx->nb_grid, NT_BLOCK, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.tiles, ll.tile_count, mode, ll.mask);
+    k_normals_tile<<<ctx->nb_grid, NT_THREADS, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.tiles, ll.tile_count, mode, ll.mask);
     LAUNCH_CHECK();
   }
   if (ctx->any_slow_leaf) {
@@ -1261,6 +1291,11 @@ static int run_flagged(DscContext *ctx, int want)
   if ((r = join_side(ctx))) return r;
   if ((r = run_collect(ctx, want))) return r;
   const int mode = ((want & F_UpdateNormals) ? NB_NORMALS : 0) | ((want & F_UpdateBB) ? NB_BOUNDS : 0);
+  if (want & F_UpdateBB) {
+    StageScope s(ctx, ST_OTHER);
+    k_reset_leaf_boxes<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->m.flag_list, &ctx->m.tot->flag_count, F_UpdateBB);
+    LAUNCH_CHECK();
+  }
   if ((r = run_normals_bounds(ctx, flag_list(ctx), mode))) return r;
   if ((want & F_UpdateBB) && (r = run_flush_full(ctx))) return r;
   return run_clear(ctx, flag_list(ctx), want);
@@ -1483,9 +1518,12 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     /* side stream: tag the ancestors of the hit leaves for the bottom-up refit while the brush runs */
     CU(cudaEventRecord(ctx->ev_fork, st));
     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    StageScope s(ctx, ST_FLUSH, ctx->stream2);
-    k_tag_ancestors<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, hits.list, hits.count);
-    LAUNCH_CHECK();
+    {
+      StageScope s(ctx, ST_FLUSH, ctx->stream2);
+      k_tag_ancestors<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, hits.list, hits.count, 1);
+      LAUNCH_CHECK();
+    }
+    CU(cudaEventRecord(ctx->ev_tag, ctx->stream2)); /* the tile kernel accumulates into the emptied leaf boxes */
     ctx->side_busy = true;
   }
   /* 2.-3. brush */
@@ -1544,6 +1582,16 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
   /* 4. normals, 5. bounds */
   if (use_hits) {
     const int mode = (do_normals ? NB_NORMALS : 0) | (do_bounds ? NB_BOUNDS : 0);
+    if (do_bounds) {
+      if (!dist) {
+        CU(cudaStreamWaitEvent(st, ctx->ev_tag, 0));
+      }
+      else {
+        StageScope s(ctx, ST_OTHER);
+        k_reset_leaf_boxes<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, hits.list, hits.count, 0);
+        LAUNCH_CHECK();
+      }
+    }
     if (mode) {
       if ((r = run_normals_bounds(ctx, hits, mode))) return r;
     }
@@ -1853,9 +1901,9 @@ int dsc_state_save(DscContext *ctx)
   int r = join_side(ctx);
   if (r) return r;
   DevMesh &m = ctx->m;
-  const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode, NT = (size_t)std::max(m.ntile, 1);
+  const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode;
   if (!ctx->d_save_v) {
-    if ((r = dev_alloc(ctx, &ctx->d_save_v, 6 * VP)) || (r = dev_alloc(ctx, &ctx->d_save_bb, 12 * N + 6 * NT)) ||
+    if ((r = dev_alloc(ctx, &ctx->d_save_v, 6 * VP)) || (r = dev_alloc(ctx, &ctx->d_save_bb, 12 * N)) ||
         (r = dev_alloc(ctx, &ctx->d_save_flag, N)))
       return r;
   }
@@ -1863,7 +1911,6 @@ int dsc_state_save(DscContext *ctx)
   for (int k = 0; k < 6; k++) CU(cudaMemcpyAsync(ctx->d_save_v + k * VP, src[k], VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_save_bb, m.bb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_save_bb + 6 * N, m.obb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_save_bb + 12 * N, m.tile_bb, 6 * NT * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_save_flag, m.node_flag, N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->save_stale_flags = ctx->stale_flags;
   ctx->have_save = true;
@@ -1877,12 +1924,11 @@ int dsc_state_restore(DscContext *ctx)
   int r = join_side(ctx);
   if (r) return r;
   DevMesh &m = ctx->m;
-  const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode, NT = (size_t)std::max(m.ntile, 1);
+  const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode;
   float *dst[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
   for (int k = 0; k < 6; k++) CU(cudaMemcpyAsync(dst[k], ctx->d_save_v + k * VP, VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(m.bb, ctx->d_save_bb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(m.obb, ctx->d_save_bb + 6 * N, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(m.tile_bb, ctx->d_save_bb + 12 * N, 6 * NT * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(m.node_flag, ctx->d_save_flag, N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemsetAsync(m.dirty, 0, sizeof(unsigned) * (size_t)ctx->nwords, ctx->stream));
   ctx->stale_flags = ctx->save_stale_flags;

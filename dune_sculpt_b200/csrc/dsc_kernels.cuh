@@ -91,9 +91,10 @@ struct DevMesh {
    * padding points at the tile's zero entry */
   const unsigned *v2_goff;    /* [slots / 32 + 1], in words */
   const unsigned *v2_idx;
-  float *tile_bb;             /* [6][ntile] box of the tile's unique + box-counted staged verts */
-  int *leaf_tcnt;             /* tiles of the leaf whose box is done (this dab) */
   const unsigned char *leaf_fast;
+  /* byte offsets of the tile kernel's shared-memory regions (sized for the largest tile of the mesh, so a region
+   * never moves between tiles): positions at 0, then poly normals, poly entries, index words, other-leaf switches */
+  int sm_off_f, sm_off_e, sm_off_v2, sm_off_h;
   /* leaves */
   int nleaf;
   int max_chunks; /* ceil(max uniq_verts / DSC_CHUNK) */
@@ -394,14 +395,39 @@ __global__ void __launch_bounds__(1024) k_collect_flagged(DevMesh m, int flags)
   }
 }
 
-/* Bottom-up refit, pass 1: tags the ancestors of the listed leaves.  pending[p] gets bit 1 / bit 2
- * when a leaf below its first / second child is listed.  A walker stops at the first node that
- * already carries its bit (somebody else tagged everything above). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, const int *list, const int *count)
+/* Before the tile kernel accumulates tile boxes into them (dsc_red_min / dsc_red_max), the boxes of
+ * the listed leaves that take the tile path start from the empty box. */
+__device__ __forceinline__ void dsc_reset_leaf_box(const DevMesh &m, int leaf)
+{
+  if (!m.leaf_fast[leaf]) return;
+  const int tn = m.totnode;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    m.bb[k * tn + leaf] = 3.402823466e+38f;
+    m.bb[(3 + k) * tn + leaf] = -3.402823466e+38f;
+  }
+}
+__global__ void __launch_bounds__(DSC_BLOCK) k_reset_leaf_boxes(DevMesh m, const int *list, const int *count, int need_flag)
 {
   const int n = *count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int4 t = m.topo[list[i]];
+    const int l = list[i];
+    if (!need_flag || (m.node_flag[l] & need_flag)) dsc_reset_leaf_box(m, l);
+  }
+}
+
+/* Bottom-up refit, pass 1: tags the ancestors of the listed leaves.  pending[p] gets bit 1 / bit 2
+ * when a leaf below its first / second child is listed.  A walker stops at the first node that
+ * already carries its bit (somebody else tagged everything above).  With reset_boxes the leaf boxes
+ * are emptied on the way: this kernel is ordered after the previous dab's refit (same stream), which
+ * is the last reader of the old boxes, and before this dab's tile kernel (event). */
+__global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, const int *list, const int *count, int reset_boxes)
+{
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int leaf = list[i];
+    if (reset_boxes) dsc_reset_leaf_box(m, leaf);
+    int4 t = m.topo[leaf];
     while (t.x >= 0) {
       const int4 tp = m.topo[t.x]; /* in flight together with the atomic */
       const int old = atomicOr(&m.pending[t.x], t.y);
@@ -977,7 +1003,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *lis
 }
 
 /* ----------------------------------------------------------- K5 + K6 fused, shared-memory form */
-#define NT_BLOCK 256
+#define NT_BLOCK 256 /* compute threads of the tile kernel */
 #define NB_NORMALS 1
 #define NB_BOUNDS 2
 /* tile_meta: 3 x int4 per tile */
@@ -986,9 +1012,9 @@ struct TileMeta {
   int xcnt, ebeg, eown, ehalo;   /* further staged verts; entries: offset (even), own-leaf, other-leaf */
   int hbeg, leaf, tile0, ntfast; /* e_halo_leaf offset; leaf; its first tile; tile count | fast << 16 */
 };
-/* shared-memory carve of one tile (host and device agree through these formulas): positions SoA
- * [3][nloc_a], poly normals float4 [ne + 1], poly entries ushort4 [ne_a], index words [v2w],
- * other-leaf entry switches [ehalo] */
+/* shared-memory regions of the tile kernel: positions SoA [3][nloc_a], poly normals float4 [ne + 1],
+ * poly entries ushort4 [ne_a], index words [v2w], other-leaf entry switches [ehalo]; each region is
+ * sized for the largest tile of the mesh (DevMesh.sm_off_*) */
 __host__ __device__ inline int dsc_tile_nloc_a(int ucnt, int sbb, int xcnt) { return (((ucnt + 3) & ~3) + sbb + xcnt + 3) & ~3; }
 __host__ __device__ inline size_t dsc_tile_smem_bytes(int nloc_a, int ne, int v2w, int ehalo)
 {
@@ -1100,127 +1126,208 @@ __device__ __forceinline__ void dsc_tile_poly_normals(const float *PX, const flo
   }
 }
 
-__global__ void __launch_bounds__(NT_BLOCK, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
-                                                              const unsigned *upd)
+/* order-free float min / max into global memory (fire-and-forget RED: no return value, no stall) */
+__device__ __forceinline__ void dsc_red_min(float *a, float v)
+{
+  v = v + 0.0f; /* -0 -> +0 */
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void dsc_red_max(float *a, float v)
+{
+  v = v + 0.0f;
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(a), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+
+#define NT_CONSUMERS 256                 /* 8 compute warps */
+#define NT_THREADS (NT_CONSUMERS + 32)   /* + 1 producer warp */
+#define NT_UPD_WORDS 512                 /* leaf bitmask words kept in shared memory */
+#define NT_ACTIVE 1
+#define NT_ANYD 2
+#define NT_DO_B 4
+
+/* Producer / consumer form.  Warp 8 is the producer: for the NEXT tile it reads the descriptor, the
+ * dirty words and the index-row offsets, publishes them in shared memory (double buffered), queues
+ * the TMA bulk copies, gathers the staged verts and resolves the other-leaf switches -- all of it
+ * while the 8 consumer warps compute the current tile, so no compute warp ever waits on a global
+ * load.  Buffers are handed over with mbarriers: full[0] / empty[0] guard positions + entries +
+ * staged verts (consumed by the box reduction and phase 2), full[1] / empty[1] the index words
+ * (consumed by phase 3).  The consumers synchronise among themselves with a named barrier. */
+__global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
+                                                                const unsigned *upd)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ __align__(16) int4 s_meta[3];
-  __shared__ float red[6][NT_BLOCK / 32];
-  __shared__ unsigned sdirty[DSC_TILE / 32];
-  __shared__ unsigned sgoff[DSC_TILE / 32 + 1];
-  __shared__ int s_dcount;
-  constexpr int NW = NT_BLOCK / 32;
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  __shared__ __align__(16) int4 s_q[2][3];
+  __shared__ __align__(16) int4 s_ent[2]; /* {tile, first slot, unique verts, NT_* flags | dirty count << 8} */
+  __shared__ float red[6][NT_CONSUMERS / 32];
+  __shared__ unsigned sdirty[2][DSC_TILE / 32];
+  __shared__ unsigned sgoff[2][DSC_TILE / 32 + 1];
+  __shared__ unsigned s_upd[NT_UPD_WORDS];
+  constexpr int NW = NT_CONSUMERS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
   const int n = *count;
-  if (tid == 0) dsc_mbar_init(&s_bar, NT_BLOCK);
-  unsigned parity = 0;
-  int h = blockIdx.x;
-  if (h >= n) return;
-  int4 ent = list[h];
-  /* warp 0 keeps the next tile's descriptor, dirty words and index offsets in flight (registers)
-   * while the current tile is processed */
-  int4 pf_q = make_int4(0, 0, 0, 0);
-  unsigned pf_dirty = 0u, pf_goff = 0u, pf_glast = 0u;
-  auto prefetch = [&](const int4 &e) {
-    if (warp != 0) return;
-    const int ngn = (e.z + 31) >> 5, g0n = e.y >> 5;
-    const bool dn = (mode & NB_NORMALS) && (e.w & DSC_ENT_NORMALS);
-    if (lane < 3) pf_q = m.tile_meta[3 * e.x + lane];
-    pf_dirty = (dn && lane < ngn) ? m.dirty[g0n + lane] : 0u;
-    pf_goff = (dn && lane < ngn) ? m.v2_goff[g0n + lane] : 0u;
-    pf_glast = (dn && lane == 0) ? m.v2_goff[g0n + ngn] : 0u;
-  };
-  prefetch(ent);
-  while (h < n) {
-    const int hn = h + (int)gridDim.x;
-    int4 ent_n = make_int4(0, 0, 0, 0);
-    if (hn < n) ent_n = list[hn];
-    const int tile = ent.x;
-    const int ub = ent.y, U = ent.z;
+  if ((int)blockIdx.x >= n) return;
+  const bool upd_shared = m.ghit_words <= NT_UPD_WORDS;
+  if (upd_shared) {
+    for (int w = tid; w < m.ghit_words; w += NT_THREADS) s_upd[w] = upd[w];
+  }
+  if (tid == 0) {
+    dsc_mbar_init(&s_full[0], 32);          /* the producer lanes (+ TMA bytes) */
+    dsc_mbar_init(&s_full[1], 1);           /* TMA bytes only */
+    dsc_mbar_init(&s_empty[0], NW);         /* one arrival per consumer warp */
+    dsc_mbar_init(&s_empty[1], NW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    /* ------------------------------------------------------------------ producer warp */
+    unsigned par_e0 = 1u, par_e1 = 1u; /* a fresh mbarrier passes a wait on the previous phase */
+    int4 ent = list[blockIdx.x];
+    int k = 0;
+    for (int h = blockIdx.x; h < n; h += gridDim.x, k++) {
+      const int set = k & 1;
+      const int hn = h + (int)gridDim.x;
+      int4 ent_n = make_int4(0, 0, 0, 0);
+      if (hn < n) ent_n = list[hn];
+      const int tile = ent.x, ub = ent.y, U = ent.z;
+      const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
+      const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
+      const int ng = (U + 31) >> 5, G0 = ub >> 5;
+      int4 q = make_int4(0, 0, 0, 0);
+      if (lane < 3) q = m.tile_meta[3 * tile + lane];
+      const unsigned dw = (do_n && lane < ng) ? m.dirty[G0 + lane] : 0u;
+      const unsigned go = (do_n && lane < ng) ? m.v2_goff[G0 + lane] : 0u;
+      unsigned glast = (do_n && lane == 0) ? m.v2_goff[G0 + ng] : 0u;
+      int dcount = __popc(dw);
+      for (int o = 16; o > 0; o >>= 1) dcount += __shfl_xor_sync(0xffffffffu, dcount, o);
+      const unsigned goff0 = __shfl_sync(0xffffffffu, go, 0);
+      glast = __shfl_sync(0xffffffffu, glast, 0);
+      const int sb = __shfl_sync(0xffffffffu, q.z, 0), SB = __shfl_sync(0xffffffffu, q.w, 0);
+      const int X = __shfl_sync(0xffffffffu, q.x, 1), eb = __shfl_sync(0xffffffffu, q.y, 1);
+      const int eown = __shfl_sync(0xffffffffu, q.z, 1), ehalo = __shfl_sync(0xffffffffu, q.w, 1);
+      const int hb = __shfl_sync(0xffffffffu, q.x, 2), ntfast = __shfl_sync(0xffffffffu, q.w, 2);
+      const bool anyd = dcount > 0;
+      const bool active = (ntfast & (1 << 16)) && (anyd || do_b);
+      /* positions / entries / staged verts / descriptor of tile k - 1 are released */
+      dsc_mbar_wait(&s_empty[0], par_e0);
+      par_e0 ^= 1u;
+      if (lane < 3) s_q[set][lane] = q;
+      sdirty[set][lane] = dw;
+      sgoff[set][lane] = go;
+      if (lane == 0) {
+        sgoff[set][ng] = glast;
+        s_ent[set] = make_int4(tile, ub, U, (active ? NT_ACTIVE : 0) | (anyd ? NT_ANYD : 0) | (do_b ? NT_DO_B : 0) | (dcount << 8));
+      }
+      const int ne = eown + ehalo;
+      const int UA = (U + 3) & ~3;
+      const int nloc_a = dsc_tile_nloc_a(U, SB, X);
+      const int v2w = anyd ? (int)(glast - goff0) : 0;
+      float *PX = reinterpret_cast<float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
+      ushort4 *E = reinterpret_cast<ushort4 *>(smem_raw + m.sm_off_e);
+      unsigned *V2 = reinterpret_cast<unsigned *>(smem_raw + m.sm_off_v2);
+      unsigned char *H = smem_raw + m.sm_off_h;
+      if (active) {
+        if (lane == 0) {
+          const unsigned pbytes = 4u * (unsigned)UA;
+          const unsigned ebytes = anyd ? 8u * (unsigned)((ne + 1) & ~1) : 0u;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (3u * pbytes + ebytes) dsc_mbar_expect_tx(&s_full[0], 3u * pbytes + ebytes);
+          if (pbytes) {
+            dsc_bulk_g2s(PX, m.cx + ub, pbytes, &s_full[0]);
+            dsc_bulk_g2s(PY, m.cy + ub, pbytes, &s_full[0]);
+            dsc_bulk_g2s(PZ, m.cz + ub, pbytes, &s_full[0]);
+          }
+          if (ebytes) dsc_bulk_g2s(E, m.e_pv + eb, ebytes, &s_full[0]);
+        }
+        /* staged verts: 4 x 32 at a time, index loads first, then the 12 position loads, then the stores */
+        const int nstaged = SB + (anyd ? X : 0);
+        for (int i0 = 0; i0 < nstaged; i0 += 128) {
+          int sl[4];
+          float x[4], y[4], z[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * 32 + lane;
+            sl[u] = (i < nstaged) ? m.stage_slots[sb + i] : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            x[u] = m.cx[sl[u]]; y[u] = m.cy[sl[u]]; z[u] = m.cz[sl[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * 32 + lane;
+            if (i < nstaged) {
+              PX[UA + i] = x[u]; PY[UA + i] = y[u]; PZ[UA + i] = z[u];
+            }
+          }
+        }
+        if (anyd) {
+          for (int i = lane; i < ehalo; i += 32) {
+            const int ol = m.e_halo_leaf[hb + i];
+            const unsigned w = upd_shared ? s_upd[ol >> 5] : upd[ol >> 5];
+            H[i] = (unsigned char)((w >> (ol & 31)) & 1u);
+          }
+        }
+      }
+      dsc_mbar_arrive(&s_full[0]);
+      if (active && anyd) {
+        /* index words: their buffer is released when phase 3 of the previous tile that had one is done */
+        dsc_mbar_wait(&s_empty[1], par_e1);
+        par_e1 ^= 1u;
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          dsc_mbar_expect_tx(&s_full[1], 4u * (unsigned)v2w);
+          dsc_bulk_g2s(V2, m.v2_idx + goff0, 4u * (unsigned)v2w, &s_full[1]);
+          asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(dsc_smem_u32(&s_full[1])) : "memory");
+        }
+      }
+      ent = ent_n;
+    }
+    return;
+  }
+
+  /* -------------------------------------------------------------------- consumer warps */
+  unsigned par_f0 = 0u, par_f1 = 0u;
+  int k = 0;
+  for (int h = blockIdx.x; h < n; h += gridDim.x, k++) {
+    const int set = k & 1;
+    dsc_mbar_wait(&s_full[0], par_f0);
+    par_f0 ^= 1u;
+    const int4 ent = s_ent[set];
+    const int flags = ent.w;
+    if (!(flags & NT_ACTIVE)) {
+      __syncwarp();
+      if (lane == 0) dsc_mbar_arrive(&s_empty[0]);
+      continue;
+    }
+    const int4 q0 = s_q[set][0], q1 = s_q[set][1], q2 = s_q[set][2];
+    const int ub = ent.y, U = ent.z, dcount = flags >> 8;
+    const bool anyd = (flags & NT_ANYD) != 0, do_b = (flags & NT_DO_B) != 0;
+    const int SB = q0.w, X = q1.x, eown = q1.z, ne = q1.z + q1.w;
     const int ng = (U + 31) >> 5, G0 = ub >> 5;
-    const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
-    const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
-    __syncthreads(); /* the previous tile is done with the shared arrays (and the mbarrier is initialised) */
-    /* phase 0: the prefetched words land in shared memory */
-    if (warp == 0) {
-      if (lane < 3) s_meta[lane] = pf_q;
-      sdirty[lane] = pf_dirty;
-      sgoff[lane] = pf_goff;
-      if (lane == 0) sgoff[ng] = pf_glast;
-      int c = __popc(pf_dirty);
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if (lane == 0) s_dcount = c;
-    }
-    __syncthreads();
-    if (hn < n) prefetch(ent_n);
-    const int4 q0 = s_meta[0], q1 = s_meta[1], q2 = s_meta[2];
-    const int dcount = s_dcount;
-    const bool anyd = dcount > 0;
-    h = hn;
-    ent = ent_n;
-    if (!(q2.w & (1 << 16)) || !(anyd || do_b)) continue;
-    const int sb = q0.z, SB = q0.w;
-    const int X = q1.x, eb = q1.y, eown = q1.z, ehalo = q1.w, ne = q1.z + q1.w;
     const int UA = (U + 3) & ~3;
-    const int nstaged = SB + (anyd ? X : 0);
     const int nloc_a = dsc_tile_nloc_a(U, SB, X);
-    const int v2w = anyd ? (int)(sgoff[ng] - sgoff[0]) : 0;
-    float *PX = reinterpret_cast<float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
-    float4 *F = reinterpret_cast<float4 *>(PZ + nloc_a); /* [ne + 1], entry ne = zero */
-    const ushort4 *E = reinterpret_cast<const ushort4 *>(F + ne + 1);
-    const unsigned *V2 = reinterpret_cast<const unsigned *>(E + ((ne + 1) & ~1));
-    unsigned char *H = reinterpret_cast<unsigned char *>(const_cast<unsigned *>(V2) + v2w);
-    /* phase 1 */
-    if (tid == 0) {
-      const unsigned pbytes = 4u * (unsigned)UA;
-      const unsigned ebytes = anyd ? 8u * (unsigned)((ne + 1) & ~1) : 0u;
-      const unsigned vbytes = 4u * (unsigned)v2w;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      dsc_mbar_expect_tx(&s_bar, 3u * pbytes + ebytes + vbytes);
-      if (pbytes) {
-        dsc_bulk_g2s(PX, m.cx + ub, pbytes, &s_bar);
-        dsc_bulk_g2s(PY, m.cy + ub, pbytes, &s_bar);
-        dsc_bulk_g2s(PZ, m.cz + ub, pbytes, &s_bar);
-      }
-      if (ebytes) dsc_bulk_g2s(const_cast<ushort4 *>(E), m.e_pv + eb, ebytes, &s_bar);
-      if (vbytes) dsc_bulk_g2s(const_cast<unsigned *>(V2), m.v2_idx + sgoff[0], vbytes, &s_bar);
-      F[ne] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
-    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    for (int i = tid; i < nstaged; i += NT_BLOCK) {
-      const int s = m.stage_slots[sb + i];
-      const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
-      PX[UA + i] = x; PY[UA + i] = y; PZ[UA + i] = z;
-      if (i < SB) {
-        mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
-        mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
-        mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
-      }
-    }
-    if (anyd) {
-      for (int i = tid; i < ehalo; i += NT_BLOCK) {
-        const int ol = m.e_halo_leaf[q2.x + i];
-        H[i] = (unsigned char)((upd[ol >> 5] >> (ol & 31)) & 1u);
-      }
-    }
-    dsc_mbar_arrive(&s_bar);
-    dsc_mbar_wait(&s_bar, parity);
-    parity ^= 1u;
+    const unsigned goff0 = sgoff[set][0];
+    const float *PX = reinterpret_cast<const float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
+    float4 *F = reinterpret_cast<float4 *>(smem_raw + m.sm_off_f); /* [ne + 1], entry ne = zero */
+    const ushort4 *E = reinterpret_cast<const ushort4 *>(smem_raw + m.sm_off_e);
+    const unsigned *V2 = reinterpret_cast<const unsigned *>(smem_raw + m.sm_off_v2);
+    const unsigned char *H = smem_raw + m.sm_off_h;
     if (do_b) {
-      /* box of the unique verts, four per thread straight from shared memory */
+      /* box of the unique verts (four per thread) and of the box-counted staged verts, from shared memory */
+      float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+      float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
       const int i0 = 4 * tid;
       if (i0 + 3 < U) {
         const float4 x4 = *reinterpret_cast<const float4 *>(PX + i0), y4 = *reinterpret_cast<const float4 *>(PY + i0),
                      z4 = *reinterpret_cast<const float4 *>(PZ + i0);
-        mn[0] = fminf(fminf(mn[0], x4.x), fminf(fminf(x4.y, x4.z), x4.w));
-        mx[0] = fmaxf(fmaxf(mx[0], x4.x), fmaxf(fmaxf(x4.y, x4.z), x4.w));
-        mn[1] = fminf(fminf(mn[1], y4.x), fminf(fminf(y4.y, y4.z), y4.w));
-        mx[1] = fmaxf(fmaxf(mx[1], y4.x), fmaxf(fmaxf(y4.y, y4.z), y4.w));
-        mn[2] = fminf(fminf(mn[2], z4.x), fminf(fminf(z4.y, z4.z), z4.w));
-        mx[2] = fmaxf(fmaxf(mx[2], z4.x), fmaxf(fmaxf(z4.y, z4.z), z4.w));
+        mn[0] = fminf(fminf(x4.x, x4.y), fminf(x4.z, x4.w)); mx[0] = fmaxf(fmaxf(x4.x, x4.y), fmaxf(x4.z, x4.w));
+        mn[1] = fminf(fminf(y4.x, y4.y), fminf(y4.z, y4.w)); mx[1] = fmaxf(fmaxf(y4.x, y4.y), fmaxf(y4.z, y4.w));
+        mn[2] = fminf(fminf(z4.x, z4.y), fminf(z4.z, z4.w)); mx[2] = fmaxf(fmaxf(z4.x, z4.y), fmaxf(z4.z, z4.w));
       }
       else {
         for (int i = i0; i < U; i++) {
@@ -1229,100 +1336,84 @@ __global__ void __launch_bounds__(NT_BLOCK, 4) k_normals_tile(DevMesh m, const i
           mn[2] = fminf(mn[2], PZ[i]); mx[2] = fmaxf(mx[2], PZ[i]);
         }
       }
+      for (int i = tid; i < SB; i += NT_CONSUMERS) {
+        mn[0] = fminf(mn[0], PX[UA + i]); mx[0] = fmaxf(mx[0], PX[UA + i]);
+        mn[1] = fminf(mn[1], PY[UA + i]); mx[1] = fmaxf(mx[1], PY[UA + i]);
+        mn[2] = fminf(mn[2], PZ[UA + i]); mx[2] = fmaxf(mx[2], PZ[UA + i]);
+      }
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
+      for (int c = 0; c < 3; c++) {
         for (int o = 16; o > 0; o >>= 1) {
-          mn[k] = fminf(mn[k], __shfl_down_sync(0xffffffffu, mn[k], o));
-          mx[k] = fmaxf(mx[k], __shfl_down_sync(0xffffffffu, mx[k], o));
+          mn[c] = fminf(mn[c], __shfl_down_sync(0xffffffffu, mn[c], o));
+          mx[c] = fmaxf(mx[c], __shfl_down_sync(0xffffffffu, mx[c], o));
         }
       }
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-          red[k][warp] = mn[k];
-          red[3 + k][warp] = mx[k];
+        for (int c = 0; c < 3; c++) {
+          red[c][warp] = mn[c];
+          red[3 + c][warp] = mx[c];
         }
       }
     }
     /* phase 2: poly normals of the local entries */
     if (anyd) {
+      if (tid == 0) F[ne] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       const bool sparse = dcount * 2 < U;
-      if (q2.w & (1 << 17)) dsc_tile_poly_normals<true>(PX, PY, PZ, E, F, H, sdirty, tid, U, eown, ne, sparse);
-      else dsc_tile_poly_normals<false>(PX, PY, PZ, E, F, H, sdirty, tid, U, eown, ne, sparse);
+      if (q2.w & (1 << 17)) dsc_tile_poly_normals<true>(PX, PY, PZ, E, F, H, sdirty[set], tid, U, eown, ne, sparse);
+      else dsc_tile_poly_normals<false>(PX, PY, PZ, E, F, H, sdirty[set], tid, U, eown, ne, sparse);
     }
-    __syncthreads();
-    if (do_b && warp == 0) {
-      /* tile box; the last tile of the leaf to get here merges them into the leaf box */
-      const int leaf = q2.y;
-      float v = 0.0f;
-      if (lane < 6) {
-        v = red[lane][0];
-        for (int w = 1; w < NW; w++) v = (lane < 3) ? fminf(v, red[lane][w]) : fmaxf(v, red[lane][w]);
-      }
-      const int nt = q2.w & 0xffff;
-      if (nt == 1) {
-        if (lane < 6) {
-          m.tile_bb[lane * m.ntile + tile] = v;
-          m.bb[lane * tn + leaf] = v;
-        }
-      }
-      else {
-        if (lane < 6) __stcg(&m.tile_bb[lane * m.ntile + tile], v);
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-          last = atomicAdd(&m.leaf_tcnt[leaf], 1) == nt - 1;
-          if (last) m.leaf_tcnt[leaf] = 0;
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-          __threadfence();
-          if (lane < 6) {
-            for (int t = 0; t < nt; t++) {
-              const float o = __ldcg(&m.tile_bb[lane * m.ntile + q2.z + t]);
-              v = (lane < 3) ? fminf(v, o) : fmaxf(v, o);
-            }
-            m.bb[lane * tn + leaf] = v;
-          }
-        }
-      }
+    __syncwarp();
+    if (lane == 0) dsc_mbar_arrive(&s_empty[0]); /* positions, entries, staged verts: the producer may refill */
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (do_b && warp == 1 && lane < 6) {
+      /* the tile's share of the leaf box (the gather reset the box of every leaf it hit) */
+      float v = red[lane][0];
+      for (int w = 1; w < NW; w++) v = (lane < 3) ? fminf(v, red[lane][w]) : fmaxf(v, red[lane][w]);
+      float *dst = &m.bb[lane * tn + q2.y];
+      if (lane < 3) dsc_red_min(dst, v);
+      else dsc_red_max(dst, v);
     }
-    if (!anyd) continue;
-    /* phase 3: one warp per group of 32 verts */
-    const unsigned goff0 = sgoff[0];
-    for (int g = warp; g < ng; g += NW) {
-      const unsigned word = sdirty[g];
-      if (word == 0u) continue; /* warp-uniform */
-      if ((word >> lane) & 1u) {
-        const unsigned off = sgoff[g];
-        const int wd = (int)((sgoff[g + 1] - off) >> 5);
-        const unsigned *rp = V2 + (off - goff0) + lane;
-        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-        if (wd == 3) {
-          const unsigned w0 = rp[0], w1 = rp[32], w2 = rp[64];
-          float4 f;
-          f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
-          f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
-          f = F[w1 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
-          f = F[w1 >> 16]; sx += f.x; sy += f.y; sz += f.z;
-          f = F[w2 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
-          f = F[w2 >> 16]; sx += f.x; sy += f.y; sz += f.z;
-        }
-        else {
-          for (int j = 0; j < wd; j++) {
-            const unsigned w0 = rp[j * 32];
+    if (anyd) {
+      /* phase 3: one warp per group of 32 verts */
+      dsc_mbar_wait(&s_full[1], par_f1);
+      par_f1 ^= 1u;
+      for (int g = warp; g < ng; g += NW) {
+        const unsigned word = sdirty[set][g];
+        if (word == 0u) continue; /* warp-uniform */
+        if ((word >> lane) & 1u) {
+          const unsigned off = sgoff[set][g];
+          const int wd = (int)((sgoff[set][g + 1] - off) >> 5);
+          const unsigned *rp = V2 + (off - goff0) + lane;
+          float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+          if (wd == 3) {
+            const unsigned w0 = rp[0], w1 = rp[32], w2 = rp[64];
             float4 f;
             f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
             f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+            f = F[w1 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+            f = F[w1 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+            f = F[w2 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+            f = F[w2 >> 16]; sx += f.x; sy += f.y; sz += f.z;
           }
+          else {
+            for (int j = 0; j < wd; j++) {
+              const unsigned w0 = rp[j * 32];
+              float4 f;
+              f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+              f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+            }
+          }
+          dsc_normalize(sx, sy, sz);
+          const int s = ub + g * 32 + lane;
+          m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
         }
-        dsc_normalize(sx, sy, sz);
-        const int s = ub + g * 32 + lane;
-        m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
+        if (lane == 0) m.dirty[G0 + g] = 0u;
       }
-      if (lane == 0) m.dirty[G0 + g] = 0u;
+      __syncwarp();
+      if (lane == 0) dsc_mbar_arrive(&s_empty[1]); /* index words: the producer may refill */
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory"); /* poly normals / box partials are free for the next tile */
   }
 }
 
