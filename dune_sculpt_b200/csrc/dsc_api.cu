@@ -29,12 +29,21 @@ struct StageEvent {
   cudaEvent_t a, b;
 };
 
+struct DabGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  int stage_launches[DSC_NUM_STAGES] = {0};
+};
+
 struct DscContext {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;  /* the dab pipeline */
   cudaStream_t stream2 = nullptr; /* bottom-up box refit, overlapped with the next dab */
   cudaEvent_t ev_fork = nullptr, ev_bb = nullptr, ev_tag = nullptr, ev_refit[DSC_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  /* the same events for launches recorded into a graph (a captured event cannot be waited on outside its graph) */
+  cudaEvent_t cap_fork = nullptr, cap_bb = nullptr, cap_tag = nullptr, cap_join = nullptr, cap_refit[DSC_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   bool side_busy = false; /* something was queued on stream2 since the last join */
   std::string error;
   std::vector<void *> allocs;
@@ -82,6 +91,14 @@ struct DscContext {
   StrokeTotals *h_tot = nullptr; /* pinned */
   int *h_list = nullptr;         /* pinned, nleaf ints */
 
+  /* dab ring: pinned host staging + device copy; executable graphs by launch-sequence signature */
+  DabEntry *h_ring = nullptr, *d_ring = nullptr;
+  int *d_ring_ctl = nullptr;
+  cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::unordered_map<unsigned, DabGraph> graphs;
+  bool use_graphs = true;
+  long long graph_launches = 0, ring_seq = 0;
+
   bool capture = false;
   bool stage_timing = false;
   std::vector<StageEvent> events;
@@ -91,6 +108,15 @@ struct DscContext {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int grid = 148 * 8;
 };
+
+static void invalidate_graphs(DscContext *ctx)
+{
+  for (auto &kv : ctx->graphs) {
+    cudaGraphExecDestroy(kv.second.exec);
+    cudaGraphDestroy(kv.second.graph);
+  }
+  ctx->graphs.clear();
+}
 
 static int fail(DscContext *ctx, int code, const char *fmt, ...)
 {
@@ -401,7 +427,22 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
             cudaEventCreateWithFlags(&ctx->ev_tag, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreate(&ctx->t0) == cudaSuccess && cudaEventCreate(&ctx->t1) == cudaSuccess &&
             cudaMallocHost((void **)&ctx->h_state, sizeof(DabState)) == cudaSuccess &&
-            cudaMallocHost((void **)&ctx->h_tot, sizeof(StrokeTotals)) == cudaSuccess;
+            cudaMallocHost((void **)&ctx->h_tot, sizeof(StrokeTotals)) == cudaSuccess &&
+            cudaMallocHost((void **)&ctx->h_ring, sizeof(DabEntry) * DSC_RING) == cudaSuccess &&
+            cudaMalloc((void **)&ctx->d_ring, sizeof(DabEntry) * DSC_RING) == cudaSuccess &&
+            cudaMalloc((void **)&ctx->d_ring_ctl, sizeof(int) * 2) == cudaSuccess &&
+            cudaMemset(ctx->d_ring_ctl, 0, sizeof(int) * 2) == cudaSuccess;
+  for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < DSC_SLOTS; i++) ok = cudaEventCreateWithFlags(&ctx->cap_refit[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->cap_fork, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->cap_bb, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->cap_tag, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->cap_join, cudaEventDisableTiming) == cudaSuccess;
+  if (ok) {
+    ctx->m.ring = ctx->d_ring;
+    ctx->m.ring_ctl = ctx->d_ring_ctl;
+    ctx->use_graphs = !getenv("DSC_NO_GRAPHS");
+  }
   for (int i = 0; ok && i < DSC_SLOTS; i++) ok = cudaEventCreateWithFlags(&ctx->ev_refit[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     fail(nullptr, DSC_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -419,7 +460,19 @@ void dsc_ctx_destroy(DscContext *ctx)
   cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  invalidate_graphs(ctx);
   for (void *p : ctx->allocs) cudaFree(p);
+  if (ctx->d_ring) cudaFree(ctx->d_ring);
+  if (ctx->d_ring_ctl) cudaFree(ctx->d_ring_ctl);
+  if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+  for (int i = 0; i < 4; i++) {
+    if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
+    if (ctx->cap_refit[i]) cudaEventDestroy(ctx->cap_refit[i]);
+  }
+  if (ctx->cap_fork) cudaEventDestroy(ctx->cap_fork);
+  if (ctx->cap_bb) cudaEventDestroy(ctx->cap_bb);
+  if (ctx->cap_tag) cudaEventDestroy(ctx->cap_tag);
+  if (ctx->cap_join) cudaEventDestroy(ctx->cap_join);
   for (auto &ev : ctx->events) {
     cudaEventDestroy(ev.a);
     cudaEventDestroy(ev.b);
@@ -786,7 +839,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     std::vector<int> own_polys, halo_polys, halo_leaves, st_bb, st_x;
     std::vector<unsigned> rows, raw, goff_local; /* entry ids of the current group, [row][lane]; bit 31 = other-leaf entry */
     int next_group_to_fill = 0;
-    size_t max_smem = 0;
     struct TileDims { int tile, nloc_a, ne, v2w, ehalo; };
     std::vector<TileDims> tile_dims;
     for (int l = 0; l < L; l++) {
@@ -986,7 +1038,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       m.sm_off_v2 = m.sm_off_e + 8 * ((mx_ne + 1) & ~1);
       m.sm_off_h = m.sm_off_v2 + 4 * mx_v2;
       ctx->nb_smem = (size_t)m.sm_off_h + (((size_t)mx_h + 15) & ~(size_t)15);
-      (void)max_smem;
       if (ctx->nb_smem > 220 * 1024) {
         /* the regions' maxima do not fit one SM together: every leaf takes the general path */
         std::fill(leaf_fast.begin(), leaf_fast.end(), (unsigned char)0);
@@ -1393,6 +1444,7 @@ int dsc_recalc_normals(DscContext *ctx)
 int dsc_set_custom_curve(DscContext *ctx, const float *table257)
 {
   NEED_PBVH();
+  invalidate_graphs(ctx); /* the mesh descriptor is baked into the captured launches */
   if (!table257) {
     ctx->m.curve = nullptr;
     return DSC_OK;
@@ -1415,6 +1467,7 @@ static int upload_per_vertex(DscContext *ctx, float *dst, const float *src)
 int dsc_set_mask(DscContext *ctx, const float *mask)
 {
   NEED_PBVH();
+  invalidate_graphs(ctx);
   if (!mask) {
     ctx->m.mask = nullptr;
     return DSC_OK;
@@ -1452,6 +1505,7 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
   if (ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "stroke already open");
   int r = join_side(ctx);
   if (r) return r;
+  const float *old_automask = ctx->m.automask;
   if (automask) {
     if ((r = upload_per_vertex(ctx, ctx->d_automask, automask))) return r;
     ctx->m.automask = ctx->d_automask;
@@ -1459,6 +1513,7 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
   else {
     ctx->m.automask = nullptr;
   }
+  if (ctx->m.automask != old_automask) invalidate_graphs(ctx);
   CU(cudaMemsetAsync(ctx->m.leaf_state, 0, sizeof(unsigned) * (size_t)std::max(ctx->m.nleaf, 1), ctx->stream));
   CU(cudaMemsetAsync(ctx->m.st, 0, sizeof(DabState) * DSC_SLOTS, ctx->stream));
   CU(cudaMemsetAsync(ctx->m.tot, 0, sizeof(StrokeTotals), ctx->stream));
@@ -1469,61 +1524,105 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
   return DSC_OK;
 }
 
-int dsc_dab(DscContext *ctx, const DscDab *dab)
+/* ---- one dab = a fixed launch sequence over the device-resident dab ring ---- */
+/* what decides the launch sequence of a dab (everything else is data in its ring entry) */
+struct DabSig {
+  int tool, needs_area, do_normals, do_bounds, smooth_iters, smooth_tail;
+  unsigned key(int batch) const
+  {
+    return (unsigned)tool | (unsigned)needs_area << 8 | (unsigned)do_normals << 9 | (unsigned)do_bounds << 10 |
+           (unsigned)smooth_iters << 11 | (unsigned)smooth_tail << 15 | (unsigned)batch << 16;
+  }
+  bool operator==(const DabSig &o) const { return key(0) == o.key(0); }
+};
+
+static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *sig)
 {
-  NEED_PBVH();
   if (!dab) return fail(ctx, DSC_ERR_INVALID, "dab is NULL");
-  if (!ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "dsc_stroke_begin first");
   const int tool = dab->tool;
   if (tool != DSC_TOOL_DRAW && tool != DSC_TOOL_SMOOTH && tool != DSC_TOOL_INFLATE && tool != DSC_TOOL_GRAB &&
       tool != DSC_TOOL_CLAY_STRIPS)
     return fail(ctx, DSC_ERR_UNSUPPORTED, "sculpt tool %d is not on the accelerated path", tool);
   if (tool == DSC_TOOL_SMOOTH && !ctx->has_nb) return fail(ctx, DSC_ERR_STATE, "smooth brush needs the neighbour CSR (DscMeshDesc.nb_offsets)");
   if (!(dab->radius > 0.0f)) return fail(ctx, DSC_ERR_INVALID, "radius must be positive");
-  DabParams d;
   static_assert(sizeof(DabParams) == sizeof(DscDab), "DabParams mirrors DscDab");
-  memcpy(&d, dab, sizeof(d));
+  static_assert(sizeof(DabEntry) == 128, "DabEntry is 128 bytes");
+  memset(e, 0, sizeof(*e));
+  memcpy(&e->d, dab, sizeof(e->d));
+  sig->tool = tool;
+  sig->do_normals = !(dab->flags & DSC_DAB_NO_NORMALS);
+  sig->do_bounds = !(dab->flags & DSC_DAB_NO_BOUNDS);
+  sig->needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS;
+  sig->smooth_iters = 0;
+  sig->smooth_tail = 0;
+  const float rs = dab->radius * dab->radius_scale;
+  float ar = sqrtf(dab->radius * dab->radius); /* radius of the normal-sampling sphere, same float steps as k_area */
+  ar *= dab->normal_radius_factor;
+  e->radius_sq = rs * rs;
+  e->area_radius_sq = ar * ar;
+  e->original = tool == DSC_TOOL_GRAB ? 1 : 0;
+  e->use_cos = tool == DSC_TOOL_CLAY_STRIPS ? 1 : 0;
+  e->ent_bits = (sig->do_normals ? DSC_ENT_NORMALS : 0) | (sig->do_bounds ? DSC_ENT_BOUNDS : 0);
+  /* flags this dab clears again before it ends are not set in the first place, unless the general
+   * path (which reads them) has work or leaves may carry older flags */
+  const int all_flags = F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw;
+  e->set_flags = all_flags;
+  if (!ctx->stale_flags && !ctx->any_slow_leaf) {
+    e->set_flags &= ~((sig->do_normals ? F_UpdateNormals : 0) | (sig->do_bounds ? F_UpdateBB : 0));
+  }
+  if (tool == DSC_TOOL_SMOOTH) {
+    const int max_iterations = 4;
+    const float fract = 1.0f / (float)max_iterations;
+    float bstrength = dab->bstrength;
+    bstrength = bstrength < 0.0f ? 0.0f : (bstrength > 1.0f ? 1.0f : bstrength);
+    const int count = (int)(bstrength * (float)max_iterations);
+    float last = (float)max_iterations * (bstrength - (float)count * fract);
+    last = last < 0.0f ? 0.0f : (last > 1.0f ? 1.0f : last);
+    e->smooth_last = last;
+    sig->smooth_iters = count; /* full-strength iterations */
+    /* a zero-strength tail iteration moves nothing and marks only verts the previous iteration
+     * already marked; it is skipped */
+    sig->smooth_tail = !(count > 0 && last == 0.0f);
+  }
+  return DSC_OK;
+}
+
+/* Queues the launch sequence of the j-th dab of a batch (ring entry ring_ctl[0] + j, state slot
+ * `slot`).  `capturing`: the calls are being recorded into a CUDA graph. */
+static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool capturing)
+{
   DevMesh &m = ctx->m;
   cudaStream_t st = ctx->stream;
-  const int slot = (int)(ctx->dab_index & (DSC_SLOTS - 1));
+  const int tool = sig.tool;
+  const bool do_normals = sig.do_normals, do_bounds = sig.do_bounds;
   const LeafList hits = hit_list(ctx, slot);
-  const bool do_normals = !(dab->flags & DSC_DAB_NO_NORMALS), do_bounds = !(dab->flags & DSC_DAB_NO_BOUNDS);
   /* the stages below walk the hit list unless some leaf may still carry flags of an earlier dab */
   const bool use_hits = !ctx->stale_flags;
   const bool dist = ctx->world > 1;
-  if (dist && (!use_hits || !do_normals || !do_bounds))
-    return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
   int r;
+  cudaEvent_t ev_fork = capturing ? ctx->cap_fork : ctx->ev_fork, ev_bb = capturing ? ctx->cap_bb : ctx->ev_bb;
+  cudaEvent_t ev_tag = capturing ? ctx->cap_tag : ctx->ev_tag;
+  cudaEvent_t *ev_refit = capturing ? ctx->cap_refit : ctx->ev_refit;
   if (ctx->capture) CU(cudaMemsetAsync(ctx->d_capture, 0, sizeof(unsigned) * (size_t)ctx->nwords, st));
 
-  /* 1. gather + undo membership + node marks.  It recycles the ring slot the refit of three dabs ago read. */
-  CU(cudaStreamWaitEvent(st, ctx->ev_refit[(slot + 1) & (DSC_SLOTS - 1)], 0));
+  /* 1. gather + undo membership + node marks.  It recycles the ring slot the refit of three dabs ago
+   * read (inside a captured batch the first three dabs follow a joined side stream). */
+  if (!capturing || j >= DSC_SLOTS - 1) CU(cudaStreamWaitEvent(st, ev_refit[(slot + 1) & (DSC_SLOTS - 1)], 0));
   {
     StageScope s(ctx, ST_GATHER);
-    const float rs = dab->radius * dab->radius_scale;
-    float ar = sqrtf(dab->radius * dab->radius); /* radius of the normal-sampling sphere, same float steps as k_area */
-    ar *= dab->normal_radius_factor;
-    /* flags this dab clears again before it ends are not set in the first place, unless the general
-     * path (which reads them) has work */
-    const int all_flags = F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw;
-    int set_flags = all_flags;
-    if (use_hits && !ctx->any_slow_leaf) set_flags &= ~((do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0));
-    const int ent_bits = (do_normals ? DSC_ENT_NORMALS : 0) | (do_bounds ? DSC_ENT_BOUNDS : 0);
-    k_gather<<<(m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st>>>(m, slot, dab->location[0], dab->location[1],
-                                                                          dab->location[2], rs * rs, ar * ar,
-                                                                          tool == DSC_TOOL_GRAB ? 1 : 0, 1, 1, set_flags, ent_bits);
+    k_gather_dab<<<(m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st>>>(m, j, slot);
     LAUNCH_CHECK();
   }
   if (do_bounds && use_hits && !dist) {
     /* side stream: tag the ancestors of the hit leaves for the bottom-up refit while the brush runs */
-    CU(cudaEventRecord(ctx->ev_fork, st));
-    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    CU(cudaEventRecord(ev_fork, st));
+    CU(cudaStreamWaitEvent(ctx->stream2, ev_fork, 0));
     {
       StageScope s(ctx, ST_FLUSH, ctx->stream2);
-      k_tag_ancestors<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, hits.list, hits.count, 1);
+      k_tag_ancestors<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, slot, 1);
       LAUNCH_CHECK();
     }
-    CU(cudaEventRecord(ctx->ev_tag, ctx->stream2)); /* the tile kernel accumulates into the emptied leaf boxes */
+    CU(cudaEventRecord(ev_tag, ctx->stream2)); /* the tile kernel accumulates into the emptied leaf boxes */
     ctx->side_busy = true;
   }
   /* 2.-3. brush */
@@ -1533,21 +1632,11 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
       k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
       LAUNCH_CHECK();
     }
-    const int max_iterations = 4;
-    const float fract = 1.0f / (float)max_iterations;
-    float bstrength = dab->bstrength;
-    bstrength = bstrength < 0.0f ? 0.0f : (bstrength > 1.0f ? 1.0f : bstrength);
-    const int count = (int)(bstrength * (float)max_iterations);
-    const float last = (float)max_iterations * (bstrength - (float)count * fract);
-    for (int it = 0; it <= count; it++) {
-      float strength = (it != count) ? 1.0f : last;
-      strength = strength < 0.0f ? 0.0f : (strength > 1.0f ? 1.0f : strength);
-      /* a zero-strength tail iteration moves nothing and marks only verts the previous iteration
-       * already marked; skip it */
-      if (it == count && count > 0 && strength == 0.0f) break;
+    const int total = sig.smooth_iters + (sig.smooth_tail ? 1 : 0);
+    for (int it = 0; it < total; it++) {
       {
         StageScope s(ctx, ST_SMOOTH);
-        k_smooth_a<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot, strength);
+        k_smooth_a<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot, it == sig.smooth_iters ? 1 : 0);
         LAUNCH_CHECK();
       }
       {
@@ -1560,20 +1649,19 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     if (dist && (r = dist_allreduce_dab(ctx, slot, false))) return r;
   }
   else {
-    const bool needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS;
-    if (needs_area) {
+    if (sig.needs_area) {
       StageScope s(ctx, ST_AREA);
-      k_area<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot, tool == DSC_TOOL_CLAY_STRIPS ? 1 : 0);
+      k_area<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot);
       LAUNCH_CHECK();
     }
-    if (dist && (r = dist_allreduce_dab(ctx, slot, needs_area))) return r;
+    if (dist && (r = dist_allreduce_dab(ctx, slot, sig.needs_area))) return r;
     {
       StageScope s(ctx, ST_BRUSH);
       switch (tool) {
-        case DSC_TOOL_DRAW: k_brush<DSC_TOOL_DRAW><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
-        case DSC_TOOL_INFLATE: k_brush<DSC_TOOL_INFLATE><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
-        case DSC_TOOL_GRAB: k_brush<DSC_TOOL_GRAB><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
-        default: k_brush<DSC_TOOL_CLAY_STRIPS><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, d, slot); break;
+        case DSC_TOOL_DRAW: k_brush<DSC_TOOL_DRAW><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        case DSC_TOOL_INFLATE: k_brush<DSC_TOOL_INFLATE><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        case DSC_TOOL_GRAB: k_brush<DSC_TOOL_GRAB><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        default: k_brush<DSC_TOOL_CLAY_STRIPS><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
       }
       LAUNCH_CHECK();
     }
@@ -1584,7 +1672,7 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     const int mode = (do_normals ? NB_NORMALS : 0) | (do_bounds ? NB_BOUNDS : 0);
     if (do_bounds) {
       if (!dist) {
-        CU(cudaStreamWaitEvent(st, ctx->ev_tag, 0));
+        CU(cudaStreamWaitEvent(st, ev_tag, 0));
       }
       else {
         StageScope s(ctx, ST_OTHER);
@@ -1597,40 +1685,177 @@ int dsc_dab(DscContext *ctx, const DscDab *dab)
     }
     if (do_bounds && !dist) {
       /* side stream: carry the refreshed leaf boxes up the tree; overlaps the next dab */
-      CU(cudaEventRecord(ctx->ev_bb, st));
-      CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_bb, 0));
+      CU(cudaEventRecord(ev_bb, st));
+      CU(cudaStreamWaitEvent(ctx->stream2, ev_bb, 0));
       {
         StageScope s(ctx, ST_FLUSH, ctx->stream2);
-        k_refit<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, hits.list, hits.count);
+        k_refit<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream2>>>(m, slot);
         LAUNCH_CHECK();
       }
-      CU(cudaEventRecord(ctx->ev_refit[slot], ctx->stream2));
+      CU(cudaEventRecord(ev_refit[slot], ctx->stream2));
       ctx->side_busy = true;
     }
     if (mode && ctx->any_slow_leaf) {
       if ((r = run_clear(ctx, hits, (do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0)))) return r;
     }
-    if (!do_normals || !do_bounds) ctx->stale_flags = true;
   }
   else {
     const int want = (do_normals ? F_UpdateNormals : 0) | (do_bounds ? F_UpdateBB : 0);
     if (want && (r = run_flagged(ctx, want))) return r;
-    if (do_normals && do_bounds) ctx->stale_flags = false;
   }
-  ctx->last_slot = slot;
-  ctx->dab_index++;
+  return DSC_OK;
+}
+
+/* host ring -> device ring for the dabs [seq, seq + count) */
+static int upload_entries(DscContext *ctx, long long seq, int count)
+{
+  int done = 0;
+  while (done < count) {
+    const int at = (int)((seq + done) & (DSC_RING - 1));
+    const int n = std::min(count - done, DSC_RING - at);
+    CU(cudaMemcpyAsync(ctx->d_ring + at, ctx->h_ring + at, sizeof(DabEntry) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    done += n;
+  }
+  return DSC_OK;
+}
+
+/* the host may overwrite a quarter of its pinned ring once the copies queued from it a ring ago ran */
+static int ring_reserve(DscContext *ctx, long long seq)
+{
+  const int q = (int)((seq & (DSC_RING - 1)) / (DSC_RING / 4));
+  if ((seq & (DSC_RING / 4 - 1)) == 0 && seq >= DSC_RING) CU(cudaEventSynchronize(ctx->ev_ring[q]));
+  return DSC_OK;
+}
+static int ring_commit(DscContext *ctx, long long seq_end)
+{
+  /* seq_end: one past the last dab whose copy was just queued */
+  if ((seq_end & (DSC_RING / 4 - 1)) == 0) {
+    const int q = (int)(((seq_end - 1) & (DSC_RING - 1)) / (DSC_RING / 4));
+    CU(cudaEventRecord(ctx->ev_ring[q], ctx->stream));
+  }
+  return DSC_OK;
+}
+
+/* the launch sequence of `batch` dabs of one signature as an executable graph (built on first use) */
+static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r_graph)
+{
+  auto it = ctx->graphs.find(sig.key(batch));
+  if (it != ctx->graphs.end()) {
+    *r_graph = &it->second;
+    return DSC_OK;
+  }
+  int r = join_side(ctx);
+  if (r) return r;
+  DabGraph g;
+  const long long launches0 = ctx->launches;
+  int stage0[DSC_NUM_STAGES];
+  memcpy(stage0, ctx->stage_launches, sizeof(stage0));
+  CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  k_batch_begin<<<1, 1, 0, ctx->stream>>>(ctx->m, batch);
+  r = DSC_OK;
+  for (int j = 0; j < batch && r == DSC_OK; j++) r = enqueue_dab(ctx, sig, j, j & (DSC_SLOTS - 1), true);
+  if (r == DSC_OK && ctx->side_busy) {
+    /* the side stream's work is part of the graph */
+    if (cudaEventRecord(ctx->cap_join, ctx->stream2) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->cap_join, 0) != cudaSuccess)
+      r = fail(ctx, DSC_ERR_CUDA, "joining the side stream into the captured batch failed");
+  }
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g.graph);
+  ctx->side_busy = false;
+  if (r != DSC_OK) {
+    if (e == cudaSuccess && g.graph) cudaGraphDestroy(g.graph);
+    return r;
+  }
+  if (e != cudaSuccess) return fail(ctx, DSC_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&g.exec, g.graph, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g.graph);
+    return fail(ctx, DSC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  g.launches = (int)(ctx->launches - launches0) + 1;
+  for (int k = 0; k < DSC_NUM_STAGES; k++) g.stage_launches[k] = ctx->stage_launches[k] - stage0[k];
+  /* capturing counted the launches once; they are counted per graph launch instead */
+  ctx->launches = launches0;
+  memcpy(ctx->stage_launches, stage0, sizeof(stage0));
+  *r_graph = &ctx->graphs.emplace(sig.key(batch), g).first->second;
   return DSC_OK;
 }
 
 int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
 {
+  NEED_PBVH();
   if (count < 0 || (count > 0 && !dabs)) return fail(ctx, DSC_ERR_INVALID, "bad dab array");
-  for (int i = 0; i < count; i++) {
-    const int r = dsc_dab(ctx, dabs + i);
-    if (r) return r;
+  if (!ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "dsc_stroke_begin first");
+  int r;
+  int i = 0;
+  while (i < count) {
+    DabEntry e;
+    DabSig sig;
+    if ((r = make_entry(ctx, dabs + i, &e, &sig))) return r;
+    const bool dist = ctx->world > 1;
+    if (dist && (ctx->stale_flags || !sig.do_normals || !sig.do_bounds))
+      return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
+    /* how many of the following dabs share the launch sequence */
+    const bool graphable = ctx->use_graphs && !ctx->stage_timing && !ctx->capture && !dist && !ctx->stale_flags &&
+                           !ctx->any_slow_leaf && sig.do_normals && sig.do_bounds;
+    int run = 1;
+    const long long seq = ctx->ring_seq; /* ring position: runs across strokes; the state slot follows dab_index */
+    if ((r = ring_reserve(ctx, seq))) return r;
+    ctx->h_ring[seq & (DSC_RING - 1)] = e;
+    int batch = 1;
+    if (graphable && (ctx->dab_index & (DSC_SLOTS - 1)) == 0) {
+      const int sizes[3] = {32, 16, 4};
+      while (run < 32 && i + run < count) {
+        DabEntry e2;
+        DabSig s2;
+        if (make_entry(ctx, dabs + i + run, &e2, &s2) != DSC_OK || !(s2 == sig)) break;
+        if ((r = ring_reserve(ctx, seq + run))) return r;
+        ctx->h_ring[(seq + run) & (DSC_RING - 1)] = e2;
+        run++;
+      }
+      batch = 1;
+      for (int k = 0; k < 3; k++) {
+        if (run >= sizes[k]) {
+          batch = sizes[k];
+          break;
+        }
+      }
+    }
+    if ((r = upload_entries(ctx, seq, batch))) return r;
+    for (int k = 1; k <= batch; k++) {
+      if ((r = ring_commit(ctx, seq + k))) return r;
+    }
+    if (batch > 1) {
+      DabGraph *g = nullptr;
+      if ((r = get_graph(ctx, sig, batch, &g))) return r;
+      if ((r = join_side(ctx))) return r; /* the graph's first dabs do not wait for an earlier refit themselves */
+      CU(cudaGraphLaunch(g->exec, ctx->stream));
+      ctx->launches += g->launches;
+      for (int k = 0; k < DSC_NUM_STAGES; k++) ctx->stage_launches[k] += g->stage_launches[k];
+      ctx->graph_launches++;
+    }
+    else {
+      const int slot = (int)(ctx->dab_index & (DSC_SLOTS - 1));
+      k_batch_begin<<<1, 1, 0, ctx->stream>>>(ctx->m, 1);
+      LAUNCH_CHECK();
+      ctx->launches++;
+      if ((r = enqueue_dab(ctx, sig, 0, slot, false))) return r;
+    }
+    /* flag bookkeeping of the sequence that just ran */
+    if (!ctx->stale_flags) {
+      if (!sig.do_normals || !sig.do_bounds) ctx->stale_flags = true;
+    }
+    else if (sig.do_normals && sig.do_bounds) {
+      ctx->stale_flags = false;
+    }
+    ctx->dab_index += batch;
+    ctx->ring_seq += batch;
+    ctx->last_slot = (int)((ctx->dab_index - 1) & (DSC_SLOTS - 1));
+    i += batch;
   }
   return DSC_OK;
 }
+
+int dsc_dab(DscContext *ctx, const DscDab *dab) { return dsc_dabs(ctx, dab, 1); }
 
 static int read_list(DscContext *ctx, const int *d_list, const int *d_count, int *r_nodes, int capacity, int *r_tot)
 {
@@ -1666,7 +1891,7 @@ int dsc_search_sphere(DscContext *ctx, const float center[3], float radius_sq, i
   {
     StageScope s(ctx, ST_GATHER);
     k_gather<<<(ctx->m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, ctx->stream>>>(
-        ctx->m, 0, center[0], center[1], center[2], radius_sq, 0.0f, original ? 1 : 0, ignore_fully_ineffective ? 1 : 0, 0, 0, 0);
+        ctx->m, center[0], center[1], center[2], radius_sq, original ? 1 : 0, ignore_fully_ineffective ? 1 : 0);
     LAUNCH_CHECK();
   }
   return read_list(ctx, ctx->m.search_list, &ctx->m.tot->search_count, r_nodes, capacity, r_tot);
@@ -1690,6 +1915,7 @@ int dsc_debug_capture(DscContext *ctx, int on)
   if (!ctx) return DSC_ERR_INVALID;
   ctx->capture = on != 0;
   ctx->m.capture = ctx->capture ? ctx->d_capture : nullptr;
+  invalidate_graphs(ctx);
   return DSC_OK;
 }
 

@@ -53,7 +53,10 @@ struct StrokeTotals {
 
 /* Nodes are renumbered on the device: ids [0, nleaf) are the leaves in traversal order, ids
  * [nleaf, totnode) the inner nodes, root first (breadth-first).  The host translates. */
+struct DabEntry;
 struct DevMesh {
+  const DabEntry *ring; /* [DSC_RING] queued dabs */
+  int *ring_ctl;        /* [0] sequence number of the running batch's first dab, [1] of the next batch */
   /* per slot */
   float *cx, *cy, *cz;    /* MVert.co */
   float *nx, *ny, *nz;    /* vert_normals */
@@ -132,6 +135,37 @@ struct DabParams {
   float loc[3], radius, view_n[3], bstrength, scale[3], hardness;
   float normal_radius_factor, plane_offset, plane_trim, tip_roundness, grab_delta[3], radius_scale;
 };
+
+/* One queued dab on the device: the descriptor plus what the host derives from it.  The per-dab
+ * kernels read their dab from this ring (DevMesh.ring) instead of from kernel arguments, so the launch
+ * sequence of a dab is the same for every dab and can be replayed as a CUDA graph: entry
+ * (ring_ctl[0] + j) of the ring for the j-th dab of the running batch.  The slot of the per-dab state
+ * ring (DSC_SLOTS) is a kernel argument: batches start at multiples of DSC_SLOTS. */
+#define DSC_RING 1024
+struct DabEntry {
+  DabParams d;
+  float radius_sq;      /* gather sphere: (radius * radius_scale)^2 */
+  float area_radius_sq; /* normal-sampling sphere */
+  float smooth_last;    /* strength of the last smoothing iteration */
+  int original;         /* gather tests the stroke-start boxes (grab) */
+  int set_flags;        /* node flags the gather sets on hit leaves */
+  int ent_bits;         /* DSC_ENT_NORMALS | DSC_ENT_BOUNDS */
+  int use_cos;          /* the area pass also samples the centre (clay strips) */
+  int pad;
+};
+
+__device__ __forceinline__ const DabEntry &dsc_dab_entry(const DevMesh &m, int j)
+{
+  return m.ring[(m.ring_ctl[0] + j) & (DSC_RING - 1)];
+}
+
+/* first node of a batch of `count` dabs: the batch's base sequence number */
+__global__ void k_batch_begin(DevMesh m, int count)
+{
+  const int base = m.ring_ctl[1];
+  m.ring_ctl[0] = base;
+  m.ring_ctl[1] = base + count;
+}
 
 /* ---------------------------------------------------------------- math, same order as the CPU */
 __device__ __forceinline__ float dsc_normalize(float &x, float &y, float &z)
@@ -264,9 +298,9 @@ __device__ __forceinline__ void dsc_poly_normal(const DevMesh &m, unsigned pos, 
  * mark != 0 is the dab: undo-node membership (first touch), BKE_pbvh_node_mark_update
  * (pbvh.c:3641-3645), the sub-list of leaves that reach the (smaller) normal-sampling sphere, and
  * the reset of the next slot of the per-dab state ring. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float cx, float cy, float cz, float radius_sq,
-                                                      float area_radius_sq, int original, int ignore_ineffective, int mark,
-                                                      int set_flags, int ent_bits)
+__device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, float cx, float cy, float cz, float radius_sq,
+                                                float area_radius_sq, int original, int ignore_ineffective, int mark,
+                                                int set_flags, int ent_bits)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const int l = blockIdx.x * DSC_BLOCK + tid;
@@ -368,6 +402,20 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, int slot, float
   }
 }
 
+/* stand-alone search (BKE_pbvh_search_gather outside a stroke) */
+__global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, float cx, float cy, float cz, float radius_sq, int original,
+                                                      int ignore_ineffective)
+{
+  dsc_gather_body(m, 0, cx, cy, cz, radius_sq, 0.0f, original, ignore_ineffective, 0, 0, 0);
+}
+/* the gather of the j-th dab of the running batch */
+__global__ void __launch_bounds__(DSC_BLOCK) k_gather_dab(DevMesh m, int j, int slot)
+{
+  const DabEntry &e = dsc_dab_entry(m, j);
+  dsc_gather_body(m, slot, e.d.loc[0], e.d.loc[1], e.d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
+                  e.ent_bits);
+}
+
 /* leaves carrying any of `flags` (update_search_cb, pbvh.c:2891-2900) */
 __global__ void __launch_bounds__(1024) k_collect_flagged(DevMesh m, int flags)
 {
@@ -421,9 +469,10 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_reset_leaf_boxes(DevMesh m, const
  * already carries its bit (somebody else tagged everything above).  With reset_boxes the leaf boxes
  * are emptied on the way: this kernel is ordered after the previous dab's refit (same stream), which
  * is the last reader of the old boxes, and before this dab's tile kernel (event). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, const int *list, const int *count, int reset_boxes)
+__global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, int slot, int reset_boxes)
 {
-  const int n = *count;
+  const int *list = m.hit_list + (size_t)slot * m.nleaf;
+  const int n = m.st[slot].hit_count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int leaf = list[i];
     if (reset_boxes) dsc_reset_leaf_box(m, leaf);
@@ -442,9 +491,10 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, const in
  * the last pending child merges the sibling's box, stores the node and carries on, the other one
  * retires.  Only nodes above a refreshed leaf are touched, as in the reference.  Runs on the side
  * stream: nothing on the device reads inner boxes (the gather is flat), only the host does. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, const int *list, const int *count)
+__global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, int slot)
 {
-  const int n = *count;
+  const int *list = m.hit_list + (size_t)slot * m.nleaf;
+  const int n = m.st[slot].hit_count;
   const int tn = m.totnode;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int leaf = list[i];
@@ -505,8 +555,11 @@ __device__ __forceinline__ unsigned dsc_pack_nibbles(unsigned nib, int lane)
 /* SURVEY.md 8a row a15.  Unique verts of hit leaves inside radius * normal_radius_factor; two
  * buckets by the sign of dot(view_normal, no); smoothstep weight; exact int64 sums.  Streams
  * float4 runs of the SoA position arrays; normals are only fetched for runs with a vert inside. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, DabParams d, int slot, int use_cos)
+__global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, int j, int slot)
 {
+  const DabEntry &ent_ = dsc_dab_entry(m, j);
+  const DabParams d = ent_.d;
+  const int use_cos = ent_.use_cos;
   DabState *st = m.st + slot;
   const int4 *alist = m.atile_list + (size_t)slot * m.ntile;
   __shared__ unsigned long long sacc[16];
@@ -763,8 +816,9 @@ __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabPara
  * consecutive slots (float4 loads / stores of the SoA arrays).  First touch of a leaf in the stroke
  * snapshots co/no into orig_co/orig_no before the vertex is moved (row a9).  Displaced verts get
  * their vert_bitmap bit (pbvh.c:3729). */
-template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, DabParams d, int slot)
+template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, int j, int slot)
 {
+  const DabParams d = dsc_dab_entry(m, j).d;
   DabState *st = m.st + slot;
   const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   __shared__ BrushDerived D;
@@ -864,8 +918,11 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m, int slot)
  * sphere = co + (neighbour average - co) * fade, into the scratch arrays (SURVEY.md 8a row a20:
  * interior verts average all edge neighbours, boundary verts only boundary neighbours, boundary
  * verts with <= 2 neighbours stay).  The CSR gather is served by L2. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, DabParams d, int slot, float strength)
+__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, int j, int slot, int last_iteration)
 {
+  const DabEntry &ent_ = dsc_dab_entry(m, j);
+  const DabParams d = ent_.d;
+  const float strength = last_iteration ? ent_.smooth_last : 1.0f;
   const DabState *st = m.st + slot;
   const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   __shared__ unsigned s_moved;

@@ -295,3 +295,39 @@ def test_checkpoint_rollback_repeats_the_stroke_bit_for_bit():
         assert np.array_equal(outs[0][2][0], outs[1][2][0]) and outs[0][3] == outs[1][3]
     finally:
         ses.close()
+
+
+def test_batched_dabs_through_cuda_graphs_match_the_oracle():
+    """dsc_dabs: runs of dabs with one launch sequence are replayed as CUDA graphs over the device dab
+    ring (batches of 32 / 16 / 4, singles for the rest) -- same bits as the oracle's dab-by-dab stroke"""
+    import ctypes as C
+    from oracle_py import Oracle
+    m = meshgen.grid(400)
+    diag = m.bbox_diag()
+    dabs = stroke.c3_radius_sweep(diag, dabs_per_radius=9)               # 63 draw dabs: 32 + 16 + 4 x 3 + 3 singles
+    dabs += _line_dabs(capi.TOOL_INFLATE, (-0.5, 0.2, 0.0), (0.5, -0.3, 0.0), 0.25, 6)   # another signature: 4 + 2
+    orc = Oracle(m)
+    ses = capi.SculptSession(m, device=0)
+    try:
+        orc.stroke_begin()
+        for d in dabs:
+            orc.dab(d)
+        orc.stroke_end()
+        arr = (capi.DscDab * len(dabs))(*dabs)
+        for _ in range(2):  # the second stroke replays the cached graphs
+            ses.checkpoint()
+            ses.stroke_begin()
+            ses.dabs(arr, len(dabs))
+            st = ses.stats()
+            ses.stroke_end()
+            assert st["vertex_dabs"] == orc.vertex_dabs() and st["dabs"] == len(dabs)
+            assert np.array_equal(ses.co(), orc.co()), "positions differ in bits"
+            assert np.array_equal(ses.no(), orc.no()), "normals differ in bits"
+            bb, obb = ses.node_bb()
+            na = orc.node_arrays()
+            assert np.array_equal(bb, na["vb"]) and np.array_equal(obb, na["orig_vb"])
+            assert np.array_equal(ses.orig_co(), orc.orig_co())
+            ses.rollback()
+    finally:
+        ses.close()
+        orc.close()
