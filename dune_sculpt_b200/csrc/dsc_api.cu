@@ -96,7 +96,7 @@ struct DscContext {
   int *d_ring_ctl = nullptr;
   cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
   std::unordered_map<unsigned, DabGraph> graphs;
-  bool use_graphs = true;
+  bool use_graphs = true, use_pdl = false;
   long long graph_launches = 0, ring_seq = 0;
 
   bool capture = false;
@@ -164,6 +164,25 @@ template<typename T> static int dev_zero(DscContext *ctx, T **p, size_t n)
   if (r) return r;
   CU(cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(T), ctx->stream));
   return DSC_OK;
+}
+
+/* kernel launch, optionally as a programmatic dependent of the launch before it on the stream (see
+ * dsc_pdl_wait in dsc_kernels.cuh) */
+template<typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 /* stage bracket: counts the launch and, when stage timing is on, records an event pair */
@@ -442,6 +461,7 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
     ctx->m.ring = ctx->d_ring;
     ctx->m.ring_ctl = ctx->d_ring_ctl;
     ctx->use_graphs = !getenv("DSC_NO_GRAPHS");
+    ctx->use_pdl = getenv("DSC_PDL") != nullptr; /* measured: no gain on small dabs, a loss on large ones (early CTAs hold SM slots) */
   }
   for (int i = 0; ok && i < DSC_SLOTS; i++) ok = cudaEventCreateWithFlags(&ctx->ev_refit[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
@@ -1300,12 +1320,11 @@ static int run_collect(DscContext *ctx, int flags)
   return DSC_OK;
 }
 /* normals and/or leaf boxes of the listed leaves (mode: NB_NORMALS | NB_BOUNDS) */
-static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode)
+static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode, bool pdl = false)
 {
   {
     StageScope s(ctx, ST_NORMALS);
-    k_normals_tile<<<ctx->nb_grid, NT_THREADS, ctx->nb_smem, ctx->stream>>>(ctx->m, ll.tiles, ll.tile_count, mode, ll.mask);
-    LAUNCH_CHECK();
+    CU(launch_k(k_normals_tile, ctx->nb_grid, NT_THREADS, ctx->nb_smem, ctx->stream, pdl, ctx->m, ll.tiles, ll.tile_count, mode, ll.mask));
   }
   if (ctx->any_slow_leaf) {
     if (mode & NB_NORMALS) {
@@ -1603,6 +1622,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   cudaEvent_t ev_fork = capturing ? ctx->cap_fork : ctx->ev_fork, ev_bb = capturing ? ctx->cap_bb : ctx->ev_bb;
   cudaEvent_t ev_tag = capturing ? ctx->cap_tag : ctx->ev_tag;
   cudaEvent_t *ev_refit = capturing ? ctx->cap_refit : ctx->ev_refit;
+  const bool pdl = ctx->use_pdl && !ctx->stage_timing && !ctx->capture;
   if (ctx->capture) CU(cudaMemsetAsync(ctx->d_capture, 0, sizeof(unsigned) * (size_t)ctx->nwords, st));
 
   /* 1. gather + undo membership + node marks.  It recycles the ring slot the refit of three dabs ago
@@ -1610,8 +1630,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   if (!capturing || j >= DSC_SLOTS - 1) CU(cudaStreamWaitEvent(st, ev_refit[(slot + 1) & (DSC_SLOTS - 1)], 0));
   {
     StageScope s(ctx, ST_GATHER);
-    k_gather_dab<<<(m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st>>>(m, j, slot);
-    LAUNCH_CHECK();
+    CU(launch_k(k_gather_dab, (m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st, pdl, m, j, slot));
   }
   if (do_bounds && use_hits && !dist) {
     /* side stream: tag the ancestors of the hit leaves for the bottom-up refit while the brush runs */
@@ -1651,19 +1670,20 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   else {
     if (sig.needs_area) {
       StageScope s(ctx, ST_AREA);
-      k_area<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot);
-      LAUNCH_CHECK();
+      CU(launch_k(k_area, ctx->grid, DSC_BLOCK, 0, st, pdl, m, j, slot));
     }
     if (dist && (r = dist_allreduce_dab(ctx, slot, sig.needs_area))) return r;
     {
       StageScope s(ctx, ST_BRUSH);
+      /* with an area pass (and no collective) between the gather and the brush, the brush may read the gather's list early */
+      const bool bpdl = pdl && !dist;
+      const int hoist = (bpdl && sig.needs_area) ? 1 : 0;
       switch (tool) {
-        case DSC_TOOL_DRAW: k_brush<DSC_TOOL_DRAW><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
-        case DSC_TOOL_INFLATE: k_brush<DSC_TOOL_INFLATE><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
-        case DSC_TOOL_GRAB: k_brush<DSC_TOOL_GRAB><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
-        default: k_brush<DSC_TOOL_CLAY_STRIPS><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        case DSC_TOOL_DRAW: CU(launch_k(k_brush<DSC_TOOL_DRAW>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
+        case DSC_TOOL_INFLATE: CU(launch_k(k_brush<DSC_TOOL_INFLATE>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
+        case DSC_TOOL_GRAB: CU(launch_k(k_brush<DSC_TOOL_GRAB>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
+        default: CU(launch_k(k_brush<DSC_TOOL_CLAY_STRIPS>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
       }
-      LAUNCH_CHECK();
     }
     if (dist && (r = dist_halo_exchange(ctx))) return r;
   }
@@ -1681,7 +1701,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
       }
     }
     if (mode) {
-      if ((r = run_normals_bounds(ctx, hits, mode))) return r;
+      if ((r = run_normals_bounds(ctx, hits, mode, pdl && !dist && tool != DSC_TOOL_SMOOTH))) return r;
     }
     if (do_bounds && !dist) {
       /* side stream: carry the refreshed leaf boxes up the tree; overlaps the next dab */

@@ -159,6 +159,16 @@ __device__ __forceinline__ const DabEntry &dsc_dab_entry(const DevMesh &m, int j
   return m.ring[(m.ring_ctl[0] + j) & (DSC_RING - 1)];
 }
 
+/* Programmatic dependent launch: the per-dab kernels of the main stream are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may start while its predecessor
+ * still runs.  Everything a kernel reads or writes that the predecessor touches comes after
+ * dsc_pdl_wait(); each kernel releases its own dependent right after its wait, so by the time a
+ * kernel starts, the launch before its predecessor has completed -- its outputs (e.g. the gather's
+ * lists for the brush and the tile kernel) may be read before the wait.  Both are no-ops for a
+ * kernel launched the ordinary way. */
+__device__ __forceinline__ void dsc_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void dsc_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 /* first node of a batch of `count` dabs: the batch's base sequence number */
 __global__ void k_batch_begin(DevMesh m, int count)
 {
@@ -411,6 +421,8 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, float cx, float
 /* the gather of the j-th dab of the running batch */
 __global__ void __launch_bounds__(DSC_BLOCK) k_gather_dab(DevMesh m, int j, int slot)
 {
+  dsc_pdl_wait(); /* leaf boxes of the previous dab's tile kernel; ring_ctl of the batch head */
+  dsc_pdl_launch();
   const DabEntry &e = dsc_dab_entry(m, j);
   dsc_gather_body(m, slot, e.d.loc[0], e.d.loc[1], e.d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
                   e.ent_bits);
@@ -557,6 +569,8 @@ __device__ __forceinline__ unsigned dsc_pack_nibbles(unsigned nib, int lane)
  * float4 runs of the SoA position arrays; normals are only fetched for runs with a vert inside. */
 __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, int j, int slot)
 {
+  dsc_pdl_wait(); /* the gather's area tile list */
+  dsc_pdl_launch();
   const DabEntry &ent_ = dsc_dab_entry(m, j);
   const DabParams d = ent_.d;
   const int use_cos = ent_.use_cos;
@@ -816,7 +830,7 @@ __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabPara
  * consecutive slots (float4 loads / stores of the SoA arrays).  First touch of a leaf in the stroke
  * snapshots co/no into orig_co/orig_no before the vertex is moved (row a9).  Displaced verts get
  * their vert_bitmap bit (pbvh.c:3729). */
-template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, int j, int slot)
+template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, int j, int slot, int hoist)
 {
   const DabParams d = dsc_dab_entry(m, j).d;
   DabState *st = m.st + slot;
@@ -824,6 +838,21 @@ template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh 
   __shared__ BrushDerived D;
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
+  /* hoist: the launch before the predecessor was the gather (an area pass sits in between), so its
+   * tile list may be read while the area pass still runs */
+  int total = 0;
+  int4 ent = make_int4(0, 0, 0, 0);
+  if (hoist) {
+    total = st->tile_count;
+    if ((int)blockIdx.x < total) ent = tl[blockIdx.x];
+  }
+  dsc_pdl_wait(); /* the area sums (or, without an area pass, the gather) */
+  dsc_pdl_launch();
+  if (!hoist) {
+    total = st->tile_count;
+    if ((int)blockIdx.x < total) ent = tl[blockIdx.x];
+  }
+  if ((int)blockIdx.x >= total && blockIdx.x != 0) return; /* block 0 publishes the plane even when nothing was gathered */
   if (tid == 0) {
     s_moved = 0;
     dsc_brush_derive(st, d, D, blockIdx.x == 0);
@@ -834,9 +863,8 @@ template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh 
   const bool need_no = (tool == 4) || (d.flags & 1);
   constexpr bool use_orig = (tool == 5);
   unsigned moved_cnt = 0;
-  const int total = st->tile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    const int4 ent = tl[u];
+    if (u != (int)blockIdx.x) ent = tl[u];
     const bool first = (ent.w & DSC_ENT_FIRST) != 0;
     const int nvalid = ent.z - 4 * tid;
     const int s0 = ent.y + 4 * tid;
@@ -1225,8 +1253,13 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
   constexpr int NW = NT_CONSUMERS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
+  /* before the PDL wait: only what the gather (at least two launches back) and the upload wrote */
   const int n = *count;
-  if ((int)blockIdx.x >= n) return;
+  if ((int)blockIdx.x >= n) {
+    dsc_pdl_wait();
+    dsc_pdl_launch();
+    return;
+  }
   const bool upd_shared = m.ghit_words <= NT_UPD_WORDS;
   if (upd_shared) {
     for (int w = tid; w < m.ghit_words; w += NT_THREADS) s_upd[w] = upd[w];
@@ -1238,12 +1271,23 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
     dsc_mbar_init(&s_empty[1], NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  /* the producer's first descriptor: tile list entry, tile meta, index-row offsets (constant tables) */
+  int4 ent = make_int4(0, 0, 0, 0), q = make_int4(0, 0, 0, 0);
+  unsigned go = 0u, glast = 0u;
+  if (warp == NW) {
+    ent = list[blockIdx.x];
+    const int ng0 = (ent.z + 31) >> 5, g00 = ent.y >> 5;
+    if (lane < 3) q = m.tile_meta[3 * ent.x + lane];
+    go = (lane < ng0) ? m.v2_goff[g00 + lane] : 0u;
+    glast = (lane == 0) ? m.v2_goff[g00 + ng0] : 0u;
+  }
+  dsc_pdl_wait(); /* positions and dirty bits of the brush; the emptied leaf boxes */
+  dsc_pdl_launch();
   __syncthreads();
 
   if (warp == NW) {
     /* ------------------------------------------------------------------ producer warp */
     unsigned par_e0 = 1u, par_e1 = 1u; /* a fresh mbarrier passes a wait on the previous phase */
-    int4 ent = list[blockIdx.x];
     int k = 0;
     for (int h = blockIdx.x; h < n; h += gridDim.x, k++) {
       const int set = k & 1;
@@ -1254,11 +1298,7 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
       const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
       const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
       const int ng = (U + 31) >> 5, G0 = ub >> 5;
-      int4 q = make_int4(0, 0, 0, 0);
-      if (lane < 3) q = m.tile_meta[3 * tile + lane];
       const unsigned dw = (do_n && lane < ng) ? m.dirty[G0 + lane] : 0u;
-      const unsigned go = (do_n && lane < ng) ? m.v2_goff[G0 + lane] : 0u;
-      unsigned glast = (do_n && lane == 0) ? m.v2_goff[G0 + ng] : 0u;
       int dcount = __popc(dw);
       for (int o = 16; o > 0; o >>= 1) dcount += __shfl_xor_sync(0xffffffffu, dcount, o);
       const unsigned goff0 = __shfl_sync(0xffffffffu, go, 0);
@@ -1342,7 +1382,15 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
           asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(dsc_smem_u32(&s_full[1])) : "memory");
         }
       }
+      /* the next tile's constant tables, one tile ahead */
       ent = ent_n;
+      if (hn < n) {
+        const int ngn = (ent.z + 31) >> 5, g0n = ent.y >> 5;
+        q = make_int4(0, 0, 0, 0);
+        if (lane < 3) q = m.tile_meta[3 * ent.x + lane];
+        go = (lane < ngn) ? m.v2_goff[g0n + lane] : 0u;
+        glast = (lane == 0) ? m.v2_goff[g0n + ngn] : 0u;
+      }
     }
     return;
   }
