@@ -96,7 +96,9 @@ struct DscContext {
   int *d_ring_ctl = nullptr;
   cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
   std::unordered_map<unsigned, DabGraph> graphs;
-  bool use_graphs = true, use_pdl = false;
+  bool use_graphs = true, use_pdl = false, use_batch_kernel = false;
+  int batch_grid[4] = {0, 0, 0, 0}; /* resident CTAs of k_dab_batch<tool> */
+  long long batch_launches = 0;
   long long graph_launches = 0, ring_seq = 0;
 
   bool capture = false;
@@ -461,6 +463,9 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
     ctx->m.ring = ctx->d_ring;
     ctx->m.ring_ctl = ctx->d_ring_ctl;
     ctx->use_graphs = !getenv("DSC_NO_GRAPHS");
+    /* measured slower than the graph replay (grid barriers cost more than the launch gaps they replace, and the
+     * area / brush stages run at the tile kernel's lower occupancy): opt-in */
+    ctx->use_batch_kernel = getenv("DSC_BATCH_KERNEL") != nullptr;
     ctx->use_pdl = getenv("DSC_PDL") != nullptr; /* measured: no gain on small dabs, a loss on large ones (early CTAs hold SM slots) */
   }
   for (int i = 0; ok && i < DSC_SLOTS; i++) ok = cudaEventCreateWithFlags(&ctx->ev_refit[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1203,8 +1208,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_upload_c(ctx, &m.child1, child1)) || (r = dev_upload_c(ctx, &m.level_off, level_off)) ||
         (r = dev_upload_c(ctx, &m.level_nodes, level_nodes)))
       return r;
-    if ((r = dev_zero(ctx, &m.node_mark, (size_t)N)) || (r = dev_zero(ctx, &m.pending, (size_t)N)) ||
-        (r = dev_zero(ctx, &m.arrived, (size_t)N)))
+    if ((r = dev_zero(ctx, &m.node_mark, (size_t)N)) || (r = dev_zero(ctx, &m.pending, (size_t)2 * N)) ||
+        (r = dev_zero(ctx, &m.arrived, (size_t)2 * N)) || (r = dev_zero(ctx, &m.grid_bar, 1)))
       return r;
     m.totnode = N;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1218,6 +1223,17 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   int occ = 1;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_tile, NT_THREADS, ctx->nb_smem));
   ctx->nb_grid = ctx->num_sms * std::max(occ, 1);
+  {
+    /* the persistent batch kernel, one instantiation per tool: every CTA must be resident */
+    const void *fn[4] = {(const void *)k_dab_batch<DSC_TOOL_DRAW>, (const void *)k_dab_batch<DSC_TOOL_INFLATE>,
+                         (const void *)k_dab_batch<DSC_TOOL_GRAB>, (const void *)k_dab_batch<DSC_TOOL_CLAY_STRIPS>};
+    for (int k = 0; k < 4; k++) {
+      CU(cudaFuncSetAttribute(fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
+      int o = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn[k], NT_THREADS, ctx->nb_smem));
+      ctx->batch_grid[k] = ctx->num_sms * o;
+    }
+  }
 
   /* multi-GPU: owned leaf run, hit-mask ring, halo index lists */
   m.own_lo = 0;
@@ -1675,14 +1691,12 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
     if (dist && (r = dist_allreduce_dab(ctx, slot, sig.needs_area))) return r;
     {
       StageScope s(ctx, ST_BRUSH);
-      /* with an area pass (and no collective) between the gather and the brush, the brush may read the gather's list early */
       const bool bpdl = pdl && !dist;
-      const int hoist = (bpdl && sig.needs_area) ? 1 : 0;
       switch (tool) {
-        case DSC_TOOL_DRAW: CU(launch_k(k_brush<DSC_TOOL_DRAW>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
-        case DSC_TOOL_INFLATE: CU(launch_k(k_brush<DSC_TOOL_INFLATE>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
-        case DSC_TOOL_GRAB: CU(launch_k(k_brush<DSC_TOOL_GRAB>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
-        default: CU(launch_k(k_brush<DSC_TOOL_CLAY_STRIPS>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot, hoist)); break;
+        case DSC_TOOL_DRAW: CU(launch_k(k_brush<DSC_TOOL_DRAW>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        case DSC_TOOL_INFLATE: CU(launch_k(k_brush<DSC_TOOL_INFLATE>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        case DSC_TOOL_GRAB: CU(launch_k(k_brush<DSC_TOOL_GRAB>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        default: CU(launch_k(k_brush<DSC_TOOL_CLAY_STRIPS>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
       }
     }
     if (dist && (r = dist_halo_exchange(ctx))) return r;
@@ -1800,6 +1814,36 @@ static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r
   return DSC_OK;
 }
 
+/* `count` dabs of one launch sequence in one cooperative launch of the persistent batch kernel */
+static int launch_batch_kernel(DscContext *ctx, const DabSig &sig, int count, int slot0)
+{
+  void (*fn)(DevMesh, int, int, int) = nullptr;
+  int k = 0;
+  switch (sig.tool) {
+    case DSC_TOOL_DRAW: fn = k_dab_batch<DSC_TOOL_DRAW>; k = 0; break;
+    case DSC_TOOL_INFLATE: fn = k_dab_batch<DSC_TOOL_INFLATE>; k = 1; break;
+    case DSC_TOOL_GRAB: fn = k_dab_batch<DSC_TOOL_GRAB>; k = 2; break;
+    default: fn = k_dab_batch<DSC_TOOL_CLAY_STRIPS>; k = 3; break;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)ctx->batch_grid[k], 1, 1);
+  cfg.blockDim = dim3(NT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = ctx->nb_smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  k_batch_begin<<<1, 1, 0, ctx->stream>>>(ctx->m, count);
+  LAUNCH_CHECK();
+  CU(cudaLaunchKernelEx(&cfg, fn, ctx->m, count, slot0, sig.needs_area));
+  ctx->launches += 2;
+  ctx->batch_launches++;
+  return DSC_OK;
+}
+
 int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
 {
   NEED_PBVH();
@@ -1822,7 +1866,19 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     if ((r = ring_reserve(ctx, seq))) return r;
     ctx->h_ring[seq & (DSC_RING - 1)] = e;
     int batch = 1;
-    if (graphable && (ctx->dab_index & (DSC_SLOTS - 1)) == 0) {
+    const bool batchable = graphable && ctx->use_batch_kernel && sig.tool != DSC_TOOL_SMOOTH && ctx->batch_grid[0] > 0;
+    if (batchable) {
+      while (run < 256 && i + run < count) {
+        DabEntry e2;
+        DabSig s2;
+        if (make_entry(ctx, dabs + i + run, &e2, &s2) != DSC_OK || !(s2 == sig)) break;
+        if ((r = ring_reserve(ctx, seq + run))) return r;
+        ctx->h_ring[(seq + run) & (DSC_RING - 1)] = e2;
+        run++;
+      }
+      batch = run;
+    }
+    else if (graphable && (ctx->dab_index & (DSC_SLOTS - 1)) == 0) {
       const int sizes[3] = {32, 16, 4};
       while (run < 32 && i + run < count) {
         DabEntry e2;
@@ -1844,7 +1900,11 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     for (int k = 1; k <= batch; k++) {
       if ((r = ring_commit(ctx, seq + k))) return r;
     }
-    if (batch > 1) {
+    if (batchable) {
+      if ((r = join_side(ctx))) return r;
+      if ((r = launch_batch_kernel(ctx, sig, batch, (int)(ctx->dab_index & (DSC_SLOTS - 1))))) return r;
+    }
+    else if (batch > 1) {
       DabGraph *g = nullptr;
       if ((r = get_graph(ctx, sig, batch, &g))) return r;
       if ((r = join_side(ctx))) return r; /* the graph's first dabs do not wait for an earlier refit themselves */

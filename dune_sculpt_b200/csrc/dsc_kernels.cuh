@@ -110,7 +110,9 @@ struct DevMesh {
   int *node_flag;
   const int4 *topo; /* x parent (-1 root), y side bit of this node in its parent (1 / 2), z sibling */
   const int *child0, *child1;
-  int *pending, *arrived; /* bottom-up refit: which children will arrive / have arrived */
+  int *pending, *arrived; /* [2][totnode] bottom-up refit: which children will arrive / have arrived (two sets: the
+                             batch kernel tags the next dab while the previous one is still refitted) */
+  unsigned *grid_bar;     /* arrival counter of the batch kernel's grid barrier */
   int *node_mark;
   int nlevel;
   const int *level_off, *level_nodes; /* inner nodes by depth, root first */
@@ -175,6 +177,7 @@ __global__ void k_batch_begin(DevMesh m, int count)
   const int base = m.ring_ctl[1];
   m.ring_ctl[0] = base;
   m.ring_ctl[1] = base + count;
+  *m.grid_bar = 0u;
 }
 
 /* ---------------------------------------------------------------- math, same order as the CPU */
@@ -299,6 +302,18 @@ __device__ __forceinline__ void dsc_poly_normal(const DevMesh &m, unsigned pos, 
   }
 }
 
+/* Before the tile kernel accumulates tile boxes into them (dsc_red_min / dsc_red_max), the boxes of
+ * the listed leaves that take the tile path start from the empty box. */
+__device__ __forceinline__ void dsc_reset_leaf_box(const DevMesh &m, int leaf)
+{
+  if (!m.leaf_fast[leaf]) return;
+  const int tn = m.totnode;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    m.bb[k * tn + leaf] = 3.402823466e+38f;
+    m.bb[(3 + k) * tn + leaf] = -3.402823466e+38f;
+  }
+}
 /* ------------------------------------------------------------------------------ K1 gather */
 /* One thread per leaf, any number of CTAs.  A leaf passes BKE_pbvh_search_gather's DFS iff it
  * passes the callback itself, because every inner AABB is the union of its children
@@ -310,12 +325,12 @@ __device__ __forceinline__ void dsc_poly_normal(const DevMesh &m, unsigned pos, 
  * the reset of the next slot of the per-dab state ring. */
 __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, float cx, float cy, float cz, float radius_sq,
                                                 float area_radius_sq, int original, int ignore_ineffective, int mark,
-                                                int set_flags, int ent_bits)
+                                                int set_flags, int ent_bits, int bidx, int tag_parity)
 {
   const int tid = threadIdx.x, lane = tid & 31;
-  const int l = blockIdx.x * DSC_BLOCK + tid;
+  const int l = bidx * DSC_BLOCK + tid;
   DabState *st = m.st + slot;
-  if (mark && blockIdx.x == 0) {
+  if (mark && bidx == 0) {
     DabState *nx = m.st + ((slot + 1) & (DSC_SLOTS - 1));
     if (tid < 16) nx->acc[tid] = 0;
     if (tid == 16) nx->hit_count = 0;
@@ -335,13 +350,13 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
   if (l < m.nleaf && (!mark || (l >= m.own_lo && l < m.own_hi))) {
     const float *bbs = original ? m.obb : m.bb;
     const int tn = m.totnode;
-    flag = m.node_flag[l];
-    if (mark) lst = m.leaf_state[l];
+    flag = __ldcg(&m.node_flag[l]);
+    if (mark) lst = __ldcg(&m.leaf_state[l]);
     const float c[3] = {cx, cy, cz};
     float t[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      const float bmin = bbs[i * tn + l], bmax = bbs[(3 + i) * tn + l];
+      const float bmin = __ldcg(&bbs[i * tn + l]), bmax = __ldcg(&bbs[(3 + i) * tn + l]);
       float nearest;
       if (bmin > c[i]) nearest = bmin;
       else if (bmax < c[i]) nearest = bmax;
@@ -404,6 +419,17 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
     m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((lst & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
     m.node_flag[l] = flag | set_flags;
     vd = (unsigned long long)m.leaf_ucnt[l];
+    if (tag_parity >= 0 && (ent_bits & DSC_ENT_BOUNDS)) {
+      /* batch kernel: what k_tag_ancestors does on the side stream otherwise (the boxes are emptied later) */
+      int *pending = m.pending + (size_t)tag_parity * m.totnode;
+      int4 t = m.topo[l];
+      while (t.x >= 0) {
+        const int4 tp = m.topo[t.x];
+        const int old = atomicOr(&pending[t.x], t.y);
+        if (old & t.y) break;
+        t = tp;
+      }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) vd += __shfl_down_sync(0xffffffffu, vd, o);
   if (lane == 0) {
@@ -416,7 +442,7 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
 __global__ void __launch_bounds__(DSC_BLOCK) k_gather(DevMesh m, float cx, float cy, float cz, float radius_sq, int original,
                                                       int ignore_ineffective)
 {
-  dsc_gather_body(m, 0, cx, cy, cz, radius_sq, 0.0f, original, ignore_ineffective, 0, 0, 0);
+  dsc_gather_body(m, 0, cx, cy, cz, radius_sq, 0.0f, original, ignore_ineffective, 0, 0, 0, blockIdx.x, -1);
 }
 /* the gather of the j-th dab of the running batch */
 __global__ void __launch_bounds__(DSC_BLOCK) k_gather_dab(DevMesh m, int j, int slot)
@@ -425,7 +451,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather_dab(DevMesh m, int j, int 
   dsc_pdl_launch();
   const DabEntry &e = dsc_dab_entry(m, j);
   dsc_gather_body(m, slot, e.d.loc[0], e.d.loc[1], e.d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
-                  e.ent_bits);
+                  e.ent_bits, blockIdx.x, -1);
 }
 
 /* leaves carrying any of `flags` (update_search_cb, pbvh.c:2891-2900) */
@@ -455,18 +481,6 @@ __global__ void __launch_bounds__(1024) k_collect_flagged(DevMesh m, int flags)
   }
 }
 
-/* Before the tile kernel accumulates tile boxes into them (dsc_red_min / dsc_red_max), the boxes of
- * the listed leaves that take the tile path start from the empty box. */
-__device__ __forceinline__ void dsc_reset_leaf_box(const DevMesh &m, int leaf)
-{
-  if (!m.leaf_fast[leaf]) return;
-  const int tn = m.totnode;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    m.bb[k * tn + leaf] = 3.402823466e+38f;
-    m.bb[(3 + k) * tn + leaf] = -3.402823466e+38f;
-  }
-}
 __global__ void __launch_bounds__(DSC_BLOCK) k_reset_leaf_boxes(DevMesh m, const int *list, const int *count, int need_flag)
 {
   const int n = *count;
@@ -503,13 +517,14 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_tag_ancestors(DevMesh m, int slot
  * the last pending child merges the sibling's box, stores the node and carries on, the other one
  * retires.  Only nodes above a refreshed leaf are touched, as in the reference.  Runs on the side
  * stream: nothing on the device reads inner boxes (the gather is flat), only the host does. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, int slot)
+__device__ __forceinline__ void dsc_refit_body(const DevMesh &m, int slot, int parity, int gtid, int gthreads)
 {
   const int *list = m.hit_list + (size_t)slot * m.nleaf;
-  const int n = m.st[slot].hit_count;
+  const int n = __ldcg(&m.st[slot].hit_count);
   const int tn = m.totnode;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int leaf = list[i];
+  int *pending = m.pending + (size_t)parity * tn, *arrived = m.arrived + (size_t)parity * tn;
+  for (int i = gtid; i < n; i += gthreads) {
+    const int leaf = __ldcg(&list[i]);
     float box[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) box[k] = __ldcg(&m.bb[k * tn + leaf]);
@@ -517,9 +532,9 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, int slot)
     while (t.x >= 0) {
       const int p = t.x;
       const int4 tp = m.topo[p];
-      const int pend = m.pending[p];
+      const int pend = __ldcg(&pending[p]);
       __threadfence(); /* my box (stored below, or by the leaf kernel) is visible before I arrive */
-      const int old = atomicOr(&m.arrived[p], t.y);
+      const int old = atomicOr(&arrived[p], t.y);
       if ((old | t.y) != pend) break; /* the sibling subtree is still on its way */
       /* ordered after the atomic: if the sibling subtree was refreshed it arrived, fenced, before
        * me; if not, its stored box is current */
@@ -530,11 +545,15 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, int slot)
       }
 #pragma unroll
       for (int k = 0; k < 6; k++) __stcg(&m.bb[k * tn + p], box[k]);
-      m.arrived[p] = 0;
-      m.pending[p] = 0;
+      arrived[p] = 0;
+      pending[p] = 0;
       t = tp;
     }
   }
+}
+__global__ void __launch_bounds__(DSC_BLOCK) k_refit(DevMesh m, int slot)
+{
+  dsc_refit_body(m, slot, 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 /* general path: work unit u of a leaf list: (leaf, chunk) -> slot range; false if the chunk is empty */
@@ -550,7 +569,8 @@ __device__ __forceinline__ bool dsc_unit(const DevMesh &m, const int *list, int 
   return true;
 }
 
-__device__ __forceinline__ float4 ld4(const float *p, int s) { return *reinterpret_cast<const float4 *>(p + s); }
+/* through L2 (ld.global.cg): the persistent batch kernel re-reads arrays other CTAs rewrote since this SM last saw them */
+__device__ __forceinline__ float4 ld4(const float *p, int s) { return __ldcg(reinterpret_cast<const float4 *>(p + s)); }
 __device__ __forceinline__ void st4(float *p, int s, const float4 &v) { *reinterpret_cast<float4 *>(p + s) = v; }
 
 /* 4-bit per-lane flags -> one 32-bit word per 8 lanes (lane & 7 == 0 holds it) */
@@ -567,17 +587,13 @@ __device__ __forceinline__ unsigned dsc_pack_nibbles(unsigned nib, int lane)
 /* SURVEY.md 8a row a15.  Unique verts of hit leaves inside radius * normal_radius_factor; two
  * buckets by the sign of dot(view_normal, no); smoothstep weight; exact int64 sums.  Streams
  * float4 runs of the SoA position arrays; normals are only fetched for runs with a vert inside. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, int j, int slot)
+__device__ __forceinline__ void dsc_area_body(const DevMesh &m, const DabParams &d, int use_cos, int slot, int cta, int ncta)
 {
-  dsc_pdl_wait(); /* the gather's area tile list */
-  dsc_pdl_launch();
-  const DabEntry &ent_ = dsc_dab_entry(m, j);
-  const DabParams d = ent_.d;
-  const int use_cos = ent_.use_cos;
   DabState *st = m.st + slot;
   const int4 *alist = m.atile_list + (size_t)slot * m.ntile;
   __shared__ unsigned long long sacc[16];
   const int tid = threadIdx.x, lane = tid & 31;
+  __syncthreads(); /* sacc of an earlier call */
   if (tid < 16) sacc[tid] = 0ull;
   __syncthreads();
   float test_radius = sqrtf(d.radius * d.radius);
@@ -586,9 +602,9 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, int j, int slot)
   long long n0x = 0, n0y = 0, n0z = 0, n1x = 0, n1y = 0, n1z = 0;
   long long c0x = 0, c0y = 0, c0z = 0, c1x = 0, c1y = 0, c1z = 0;
   long long cnt0 = 0, cnt1 = 0;
-  const int total = st->atile_count;
-  for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    const int4 ent = alist[u];
+  const int total = __ldcg(&st->atile_count);
+  for (int u = cta; u < total; u += ncta) {
+    const int4 ent = __ldcg(&alist[u]);
     const int nvalid = ent.z - 4 * tid;
     if (nvalid <= 0) continue;
     const int s0 = ent.y + 4 * tid;
@@ -638,6 +654,14 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, int j, int slot)
   __syncthreads();
   if (tid < 16 && sacc[tid] != 0ull) atomicAdd((unsigned long long *)&st->acc[tid], sacc[tid]);
 }
+__global__ void __launch_bounds__(DSC_BLOCK) k_area(DevMesh m, int j, int slot)
+{
+  dsc_pdl_wait(); /* the gather's area tile list */
+  dsc_pdl_launch();
+  const DabEntry &e = dsc_dab_entry(m, j);
+  const DabParams d = e.d;
+  dsc_area_body(m, d, e.use_cos, slot, blockIdx.x, gridDim.x);
+}
 
 /* finalisation of the sums, same float/double steps as the CPU path */
 __device__ __forceinline__ void dsc_area_finalize(const DabState *st, const DabParams &d, bool use_cos, float no[3],
@@ -645,9 +669,9 @@ __device__ __forceinline__ void dsc_area_finalize(const DabState *st, const DabP
 {
   no[0] = no[1] = no[2] = 0.0f;
   for (int i = 0; i < 2; i++) {
-    float tx = (float)((double)st->acc[i * 3 + 0] * (1.0 / 4294967296.0));
-    float ty = (float)((double)st->acc[i * 3 + 1] * (1.0 / 4294967296.0));
-    float tz = (float)((double)st->acc[i * 3 + 2] * (1.0 / 4294967296.0));
+    float tx = (float)((double)__ldcg(&st->acc[i * 3 + 0]) * (1.0 / 4294967296.0));
+    float ty = (float)((double)__ldcg(&st->acc[i * 3 + 1]) * (1.0 / 4294967296.0));
+    float tz = (float)((double)__ldcg(&st->acc[i * 3 + 2]) * (1.0 / 4294967296.0));
     if (dsc_normalize(tx, ty, tz) != 0.0f) {
       no[0] = tx; no[1] = ty; no[2] = tz;
       break;
@@ -658,10 +682,10 @@ __device__ __forceinline__ void dsc_area_finalize(const DabState *st, const DabP
     float test_radius = sqrtf(d.radius * d.radius);
     test_radius *= d.normal_radius_factor;
     for (int i = 0; i < 2; i++) {
-      const long long cnt = st->acc[14 + i];
+      const long long cnt = __ldcg(&st->acc[14 + i]);
       if (cnt == 0) continue;
       for (int k = 0; k < 3; k++) {
-        const double mean = (double)st->acc[6 + i * 3 + k] / ((double)cnt * 4294967296.0);
+        const double mean = (double)__ldcg(&st->acc[6 + i * 3 + k]) / ((double)cnt * 4294967296.0);
         co[k] = (float)((double)d.loc[k] + (double)test_radius * mean);
       }
       break;
@@ -830,32 +854,20 @@ __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabPara
  * consecutive slots (float4 loads / stores of the SoA arrays).  First touch of a leaf in the stroke
  * snapshots co/no into orig_co/orig_no before the vertex is moved (row a9).  Displaced verts get
  * their vert_bitmap bit (pbvh.c:3729). */
-template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, int j, int slot, int hoist)
+template<int TOOL>
+__device__ __forceinline__ void dsc_brush_body(const DevMesh &m, const DabParams &d, int slot, int cta, int ncta)
 {
-  const DabParams d = dsc_dab_entry(m, j).d;
   DabState *st = m.st + slot;
   const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   __shared__ BrushDerived D;
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
-  /* hoist: the launch before the predecessor was the gather (an area pass sits in between), so its
-   * tile list may be read while the area pass still runs */
-  int total = 0;
-  int4 ent = make_int4(0, 0, 0, 0);
-  if (hoist) {
-    total = st->tile_count;
-    if ((int)blockIdx.x < total) ent = tl[blockIdx.x];
-  }
-  dsc_pdl_wait(); /* the area sums (or, without an area pass, the gather) */
-  dsc_pdl_launch();
-  if (!hoist) {
-    total = st->tile_count;
-    if ((int)blockIdx.x < total) ent = tl[blockIdx.x];
-  }
-  if ((int)blockIdx.x >= total && blockIdx.x != 0) return; /* block 0 publishes the plane even when nothing was gathered */
+  const int total = __ldcg(&st->tile_count);
+  if (cta >= total && cta != 0) return; /* CTA 0 publishes the plane even when nothing was gathered */
+  __syncthreads(); /* D / s_moved of an earlier call */
   if (tid == 0) {
     s_moved = 0;
-    dsc_brush_derive(st, d, D, blockIdx.x == 0);
+    dsc_brush_derive(st, d, D, cta == 0);
   }
   __syncthreads();
   constexpr int tool = TOOL;
@@ -863,8 +875,8 @@ template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh 
   const bool need_no = (tool == 4) || (d.flags & 1);
   constexpr bool use_orig = (tool == 5);
   unsigned moved_cnt = 0;
-  for (int u = blockIdx.x; u < total; u += gridDim.x) {
-    if (u != (int)blockIdx.x) ent = tl[u];
+  for (int u = cta; u < total; u += ncta) {
+    const int4 ent = __ldcg(&tl[u]);
     const bool first = (ent.w & DSC_ENT_FIRST) != 0;
     const int nvalid = ent.z - 4 * tid;
     const int s0 = ent.y + 4 * tid;
@@ -922,6 +934,13 @@ template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh 
   if (moved_cnt) atomicAdd(&s_moved, moved_cnt);
   __syncthreads();
   if (tid == 0 && s_moved) atomicAdd(&m.tot->moved_total, (unsigned long long)s_moved);
+}
+template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh m, int j, int slot)
+{
+  dsc_pdl_wait(); /* the area sums (or, without an area pass, the gather) */
+  dsc_pdl_launch();
+  const DabParams d = dsc_dab_entry(m, j).d;
+  dsc_brush_body<TOOL>(m, d, slot, blockIdx.x, gridDim.x);
 }
 
 /* snapshot only (smooth brush: first touch, before iteration 0) */
@@ -1239,8 +1258,8 @@ __device__ __forceinline__ void dsc_red_max(float *a, float v)
  * load.  Buffers are handed over with mbarriers: full[0] / empty[0] guard positions + entries +
  * staged verts (consumed by the box reduction and phase 2), full[1] / empty[1] the index words
  * (consumed by phase 3).  The consumers synchronise among themselves with a named barrier. */
-__global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
-                                                                const unsigned *upd)
+__device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const int4 *list, const int *count, int mode,
+                                                      const unsigned *upd, const int cta, const int ncta, const bool pdl)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
@@ -1254,15 +1273,18 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
   /* before the PDL wait: only what the gather (at least two launches back) and the upload wrote */
-  const int n = *count;
-  if ((int)blockIdx.x >= n) {
-    dsc_pdl_wait();
-    dsc_pdl_launch();
+  const int n = __ldcg(count);
+  if (cta >= n) {
+    if (pdl) {
+      dsc_pdl_wait();
+      dsc_pdl_launch();
+    }
     return;
   }
+  __syncthreads(); /* an earlier call is done with the static shared arrays and the mbarriers */
   const bool upd_shared = m.ghit_words <= NT_UPD_WORDS;
   if (upd_shared) {
-    for (int w = tid; w < m.ghit_words; w += NT_THREADS) s_upd[w] = upd[w];
+    for (int w = tid; w < m.ghit_words; w += NT_THREADS) s_upd[w] = __ldcg(&upd[w]);
   }
   if (tid == 0) {
     dsc_mbar_init(&s_full[0], 32);          /* the producer lanes (+ TMA bytes) */
@@ -1275,30 +1297,32 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
   int4 ent = make_int4(0, 0, 0, 0), q = make_int4(0, 0, 0, 0);
   unsigned go = 0u, glast = 0u;
   if (warp == NW) {
-    ent = list[blockIdx.x];
+    ent = __ldcg(&list[cta]);
     const int ng0 = (ent.z + 31) >> 5, g00 = ent.y >> 5;
     if (lane < 3) q = m.tile_meta[3 * ent.x + lane];
     go = (lane < ng0) ? m.v2_goff[g00 + lane] : 0u;
     glast = (lane == 0) ? m.v2_goff[g00 + ng0] : 0u;
   }
-  dsc_pdl_wait(); /* positions and dirty bits of the brush; the emptied leaf boxes */
-  dsc_pdl_launch();
+  if (pdl) {
+    dsc_pdl_wait(); /* positions and dirty bits of the brush; the emptied leaf boxes */
+    dsc_pdl_launch();
+  }
   __syncthreads();
 
   if (warp == NW) {
     /* ------------------------------------------------------------------ producer warp */
     unsigned par_e0 = 1u, par_e1 = 1u; /* a fresh mbarrier passes a wait on the previous phase */
     int k = 0;
-    for (int h = blockIdx.x; h < n; h += gridDim.x, k++) {
+    for (int h = cta; h < n; h += ncta, k++) {
       const int set = k & 1;
-      const int hn = h + (int)gridDim.x;
+      const int hn = h + ncta;
       int4 ent_n = make_int4(0, 0, 0, 0);
-      if (hn < n) ent_n = list[hn];
+      if (hn < n) ent_n = __ldcg(&list[hn]);
       const int tile = ent.x, ub = ent.y, U = ent.z;
       const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
       const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
       const int ng = (U + 31) >> 5, G0 = ub >> 5;
-      const unsigned dw = (do_n && lane < ng) ? m.dirty[G0 + lane] : 0u;
+      const unsigned dw = (do_n && lane < ng) ? __ldcg(&m.dirty[G0 + lane]) : 0u;
       int dcount = __popc(dw);
       for (int o = 16; o > 0; o >>= 1) dcount += __shfl_xor_sync(0xffffffffu, dcount, o);
       const unsigned goff0 = __shfl_sync(0xffffffffu, go, 0);
@@ -1352,7 +1376,7 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) {
-            x[u] = m.cx[sl[u]]; y[u] = m.cy[sl[u]]; z[u] = m.cz[sl[u]];
+            x[u] = __ldcg(&m.cx[sl[u]]); y[u] = __ldcg(&m.cy[sl[u]]); z[u] = __ldcg(&m.cz[sl[u]]);
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) {
@@ -1365,7 +1389,7 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
         if (anyd) {
           for (int i = lane; i < ehalo; i += 32) {
             const int ol = m.e_halo_leaf[hb + i];
-            const unsigned w = upd_shared ? s_upd[ol >> 5] : upd[ol >> 5];
+            const unsigned w = upd_shared ? s_upd[ol >> 5] : __ldcg(&upd[ol >> 5]);
             H[i] = (unsigned char)((w >> (ol & 31)) & 1u);
           }
         }
@@ -1392,13 +1416,13 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
         glast = (lane == 0) ? m.v2_goff[g0n + ngn] : 0u;
       }
     }
-    return;
+    return; /* the caller joins the warps (end of the kernel, or a CTA barrier of the batch kernel) */
   }
 
   /* -------------------------------------------------------------------- consumer warps */
   unsigned par_f0 = 0u, par_f1 = 0u;
   int k = 0;
-  for (int h = blockIdx.x; h < n; h += gridDim.x, k++) {
+  for (int h = cta; h < n; h += ncta, k++) {
     const int set = k & 1;
     dsc_mbar_wait(&s_full[0], par_f0);
     par_f0 ^= 1u;
@@ -1520,6 +1544,76 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const
     }
     asm volatile("bar.sync 1, 256;" ::: "memory"); /* poly normals / box partials are free for the next tile */
   }
+}
+__global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
+                                                                const unsigned *upd)
+{
+  dsc_normals_tile_body(m, list, count, mode, upd, blockIdx.x, gridDim.x, true);
+}
+
+/* ------------------------------------------------------------------ the whole dab path, persistent */
+/* grid-wide barrier of a cooperative launch (all CTAs resident): arrive on a global counter, spin on
+ * an acquire load until every CTA of this round has arrived */
+__device__ __forceinline__ void dsc_grid_sync(unsigned *bar, unsigned &target, unsigned ncta)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += ncta;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+/* A run of `batch` dabs of one tool in ONE cooperative launch: gather -> (area) -> brush -> normals +
+ * boxes, the stages separated by grid barriers instead of kernel boundaries, the bottom-up refit of a
+ * dab riding along with the gather of the next one.  The per-dab cost that is left is the barriers
+ * (~1 us each) and each stage's own dependent loads -- no launch gaps, no host calls, no events.
+ * CTA shape and shared memory are the tile kernel's; area and brush use its 8 compute warps.  Everything
+ * a stage reads that an earlier stage of the same launch wrote goes through L2 (__ldcg / ld4). */
+template<int TOOL>
+__global__ void __launch_bounds__(NT_THREADS, 4) k_dab_batch(DevMesh m, int batch, int slot0, int needs_area)
+{
+  const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
+  unsigned target = 0u;
+  const int gblocks = (m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK;
+  for (int j = 0; j < batch; j++) {
+    const int slot = (slot0 + j) & (DSC_SLOTS - 1);
+    const DabEntry &e = dsc_dab_entry(m, j);
+    const DabParams d = e.d;
+    const int mode = ((e.ent_bits & DSC_ENT_NORMALS) ? NB_NORMALS : 0) | ((e.ent_bits & DSC_ENT_BOUNDS) ? NB_BOUNDS : 0);
+    /* 1. gather + ancestor tags (first CTAs); the previous dab's refit rides along (last CTAs) */
+    if (tid < DSC_BLOCK) {
+      for (int b = cta; b < gblocks; b += ncta) {
+        dsc_gather_body(m, slot, d.loc[0], d.loc[1], d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
+                        e.ent_bits, b, j & 1);
+      }
+    }
+    if (j > 0) dsc_refit_body(m, (slot0 + j - 1) & (DSC_SLOTS - 1), (j - 1) & 1, (ncta - 1 - cta) * NT_THREADS + tid, ncta * NT_THREADS);
+    dsc_grid_sync(m.grid_bar, target, ncta);
+    /* 2. area normal / centre */
+    if (needs_area) {
+      dsc_area_body(m, d, e.use_cos, slot, cta, ncta);
+      dsc_grid_sync(m.grid_bar, target, ncta);
+    }
+    /* 3. brush; the boxes of the gathered leaves are emptied for the tile stage */
+    if (mode & NB_BOUNDS) {
+      const int *hl = m.hit_list + (size_t)slot * m.nleaf;
+      const int nh = __ldcg(&m.st[slot].hit_count);
+      for (int i = cta * NT_THREADS + tid; i < nh; i += ncta * NT_THREADS) dsc_reset_leaf_box(m, __ldcg(&hl[i]));
+    }
+    dsc_brush_body<TOOL>(m, d, slot, cta, ncta);
+    dsc_grid_sync(m.grid_bar, target, ncta);
+    /* 4. + 5. normals and boxes, tile by tile */
+    dsc_normals_tile_body(m, m.tile_list + (size_t)slot * m.ntile, &m.st[slot].tile_count, mode,
+                          m.ghit + (size_t)slot * m.ghit_words, cta, ncta, false);
+    dsc_grid_sync(m.grid_bar, target, ncta);
+  }
+  dsc_refit_body(m, (slot0 + batch - 1) & (DSC_SLOTS - 1), (batch - 1) & 1, cta * NT_THREADS + tid, ncta * NT_THREADS);
 }
 
 /* ------------------------------------------------------------------------------ K6 leaf BB */
