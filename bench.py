@@ -151,7 +151,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, mesh, ndabs):
@@ -264,6 +264,7 @@ def run_ours(args, rank, world):
         device_stroke()
     ses.synchronize()
     barrier()
+    log("[bench] rank %d: warm-up done (%.1fs since upload)" % (rank, time.time() - t0))
     sampler = ClockSampler(local_rank)
     sampler.start()
     vd = 0
@@ -277,6 +278,7 @@ def run_ours(args, rank, world):
     ms = ses.timer_stop()
     clocks = sampler.stop()
     barrier()
+    log("[bench] rank %d: timed strokes done, %.3f ms/step" % (rank, ms / args.steps))
 
     # ---- end-to-end timing through the host API: `e2e`
     H = ses.H
@@ -297,6 +299,7 @@ def run_ours(args, rank, world):
     ses.synchronize()
     dt_e = time.perf_counter() - t0
     barrier()
+    log("[bench] rank %d: end-to-end strokes done, %.3f ms/step" % (rank, 1e3 * dt_e / args.steps))
 
     # ---- max over ranks
     if world > 1:
@@ -328,8 +331,10 @@ def run_ours(args, rank, world):
     ses._chk(D.dsc_stroke_end(ctx))
     ses.synchronize()
 
+    log("[bench] rank %d: radius sweep done" % rank)
     # ---- roofline of the dominant kernel (untimed analysis stroke, CUDA events per stage)
     tot, stage_bytes, times = analysis_pass(ses, dabs, na)
+    log("[bench] rank %d: analysis stroke done" % rank)
     peak, peak_src = measured_peaks()
     dom = max((k for k in stage_bytes), key=lambda k: times[k][0])
     dom_ms, dom_launches = times[dom]
@@ -371,7 +376,7 @@ def run_ours(args, rank, world):
     }
     if cpu:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out), flush=True)
+    emit(out)
     ses.close()
 
 
@@ -402,7 +407,28 @@ def cpu_baseline(args, mesh, dabs):
             "ms_per_dab": 1e3 * dt / len(sample)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the one JSON line, on the process's original stdout"""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line.encode())
+    else:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+
+
 def main():
+    # libraries (NCCL's version banner, ...) may write to fd 1: route it to stderr and keep the real stdout for the JSON line
+    global _REAL_STDOUT
+    try:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:
+        _REAL_STDOUT = None
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
