@@ -64,6 +64,8 @@ class PBVH(C.Structure):
         ("vert_normals", c_float_p), ("verts", C.c_void_p), ("mpoly", C.c_void_p), ("mloop", C.c_void_p),
         ("looptri", C.c_void_p), ("totpoly", C.c_int), ("totloop", C.c_int), ("vmask", c_float_p),
         ("vert_bitmap", C.POINTER(C.c_uint)), ("deformed", C.c_bool), ("owns_normals", C.c_bool),
+        ("is_grids", C.c_int), ("grids", C.c_void_p), ("gridfaces", C.c_void_p), ("grid_flag_mats", C.c_void_p),
+        ("totgrid", C.c_int), ("gridkey", C.c_int * 9), ("grid_hidden", C.c_void_p), ("subdiv_ccg", C.c_void_p),
         ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
         ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool),
         ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
@@ -87,7 +89,7 @@ class SculptSearchSphereData(C.Structure):
 CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
     "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
-    "dsc_dabs", "dsc_state_save", "dsc_state_restore",
+    "dsc_dabs", "dsc_state_save", "dsc_state_restore", "dsc_grids_upload", "dsc_download_mask",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
     "dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
@@ -100,7 +102,8 @@ HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
     "DUNE_pbvh_mesh_sizes_set", "DUNE_pbvh_mask_layer_set", "DUNE_pbvh_vert_normals_set", "DUNE_pbvh_leaf_limit_set",
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
-    "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback",
+    "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
+    "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
     "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
     "BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_hidden_get", "BKE_pbvh_node_fully_masked_set",
     "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
@@ -153,6 +156,7 @@ def cuda_lib():
         L.dsc_update_bounds.argtypes = [C.c_void_p, C.c_int]
         L.dsc_node_mark_update.argtypes = [C.c_void_p, C.c_int]
         L.dsc_node_flag_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.dsc_download_mask.argtypes = [C.c_void_p, c_float_p]
         for fn in ("dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_upload_co",
                    "dsc_set_custom_curve", "dsc_set_mask"):
             getattr(L, fn).argtypes = [C.c_void_p, c_float_p]
@@ -191,6 +195,16 @@ def host_lib():
         L.DUNE_pbvh_device_detach.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_attach_dist.argtypes = [C.POINTER(PBVH), C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.DUNE_pbvh_device_sync_to_host.argtypes = [C.POINTER(PBVH)]
+        L.BKE_pbvh_build_grids.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.BKE_pbvh_build_grids.restype = None
+        L.BKE_subdiv_ccg_key_top_level.argtypes = [C.c_void_p, C.c_void_p]
+        L.BKE_subdiv_ccg_key_top_level.restype = None
+        L.DUNE_subdiv_ccg_from_tables.restype = C.c_void_p
+        L.DUNE_subdiv_ccg_from_tables.argtypes = [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p,
+                                                  C.c_int, c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
+        L.DUNE_subdiv_ccg_free.argtypes = [C.c_void_p]
+        L.DUNE_subdiv_ccg_free.restype = None
+        L.DUNE_pbvh_device_attach_grids.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int]
         L.DUNE_pbvh_device_checkpoint.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_rollback.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_error.argtypes = [C.POINTER(PBVH)]
@@ -567,3 +581,69 @@ class SculptSession:
             self.close()
         except Exception:
             pass
+
+
+class SubdivCCGStruct(C.Structure):
+    _fields_ = [
+        ("level", C.c_int), ("grid_size", C.c_int), ("grid_element_size", C.c_int), ("num_grids", C.c_int),
+        ("grids", C.c_void_p), ("grids_storage", C.c_void_p), ("has_normal", C.c_bool), ("has_mask", C.c_bool),
+        ("normal_offset", C.c_int), ("mask_offset", C.c_int), ("num_faces", C.c_int), ("faces", C.c_void_p),
+        ("grid_faces", C.c_void_p), ("num_adjacent_edges", C.c_int), ("adjacent_edges", C.c_void_p),
+        ("num_adjacent_vertices", C.c_int), ("adjacent_vertices", C.c_void_p), ("grid_edge", c_int_p), ("grid_vertex", c_int_p),
+    ]
+
+
+class GridSession(SculptSession):
+    """a multires CCG (meshgen.Multires) behind the reference's grids entry points: SubdivCCG ->
+    BKE_pbvh_build_grids -> DUNE_pbvh_device_attach_grids; the dab / download methods are the mesh ones
+    (a grid element is a vertex to them)"""
+
+    def __init__(self, mr, leaf_limit=0, device=0):
+        H = host_lib()
+        self.H = H
+        self.mesh = mr
+        self.dist = None
+        level = int(np.log2(mr.grid_size - 1)) + 1
+        assert (1 << (level - 1)) + 1 == mr.grid_size
+        co = np.ascontiguousarray(mr.co, dtype=np.float32)
+        no = np.ascontiguousarray(mr.no, dtype=np.float32)
+        mask = None if mr.mask is None else np.ascontiguousarray(mr.mask, dtype=np.float32)
+        have_no = bool(np.any(no != 0.0))
+        self.ccg = C.c_void_p(H.DUNE_subdiv_ccg_from_tables(
+            level, mr.totgrid, fptr(co), fptr(no) if have_no else None, None if mask is None else fptr(mask),
+            int(mr.face_start.shape[0]), iptr(mr.face_start), iptr(mr.face_num), int(mr.edge_off.shape[0] - 1), iptr(mr.edge_off),
+            iptr(mr.edge_elems), int(mr.cvert_off.shape[0] - 1), iptr(mr.cvert_off), iptr(mr.cvert_elems), iptr(mr.grid_edge),
+            iptr(mr.grid_cvert)))
+        self.key = (C.c_int * 9)()
+        H.BKE_subdiv_ccg_key_top_level(self.key, self.ccg)
+        ccg = C.cast(self.ccg, C.POINTER(SubdivCCGStruct)).contents
+        self.pbvh = H.BKE_pbvh_new()
+        if leaf_limit:
+            H.DUNE_pbvh_leaf_limit_set(self.pbvh, int(leaf_limit))
+        H.BKE_pbvh_build_grids(self.pbvh, ccg.grids, mr.totgrid, self.key, ccg.grid_faces, None, None)
+        self.ctx = None
+        if device is not None:
+            self._chk(H.DUNE_pbvh_device_attach_grids(self.pbvh, self.ccg, int(device)))
+            self.ctx = C.c_void_p(self.pbvh.contents.device)
+            self.D = cuda_lib()
+
+    def mask(self):
+        out = np.zeros(self.mesh.totelem, dtype=np.float32)
+        self._chk(self.D.dsc_download_mask(self.ctx, fptr(out)))
+        return out
+
+    def host_elements(self):
+        """(co, no, mask) as the host's CCGElem storage holds them after a sync"""
+        ccg = C.cast(self.ccg, C.POINTER(SubdivCCGStruct)).contents
+        nfl = ccg.grid_element_size // 4
+        raw = np.ctypeslib.as_array(C.cast(ccg.grids_storage, c_float_p), shape=(self.mesh.totelem * nfl,)).reshape(-1, nfl)
+        co = raw[:, 0:3].copy()
+        no = raw[:, ccg.normal_offset // 4:ccg.normal_offset // 4 + 3].copy()
+        mask = raw[:, ccg.mask_offset // 4].copy() if ccg.has_mask else None
+        return co, no, mask
+
+    def close(self):
+        super().close()
+        if getattr(self, "ccg", None):
+            self.H.DUNE_subdiv_ccg_free(self.ccg)
+            self.ccg = None

@@ -1,6 +1,7 @@
 /* libdune_sculpt_cuda: C ABI + host-side layout construction (see include/dune_sculpt_cuda.h). */
 #include "../../include/dune_sculpt_cuda.h"
 #include "dsc_kernels.cuh"
+#include "dsc_grids.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -57,6 +58,15 @@ struct DscContext {
   std::vector<int> h_poly_start, h_poly_len, h_loop_v, h_tri_vert, h_tri_poly, h_nb_off, h_nb_idx;
   std::vector<unsigned char> h_boundary;
   bool has_no = false, has_mask = false, has_nb = false;
+
+  /* multires grids (dsc_grids_upload) */
+  bool is_grids = false;
+  int grid_size = 0, totgrid = 0;
+  std::vector<int> h_face_start, h_face_num, h_edge_off, h_edge_elems, h_cvert_off, h_cvert_elems, h_grid_edge, h_grid_cvert;
+  DevGrids g;
+  int grid_seq = 0;
+  size_t gn_smem = 0;
+  bool has_odd_edges = false; /* some coarse edge has more than two faces */
 
   std::vector<int> slot_of;     /* vertex -> slot */
   std::vector<int> leaf_node;   /* leaf (= device id) -> host node index */
@@ -639,6 +649,42 @@ int dsc_mesh_upload(DscContext *ctx, const DscMeshDesc *me)
   return DSC_OK;
 }
 
+int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *gr)
+{
+  if (!ctx || !gr) return fail(ctx, DSC_ERR_INVALID, "NULL argument");
+  if (ctx->have_mesh) return fail(ctx, DSC_ERR_STATE, "a mesh is already resident in this context");
+  if (ctx->world > 1) return fail(ctx, DSC_ERR_UNSUPPORTED, "grids are not partitioned across GPUs yet");
+  if (gr->totgrid <= 0 || gr->grid_size < 2 || !gr->co) return fail(ctx, DSC_ERR_INVALID, "empty grid set");
+  if (!gr->face_start_grid || !gr->face_num_grids || !gr->edge_offsets || !gr->edge_elems || !gr->cvert_offsets ||
+      !gr->cvert_elems || !gr->grid_edge || !gr->grid_cvert)
+    return fail(ctx, DSC_ERR_INVALID, "grid adjacency tables missing");
+  const long long E = (long long)gr->totgrid * gr->grid_size * gr->grid_size;
+  if (E > 0x7fff0000ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 grid elements");
+  if (dsc_grid_normals_smem(gr->grid_size) > 200 * 1024)
+    return fail(ctx, DSC_ERR_UNSUPPORTED, "grid size %d: one grid does not fit the normal kernel's shared memory", gr->grid_size);
+  ctx->is_grids = true;
+  ctx->grid_size = gr->grid_size;
+  ctx->totgrid = gr->totgrid;
+  ctx->totvert = (int)E;
+  ctx->h_co.assign(gr->co, gr->co + (size_t)3 * E);
+  ctx->has_no = gr->no != nullptr;
+  if (gr->no) ctx->h_no.assign(gr->no, gr->no + (size_t)3 * E);
+  ctx->has_mask = gr->mask != nullptr;
+  if (gr->mask) ctx->h_mask.assign(gr->mask, gr->mask + E);
+  ctx->h_face_start.assign(gr->face_start_grid, gr->face_start_grid + gr->totface);
+  ctx->h_face_num.assign(gr->face_num_grids, gr->face_num_grids + gr->totface);
+  ctx->h_edge_off.assign(gr->edge_offsets, gr->edge_offsets + gr->totedge + 1);
+  ctx->h_edge_elems.assign(gr->edge_elems, gr->edge_elems + (size_t)gr->edge_offsets[gr->totedge] * 2 * gr->grid_size);
+  ctx->h_cvert_off.assign(gr->cvert_offsets, gr->cvert_offsets + gr->totcvert + 1);
+  ctx->h_cvert_elems.assign(gr->cvert_elems, gr->cvert_elems + gr->cvert_offsets[gr->totcvert]);
+  ctx->h_grid_edge.assign(gr->grid_edge, gr->grid_edge + gr->totgrid);
+  ctx->h_grid_cvert.assign(gr->grid_cvert, gr->grid_cvert + gr->totgrid);
+  ctx->tottri = gr->totgrid; /* the PBVH's prims */
+  ctx->has_nb = false;
+  ctx->have_mesh = true;
+  return DSC_OK;
+}
+
 int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
 {
   if (!ctx || !pb) return fail(ctx, DSC_ERR_INVALID, "NULL argument");
@@ -670,7 +716,41 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   std::vector<int> tile_leaf;
   long long cur = 0;
   int expect_prim = 0;
-  {
+  std::vector<int> grid_slot0;
+  if (ctx->is_grids) {
+    /* a leaf's elements: its grids in prim order, each grid's grid_size^2 elements in (y, x) order
+     * (the order pbvh_vertex_iter walks them, pbvh.c:4840-4897); tiles = runs of DSC_TILE slots */
+    const int gs2 = ctx->grid_size * ctx->grid_size;
+    grid_slot0.assign((size_t)ctx->totgrid, -1);
+    for (int l = 0; l < L; l++) {
+      const int n = leaves[l];
+      cur = (cur + 31) & ~31ll;
+      leaf_ubeg[l] = (int)cur;
+      leaf_pbeg[l] = pb->prim_offset[n];
+      leaf_pcnt[l] = pb->totprim[n];
+      leaf_ucnt[l] = leaf_pcnt[l] * gs2;
+      leaf_scnt[l] = 0;
+      if (pb->uniq_verts[n] != leaf_ucnt[l] || pb->face_verts[n] != 0)
+        return fail(ctx, DSC_ERR_INVALID, "grid leaf %d: uniq_verts must be totprim * grid_size^2, face_verts 0", n);
+      if (leaf_pbeg[l] != expect_prim) return fail(ctx, DSC_ERR_INVALID, "leaf prim ranges do not tile prim_indices");
+      expect_prim += leaf_pcnt[l];
+      for (int k = 0; k < leaf_pcnt[l]; k++) {
+        const int g = pb->prim_indices[leaf_pbeg[l] + k];
+        if (g < 0 || g >= ctx->totgrid || grid_slot0[g] != -1) return fail(ctx, DSC_ERR_INVALID, "grid %d is not in exactly one leaf", g);
+        grid_slot0[g] = (int)cur + k * gs2;
+        for (int j = 0; j < gs2; j++) ctx->slot_of[(size_t)g * gs2 + j] = (int)cur + k * gs2 + j;
+      }
+      leaf_tile0[l] = (int)tile_range.size();
+      for (int o = 0; o < leaf_ucnt[l]; o += DSC_TILE) {
+        tile_range.push_back(make_int2((int)cur + o, std::min(DSC_TILE, leaf_ucnt[l] - o)));
+        tile_leaf.push_back(l);
+      }
+      cur += leaf_ucnt[l];
+      if (cur > 0x7fffff00ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 slots");
+    }
+    leaf_tile0[L] = (int)tile_range.size();
+  }
+  else {
     std::vector<int> ord;
     const float *hco = ctx->h_co.data();
     for (int l = 0; l < L; l++) {
@@ -819,9 +899,93 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     CU(cudaStreamSynchronize(ctx->stream));
   }
 
-  /* looptris by position; vertex -> looptri CSR; per-tile local tables of the shared-memory normals kernel */
   std::vector<int> leaf_sbeg(L);
   std::vector<unsigned char> leaf_fast(L, 1);
+  if (ctx->is_grids) {
+    /* grids: no mesh connectivity tables; the tile kernel is not used (leaf_fast = 0 keeps the box
+     * reset of the refit tagging off: k_grid_leaf_bb stores whole boxes) */
+    std::fill(leaf_fast.begin(), leaf_fast.end(), (unsigned char)0);
+    std::vector<TileMeta> tmeta((size_t)std::max(NT, 1));
+    for (int t = 0; t < NT; t++) {
+      tmeta[t].ubeg = tile_range[t].x;
+      tmeta[t].ucnt = tile_range[t].y;
+      tmeta[t].leaf = tile_leaf[t];
+      tmeta[t].tile0 = leaf_tile0[tile_leaf[t]];
+      tmeta[t].ntfast = leaf_tile0[tile_leaf[t] + 1] - leaf_tile0[tile_leaf[t]];
+    }
+    std::vector<int> one(1, 0);
+    std::vector<unsigned> oneu(1, 0u);
+    std::vector<unsigned short> e_pv(8, 0);
+    std::vector<unsigned> v2_goff((size_t)VP / 32 + 1, 0u);
+    if ((r = dev_upload_c(ctx, &m.stage_slots, one)) || (r = dev_upload_c(ctx, &m.e_pv, e_pv)) ||
+        (r = dev_upload_c(ctx, &m.e_halo_leaf, one)) || (r = dev_upload_c(ctx, &m.tile_meta, tmeta)) ||
+        (r = dev_upload_c(ctx, &m.tile_range, tile_range)) || (r = dev_upload_c(ctx, &m.leaf_tile0, leaf_tile0)) ||
+        (r = dev_upload_c(ctx, &m.v2_goff, v2_goff)) || (r = dev_upload_c(ctx, &m.v2_idx, oneu)) ||
+        (r = dev_upload_c(ctx, &m.leaf_fast, leaf_fast)))
+      return r;
+    m.ntile = NT;
+    ctx->nb_smem = 1024;
+    m.sm_off_f = m.sm_off_e = m.sm_off_v2 = m.sm_off_h = 0;
+    if ((r = dev_zero(ctx, &m.tile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
+        (r = dev_zero(ctx, &m.atile_list, (size_t)std::max(NT, 1) * DSC_SLOTS)) ||
+        (r = dev_zero(ctx, &m.flag_tile_list, (size_t)std::max(NT, 1))))
+      return r;
+    /* grid tables, element indices -> slots */
+    DevGrids &g = ctx->g;
+    memset(&g, 0, sizeof(g));
+    g.gs = ctx->grid_size;
+    g.gs2 = g.gs * g.gs;
+    g.totgrid = ctx->totgrid;
+    g.totface = (int)ctx->h_face_start.size();
+    g.totedge = (int)ctx->h_edge_off.size() - 1;
+    g.totcvert = (int)ctx->h_cvert_off.size() - 1;
+    std::vector<int> grid_face((size_t)g.totgrid, 0), leaf_gbeg((size_t)L + 1, 0), leaf_grids((size_t)T);
+    for (int f = 0; f < g.totface; f++) {
+      for (int c = 0; c < ctx->h_face_num[f]; c++) {
+        const int gr = ctx->h_face_start[f] + c;
+        if (gr < 0 || gr >= g.totgrid) return fail(ctx, DSC_ERR_INVALID, "face %d names grid %d", f, gr);
+        grid_face[gr] = f;
+      }
+    }
+    for (int l = 0; l < L; l++) {
+      leaf_gbeg[l] = leaf_pbeg[l];
+      for (int k = 0; k < leaf_pcnt[l]; k++) leaf_grids[leaf_pbeg[l] + k] = pb->prim_indices[leaf_pbeg[l] + k];
+    }
+    leaf_gbeg[L] = T;
+    auto to_slot = [&](const std::vector<int> &elems, std::vector<int> &out) -> bool {
+      out.resize(elems.size());
+      for (size_t i = 0; i < elems.size(); i++) {
+        if (elems[i] < 0 || elems[i] >= V) return false;
+        out[i] = ctx->slot_of[elems[i]];
+      }
+      return true;
+    };
+    std::vector<int> edge_slots, cvert_slots;
+    if (!to_slot(ctx->h_edge_elems, edge_slots) || !to_slot(ctx->h_cvert_elems, cvert_slots))
+      return fail(ctx, DSC_ERR_INVALID, "grid adjacency names an element out of range");
+    ctx->has_odd_edges = false;
+    for (int e = 0; e < g.totedge; e++) {
+      if (ctx->h_edge_off[e + 1] - ctx->h_edge_off[e] > 2) ctx->has_odd_edges = true;
+    }
+    if ((r = dev_upload_c(ctx, &g.grid_slot0, grid_slot0)) || (r = dev_upload_c(ctx, &g.leaf_gbeg, leaf_gbeg)) ||
+        (r = dev_upload_c(ctx, &g.leaf_grids, leaf_grids)) || (r = dev_upload_c(ctx, &g.face_start, ctx->h_face_start)) ||
+        (r = dev_upload_c(ctx, &g.face_num, ctx->h_face_num)) || (r = dev_upload_c(ctx, &g.grid_face, grid_face)) ||
+        (r = dev_upload_c(ctx, &g.grid_edge, ctx->h_grid_edge)) || (r = dev_upload_c(ctx, &g.grid_cvert, ctx->h_grid_cvert)) ||
+        (r = dev_upload_c(ctx, &g.edge_off, ctx->h_edge_off)) || (r = dev_upload_c(ctx, &g.edge_slots, edge_slots)) ||
+        (r = dev_upload_c(ctx, &g.cvert_off, ctx->h_cvert_off)) || (r = dev_upload_c(ctx, &g.cvert_slots, cvert_slots)))
+      return r;
+    if ((r = dev_zero(ctx, &g.face_stamp, (size_t)g.totface + 1)) || (r = dev_zero(ctx, &g.edge_stamp, (size_t)g.totedge + 1)) ||
+        (r = dev_zero(ctx, &g.cvert_stamp, (size_t)g.totcvert + 1)) || (r = dev_zero(ctx, &g.face_list, (size_t)g.totface + 1)) ||
+        (r = dev_zero(ctx, &g.edge_list, (size_t)g.totedge + 1)) || (r = dev_zero(ctx, &g.cvert_list, (size_t)g.totcvert + 1)) ||
+        (r = dev_zero(ctx, &g.cnt, 1)))
+      return r;
+    g.mask = ctx->has_mask ? ctx->d_mask : nullptr;
+    ctx->gn_smem = dsc_grid_normals_smem(g.gs);
+    CU(cudaFuncSetAttribute(k_grid_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->gn_smem));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  else
+  /* looptris by position; vertex -> looptri CSR; per-tile local tables of the shared-memory normals kernel */
   {
     std::vector<int> tri_leaf((size_t)std::max(T, 1), 0);
     std::vector<unsigned> deg((size_t)VP + 1, 0);
@@ -1464,9 +1628,87 @@ static int dist_gather_all(DscContext *ctx)
   return DSC_OK;
 }
 
+/* ---- multires grids: the stages after the brush ---- */
+static int grids_reset_counts(DscContext *ctx)
+{
+  CU(cudaMemsetAsync(ctx->g.cnt, 0, sizeof(GridCounts), ctx->stream));
+  return DSC_OK;
+}
+/* KERNEL_subdiv_ccg_average_grids (subdiv_ccg.c:1170-1189): every face, edge and vertex */
+static int grids_average_all(DscContext *ctx)
+{
+  DevGrids &g = ctx->g;
+  std::vector<int> iota((size_t)g.totface);
+  for (int f = 0; f < g.totface; f++) iota[f] = f;
+  GridCounts c = {g.totface, 0, 0, 0};
+  CU(cudaMemcpyAsync(g.face_list, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(g.cnt, &c, sizeof(c), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  k_grid_inner<<<ctx->num_sms * 4, 128, 0, ctx->stream>>>(ctx->m, g);
+  LAUNCH_CHECK();
+  k_grid_edges<<<ctx->num_sms * 4, 128, 0, ctx->stream>>>(ctx->m, g, 2, 0);
+  LAUNCH_CHECK();
+  k_grid_cverts<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, g, 1);
+  LAUNCH_CHECK();
+  ctx->launches += 3;
+  return DSC_OK;
+}
+/* KERNEL_subdiv_ccg_recalc_normals (subdiv_ccg.c:782-790) */
+static int grids_recalc_normals(DscContext *ctx)
+{
+  k_grid_normals<<<ctx->num_sms * 2, GN_BLOCK, ctx->gn_smem, ctx->stream>>>(ctx->m, ctx->g, 1);
+  LAUNCH_CHECK();
+  ctx->launches++;
+  return grids_average_all(ctx);
+}
+/* after the brush of a dab on grids: stitch, CCG normals of the gathered leaves' faces, leaf boxes */
+static int grids_after_brush(DscContext *ctx, LeafList hits)
+{
+  DevGrids &g = ctx->g;
+  DevMesh &m = ctx->m;
+  cudaStream_t st = ctx->stream;
+  int r;
+  const int seq = ++ctx->grid_seq;
+  if ((r = grids_reset_counts(ctx))) return r;
+  StageScope s(ctx, ST_NORMALS);
+  k_grid_faces<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, hits.list, hits.count, seq);
+  LAUNCH_CHECK();
+  k_grid_adjacency<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(g, seq);
+  LAUNCH_CHECK();
+  /* multires_stitch_grids (multires.c:1171-1196 -> subdiv_ccg.c:1303-1324): the faces' inner boundaries, then
+   * all coarse edges (two-face edges no dab touched average to themselves: only the touched ones and those with
+   * more faces run) and all coarse vertices */
+  k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
+  LAUNCH_CHECK();
+  k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 0, seq);
+  LAUNCH_CHECK();
+  if (ctx->has_odd_edges) {
+    k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 1, seq);
+    LAUNCH_CHECK();
+    ctx->launches++;
+  }
+  k_grid_cverts<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, 1);
+  LAUNCH_CHECK();
+  /* BKE_pbvh_update_normals, PBVH_GRIDS branch (pbvh.c:4575-4583 -> subdiv_ccg.c:847-866) */
+  k_grid_normals<<<ctx->num_sms * 2, GN_BLOCK, ctx->gn_smem, st>>>(m, g, 0);
+  LAUNCH_CHECK();
+  k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
+  LAUNCH_CHECK();
+  k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 0, seq);
+  LAUNCH_CHECK();
+  k_grid_cverts<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, 0);
+  LAUNCH_CHECK();
+  /* BKE_pbvh_update_bounds: leaf boxes (the refit follows on the side stream) */
+  k_grid_leaf_bb<<<ctx->num_sms * 4, DSC_BLOCK, 0, st>>>(m, hits.list, hits.count);
+  LAUNCH_CHECK();
+  ctx->launches += 10;
+  return DSC_OK;
+}
+
 int dsc_recalc_normals(DscContext *ctx)
 {
   NEED_PBVH();
+  if (ctx->is_grids) return grids_recalc_normals(ctx);
   {
     StageScope s(ctx, ST_OTHER);
     const int n = std::max(ctx->m.nleaf, 1);
@@ -1580,6 +1822,11 @@ static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *s
     return fail(ctx, DSC_ERR_UNSUPPORTED, "sculpt tool %d is not on the accelerated path", tool);
   if (tool == DSC_TOOL_SMOOTH && !ctx->has_nb) return fail(ctx, DSC_ERR_STATE, "smooth brush needs the neighbour CSR (DscMeshDesc.nb_offsets)");
   if (!(dab->radius > 0.0f)) return fail(ctx, DSC_ERR_INVALID, "radius must be positive");
+  if (ctx->is_grids) {
+    if (tool == DSC_TOOL_SMOOTH) return fail(ctx, DSC_ERR_UNSUPPORTED, "the smooth brush is not on the grids path (grid neighbours, subdiv_ccg.c:1882-1909)");
+    if (dab->flags & (DSC_DAB_NO_NORMALS | DSC_DAB_NO_BOUNDS))
+      return fail(ctx, DSC_ERR_UNSUPPORTED, "on grids every dab stitches, updates normals and bounds");
+  }
   static_assert(sizeof(DabParams) == sizeof(DscDab), "DabParams mirrors DscDab");
   static_assert(sizeof(DabEntry) == 128, "DabEntry is 128 bytes");
   memset(e, 0, sizeof(*e));
@@ -1714,7 +1961,10 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
         LAUNCH_CHECK();
       }
     }
-    if (mode) {
+    if (ctx->is_grids) {
+      if ((r = grids_after_brush(ctx, hits))) return r;
+    }
+    else if (mode) {
       if ((r = run_normals_bounds(ctx, hits, mode, pdl && !dist && tool != DSC_TOOL_SMOOTH))) return r;
     }
     if (do_bounds && !dist) {
@@ -1859,7 +2109,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     if (dist && (ctx->stale_flags || !sig.do_normals || !sig.do_bounds))
       return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
     /* how many of the following dabs share the launch sequence */
-    const bool graphable = ctx->use_graphs && !ctx->stage_timing && !ctx->capture && !dist && !ctx->stale_flags &&
+    const bool graphable = ctx->use_graphs && !ctx->is_grids && !ctx->stage_timing && !ctx->capture && !dist && !ctx->stale_flags &&
                            !ctx->any_slow_leaf && sig.do_normals && sig.do_bounds;
     int run = 1;
     const long long seq = ctx->ring_seq; /* ring position: runs across strokes; the state slot follows dab_index */
@@ -2035,6 +2285,7 @@ int dsc_stroke_stats(DscContext *ctx, DscStrokeStats *r)
 int dsc_update_normals(DscContext *ctx)
 {
   NEED_PBVH();
+  if (ctx->is_grids) return DSC_OK; /* every dab on grids updates its normals; nothing is ever left flagged */
   return run_flagged(ctx, F_UpdateNormals);
 }
 
@@ -2055,7 +2306,7 @@ int dsc_update_bounds(DscContext *ctx, int flag)
 {
   NEED_PBVH();
   int r;
-  if (flag & DSC_PBVH_UpdateBB) {
+  if ((flag & DSC_PBVH_UpdateBB) && !ctx->is_grids) {
     if ((r = run_flagged(ctx, F_UpdateBB))) return r;
   }
   if (flag & DSC_PBVH_UpdateOriginalBB) {
@@ -2113,6 +2364,23 @@ int dsc_host_unregister(DscContext *ctx, void *ptr)
 {
   if (!ctx || !ptr) return DSC_ERR_INVALID;
   CU(cudaHostUnregister(ptr));
+  return DSC_OK;
+}
+__global__ void k_export1(float *__restrict__ out, const float *__restrict__ a, const int *__restrict__ slot_of, int totvert)
+{
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < totvert; v += gridDim.x * blockDim.x) out[v] = a[slot_of[v]];
+}
+int dsc_download_mask(DscContext *ctx, float *r_mask)
+{
+  NEED_PBVH();
+  if (!r_mask) return fail(ctx, DSC_ERR_INVALID, "output pointer is NULL");
+  if (!ctx->m.mask) return fail(ctx, DSC_ERR_STATE, "no mask layer resident");
+  int r = join_side(ctx);
+  if (r) return r;
+  k_export1<<<ctx->grid, 256, 0, ctx->stream>>>(ctx->d_stage3, ctx->m.mask, ctx->d_slot_of, ctx->totvert);
+  LAUNCH_CHECK();
+  CU(cudaMemcpyAsync(r_mask, ctx->d_stage3, sizeof(float) * (size_t)ctx->totvert, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return DSC_OK;
 }
 int dsc_download_no(DscContext *ctx, float *r_no)
@@ -2180,6 +2448,7 @@ int dsc_upload_co(DscContext *ctx, const float *co)
 {
   NEED_PBVH();
   if (!co) return fail(ctx, DSC_ERR_INVALID, "co is NULL");
+  if (ctx->is_grids) return fail(ctx, DSC_ERR_UNSUPPORTED, "vert_coords_apply is a mesh entry point (pbvh.c:4707 asserts PBVH_FACES data)");
   int r = join_side(ctx);
   if (r) return r;
   CU(cudaMemcpyAsync(ctx->d_stage3, co, sizeof(float) * 3 * (size_t)ctx->totvert, cudaMemcpyHostToDevice, ctx->stream));
@@ -2209,12 +2478,13 @@ int dsc_state_save(DscContext *ctx)
   DevMesh &m = ctx->m;
   const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode;
   if (!ctx->d_save_v) {
-    if ((r = dev_alloc(ctx, &ctx->d_save_v, 6 * VP)) || (r = dev_alloc(ctx, &ctx->d_save_bb, 12 * N)) ||
+    if ((r = dev_alloc(ctx, &ctx->d_save_v, 7 * VP)) || (r = dev_alloc(ctx, &ctx->d_save_bb, 12 * N)) ||
         (r = dev_alloc(ctx, &ctx->d_save_flag, N)))
       return r;
   }
   float *src[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
   for (int k = 0; k < 6; k++) CU(cudaMemcpyAsync(ctx->d_save_v + k * VP, src[k], VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->is_grids && m.mask) CU(cudaMemcpyAsync(ctx->d_save_v + 6 * VP, m.mask, VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_save_bb, m.bb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_save_bb + 6 * N, m.obb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_save_flag, m.node_flag, N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -2233,6 +2503,7 @@ int dsc_state_restore(DscContext *ctx)
   const size_t VP = (size_t)ctx->vpad, N = (size_t)ctx->totnode;
   float *dst[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
   for (int k = 0; k < 6; k++) CU(cudaMemcpyAsync(dst[k], ctx->d_save_v + k * VP, VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->is_grids && m.mask) CU(cudaMemcpyAsync(ctx->d_mask, ctx->d_save_v + 6 * VP, VP * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(m.bb, ctx->d_save_bb, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(m.obb, ctx->d_save_bb + 6 * N, 6 * N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(m.node_flag, ctx->d_save_flag, N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -1,0 +1,276 @@
+/* Multires grids (PBVH_GRIDS) on the device: what runs after the brush when the resident mesh is a
+ * SubdivCCG -- the stitch of duplicated boundary elements (kernel/intern/multires.c:1171-1196 ->
+ * subdiv_ccg.c:1303-1324), the CCG normal update of the faces of the gathered leaves
+ * (pbvh.c:3523-3566, subdiv_ccg.c:670-866, 1237-1281) and the leaf boxes.  Gather, area normal and
+ * brush are the mesh kernels: a leaf's grid elements are one contiguous run of slots
+ * (slot = first slot of the grid + y * grid_size + x), so to those kernels a grid element is a vertex.
+ *
+ * The reference runs every averaging phase as a parallel loop over faces / coarse edges / coarse
+ * vertices whose tasks write disjoint elements; the phases below keep its order, and every sum runs
+ * in the order of the reference's lists, so the results are bit-identical to the CPU path. */
+#pragma once
+#include "dsc_kernels.cuh"
+
+struct GridCounts {
+  int faces, edges, cverts, pad;
+};
+
+struct DevGrids {
+  int gs, gs2, totgrid, totface, totedge, totcvert;
+  const int *grid_slot0;              /* [totgrid] slot of element (0, 0) */
+  const int *leaf_gbeg, *leaf_grids;  /* [nleaf + 1] into leaf_grids: the grids of a leaf (PBVHNode.prim_indices) */
+  const int *face_start, *face_num, *grid_face, *grid_edge, *grid_cvert;
+  const int *edge_off, *edge_slots;   /* SubdivCCGAdjacentEdge.boundary_coords as slots: [edge_off[e] + f][2 * gs] */
+  const int *cvert_off, *cvert_slots; /* SubdivCCGAdjacentVertex.corner_coords as slots */
+  int *face_stamp, *edge_stamp, *cvert_stamp;
+  int *face_list, *edge_list, *cvert_list;
+  GridCounts *cnt;
+  float *mask; /* per-slot mask layer (averaged along with co / no), or NULL */
+};
+
+/* BKE_pbvh_get_grid_updates (pbvh.c:3523-3566): the faces of the grids of the listed leaves, each once */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_faces(DevMesh m, DevGrids g, const int *list, const int *count, int seq)
+{
+  const int n = *count;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int l = list[h];
+    const int b = g.leaf_gbeg[l], e = g.leaf_gbeg[l + 1];
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int f = g.grid_face[g.leaf_grids[i]];
+      if (atomicExch(&g.face_stamp[f], seq) != seq) g.face_list[atomicAdd(&g.cnt->faces, 1)] = f;
+    }
+  }
+}
+
+/* subdiv_ccg_affected_face_adjacency (subdiv_ccg.c:1191-1235): coarse edges and vertices of those faces */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_adjacency(DevGrids g, int seq)
+{
+  const int n = g.cnt->faces;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = g.face_list[i];
+    for (int c = 0; c < g.face_num[f]; c++) {
+      const int gr = g.face_start[f] + c;
+      const int e = g.grid_edge[gr], v = g.grid_cvert[gr];
+      if (atomicExch(&g.edge_stamp[e], seq) != seq) g.edge_list[atomicAdd(&g.cnt->edges, 1)] = e;
+      if (atomicExch(&g.cvert_stamp[v], seq) != seq) g.cvert_list[atomicAdd(&g.cnt->cverts, 1)] = v;
+    }
+  }
+}
+
+/* average_grid_element (subdiv_ccg.c:873-897) */
+__device__ __forceinline__ void dsc_grid_average_pair(const DevMesh &m, const DevGrids &g, int a, int b)
+{
+  float *arr[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    float v = arr[k][a] + arr[k][b];
+    v = v * 0.5f;
+    arr[k][a] = v;
+    arr[k][b] = v;
+  }
+  if (g.mask) {
+    const float mk = (g.mask[a] + g.mask[b]) * 0.5f;
+    g.mask[a] = mk;
+    g.mask[b] = mk;
+  }
+}
+
+/* element_accumulator_* (subdiv_ccg.c:899-949): sum in list order, scale by 1 / n, copy to all */
+__device__ __forceinline__ void dsc_grid_average_list(const DevMesh &m, const DevGrids &g, const int *slots, int n, int stride)
+{
+  float acc[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < n; i++) {
+    const int s = slots[(size_t)i * stride];
+    acc[0] += m.cx[s]; acc[1] += m.cy[s]; acc[2] += m.cz[s];
+    acc[3] += m.nx[s]; acc[4] += m.ny[s]; acc[5] += m.nz[s];
+    if (g.mask) acc[6] += g.mask[s];
+  }
+  const float f = 1.0f / (float)n;
+#pragma unroll
+  for (int k = 0; k < 7; k++) acc[k] *= f;
+  for (int i = 0; i < n; i++) {
+    const int s = slots[(size_t)i * stride];
+    m.cx[s] = acc[0]; m.cy[s] = acc[1]; m.cz[s] = acc[2];
+    m.nx[s] = acc[3]; m.ny[s] = acc[4]; m.nz[s] = acc[5];
+    if (g.mask) g.mask[s] = acc[6];
+  }
+}
+
+/* subdiv_ccg_average_inner_face_grids (subdiv_ccg.c:951-984) of the listed faces: one CTA per face */
+__global__ void __launch_bounds__(128) k_grid_inner(DevMesh m, DevGrids g)
+{
+  const int n = g.cnt->faces;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int f = g.face_list[h];
+    const int nc = g.face_num[f], start = g.face_start[f];
+    const int per = g.gs - 1;
+    for (int t = threadIdx.x; t < nc * per; t += blockDim.x) {
+      const int corner = t / per, i = 1 + t % per;
+      const int grid = start + corner, prev = start + (corner + nc - 1) % nc;
+      dsc_grid_average_pair(m, g, g.grid_slot0[prev] + i, g.grid_slot0[grid] + i * g.gs);
+    }
+    if (threadIdx.x == 0) dsc_grid_average_list(m, g, g.grid_slot0 + start, nc, 1);
+  }
+}
+
+/* subdiv_ccg_average_grids_boundary (subdiv_ccg.c:1010-1048): listed coarse edges (all == 0), every edge
+ * (all == 2), or every edge that is not in the list and has more than two faces (all == 1: averaging two equal values is
+ * exact, so untouched two-face edges need no pass) */
+__global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int all, int seq)
+{
+  const int n = all ? g.totedge : g.cnt->edges;
+  const int gs2 = 2 * g.gs;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int e = all ? h : g.edge_list[h];
+    const int nf = g.edge_off[e + 1] - g.edge_off[e];
+    if (nf == 1) continue;
+    if (all == 1 && (nf == 2 || g.edge_stamp[e] == seq)) continue;
+    const int *base = g.edge_slots + (size_t)g.edge_off[e] * gs2;
+    for (int i = 1 + threadIdx.x; i < gs2 - 1; i += blockDim.x) dsc_grid_average_list(m, g, base + i, nf, gs2);
+  }
+}
+
+/* subdiv_ccg_average_grids_corners (subdiv_ccg.c:1081-1104): listed coarse vertices, or all of them */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g, int all)
+{
+  const int n = all ? g.totcvert : g.cnt->cverts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = all ? i : g.cvert_list[i];
+    const int nf = g.cvert_off[v + 1] - g.cvert_off[v];
+    if (nf == 1) continue;
+    dsc_grid_average_list(m, g, g.cvert_slots + g.cvert_off[v], nf, 1);
+  }
+}
+
+/* subdiv_ccg_recalc_inner_face_normals + subdiv_ccg_average_inner_face_normals (subdiv_ccg.c:670-740)
+ * of every grid of the listed faces (all == 0) or of all grids: one CTA per grid, positions and quad
+ * normals in shared memory */
+#define GN_BLOCK 256
+__host__ __device__ inline size_t dsc_grid_normals_smem(int gs) { return sizeof(float) * 3 * ((size_t)gs * gs + (size_t)(gs - 1) * (gs - 1)); }
+__global__ void __launch_bounds__(GN_BLOCK) k_grid_normals(DevMesh m, DevGrids g, int all)
+{
+  extern __shared__ float gsm[];
+  const int gs = g.gs, gs1 = gs - 1, gs2 = g.gs2;
+  float *P = gsm;           /* [gs2][3] */
+  float *Fn = gsm + 3 * gs2; /* [gs1 * gs1][3] */
+  const int units = all ? g.totgrid : g.cnt->faces * 4; /* listed faces: up to 4 corners each, more via the loop below */
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    int grid;
+    if (all) {
+      grid = u;
+    }
+    else {
+      const int f = g.face_list[u >> 2], c = u & 3;
+      if (c >= g.face_num[f]) continue;
+      grid = g.face_start[f] + c;
+    }
+    /* faces with more than 4 corners: corner c also takes c + 4, c + 8, ... */
+    for (;;) {
+      const int s0 = g.grid_slot0[grid];
+      __syncthreads();
+      for (int i = threadIdx.x; i < gs2; i += GN_BLOCK) {
+        P[3 * i] = m.cx[s0 + i]; P[3 * i + 1] = m.cy[s0 + i]; P[3 * i + 2] = m.cz[s0 + i];
+      }
+      __syncthreads();
+      for (int q = threadIdx.x; q < gs1 * gs1; q += GN_BLOCK) {
+        const int y = q / gs1, x = q - y * gs1;
+        /* normal_quad_v3(co(x, y+1), co(x+1, y+1), co(x+1, y), co(x, y)), subdiv_ccg.c:684-698 */
+        const float *v1 = P + 3 * ((y + 1) * gs + x), *v2 = P + 3 * ((y + 1) * gs + x + 1);
+        const float *v3 = P + 3 * (y * gs + x + 1), *v4 = P + 3 * (y * gs + x);
+        const float n1x = v1[0] - v3[0], n1y = v1[1] - v3[1], n1z = v1[2] - v3[2];
+        const float n2x = v2[0] - v4[0], n2y = v2[1] - v4[1], n2z = v2[2] - v4[2];
+        float ox = n1y * n2z - n1z * n2y;
+        float oy = n1z * n2x - n1x * n2z;
+        float oz = n1x * n2y - n1y * n2x;
+        dsc_normalize(ox, oy, oz);
+        Fn[3 * q] = ox; Fn[3 * q + 1] = oy; Fn[3 * q + 2] = oz;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < gs2; i += GN_BLOCK) {
+        const int y = i / gs, x = i - y * gs;
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        int counter = 0;
+        if (x < gs1 && y < gs1) {
+          const float *f = Fn + 3 * (y * gs1 + x);
+          ax += f[0]; ay += f[1]; az += f[2];
+          counter++;
+        }
+        if (x >= 1) {
+          if (y < gs1) {
+            const float *f = Fn + 3 * (y * gs1 + (x - 1));
+            ax += f[0]; ay += f[1]; az += f[2];
+            counter++;
+          }
+          if (y >= 1) {
+            const float *f = Fn + 3 * ((y - 1) * gs1 + (x - 1));
+            ax += f[0]; ay += f[1]; az += f[2];
+            counter++;
+          }
+        }
+        if (y >= 1 && x < gs1) {
+          const float *f = Fn + 3 * ((y - 1) * gs1 + x);
+          ax += f[0]; ay += f[1]; az += f[2];
+          counter++;
+        }
+        const float sc = 1.0f / (float)counter;
+        m.nx[s0 + i] = ax * sc; m.ny[s0 + i] = ay * sc; m.nz[s0 + i] = az * sc;
+      }
+      if (all) break;
+      const int f = g.face_list[u >> 2];
+      const int c = grid - g.face_start[f] + 4;
+      if (c >= g.face_num[f]) break;
+      grid = g.face_start[f] + c;
+    }
+  }
+}
+
+/* update_node_vb leaf branch for grid leaves (pbvh.c:2033-2041 with PBVH_ITER_ALL over the node's
+ * grids): box of every element of the listed leaves; the leaf's vert_bitmap words are cleared on the
+ * way (the grid normal pass does not use them) */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_leaf_bb(DevMesh m, const int *list, const int *count)
+{
+  __shared__ float red[6][DSC_BLOCK / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tn = m.totnode;
+  const int n = *count;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int l = list[h];
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    const int ub = m.leaf_ubeg[l], uc = m.leaf_ucnt[l];
+    for (int i = 4 * tid; i < uc; i += 4 * DSC_BLOCK) {
+      const float4 X = ld4(m.cx, ub + i), Y = ld4(m.cy, ub + i), Z = ld4(m.cz, ub + i);
+      const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (i + j < uc) {
+          mn[0] = fminf(mn[0], xs[j]); mx[0] = fmaxf(mx[0], xs[j]);
+          mn[1] = fminf(mn[1], ys[j]); mx[1] = fmaxf(mx[1], ys[j]);
+          mn[2] = fminf(mn[2], zs[j]); mx[2] = fmaxf(mx[2], zs[j]);
+        }
+      }
+    }
+    for (int w = tid; w < (uc + 31) / 32; w += DSC_BLOCK) m.dirty[(ub >> 5) + w] = 0u;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[k] = fminf(mn[k], __shfl_down_sync(0xffffffffu, mn[k], o));
+        mx[k] = fmaxf(mx[k], __shfl_down_sync(0xffffffffu, mx[k], o));
+      }
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        red[k][warp] = mn[k];
+        red[3 + k][warp] = mx[k];
+      }
+    }
+    __syncthreads();
+    if (tid < 6) {
+      float v = red[tid][0];
+      for (int w = 1; w < DSC_BLOCK / 32; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+      m.bb[tid * tn + l] = v;
+    }
+  }
+}

@@ -85,6 +85,8 @@ typedef struct BuildJob {
   bool root_cb;
 } BuildJob;
 
+static char g_attach_error[512];
+
 static inline float minf(float a, float b) { return (a < b) ? a : b; }
 static inline float maxf(float a, float b) { return (a > b) ? a : b; }
 
@@ -188,7 +190,7 @@ static int split_by_centroid(int *prims, int lo, int hi, int axis, float mid, co
 PBVH *BKE_pbvh_new(void)
 {
   PBVH *pbvh = calloc(1, sizeof(PBVH));
-  pbvh->leaf_limit = LEAF_LIMIT;
+  pbvh->leaf_limit = 0; /* the build picks LEAF_LIMIT (pbvh.c:2482) or LEAF_LIMIT / gridsize^2 (pbvh.c:2533) */
   return pbvh;
 }
 
@@ -204,7 +206,70 @@ void DUNE_pbvh_vert_normals_set(PBVH *pbvh, float (*vert_normals)[3])
   pbvh->vert_normals = vert_normals;
   pbvh->owns_normals = false;
 }
-void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit) { pbvh->leaf_limit = leaf_limit > 0 ? leaf_limit : LEAF_LIMIT; }
+void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit) { pbvh->leaf_limit = leaf_limit > 0 ? leaf_limit : 0; }
+
+/* pbvh_build / build_sub (pbvh.c:2372-2450) over the prim boxes `pb` */
+static void build_tree(PBVH *pbvh, const PrimBox *pb, int nprims, const BB *cb, int *stamp, int *local)
+{
+  /* pre-order walk, left subtree first: node numbering and vertex ownership then come out as in
+   * the recursive build_sub (pbvh.c:2372-2425) */
+  int cap = 128, top = 0;
+  BuildJob *stack = malloc(sizeof(BuildJob) * (size_t)cap);
+  stack[top++] = (BuildJob){0, 0, nprims, true};
+  while (top) {
+    const BuildJob job = stack[--top];
+    if (job.count <= pbvh->leaf_limit) {
+      PBVHNode *node = &pbvh->nodes[job.node];
+      node->flag |= PBVH_Leaf;
+      node->prim_indices = pbvh->prim_indices + job.offset;
+      node->totprim = (unsigned)job.count;
+      node_box_from_prims(pbvh, node, pb, job.offset, job.count);
+      if (pbvh->is_grids) {
+        /* build_grid_leaf_node: no vertex list, the node's elements are its grids' elements */
+        node->uniq_verts = (unsigned)(job.count * pbvh->gridkey.grid_area);
+        node->face_verts = 0;
+        node->flag |= PBVH_UpdateDrawBuffers;
+      }
+      else {
+        leaf_collect_verts(pbvh, node, job.node, stamp, local);
+      }
+      continue;
+    }
+    const int child = pbvh->totnode;
+    ensure_nodes(pbvh, pbvh->totnode + 2);
+    PBVHNode *node = &pbvh->nodes[job.node];
+    node->children_offset = child;
+    node_box_from_prims(pbvh, node, pb, job.offset, job.count);
+    BB c;
+    if (job.root_cb) {
+      c = *cb;
+    }
+    else {
+      bb_clear(&c);
+      for (int i = job.offset + job.count - 1; i >= job.offset; i--) {
+        const float *mid = pb[pbvh->prim_indices[i]].mid;
+        for (int k = 0; k < 3; k++) {
+          c.bmin[k] = minf(c.bmin[k], mid[k]);
+          c.bmax[k] = maxf(c.bmax[k], mid[k]);
+        }
+      }
+    }
+    /* widest centroid extent (pbvh.c:1995-2016), split at the midpoint (pbvh.c:2402-2410) */
+    const float dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
+    int axis;
+    if (dx > dy) axis = (dx > dz) ? 0 : 2;
+    else axis = (dy > dz) ? 1 : 2;
+    const int end = split_by_centroid(pbvh->prim_indices, job.offset, job.offset + job.count - 1, axis,
+                                      (c.bmax[axis] + c.bmin[axis]) * 0.5f, pb);
+    if (top + 2 > cap) {
+      cap *= 2;
+      stack = realloc(stack, sizeof(BuildJob) * (size_t)cap);
+    }
+    stack[top++] = (BuildJob){child + 1, end, job.offset + job.count - end, false};
+    stack[top++] = (BuildJob){child, job.offset, end - job.offset, false};
+  }
+  free(stack);
+}
 
 void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, const MLoop *mloop, MVert *verts,
                          int totvert, struct CustomData *vdata, struct CustomData *ldata, struct CustomData *pdata,
@@ -260,60 +325,342 @@ void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, cons
   int *local = malloc(sizeof(int) * (size_t)totvert);
   for (int i = 0; i < totvert; i++) stamp[i] = -1;
 
-  /* pre-order walk, left subtree first: node numbering and vertex ownership then come out as in
-   * the recursive build_sub (pbvh.c:2372-2425) */
-  int cap = 128, top = 0;
-  BuildJob *stack = malloc(sizeof(BuildJob) * (size_t)cap);
-  stack[top++] = (BuildJob){0, 0, looptri_num, true};
-  while (top) {
-    const BuildJob job = stack[--top];
-    if (job.count <= pbvh->leaf_limit) {
-      PBVHNode *node = &pbvh->nodes[job.node];
-      node->flag |= PBVH_Leaf;
-      node->prim_indices = pbvh->prim_indices + job.offset;
-      node->totprim = (unsigned)job.count;
-      node_box_from_prims(pbvh, node, pb, job.offset, job.count);
-      leaf_collect_verts(pbvh, node, job.node, stamp, local);
-      continue;
-    }
-    const int child = pbvh->totnode;
-    ensure_nodes(pbvh, pbvh->totnode + 2);
-    PBVHNode *node = &pbvh->nodes[job.node];
-    node->children_offset = child;
-    node_box_from_prims(pbvh, node, pb, job.offset, job.count);
-    BB c;
-    if (job.root_cb) {
-      c = cb;
-    }
-    else {
-      bb_clear(&c);
-      for (int i = job.offset + job.count - 1; i >= job.offset; i--) {
-        const float *mid = pb[pbvh->prim_indices[i]].mid;
-        for (int k = 0; k < 3; k++) {
-          c.bmin[k] = minf(c.bmin[k], mid[k]);
-          c.bmax[k] = maxf(c.bmax[k], mid[k]);
-        }
-      }
-    }
-    /* widest centroid extent (pbvh.c:1995-2016), split at the midpoint (pbvh.c:2402-2410) */
-    const float dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
-    int axis;
-    if (dx > dy) axis = (dx > dz) ? 0 : 2;
-    else axis = (dy > dz) ? 1 : 2;
-    const int end = split_by_centroid(pbvh->prim_indices, job.offset, job.offset + job.count - 1, axis,
-                                      (c.bmax[axis] + c.bmin[axis]) * 0.5f, pb);
-    if (top + 2 > cap) {
-      cap *= 2;
-      stack = realloc(stack, sizeof(BuildJob) * (size_t)cap);
-    }
-    stack[top++] = (BuildJob){child + 1, end, job.offset + job.count - end, false};
-    stack[top++] = (BuildJob){child, job.offset, end - job.offset, false};
-  }
-  free(stack);
+  build_tree(pbvh, pb, looptri_num, &cb, stamp, local);
   free(stamp);
   free(local);
   free(pb);
   memset(pbvh->vert_bitmap, 0, sizeof(unsigned) * ((size_t)totvert / 32 + 1)); /* pbvh.c:2512-2513 */
+}
+
+
+/* ------------------------------------------------------------------------------ multires grids */
+
+static inline float *ccg_elem_co(const CCGKey *key, CCGElem *grid, int j)
+{
+  return (float *)((unsigned char *)grid + (size_t)key->elem_size * (size_t)j);
+}
+
+/* pbvh.c:2516-2561 BKE_pbvh_build_grids: per-grid box over all its elements, then the same tree build
+ * as for looptris; a grid leaf keeps no vertex list (its elements are its grids' elements) */
+void BKE_pbvh_build_grids(PBVH *pbvh, CCGElem **grids, int totgrid, CCGKey *key, void **gridfaces, DMFlagMat *flagmats,
+                          BLI_bitmap **grid_hidden)
+{
+  const int gridsize = key->grid_size;
+  pbvh->is_grids = 1;
+  pbvh->grids = grids;
+  pbvh->gridfaces = gridfaces;
+  pbvh->grid_flag_mats = flagmats;
+  pbvh->totgrid = totgrid;
+  pbvh->gridkey = *key;
+  pbvh->grid_hidden = grid_hidden;
+  if (pbvh->leaf_limit <= 0) {
+    pbvh->leaf_limit = LEAF_LIMIT / (gridsize * gridsize);
+    if (pbvh->leaf_limit < 1) pbvh->leaf_limit = 1;
+  }
+  pbvh->totvert = totgrid * gridsize * gridsize;
+  if (!totgrid) return;
+
+  PrimBox *pb = malloc(sizeof(PrimBox) * (size_t)totgrid);
+  BB cb;
+  bb_clear(&cb);
+  for (int i = 0; i < totgrid; i++) {
+    PrimBox *b = &pb[i];
+    for (int k = 0; k < 3; k++) {
+      b->lo[k] = FLT_MAX;
+      b->hi[k] = -FLT_MAX;
+    }
+    for (int j = 0; j < gridsize * gridsize; j++) {
+      const float *co = ccg_elem_co(key, grids[i], j);
+      for (int k = 0; k < 3; k++) {
+        b->lo[k] = minf(b->lo[k], co[k]);
+        b->hi[k] = maxf(b->hi[k], co[k]);
+      }
+    }
+    for (int k = 0; k < 3; k++) {
+      b->mid[k] = (b->lo[k] + b->hi[k]) * 0.5f;
+      cb.bmin[k] = minf(cb.bmin[k], b->mid[k]);
+      cb.bmax[k] = maxf(cb.bmax[k], b->mid[k]);
+    }
+  }
+  pbvh->totprim = totgrid;
+  pbvh->prim_indices = malloc(sizeof(int) * (size_t)totgrid);
+  for (int i = 0; i < totgrid; i++) pbvh->prim_indices[i] = i;
+  pbvh->node_mem_count = 0;
+  pbvh->totnode = 0;
+  ensure_nodes(pbvh, 100);
+  pbvh->totnode = 1;
+  build_tree(pbvh, pb, totgrid, &cb, NULL, NULL);
+  free(pb);
+}
+
+void BKE_pbvh_node_get_grids(PBVH *pbvh, PBVHNode *node, int **r_grid_indices, int *r_totgrid, int *r_maxgrid, int *r_gridsize,
+                             CCGElem ***r_griddata)
+{
+  /* pbvh.c:3770-3800, PBVH_GRIDS case */
+  if (r_grid_indices) *r_grid_indices = node->prim_indices;
+  if (r_totgrid) *r_totgrid = (int)node->totprim;
+  if (r_maxgrid) *r_maxgrid = pbvh->totgrid;
+  if (r_gridsize) *r_gridsize = pbvh->gridkey.grid_size;
+  if (r_griddata) *r_griddata = pbvh->grids;
+}
+
+void BKE_subdiv_ccg_key_top_level(CCGKey *key, const SubdivCCG *subdiv_ccg)
+{
+  /* subdiv_ccg.c:633-651 */
+  key->level = subdiv_ccg->level;
+  key->elem_size = subdiv_ccg->grid_element_size;
+  key->grid_size = subdiv_ccg->grid_size;
+  key->grid_area = key->grid_size * key->grid_size;
+  key->grid_bytes = key->elem_size * key->grid_area;
+  key->normal_offset = subdiv_ccg->normal_offset;
+  key->mask_offset = subdiv_ccg->mask_offset;
+  key->has_normals = subdiv_ccg->has_normal;
+  key->has_mask = subdiv_ccg->has_mask;
+}
+
+SubdivCCG *DUNE_subdiv_ccg_from_tables(int level, int num_grids, const float *co, const float *no, const float *mask,
+                                       int num_faces, const int *face_start_grid, const int *face_num_grids, int num_edges,
+                                       const int *edge_offsets, const int *edge_elems, int num_vertices,
+                                       const int *vert_offsets, const int *vert_elems, const int *grid_edge,
+                                       const int *grid_vertex)
+{
+  SubdivCCG *ccg = calloc(1, sizeof(SubdivCCG));
+  const int gs = (1 << (level - 1)) + 1, area = gs * gs; /* BKE_subdiv_grid_size_from_level */
+  ccg->level = level;
+  ccg->grid_size = gs;
+  ccg->num_grids = num_grids;
+  /* layers: co, then mask, then normals (subdiv_ccg.c:62-90); normals are always kept here */
+  int off = (int)sizeof(float[3]);
+  ccg->has_mask = mask != NULL;
+  ccg->mask_offset = ccg->has_mask ? off : -1;
+  if (ccg->has_mask) off += (int)sizeof(float);
+  ccg->has_normal = true;
+  ccg->normal_offset = off;
+  off += (int)sizeof(float[3]);
+  ccg->grid_element_size = off;
+  ccg->grids = calloc((size_t)(num_grids ? num_grids : 1), sizeof(CCGElem *));
+  ccg->grids_storage = calloc((size_t)num_grids * (size_t)area, (size_t)off);
+  for (int g = 0; g < num_grids; g++) {
+    ccg->grids[g] = (CCGElem *)(ccg->grids_storage + (size_t)g * (size_t)area * (size_t)off);
+    for (int j = 0; j < area; j++) {
+      unsigned char *e = (unsigned char *)ccg->grids[g] + (size_t)j * (size_t)off;
+      const size_t idx = (size_t)g * (size_t)area + (size_t)j;
+      memcpy(e, co + 3 * idx, sizeof(float[3]));
+      if (mask) memcpy(e + ccg->mask_offset, mask + idx, sizeof(float));
+      if (no) memcpy(e + ccg->normal_offset, no + 3 * idx, sizeof(float[3]));
+    }
+  }
+  ccg->num_faces = num_faces;
+  ccg->faces = calloc((size_t)(num_faces ? num_faces : 1), sizeof(SubdivCCGFace));
+  ccg->grid_faces = calloc((size_t)(num_grids ? num_grids : 1), sizeof(SubdivCCGFace *));
+  for (int f = 0; f < num_faces; f++) {
+    ccg->faces[f].start_grid_index = face_start_grid[f];
+    ccg->faces[f].num_grids = face_num_grids[f];
+    for (int c = 0; c < face_num_grids[f]; c++) ccg->grid_faces[face_start_grid[f] + c] = &ccg->faces[f];
+  }
+  ccg->num_adjacent_edges = num_edges;
+  ccg->adjacent_edges = calloc((size_t)(num_edges ? num_edges : 1), sizeof(SubdivCCGAdjacentEdge));
+  for (int e = 0; e < num_edges; e++) {
+    SubdivCCGAdjacentEdge *ae = &ccg->adjacent_edges[e];
+    ae->num_adjacent_faces = edge_offsets[e + 1] - edge_offsets[e];
+    ae->boundary_coords = calloc((size_t)(ae->num_adjacent_faces ? ae->num_adjacent_faces : 1), sizeof(SubdivCCGCoord *));
+    for (int f = 0; f < ae->num_adjacent_faces; f++) {
+      ae->boundary_coords[f] = malloc(sizeof(SubdivCCGCoord) * (size_t)(2 * gs));
+      const int *row = edge_elems + (size_t)(edge_offsets[e] + f) * (size_t)(2 * gs);
+      for (int i = 0; i < 2 * gs; i++) {
+        SubdivCCGCoord *c = &ae->boundary_coords[f][i];
+        c->grid_index = row[i] / area;
+        c->y = (short)((row[i] % area) / gs);
+        c->x = (short)((row[i] % area) % gs);
+      }
+    }
+  }
+  ccg->num_adjacent_vertices = num_vertices;
+  ccg->adjacent_vertices = calloc((size_t)(num_vertices ? num_vertices : 1), sizeof(SubdivCCGAdjacentVertex));
+  for (int v = 0; v < num_vertices; v++) {
+    SubdivCCGAdjacentVertex *av = &ccg->adjacent_vertices[v];
+    av->num_adjacent_faces = vert_offsets[v + 1] - vert_offsets[v];
+    av->corner_coords = malloc(sizeof(SubdivCCGCoord) * (size_t)(av->num_adjacent_faces ? av->num_adjacent_faces : 1));
+    for (int f = 0; f < av->num_adjacent_faces; f++) {
+      const int el = vert_elems[vert_offsets[v] + f];
+      av->corner_coords[f].grid_index = el / area;
+      av->corner_coords[f].y = (short)((el % area) / gs);
+      av->corner_coords[f].x = (short)((el % area) % gs);
+    }
+  }
+  ccg->grid_edge = malloc(sizeof(int) * (size_t)(num_grids ? num_grids : 1));
+  ccg->grid_vertex = malloc(sizeof(int) * (size_t)(num_grids ? num_grids : 1));
+  memcpy(ccg->grid_edge, grid_edge, sizeof(int) * (size_t)num_grids);
+  memcpy(ccg->grid_vertex, grid_vertex, sizeof(int) * (size_t)num_grids);
+  return ccg;
+}
+
+void DUNE_subdiv_ccg_free(SubdivCCG *ccg)
+{
+  if (!ccg) return;
+  for (int e = 0; e < ccg->num_adjacent_edges; e++) {
+    for (int f = 0; f < ccg->adjacent_edges[e].num_adjacent_faces; f++) free(ccg->adjacent_edges[e].boundary_coords[f]);
+    free(ccg->adjacent_edges[e].boundary_coords);
+  }
+  for (int v = 0; v < ccg->num_adjacent_vertices; v++) free(ccg->adjacent_vertices[v].corner_coords);
+  free(ccg->adjacent_edges); free(ccg->adjacent_vertices); free(ccg->faces); free(ccg->grid_faces);
+  free(ccg->grids); free(ccg->grids_storage); free(ccg->grid_edge); free(ccg->grid_vertex);
+  free(ccg);
+}
+
+/* the CCG's elements and adjacency as the flat tables of DscGridsDesc, the grids PBVH as DscPbvhDesc */
+int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *ccg, int device)
+{
+  g_attach_error[0] = 0;
+  if (!pbvh || !pbvh->nodes || !pbvh->is_grids || !ccg) return DSC_ERR_INVALID;
+  if (pbvh->device) return DSC_OK;
+  DscContext *ctx = NULL;
+  int r = dsc_ctx_create(device, &ctx);
+  if (r != DSC_OK) {
+    snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(NULL));
+    return r;
+  }
+  const CCGKey *key = &pbvh->gridkey;
+  const int gs = key->grid_size, area = key->grid_area, G = pbvh->totgrid, N = pbvh->totnode;
+  const size_t E = (size_t)G * (size_t)area;
+  float *co = malloc(sizeof(float[3]) * E), *no = malloc(sizeof(float[3]) * E);
+  float *mask = key->has_mask ? malloc(sizeof(float) * E) : NULL;
+  bool have_no = false;
+  for (int g = 0; g < G; g++) {
+    for (int j = 0; j < area; j++) {
+      const unsigned char *e = (const unsigned char *)pbvh->grids[g] + (size_t)key->elem_size * (size_t)j;
+      const size_t idx = (size_t)g * (size_t)area + (size_t)j;
+      memcpy(co + 3 * idx, e, sizeof(float[3]));
+      if (key->has_normals) {
+        memcpy(no + 3 * idx, e + key->normal_offset, sizeof(float[3]));
+        have_no = have_no || no[3 * idx] != 0.0f || no[3 * idx + 1] != 0.0f || no[3 * idx + 2] != 0.0f;
+      }
+      if (mask) memcpy(mask + idx, e + key->mask_offset, sizeof(float));
+    }
+  }
+  int *face_start = malloc(sizeof(int) * (size_t)(ccg->num_faces + 1)), *face_num = malloc(sizeof(int) * (size_t)(ccg->num_faces + 1));
+  for (int f = 0; f < ccg->num_faces; f++) {
+    face_start[f] = ccg->faces[f].start_grid_index;
+    face_num[f] = ccg->faces[f].num_grids;
+  }
+  int *edge_off = malloc(sizeof(int) * (size_t)(ccg->num_adjacent_edges + 1));
+  edge_off[0] = 0;
+  for (int e = 0; e < ccg->num_adjacent_edges; e++) edge_off[e + 1] = edge_off[e] + ccg->adjacent_edges[e].num_adjacent_faces;
+  int *edge_elems = malloc(sizeof(int) * ((size_t)edge_off[ccg->num_adjacent_edges] * 2 * (size_t)gs + 1));
+  for (int e = 0; e < ccg->num_adjacent_edges; e++) {
+    for (int f = 0; f < ccg->adjacent_edges[e].num_adjacent_faces; f++) {
+      const SubdivCCGCoord *row = ccg->adjacent_edges[e].boundary_coords[f];
+      int *out = edge_elems + (size_t)(edge_off[e] + f) * 2 * (size_t)gs;
+      for (int i = 0; i < 2 * gs; i++) out[i] = row[i].grid_index * area + row[i].y * gs + row[i].x;
+    }
+  }
+  int *vert_off = malloc(sizeof(int) * (size_t)(ccg->num_adjacent_vertices + 1));
+  vert_off[0] = 0;
+  for (int v = 0; v < ccg->num_adjacent_vertices; v++) vert_off[v + 1] = vert_off[v] + ccg->adjacent_vertices[v].num_adjacent_faces;
+  int *vert_elems = malloc(sizeof(int) * ((size_t)vert_off[ccg->num_adjacent_vertices] + 1));
+  for (int v = 0; v < ccg->num_adjacent_vertices; v++) {
+    for (int f = 0; f < ccg->adjacent_vertices[v].num_adjacent_faces; f++) {
+      const SubdivCCGCoord *c = &ccg->adjacent_vertices[v].corner_coords[f];
+      vert_elems[vert_off[v] + f] = c->grid_index * area + c->y * gs + c->x;
+    }
+  }
+  DscGridsDesc gd = {0};
+  gd.totgrid = G;
+  gd.grid_size = gs;
+  gd.co = co;
+  gd.no = have_no ? no : NULL;
+  gd.mask = mask;
+  gd.totface = ccg->num_faces;
+  gd.face_start_grid = face_start;
+  gd.face_num_grids = face_num;
+  gd.totedge = ccg->num_adjacent_edges;
+  gd.edge_offsets = edge_off;
+  gd.edge_elems = edge_elems;
+  gd.totcvert = ccg->num_adjacent_vertices;
+  gd.cvert_offsets = vert_off;
+  gd.cvert_elems = vert_elems;
+  gd.grid_edge = ccg->grid_edge;
+  gd.grid_cvert = ccg->grid_vertex;
+  r = dsc_grids_upload(ctx, &gd);
+
+  float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
+  int *child = malloc(sizeof(int) * (size_t)N), *flag = malloc(sizeof(int) * (size_t)N), *prim_off = malloc(sizeof(int) * (size_t)N);
+  int *totprim = malloc(sizeof(int) * (size_t)N), *uniq = malloc(sizeof(int) * (size_t)N), *face = malloc(sizeof(int) * (size_t)N);
+  for (int n = 0; n < N; n++) {
+    const PBVHNode *node = &pbvh->nodes[n];
+    memcpy(bb + 6 * (size_t)n, &node->vb, sizeof(float[6]));
+    memcpy(obb + 6 * (size_t)n, &node->orig_vb, sizeof(float[6]));
+    child[n] = node->children_offset;
+    flag[n] = (int)node->flag;
+    const bool leaf = (node->flag & PBVH_Leaf) != 0;
+    prim_off[n] = leaf ? (int)(node->prim_indices - pbvh->prim_indices) : 0;
+    totprim[n] = leaf ? (int)node->totprim : 0;
+    uniq[n] = leaf ? (int)node->totprim * area : 0;
+    face[n] = 0;
+  }
+  DscPbvhDesc pd = {0};
+  pd.totnode = N;
+  pd.node_bb = bb;
+  pd.node_orig_bb = obb;
+  pd.children_offset = child;
+  pd.flag = flag;
+  pd.prim_offset = prim_off;
+  pd.totprim = totprim;
+  pd.prim_indices = pbvh->prim_indices;
+  pd.uniq_verts = uniq;
+  pd.face_verts = face;
+  if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
+  free(co); free(no); free(mask); free(face_start); free(face_num); free(edge_off); free(edge_elems); free(vert_off);
+  free(vert_elems); free(bb); free(obb); free(child); free(flag); free(prim_off); free(totprim); free(uniq); free(face);
+  if (r != DSC_OK) {
+    snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(ctx));
+    dsc_ctx_destroy(ctx);
+    return r;
+  }
+  pbvh->device = ctx;
+  pbvh->subdiv_ccg = ccg;
+  pbvh->device_dirty = !have_no; /* the device computed the normals */
+  return DSC_OK;
+}
+
+/* device -> CCGElem storage (co, no, mask) and node boxes / flags */
+static int sync_grids_to_host(PBVH *pbvh)
+{
+  const CCGKey *key = &pbvh->gridkey;
+  const int area = key->grid_area, G = pbvh->totgrid, N = pbvh->totnode;
+  const size_t E = (size_t)G * (size_t)area;
+  float *co = malloc(sizeof(float[3]) * E), *no = malloc(sizeof(float[3]) * E);
+  float *mask = key->has_mask ? malloc(sizeof(float) * E) : NULL;
+  int r = dsc_download_co(pbvh->device, co);
+  if (r == DSC_OK) r = dsc_download_no(pbvh->device, no);
+  if (r == DSC_OK && mask) r = dsc_download_mask(pbvh->device, mask);
+  if (r == DSC_OK) {
+    for (int g = 0; g < G; g++) {
+      for (int j = 0; j < area; j++) {
+        unsigned char *e = (unsigned char *)pbvh->grids[g] + (size_t)key->elem_size * (size_t)j;
+        const size_t idx = (size_t)g * (size_t)area + (size_t)j;
+        memcpy(e, co + 3 * idx, sizeof(float[3]));
+        if (key->has_normals) memcpy(e + key->normal_offset, no + 3 * idx, sizeof(float[3]));
+        if (mask) memcpy(e + key->mask_offset, mask + idx, sizeof(float));
+      }
+    }
+  }
+  free(co); free(no); free(mask);
+  if (r != DSC_OK) return r;
+  float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
+  int *flag = malloc(sizeof(int) * (size_t)N);
+  r = dsc_download_node_bb(pbvh->device, bb, obb);
+  if (r == DSC_OK) r = dsc_download_node_flags(pbvh->device, flag);
+  if (r == DSC_OK) {
+    for (int n = 0; n < N; n++) {
+      memcpy(&pbvh->nodes[n].vb, bb + 6 * (size_t)n, sizeof(float[6]));
+      memcpy(&pbvh->nodes[n].orig_vb, obb + 6 * (size_t)n, sizeof(float[6]));
+      pbvh->nodes[n].flag = (unsigned)flag[n];
+    }
+    pbvh->device_dirty = false;
+  }
+  free(bb); free(obb); free(flag);
+  return r;
 }
 
 void BKE_pbvh_free(PBVH *pbvh)
@@ -414,8 +761,6 @@ static void build_neighbor_tables(PBVH *pbvh)
 }
 
 /* -------------------------------------------------------------------------- device hooks */
-
-static char g_attach_error[512];
 
 const char *DUNE_pbvh_device_error(const PBVH *pbvh)
 {
@@ -576,6 +921,7 @@ int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
 {
   if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
   if (!pbvh->device_dirty) return DSC_OK;
+  if (pbvh->is_grids) return sync_grids_to_host(pbvh);
   const int V = pbvh->totvert, N = pbvh->totnode;
   if (!pbvh->deformed) {
     /* first write: take a private copy like BKE_pbvh_vert_coords_apply (pbvh.c:4714-4725) */

@@ -59,7 +59,58 @@ typedef struct MLoopTri {
 
 struct Mesh;       /* opaque here */
 struct CustomData; /* opaque here */
-struct SubdivCCG;
+
+/* ---- multires grids: the CCG types behind BKE_pbvh_build_grids (pbvh.c:2516-2561).  Their headers are
+ * absent from the reference; field names are the ones kernel/intern/subdiv_ccg.c uses. ---- */
+typedef struct CCGElem CCGElem; /* co[3], then mask, then no[3]: subdiv_ccg.c:62-90 */
+typedef struct CCGKey {          /* subdiv_ccg.c:633-646 */
+  int level;
+  int elem_size;
+  int grid_size, grid_area, grid_bytes;
+  int normal_offset, mask_offset;
+  int has_normals, has_mask;
+} CCGKey;
+typedef struct DMFlagMat {
+  short mat_nr;
+  char flag;
+} DMFlagMat;
+typedef unsigned int BLI_bitmap;
+typedef struct SubdivCCGCoord { /* subdiv_ccg.c:368-372 */
+  int grid_index;
+  short x, y;
+} SubdivCCGCoord;
+typedef struct SubdivCCGFace { /* subdiv_ccg.c:134-140 */
+  int num_grids;
+  int start_grid_index;
+} SubdivCCGFace;
+typedef struct SubdivCCGAdjacentEdge { /* subdiv_ccg.c:383-397 */
+  int num_adjacent_faces;
+  SubdivCCGCoord **boundary_coords; /* [num_adjacent_faces][2 * grid_size] */
+} SubdivCCGAdjacentEdge;
+typedef struct SubdivCCGAdjacentVertex { /* subdiv_ccg.c:472-483 */
+  int num_adjacent_faces;
+  SubdivCCGCoord *corner_coords;
+} SubdivCCGAdjacentVertex;
+typedef struct SubdivCCG { /* subdiv_ccg.c:104-140 */
+  int level;
+  int grid_size;
+  int grid_element_size;
+  int num_grids;
+  CCGElem **grids;
+  unsigned char *grids_storage;
+  bool has_normal, has_mask;
+  int normal_offset, mask_offset;
+  int num_faces;
+  SubdivCCGFace *faces;
+  SubdivCCGFace **grid_faces;
+  int num_adjacent_edges;
+  SubdivCCGAdjacentEdge *adjacent_edges;
+  int num_adjacent_vertices;
+  SubdivCCGAdjacentVertex *adjacent_vertices;
+  /* in place of the OpenSubdiv topology refiner the reference asks for a face's edges and vertices
+   * (subdiv_ccg.c:1198-1223): per grid, the coarse edge / vertex of its face corner */
+  int *grid_edge, *grid_vertex;
+} SubdivCCG;
 
 /* kernel/intern/pbvh_intern.h:4-7 */
 typedef struct BB {
@@ -115,6 +166,16 @@ typedef struct PBVH {
   bool deformed;
   bool owns_normals;
 
+  /* PBVH_GRIDS (pbvh.c:2527-2533) */
+  int is_grids;
+  CCGElem **grids;
+  void **gridfaces;
+  const DMFlagMat *grid_flag_mats;
+  int totgrid;
+  CCGKey gridkey;
+  BLI_bitmap **grid_hidden;
+  struct SubdivCCG *subdiv_ccg; /* set by DUNE_pbvh_device_attach_grids */
+
   /* device side */
   DscContext *device;
   bool device_dirty; /* the device holds newer positions / normals / boxes than the host arrays */
@@ -138,7 +199,22 @@ PBVH *BKE_pbvh_new(void);
 void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, const MLoop *mloop, MVert *verts,
                          int totvert, struct CustomData *vdata, struct CustomData *ldata, struct CustomData *pdata,
                          const MLoopTri *looptri, int looptri_num);
+void BKE_pbvh_build_grids(PBVH *pbvh, CCGElem **grids, int totgrid, CCGKey *key, void **gridfaces, DMFlagMat *flagmats,
+                          BLI_bitmap **grid_hidden);
 void BKE_pbvh_free(PBVH *pbvh);
+/* pbvh.c:3770-3800 */
+void BKE_pbvh_node_get_grids(PBVH *pbvh, PBVHNode *node, int **r_grid_indices, int *r_totgrid, int *r_maxgrid,
+                             int *r_gridsize, CCGElem ***r_griddata);
+/* subdiv_ccg.c:633-651 */
+void BKE_subdiv_ccg_key_top_level(CCGKey *key, const SubdivCCG *subdiv_ccg);
+/* not in the reference: a SubdivCCG from flat tables (what BKE_subdiv_to_ccg builds through OpenSubdiv,
+ * subdiv_ccg.c:104-140, 397-530); element index = grid * grid_size^2 + y * grid_size + x.  Copies everything. */
+SubdivCCG *DUNE_subdiv_ccg_from_tables(int level, int num_grids, const float *co, const float *no, const float *mask,
+                                       int num_faces, const int *face_start_grid, const int *face_num_grids, int num_edges,
+                                       const int *edge_offsets, const int *edge_elems, int num_vertices,
+                                       const int *vert_offsets, const int *vert_elems, const int *grid_edge,
+                                       const int *grid_vertex);
+void DUNE_subdiv_ccg_free(SubdivCCG *subdiv_ccg);
 /* not in the reference: sizes and layers the reference pulls out of Mesh / CustomData */
 void DUNE_pbvh_mesh_sizes_set(PBVH *pbvh, int totpoly, int totloop);
 void DUNE_pbvh_mask_layer_set(PBVH *pbvh, float *vmask);
@@ -147,6 +223,8 @@ void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit);
 
 /* ---- device hooks (new) ---- */
 int DUNE_pbvh_device_attach(PBVH *pbvh, int device);
+/* the same for a grids PBVH: the CCG's elements and adjacency go to the device */
+int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device);
 /* one rank of a PBVH partitioned across the GPUs of one box (see dsc_dist_init) */
 int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, const char *nccl_id);
 void DUNE_pbvh_device_detach(PBVH *pbvh);

@@ -95,7 +95,31 @@ typedef struct DscMeshDesc {
   const unsigned int *vert_tail;
 } DscMeshDesc;
 
-/* The built PBVH, flattened.  Replaces PBVH.nodes / PBVHNode (kernel/intern/pbvh_intern.h:15-162). */
+/* Multires grids instead of a mesh: a SubdivCCG (kernel/intern/subdiv_ccg.c) as flat tables.  Replaces
+ * the arrays BKE_pbvh_build_grids borrows (pbvh.c:2516-2561: grids, gridkey, gridfaces) and the
+ * adjacency SubdivCCG keeps (faces, adjacent_edges, adjacent_vertices, subdiv_ccg.c:397-530).  Element
+ * index = grid * grid_size^2 + y * grid_size + x; CCGElem fields de-interleaved. */
+typedef struct DscGridsDesc {
+  int totgrid, grid_size;
+  const float *co;   /* [totgrid * grid_size^2][3] CCG_elem_co */
+  const float *no;   /* same shape, CCG_elem_no, or NULL: computed on the device */
+  const float *mask; /* [totgrid * grid_size^2] CCG_elem_mask, or NULL */
+  int totface;
+  const int *face_start_grid; /* SubdivCCGFace.start_grid_index */
+  const int *face_num_grids;  /* SubdivCCGFace.num_grids */
+  int totedge;
+  const int *edge_offsets;    /* [totedge + 1] in adjacent faces (SubdivCCGAdjacentEdge.num_adjacent_faces) */
+  const int *edge_elems;      /* [edge_offsets[totedge]][2 * grid_size] boundary_coords as element indices */
+  int totcvert;
+  const int *cvert_offsets;   /* [totcvert + 1] (SubdivCCGAdjacentVertex.num_adjacent_faces) */
+  const int *cvert_elems;     /* corner_coords as element indices */
+  const int *grid_edge;       /* [totgrid] coarse edge of the grid's face corner (getFaceEdges order) */
+  const int *grid_cvert;      /* [totgrid] coarse vertex of the grid's face corner (getFaceVertices order) */
+} DscGridsDesc;
+
+/* The built PBVH, flattened.  Replaces PBVH.nodes / PBVHNode (kernel/intern/pbvh_intern.h:15-162).
+ * For grids the prims are grids, uniq_verts = totprim * grid_size^2, face_verts = 0 and vert_offset /
+ * vert_indices are not read (a grid leaf's elements are its grids' elements in order). */
 typedef struct DscPbvhDesc {
   int totnode;
   const float *node_bb;      /* [totnode][6] PBVHNode.vb (bmin, bmax) */
@@ -148,6 +172,10 @@ int dsc_abi_version(void);
 
 /* --- session start: behind BKE_pbvh_build_mesh (pbvh.c:2452-2514) ------------------------- */
 int dsc_mesh_upload(DscContext *ctx, const DscMeshDesc *mesh);
+/* behind BKE_pbvh_build_grids (pbvh.c:2516-2561): instead of dsc_mesh_upload.  On grids the dab runs
+ * gather -> brush -> stitch of duplicated boundary elements (multires.c:1171-1196) -> CCG normal update
+ * of the gathered leaves' faces (subdiv_ccg.c:847-866) -> bounds; draw / inflate / grab / clay strips. */
+int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *grids);
 int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pbvh);
 /* vertex normals of the whole mesh from the current positions (all vertices dirty, all leaves
  * flagged): what BKE_pbvh_vert_coords_apply triggers (pbvh.c:4739-4747) */
@@ -194,6 +222,7 @@ int dsc_download_mvert(DscContext *ctx, void *r_mvert /* [totvert] MVert */);
 int dsc_host_register(DscContext *ctx, void *ptr, size_t bytes);
 int dsc_host_unregister(DscContext *ctx, void *ptr);
 int dsc_download_no(DscContext *ctx, float *r_no /* [totvert][3] */);
+int dsc_download_mask(DscContext *ctx, float *r_mask /* [totvert]: the mask layer (grids average it when stitching) */);
 int dsc_download_orig_co(DscContext *ctx, float *r_co /* [totvert][3] */);
 int dsc_download_orig_no(DscContext *ctx, float *r_no /* [totvert][3] */);
 int dsc_download_node_bb(DscContext *ctx, float *r_bb /* [totnode][6] */, float *r_orig_bb /* or NULL */);

@@ -99,6 +99,18 @@ int or_vert_neighbors(int totvert, int totpoly, const int *poly_start, const int
 OrPbvh *or_pbvh_build_mesh(int totvert, const float (*co)[3], const float (*no)[3], const float *mask,
                            int totpoly, const int *poly_start, const int *poly_len, int totloop,
                            const int *loop_v, int leaf_limit /* 0 = LEAF_LIMIT */);
+/* BKE_pbvh_build_grids (pbvh.c:2516-2561) over a SubdivCCG given as flat tables: elements
+ * [totgrid * grid_size^2] (index = grid * gs^2 + y * gs + x), faces (start grid, grid count), adjacent
+ * edges (per edge and adjacent face 2 * gs element indices, subdiv_ccg.c:397-463), adjacent vertices
+ * (corner elements, subdiv_ccg.c:483-530), and per grid the coarse edge / vertex of its face corner
+ * (the order subdiv_ccg.c:1198-1223 walks them) */
+OrPbvh *or_pbvh_build_grids(int totgrid, int grid_size, const float (*co)[3], const float (*no)[3], const float *mask,
+                            int totface, const int *face_start, const int *face_num, int totedge, const int *edge_off,
+                            const int *edge_elems, int totcvert, const int *cvert_off, const int *cvert_elems,
+                            const int *grid_edge, const int *grid_cvert, int leaf_limit /* 0 = LEAF_LIMIT / gs^2 */);
+void or_grids_average_all(OrPbvh *p);  /* KERNEL_subdiv_ccg_average_grids, subdiv_ccg.c:1170-1189 */
+void or_grids_recalc_normals(OrPbvh *p); /* KERNEL_subdiv_ccg_recalc_normals, subdiv_ccg.c:782-790 */
+float *or_pbvh_mask(OrPbvh *p);
 void or_pbvh_free(OrPbvh *p);
 int or_pbvh_totnode(const OrPbvh *p);
 int or_pbvh_tottri(const OrPbvh *p);

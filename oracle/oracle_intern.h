@@ -55,7 +55,21 @@ struct OrPbvh {
   unsigned char *iter_flag; /* smooth: vertex moved in this iteration */
   int *moved_stamp;         /* dab serial at which the vertex was last listed in last_moved */
   int dab_serial;
+
+  /* PBVH_GRIDS (pbvh.c:2516-2561, subdiv_ccg.c): "vertices" are grid elements, element index =
+   * grid * grid_size^2 + y * grid_size + x; prims are grids */
+  int is_grids, totgrid, grid_size;
+  int totface, *face_start, *face_num, *grid_face; /* SubdivCCGFace: start_grid_index, num_grids */
+  int totedge, *edge_off, *edge_elems;             /* SubdivCCGAdjacentEdge.boundary_coords as element indices */
+  int totcvert, *cvert_off, *cvert_elems;          /* SubdivCCGAdjacentVertex.corner_coords */
+  int *grid_edge, *grid_cvert;                     /* coarse edge / vertex at the face corner of each grid */
+  int *face_stamp, *edge_stamp, *cvert_stamp, stamp;
 };
+
+/* oracle_grids.c */
+void or_grids_update_normals(OrPbvh *p, const int *faces, int totface); /* KERNEL_subdiv_ccg_update_normals */
+void or_grids_stitch_faces(OrPbvh *p, const int *faces, int totface);   /* KERNEL_subdiv_ccg_average_stitch_faces */
+int or_grids_get_updates(OrPbvh *p, int clear, int *r_faces);           /* BKE_pbvh_get_grid_updates */
 
 extern int or_threads;
 

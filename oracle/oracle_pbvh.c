@@ -185,6 +185,21 @@ static void build_leaf(OrPbvh *p, LeafMap *map, int node_index, const OrBBC *pri
   p->nodes[node_index].prim_offset = offset;
   p->nodes[node_index].totprim = count;
   update_vb(p, &p->nodes[node_index], prim_bbc, offset, count);
+  if (p->is_grids) {
+    /* build_grid_leaf_node (pbvh.c:2240-2247 neighbourhood): the node's "verts" are the elements of its
+     * grids in the order the vertex iterator walks them (pbvh.c:4840-4897): grid by grid, y, x */
+    OrNode *node = &p->nodes[node_index];
+    const int gs2 = p->grid_size * p->grid_size;
+    node->uniq_verts = count * gs2;
+    node->face_verts = 0;
+    node->vert_indices = malloc(sizeof(int) * (size_t)(node->uniq_verts > 0 ? node->uniq_verts : 1));
+    for (int i = 0; i < count; i++) {
+      const int g = p->prim_indices[offset + i];
+      for (int j = 0; j < gs2; j++) node->vert_indices[i * gs2 + j] = g * gs2 + j;
+    }
+    node->flag |= OR_PBVH_UpdateDrawBuffers;
+    return;
+  }
   build_mesh_leaf_node(p, map, node_index);
 }
 
@@ -312,6 +327,90 @@ OrPbvh *or_pbvh_build_mesh(int totvert, const float (*co)[3], const float (*no)[
   return p;
 }
 
+static int *dup_ints(const int *src, size_t n)
+{
+  int *d = malloc(sizeof(int) * (n ? n : 1));
+  if (n) memcpy(d, src, sizeof(int) * n);
+  return d;
+}
+
+/* pbvh.c:2516-2561 BKE_pbvh_build_grids (+ pbvh_build 2427-2450) */
+OrPbvh *or_pbvh_build_grids(int totgrid, int grid_size, const float (*co)[3], const float (*no)[3], const float *mask,
+                            int totface, const int *face_start, const int *face_num, int totedge, const int *edge_off,
+                            const int *edge_elems, int totcvert, const int *cvert_off, const int *cvert_elems,
+                            const int *grid_edge, const int *grid_cvert, int leaf_limit)
+{
+  OrPbvh *p = calloc(1, sizeof(OrPbvh));
+  const int gs2 = grid_size * grid_size;
+  const size_t totelem = (size_t)totgrid * (size_t)gs2;
+  p->is_grids = 1;
+  p->totgrid = totgrid;
+  p->grid_size = grid_size;
+  p->totvert = (int)totelem;
+  {
+    const int lim = LEAF_LIMIT / gs2; /* pbvh.c:2533 */
+    p->leaf_limit = leaf_limit > 0 ? leaf_limit : (lim > 1 ? lim : 1);
+  }
+  p->co = malloc(sizeof(float[3]) * totelem);
+  memcpy(p->co, co, sizeof(float[3]) * totelem);
+  p->no = calloc(totelem, sizeof(float[3]));
+  if (no) memcpy(p->no, no, sizeof(float[3]) * totelem);
+  if (mask) {
+    p->mask = malloc(sizeof(float) * totelem);
+    memcpy(p->mask, mask, sizeof(float) * totelem);
+  }
+  p->totface = totface;
+  p->face_start = dup_ints(face_start, (size_t)totface);
+  p->face_num = dup_ints(face_num, (size_t)totface);
+  p->grid_face = malloc(sizeof(int) * (size_t)(totgrid ? totgrid : 1));
+  for (int f = 0; f < totface; f++) {
+    for (int c = 0; c < face_num[f]; c++) p->grid_face[face_start[f] + c] = f;
+  }
+  p->totedge = totedge;
+  p->edge_off = dup_ints(edge_off, (size_t)totedge + 1);
+  p->edge_elems = dup_ints(edge_elems, (size_t)edge_off[totedge] * 2 * (size_t)grid_size);
+  p->totcvert = totcvert;
+  p->cvert_off = dup_ints(cvert_off, (size_t)totcvert + 1);
+  p->cvert_elems = dup_ints(cvert_elems, (size_t)cvert_off[totcvert]);
+  p->grid_edge = dup_ints(grid_edge, (size_t)totgrid);
+  p->grid_cvert = dup_ints(grid_cvert, (size_t)totgrid);
+  p->face_stamp = calloc((size_t)totface + 1, sizeof(int));
+  p->edge_stamp = calloc((size_t)totedge + 1, sizeof(int));
+  p->cvert_stamp = calloc((size_t)totcvert + 1, sizeof(int));
+  p->vert_bitmap = calloc(totelem + 1, 1);
+
+  OrBB cb;
+  BB_reset(&cb);
+  OrBBC *prim_bbc = malloc(sizeof(OrBBC) * (size_t)(totgrid > 0 ? totgrid : 1));
+  for (int i = 0; i < totgrid; i++) {
+    OrBBC *bbc = prim_bbc + i;
+    BB_reset((OrBB *)bbc);
+    for (int j = 0; j < gs2; j++) BB_expand((OrBB *)bbc, p->co[(size_t)i * gs2 + j]);
+    for (int k = 0; k < 3; k++) bbc->bcentroid[k] = (bbc->bmin[k] + bbc->bmax[k]) * 0.5f;
+    BB_expand(&cb, bbc->bcentroid);
+  }
+  if (totgrid) {
+    p->totprim = totgrid;
+    p->prim_indices = malloc(sizeof(int) * (size_t)totgrid);
+    for (int i = 0; i < totgrid; i++) p->prim_indices[i] = i;
+    p->node_mem_count = 100;
+    p->nodes = calloc((size_t)p->node_mem_count, sizeof(OrNode));
+    p->totnode = 1;
+    build_sub(p, NULL, 0, &cb, prim_bbc, 0, totgrid);
+  }
+  free(prim_bbc);
+
+  p->orig_co = calloc(totelem, sizeof(float[3]));
+  p->orig_no = calloc(totelem, sizeof(float[3]));
+  p->touched = calloc((size_t)p->totnode + 1, 1);
+  p->last_hits = malloc(sizeof(int) * (size_t)(p->totnode + 1));
+  p->last_moved = malloc(sizeof(int) * (totelem + 1));
+  p->moved_stamp = calloc(totelem + 1, sizeof(int));
+  return p;
+}
+
+float *or_pbvh_mask(OrPbvh *p) { return p->mask; }
+
 /* pbvh.c:2570-2620 */
 void or_pbvh_free(OrPbvh *p)
 {
@@ -327,6 +426,9 @@ void or_pbvh_free(OrPbvh *p)
   free(p->nodes); free(p->prim_indices); free(p->co); free(p->no); free(p->mask);
   free(p->poly_start); free(p->poly_len); free(p->loop_v); free(p->tri_loop); free(p->tri_v);
   free(p->tri_poly); free(p->vert_bitmap); free(p->nb_off); free(p->nb_idx); free(p->boundary);
+  free(p->face_start); free(p->face_num); free(p->grid_face); free(p->edge_off); free(p->edge_elems);
+  free(p->cvert_off); free(p->cvert_elems); free(p->grid_edge); free(p->grid_cvert);
+  free(p->face_stamp); free(p->edge_stamp); free(p->cvert_stamp);
   free(p->automask); free(p->orig_co); free(p->orig_no); free(p->touched); free(p->last_hits);
   free(p->last_moved); free(p->scratch); free(p->iter_flag); free(p->moved_stamp);
   free(p);
@@ -626,7 +728,16 @@ void or_update_normals(OrPbvh *p)
   int *nodes = malloc(sizeof(int) * (size_t)(p->totnode + 1));
   const int totnode = or_gather_flag(p, OR_PBVH_UpdateNormals, nodes);
   if (totnode > 0) {
-    faces_update_normals(p, nodes, totnode);
+    if (p->is_grids) {
+      /* PBVH_GRIDS branch, pbvh.c:4575-4583 */
+      int *faces = malloc(sizeof(int) * (size_t)(p->totface + 1));
+      const int num_faces = or_grids_get_updates(p, 1, faces);
+      if (num_faces > 0) or_grids_update_normals(p, faces, num_faces);
+      free(faces);
+    }
+    else {
+      faces_update_normals(p, nodes, totnode);
+    }
   }
   free(nodes);
 }

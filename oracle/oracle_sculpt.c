@@ -568,11 +568,24 @@ int or_dab(OrPbvh *p, const OrDab *d)
         do_clay_strips_brush(p, d, nodes, totnode);
         break;
       case OR_TOOL_SMOOTH:
+        if (p->is_grids) {
+          return -1; /* grid neighbours (subdiv_ccg.c:1882-1909) are not restated */
+        }
         do_smooth_brush(p, d, nodes, totnode);
         break;
       default:
         return -1;
     }
+  }
+  if (p->is_grids && totnode) {
+    /* multires_stitch_grids (kernel/intern/multires.c:1171-1196): duplicated boundary elements of the
+     * faces of flagged nodes are averaged after the displacement */
+    int *faces = malloc(sizeof(int) * (size_t)(p->totface + 1));
+    const int num_faces = or_grids_get_updates(p, 0, faces);
+    if (num_faces) {
+      or_grids_stitch_faces(p, faces, num_faces);
+    }
+    free(faces);
   }
   if (!(d->flags & OR_DAB_NO_NORMALS)) {
     or_update_normals(p);

@@ -74,6 +74,13 @@ def lib():
         L.or_looptri_count.argtypes = [C.c_int, c_int_p]
         L.or_looptri_calc.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p]
         L.or_vert_neighbors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_void_p]
+        L.or_pbvh_build_grids.restype = C.c_void_p
+        L.or_pbvh_build_grids.argtypes = [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p, C.c_int,
+                                          c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, C.c_int]
+        L.or_grids_average_all.argtypes = [C.c_void_p]
+        L.or_grids_recalc_normals.argtypes = [C.c_void_p]
+        L.or_pbvh_mask.restype = c_float_p
+        L.or_pbvh_mask.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -228,3 +235,33 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+
+class GridOracle(Oracle):
+    """the oracle over a multires CCG (meshgen.Multires): PBVH_GRIDS, prims are grids, "vertices" are
+    grid elements"""
+
+    def __init__(self, mr, leaf_limit=0, threads=1, recalc_normals=True):
+        L = lib()
+        self.L = L
+        self.mesh = mr
+        L.or_set_threads(int(threads))
+        co = np.ascontiguousarray(mr.co, dtype=np.float32)
+        no = np.ascontiguousarray(mr.no, dtype=np.float32)
+        mask = None if mr.mask is None else np.ascontiguousarray(mr.mask, dtype=np.float32)
+        self.p = C.c_void_p(L.or_pbvh_build_grids(
+            mr.totgrid, mr.grid_size, fptr(co), fptr(no), None if mask is None else fptr(mask), int(mr.face_start.shape[0]),
+            iptr(mr.face_start), iptr(mr.face_num), int(mr.edge_off.shape[0] - 1), iptr(mr.edge_off), iptr(mr.edge_elems),
+            int(mr.cvert_off.shape[0] - 1), iptr(mr.cvert_off), iptr(mr.cvert_elems), iptr(mr.grid_edge), iptr(mr.grid_cvert),
+            int(leaf_limit)))
+        self.totnode = L.or_pbvh_totnode(self.p)
+        self.tottri = L.or_pbvh_tottri(self.p)  # prims = grids
+        self.totvert = mr.totelem
+        if recalc_normals:
+            L.or_grids_recalc_normals(self.p)
+
+    def mask(self):
+        ptr = self.L.or_pbvh_mask(self.p)
+        if not ptr:
+            return None
+        return np.ctypeslib.as_array(ptr, shape=(self.totvert,)).copy()

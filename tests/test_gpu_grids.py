@@ -1,0 +1,111 @@
+"""Multires grids on the device vs the CPU oracle: BKE_pbvh_build_grids -> dab (gather, brush, stitch,
+CCG normals, bounds) through the host API and the C ABI, bit for bit."""
+import numpy as np
+import pytest
+
+from dune_sculpt_b200 import capi, meshgen, stroke
+from oracle_py import GridOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_parity(mr, dabs, leaf_limit=0, automask=None):
+    orc = GridOracle(mr, leaf_limit=leaf_limit)
+    ses = capi.GridSession(mr, leaf_limit=leaf_limit, device=0)
+    try:
+        assert orc.totnode == ses.totnode
+        assert np.array_equal(orc.no(), ses.no()), "initial CCG normals differ in bits"
+        assert np.array_equal(orc.co(), ses.co())
+        orc.stroke_begin(automask)
+        ses.stroke_begin(automask)
+        ses.capture(True)
+        for i, d in enumerate(dabs):
+            orc.dab(d)
+            ses.dab(d)
+            assert np.array_equal(orc.hits(), ses.hits()), "dab %d: node-hit list" % i
+            assert np.array_equal(np.sort(orc.moved()), ses.moved()), "dab %d: moved elements" % i
+            ano, aco = orc.last_area()
+            bno, bco = ses.last_area()
+            assert np.array_equal(ano, bno) and np.array_equal(aco, bco), "dab %d: area normal" % i
+        assert np.array_equal(orc.touched(), ses.touched())
+        orc.stroke_end()
+        ses.stroke_end()
+        assert ses.stats()["vertex_dabs"] == orc.vertex_dabs()
+        assert np.array_equal(orc.co(), ses.co()), "positions differ in bits"
+        assert np.array_equal(orc.no(), ses.no()), "normals differ in bits"
+        if mr.mask is not None:
+            assert np.array_equal(orc.mask(), ses.mask()), "mask layer differs in bits"
+        na = orc.node_arrays()
+        bb, obb = ses.node_bb()
+        assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "boxes differ in bits"
+        assert np.array_equal(orc.orig_co(), ses.orig_co()) and np.array_equal(orc.orig_no(), ses.orig_no())
+        keep = capi.PBVH_Leaf | capi.PBVH_UpdateNormals | capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB
+        assert np.array_equal(na["flag"] & keep, ses.node_flags() & keep)
+        # the host's CCGElem storage was refreshed by stroke end
+        hco, hno, hmask = ses.host_elements()
+        assert np.array_equal(hco, orc.co()) and np.array_equal(hno, orc.no())
+        if mr.mask is not None:
+            assert np.array_equal(hmask, orc.mask())
+        return ses.stats()
+    finally:
+        ses.close()
+        orc.close()
+
+
+def _sweep(mr, per=2, tool=None, radii=(4.0, 10.0, 25.0, 45.0), seed=3):
+    """dabs at seeded points of the unit sphere, radius in % of the diagonal"""
+    tool = capi.TOOL_DRAW if tool is None else tool
+    rng = np.random.default_rng(seed)
+    diag = mr.bbox_diag()
+    bs = stroke._strength(tool, 0.5)
+    out = []
+    for pct in radii:
+        for _ in range(per):
+            p = rng.normal(size=3)
+            p /= np.linalg.norm(p)
+            kw = dict(bstrength=bs, view_normal=tuple(p), flags=capi.DAB_FIRST_STEP if not out else 0)
+            if tool in (capi.TOOL_GRAB, capi.TOOL_CLAY_STRIPS):
+                kw["grab_delta"] = tuple(0.05 * rng.normal(size=3))
+            out.append(capi.make_dab(tool, p.astype(np.float32), diag * pct / 100.0, **kw))
+    return out
+
+
+def test_grids_draw_radius_sweep():
+    mr = meshgen.multires_cube(2, 4)           # 96 faces, 384 grids of 9 x 9
+    st = _grid_parity(mr, _sweep(mr), leaf_limit=6)
+    assert st["moved_verts"] > 0
+
+
+def test_grids_with_mask_single_grid_leaves_level5():
+    mr = meshgen.multires_cube(1, 5, with_mask=True)   # 96 grids of 17 x 17, one grid per leaf
+    st = _grid_parity(mr, _sweep(mr, per=2, radii=(6.0, 20.0, 50.0)), leaf_limit=1)
+    assert st["moved_verts"] > 0
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_INFLATE, capi.TOOL_GRAB, capi.TOOL_CLAY_STRIPS])
+def test_grids_other_tools(tool):
+    mr = meshgen.multires_cube(1, 4)
+    _grid_parity(mr, _sweep(mr, per=2, tool=tool, radii=(15.0, 35.0)), leaf_limit=4)
+
+
+def test_grids_default_leaf_limit_c5_shape_reduced():
+    """C5's shape at 1/100 of its size: 6 x 5 x 5 base quads, level 6 (33 x 33 per grid, 653,400
+    elements), default leaf limit (10000 / 1089 = 9 grids per leaf)"""
+    mr = meshgen.multires_cube_n(5, 6)
+    assert mr.totelem == 600 * 33 * 33
+    st = _grid_parity(mr, _sweep(mr, per=2, radii=(8.0, 30.0)))
+    assert st["moved_verts"] > 0
+
+
+def test_grids_reject_what_the_path_does_not_cover():
+    mr = meshgen.multires_cube(1, 3)
+    ses = capi.GridSession(mr, device=0)
+    try:
+        ses.stroke_begin()
+        with pytest.raises(capi.DeviceError):
+            ses.dab(capi.make_dab(capi.TOOL_SMOOTH, (0, 0, 1), 0.5, bstrength=0.5))
+        with pytest.raises(capi.DeviceError):
+            ses.dab(capi.make_dab(capi.TOOL_DRAW, (0, 0, 1), 0.5, bstrength=0.5, flags=capi.DAB_NO_NORMALS))
+        ses.stroke_end()
+    finally:
+        ses.close()

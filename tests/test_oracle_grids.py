@@ -1,0 +1,116 @@
+"""CPU: the grids (multires CCG) part of the oracle -- invariants of kernel/intern/subdiv_ccg.c and of
+BKE_pbvh_build_grids (pbvh.c:2516-2561) -- and the host library's grids PBVH against it."""
+import numpy as np
+
+from dune_sculpt_b200 import capi, meshgen
+from oracle_py import GridOracle
+
+
+def _dups_equal(mr, arr):
+    gs = mr.grid_size
+    rows = mr.edge_elems.reshape(-1, 2 * gs)
+    for e in range(mr.edge_off.shape[0] - 1):
+        a, b = mr.edge_off[e], mr.edge_off[e + 1]
+        for f in range(a + 1, b):
+            if not np.array_equal(arr[rows[a]], arr[rows[f]]):
+                return False
+    for v in range(mr.cvert_off.shape[0] - 1):
+        el = mr.cvert_elems[mr.cvert_off[v]:mr.cvert_off[v + 1]]
+        if not np.all(arr[el] == arr[el[0]]):
+            return False
+    gs2 = gs * gs
+    for f in range(mr.face_start.shape[0]):
+        n = mr.face_num[f]
+        for c in range(n):
+            prev = mr.face_start[f] + (c + n - 1) % n
+            cur = mr.face_start[f] + c
+            i = np.arange(gs)
+            if not np.array_equal(arr[prev * gs2 + i], arr[cur * gs2 + i * gs]):
+                return False
+    return True
+
+
+def test_generator_tables_are_consistent():
+    mr = meshgen.multires_cube(1, 4, with_mask=True)
+    assert mr.grid_size == 9 and mr.totgrid == 6 * 4 * 4
+    assert np.all(np.diff(mr.edge_off) == 2)            # closed cube: every coarse edge has two faces
+    assert set(np.diff(mr.cvert_off).tolist()) == {3, 4}  # cube corners have 3 faces, the other verts 4
+    assert _dups_equal(mr, mr.co) and _dups_equal(mr, mr.mask)
+
+
+def test_grids_pbvh_structure_and_host_library_agree():
+    mr = meshgen.multires_cube(1, 4)
+    for leaf_limit in (0, 5, 1):
+        orc = GridOracle(mr, leaf_limit=leaf_limit)
+        ses = capi.GridSession(mr, leaf_limit=leaf_limit, device=None)
+        na, nb = orc.node_arrays(), ses.node_arrays()
+        for k in ("vb", "orig_vb", "children_offset", "totprim", "uniq_verts", "face_verts"):
+            assert np.array_equal(na[k], nb[k]), k
+        assert np.array_equal(na["flag"] & 1, nb["flag"] & 1)
+        assert np.array_equal(orc.prim_indices(), ses.prim_indices())
+        leaf = (na["flag"] & 1) != 0
+        # pbvh.c:2533: leaf_limit = max(LEAF_LIMIT / gridsize^2, 1); every grid in exactly one leaf
+        lim = leaf_limit if leaf_limit else max(10000 // (mr.grid_size ** 2), 1)
+        assert na["totprim"][leaf].max() <= lim
+        assert sorted(orc.prim_indices().tolist()) == list(range(mr.totgrid))
+        assert np.array_equal(na["uniq_verts"][leaf], na["totprim"][leaf] * mr.grid_size ** 2)
+        ses.close()
+        orc.close()
+
+
+def test_ccg_normals_of_a_flat_grid_and_unit_length_on_the_sphere():
+    mr = meshgen.multires_cube(1, 3, noise=0.0, spherify=False)   # flat faces
+    orc = GridOracle(mr)
+    no, co = orc.no(), orc.co()
+    gs2 = mr.grid_size ** 2
+    # interior elements of a +Z face grid point along +Z exactly
+    g_top = [g for g in range(mr.totgrid) if np.all(co[g * gs2:(g + 1) * gs2, 2] == 1.0)]
+    assert g_top
+    inner = g_top[0] * gs2 + 1 * mr.grid_size + 1
+    assert np.array_equal(no[inner], np.array([0, 0, 1], np.float32))
+    orc.close()
+    mr = meshgen.multires_cube(1, 4)
+    orc = GridOracle(mr)
+    ln = np.linalg.norm(orc.no(), axis=1)
+    assert ln.min() > 0.99 and ln.max() < 1.001    # mean of up to four unit quad normals, not renormalised
+    assert _dups_equal(mr, orc.no())
+    orc.close()
+
+
+def test_dab_keeps_duplicates_stitched_and_updates_only_gathered_leaves():
+    mr = meshgen.multires_cube(1, 4, with_mask=True)
+    orc = GridOracle(mr, leaf_limit=4)
+    co0, no0 = orc.co(), orc.no()
+    d = capi.make_dab(capi.TOOL_DRAW, (0.0, 0.0, 1.0), 0.6, bstrength=0.3, view_normal=(0, 0, 1))
+    orc.stroke_begin()
+    nh = orc.dab(d)
+    orc.stroke_end()
+    assert 0 < nh < (orc.node_arrays()["flag"] & 1).sum()
+    co1 = orc.co()
+    assert np.abs(co1 - co0).max() > 0.01
+    assert _dups_equal(mr, co1) and _dups_equal(mr, orc.no()) and _dups_equal(mr, orc.mask())
+    na = orc.node_arrays()
+    assert not np.any(na["flag"] & (capi.PBVH_UpdateNormals | capi.PBVH_UpdateBB))
+    # leaf boxes contain their elements
+    prims = orc.prim_indices()
+    gs2 = mr.grid_size ** 2
+    for n in np.nonzero(na["flag"] & 1)[0]:
+        g = prims[na["prim_offset"][n]:na["prim_offset"][n] + na["totprim"][n]]
+        el = (g[:, None] * gs2 + np.arange(gs2)[None, :]).reshape(-1)
+        assert np.all(co1[el].min(axis=0) == na["vb"][n, :3]) and np.all(co1[el].max(axis=0) == na["vb"][n, 3:])
+    assert orc.vertex_dabs() == int(na["uniq_verts"][orc.hits()].sum())
+    orc.close()
+
+
+def test_openmp_and_single_thread_agree_on_grids():
+    mr = meshgen.multires_cube(1, 4)
+    outs = []
+    for threads in (1, 4):
+        orc = GridOracle(mr, leaf_limit=3, threads=threads)
+        orc.stroke_begin()
+        for k in range(4):
+            orc.dab(capi.make_dab(capi.TOOL_DRAW, (0.2 * k - 0.3, 0.1, 1.0), 0.5, bstrength=0.2, view_normal=(0, 0, 1)))
+        orc.stroke_end()
+        outs.append((orc.co(), orc.no()))
+        orc.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
