@@ -101,6 +101,22 @@ class ClockSampler:
 def build_workload(args):
     from dune_sculpt_b200 import meshgen, stroke
     t0 = time.time()
+    if args.config == "c5":
+        # C5: multires cube, `c5_base`^2 base quads per side, level `c5_level`; draw stroke, r = 8 % of the diagonal
+        from dune_sculpt_b200 import capi
+        mesh = meshgen.multires_cube_n(args.c5_base, args.c5_level)
+        diag = mesh.bbox_diag()
+        rng = np.random.default_rng(5)
+        bs = stroke._strength(capi.TOOL_DRAW, 0.5)
+        dabs = []
+        for i in range(args.c5_dabs):
+            p = rng.normal(size=3)
+            p /= np.linalg.norm(p)
+            dabs.append(capi.make_dab(capi.TOOL_DRAW, p.astype(np.float32), diag * 0.08, bstrength=bs, view_normal=tuple(p),
+                                      flags=capi.DAB_FIRST_STEP if i == 0 else 0))
+        log("[bench] multires cube %d^2 x 6 base quads, level %d: %d grids of %d^2 = %d elements, diag=%.4f, %d dabs/stroke (%.1fs)" %
+            (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, diag, len(dabs), time.time() - t0))
+        return mesh, diag, dabs
     mesh = meshgen.grid(args.grid)
     diag = mesh.bbox_diag()
     dabs = stroke.c3_radius_sweep(diag, dabs_per_radius=args.dabs_per_radius)
@@ -117,16 +133,20 @@ def run_reference(args, rank):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from dune_sculpt_b200 import build as b
     b.build_oracle()
-    from oracle_py import Oracle
+    from oracle_py import GridOracle, Oracle
     mesh, diag, dabs = build_workload(args)
     cores = os.cpu_count() or 1
     t0 = time.time()
-    orc = Oracle(mesh, threads=cores)
+    orc = GridOracle(mesh, threads=cores) if args.config == "c5" else Oracle(mesh, threads=cores)
     log("[bench] oracle PBVH build %.1fs, %d nodes, %d threads" % (time.time() - t0, orc.totnode, cores))
     # bounded sample: `sample_per_radius` dabs of every radius of the sweep per step
     per = args.dabs_per_radius
     nrad = len(dabs) // per
-    sample = [dabs[r * per + k] for r in range(nrad) for k in range(args.cpu_sample_per_radius)]
+    if args.config == "c5":
+        sample = dabs[:args.c5_cpu_dabs]
+        nrad = 1
+    else:
+        sample = [dabs[r * per + k] for r in range(nrad) for k in range(args.cpu_sample_per_radius)]
     orc.stroke_begin()
     for _ in range(args.warmup_ref):
         for d in sample[:2]:
@@ -142,6 +162,8 @@ def run_reference(args, rank):
     value = vd / dt
     sample_desc = "%d dabs per radius x %d radii of the C3 sweep per step (%d dabs), %d steps" % (
         args.cpu_sample_per_radius, nrad, len(sample), args.steps_ref)
+    if args.config == "c5":
+        sample_desc = "the first %d dabs of the C5 stroke per step, %d steps" % (len(sample), args.steps_ref)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps_ref,
         "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps_ref, "higher_is_better": True, "scaling": "weak",
@@ -156,6 +178,14 @@ def run_reference(args, rank):
 
 def workload_config(args, mesh, ndabs):
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.config == "c5":
+        return {"workload": "C5 multires grids: cube %d^2 x 6 base quads, level %d (%d grids of %d^2 = %d elements), draw + stitch + "
+                            "CCG normals + BB, r = 8%% bbox diag, %d dabs/stroke" %
+                            (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, ndabs),
+                "parallelism": "single GPU", "verts": mesh.totelem, "dabs_per_step": ndabs,
+                "brush": "draw, SMOOTH falloff, area-normal direction",
+                "l2": "inputs larger than L2 (resident element arrays > 2 GB)" if mesh.totelem > 8000000 else "small mesh: L2 resident",
+                "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
     return {"workload": "C3 draw+normals+BB radius sweep 1-50%% bbox diag, grid %d^2 (V=%d), %d dabs/stroke" %
                         (args.grid, mesh.totvert, ndabs) +
                         ("" if world == 1 else "; PBVH partitioned spatially over %d GPUs (same mesh: strong scaling), per dab one "
@@ -166,7 +196,7 @@ def workload_config(args, mesh, ndabs):
             "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
 
 
-def analysis_pass(ses, dabs, na):
+def analysis_pass(ses, dabs, na, grids=False):
     """One untimed stroke with a sync after every dab: per-dab U/A/T/M and per-stage device times,
     for the roofline object."""
     uniq, face, totprim = na["uniq_verts"].astype(np.int64), na["face_verts"].astype(np.int64), na["totprim"].astype(np.int64)
@@ -209,7 +239,11 @@ def analysis_pass(ses, dabs, na):
         stage_bytes["gather"] += 48 * nleaf
         stage_bytes["area_normal"] += U * 12 + M * 12
         stage_bytes["brush"] += U * 12 + M * 12 + first_A * 24
-        stage_bytes["normals_bb"] += T * 12 + A * 12 + M * 12 + 24 * h.size
+        if grids:
+            # stitch + CCG normals: positions of the gathered leaves' grids read, normals written; leaf boxes read them again
+            stage_bytes["normals_bb"] += U * 12 + U * 12 + U * 12 + 24 * h.size
+        else:
+            stage_bytes["normals_bb"] += T * 12 + A * 12 + M * 12 + 24 * h.size
         stage_bytes["bb_refit"] += 72 * anc
     ses.stroke_end()
     times = ses.stage_times()
@@ -235,7 +269,12 @@ def run_ours(args, rank, world):
             idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         dist_arg = (world, rank, bytes(idt.cpu().numpy().tobytes()))
-    ses = capi.SculptSession(mesh, device=local_rank, dist=dist_arg)  # fails loudly without a device / the .so
+    if args.config == "c5":
+        if world > 1:
+            raise SystemExit("config c5: the grids path is single-GPU (DESIGN.md section 5)")
+        ses = capi.GridSession(mesh, device=local_rank)
+    else:
+        ses = capi.SculptSession(mesh, device=local_rank, dist=dist_arg)  # fails loudly without a device / the .so
     na = ses.node_arrays()
     log("[bench] host PBVH build + device upload %.1fs, %d nodes (%d leaves)" %
         (time.time() - t0, ses.totnode, int((na["flag"] & 1).sum())))
@@ -313,7 +352,7 @@ def run_ours(args, rank, world):
         vd, vd_e, launches = int(s[0]), int(s[1]), int(s[2])
 
     # ---- the sweep radius by radius (untimed for `value`: one more stroke, CUDA events around each radius group)
-    per = args.dabs_per_radius
+    per = args.dabs_per_radius if args.config == "c3" else len(dabs)
     sweep = []
     ses._chk(D.dsc_state_restore(ctx))
     ses._chk(D.dsc_stroke_begin(ctx, None))
@@ -333,7 +372,7 @@ def run_ours(args, rank, world):
 
     log("[bench] rank %d: radius sweep done" % rank)
     # ---- roofline of the dominant kernel (untimed analysis stroke, CUDA events per stage)
-    tot, stage_bytes, times = analysis_pass(ses, dabs, na)
+    tot, stage_bytes, times = analysis_pass(ses, dabs, na, grids=args.config == "c5")
     log("[bench] rank %d: analysis stroke done" % rank)
     peak, peak_src = measured_peaks()
     dom = max((k for k in stage_bytes), key=lambda k: times[k][0])
@@ -344,8 +383,19 @@ def run_ours(args, rank, world):
     stages = {k: {"ms": round(times[k][0], 4), "launches": times[k][1], "alg_bytes": int(stage_bytes.get(k, 0)),
                   "gbs": round(stage_bytes.get(k, 0) / (times[k][0] * 1e-3) / 1e9, 1) if times[k][0] > 0 else None}
               for k in times}
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture (profiles/r1_traffic.json) gives measured
+    # bytes / algorithmic bytes for one launch; scaled to the average launch the `achieved` figure is quoted on
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if dom == "normals_bb" and args.config == "c3":
+            traffic = int(stage_bytes[dom] / max(dom_launches, 1) * float(tr["traffic_over_algorithmic"]))
+            traffic_note = ("ncu dram__bytes_read+write of %s = %.3f x its algorithmic bytes on the captured launch (%s); "
+                            "scaled to the average launch" % (tr["kernel"], tr["traffic_over_algorithmic"], "profiles/r1_traffic.json"))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "alg_bytes_per_launch": int(stage_bytes[dom] / max(dom_launches, 1)),
                 "whole_path": {"achieved": round(total_bytes / (total_ms * 1e-3) / 1e9, 1) if total_ms > 0 else None,
                                "frac": round(total_bytes / (total_ms * 1e-3) / 1e9 / peak, 4) if total_ms > 0 else None,
@@ -384,9 +434,25 @@ def cpu_baseline(args, mesh, dabs):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from dune_sculpt_b200 import build as b
     b.build_oracle()
-    from oracle_py import Oracle
+    from oracle_py import GridOracle, Oracle
     cores = os.cpu_count() or 1
     t0 = time.time()
+    if args.config == "c5":
+        orc = GridOracle(mesh, threads=cores)
+        log("[bench] cpu_baseline: grids oracle build %.1fs" % (time.time() - t0))
+        sample = dabs[:args.c5_cpu_dabs]
+        orc.stroke_begin()
+        orc.dab(sample[0])
+        vd0 = orc.vertex_dabs()
+        t0 = time.perf_counter()
+        for d in sample:
+            orc.dab(d)
+        dt = time.perf_counter() - t0
+        vd = orc.vertex_dabs() - vd0
+        orc.close()
+        return {"value": vd / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "the first %d dabs of the same stroke (%.1f s), OpenMP over faces / edges / nodes" % (len(sample), dt),
+                "ms_per_dab": 1e3 * dt / len(sample)}
     orc = Oracle(mesh, threads=cores)
     log("[bench] cpu_baseline: oracle PBVH build %.1fs" % (time.time() - t0))
     per = args.dabs_per_radius
@@ -438,6 +504,12 @@ def main():
     ap.add_argument("--dabs-per-radius", type=int, default=32)
     ap.add_argument("--cpu-sample-per-radius", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"],
+                    help="c3 (default): the headline 16.7M-vertex draw sweep; c5: multires grids, draw stroke")
+    ap.add_argument("--c5-base", type=int, default=25)
+    ap.add_argument("--c5-level", type=int, default=7)
+    ap.add_argument("--c5-dabs", type=int, default=100)
+    ap.add_argument("--c5-cpu-dabs", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # the CPU arm's steps are bounded samples: cap them so the run ends within minutes
