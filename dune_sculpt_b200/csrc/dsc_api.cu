@@ -119,6 +119,7 @@ struct DscContext {
   long long launches = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int grid = 148 * 8;
+  int grid_area = 148 * 8, grid_brush = 148 * 8; /* per-dab kernels: SMs x a multiple from DSC_GRID_AREA / DSC_GRID_BRUSH */
 };
 
 static void invalidate_graphs(DscContext *ctx)
@@ -450,6 +451,7 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->grid = ctx->num_sms * 8;
+  ctx->grid_area = ctx->grid_brush = ctx->grid;
   memset(&ctx->m, 0, sizeof(ctx->m));
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
@@ -473,6 +475,8 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
     ctx->m.ring = ctx->d_ring;
     ctx->m.ring_ctl = ctx->d_ring_ctl;
     ctx->use_graphs = !getenv("DSC_NO_GRAPHS");
+    if (getenv("DSC_GRID_AREA")) ctx->grid_area = ctx->num_sms * std::max(1, atoi(getenv("DSC_GRID_AREA")));
+    if (getenv("DSC_GRID_BRUSH")) ctx->grid_brush = ctx->num_sms * std::max(1, atoi(getenv("DSC_GRID_BRUSH")));
     /* measured slower than the graph replay (grid barriers cost more than the launch gaps they replace, and the
      * area / brush stages run at the tile kernel's lower occupancy): opt-in */
     ctx->use_batch_kernel = getenv("DSC_BATCH_KERNEL") != nullptr;
@@ -1933,17 +1937,17 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   else {
     if (sig.needs_area) {
       StageScope s(ctx, ST_AREA);
-      CU(launch_k(k_area, ctx->grid, DSC_BLOCK, 0, st, pdl, m, j, slot));
+      CU(launch_k(k_area, ctx->grid_area, DSC_BLOCK, 0, st, pdl, m, j, slot));
     }
     if (dist && (r = dist_allreduce_dab(ctx, slot, sig.needs_area))) return r;
     {
       StageScope s(ctx, ST_BRUSH);
       const bool bpdl = pdl && !dist;
       switch (tool) {
-        case DSC_TOOL_DRAW: CU(launch_k(k_brush<DSC_TOOL_DRAW>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
-        case DSC_TOOL_INFLATE: CU(launch_k(k_brush<DSC_TOOL_INFLATE>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
-        case DSC_TOOL_GRAB: CU(launch_k(k_brush<DSC_TOOL_GRAB>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
-        default: CU(launch_k(k_brush<DSC_TOOL_CLAY_STRIPS>, ctx->grid, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        case DSC_TOOL_DRAW: CU(launch_k(k_brush<DSC_TOOL_DRAW>, ctx->grid_brush, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        case DSC_TOOL_INFLATE: CU(launch_k(k_brush<DSC_TOOL_INFLATE>, ctx->grid_brush, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        case DSC_TOOL_GRAB: CU(launch_k(k_brush<DSC_TOOL_GRAB>, ctx->grid_brush, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
+        default: CU(launch_k(k_brush<DSC_TOOL_CLAY_STRIPS>, ctx->grid_brush, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
       }
     }
     if (dist && (r = dist_halo_exchange(ctx))) return r;
