@@ -359,3 +359,34 @@ def _multires_make_consistent(m):
         idx = m.cvert_off[v][:, None] + np.arange(k)[None, :]
         avg(m.cvert_elems.astype(np.int64)[idx])
     assert F > 0
+
+
+def mixed_grid(n, height=0.05, freq=8.0):
+    """the height-field grid with mixed polygon sizes: every third cell pair of every other row is
+    merged into a hexagon, every fifth remaining cell is split into two triangles.  N-gons push their
+    leaves onto the general normals / bounds path; the rest stay on the tile path."""
+    base = grid(n, height, freq)
+    polys = []
+    used = np.zeros((n - 1, n - 1), dtype=bool)
+
+    def vid(i, j):
+        return j * n + i
+
+    for j in range(n - 1):
+        for i in range(n - 1):
+            if used[j, i]:
+                continue
+            if j % 2 == 0 and i % 3 == 0 and i + 1 < n - 1 and not used[j, i + 1]:
+                used[j, i] = used[j, i + 1] = True
+                polys.append([vid(i, j), vid(i + 1, j), vid(i + 2, j), vid(i + 2, j + 1), vid(i + 1, j + 1), vid(i, j + 1)])
+            elif (i + j) % 5 == 1:
+                used[j, i] = True
+                polys.append([vid(i, j), vid(i + 1, j), vid(i + 1, j + 1)])
+                polys.append([vid(i, j), vid(i + 1, j + 1), vid(i, j + 1)])
+            else:
+                used[j, i] = True
+                polys.append([vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)])
+    lens = np.array([len(p) for p in polys], dtype=np.int32)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    loops = np.concatenate([np.asarray(p, dtype=np.int32) for p in polys])
+    return Mesh(co=base.co.copy(), poly_start=starts, poly_len=lens, loop_v=loops)

@@ -331,3 +331,61 @@ def test_batched_dabs_through_cuda_graphs_match_the_oracle():
     finally:
         ses.close()
         orc.close()
+
+
+def test_mixed_polygons_general_and_tile_paths_together():
+    """triangles, quads and hexagons in one mesh: leaves with an n-gon take the general normals / bounds
+    kernels (and keep their update flags until the dab's clear pass), their neighbours the tile kernel;
+    draw, inflate and smooth strokes across both"""
+    m = meshgen.mixed_grid(97)
+    assert set(np.unique(m.poly_len).tolist()) == {3, 4, 6}
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.7, -0.6, 0.0), (0.7, 0.5, 0.0), 0.22, 6)
+    dabs += _line_dabs(capi.TOOL_INFLATE, (0.6, -0.6, 0.0), (-0.6, 0.6, 0.0), 0.3, 4)
+    r = run_parity(m, dabs, leaf_limit=300)
+    assert r["moved"] > 0
+    r = run_parity(m, _line_dabs(capi.TOOL_SMOOTH, (-0.5, 0.0, 0.0), (0.5, 0.1, 0.0), 0.35, 4, alpha=0.8), leaf_limit=300)
+    assert r["moved"] > 0
+    # batched submission on a mesh with slow leaves goes dab by dab (no graph) and still matches
+    arr = (capi.DscDab * len(dabs))(*dabs)
+    ses = capi.SculptSession(m, leaf_limit=300, device=0)
+    from oracle_py import Oracle
+    orc = Oracle(m, leaf_limit=300)
+    try:
+        orc.stroke_begin()
+        for d in dabs:
+            orc.dab(d)
+        orc.stroke_end()
+        ses.stroke_begin()
+        ses.dabs(arr, len(dabs))
+        ses.stroke_end()
+        assert np.array_equal(ses.co(), orc.co()) and np.array_equal(ses.no(), orc.no())
+        bb, _ = ses.node_bb()
+        assert np.array_equal(bb, orc.node_arrays()["vb"])
+    finally:
+        ses.close()
+        orc.close()
+
+
+def test_dab_that_gathers_nothing_and_degenerate_inputs():
+    """a dab far from the mesh gathers no node (BKE_pbvh_search_gather returns NULL, 0, pbvh.c:2760-2766)
+    and changes nothing; a zero-radius dab is refused; a one-quad mesh is one leaf"""
+    m = meshgen.grid(33)
+    far = capi.make_dab(capi.TOOL_DRAW, (5.0, 5.0, 5.0), 0.3, bstrength=0.3, view_normal=(0, 0, 1))
+    r = run_parity(m, [far, capi.make_dab(capi.TOOL_DRAW, (0.1, 0.1, 0.0), 0.3, bstrength=0.3, view_normal=(0, 0, 1)), far], leaf_limit=100)
+    assert r["moved"] > 0
+    ses = capi.SculptSession(m, leaf_limit=100, device=0)
+    try:
+        ses.capture(True)
+        ses.stroke_begin()
+        ses.dab(far)
+        assert ses.hits().size == 0 and ses.moved().size == 0
+        bad = capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.3, bstrength=0.3)
+        bad.radius = 0.0
+        with pytest.raises(capi.DeviceError):
+            ses.dab(bad)
+        ses.stroke_end()
+    finally:
+        ses.close()
+    tiny = meshgen.grid(2)
+    r = run_parity(tiny, [capi.make_dab(capi.TOOL_DRAW, (0.0, 0.0, 0.0), 2.0, bstrength=0.2, view_normal=(0, 0, 1))])
+    assert r["moved"] == 4
