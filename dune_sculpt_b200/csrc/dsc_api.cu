@@ -67,6 +67,7 @@ struct DscContext {
   int grid_seq = 0;
   size_t gn_smem = 0;
   bool has_odd_edges = false; /* some coarse edge has more than two faces */
+  bool grid_fused = false;    /* DSC_GRID_FUSED=1: the stages after the brush as one cooperative kernel instead of nine launches */
 
   std::vector<int> slot_of;     /* vertex -> slot */
   std::vector<int> leaf_node;   /* leaf (= device id) -> host node index */
@@ -984,8 +985,13 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_zero(ctx, &g.cnt, 1)))
       return r;
     g.mask = ctx->has_mask ? ctx->d_mask : nullptr;
+    g.has_odd_edges = ctx->has_odd_edges ? 1 : 0;
+    g.max_face_grids = 1;
+    for (int f = 0; f < g.totface; f++) g.max_face_grids = std::max(g.max_face_grids, ctx->h_face_num[f]);
     ctx->gn_smem = dsc_grid_normals_smem(g.gs);
+    ctx->grid_fused = getenv("DSC_GRID_FUSED") != nullptr; /* measured slower than the nine launches (119 -> 141 us per C5 dab): opt-in */
     CU(cudaFuncSetAttribute(k_grid_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->gn_smem));
+    CU(cudaFuncSetAttribute(k_grid_dab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->gn_smem));
     CU(cudaStreamSynchronize(ctx->stream));
   }
   else
@@ -1675,9 +1681,24 @@ static int grids_after_brush(DscContext *ctx, LeafList hits)
   const int seq = ++ctx->grid_seq;
   if ((r = grids_reset_counts(ctx))) return r;
   StageScope s(ctx, ST_NORMALS);
-  k_grid_faces<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, hits.list, hits.count, seq);
-  LAUNCH_CHECK();
-  k_grid_adjacency<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(g, seq);
+  if (ctx->grid_fused) {
+    /* one cooperative launch, the stages separated by grid barriers */
+    CU(cudaMemsetAsync(m.grid_bar, 0, sizeof(unsigned), st));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctx->num_sms, 1, 1);
+    cfg.blockDim = dim3(GN_BLOCK, 1, 1);
+    cfg.dynamicSmemBytes = ctx->gn_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k_grid_dab, m, g, hits.list, hits.count, seq));
+    return DSC_OK;
+  }
+  k_grid_faces<<<ctx->num_sms * 2, DSC_BLOCK, 0, st>>>(m, g, hits.list, hits.count, seq);
   LAUNCH_CHECK();
   /* multires_stitch_grids (multires.c:1171-1196 -> subdiv_ccg.c:1303-1324): the faces' inner boundaries, then
    * all coarse edges (two-face edges no dab touched average to themselves: only the touched ones and those with
@@ -1705,7 +1726,7 @@ static int grids_after_brush(DscContext *ctx, LeafList hits)
   /* BKE_pbvh_update_bounds: leaf boxes (the refit follows on the side stream) */
   k_grid_leaf_bb<<<ctx->num_sms * 4, DSC_BLOCK, 0, st>>>(m, hits.list, hits.count);
   LAUNCH_CHECK();
-  ctx->launches += 10;
+  ctx->launches += 8;
   return DSC_OK;
 }
 

@@ -26,33 +26,33 @@ struct DevGrids {
   int *face_list, *edge_list, *cvert_list;
   GridCounts *cnt;
   float *mask; /* per-slot mask layer (averaged along with co / no), or NULL */
+  int max_face_grids; /* most corners of a face */
+  int has_odd_edges;  /* some coarse edge has more than two faces */
 };
 
-/* BKE_pbvh_get_grid_updates (pbvh.c:3523-3566): the faces of the grids of the listed leaves, each once */
-__global__ void __launch_bounds__(DSC_BLOCK) k_grid_faces(DevMesh m, DevGrids g, const int *list, const int *count, int seq)
+/* Every stage below is a __device__ body over (cta, ncta) so that it runs either as its own kernel or as
+ * one phase of k_grid_dab, the fused per-dab kernel (phases separated by grid barriers).  What a phase
+ * reads that an earlier phase wrote -- lists, counters, element data -- goes through L2 (__ldcg). */
+
+/* BKE_pbvh_get_grid_updates (pbvh.c:3523-3566): the faces of the grids of the listed leaves, each once; the
+ * thread that claims a face also claims its coarse edges and vertices (subdiv_ccg_affected_face_adjacency,
+ * subdiv_ccg.c:1191-1235) */
+__device__ __forceinline__ void dsc_grid_faces_body(const DevGrids &g, const int *list, const int *count, int seq, int cta, int ncta)
 {
-  const int n = *count;
-  for (int h = blockIdx.x; h < n; h += gridDim.x) {
-    const int l = list[h];
+  const int n = __ldcg(count);
+  for (int h = cta; h < n; h += ncta) {
+    const int l = __ldcg(&list[h]);
     const int b = g.leaf_gbeg[l], e = g.leaf_gbeg[l + 1];
     for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
       const int f = g.grid_face[g.leaf_grids[i]];
-      if (atomicExch(&g.face_stamp[f], seq) != seq) g.face_list[atomicAdd(&g.cnt->faces, 1)] = f;
-    }
-  }
-}
-
-/* subdiv_ccg_affected_face_adjacency (subdiv_ccg.c:1191-1235): coarse edges and vertices of those faces */
-__global__ void __launch_bounds__(DSC_BLOCK) k_grid_adjacency(DevGrids g, int seq)
-{
-  const int n = g.cnt->faces;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int f = g.face_list[i];
-    for (int c = 0; c < g.face_num[f]; c++) {
-      const int gr = g.face_start[f] + c;
-      const int e = g.grid_edge[gr], v = g.grid_cvert[gr];
-      if (atomicExch(&g.edge_stamp[e], seq) != seq) g.edge_list[atomicAdd(&g.cnt->edges, 1)] = e;
-      if (atomicExch(&g.cvert_stamp[v], seq) != seq) g.cvert_list[atomicAdd(&g.cnt->cverts, 1)] = v;
+      if (atomicExch(&g.face_stamp[f], seq) == seq) continue;
+      g.face_list[atomicAdd(&g.cnt->faces, 1)] = f;
+      const int start = g.face_start[f], nc = g.face_num[f];
+      for (int c = 0; c < nc; c++) {
+        const int ed = g.grid_edge[start + c], v = g.grid_cvert[start + c];
+        if (atomicExch(&g.edge_stamp[ed], seq) != seq) g.edge_list[atomicAdd(&g.cnt->edges, 1)] = ed;
+        if (atomicExch(&g.cvert_stamp[v], seq) != seq) g.cvert_list[atomicAdd(&g.cnt->cverts, 1)] = v;
+      }
     }
   }
 }
@@ -61,29 +61,75 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_grid_adjacency(DevGrids g, int se
 __device__ __forceinline__ void dsc_grid_average_pair(const DevMesh &m, const DevGrids &g, int a, int b)
 {
   float *arr[6] = {m.cx, m.cy, m.cz, m.nx, m.ny, m.nz};
+  float va[6], vb[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    float v = arr[k][a] + arr[k][b];
+    va[k] = __ldcg(&arr[k][a]);
+    vb[k] = __ldcg(&arr[k][b]);
+  }
+  float ma = 0.0f, mb = 0.0f;
+  if (g.mask) {
+    ma = __ldcg(&g.mask[a]);
+    mb = __ldcg(&g.mask[b]);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    float v = va[k] + vb[k];
     v = v * 0.5f;
     arr[k][a] = v;
     arr[k][b] = v;
   }
   if (g.mask) {
-    const float mk = (g.mask[a] + g.mask[b]) * 0.5f;
+    const float mk = (ma + mb) * 0.5f;
     g.mask[a] = mk;
     g.mask[b] = mk;
   }
 }
 
-/* element_accumulator_* (subdiv_ccg.c:899-949): sum in list order, scale by 1 / n, copy to all */
+/* element_accumulator_* (subdiv_ccg.c:899-949): sum in list order, scale by 1 / n, copy to all.  Up to 4
+ * members have their slots, then all their values, loaded together (two round trips, not two per member);
+ * the sums still run in list order. */
 __device__ __forceinline__ void dsc_grid_average_list(const DevMesh &m, const DevGrids &g, const int *slots, int n, int stride)
 {
   float acc[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (n <= 4) {
+    int sl[4];
+    float v[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; i++) sl[i] = (i < n) ? slots[(size_t)i * stride] : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (i < n) {
+        v[i][0] = __ldcg(&m.cx[sl[i]]); v[i][1] = __ldcg(&m.cy[sl[i]]); v[i][2] = __ldcg(&m.cz[sl[i]]);
+        v[i][3] = __ldcg(&m.nx[sl[i]]); v[i][4] = __ldcg(&m.ny[sl[i]]); v[i][5] = __ldcg(&m.nz[sl[i]]);
+        v[i][6] = g.mask ? __ldcg(&g.mask[sl[i]]) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (i < n) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc[k] += v[i][k];
+      }
+    }
+    const float f = 1.0f / (float)n;
+#pragma unroll
+    for (int k = 0; k < 7; k++) acc[k] *= f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (i < n) {
+        m.cx[sl[i]] = acc[0]; m.cy[sl[i]] = acc[1]; m.cz[sl[i]] = acc[2];
+        m.nx[sl[i]] = acc[3]; m.ny[sl[i]] = acc[4]; m.nz[sl[i]] = acc[5];
+        if (g.mask) g.mask[sl[i]] = acc[6];
+      }
+    }
+    return;
+  }
   for (int i = 0; i < n; i++) {
     const int s = slots[(size_t)i * stride];
-    acc[0] += m.cx[s]; acc[1] += m.cy[s]; acc[2] += m.cz[s];
-    acc[3] += m.nx[s]; acc[4] += m.ny[s]; acc[5] += m.nz[s];
-    if (g.mask) acc[6] += g.mask[s];
+    acc[0] += __ldcg(&m.cx[s]); acc[1] += __ldcg(&m.cy[s]); acc[2] += __ldcg(&m.cz[s]);
+    acc[3] += __ldcg(&m.nx[s]); acc[4] += __ldcg(&m.ny[s]); acc[5] += __ldcg(&m.nz[s]);
+    if (g.mask) acc[6] += __ldcg(&g.mask[s]);
   }
   const float f = 1.0f / (float)n;
 #pragma unroll
@@ -96,46 +142,53 @@ __device__ __forceinline__ void dsc_grid_average_list(const DevMesh &m, const De
   }
 }
 
-/* subdiv_ccg_average_inner_face_grids (subdiv_ccg.c:951-984) of the listed faces: one CTA per face */
-__global__ void __launch_bounds__(128) k_grid_inner(DevMesh m, DevGrids g)
+/* subdiv_ccg_average_inner_face_grids (subdiv_ccg.c:951-984) of the listed faces: one thread per pair of
+ * elements (the pairs of a face are disjoint), one per face centre */
+__device__ __forceinline__ void dsc_grid_inner_body(const DevMesh &m, const DevGrids &g, int cta, int ncta)
 {
-  const int n = g.cnt->faces;
-  for (int h = blockIdx.x; h < n; h += gridDim.x) {
-    const int f = g.face_list[h];
+  const int n = __ldcg(&g.cnt->faces);
+  const int per = g.gs - 1, per_face = g.max_face_grids * per;
+  const long long items = (long long)n * per_face;
+  for (long long t = (long long)cta * blockDim.x + threadIdx.x; t < items; t += (long long)ncta * blockDim.x) {
+    const int h = (int)(t / per_face), r = (int)(t - (long long)h * per_face);
+    const int f = __ldcg(&g.face_list[h]);
     const int nc = g.face_num[f], start = g.face_start[f];
-    const int per = g.gs - 1;
-    for (int t = threadIdx.x; t < nc * per; t += blockDim.x) {
-      const int corner = t / per, i = 1 + t % per;
-      const int grid = start + corner, prev = start + (corner + nc - 1) % nc;
-      dsc_grid_average_pair(m, g, g.grid_slot0[prev] + i, g.grid_slot0[grid] + i * g.gs);
-    }
-    if (threadIdx.x == 0) dsc_grid_average_list(m, g, g.grid_slot0 + start, nc, 1);
+    const int corner = r / per, i = 1 + r % per;
+    if (corner >= nc) continue;
+    const int grid = start + corner, prev = start + (corner + nc - 1) % nc;
+    dsc_grid_average_pair(m, g, g.grid_slot0[prev] + i, g.grid_slot0[grid] + i * g.gs);
+  }
+  for (int h = cta * blockDim.x + threadIdx.x; h < n; h += ncta * blockDim.x) {
+    const int f = __ldcg(&g.face_list[h]);
+    dsc_grid_average_list(m, g, g.grid_slot0 + g.face_start[f], g.face_num[f], 1);
   }
 }
 
 /* subdiv_ccg_average_grids_boundary (subdiv_ccg.c:1010-1048): listed coarse edges (all == 0), every edge
- * (all == 2), or every edge that is not in the list and has more than two faces (all == 1: averaging two equal values is
- * exact, so untouched two-face edges need no pass) */
-__global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int all, int seq)
+ * (all == 2), or every edge that is not in the list and has more than two faces (all == 1: averaging two
+ * equal values is exact, so untouched two-face edges need no pass); one thread per
+ * boundary element */
+__device__ __forceinline__ void dsc_grid_edges_body(const DevMesh &m, const DevGrids &g, int all, int seq, int cta, int ncta)
 {
-  const int n = all ? g.totedge : g.cnt->edges;
-  const int gs2 = 2 * g.gs;
-  for (int h = blockIdx.x; h < n; h += gridDim.x) {
-    const int e = all ? h : g.edge_list[h];
+  const int n = all ? g.totedge : __ldcg(&g.cnt->edges);
+  const int gs2 = 2 * g.gs, per = gs2 - 2;
+  const long long items = (long long)n * per;
+  for (long long t = (long long)cta * blockDim.x + threadIdx.x; t < items; t += (long long)ncta * blockDim.x) {
+    const int h = (int)(t / per), i = 1 + (int)(t - (long long)h * per);
+    const int e = all ? h : __ldcg(&g.edge_list[h]);
     const int nf = g.edge_off[e + 1] - g.edge_off[e];
     if (nf == 1) continue;
     if (all == 1 && (nf == 2 || g.edge_stamp[e] == seq)) continue;
-    const int *base = g.edge_slots + (size_t)g.edge_off[e] * gs2;
-    for (int i = 1 + threadIdx.x; i < gs2 - 1; i += blockDim.x) dsc_grid_average_list(m, g, base + i, nf, gs2);
+    dsc_grid_average_list(m, g, g.edge_slots + (size_t)g.edge_off[e] * gs2 + i, nf, gs2);
   }
 }
 
 /* subdiv_ccg_average_grids_corners (subdiv_ccg.c:1081-1104): listed coarse vertices, or all of them */
-__global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g, int all)
+__device__ __forceinline__ void dsc_grid_cverts_body(const DevMesh &m, const DevGrids &g, int all, int cta, int ncta)
 {
-  const int n = all ? g.totcvert : g.cnt->cverts;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int v = all ? i : g.cvert_list[i];
+  const int n = all ? g.totcvert : __ldcg(&g.cnt->cverts);
+  for (int i = cta * blockDim.x + threadIdx.x; i < n; i += ncta * blockDim.x) {
+    const int v = all ? i : __ldcg(&g.cvert_list[i]);
     const int nf = g.cvert_off[v + 1] - g.cvert_off[v];
     if (nf == 1) continue;
     dsc_grid_average_list(m, g, g.cvert_slots + g.cvert_off[v], nf, 1);
@@ -145,81 +198,74 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g
 /* subdiv_ccg_recalc_inner_face_normals + subdiv_ccg_average_inner_face_normals (subdiv_ccg.c:670-740)
  * of every grid of the listed faces (all == 0) or of all grids: one CTA per grid, positions and quad
  * normals in shared memory */
-#define GN_BLOCK 256
+#define GN_BLOCK 1024
 __host__ __device__ inline size_t dsc_grid_normals_smem(int gs) { return sizeof(float) * 3 * ((size_t)gs * gs + (size_t)(gs - 1) * (gs - 1)); }
-__global__ void __launch_bounds__(GN_BLOCK) k_grid_normals(DevMesh m, DevGrids g, int all)
+__device__ __forceinline__ void dsc_grid_normals_body(const DevMesh &m, const DevGrids &g, int all, float *gsm, int cta, int ncta)
 {
-  extern __shared__ float gsm[];
   const int gs = g.gs, gs1 = gs - 1, gs2 = g.gs2;
-  float *P = gsm;           /* [gs2][3] */
+  const int bd = blockDim.x;
+  float *P = gsm;            /* [gs2][3] */
   float *Fn = gsm + 3 * gs2; /* [gs1 * gs1][3] */
-  const int units = all ? g.totgrid : g.cnt->faces * 4; /* listed faces: up to 4 corners each, more via the loop below */
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+  const int mfg = g.max_face_grids;
+  const int units = all ? g.totgrid : __ldcg(&g.cnt->faces) * mfg;
+  for (int u = cta; u < units; u += ncta) {
     int grid;
     if (all) {
       grid = u;
     }
     else {
-      const int f = g.face_list[u >> 2], c = u & 3;
+      const int f = __ldcg(&g.face_list[u / mfg]), c = u % mfg;
       if (c >= g.face_num[f]) continue;
       grid = g.face_start[f] + c;
     }
-    /* faces with more than 4 corners: corner c also takes c + 4, c + 8, ... */
-    for (;;) {
-      const int s0 = g.grid_slot0[grid];
-      __syncthreads();
-      for (int i = threadIdx.x; i < gs2; i += GN_BLOCK) {
-        P[3 * i] = m.cx[s0 + i]; P[3 * i + 1] = m.cy[s0 + i]; P[3 * i + 2] = m.cz[s0 + i];
+    const int s0 = g.grid_slot0[grid];
+    __syncthreads();
+    for (int i = threadIdx.x; i < gs2; i += bd) {
+      P[3 * i] = __ldcg(&m.cx[s0 + i]); P[3 * i + 1] = __ldcg(&m.cy[s0 + i]); P[3 * i + 2] = __ldcg(&m.cz[s0 + i]);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < gs1 * gs1; q += bd) {
+      const int y = q / gs1, x = q - y * gs1;
+      /* normal_quad_v3(co(x, y+1), co(x+1, y+1), co(x+1, y), co(x, y)), subdiv_ccg.c:684-698 */
+      const float *v1 = P + 3 * ((y + 1) * gs + x), *v2 = P + 3 * ((y + 1) * gs + x + 1);
+      const float *v3 = P + 3 * (y * gs + x + 1), *v4 = P + 3 * (y * gs + x);
+      const float n1x = v1[0] - v3[0], n1y = v1[1] - v3[1], n1z = v1[2] - v3[2];
+      const float n2x = v2[0] - v4[0], n2y = v2[1] - v4[1], n2z = v2[2] - v4[2];
+      float ox = n1y * n2z - n1z * n2y;
+      float oy = n1z * n2x - n1x * n2z;
+      float oz = n1x * n2y - n1y * n2x;
+      dsc_normalize(ox, oy, oz);
+      Fn[3 * q] = ox; Fn[3 * q + 1] = oy; Fn[3 * q + 2] = oz;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < gs2; i += bd) {
+      const int y = i / gs, x = i - y * gs;
+      float ax = 0.0f, ay = 0.0f, az = 0.0f;
+      int counter = 0;
+      if (x < gs1 && y < gs1) {
+        const float *f = Fn + 3 * (y * gs1 + x);
+        ax += f[0]; ay += f[1]; az += f[2];
+        counter++;
       }
-      __syncthreads();
-      for (int q = threadIdx.x; q < gs1 * gs1; q += GN_BLOCK) {
-        const int y = q / gs1, x = q - y * gs1;
-        /* normal_quad_v3(co(x, y+1), co(x+1, y+1), co(x+1, y), co(x, y)), subdiv_ccg.c:684-698 */
-        const float *v1 = P + 3 * ((y + 1) * gs + x), *v2 = P + 3 * ((y + 1) * gs + x + 1);
-        const float *v3 = P + 3 * (y * gs + x + 1), *v4 = P + 3 * (y * gs + x);
-        const float n1x = v1[0] - v3[0], n1y = v1[1] - v3[1], n1z = v1[2] - v3[2];
-        const float n2x = v2[0] - v4[0], n2y = v2[1] - v4[1], n2z = v2[2] - v4[2];
-        float ox = n1y * n2z - n1z * n2y;
-        float oy = n1z * n2x - n1x * n2z;
-        float oz = n1x * n2y - n1y * n2x;
-        dsc_normalize(ox, oy, oz);
-        Fn[3 * q] = ox; Fn[3 * q + 1] = oy; Fn[3 * q + 2] = oz;
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < gs2; i += GN_BLOCK) {
-        const int y = i / gs, x = i - y * gs;
-        float ax = 0.0f, ay = 0.0f, az = 0.0f;
-        int counter = 0;
-        if (x < gs1 && y < gs1) {
-          const float *f = Fn + 3 * (y * gs1 + x);
+      if (x >= 1) {
+        if (y < gs1) {
+          const float *f = Fn + 3 * (y * gs1 + (x - 1));
           ax += f[0]; ay += f[1]; az += f[2];
           counter++;
         }
-        if (x >= 1) {
-          if (y < gs1) {
-            const float *f = Fn + 3 * (y * gs1 + (x - 1));
-            ax += f[0]; ay += f[1]; az += f[2];
-            counter++;
-          }
-          if (y >= 1) {
-            const float *f = Fn + 3 * ((y - 1) * gs1 + (x - 1));
-            ax += f[0]; ay += f[1]; az += f[2];
-            counter++;
-          }
-        }
-        if (y >= 1 && x < gs1) {
-          const float *f = Fn + 3 * ((y - 1) * gs1 + x);
+        if (y >= 1) {
+          const float *f = Fn + 3 * ((y - 1) * gs1 + (x - 1));
           ax += f[0]; ay += f[1]; az += f[2];
           counter++;
         }
-        const float sc = 1.0f / (float)counter;
-        m.nx[s0 + i] = ax * sc; m.ny[s0 + i] = ay * sc; m.nz[s0 + i] = az * sc;
       }
-      if (all) break;
-      const int f = g.face_list[u >> 2];
-      const int c = grid - g.face_start[f] + 4;
-      if (c >= g.face_num[f]) break;
-      grid = g.face_start[f] + c;
+      if (y >= 1 && x < gs1) {
+        const float *f = Fn + 3 * ((y - 1) * gs1 + x);
+        ax += f[0]; ay += f[1]; az += f[2];
+        counter++;
+      }
+      const float sc = 1.0f / (float)counter;
+      m.nx[s0 + i] = ax * sc; m.ny[s0 + i] = ay * sc; m.nz[s0 + i] = az * sc;
     }
   }
 }
@@ -227,18 +273,18 @@ __global__ void __launch_bounds__(GN_BLOCK) k_grid_normals(DevMesh m, DevGrids g
 /* update_node_vb leaf branch for grid leaves (pbvh.c:2033-2041 with PBVH_ITER_ALL over the node's
  * grids): box of every element of the listed leaves; the leaf's vert_bitmap words are cleared on the
  * way (the grid normal pass does not use them) */
-__global__ void __launch_bounds__(DSC_BLOCK) k_grid_leaf_bb(DevMesh m, const int *list, const int *count)
+__device__ __forceinline__ void dsc_grid_leaf_bb_body(const DevMesh &m, const int *list, const int *count, int cta, int ncta)
 {
-  __shared__ float red[6][DSC_BLOCK / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float red[6][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bd = blockDim.x, nw = bd >> 5;
   const int tn = m.totnode;
-  const int n = *count;
-  for (int h = blockIdx.x; h < n; h += gridDim.x) {
-    const int l = list[h];
+  const int n = __ldcg(count);
+  for (int h = cta; h < n; h += ncta) {
+    const int l = __ldcg(&list[h]);
     float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
     float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
     const int ub = m.leaf_ubeg[l], uc = m.leaf_ucnt[l];
-    for (int i = 4 * tid; i < uc; i += 4 * DSC_BLOCK) {
+    for (int i = 4 * tid; i < uc; i += 4 * bd) {
       const float4 X = ld4(m.cx, ub + i), Y = ld4(m.cy, ub + i), Z = ld4(m.cz, ub + i);
       const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
@@ -250,7 +296,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_grid_leaf_bb(DevMesh m, const int
         }
       }
     }
-    for (int w = tid; w < (uc + 31) / 32; w += DSC_BLOCK) m.dirty[(ub >> 5) + w] = 0u;
+    for (int w = tid; w < (uc + 31) / 32; w += bd) m.dirty[(ub >> 5) + w] = 0u;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       for (int o = 16; o > 0; o >>= 1) {
@@ -269,8 +315,56 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_grid_leaf_bb(DevMesh m, const int
     __syncthreads();
     if (tid < 6) {
       float v = red[tid][0];
-      for (int w = 1; w < DSC_BLOCK / 32; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+      for (int w = 1; w < nw; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
       m.bb[tid * tn + l] = v;
     }
   }
+}
+
+/* ---- the stages as kernels of their own (session start, full averages) ---- */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_faces(DevMesh m, DevGrids g, const int *list, const int *count, int seq)
+{
+  dsc_grid_faces_body(g, list, count, seq, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(128) k_grid_inner(DevMesh m, DevGrids g) { dsc_grid_inner_body(m, g, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int all, int seq)
+{
+  dsc_grid_edges_body(m, g, all, seq, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g, int all) { dsc_grid_cverts_body(m, g, all, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(GN_BLOCK) k_grid_normals(DevMesh m, DevGrids g, int all)
+{
+  extern __shared__ float gsm[];
+  dsc_grid_normals_body(m, g, all, gsm, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_leaf_bb(DevMesh m, const int *list, const int *count)
+{
+  dsc_grid_leaf_bb_body(m, list, count, blockIdx.x, gridDim.x);
+}
+
+/* ---- everything a dab does on grids after the brush, in ONE cooperative launch ----
+ * faces of the gathered leaves -> stitch (inner boundaries, coarse edges, all coarse vertices) -> CCG normals
+ * of those faces' grids -> their averaging (inner, edges, vertices) -> leaf boxes; the phases are separated by
+ * grid barriers (dsc_grid_sync) instead of nine kernel boundaries.  One CTA of GN_BLOCK threads per SM. */
+__global__ void __launch_bounds__(GN_BLOCK, 1) k_grid_dab(DevMesh m, DevGrids g, const int *list, const int *count, int seq)
+{
+  extern __shared__ float gsm[];
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  unsigned target = 0u;
+  dsc_grid_faces_body(g, list, count, seq, cta, ncta);
+  dsc_grid_sync(m.grid_bar, target, ncta);
+  dsc_grid_inner_body(m, g, cta, ncta);
+  dsc_grid_sync(m.grid_bar, target, ncta);
+  dsc_grid_edges_body(m, g, 0, seq, cta, ncta);
+  if (g.has_odd_edges) dsc_grid_edges_body(m, g, 1, seq, cta, ncta);
+  dsc_grid_cverts_body(m, g, 1, cta, ncta); /* coarse vertices are not on any edge's list: same phase */
+  dsc_grid_sync(m.grid_bar, target, ncta);
+  dsc_grid_normals_body(m, g, 0, gsm, cta, ncta);
+  dsc_grid_sync(m.grid_bar, target, ncta);
+  dsc_grid_inner_body(m, g, cta, ncta);
+  dsc_grid_sync(m.grid_bar, target, ncta);
+  dsc_grid_edges_body(m, g, 0, seq, cta, ncta);
+  dsc_grid_cverts_body(m, g, 0, cta, ncta);
+  dsc_grid_sync(m.grid_bar, target, ncta);
+  dsc_grid_leaf_bb_body(m, list, count, cta, ncta);
 }

@@ -109,3 +109,12 @@ def test_grids_reject_what_the_path_does_not_cover():
         ses.stroke_end()
     finally:
         ses.close()
+
+
+def test_grids_fused_cooperative_kernel_is_bit_identical(monkeypatch):
+    """DSC_GRID_FUSED=1: the nine launches after the brush as one cooperative kernel with grid barriers
+    (an experiment that measured slower; kept honest here)"""
+    monkeypatch.setenv("DSC_GRID_FUSED", "1")
+    mr = meshgen.multires_cube(2, 4, with_mask=True)
+    st = _grid_parity(mr, _sweep(mr, per=2, radii=(6.0, 20.0, 45.0)), leaf_limit=6)
+    assert st["moved_verts"] > 0

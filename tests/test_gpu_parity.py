@@ -389,3 +389,34 @@ def test_dab_that_gathers_nothing_and_degenerate_inputs():
     tiny = meshgen.grid(2)
     r = run_parity(tiny, [capi.make_dab(capi.TOOL_DRAW, (0.0, 0.0, 0.0), 2.0, bstrength=0.2, view_normal=(0, 0, 1))])
     assert r["moved"] == 4
+
+
+def test_persistent_batch_kernel_is_bit_identical(monkeypatch):
+    """DSC_BATCH_KERNEL=1: a run of dabs in one cooperative launch, stages separated by grid barriers (an
+    experiment that measured slower than graph replay; kept honest here)"""
+    from oracle_py import Oracle
+    monkeypatch.setenv("DSC_BATCH_KERNEL", "1")
+    m = meshgen.grid(300)
+    dabs = stroke.c3_radius_sweep(m.bbox_diag(), dabs_per_radius=3)
+    dabs += _line_dabs(capi.TOOL_CLAY_STRIPS, (-0.5, 0.2, 0.0), (0.5, -0.3, 0.0), 0.25, 5)
+    orc = Oracle(m)
+    ses = capi.SculptSession(m, device=0)
+    try:
+        orc.stroke_begin()
+        for d in dabs:
+            orc.dab(d)
+        orc.stroke_end()
+        arr = (capi.DscDab * len(dabs))(*dabs)
+        ses.stroke_begin()
+        ses.dabs(arr, len(dabs))
+        st = ses.stats()
+        ses.stroke_end()
+        assert st["vertex_dabs"] == orc.vertex_dabs()
+        assert st["kernel_launches"] < 3 * len(dabs), "the batch kernel was not used"
+        assert np.array_equal(ses.co(), orc.co()) and np.array_equal(ses.no(), orc.no())
+        bb, obb = ses.node_bb()
+        na = orc.node_arrays()
+        assert np.array_equal(bb, na["vb"]) and np.array_equal(obb, na["orig_vb"])
+    finally:
+        ses.close()
+        orc.close()
