@@ -28,6 +28,7 @@ DIR_AREA, DIR_VIEW, DIR_X, DIR_Y, DIR_Z = 0, 1, 2, 3, 4
 DAB_FRONTFACE, DAB_PLANE_TRIM, DAB_FIRST_STEP, DAB_NO_NORMALS, DAB_NO_BOUNDS = 1, 2, 4, 8, 16
 PBVH_Leaf, PBVH_UpdateNormals, PBVH_UpdateBB, PBVH_UpdateOriginalBB = 1, 2, 4, 8
 PBVH_FullyHidden, PBVH_FullyMasked = 1 << 10, 1 << 11
+PBVH_UpdateDrawBuffers, PBVH_UpdateRedraw, PBVH_RebuildDrawBuffers = 1 << 4, 1 << 5, 1 << 9
 
 
 class DscDab(C.Structure):
@@ -66,6 +67,7 @@ class PBVH(C.Structure):
         ("vert_bitmap", C.POINTER(C.c_uint)), ("deformed", C.c_bool), ("owns_normals", C.c_bool),
         ("is_grids", C.c_int), ("grids", C.c_void_p), ("gridfaces", C.c_void_p), ("grid_flag_mats", C.c_void_p),
         ("totgrid", C.c_int), ("gridkey", C.c_int * 9), ("grid_hidden", C.c_void_p), ("subdiv_ccg", C.c_void_p),
+        ("want_draw_buffers", C.c_int),
         ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
         ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool),
         ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
@@ -90,6 +92,7 @@ CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
     "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
     "dsc_dabs", "dsc_state_save", "dsc_state_restore", "dsc_grids_upload", "dsc_download_mask",
+    "dsc_draw_enable", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
     "dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
@@ -104,6 +107,7 @@ HOST_SYMBOLS = [
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
     "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
+    "DUNE_pbvh_draw_buffers_enable", "DUNE_pbvh_update_draw_buffers", "DUNE_pbvh_node_draw_buffer",
     "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
     "BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_hidden_get", "BKE_pbvh_node_fully_masked_set",
     "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
@@ -157,6 +161,10 @@ def cuda_lib():
         L.dsc_node_mark_update.argtypes = [C.c_void_p, C.c_int]
         L.dsc_node_flag_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.dsc_download_mask.argtypes = [C.c_void_p, c_float_p]
+        L.dsc_draw_enable.argtypes = [C.c_void_p]
+        L.dsc_draw_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.dsc_draw_node_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), c_int_p]
+        L.dsc_draw_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, c_int_p]
         for fn in ("dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_upload_co",
                    "dsc_set_custom_curve", "dsc_set_mask"):
             getattr(L, fn).argtypes = [C.c_void_p, c_float_p]
@@ -205,6 +213,10 @@ def host_lib():
         L.DUNE_subdiv_ccg_free.argtypes = [C.c_void_p]
         L.DUNE_subdiv_ccg_free.restype = None
         L.DUNE_pbvh_device_attach_grids.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int]
+        L.DUNE_pbvh_draw_buffers_enable.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_draw_buffers_enable.restype = None
+        L.DUNE_pbvh_update_draw_buffers.argtypes = [C.POINTER(PBVH), C.c_bool, C.c_bool]
+        L.DUNE_pbvh_node_draw_buffer.argtypes = [C.POINTER(PBVH), C.c_void_p, C.POINTER(C.c_void_p), c_int_p]
         L.DUNE_pbvh_device_checkpoint.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_rollback.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_error.argtypes = [C.POINTER(PBVH)]
@@ -296,7 +308,7 @@ def make_dab(tool, location, radius, **kw):
 class SculptSession:
     """A mesh + its PBVH through the reference-named host API, optionally attached to a device."""
 
-    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None):
+    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None, draw_buffers=False):
         """dist = (world, rank, nccl_id_bytes) attaches this process as one rank of a partitioned PBVH"""
         H = host_lib()
         self.H = H
@@ -326,6 +338,8 @@ class SculptSession:
                               mesh.totvert, None, None, None, self.looptri.ctypes.data, self.tottri)
         self.ctx = None
         self.dist = dist
+        if draw_buffers:
+            H.DUNE_pbvh_draw_buffers_enable(self.pbvh)
         if device is not None:
             self.attach(device)
 
@@ -466,6 +480,18 @@ class SculptSession:
 
     def stroke_end(self):
         self._chk(self.H.DUNE_sculpt_stroke_end(self.pbvh))
+
+    def update_draw_buffers(self, smooth=True, show_mask=True):
+        """pack the vertex buffers of the leaves flagged for a draw update, on the device"""
+        self._chk(self.H.DUNE_pbvh_update_draw_buffers(self.pbvh, bool(smooth), bool(show_mask)))
+
+    def draw_buffer(self, node):
+        """the packed vertex buffer of a leaf, (verts, 36) bytes"""
+        n = C.c_int(0)
+        self._chk(self.D.dsc_draw_download(self.ctx, int(node), None, 0, C.byref(n)))
+        out = np.zeros((n.value, 36), dtype=np.uint8)
+        self._chk(self.D.dsc_draw_download(self.ctx, int(node), out.ctypes.data, out.nbytes, C.byref(n)))
+        return out
 
     def checkpoint(self):
         """remember the resident mesh state (device-to-device)"""

@@ -66,11 +66,16 @@ struct DscContext {
   DevGrids g;
   int grid_seq = 0;
   size_t gn_smem = 0;
+  /* draw-buffer fill (dsc_draw_*) */
+  bool want_draw = false;
+  const int4 *d_tri_slots = nullptr;
+  unsigned *d_vbo = nullptr; /* [tottri * 3][9] packed vertex records, by looptri position */
   bool has_odd_edges = false; /* some coarse edge has more than two faces */
   bool grid_fused = false;    /* DSC_GRID_FUSED=1: the stages after the brush as one cooperative kernel instead of nine launches */
 
   std::vector<int> slot_of;     /* vertex -> slot */
   std::vector<int> leaf_node;   /* leaf (= device id) -> host node index */
+  std::vector<int> h_leaf_pbeg, h_leaf_pcnt; /* leaf -> its run of looptri positions */
   std::vector<int> dev_of_node; /* host node index -> device node id */
   std::vector<int> node_of_dev;
   bool stale_flags = false; /* leaves may carry update flags from an earlier dab or from the host */
@@ -1260,7 +1265,17 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       return r;
     CU(cudaStreamSynchronize(ctx->stream));
 
-    if (ctx->any_slow_leaf) {
+    if (ctx->want_draw) {
+      /* draw-buffer fill: the three corners of every looptri, as slots, by looptri position */
+      std::vector<int4> tri_slots((size_t)std::max(T, 1));
+      for (int pos = 0; pos < T; pos++) {
+        const int t = pb->prim_indices[pos];
+        tri_slots[pos] = make_int4(ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t]], ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + 1]],
+                                   ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + 2]], ctx->h_tri_poly[t]);
+      }
+      if ((r = dev_upload_c(ctx, &ctx->d_tri_slots, tri_slots))) return r;
+    }
+    if (ctx->any_slow_leaf || ctx->want_draw) {
       /* general path tables: poly verts as slots per looptri position, n-gon lists */
       std::vector<int> pv[4];
       for (int k = 0; k < 4; k++) pv[k].assign((size_t)std::max(T, 1), -1);
@@ -1303,6 +1318,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_upload_c(ctx, &m.leaf_pbeg, leaf_pbeg)) || (r = dev_upload_c(ctx, &m.leaf_pcnt, leaf_pcnt)))
       return r;
     m.nleaf = L;
+    ctx->h_leaf_pbeg = leaf_pbeg;
+    ctx->h_leaf_pcnt = leaf_pcnt;
     int max_u = 1;
     for (int l = 0; l < L; l++) max_u = std::max(max_u, leaf_ucnt[l]);
     m.max_chunks = (max_u + DSC_CHUNK - 1) / DSC_CHUNK;
@@ -2488,6 +2505,55 @@ int dsc_upload_co(DscContext *ctx, const float *co)
   if ((r = run_flagged(ctx, F_UpdateNormals | F_UpdateBB))) return r;
   if ((r = run_orig_flush(ctx))) return r;
   return sync_all(ctx);
+}
+
+/* ---- draw-buffer fill from the device ---- */
+int dsc_draw_enable(DscContext *ctx)
+{
+  if (!ctx) return DSC_ERR_INVALID;
+  if (ctx->have_pbvh) return fail(ctx, DSC_ERR_STATE, "dsc_draw_enable comes before dsc_pbvh_upload");
+  if (ctx->is_grids) return fail(ctx, DSC_ERR_UNSUPPORTED, "the grids draw buffers (gpu_buffers.c:548-725) are not on the device yet");
+  ctx->want_draw = true;
+  return DSC_OK;
+}
+int dsc_draw_update(DscContext *ctx, int smooth, int show_mask)
+{
+  NEED_PBVH();
+  if (!ctx->want_draw) return fail(ctx, DSC_ERR_STATE, "dsc_draw_enable first");
+  int r = join_side(ctx);
+  if (r) return r;
+  if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, (size_t)std::max(ctx->tottri, 1) * 3 * 9))) return r;
+  const int flags = DSC_PBVH_UpdateDrawBuffers | DSC_PBVH_RebuildDrawBuffers;
+  if ((r = run_collect(ctx, flags))) return r;
+  k_draw_fill<<<ctx->num_sms * 4, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->d_tri_slots, ctx->m.flag_list, &ctx->m.tot->flag_count,
+                                                                smooth ? 1 : 0, (show_mask && ctx->m.mask) ? 1 : 0, ctx->d_vbo);
+  LAUNCH_CHECK();
+  ctx->launches++;
+  return run_clear(ctx, flag_list(ctx), flags); /* pbvh.c:3276 */
+}
+int dsc_draw_node_buffer(DscContext *ctx, int node, void **r_device_ptr, int *r_vert_len)
+{
+  NEED_PBVH();
+  if (!ctx->d_vbo) return fail(ctx, DSC_ERR_STATE, "dsc_draw_update first");
+  if (node < 0 || node >= ctx->totnode || ctx->dev_of_node[node] >= ctx->m.nleaf) return fail(ctx, DSC_ERR_INVALID, "node %d is not a leaf", node);
+  const int l = ctx->dev_of_node[node];
+  if (r_device_ptr) *r_device_ptr = ctx->d_vbo + (size_t)ctx->h_leaf_pbeg[l] * 3 * 9;
+  if (r_vert_len) *r_vert_len = ctx->h_leaf_pcnt[l] * 3;
+  return DSC_OK;
+}
+int dsc_draw_download(DscContext *ctx, int node, void *r_host, size_t capacity_bytes, int *r_vert_len)
+{
+  void *dp = nullptr;
+  int n = 0;
+  int r = dsc_draw_node_buffer(ctx, node, &dp, &n);
+  if (r) return r;
+  if (r_vert_len) *r_vert_len = n;
+  if (!r_host) return DSC_OK;
+  if (capacity_bytes < (size_t)n * 36) return fail(ctx, DSC_ERR_INVALID, "buffer too small for %d vertices", n);
+  if ((r = join_side(ctx))) return r;
+  CU(cudaMemcpyAsync(r_host, dp, (size_t)n * 36, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSC_OK;
 }
 
 /* Checkpoint / rollback of the resident mesh state (positions, normals, node boxes, node flags):

@@ -1733,6 +1733,58 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_orig_inner(DevMesh m)
   }
 }
 
+/* ------------------------------------------------------------------- draw-buffer fill */
+/* GPU_pbvh_mesh_buffers_update (gpu/intern/gpu_buffers.c:174-305) for the listed leaves: one 36-byte record
+ * per looptri corner in the vertex format of gpu_pbvh_init (gpu_buffers.c:84-100, offsets from
+ * VertexFormat_pack, gpu_vertex_format.cc:300-325): pos f32 x 3 @0, nor i16 x 3 @16, msk u8 @22,
+ * col u16 x 4 @24 (not shown on this path: zero), fset u8 x 3 @32 (white).  Flat shading: the poly normal
+ * and the mean mask of the looptri; smooth: the vertex normal and mask.  The buffer is indexed by looptri
+ * position, so a leaf's VBO is one contiguous run. */
+__device__ __forceinline__ unsigned dsc_normal_short(float f) { return (unsigned)(unsigned short)(short)(int)(f * 32767.0f); }
+__global__ void __launch_bounds__(DSC_BLOCK) k_draw_fill(DevMesh m, const int4 *tri_slots, const int *list, const int *count, int smooth,
+                                                         int show_mask, unsigned *vbo)
+{
+  const int n = *count;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int l = list[h];
+    const int pb = m.leaf_pbeg[l], pe = pb + m.leaf_pcnt[l];
+    for (int pos = pb + threadIdx.x; pos < pe; pos += blockDim.x) {
+      const int4 tv = tri_slots[pos];
+      const int sl[3] = {tv.x, tv.y, tv.z};
+      unsigned n01 = 0u, n2 = 0u, cmask = 0u;
+      if (!smooth) {
+        float fx, fy, fz;
+        dsc_poly_normal(m, (unsigned)pos, fx, fy, fz);
+        n01 = dsc_normal_short(fx) | (dsc_normal_short(fy) << 16);
+        n2 = dsc_normal_short(fz);
+        if (show_mask) {
+          const float fmask = (m.mask[sl[0]] + m.mask[sl[1]] + m.mask[sl[2]]) / 3.0f;
+          cmask = (unsigned)(unsigned char)(int)(fmask * 255);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int s = sl[j];
+        if (smooth) {
+          n01 = dsc_normal_short(m.nx[s]) | (dsc_normal_short(m.ny[s]) << 16);
+          n2 = dsc_normal_short(m.nz[s]);
+          if (show_mask) cmask = (unsigned)(unsigned char)(int)(m.mask[s] * 255);
+        }
+        unsigned *rec = vbo + ((size_t)pos * 3 + j) * 9;
+        rec[0] = __float_as_uint(m.cx[s]);
+        rec[1] = __float_as_uint(m.cy[s]);
+        rec[2] = __float_as_uint(m.cz[s]);
+        rec[3] = 0u;
+        rec[4] = n01;
+        rec[5] = n2 | (cmask << 16);
+        rec[6] = 0u;
+        rec[7] = 0u;
+        rec[8] = 0x00ffffffu;
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------- multi-GPU halo pack / unpack */
 /* positions of the halo slots, [3][n] in the buffer */
 __global__ void k_halo_pack(float *__restrict__ buf, const int *__restrict__ idx, int n, const float *__restrict__ ax,

@@ -875,6 +875,7 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
   pd.face_verts = face;
   pd.vert_offset = vert_off;
   pd.vert_indices = vert_indices;
+  if (r == DSC_OK && pbvh->want_draw_buffers) r = dsc_draw_enable(ctx);
   if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
 
   free(tail); free(co); free(poly_start); free(poly_len); free(loop_v); free(tri_vert); free(tri_poly);
@@ -901,6 +902,20 @@ void DUNE_pbvh_device_detach(PBVH *pbvh)
     dsc_ctx_destroy(pbvh->device);
     pbvh->device = NULL;
   }
+}
+
+void DUNE_pbvh_draw_buffers_enable(PBVH *pbvh) { pbvh->want_draw_buffers = 1; }
+
+int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask)
+{
+  if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
+  return dsc_draw_update(pbvh->device, smooth ? 1 : 0, show_mask ? 1 : 0);
+}
+
+int DUNE_pbvh_node_draw_buffer(PBVH *pbvh, PBVHNode *node, void **r_device_ptr, int *r_vert_len)
+{
+  if (!pbvh || !pbvh->device || !node) return DSC_ERR_STATE;
+  return dsc_draw_node_buffer(pbvh->device, (int)(node - pbvh->nodes), r_device_ptr, r_vert_len);
 }
 
 int DUNE_pbvh_device_checkpoint(PBVH *pbvh)

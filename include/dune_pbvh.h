@@ -175,6 +175,7 @@ typedef struct PBVH {
   CCGKey gridkey;
   BLI_bitmap **grid_hidden;
   struct SubdivCCG *subdiv_ccg; /* set by DUNE_pbvh_device_attach_grids */
+  int want_draw_buffers;
 
   /* device side */
   DscContext *device;
@@ -223,6 +224,13 @@ void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit);
 
 /* ---- device hooks (new) ---- */
 int DUNE_pbvh_device_attach(PBVH *pbvh, int device);
+/* before the attach: also keep the tables the device-side draw-buffer fill needs (dsc_draw_enable) */
+void DUNE_pbvh_draw_buffers_enable(PBVH *pbvh);
+/* pbvh_update_draw_buffers (pbvh.c:3169-3285) on the device: pack the vertex buffers of the leaves flagged
+ * PBVH_UpdateDrawBuffers / PBVH_RebuildDrawBuffers (gpu_buffers.c:174-305) and clear the flags; then the
+ * device pointer and vertex count of a node's buffer for the GL copy */
+int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask);
+int DUNE_pbvh_node_draw_buffer(PBVH *pbvh, PBVHNode *node, void **r_device_ptr, int *r_vert_len);
 /* the same for a grids PBVH: the CCG's elements and adjacency go to the device */
 int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device);
 /* one rank of a PBVH partitioned across the GPUs of one box (see dsc_dist_init) */

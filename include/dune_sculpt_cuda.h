@@ -230,6 +230,19 @@ int dsc_download_node_flags(DscContext *ctx, int *r_flags /* [totnode] */);
 /* undo-node membership of the running / last stroke: r_touched[node] = 1 */
 int dsc_download_touched(DscContext *ctx, unsigned char *r_touched /* [totnode] */);
 int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_coords_apply */
+/* --- draw-buffer fill from the device: behind pbvh_update_draw_buffers (pbvh.c:3169-3285) ->
+ *     GPU_pbvh_mesh_buffers_update (gpu/intern/gpu_buffers.c:174-305).  Every leaf flagged
+ *     PBVH_UpdateDrawBuffers / PBVH_RebuildDrawBuffers gets its vertex buffer packed on the device in the
+ *     format of gpu_pbvh_init (gpu_buffers.c:84-100): 36 bytes per looptri corner -- pos f32 x 3 @0,
+ *     nor i16 x 3 @16, msk u8 @22, col u16 x 4 @24 (zero), fset u8 x 3 @32 (white); the flags are cleared
+ *     (pbvh.c:3276).  The reference's caller copies the node's run into its GL buffer (CUDA-GL interop
+ *     on the pointer dsc_draw_node_buffer returns) instead of re-reading the node's triangles on the CPU.
+ *     Meshes only.  dsc_draw_enable comes between dsc_mesh_upload and dsc_pbvh_upload. ------------------- */
+int dsc_draw_enable(DscContext *ctx);
+int dsc_draw_update(DscContext *ctx, int smooth /* ME_SMOOTH of the node's faces */, int show_mask);
+int dsc_draw_node_buffer(DscContext *ctx, int node, void **r_device_ptr, int *r_vert_len);
+int dsc_draw_download(DscContext *ctx, int node, void *r_host, size_t capacity_bytes, int *r_vert_len);
+
 /* Checkpoint / rollback of the resident mesh state (positions, normals, node boxes and flags) by
  * device-to-device copies: what operator cancel / the undo restore do on the host side of the
  * reference (undo nodes written back, paint_hide.c:78, then BKE_pbvh_update_bounds), without the

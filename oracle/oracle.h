@@ -138,6 +138,9 @@ void or_vert_mark_update(OrPbvh *p, int v);
 void or_node_mark_update(OrPbvh *p, int node);
 void or_update_normals(OrPbvh *p);
 void or_update_bounds(OrPbvh *p, int flag);
+/* GPU_pbvh_mesh_buffers_update (gpu/intern/gpu_buffers.c:174-305) of one leaf into `out` (totprim * 3 records of
+ * 36 bytes); returns the vertex count */
+int or_draw_buffers_update(OrPbvh *p, int node, int smooth, int show_mask, unsigned char *out);
 /* full-mesh vertex normals the way the accumulate pass would produce them with every vertex dirty */
 void or_recalc_all_normals(OrPbvh *p);
 void or_set_threads(int n);

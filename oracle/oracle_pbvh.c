@@ -753,6 +753,51 @@ void or_recalc_all_normals(OrPbvh *p)
   or_update_normals(p);
 }
 
+/* gpu/intern/gpu_buffers.c:174-305 GPU_pbvh_mesh_buffers_update for one leaf, into the packed vertex
+ * format of gpu_pbvh_init (gpu_buffers.c:84-100; offsets by VertexFormat_pack, gpu_vertex_format.cc:300-325):
+ * 36 bytes per looptri corner -- pos f32 x 3 @0, nor i16 x 3 @16, msk u8 @22, col u16 x 4 @24, fset u8 x 3 @32.
+ * No hidden faces, no face sets, no vertex colours on this path: every looptri is visible, col stays zero,
+ * fset is white.  Clears PBVH_RebuildDrawBuffers | PBVH_UpdateDrawBuffers like pbvh.c:3276. */
+int or_draw_buffers_update(OrPbvh *p, int ni, int smooth, int show_mask, unsigned char *out)
+{
+  OrNode *node = &p->nodes[ni];
+  if (!(node->flag & OR_PBVH_Leaf) || p->is_grids) return 0;
+  const int stride = 36;
+  const int *faces = p->prim_indices + node->prim_offset;
+  const int use_mask = show_mask && p->mask;
+  int mpoly_prev = -1;
+  short no[3] = {0, 0, 0};
+  memset(out, 0, (size_t)node->totprim * 3 * stride);
+  for (int i = 0; i < node->totprim; i++) {
+    const int t = faces[i];
+    const int *vtri = p->tri_v[t];
+    if (p->tri_poly[t] != mpoly_prev && !smooth) {
+      float fno[3];
+      calc_poly_normal(p, p->tri_poly[t], fno);
+      for (int k = 0; k < 3; k++) no[k] = (short)(fno[k] * 32767.0f); /* normal_float_to_short_v3 */
+      mpoly_prev = p->tri_poly[t];
+    }
+    unsigned char cmask = 0;
+    if (use_mask && !smooth) {
+      const float fmask = (p->mask[vtri[0]] + p->mask[vtri[1]] + p->mask[vtri[2]]) / 3.0f;
+      cmask = (unsigned char)(fmask * 255);
+    }
+    for (int j = 0; j < 3; j++) {
+      unsigned char *rec = out + ((size_t)i * 3 + j) * stride;
+      memcpy(rec, p->co[vtri[j]], sizeof(float[3]));
+      if (smooth) {
+        for (int k = 0; k < 3; k++) no[k] = (short)(p->no[vtri[j]][k] * 32767.0f);
+      }
+      memcpy(rec + 16, no, sizeof(short[3]));
+      if (use_mask && smooth) cmask = (unsigned char)(p->mask[vtri[j]] * 255);
+      rec[22] = cmask;
+      rec[32] = rec[33] = rec[34] = 255;
+    }
+  }
+  node->flag &= ~(unsigned)(OR_PBVH_RebuildDrawBuffers | OR_PBVH_UpdateDrawBuffers);
+  return node->totprim * 3;
+}
+
 /* pbvh.c:3287-3317 pbvh_flush_bb */
 static int pbvh_flush_bb(OrPbvh *p, OrNode *node, int flag)
 {

@@ -74,6 +74,7 @@ def lib():
         L.or_looptri_count.argtypes = [C.c_int, c_int_p]
         L.or_looptri_calc.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p]
         L.or_vert_neighbors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_void_p]
+        L.or_draw_buffers_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.or_pbvh_build_grids.restype = C.c_void_p
         L.or_pbvh_build_grids.argtypes = [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p, C.c_int,
                                           c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, C.c_int]
@@ -221,6 +222,13 @@ class Oracle:
 
     def update_bounds(self, flag):
         self.L.or_update_bounds(self.p, int(flag))
+
+    def draw_buffer(self, node, totprim, smooth=True, show_mask=True):
+        """the leaf's packed VBO (gpu_buffers.c:174-305), (totprim * 3, 36) bytes"""
+        out = np.zeros((totprim * 3, 36), dtype=np.uint8)
+        n = self.L.or_draw_buffers_update(self.p, int(node), int(smooth), int(show_mask), out.ctypes.data)
+        assert n == totprim * 3
+        return out
 
     def curve_strength(self, preset, p, length):
         return float(self.L.or_brush_curve_strength(self.p, int(preset), C.c_float(p), C.c_float(length)))

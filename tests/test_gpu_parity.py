@@ -420,3 +420,40 @@ def test_persistent_batch_kernel_is_bit_identical(monkeypatch):
     finally:
         ses.close()
         orc.close()
+
+
+@pytest.mark.parametrize("smooth", [True, False])
+def test_draw_buffers_filled_on_the_device_match_gpu_pbvh_mesh_buffers_update(smooth):
+    """after a stroke the leaves flagged PBVH_UpdateDrawBuffers get their 36-byte-per-corner
+    vertex buffers (gpu_buffers.c:84-100, 174-305) packed on the device; bytes equal the oracle's; flags cleared;
+    leaves the stroke did not touch are only filled by the first (rebuild) pass"""
+    from oracle_py import Oracle
+    m = meshgen.mixed_grid(65) if not smooth else meshgen.grid(129)
+    mask = meshgen.low_freq_mask(m)
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.6, -0.5, 0.0), (0.5, 0.4, 0.0), 0.2, 5)
+    orc = Oracle(m, mask=mask, leaf_limit=200)
+    ses = capi.SculptSession(m, mask=mask, leaf_limit=200, device=0, draw_buffers=True)
+    try:
+        na = orc.node_arrays()
+        leaves = np.nonzero(na["flag"] & 1)[0]
+        for rnd in range(2):
+            if rnd == 1:
+                orc.stroke_begin()
+                ses.stroke_begin()
+                for d in dabs:
+                    orc.dab(d)
+                    ses.dab(d)
+                orc.stroke_end()
+                ses.stroke_end()
+            flagged = [int(n) for n in leaves if orc.node_arrays()["flag"][n] & (capi.PBVH_UpdateDrawBuffers | capi.PBVH_RebuildDrawBuffers)]
+            assert flagged and (rnd == 0 or len(flagged) < leaves.size)
+            ses.update_draw_buffers(smooth=smooth, show_mask=True)
+            for n in flagged:
+                ref = orc.draw_buffer(n, int(na["totprim"][n]), smooth=smooth, show_mask=True)
+                got = ses.draw_buffer(n)
+                assert got.shape == ref.shape and np.array_equal(got, ref), "leaf %d round %d" % (n, rnd)
+            keep = capi.PBVH_UpdateDrawBuffers | capi.PBVH_RebuildDrawBuffers
+            assert not np.any(ses.node_flags() & keep) and not np.any(orc.node_arrays()["flag"] & keep)
+    finally:
+        ses.close()
+        orc.close()
