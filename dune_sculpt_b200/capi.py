@@ -92,7 +92,7 @@ CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
     "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
     "dsc_dabs", "dsc_state_save", "dsc_state_restore", "dsc_grids_upload", "dsc_download_mask",
-    "dsc_draw_enable", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
+    "dsc_raycast_enable", "dsc_raycast", "dsc_draw_enable", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
     "dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
@@ -108,6 +108,7 @@ HOST_SYMBOLS = [
     "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
     "DUNE_pbvh_draw_buffers_enable", "DUNE_pbvh_update_draw_buffers", "DUNE_pbvh_node_draw_buffer",
+    "DUNE_pbvh_raycast_enable", "DUNE_pbvh_raycast_nearest",
     "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
     "BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_hidden_get", "BKE_pbvh_node_fully_masked_set",
     "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
@@ -216,6 +217,11 @@ def host_lib():
         L.DUNE_pbvh_draw_buffers_enable.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_draw_buffers_enable.restype = None
         L.DUNE_pbvh_update_draw_buffers.argtypes = [C.POINTER(PBVH), C.c_bool, C.c_bool]
+        L.DUNE_pbvh_raycast_enable.argtypes = [C.POINTER(PBVH)]
+        L.DUNE_pbvh_raycast_enable.restype = None
+        L.DUNE_pbvh_raycast_nearest.argtypes = [C.POINTER(PBVH), c_float_p, c_float_p, C.c_bool, C.c_float, c_float_p, c_int_p, c_int_p,
+                                                c_float_p, C.POINTER(C.c_void_p)]
+        L.DUNE_pbvh_raycast_nearest.restype = C.c_bool
         L.DUNE_pbvh_node_draw_buffer.argtypes = [C.POINTER(PBVH), C.c_void_p, C.POINTER(C.c_void_p), c_int_p]
         L.DUNE_pbvh_device_checkpoint.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_rollback.argtypes = [C.POINTER(PBVH)]
@@ -308,7 +314,7 @@ def make_dab(tool, location, radius, **kw):
 class SculptSession:
     """A mesh + its PBVH through the reference-named host API, optionally attached to a device."""
 
-    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None, draw_buffers=False):
+    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None, draw_buffers=False, raycast=False):
         """dist = (world, rank, nccl_id_bytes) attaches this process as one rank of a partitioned PBVH"""
         H = host_lib()
         self.H = H
@@ -340,6 +346,9 @@ class SculptSession:
         self.dist = dist
         if draw_buffers:
             H.DUNE_pbvh_draw_buffers_enable(self.pbvh)
+        self.raycast_enabled = bool(raycast)
+        if raycast:
+            H.DUNE_pbvh_raycast_enable(self.pbvh)
         if device is not None:
             self.attach(device)
 
@@ -480,6 +489,24 @@ class SculptSession:
 
     def stroke_end(self):
         self._chk(self.H.DUNE_sculpt_stroke_end(self.pbvh))
+
+    def raycast(self, start, normal, original=False, max_depth=3.4028234663852886e38):
+        """BKE_pbvh_raycast + the stroke operator's hit callback: None or dict(depth, vertex, face, normal, node)"""
+        if not self.raycast_enabled:
+            raise DeviceError("SculptSession(raycast=True) keeps the tables the device ray-cast needs")
+        s_ = np.ascontiguousarray(start, dtype=np.float32)
+        n_ = np.ascontiguousarray(normal, dtype=np.float32)
+        depth = C.c_float(0)
+        vert = C.c_int(0)
+        face = C.c_int(0)
+        fno = np.zeros(3, np.float32)
+        node = C.c_void_p(0)
+        if not self.H.DUNE_pbvh_raycast_nearest(self.pbvh, fptr(s_), fptr(n_), bool(original), C.c_float(max_depth), C.byref(depth), C.byref(vert),
+                                                C.byref(face), fptr(fno), C.byref(node)):
+            return None
+        base = C.addressof(self.pbvh.contents.nodes.contents)
+        return {"depth": np.float32(depth.value), "vertex": vert.value, "face": face.value, "normal": fno,
+                "node": (node.value - base) // C.sizeof(PBVHNode)}
 
     def update_draw_buffers(self, smooth=True, show_mask=True):
         """pack the vertex buffers of the leaves flagged for a draw update, on the device"""

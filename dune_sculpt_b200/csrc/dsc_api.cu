@@ -67,7 +67,11 @@ struct DscContext {
   int grid_seq = 0;
   size_t gn_smem = 0;
   /* draw-buffer fill (dsc_draw_*) */
-  bool want_draw = false;
+  bool want_draw = false, want_raycast = false;
+  const int *d_slot_leaf = nullptr; /* [slots / 32] leaf owning the 32-slot group (ray-cast: undo-node lookup per vert) */
+  RayLeafHit *d_ray_out = nullptr, *h_ray_out = nullptr; /* [nleaf] on the device, the first DSC_RAY_FIRST pinned */
+  int *d_ray_count = nullptr, *h_ray_count = nullptr;
+  std::vector<int> vert_of_slot;
   const int4 *d_tri_slots = nullptr;
   unsigned *d_vbo = nullptr; /* [tottri * 3][9] packed vertex records, by looptri position */
   bool has_odd_edges = false; /* some coarse edge has more than two faces */
@@ -525,6 +529,8 @@ void dsc_ctx_destroy(DscContext *ctx)
   if (ctx->h_state) cudaFreeHost(ctx->h_state);
   if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
   if (ctx->h_list) cudaFreeHost(ctx->h_list);
+  if (ctx->h_ray_out) cudaFreeHost(ctx->h_ray_out);
+  if (ctx->h_ray_count) cudaFreeHost(ctx->h_ray_count);
   cudaEventDestroy(ctx->t0);
   cudaEventDestroy(ctx->t1);
   cudaEventDestroy(ctx->ev_fork);
@@ -1265,6 +1271,13 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       return r;
     CU(cudaStreamSynchronize(ctx->stream));
 
+    if (ctx->want_raycast) {
+      std::vector<int> slot_leaf((size_t)VP / 32 + 1, 0);
+      for (int l = 0; l < L; l++) {
+        for (int gq = leaf_ubeg[l] / 32; gq <= (leaf_ubeg[l] + std::max(leaf_ucnt[l], 1) - 1) / 32; gq++) slot_leaf[gq] = l;
+      }
+      if ((r = dev_upload_c(ctx, &ctx->d_slot_leaf, slot_leaf))) return r;
+    }
     if (ctx->want_draw) {
       /* draw-buffer fill: the three corners of every looptri, as slots, by looptri position */
       std::vector<int4> tri_slots((size_t)std::max(T, 1));
@@ -2505,6 +2518,139 @@ int dsc_upload_co(DscContext *ctx, const float *co)
   if ((r = run_flagged(ctx, F_UpdateNormals | F_UpdateBB))) return r;
   if ((r = run_orig_flush(ctx))) return r;
   return sync_all(ctx);
+}
+
+/* ---- ray-cast ---- */
+#define DSC_RAY_FIRST 64
+int dsc_raycast_enable(DscContext *ctx)
+{
+  if (!ctx) return DSC_ERR_INVALID;
+  if (ctx->have_pbvh) return fail(ctx, DSC_ERR_STATE, "dsc_raycast_enable comes before dsc_pbvh_upload");
+  if (ctx->is_grids) return fail(ctx, DSC_ERR_UNSUPPORTED, "the grids ray-cast (pbvh.c:4102-4200) is not on the device yet");
+  ctx->want_draw = true; /* the looptri corner table */
+  ctx->want_raycast = true;
+  return DSC_OK;
+}
+int dsc_raycast(DscContext *ctx, const float ray_start[3], const float ray_normal[3], int original, float max_depth, DscRayHit *r_hit)
+{
+  NEED_PBVH();
+  if (!ray_start || !ray_normal || !r_hit) return fail(ctx, DSC_ERR_INVALID, "NULL argument");
+  if (!ctx->want_raycast) return fail(ctx, DSC_ERR_STATE, "dsc_raycast_enable first");
+  int r = join_side(ctx);
+  if (r) return r;
+  memset(r_hit, 0, sizeof(*r_hit));
+  RayParams rp;
+  for (int k = 0; k < 3; k++) {
+    rp.o[k] = ray_start[k];
+    rp.inv_dir[k] = 1.0f / ray_normal[k]; /* isect_ray_aabb_v3_precalc, math_geom.cc:3017-3030 */
+    rp.sign[k] = rp.inv_dir[k] < 0.0f;
+  }
+  {
+    /* isect_ray_tri_watertight_v3_precalc, math_geom.cc:1755-1780 */
+    const float x = fabsf(ray_normal[0]), y = fabsf(ray_normal[1]), z = fabsf(ray_normal[2]);
+    int kz = ((x > y) ? ((x > z) ? 0 : 2) : ((y > z) ? 1 : 2));
+    int kx = (kz != 2) ? (kz + 1) : 0;
+    int ky = (kx != 2) ? (kx + 1) : 0;
+    if (ray_normal[kz] < 0.0f) std::swap(kx, ky);
+    const float inv_dir_z = 1.0f / ray_normal[kz];
+    rp.sx = ray_normal[kx] * inv_dir_z;
+    rp.sy = ray_normal[ky] * inv_dir_z;
+    rp.sz = inv_dir_z;
+    rp.kx = kx; rp.ky = ky; rp.kz = kz;
+  }
+  rp.original = original ? 1 : 0;
+  const int L = ctx->m.nleaf;
+  if (!ctx->d_ray_out) {
+    if ((r = dev_zero(ctx, &ctx->d_ray_out, (size_t)L))) return r;
+    if ((r = dev_zero(ctx, &ctx->d_ray_count, 1))) return r;
+    CU(cudaMallocHost((void **)&ctx->h_ray_out, sizeof(RayLeafHit) * DSC_RAY_FIRST));
+    CU(cudaMallocHost((void **)&ctx->h_ray_count, sizeof(int)));
+  }
+  CU(cudaMemsetAsync(ctx->d_ray_count, 0, sizeof(int), ctx->stream));
+  k_raycast<<<std::min(L, ctx->num_sms * 8), DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->d_tri_slots, ctx->d_slot_leaf, rp, ctx->d_ray_count,
+                                                                           ctx->d_ray_out);
+  LAUNCH_CHECK();
+  ctx->launches += 1;
+  /* the entered leaves with a hit: a handful for any real mesh; one copy brings the count and the first few */
+  CU(cudaMemcpyAsync(ctx->h_ray_count, ctx->d_ray_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_ray_out, ctx->d_ray_out, sizeof(RayLeafHit) * (size_t)std::min(L, DSC_RAY_FIRST), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int nh = *ctx->h_ray_count;
+  if (nh <= 0) return DSC_OK;
+  std::vector<RayLeafHit> hits((size_t)nh);
+  memcpy(hits.data(), ctx->h_ray_out, sizeof(RayLeafHit) * (size_t)std::min(nh, DSC_RAY_FIRST));
+  if (nh > DSC_RAY_FIRST) {
+    CU(cudaMemcpyAsync(hits.data() + DSC_RAY_FIRST, ctx->d_ray_out + DSC_RAY_FIRST, sizeof(RayLeafHit) * (size_t)(nh - DSC_RAY_FIRST),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  /* BKE_pbvh_search_callback_occluded (pbvh.c:2852-2889): leaves by entry distance, ties in traversal order (the
+   * looptri ranges of the leaves ascend in traversal order) */
+  std::stable_sort(hits.begin(), hits.end(), [](const RayLeafHit &a, const RayLeafHit &b) {
+    return a.tmin < b.tmin || (!(b.tmin < a.tmin) && a.pos < b.pos);
+  });
+  /* the stroke operator's hit callback (sculpt_raycast_cb): a leaf entered behind the best hit is not looked at */
+  float depth = max_depth, tmin = FLT_MAX;
+  const RayLeafHit *win = nullptr;
+  for (const RayLeafHit &h : hits) {
+    if (!(h.tmin < tmin)) continue;
+    if (h.depth < depth) {
+      depth = h.depth;
+      tmin = depth;
+      win = &h;
+    }
+  }
+  if (!win) return DSC_OK;
+  const RayLeafHit &c = *win;
+  r_hit->hit = 1;
+  r_hit->depth = depth;
+  r_hit->face = c.poly;
+  r_hit->node = ctx->leaf_node[c.leaf];
+  {
+    /* normal_tri_v3, lib/intern/math_geom.cc:31-49 */
+    float n1[3], n2[3], n[3];
+    for (int k = 0; k < 3; k++) {
+      n1[k] = c.co[0][k] - c.co[1][k];
+      n2[k] = c.co[1][k] - c.co[2][k];
+    }
+    n[0] = n1[1] * n2[2] - n1[2] * n2[1];
+    n[1] = n1[2] * n2[0] - n1[0] * n2[2];
+    n[2] = n1[0] * n2[1] - n1[1] * n2[0];
+    float d = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    if (d > 1.0e-35f) {
+      d = sqrtf(d);
+      const float f = 1.0f / d;
+      for (int k = 0; k < 3; k++) n[k] = n[k] * f;
+    }
+    else {
+      n[0] = n[1] = n[2] = 0.0f;
+    }
+    memcpy(r_hit->face_normal, n, sizeof(n));
+  }
+  {
+    /* the corner nearest to the hit point (pbvh.c:4084-4098) */
+    float location[3], nearest[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < 3; k++) location[k] = ray_start[k] + ray_normal[k] * depth;
+    int sl = c.slot[0];
+    for (int j = 0; j < 3; j++) {
+      float da = 0.0f, db = 0.0f;
+      for (int k = 0; k < 3; k++) {
+        da += (location[k] - c.co[j][k]) * (location[k] - c.co[j][k]);
+        db += (location[k] - nearest[k]) * (location[k] - nearest[k]);
+      }
+      if (j == 0 || da < db) {
+        memcpy(nearest, c.co[j], sizeof(float[3]));
+        sl = c.slot[j];
+      }
+    }
+    if (ctx->vert_of_slot.empty()) {
+      ctx->vert_of_slot.assign((size_t)ctx->vpad, -1);
+      for (int v = 0; v < ctx->totvert; v++) ctx->vert_of_slot[ctx->slot_of[v]] = v;
+    }
+    r_hit->vertex = ctx->vert_of_slot[sl];
+  }
+  return DSC_OK;
 }
 
 /* ---- draw-buffer fill from the device ---- */

@@ -1733,6 +1733,134 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_orig_inner(DevMesh m)
   }
 }
 
+/* ------------------------------------------------------------------- ray-cast */
+/* BKE_pbvh_raycast (pbvh.c:3896-3928) + pbvh_faces_node_raycast (pbvh.c:4041-4100): nearest intersection of a
+ * ray with the looptris of the leaves whose box it enters.  The reference walks the leaves in order of entry
+ * distance; inside a leaf it walks the looptris in order and keeps a hit only if strictly nearer, so what a leaf
+ * contributes is its nearest depth and the FIRST looptri attaining it.  One CTA per entered leaf reduces exactly
+ * that (a min over the key depth-bits:position, depths being >= 0) and appends it with the leaf's entry
+ * distance; the walk over the few entered leaves (skip a leaf entered behind the best hit so far) is done on the
+ * host in the reference's order.  `original`: stroke-start boxes, and for leaves with an undo node the
+ * stroke-start coordinates (a vert the leaf shares: its owner's snapshot if the owner has one). */
+struct RayParams {
+  float o[3], inv_dir[3];
+  int sign[3];
+  int kx, ky, kz;
+  float sx, sy, sz;
+  int original;
+};
+struct RayLeafHit {
+  int pos, leaf, poly, pad;
+  float tmin, depth;
+  int slot[3];
+  float co[3][3];
+};
+
+__device__ __forceinline__ bool dsc_ray_leaf(const DevMesh &m, const RayParams &r, int l, float &tmin_out)
+{
+  /* isect_ray_aabb_v3, lib/intern/math_geom.cc:3032-3080 */
+  const float *bbs = r.original ? m.obb : m.bb;
+  const int tn = m.totnode;
+  float bbox[2][3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    bbox[0][k] = bbs[k * tn + l];
+    bbox[1][k] = bbs[(3 + k) * tn + l];
+  }
+  float tmin = (bbox[r.sign[0]][0] - r.o[0]) * r.inv_dir[0];
+  float tmax = (bbox[1 - r.sign[0]][0] - r.o[0]) * r.inv_dir[0];
+  const float tymin = (bbox[r.sign[1]][1] - r.o[1]) * r.inv_dir[1];
+  const float tymax = (bbox[1 - r.sign[1]][1] - r.o[1]) * r.inv_dir[1];
+  if ((tmin > tymax) || (tymin > tmax)) return false;
+  if (tymin > tmin) tmin = tymin;
+  if (tymax < tmax) tmax = tymax;
+  const float tzmin = (bbox[r.sign[2]][2] - r.o[2]) * r.inv_dir[2];
+  const float tzmax = (bbox[1 - r.sign[2]][2] - r.o[2]) * r.inv_dir[2];
+  if ((tmin > tzmax) || (tzmin > tmax)) return false;
+  if (tzmin > tmin) tmin = tzmin;
+  tmin_out = tmin;
+  return true;
+}
+
+__device__ __forceinline__ void dsc_ray_vert(const DevMesh &m, const int *slot_leaf, bool use_orig, int s, float co[3])
+{
+  if (use_orig && (m.leaf_state[slot_leaf[s >> 5]] & DSC_LEAF_TOUCHED)) {
+    co[0] = m.ox[s]; co[1] = m.oy[s]; co[2] = m.oz[s];
+  }
+  else {
+    co[0] = m.cx[s]; co[1] = m.cy[s]; co[2] = m.cz[s];
+  }
+}
+
+/* isect_ray_tri_watertight_v3, lib/intern/math_geom.cc:1782-1857 */
+__device__ __forceinline__ bool dsc_ray_tri(const RayParams &r, const float v0[3], const float v1[3], const float v2[3], float &lambda)
+{
+  const float a[3] = {v0[0] - r.o[0], v0[1] - r.o[1], v0[2] - r.o[2]};
+  const float b[3] = {v1[0] - r.o[0], v1[1] - r.o[1], v1[2] - r.o[2]};
+  const float c[3] = {v2[0] - r.o[0], v2[1] - r.o[1], v2[2] - r.o[2]};
+  const float a_kx = a[r.kx], a_ky = a[r.ky], a_kz = a[r.kz];
+  const float b_kx = b[r.kx], b_ky = b[r.ky], b_kz = b[r.kz];
+  const float c_kx = c[r.kx], c_ky = c[r.ky], c_kz = c[r.kz];
+  const float ax = a_kx - r.sx * a_kz, ay = a_ky - r.sy * a_kz;
+  const float bx = b_kx - r.sx * b_kz, by = b_ky - r.sy * b_kz;
+  const float cx = c_kx - r.sx * c_kz, cy = c_ky - r.sy * c_kz;
+  const float u = cx * by - cy * bx;
+  const float v = ax * cy - ay * cx;
+  const float w = bx * ay - by * ax;
+  if ((u < 0.0f || v < 0.0f || w < 0.0f) && (u > 0.0f || v > 0.0f || w > 0.0f)) return false;
+  const float det = u + v + w;
+  if (det == 0.0f || !isfinite(det)) return false;
+  const unsigned sign_det = __float_as_uint(det) & 0x80000000u;
+  const float t = (u * a_kz + v * b_kz + w * c_kz) * r.sz;
+  if (__uint_as_float(__float_as_uint(t) ^ sign_det) < 0.0f) return false;
+  const float inv_det = 1.0f / det;
+  lambda = t * inv_det;
+  return true;
+}
+
+__global__ void __launch_bounds__(DSC_BLOCK) k_raycast(DevMesh m, const int4 *tri_slots, const int *slot_leaf, RayParams r, int *count,
+                                                       RayLeafHit *out)
+{
+  __shared__ unsigned long long s_min;
+  for (int l = blockIdx.x; l < m.nleaf; l += gridDim.x) {
+    float tmin;
+    if (!dsc_ray_leaf(m, r, l, tmin)) continue; /* CTA-uniform */
+    const bool use_orig = r.original && (m.leaf_state[l] & DSC_LEAF_TOUCHED);
+    const int pb = m.leaf_pbeg[l], pe = pb + m.leaf_pcnt[l];
+    if (threadIdx.x == 0) s_min = ~0ull;
+    __syncthreads();
+    unsigned long long best = ~0ull;
+    for (int pos = pb + threadIdx.x; pos < pe; pos += blockDim.x) {
+      const int4 tv = tri_slots[pos];
+      float c0[3], c1[3], c2[3], lambda;
+      dsc_ray_vert(m, slot_leaf, use_orig, tv.x, c0);
+      dsc_ray_vert(m, slot_leaf, use_orig, tv.y, c1);
+      dsc_ray_vert(m, slot_leaf, use_orig, tv.z, c2);
+      if (!dsc_ray_tri(r, c0, c1, c2, lambda)) continue;
+      /* lambda >= 0 or -0 (the sign test above), never NaN past the det test unless t overflowed: +0 canonical */
+      const unsigned long long key = ((unsigned long long)__float_as_uint(lambda + 0.0f) << 32) | (unsigned)pos;
+      best = min(best, key);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&s_min, best);
+    __syncthreads();
+    const unsigned long long win = s_min;
+    if (win != ~0ull && threadIdx.x == 0) {
+      const int pos = (int)(unsigned)(win & 0xffffffffull);
+      const int4 tv = tri_slots[pos];
+      RayLeafHit &h = out[atomicAdd(count, 1)];
+      h.pos = pos; h.leaf = l; h.poly = tv.w; h.pad = 0;
+      h.tmin = tmin;
+      h.depth = __uint_as_float((unsigned)(win >> 32));
+      h.slot[0] = tv.x; h.slot[1] = tv.y; h.slot[2] = tv.z;
+      dsc_ray_vert(m, slot_leaf, use_orig, tv.x, h.co[0]);
+      dsc_ray_vert(m, slot_leaf, use_orig, tv.y, h.co[1]);
+      dsc_ray_vert(m, slot_leaf, use_orig, tv.z, h.co[2]);
+    }
+    __syncthreads();
+  }
+}
+
 /* ------------------------------------------------------------------- draw-buffer fill */
 /* GPU_pbvh_mesh_buffers_update (gpu/intern/gpu_buffers.c:174-305) for the listed leaves: one 36-byte record
  * per looptri corner in the vertex format of gpu_pbvh_init (gpu_buffers.c:84-100, offsets from

@@ -875,7 +875,8 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
   pd.face_verts = face;
   pd.vert_offset = vert_off;
   pd.vert_indices = vert_indices;
-  if (r == DSC_OK && pbvh->want_draw_buffers) r = dsc_draw_enable(ctx);
+  if (r == DSC_OK && (pbvh->want_draw_buffers & 1)) r = dsc_draw_enable(ctx);
+  if (r == DSC_OK && (pbvh->want_draw_buffers & 2)) r = dsc_raycast_enable(ctx);
   if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
 
   free(tail); free(co); free(poly_start); free(poly_len); free(loop_v); free(tri_vert); free(tri_poly);
@@ -904,7 +905,26 @@ void DUNE_pbvh_device_detach(PBVH *pbvh)
   }
 }
 
-void DUNE_pbvh_draw_buffers_enable(PBVH *pbvh) { pbvh->want_draw_buffers = 1; }
+void DUNE_pbvh_draw_buffers_enable(PBVH *pbvh) { pbvh->want_draw_buffers |= 1; }
+void DUNE_pbvh_raycast_enable(PBVH *pbvh) { pbvh->want_draw_buffers |= 2; }
+
+/* BKE_pbvh_raycast (pbvh.c:3915-3928) with the stroke operator's per-node callback folded in: that callback
+ * (sculpt_raycast_cb, editors/sculpt_paint/sculpt.c) does nothing but call BKE_pbvh_node_raycast
+ * (pbvh.c:4203-4260) on each leaf the ray enters and keep the nearest hit, which is what the device returns. */
+bool DUNE_pbvh_raycast_nearest(PBVH *pbvh, const float ray_start[3], const float ray_normal[3], bool original,
+                               float max_depth, float *r_depth, int *r_active_vertex_index, int *r_active_face_index,
+                               float r_face_normal[3], PBVHNode **r_node)
+{
+  DscRayHit hit;
+  if (!pbvh || !pbvh->device) return false;
+  if (dsc_raycast(pbvh->device, ray_start, ray_normal, original ? 1 : 0, max_depth, &hit) != DSC_OK || !hit.hit) return false;
+  if (r_depth) *r_depth = hit.depth;
+  if (r_active_vertex_index) *r_active_vertex_index = hit.vertex;
+  if (r_active_face_index) *r_active_face_index = hit.face;
+  if (r_face_normal) memcpy(r_face_normal, hit.face_normal, sizeof(float[3]));
+  if (r_node) *r_node = &pbvh->nodes[hit.node];
+  return true;
+}
 
 int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask)
 {

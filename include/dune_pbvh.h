@@ -231,6 +231,15 @@ void DUNE_pbvh_draw_buffers_enable(PBVH *pbvh);
  * device pointer and vertex count of a node's buffer for the GL copy */
 int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask);
 int DUNE_pbvh_node_draw_buffer(PBVH *pbvh, PBVHNode *node, void **r_device_ptr, int *r_vert_len);
+/* before the attach: keep the tables the device ray-cast needs (dsc_raycast_enable) */
+void DUNE_pbvh_raycast_enable(PBVH *pbvh);
+/* BKE_pbvh_raycast (pbvh.c:3915-3928) + BKE_pbvh_node_raycast (pbvh.c:4203-4260) in one call: the nearest hit of
+ * the ray with the mesh -- its depth, the active vertex and face (MLoopTri.poly), the triangle normal and the
+ * leaf -- as the stroke operator's hit callback accumulates them, starting from `max_depth` (the ray's length).
+ * False when nothing nearer than that is hit. */
+bool DUNE_pbvh_raycast_nearest(PBVH *pbvh, const float ray_start[3], const float ray_normal[3], bool original,
+                               float max_depth, float *r_depth, int *r_active_vertex_index, int *r_active_face_index,
+                               float r_face_normal[3], PBVHNode **r_node);
 /* the same for a grids PBVH: the CCG's elements and adjacency go to the device */
 int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device);
 /* one rank of a PBVH partitioned across the GPUs of one box (see dsc_dist_init) */

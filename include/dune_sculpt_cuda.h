@@ -239,6 +239,24 @@ int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_
  *     on the pointer dsc_draw_node_buffer returns) instead of re-reading the node's triangles on the CPU.
  *     Meshes only.  dsc_draw_enable comes between dsc_mesh_upload and dsc_pbvh_upload. ------------------- */
 int dsc_draw_enable(DscContext *ctx);
+
+/* --- ray-cast: behind BKE_pbvh_raycast (pbvh.c:3896-3928) + BKE_pbvh_node_raycast (pbvh.c:4041-4100), the step
+ *     that finds the dab location under the cursor.  Nearest intersection of the ray with
+ *     the mesh: depth, the looptri's MLoopTri.poly, the corner nearest to the hit point, the triangle normal and
+ *     the leaf.  `original`: stroke-start boxes and, for leaves with an undo node, stroke-start coordinates.
+ *     `max_depth`: the depth the caller's search starts from (the ray's length to the far clip); only nearer hits count.
+ *     dsc_raycast_enable comes between dsc_mesh_upload and dsc_pbvh_upload.  Meshes only.  Synchronises. ---- */
+typedef struct DscRayHit {
+  int hit;
+  float depth;
+  int vertex; /* active vertex (original index) */
+  int face;   /* MLoopTri.poly */
+  int node;
+  float face_normal[3];
+} DscRayHit;
+int dsc_raycast_enable(DscContext *ctx);
+int dsc_raycast(DscContext *ctx, const float ray_start[3], const float ray_normal[3], int original, float max_depth,
+                DscRayHit *r_hit);
 int dsc_draw_update(DscContext *ctx, int smooth /* ME_SMOOTH of the node's faces */, int show_mask);
 int dsc_draw_node_buffer(DscContext *ctx, int node, void **r_device_ptr, int *r_vert_len);
 int dsc_draw_download(DscContext *ctx, int node, void *r_host, size_t capacity_bytes, int *r_vert_len);

@@ -19,6 +19,7 @@ typedef struct OrNode {
   int uniq_verts, face_verts;
   int (*face_vert_indices)[3];
   unsigned flag;
+  float tmin; /* ray-cast: entry distance of the ray into vb (pbvh_intern.h:81) */
 } OrNode;
 
 /* kernel/intern/pbvh_intern.h:98-162 plus the sculpt-session state the brushes need */

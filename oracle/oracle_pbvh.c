@@ -753,6 +753,201 @@ void or_recalc_all_normals(OrPbvh *p)
   or_update_normals(p);
 }
 
+/* ------------------------------------------------------------------------------ ray-cast */
+/* lib/intern/math_geom.cc:3017-3030 */
+typedef struct RayAABB {
+  float ray_origin[3], ray_inv_dir[3];
+  int sign[3];
+  int original;
+} RayAABB;
+
+/* lib/intern/math_geom.cc:3032-3080 isect_ray_aabb_v3 */
+static int isect_ray_aabb(const RayAABB *d, const float bb_min[3], const float bb_max[3], float *tmin_out)
+{
+  float bbox[2][3];
+  memcpy(bbox[0], bb_min, sizeof(float[3]));
+  memcpy(bbox[1], bb_max, sizeof(float[3]));
+  float tmin = (bbox[d->sign[0]][0] - d->ray_origin[0]) * d->ray_inv_dir[0];
+  float tmax = (bbox[1 - d->sign[0]][0] - d->ray_origin[0]) * d->ray_inv_dir[0];
+  const float tymin = (bbox[d->sign[1]][1] - d->ray_origin[1]) * d->ray_inv_dir[1];
+  const float tymax = (bbox[1 - d->sign[1]][1] - d->ray_origin[1]) * d->ray_inv_dir[1];
+  if ((tmin > tymax) || (tymin > tmax)) return 0;
+  if (tymin > tmin) tmin = tymin;
+  if (tymax < tmax) tmax = tymax;
+  const float tzmin = (bbox[d->sign[2]][2] - d->ray_origin[2]) * d->ray_inv_dir[2];
+  const float tzmax = (bbox[1 - d->sign[2]][2] - d->ray_origin[2]) * d->ray_inv_dir[2];
+  if ((tmin > tzmax) || (tzmin > tmax)) return 0;
+  if (tzmin > tmin) tmin = tzmin;
+  *tmin_out = tmin;
+  return 1;
+}
+
+/* pbvh.c:3897-3915 ray_aabb_intersect */
+static int ray_aabb_cb(OrPbvh *p, OrNode *node, void *data_v)
+{
+  (void)p;
+  const RayAABB *d = data_v;
+  const OrBB *bb = d->original ? &node->orig_vb : &node->vb;
+  return isect_ray_aabb(d, bb->bmin, bb->bmax, &node->tmin);
+}
+
+/* lib/intern/math_geom.cc:1755-1780, 1782-1857 isect_ray_tri_watertight_v3 */
+typedef struct RayTri {
+  int kx, ky, kz;
+  float sx, sy, sz;
+} RayTri;
+
+static void ray_tri_precalc(RayTri *pc, const float dir[3])
+{
+  const float x = fabsf(dir[0]), y = fabsf(dir[1]), z = fabsf(dir[2]);
+  int kz = ((x > y) ? ((x > z) ? 0 : 2) : ((y > z) ? 1 : 2));
+  int kx = (kz != 2) ? (kz + 1) : 0;
+  int ky = (kx != 2) ? (kx + 1) : 0;
+  if (dir[kz] < 0.0f) {
+    const int t = kx;
+    kx = ky;
+    ky = t;
+  }
+  const float inv_dir_z = 1.0f / dir[kz];
+  pc->sx = dir[kx] * inv_dir_z;
+  pc->sy = dir[ky] * inv_dir_z;
+  pc->sz = inv_dir_z;
+  pc->kx = kx; pc->ky = ky; pc->kz = kz;
+}
+
+static int ray_tri_watertight(const float o[3], const RayTri *pc, const float v0[3], const float v1[3], const float v2[3],
+                              float *r_lambda)
+{
+  const int kx = pc->kx, ky = pc->ky, kz = pc->kz;
+  const float sx = pc->sx, sy = pc->sy, sz = pc->sz;
+  const float a[3] = {v0[0] - o[0], v0[1] - o[1], v0[2] - o[2]};
+  const float b[3] = {v1[0] - o[0], v1[1] - o[1], v1[2] - o[2]};
+  const float c[3] = {v2[0] - o[0], v2[1] - o[1], v2[2] - o[2]};
+  const float a_kx = a[kx], a_ky = a[ky], a_kz = a[kz];
+  const float b_kx = b[kx], b_ky = b[ky], b_kz = b[kz];
+  const float c_kx = c[kx], c_ky = c[ky], c_kz = c[kz];
+  const float ax = a_kx - sx * a_kz, ay = a_ky - sy * a_kz;
+  const float bx = b_kx - sx * b_kz, by = b_ky - sy * b_kz;
+  const float cx = c_kx - sx * c_kz, cy = c_ky - sy * c_kz;
+  const float u = cx * by - cy * bx;
+  const float v = ax * cy - ay * cx;
+  const float w = bx * ay - by * ax;
+  if ((u < 0.0f || v < 0.0f || w < 0.0f) && (u > 0.0f || v > 0.0f || w > 0.0f)) return 0;
+  const float det = u + v + w;
+  if (det == 0.0f || !isfinite(det)) return 0;
+  union { float f; unsigned i; } ud, ut;
+  ud.f = det;
+  const unsigned sign_det = ud.i & 0x80000000u;
+  const float t = (u * a_kz + v * b_kz + w * c_kz) * sz;
+  ut.f = t;
+  ut.i ^= sign_det; /* xor_fl */
+  if (ut.f < 0.0f) return 0;
+  const float inv_det = 1.0f / det;
+  *r_lambda = t * inv_det;
+  return 1;
+}
+
+typedef struct RayNodeRef {
+  int node;
+  float tmin;
+} RayNodeRef;
+
+int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], int original, float max_depth, float *r_depth,
+               int *r_vertex, int *r_face, float r_face_normal[3], int *r_node)
+{
+  if (p->is_grids || p->totnode == 0) return 0;
+  RayAABB d;
+  memcpy(d.ray_origin, ray_start, sizeof(float[3]));
+  for (int k = 0; k < 3; k++) {
+    d.ray_inv_dir[k] = 1.0f / ray_normal[k];
+    d.sign[k] = d.ray_inv_dir[k] < 0.0f;
+  }
+  d.original = original;
+  int *nodes = malloc(sizeof(int) * (size_t)(p->totnode + 1));
+  const int tot = search_gather(p, ray_aabb_cb, &d, nodes);
+  /* BKE_pbvh_search_callback_occluded (pbvh.c:2852-2889): an unbalanced tree keyed by tmin, ties to the right,
+   * walked in order = a stable sort of the leaves by tmin */
+  RayNodeRef *ord = malloc(sizeof(RayNodeRef) * (size_t)(tot + 1));
+  for (int i = 0; i < tot; i++) {
+    RayNodeRef r = {nodes[i], p->nodes[nodes[i]].tmin};
+    int k = i;
+    while (k > 0 && r.tmin < ord[k - 1].tmin) {
+      ord[k] = ord[k - 1];
+      k--;
+    }
+    ord[k] = r;
+  }
+  /* an undo node holds the coordinates of ALL verts of its leaf as they were when it was pushed (row a9); for a
+   * vert the leaf shares, that is the owner's snapshot if the owner was pushed too, else the (unmoved) current one */
+  int *owner = NULL;
+  if (original) {
+    owner = malloc(sizeof(int) * (size_t)(p->totvert + 1));
+    for (int n = 0; n < p->totnode; n++) {
+      if (p->nodes[n].flag & OR_PBVH_Leaf) {
+        for (int i = 0; i < p->nodes[n].uniq_verts; i++) owner[p->nodes[n].vert_indices[i]] = n;
+      }
+    }
+  }
+  RayTri pc;
+  ray_tri_precalc(&pc, ray_normal);
+  float depth = max_depth; /* the caller starts from the ray's length to the far clip (SCULPT_raycast_init) */
+  int hit = 0;
+  float tmin = 3.402823466e+38f;
+  for (int i = 0; i < tot; i++) {
+    const OrNode *node = &p->nodes[ord[i].node];
+    if (!(node->tmin < tmin)) continue; /* DAGGER sculpt_raycast_cb: only nodes the ray enters before the best hit */
+    const int use_orig = original && p->touched[ord[i].node];
+    const int *faces = p->prim_indices + node->prim_offset;
+    int node_hit = 0;
+    for (int f = 0; f < node->totprim; f++) {
+      const int *vt = p->tri_v[faces[f]];
+      const float *co[3];
+      for (int j = 0; j < 3; j++) co[j] = (use_orig && p->touched[owner[vt[j]]]) ? p->orig_co[vt[j]] : p->co[vt[j]];
+      float depth_test;
+      if (ray_tri_watertight(ray_start, &pc, co[0], co[1], co[2], &depth_test) && depth_test < depth) {
+        depth = depth_test;
+        node_hit = 1;
+        if (r_face_normal) {
+          /* normal_tri_v3 */
+          float n1[3], n2[3];
+          for (int k = 0; k < 3; k++) {
+            n1[k] = co[0][k] - co[1][k];
+            n2[k] = co[1][k] - co[2][k];
+          }
+          r_face_normal[0] = n1[1] * n2[2] - n1[2] * n2[1];
+          r_face_normal[1] = n1[2] * n2[0] - n1[0] * n2[2];
+          r_face_normal[2] = n1[0] * n2[1] - n1[1] * n2[0];
+          normalize_v3(r_face_normal);
+        }
+        float location[3], nearest[3] = {0.0f, 0.0f, 0.0f};
+        for (int k = 0; k < 3; k++) location[k] = ray_start[k] + ray_normal[k] * depth;
+        for (int j = 0; j < 3; j++) {
+          float da = 0.0f, db = 0.0f;
+          for (int k = 0; k < 3; k++) {
+            da += (location[k] - co[j][k]) * (location[k] - co[j][k]);
+            db += (location[k] - nearest[k]) * (location[k] - nearest[k]);
+          }
+          if (j == 0 || da < db) {
+            memcpy(nearest, co[j], sizeof(float[3]));
+            if (r_vertex) *r_vertex = vt[j];
+            if (r_face) *r_face = p->tri_poly[faces[f]];
+          }
+        }
+        if (r_node) *r_node = ord[i].node;
+      }
+    }
+    if (node_hit) {
+      hit = 1;
+      tmin = depth;
+    }
+  }
+  free(ord);
+  free(nodes);
+  free(owner);
+  if (hit && r_depth) *r_depth = depth;
+  return hit;
+}
+
 /* gpu/intern/gpu_buffers.c:174-305 GPU_pbvh_mesh_buffers_update for one leaf, into the packed vertex
  * format of gpu_pbvh_init (gpu_buffers.c:84-100; offsets by VertexFormat_pack, gpu_vertex_format.cc:300-325):
  * 36 bytes per looptri corner -- pos f32 x 3 @0, nor i16 x 3 @16, msk u8 @22, col u16 x 4 @24, fset u8 x 3 @32.

@@ -74,6 +74,7 @@ def lib():
         L.or_looptri_count.argtypes = [C.c_int, c_int_p]
         L.or_looptri_calc.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p]
         L.or_vert_neighbors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_void_p]
+        L.or_raycast.argtypes = [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_float, c_float_p, c_int_p, c_int_p, c_float_p, c_int_p]
         L.or_draw_buffers_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.or_pbvh_build_grids.restype = C.c_void_p
         L.or_pbvh_build_grids.argtypes = [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p, C.c_int,
@@ -222,6 +223,19 @@ class Oracle:
 
     def update_bounds(self, flag):
         self.L.or_update_bounds(self.p, int(flag))
+
+    def raycast(self, start, normal, original=False, max_depth=3.4028234663852886e38):
+        """BKE_pbvh_raycast + the stroke operator's hit callback: None or dict(depth, vertex, face, normal, node)"""
+        s_ = np.asarray(start, dtype=np.float32)
+        n_ = np.asarray(normal, dtype=np.float32)
+        depth = np.zeros(1, np.float32)
+        vert = np.zeros(1, np.int32)
+        face = np.zeros(1, np.int32)
+        node = np.zeros(1, np.int32)
+        fno = np.zeros(3, np.float32)
+        if not self.L.or_raycast(self.p, fptr(s_), fptr(n_), int(original), C.c_float(max_depth), fptr(depth), iptr(vert), iptr(face), fptr(fno), iptr(node)):
+            return None
+        return {"depth": depth[0], "vertex": int(vert[0]), "face": int(face[0]), "normal": fno, "node": int(node[0])}
 
     def draw_buffer(self, node, totprim, smooth=True, show_mask=True):
         """the leaf's packed VBO (gpu_buffers.c:174-305), (totprim * 3, 36) bytes"""

@@ -457,3 +457,96 @@ def test_draw_buffers_filled_on_the_device_match_gpu_pbvh_mesh_buffers_update(sm
     finally:
         ses.close()
         orc.close()
+
+
+def _ray_cases(m, rng, count):
+    """rays at a mesh from outside its box: at random points, exactly at vertices and edge midpoints (ties between
+    the looptris round them, across leaf borders too), axis-parallel ones, and ones that miss"""
+    co = m.co
+    lo, hi = co.min(axis=0), co.max(axis=0)
+    ctr, ext = 0.5 * (lo + hi), float(np.linalg.norm(hi - lo))
+    rays = []
+    for i in range(count):
+        kind = i % 5
+        if kind == 0:
+            target = lo + rng.random(3).astype(np.float32) * (hi - lo)
+        elif kind == 1:
+            target = co[rng.integers(m.totvert)]
+        elif kind == 2:
+            f = rng.integers(m.totpoly)
+            a, b = m.loop_v[m.poly_start[f]], m.loop_v[m.poly_start[f] + 1]
+            target = (0.5 * (co[a] + co[b])).astype(np.float32)
+        elif kind == 3:
+            target = co[rng.integers(m.totvert)]
+        else:
+            target = ctr + (hi - lo) * 3.0 * np.sign(rng.normal(size=3)).astype(np.float32)  # far off: a miss
+        if kind == 3:
+            d = np.zeros(3, np.float32)
+            d[rng.integers(3)] = 1.0 if rng.random() < 0.5 else -1.0
+        else:
+            d = rng.normal(size=3).astype(np.float32)
+            if abs(d[2]) < 0.3:
+                d[2] = 0.7
+            d /= np.float32(np.linalg.norm(d))
+        start = (np.asarray(target, np.float32) - d * np.float32(2.0 * ext)).astype(np.float32)
+        rays.append((start, d.astype(np.float32)))
+    return rays
+
+
+def _same_hit(ref, got, what):
+    assert (ref is None) == (got is None), what
+    if ref is None:
+        return 0
+    assert np.float32(ref["depth"]).tobytes() == np.float32(got["depth"]).tobytes(), what
+    assert ref["face"] == got["face"] and ref["vertex"] == got["vertex"] and ref["node"] == got["node"], (what, ref, got)
+    assert np.array_equal(ref["normal"].view(np.uint32), got["normal"].view(np.uint32)), what
+    return 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["grid", "mixed", "sphere"])
+def test_raycast_matches_bke_pbvh_raycast(name):
+    """the nearest hit of a ray -- depth, active vertex, face, triangle normal, leaf -- as
+    BKE_pbvh_raycast (pbvh.c:3915-3928) with the stroke operator's per-leaf callback over BKE_pbvh_node_raycast
+    (pbvh.c:4041-4100, 4203-4260) returns it; bit-equal, including which of several tied looptris wins.  Mid-stroke:
+    original=True sees the stroke-start surface, original=False the deformed one."""
+    from oracle_py import Oracle
+    m = {"grid": lambda: meshgen.grid(129), "mixed": lambda: meshgen.mixed_grid(65), "sphere": lambda: meshgen.icosphere(24, noise=0.02)}[name]()
+    orc = Oracle(m, leaf_limit=300)
+    ses = capi.SculptSession(m, leaf_limit=300, device=0, raycast=True)
+    try:
+        rng = np.random.default_rng(17)
+        rays = _ray_cases(m, rng, 150)
+        hits = 0
+        for i, (s, d) in enumerate(rays):
+            hits += _same_hit(orc.raycast(s, d), ses.raycast(s, d), "ray %d" % i)
+        assert hits > 60 and hits < len(rays)
+        # a depth limit in front of / behind the surface
+        s, d = rays[0]
+        full = orc.raycast(s, d)
+        if full is not None:
+            for md in (float(full["depth"]) * 0.5, float(full["depth"]), float(full["depth"]) * 1.5):
+                _same_hit(orc.raycast(s, d, max_depth=md), ses.raycast(s, d, max_depth=md), "max_depth %g" % md)
+        # mid-stroke: some leaves hold undo coordinates
+        top = m.co[np.argmax(m.co[:, 2])]
+        dabs = _line_dabs(capi.TOOL_DRAW, tuple(top - np.float32([0.3, 0.2, 0.0])), tuple(top + np.float32([0.2, 0.3, 0.0])), 0.25, 4)
+        orc.stroke_begin()
+        ses.stroke_begin()
+        for dab in dabs:
+            orc.dab(dab)
+            ses.dab(dab)
+        differ = 0
+        for i, (s, d) in enumerate(rays):
+            a = orc.raycast(s, d, original=True)
+            b = orc.raycast(s, d, original=False)
+            _same_hit(a, ses.raycast(s, d, original=True), "mid-stroke original ray %d" % i)
+            _same_hit(b, ses.raycast(s, d, original=False), "mid-stroke current ray %d" % i)
+            differ += (a is not None and b is not None and a["depth"] != b["depth"])
+        assert differ > 0
+        orc.stroke_end()
+        ses.stroke_end()
+        for i, (s, d) in enumerate(rays[:40]):
+            _same_hit(orc.raycast(s, d), ses.raycast(s, d), "after stroke ray %d" % i)
+    finally:
+        ses.close()
+        orc.close()

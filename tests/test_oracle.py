@@ -166,3 +166,50 @@ def test_golden_fixtures():
     want = json.load(open(os.path.join(here, "golden", "oracle_strokes.json")))
     got = make_golden.compute()
     assert got == want
+
+
+def test_raycast_closed_forms():
+    """BKE_pbvh_raycast + pbvh_faces_node_raycast (pbvh.c:3896-3928, 4041-4100) on shapes with known answers: a unit
+    sphere is hit at |start| - 1 from outside along a radius; the hit vertex is a corner of the hit polygon and the
+    nearest of them; a ray pointing away misses; max_depth cuts the search; brute force over all triangles agrees"""
+    from oracle_py import Oracle
+    m = meshgen.icosphere(16)
+    orc = Oracle(m, leaf_limit=200)
+    try:
+        rng = np.random.default_rng(5)
+        co = m.co.astype(np.float64)
+        tri_v = orc.tri_verts()
+        for i in range(40):
+            d = rng.normal(size=3)
+            d /= np.linalg.norm(d)
+            start = (-3.0 * d).astype(np.float32)
+            nrm = d.astype(np.float32)
+            hit = orc.raycast(start, nrm)
+            assert hit is not None
+            # facets lie just inside the unit sphere
+            assert 2.0 - 1e-5 <= hit["depth"] < 2.02
+            # brute force (Moeller-Trumbore in f64) over all looptris
+            a, b, c = co[tri_v[:, 0]], co[tri_v[:, 1]], co[tri_v[:, 2]]
+            e1, e2 = b - a, c - a
+            pv = np.cross(d, e2)
+            det = np.einsum("ij,ij->i", e1, pv)
+            ok = np.abs(det) > 1e-14
+            inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+            tv = start.astype(np.float64) - a
+            u = np.einsum("ij,ij->i", tv, pv) * inv
+            qv = np.cross(tv, e1)
+            v = (qv @ d) * inv
+            t = np.einsum("ij,ij->i", e2, qv) * inv
+            inside = ok & (u >= -1e-9) & (v >= -1e-9) & (u + v <= 1 + 1e-9) & (t > 0)
+            assert abs(t[inside].min() - hit["depth"]) < 1e-5
+            f = hit["face"]
+            poly = [int(x) for x in m.loop_v[m.poly_start[f]:m.poly_start[f] + m.poly_len[f]]]
+            assert hit["vertex"] in poly
+            loc = start.astype(np.float64) + d * float(hit["depth"])
+            near = min(poly, key=lambda vv: np.sum((co[vv] - loc) ** 2))
+            assert np.sum((co[hit["vertex"]] - loc) ** 2) <= np.sum((co[near] - loc) ** 2) + 1e-9
+            assert np.dot(hit["normal"], d) < 0  # the outward facet faces the ray
+            assert orc.raycast(start, (-d).astype(np.float32)) is None
+            assert orc.raycast(start, nrm, max_depth=1.5) is None
+    finally:
+        orc.close()
