@@ -189,6 +189,11 @@ class Multires:
     cvert_elems: np.ndarray  # (cvert_off[-1],) int32: SubdivCCGAdjacentVertex.corner_coords
     grid_edge: np.ndarray    # (G,) int32: coarse edge leaving the grid's corner vertex (MLoop order)
     grid_cvert: np.ndarray   # (G,) int32: the grid's corner vertex
+    # the topology-refiner queries KERNEL_subdiv_ccg_neighbor_coords_get makes (subdiv_ccg.c:1558-1582, 1649-1651);
+    # OpenSubdiv is not in the reference tree, so the order is this generator's: a vertex's edges ascend
+    edge_verts: np.ndarray = None      # (NE, 2) int32: getEdgeVertices
+    cvert_edge_off: np.ndarray = None  # (NV + 1,) int32
+    cvert_edges: np.ndarray = None     # getVertexEdges, ascending edge index
 
     @property
     def totgrid(self):
@@ -219,6 +224,12 @@ def multires_cube_n(n_per_side, level, **kw):
     """same with n x n base quads per side (n need not be a power of two)"""
     return _multires_from_base(_cube_n(n_per_side), level, kw.get("noise", 0.01), kw.get("freq", 5.0),
                                kw.get("with_mask", False), kw.get("spherify", True))
+
+
+def multires_plane(n_per_side, level, noise=0.01, freq=5.0, with_mask=False):
+    """open base: n x n quads of a planar height field; coarse boundary edges have one face, so the elements
+    along them are boundary elements of the smooth brush"""
+    return _multires_from_base(grid(n_per_side + 1, height=0.1, freq=3.0), level, noise, freq, with_mask, False)
 
 
 def _cube_n(n):
@@ -309,6 +320,13 @@ def _multires_from_base(base, level, noise, freq, with_mask, spherify):
                  face_start=(np.arange(F, dtype=np.int32) * 4), face_num=np.full(F, 4, dtype=np.int32),
                  edge_off=edge_off, edge_elems=edge_elems, cvert_off=cvert_off, cvert_elems=cvert_elems,
                  grid_edge=grid_edge, grid_cvert=grid_cvert)
+    ev = np.stack([edge_v0, eb[first]], axis=1).astype(np.int32)
+    inc_v = ev.reshape(-1).astype(np.int64)
+    inc_e = np.repeat(np.arange(NE, dtype=np.int64), 2)
+    o = np.lexsort((inc_e, inc_v))
+    m.edge_verts = ev
+    m.cvert_edge_off = np.concatenate([[0], np.cumsum(np.bincount(inc_v, minlength=NV))]).astype(np.int32)
+    m.cvert_edges = inc_e[o].astype(np.int32)
     _multires_make_consistent(m)
     return m
 

@@ -108,6 +108,14 @@ OrPbvh *or_pbvh_build_grids(int totgrid, int grid_size, const float (*co)[3], co
                             int totface, const int *face_start, const int *face_num, int totedge, const int *edge_off,
                             const int *edge_elems, int totcvert, const int *cvert_off, const int *cvert_elems,
                             const int *grid_edge, const int *grid_cvert, int leaf_limit /* 0 = LEAF_LIMIT / gs^2 */);
+/* the two topology-refiner queries the element-neighbour lookup makes beyond the tables above:
+ * edge_verts[totedge][2] (getEdgeVertices), cvert_edges CSR (getVertexEdges); needed by the smooth brush */
+void or_grids_set_topology(OrPbvh *p, const int *edge_verts, const int *cvert_edge_off, const int *cvert_edges);
+/* KERNEL_subdiv_ccg_neighbor_coords_get (subdiv_ccg.c:1882-1909), include_duplicates = false: neighbours of an
+ * element in the reference's order; r holds or_grids_max_neighbors() ints; returns the count */
+int or_grids_neighbors(const OrPbvh *p, int elem, int *r);
+int or_grids_max_neighbors(const OrPbvh *p);
+int or_grids_is_boundary(const OrPbvh *p, int elem); /* DAGGER SCULPT_vertex_is_boundary, subdiv_ccg.c:1949-2008 */
 void or_grids_average_all(OrPbvh *p);  /* KERNEL_subdiv_ccg_average_grids, subdiv_ccg.c:1170-1189 */
 void or_grids_recalc_normals(OrPbvh *p); /* KERNEL_subdiv_ccg_recalc_normals, subdiv_ccg.c:782-790 */
 float *or_pbvh_mask(OrPbvh *p);

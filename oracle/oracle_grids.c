@@ -273,3 +273,154 @@ void or_grids_recalc_normals(OrPbvh *p)
   free(fn);
   or_grids_average_all(p);
 }
+
+/* ---- element neighbours (smooth brush on grids) -------------------------
+ * KERNEL_subdiv_ccg_neighbor_coords_get (subdiv_ccg.c:1882-1909) with include_duplicates = false, the way
+ * the brushes' neighbour iterator calls it, over the flat tables.  The three OpenSubdiv queries it makes
+ * -- getFaceEdges / getFaceVertices (grid_edge / grid_cvert, already held), getEdgeVertices and
+ * getVertexEdges (subdiv_ccg.c:1558-1582, 1649-1651) -- are tables the caller gives through
+ * or_grids_set_topology.  Neighbours come out in the reference's order (the average sums them in it). */
+void or_grids_set_topology(OrPbvh *p, const int *edge_verts, const int *cvert_edge_off, const int *cvert_edges)
+{
+  free(p->edge_verts); free(p->cvert_edge_off); free(p->cvert_edges); free(p->cvert_boundary);
+  p->edge_verts = malloc(sizeof(int) * 2 * (size_t)(p->totedge + 1));
+  memcpy(p->edge_verts, edge_verts, sizeof(int) * 2 * (size_t)p->totedge);
+  p->cvert_edge_off = malloc(sizeof(int) * (size_t)(p->totcvert + 1));
+  memcpy(p->cvert_edge_off, cvert_edge_off, sizeof(int) * (size_t)(p->totcvert + 1));
+  p->cvert_edges = malloc(sizeof(int) * (size_t)(cvert_edge_off[p->totcvert] + 1));
+  memcpy(p->cvert_edges, cvert_edges, sizeof(int) * (size_t)cvert_edge_off[p->totcvert]);
+  /* DAGGER boundary vertices of the base mesh (upstream's vertex_info.boundary): both ends of every
+   * coarse edge with fewer than two faces */
+  p->cvert_boundary = calloc((size_t)p->totcvert + 1, 1);
+  if (!p->scratch) { /* Jacobi buffers of the smooth brush */
+    p->scratch = malloc(sizeof(float[3]) * ((size_t)p->totvert + 1));
+    p->iter_flag = calloc((size_t)p->totvert + 1, 1);
+  }
+  for (int e = 0; e < p->totedge; e++) {
+    if (p->edge_off[e + 1] - p->edge_off[e] < 2) {
+      p->cvert_boundary[edge_verts[2 * e]] = 1;
+      p->cvert_boundary[edge_verts[2 * e + 1]] = 1;
+    }
+  }
+}
+
+/* subdiv_ccg.c:1448-1471 coord_step_inside_from_boundary, on an element index */
+static int step_inside(const OrPbvh *p, int elem)
+{
+  const int gs = p->grid_size, gs2 = gs * gs, gs1 = gs - 1;
+  const int g = elem / gs2, y = (elem % gs2) / gs, x = (elem % gs2) % gs;
+  if (x == gs1) return elem_index(p, g, x - 1, y);
+  if (y == gs1) return elem_index(p, g, x, y - 1);
+  if (x == 0) return elem_index(p, g, x + 1, y);
+  return elem_index(p, g, x, y + 1);
+}
+
+/* subdiv_ccg.c:1714-1772 neighbor_coords_edge_get: the element lies on a coarse edge (not at a coarse vertex) */
+static int neighbors_on_edge(const OrPbvh *p, int g, int x, int y, int *r)
+{
+  const int gs = p->grid_size, gs1 = gs - 1;
+  const int f = p->grid_face[g], start = p->face_start[f], num = p->face_num[f], c = g - start;
+  /* adjacent_edge_index_from_coord (1612-1641) */
+  const int e = (x == gs1) ? p->grid_edge[start + c] : p->grid_edge[start + (c == 0 ? num - 1 : c - 1)];
+  const int nf = p->edge_off[e + 1] - p->edge_off[e];
+  /* adjacent_edge_point_index_from_coord (1643-1679) */
+  const int v = p->grid_cvert[g];
+  int pt, dirv;
+  if (x == gs1) {
+    pt = gs - y - 1;
+    dirv = p->edge_verts[2 * e];
+  }
+  else {
+    pt = gs + x;
+    dirv = p->edge_verts[2 * e + 1];
+  }
+  if (v != dirv) pt = 2 * gs - pt - 1;
+  const int next = (pt == gs - 1) ? pt + 2 : pt + 1; /* 1685-1691 */
+  const int prev = (pt == gs) ? pt - 2 : pt - 1;     /* 1692-1698 */
+  for (int i = 0; i < nf; i++) {
+    const int *row = p->edge_elems + (size_t)(p->edge_off[e] + i) * 2 * (size_t)gs;
+    r[i + 2] = step_inside(p, row[pt]);
+    if (row[pt] / (gs * gs) == g) {
+      r[0] = row[prev];
+      r[1] = row[next];
+    }
+  }
+  return nf + 2;
+}
+
+int or_grids_neighbors(const OrPbvh *p, int elem, int *r)
+{
+  const int gs = p->grid_size, gs2 = gs * gs, gs1 = gs - 1;
+  const int g = elem / gs2, y = (elem % gs2) / gs, x = (elem % gs2) % gs;
+  const int f = p->grid_face[g], start = p->face_start[f], num = p->face_num[f];
+  const int corner = (x == 0 || x == gs1) && (y == 0 || y == gs1);
+  if (corner) {
+    if (x == 0 && y == 0) { /* 1496-1520: the face centre */
+      for (int c = 0; c < num; c++) r[c] = elem_index(p, start + c, 1, 0);
+      return num;
+    }
+    if (x == gs1 && y == gs1) { /* 1547-1610: a coarse vertex */
+      const int v = p->grid_cvert[g];
+      const int ne = p->cvert_edge_off[v + 1] - p->cvert_edge_off[v];
+      for (int i = 0; i < ne; i++) {
+        const int e = p->cvert_edges[p->cvert_edge_off[v] + i];
+        const int pt = (p->edge_verts[2 * e] == v) ? 1 : 2 * gs - 2;
+        r[i] = p->edge_elems[(size_t)p->edge_off[e] * 2 * (size_t)gs + pt]; /* first face of the edge */
+      }
+      return ne;
+    }
+    return neighbors_on_edge(p, g, x, y, r);
+  }
+  if (x == 0 || y == 0 || x == gs1 || y == gs1) {
+    if (x == 0) { /* 1807-1843: boundary between two grids of one face */
+      const int prev = start + ((g - start) == 0 ? num - 1 : g - start - 1);
+      r[0] = elem_index(p, g, x, y - 1);
+      r[1] = elem_index(p, g, x, y + 1);
+      r[2] = elem_index(p, g, x + 1, y);
+      r[3] = elem_index(p, prev, y, 1);
+      return 4;
+    }
+    if (y == 0) {
+      const int next = start + ((g - start + 1) == num ? 0 : g - start + 1);
+      r[0] = elem_index(p, g, x - 1, y);
+      r[1] = elem_index(p, g, x + 1, y);
+      r[2] = elem_index(p, g, x, y + 1);
+      r[3] = elem_index(p, next, 1, x);
+      return 4;
+    }
+    return neighbors_on_edge(p, g, x, y, r);
+  }
+  r[0] = elem_index(p, g, x, y - 1); /* 1870-1880 */
+  r[1] = elem_index(p, g, x, y + 1);
+  r[2] = elem_index(p, g, x - 1, y);
+  r[3] = elem_index(p, g, x + 1, y);
+  return 4;
+}
+
+/* DAGGER SCULPT_vertex_is_boundary for grids over KERNEL_subdiv_ccg_coarse_mesh_adjacency_info_get
+ * (subdiv_ccg.c:1949-2008): an element at a coarse vertex is a boundary element when that vertex is a boundary
+ * vertex of the base mesh, one on a coarse edge when both ends of the edge are; everything else is interior */
+int or_grids_is_boundary(const OrPbvh *p, int elem)
+{
+  const int gs = p->grid_size, gs2 = gs * gs, gs1 = gs - 1;
+  const int g = elem / gs2, y = (elem % gs2) / gs, x = (elem % gs2) % gs;
+  if (x != gs1 && y != gs1) return 0; /* interior, face centre or an inner boundary */
+  const int f = p->grid_face[g], start = p->face_start[f], num = p->face_num[f], c = g - start;
+  const int v1 = p->grid_cvert[g];
+  if (x == gs1 && y == gs1) return p->cvert_boundary[v1];
+  int v2 = v1;
+  if (x == gs1) v2 = p->grid_cvert[start + (c + 1) % num];
+  if (y == gs1) v2 = p->grid_cvert[start + (c + num - 1) % num];
+  return p->cvert_boundary[v1] && p->cvert_boundary[v2];
+}
+
+int or_grids_max_neighbors(const OrPbvh *p)
+{
+  int w = 4;
+  for (int f = 0; f < p->totface; f++) w = p->face_num[f] > w ? p->face_num[f] : w;
+  for (int e = 0; e < p->totedge; e++) w = (p->edge_off[e + 1] - p->edge_off[e] + 2) > w ? (p->edge_off[e + 1] - p->edge_off[e] + 2) : w;
+  if (p->cvert_edge_off) {
+    for (int v = 0; v < p->totcvert; v++) w = (p->cvert_edge_off[v + 1] - p->cvert_edge_off[v]) > w ? (p->cvert_edge_off[v + 1] - p->cvert_edge_off[v]) : w;
+  }
+  return w;
+}

@@ -65,6 +65,9 @@ struct OrPbvh {
   int totcvert, *cvert_off, *cvert_elems;          /* SubdivCCGAdjacentVertex.corner_coords */
   int *grid_edge, *grid_cvert;                     /* coarse edge / vertex at the face corner of each grid */
   int *face_stamp, *edge_stamp, *cvert_stamp, stamp;
+  /* stand-ins for the topology refiner's getEdgeVertices / getVertexEdges (or_grids_set_topology) */
+  int *edge_verts, *cvert_edge_off, *cvert_edges;
+  unsigned char *cvert_boundary;
 };
 
 /* oracle_grids.c */

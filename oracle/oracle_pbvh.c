@@ -428,6 +428,7 @@ void or_pbvh_free(OrPbvh *p)
   free(p->tri_poly); free(p->vert_bitmap); free(p->nb_off); free(p->nb_idx); free(p->boundary);
   free(p->face_start); free(p->face_num); free(p->grid_face); free(p->edge_off); free(p->edge_elems);
   free(p->cvert_off); free(p->cvert_elems); free(p->grid_edge); free(p->grid_cvert);
+  free(p->edge_verts); free(p->cvert_edge_off); free(p->cvert_edges); free(p->cvert_boundary);
   free(p->face_stamp); free(p->edge_stamp); free(p->cvert_stamp);
   free(p->automask); free(p->orig_co); free(p->orig_no); free(p->touched); free(p->last_hits);
   free(p->last_moved); free(p->scratch); free(p->iter_flag); free(p->moved_stamp);

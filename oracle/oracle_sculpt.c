@@ -466,12 +466,28 @@ static void neighbor_average(const OrPbvh *p, const float (*src)[3], int v, floa
 {
   float avg[3] = {0.0f, 0.0f, 0.0f};
   int total = 0, neighbor_count = 0;
-  const int is_boundary = p->boundary[v];
-  for (int q = p->nb_off[v]; q < p->nb_off[v + 1]; q++) {
-    const int u = p->nb_idx[q];
+  /* grids: the neighbour iterator asks KERNEL_subdiv_ccg_neighbor_coords_get (subdiv_ccg.c:1882-1909, no
+   * duplicates) and the boundary test goes through the coarse mesh (subdiv_ccg.c:1972-2008) */
+  int gnb[64], *nb_heap = NULL;
+  const int *nb;
+  int nb_count, is_boundary;
+  if (p->is_grids) {
+    int *dst = gnb;
+    if (or_grids_max_neighbors(p) > 64) dst = nb_heap = malloc(sizeof(int) * (size_t)or_grids_max_neighbors(p));
+    nb_count = or_grids_neighbors(p, v, dst);
+    nb = dst;
+    is_boundary = or_grids_is_boundary(p, v);
+  }
+  else {
+    nb = p->nb_idx + p->nb_off[v];
+    nb_count = p->nb_off[v + 1] - p->nb_off[v];
+    is_boundary = p->boundary[v];
+  }
+  for (int q = 0; q < nb_count; q++) {
+    const int u = nb[q];
     neighbor_count++;
     if (is_boundary) {
-      if (p->boundary[u]) {
+      if (p->is_grids ? or_grids_is_boundary(p, u) : p->boundary[u]) {
         avg[0] += src[u][0]; avg[1] += src[u][1]; avg[2] += src[u][2];
         total++;
       }
@@ -481,6 +497,7 @@ static void neighbor_average(const OrPbvh *p, const float (*src)[3], int v, floa
       total++;
     }
   }
+  free(nb_heap);
   if ((neighbor_count <= 2 && is_boundary) || total == 0) {
     memcpy(result, src[v], sizeof(float[3]));
     return;
@@ -568,8 +585,8 @@ int or_dab(OrPbvh *p, const OrDab *d)
         do_clay_strips_brush(p, d, nodes, totnode);
         break;
       case OR_TOOL_SMOOTH:
-        if (p->is_grids) {
-          return -1; /* grid neighbours (subdiv_ccg.c:1882-1909) are not restated */
+        if (p->is_grids && !p->edge_verts) {
+          return -1; /* grid neighbours need or_grids_set_topology */
         }
         do_smooth_brush(p, d, nodes, totnode);
         break;

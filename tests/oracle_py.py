@@ -81,6 +81,10 @@ def lib():
                                           c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, C.c_int]
         L.or_grids_average_all.argtypes = [C.c_void_p]
         L.or_grids_recalc_normals.argtypes = [C.c_void_p]
+        L.or_grids_set_topology.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p]
+        L.or_grids_neighbors.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.or_grids_max_neighbors.argtypes = [C.c_void_p]
+        L.or_grids_is_boundary.argtypes = [C.c_void_p, C.c_int]
         L.or_pbvh_mask.restype = c_float_p
         L.or_pbvh_mask.argtypes = [C.c_void_p]
         _LIB = L
@@ -279,8 +283,21 @@ class GridOracle(Oracle):
         self.totnode = L.or_pbvh_totnode(self.p)
         self.tottri = L.or_pbvh_tottri(self.p)  # prims = grids
         self.totvert = mr.totelem
+        if getattr(mr, "edge_verts", None) is not None:
+            L.or_grids_set_topology(self.p, iptr(np.ascontiguousarray(mr.edge_verts, dtype=np.int32)),
+                                    iptr(np.ascontiguousarray(mr.cvert_edge_off, dtype=np.int32)),
+                                    iptr(np.ascontiguousarray(mr.cvert_edges, dtype=np.int32)))
         if recalc_normals:
             L.or_grids_recalc_normals(self.p)
+
+    def neighbors(self, elem):
+        """KERNEL_subdiv_ccg_neighbor_coords_get without duplicates: element indices, reference order"""
+        buf = np.zeros(self.L.or_grids_max_neighbors(self.p), dtype=np.int32)
+        n = self.L.or_grids_neighbors(self.p, int(elem), iptr(buf))
+        return buf[:n].copy()
+
+    def is_boundary(self, elem):
+        return bool(self.L.or_grids_is_boundary(self.p, int(elem)))
 
     def mask(self):
         ptr = self.L.or_pbvh_mask(self.p)
