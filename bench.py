@@ -109,6 +109,13 @@ def build_workload(args):
         rng = np.random.default_rng(5)
         bs = stroke._strength(capi.TOOL_DRAW, 0.5)
         dabs = []
+        # C5: a smooth stroke, then a draw stroke, same radius
+        bsm = stroke._strength(capi.TOOL_SMOOTH, 0.75)
+        for i in range(args.c5_smooth_dabs):
+            p = rng.normal(size=3)
+            p /= np.linalg.norm(p)
+            dabs.append(capi.make_dab(capi.TOOL_SMOOTH, p.astype(np.float32), diag * 0.08, bstrength=bsm, view_normal=tuple(p),
+                                      flags=capi.DAB_FIRST_STEP if i == 0 else 0))
         for i in range(args.c5_dabs):
             p = rng.normal(size=3)
             p /= np.linalg.norm(p)
@@ -179,11 +186,12 @@ def run_reference(args, rank):
 def workload_config(args, mesh, ndabs):
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.config == "c5":
-        return {"workload": "C5 multires grids: cube %d^2 x 6 base quads, level %d (%d grids of %d^2 = %d elements), draw + stitch + "
-                            "CCG normals + BB, r = 8%% bbox diag, %d dabs/stroke" %
-                            (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, ndabs),
+        return {"workload": "C5 multires grids: cube %d^2 x 6 base quads, level %d (%d grids of %d^2 = %d elements), %d smooth dabs (3 iterations) "
+                            "then %d draw dabs, each + stitch + CCG normals + BB, r = 8%% bbox diag, %d dabs/stroke" %
+                            (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, args.c5_smooth_dabs,
+                             args.c5_dabs, ndabs),
                 "parallelism": "single GPU", "verts": mesh.totelem, "dabs_per_step": ndabs,
-                "brush": "draw, SMOOTH falloff, area-normal direction",
+                "brush": "smooth (alpha 0.75) then draw (alpha 0.5), SMOOTH falloff, area-normal direction",
                 "l2": "inputs larger than L2 (resident element arrays > 2 GB)" if mesh.totelem > 8000000 else "small mesh: L2 resident",
                 "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
     return {"workload": "C3 draw+normals+BB radius sweep 1-50%% bbox diag, grid %d^2 (V=%d), %d dabs/stroke" %
@@ -211,7 +219,7 @@ def analysis_pass(ses, dabs, na, grids=False):
     moved_prev = 0
     touched = np.zeros(n, dtype=bool)
     tot = {"U": 0, "A": 0, "T": 0, "M": 0, "first_A": 0, "hits": 0}
-    stage_bytes = {"gather": 0, "area_normal": 0, "brush": 0, "normals_bb": 0, "bb_refit": 0}
+    stage_bytes = {"gather": 0, "area_normal": 0, "brush": 0, "smooth": 0, "normals_bb": 0, "bb_refit": 0}
     nleaf = int((na["flag"] & 1).sum())
     for d in dabs:
         ses.dab(d)
@@ -237,8 +245,15 @@ def analysis_pass(ses, dabs, na, grids=False):
             f = f[f >= 0]
         tot["U"] += U; tot["A"] += A; tot["T"] += T; tot["M"] += M; tot["first_A"] += first_A; tot["hits"] += h.size
         stage_bytes["gather"] += 48 * nleaf
-        stage_bytes["area_normal"] += U * 12 + M * 12
-        stage_bytes["brush"] += U * 12 + M * 12 + first_A * 24
+        if d.tool == 2:
+            # SURVEY.md 8d smooth, per iteration U * (12 [+ 4 mask]) + M * (deg * (4 + 12) + 8 + 12); M here is already the
+            # sum over the dab's iterations; grids: deg = 4 and the neighbours need no index (element's place in its grid)
+            bs = min(max(float(d.bstrength), 0.0), 1.0)
+            iters = int(bs * 4) + (0 if (int(bs * 4) > 0 and 4.0 * (bs - int(bs * 4) * 0.25) == 0.0) else 1)
+            stage_bytes["smooth"] += iters * U * 12 + M * ((4 * 12 + 12) if grids else (6 * 16 + 8 + 12)) + first_A * 24
+        else:
+            stage_bytes["area_normal"] += U * 12 + M * 12
+            stage_bytes["brush"] += U * 12 + M * 12 + first_A * 24
         if grids:
             # stitch + CCG normals: positions of the gathered leaves' grids read, normals written; leaf boxes read them again
             stage_bytes["normals_bb"] += U * 12 + U * 12 + U * 12 + 24 * h.size
@@ -508,7 +523,8 @@ def main():
                     help="c3 (default): the headline 16.7M-vertex draw sweep; c5: multires grids, draw stroke")
     ap.add_argument("--c5-base", type=int, default=25)
     ap.add_argument("--c5-level", type=int, default=7)
-    ap.add_argument("--c5-dabs", type=int, default=100)
+    ap.add_argument("--c5-dabs", type=int, default=100, help="draw dabs of the C5 stroke")
+    ap.add_argument("--c5-smooth-dabs", type=int, default=100, help="smooth dabs ahead of them")
     ap.add_argument("--c5-cpu-dabs", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

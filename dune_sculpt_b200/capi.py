@@ -107,6 +107,7 @@ HOST_SYMBOLS = [
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
     "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
+    "DUNE_subdiv_ccg_topology_set", "BKE_subdiv_ccg_neighbor_coords_get", "BKE_subdiv_ccg_coarse_mesh_adjacency_info_get",
     "DUNE_pbvh_draw_buffers_enable", "DUNE_pbvh_update_draw_buffers", "DUNE_pbvh_node_draw_buffer",
     "DUNE_pbvh_raycast_enable", "DUNE_pbvh_raycast_nearest",
     "BKE_pbvh_search_gather", "SCULPT_search_sphere_cb", "BKE_pbvh_node_mark_update", "BKE_pbvh_vert_mark_update",
@@ -213,6 +214,10 @@ def host_lib():
                                                   C.c_int, c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
         L.DUNE_subdiv_ccg_free.argtypes = [C.c_void_p]
         L.DUNE_subdiv_ccg_free.restype = None
+        L.DUNE_subdiv_ccg_topology_set.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p]
+        L.DUNE_subdiv_ccg_topology_set.restype = None
+        L.BKE_subdiv_ccg_neighbor_coords_get.argtypes = [C.c_void_p, C.c_void_p, C.c_bool, C.c_void_p]
+        L.BKE_subdiv_ccg_neighbor_coords_get.restype = None
         L.DUNE_pbvh_device_attach_grids.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int]
         L.DUNE_pbvh_draw_buffers_enable.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_draw_buffers_enable.restype = None
@@ -643,7 +648,17 @@ class SubdivCCGStruct(C.Structure):
         ("normal_offset", C.c_int), ("mask_offset", C.c_int), ("num_faces", C.c_int), ("faces", C.c_void_p),
         ("grid_faces", C.c_void_p), ("num_adjacent_edges", C.c_int), ("adjacent_edges", C.c_void_p),
         ("num_adjacent_vertices", C.c_int), ("adjacent_vertices", C.c_void_p), ("grid_edge", c_int_p), ("grid_vertex", c_int_p),
+        ("edge_vertices", c_int_p), ("vertex_edge_offsets", c_int_p), ("vertex_edges", c_int_p),
     ]
+
+
+class SubdivCCGCoord(C.Structure):
+    _fields_ = [("grid_index", C.c_int), ("x", C.c_short), ("y", C.c_short)]
+
+
+class SubdivCCGNeighbors(C.Structure):
+    _fields_ = [("coords", C.POINTER(SubdivCCGCoord)), ("size", C.c_int), ("num_duplicates", C.c_int),
+                ("coords_fixed", SubdivCCGCoord * 256)]
 
 
 class GridSession(SculptSession):
@@ -667,6 +682,11 @@ class GridSession(SculptSession):
             int(mr.face_start.shape[0]), iptr(mr.face_start), iptr(mr.face_num), int(mr.edge_off.shape[0] - 1), iptr(mr.edge_off),
             iptr(mr.edge_elems), int(mr.cvert_off.shape[0] - 1), iptr(mr.cvert_off), iptr(mr.cvert_elems), iptr(mr.grid_edge),
             iptr(mr.grid_cvert)))
+        if getattr(mr, "edge_verts", None) is not None:
+            # the coarse topology the element-neighbour lookup asks the refiner for (smooth brush)
+            H.DUNE_subdiv_ccg_topology_set(self.ccg, iptr(np.ascontiguousarray(mr.edge_verts, dtype=np.int32)),
+                                           iptr(np.ascontiguousarray(mr.cvert_edge_off, dtype=np.int32)),
+                                           iptr(np.ascontiguousarray(mr.cvert_edges, dtype=np.int32)))
         self.key = (C.c_int * 9)()
         H.BKE_subdiv_ccg_key_top_level(self.key, self.ccg)
         ccg = C.cast(self.ccg, C.POINTER(SubdivCCGStruct)).contents
@@ -684,6 +704,18 @@ class GridSession(SculptSession):
         out = np.zeros(self.mesh.totelem, dtype=np.float32)
         self._chk(self.D.dsc_download_mask(self.ctx, fptr(out)))
         return out
+
+    def neighbors(self, elem, include_duplicates=False):
+        """BKE_subdiv_ccg_neighbor_coords_get of the host library -> (element indices, num_duplicates)"""
+        gs = self.mesh.grid_size
+        c = SubdivCCGCoord(int(elem) // (gs * gs), (int(elem) % (gs * gs)) % gs, (int(elem) % (gs * gs)) // gs)
+        nb = SubdivCCGNeighbors()
+        self.H.BKE_subdiv_ccg_neighbor_coords_get(self.ccg, C.byref(c), bool(include_duplicates), C.byref(nb))
+        out = np.array([nb.coords[i].grid_index * gs * gs + nb.coords[i].y * gs + nb.coords[i].x for i in range(nb.size)],
+                       dtype=np.int64)
+        if C.addressof(nb.coords.contents) != C.addressof(nb.coords_fixed):
+            self.H.MEM_freeN(nb.coords)
+        return out, nb.num_duplicates
 
     def host_elements(self):
         """(co, no, mask) as the host's CCGElem storage holds them after a sync"""

@@ -64,6 +64,10 @@ struct DscContext {
   int grid_size = 0, totgrid = 0;
   std::vector<int> h_face_start, h_face_num, h_edge_off, h_edge_elems, h_cvert_off, h_cvert_elems, h_grid_edge, h_grid_cvert;
   DevGrids g;
+  GridNb gnb = {}; /* smooth brush on grids: rim neighbour table in slot space */
+  std::vector<int> h_rim_nb;
+  std::vector<unsigned char> h_rim_bnd;
+  int rim_width = 0;
   int grid_seq = 0;
   size_t gn_smem = 0;
   /* draw-buffer fill (dsc_draw_*) */
@@ -696,7 +700,14 @@ int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *gr)
   ctx->h_grid_edge.assign(gr->grid_edge, gr->grid_edge + gr->totgrid);
   ctx->h_grid_cvert.assign(gr->grid_cvert, gr->grid_cvert + gr->totgrid);
   ctx->tottri = gr->totgrid; /* the PBVH's prims */
-  ctx->has_nb = false;
+  ctx->has_nb = gr->rim_neighbors != nullptr;
+  if (ctx->has_nb) {
+    if (gr->rim_width < 4) return fail(ctx, DSC_ERR_INVALID, "rim_width %d: a rim element has up to four neighbours or more", gr->rim_width);
+    const size_t rows = (size_t)gr->totgrid * (size_t)(4 * gr->grid_size - 4);
+    ctx->rim_width = gr->rim_width;
+    ctx->h_rim_nb.assign(gr->rim_neighbors, gr->rim_neighbors + rows * (size_t)gr->rim_width);
+    if (gr->rim_boundary) ctx->h_rim_bnd.assign(gr->rim_boundary, gr->rim_boundary + rows);
+  }
   ctx->have_mesh = true;
   return DSC_OK;
 }
@@ -894,7 +905,39 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   if ((r = dev_alloc(ctx, &ctx->d_list, (size_t)std::max(V, L))) || (r = dev_zero(ctx, &ctx->d_count, 1))) return r;
 
   /* smooth adjacency in slot order */
-  if (ctx->has_nb) {
+  if (ctx->has_nb && ctx->is_grids) {
+    /* the rim table, element indices -> slots; per-slot boundary flags only when the base mesh is open */
+    if ((r = dev_zero(ctx, &m.tx, (size_t)VP)) || (r = dev_zero(ctx, &m.ty, (size_t)VP)) || (r = dev_zero(ctx, &m.tz, (size_t)VP))) return r;
+    const int gs = ctx->grid_size, gs2 = gs * gs, rim = 4 * gs - 4;
+    std::vector<int> rim_slots(ctx->h_rim_nb.size());
+    for (size_t i = 0; i < rim_slots.size(); i++) {
+      const int e = ctx->h_rim_nb[i];
+      if (e >= V) return fail(ctx, DSC_ERR_INVALID, "rim neighbour table names element %d", e);
+      rim_slots[i] = e < 0 ? -1 : ctx->slot_of[e];
+    }
+    GridNb &gn = ctx->gnb;
+    gn.gs = gs;
+    gn.gs2 = gs2;
+    gn.rim_w = ctx->rim_width;
+    if ((r = dev_upload_c(ctx, &gn.rim_nb, rim_slots))) return r;
+    bool any_boundary = false;
+    for (unsigned char b : ctx->h_rim_bnd) any_boundary = any_boundary || b;
+    if (any_boundary) {
+      std::vector<unsigned char> bnd((size_t)VP, 0);
+      for (int g = 0; g < ctx->totgrid; g++) {
+        for (int b = 0; b < rim; b++) {
+          if (!ctx->h_rim_bnd[(size_t)g * rim + b]) continue;
+          const int x = b < gs ? b : (b < 2 * gs ? b - gs : (b < 3 * gs - 2 ? 0 : gs - 1));
+          const int y = b < gs ? 0 : (b < 2 * gs ? gs - 1 : (b < 3 * gs - 2 ? b - 2 * gs + 1 : b - (3 * gs - 2) + 1));
+          bnd[(size_t)ctx->slot_of[(size_t)g * gs2 + (size_t)y * gs + x]] = 1;
+        }
+      }
+      if ((r = dev_upload_c(ctx, &gn.rim_bnd, ctx->h_rim_bnd)) || (r = dev_upload_c(ctx, &m.boundary, bnd))) return r;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int>().swap(ctx->h_rim_nb);
+  }
+  if (ctx->has_nb && !ctx->is_grids) {
     if ((r = dev_zero(ctx, &m.tx, (size_t)VP)) || (r = dev_zero(ctx, &m.ty, (size_t)VP)) || (r = dev_zero(ctx, &m.tz, (size_t)VP))) return r;
     std::vector<int> vert_of((size_t)VP, -1);
     for (int v = 0; v < V; v++) vert_of[ctx->slot_of[v]] = v;
@@ -995,6 +1038,8 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_zero(ctx, &g.edge_list, (size_t)g.totedge + 1)) || (r = dev_zero(ctx, &g.cvert_list, (size_t)g.totcvert + 1)) ||
         (r = dev_zero(ctx, &g.cnt, 1)))
       return r;
+    ctx->gnb.leaf_gbeg = g.leaf_gbeg;
+    ctx->gnb.leaf_grids = g.leaf_grids;
     g.mask = ctx->has_mask ? ctx->d_mask : nullptr;
     g.has_odd_edges = ctx->has_odd_edges ? 1 : 0;
     g.max_face_grids = 1;
@@ -1875,10 +1920,11 @@ static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *s
   if (tool != DSC_TOOL_DRAW && tool != DSC_TOOL_SMOOTH && tool != DSC_TOOL_INFLATE && tool != DSC_TOOL_GRAB &&
       tool != DSC_TOOL_CLAY_STRIPS)
     return fail(ctx, DSC_ERR_UNSUPPORTED, "sculpt tool %d is not on the accelerated path", tool);
-  if (tool == DSC_TOOL_SMOOTH && !ctx->has_nb) return fail(ctx, DSC_ERR_STATE, "smooth brush needs the neighbour CSR (DscMeshDesc.nb_offsets)");
+  if (tool == DSC_TOOL_SMOOTH && !ctx->has_nb)
+    return fail(ctx, DSC_ERR_STATE, ctx->is_grids ? "smooth brush needs the rim neighbour table (DscGridsDesc.rim_neighbors)" :
+                                                    "smooth brush needs the neighbour CSR (DscMeshDesc.nb_offsets)");
   if (!(dab->radius > 0.0f)) return fail(ctx, DSC_ERR_INVALID, "radius must be positive");
   if (ctx->is_grids) {
-    if (tool == DSC_TOOL_SMOOTH) return fail(ctx, DSC_ERR_UNSUPPORTED, "the smooth brush is not on the grids path (grid neighbours, subdiv_ccg.c:1882-1909)");
     if (dab->flags & (DSC_DAB_NO_NORMALS | DSC_DAB_NO_BOUNDS))
       return fail(ctx, DSC_ERR_UNSUPPORTED, "on grids every dab stitches, updates normals and bounds");
   }
@@ -1973,7 +2019,8 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
     for (int it = 0; it < total; it++) {
       {
         StageScope s(ctx, ST_SMOOTH);
-        k_smooth_a<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, j, slot, it == sig.smooth_iters ? 1 : 0);
+        if (ctx->is_grids) k_smooth_a<true><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0);
+        else k_smooth_a<false><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0);
         LAUNCH_CHECK();
       }
       {

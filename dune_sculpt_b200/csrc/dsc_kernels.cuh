@@ -964,8 +964,17 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m, int slot)
 /* One Jacobi iteration, part A: new position of every unique vert of a hit leaf inside the
  * sphere = co + (neighbour average - co) * fade, into the scratch arrays (SURVEY.md 8a row a20:
  * interior verts average all edge neighbours, boundary verts only boundary neighbours, boundary
- * verts with <= 2 neighbours stay).  The CSR gather is served by L2. */
-__global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, int j, int slot, int last_iteration)
+ * verts with <= 2 neighbours stay).  The CSR gather is served by L2.
+ * GRIDS: the neighbours of a grid element come from its place in the grid (subdiv_ccg.c:1870-1880: previous row,
+ * next row, previous column, next column -- four unit-stride streams, no index traffic) or, on the grid's rim,
+ * from the per-grid rim table (KERNEL_subdiv_ccg_neighbor_coords_get asked once at upload, subdiv_ccg.c:1882-1909). */
+struct GridNb {
+  int gs, gs2, rim_w;
+  const int *leaf_gbeg, *leaf_grids;
+  const int *rim_nb;              /* [totgrid][4 gs - 4][rim_w] slots, -1 = none */
+  const unsigned char *rim_bnd;   /* [totgrid][4 gs - 4] or NULL */
+};
+template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, GridNb gn, int j, int slot, int last_iteration)
 {
   const DabEntry &ent_ = dsc_dab_entry(m, j);
   const DabParams d = ent_.d;
@@ -983,6 +992,11 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, int j, int sl
     const int4 ent = tl[u];
     const int beg = ent.y, cnt = ent.z;
     const int cnt32 = (cnt + 31) & ~31;
+    int leaf = 0, leaf_beg = 0;
+    if (GRIDS) {
+      leaf = m.tile_meta[3 * ent.x + 2].y;
+      leaf_beg = m.leaf_ubeg[leaf];
+    }
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
       bool moved = false;
@@ -995,15 +1009,49 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, int j, int sl
           if (d.flags & 1) { vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s]; }
           const float fade = strength * dsc_strength_factor(m, d, sqrtf(distsq), vnx, vny, vnz, s);
           float ax = 0.0f, ay = 0.0f, az = 0.0f;
-          int tot = 0;
-          const unsigned qb = m.nb_off[s], qe = m.nb_off[s + 1];
-          const int neighbor_count = (int)(qe - qb);
-          const bool is_boundary = m.boundary[s] != 0;
-          for (unsigned q = qb; q < qe; q++) {
-            const int v = m.nb_idx[q];
-            if (!is_boundary || m.boundary[v]) {
-              ax += m.cx[v]; ay += m.cy[v]; az += m.cz[v];
-              tot++;
+          int tot = 0, neighbor_count;
+          bool is_boundary;
+          if (GRIDS) {
+            const int local = s - leaf_beg;
+            const int gi = local / gn.gs2, e = local - gi * gn.gs2;
+            const int ey = e / gn.gs, ex = e - ey * gn.gs, last = gn.gs - 1;
+            if (ex > 0 && ey > 0 && ex < last && ey < last) {
+              const int a = s - gn.gs, b = s + gn.gs;
+              ax += m.cx[a]; ay += m.cy[a]; az += m.cz[a];
+              ax += m.cx[b]; ay += m.cy[b]; az += m.cz[b];
+              ax += m.cx[s - 1]; ay += m.cy[s - 1]; az += m.cz[s - 1];
+              ax += m.cx[s + 1]; ay += m.cy[s + 1]; az += m.cz[s + 1];
+              tot = neighbor_count = 4;
+              is_boundary = false;
+            }
+            else {
+              const int grid = gn.leaf_grids[gn.leaf_gbeg[leaf] + gi];
+              const int rim = 4 * gn.gs - 4;
+              const int b = ey == 0 ? ex : (ey == last ? gn.gs + ex : (ex == 0 ? 2 * gn.gs + ey - 1 : 3 * gn.gs - 2 + ey - 1));
+              const int *row = gn.rim_nb + ((size_t)grid * rim + b) * gn.rim_w;
+              is_boundary = gn.rim_bnd && gn.rim_bnd[(size_t)grid * rim + b] != 0;
+              neighbor_count = 0;
+              for (int q = 0; q < gn.rim_w; q++) {
+                const int v = row[q];
+                if (v < 0) break;
+                neighbor_count++;
+                if (!is_boundary || m.boundary[v]) {
+                  ax += m.cx[v]; ay += m.cy[v]; az += m.cz[v];
+                  tot++;
+                }
+              }
+            }
+          }
+          else {
+            const unsigned qb = m.nb_off[s], qe = m.nb_off[s + 1];
+            neighbor_count = (int)(qe - qb);
+            is_boundary = m.boundary[s] != 0;
+            for (unsigned q = qb; q < qe; q++) {
+              const int v = m.nb_idx[q];
+              if (!is_boundary || m.boundary[v]) {
+                ax += m.cx[v]; ay += m.cy[v]; az += m.cz[v];
+                tot++;
+              }
             }
           }
           float rx, ry, rz;

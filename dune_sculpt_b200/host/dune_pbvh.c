@@ -495,6 +495,166 @@ SubdivCCG *DUNE_subdiv_ccg_from_tables(int level, int num_grids, const float *co
   return ccg;
 }
 
+void DUNE_subdiv_ccg_topology_set(SubdivCCG *ccg, const int *edge_vertices, const int *vertex_edge_offsets, const int *vertex_edges)
+{
+  free(ccg->edge_vertices); free(ccg->vertex_edge_offsets); free(ccg->vertex_edges);
+  const int ne = ccg->num_adjacent_edges, nv = ccg->num_adjacent_vertices;
+  ccg->edge_vertices = malloc(sizeof(int[2]) * (size_t)(ne ? ne : 1));
+  memcpy(ccg->edge_vertices, edge_vertices, sizeof(int[2]) * (size_t)ne);
+  ccg->vertex_edge_offsets = malloc(sizeof(int) * (size_t)(nv + 1));
+  memcpy(ccg->vertex_edge_offsets, vertex_edge_offsets, sizeof(int) * (size_t)(nv + 1));
+  ccg->vertex_edges = malloc(sizeof(int) * (size_t)(vertex_edge_offsets[nv] + 1));
+  memcpy(ccg->vertex_edges, vertex_edges, sizeof(int) * (size_t)vertex_edge_offsets[nv]);
+}
+
+/* ---- element neighbours: subdiv_ccg.c:1365-1909.  An element is classified by where it sits in its grid --
+ * interior, on a boundary shared with the next / previous grid of the same face (x == 0 or y == 0), on a coarse edge
+ * (x or y == grid_size - 1), at the face centre (0, 0) or at a coarse vertex (both maximal) -- and each class has its own
+ * fixed neighbour order; `include_duplicates` appends the other copies of the element itself. ---- */
+static SubdivCCGCoord ccg_coord(int grid, int x, int y)
+{
+  SubdivCCGCoord c;
+  c.grid_index = grid;
+  c.x = (short)x;
+  c.y = (short)y;
+  return c;
+}
+
+static void neighbors_reserve(SubdivCCGNeighbors *nb, int num_unique, int num_duplicates)
+{
+  nb->size = num_unique + num_duplicates;
+  nb->num_duplicates = num_duplicates;
+  nb->coords = nb->size < (int)(sizeof(nb->coords_fixed) / sizeof(nb->coords_fixed[0])) ?
+                   nb->coords_fixed :
+                   MEM_mallocN(sizeof(SubdivCCGCoord) * (size_t)nb->size, "SubdivCCGNeighbors.coords");
+}
+
+/* one step off the grid's rim (subdiv_ccg.c:1448-1471) */
+static SubdivCCGCoord step_off_rim(const SubdivCCG *ccg, SubdivCCGCoord c)
+{
+  const int last = ccg->grid_size - 1;
+  if (c.x == last) c.x--;
+  else if (c.y == last) c.y--;
+  else if (c.x == 0) c.x++;
+  else c.y++;
+  return c;
+}
+
+/* the element lies on a coarse edge and is not a coarse vertex (subdiv_ccg.c:1612-1772) */
+static void neighbors_coarse_edge(const SubdivCCG *ccg, const SubdivCCGCoord *co, bool dups, SubdivCCGNeighbors *nb)
+{
+  const int gs = ccg->grid_size, last = gs - 1;
+  const SubdivCCGFace *face = ccg->grid_faces[co->grid_index];
+  const int corner = co->grid_index - face->start_grid_index;
+  const bool on_x = co->x == last;
+  const bool at_grid_corner = (co->x == 0 || co->x == last) && (co->y == 0 || co->y == last);
+  /* the face's edge leaving this corner, or the one arriving at it */
+  const int edge = on_x ? ccg->grid_edge[co->grid_index] :
+                          ccg->grid_edge[face->start_grid_index + (corner == 0 ? face->num_grids - 1 : corner - 1)];
+  const SubdivCCGAdjacentEdge *ae = &ccg->adjacent_edges[edge];
+  const int nf = ae->num_adjacent_faces;
+  /* position along the 2 * grid_size boundary points, flipped when the edge runs against this face's winding */
+  int pt = on_x ? gs - co->y - 1 : gs + co->x;
+  if (ccg->grid_vertex[co->grid_index] != ccg->edge_vertices[edge][on_x ? 0 : 1]) pt = 2 * gs - pt - 1;
+  /* the two middle points of the edge are one vertex (two grid corners): step over the twin */
+  const int pt_next = pt == gs - 1 ? pt + 2 : pt + 1;
+  const int pt_prev = pt == gs ? pt - 2 : pt - 1;
+  const int pt_twin = pt == gs ? pt - 1 : pt + 1;
+  neighbors_reserve(nb, nf + 2, dups ? (nf - 1) + (at_grid_corner ? nf : 0) : 0);
+  int dup_at = nf + 2;
+  for (int i = 0; i < nf; i++) {
+    const SubdivCCGCoord *row = ae->boundary_coords[i];
+    nb->coords[2 + i] = step_off_rim(ccg, row[pt]);
+    if (row[pt].grid_index == co->grid_index) {
+      nb->coords[0] = row[pt_prev];
+      nb->coords[1] = row[pt_next];
+    }
+    else if (dups) {
+      nb->coords[dup_at++] = row[pt];
+    }
+    if (dups && at_grid_corner) nb->coords[dup_at++] = row[pt_twin];
+  }
+}
+
+void BKE_subdiv_ccg_neighbor_coords_get(const SubdivCCG *ccg, const SubdivCCGCoord *co, const bool dups, SubdivCCGNeighbors *nb)
+{
+  const int gs = ccg->grid_size, last = gs - 1;
+  const int g = co->grid_index, x = co->x, y = co->y;
+  const SubdivCCGFace *face = ccg->grid_faces[g];
+  const int n = face->num_grids, first = face->start_grid_index, corner = g - first;
+  if (x > 0 && y > 0 && x < last && y < last) { /* interior: previous / next row, previous / next column */
+    neighbors_reserve(nb, 4, 0);
+    nb->coords[0] = ccg_coord(g, x, y - 1);
+    nb->coords[1] = ccg_coord(g, x, y + 1);
+    nb->coords[2] = ccg_coord(g, x - 1, y);
+    nb->coords[3] = ccg_coord(g, x + 1, y);
+    return;
+  }
+  if (x == 0 && y == 0) { /* the face centre: one step along every grid of the face */
+    neighbors_reserve(nb, n, dups ? n - 1 : 0);
+    int dup_at = n;
+    for (int c = 0; c < n; c++) {
+      nb->coords[c] = ccg_coord(first + c, 1, 0);
+      if (dups && first + c != g) nb->coords[dup_at++] = ccg_coord(first + c, 0, 0);
+    }
+    return;
+  }
+  if (x == last && y == last) { /* a coarse vertex: the second point of every edge around it, on the edge's first face */
+    const int v = ccg->grid_vertex[g];
+    const int *edges = ccg->vertex_edges + ccg->vertex_edge_offsets[v];
+    const int ne = ccg->vertex_edge_offsets[v + 1] - ccg->vertex_edge_offsets[v];
+    const SubdivCCGAdjacentVertex *av = &ccg->adjacent_vertices[v];
+    neighbors_reserve(nb, ne, dups ? av->num_adjacent_faces - 1 : 0);
+    for (int i = 0; i < ne; i++) {
+      const int pt = ccg->edge_vertices[edges[i]][0] == v ? 1 : 2 * gs - 2;
+      nb->coords[i] = ccg->adjacent_edges[edges[i]].boundary_coords[0][pt];
+    }
+    if (dups) {
+      int dup_at = ne;
+      for (int i = 0; i < av->num_adjacent_faces; i++) {
+        if (av->corner_coords[i].grid_index != g) nb->coords[dup_at++] = av->corner_coords[i];
+      }
+    }
+    return;
+  }
+  if (x == last || y == last) {
+    neighbors_coarse_edge(ccg, co, dups, nb);
+    return;
+  }
+  /* on the boundary with a sibling grid: column 0 is row 0 of the previous grid, row 0 is column 0 of the next */
+  neighbors_reserve(nb, 4, dups ? 1 : 0);
+  if (x == 0) {
+    const int prev = first + (corner == 0 ? n - 1 : corner - 1);
+    nb->coords[0] = ccg_coord(g, x, y - 1);
+    nb->coords[1] = ccg_coord(g, x, y + 1);
+    nb->coords[2] = ccg_coord(g, x + 1, y);
+    nb->coords[3] = ccg_coord(prev, y, 1);
+    if (dups) nb->coords[4] = ccg_coord(prev, y, 0);
+  }
+  else {
+    const int next = first + (corner + 1 == n ? 0 : corner + 1);
+    nb->coords[0] = ccg_coord(g, x - 1, y);
+    nb->coords[1] = ccg_coord(g, x + 1, y);
+    nb->coords[2] = ccg_coord(g, x, y + 1);
+    nb->coords[3] = ccg_coord(next, 1, x);
+    if (dups) nb->coords[4] = ccg_coord(next, 0, x);
+  }
+}
+
+SubdivCCGAdjacencyType BKE_subdiv_ccg_coarse_mesh_adjacency_info_get(const SubdivCCG *ccg, const SubdivCCGCoord *co, int *r_v1, int *r_v2)
+{
+  const int last = ccg->grid_size - 1;
+  if (co->x != last && co->y != last) return SUBDIV_CCG_ADJACENT_NONE; /* interior, face centre, sibling boundary */
+  const SubdivCCGFace *face = ccg->grid_faces[co->grid_index];
+  const int n = face->num_grids, first = face->start_grid_index, corner = co->grid_index - first;
+  *r_v1 = *r_v2 = ccg->grid_vertex[co->grid_index];
+  if (co->x == last && co->y == last) return SUBDIV_CCG_ADJACENT_VERTEX;
+  /* the other end of the coarse edge: the next loop's vertex along x, the previous loop's along y */
+  if (co->x == last) *r_v2 = ccg->grid_vertex[first + (corner + 1) % n];
+  if (co->y == last) *r_v2 = ccg->grid_vertex[first + (corner + n - 1) % n];
+  return SUBDIV_CCG_ADJACENT_EDGE;
+}
+
 void DUNE_subdiv_ccg_free(SubdivCCG *ccg)
 {
   if (!ccg) return;
@@ -505,6 +665,7 @@ void DUNE_subdiv_ccg_free(SubdivCCG *ccg)
   for (int v = 0; v < ccg->num_adjacent_vertices; v++) free(ccg->adjacent_vertices[v].corner_coords);
   free(ccg->adjacent_edges); free(ccg->adjacent_vertices); free(ccg->faces); free(ccg->grid_faces);
   free(ccg->grids); free(ccg->grids_storage); free(ccg->grid_edge); free(ccg->grid_vertex);
+  free(ccg->edge_vertices); free(ccg->vertex_edge_offsets); free(ccg->vertex_edges);
   free(ccg);
 }
 
@@ -581,7 +742,63 @@ int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *ccg, int device)
   gd.cvert_elems = vert_elems;
   gd.grid_edge = ccg->grid_edge;
   gd.grid_cvert = ccg->grid_vertex;
+  int *rim_nb = NULL;
+  unsigned char *rim_bnd = NULL;
+  if (ccg->edge_vertices) {
+    /* what the smooth brush's neighbour iterator would ask per element per iteration, asked once: the rim elements of
+     * every grid through BKE_subdiv_ccg_neighbor_coords_get, flattened to element indices */
+    const int rim = 4 * gs - 4;
+    unsigned char *vbnd = calloc((size_t)ccg->num_adjacent_vertices + 1, 1); /* boundary vertices of the base mesh */
+    for (int e = 0; e < ccg->num_adjacent_edges; e++) {
+      if (ccg->adjacent_edges[e].num_adjacent_faces < 2) {
+        vbnd[ccg->edge_vertices[e][0]] = 1;
+        vbnd[ccg->edge_vertices[e][1]] = 1;
+      }
+    }
+    int width = 4;
+    for (int f = 0; f < ccg->num_faces; f++) width = ccg->faces[f].num_grids > width ? ccg->faces[f].num_grids : width;
+    for (int e = 0; e < ccg->num_adjacent_edges; e++) {
+      const int k = ccg->adjacent_edges[e].num_adjacent_faces + 2;
+      width = k > width ? k : width;
+    }
+    for (int v = 0; v < ccg->num_adjacent_vertices; v++) {
+      const int k = ccg->vertex_edge_offsets[v + 1] - ccg->vertex_edge_offsets[v];
+      width = k > width ? k : width;
+    }
+    rim_nb = malloc(sizeof(int) * (size_t)G * (size_t)rim * (size_t)width);
+    rim_bnd = calloc((size_t)G * (size_t)rim, 1);
+    SubdivCCGNeighbors *nb = malloc(sizeof(SubdivCCGNeighbors));
+    for (int g = 0; g < G; g++) {
+      for (int b = 0; b < rim; b++) {
+        SubdivCCGCoord c;
+        c.grid_index = g;
+        if (b < gs) { c.x = (short)b; c.y = 0; }
+        else if (b < 2 * gs) { c.x = (short)(b - gs); c.y = (short)(gs - 1); }
+        else if (b < 3 * gs - 2) { c.x = 0; c.y = (short)(b - 2 * gs + 1); }
+        else { c.x = (short)(gs - 1); c.y = (short)(b - (3 * gs - 2) + 1); }
+        BKE_subdiv_ccg_neighbor_coords_get(ccg, &c, false, nb);
+        int *row = rim_nb + ((size_t)g * (size_t)rim + (size_t)b) * (size_t)width;
+        for (int i = 0; i < width; i++) {
+          row[i] = i < nb->size ? nb->coords[i].grid_index * area + nb->coords[i].y * gs + nb->coords[i].x : -1;
+        }
+        if (nb->coords != nb->coords_fixed) MEM_freeN(nb->coords);
+        int v1 = 0, v2 = 0;
+        switch (BKE_subdiv_ccg_coarse_mesh_adjacency_info_get(ccg, &c, &v1, &v2)) {
+          case SUBDIV_CCG_ADJACENT_VERTEX: rim_bnd[(size_t)g * (size_t)rim + (size_t)b] = vbnd[v1]; break;
+          case SUBDIV_CCG_ADJACENT_EDGE: rim_bnd[(size_t)g * (size_t)rim + (size_t)b] = vbnd[v1] && vbnd[v2]; break;
+          default: break;
+        }
+      }
+    }
+    free(nb);
+    free(vbnd);
+    gd.rim_width = width;
+    gd.rim_neighbors = rim_nb;
+    gd.rim_boundary = rim_bnd;
+  }
   r = dsc_grids_upload(ctx, &gd);
+  free(rim_nb);
+  free(rim_bnd);
 
   float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
   int *child = malloc(sizeof(int) * (size_t)N), *flag = malloc(sizeof(int) * (size_t)N), *prim_off = malloc(sizeof(int) * (size_t)N);

@@ -110,7 +110,22 @@ typedef struct SubdivCCG { /* subdiv_ccg.c:104-140 */
   /* in place of the OpenSubdiv topology refiner the reference asks for a face's edges and vertices
    * (subdiv_ccg.c:1198-1223): per grid, the coarse edge / vertex of its face corner */
   int *grid_edge, *grid_vertex;
+  /* the refiner's getEdgeVertices / getNumVertexEdges / getVertexEdges, which the element-neighbour lookup asks
+   * (subdiv_ccg.c:1558-1582, 1649-1651): NULL until DUNE_subdiv_ccg_topology_set */
+  int (*edge_vertices)[2];
+  int *vertex_edge_offsets, *vertex_edges;
 } SubdivCCG;
+typedef struct SubdivCCGNeighbors { /* subdiv_ccg.c:1365-1380: the header is absent; fields as the code uses them */
+  SubdivCCGCoord *coords;
+  int size;
+  int num_duplicates;
+  SubdivCCGCoord coords_fixed[256];
+} SubdivCCGNeighbors;
+typedef enum SubdivCCGAdjacencyType { /* subdiv_ccg.c:1972-2008 */
+  SUBDIV_CCG_ADJACENT_NONE,
+  SUBDIV_CCG_ADJACENT_VERTEX,
+  SUBDIV_CCG_ADJACENT_EDGE,
+} SubdivCCGAdjacencyType;
 
 /* kernel/intern/pbvh_intern.h:4-7 */
 typedef struct BB {
@@ -216,6 +231,17 @@ SubdivCCG *DUNE_subdiv_ccg_from_tables(int level, int num_grids, const float *co
                                        const int *vert_offsets, const int *vert_elems, const int *grid_edge,
                                        const int *grid_vertex);
 void DUNE_subdiv_ccg_free(SubdivCCG *subdiv_ccg);
+/* not in the reference: the coarse topology the neighbour lookup needs (edge -> its two vertices, vertex -> its
+ * edges in the refiner's order); copies.  Without it the smooth brush is refused on grids. */
+void DUNE_subdiv_ccg_topology_set(SubdivCCG *subdiv_ccg, const int *edge_vertices, const int *vertex_edge_offsets,
+                                  const int *vertex_edges);
+/* subdiv_ccg.c:1882-1909: the neighbours of a grid element; coords is coords_fixed or MEM-allocated when larger
+ * (free with MEM_freeN when coords != coords_fixed, as the reference's callers do) */
+void BKE_subdiv_ccg_neighbor_coords_get(const SubdivCCG *subdiv_ccg, const SubdivCCGCoord *coord, const bool include_duplicates,
+                                        SubdivCCGNeighbors *r_neighbors);
+/* subdiv_ccg.c:1972-2008, with the base mesh's loop vertices taken from grid_vertex (mloop[grid_index].v) */
+SubdivCCGAdjacencyType BKE_subdiv_ccg_coarse_mesh_adjacency_info_get(const SubdivCCG *subdiv_ccg, const SubdivCCGCoord *coord,
+                                                                     int *r_v1, int *r_v2);
 /* not in the reference: sizes and layers the reference pulls out of Mesh / CustomData */
 void DUNE_pbvh_mesh_sizes_set(PBVH *pbvh, int totpoly, int totloop);
 void DUNE_pbvh_mask_layer_set(PBVH *pbvh, float *vmask);

@@ -115,6 +115,15 @@ typedef struct DscGridsDesc {
   const int *cvert_elems;     /* corner_coords as element indices */
   const int *grid_edge;       /* [totgrid] coarse edge of the grid's face corner (getFaceEdges order) */
   const int *grid_cvert;      /* [totgrid] coarse vertex of the grid's face corner (getFaceVertices order) */
+  /* smooth brush on grids: the neighbours of the elements on the rim of every grid, as
+   * KERNEL_subdiv_ccg_neighbor_coords_get (subdiv_ccg.c:1882-1909, no duplicates) lists them -- the neighbours of
+   * interior elements are (x, y - 1), (x, y + 1), (x - 1, y), (x + 1, y) (subdiv_ccg.c:1870-1880) and need no table.
+   * Rim index b of element (x, y), gs = grid_size: y == 0: x;  y == gs - 1: gs + x;  x == 0: 2 gs + y - 1;
+   * x == gs - 1: 3 gs - 2 + y - 1  (4 gs - 4 per grid).  NULL: the smooth brush is refused. */
+  int rim_width;               /* row length: the most neighbours any rim element has */
+  const int *rim_neighbors;    /* [totgrid][4 * grid_size - 4][rim_width] element indices, -1 = none */
+  const unsigned char *rim_boundary; /* [totgrid][4 * grid_size - 4] element is a boundary element of the coarse mesh
+                                        (subdiv_ccg.c:1972-2008), or NULL: none is */
 } DscGridsDesc;
 
 /* The built PBVH, flattened.  Replaces PBVH.nodes / PBVHNode (kernel/intern/pbvh_intern.h:15-162).
@@ -174,7 +183,8 @@ int dsc_abi_version(void);
 int dsc_mesh_upload(DscContext *ctx, const DscMeshDesc *mesh);
 /* behind BKE_pbvh_build_grids (pbvh.c:2516-2561): instead of dsc_mesh_upload.  On grids the dab runs
  * gather -> brush -> stitch of duplicated boundary elements (multires.c:1171-1196) -> CCG normal update
- * of the gathered leaves' faces (subdiv_ccg.c:847-866) -> bounds; draw / inflate / grab / clay strips. */
+ * of the gathered leaves' faces (subdiv_ccg.c:847-866) -> bounds; draw / inflate / grab / clay strips, and smooth
+ * when the rim neighbour table is given. */
 int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *grids);
 int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pbvh);
 /* vertex normals of the whole mesh from the current positions (all vertices dirty, all leaves

@@ -292,6 +292,8 @@ void or_grids_set_topology(OrPbvh *p, const int *edge_verts, const int *cvert_ed
   /* DAGGER boundary vertices of the base mesh (upstream's vertex_info.boundary): both ends of every
    * coarse edge with fewer than two faces */
   p->cvert_boundary = calloc((size_t)p->totcvert + 1, 1);
+  p->max_neighbors = 0;
+  p->max_neighbors = or_grids_max_neighbors(p);
   if (!p->scratch) { /* Jacobi buffers of the smooth brush */
     p->scratch = malloc(sizeof(float[3]) * ((size_t)p->totvert + 1));
     p->iter_flag = calloc((size_t)p->totvert + 1, 1);
@@ -416,6 +418,7 @@ int or_grids_is_boundary(const OrPbvh *p, int elem)
 
 int or_grids_max_neighbors(const OrPbvh *p)
 {
+  if (p->max_neighbors) return p->max_neighbors;
   int w = 4;
   for (int f = 0; f < p->totface; f++) w = p->face_num[f] > w ? p->face_num[f] : w;
   for (int e = 0; e < p->totedge; e++) w = (p->edge_off[e + 1] - p->edge_off[e] + 2) > w ? (p->edge_off[e + 1] - p->edge_off[e] + 2) : w;

@@ -68,6 +68,7 @@ struct OrPbvh {
   /* stand-ins for the topology refiner's getEdgeVertices / getVertexEdges (or_grids_set_topology) */
   int *edge_verts, *cvert_edge_off, *cvert_edges;
   unsigned char *cvert_boundary;
+  int max_neighbors;
 };
 
 /* oracle_grids.c */

@@ -99,6 +99,7 @@ def test_grids_default_leaf_limit_c5_shape_reduced():
 
 def test_grids_reject_what_the_path_does_not_cover():
     mr = meshgen.multires_cube(1, 3)
+    mr.edge_verts = None   # no coarse topology -> no rim neighbour table -> no smooth brush
     ses = capi.GridSession(mr, device=0)
     try:
         ses.stroke_begin()
@@ -117,4 +118,48 @@ def test_grids_fused_cooperative_kernel_is_bit_identical(monkeypatch):
     monkeypatch.setenv("DSC_GRID_FUSED", "1")
     mr = meshgen.multires_cube(2, 4, with_mask=True)
     st = _grid_parity(mr, _sweep(mr, per=2, radii=(6.0, 20.0, 45.0)), leaf_limit=6)
+    assert st["moved_verts"] > 0
+
+
+def _smooth_dabs(mr, n=4, pct=(12.0, 30.0), alpha=0.75, seed=5, around=None):
+    rng = np.random.default_rng(seed)
+    diag = mr.bbox_diag()
+    out = []
+    for r in pct:
+        for _ in range(n):
+            if around is None:
+                p = rng.normal(size=3)
+                p /= np.linalg.norm(p)
+            else:
+                p = np.asarray(around, dtype=np.float64) + 0.3 * rng.normal(size=3) * np.array([1.0, 1.0, 0.0])
+            out.append(capi.make_dab(capi.TOOL_SMOOTH, p.astype(np.float32), diag * r / 100.0,
+                                     bstrength=stroke._strength(capi.TOOL_SMOOTH, alpha)))
+    return out
+
+
+@pytest.mark.parametrize("alpha", [0.75, 0.5, 0.2])
+def test_grids_smooth_brush(alpha):
+    """smooth on grids: neighbours from the element's place in its grid or from the rim table
+    (KERNEL_subdiv_ccg_neighbor_coords_get, subdiv_ccg.c:1882-1909); alpha 0.75 = 3 full iterations,
+    0.5 = 2, 0.2 = a partial one only"""
+    mr = meshgen.multires_cube(2, 4, noise=0.03, freq=17.0, with_mask=True)
+    st = _grid_parity(mr, _smooth_dabs(mr, n=2, alpha=alpha), leaf_limit=6)
+    assert st["moved_verts"] > 0
+
+
+def test_grids_smooth_open_base_boundary_elements():
+    """open base mesh: coarse boundary edges / vertices -> boundary elements average boundary neighbours only,
+    corner elements of the sheet (two neighbours) stay"""
+    mr = meshgen.multires_plane(4, 4, noise=0.05, freq=11.0)
+    dabs = _smooth_dabs(mr, n=3, pct=(15.0, 45.0), around=(0.0, 0.0, 0.0))
+    dabs.append(capi.make_dab(capi.TOOL_SMOOTH, mr.co[np.argmax(mr.co[:, 0] + mr.co[:, 1])], mr.bbox_diag() * 0.2, bstrength=0.75))
+    st = _grid_parity(mr, dabs, leaf_limit=3)
+    assert st["moved_verts"] > 0
+
+
+def test_grids_smooth_then_draw_c5_shape_reduced():
+    """C5's stroke pair (smooth, then draw) on its shape at 1/100 of the size, default leaf limit"""
+    mr = meshgen.multires_cube_n(5, 6, noise=0.02, freq=23.0)
+    dabs = _smooth_dabs(mr, n=2, pct=(8.0,)) + _sweep(mr, per=2, radii=(8.0,))
+    st = _grid_parity(mr, dabs)
     assert st["moved_verts"] > 0

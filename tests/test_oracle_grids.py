@@ -183,3 +183,23 @@ def test_grid_smooth_brush_oracle_runs_and_is_thread_invariant():
         orc.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert not np.array_equal(out[0][0], mr.co)
+
+
+def test_host_library_neighbours_match_the_oracle_and_duplicates_are_the_other_copies():
+    """the host library's BKE_subdiv_ccg_neighbor_coords_get against the oracle's restatement (order included), and
+    include_duplicates = true appends exactly the other elements welded to the same vertex"""
+    for mr in (meshgen.multires_cube(1, 3), meshgen.multires_plane(3, 3)):
+        orc = GridOracle(mr, leaf_limit=4)
+        ses = capi.GridSession(mr, leaf_limit=4, device=None)
+        weld, _ = _welded_graph(mr)
+        copies = {}
+        for e, w in enumerate(weld):
+            copies.setdefault(int(w), set()).add(e)
+        for e in range(mr.totelem):
+            nb, nd = ses.neighbors(e)
+            assert nd == 0 and nb.tolist() == orc.neighbors(e).tolist(), "element %d" % e
+            nb2, nd2 = ses.neighbors(e, True)
+            assert nb2[:nb2.size - nd2].tolist() == nb.tolist()
+            assert set(nb2[nb2.size - nd2:].tolist()) == copies[int(weld[e])] - {e} and nd2 == len(copies[int(weld[e])]) - 1, e
+        ses.close()
+        orc.close()
