@@ -99,7 +99,7 @@ CUDA_SYMBOLS = [
     "dsc_download_node_flags", "dsc_download_touched", "dsc_upload_co", "dsc_synchronize", "dsc_timer_start",
     "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
     "dsc_dist_unique_id", "dsc_dist_init", "dsc_dist_partition", "dsc_dist_halo_plan", "dsc_dist_free",
-    "dsc_dist_owned_range",
+    "dsc_dist_owned_range", "dsc_dist_grids_plan",
 ]
 HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
@@ -107,6 +107,7 @@ HOST_SYMBOLS = [
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
     "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
+    "DUNE_pbvh_device_attach_grids_dist",
     "DUNE_subdiv_ccg_topology_set", "BKE_subdiv_ccg_neighbor_coords_get", "BKE_subdiv_ccg_coarse_mesh_adjacency_info_get",
     "DUNE_pbvh_draw_buffers_enable", "DUNE_pbvh_update_draw_buffers", "DUNE_pbvh_node_draw_buffer",
     "DUNE_pbvh_raycast_enable", "DUNE_pbvh_raycast_nearest",
@@ -178,6 +179,8 @@ def cuda_lib():
         L.dsc_stage_times.argtypes = [C.c_void_p, c_float_p, c_int_p]
         L.dsc_dist_unique_id.argtypes = [C.c_char_p]
         L.dsc_dist_owned_range.argtypes = [C.c_void_p, c_int_p]
+        L.dsc_dist_grids_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_int_p, c_ubyte_p, c_ubyte_p, c_ubyte_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dsc_dist_free.argtypes = [C.c_void_p]
         L.dsc_dist_free.restype = None
         _cuda = L
@@ -219,6 +222,7 @@ def host_lib():
         L.BKE_subdiv_ccg_neighbor_coords_get.argtypes = [C.c_void_p, C.c_void_p, C.c_bool, C.c_void_p]
         L.BKE_subdiv_ccg_neighbor_coords_get.restype = None
         L.DUNE_pbvh_device_attach_grids.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int]
+        L.DUNE_pbvh_device_attach_grids_dist.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.DUNE_pbvh_draw_buffers_enable.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_draw_buffers_enable.restype = None
         L.DUNE_pbvh_update_draw_buffers.argtypes = [C.POINTER(PBVH), C.c_bool, C.c_bool]
@@ -280,6 +284,14 @@ class DscMeshDesc(C.Structure):
                 ("totloop", C.c_int), ("poly_loopstart", c_int_p), ("poly_totloop", c_int_p), ("loop_vert", c_int_p),
                 ("tottri", C.c_int), ("tri_vert", c_int_p), ("tri_poly", c_int_p), ("nb_offsets", c_int_p),
                 ("nb_indices", c_int_p), ("boundary", c_ubyte_p), ("vert_tail", C.POINTER(C.c_uint))]
+
+
+class DscGridsDesc(C.Structure):
+    _fields_ = [("totgrid", C.c_int), ("grid_size", C.c_int), ("co", c_float_p), ("no", c_float_p), ("mask", c_float_p),
+                ("totface", C.c_int), ("face_start_grid", c_int_p), ("face_num_grids", c_int_p), ("totedge", C.c_int),
+                ("edge_offsets", c_int_p), ("edge_elems", c_int_p), ("totcvert", C.c_int), ("cvert_offsets", c_int_p),
+                ("cvert_elems", c_int_p), ("grid_edge", c_int_p), ("grid_cvert", c_int_p), ("rim_width", C.c_int),
+                ("rim_neighbors", c_int_p), ("rim_boundary", c_ubyte_p)]
 
 
 class DscPbvhDesc(C.Structure):
@@ -666,11 +678,11 @@ class GridSession(SculptSession):
     BKE_pbvh_build_grids -> DUNE_pbvh_device_attach_grids; the dab / download methods are the mesh ones
     (a grid element is a vertex to them)"""
 
-    def __init__(self, mr, leaf_limit=0, device=0):
+    def __init__(self, mr, leaf_limit=0, device=0, dist=None):
         H = host_lib()
         self.H = H
         self.mesh = mr
-        self.dist = None
+        self.dist = dist
         level = int(np.log2(mr.grid_size - 1)) + 1
         assert (1 << (level - 1)) + 1 == mr.grid_size
         co = np.ascontiguousarray(mr.co, dtype=np.float32)
@@ -696,7 +708,11 @@ class GridSession(SculptSession):
         H.BKE_pbvh_build_grids(self.pbvh, ccg.grids, mr.totgrid, self.key, ccg.grid_faces, None, None)
         self.ctx = None
         if device is not None:
-            self._chk(H.DUNE_pbvh_device_attach_grids(self.pbvh, self.ccg, int(device)))
+            if dist is None:
+                self._chk(H.DUNE_pbvh_device_attach_grids(self.pbvh, self.ccg, int(device)))
+            else:
+                world, rank, nid = dist
+                self._chk(H.DUNE_pbvh_device_attach_grids_dist(self.pbvh, self.ccg, int(device), int(world), int(rank), nid))
             self.ctx = C.c_void_p(self.pbvh.contents.device)
             self.D = cuda_lib()
 
@@ -704,6 +720,62 @@ class GridSession(SculptSession):
         out = np.zeros(self.mesh.totelem, dtype=np.float32)
         self._chk(self.D.dsc_download_mask(self.ctx, fptr(out)))
         return out
+
+    def descs(self, with_neighbors=True):
+        """(DscGridsDesc, DscPbvhDesc, keep-alive) of the C ABI from the generator's tables and the host-side grids PBVH;
+        with_neighbors builds the rim neighbour table through the host's BKE_subdiv_ccg_neighbor_coords_get (small meshes)"""
+        mr = self.mesh
+        na = self.node_arrays()
+        keep = {"na": na, "co": np.ascontiguousarray(mr.co, dtype=np.float32), "prims": self.prim_indices().astype(np.int32),
+                "vb": np.ascontiguousarray(na["vb"]), "ovb": np.ascontiguousarray(na["orig_vb"])}
+        gd = DscGridsDesc()
+        gd.totgrid, gd.grid_size, gd.co = mr.totgrid, mr.grid_size, fptr(keep["co"])
+        gd.totface, gd.face_start_grid, gd.face_num_grids = int(mr.face_start.shape[0]), iptr(mr.face_start), iptr(mr.face_num)
+        gd.totedge, gd.edge_offsets, gd.edge_elems = int(mr.edge_off.shape[0] - 1), iptr(mr.edge_off), iptr(mr.edge_elems)
+        gd.totcvert, gd.cvert_offsets, gd.cvert_elems = int(mr.cvert_off.shape[0] - 1), iptr(mr.cvert_off), iptr(mr.cvert_elems)
+        gd.grid_edge, gd.grid_cvert = iptr(mr.grid_edge), iptr(mr.grid_cvert)
+        if with_neighbors and getattr(mr, "edge_verts", None) is not None:
+            gs = mr.grid_size
+            rim = [(b, 0) for b in range(gs)] + [(b, gs - 1) for b in range(gs)] + [(0, y) for y in range(1, gs - 1)] + \
+                  [(gs - 1, y) for y in range(1, gs - 1)]
+            rows = [[self.neighbors(g * gs * gs + y * gs + x)[0] for (x, y) in rim] for g in range(mr.totgrid)]
+            width = max(4, max(len(r) for gr in rows for r in gr))
+            tab = np.full((mr.totgrid, len(rim), width), -1, dtype=np.int32)
+            for g, gr in enumerate(rows):
+                for b, r in enumerate(gr):
+                    tab[g, b, :len(r)] = r
+            keep["rim"] = tab
+            gd.rim_width, gd.rim_neighbors = width, iptr(tab)
+        pd = DscPbvhDesc()
+        pd.totnode = self.totnode
+        pd.node_bb, pd.node_orig_bb = fptr(keep["vb"]), fptr(keep["ovb"])
+        pd.children_offset, pd.flag = iptr(na["children_offset"]), iptr(na["flag"])
+        pd.prim_offset, pd.totprim, pd.prim_indices = iptr(na["prim_offset"]), iptr(na["totprim"]), iptr(keep["prims"])
+        pd.uniq_verts, pd.face_verts = iptr(na["uniq_verts"]), iptr(na["face_verts"])
+        return gd, pd, keep
+
+    def grids_plan(self, world, rank, with_neighbors=True):
+        """dsc_dist_grids_plan of one rank (host only): dict of grid_owner, face_dom, edge_mine, cvert_mine and the
+        per-peer send / receive element lists"""
+        gd, pd, keep = self.descs(with_neighbors=with_neighbors)
+        L = cuda_lib()
+        owner = np.zeros(gd.totgrid, np.int32)
+        face_dom = np.zeros(max(gd.totface, 1), np.uint8)
+        edge_mine = np.zeros(max(gd.totedge, 1), np.uint8)
+        cvert_mine = np.zeros(max(gd.totcvert, 1), np.uint8)
+        ptrs = [c_int_p() for _ in range(4)]
+        r = L.dsc_dist_grids_plan(C.byref(gd), C.byref(pd), int(world), int(rank), iptr(owner), face_dom.ctypes.data_as(c_ubyte_p),
+                                  edge_mine.ctypes.data_as(c_ubyte_p), cvert_mine.ctypes.data_as(c_ubyte_p),
+                                  *[C.byref(p) for p in ptrs])
+        assert r == 0
+        soff = np.ctypeslib.as_array(ptrs[0], shape=(world + 1,)).copy()
+        roff = np.ctypeslib.as_array(ptrs[2], shape=(world + 1,)).copy()
+        se = np.ctypeslib.as_array(ptrs[1], shape=(max(int(soff[-1]), 1),)).copy()[:soff[-1]]
+        re_ = np.ctypeslib.as_array(ptrs[3], shape=(max(int(roff[-1]), 1),)).copy()[:roff[-1]]
+        for p in ptrs:
+            L.dsc_dist_free(p)
+        return dict(grid_owner=owner, face_dom=face_dom[:gd.totface], edge_mine=edge_mine[:gd.totedge],
+                    cvert_mine=cvert_mine[:gd.totcvert], send_off=soff, send_elem=se, recv_off=roff, recv_elem=re_)
 
     def neighbors(self, elem, include_duplicates=False):
         """BKE_subdiv_ccg_neighbor_coords_get of the host library -> (element indices, num_duplicates)"""

@@ -100,6 +100,7 @@ struct DscContext {
   std::vector<int> slot_range;            /* [world + 1] slot bounds of the owned unique-vert runs */
   std::vector<int> send_off, recv_off;    /* [world + 1] into the index lists below */
   int *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  int *d_glist = nullptr, *d_gcount = nullptr; /* partitioned grids: the leaves all ranks gathered this dab */
   float *d_send_buf = nullptr, *d_recv_buf = nullptr;
 
   int *d_slot_of = nullptr;
@@ -383,6 +384,149 @@ struct HaloTriple {
   bool operator==(const HaloTriple &o) const { return reader == o.reader && owner == o.owner && vert == o.vert; }
 };
 
+
+/* ---- partitioned grids: what a rank computes and what it must be sent ----
+ * A rank owns the grids of its leaves.  After the brush it runs the averaging of every group of duplicated elements
+ * that holds an element it owns -- the pairs along the boundaries between the grids of a face and the face centre
+ * (subdiv_ccg.c:951-984), the points of a coarse edge (1010-1048), the corners at a coarse vertex (1081-1104) --
+ * on copies of the other ranks' elements that the halo exchange has made current; every rank that shares a group
+ * computes the same value from the same inputs, so nothing has to be sent back.  One dependency crosses phases:
+ * the two middle points of a coarse edge are first averaged inside each face (they are the last pair of the boundary
+ * between its two grids there), so a rank that averages one half of an edge also runs that pair for every face on
+ * the edge.  The plan below is that closure, enumerated over the tables:
+ *   face_dom[f]   bit 0: some grid of f is owned -- all its pairs and its centre run; bit 1 (alone): only middle pairs on
+ *                 owned edges; bit 2: the face has an owned coarse vertex (it lists it when a dab reaches the face)
+ *   edge_mine[e]  bit h: half h of the edge's 2 * grid_size points (one grid per face and half) holds an owned element
+ *   cvert_mine[v] some corner at the coarse vertex is owned
+ *   need          the elements of other ranks those groups read, plus the neighbours of owned rim elements the smooth
+ *                 brush reads (rim table) */
+struct GridPlan {
+  std::vector<unsigned char> face_dom, edge_mine, cvert_mine;
+  std::vector<int> need; /* ascending element indices, none owned by the rank */
+};
+struct GridTables {
+  int totgrid, gs, totface, totedge, totcvert;
+  const int *face_start, *face_num, *edge_off, *edge_elems, *cvert_off, *cvert_elems, *grid_edge, *grid_cvert;
+  int rim_w;
+  const int *rim_nb; /* or NULL */
+};
+static void plan_grids_rank(const GridTables &t, const std::vector<int> &grid_owner, int rank, GridPlan &pl)
+{
+  const int gs = t.gs, gs2 = gs * gs, rows2 = 2 * gs;
+  auto owner_of = [&](int elem) { return grid_owner[elem / gs2]; };
+  pl.face_dom.assign((size_t)t.totface, 0);
+  pl.edge_mine.assign((size_t)t.totedge, 0);
+  pl.cvert_mine.assign((size_t)t.totcvert, 0);
+  std::vector<int> need;
+  auto want = [&](int elem) {
+    if (owner_of(elem) != rank) need.push_back(elem);
+  };
+  for (int f = 0; f < t.totface; f++) {
+    bool any = false;
+    for (int c = 0; c < t.face_num[f]; c++) any = any || grid_owner[t.face_start[f] + c] == rank;
+    if (!any) continue;
+    pl.face_dom[f] = 1;
+    for (int c = 0; c < t.face_num[f]; c++) {
+      const int g = t.face_start[f] + c;
+      for (int i = 0; i < gs; i++) { /* row y == 0 and column x == 0: every pair of the face and its centre */
+        want(g * gs2 + i);
+        want(g * gs2 + i * gs);
+      }
+    }
+  }
+  for (int e = 0; e < t.totedge; e++) {
+    const int nf = t.edge_off[e + 1] - t.edge_off[e];
+    for (int h = 0; h < 2; h++) {
+      for (int k = 0; k < nf; k++) {
+        if (owner_of(t.edge_elems[(size_t)(t.edge_off[e] + k) * rows2 + h * gs]) == rank) pl.edge_mine[e] |= (unsigned char)(1 << h);
+      }
+    }
+    if (!pl.edge_mine[e]) continue;
+    for (int k = 0; k < nf; k++) {
+      const int *row = t.edge_elems + (size_t)(t.edge_off[e] + k) * rows2;
+      for (int h = 0; h < 2; h++) {
+        if (!(pl.edge_mine[e] & (1 << h))) continue;
+        for (int i = 0; i < gs; i++) want(row[h * gs + i]);
+      }
+      want(row[gs - 1]); /* the middle pair of every face on the edge */
+      want(row[gs]);
+    }
+  }
+  /* faces that only contribute middle pairs: a face with no owned grid on an edge with an owned half */
+  for (int f = 0; f < t.totface; f++) {
+    if (pl.face_dom[f]) continue;
+    for (int c = 0; c < t.face_num[f]; c++) {
+      if (pl.edge_mine[t.grid_edge[t.face_start[f] + c]]) pl.face_dom[f] = 2;
+    }
+  }
+  for (int v = 0; v < t.totcvert; v++) {
+    bool any = false;
+    for (int k = t.cvert_off[v]; k < t.cvert_off[v + 1]; k++) any = any || owner_of(t.cvert_elems[k]) == rank;
+    if (!any) continue;
+    pl.cvert_mine[v] = 1;
+    for (int k = t.cvert_off[v]; k < t.cvert_off[v + 1]; k++) want(t.cvert_elems[k]);
+  }
+  /* a face none of whose grids or edges is ours still lists our coarse vertices when a dab reaches it */
+  for (int f = 0; f < t.totface; f++) {
+    for (int c = 0; c < t.face_num[f]; c++) {
+      if (pl.cvert_mine[t.grid_cvert[t.face_start[f] + c]]) pl.face_dom[f] |= 4;
+    }
+  }
+  if (t.rim_nb) {
+    const int rim = 4 * gs - 4;
+    for (int g = 0; g < t.totgrid; g++) {
+      if (grid_owner[g] != rank) continue;
+      const int *rows = t.rim_nb + (size_t)g * rim * t.rim_w;
+      for (int i = 0; i < rim * t.rim_w; i++) {
+        if (rows[i] >= 0) want(rows[i]);
+      }
+    }
+  }
+  std::sort(need.begin(), need.end());
+  need.erase(std::unique(need.begin(), need.end()), need.end());
+  pl.need.swap(need);
+}
+/* owner rank of every grid: the rank of the leaf that holds it */
+static void plan_grid_owner(const DscPbvhDesc *pb, int world, int totgrid, std::vector<int> &leaves, std::vector<int> &range,
+                            std::vector<int> &grid_owner)
+{
+  plan_partition(pb, world, leaves, range);
+  grid_owner.assign((size_t)totgrid, 0);
+  for (int r = 0; r < world; r++) {
+    for (int l = range[r]; l < range[r + 1]; l++) {
+      const int n = leaves[l];
+      for (int k = 0; k < pb->totprim[n]; k++) grid_owner[pb->prim_indices[pb->prim_offset[n] + k]] = r;
+    }
+  }
+}
+/* send / receive lists of one rank: per peer, ascending element indices (both sides enumerate the same order) */
+static void plan_grids_lists(const GridTables &t, const std::vector<int> &grid_owner, int world, int rank, GridPlan &mine,
+                             std::vector<int> &send_off, std::vector<int> &send_elem, std::vector<int> &recv_off,
+                             std::vector<int> &recv_elem)
+{
+  const int gs2 = t.gs * t.gs;
+  send_off.assign(world + 1, 0);
+  recv_off.assign(world + 1, 0);
+  send_elem.clear();
+  recv_elem.clear();
+  plan_grids_rank(t, grid_owner, rank, mine);
+  for (int q = 0; q < world; q++) {
+    send_off[q] = (int)send_elem.size();
+    recv_off[q] = (int)recv_elem.size();
+    if (q == rank) continue;
+    for (int e : mine.need) {
+      if (grid_owner[e / gs2] == q) recv_elem.push_back(e);
+    }
+    GridPlan theirs;
+    plan_grids_rank(t, grid_owner, q, theirs);
+    for (int e : theirs.need) {
+      if (grid_owner[e / gs2] == rank) send_elem.push_back(e);
+    }
+  }
+  send_off[world] = (int)send_elem.size();
+  recv_off[world] = (int)recv_elem.size();
+}
+
 static void plan_halo(const DscMeshDesc *me, const DscPbvhDesc *pb, int world, const std::vector<int> &leaves,
                       const std::vector<int> &range, std::vector<HaloTriple> &out)
 {
@@ -623,6 +767,42 @@ int dsc_dist_halo_plan(const DscMeshDesc *me, const DscPbvhDesc *pb, int world, 
   return DSC_OK;
 }
 
+
+static GridTables grid_tables_of(const DscGridsDesc *gr)
+{
+  GridTables t;
+  t.totgrid = gr->totgrid; t.gs = gr->grid_size; t.totface = gr->totface; t.totedge = gr->totedge; t.totcvert = gr->totcvert;
+  t.face_start = gr->face_start_grid; t.face_num = gr->face_num_grids; t.edge_off = gr->edge_offsets; t.edge_elems = gr->edge_elems;
+  t.cvert_off = gr->cvert_offsets; t.cvert_elems = gr->cvert_elems; t.grid_edge = gr->grid_edge; t.grid_cvert = gr->grid_cvert;
+  t.rim_w = gr->rim_width; t.rim_nb = gr->rim_neighbors;
+  return t;
+}
+
+int dsc_dist_grids_plan(const DscGridsDesc *gr, const DscPbvhDesc *pb, int world, int rank, int *r_grid_owner,
+                        unsigned char *r_face_dom, unsigned char *r_edge_mine, unsigned char *r_cvert_mine, int **r_send_off,
+                        int **r_send_elem, int **r_recv_off, int **r_recv_elem)
+{
+  if (!gr || !pb || world < 1 || rank < 0 || rank >= world) return DSC_ERR_INVALID;
+  std::vector<int> leaves, range, owner, soff, se, roff, re;
+  plan_grid_owner(pb, world, gr->totgrid, leaves, range, owner);
+  GridPlan pl;
+  plan_grids_lists(grid_tables_of(gr), owner, world, rank, pl, soff, se, roff, re);
+  if (r_grid_owner) memcpy(r_grid_owner, owner.data(), sizeof(int) * owner.size());
+  if (r_face_dom) memcpy(r_face_dom, pl.face_dom.data(), pl.face_dom.size());
+  if (r_edge_mine) memcpy(r_edge_mine, pl.edge_mine.data(), pl.edge_mine.size());
+  if (r_cvert_mine) memcpy(r_cvert_mine, pl.cvert_mine.data(), pl.cvert_mine.size());
+  auto dup = [](const std::vector<int> &v) {
+    int *p = (int *)malloc(sizeof(int) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(int) * v.size());
+    return p;
+  };
+  if (r_send_off) *r_send_off = dup(soff);
+  if (r_send_elem) *r_send_elem = dup(se);
+  if (r_recv_off) *r_recv_off = dup(roff);
+  if (r_recv_elem) *r_recv_elem = dup(re);
+  return DSC_OK;
+}
+
 void dsc_dist_free(void *p) { free(p); }
 
 int dsc_dist_owned_range(DscContext *ctx, int r_range[2])
@@ -673,7 +853,6 @@ int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *gr)
 {
   if (!ctx || !gr) return fail(ctx, DSC_ERR_INVALID, "NULL argument");
   if (ctx->have_mesh) return fail(ctx, DSC_ERR_STATE, "a mesh is already resident in this context");
-  if (ctx->world > 1) return fail(ctx, DSC_ERR_UNSUPPORTED, "grids are not partitioned across GPUs yet");
   if (gr->totgrid <= 0 || gr->grid_size < 2 || !gr->co) return fail(ctx, DSC_ERR_INVALID, "empty grid set");
   if (!gr->face_start_grid || !gr->face_num_grids || !gr->edge_offsets || !gr->edge_elems || !gr->cvert_offsets ||
       !gr->cvert_elems || !gr->grid_edge || !gr->grid_cvert)
@@ -935,7 +1114,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       if ((r = dev_upload_c(ctx, &gn.rim_bnd, ctx->h_rim_bnd)) || (r = dev_upload_c(ctx, &m.boundary, bnd))) return r;
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    std::vector<int>().swap(ctx->h_rim_nb);
   }
   if (ctx->has_nb && !ctx->is_grids) {
     if ((r = dev_zero(ctx, &m.tx, (size_t)VP)) || (r = dev_zero(ctx, &m.ty, (size_t)VP)) || (r = dev_zero(ctx, &m.tz, (size_t)VP))) return r;
@@ -1499,6 +1677,42 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       const int l = ctx->leaf_range[q];
       ctx->slot_range[q] = (l < L) ? leaf_ubeg[l] : ((L ? leaf_ubeg[L - 1] + leaf_ucnt[L - 1] + 31 : 0) & ~31);
     }
+    std::vector<int> sidx, ridx;
+    if (ctx->is_grids) {
+      /* partitioned grids: what this rank averages after the brush, and the halo elements (plan_grids_rank) */
+      GridTables t;
+      t.totgrid = ctx->totgrid; t.gs = ctx->grid_size; t.totface = (int)ctx->h_face_start.size();
+      t.totedge = (int)ctx->h_edge_off.size() - 1; t.totcvert = (int)ctx->h_cvert_off.size() - 1;
+      t.face_start = ctx->h_face_start.data(); t.face_num = ctx->h_face_num.data(); t.edge_off = ctx->h_edge_off.data();
+      t.edge_elems = ctx->h_edge_elems.data(); t.cvert_off = ctx->h_cvert_off.data(); t.cvert_elems = ctx->h_cvert_elems.data();
+      t.grid_edge = ctx->h_grid_edge.data(); t.grid_cvert = ctx->h_grid_cvert.data();
+      t.rim_w = ctx->rim_width; t.rim_nb = ctx->h_rim_nb.empty() ? nullptr : ctx->h_rim_nb.data();
+      std::vector<int> grid_owner((size_t)ctx->totgrid, 0);
+      for (int q = 0; q < ctx->world; q++) {
+        for (int l = ctx->leaf_range[q]; l < ctx->leaf_range[q + 1]; l++) {
+          for (int k = 0; k < leaf_pcnt[l]; k++) grid_owner[pb->prim_indices[leaf_pbeg[l] + k]] = q;
+        }
+      }
+      GridPlan plan;
+      std::vector<int> se, re;
+      plan_grids_lists(t, grid_owner, ctx->world, ctx->rank, plan, ctx->send_off, se, ctx->recv_off, re);
+      sidx.resize(se.size());
+      ridx.resize(re.size());
+      for (size_t i = 0; i < se.size(); i++) sidx[i] = ctx->slot_of[se[i]];
+      for (size_t i = 0; i < re.size(); i++) ridx[i] = ctx->slot_of[re[i]];
+      DevGrids &g = ctx->g;
+      if ((r = dev_upload_c(ctx, &g.face_dom, plan.face_dom)) || (r = dev_upload_c(ctx, &g.edge_mine, plan.edge_mine)) ||
+          (r = dev_upload_c(ctx, &g.cvert_mine, plan.cvert_mine)) || (r = dev_upload_c(ctx, &g.grid_owner, grid_owner)) ||
+          (r = dev_zero(ctx, &ctx->d_glist, (size_t)L + 1)) || (r = dev_zero(ctx, &ctx->d_gcount, 1)))
+        return r;
+      g.rank = ctx->rank;
+      ctx->grid_fused = false;
+      if ((r = dev_upload(ctx, &ctx->d_send_idx, sidx)) || (r = dev_upload(ctx, &ctx->d_recv_idx, ridx)) ||
+          (r = dev_alloc(ctx, &ctx->d_send_buf, 3 * sidx.size() + 1)) || (r = dev_alloc(ctx, &ctx->d_recv_buf, 3 * ridx.size() + 1)))
+        return r;
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    else {
     DscMeshDesc me;
     memset(&me, 0, sizeof(me));
     me.totvert = V;
@@ -1514,7 +1728,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     me.nb_indices = ctx->has_nb ? ctx->h_nb_idx.data() : nullptr;
     std::vector<HaloTriple> tr;
     plan_halo(&me, pb, ctx->world, pl, ctx->leaf_range, tr);
-    std::vector<int> sidx, ridx;
     ctx->send_off.assign(ctx->world + 1, 0);
     ctx->recv_off.assign(ctx->world + 1, 0);
     for (int q = 0; q < ctx->world; q++) {
@@ -1531,9 +1744,11 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         (r = dev_alloc(ctx, &ctx->d_send_buf, 3 * sidx.size() + 1)) || (r = dev_alloc(ctx, &ctx->d_recv_buf, 3 * ridx.size() + 1)))
       return r;
     CU(cudaStreamSynchronize(ctx->stream));
+    }
   }
 
   /* the host staging copies are no longer needed */
+  std::vector<int>().swap(ctx->h_rim_nb);
   std::vector<float>().swap(ctx->h_co);
   std::vector<float>().swap(ctx->h_no);
   std::vector<float>().swap(ctx->h_mask);
@@ -1652,16 +1867,17 @@ static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
   return DSC_OK;
 }
 /* one-ring halo: owners push the positions other ranks' leaves read */
-static int dist_halo_exchange(DscContext *ctx)
+static int dist_halo_exchange(DscContext *ctx, bool normals = false)
 {
   const int W = ctx->world;
+  float *ax = normals ? ctx->m.nx : ctx->m.cx, *ay = normals ? ctx->m.ny : ctx->m.cy, *az = normals ? ctx->m.nz : ctx->m.cz;
   const int ns = ctx->send_off[W], nr = ctx->recv_off[W];
   /* per peer the buffer holds [3][count] */
   for (int q = 0; q < W; q++) {
     const int n = ctx->send_off[q + 1] - ctx->send_off[q];
     if (n) {
       k_halo_pack<<<std::min((n + 255) / 256, ctx->num_sms * 4), 256, 0, ctx->stream>>>(
-          ctx->d_send_buf + 3 * (size_t)ctx->send_off[q], ctx->d_send_idx + ctx->send_off[q], n, ctx->m.cx, ctx->m.cy, ctx->m.cz);
+          ctx->d_send_buf + 3 * (size_t)ctx->send_off[q], ctx->d_send_idx + ctx->send_off[q], n, ax, ay, az);
       LAUNCH_CHECK();
       ctx->launches++;
     }
@@ -1679,7 +1895,7 @@ static int dist_halo_exchange(DscContext *ctx)
     const int k = ctx->recv_off[q + 1] - ctx->recv_off[q];
     if (k) {
       k_halo_unpack<<<std::min((k + 255) / 256, ctx->num_sms * 4), 256, 0, ctx->stream>>>(
-          ctx->d_recv_buf + 3 * (size_t)ctx->recv_off[q], ctx->d_recv_idx + ctx->recv_off[q], k, ctx->m.cx, ctx->m.cy, ctx->m.cz);
+          ctx->d_recv_buf + 3 * (size_t)ctx->recv_off[q], ctx->d_recv_idx + ctx->recv_off[q], k, ax, ay, az);
       LAUNCH_CHECK();
       ctx->launches++;
     }
@@ -1699,6 +1915,8 @@ static int dist_gather_all(DscContext *ctx)
     const int l0 = ctx->leaf_range[q], ln = ctx->leaf_range[q + 1] - l0;
     if (sn > 0) {
       for (int a = 0; a < 12; a++) NC(g_nccl.Broadcast(vert_arrays[a] + s0, vert_arrays[a] + s0, (size_t)sn, ncclFloat, q, ctx->comm, ctx->stream));
+      /* grids: the stitch averages the mask layer too */
+      if (ctx->is_grids && ctx->g.mask) NC(g_nccl.Broadcast(ctx->g.mask + s0, ctx->g.mask + s0, (size_t)sn, ncclFloat, q, ctx->comm, ctx->stream));
     }
     if (ln > 0) {
       for (int k = 0; k < 6; k++) NC(g_nccl.Broadcast(m.bb + (size_t)k * N + l0, m.bb + (size_t)k * N + l0, (size_t)ln, ncclFloat, q, ctx->comm, ctx->stream));
@@ -1722,7 +1940,9 @@ static int grids_reset_counts(DscContext *ctx)
 /* KERNEL_subdiv_ccg_average_grids (subdiv_ccg.c:1170-1189): every face, edge and vertex */
 static int grids_average_all(DscContext *ctx)
 {
-  DevGrids &g = ctx->g;
+  DevGrids g = ctx->g;
+  g.face_dom = g.edge_mine = g.cvert_mine = nullptr; /* every replica averages everything */
+  g.grid_owner = nullptr;
   std::vector<int> iota((size_t)g.totface);
   for (int f = 0; f < g.totface; f++) iota[f] = f;
   GridCounts c = {g.totface, 0, 0, 0};
@@ -1773,7 +1993,16 @@ static int grids_after_brush(DscContext *ctx, LeafList hits)
     CU(cudaLaunchKernelEx(&cfg, k_grid_dab, m, g, hits.list, hits.count, seq));
     return DSC_OK;
   }
-  k_grid_faces<<<ctx->num_sms * 2, DSC_BLOCK, 0, st>>>(m, g, hits.list, hits.count, seq);
+  const bool dist = ctx->world > 1;
+  if (dist) {
+    /* the faces of the leaves ALL ranks gathered (the all-reduced bitmask), restricted to what this rank averages */
+    CU(cudaMemsetAsync(ctx->d_gcount, 0, sizeof(int), st));
+    k_ghit_expand<<<std::max(1, std::min(ctx->num_sms, (m.ghit_words + DSC_BLOCK - 1) / DSC_BLOCK)), DSC_BLOCK, 0, st>>>(m, hits.mask, ctx->d_glist, ctx->d_gcount);
+    LAUNCH_CHECK();
+    k_grid_faces<<<ctx->num_sms * 2, DSC_BLOCK, 0, st>>>(m, g, ctx->d_glist, ctx->d_gcount, seq);
+    ctx->launches++;
+  }
+  else k_grid_faces<<<ctx->num_sms * 2, DSC_BLOCK, 0, st>>>(m, g, hits.list, hits.count, seq);
   LAUNCH_CHECK();
   /* multires_stitch_grids (multires.c:1171-1196 -> subdiv_ccg.c:1303-1324): the faces' inner boundaries, then
    * all coarse edges (two-face edges no dab touched average to themselves: only the touched ones and those with
@@ -1792,6 +2021,7 @@ static int grids_after_brush(DscContext *ctx, LeafList hits)
   /* BKE_pbvh_update_normals, PBVH_GRIDS branch (pbvh.c:4575-4583 -> subdiv_ccg.c:847-866) */
   k_grid_normals<<<ctx->num_sms * 2, GN_BLOCK, ctx->gn_smem, st>>>(m, g, 0);
   LAUNCH_CHECK();
+  if (dist && (r = dist_halo_exchange(ctx, true))) return r; /* the new normals of the other ranks' halo elements */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
   LAUNCH_CHECK();
   k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 0, seq);

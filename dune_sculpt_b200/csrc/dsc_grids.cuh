@@ -28,6 +28,12 @@ struct DevGrids {
   float *mask; /* per-slot mask layer (averaged along with co / no), or NULL */
   int max_face_grids; /* most corners of a face */
   int has_odd_edges;  /* some coarse edge has more than two faces */
+  /* partitioned across GPUs (NULL on one): what this rank averages after the brush -- see plan_grids_rank in dsc_api.cu.
+   * face_dom bit 0: a grid of the face is owned (all pairs + centre), bit 1: only middle pairs on edges with an owned
+   * half, bit 2: only lists an owned coarse vertex; edge_mine bit h: half h of the edge's points; cvert_mine */
+  const unsigned char *face_dom, *edge_mine, *cvert_mine;
+  const int *grid_owner;
+  int rank;
 };
 
 /* Every stage below is a __device__ body over (cta, ncta) so that it runs either as its own kernel or as
@@ -45,13 +51,15 @@ __device__ __forceinline__ void dsc_grid_faces_body(const DevGrids &g, const int
     const int b = g.leaf_gbeg[l], e = g.leaf_gbeg[l + 1];
     for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
       const int f = g.grid_face[g.leaf_grids[i]];
+      const int dom = g.face_dom ? g.face_dom[f] : 1;
+      if (!dom) continue;
       if (atomicExch(&g.face_stamp[f], seq) == seq) continue;
-      g.face_list[atomicAdd(&g.cnt->faces, 1)] = f;
+      if (dom & 3) g.face_list[atomicAdd(&g.cnt->faces, 1)] = f;
       const int start = g.face_start[f], nc = g.face_num[f];
       for (int c = 0; c < nc; c++) {
         const int ed = g.grid_edge[start + c], v = g.grid_cvert[start + c];
-        if (atomicExch(&g.edge_stamp[ed], seq) != seq) g.edge_list[atomicAdd(&g.cnt->edges, 1)] = ed;
-        if (atomicExch(&g.cvert_stamp[v], seq) != seq) g.cvert_list[atomicAdd(&g.cnt->cverts, 1)] = v;
+        if ((!g.edge_mine || g.edge_mine[ed]) && atomicExch(&g.edge_stamp[ed], seq) != seq) g.edge_list[atomicAdd(&g.cnt->edges, 1)] = ed;
+        if ((!g.cvert_mine || g.cvert_mine[v]) && atomicExch(&g.cvert_stamp[v], seq) != seq) g.cvert_list[atomicAdd(&g.cnt->cverts, 1)] = v;
       }
     }
   }
@@ -156,10 +164,15 @@ __device__ __forceinline__ void dsc_grid_inner_body(const DevMesh &m, const DevG
     const int corner = r / per, i = 1 + r % per;
     if (corner >= nc) continue;
     const int grid = start + corner, prev = start + (corner + nc - 1) % nc;
+    if (g.face_dom && !(g.face_dom[f] & 1)) {
+      /* no grid of this face is ours: only the middle pair of an edge we average (it sits on the edge leaving `prev`) */
+      if (i != per || !g.edge_mine[g.grid_edge[prev]]) continue;
+    }
     dsc_grid_average_pair(m, g, g.grid_slot0[prev] + i, g.grid_slot0[grid] + i * g.gs);
   }
   for (int h = cta * blockDim.x + threadIdx.x; h < n; h += ncta * blockDim.x) {
     const int f = __ldcg(&g.face_list[h]);
+    if (g.face_dom && !(g.face_dom[f] & 1)) continue;
     dsc_grid_average_list(m, g, g.grid_slot0 + g.face_start[f], g.face_num[f], 1);
   }
 }
@@ -179,6 +192,7 @@ __device__ __forceinline__ void dsc_grid_edges_body(const DevMesh &m, const DevG
     const int nf = g.edge_off[e + 1] - g.edge_off[e];
     if (nf == 1) continue;
     if (all == 1 && (nf == 2 || g.edge_stamp[e] == seq)) continue;
+    if (g.edge_mine && !((g.edge_mine[e] >> (i >= g.gs ? 1 : 0)) & 1)) continue;
     dsc_grid_average_list(m, g, g.edge_slots + (size_t)g.edge_off[e] * gs2 + i, nf, gs2);
   }
 }
@@ -191,6 +205,7 @@ __device__ __forceinline__ void dsc_grid_cverts_body(const DevMesh &m, const Dev
     const int v = all ? i : __ldcg(&g.cvert_list[i]);
     const int nf = g.cvert_off[v + 1] - g.cvert_off[v];
     if (nf == 1) continue;
+    if (g.cvert_mine && !g.cvert_mine[v]) continue;
     dsc_grid_average_list(m, g, g.cvert_slots + g.cvert_off[v], nf, 1);
   }
 }
@@ -217,6 +232,7 @@ __device__ __forceinline__ void dsc_grid_normals_body(const DevMesh &m, const De
       const int f = __ldcg(&g.face_list[u / mfg]), c = u % mfg;
       if (c >= g.face_num[f]) continue;
       grid = g.face_start[f] + c;
+      if (g.grid_owner && g.grid_owner[grid] != g.rank) continue; /* its owner sends the rim normals */
     }
     const int s0 = g.grid_slot0[grid];
     __syncthreads();
@@ -317,6 +333,21 @@ __device__ __forceinline__ void dsc_grid_leaf_bb_body(const DevMesh &m, const in
       float v = red[tid][0];
       for (int w = 1; w < nw; w++) v = (tid < 3) ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
       m.bb[tid * tn + l] = v;
+    }
+  }
+}
+
+/* partitioned: the leaves every rank gathered this dab (the all-reduced bitmask) as a list, any order */
+__global__ void __launch_bounds__(DSC_BLOCK) k_ghit_expand(DevMesh m, const unsigned *ghit, int *list, int *count)
+{
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < m.ghit_words; w += gridDim.x * blockDim.x) {
+    unsigned bits = ghit[w];
+    if (!bits) continue;
+    int at = atomicAdd(count, __popc(bits));
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      list[at++] = 32 * w + b;
     }
   }
 }

@@ -672,6 +672,11 @@ void DUNE_subdiv_ccg_free(SubdivCCG *ccg)
 /* the CCG's elements and adjacency as the flat tables of DscGridsDesc, the grids PBVH as DscPbvhDesc */
 int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *ccg, int device)
 {
+  return DUNE_pbvh_device_attach_grids_dist(pbvh, ccg, device, 1, 0, NULL);
+}
+
+int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, int world, int rank, const char *nccl_id)
+{
   g_attach_error[0] = 0;
   if (!pbvh || !pbvh->nodes || !pbvh->is_grids || !ccg) return DSC_ERR_INVALID;
   if (pbvh->device) return DSC_OK;
@@ -680,6 +685,14 @@ int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *ccg, int device)
   if (r != DSC_OK) {
     snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(NULL));
     return r;
+  }
+  if (world > 1) {
+    r = dsc_dist_init(ctx, world, rank, nccl_id);
+    if (r != DSC_OK) {
+      snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(ctx));
+      dsc_ctx_destroy(ctx);
+      return r;
+    }
   }
   const CCGKey *key = &pbvh->gridkey;
   const int gs = key->grid_size, area = key->grid_area, G = pbvh->totgrid, N = pbvh->totnode;

@@ -268,6 +268,8 @@ bool DUNE_pbvh_raycast_nearest(PBVH *pbvh, const float ray_start[3], const float
                                float r_face_normal[3], PBVHNode **r_node);
 /* the same for a grids PBVH: the CCG's elements and adjacency go to the device */
 int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device);
+/* one rank of a grids PBVH partitioned across the GPUs of one box (multires meshes too large or too slow for one) */
+int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device, int world, int rank, const char *nccl_id);
 /* one rank of a PBVH partitioned across the GPUs of one box (see dsc_dist_init) */
 int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, const char *nccl_id);
 void DUNE_pbvh_device_detach(PBVH *pbvh);

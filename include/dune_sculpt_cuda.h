@@ -285,7 +285,10 @@ int dsc_synchronize(DscContext *ctx);
  *     the bitmask of gathered leaves) and one exchange of the one-ring halo positions; at stroke
  *     end the owned vertex runs and leaf boxes are all-gathered (the BB-root reduction) so every
  *     replica is whole again.  Call order: dsc_ctx_create, dsc_dist_init, dsc_mesh_upload,
- *     dsc_pbvh_upload.  Not in the reference. ------------------------- */
+ *     dsc_pbvh_upload.  Not in the reference.
+ *     Grids (dsc_grids_upload instead of dsc_mesh_upload): per dab two more exchanges -- the positions of the halo
+ *     elements after the brush (and after every smoothing iteration), their normals after the CCG normal pass -- and
+ *     every rank averages the groups of duplicated elements that hold one of its own (see dsc_dist_grids_plan). --- */
 #define DSC_NCCL_ID_BYTES 128
 int dsc_dist_unique_id(char id[DSC_NCCL_ID_BYTES]); /* rank 0 makes it, the host broadcasts it */
 int dsc_dist_init(DscContext *ctx, int world, int rank, const char id[DSC_NCCL_ID_BYTES]);
@@ -297,6 +300,14 @@ int dsc_dist_partition(const DscPbvhDesc *pbvh, int world, int *r_leaf_range, in
  * dsc_dist_free.  r_send_off / r_recv_off have world + 1 entries. */
 int dsc_dist_halo_plan(const DscMeshDesc *mesh, const DscPbvhDesc *pbvh, int world, int rank, int **r_send_off,
                        int **r_send_vert, int **r_recv_off, int **r_recv_vert);
+/* the same for partitioned grids, no device needed: r_grid_owner[totgrid]; what the rank computes after the brush --
+ * r_face_dom[totface] (1: a grid of the face is owned, all its inner boundaries and its centre are averaged here; 2: only
+ * the middle pairs on edges with an owned half), r_edge_mine[totedge] (bit h: half h of the coarse edge's points),
+ * r_cvert_mine[totcvert] -- and per peer the elements it sends (owns) and receives (other ranks' elements those groups and
+ * the smooth brush's neighbour lookups read), ascending element indices.  Arrays malloc'd; dsc_dist_free. */
+int dsc_dist_grids_plan(const DscGridsDesc *grids, const DscPbvhDesc *pbvh, int world, int rank, int *r_grid_owner,
+                        unsigned char *r_face_dom, unsigned char *r_edge_mine, unsigned char *r_cvert_mine, int **r_send_off,
+                        int **r_send_elem, int **r_recv_off, int **r_recv_elem);
 void dsc_dist_free(void *p);
 /* leaf nodes this rank owns: r_range[2] = first and one-past-last leaf in traversal order */
 int dsc_dist_owned_range(DscContext *ctx, int r_range[2]);

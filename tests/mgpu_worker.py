@@ -12,7 +12,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 
 from dune_sculpt_b200 import capi, meshgen, stroke  # noqa: E402
-from oracle_py import Oracle  # noqa: E402
+from oracle_py import GridOracle, Oracle  # noqa: E402
 
 
 def main():
@@ -28,6 +28,8 @@ def main():
             time.sleep(0.05)
             assert time.time() - t0 < 120, "no NCCL id from rank 0"
         nid = open(idfile, "rb").read()
+    if scenario.startswith("multires"):
+        return multires(world, rank, nid, scenario)
     if scenario == "grid":
         mesh, ll = meshgen.grid(257), 900
         diag = mesh.bbox_diag()
@@ -67,6 +69,63 @@ def main():
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
     print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d" %
           (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs()), flush=True)
+    ses.close()
+
+
+def multires(world, rank, nid, scenario):
+    """partitioned multires grids: smooth, draw, inflate, grab and clay strips dabs that straddle the partition cuts;
+    after stroke end every replica must hold the oracle's elements, normals, mask layer and boxes, bit for bit"""
+    if scenario == "multires_open":
+        mr, ll = meshgen.multires_plane(6, 4, noise=0.04, freq=9.0, with_mask=True), 3
+        centres = [(-0.5 + 0.25 * i, 0.1 * i - 0.2, 0.0) for i in range(5)]
+    else:
+        mr, ll = meshgen.multires_cube(2, 4, noise=0.03, freq=13.0, with_mask=True), 5
+        rng_ = np.random.default_rng(11)
+        centres = [p / np.linalg.norm(p) for p in rng_.normal(size=(6, 3))]
+    diag = mr.bbox_diag()
+    dabs = []
+    for i, c in enumerate(centres):
+        c = np.asarray(c, dtype=np.float32)
+        n = tuple(c / max(np.linalg.norm(c), 1e-9)) if scenario != "multires_open" else (0.0, 0.0, 1.0)
+        dabs.append(capi.make_dab(capi.TOOL_SMOOTH, c, diag * 0.22, bstrength=stroke._strength(capi.TOOL_SMOOTH, 0.6)))
+        dabs.append(capi.make_dab(capi.TOOL_DRAW, c, diag * (0.12 + 0.05 * i), bstrength=stroke._strength(capi.TOOL_DRAW, 0.5),
+                                  view_normal=n, flags=capi.DAB_FIRST_STEP if i == 0 else 0))
+        dabs.append(capi.make_dab(capi.TOOL_INFLATE, c, diag * 0.3, bstrength=stroke._strength(capi.TOOL_INFLATE, 0.5), view_normal=n))
+        dabs.append(capi.make_dab(capi.TOOL_CLAY_STRIPS, c, diag * 0.25, bstrength=stroke._strength(capi.TOOL_CLAY_STRIPS, 0.5),
+                                  view_normal=n, grab_delta=(0.03, 0.01, 0.02)))
+    dabs.append(capi.make_dab(capi.TOOL_GRAB, np.asarray(centres[0], dtype=np.float32), diag * 0.3,
+                              bstrength=stroke._strength(capi.TOOL_GRAB, 0.5), grab_delta=(0.02, -0.03, 0.04)))
+    orc = GridOracle(mr, leaf_limit=ll)
+    ses = capi.GridSession(mr, leaf_limit=ll, device=rank, dist=(world, rank, nid))
+    rng, owner = ses.partition(world)
+    orc.stroke_begin(None)
+    ses.stroke_begin(None)
+    for i, d in enumerate(dabs):
+        orc.dab(d)
+        ses.dab(d)
+        ho = orc.hits()
+        mine = ho[owner[ho] == rank]
+        hg = ses.hits()
+        assert np.array_equal(mine, hg), "rank %d dab %d: own hit list differs (%d vs %d)" % (rank, i, mine.size, hg.size)
+    orc.stroke_end()
+    ses.stroke_end()
+    co_o, co_g = orc.co(), ses.co()
+    bad = np.nonzero((co_o != co_g).any(axis=1))[0]
+    gs2 = mr.grid_size ** 2
+    assert bad.size == 0, "rank %d: %d positions differ (max %g), first elements %s (grid, y, x) %s" % (
+        rank, bad.size, np.abs(co_o - co_g).max(), bad[:8], [(int(b) // gs2, (int(b) % gs2) // mr.grid_size, int(b) % mr.grid_size) for b in bad[:8]])
+    no_o, no_g = orc.no(), ses.no()
+    badn = np.nonzero((no_o != no_g).any(axis=1))[0]
+    assert badn.size == 0, "rank %d: %d normals differ, first (grid, y, x) %s" % (
+        rank, badn.size, [(int(b) // gs2, (int(b) % gs2) // mr.grid_size, int(b) % mr.grid_size) for b in badn[:8]])
+    assert np.array_equal(orc.mask(), ses.mask()), "rank %d: mask layer differs" % rank
+    na = orc.node_arrays()
+    bb, obb = ses.node_bb()
+    assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: boxes differ" % rank
+    assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
+    assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
+    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d" %
+          (rank, world, scenario, rng[rank], rng[rank + 1], ses.stats()["vertex_dabs"], orc.vertex_dabs()), flush=True)
     ses.close()
 
 

@@ -124,3 +124,111 @@ def test_partition_shapes():
     for n in depth2:
         assert len(set(owner[leaves_under(int(n))].tolist())) == 1
     ses.close()
+
+
+def _grids_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dune_sculpt_b200 import capi, meshgen
+        mr = meshgen.multires_cube(1, 3)      # 24 faces, 96 grids of 5 x 5
+        gs, gs2 = mr.grid_size, mr.grid_size ** 2
+        ses = capi.GridSession(mr, leaf_limit=3, device=None)
+        plan = ses.grids_plan(world, rank)
+        rng, node_owner = ses.partition(world)
+        na = ses.node_arrays()
+        prims = ses.prim_indices()
+        # a grid belongs to the rank of its leaf
+        gowner = np.full(mr.totgrid, -1)
+        for n in np.nonzero(na["flag"] & 1)[0]:
+            gowner[prims[na["prim_offset"][n]:na["prim_offset"][n] + na["totprim"][n]]] = node_owner[n]
+        assert np.array_equal(gowner, plan["grid_owner"]) and set(gowner.tolist()) == set(range(world))
+        eowner = np.repeat(gowner, gs2)
+        mine = eowner == rank
+        have = mine.copy()
+        have[plan["recv_elem"]] = True
+        assert not mine[plan["recv_elem"]].any() and mine[plan["send_elem"]].all()
+        # every group of duplicated elements with an owned member is computed here, on current inputs
+        F = mr.face_start.shape[0]
+        fdom = np.array([(gowner[mr.face_start[f]:mr.face_start[f] + mr.face_num[f]] == rank).any() for f in range(F)])
+        assert np.array_equal((plan["face_dom"] & 1).astype(bool), fdom)
+        for f in np.nonzero(fdom)[0]:
+            for c in range(mr.face_num[f]):
+                g = mr.face_start[f] + c
+                i = np.arange(gs)
+                assert have[g * gs2 + i].all() and have[g * gs2 + i * gs].all()
+        rows = mr.edge_elems.reshape(-1, 2 * gs)
+        for e in range(mr.edge_off.shape[0] - 1):
+            r_ = rows[mr.edge_off[e]:mr.edge_off[e + 1]]
+            for h in range(2):
+                owned_half = mine[r_[:, h * gs:(h + 1) * gs]].any()
+                assert bool((plan["edge_mine"][e] >> h) & 1) == bool(owned_half), (e, h)
+                if owned_half:
+                    assert have[r_[:, h * gs:(h + 1) * gs]].all()
+                    assert have[r_[:, gs - 1:gs + 1]].all()           # the middle pair of every face on the edge
+                    for k in range(r_.shape[0]):                       # ... which that face's inner pass runs here
+                        f = int(np.searchsorted(mr.face_start, r_[k, 0] // gs2, side="right") - 1)
+                        assert plan["face_dom"][f] & 3
+        for v in range(mr.cvert_off.shape[0] - 1):
+            el = mr.cvert_elems[mr.cvert_off[v]:mr.cvert_off[v + 1]]
+            assert bool(plan["cvert_mine"][v]) == bool(mine[el].any())
+            if mine[el].any():
+                assert have[el].all()
+                for x in el:                                            # every face around it lists it
+                    f = int(np.searchsorted(mr.face_start, x // gs2, side="right") - 1)
+                    assert plan["face_dom"][f] != 0
+        # smooth brush: the neighbours of every owned element
+        for e in np.nonzero(mine)[0]:
+            assert have[ses.neighbors(int(e))[0]].all(), "element %d reads a stale neighbour" % e
+        # symmetry with the peer over the wire, then a simulated exchange
+        peer = 1 - rank
+        so, ro = plan["send_off"], plan["recv_off"]
+        send_ids = torch.from_numpy(plan["send_elem"][so[peer]:so[peer + 1]].astype(np.int64))
+        n_recv = torch.zeros(1, dtype=torch.long)
+        n_send = torch.tensor([send_ids.numel()], dtype=torch.long)
+        if rank == 0:
+            dist.send(n_send, peer); dist.recv(n_recv, peer)
+        else:
+            dist.recv(n_recv, peer); dist.send(n_send, peer)
+        assert int(n_recv) == ro[peer + 1] - ro[peer]
+        recv_ids = torch.zeros(int(n_recv), dtype=torch.long)
+        truth = mr.co.astype(np.float64) * (1.0 + 0.01 * (eowner[:, None] + 1))
+        local = mr.co.astype(np.float64).copy()
+        local[mine] = truth[mine]
+        payload = torch.from_numpy(local[send_ids.numpy()])
+        got = torch.zeros((int(n_recv), 3), dtype=torch.float64)
+        if rank == 0:
+            dist.send(send_ids, peer); dist.recv(recv_ids, peer); dist.send(payload, peer); dist.recv(got, peer)
+        else:
+            dist.recv(recv_ids, peer); dist.send(send_ids, peer); dist.recv(got, peer); dist.send(payload, peer)
+        assert np.array_equal(recv_ids.numpy(), plan["recv_elem"][ro[peer]:ro[peer + 1]])
+        local[recv_ids.numpy()] = got.numpy()
+        assert np.array_equal(local[have], truth[have])
+        ses.close()
+        q.put((rank, "ok", int(plan["send_elem"].size), int(plan["recv_elem"].size)))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc()), 0, 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grids_partition_plan_world2_gloo():
+    """partitioned multires grids: ownership, the groups a rank averages, the halo closure (incl. the middle pairs
+    of shared edges and the smooth brush's neighbours) and the symmetry of the send / receive lists"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grids_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, ns, nr in sorted(res):
+        assert status == "ok", "rank %d: %s" % (rank, status)
+        assert ns > 0 and nr > 0

@@ -19,7 +19,7 @@ def _device_count():
         return 0
 
 
-@pytest.mark.parametrize("scenario", ["grid", "ico"])
+@pytest.mark.parametrize("scenario", ["grid", "ico", "multires", "multires_open"])
 def test_partitioned_stroke_matches_oracle(scenario):
     n = _device_count()
     if n < 2:
