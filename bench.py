@@ -190,7 +190,11 @@ def workload_config(args, mesh, ndabs):
                             "then %d draw dabs, each + stitch + CCG normals + BB, r = 8%% bbox diag, %d dabs/stroke" %
                             (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, args.c5_smooth_dabs,
                              args.c5_dabs, ndabs),
-                "parallelism": "single GPU", "verts": mesh.totelem, "dabs_per_step": ndabs,
+                "parallelism": "single GPU" if world == 1 else
+                               "grids PBVH partitioned spatially over %d GPUs (same mesh: strong scaling); per dab one NCCL all-reduce "
+                               "(area sums + hit mask), the rim positions after the brush / every smoothing iteration and the rim "
+                               "normals after the CCG normal pass exchanged with the neighbouring ranks" % world,
+                "verts": mesh.totelem, "dabs_per_step": ndabs,
                 "brush": "smooth (alpha 0.75) then draw (alpha 0.5), SMOOTH falloff, area-normal direction",
                 "l2": "inputs larger than L2 (resident element arrays > 2 GB)" if mesh.totelem > 8000000 else "small mesh: L2 resident",
                 "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
@@ -285,9 +289,7 @@ def run_ours(args, rank, world):
         dist.broadcast(idt, 0)
         dist_arg = (world, rank, bytes(idt.cpu().numpy().tobytes()))
     if args.config == "c5":
-        if world > 1:
-            raise SystemExit("config c5: the grids path is single-GPU (DESIGN.md section 5)")
-        ses = capi.GridSession(mesh, device=local_rank)
+        ses = capi.GridSession(mesh, device=local_rank, dist=dist_arg)
     else:
         ses = capi.SculptSession(mesh, device=local_rank, dist=dist_arg)  # fails loudly without a device / the .so
     na = ses.node_arrays()

@@ -2240,6 +2240,11 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   }
   /* 2.-3. brush */
   if (tool == DSC_TOOL_SMOOTH) {
+    /* partitioned grids: the halo elements the averaging groups of this rank hold are kept current by those groups, but
+     * the smooth brush also reads neighbours that are in none of them (the next point along a coarse edge in the
+     * sibling grid, one step inside another rank's grid): their owners' stitch may have moved them since the last
+     * exchange, so the first iteration starts from a fresh halo */
+    if (dist && ctx->is_grids && (r = dist_halo_exchange(ctx))) return r;
     {
       StageScope s(ctx, ST_SMOOTH);
       k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
