@@ -101,6 +101,12 @@ struct DscContext {
   std::vector<int> send_off, recv_off;    /* [world + 1] into the index lists below */
   int *d_send_idx = nullptr, *d_recv_idx = nullptr;
   int *d_glist = nullptr, *d_gcount = nullptr; /* partitioned grids: the leaves all ranks gathered this dab */
+  /* exchanges over peer memory (see PeerLink in dsc_kernels.cuh); NCCL carries them when the mapping is refused */
+  bool p2p = false;
+  PeerLink link = {};
+  void *p2p_region = nullptr;
+  void *p2p_peer_region[DSC_MAX_RANKS] = {nullptr};
+  int p2p_round = 0;
   float *d_send_buf = nullptr, *d_recv_buf = nullptr;
 
   int *d_slot_of = nullptr;
@@ -656,6 +662,9 @@ void dsc_ctx_destroy(DscContext *ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);
+  for (int q = 0; q < DSC_MAX_RANKS; q++) {
+    if (ctx->p2p_peer_region[q]) cudaIpcCloseMemHandle(ctx->p2p_peer_region[q]);
+  }
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   invalidate_graphs(ctx);
   for (void *p : ctx->allocs) cudaFree(p);
@@ -805,6 +814,8 @@ int dsc_dist_grids_plan(const DscGridsDesc *gr, const DscPbvhDesc *pb, int world
 
 void dsc_dist_free(void *p) { free(p); }
 
+int dsc_dist_uses_peer_memory(DscContext *ctx) { return ctx && ctx->p2p ? 1 : 0; }
+
 int dsc_dist_owned_range(DscContext *ctx, int r_range[2])
 {
   if (!ctx || !ctx->have_pbvh) return DSC_ERR_STATE;
@@ -890,6 +901,8 @@ int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *gr)
   ctx->have_mesh = true;
   return DSC_OK;
 }
+
+static int dist_p2p_setup(DscContext *ctx);
 
 int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
 {
@@ -1745,6 +1758,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       return r;
     CU(cudaStreamSynchronize(ctx->stream));
     }
+    if ((r = dist_p2p_setup(ctx))) return r;
   }
 
   /* the host staging copies are no longer needed */
@@ -1851,11 +1865,113 @@ static int run_flagged(DscContext *ctx, int want)
   return run_clear(ctx, flag_list(ctx), want);
 }
 
+
+/* maps every peer's exchange region (flags | reduce inbox | halo inbox) into this process: cudaIpc handles travel
+ * through NCCL broadcasts, as do the peers' receive offsets.  On any refusal the context keeps using NCCL. */
+static int dist_p2p_setup(DscContext *ctx)
+{
+  const int W = ctx->world;
+  ctx->p2p = false;
+  if (W < 2 || W > DSC_MAX_RANKS || getenv("DSC_NO_P2P")) return DSC_OK;
+  const int words = ctx->m.ghit_words;
+  const int red_stride = 16 + (words + 1) / 2 + 2; /* 8-byte words per source rank: 16 sums, the bitmask, padding */
+  const size_t flag_bytes = 256, red_bytes = ((size_t)W * red_stride * 8 + 255) & ~(size_t)255;
+  /* everyone allocates an inbox for the largest receive list so the regions have one layout */
+  int my_recv = ctx->recv_off[W];
+  int *d_meta = nullptr;
+  int r;
+  if ((r = dev_zero(ctx, &d_meta, (size_t)W * (W + 2) + 16 * (size_t)W * 2))) return r;
+  std::vector<int> meta((size_t)W + 2);
+  for (int q = 0; q <= W; q++) meta[q] = ctx->recv_off[q];
+  meta[W + 1] = my_recv;
+  CU(cudaMemcpyAsync(d_meta + (size_t)ctx->rank * (W + 2), meta.data(), sizeof(int) * (W + 2), cudaMemcpyHostToDevice, ctx->stream));
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < W; q++) NC(g_nccl.Broadcast(d_meta + (size_t)q * (W + 2), d_meta + (size_t)q * (W + 2), (size_t)(W + 2), ncclInt32, q, ctx->comm, ctx->stream));
+  NC(g_nccl.GroupEnd());
+  std::vector<int> all((size_t)W * (W + 2));
+  CU(cudaMemcpyAsync(all.data(), d_meta, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int max_recv = 0;
+  for (int q = 0; q < W; q++) max_recv = std::max(max_recv, all[(size_t)q * (W + 2) + W + 1]);
+  const size_t inbox_bytes = ((size_t)3 * max_recv * sizeof(float) + 255) & ~(size_t)255;
+  const size_t total = flag_bytes + red_bytes + inbox_bytes + 256;
+  char *region = nullptr;
+  if (cudaMalloc((void **)&region, total) != cudaSuccess) {
+    cudaGetLastError();
+    return DSC_OK;
+  }
+  ctx->allocs.push_back(region);
+  ctx->p2p_region = region;
+  CU(cudaMemsetAsync(region, 0, total, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t mine;
+  int ok = cudaIpcGetMemHandle(&mine, region) == cudaSuccess ? 1 : 0;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  int *d_handles = d_meta + (size_t)W * (W + 2); /* [W][16 ints] handles, then [W] ok flags packed behind */
+  CU(cudaMemcpyAsync(d_handles + 16 * (size_t)ctx->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < W; q++) NC(g_nccl.Broadcast(d_handles + 16 * (size_t)q, d_handles + 16 * (size_t)q, 16, ncclInt32, q, ctx->comm, ctx->stream));
+  NC(g_nccl.GroupEnd());
+  std::vector<cudaIpcMemHandle_t> handles((size_t)W);
+  CU(cudaMemcpyAsync(handles.data(), d_handles, 64 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int q = 0; q < W && ok; q++) {
+    if (q == ctx->rank) continue;
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, handles[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    ctx->p2p_peer_region[q] = p;
+  }
+  /* all ranks or none */
+  int *d_ok = d_handles + 16 * (size_t)W;
+  CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+  int sum = 0;
+  CU(cudaMemcpyAsync(&sum, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (sum != W) return DSC_OK;
+  PeerLink &L = ctx->link;
+  memset(&L, 0, sizeof(L));
+  L.world = W;
+  L.rank = ctx->rank;
+  L.red_stride = red_stride;
+  for (int q = 0; q < W; q++) {
+    char *base = q == ctx->rank ? region : (char *)ctx->p2p_peer_region[q];
+    L.peer_flags[q] = (int *)base;
+    L.peer_red[q] = (long long *)(base + flag_bytes);
+    L.peer_inbox[q] = (float *)(base + flag_bytes + red_bytes);
+    L.peer_off[q] = all[(size_t)q * (W + 2) + ctx->rank];
+  }
+  L.flags = L.peer_flags[ctx->rank];
+  L.red = L.peer_red[ctx->rank];
+  L.inbox = L.peer_inbox[ctx->rank];
+  for (int q = 0; q <= W; q++) {
+    L.send_off[q] = ctx->send_off[q];
+    L.recv_off[q] = ctx->recv_off[q];
+  }
+  ctx->p2p = true;
+  ctx->p2p_round = 0;
+  return DSC_OK;
+}
+
 /* ---- multi-GPU steps of a dab ---- */
 /* one all-reduce pair per dab: the exact area sums and the bitmask of gathered leaves (disjoint per
  * rank, so sum == or) */
 static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
 {
+  if (ctx->p2p) {
+    const int round = ++ctx->p2p_round;
+    unsigned *gh = ctx->m.ghit + (size_t)slot * ctx->m.ghit_words;
+    k_p2p_reduce_push<<<dim3(1, ctx->world), 256, 0, ctx->stream>>>(ctx->link, round, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
+    LAUNCH_CHECK();
+    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->link, round, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
+    LAUNCH_CHECK();
+    ctx->launches += 2;
+    return DSC_OK;
+  }
   NC(g_nccl.GroupStart());
   if (with_area) {
     NC(g_nccl.AllReduce(ctx->m.st[slot].acc, ctx->m.st[slot].acc, 16, ncclInt64, ncclSum, ctx->comm, ctx->stream));
@@ -1871,6 +1987,19 @@ static int dist_halo_exchange(DscContext *ctx, bool normals = false)
 {
   const int W = ctx->world;
   float *ax = normals ? ctx->m.nx : ctx->m.cx, *ay = normals ? ctx->m.ny : ctx->m.cy, *az = normals ? ctx->m.nz : ctx->m.cz;
+  if (ctx->p2p) {
+    /* gather from the arrays straight into the peers' inboxes, then scatter what arrived */
+    const int round = ++ctx->p2p_round;
+    int most = 1;
+    for (int q = 0; q < W; q++) most = std::max(most, std::max(ctx->send_off[q + 1] - ctx->send_off[q], ctx->recv_off[q + 1] - ctx->recv_off[q]));
+    const int ctas = std::max(1, std::min((most + 1023) / 1024, std::max(1, ctx->num_sms / (2 * W))));
+    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, round, ctx->d_send_idx, ax, ay, az);
+    LAUNCH_CHECK();
+    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, round, ctx->d_recv_idx, ax, ay, az);
+    LAUNCH_CHECK();
+    ctx->launches += 2;
+    return DSC_OK;
+  }
   const int ns = ctx->send_off[W], nr = ctx->recv_off[W];
   /* per peer the buffer holds [3][count] */
   for (int q = 0; q < W; q++) {
@@ -2658,6 +2787,12 @@ int dsc_stroke_end(DscContext *ctx)
   if (!ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "no stroke open");
   int r;
   if (ctx->world > 1 && (r = dist_gather_all(ctx))) return r;
+  if (ctx->p2p) {
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, ctx->link.flags + P2P_ERR, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (err) return fail(ctx, DSC_ERR_NCCL, "a peer-memory exchange timed out: a rank did not queue the same exchanges");
+  }
   r = run_orig_flush(ctx);
   if (r) return r;
   ctx->in_stroke = false;

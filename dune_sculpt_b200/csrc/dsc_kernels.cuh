@@ -1984,6 +1984,137 @@ __global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restri
   }
 }
 
+/* ---- multi-GPU exchanges over peer memory (NVLink): every rank maps one small region of every other rank's HBM
+ * (cudaIpc) -- flags, a reduce inbox, a halo inbox -- and the per-dab exchanges are stores into the peers' inboxes
+ * instead of NCCL send / recv pairs.  One exchange = a push kernel and a receive kernel on every rank, numbered by a
+ * round counter all ranks advance together:
+ *   push:    tell every peer "my inbox is free for round r" (all earlier kernels of this stream have finished: stream
+ *            order), wait for the peer's own such flag, gather the halo elements of this rank from its arrays straight
+ *            into the peer's inbox (coalesced remote stores), fence, raise "round r delivered" at the peer;
+ *   receive: wait for "round r delivered" from every peer, scatter the inbox into the arrays (or sum the reduce inbox).
+ * No CTA waits for anything that is not raised unconditionally at the start of the peer's push kernel, so the ranks
+ * cannot deadlock as long as they queue the same sequence of exchanges (they do: the dab sequence is replicated). */
+#define DSC_MAX_RANKS 8
+#define P2P_READY 0
+#define P2P_DONE 16
+#define P2P_COUNT 32
+#define P2P_ERR 48 /* a wait gave up (a peer never arrived): the host reports it at stroke end instead of hanging */
+struct PeerLink {
+  int world, rank;
+  int *flags;                      /* mine: [P2P_READY + q], [P2P_DONE + q] raised by rank q; [P2P_COUNT + q] local CTA counter */
+  int *peer_flags[DSC_MAX_RANKS];
+  float *inbox;                    /* mine: halo inbox, the block from rank q at 3 * recv_off[q] */
+  float *peer_inbox[DSC_MAX_RANKS];
+  long long *red;                  /* mine: reduce inbox, [q * red_stride] */
+  long long *peer_red[DSC_MAX_RANKS];
+  int red_stride;                  /* in 8-byte words */
+  int send_off[DSC_MAX_RANKS + 1], recv_off[DSC_MAX_RANKS + 1];
+  int peer_off[DSC_MAX_RANKS];     /* where this rank's block starts in rank q's inbox (q's recv_off[rank]) */
+};
+__device__ __forceinline__ void dsc_flag_raise(int *p, int v)
+{
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int dsc_flag_read(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsc_flag_wait(const int *p, int round, int *err)
+{
+  for (long long spin = 0; dsc_flag_read(p) < round; spin++) {
+    __nanosleep(100);
+    if (spin > (1ll << 26)) { /* tens of seconds */
+      *err = 1;
+      return;
+    }
+  }
+}
+/* grid (ctas_per_peer, world): blockIdx.y = peer */
+__global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, int round, const int *__restrict__ idx, const float *__restrict__ ax,
+                                                       const float *__restrict__ ay, const float *__restrict__ az)
+{
+  const int q = blockIdx.y;
+  if (q == L.rank) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_READY + L.rank, round);
+  if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_READY + q, round, L.flags + P2P_ERR);
+  __syncthreads();
+  const int n = L.send_off[q + 1] - L.send_off[q];
+  const int *id = idx + L.send_off[q];
+  float *dst = L.peer_inbox[q] + 3 * (size_t)L.peer_off[q];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = id[i];
+    dst[i] = ax[s];
+    dst[n + i] = ay[s];
+    dst[2 * n + i] = az[s];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(L.flags + P2P_COUNT + q, 1) + 1;
+    if (arrived == (int)gridDim.x) {
+      L.flags[P2P_COUNT + q] = 0;
+      __threadfence_system();
+      dsc_flag_raise(L.peer_flags[q] + P2P_DONE + L.rank, round);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, int round, const int *__restrict__ idx, float *__restrict__ ax,
+                                                       float *__restrict__ ay, float *__restrict__ az)
+{
+  const int q = blockIdx.y;
+  if (q == L.rank) return;
+  if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_DONE + q, round, L.flags + P2P_ERR);
+  __syncthreads();
+  const int n = L.recv_off[q + 1] - L.recv_off[q];
+  const int *id = idx + L.recv_off[q];
+  const float *src = L.inbox + 3 * (size_t)L.recv_off[q];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = id[i];
+    ax[s] = __ldcg(&src[i]);
+    ay[s] = __ldcg(&src[n + i]);
+    az[s] = __ldcg(&src[2 * n + i]);
+  }
+}
+/* the per-dab all-reduce: the 16 exact area sums (int64) and the bitmask of gathered leaves.  grid (1, world) */
+__global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, int round, const long long *__restrict__ acc, const unsigned *__restrict__ ghit,
+                                                         int words, int with_area)
+{
+  const int q = blockIdx.y;
+  if (q == L.rank) return;
+  if (threadIdx.x == 0) {
+    dsc_flag_raise(L.peer_flags[q] + P2P_READY + L.rank, round);
+    dsc_flag_wait(L.flags + P2P_READY + q, round, L.flags + P2P_ERR);
+  }
+  __syncthreads();
+  long long *dst = L.peer_red[q] + (size_t)L.rank * L.red_stride;
+  if (with_area && threadIdx.x < 16) dst[threadIdx.x] = acc[threadIdx.x];
+  unsigned *dw = reinterpret_cast<unsigned *>(dst + 16);
+  for (int w = threadIdx.x; w < words; w += blockDim.x) dw[w] = ghit[w];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_DONE + L.rank, round);
+}
+__global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, int round, long long *__restrict__ acc, unsigned *__restrict__ ghit, int words,
+                                                         int with_area)
+{
+  if (threadIdx.x < L.world && threadIdx.x != L.rank) dsc_flag_wait(L.flags + P2P_DONE + threadIdx.x, round, L.flags + P2P_ERR);
+  __syncthreads();
+  if (with_area && threadIdx.x < 16) {
+    long long sum = 0;
+    for (int r = 0; r < L.world; r++) sum += r == L.rank ? acc[threadIdx.x] : __ldcg(&L.red[(size_t)r * L.red_stride + threadIdx.x]);
+    acc[threadIdx.x] = sum;
+  }
+  for (int w = threadIdx.x; w < words; w += blockDim.x) {
+    unsigned bits = ghit[w];
+    for (int r = 0; r < L.world; r++) {
+      if (r != L.rank) bits |= __ldcg(reinterpret_cast<const unsigned *>(L.red + (size_t)r * L.red_stride + 16) + w);
+    }
+    ghit[w] = bits;
+  }
+}
+
 /* ------------------------------------------------------------------------------ misc */
 __global__ void k_mark_all(DevMesh m, int flags, int all_dirty, int nwords)
 {

@@ -311,6 +311,9 @@ int dsc_dist_grids_plan(const DscGridsDesc *grids, const DscPbvhDesc *pbvh, int 
 void dsc_dist_free(void *p);
 /* leaf nodes this rank owns: r_range[2] = first and one-past-last leaf in traversal order */
 int dsc_dist_owned_range(DscContext *ctx, int r_range[2]);
+/* 1 when the per-dab exchanges run as stores into the peers' HBM over NVLink (cudaIpc-mapped inboxes, flag
+ * handshakes), 0 when NCCL send / recv / all-reduce carries them (mapping refused, or DSC_NO_P2P set) */
+int dsc_dist_uses_peer_memory(DscContext *ctx);
 
 /* --- timing helpers (CUDA events on the context's stream) --------------------------------- */
 int dsc_timer_start(DscContext *ctx);

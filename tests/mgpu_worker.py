@@ -67,8 +67,8 @@ def main():
     assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: boxes differ" % rank
     assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
-    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d" %
-          (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs()), flush=True)
+    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d" %
+          (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs(), ses.D.dsc_dist_uses_peer_memory(ses.ctx)), flush=True)
     ses.close()
 
 
@@ -124,8 +124,9 @@ def multires(world, rank, nid, scenario):
     assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: boxes differ" % rank
     assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
-    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d" %
-          (rank, world, scenario, rng[rank], rng[rank + 1], ses.stats()["vertex_dabs"], orc.vertex_dabs()), flush=True)
+    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d" %
+          (rank, world, scenario, rng[rank], rng[rank + 1], ses.stats()["vertex_dabs"], orc.vertex_dabs(),
+           ses.D.dsc_dist_uses_peer_memory(ses.ctx)), flush=True)
     ses.close()
 
 

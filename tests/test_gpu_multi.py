@@ -19,16 +19,21 @@ def _device_count():
         return 0
 
 
+@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
 @pytest.mark.parametrize("scenario", ["grid", "ico", "multires", "multires_open"])
-def test_partitioned_stroke_matches_oracle(scenario):
+def test_partitioned_stroke_matches_oracle(scenario, transport):
+    """transport: the per-dab exchanges as stores into the peers' HBM (default) or through NCCL (DSC_NO_P2P)"""
     n = _device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 4 if n >= 4 else 2
     with tempfile.TemporaryDirectory() as td:
         idfile = os.path.join(td, "nccl_id")
+        env = dict(os.environ)
+        if transport == "nccl":
+            env["DSC_NO_P2P"] = "1"
         procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "mgpu_worker.py"), str(world), str(r), idfile, scenario],
-                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
         outs = []
         for p in procs:
             try:
@@ -40,3 +45,6 @@ def test_partitioned_stroke_matches_oracle(scenario):
             outs.append(o)
         for r, (p, o) in enumerate(zip(procs, outs)):
             assert p.returncode == 0 and "MGPU_OK" in o, "rank %d failed:\n%s" % (r, o[-3000:])
+            if transport == "nccl":
+                assert "peer_memory 0" in o
+        print("\n".join(ln for o in outs for ln in o.splitlines() if "MGPU_OK" in ln))
