@@ -1963,11 +1963,10 @@ static int dist_p2p_setup(DscContext *ctx)
 static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
 {
   if (ctx->p2p) {
-    const int round = ++ctx->p2p_round;
     unsigned *gh = ctx->m.ghit + (size_t)slot * ctx->m.ghit_words;
-    k_p2p_reduce_push<<<dim3(1, ctx->world), 256, 0, ctx->stream>>>(ctx->link, round, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
+    k_p2p_reduce_push<<<dim3(1, ctx->world), 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
     LAUNCH_CHECK();
-    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->link, round, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
+    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
     LAUNCH_CHECK();
     ctx->launches += 2;
     return DSC_OK;
@@ -1989,13 +1988,12 @@ static int dist_halo_exchange(DscContext *ctx, bool normals = false)
   float *ax = normals ? ctx->m.nx : ctx->m.cx, *ay = normals ? ctx->m.ny : ctx->m.cy, *az = normals ? ctx->m.nz : ctx->m.cz;
   if (ctx->p2p) {
     /* gather from the arrays straight into the peers' inboxes, then scatter what arrived */
-    const int round = ++ctx->p2p_round;
     int most = 1;
     for (int q = 0; q < W; q++) most = std::max(most, std::max(ctx->send_off[q + 1] - ctx->send_off[q], ctx->recv_off[q + 1] - ctx->recv_off[q]));
     const int ctas = std::max(1, std::min((most + 1023) / 1024, std::max(1, ctx->num_sms / (2 * W))));
-    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, round, ctx->d_send_idx, ax, ay, az);
+    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_send_idx, ax, ay, az);
     LAUNCH_CHECK();
-    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, round, ctx->d_recv_idx, ax, ay, az);
+    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_recv_idx, ax, ay, az);
     LAUNCH_CHECK();
     ctx->launches += 2;
     return DSC_OK;
@@ -2096,13 +2094,13 @@ static int grids_recalc_normals(DscContext *ctx)
   return grids_average_all(ctx);
 }
 /* after the brush of a dab on grids: stitch, CCG normals of the gathered leaves' faces, leaf boxes */
-static int grids_after_brush(DscContext *ctx, LeafList hits)
+static int grids_after_brush(DscContext *ctx, LeafList hits, int j)
 {
   DevGrids &g = ctx->g;
   DevMesh &m = ctx->m;
   cudaStream_t st = ctx->stream;
   int r;
-  const int seq = ++ctx->grid_seq;
+  const int seq = j; /* the kernels turn the dab's position in the running batch into its stamp (dsc_grid_seq) */
   if ((r = grids_reset_counts(ctx))) return r;
   StageScope s(ctx, ST_NORMALS);
   if (ctx->grid_fused) {
@@ -2428,7 +2426,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
       }
     }
     if (ctx->is_grids) {
-      if ((r = grids_after_brush(ctx, hits))) return r;
+      if ((r = grids_after_brush(ctx, hits, j))) return r;
     }
     else if (mode) {
       if ((r = run_normals_bounds(ctx, hits, mode, pdl && !dist && tool != DSC_TOOL_SMOOTH))) return r;
@@ -2575,7 +2573,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     if (dist && (ctx->stale_flags || !sig.do_normals || !sig.do_bounds))
       return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
     /* how many of the following dabs share the launch sequence */
-    const bool graphable = ctx->use_graphs && !ctx->is_grids && !ctx->stage_timing && !ctx->capture && !dist && !ctx->stale_flags &&
+    const bool graphable = ctx->use_graphs && !(ctx->is_grids && ctx->grid_fused) && !ctx->stage_timing && !ctx->capture && (!dist || ctx->p2p) && !ctx->stale_flags &&
                            !ctx->any_slow_leaf && sig.do_normals && sig.do_bounds;
     int run = 1;
     const long long seq = ctx->ring_seq; /* ring position: runs across strokes; the state slot follows dab_index */

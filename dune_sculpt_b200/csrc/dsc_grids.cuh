@@ -353,14 +353,17 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_ghit_expand(DevMesh m, const unsi
 }
 
 /* ---- the stages as kernels of their own (session start, full averages) ---- */
-__global__ void __launch_bounds__(DSC_BLOCK) k_grid_faces(DevMesh m, DevGrids g, const int *list, const int *count, int seq)
+/* the stamp of a dab is its sequence number (ring position + 1, read on the device so that the launch can be replayed
+ * from a CUDA graph): faces / edges / vertices claimed by this dab carry it */
+__device__ __forceinline__ int dsc_grid_seq(const DevMesh &m, int j) { return m.ring_ctl[0] + j + 1; }
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_faces(DevMesh m, DevGrids g, const int *list, const int *count, int j)
 {
-  dsc_grid_faces_body(g, list, count, seq, blockIdx.x, gridDim.x);
+  dsc_grid_faces_body(g, list, count, dsc_grid_seq(m, j), blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(128) k_grid_inner(DevMesh m, DevGrids g) { dsc_grid_inner_body(m, g, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int all, int seq)
+__global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int all, int j)
 {
-  dsc_grid_edges_body(m, g, all, seq, blockIdx.x, gridDim.x);
+  dsc_grid_edges_body(m, g, all, dsc_grid_seq(m, j), blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g, int all) { dsc_grid_cverts_body(m, g, all, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(GN_BLOCK) k_grid_normals(DevMesh m, DevGrids g, int all)
@@ -377,9 +380,10 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_grid_leaf_bb(DevMesh m, const int
  * faces of the gathered leaves -> stitch (inner boundaries, coarse edges, all coarse vertices) -> CCG normals
  * of those faces' grids -> their averaging (inner, edges, vertices) -> leaf boxes; the phases are separated by
  * grid barriers (dsc_grid_sync) instead of nine kernel boundaries.  One CTA of GN_BLOCK threads per SM. */
-__global__ void __launch_bounds__(GN_BLOCK, 1) k_grid_dab(DevMesh m, DevGrids g, const int *list, const int *count, int seq)
+__global__ void __launch_bounds__(GN_BLOCK, 1) k_grid_dab(DevMesh m, DevGrids g, const int *list, const int *count, int j)
 {
   extern __shared__ float gsm[];
+  const int seq = dsc_grid_seq(m, j);
   const int cta = blockIdx.x, ncta = gridDim.x;
   unsigned target = 0u;
   dsc_grid_faces_body(g, list, count, seq, cta, ncta);

@@ -1998,6 +1998,8 @@ __global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restri
 #define P2P_READY 0
 #define P2P_DONE 16
 #define P2P_COUNT 32
+#define P2P_ROUND 49 /* exchanges completed so far: the kernels read their round here, so a dab's exchanges replay from a graph */
+#define P2P_RCOUNT 50 /* CTA counter of the receive kernel */
 #define P2P_ERR 48 /* a wait gave up (a peer never arrived): the host reports it at stroke end instead of hanging */
 struct PeerLink {
   int world, rank;
@@ -2032,11 +2034,12 @@ __device__ __forceinline__ void dsc_flag_wait(const int *p, int round, int *err)
   }
 }
 /* grid (ctas_per_peer, world): blockIdx.y = peer */
-__global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, int round, const int *__restrict__ idx, const float *__restrict__ ax,
+__global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, const int *__restrict__ idx, const float *__restrict__ ax,
                                                        const float *__restrict__ ay, const float *__restrict__ az)
 {
   const int q = blockIdx.y;
   if (q == L.rank) return;
+  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_READY + L.rank, round);
   if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_READY + q, round, L.flags + P2P_ERR);
   __syncthreads();
@@ -2060,29 +2063,41 @@ __global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, int round, co
     }
   }
 }
-__global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, int round, const int *__restrict__ idx, float *__restrict__ ax,
+__global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, const int *__restrict__ idx, float *__restrict__ ax,
                                                        float *__restrict__ ay, float *__restrict__ az)
 {
   const int q = blockIdx.y;
-  if (q == L.rank) return;
-  if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_DONE + q, round, L.flags + P2P_ERR);
+  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
+  if (q != L.rank) {
+    if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_DONE + q, round, L.flags + P2P_ERR);
+    __syncthreads();
+    const int n = L.recv_off[q + 1] - L.recv_off[q];
+    const int *id = idx + L.recv_off[q];
+    const float *src = L.inbox + 3 * (size_t)L.recv_off[q];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int s = id[i];
+      ax[s] = __ldcg(&src[i]);
+      ay[s] = __ldcg(&src[n + i]);
+      az[s] = __ldcg(&src[2 * n + i]);
+    }
+  }
+  /* the last CTA to leave closes the round (every CTA has read the counter by then) */
   __syncthreads();
-  const int n = L.recv_off[q + 1] - L.recv_off[q];
-  const int *id = idx + L.recv_off[q];
-  const float *src = L.inbox + 3 * (size_t)L.recv_off[q];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int s = id[i];
-    ax[s] = __ldcg(&src[i]);
-    ay[s] = __ldcg(&src[n + i]);
-    az[s] = __ldcg(&src[2 * n + i]);
+  if (threadIdx.x == 0) {
+    const int total = (int)(gridDim.x * gridDim.y);
+    if (atomicAdd(L.flags + P2P_RCOUNT, 1) + 1 == total) {
+      L.flags[P2P_RCOUNT] = 0;
+      L.flags[P2P_ROUND] = round;
+    }
   }
 }
 /* the per-dab all-reduce: the 16 exact area sums (int64) and the bitmask of gathered leaves.  grid (1, world) */
-__global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, int round, const long long *__restrict__ acc, const unsigned *__restrict__ ghit,
+__global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, const long long *__restrict__ acc, const unsigned *__restrict__ ghit,
                                                          int words, int with_area)
 {
   const int q = blockIdx.y;
   if (q == L.rank) return;
+  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   if (threadIdx.x == 0) {
     dsc_flag_raise(L.peer_flags[q] + P2P_READY + L.rank, round);
     dsc_flag_wait(L.flags + P2P_READY + q, round, L.flags + P2P_ERR);
@@ -2096,9 +2111,10 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, int round, 
   __syncthreads();
   if (threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_DONE + L.rank, round);
 }
-__global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, int round, long long *__restrict__ acc, unsigned *__restrict__ ghit, int words,
+__global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, long long *__restrict__ acc, unsigned *__restrict__ ghit, int words,
                                                          int with_area)
 {
+  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   if (threadIdx.x < L.world && threadIdx.x != L.rank) dsc_flag_wait(L.flags + P2P_DONE + threadIdx.x, round, L.flags + P2P_ERR);
   __syncthreads();
   if (with_area && threadIdx.x < 16) {
@@ -2113,6 +2129,8 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, int round, 
     }
     ghit[w] = bits;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) L.flags[P2P_ROUND] = round;
 }
 
 /* ------------------------------------------------------------------------------ misc */

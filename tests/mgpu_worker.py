@@ -15,6 +15,25 @@ from dune_sculpt_b200 import capi, meshgen, stroke  # noqa: E402
 from oracle_py import GridOracle, Oracle  # noqa: E402
 
 
+def batched_stroke(orc, ses, dabs, rank, what):
+    """a second stroke submitted as ONE dsc_dabs call: runs of one launch sequence replay as CUDA graphs, the
+    peer-memory exchanges inside them (their round numbers live on the device)"""
+    dabs = sorted(dabs, key=lambda d: d.tool)       # runs of equal signature
+    arr = (capi.DscDab * len(dabs))(*dabs)
+    orc.stroke_begin(None)
+    for d in dabs:
+        orc.dab(d)
+    orc.stroke_end()
+    ses.stroke_begin(None)
+    ses.dabs(arr, len(dabs))
+    ses.stroke_end()
+    assert np.array_equal(orc.co(), ses.co()), "rank %d: batched %s stroke: positions differ" % (rank, what)
+    assert np.array_equal(orc.no(), ses.no()), "rank %d: batched %s stroke: normals differ" % (rank, what)
+    na = orc.node_arrays()
+    bb, obb = ses.node_bb()
+    assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: batched stroke: boxes differ" % rank
+
+
 def main():
     world, rank, idfile, scenario = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
     if rank == 0:
@@ -67,6 +86,7 @@ def main():
     assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: boxes differ" % rank
     assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
+    batched_stroke(orc, ses, dabs, rank, scenario)
     print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d" %
           (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs(), ses.D.dsc_dist_uses_peer_memory(ses.ctx)), flush=True)
     ses.close()
@@ -124,6 +144,8 @@ def multires(world, rank, nid, scenario):
     assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb), "rank %d: boxes differ" % rank
     assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
+    batched_stroke(orc, ses, dabs, rank, scenario)
+    assert np.array_equal(orc.mask(), ses.mask()), "rank %d: mask layer differs after the batched stroke" % rank
     print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d" %
           (rank, world, scenario, rng[rank], rng[rank + 1], ses.stats()["vertex_dabs"], orc.vertex_dabs(),
            ses.D.dsc_dist_uses_peer_memory(ses.ctx)), flush=True)

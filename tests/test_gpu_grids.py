@@ -163,3 +163,35 @@ def test_grids_smooth_then_draw_c5_shape_reduced():
     dabs = _smooth_dabs(mr, n=2, pct=(8.0,)) + _sweep(mr, per=2, radii=(8.0,))
     st = _grid_parity(mr, dabs)
     assert st["moved_verts"] > 0
+
+
+def test_grids_batched_dabs_through_cuda_graphs():
+    """dsc_dabs on grids: runs of one launch sequence (smooth with its iteration count, draw) replayed as CUDA graphs;
+    the face / edge / vertex stamps of a dab come from its ring position on the device.  Two strokes: the second
+    replays the cached graphs on stamps the first left behind."""
+    mr = meshgen.multires_cube(2, 4, noise=0.03, freq=17.0, with_mask=True)
+    dabs = _smooth_dabs(mr, n=9, pct=(10.0,)) + _sweep(mr, per=11, radii=(9.0, 22.0))   # 9 smooth, 22 draw
+    orc = GridOracle(mr, leaf_limit=6)
+    ses = capi.GridSession(mr, leaf_limit=6, device=0)
+    try:
+        arr = (capi.DscDab * len(dabs))(*dabs)
+        for stroke_no in range(2):
+            orc.stroke_begin(None)
+            for d in dabs:
+                orc.dab(d)
+            orc.stroke_end()
+            ses.stroke_begin(None)
+            ses.dabs(arr, len(dabs))
+            st = ses.stats()
+            ses.stroke_end()
+            assert st["dabs"] == len(dabs)
+            assert np.array_equal(orc.co(), ses.co()), "stroke %d: positions differ in bits" % stroke_no
+            assert np.array_equal(orc.no(), ses.no()), "stroke %d: normals differ in bits" % stroke_no
+            assert np.array_equal(orc.mask(), ses.mask())
+            na = orc.node_arrays()
+            bb, obb = ses.node_bb()
+            assert np.array_equal(na["vb"], bb) and np.array_equal(na["orig_vb"], obb)
+        assert ses.stats()["kernel_launches"] > 0
+    finally:
+        ses.close()
+        orc.close()
