@@ -1875,7 +1875,7 @@ static int dist_p2p_setup(DscContext *ctx)
   if (W < 2 || W > DSC_MAX_RANKS || getenv("DSC_NO_P2P")) return DSC_OK;
   const int words = ctx->m.ghit_words;
   const int red_stride = 16 + (words + 1) / 2 + 2; /* 8-byte words per source rank: 16 sums, the bitmask, padding */
-  const size_t flag_bytes = 256, red_bytes = ((size_t)W * red_stride * 8 + 255) & ~(size_t)255;
+  const size_t flag_bytes = 256, red_half_bytes = ((size_t)W * red_stride * 8 + 255) & ~(size_t)255, red_bytes = 2 * red_half_bytes;
   /* everyone allocates an inbox for the largest receive list so the regions have one layout */
   int my_recv = ctx->recv_off[W];
   int *d_meta = nullptr;
@@ -1893,7 +1893,7 @@ static int dist_p2p_setup(DscContext *ctx)
   CU(cudaStreamSynchronize(ctx->stream));
   int max_recv = 0;
   for (int q = 0; q < W; q++) max_recv = std::max(max_recv, all[(size_t)q * (W + 2) + W + 1]);
-  const size_t inbox_bytes = ((size_t)3 * max_recv * sizeof(float) + 255) & ~(size_t)255;
+  const size_t inbox_half_bytes = ((size_t)3 * max_recv * sizeof(float) + 255) & ~(size_t)255, inbox_bytes = 2 * inbox_half_bytes;
   const size_t total = flag_bytes + red_bytes + inbox_bytes + 256;
   char *region = nullptr;
   if (cudaMalloc((void **)&region, total) != cudaSuccess) {
@@ -1938,6 +1938,8 @@ static int dist_p2p_setup(DscContext *ctx)
   L.world = W;
   L.rank = ctx->rank;
   L.red_stride = red_stride;
+  L.red_half = (int)(red_half_bytes / 8);
+  L.inbox_half = (int)(inbox_half_bytes / sizeof(float));
   for (int q = 0; q < W; q++) {
     char *base = q == ctx->rank ? region : (char *)ctx->p2p_peer_region[q];
     L.peer_flags[q] = (int *)base;

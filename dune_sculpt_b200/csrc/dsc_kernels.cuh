@@ -1985,17 +1985,19 @@ __global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restri
 }
 
 /* ---- multi-GPU exchanges over peer memory (NVLink): every rank maps one small region of every other rank's HBM
- * (cudaIpc) -- flags, a reduce inbox, a halo inbox -- and the per-dab exchanges are stores into the peers' inboxes
- * instead of NCCL send / recv pairs.  One exchange = a push kernel and a receive kernel on every rank, numbered by a
- * round counter all ranks advance together:
- *   push:    tell every peer "my inbox is free for round r" (all earlier kernels of this stream have finished: stream
- *            order), wait for the peer's own such flag, gather the halo elements of this rank from its arrays straight
- *            into the peer's inbox (coalesced remote stores), fence, raise "round r delivered" at the peer;
- *   receive: wait for "round r delivered" from every peer, scatter the inbox into the arrays (or sum the reduce inbox).
- * No CTA waits for anything that is not raised unconditionally at the start of the peer's push kernel, so the ranks
- * cannot deadlock as long as they queue the same sequence of exchanges (they do: the dab sequence is replicated). */
+ * (cudaIpc) -- flags, a reduce inbox, a halo inbox, the inboxes double buffered -- and the per-dab exchanges are stores
+ * into the peers' inboxes instead of NCCL send / recv pairs.  One exchange = a push kernel and a receive kernel on every
+ * rank, numbered by a round counter all ranks advance together (it lives in device memory, so the pair replays from a
+ * CUDA graph):
+ *   push:    gather the halo elements of this rank from its arrays straight into half (round & 1) of the peer's inbox
+ *            (coalesced remote stores), fence, raise "round r delivered" at the peer;
+ *   receive: wait for "round r delivered" from every peer, scatter that half of the inbox into the arrays (or sum the
+ *            reduce inbox), close the round.
+ * No "inbox free" handshake is needed: a rank pushes round r only after its own receive of round r - 1, i.e. after every
+ * peer delivered round r - 1, which a peer does only after ITS receive of round r - 2 -- the last reader of the half
+ * round r overwrites.  Nothing waits for anything but a delivery that the peer's push raises unconditionally, so the
+ * ranks cannot deadlock as long as they queue the same sequence of exchanges (they do: the dab sequence is replicated). */
 #define DSC_MAX_RANKS 8
-#define P2P_READY 0
 #define P2P_DONE 16
 #define P2P_COUNT 32
 #define P2P_ROUND 49 /* exchanges completed so far: the kernels read their round here, so a dab's exchanges replay from a graph */
@@ -2003,13 +2005,15 @@ __global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restri
 #define P2P_ERR 48 /* a wait gave up (a peer never arrived): the host reports it at stroke end instead of hanging */
 struct PeerLink {
   int world, rank;
-  int *flags;                      /* mine: [P2P_READY + q], [P2P_DONE + q] raised by rank q; [P2P_COUNT + q] local CTA counter */
+  int *flags;                      /* mine: [P2P_DONE + q] raised by rank q; [P2P_COUNT + q], [P2P_RCOUNT] local CTA counters; [P2P_ROUND]; [P2P_ERR] */
   int *peer_flags[DSC_MAX_RANKS];
   float *inbox;                    /* mine: halo inbox, the block from rank q at 3 * recv_off[q] */
   float *peer_inbox[DSC_MAX_RANKS];
   long long *red;                  /* mine: reduce inbox, [q * red_stride] */
   long long *peer_red[DSC_MAX_RANKS];
-  int red_stride;                  /* in 8-byte words */
+  int red_stride;                  /* in 8-byte words, per source rank */
+  int red_half;                    /* 8-byte words of one half of the reduce inbox */
+  int inbox_half;                  /* floats of one half of the halo inbox */
   int send_off[DSC_MAX_RANKS + 1], recv_off[DSC_MAX_RANKS + 1];
   int peer_off[DSC_MAX_RANKS];     /* where this rank's block starts in rank q's inbox (q's recv_off[rank]) */
 };
@@ -2040,12 +2044,9 @@ __global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, const int *__
   const int q = blockIdx.y;
   if (q == L.rank) return;
   const int round = __ldcg(L.flags + P2P_ROUND) + 1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_READY + L.rank, round);
-  if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_READY + q, round, L.flags + P2P_ERR);
-  __syncthreads();
   const int n = L.send_off[q + 1] - L.send_off[q];
   const int *id = idx + L.send_off[q];
-  float *dst = L.peer_inbox[q] + 3 * (size_t)L.peer_off[q];
+  float *dst = L.peer_inbox[q] + (size_t)(round & 1) * L.inbox_half + 3 * (size_t)L.peer_off[q];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int s = id[i];
     dst[i] = ax[s];
@@ -2073,7 +2074,7 @@ __global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, const int *__
     __syncthreads();
     const int n = L.recv_off[q + 1] - L.recv_off[q];
     const int *id = idx + L.recv_off[q];
-    const float *src = L.inbox + 3 * (size_t)L.recv_off[q];
+    const float *src = L.inbox + (size_t)(round & 1) * L.inbox_half + 3 * (size_t)L.recv_off[q];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const int s = id[i];
       ax[s] = __ldcg(&src[i]);
@@ -2098,12 +2099,7 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, const long 
   const int q = blockIdx.y;
   if (q == L.rank) return;
   const int round = __ldcg(L.flags + P2P_ROUND) + 1;
-  if (threadIdx.x == 0) {
-    dsc_flag_raise(L.peer_flags[q] + P2P_READY + L.rank, round);
-    dsc_flag_wait(L.flags + P2P_READY + q, round, L.flags + P2P_ERR);
-  }
-  __syncthreads();
-  long long *dst = L.peer_red[q] + (size_t)L.rank * L.red_stride;
+  long long *dst = L.peer_red[q] + (size_t)(round & 1) * L.red_half + (size_t)L.rank * L.red_stride;
   if (with_area && threadIdx.x < 16) dst[threadIdx.x] = acc[threadIdx.x];
   unsigned *dw = reinterpret_cast<unsigned *>(dst + 16);
   for (int w = threadIdx.x; w < words; w += blockDim.x) dw[w] = ghit[w];
@@ -2117,15 +2113,16 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, long long *
   const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   if (threadIdx.x < L.world && threadIdx.x != L.rank) dsc_flag_wait(L.flags + P2P_DONE + threadIdx.x, round, L.flags + P2P_ERR);
   __syncthreads();
+  const long long *red = L.red + (size_t)(round & 1) * L.red_half;
   if (with_area && threadIdx.x < 16) {
     long long sum = 0;
-    for (int r = 0; r < L.world; r++) sum += r == L.rank ? acc[threadIdx.x] : __ldcg(&L.red[(size_t)r * L.red_stride + threadIdx.x]);
+    for (int r = 0; r < L.world; r++) sum += r == L.rank ? acc[threadIdx.x] : __ldcg(&red[(size_t)r * L.red_stride + threadIdx.x]);
     acc[threadIdx.x] = sum;
   }
   for (int w = threadIdx.x; w < words; w += blockDim.x) {
     unsigned bits = ghit[w];
     for (int r = 0; r < L.world; r++) {
-      if (r != L.rank) bits |= __ldcg(reinterpret_cast<const unsigned *>(L.red + (size_t)r * L.red_stride + 16) + w);
+      if (r != L.rank) bits |= __ldcg(reinterpret_cast<const unsigned *>(red + (size_t)r * L.red_stride + 16) + w);
     }
     ghit[w] = bits;
   }

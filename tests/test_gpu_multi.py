@@ -26,7 +26,7 @@ def test_partitioned_stroke_matches_oracle(scenario, transport):
     n = _device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    world = 4 if n >= 4 else 2
+    world = 8 if n >= 8 else 4 if n >= 4 else 2
     with tempfile.TemporaryDirectory() as td:
         idfile = os.path.join(td, "nccl_id")
         env = dict(os.environ)
