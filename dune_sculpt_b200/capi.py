@@ -107,7 +107,7 @@ HOST_SYMBOLS = [
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
     "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
-    "DUNE_pbvh_device_attach_grids_dist",
+    "DUNE_pbvh_device_attach_grids_dist", "DUNE_multires_reshape_assign_final_coords",
     "DUNE_subdiv_ccg_topology_set", "BKE_subdiv_ccg_neighbor_coords_get", "BKE_subdiv_ccg_coarse_mesh_adjacency_info_get",
     "DUNE_pbvh_draw_buffers_enable", "DUNE_pbvh_update_draw_buffers", "DUNE_pbvh_node_draw_buffer",
     "DUNE_pbvh_raycast_enable", "DUNE_pbvh_raycast_nearest",
@@ -218,6 +218,8 @@ def host_lib():
                                                   C.c_int, c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
         L.DUNE_subdiv_ccg_free.argtypes = [C.c_void_p]
         L.DUNE_subdiv_ccg_free.restype = None
+        L.DUNE_multires_reshape_assign_final_coords.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.DUNE_multires_reshape_assign_final_coords.restype = C.c_bool
         L.DUNE_subdiv_ccg_topology_set.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p]
         L.DUNE_subdiv_ccg_topology_set.restype = None
         L.BKE_subdiv_ccg_neighbor_coords_get.argtypes = [C.c_void_p, C.c_void_p, C.c_bool, C.c_void_p]
@@ -665,6 +667,14 @@ class SubdivCCGStruct(C.Structure):
     ]
 
 
+class MDisps(C.Structure):
+    _fields_ = [("totdisp", C.c_int), ("level", C.c_int), ("disps", c_float_p), ("hidden", C.c_void_p)]
+
+
+class GridPaintMask(C.Structure):
+    _fields_ = [("data", c_float_p), ("level", C.c_uint), ("_pad", C.c_char * 4)]
+
+
 class SubdivCCGCoord(C.Structure):
     _fields_ = [("grid_index", C.c_int), ("x", C.c_short), ("y", C.c_short)]
 
@@ -777,6 +787,25 @@ class GridSession(SculptSession):
             L.dsc_dist_free(p)
         return dict(grid_owner=owner, face_dom=face_dom[:gd.totface], edge_mine=edge_mine[:gd.totedge],
                     cvert_mine=cvert_mine[:gd.totcvert], send_off=soff, send_elem=se, recv_off=roff, recv_elem=re_)
+
+    def multires_write_back(self, with_mask=True):
+        """multires_reshape_assign_final_coords_from_ccg through the host library: (disps [G, gs^2, 3], masks [G, gs^2] or
+        None) as the per-loop MDisps / GridPaintMask arrays receive them"""
+        mr = self.mesh
+        G, area = mr.totgrid, mr.grid_size ** 2
+        level = int(np.log2(mr.grid_size - 1)) + 1
+        disps = np.full((G, area, 3), np.nan, dtype=np.float32)
+        masks = np.full((G, area), np.nan, dtype=np.float32) if (with_mask and mr.mask is not None) else None
+        md = (MDisps * G)()
+        gm = (GridPaintMask * G)() if masks is not None else None
+        for g in range(G):
+            md[g].totdisp, md[g].level = area, level
+            md[g].disps = disps[g].ctypes.data_as(c_float_p)
+            if gm is not None:
+                gm[g].data, gm[g].level = masks[g].ctypes.data_as(c_float_p), level
+        ok = self.H.DUNE_multires_reshape_assign_final_coords(self.pbvh, self.ccg, md, gm)
+        assert ok
+        return disps, masks
 
     def neighbors(self, elem, include_duplicates=False):
         """BKE_subdiv_ccg_neighbor_coords_get of the host library -> (element indices, num_duplicates)"""

@@ -79,6 +79,7 @@ struct DscContext {
   const int4 *d_tri_slots = nullptr;
   unsigned *d_vbo = nullptr; /* [tottri * 3][9] packed vertex records, by looptri position */
   bool has_odd_edges = false; /* some coarse edge has more than two faces */
+  bool grid_normals_flat = false; /* DSC_GRID_NORMALS_FLAT=1: the element-parallel normal pass (measured slower: 4 x the IEEE sqrt / div work) */
   bool grid_fused = false;    /* DSC_GRID_FUSED=1: the stages after the brush as one cooperative kernel instead of nine launches */
 
   std::vector<int> slot_of;     /* vertex -> slot */
@@ -1236,6 +1237,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     g.max_face_grids = 1;
     for (int f = 0; f < g.totface; f++) g.max_face_grids = std::max(g.max_face_grids, ctx->h_face_num[f]);
     ctx->gn_smem = dsc_grid_normals_smem(g.gs);
+    ctx->grid_normals_flat = getenv("DSC_GRID_NORMALS_FLAT") != nullptr;
     ctx->grid_fused = getenv("DSC_GRID_FUSED") != nullptr; /* measured slower than the nine launches (119 -> 141 us per C5 dab): opt-in */
     CU(cudaFuncSetAttribute(k_grid_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->gn_smem));
     CU(cudaFuncSetAttribute(k_grid_dab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->gn_smem));
@@ -2148,7 +2150,8 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j)
   k_grid_cverts<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, 1);
   LAUNCH_CHECK();
   /* BKE_pbvh_update_normals, PBVH_GRIDS branch (pbvh.c:4575-4583 -> subdiv_ccg.c:847-866) */
-  k_grid_normals<<<ctx->num_sms * 2, GN_BLOCK, ctx->gn_smem, st>>>(m, g, 0);
+  if (ctx->grid_normals_flat) k_grid_normals_flat<<<ctx->num_sms * 8, 256, 0, st>>>(m, g, 0);
+  else k_grid_normals<<<ctx->num_sms * 2, GN_BLOCK, ctx->gn_smem, st>>>(m, g, 0);
   LAUNCH_CHECK();
   if (dist && (r = dist_halo_exchange(ctx, true))) return r; /* the new normals of the other ranks' halo elements */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);

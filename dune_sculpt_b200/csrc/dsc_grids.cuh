@@ -286,6 +286,72 @@ __device__ __forceinline__ void dsc_grid_normals_body(const DevMesh &m, const De
   }
 }
 
+/* The same pass, element-parallel (opt-in experiment, DSC_GRID_NORMALS_FLAT=1; measured slower on B200: 41.8 vs 39.2 ms per
+ * C5 stroke -- the IEEE sqrt / div of a quad normal, kept for bit parity, is paid four times): one thread per element, no shared memory.  An element's normal is the mean of the
+ * normals of the <= 4 quads around it, each quad normal recomputed from its four corners by every element that uses it
+ * (4 x the arithmetic of the staged version, all of it hidden under the loads; the 3 x 3 neighbourhood of positions
+ * comes from L1 / L2 -- a grid row is a unit-stride run).  Same expressions in the same order as
+ * dsc_grid_normals_body, so the bits are the same; any number of CTAs, no phase barriers, no per-grid serial tail. */
+__device__ __forceinline__ void dsc_grid_quad_normal(const DevMesh &m, int s_xy, int gs, float &ox, float &oy, float &oz)
+{
+  /* normal_quad_v3(co(x, y+1), co(x+1, y+1), co(x+1, y), co(x, y)), subdiv_ccg.c:684-698; s_xy = slot of (x, y) */
+  const int a = s_xy + gs, b = s_xy + gs + 1, c = s_xy + 1, d = s_xy;
+  const float n1x = __ldg(&m.cx[a]) - __ldg(&m.cx[c]), n1y = __ldg(&m.cy[a]) - __ldg(&m.cy[c]), n1z = __ldg(&m.cz[a]) - __ldg(&m.cz[c]);
+  const float n2x = __ldg(&m.cx[b]) - __ldg(&m.cx[d]), n2y = __ldg(&m.cy[b]) - __ldg(&m.cy[d]), n2z = __ldg(&m.cz[b]) - __ldg(&m.cz[d]);
+  ox = n1y * n2z - n1z * n2y;
+  oy = n1z * n2x - n1x * n2z;
+  oz = n1x * n2y - n1y * n2x;
+  dsc_normalize(ox, oy, oz);
+}
+__global__ void __launch_bounds__(256) k_grid_normals_flat(DevMesh m, DevGrids g, int all)
+{
+  const int gs = g.gs, gs1 = gs - 1, gs2 = g.gs2;
+  const int mfg = g.max_face_grids;
+  const long long units = all ? g.totgrid : (long long)__ldcg(&g.cnt->faces) * mfg;
+  const long long items = units * gs2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(t / gs2), i = (int)(t - (long long)u * gs2);
+    int grid;
+    if (all) {
+      grid = u;
+    }
+    else {
+      const int f = __ldcg(&g.face_list[u / mfg]), c = u % mfg;
+      if (c >= g.face_num[f]) continue;
+      grid = g.face_start[f] + c;
+      if (g.grid_owner && g.grid_owner[grid] != g.rank) continue; /* its owner sends the rim normals */
+    }
+    const int s0 = g.grid_slot0[grid];
+    const int y = i / gs, x = i - y * gs;
+    float ax = 0.0f, ay = 0.0f, az = 0.0f, fx, fy, fz;
+    int counter = 0;
+    if (x < gs1 && y < gs1) {
+      dsc_grid_quad_normal(m, s0 + y * gs + x, gs, fx, fy, fz);
+      ax += fx; ay += fy; az += fz;
+      counter++;
+    }
+    if (x >= 1) {
+      if (y < gs1) {
+        dsc_grid_quad_normal(m, s0 + y * gs + (x - 1), gs, fx, fy, fz);
+        ax += fx; ay += fy; az += fz;
+        counter++;
+      }
+      if (y >= 1) {
+        dsc_grid_quad_normal(m, s0 + (y - 1) * gs + (x - 1), gs, fx, fy, fz);
+        ax += fx; ay += fy; az += fz;
+        counter++;
+      }
+    }
+    if (y >= 1 && x < gs1) {
+      dsc_grid_quad_normal(m, s0 + (y - 1) * gs + x, gs, fx, fy, fz);
+      ax += fx; ay += fy; az += fz;
+      counter++;
+    }
+    const float sc = 1.0f / (float)counter;
+    m.nx[s0 + i] = ax * sc; m.ny[s0 + i] = ay * sc; m.nz[s0 + i] = az * sc;
+  }
+}
+
 /* update_node_vb leaf branch for grid leaves (pbvh.c:2033-2041 with PBVH_ITER_ALL over the node's
  * grids): box of every element of the listed leaves; the leaf's vert_bitmap words are cleared on the
  * way (the grid normal pass does not use them) */

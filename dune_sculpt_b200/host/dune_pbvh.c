@@ -893,6 +893,45 @@ static int sync_grids_to_host(PBVH *pbvh)
   return r;
 }
 
+/* kernel/intern/multires_reshape_ccg.c:10-70 + multires_reshape_util.c:417-438 */
+bool DUNE_multires_reshape_assign_final_coords(PBVH *pbvh, SubdivCCG *ccg, MDisps *mdisps, GridPaintMask *grid_paint_masks)
+{
+  if (!ccg || (!mdisps && !grid_paint_masks)) return false;
+  const int gs = ccg->grid_size, area = gs * gs, G = ccg->num_grids;
+  const bool want_mask = ccg->has_mask && grid_paint_masks != NULL;
+  if (pbvh && pbvh->device && pbvh->is_grids) {
+    /* the device is authoritative during and after a stroke: element order on the wire is grid, y, x -- a grid's run
+     * is its MDisps.disps array */
+    const size_t E = (size_t)G * (size_t)area;
+    float *co = mdisps ? malloc(sizeof(float[3]) * E) : NULL;
+    float *mask = want_mask ? malloc(sizeof(float) * E) : NULL;
+    int r = DSC_OK;
+    if (co) r = dsc_download_co(pbvh->device, co);
+    if (r == DSC_OK && mask) r = dsc_download_mask(pbvh->device, mask);
+    if (r == DSC_OK) {
+      for (int g = 0; g < G; g++) {
+        if (co && mdisps[g].disps) memcpy(mdisps[g].disps, co + 3 * (size_t)g * (size_t)area, sizeof(float[3]) * (size_t)area);
+        if (mask && grid_paint_masks[g].data) memcpy(grid_paint_masks[g].data, mask + (size_t)g * (size_t)area, sizeof(float) * (size_t)area);
+      }
+    }
+    free(co);
+    free(mask);
+    return r == DSC_OK;
+  }
+  for (int g = 0; g < G; g++) {
+    const unsigned char *grid = (const unsigned char *)ccg->grids[g];
+    for (int y = 0; y < gs; y++) {
+      for (int x = 0; x < gs; x++) {
+        const int idx = y * gs + x;
+        const unsigned char *e = grid + (size_t)ccg->grid_element_size * (size_t)idx;
+        if (mdisps && mdisps[g].disps) memcpy(mdisps[g].disps[idx], e, sizeof(float[3]));
+        if (want_mask && grid_paint_masks[g].data) memcpy(&grid_paint_masks[g].data[idx], e + ccg->mask_offset, sizeof(float));
+      }
+    }
+  }
+  return true;
+}
+
 void BKE_pbvh_free(PBVH *pbvh)
 {
   if (!pbvh) return;

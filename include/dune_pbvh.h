@@ -248,6 +248,27 @@ void DUNE_pbvh_mask_layer_set(PBVH *pbvh, float *vmask);
 void DUNE_pbvh_vert_normals_set(PBVH *pbvh, float (*vert_normals)[3]);
 void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit);
 
+/* types/types_meshdata.h:274-297: the per-loop displacement grid and paint-mask grid of a multires mesh */
+typedef struct MDisps {
+  int totdisp;
+  int level;
+  float (*disps)[3];
+  unsigned int *hidden;
+} MDisps;
+typedef struct GridPaintMask {
+  float *data;
+  unsigned int level;
+  char _pad[4];
+} GridPaintMask;
+/* multires_reshape_assign_final_coords_from_ccg (kernel/intern/multires_reshape_ccg.c:10-70), the first step of
+ * multires_flush_sculpt_updates -> multiresModifier_reshapeFromCCG (kernel/intern/multires.c:401-428): every grid's
+ * element coordinates into mdisps[grid].disps[y * grid_size + x] and, when both sides have one, its mask into
+ * grid_paint_masks[grid].data[...].  With a device attached the elements come straight from the device (one download,
+ * one memcpy per grid -- the CCG storage is not touched); without one, from the CCG as in the reference.  `mdisps` /
+ * `grid_paint_masks` may be NULL (multires_reshape_util.c:427-435).  Top level only (reshape level == CCG level). */
+bool DUNE_multires_reshape_assign_final_coords(PBVH *pbvh, struct SubdivCCG *subdiv_ccg, MDisps *mdisps,
+                                               GridPaintMask *grid_paint_masks);
+
 /* ---- device hooks (new) ---- */
 int DUNE_pbvh_device_attach(PBVH *pbvh, int device);
 /* before the attach: also keep the tables the device-side draw-buffer fill needs (dsc_draw_enable) */

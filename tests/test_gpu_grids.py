@@ -46,6 +46,11 @@ def _grid_parity(mr, dabs, leaf_limit=0, automask=None):
         assert np.array_equal(hco, orc.co()) and np.array_equal(hno, orc.no())
         if mr.mask is not None:
             assert np.array_equal(hmask, orc.mask())
+        # multires write-back (multires_reshape_ccg.c:10-70): straight from the device into the MDisps / GridPaintMask arrays
+        disps, masks = ses.multires_write_back()
+        assert np.array_equal(disps.reshape(-1, 3), orc.co())
+        if masks is not None:
+            assert np.array_equal(masks.reshape(-1), orc.mask())
         return ses.stats()
     finally:
         ses.close()
@@ -195,3 +200,11 @@ def test_grids_batched_dabs_through_cuda_graphs():
     finally:
         ses.close()
         orc.close()
+
+
+def test_grids_element_parallel_normal_pass_is_bit_identical(monkeypatch):
+    """DSC_GRID_NORMALS_FLAT=1: one thread per element instead of one CTA per grid (an experiment that measured slower)"""
+    monkeypatch.setenv("DSC_GRID_NORMALS_FLAT", "1")
+    mr = meshgen.multires_cube(2, 4, with_mask=True)
+    st = _grid_parity(mr, _sweep(mr, per=2, radii=(6.0, 20.0, 45.0)), leaf_limit=6)
+    assert st["moved_verts"] > 0

@@ -203,3 +203,13 @@ def test_host_library_neighbours_match_the_oracle_and_duplicates_are_the_other_c
             assert set(nb2[nb2.size - nd2:].tolist()) == copies[int(weld[e])] - {e} and nd2 == len(copies[int(weld[e])]) - 1, e
         ses.close()
         orc.close()
+
+
+def test_multires_write_back_from_the_ccg_without_a_device():
+    """multires_reshape_assign_final_coords_from_ccg (multires_reshape_ccg.c:10-70): element (x, y) of grid g lands in
+    mdisps[g].disps[y * gs + x], its mask in grid_paint_masks[g].data[...]"""
+    mr = meshgen.multires_cube(1, 3, with_mask=True)
+    ses = capi.GridSession(mr, leaf_limit=4, device=None)
+    disps, masks = ses.multires_write_back()
+    assert np.array_equal(disps.reshape(-1, 3), mr.co) and np.array_equal(masks.reshape(-1), mr.mask)
+    ses.close()
