@@ -2140,14 +2140,7 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j)
    * more faces run) and all coarse vertices */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
   LAUNCH_CHECK();
-  k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 0, seq);
-  LAUNCH_CHECK();
-  if (ctx->has_odd_edges) {
-    k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 1, seq);
-    LAUNCH_CHECK();
-    ctx->launches++;
-  }
-  k_grid_cverts<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, 1);
+  k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, ctx->has_odd_edges ? 1 : 0, 1, seq, ctx->num_sms * 4);
   LAUNCH_CHECK();
   /* BKE_pbvh_update_normals, PBVH_GRIDS branch (pbvh.c:4575-4583 -> subdiv_ccg.c:847-866) */
   if (ctx->grid_normals_flat) k_grid_normals_flat<<<ctx->num_sms * 8, 256, 0, st>>>(m, g, 0);
@@ -2156,14 +2149,12 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j)
   if (dist && (r = dist_halo_exchange(ctx, true))) return r; /* the new normals of the other ranks' halo elements */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
   LAUNCH_CHECK();
-  k_grid_edges<<<ctx->num_sms * 4, 128, 0, st>>>(m, g, 0, seq);
-  LAUNCH_CHECK();
-  k_grid_cverts<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, g, 0);
+  k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, 0, 0, seq, ctx->num_sms * 4);
   LAUNCH_CHECK();
   /* BKE_pbvh_update_bounds: leaf boxes (the refit follows on the side stream) */
   k_grid_leaf_bb<<<ctx->num_sms * 4, DSC_BLOCK, 0, st>>>(m, hits.list, hits.count);
   LAUNCH_CHECK();
-  ctx->launches += 8;
+  ctx->launches += 7;
   return DSC_OK;
 }
 

@@ -432,6 +432,20 @@ __global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int a
   dsc_grid_edges_body(m, g, all, dsc_grid_seq(m, j), blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g, int all) { dsc_grid_cverts_body(m, g, all, blockIdx.x, gridDim.x); }
+/* coarse edges and coarse vertices in one launch: no element is in both a coarse-edge group and a corner group (the
+ * edge pass leaves out the two end points of an edge, subdiv_ccg.c:1035), so the two passes -- and the pass over
+ * untouched edges with more than two faces -- are independent.  The first `edge_ctas` CTAs take the edges. */
+__global__ void __launch_bounds__(128) k_grid_edges_cverts(DevMesh m, DevGrids g, int odd_too, int all_cverts, int j, int edge_ctas)
+{
+  if ((int)blockIdx.x < edge_ctas) {
+    const int seq = dsc_grid_seq(m, j);
+    dsc_grid_edges_body(m, g, 0, seq, blockIdx.x, edge_ctas);
+    if (odd_too) dsc_grid_edges_body(m, g, 1, seq, blockIdx.x, edge_ctas);
+  }
+  else {
+    dsc_grid_cverts_body(m, g, all_cverts, blockIdx.x - edge_ctas, gridDim.x - edge_ctas);
+  }
+}
 __global__ void __launch_bounds__(GN_BLOCK) k_grid_normals(DevMesh m, DevGrids g, int all)
 {
   extern __shared__ float gsm[];

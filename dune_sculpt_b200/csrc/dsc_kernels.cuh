@@ -1085,7 +1085,9 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
   if (tid == 0 && s_moved) atomicAdd(&m.tot->moved_total, (unsigned long long)s_moved);
 }
 
-/* part B: commit the scratch positions */
+/* part B: commit the scratch positions.  Four slots per thread: a group whose four moved bits are all set is one
+ * float4 copy per coordinate (the interior of the brush sphere), a mixed group goes slot by slot -- so a tile is one
+ * iteration with three independent 16-byte loads in flight instead of four dependent scalar rounds. */
 __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m, int slot)
 {
   const DabState *st = m.st + slot;
@@ -1093,11 +1095,21 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_b(DevMesh m, int slot)
   const int total = st->tile_count;
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
     const int4 ent = tl[u];
-    const int beg = ent.y, cnt = ent.z;
-    for (int i = threadIdx.x; i < cnt; i += DSC_BLOCK) {
+    const int beg = ent.y, cnt = ent.z; /* beg is a multiple of 32 */
+    for (int i = 4 * threadIdx.x; i < cnt; i += 4 * DSC_BLOCK) {
       const int s = beg + i;
-      if ((m.iter_moved[s >> 5] >> (s & 31)) & 1u) {
-        m.cx[s] = m.tx[s]; m.cy[s] = m.ty[s]; m.cz[s] = m.tz[s];
+      const unsigned bits = (m.iter_moved[s >> 5] >> (s & 31)) & 0xfu;
+      if (bits == 0u) continue;
+      if (bits == 0xfu && i + 4 <= cnt) {
+        st4(m.cx, s, ld4(m.tx, s)); st4(m.cy, s, ld4(m.ty, s)); st4(m.cz, s, ld4(m.tz, s));
+      }
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (i + k < cnt && ((bits >> k) & 1u)) {
+            m.cx[s + k] = m.tx[s + k]; m.cy[s + k] = m.ty[s + k]; m.cz[s + k] = m.tz[s + k];
+          }
+        }
       }
     }
   }
