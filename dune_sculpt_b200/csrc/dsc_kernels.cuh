@@ -982,6 +982,11 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
   const DabState *st = m.st + slot;
   const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
   __shared__ unsigned s_moved;
+  /* grids: the rim elements of a tile (about one in sixteen, but one in most warps) are set aside and finished by a
+   * few converged warps after the interior ones, instead of dragging every warp through the table lookup */
+  __shared__ int s_rim_n;
+  __shared__ int s_rim_slot[GRIDS ? DSC_TILE : 1];
+  __shared__ float s_rim_fade[GRIDS ? DSC_TILE : 1];
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) s_moved = 0;
   __syncthreads();
@@ -996,6 +1001,8 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
     if (GRIDS) {
       leaf = m.tile_meta[3 * ent.x + 2].y;
       leaf_beg = m.leaf_ubeg[leaf];
+      if (tid == 0) s_rim_n = 0;
+      __syncthreads();
     }
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
@@ -1009,8 +1016,8 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
           if (d.flags & 1) { vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s]; }
           const float fade = strength * dsc_strength_factor(m, d, sqrtf(distsq), vnx, vny, vnz, s);
           float ax = 0.0f, ay = 0.0f, az = 0.0f;
-          int tot = 0, neighbor_count;
-          bool is_boundary;
+          int tot = 0, neighbor_count = 0;
+          bool is_boundary = false, deferred = false;
           if (GRIDS) {
             const int local = s - leaf_beg;
             const int gi = local / gn.gs2, e = local - gi * gn.gs2;
@@ -1022,24 +1029,12 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
               ax += m.cx[s - 1]; ay += m.cy[s - 1]; az += m.cz[s - 1];
               ax += m.cx[s + 1]; ay += m.cy[s + 1]; az += m.cz[s + 1];
               tot = neighbor_count = 4;
-              is_boundary = false;
             }
             else {
-              const int grid = gn.leaf_grids[gn.leaf_gbeg[leaf] + gi];
-              const int rim = 4 * gn.gs - 4;
-              const int b = ey == 0 ? ex : (ey == last ? gn.gs + ex : (ex == 0 ? 2 * gn.gs + ey - 1 : 3 * gn.gs - 2 + ey - 1));
-              const int *row = gn.rim_nb + ((size_t)grid * rim + b) * gn.rim_w;
-              is_boundary = gn.rim_bnd && gn.rim_bnd[(size_t)grid * rim + b] != 0;
-              neighbor_count = 0;
-              for (int q = 0; q < gn.rim_w; q++) {
-                const int v = row[q];
-                if (v < 0) break;
-                neighbor_count++;
-                if (!is_boundary || m.boundary[v]) {
-                  ax += m.cx[v]; ay += m.cy[v]; az += m.cz[v];
-                  tot++;
-                }
-              }
+              const int k = atomicAdd(&s_rim_n, 1);
+              s_rim_slot[k] = s;
+              s_rim_fade[k] = fade;
+              deferred = true;
             }
           }
           else {
@@ -1054,18 +1049,20 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
               }
             }
           }
-          float rx, ry, rz;
-          if ((neighbor_count <= 2 && is_boundary) || tot == 0) {
-            rx = x; ry = y; rz = z;
+          if (!deferred) {
+            float rx, ry, rz;
+            if ((neighbor_count <= 2 && is_boundary) || tot == 0) {
+              rx = x; ry = y; rz = z;
+            }
+            else {
+              const float f = 1.0f / (float)tot;
+              rx = ax * f; ry = ay * f; rz = az * f;
+            }
+            const float vx = rx - x, vy = ry - y, vz = rz - z;
+            m.tx[s] = x + vx * fade;
+            m.ty[s] = y + vy * fade;
+            m.tz[s] = z + vz * fade;
           }
-          else {
-            const float f = 1.0f / (float)tot;
-            rx = ax * f; ry = ay * f; rz = az * f;
-          }
-          const float vx = rx - x, vy = ry - y, vz = rz - z;
-          m.tx[s] = x + vx * fade;
-          m.ty[s] = y + vy * fade;
-          m.tz[s] = z + vz * fade;
           moved = true;
         }
       }
@@ -1078,6 +1075,47 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
           moved_cnt += __popc(bal);
         }
       }
+    }
+    if (GRIDS) {
+      __syncthreads();
+      const int nrim = s_rim_n;
+      for (int k = tid; k < nrim; k += DSC_BLOCK) {
+        const int s = s_rim_slot[k];
+        const float fade = s_rim_fade[k];
+        const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
+        const int local = s - leaf_beg;
+        const int gi = local / gn.gs2, e = local - gi * gn.gs2;
+        const int ey = e / gn.gs, ex = e - ey * gn.gs, last = gn.gs - 1;
+        const int grid = gn.leaf_grids[gn.leaf_gbeg[leaf] + gi];
+        const int rim = 4 * gn.gs - 4;
+        const int b = ey == 0 ? ex : (ey == last ? gn.gs + ex : (ex == 0 ? 2 * gn.gs + ey - 1 : 3 * gn.gs - 2 + ey - 1));
+        const int *row = gn.rim_nb + ((size_t)grid * rim + b) * gn.rim_w;
+        const bool is_boundary = gn.rim_bnd && gn.rim_bnd[(size_t)grid * rim + b] != 0;
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        int tot = 0, neighbor_count = 0;
+        for (int q = 0; q < gn.rim_w; q++) {
+          const int v = row[q];
+          if (v < 0) break;
+          neighbor_count++;
+          if (!is_boundary || m.boundary[v]) {
+            ax += m.cx[v]; ay += m.cy[v]; az += m.cz[v];
+            tot++;
+          }
+        }
+        float rx, ry, rz;
+        if ((neighbor_count <= 2 && is_boundary) || tot == 0) {
+          rx = x; ry = y; rz = z;
+        }
+        else {
+          const float f = 1.0f / (float)tot;
+          rx = ax * f; ry = ay * f; rz = az * f;
+        }
+        const float vx = rx - x, vy = ry - y, vz = rz - z;
+        m.tx[s] = x + vx * fade;
+        m.ty[s] = y + vy * fade;
+        m.tz[s] = z + vz * fade;
+      }
+      __syncthreads(); /* the list is reset for the next tile */
     }
   }
   if (moved_cnt) atomicAdd(&s_moved, moved_cnt);
