@@ -68,7 +68,6 @@ struct DscContext {
   std::vector<int> h_rim_nb;
   std::vector<unsigned char> h_rim_bnd;
   int rim_width = 0;
-  int grid_seq = 0;
   size_t gn_smem = 0;
   /* draw-buffer fill (dsc_draw_*) */
   bool want_draw = false, want_raycast = false;
@@ -107,7 +106,6 @@ struct DscContext {
   PeerLink link = {};
   void *p2p_region = nullptr;
   void *p2p_peer_region[DSC_MAX_RANKS] = {nullptr};
-  int p2p_round = 0;
   float *d_send_buf = nullptr, *d_recv_buf = nullptr;
 
   int *d_slot_of = nullptr;
@@ -1957,7 +1955,6 @@ static int dist_p2p_setup(DscContext *ctx)
     L.recv_off[q] = ctx->recv_off[q];
   }
   ctx->p2p = true;
-  ctx->p2p_round = 0;
   return DSC_OK;
 }
 
