@@ -69,7 +69,7 @@ class PBVH(C.Structure):
         ("totgrid", C.c_int), ("gridkey", C.c_int * 9), ("grid_hidden", C.c_void_p), ("subdiv_ccg", C.c_void_p),
         ("want_draw_buffers", C.c_int),
         ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
-        ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool),
+        ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool), ("grids_pinned", C.c_bool),
         ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
     ]
 
@@ -95,7 +95,7 @@ CUDA_SYMBOLS = [
     "dsc_raycast_enable", "dsc_raycast", "dsc_draw_enable", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
-    "dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
+    "dsc_download_co", "dsc_download_mvert", "dsc_download_ccg", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
     "dsc_download_node_flags", "dsc_download_touched", "dsc_upload_co", "dsc_synchronize", "dsc_timer_start",
     "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
     "dsc_dist_unique_id", "dsc_dist_init", "dsc_dist_partition", "dsc_dist_halo_plan", "dsc_dist_free",

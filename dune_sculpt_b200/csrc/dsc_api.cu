@@ -2816,6 +2816,44 @@ int dsc_download_mvert(DscContext *ctx, void *r_mvert)
   CU(cudaStreamSynchronize(ctx->stream));
   return DSC_OK;
 }
+
+/* whole CCGElem records (co, [mask], no interleaved: subdiv_ccg.c:62-90) in element order, packed on the device */
+__global__ void k_export_ccg(float *__restrict__ out, const float *__restrict__ cx, const float *__restrict__ cy, const float *__restrict__ cz,
+                             const float *__restrict__ nx, const float *__restrict__ ny, const float *__restrict__ nz,
+                             const float *__restrict__ mask, const int *__restrict__ slot_of, int first, int count, int ef, int mask_off,
+                             int no_off)
+{
+  const long long items = (long long)count * ef;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t / ef), k = (int)(t - (long long)v * ef);
+    const int s = slot_of[first + v];
+    float val = 0.0f;
+    if (k < 3) val = (k == 0 ? cx : (k == 1 ? cy : cz))[s];
+    else if (k == mask_off) val = mask ? mask[s] : 0.0f;
+    else if (no_off >= 0 && k >= no_off && k < no_off + 3) val = (k == no_off ? nx : (k == no_off + 1 ? ny : nz))[s];
+    out[t] = val;
+  }
+}
+int dsc_download_ccg(DscContext *ctx, void *r_elems, int elem_floats, int mask_offset_floats, int normal_offset_floats)
+{
+  NEED_PBVH();
+  if (!r_elems || elem_floats < 3 || elem_floats > 16) return fail(ctx, DSC_ERR_INVALID, "bad CCG element layout");
+  int r = join_side(ctx);
+  if (r) return r;
+  const int V = ctx->totvert;
+  const int chunk = (int)(((size_t)4 * V) / (size_t)elem_floats); /* elements per pass through the staging array */
+  for (int first = 0; first < V; first += chunk) {
+    const int count = std::min(chunk, V - first);
+    k_export_ccg<<<ctx->grid, 256, 0, ctx->stream>>>(ctx->d_stage3, ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny, ctx->m.nz,
+                                                     ctx->m.mask, ctx->d_slot_of, first, count, elem_floats, mask_offset_floats,
+                                                     normal_offset_floats);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync((float *)r_elems + (size_t)first * elem_floats, ctx->d_stage3, sizeof(float) * (size_t)count * elem_floats,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSC_OK;
+}
 int dsc_host_register(DscContext *ctx, void *ptr, size_t bytes)
 {
   if (!ctx || !ptr) return DSC_ERR_INVALID;

@@ -859,23 +859,38 @@ static int sync_grids_to_host(PBVH *pbvh)
   const CCGKey *key = &pbvh->gridkey;
   const int area = key->grid_area, G = pbvh->totgrid, N = pbvh->totnode;
   const size_t E = (size_t)G * (size_t)area;
-  float *co = malloc(sizeof(float[3]) * E), *no = malloc(sizeof(float[3]) * E);
-  float *mask = key->has_mask ? malloc(sizeof(float) * E) : NULL;
-  int r = dsc_download_co(pbvh->device, co);
-  if (r == DSC_OK) r = dsc_download_no(pbvh->device, no);
-  if (r == DSC_OK && mask) r = dsc_download_mask(pbvh->device, mask);
-  if (r == DSC_OK) {
-    for (int g = 0; g < G; g++) {
-      for (int j = 0; j < area; j++) {
-        unsigned char *e = (unsigned char *)pbvh->grids[g] + (size_t)key->elem_size * (size_t)j;
-        const size_t idx = (size_t)g * (size_t)area + (size_t)j;
-        memcpy(e, co + 3 * idx, sizeof(float[3]));
-        if (key->has_normals) memcpy(e + key->normal_offset, no + 3 * idx, sizeof(float[3]));
-        if (mask) memcpy(e + key->mask_offset, mask + idx, sizeof(float));
+  int r;
+  /* the grids of a SubdivCCG are one block (grids_storage, subdiv_ccg.c:116-122): whole CCGElem records are packed on
+   * the device and land in it by DMA; grids allocated one by one take the layer-by-layer path */
+  bool contiguous = G > 0 && key->elem_size % (int)sizeof(float) == 0;
+  for (int g = 1; g < G && contiguous; g++) {
+    contiguous = (unsigned char *)pbvh->grids[g] == (unsigned char *)pbvh->grids[0] + (size_t)g * (size_t)area * (size_t)key->elem_size;
+  }
+  if (contiguous) {
+    if (!pbvh->grids_pinned && dsc_host_register(pbvh->device, pbvh->grids[0], E * (size_t)key->elem_size) == DSC_OK) pbvh->grids_pinned = true;
+    r = dsc_download_ccg(pbvh->device, pbvh->grids[0], key->elem_size / (int)sizeof(float),
+                         key->has_mask ? key->mask_offset / (int)sizeof(float) : -1,
+                         key->has_normals ? key->normal_offset / (int)sizeof(float) : -1);
+  }
+  else {
+    float *co = malloc(sizeof(float[3]) * E), *no = malloc(sizeof(float[3]) * E);
+    float *mask = key->has_mask ? malloc(sizeof(float) * E) : NULL;
+    r = dsc_download_co(pbvh->device, co);
+    if (r == DSC_OK) r = dsc_download_no(pbvh->device, no);
+    if (r == DSC_OK && mask) r = dsc_download_mask(pbvh->device, mask);
+    if (r == DSC_OK) {
+      for (int g = 0; g < G; g++) {
+        for (int j = 0; j < area; j++) {
+          unsigned char *e = (unsigned char *)pbvh->grids[g] + (size_t)key->elem_size * (size_t)j;
+          const size_t idx = (size_t)g * (size_t)area + (size_t)j;
+          memcpy(e, co + 3 * idx, sizeof(float[3]));
+          if (key->has_normals) memcpy(e + key->normal_offset, no + 3 * idx, sizeof(float[3]));
+          if (mask) memcpy(e + key->mask_offset, mask + idx, sizeof(float));
+        }
       }
     }
+    free(co); free(no); free(mask);
   }
-  free(co); free(no); free(mask);
   if (r != DSC_OK) return r;
   float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
   int *flag = malloc(sizeof(int) * (size_t)N);
@@ -1168,7 +1183,8 @@ void DUNE_pbvh_device_detach(PBVH *pbvh)
   if (pbvh && pbvh->device) {
     if (pbvh->normals_pinned) dsc_host_unregister(pbvh->device, pbvh->vert_normals);
     if (pbvh->verts_pinned) dsc_host_unregister(pbvh->device, pbvh->verts);
-    pbvh->normals_pinned = pbvh->verts_pinned = false;
+    if (pbvh->grids_pinned) dsc_host_unregister(pbvh->device, pbvh->grids[0]);
+    pbvh->normals_pinned = pbvh->verts_pinned = pbvh->grids_pinned = false;
     dsc_ctx_destroy(pbvh->device);
     pbvh->device = NULL;
   }

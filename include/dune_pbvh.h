@@ -196,7 +196,7 @@ typedef struct PBVH {
   DscContext *device;
   bool device_dirty; /* the device holds newer positions / normals / boxes than the host arrays */
   bool in_stroke;
-  bool normals_pinned, verts_pinned; /* host arrays page-locked for the stroke-end DMA */
+  bool normals_pinned, verts_pinned, grids_pinned; /* host arrays page-locked for the stroke-end DMA */
   /* session tables (kernel/intern/paint.c:1685-1688 pmap, boundary info) */
   int *nb_offsets, *nb_indices;
   unsigned char *boundary;

@@ -233,6 +233,9 @@ int dsc_host_register(DscContext *ctx, void *ptr, size_t bytes);
 int dsc_host_unregister(DscContext *ctx, void *ptr);
 int dsc_download_no(DscContext *ctx, float *r_no /* [totvert][3] */);
 int dsc_download_mask(DscContext *ctx, float *r_mask /* [totvert]: the mask layer (grids average it when stitching) */);
+/* grids: whole CCGElem records (co, then mask, then no -- subdiv_ccg.c:62-90) in element order, interleaved on the
+ * device and copied by DMA straight into the CCG's storage; offsets in floats, -1 = the layer is absent */
+int dsc_download_ccg(DscContext *ctx, void *r_elems, int elem_floats, int mask_offset_floats, int normal_offset_floats);
 int dsc_download_orig_co(DscContext *ctx, float *r_co /* [totvert][3] */);
 int dsc_download_orig_no(DscContext *ctx, float *r_no /* [totvert][3] */);
 int dsc_download_node_bb(DscContext *ctx, float *r_bb /* [totnode][6] */, float *r_orig_bb /* or NULL */);
