@@ -99,7 +99,7 @@ CUDA_SYMBOLS = [
     "dsc_download_node_flags", "dsc_download_touched", "dsc_upload_co", "dsc_synchronize", "dsc_timer_start",
     "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
     "dsc_dist_unique_id", "dsc_dist_init", "dsc_dist_partition", "dsc_dist_halo_plan", "dsc_dist_free",
-    "dsc_dist_owned_range", "dsc_dist_grids_plan", "dsc_dist_uses_peer_memory",
+    "dsc_dist_owned_range", "dsc_dist_grids_plan", "dsc_dist_uses_peer_memory", "dsc_dist_exchanges_skipped",
 ]
 HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
@@ -182,6 +182,7 @@ def cuda_lib():
         L.dsc_dist_grids_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_int_p, c_ubyte_p, c_ubyte_p, c_ubyte_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dsc_dist_uses_peer_memory.argtypes = [C.c_void_p]
+        L.dsc_dist_exchanges_skipped.argtypes = [C.c_void_p, c_int_p]
         L.dsc_dist_free.argtypes = [C.c_void_p]
         L.dsc_dist_free.restype = None
         _cuda = L

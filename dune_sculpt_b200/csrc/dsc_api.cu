@@ -103,6 +103,7 @@ struct DscContext {
   int *d_glist = nullptr, *d_gcount = nullptr; /* partitioned grids: the leaves all ranks gathered this dab */
   /* exchanges over peer memory (see PeerLink in dsc_kernels.cuh); NCCL carries them when the mapping is refused */
   bool p2p = false;
+  unsigned *d_near_mask = nullptr; /* bit per leaf: gathering it can change a halo element on some rank */
   PeerLink link = {};
   void *p2p_region = nullptr;
   void *p2p_peer_region[DSC_MAX_RANKS] = {nullptr};
@@ -507,14 +508,18 @@ static void plan_grid_owner(const DscPbvhDesc *pb, int world, int totgrid, std::
 /* send / receive lists of one rank: per peer, ascending element indices (both sides enumerate the same order) */
 static void plan_grids_lists(const GridTables &t, const std::vector<int> &grid_owner, int world, int rank, GridPlan &mine,
                              std::vector<int> &send_off, std::vector<int> &send_elem, std::vector<int> &recv_off,
-                             std::vector<int> &recv_elem)
+                             std::vector<int> &recv_elem, std::vector<unsigned char> *halo_grid = nullptr)
 {
   const int gs2 = t.gs * t.gs;
+  if (halo_grid) halo_grid->assign((size_t)t.totgrid, 0);
   send_off.assign(world + 1, 0);
   recv_off.assign(world + 1, 0);
   send_elem.clear();
   recv_elem.clear();
   plan_grids_rank(t, grid_owner, rank, mine);
+  if (halo_grid) {
+    for (int e : mine.need) (*halo_grid)[e / gs2] = 1;
+  }
   for (int q = 0; q < world; q++) {
     send_off[q] = (int)send_elem.size();
     recv_off[q] = (int)recv_elem.size();
@@ -526,6 +531,7 @@ static void plan_grids_lists(const GridTables &t, const std::vector<int> &grid_o
     plan_grids_rank(t, grid_owner, q, theirs);
     for (int e : theirs.need) {
       if (grid_owner[e / gs2] == rank) send_elem.push_back(e);
+      if (halo_grid) (*halo_grid)[e / gs2] = 1;
     }
   }
   send_off[world] = (int)send_elem.size();
@@ -814,6 +820,16 @@ int dsc_dist_grids_plan(const DscGridsDesc *gr, const DscPbvhDesc *pb, int world
 void dsc_dist_free(void *p) { free(p); }
 
 int dsc_dist_uses_peer_memory(DscContext *ctx) { return ctx && ctx->p2p ? 1 : 0; }
+int dsc_dist_exchanges_skipped(DscContext *ctx, int *r_skipped)
+{
+  if (!ctx || !r_skipped) return DSC_ERR_INVALID;
+  *r_skipped = 0;
+  if (!ctx->p2p) return DSC_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(r_skipped, ctx->link.flags + P2P_SKIPPED, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSC_OK;
+}
 
 int dsc_dist_owned_range(DscContext *ctx, int r_range[2])
 {
@@ -1708,7 +1724,46 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
       }
       GridPlan plan;
       std::vector<int> se, re;
-      plan_grids_lists(t, grid_owner, ctx->world, ctx->rank, plan, ctx->send_off, se, ctx->recv_off, re);
+      std::vector<unsigned char> halo_grid;
+      plan_grids_lists(t, grid_owner, ctx->world, ctx->rank, plan, ctx->send_off, se, ctx->recv_off, re, &halo_grid);
+      {
+        /* leaves whose gathering can change a halo element on some rank: the dab moves the elements of the leaf's grids,
+         * the stitch and the normal pass reach every grid of those grids' faces and the rims of the faces that share a
+         * coarse edge or vertex with them -- so a leaf is "near a cut" when one of those faces holds a halo grid */
+        const int F = t.totface;
+        std::vector<int> grid_face_h((size_t)t.totgrid, 0);
+        std::vector<unsigned char> face_halo((size_t)F, 0), edge_halo((size_t)t.totedge, 0), vert_halo((size_t)t.totcvert, 0);
+        for (int f = 0; f < F; f++) {
+          for (int c = 0; c < t.face_num[f]; c++) {
+            grid_face_h[t.face_start[f] + c] = f;
+            if (halo_grid[t.face_start[f] + c]) face_halo[f] = 1;
+          }
+        }
+        const int gs2h = t.gs * t.gs;
+        for (int e = 0; e < t.totedge; e++) {
+          for (int k = t.edge_off[e]; k < t.edge_off[e + 1]; k++) {
+            if (face_halo[grid_face_h[t.edge_elems[(size_t)k * 2 * t.gs] / gs2h]]) edge_halo[e] = 1;
+          }
+        }
+        for (int v = 0; v < t.totcvert; v++) {
+          for (int k = t.cvert_off[v]; k < t.cvert_off[v + 1]; k++) {
+            if (face_halo[grid_face_h[t.cvert_elems[k] / gs2h]]) vert_halo[v] = 1;
+          }
+        }
+        std::vector<unsigned> near_mask((size_t)m.ghit_words, 0u);
+        for (int l = 0; l < L; l++) {
+          bool near = false;
+          for (int k = 0; k < leaf_pcnt[l] && !near; k++) {
+            const int f = grid_face_h[pb->prim_indices[leaf_pbeg[l] + k]];
+            near = face_halo[f] != 0;
+            for (int c = 0; c < t.face_num[f] && !near; c++) {
+              near = edge_halo[t.grid_edge[t.face_start[f] + c]] || vert_halo[t.grid_cvert[t.face_start[f] + c]];
+            }
+          }
+          if (near) near_mask[l >> 5] |= 1u << (l & 31);
+        }
+        if ((r = dev_upload(ctx, &ctx->d_near_mask, near_mask))) return r;
+      }
       sidx.resize(se.size());
       ridx.resize(re.size());
       for (size_t i = 0; i < se.size(); i++) sidx[i] = ctx->slot_of[se[i]];
@@ -1741,6 +1796,16 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     me.nb_indices = ctx->has_nb ? ctx->h_nb_idx.data() : nullptr;
     std::vector<HaloTriple> tr;
     plan_halo(&me, pb, ctx->world, pl, ctx->leaf_range, tr);
+    {
+      /* leaves that own a vertex some other rank reads: only a dab that gathers one of them changes a halo vertex */
+      std::vector<unsigned> near_mask((size_t)m.ghit_words, 0u);
+      for (const HaloTriple &t3 : tr) {
+        const int sl = ctx->slot_of[t3.vert];
+        const int l = (int)(std::upper_bound(leaf_ubeg.begin(), leaf_ubeg.end(), sl) - leaf_ubeg.begin()) - 1;
+        if (l >= 0 && l < L) near_mask[l >> 5] |= 1u << (l & 31);
+      }
+      if ((r = dev_upload(ctx, &ctx->d_near_mask, near_mask))) return r;
+    }
     ctx->send_off.assign(ctx->world + 1, 0);
     ctx->recv_off.assign(ctx->world + 1, 0);
     for (int q = 0; q < ctx->world; q++) {
@@ -1967,7 +2032,7 @@ static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
     unsigned *gh = ctx->m.ghit + (size_t)slot * ctx->m.ghit_words;
     k_p2p_reduce_push<<<dim3(1, ctx->world), 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
     LAUNCH_CHECK();
-    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
+    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0, ctx->d_near_mask);
     LAUNCH_CHECK();
     ctx->launches += 2;
     return DSC_OK;
@@ -1983,7 +2048,7 @@ static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
   return DSC_OK;
 }
 /* one-ring halo: owners push the positions other ranks' leaves read */
-static int dist_halo_exchange(DscContext *ctx, bool normals = false)
+static int dist_halo_exchange(DscContext *ctx, bool normals = false, int cond = 1)
 {
   const int W = ctx->world;
   float *ax = normals ? ctx->m.nx : ctx->m.cx, *ay = normals ? ctx->m.ny : ctx->m.cy, *az = normals ? ctx->m.nz : ctx->m.cz;
@@ -1992,9 +2057,9 @@ static int dist_halo_exchange(DscContext *ctx, bool normals = false)
     int most = 1;
     for (int q = 0; q < W; q++) most = std::max(most, std::max(ctx->send_off[q + 1] - ctx->send_off[q], ctx->recv_off[q + 1] - ctx->recv_off[q]));
     const int ctas = std::max(1, std::min((most + 1023) / 1024, std::max(1, ctx->num_sms / (2 * W))));
-    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_send_idx, ax, ay, az);
+    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_near_mask ? cond : 0, ctx->d_send_idx, ax, ay, az);
     LAUNCH_CHECK();
-    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_recv_idx, ax, ay, az);
+    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_near_mask ? cond : 0, ctx->d_recv_idx, ax, ay, az);
     LAUNCH_CHECK();
     ctx->launches += 2;
     return DSC_OK;
@@ -2364,7 +2429,9 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
      * the smooth brush also reads neighbours that are in none of them (the next point along a coarse edge in the
      * sibling grid, one step inside another rank's grid): their owners' stitch may have moved them since the last
      * exchange, so the first iteration starts from a fresh halo */
-    if (dist && ctx->is_grids && (r = dist_halo_exchange(ctx))) return r;
+    if (dist && ctx->is_grids && (r = dist_halo_exchange(ctx, false, 2))) return r;
+    /* the bitmask of gathered leaves first: it tells every rank whether this dab's exchanges carry anything */
+    if (dist && (r = dist_allreduce_dab(ctx, slot, false))) return r;
     {
       StageScope s(ctx, ST_SMOOTH);
       k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
@@ -2385,7 +2452,6 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
       }
       if (dist && (r = dist_halo_exchange(ctx))) return r; /* the next iteration reads the ring */
     }
-    if (dist && (r = dist_allreduce_dab(ctx, slot, false))) return r;
   }
   else {
     if (sig.needs_area) {

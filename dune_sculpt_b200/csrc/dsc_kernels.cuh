@@ -2046,12 +2046,17 @@ __global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restri
  * No "inbox free" handshake is needed: a rank pushes round r only after its own receive of round r - 1, i.e. after every
  * peer delivered round r - 1, which a peer does only after ITS receive of round r - 2 -- the last reader of the half
  * round r overwrites.  Nothing waits for anything but a delivery that the peer's push raises unconditionally, so the
- * ranks cannot deadlock as long as they queue the same sequence of exchanges (they do: the dab sequence is replicated). */
+ * ranks cannot deadlock as long as they queue the same sequence of exchanges (they do: the dab sequence is replicated).
+ * A dab that gathers no leaf near a partition cut changes no halo element anywhere; every rank sees that in the
+ * all-reduced bitmask of gathered leaves, and the halo exchanges of such a dab return at once on all ranks (`cond`). */
 #define DSC_MAX_RANKS 8
 #define P2P_DONE 16
 #define P2P_COUNT 32
 #define P2P_ROUND 49 /* exchanges completed so far: the kernels read their round here, so a dab's exchanges replay from a graph */
 #define P2P_RCOUNT 50 /* CTA counter of the receive kernel */
+#define P2P_NEAR 51    /* this dab gathered a leaf near a partition cut: its halo exchanges run */
+#define P2P_DIRTY 52   /* a dab near a cut has run since the last refresh of the smooth brush's halo */
+#define P2P_SKIPPED 53 /* exchanges skipped so far (statistics) */
 #define P2P_ERR 48 /* a wait gave up (a peer never arrived): the host reports it at stroke end instead of hanging */
 struct PeerLink {
   int world, rank;
@@ -2087,12 +2092,19 @@ __device__ __forceinline__ void dsc_flag_wait(const int *p, int round, int *err)
     }
   }
 }
+/* cond 0: always; 1: only when this dab is near a cut; 2: only when the halo is stale for the smooth brush */
+__device__ __forceinline__ bool dsc_p2p_skip(const PeerLink &L, int cond)
+{
+  if (cond == 1) return __ldcg(L.flags + P2P_NEAR) == 0;
+  if (cond == 2) return __ldcg(L.flags + P2P_DIRTY) == 0;
+  return false;
+}
 /* grid (ctas_per_peer, world): blockIdx.y = peer */
-__global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, const int *__restrict__ idx, const float *__restrict__ ax,
+__global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, int cond, const int *__restrict__ idx, const float *__restrict__ ax,
                                                        const float *__restrict__ ay, const float *__restrict__ az)
 {
   const int q = blockIdx.y;
-  if (q == L.rank) return;
+  if (q == L.rank || dsc_p2p_skip(L, cond)) return;
   const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   const int n = L.send_off[q + 1] - L.send_off[q];
   const int *id = idx + L.send_off[q];
@@ -2114,10 +2126,14 @@ __global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, const int *__
     }
   }
 }
-__global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, const int *__restrict__ idx, float *__restrict__ ax,
+__global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, int cond, const int *__restrict__ idx, float *__restrict__ ax,
                                                        float *__restrict__ ay, float *__restrict__ az)
 {
   const int q = blockIdx.y;
+  if (dsc_p2p_skip(L, cond)) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) L.flags[P2P_SKIPPED] += 1;
+    return;
+  }
   const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   if (q != L.rank) {
     if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_DONE + q, round, L.flags + P2P_ERR);
@@ -2139,6 +2155,7 @@ __global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, const int *__
     if (atomicAdd(L.flags + P2P_RCOUNT, 1) + 1 == total) {
       L.flags[P2P_RCOUNT] = 0;
       L.flags[P2P_ROUND] = round;
+      if (cond == 2) L.flags[P2P_DIRTY] = 0; /* every CTA read it when it started */
     }
   }
 }
@@ -2158,12 +2175,13 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, const long 
   if (threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_DONE + L.rank, round);
 }
 __global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, long long *__restrict__ acc, unsigned *__restrict__ ghit, int words,
-                                                         int with_area)
+                                                         int with_area, const unsigned *__restrict__ near_mask)
 {
   const int round = __ldcg(L.flags + P2P_ROUND) + 1;
   if (threadIdx.x < L.world && threadIdx.x != L.rank) dsc_flag_wait(L.flags + P2P_DONE + threadIdx.x, round, L.flags + P2P_ERR);
   __syncthreads();
   const long long *red = L.red + (size_t)(round & 1) * L.red_half;
+  int near = 0;
   if (with_area && threadIdx.x < 16) {
     long long sum = 0;
     for (int r = 0; r < L.world; r++) sum += r == L.rank ? acc[threadIdx.x] : __ldcg(&red[(size_t)r * L.red_stride + threadIdx.x]);
@@ -2175,9 +2193,14 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, long long *
       if (r != L.rank) bits |= __ldcg(reinterpret_cast<const unsigned *>(red + (size_t)r * L.red_stride + 16) + w);
     }
     ghit[w] = bits;
+    if (near_mask && (bits & near_mask[w])) near = 1;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) L.flags[P2P_ROUND] = round;
+  near = __syncthreads_or(near);
+  if (threadIdx.x == 0) {
+    L.flags[P2P_ROUND] = round;
+    L.flags[P2P_NEAR] = near_mask ? near : 1;
+    if (near || !near_mask) L.flags[P2P_DIRTY] = 1;
+  }
 }
 
 /* ------------------------------------------------------------------------------ misc */

@@ -317,6 +317,9 @@ int dsc_dist_owned_range(DscContext *ctx, int r_range[2]);
 /* 1 when the per-dab exchanges run as stores into the peers' HBM over NVLink (cudaIpc-mapped inboxes, flag
  * handshakes), 0 when NCCL send / recv / all-reduce carries them (mapping refused, or DSC_NO_P2P set) */
 int dsc_dist_uses_peer_memory(DscContext *ctx);
+/* halo exchanges that returned at once because the dab gathered no leaf near a partition cut (peer-memory transport:
+ * every rank reads that off the all-reduced bitmask of gathered leaves).  Synchronises. */
+int dsc_dist_exchanges_skipped(DscContext *ctx, int *r_skipped);
 
 /* --- timing helpers (CUDA events on the context's stream) --------------------------------- */
 int dsc_timer_start(DscContext *ctx);

@@ -15,6 +15,13 @@ from dune_sculpt_b200 import capi, meshgen, stroke  # noqa: E402
 from oracle_py import GridOracle, Oracle  # noqa: E402
 
 
+def skipped(ses):
+    import ctypes
+    n = ctypes.c_int(0)
+    ses.D.dsc_dist_exchanges_skipped(ses.ctx, ctypes.byref(n))
+    return n.value
+
+
 def batched_stroke(orc, ses, dabs, rank, what):
     """a second stroke submitted as ONE dsc_dabs call: runs of one launch sequence replay as CUDA graphs, the
     peer-memory exchanges inside them (their round numbers live on the device)"""
@@ -56,6 +63,10 @@ def main():
         for tool in (capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_CLAY_STRIPS, capi.TOOL_GRAB):
             dabs += stroke.c4_tool_stroke(tool, diag, dabs=6, radius_pct=14.0)
         dabs += [capi.make_dab(capi.TOOL_SMOOTH, (0.12 * i - 0.5, 0.05 * i - 0.1, 0.0), 0.45, bstrength=0.8) for i in range(6)]
+        # small dabs well inside one rank's region: their halo exchanges are skipped on every rank
+        for c in ((-0.8, -0.8, 0.0), (0.8, 0.8, 0.0), (-0.8, 0.8, 0.0), (0.8, -0.8, 0.0)):
+            dabs.append(capi.make_dab(capi.TOOL_DRAW, c, 0.08, bstrength=0.2, view_normal=(0, 0, 1)))
+            dabs.append(capi.make_dab(capi.TOOL_SMOOTH, c, 0.1, bstrength=0.6))
         mask = meshgen.low_freq_mask(mesh)
     else:
         mesh, ll = meshgen.icosphere(48, noise=0.003), 700
@@ -87,8 +98,9 @@ def main():
     assert np.array_equal(orc.orig_co(), ses.orig_co()), "rank %d: undo snapshot differs" % rank
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
     batched_stroke(orc, ses, dabs, rank, scenario)
-    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d" %
-          (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs(), ses.D.dsc_dist_uses_peer_memory(ses.ctx)), flush=True)
+    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d skipped_exchanges %d" %
+          (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs(), ses.D.dsc_dist_uses_peer_memory(ses.ctx),
+           skipped(ses)), flush=True)
     ses.close()
 
 
@@ -115,6 +127,20 @@ def multires(world, rank, nid, scenario):
                                   view_normal=n, grab_delta=(0.03, 0.01, 0.02)))
     dabs.append(capi.make_dab(capi.TOOL_GRAB, np.asarray(centres[0], dtype=np.float32), diag * 0.3,
                               bstrength=stroke._strength(capi.TOOL_GRAB, 0.5), grab_delta=(0.02, -0.03, 0.04)))
+    # small dabs: some of them gather no leaf near a partition cut, and their halo exchanges are skipped on every rank
+    rs = np.random.default_rng(23)
+    for k in range(16):
+        if scenario == "multires_open":
+            c = np.array([rs.uniform(-0.9, 0.9), rs.uniform(-0.9, 0.9), 0.0], dtype=np.float32)
+            n = (0.0, 0.0, 1.0)
+        else:
+            c = rs.normal(size=3)
+            c = (c / np.linalg.norm(c)).astype(np.float32)
+            n = tuple(c)
+        if k % 2:
+            dabs.append(capi.make_dab(capi.TOOL_SMOOTH, c, diag * 0.04, bstrength=stroke._strength(capi.TOOL_SMOOTH, 0.6)))
+        else:
+            dabs.append(capi.make_dab(capi.TOOL_DRAW, c, diag * 0.04, bstrength=stroke._strength(capi.TOOL_DRAW, 0.5), view_normal=n))
     orc = GridOracle(mr, leaf_limit=ll)
     ses = capi.GridSession(mr, leaf_limit=ll, device=rank, dist=(world, rank, nid))
     rng, owner = ses.partition(world)
@@ -146,9 +172,9 @@ def multires(world, rank, nid, scenario):
     assert np.array_equal(orc.touched(), ses.touched()), "rank %d: undo membership differs" % rank
     batched_stroke(orc, ses, dabs, rank, scenario)
     assert np.array_equal(orc.mask(), ses.mask()), "rank %d: mask layer differs after the batched stroke" % rank
-    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d" %
+    print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d skipped_exchanges %d" %
           (rank, world, scenario, rng[rank], rng[rank + 1], ses.stats()["vertex_dabs"], orc.vertex_dabs(),
-           ses.D.dsc_dist_uses_peer_memory(ses.ctx)), flush=True)
+           ses.D.dsc_dist_uses_peer_memory(ses.ctx), skipped(ses)), flush=True)
     ses.close()
 
 
