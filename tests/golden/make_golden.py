@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from dune_sculpt_b200 import capi, meshgen, stroke  # noqa: E402
-from oracle_py import Oracle  # noqa: E402
+from oracle_py import GridOracle, Oracle  # noqa: E402
 
 
 def _digest(*arrays):
@@ -56,6 +56,29 @@ def compute():
         rec["vertex_dabs"] = int(o.vertex_dabs())
         out[name] = rec
         o.close()
+    # multires grids: the element-neighbour lists (closed cube and open sheet), a smooth + draw stroke with the mask layer
+    for name, mr in (("mr_cube_neighbours", meshgen.multires_cube(1, 3)), ("mr_plane_neighbours", meshgen.multires_plane(3, 3))):
+        o = GridOracle(mr, leaf_limit=4)
+        nb = [o.neighbors(e) for e in range(mr.totelem)]
+        out[name] = {"counts": _digest(np.array([len(x) for x in nb], dtype=np.int32)), "lists": _digest(*nb),
+                     "boundary": _digest(np.array([o.is_boundary(e) for e in range(mr.totelem)], dtype=np.uint8))}
+        o.close()
+    mr = meshgen.multires_cube(2, 4, noise=0.03, freq=17.0, with_mask=True)
+    o = GridOracle(mr, leaf_limit=6)
+    o.stroke_begin(None)
+    rng = np.random.default_rng(5)
+    hits = []
+    for i in range(6):
+        p = rng.normal(size=3)
+        p = (p / np.linalg.norm(p)).astype(np.float32)
+        tool = capi.TOOL_SMOOTH if i < 3 else capi.TOOL_DRAW
+        o.dab(capi.make_dab(tool, p, mr.bbox_diag() * 0.15, bstrength=stroke._strength(tool, 0.6), view_normal=tuple(p)))
+        hits.append(o.hits())
+    o.stroke_end()
+    out["mr_cube_smooth_draw"] = {"hits": _digest(*hits), "co": _digest(o.co()), "no": _digest(o.no() + np.float32(0.0)),
+                                  "mask": _digest(o.mask()), "vb": _digest(o.node_arrays()["vb"] + np.float32(0.0)),
+                                  "vertex_dabs": int(o.vertex_dabs())}
+    o.close()
     return out
 
 
