@@ -519,7 +519,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--dabs-per-radius", type=int, default=32)
-    ap.add_argument("--cpu-sample-per-radius", type=int, default=2)
+    ap.add_argument("--cpu-sample-per-radius", type=int, default=32,
+                    help="CPU legs: dabs of every radius of the sweep (32 = the whole stroke, ~ 13 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c3", choices=["c3", "c5"],
                     help="c3 (default): the headline 16.7M-vertex draw sweep; c5: multires grids, draw stroke")
@@ -527,10 +528,13 @@ def main():
     ap.add_argument("--c5-level", type=int, default=7)
     ap.add_argument("--c5-dabs", type=int, default=100, help="draw dabs of the C5 stroke")
     ap.add_argument("--c5-smooth-dabs", type=int, default=100, help="smooth dabs ahead of them")
-    ap.add_argument("--c5-cpu-dabs", type=int, default=6)
+    ap.add_argument("--c5-cpu-dabs", type=int, default=0, help="CPU legs of c5: the first N dabs of the stroke (0 = all of it, ~ 8 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # the CPU arm's steps are bounded samples: cap them so the run ends within minutes
+    if args.c5_cpu_dabs <= 0:
+        args.c5_cpu_dabs = args.c5_dabs + args.c5_smooth_dabs
+    args.cpu_sample_per_radius = max(1, min(args.cpu_sample_per_radius, args.dabs_per_radius))
     args.steps_ref = max(1, min(args.steps, 3))
     args.warmup_ref = max(0, min(args.warmup, 1))
 
