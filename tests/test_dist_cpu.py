@@ -232,3 +232,67 @@ def test_grids_partition_plan_world2_gloo():
     for rank, status, ns, nr in sorted(res):
         assert status == "ok", "rank %d: %s" % (rank, status)
         assert ns > 0 and nr > 0
+
+
+def test_grids_partition_plans_are_symmetric_and_closed_for_every_world_size():
+    """the same plan for 3, 4 and 8 ranks, all ranks evaluated in one process: what rank a sends to rank b is what b
+    expects from a (same elements, same order), nobody receives an element it owns, and every averaging group with an
+    owned member reads only owned or received elements"""
+    sys.path.insert(0, ROOT)
+    from dune_sculpt_b200 import capi, meshgen
+    mr = meshgen.multires_cube(2, 3)     # 96 faces, 384 grids of 5 x 5
+    gs, gs2 = mr.grid_size, mr.grid_size ** 2
+    ses = capi.GridSession(mr, leaf_limit=4, device=None)
+    rows = mr.edge_elems.reshape(-1, 2 * gs)
+    for world in (3, 4, 8):
+        plans = [ses.grids_plan(world, r, with_neighbors=(world == 4)) for r in range(world)]
+        owner = plans[0]["grid_owner"]
+        assert set(owner.tolist()) == set(range(world))
+        eowner = np.repeat(owner, gs2)
+        for a in range(world):
+            pa = plans[a]
+            assert np.array_equal(pa["grid_owner"], owner)
+            assert (eowner[pa["send_elem"]] == a).all() and (eowner[pa["recv_elem"]] != a).all()
+            for b in range(world):
+                if a == b:
+                    continue
+                sent = pa["send_elem"][pa["send_off"][b]:pa["send_off"][b + 1]]
+                want = plans[b]["recv_elem"][plans[b]["recv_off"][a]:plans[b]["recv_off"][a + 1]]
+                assert np.array_equal(sent, want), (world, a, b)
+            have = eowner == a
+            have[pa["recv_elem"]] = True
+            for e in range(mr.edge_off.shape[0] - 1):
+                r_ = rows[mr.edge_off[e]:mr.edge_off[e + 1]]
+                for h in range(2):
+                    if (eowner[r_[:, h * gs:(h + 1) * gs]] == a).any():
+                        assert (pa["edge_mine"][e] >> h) & 1
+                        assert have[r_[:, h * gs:(h + 1) * gs]].all() and have[r_[:, gs - 1:gs + 1]].all()
+            for v in range(mr.cvert_off.shape[0] - 1):
+                el = mr.cvert_elems[mr.cvert_off[v]:mr.cvert_off[v + 1]]
+                if (eowner[el] == a).any():
+                    assert pa["cvert_mine"][v] and have[el].all()
+            for f in range(mr.face_start.shape[0]):
+                g0 = mr.face_start[f]
+                if (owner[g0:g0 + mr.face_num[f]] == a).any():
+                    assert pa["face_dom"][f] & 1
+                    for c in range(mr.face_num[f]):
+                        i = np.arange(gs)
+                        assert have[(g0 + c) * gs2 + i].all() and have[(g0 + c) * gs2 + i * gs].all()
+    ses.close()
+
+
+def test_mesh_halo_plans_are_symmetric_for_every_world_size():
+    sys.path.insert(0, ROOT)
+    from dune_sculpt_b200 import capi, meshgen
+    ses = capi.SculptSession(meshgen.icosphere(20, noise=0.002), leaf_limit=200)
+    for world in (3, 4, 8):
+        plans = [ses.halo_plan(world, r) for r in range(world)]
+        for a in range(world):
+            soff, sv, roff, rv = plans[a]
+            for b in range(world):
+                if a == b:
+                    assert soff[b + 1] == soff[b] and roff[b + 1] == roff[b]
+                    continue
+                boff, bsv, broff, brv = plans[b]
+                assert np.array_equal(sv[soff[b]:soff[b + 1]], brv[broff[a]:broff[a + 1]]), (world, a, b)
+    ses.close()
