@@ -148,7 +148,8 @@ void or_update_normals(OrPbvh *p);
 void or_update_bounds(OrPbvh *p, int flag);
 /* BKE_pbvh_raycast (pbvh.c:3896-3928) with the stroke operator's hit callback (DAGGER sculpt_raycast_cb ->
  * BKE_pbvh_node_raycast -> pbvh_faces_node_raycast, pbvh.c:4041-4100): nearest hit of the ray with the mesh.
- * Returns 1 on a hit; r_face = MLoopTri.poly of the hit, r_vertex = its corner nearest to the hit point. */
+ * Returns 1 on a hit; r_face = MLoopTri.poly of the hit, r_vertex = its corner nearest to the hit point.  Grids
+ * (pbvh_grids_node_raycast, pbvh.c:4102-4200): r_face = the grid of the hit quad, r_vertex = its nearest element. */
 int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], int original, float max_depth, float *r_depth,
                int *r_vertex, int *r_face, float r_face_normal[3], int *r_node);
 /* GPU_pbvh_mesh_buffers_update (gpu/intern/gpu_buffers.c:174-305) of one leaf into `out` (totprim * 3 records of

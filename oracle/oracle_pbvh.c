@@ -856,7 +856,7 @@ typedef struct RayNodeRef {
 int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], int original, float max_depth, float *r_depth,
                int *r_vertex, int *r_face, float r_face_normal[3], int *r_node)
 {
-  if (p->is_grids || p->totnode == 0) return 0;
+  if (p->totnode == 0) return 0;
   RayAABB d;
   memcpy(d.ray_origin, ray_start, sizeof(float[3]));
   for (int k = 0; k < 3; k++) {
@@ -881,7 +881,7 @@ int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], i
   /* an undo node holds the coordinates of ALL verts of its leaf as they were when it was pushed (row a9); for a
    * vert the leaf shares, that is the owner's snapshot if the owner was pushed too, else the (unmoved) current one */
   int *owner = NULL;
-  if (original) {
+  if (original && !p->is_grids) {
     owner = malloc(sizeof(int) * (size_t)(p->totvert + 1));
     for (int n = 0; n < p->totnode; n++) {
       if (p->nodes[n].flag & OR_PBVH_Leaf) {
@@ -900,6 +900,56 @@ int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], i
     const int use_orig = original && p->touched[ord[i].node];
     const int *faces = p->prim_indices + node->prim_offset;
     int node_hit = 0;
+    if (p->is_grids) {
+      /* pbvh_grids_node_raycast (pbvh.c:4102-4200): the quads of the node's grids in grid, y, x order; a quad is its
+       * two triangles (0, 1, 2) then (0, 2, 3), the second only looked at when the first is not a nearer hit
+       * (ray_face_intersection_quad, pbvh.c:3930-3949).  No hidden grid faces on this path.  r_face = the active grid. */
+      const int gs = p->grid_size, gs2 = gs * gs;
+      float (*src)[3] = use_orig ? p->orig_co : p->co;
+      for (int gi = 0; gi < node->totprim; gi++) {
+        const int g = faces[gi];
+        for (int y = 0; y < gs - 1; y++) {
+          for (int x = 0; x < gs - 1; x++) {
+            const int e[4] = {g * gs2 + y * gs + x, g * gs2 + y * gs + x + 1, g * gs2 + (y + 1) * gs + x + 1, g * gs2 + (y + 1) * gs + x};
+            const float *co[4] = {src[e[0]], src[e[1]], src[e[2]], src[e[3]]};
+            float depth_test;
+            if (!((ray_tri_watertight(ray_start, &pc, co[0], co[1], co[2], &depth_test) && depth_test < depth) ||
+                  (ray_tri_watertight(ray_start, &pc, co[0], co[2], co[3], &depth_test) && depth_test < depth)))
+              continue;
+            depth = depth_test;
+            node_hit = 1;
+            if (r_face_normal) {
+              /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
+              float n1[3], n2[3];
+              for (int k = 0; k < 3; k++) {
+                n1[k] = co[0][k] - co[2][k];
+                n2[k] = co[1][k] - co[3][k];
+              }
+              r_face_normal[0] = n1[1] * n2[2] - n1[2] * n2[1];
+              r_face_normal[1] = n1[2] * n2[0] - n1[0] * n2[2];
+              r_face_normal[2] = n1[0] * n2[1] - n1[1] * n2[0];
+              normalize_v3(r_face_normal);
+            }
+            float location[3], nearest[3] = {0.0f, 0.0f, 0.0f};
+            for (int k = 0; k < 3; k++) location[k] = ray_start[k] + ray_normal[k] * depth;
+            for (int j = 0; j < 4; j++) {
+              float da = 0.0f, db = 0.0f;
+              for (int k = 0; k < 3; k++) {
+                da += (location[k] - co[j][k]) * (location[k] - co[j][k]);
+                db += (location[k] - nearest[k]) * (location[k] - nearest[k]);
+              }
+              if (j == 0 || da < db) {
+                memcpy(nearest, co[j], sizeof(float[3]));
+                if (r_vertex) *r_vertex = e[j];
+              }
+            }
+            if (r_face) *r_face = g;
+            if (r_node) *r_node = ord[i].node;
+          }
+        }
+      }
+    }
+    else
     for (int f = 0; f < node->totprim; f++) {
       const int *vt = p->tri_v[faces[f]];
       const float *co[3];

@@ -213,3 +213,32 @@ def test_multires_write_back_from_the_ccg_without_a_device():
     disps, masks = ses.multires_write_back()
     assert np.array_equal(disps.reshape(-1, 3), mr.co) and np.array_equal(masks.reshape(-1), mr.mask)
     ses.close()
+
+
+def test_grids_raycast_oracle_closed_forms():
+    """pbvh_grids_node_raycast restated (pbvh.c:4102-4200): a ray down the z axis onto the spherified multires cube
+    hits just inside the unit sphere (the quads are chords), at the element nearest to the pole; rays that leave, or
+    whose search starts nearer than the surface, hit nothing; mid-stroke the original coordinates answer for the
+    leaves that carry an undo node"""
+    mr = meshgen.multires_cube(1, 5, noise=0.0)
+    orc = GridOracle(mr, leaf_limit=2)
+    hit = orc.raycast((0.02, 0.01, 3.0), (0.0, 0.0, -1.0))
+    assert hit is not None and 2.0 <= hit["depth"] < 2.01
+    assert abs(abs(hit["normal"][2]) - 1.0) < 0.02
+    v = mr.co[hit["vertex"]]
+    assert v[2] > 0.99 and np.hypot(v[0] - 0.02, v[1] - 0.01) < 0.08
+    assert hit["face"] == hit["vertex"] // (mr.grid_size ** 2)          # the active grid holds the active element
+    assert orc.raycast((0.02, 0.01, 3.0), (0.0, 0.0, 1.0)) is None
+    assert orc.raycast((0.02, 0.01, 3.0), (0.0, 0.0, -1.0), max_depth=1.5) is None
+    # from inside the sphere the far side is hit (no back-face culling in the ray test)
+    inside = orc.raycast((0.0, 0.0, 0.0), (0.0, 1.0, 0.0))
+    assert inside is not None and 0.99 < inside["depth"] <= 1.0
+    # a draw dab raises the pole; the original coordinates still answer with the rest surface
+    d0 = hit["depth"]
+    orc.stroke_begin(None)
+    orc.dab(capi.make_dab(capi.TOOL_DRAW, (0.0, 0.0, 1.0), 0.4, bstrength=0.5, view_normal=(0.0, 0.0, 1.0)))
+    now = orc.raycast((0.02, 0.01, 3.0), (0.0, 0.0, -1.0))
+    orig = orc.raycast((0.02, 0.01, 3.0), (0.0, 0.0, -1.0), original=True)
+    assert now["depth"] < d0 - 0.01 and orig["depth"] == d0
+    orc.stroke_end()
+    orc.close()
