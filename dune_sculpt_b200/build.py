@@ -56,7 +56,7 @@ def build_host(force=False):
     deps = [src, os.path.join(ROOT, "include", "dune_pbvh.h"), os.path.join(ROOT, "include", "dune_sculpt_cuda.h")]
     out = os.path.join(LIB, "libdune_sculpt_host.so")
     if force or _newer(out, deps):
-        cmd = [GCC, "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wextra", "-o", out, src,
+        cmd = [GCC, "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fopenmp", "-Wall", "-Wextra", "-o", out, src,
                "-L" + LIB, "-ldune_sculpt_cuda", "-Wl,-rpath,$ORIGIN", "-lm"]
         subprocess.run(cmd, check=True)
     return out

@@ -6,6 +6,8 @@
  */
 #include "../../include/dune_pbvh.h"
 
+#define _POSIX_C_SOURCE 199309L
+#include <time.h>
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
@@ -80,11 +82,6 @@ typedef struct PrimBox {
   float lo[3], hi[3], mid[3];
 } PrimBox;
 
-typedef struct BuildJob {
-  int node, offset, count;
-  bool root_cb;
-} BuildJob;
-
 static char g_attach_error[512];
 
 static inline float minf(float a, float b) { return (a < b) ? a : b; }
@@ -113,20 +110,6 @@ static void ensure_nodes(PBVH *pbvh, int totnode)
     pbvh->node_mem_count = cap;
   }
   pbvh->totnode = totnode;
-}
-
-static void node_box_from_prims(PBVH *pbvh, PBVHNode *node, const PrimBox *pb, int offset, int count)
-{
-  /* pbvh.c:2240-2247 */
-  bb_clear(&node->vb);
-  for (int i = offset + count - 1; i >= offset; i--) {
-    const PrimBox *b = &pb[pbvh->prim_indices[i]];
-    for (int k = 0; k < 3; k++) {
-      node->vb.bmin[k] = minf(node->vb.bmin[k], b->lo[k]);
-      node->vb.bmax[k] = maxf(node->vb.bmax[k], b->hi[k]);
-    }
-  }
-  node->orig_vb = node->vb;
 }
 
 static void leaf_collect_verts(PBVH *pbvh, PBVHNode *node, int node_index, int *stamp, int *local)
@@ -208,67 +191,118 @@ void DUNE_pbvh_vert_normals_set(PBVH *pbvh, float (*vert_normals)[3])
 }
 void DUNE_pbvh_leaf_limit_set(PBVH *pbvh, int leaf_limit) { pbvh->leaf_limit = leaf_limit > 0 ? leaf_limit : 0; }
 
-/* pbvh_build / build_sub (pbvh.c:2372-2450) over the prim boxes `pb` */
-static void build_tree(PBVH *pbvh, const PrimBox *pb, int nprims, const BB *cb, int *stamp, int *local)
+/* pbvh_build / build_sub (pbvh.c:2372-2450) over the prim boxes `pb`, in two passes.
+ *
+ * Pass 1 partitions.  What a node does to prim_indices -- box, centroid box, widest axis, Hoare split at the midpoint --
+ * touches only its own run of the array, so the two children of a split are independent and run as OpenMP tasks: the
+ * root's pass over all prims is serial, the two halves below it run side by side, and so on (about 2 N element visits
+ * on the critical path instead of depth x N).  The permutation each node leaves behind is the serial one.
+ * Pass 2 is serial and cheap: it numbers the nodes in the order the recursive build_sub creates them (a node's two
+ * children take the next two indices when the node is visited, the left subtree is finished before the right one,
+ * pbvh.c:2387-2425) and collects the leaves' vertices in that order -- vertex ownership is "first leaf in build
+ * order", which only a serial walk defines. */
+typedef struct TmpNode {
+  struct TmpNode *child[2]; /* NULL, NULL: leaf */
+  int offset, count;
+  BB vb;
+} TmpNode;
+
+#define BUILD_TASK_MIN 32768 /* prims below which a subtree is built by the thread that reached it */
+
+static void box_of_run(const int *prims, const PrimBox *pb, int offset, int count, BB *vb, BB *cb)
 {
-  /* pre-order walk, left subtree first: node numbering and vertex ownership then come out as in
-   * the recursive build_sub (pbvh.c:2372-2425) */
-  int cap = 128, top = 0;
-  BuildJob *stack = malloc(sizeof(BuildJob) * (size_t)cap);
-  stack[top++] = (BuildJob){0, 0, nprims, true};
-  while (top) {
-    const BuildJob job = stack[--top];
-    if (job.count <= pbvh->leaf_limit) {
-      PBVHNode *node = &pbvh->nodes[job.node];
-      node->flag |= PBVH_Leaf;
-      node->prim_indices = pbvh->prim_indices + job.offset;
-      node->totprim = (unsigned)job.count;
-      node_box_from_prims(pbvh, node, pb, job.offset, job.count);
-      if (pbvh->is_grids) {
-        /* build_grid_leaf_node: no vertex list, the node's elements are its grids' elements */
-        node->uniq_verts = (unsigned)(job.count * pbvh->gridkey.grid_area);
-        node->face_verts = 0;
-        node->flag |= PBVH_UpdateDrawBuffers;
+  bb_clear(vb);
+  if (cb) bb_clear(cb);
+  for (int i = offset + count - 1; i >= offset; i--) {
+    const PrimBox *b = &pb[prims[i]];
+    for (int k = 0; k < 3; k++) {
+      vb->bmin[k] = minf(vb->bmin[k], b->lo[k]);
+      vb->bmax[k] = maxf(vb->bmax[k], b->hi[k]);
+      if (cb) {
+        cb->bmin[k] = minf(cb->bmin[k], b->mid[k]);
+        cb->bmax[k] = maxf(cb->bmax[k], b->mid[k]);
       }
-      else {
-        leaf_collect_verts(pbvh, node, job.node, stamp, local);
-      }
-      continue;
     }
-    const int child = pbvh->totnode;
-    ensure_nodes(pbvh, pbvh->totnode + 2);
-    PBVHNode *node = &pbvh->nodes[job.node];
-    node->children_offset = child;
-    node_box_from_prims(pbvh, node, pb, job.offset, job.count);
-    BB c;
-    if (job.root_cb) {
-      c = *cb;
+  }
+}
+
+static TmpNode *partition_rec(PBVH *pbvh, const PrimBox *pb, int offset, int count, const BB *root_cb)
+{
+  TmpNode *t = calloc(1, sizeof(TmpNode));
+  t->offset = offset;
+  t->count = count;
+  if (count <= pbvh->leaf_limit) {
+    box_of_run(pbvh->prim_indices, pb, offset, count, &t->vb, NULL); /* pbvh.c:2240-2247 */
+    return t;
+  }
+  BB c;
+  box_of_run(pbvh->prim_indices, pb, offset, count, &t->vb, &c);
+  if (root_cb) c = *root_cb; /* the root splits on the centroid box BKE_pbvh_build_* accumulated (pbvh.c:2440) */
+  /* widest centroid extent (pbvh.c:1995-2016), split at the midpoint (pbvh.c:2402-2410) */
+  const float dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
+  int axis;
+  if (dx > dy) axis = (dx > dz) ? 0 : 2;
+  else axis = (dy > dz) ? 1 : 2;
+  const int end = split_by_centroid(pbvh->prim_indices, offset, offset + count - 1, axis, (c.bmax[axis] + c.bmin[axis]) * 0.5f, pb);
+  const int nl = end - offset, nr = offset + count - end;
+  if (count >= 2 * BUILD_TASK_MIN) {
+#pragma omp task shared(t) firstprivate(pbvh, pb, offset, nl)
+    t->child[0] = partition_rec(pbvh, pb, offset, nl, NULL);
+#pragma omp task shared(t) firstprivate(pbvh, pb, end, nr)
+    t->child[1] = partition_rec(pbvh, pb, end, nr, NULL);
+#pragma omp taskwait
+  }
+  else {
+    t->child[0] = partition_rec(pbvh, pb, offset, nl, NULL);
+    t->child[1] = partition_rec(pbvh, pb, end, nr, NULL);
+  }
+  return t;
+}
+
+static void number_rec(PBVH *pbvh, TmpNode *t, int index, int *stamp, int *local)
+{
+  if (!t->child[0]) {
+    PBVHNode *node = &pbvh->nodes[index];
+    node->flag |= PBVH_Leaf;
+    node->prim_indices = pbvh->prim_indices + t->offset;
+    node->totprim = (unsigned)t->count;
+    node->vb = t->vb;
+    node->orig_vb = t->vb;
+    if (pbvh->is_grids) {
+      /* build_grid_leaf_node: no vertex list, the node's elements are its grids' elements */
+      node->uniq_verts = (unsigned)(t->count * pbvh->gridkey.grid_area);
+      node->face_verts = 0;
+      node->flag |= PBVH_UpdateDrawBuffers;
     }
     else {
-      bb_clear(&c);
-      for (int i = job.offset + job.count - 1; i >= job.offset; i--) {
-        const float *mid = pb[pbvh->prim_indices[i]].mid;
-        for (int k = 0; k < 3; k++) {
-          c.bmin[k] = minf(c.bmin[k], mid[k]);
-          c.bmax[k] = maxf(c.bmax[k], mid[k]);
-        }
-      }
+      leaf_collect_verts(pbvh, node, index, stamp, local);
     }
-    /* widest centroid extent (pbvh.c:1995-2016), split at the midpoint (pbvh.c:2402-2410) */
-    const float dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
-    int axis;
-    if (dx > dy) axis = (dx > dz) ? 0 : 2;
-    else axis = (dy > dz) ? 1 : 2;
-    const int end = split_by_centroid(pbvh->prim_indices, job.offset, job.offset + job.count - 1, axis,
-                                      (c.bmax[axis] + c.bmin[axis]) * 0.5f, pb);
-    if (top + 2 > cap) {
-      cap *= 2;
-      stack = realloc(stack, sizeof(BuildJob) * (size_t)cap);
-    }
-    stack[top++] = (BuildJob){child + 1, end, job.offset + job.count - end, false};
-    stack[top++] = (BuildJob){child, job.offset, end - job.offset, false};
+    free(t);
+    return;
   }
-  free(stack);
+  const int child = pbvh->totnode;
+  ensure_nodes(pbvh, pbvh->totnode + 2);
+  PBVHNode *node = &pbvh->nodes[index]; /* after ensure_nodes: the array may have moved */
+  node->children_offset = child;
+  node->vb = t->vb;
+  node->orig_vb = t->vb;
+  number_rec(pbvh, t->child[0], child, stamp, local);
+  number_rec(pbvh, t->child[1], child + 1, stamp, local);
+  free(t);
+}
+
+static void build_tree(PBVH *pbvh, const PrimBox *pb, int nprims, const BB *cb, int *stamp, int *local)
+{
+  TmpNode *root = NULL;
+  struct timespec t0, t1, t2;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel
+#pragma omp single
+  root = partition_rec(pbvh, pb, 0, nprims, cb);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  number_rec(pbvh, root, 0, stamp, local);
+  clock_gettime(CLOCK_MONOTONIC, &t2);
+  if (getenv("DUNE_PBVH_TIMING")) fprintf(stderr, "partition %.3f number %.3f\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), (t2.tv_sec - t1.tv_sec) + 1e-9 * (t2.tv_nsec - t1.tv_nsec));
 }
 
 void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, const MLoop *mloop, MVert *verts,
