@@ -167,3 +167,24 @@ def test_node_accessors():
     f = s.pbvh.contents.nodes[leaf].flag
     assert f & capi.PBVH_UpdateNormals and f & capi.PBVH_UpdateBB and f & capi.PBVH_UpdateOriginalBB
     s.close()
+
+
+def test_host_build_matches_the_oracle_at_sizes_that_run_the_task_parallel_partition():
+    """BKE_pbvh_build_mesh splits subtrees of >= 65536 prims into OpenMP tasks; the tree, the prim order and the leaves'
+    vertex lists must still be the serial build's (the oracle's), default leaf limit and a small one"""
+    import numpy as np
+    from dune_sculpt_b200 import capi, meshgen
+    from oracle_py import Oracle
+    for mesh, ll in ((meshgen.grid(420), 0), (meshgen.icosphere(130, noise=0.002), 2500)):
+        assert mesh.totloop - 2 * mesh.totpoly >= 3 * 65536   # looptris: several levels of tasks
+        ses = capi.SculptSession(mesh, leaf_limit=ll, device=None)
+        orc = Oracle(mesh, leaf_limit=ll)
+        na, nb = orc.node_arrays(), ses.node_arrays()
+        for k in ("vb", "orig_vb", "children_offset", "totprim", "uniq_verts", "face_verts", "prim_offset"):
+            assert np.array_equal(na[k], nb[k]), k
+        assert np.array_equal(orc.prim_indices(), ses.prim_indices())
+        for n in np.nonzero(na["flag"] & 1)[0]:
+            cnt = int(na["uniq_verts"][n] + na["face_verts"][n])
+            assert np.array_equal(orc.node_vert_indices(int(n), cnt), ses.node_vert_indices(int(n))), n
+        ses.close()
+        orc.close()
