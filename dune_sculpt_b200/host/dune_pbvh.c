@@ -4,9 +4,11 @@
  * ordering -- with the split rule, leaf limit and first-touch vertex ownership of
  * kernel/intern/pbvh.c:2070-2514; everything per-dab runs on the device.
  */
+#ifndef _POSIX_C_SOURCE
+#define _POSIX_C_SOURCE 199309L /* clock_gettime */
+#endif
 #include "../../include/dune_pbvh.h"
 
-#define _POSIX_C_SOURCE 199309L
 #include <time.h>
 #include <float.h>
 #include <math.h>
@@ -323,27 +325,39 @@ void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, cons
   if (pbvh->leaf_limit <= 0) pbvh->leaf_limit = LEAF_LIMIT;
   if (!looptri_num) return;
 
-  /* per-looptri box and centroid (pbvh.c:2490-2504) */
+  /* per-looptri box and centroid (pbvh.c:2490-2504): independent per looptri; the centroid box is a min / max, exact
+   * in any order */
   PrimBox *pb = malloc(sizeof(PrimBox) * (size_t)looptri_num);
   BB cb;
   bb_clear(&cb);
-  for (int i = 0; i < looptri_num; i++) {
-    PrimBox *b = &pb[i];
-    for (int k = 0; k < 3; k++) {
-      b->lo[k] = FLT_MAX;
-      b->hi[k] = -FLT_MAX;
-    }
-    for (int j = 0; j < 3; j++) {
-      const float *co = verts[mloop[looptri[i].tri[j]].v].co;
+#pragma omp parallel
+  {
+    BB mine;
+    bb_clear(&mine);
+#pragma omp for schedule(static) nowait
+    for (int i = 0; i < looptri_num; i++) {
+      PrimBox *b = &pb[i];
       for (int k = 0; k < 3; k++) {
-        b->lo[k] = minf(b->lo[k], co[k]);
-        b->hi[k] = maxf(b->hi[k], co[k]);
+        b->lo[k] = FLT_MAX;
+        b->hi[k] = -FLT_MAX;
+      }
+      for (int j = 0; j < 3; j++) {
+        const float *co = verts[mloop[looptri[i].tri[j]].v].co;
+        for (int k = 0; k < 3; k++) {
+          b->lo[k] = minf(b->lo[k], co[k]);
+          b->hi[k] = maxf(b->hi[k], co[k]);
+        }
+      }
+      for (int k = 0; k < 3; k++) {
+        b->mid[k] = (b->lo[k] + b->hi[k]) * 0.5f;
+        mine.bmin[k] = minf(mine.bmin[k], b->mid[k]);
+        mine.bmax[k] = maxf(mine.bmax[k], b->mid[k]);
       }
     }
+#pragma omp critical
     for (int k = 0; k < 3; k++) {
-      b->mid[k] = (b->lo[k] + b->hi[k]) * 0.5f;
-      cb.bmin[k] = minf(cb.bmin[k], b->mid[k]);
-      cb.bmax[k] = maxf(cb.bmax[k], b->mid[k]);
+      cb.bmin[k] = minf(cb.bmin[k], mine.bmin[k]);
+      cb.bmax[k] = maxf(cb.bmax[k], mine.bmax[k]);
     }
   }
 
@@ -397,23 +411,34 @@ void BKE_pbvh_build_grids(PBVH *pbvh, CCGElem **grids, int totgrid, CCGKey *key,
   PrimBox *pb = malloc(sizeof(PrimBox) * (size_t)totgrid);
   BB cb;
   bb_clear(&cb);
-  for (int i = 0; i < totgrid; i++) {
-    PrimBox *b = &pb[i];
-    for (int k = 0; k < 3; k++) {
-      b->lo[k] = FLT_MAX;
-      b->hi[k] = -FLT_MAX;
-    }
-    for (int j = 0; j < gridsize * gridsize; j++) {
-      const float *co = ccg_elem_co(key, grids[i], j);
+#pragma omp parallel
+  {
+    BB mine;
+    bb_clear(&mine);
+#pragma omp for schedule(static) nowait
+    for (int i = 0; i < totgrid; i++) {
+      PrimBox *b = &pb[i];
       for (int k = 0; k < 3; k++) {
-        b->lo[k] = minf(b->lo[k], co[k]);
-        b->hi[k] = maxf(b->hi[k], co[k]);
+        b->lo[k] = FLT_MAX;
+        b->hi[k] = -FLT_MAX;
+      }
+      for (int j = 0; j < gridsize * gridsize; j++) {
+        const float *co = ccg_elem_co(key, grids[i], j);
+        for (int k = 0; k < 3; k++) {
+          b->lo[k] = minf(b->lo[k], co[k]);
+          b->hi[k] = maxf(b->hi[k], co[k]);
+        }
+      }
+      for (int k = 0; k < 3; k++) {
+        b->mid[k] = (b->lo[k] + b->hi[k]) * 0.5f;
+        mine.bmin[k] = minf(mine.bmin[k], b->mid[k]);
+        mine.bmax[k] = maxf(mine.bmax[k], b->mid[k]);
       }
     }
+#pragma omp critical
     for (int k = 0; k < 3; k++) {
-      b->mid[k] = (b->lo[k] + b->hi[k]) * 0.5f;
-      cb.bmin[k] = minf(cb.bmin[k], b->mid[k]);
-      cb.bmax[k] = maxf(cb.bmax[k], b->mid[k]);
+      cb.bmin[k] = minf(cb.bmin[k], mine.bmin[k]);
+      cb.bmax[k] = maxf(cb.bmax[k], mine.bmax[k]);
     }
   }
   pbvh->totprim = totgrid;
