@@ -153,7 +153,8 @@ void or_update_bounds(OrPbvh *p, int flag);
 int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], int original, float max_depth, float *r_depth,
                int *r_vertex, int *r_face, float r_face_normal[3], int *r_node);
 /* GPU_pbvh_mesh_buffers_update (gpu/intern/gpu_buffers.c:174-305) of one leaf into `out` (totprim * 3 records of
- * 36 bytes); returns the vertex count */
+ * 36 bytes); returns the vertex count.  Grid leaves (gpu_pbvh_grid_buffers_update, gpu_buffers.c:548-725): smooth -- one
+ * record per element, totprim * grid_size^2; flat -- four per quad, totprim * (grid_size - 1)^2 * 4 */
 int or_draw_buffers_update(OrPbvh *p, int node, int smooth, int show_mask, unsigned char *out);
 /* full-mesh vertex normals the way the accumulate pass would produce them with every vertex dirty */
 void or_recalc_all_normals(OrPbvh *p);

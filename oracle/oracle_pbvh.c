@@ -1004,10 +1004,71 @@ int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], i
  * 36 bytes per looptri corner -- pos f32 x 3 @0, nor i16 x 3 @16, msk u8 @22, col u16 x 4 @24, fset u8 x 3 @32.
  * No hidden faces, no face sets, no vertex colours on this path: every looptri is visible, col stays zero,
  * fset is white.  Clears PBVH_RebuildDrawBuffers | PBVH_UpdateDrawBuffers like pbvh.c:3276. */
+/* gpu/intern/gpu_buffers.c:548-725 gpu_pbvh_grid_buffers_update for one grid leaf, same record format: smooth -- one
+ * record per element in (grid, y, x) order with its own normal and mask; flat -- four records per quad (x, y), (x+1, y),
+ * (x+1, y+1), (x, y+1), the quad normal taken with the corners reversed (gpu_buffers.c:664-666) and the mean of the four
+ * masks.  On this branch col is written too (white, gpu_buffers.c:640-643 with show_vcol, 686-690 always when flat);
+ * here: flat writes it, smooth leaves it zero (no vertex colours on this path).  Returns the record count. */
+static int grid_draw_buffers_update(OrPbvh *p, OrNode *node, int smooth, int show_mask, unsigned char *out)
+{
+  const int stride = 36, gs = p->grid_size, gs2 = gs * gs;
+  const int *grids = p->prim_indices + node->prim_offset;
+  const int use_mask = show_mask && p->mask;
+  const int per_grid = smooth ? gs2 : (gs - 1) * (gs - 1) * 4;
+  memset(out, 0, (size_t)node->totprim * (size_t)per_grid * stride);
+  unsigned char *rec = out;
+  for (int i = 0; i < node->totprim; i++) {
+    const int g = grids[i];
+    if (smooth) {
+      for (int e = g * gs2; e < (g + 1) * gs2; e++, rec += stride) {
+        short no[3];
+        for (int k = 0; k < 3; k++) no[k] = (short)(p->no[e][k] * 32767.0f);
+        memcpy(rec, p->co[e], sizeof(float[3]));
+        memcpy(rec + 16, no, sizeof(no));
+        if (use_mask) rec[22] = (unsigned char)(p->mask[e] * 255);
+        rec[32] = rec[33] = rec[34] = 255;
+      }
+      continue;
+    }
+    for (int y = 0; y < gs - 1; y++) {
+      for (int x = 0; x < gs - 1; x++) {
+        const int e[4] = {g * gs2 + y * gs + x, g * gs2 + y * gs + x + 1, g * gs2 + (y + 1) * gs + x + 1, g * gs2 + (y + 1) * gs + x};
+        /* normal_quad_v3(fno, co[3], co[2], co[1], co[0]) */
+        float n1[3], n2[3], fno[3];
+        for (int k = 0; k < 3; k++) {
+          n1[k] = p->co[e[3]][k] - p->co[e[1]][k];
+          n2[k] = p->co[e[2]][k] - p->co[e[0]][k];
+        }
+        fno[0] = n1[1] * n2[2] - n1[2] * n2[1];
+        fno[1] = n1[2] * n2[0] - n1[0] * n2[2];
+        fno[2] = n1[0] * n2[1] - n1[1] * n2[0];
+        normalize_v3(fno);
+        short no[3];
+        for (int k = 0; k < 3; k++) no[k] = (short)(fno[k] * 32767.0f);
+        unsigned char cmask = 0;
+        if (use_mask) {
+          const float fmask = (p->mask[e[0]] + p->mask[e[1]] + p->mask[e[2]] + p->mask[e[3]]) * 0.25f;
+          cmask = (unsigned char)(fmask * 255);
+        }
+        for (int j = 0; j < 4; j++, rec += stride) {
+          memcpy(rec, p->co[e[j]], sizeof(float[3]));
+          memcpy(rec + 16, no, sizeof(no));
+          rec[22] = cmask;
+          memset(rec + 24, 0xff, 8); /* col u16 x 4 = USHRT_MAX */
+          rec[32] = rec[33] = rec[34] = 255;
+        }
+      }
+    }
+  }
+  node->flag &= ~(unsigned)(OR_PBVH_RebuildDrawBuffers | OR_PBVH_UpdateDrawBuffers);
+  return node->totprim * per_grid;
+}
+
 int or_draw_buffers_update(OrPbvh *p, int ni, int smooth, int show_mask, unsigned char *out)
 {
   OrNode *node = &p->nodes[ni];
-  if (!(node->flag & OR_PBVH_Leaf) || p->is_grids) return 0;
+  if (!(node->flag & OR_PBVH_Leaf)) return 0;
+  if (p->is_grids) return grid_draw_buffers_update(p, node, smooth, show_mask, out);
   const int stride = 36;
   const int *faces = p->prim_indices + node->prim_offset;
   const int use_mask = show_mask && p->mask;

@@ -290,6 +290,15 @@ class GridOracle(Oracle):
         if recalc_normals:
             L.or_grids_recalc_normals(self.p)
 
+    def draw_buffer(self, node, totprim, smooth=True, show_mask=True):
+        """the grid leaf's packed VBO (gpu_buffers.c:548-725): (records, 36) bytes"""
+        gs = self.mesh.grid_size
+        per = gs * gs if smooth else (gs - 1) * (gs - 1) * 4
+        out = np.zeros((totprim * per, 36), dtype=np.uint8)
+        n = self.L.or_draw_buffers_update(self.p, int(node), int(smooth), int(show_mask), out.ctypes.data)
+        assert n == totprim * per
+        return out
+
     def neighbors(self, elem):
         """KERNEL_subdiv_ccg_neighbor_coords_get without duplicates: element indices, reference order"""
         buf = np.zeros(self.L.or_grids_max_neighbors(self.p), dtype=np.int32)

@@ -242,3 +242,32 @@ def test_grids_raycast_oracle_closed_forms():
     assert now["depth"] < d0 - 0.01 and orig["depth"] == d0
     orc.stroke_end()
     orc.close()
+
+
+def test_grids_draw_buffer_oracle_layout():
+    """gpu_pbvh_grid_buffers_update restated (gpu_buffers.c:548-725): smooth = one 36-byte record per element with its
+    position, i16 normal and u8 mask; flat = four records per quad sharing the quad normal (which faces outwards on the
+    spherified cube) and the mean mask; the draw flags are cleared"""
+    mr = meshgen.multires_cube(1, 3, noise=0.0, with_mask=True)
+    orc = GridOracle(mr, leaf_limit=2)
+    na = orc.node_arrays()
+    leaf = int(np.nonzero(na["flag"] & 1)[0][3])
+    grids = orc.prim_indices()[na["prim_offset"][leaf]:na["prim_offset"][leaf] + na["totprim"][leaf]]
+    gs, gs2 = mr.grid_size, mr.grid_size ** 2
+    buf = orc.draw_buffer(leaf, int(na["totprim"][leaf]), smooth=True)
+    el = np.concatenate([np.arange(g * gs2, (g + 1) * gs2) for g in grids])
+    assert np.array_equal(buf[:, 0:12].copy().view(np.float32).reshape(-1, 3), orc.co()[el])
+    assert np.array_equal(buf[:, 16:22].copy().view(np.int16).reshape(-1, 3), (orc.no()[el] * np.float32(32767.0)).astype(np.int16))
+    assert np.array_equal(buf[:, 22], (orc.mask()[el] * np.float32(255)).astype(np.uint8))
+    assert (buf[:, 32:35] == 255).all() and (buf[:, 24:32] == 0).all()
+    assert not (orc.node_arrays()["flag"][leaf] & (capi.PBVH_UpdateDrawBuffers | capi.PBVH_RebuildDrawBuffers))
+    flat = orc.draw_buffer(leaf, int(na["totprim"][leaf]), smooth=False)
+    assert flat.shape[0] == len(grids) * (gs - 1) ** 2 * 4
+    pos = flat[:, 0:12].copy().view(np.float32).reshape(-1, 4, 3)
+    nor = flat[:, 16:22].copy().view(np.int16).reshape(-1, 4, 3).astype(np.float32) / 32767.0
+    assert np.array_equal(pos[0, 0], orc.co()[grids[0] * gs2]) and np.array_equal(pos[0, 2], orc.co()[grids[0] * gs2 + gs + 1])
+    assert (nor[:, 0] == nor[:, 1]).all() and (nor[:, 0] == nor[:, 3]).all()
+    centre = pos.mean(axis=1)
+    assert (np.einsum("ij,ij->i", nor[:, 0], centre / np.linalg.norm(centre, axis=1, keepdims=True)) > 0.9).all()
+    assert (flat[:, 24:32] == 255).all()
+    orc.close()
