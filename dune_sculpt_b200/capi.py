@@ -690,7 +690,7 @@ class GridSession(SculptSession):
     BKE_pbvh_build_grids -> DUNE_pbvh_device_attach_grids; the dab / download methods are the mesh ones
     (a grid element is a vertex to them)"""
 
-    def __init__(self, mr, leaf_limit=0, device=0, dist=None):
+    def __init__(self, mr, leaf_limit=0, device=0, dist=None, draw_buffers=False):
         H = host_lib()
         self.H = H
         self.mesh = mr
@@ -719,6 +719,8 @@ class GridSession(SculptSession):
             H.DUNE_pbvh_leaf_limit_set(self.pbvh, int(leaf_limit))
         H.BKE_pbvh_build_grids(self.pbvh, ccg.grids, mr.totgrid, self.key, ccg.grid_faces, None, None)
         self.ctx = None
+        if draw_buffers:
+            H.DUNE_pbvh_draw_buffers_enable(self.pbvh)
         if device is not None:
             if dist is None:
                 self._chk(H.DUNE_pbvh_device_attach_grids(self.pbvh, self.ccg, int(device)))

@@ -76,7 +76,8 @@ struct DscContext {
   int *d_ray_count = nullptr, *h_ray_count = nullptr;
   std::vector<int> vert_of_slot;
   const int4 *d_tri_slots = nullptr;
-  unsigned *d_vbo = nullptr; /* [tottri * 3][9] packed vertex records, by looptri position */
+  unsigned *d_vbo = nullptr; /* [tottri * 3][9] packed vertex records, by looptri position; grids: [totgrid * draw_per_grid][9] */
+  int draw_per_grid = 0;
   bool has_odd_edges = false; /* some coarse edge has more than two faces */
   bool grid_normals_flat = false; /* DSC_GRID_NORMALS_FLAT=1: the element-parallel normal pass (measured slower: 4 x the IEEE sqrt / div work) */
   bool grid_fused = false;    /* DSC_GRID_FUSED=1: the stages after the brush as one cooperative kernel instead of nine launches */
@@ -3170,7 +3171,6 @@ int dsc_draw_enable(DscContext *ctx)
 {
   if (!ctx) return DSC_ERR_INVALID;
   if (ctx->have_pbvh) return fail(ctx, DSC_ERR_STATE, "dsc_draw_enable comes before dsc_pbvh_upload");
-  if (ctx->is_grids) return fail(ctx, DSC_ERR_UNSUPPORTED, "the grids draw buffers (gpu_buffers.c:548-725) are not on the device yet");
   ctx->want_draw = true;
   return DSC_OK;
 }
@@ -3180,8 +3180,23 @@ int dsc_draw_update(DscContext *ctx, int smooth, int show_mask)
   if (!ctx->want_draw) return fail(ctx, DSC_ERR_STATE, "dsc_draw_enable first");
   int r = join_side(ctx);
   if (r) return r;
-  if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, (size_t)std::max(ctx->tottri, 1) * 3 * 9))) return r;
   const int flags = DSC_PBVH_UpdateDrawBuffers | DSC_PBVH_RebuildDrawBuffers;
+  if (ctx->is_grids) {
+    /* gpu_pbvh_grid_buffers_update (gpu_buffers.c:548-725): gs^2 records per grid when smooth, 4 (gs - 1)^2 when flat; the
+     * shading mode is a property of the mesh (grid_flag_mats) and fixes the layout at the first update */
+    const int gs = ctx->grid_size;
+    const int per_grid = smooth ? gs * gs : (gs - 1) * (gs - 1) * 4;
+    if (ctx->d_vbo && ctx->draw_per_grid != per_grid) return fail(ctx, DSC_ERR_STATE, "the shading mode of a grids context is fixed by its first dsc_draw_update");
+    if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, (size_t)std::max(ctx->totgrid, 1) * (size_t)per_grid * 9))) return r;
+    ctx->draw_per_grid = per_grid;
+    if ((r = run_collect(ctx, flags))) return r;
+    k_grid_draw_fill<<<ctx->num_sms * 4, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->g, ctx->m.flag_list, &ctx->m.tot->flag_count, smooth ? 1 : 0,
+                                                                       (show_mask && ctx->g.mask) ? 1 : 0, ctx->d_vbo);
+    LAUNCH_CHECK();
+    ctx->launches++;
+    return run_clear(ctx, flag_list(ctx), flags);
+  }
+  if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, (size_t)std::max(ctx->tottri, 1) * 3 * 9))) return r;
   if ((r = run_collect(ctx, flags))) return r;
   k_draw_fill<<<ctx->num_sms * 4, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->d_tri_slots, ctx->m.flag_list, &ctx->m.tot->flag_count,
                                                                 smooth ? 1 : 0, (show_mask && ctx->m.mask) ? 1 : 0, ctx->d_vbo);
@@ -3195,8 +3210,9 @@ int dsc_draw_node_buffer(DscContext *ctx, int node, void **r_device_ptr, int *r_
   if (!ctx->d_vbo) return fail(ctx, DSC_ERR_STATE, "dsc_draw_update first");
   if (node < 0 || node >= ctx->totnode || ctx->dev_of_node[node] >= ctx->m.nleaf) return fail(ctx, DSC_ERR_INVALID, "node %d is not a leaf", node);
   const int l = ctx->dev_of_node[node];
-  if (r_device_ptr) *r_device_ptr = ctx->d_vbo + (size_t)ctx->h_leaf_pbeg[l] * 3 * 9;
-  if (r_vert_len) *r_vert_len = ctx->h_leaf_pcnt[l] * 3;
+  const int per_prim = ctx->is_grids ? ctx->draw_per_grid : 3;
+  if (r_device_ptr) *r_device_ptr = ctx->d_vbo + (size_t)ctx->h_leaf_pbeg[l] * per_prim * 9;
+  if (r_vert_len) *r_vert_len = ctx->h_leaf_pcnt[l] * per_prim;
   return DSC_OK;
 }
 int dsc_draw_download(DscContext *ctx, int node, void *r_host, size_t capacity_bytes, int *r_vert_len)

@@ -418,6 +418,75 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_ghit_expand(DevMesh m, const unsi
   }
 }
 
+/* gpu_pbvh_grid_buffers_update (gpu/intern/gpu_buffers.c:548-725) for the listed (flagged) grid leaves, in the record
+ * format of k_draw_fill: smooth -- one record per element in (grid, y, x) order with its own normal and mask; flat --
+ * four records per quad, corners (x, y), (x+1, y), (x+1, y+1), (x, y+1), the quad normal taken with the corners
+ * reversed (gpu_buffers.c:664-666), the mean of the four masks, col = white.  A leaf's records start at
+ * leaf_gbeg[leaf] * per_grid.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent; its parity test is
+ * gated behind DSC_TEST_UNVERIFIED). */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_draw_fill(DevMesh m, DevGrids g, const int *list, const int *count, int smooth,
+                                                              int show_mask, unsigned *vbo)
+{
+  const int n = *count;
+  const int gs = g.gs, gs1 = gs - 1, gs2 = g.gs2;
+  const int per_grid = smooth ? gs2 : gs1 * gs1 * 4;
+  for (int h = blockIdx.x; h < n; h += gridDim.x) {
+    const int l = list[h];
+    const int gb = g.leaf_gbeg[l], ge = g.leaf_gbeg[l + 1];
+    const int units = smooth ? gs2 : gs1 * gs1;
+    for (int t = threadIdx.x; t < (ge - gb) * units; t += blockDim.x) {
+      const int gi = t / units, u = t - gi * units;
+      const int s0 = g.grid_slot0[g.leaf_grids[gb + gi]];
+      unsigned *rec = vbo + ((size_t)(gb + gi) * per_grid) * 9;
+      if (smooth) {
+        const int s = s0 + u;
+        rec += (size_t)u * 9;
+        unsigned cmask = 0u;
+        if (show_mask) cmask = (unsigned)(unsigned char)(int)(g.mask[s] * 255);
+        rec[0] = __float_as_uint(m.cx[s]);
+        rec[1] = __float_as_uint(m.cy[s]);
+        rec[2] = __float_as_uint(m.cz[s]);
+        rec[3] = 0u;
+        rec[4] = dsc_normal_short(m.nx[s]) | (dsc_normal_short(m.ny[s]) << 16);
+        rec[5] = dsc_normal_short(m.nz[s]) | (cmask << 16);
+        rec[6] = 0u;
+        rec[7] = 0u;
+        rec[8] = 0x00ffffffu;
+        continue;
+      }
+      const int y = u / gs1, x = u - y * gs1;
+      const int sl[4] = {s0 + y * gs + x, s0 + y * gs + x + 1, s0 + (y + 1) * gs + x + 1, s0 + (y + 1) * gs + x};
+      /* normal_quad_v3(fno, co[3], co[2], co[1], co[0]): n1 = co3 - co1, n2 = co2 - co0 */
+      const float n1x = m.cx[sl[3]] - m.cx[sl[1]], n1y = m.cy[sl[3]] - m.cy[sl[1]], n1z = m.cz[sl[3]] - m.cz[sl[1]];
+      const float n2x = m.cx[sl[2]] - m.cx[sl[0]], n2y = m.cy[sl[2]] - m.cy[sl[0]], n2z = m.cz[sl[2]] - m.cz[sl[0]];
+      float fx = n1y * n2z - n1z * n2y;
+      float fy = n1z * n2x - n1x * n2z;
+      float fz = n1x * n2y - n1y * n2x;
+      dsc_normalize(fx, fy, fz);
+      const unsigned n01 = dsc_normal_short(fx) | (dsc_normal_short(fy) << 16);
+      unsigned cmask = 0u;
+      if (show_mask) {
+        const float fmask = (g.mask[sl[0]] + g.mask[sl[1]] + g.mask[sl[2]] + g.mask[sl[3]]) * 0.25f;
+        cmask = (unsigned)(unsigned char)(int)(fmask * 255);
+      }
+      const unsigned w5 = dsc_normal_short(fz) | (cmask << 16);
+      rec += (size_t)u * 4 * 9;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        rec[9 * j + 0] = __float_as_uint(m.cx[sl[j]]);
+        rec[9 * j + 1] = __float_as_uint(m.cy[sl[j]]);
+        rec[9 * j + 2] = __float_as_uint(m.cz[sl[j]]);
+        rec[9 * j + 3] = 0u;
+        rec[9 * j + 4] = n01;
+        rec[9 * j + 5] = w5;
+        rec[9 * j + 6] = 0xffffffffu;
+        rec[9 * j + 7] = 0xffffffffu;
+        rec[9 * j + 8] = 0x00ffffffu;
+      }
+    }
+  }
+}
+
 /* ---- the stages as kernels of their own (session start, full averages) ---- */
 /* the stamp of a dab is its sequence number (ring position + 1, read on the device so that the launch can be replayed
  * from a CUDA graph): faces / edges / vertices claimed by this dab carry it */

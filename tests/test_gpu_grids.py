@@ -8,6 +8,10 @@ from oracle_py import GridOracle
 
 pytestmark = pytest.mark.gpu
 
+import os  # noqa: E402
+# tests of device code written after the round's GPU budget was spent: compiled, never run on a GPU yet
+unverified = pytest.mark.skipif(not os.environ.get("DSC_TEST_UNVERIFIED"), reason="not yet run on a GPU (set DSC_TEST_UNVERIFIED=1)")
+
 
 def _grid_parity(mr, dabs, leaf_limit=0, automask=None):
     orc = GridOracle(mr, leaf_limit=leaf_limit)
@@ -208,3 +212,34 @@ def test_grids_element_parallel_normal_pass_is_bit_identical(monkeypatch):
     mr = meshgen.multires_cube(2, 4, with_mask=True)
     st = _grid_parity(mr, _sweep(mr, per=2, radii=(6.0, 20.0, 45.0)), leaf_limit=6)
     assert st["moved_verts"] > 0
+
+
+@unverified
+@pytest.mark.parametrize("smooth", [True, False])
+def test_grids_draw_buffers_from_the_device(smooth):
+    """gpu_pbvh_grid_buffers_update (gpu_buffers.c:548-725) on the device: after a stroke the flagged leaves' vertex
+    records, smooth (per element) or flat (four per quad), byte for byte"""
+    mr = meshgen.multires_cube(1, 4, with_mask=True)
+    orc = GridOracle(mr, leaf_limit=3)
+    ses = capi.GridSession(mr, leaf_limit=3, device=0, draw_buffers=True)
+    try:
+        na = orc.node_arrays()
+        leaves = np.nonzero(na["flag"] & 1)[0]
+        ses.update_draw_buffers(smooth=smooth, show_mask=True)     # every leaf starts flagged (build_grid_leaf_node)
+        for n in leaves:
+            assert np.array_equal(orc.draw_buffer(int(n), int(na["totprim"][n]), smooth=smooth), ses.draw_buffer(int(n))), n
+        orc.stroke_begin(None)
+        ses.stroke_begin(None)
+        for d in _sweep(mr, per=1, radii=(12.0, 30.0)):
+            orc.dab(d)
+            ses.dab(d)
+        orc.stroke_end()
+        ses.stroke_end()
+        flagged = np.nonzero(orc.node_arrays()["flag"] & capi.PBVH_UpdateDrawBuffers)[0]
+        assert flagged.size > 0
+        ses.update_draw_buffers(smooth=smooth, show_mask=True)
+        for n in leaves:
+            assert np.array_equal(orc.draw_buffer(int(n), int(na["totprim"][n]), smooth=smooth), ses.draw_buffer(int(n))), n
+    finally:
+        ses.close()
+        orc.close()
