@@ -422,8 +422,7 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_ghit_expand(DevMesh m, const unsi
  * format of k_draw_fill: smooth -- one record per element in (grid, y, x) order with its own normal and mask; flat --
  * four records per quad, corners (x, y), (x+1, y), (x+1, y+1), (x, y+1), the quad normal taken with the corners
  * reversed (gpu_buffers.c:664-666), the mean of the four masks, col = white.  A leaf's records start at
- * leaf_gbeg[leaf] * per_grid.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent; its parity test is
- * gated behind DSC_TEST_UNVERIFIED). */
+ * leaf_gbeg[leaf] * per_grid.  Byte-exact against the oracle on B200 (tests/test_gpu_grids.py). */
 __global__ void __launch_bounds__(DSC_BLOCK) k_grid_draw_fill(DevMesh m, DevGrids g, const int *list, const int *count, int smooth,
                                                               int show_mask, unsigned *vbo)
 {

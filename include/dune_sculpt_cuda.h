@@ -252,8 +252,8 @@ int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_
  *     on the pointer dsc_draw_node_buffer returns) instead of re-reading the node's triangles on the CPU.
  *     dsc_draw_enable comes between dsc_mesh_upload and dsc_pbvh_upload.  Grids (gpu_pbvh_grid_buffers_update,
  *     gpu_buffers.c:548-725): grid_size^2 records per grid when smooth, 4 (grid_size - 1)^2 when flat -- the shading
- *     mode of a grids context is fixed by its first dsc_draw_update; this branch is compiled but has not been run on
- *     a GPU yet (its parity test is gated behind DSC_TEST_UNVERIFIED). ------------------- */
+ *     mode of a grids context is fixed by its first dsc_draw_update.  Only flagged leaves are refilled, like the
+ *     reference (an unflagged leaf keeps its last records even when a neighbour's stitch moved its rim). ---------- */
 int dsc_draw_enable(DscContext *ctx);
 
 /* --- ray-cast: behind BKE_pbvh_raycast (pbvh.c:3896-3928) + BKE_pbvh_node_raycast (pbvh.c:4041-4100), the step
