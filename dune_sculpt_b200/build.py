@@ -70,10 +70,25 @@ def build_oracle(force=False):
     return os.path.join(d, "build", "liboracle.so")
 
 
+def build_oracle_ref(force=False):
+    """oracle/_ref/libref.so: the reference's own hot-path functions, cut out of /root/reference at build time
+    (oracle/ref_extract.py) -- test infrastructure that pins the oracle.  Where /root/reference is absent (the GPU box)
+    the prebuilt library travels with the tree; returns None when there is neither."""
+    d = os.path.join(ROOT, "oracle")
+    so = os.path.join(d, "_ref", "libref.so")
+    srcs = [os.path.join(d, f) for f in ("ref_extract.py", "ref_shim.h", "ref_api.c", "ref_glue.inc")]
+    if os.path.isdir("/root/reference") and (force or _newer(so, srcs)):
+        subprocess.run([sys.executable, os.path.join(d, "ref_extract.py")], check=True, stdout=subprocess.DEVNULL)
+    return so if os.path.exists(so) else None
+
+
 def build_all(force=False, oracle=False, verbose=False):
     outs = [build_cuda(force, verbose), build_host(force)]
     if oracle:
         outs.append(build_oracle(force))
+        ref = build_oracle_ref(force)
+        if ref:
+            outs.append(ref)
     return outs
 
 

@@ -105,7 +105,7 @@ HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
     "DUNE_pbvh_mesh_sizes_set", "DUNE_pbvh_mask_layer_set", "DUNE_pbvh_vert_normals_set", "DUNE_pbvh_leaf_limit_set",
     "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
-    "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_node_get_grids",
+    "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_count_grid_quads", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
     "DUNE_pbvh_device_attach_grids_dist", "DUNE_multires_reshape_assign_final_coords",
     "DUNE_subdiv_ccg_topology_set", "BKE_subdiv_ccg_neighbor_coords_get", "BKE_subdiv_ccg_coarse_mesh_adjacency_info_get",
@@ -335,16 +335,24 @@ def make_dab(tool, location, radius, **kw):
 class SculptSession:
     """A mesh + its PBVH through the reference-named host API, optionally attached to a device."""
 
-    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None, draw_buffers=False, raycast=False):
-        """dist = (world, rank, nccl_id_bytes) attaches this process as one rank of a partitioned PBVH"""
+    def __init__(self, mesh: Mesh, mask=None, no=None, leaf_limit=0, device=None, dist=None, draw_buffers=False, raycast=False,
+                 poly_mat=None, poly_flag=None, vert_flag=None):
+        """dist = (world, rank, nccl_id_bytes) attaches this process as one rank of a partitioned PBVH;
+        poly_mat / poly_flag = MPoly.mat_nr / .flag (ME_SMOOTH), vert_flag = MVert.flag (ME_HIDE)"""
         H = host_lib()
         self.H = H
         self.mesh = mesh
         self.mvert = np.zeros(mesh.totvert, dtype=MVERT)
         self.mvert["co"] = mesh.co
+        if vert_flag is not None:
+            self.mvert["flag"] = np.asarray(vert_flag).astype(np.int8)
         self.mpoly = np.zeros(mesh.totpoly, dtype=MPOLY)
         self.mpoly["loopstart"] = mesh.poly_start
         self.mpoly["totloop"] = mesh.poly_len
+        if poly_mat is not None:
+            self.mpoly["mat_nr"] = poly_mat
+        if poly_flag is not None:
+            self.mpoly["flag"] = np.asarray(poly_flag).astype(np.int8)
         self.mloop = np.zeros(mesh.totloop, dtype=MLOOP)
         self.mloop["v"] = mesh.loop_v.astype(np.uint32)
         self.tottri = int(H.BKE_mesh_poly_to_tri_count(mesh.totpoly, mesh.totloop))
@@ -690,10 +698,33 @@ class GridSession(SculptSession):
     BKE_pbvh_build_grids -> DUNE_pbvh_device_attach_grids; the dab / download methods are the mesh ones
     (a grid element is a vertex to them)"""
 
-    def __init__(self, mr, leaf_limit=0, device=0, dist=None, draw_buffers=False):
+    def __init__(self, mr, leaf_limit=0, device=0, dist=None, draw_buffers=False, grid_mat=None, grid_flag=None, hidden=None):
+        """grid_mat / grid_flag = DMFlagMat per grid; hidden = [totelem] grid_hidden bit per element"""
         H = host_lib()
         self.H = H
         self.mesh = mr
+        self.flagmats = None
+        if grid_mat is not None or grid_flag is not None:
+            self.flagmats = np.zeros(mr.totgrid, dtype=np.dtype([("mat_nr", np.int16), ("flag", np.int8), ("_pad", np.int8)]))
+            if grid_mat is not None:
+                self.flagmats["mat_nr"] = grid_mat
+            if grid_flag is not None:
+                self.flagmats["flag"] = np.asarray(grid_flag).astype(np.int8)
+        self.grid_hidden = None
+        if hidden is not None:
+            # BLI_bitmap ** : one bitmap per grid that hides something, NULL otherwise
+            area = mr.grid_size * mr.grid_size
+            h = np.asarray(hidden, dtype=np.uint8).reshape(mr.totgrid, area)
+            self._gh_maps = []
+            self.grid_hidden = (C.c_void_p * mr.totgrid)()
+            for g in range(mr.totgrid):
+                if not h[g].any():
+                    continue
+                words = np.zeros((area >> 5) + 1, dtype=np.uint32)
+                idx = np.nonzero(h[g])[0]
+                np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+                self._gh_maps.append(words)
+                self.grid_hidden[g] = words.ctypes.data
         self.dist = dist
         level = int(np.log2(mr.grid_size - 1)) + 1
         assert (1 << (level - 1)) + 1 == mr.grid_size
@@ -717,7 +748,8 @@ class GridSession(SculptSession):
         self.pbvh = H.BKE_pbvh_new()
         if leaf_limit:
             H.DUNE_pbvh_leaf_limit_set(self.pbvh, int(leaf_limit))
-        H.BKE_pbvh_build_grids(self.pbvh, ccg.grids, mr.totgrid, self.key, ccg.grid_faces, None, None)
+        H.BKE_pbvh_build_grids(self.pbvh, ccg.grids, mr.totgrid, self.key, ccg.grid_faces,
+                               None if self.flagmats is None else self.flagmats.ctypes.data, self.grid_hidden)
         self.ctx = None
         if draw_buffers:
             H.DUNE_pbvh_draw_buffers_enable(self.pbvh)

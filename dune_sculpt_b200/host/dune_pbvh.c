@@ -155,6 +155,84 @@ static void leaf_collect_verts(PBVH *pbvh, PBVHNode *node, int node_index, int *
   node->vert_indices = vi;
   node->face_vert_indices = (const int(*)[3])fvi;
   node->flag |= PBVH_RebuildDrawBuffers | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw;
+  /* pbvh.c:2188-2208, 2235: a leaf none of whose looptris is visible is fully hidden (respect_hide, pbvh.c:2566);
+   * a looptri is hidden when one of its corners is (paint.c:1227-1232) */
+  bool has_visible = false;
+  for (int i = 0; i < totface && !has_visible; i++) {
+    const MLoopTri *lt = &pbvh->looptri[node->prim_indices[i]];
+    has_visible = !((pbvh->verts[pbvh->mloop[lt->tri[0]].v].flag | pbvh->verts[pbvh->mloop[lt->tri[1]].v].flag |
+                     pbvh->verts[pbvh->mloop[lt->tri[2]].v].flag) & ME_HIDE);
+  }
+  if (!has_visible) node->flag |= PBVH_FullyHidden;
+}
+
+/* paint.c:1234-1241 */
+static bool grid_face_hidden(const BLI_bitmap *gh, int gridsize, int x, int y)
+{
+#define GH_TEST(i) ((gh[(i) >> 5] >> ((i)&31)) & 1u)
+  return GH_TEST(y * gridsize + x) || GH_TEST(y * gridsize + x + 1) || GH_TEST((y + 1) * gridsize + x + 1) || GH_TEST((y + 1) * gridsize + x);
+#undef GH_TEST
+}
+
+/* pbvh.c:2249-2279 */
+int BKE_pbvh_count_grid_quads(BLI_bitmap **grid_hidden, const int *grid_indices, int totgrid, int gridsize)
+{
+  const int gridarea = (gridsize - 1) * (gridsize - 1);
+  int totquad = 0;
+  for (int i = 0; i < totgrid; i++) {
+    const BLI_bitmap *gh = grid_hidden ? grid_hidden[grid_indices[i]] : NULL;
+    if (gh) {
+      for (int y = 0; y < gridsize - 1; y++) {
+        for (int x = 0; x < gridsize - 1; x++) {
+          if (!grid_face_hidden(gh, gridsize, x, y)) totquad++;
+        }
+      }
+    }
+    else {
+      totquad += gridarea;
+    }
+  }
+  return totquad;
+}
+
+/* pbvh.c:2058-2066 face_materials_match / grid_materials_match on the prims' material records */
+static bool prim_materials_match(const PBVH *pbvh, int prim_a, int prim_b)
+{
+  if (pbvh->is_grids) {
+    const DMFlagMat *a = &pbvh->grid_flag_mats[prim_a], *b = &pbvh->grid_flag_mats[prim_b];
+    return (a->flag & ME_SMOOTH) == (b->flag & ME_SMOOTH) && a->mat_nr == b->mat_nr;
+  }
+  const MPoly *a = &pbvh->mpoly[pbvh->looptri[prim_a].poly], *b = &pbvh->mpoly[pbvh->looptri[prim_b].poly];
+  return (a->flag & ME_SMOOTH) == (b->flag & ME_SMOOTH) && a->mat_nr == b->mat_nr;
+}
+
+/* pbvh.c:2329-2359 */
+static bool leaf_needs_material_split(const PBVH *pbvh, int offset, int count)
+{
+  if (count <= 1) return false;
+  if (pbvh->is_grids ? !pbvh->grid_flag_mats : !pbvh->mpoly) return false;
+  const int first = pbvh->prim_indices[offset];
+  for (int i = offset + count - 1; i > offset; i--) {
+    if (!prim_materials_match(pbvh, first, pbvh->prim_indices[i])) return true;
+  }
+  return false;
+}
+
+/* pbvh.c:2091-2132: Hoare partition, prims of the first prim's material to the left */
+static int split_by_material(PBVH *pbvh, int lo, int hi)
+{
+  int *prims = pbvh->prim_indices;
+  const int first = prims[lo];
+  int i = lo, j = hi;
+  for (;;) {
+    while (prim_materials_match(pbvh, first, prims[i])) i++;
+    while (!prim_materials_match(pbvh, first, prims[j])) j--;
+    if (!(i < j)) return i;
+    const int t = prims[i];
+    prims[i] = prims[j];
+    prims[j] = t;
+    i++;
+  }
 }
 
 static int split_by_centroid(int *prims, int lo, int hi, int axis, float mid, const PrimBox *pb)
@@ -235,6 +313,11 @@ static TmpNode *partition_rec(PBVH *pbvh, const PrimBox *pb, int offset, int cou
   t->count = count;
   if (count <= pbvh->leaf_limit) {
     box_of_run(pbvh->prim_indices, pb, offset, count, &t->vb, NULL); /* pbvh.c:2240-2247 */
+    if (!leaf_needs_material_split(pbvh, offset, count)) return t;
+    /* one draw batch per material and shading mode: split by material instead of by position (pbvh.c:2411-2414) */
+    const int end = split_by_material(pbvh, offset, offset + count - 1);
+    t->child[0] = partition_rec(pbvh, pb, offset, end - offset, NULL);
+    t->child[1] = partition_rec(pbvh, pb, end, offset + count - end, NULL);
     return t;
   }
   BB c;
@@ -274,7 +357,10 @@ static void number_rec(PBVH *pbvh, TmpNode *t, int index, int *stamp, int *local
       /* build_grid_leaf_node: no vertex list, the node's elements are its grids' elements */
       node->uniq_verts = (unsigned)(t->count * pbvh->gridkey.grid_area);
       node->face_verts = 0;
-      node->flag |= PBVH_UpdateDrawBuffers;
+      /* pbvh.c:2301-2307: BKE_pbvh_node_fully_hidden_set(totquads == 0), BKE_pbvh_node_mark_rebuild_draw */
+      if (BKE_pbvh_count_grid_quads(pbvh->grid_hidden, node->prim_indices, (int)node->totprim, pbvh->gridkey.grid_size) == 0)
+        node->flag |= PBVH_FullyHidden;
+      node->flag |= PBVH_RebuildDrawBuffers | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw;
     }
     else {
       leaf_collect_verts(pbvh, node, index, stamp, local);

@@ -42,6 +42,8 @@ typedef struct MVert {
   char flag, bweight;
   char _pad[2];
 } MVert;
+enum { ME_HIDE = (1 << 4) };   /* MVert.flag, types/types_meshdata.h:20-24 */
+enum { ME_SMOOTH = (1 << 0) }; /* MPoly.flag / DMFlagMat.flag */
 typedef struct MPoly {
   int loopstart;
   int totloop;
@@ -218,6 +220,8 @@ void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, cons
 void BKE_pbvh_build_grids(PBVH *pbvh, CCGElem **grids, int totgrid, CCGKey *key, void **gridfaces, DMFlagMat *flagmats,
                           BLI_bitmap **grid_hidden);
 void BKE_pbvh_free(PBVH *pbvh);
+/* visible quads of the listed grids (pbvh.c:2249-2279); grid_hidden may be NULL, and so may any of its entries */
+int BKE_pbvh_count_grid_quads(BLI_bitmap **grid_hidden, const int *grid_indices, int totgrid, int gridsize);
 /* pbvh.c:3770-3800 */
 void BKE_pbvh_node_get_grids(PBVH *pbvh, PBVHNode *node, int **r_grid_indices, int *r_totgrid, int *r_maxgrid,
                              int *r_gridsize, CCGElem ***r_griddata);

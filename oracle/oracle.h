@@ -99,6 +99,10 @@ int or_vert_neighbors(int totvert, int totpoly, const int *poly_start, const int
 OrPbvh *or_pbvh_build_mesh(int totvert, const float (*co)[3], const float (*no)[3], const float *mask,
                            int totpoly, const int *poly_start, const int *poly_len, int totloop,
                            const int *loop_v, int leaf_limit /* 0 = LEAF_LIMIT */);
+/* optional inputs of the NEXT or_pbvh_build_mesh / _grids call (copied by it): MPoly.mat_nr / .flag, MVert.flag,
+ * DMFlagMat.mat_nr / .flag, grid_hidden per element -- material split, fully hidden leaves, hidden vertices */
+void or_pbvh_next_build_attrs(const short *poly_mat, const unsigned char *poly_flag, const unsigned char *vert_flag,
+                              const short *grid_mat, const unsigned char *grid_flag, const unsigned char *grid_hidden);
 /* BKE_pbvh_build_grids (pbvh.c:2516-2561) over a SubdivCCG given as flat tables: elements
  * [totgrid * grid_size^2] (index = grid * gs^2 + y * gs + x), faces (start grid, grid count), adjacent
  * edges (per edge and adjacent face 2 * gs element indices, subdiv_ccg.c:397-463), adjacent vertices
@@ -118,6 +122,7 @@ int or_grids_max_neighbors(const OrPbvh *p);
 int or_grids_is_boundary(const OrPbvh *p, int elem); /* DAGGER SCULPT_vertex_is_boundary, subdiv_ccg.c:1949-2008 */
 void or_grids_average_all(OrPbvh *p);  /* KERNEL_subdiv_ccg_average_grids, subdiv_ccg.c:1170-1189 */
 void or_grids_recalc_normals(OrPbvh *p); /* KERNEL_subdiv_ccg_recalc_normals, subdiv_ccg.c:782-790 */
+void or_grids_inner_normals(OrPbvh *p);  /* its first half alone: subdiv_ccg.c:670-740 on every grid (pin tests) */
 float *or_pbvh_mask(OrPbvh *p);
 void or_pbvh_free(OrPbvh *p);
 int or_pbvh_totnode(const OrPbvh *p);

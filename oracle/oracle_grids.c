@@ -264,6 +264,14 @@ void or_grids_average_all(OrPbvh *p)
   for (int v = 0; v < p->totcvert; v++) average_cvert(p, v);
 }
 
+void or_grids_inner_normals(OrPbvh *p)
+{
+  const int gs1 = p->grid_size - 1;
+  float(*fn)[3] = malloc(sizeof(float[3]) * (size_t)(gs1 * gs1 > 0 ? gs1 * gs1 : 1));
+  for (int g = 0; g < p->totgrid; g++) grid_inner_normals(p, g, fn);
+  free(fn);
+}
+
 /* subdiv_ccg.c:782-790 KERNEL_subdiv_ccg_recalc_normals */
 void or_grids_recalc_normals(OrPbvh *p)
 {

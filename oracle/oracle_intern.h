@@ -38,6 +38,11 @@ struct OrPbvh {
   int (*tri_v)[3];    /* mloop[tri].v resolved */
   int *tri_poly;
   unsigned char *vert_bitmap; /* one byte per vertex */
+  /* material / visibility inputs of the build and the vertex iterator (NULL: one material, nothing hidden) */
+  short *poly_mat, *grid_mat;           /* MPoly.mat_nr, DMFlagMat.mat_nr */
+  unsigned char *poly_flag, *grid_flag; /* MPoly.flag, DMFlagMat.flag (ME_SMOOTH = 1) */
+  unsigned char *vert_flag;             /* MVert.flag (ME_HIDE = 16) */
+  unsigned char *grid_hidden;           /* [totgrid * grid_size^2] grid_hidden bit of the element */
 
   /* sculpt session DAGGER */
   int *nb_off, *nb_idx; /* vertex neighbours, reference order */

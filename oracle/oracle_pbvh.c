@@ -74,6 +74,80 @@ static void update_node_vb(OrPbvh *p, OrNode *node)
   node->vb = vb;
 }
 
+/* Inputs BKE_pbvh_build_mesh / _grids read besides the geometry: MPoly.mat_nr / .flag & ME_SMOOTH (material split,
+ * pbvh.c:2058-2066, 2091-2132, 2329-2359), MVert.flag & ME_HIDE (fully hidden leaves, pbvh.c:2192-2208;
+ * paint.c:1227-1232), DMFlagMat and grid_hidden for grids (pbvh.c:2249-2307; paint.c:1234-1241).  Given for the NEXT
+ * build through or_pbvh_next_build_attrs (all optional); the build copies them. */
+static struct {
+  const short *poly_mat, *grid_mat;
+  const unsigned char *poly_flag, *vert_flag, *grid_flag, *grid_hidden;
+} g_next_attrs;
+void or_pbvh_next_build_attrs(const short *poly_mat, const unsigned char *poly_flag, const unsigned char *vert_flag,
+                              const short *grid_mat, const unsigned char *grid_flag, const unsigned char *grid_hidden)
+{
+  g_next_attrs.poly_mat = poly_mat; g_next_attrs.poly_flag = poly_flag; g_next_attrs.vert_flag = vert_flag;
+  g_next_attrs.grid_mat = grid_mat; g_next_attrs.grid_flag = grid_flag; g_next_attrs.grid_hidden = grid_hidden;
+}
+static void *dup_bytes(const void *src, size_t n)
+{
+  if (!src) return NULL;
+  void *d = malloc(n ? n : 1);
+  memcpy(d, src, n);
+  return d;
+}
+#define OR_ME_SMOOTH 1
+#define OR_ME_HIDE 16
+
+/* pbvh.c:2058-2066 face_materials_match / grid_materials_match over the prim's material record */
+static int prim_materials_match(const OrPbvh *p, int prim_a, int prim_b)
+{
+  int a = prim_a, b = prim_b;
+  const short *mat = p->grid_mat;
+  const unsigned char *flag = p->grid_flag;
+  if (!p->is_grids) {
+    a = p->tri_poly[prim_a];
+    b = p->tri_poly[prim_b];
+    mat = p->poly_mat;
+    flag = p->poly_flag;
+  }
+  const int sa = flag ? (flag[a] & OR_ME_SMOOTH) : 0, sb = flag ? (flag[b] & OR_ME_SMOOTH) : 0;
+  const int ma = mat ? mat[a] : 0, mb = mat ? mat[b] : 0;
+  return sa == sb && ma == mb;
+}
+
+/* pbvh.c:2329-2359 */
+static int leaf_needs_material_split(const OrPbvh *p, int offset, int count)
+{
+  if (count <= 1) return 0;
+  if (p->is_grids ? !(p->grid_mat || p->grid_flag) : !(p->poly_mat || p->poly_flag)) return 0;
+  const int first = p->prim_indices[offset];
+  for (int i = offset + count - 1; i > offset; i--) {
+    if (!prim_materials_match(p, first, p->prim_indices[i])) return 1;
+  }
+  return 0;
+}
+
+/* pbvh.c:2091-2132 */
+static int partition_indices_material(OrPbvh *p, int lo, int hi)
+{
+  const int *indices = p->prim_indices;
+  const int first = p->prim_indices[lo];
+  int i = lo, j = hi;
+  for (;;) {
+    for (; prim_materials_match(p, first, indices[i]); i++) {
+    }
+    for (; !prim_materials_match(p, first, indices[j]); j--) {
+    }
+    if (!(i < j)) {
+      return i;
+    }
+    int t = p->prim_indices[i];
+    p->prim_indices[i] = p->prim_indices[j];
+    p->prim_indices[j] = t;
+    i++;
+  }
+}
+
 /* pbvh.c:2070-2088 */
 static int partition_indices(int *prim_indices, int lo, int hi, int axis, float mid, const OrBBC *prim_bbc)
 {
@@ -166,6 +240,38 @@ static void build_mesh_leaf_node(OrPbvh *p, LeafMap *map, int node_index)
     }
   }
   node->flag |= OR_PBVH_RebuildDrawBuffers | OR_PBVH_UpdateDrawBuffers | OR_PBVH_UpdateRedraw; /* pbvh.c:3663 */
+  /* pbvh.c:2188-2208, 2235: respect_hide is set by BKE_pbvh_new (pbvh.c:2566); a looptri is hidden when any of its
+   * corners is (paint.c:1227-1232) */
+  int has_visible = 0;
+  for (int i = 0; i < totface && !has_visible; i++) {
+    const int *vt = p->tri_v[prims[i]];
+    has_visible = !(p->vert_flag && ((p->vert_flag[vt[0]] | p->vert_flag[vt[1]] | p->vert_flag[vt[2]]) & OR_ME_HIDE));
+  }
+  if (!has_visible) node->flag |= OR_PBVH_FullyHidden;
+}
+
+/* pbvh.c:2249-2279 BKE_pbvh_count_grid_quads; paint.c:1234-1241 */
+static int count_grid_quads(const OrPbvh *p, const int *grid_indices, int totgrid)
+{
+  const int gs = p->grid_size, gridarea = (gs - 1) * (gs - 1);
+  int totquad = 0;
+  for (int i = 0; i < totgrid; i++) {
+    const unsigned char *gh = p->grid_hidden ? p->grid_hidden + (size_t)grid_indices[i] * (size_t)(gs * gs) : NULL;
+    int any = 0;
+    if (gh) {
+      for (int e = 0; e < gs * gs && !any; e++) any = gh[e];
+    }
+    if (!any) { /* no bitmap for this grid */
+      totquad += gridarea;
+      continue;
+    }
+    for (int y = 0; y < gs - 1; y++) {
+      for (int x = 0; x < gs - 1; x++) {
+        if (!(gh[y * gs + x] || gh[y * gs + x + 1] || gh[(y + 1) * gs + x + 1] || gh[(y + 1) * gs + x])) totquad++;
+      }
+    }
+  }
+  return totquad;
 }
 
 /* pbvh.c:2240-2247 */
@@ -197,13 +303,15 @@ static void build_leaf(OrPbvh *p, LeafMap *map, int node_index, const OrBBC *pri
       const int g = p->prim_indices[offset + i];
       for (int j = 0; j < gs2; j++) node->vert_indices[i * gs2 + j] = g * gs2 + j;
     }
-    node->flag |= OR_PBVH_UpdateDrawBuffers;
+    /* build_grid_leaf_node, pbvh.c:2301-2307 */
+    if (count_grid_quads(p, p->prim_indices + offset, count) == 0) node->flag |= OR_PBVH_FullyHidden;
+    node->flag |= OR_PBVH_RebuildDrawBuffers | OR_PBVH_UpdateDrawBuffers | OR_PBVH_UpdateRedraw; /* pbvh.c:3663 */
     return;
   }
   build_mesh_leaf_node(p, map, node_index);
 }
 
-/* pbvh.c:2372-2425 build_sub (single material: leaf_needs_material_split is always false) */
+/* pbvh.c:2372-2425 build_sub */
 static void build_sub(OrPbvh *p, LeafMap *map, int node_index, OrBB *cb, const OrBBC *prim_bbc, int offset, int count)
 {
   int end;
@@ -211,8 +319,10 @@ static void build_sub(OrPbvh *p, LeafMap *map, int node_index, OrBB *cb, const O
 
   const int below_leaf_limit = count <= p->leaf_limit;
   if (below_leaf_limit) {
-    build_leaf(p, map, node_index, prim_bbc, offset, count);
-    return;
+    if (!leaf_needs_material_split(p, offset, count)) {
+      build_leaf(p, map, node_index, prim_bbc, offset, count);
+      return;
+    }
   }
 
   p->nodes[node_index].children_offset = p->totnode;
@@ -220,16 +330,21 @@ static void build_sub(OrPbvh *p, LeafMap *map, int node_index, OrBB *cb, const O
 
   update_vb(p, &p->nodes[node_index], prim_bbc, offset, count);
 
-  if (!cb) {
-    cb = &cb_backing;
-    BB_reset(cb);
-    for (int i = offset + count - 1; i >= offset; i--) {
-      BB_expand(cb, prim_bbc[p->prim_indices[i]].bcentroid);
+  if (!below_leaf_limit) {
+    if (!cb) {
+      cb = &cb_backing;
+      BB_reset(cb);
+      for (int i = offset + count - 1; i >= offset; i--) {
+        BB_expand(cb, prim_bbc[p->prim_indices[i]].bcentroid);
+      }
     }
+    const int axis = BB_widest_axis(cb);
+    end = partition_indices(p->prim_indices, offset, offset + count - 1, axis,
+                            (cb->bmax[axis] + cb->bmin[axis]) * 0.5f, prim_bbc);
   }
-  const int axis = BB_widest_axis(cb);
-  end = partition_indices(p->prim_indices, offset, offset + count - 1, axis,
-                          (cb->bmax[axis] + cb->bmin[axis]) * 0.5f, prim_bbc);
+  else {
+    end = partition_indices_material(p, offset, offset + count - 1); /* pbvh.c:2411-2414 */
+  }
 
   build_sub(p, map, p->nodes[node_index].children_offset, NULL, prim_bbc, offset, end - offset);
   build_sub(p, map, p->nodes[node_index].children_offset + 1, NULL, prim_bbc, end, offset + count - end);
@@ -261,6 +376,11 @@ OrPbvh *or_pbvh_build_mesh(int totvert, const float (*co)[3], const float (*no)[
   memcpy(p->poly_start, poly_start, sizeof(int) * (size_t)totpoly);
   memcpy(p->poly_len, poly_len, sizeof(int) * (size_t)totpoly);
   memcpy(p->loop_v, loop_v, sizeof(int) * (size_t)totloop);
+
+  p->poly_mat = dup_bytes(g_next_attrs.poly_mat, sizeof(short) * (size_t)totpoly);
+  p->poly_flag = dup_bytes(g_next_attrs.poly_flag, (size_t)totpoly);
+  p->vert_flag = dup_bytes(g_next_attrs.vert_flag, (size_t)totvert);
+  memset(&g_next_attrs, 0, sizeof(g_next_attrs));
 
   const int looptri_num = or_looptri_count(totpoly, poly_len);
   p->tri_loop = malloc(sizeof(int[3]) * (size_t)(looptri_num > 0 ? looptri_num : 1));
@@ -374,6 +494,10 @@ OrPbvh *or_pbvh_build_grids(int totgrid, int grid_size, const float (*co)[3], co
   p->cvert_elems = dup_ints(cvert_elems, (size_t)cvert_off[totcvert]);
   p->grid_edge = dup_ints(grid_edge, (size_t)totgrid);
   p->grid_cvert = dup_ints(grid_cvert, (size_t)totgrid);
+  p->grid_mat = dup_bytes(g_next_attrs.grid_mat, sizeof(short) * (size_t)totgrid);
+  p->grid_flag = dup_bytes(g_next_attrs.grid_flag, (size_t)totgrid);
+  p->grid_hidden = dup_bytes(g_next_attrs.grid_hidden, totelem);
+  memset(&g_next_attrs, 0, sizeof(g_next_attrs));
   p->face_stamp = calloc((size_t)totface + 1, sizeof(int));
   p->edge_stamp = calloc((size_t)totedge + 1, sizeof(int));
   p->cvert_stamp = calloc((size_t)totcvert + 1, sizeof(int));
@@ -425,6 +549,7 @@ void or_pbvh_free(OrPbvh *p)
   }
   free(p->nodes); free(p->prim_indices); free(p->co); free(p->no); free(p->mask);
   free(p->poly_start); free(p->poly_len); free(p->loop_v); free(p->tri_loop); free(p->tri_v);
+  free(p->poly_mat); free(p->grid_mat); free(p->poly_flag); free(p->grid_flag); free(p->vert_flag); free(p->grid_hidden);
   free(p->tri_poly); free(p->vert_bitmap); free(p->nb_off); free(p->nb_idx); free(p->boundary);
   free(p->face_start); free(p->face_num); free(p->grid_face); free(p->edge_off); free(p->edge_elems);
   free(p->cvert_off); free(p->cvert_elems); free(p->grid_edge); free(p->grid_cvert);

@@ -81,6 +81,8 @@ def lib():
                                           c_int_p, c_int_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, C.c_int]
         L.or_grids_average_all.argtypes = [C.c_void_p]
         L.or_grids_recalc_normals.argtypes = [C.c_void_p]
+        L.or_grids_inner_normals.argtypes = [C.c_void_p]
+        L.or_pbvh_next_build_attrs.argtypes = [C.c_void_p] * 6
         L.or_grids_set_topology.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p]
         L.or_grids_neighbors.argtypes = [C.c_void_p, C.c_int, c_int_p]
         L.or_grids_max_neighbors.argtypes = [C.c_void_p]
@@ -106,9 +108,25 @@ def dab_from(d):
     return o
 
 
+def _next_attrs(L, poly_mat=None, poly_flag=None, vert_flag=None, grid_mat=None, grid_flag=None, grid_hidden=None):
+    """material / visibility inputs of the next build (the build copies them)"""
+    keep = []
+
+    def opt(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+    L.or_pbvh_next_build_attrs(opt(poly_mat, np.int16), opt(poly_flag, np.uint8), opt(vert_flag, np.uint8), opt(grid_mat, np.int16),
+                               opt(grid_flag, np.uint8), opt(grid_hidden, np.uint8))
+    L._attrs_keep = keep  # alive until the build has copied them
+
+
 class Oracle:
-    def __init__(self, mesh, mask=None, no=None, leaf_limit=0, threads=1):
+    def __init__(self, mesh, mask=None, no=None, leaf_limit=0, threads=1, poly_mat=None, poly_flag=None, vert_flag=None):
         L = lib()
+        _next_attrs(L, poly_mat=poly_mat, poly_flag=poly_flag, vert_flag=vert_flag)
         self.L = L
         self.mesh = mesh
         co = np.ascontiguousarray(mesh.co, dtype=np.float32)
@@ -267,8 +285,9 @@ class GridOracle(Oracle):
     """the oracle over a multires CCG (meshgen.Multires): PBVH_GRIDS, prims are grids, "vertices" are
     grid elements"""
 
-    def __init__(self, mr, leaf_limit=0, threads=1, recalc_normals=True):
+    def __init__(self, mr, leaf_limit=0, threads=1, recalc_normals=True, grid_mat=None, grid_flag=None, hidden=None):
         L = lib()
+        _next_attrs(L, grid_mat=grid_mat, grid_flag=grid_flag, grid_hidden=hidden)
         self.L = L
         self.mesh = mr
         L.or_set_threads(int(threads))

@@ -188,3 +188,59 @@ def test_host_build_matches_the_oracle_at_sizes_that_run_the_task_parallel_parti
             assert np.array_equal(orc.node_vert_indices(int(n), cnt), ses.node_vert_indices(int(n))), n
         ses.close()
         orc.close()
+
+
+def _patchy(n, seed, nmat=3):
+    rng = np.random.default_rng(seed)
+    mat = np.zeros(n, dtype=np.int16)
+    flag = np.zeros(n, dtype=np.uint8)
+    i = 0
+    while i < n:
+        run = int(rng.integers(1, max(2, n // 12)))
+        mat[i:i + run] = rng.integers(0, nmat)
+        flag[i:i + run] = rng.integers(0, 2)
+        i += run
+    return mat, flag
+
+
+@pytest.mark.parametrize("mk,ll", [(lambda: meshgen.grid(96), 700), (lambda: meshgen.mixed_grid(40), 300)])
+def test_build_mesh_material_split_and_hidden_leaves(mk, ll):
+    """leaf_needs_material_split / partition_indices_material (pbvh.c:2091-2132, 2329-2359) and the fully-hidden leaf flag
+    (pbvh.c:2188-2208) -- the oracle these are compared with is itself pinned to the reference (tests/test_ref_pin.py)"""
+    m = mk()
+    mat, pflag = _patchy(m.totpoly, 1)
+    co = np.asarray(m.co)
+    vflag = np.where((co[:, 0] > 0.2) & (co[:, 1] > -0.1), 16, 0).astype(np.uint8)
+    o = Oracle(m, leaf_limit=ll, poly_mat=mat, poly_flag=pflag, vert_flag=vflag)
+    s = capi.SculptSession(m, leaf_limit=ll, poly_mat=mat, poly_flag=pflag, vert_flag=vflag)
+    a, b = o.node_arrays(), s.node_arrays()
+    assert o.totnode == s.totnode
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(o.prim_indices(), s.prim_indices())
+    leaves = np.nonzero(a["flag"] & 1)[0]
+    assert 0 < ((a["flag"][leaves] & capi.PBVH_FullyHidden) != 0).sum() < leaves.size
+    for i in leaves:
+        assert np.array_equal(o.node_vert_indices(int(i), a["uniq_verts"][i] + a["face_verts"][i]), s.node_vert_indices(int(i)))
+    s.close()
+    o.close()
+
+
+def test_build_grids_material_split_and_hidden_leaves():
+    from oracle_py import GridOracle
+    mr = meshgen.multires_cube(2, 4)
+    mat, gflag = _patchy(mr.totgrid, 2)
+    gs2 = mr.grid_size * mr.grid_size
+    hidden = np.zeros(mr.totelem, dtype=np.uint8)
+    hidden[:gs2 * 24] = 1
+    hidden[gs2 * 40 + 5:gs2 * 40 + 9] = 1
+    for ll in (0, 2):
+        o = GridOracle(mr, leaf_limit=ll, recalc_normals=False, grid_mat=mat, grid_flag=gflag, hidden=hidden)
+        s = capi.GridSession(mr, leaf_limit=ll, device=None, grid_mat=mat, grid_flag=gflag, hidden=hidden)
+        a, b = o.node_arrays(), s.node_arrays()
+        assert o.totnode == s.totnode
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (ll, k)
+        assert np.array_equal(o.prim_indices(), s.prim_indices())
+        s.close()
+        o.close()
