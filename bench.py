@@ -1,21 +1,30 @@
 #!/usr/bin/env python
-"""Headline benchmark of the sculpt-stroke hot path (BASELINE.json: vertex-dabs/sec and ms/dab,
+"""Headline benchmark of the sculpt-stroke hot path (BASELINE.json: vertex-dabs/sec and ms/dab at 1M / 16M verts,
 % of HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid 4096]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c3|c1|c2|c4|c5]
 
-N = 1 workload (config.workload): C3 -- draw brush + normal recompute + BB refit on the 16,777,216-
-vertex height-field grid, radius sweep 1-50 % of the bounding-box diagonal, 32 dabs per radius.
-One *step* = a device-to-device rollback of the mesh to its rest state + one pass of the whole 224-dab
-stroke script (so every step does identical work).  `value` = vertex-dabs / second with the
-mesh resident in HBM (CUDA events around the K strokes); `e2e` = the same strokes driven through
-the reference-named host API with host buffers: per dab the descriptor goes host->device, at stroke
-end positions, normals, node boxes and flags come back device->host, all inside the timed region.
+Headline workload (config.workload): C3 -- draw brush + normal recompute + BB refit on the 16,777,216-vertex
+height-field grid, radius sweep 1-50 % of the bounding-box diagonal, 32 dabs per radius.  One *step* = a
+device-to-device rollback of the mesh to its rest state + one pass of the whole stroke script (every step does identical
+work).  `value` = vertex-dabs / second with the mesh resident in HBM (CUDA events around the K steps); `e2e` = the same
+steps driven through the reference-named host API with host buffers: descriptors go host->device, at stroke end
+positions, normals, node boxes and flags come back device->host, all inside the timed region.
 
-Prints ONE JSON line on rank 0.  --impl reference times the CPU oracle (OpenMP, all host threads)
-on a bounded sample of the same workload.
+`roofline`: the dominant kernel's algorithmic bytes (SURVEY.md 8d formulas over device-counted U / A / T / M / U' / M')
+divided by its duration INSIDE the replayed graphs (event-record nodes, dsc_stage_timing mode 2: the path that is
+timed), against the measured copy bandwidth; per radius too.  `whole_path` = SURVEY.md 8d's headline formula
+(U 12 + M 12 + T 12 + A 12 + D 12, area pass excluded) / device time of a timed step.
+`cpu_baseline` + `parity_fullsize`: the CPU oracle (OpenMP) runs the very same full-size stroke; its result is
+compared with the device's -- per-dab node-hit lists, undo-node membership, final positions / normals / boxes.
+
+At N = 1 the line also carries `configs`: the same measurements for C1, C2, C4, C5 (and `c5` again at top level, which
+N > 1 runs carry too: the partitioned multires config the north star names for scaling).
+--impl reference times the CPU oracle (OpenMP, all host threads) on a bounded sample of the headline workload.
+Prints ONE JSON line on rank 0.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -30,10 +39,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "vertex_dabs_per_sec"
 UNIT = "vertex-dabs/s"
+T0 = time.time()
 
 
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print("[bench %6.1fs]" % (time.time() - T0), *a, file=sys.stderr, flush=True)
 
 
 def measured_peaks():
@@ -98,396 +108,586 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(args):
-    from dune_sculpt_b200 import meshgen, stroke
+# ------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """a mesh + the strokes of one step.  stroke = dict(label, dabs, automask, mask_on); groups = dabs per timed group
+    of the sweep (C3: one radius), 0 = the whole stroke"""
+
+    def __init__(self, name, mesh, grids, strokes, desc, brush, mask=None, group=0):
+        self.name, self.mesh, self.grids, self.strokes, self.desc, self.brush = name, mesh, grids, strokes, desc, brush
+        self.mask, self.group = mask, group
+        self.diag = mesh.bbox_diag()
+        self.verts = mesh.totelem if grids else mesh.totvert
+
+    @property
+    def ndabs(self):
+        return sum(len(s["dabs"]) for s in self.strokes)
+
+
+def build_workload(name, args):
+    from dune_sculpt_b200 import capi, meshgen, stroke
     t0 = time.time()
-    if args.config == "c5":
-        # C5: multires cube, `c5_base`^2 base quads per side, level `c5_level`; draw stroke, r = 8 % of the diagonal
-        from dune_sculpt_b200 import capi
+    if name == "c1":
+        mesh = meshgen.cube(args.c1_levels)
+        w = Workload("c1", mesh, False, [dict(label="draw line", dabs=stroke.c1_draw_stroke(), automask=None, mask_on=False)],
+                     "C1 draw, 100-dab straight stroke across the +Z face, r = 0.15, cube subdivided x%d (V=%d)" % (args.c1_levels, mesh.totvert),
+                     "draw (alpha 0.5), SMOOTH falloff, area-normal direction")
+    elif name == "c2":
+        mesh = meshgen.icosphere(args.c2_freq, noise=0.002)
+        w = Workload("c2", mesh, False, [dict(label="smooth arc", dabs=stroke.c2_smooth_stroke(), automask=None, mask_on=False)],
+                     "C2 smooth (CSR one-ring averaging, 3 iterations / dab), 200-dab great-circle stroke, r = 0.2, icosphere f=%d (V=%d)" %
+                     (args.c2_freq, mesh.totvert), "smooth (alpha 0.75), SMOOTH falloff")
+    elif name == "c3":
+        mesh = meshgen.grid(args.grid)
+        dabs = stroke.c3_radius_sweep(mesh.bbox_diag(), dabs_per_radius=args.dabs_per_radius)
+        w = Workload("c3", mesh, False, [dict(label="radius sweep", dabs=dabs, automask=None, mask_on=False)],
+                     "C3 draw+normals+BB radius sweep 1-50%% bbox diag, grid %d^2 (V=%d), %d dabs/stroke" % (args.grid, mesh.totvert, len(dabs)),
+                     "draw (alpha 0.5), SMOOTH falloff, area-normal direction", group=args.dabs_per_radius)
+    elif name == "c4":
+        mesh = meshgen.grid(args.c4_grid)
+        diag = mesh.bbox_diag()
+        mask = meshgen.low_freq_mask(mesh)
+        # automask factors come from the host library's session helpers (boundary-edge propagation, 1 step; topology flood fill
+        # from the vertex nearest the first dab)
+        ses = capi.SculptSession(mesh)
+        auto_b = np.zeros(mesh.totvert, dtype=np.float32)
+        capi.host_lib().DUNE_sculpt_automask_boundary_edges(ses.pbvh, 1, capi.fptr(auto_b))
+        strokes = []
+        tools = (("draw", capi.TOOL_DRAW), ("inflate", capi.TOOL_INFLATE), ("clay strips", capi.TOOL_CLAY_STRIPS), ("grab", capi.TOOL_GRAB))
+        for tname, tool in tools:
+            dabs = stroke.c4_tool_stroke(tool, diag, dabs=args.c4_dabs)
+            strokes.append(dict(label=tname + ", mask off", dabs=dabs, automask=None, mask_on=False))
+        for tname, tool in tools:
+            dabs = stroke.c4_tool_stroke(tool, diag, dabs=args.c4_dabs)
+            strokes.append(dict(label=tname + ", mask + boundary automask", dabs=dabs, automask=auto_b, mask_on=True))
+        dabs = stroke.c4_tool_stroke(capi.TOOL_DRAW, diag, dabs=args.c4_dabs)
+        loc = np.array(dabs[0].location[:], dtype=np.float32)
+        seed = int(np.argmin(((np.asarray(mesh.co) - loc) ** 2).sum(axis=1)))
+        auto_t = np.zeros(mesh.totvert, dtype=np.float32)
+        capi.host_lib().DUNE_sculpt_automask_topology(ses.pbvh, seed, capi.fptr(loc), C_float(0.0), capi.fptr(auto_t))
+        ses.close()
+        strokes.append(dict(label="draw, mask + topology automask", dabs=dabs, automask=auto_t, mask_on=True))
+        w = Workload("c4", mesh, False, strokes,
+                     "C4 tool sweep draw / inflate / clay strips / grab x {mask off, mask layer + boundary automask} + draw with topology "
+                     "automask, r = 10%% bbox diag, %d dabs each, grid %d^2 (V=%d)" % (args.c4_dabs, args.c4_grid, mesh.totvert),
+                     "draw / inflate / clay strips / grab (alpha 0.5)", mask=mask)
+    elif name == "c5":
         mesh = meshgen.multires_cube_n(args.c5_base, args.c5_level)
         diag = mesh.bbox_diag()
         rng = np.random.default_rng(5)
         bs = stroke._strength(capi.TOOL_DRAW, 0.5)
-        dabs = []
-        # C5: a smooth stroke, then a draw stroke, same radius
         bsm = stroke._strength(capi.TOOL_SMOOTH, 0.75)
-        for i in range(args.c5_smooth_dabs):
-            p = rng.normal(size=3)
-            p /= np.linalg.norm(p)
-            dabs.append(capi.make_dab(capi.TOOL_SMOOTH, p.astype(np.float32), diag * 0.08, bstrength=bsm, view_normal=tuple(p),
-                                      flags=capi.DAB_FIRST_STEP if i == 0 else 0))
-        for i in range(args.c5_dabs):
-            p = rng.normal(size=3)
-            p /= np.linalg.norm(p)
-            dabs.append(capi.make_dab(capi.TOOL_DRAW, p.astype(np.float32), diag * 0.08, bstrength=bs, view_normal=tuple(p),
-                                      flags=capi.DAB_FIRST_STEP if i == 0 else 0))
-        log("[bench] multires cube %d^2 x 6 base quads, level %d: %d grids of %d^2 = %d elements, diag=%.4f, %d dabs/stroke (%.1fs)" %
-            (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, diag, len(dabs), time.time() - t0))
-        return mesh, diag, dabs
-    mesh = meshgen.grid(args.grid)
-    diag = mesh.bbox_diag()
-    dabs = stroke.c3_radius_sweep(diag, dabs_per_radius=args.dabs_per_radius)
-    log("[bench] mesh grid %d^2: V=%d polys=%d diag=%.4f, %d dabs/stroke (%.1fs)" %
-        (args.grid, mesh.totvert, mesh.totpoly, diag, len(dabs), time.time() - t0))
-    return mesh, diag, dabs
+        dabs = []
+        for tool, n, b in ((capi.TOOL_SMOOTH, args.c5_smooth_dabs, bsm), (capi.TOOL_DRAW, args.c5_dabs, bs)):
+            for i in range(n):
+                p = rng.normal(size=3)
+                p /= np.linalg.norm(p)
+                dabs.append(capi.make_dab(tool, p.astype(np.float32), diag * 0.08, bstrength=b, view_normal=tuple(p),
+                                          flags=capi.DAB_FIRST_STEP if not dabs else 0))
+        w = Workload("c5", mesh, True, [dict(label="smooth then draw", dabs=dabs, automask=None, mask_on=False)],
+                     "C5 multires grids: cube %d^2 x 6 base quads, level %d (%d grids of %d^2 = %d elements), %d smooth dabs (3 iterations) then "
+                     "%d draw dabs, each + stitch + CCG normals + BB, r = 8%% bbox diag" %
+                     (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, args.c5_smooth_dabs, args.c5_dabs),
+                     "smooth (alpha 0.75) then draw (alpha 0.5), SMOOTH falloff, area-normal direction")
+    else:
+        raise ValueError(name)
+    log("%s: %s -- built in %.1fs" % (name, w.desc, time.time() - t0))
+    return w
 
 
+def C_float(x):
+    import ctypes
+    return ctypes.c_float(x)
+
+
+def config_of(w, world):
+    par = "single GPU"
+    if world > 1:
+        par = ("PBVH partitioned spatially over %d GPUs (the same mesh: strong scaling); per dab the halo exchanges over NVLink peer "
+               "memory" % world)
+    return {"workload": w.desc, "parallelism": par, "verts": w.verts, "dabs_per_step": w.ndabs, "strokes_per_step": len(w.strokes),
+            "brush": w.brush,
+            "l2": ("inputs larger than L2 (resident arrays > 1 GB; every stroke sweeps them)" if w.verts > 4000000 else
+                   "flushed between steps by the rollback: a device-to-device copy of every position / normal array (> L2 for C2; C1's "
+                   "arrays fit in L2 -- an L2-resident config by the north star's own sizing)"),
+            "step": "device-to-device rollback to the rest state + %d stroke%s (%d dabs)" % (len(w.strokes), "" if len(w.strokes) == 1 else "s", w.ndabs)}
+
+
+# --------------------------------------------------------------------------------- byte accounting
+def smooth_iterations(bstrength):
+    bs = min(max(float(bstrength), 0.0), 1.0)
+    full = int(bs * 4)
+    return full + (0 if (full > 0 and 4.0 * (bs - full * 0.25) == 0.0) else 1)
+
+
+def stage_bytes_of(st, dabs, nleaf, grids, mask_on, automask_on):
+    """Algorithmic bytes per stage of a run of dabs of ONE tool, from the device's counters `st` (deltas
+    over the run): U vertex_dabs, A all_verts, T prims, M moved_verts, first_A first_touch_verts, U' area_verts,
+    M' area_inside, hits, refit nodes."""
+    U, A, T, M = st["vertex_dabs"], st["all_verts"], st["prims"], st["moved_verts"]
+    fa, Ua, Ma, hits = st["first_touch_verts"], st["area_verts"], st["area_inside"], st["node_hits"]
+    n = len(dabs)
+    tool = dabs[0].tool
+    per_u = 12 + (4 if mask_on else 0) + (4 if automask_on else 0)
+    b = {"gather": 48 * nleaf * n, "area_normal": 0, "brush": 0, "smooth": 0, "normals_bb": 0, "bb_refit": 72 * st["refit_nodes"] + 24 * hits}
+    if tool == 2:
+        it = smooth_iterations(dabs[0].bstrength)
+        # M counts every iteration's moved verts; the verts whose normals are recomputed are those of one iteration
+        b["smooth"] = it * U * per_u + M * ((4 * 12 + 12) if grids else (6 * 16 + 8 + 12)) + fa * 24
+        D = M // max(it, 1)
+    else:
+        if tool == 4 or (dabs[0].flags & 1):
+            per_u += 12
+        b["brush"] = U * per_u + M * 12 + fa * 24
+        b["area_normal"] = Ua * 12 + Ma * 12  # zero when the tool samples no plane: the counters stay put
+        D = M
+    if grids:
+        b["normals_bb"] = U * 36 + 24 * hits  # stitch + CCG normals: positions twice, normals once
+    else:
+        b["normals_bb"] = T * 12 + A * 12 + D * 12 + 24 * hits
+    b["headline_8d"] = 0 if grids else U * 12 + M * 12 + T * 12 + A * 12 + D * 12
+    return b
+
+
+def tool_runs(dabs):
+    """maximal runs of equal tool"""
+    runs, i = [], 0
+    while i < len(dabs):
+        j = i
+        while j < len(dabs) and dabs[j].tool == dabs[i].tool:
+            j += 1
+        runs.append((i, j))
+        i = j
+    return runs
+
+
+# --------------------------------------------------------------------------------------- measurement
+class Runner:
+    def __init__(self, w, args, rank, world, local_rank):
+        from dune_sculpt_b200 import capi
+        import ctypes as C
+        self.w, self.args, self.rank, self.world, self.capi, self.C = w, args, rank, world, capi, C
+        t0 = time.time()
+        dist_arg = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda:%d" % local_rank)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            dist_arg = (world, rank, bytes(idt.cpu().numpy().tobytes()))
+        if w.grids:
+            self.ses = capi.GridSession(w.mesh, device=local_rank, dist=dist_arg)
+        else:
+            self.ses = capi.SculptSession(w.mesh, mask=w.mask, device=local_rank, dist=dist_arg)  # fails loudly without a device / the .so
+        self.na = self.ses.node_arrays()
+        self.nleaf = int((self.na["flag"] & 1).sum())
+        self.session_start_s = time.time() - t0
+        log("%s rank %d: host PBVH build + device upload %.1fs, %d nodes (%d leaves)" % (w.name, rank, self.session_start_s, self.ses.totnode, self.nleaf))
+        self.arrs = [(capi.DscDab * len(s["dabs"]))(*s["dabs"]) for s in w.strokes]
+        self.mask_state = w.mask is not None
+        self.ses.checkpoint()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def _set_mask(self, on):
+        if self.w.mask is None or on == self.mask_state:
+            return 0
+        ses = self.ses
+        ses._chk(ses.D.dsc_set_mask(ses.ctx, self.capi.fptr(self.w.mask) if on else None))
+        self.mask_state = on
+        return self.w.mask.nbytes if on else 0
+
+    def device_step(self):
+        ses, D, ctx = self.ses, self.ses.D, self.ses.ctx
+        for s, arr in zip(self.w.strokes, self.arrs):
+            ses._chk(D.dsc_state_restore(ctx))
+            self._set_mask(s["mask_on"])
+            a = s["automask"]
+            ses._chk(D.dsc_stroke_begin(ctx, None if a is None else self.capi.fptr(a)))
+            ses._chk(D.dsc_dabs(ctx, arr, len(arr)))
+            ses._chk(D.dsc_stroke_end(ctx))
+
+    def host_step(self):
+        """the same through the reference-named host API: stroke end brings the mesh back to host memory"""
+        ses = self.ses
+        h2d = 0
+        for s, arr in zip(self.w.strokes, self.arrs):
+            ses.rollback()
+            h2d += self._set_mask(s["mask_on"])
+            ses.stroke_begin(s["automask"])
+            if s["automask"] is not None:
+                h2d += s["automask"].nbytes
+            ses.dabs(arr, len(arr))
+            ses.stroke_end()
+            h2d += len(arr) * self.C.sizeof(self.capi.DscDab)
+        return h2d
+
+    def run(self):
+        args, ses, w = self.args, self.ses, self.w
+        steps, warmup = args.steps, args.warmup
+        if w.name != args.config:  # side configs: bounded
+            steps, warmup = min(steps, args.side_steps), min(warmup, 3)
+        for _ in range(warmup):
+            self.device_step()
+        ses.synchronize()
+        self.barrier()
+        sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", self.rank)))
+        sampler.start()
+        ses.timer_start()
+        for _ in range(steps):
+            self.device_step()
+        ms = ses.timer_stop()
+        clocks = sampler.stop()
+        self.barrier()
+        # vertex-dabs of one step: the strokes' counters reset at stroke begin, so count them stroke by stroke once
+        vd_step, launches_step = self.count_step()
+        vd = vd_step * steps
+        launches = launches_step * steps
+        log("%s rank %d: timed steps done, %.3f ms/step" % (w.name, self.rank, ms / steps))
+
+        # ---- end to end through the host API
+        self.host_step()
+        ses.synchronize()
+        self.barrier()
+        t0 = time.perf_counter()
+        h2d = 0
+        for _ in range(steps):
+            h2d = self.host_step()
+        ses.synchronize()
+        dt_e = time.perf_counter() - t0
+        self.barrier()
+        # whole MVert records + normals (mesh) or whole CCGElem records (grids), node boxes and flags, once per stroke
+        d2h = len(w.strokes) * (w.verts * 28 + ses.totnode * (48 + 4))
+        log("%s rank %d: end-to-end steps done, %.3f ms/step" % (w.name, self.rank, 1e3 * dt_e / steps))
+
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", self.rank))
+            t = torch.tensor([ms, dt_e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, dt_e = float(t[0]), float(t[1])
+            s_ = torch.tensor([float(vd_step), float(launches_step)], dtype=torch.float64, device=dev)
+            dist.all_reduce(s_, op=dist.ReduceOp.SUM)
+            vd_step, launches_step = int(s_[0]), int(s_[1])
+            vd, launches = vd_step * steps, launches_step * steps
+
+        out = {"value": vd / (ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+               "ms_per_dab": ms / (steps * w.ndabs), "vertex_dabs_per_step": vd_step, "gpu_launches": launches,
+               "session_start_s": round(self.session_start_s, 2),
+               "e2e": {"value": vd / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": 1e3 * dt_e / steps}}
+        if self.world == 1:
+            out["roofline"] = self.roofline(ms / steps)
+        return out, clocks
+
+    def count_step(self):
+        ses, D, ctx = self.ses, self.ses.D, self.ses.ctx
+        vd = launches = 0
+        for s, arr in zip(self.w.strokes, self.arrs):
+            ses._chk(D.dsc_state_restore(ctx))
+            self._set_mask(s["mask_on"])
+            a = s["automask"]
+            ses._chk(D.dsc_stroke_begin(ctx, None if a is None else self.capi.fptr(a)))
+            ses._chk(D.dsc_dabs(ctx, arr, len(arr)))
+            st = ses.stats()
+            ses._chk(D.dsc_stroke_end(ctx))
+            vd += st["vertex_dabs"]
+            launches += st["kernel_launches"]
+        ses.synchronize()
+        return vd, launches
+
+    # ---- roofline: device counters + kernel durations inside the replayed graphs
+    def roofline(self, step_ms):
+        ses, D, ctx, w, capi = self.ses, self.ses.D, self.ses.ctx, self.w, self.capi
+        peak, peak_src = measured_peaks()
+        keys = ("vertex_dabs", "all_verts", "prims", "moved_verts", "first_touch_verts", "area_verts", "area_inside", "node_hits", "refit_nodes")
+        # (1) the sweep group by group, un-instrumented (CUDA events around each group's graph replays)
+        groups = []
+        for si, (s, arr) in enumerate(zip(w.strokes, self.arrs)):
+            dabs = s["dabs"]
+            cuts = [(a, b) for (a, b) in tool_runs(dabs)]
+            if w.group:
+                cuts = [(a, min(a + w.group, len(dabs))) for a in range(0, len(dabs), w.group)]
+            ses._chk(D.dsc_state_restore(ctx))
+            self._set_mask(s["mask_on"])
+            a_ = s["automask"]
+            ses._chk(D.dsc_stroke_begin(ctx, None if a_ is None else capi.fptr(a_)))
+            prev = {k: 0 for k in keys}
+            for (a, b) in cuts:
+                grp = (capi.DscDab * (b - a))(*dabs[a:b])
+                ses.timer_start()
+                ses._chk(D.dsc_dabs(ctx, grp, b - a))
+                g_ms = ses.timer_stop()
+                st = ses.stats()
+                delta = {k: st[k] - prev[k] for k in keys}
+                prev = {k: st[k] for k in keys}
+                groups.append({"stroke": si, "a": a, "b": b, "ms": g_ms, "st": delta,
+                               "bytes": stage_bytes_of(delta, dabs[a:b], self.nleaf, w.grids, s["mask_on"], a_ is not None)})
+            ses._chk(D.dsc_stroke_end(ctx))
+        ses.synchronize()
+        # (2) the same again with the event-record nodes: kernel durations per group and stage
+        ses.stage_timing(2)
+        gi = 0
+        for si, (s, arr) in enumerate(zip(w.strokes, self.arrs)):
+            dabs = s["dabs"]
+            ses._chk(D.dsc_state_restore(ctx))
+            self._set_mask(s["mask_on"])
+            a_ = s["automask"]
+            ses._chk(D.dsc_stroke_begin(ctx, None if a_ is None else capi.fptr(a_)))
+            prev_t = {k: v[0] for k, v in ses.stage_times().items()}
+            while gi < len(groups) and groups[gi]["stroke"] == si:
+                g = groups[gi]
+                grp = (capi.DscDab * (g["b"] - g["a"]))(*dabs[g["a"]:g["b"]])
+                ses._chk(D.dsc_dabs(ctx, grp, g["b"] - g["a"]))
+                now = ses.stage_times()
+                g["stage_ms"] = {k: now[k][0] - prev_t.get(k, 0.0) for k in now}
+                prev_t = {k: v[0] for k, v in now.items()}
+                gi += 1
+            ses._chk(D.dsc_stroke_end(ctx))
+        times = ses.stage_times()
+        ses.stage_timing(0)
+        ses.synchronize()
+
+        stage_names = [k for k in times if k not in ("other", "leaf_bb")]
+        tot_b = {k: sum(g["bytes"].get(k, 0) for g in groups) for k in stage_names}
+        tot_ms = {k: sum(g["stage_ms"].get(k, 0.0) for g in groups) for k in stage_names}
+        dom = max(stage_names, key=lambda k: tot_ms[k])
+        dom_launches = max(times[dom][1], 1)
+        ach = tot_b[dom] / (tot_ms[dom] * 1e-3) / 1e9 if tot_ms[dom] > 0 else 0.0
+        stages = {k: {"ms": round(tot_ms[k], 4), "launches": times[k][1], "alg_bytes": int(tot_b[k]),
+                      "gbs": round(tot_b[k] / (tot_ms[k] * 1e-3) / 1e9, 1) if tot_ms[k] > 0 else None} for k in stage_names}
+        total_bytes = sum(tot_b[k] for k in stage_names)
+        head = sum(g["bytes"]["headline_8d"] for g in groups)
+        kernels_ms = sum(tot_ms[k] for k in stage_names if k != "bb_refit")  # the refit overlaps on the side stream
+        U = sum(g["st"]["vertex_dabs"] for g in groups)
+        M = sum(g["st"]["moved_verts"] for g in groups)
+        sweep = []
+        for g in groups:
+            d0 = w.strokes[g["stroke"]]["dabs"][g["a"]]
+            n = g["b"] - g["a"]
+            dm = g["stage_ms"].get(dom, 0.0)
+            sweep.append({"stroke": w.strokes[g["stroke"]]["label"], "tool": int(d0.tool), "radius_pct_diag": round(100.0 * float(d0.radius) / w.diag, 2),
+                          "dabs": n, "us_per_dab": round(1e3 * g["ms"] / n, 2), "vertex_dabs_per_dab": g["st"]["vertex_dabs"] // n,
+                          "gvd_per_s": round(g["st"]["vertex_dabs"] / (g["ms"] * 1e-3) / 1e9, 2) if g["ms"] > 0 else None,
+                          "moved_frac": round(g["st"]["moved_verts"] / max(g["st"]["vertex_dabs"], 1), 3),
+                          "dominant_kernel_us_per_dab": round(1e3 * dm / n, 2),
+                          "dominant_kernel_frac": round(g["bytes"].get(dom, 0) / (dm * 1e-3) / 1e9 / peak, 4) if dm > 0 else None,
+                          "whole_path_frac": round(sum(g["bytes"][k] for k in stage_names) / (g["ms"] * 1e-3) / 1e9 / peak, 4) if g["ms"] > 0 else None})
+        rl = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+              "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": int(tot_b[dom] / dom_launches),
+              "how": "algorithmic bytes of the stage (SURVEY.md 8d over device-counted U/A/T/M/U'/M') / its kernels' durations inside the replayed "
+                     "graphs (event-record nodes), one instrumented step",
+              "whole_path": {"achieved": round(total_bytes / (step_ms * 1e-3) / 1e9, 1), "frac": round(total_bytes / (step_ms * 1e-3) / 1e9 / peak, 4),
+                             "frac_of_8TBs_nominal": round(total_bytes / (step_ms * 1e-3) / 1e9 / 8000.0, 4),
+                             "bytes_per_vertex_dab": round(total_bytes / max(U, 1), 2),
+                             "headline_8d": None if w.grids else {"bytes": int(head), "bytes_per_vertex_dab": round(head / max(U, 1), 2),
+                                                                   "frac": round(head / (step_ms * 1e-3) / 1e9 / peak, 4),
+                                                                   "formula": "U 12 + M 12 + T 12 + A 12 + D 12 (area pass excluded)"},
+                             "moved_frac": round(M / max(U, 1), 3),
+                             "how": "algorithmic bytes of one step (all stages, area pass charged with U' 12 + M' 12) / device time of a timed step"},
+              "kernel_time_in_step": {"kernels_ms": round(kernels_ms, 4), "step_ms": round(step_ms, 4),
+                                      "note": "sum of the main-stream kernels' durations inside the graphs vs the timed step (the rest is launch "
+                                              "gaps and the rollback copy)"},
+              "stages": stages, "groups": sweep}
+        # DRAM traffic of the dominant kernel from the committed ncu capture, if one was made for this kernel
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if tr.get("stage") == dom and tr.get("config") == w.name:
+                rl["traffic"] = int(rl["alg_bytes_per_launch"] * float(tr["traffic_over_algorithmic"]))
+                rl["traffic_note"] = ("ncu dram__bytes_read+write of %s = %.3f x its algorithmic bytes on the captured launch (profiles/r2_traffic.json), "
+                                      "scaled to the average launch" % (tr["kernel"], tr["traffic_over_algorithmic"]))
+                if "l2_hit_rate" in tr:
+                    rl["l2_hit_rate"] = tr["l2_hit_rate"]
+        except Exception:
+            pass
+        return rl
+
+    # ---- the device result of one full-size step, dab by dab, for the parity leg
+    def parity_device(self):
+        ses, w = self.ses, self.w
+        out = []
+        for s in w.strokes:
+            ses.rollback()
+            self._set_mask(s["mask_on"])
+            ses.stroke_begin(s["automask"])
+            h = hashlib.sha1()
+            for d in s["dabs"]:
+                ses.dab(d)
+                h.update(ses.hits().tobytes())
+                h.update(b"|")
+            touched = ses.touched()
+            ses.stroke_end()
+            bb, obb = ses.node_bb()
+            out.append({"hits": h.hexdigest(), "touched": touched, "co": ses.co(), "no": ses.no(), "bb": bb, "vd": ses.stats()["vertex_dabs"]})
+        return out
+
+    def close(self):
+        self.ses.close()
+
+
+def cpu_leg(w, args, device_results, sample=None):
+    """The CPU oracle (OpenMP over hit nodes) over the same full-size strokes: timed (`cpu_baseline`) and, when the device
+    results are given, compared with them (`parity_fullsize`)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dune_sculpt_b200 import build as b
+    b.build_oracle()
+    from oracle_py import GridOracle, Oracle
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    # threaded, but vertex normals summed in the serial loop's order: bit-identical to the single-threaded restatement
+    from oracle_py import lib as oracle_lib
+    oracle_lib().or_set_ordered_normals(1 if device_results is not None else 0)
+    orc = GridOracle(w.mesh, threads=cores) if w.grids else Oracle(w.mesh, threads=cores, mask=w.mask)
+    log("%s cpu: oracle PBVH build %.1fs" % (w.name, time.time() - t0))
+    co0, no0 = orc.co(), orc.no()
+    na0 = orc.node_arrays()
+    vd = 0
+    dt = 0.0
+    ndabs = 0
+    par = {"strokes": [], "tolerance": "1e-5 x bbox diagonal (BASELINE.json north star); bit equality reported beside it"}
+    tol = 1e-5 * w.diag
+    ok = True
+    for si, s in enumerate(w.strokes):
+        if si:
+            # back to the rest state: coordinates, normals, boxes, flags
+            orc.set_co(co0)
+            np.ctypeslib.as_array(orc.L.or_pbvh_no(orc.p), shape=(orc.totvert * 3,))[:] = no0.reshape(-1)
+            for n in np.nonzero(na0["flag"] & 1)[0]:
+                orc.L.or_node_mark_update(orc.p, int(n))
+            orc.update_bounds(4 | 8)
+            for n in np.nonzero(na0["flag"] & 1)[0]:
+                orc.set_node_flag(int(n), 2 | 4 | 8 | 16 | 32, False)
+        if w.mask is not None:
+            m = np.ctypeslib.as_array(orc.L.or_pbvh_mask(orc.p), shape=(orc.totvert,))
+            m[:] = w.mask if s["mask_on"] else 0.0
+        orc.stroke_begin(s["automask"])
+        h = hashlib.sha1()
+        t0 = time.perf_counter()
+        for d in s["dabs"]:
+            orc.dab(d)
+            if device_results is not None:
+                h.update(orc.hits().tobytes())
+                h.update(b"|")
+        dt += time.perf_counter() - t0
+        ndabs += len(s["dabs"])
+        vd += orc.vertex_dabs()
+        touched = orc.touched()
+        orc.stroke_end()
+        if device_results is not None:
+            dv = device_results[si]
+            co, no = orc.co(), orc.no()
+            dco, dno = float(np.abs(co - dv["co"]).max()), float(np.abs(no - dv["no"]).max())
+            dbb = float(np.abs(orc.node_arrays()["vb"] - dv["bb"]).max())
+            rec = {"stroke": s["label"], "dabs": len(s["dabs"]), "hit_lists_equal": h.hexdigest() == dv["hits"],
+                   "touched_equal": bool(np.array_equal(touched, dv["touched"])), "vertex_dabs_equal": int(orc.vertex_dabs()) == int(dv["vd"]),
+                   "max_dco": dco, "max_dno": dno, "max_dbb": dbb, "within_tolerance": bool(dco <= tol and dno <= tol and dbb <= tol),
+                   "bit_exact": bool(np.array_equal(co, dv["co"]) and np.array_equal(no, dv["no"]))}
+            ok = ok and rec["hit_lists_equal"] and rec["touched_equal"] and rec["vertex_dabs_equal"] and rec["within_tolerance"]
+            par["strokes"].append(rec)
+    orc.L.or_set_ordered_normals(0)
+    orc.close()
+    par["ok"] = bool(ok)
+    par["bit_exact"] = bool(all(r["bit_exact"] for r in par["strokes"])) if par["strokes"] else None
+    cpu = {"value": vd / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "the whole step: %d stroke%s, %d dabs (%.1f s), OpenMP over hit nodes" % (len(w.strokes), "" if len(w.strokes) == 1 else "s", ndabs, dt),
+           "ms_per_dab": 1e3 * dt / max(ndabs, 1)}
+    return cpu, (par if device_results is not None else None)
+
+
+def measure(name, args, rank, world, local_rank, with_cpu):
+    w = build_workload(name, args)
+    r = Runner(w, args, rank, world, local_rank)
+    res, clocks = r.run()
+    res["config"] = config_of(w, world)
+    if with_cpu and rank == 0 and world == 1:
+        dev = r.parity_device()
+        log("%s: device parity stroke done" % name)
+        cpu, par = cpu_leg(w, args, dev)
+        res["cpu_baseline"] = cpu
+        res["parity_fullsize"] = par
+        log("%s: cpu leg done, parity ok = %s" % (name, par["ok"]))
+    elif world > 1 and args.verify_partition:
+        res["parity_vs_1gpu"] = partition_digest(w, r, rank, local_rank)
+    r.close()
+    return res, clocks
+
+
+def partition_digest(w, r, rank, local_rank):
+    """N > 1: the partitioned stroke-end mesh on rank 0 against the same stroke on one GPU (a second, unpartitioned session)"""
+    ses = r.ses
+    res = None
+    s = w.strokes[0]
+    ses.rollback()
+    ses.stroke_begin(s["automask"])
+    ses.dabs(r.arrs[0], len(r.arrs[0]))
+    ses.stroke_end()
+    co, no = ses.co(), ses.no()
+    r.barrier()
+    if rank == 0:
+        capi = r.capi
+        one = capi.GridSession(w.mesh, device=local_rank) if w.grids else capi.SculptSession(w.mesh, mask=w.mask, device=local_rank)
+        one.stroke_begin(s["automask"])
+        one.dabs(r.arrs[0], len(r.arrs[0]))
+        one.stroke_end()
+        res = {"co_bit_equal": bool(np.array_equal(co, one.co())), "no_bit_equal": bool(np.array_equal(no, one.no())),
+               "sha1_co": hashlib.sha1(co.tobytes()).hexdigest()[:16]}
+        one.close()
+    r.barrier()
+    return res
+
+
+# ---------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
-    """CPU arm: the oracle (a port -- the reference itself does not compile here) with
-    OpenMP over hit nodes, the decomposition the reference uses (lib/intern/task_range.cc:89-127)."""
+    """CPU arm: the oracle (a port, pinned to the reference's own functions by tests/test_ref_pin.py) with OpenMP over hit
+    nodes -- the decomposition the reference uses (lib/intern/task_range.cc:89-127) -- on the headline workload, every step a
+    bounded sample of it sized so that the K + W steps end within a few minutes."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from dune_sculpt_b200 import build as b
     b.build_oracle()
     from oracle_py import GridOracle, Oracle
-    mesh, diag, dabs = build_workload(args)
+    w = build_workload(args.config, args)
+    dabs = w.strokes[0]["dabs"]
     cores = os.cpu_count() or 1
     t0 = time.time()
-    orc = GridOracle(mesh, threads=cores) if args.config == "c5" else Oracle(mesh, threads=cores)
-    log("[bench] oracle PBVH build %.1fs, %d nodes, %d threads" % (time.time() - t0, orc.totnode, cores))
-    # bounded sample: `sample_per_radius` dabs of every radius of the sweep per step
-    per = args.dabs_per_radius
-    nrad = len(dabs) // per
-    if args.config == "c5":
-        sample = dabs[:args.c5_cpu_dabs]
-        nrad = 1
-    else:
-        sample = [dabs[r * per + k] for r in range(nrad) for k in range(args.cpu_sample_per_radius)]
-    orc.stroke_begin()
-    for _ in range(args.warmup_ref):
-        for d in sample[:2]:
+    orc = GridOracle(w.mesh, threads=cores) if w.grids else Oracle(w.mesh, threads=cores, mask=w.mask)
+    log("reference arm: oracle PBVH build %.1fs, %d nodes, %d threads" % (time.time() - t0, orc.totnode, cores))
+    per = w.group or len(dabs)
+    nrad = max(len(dabs) // per, 1)
+    orc.stroke_begin(w.strokes[0]["automask"])
+    # calibrate: one dab of every group, then size the per-step sample for the time budget
+    t0 = time.perf_counter()
+    for r_ in range(nrad):
+        orc.dab(dabs[r_ * per])
+    one = time.perf_counter() - t0
+    budget = args.ref_budget_s / max(args.steps + args.warmup, 1)
+    k = int(max(1, min(per, budget / max(one, 1e-6))))
+    sample = [dabs[r_ * per + j] for r_ in range(nrad) for j in range(k)]
+    for _ in range(args.warmup):
+        for d in sample:
             orc.dab(d)
     vd0 = orc.vertex_dabs()
     t0 = time.perf_counter()
-    for _ in range(args.steps_ref):
+    for _ in range(args.steps):
         for d in sample:
             orc.dab(d)
     dt = time.perf_counter() - t0
     vd = orc.vertex_dabs() - vd0
     orc.stroke_end()
     value = vd / dt
-    sample_desc = "%d dabs per radius x %d radii of the C3 sweep per step (%d dabs), %d steps" % (
-        args.cpu_sample_per_radius, nrad, len(sample), args.steps_ref)
-    if args.config == "c5":
-        sample_desc = "the first %d dabs of the C5 stroke per step, %d steps" % (len(sample), args.steps_ref)
-    out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps_ref,
-        "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps_ref, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, mesh, len(dabs)),
-        "ms_per_dab": 1e3 * dt / (args.steps_ref * len(sample)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(out)
-
-
-def workload_config(args, mesh, ndabs):
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.config == "c5":
-        return {"workload": "C5 multires grids: cube %d^2 x 6 base quads, level %d (%d grids of %d^2 = %d elements), %d smooth dabs (3 iterations) "
-                            "then %d draw dabs, each + stitch + CCG normals + BB, r = 8%% bbox diag, %d dabs/stroke" %
-                            (args.c5_base, args.c5_level, mesh.totgrid, mesh.grid_size, mesh.totelem, args.c5_smooth_dabs,
-                             args.c5_dabs, ndabs),
-                "parallelism": "single GPU" if world == 1 else
-                               "grids PBVH partitioned spatially over %d GPUs (same mesh: strong scaling); per dab one NCCL all-reduce "
-                               "(area sums + hit mask), the rim positions after the brush / every smoothing iteration and the rim "
-                               "normals after the CCG normal pass exchanged with the neighbouring ranks" % world,
-                "verts": mesh.totelem, "dabs_per_step": ndabs,
-                "brush": "smooth (alpha 0.75) then draw (alpha 0.5), SMOOTH falloff, area-normal direction",
-                "l2": "inputs larger than L2 (resident element arrays > 2 GB)" if mesh.totelem > 8000000 else "small mesh: L2 resident",
-                "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
-    return {"workload": "C3 draw+normals+BB radius sweep 1-50%% bbox diag, grid %d^2 (V=%d), %d dabs/stroke" %
-                        (args.grid, mesh.totvert, ndabs) +
-                        ("" if world == 1 else "; PBVH partitioned spatially over %d GPUs (same mesh: strong scaling), per dab one "
-                         "NCCL all-reduce (area sums + hit mask) and one one-ring halo exchange" % world),
-            "parallelism": "single GPU" if world == 1 else "pbvh-partition x%d" % world,
-            "verts": mesh.totvert, "dabs_per_step": ndabs, "brush": "draw, SMOOTH falloff, area-normal direction",
-            "l2": "inputs larger than L2 (resident mesh arrays > 2 GB; every stroke sweeps all of them)",
-            "step": "device-to-device rollback to the rest state + one %d-dab stroke" % ndabs}
-
-
-def analysis_pass(ses, dabs, na, grids=False):
-    """One untimed stroke with a sync after every dab: per-dab U/A/T/M and per-stage device times,
-    for the roofline object."""
-    uniq, face, totprim = na["uniq_verts"].astype(np.int64), na["face_verts"].astype(np.int64), na["totprim"].astype(np.int64)
-    n = ses.totnode
-    parent = np.full(n, -1, dtype=np.int64)
-    inner = np.nonzero((na["flag"] & 1) == 0)[0]
-    parent[na["children_offset"][inner]] = inner
-    parent[na["children_offset"][inner] + 1] = inner
-    ses.rollback()
-    ses.stage_timing(True)
-    ses.stroke_begin()
-    moved_prev = 0
-    touched = np.zeros(n, dtype=bool)
-    tot = {"U": 0, "A": 0, "T": 0, "M": 0, "first_A": 0, "hits": 0}
-    stage_bytes = {"gather": 0, "area_normal": 0, "brush": 0, "smooth": 0, "normals_bb": 0, "bb_refit": 0}
-    nleaf = int((na["flag"] & 1).sum())
-    for d in dabs:
-        ses.dab(d)
-        h = ses.hits()
-        st = ses.stats()
-        M = st["moved_verts"] - moved_prev
-        moved_prev = st["moved_verts"]
-        U = int(uniq[h].sum())
-        A = U + int(face[h].sum())
-        T = int(totprim[h].sum())
-        new = h[~touched[h]]
-        touched[h] = True
-        first_A = int(uniq[new].sum() + face[new].sum())
-        anc = 0
-        f = np.unique(parent[h])
-        f = f[f >= 0]
-        seen = np.zeros(n, dtype=bool)
-        while f.size:
-            f = f[~seen[f]]
-            seen[f] = True
-            anc += f.size
-            f = np.unique(parent[f])
-            f = f[f >= 0]
-        tot["U"] += U; tot["A"] += A; tot["T"] += T; tot["M"] += M; tot["first_A"] += first_A; tot["hits"] += h.size
-        stage_bytes["gather"] += 48 * nleaf
-        if d.tool == 2:
-            # SURVEY.md 8d smooth, per iteration U * (12 [+ 4 mask]) + M * (deg * (4 + 12) + 8 + 12); M here is already the
-            # sum over the dab's iterations; grids: deg = 4 and the neighbours need no index (element's place in its grid)
-            bs = min(max(float(d.bstrength), 0.0), 1.0)
-            iters = int(bs * 4) + (0 if (int(bs * 4) > 0 and 4.0 * (bs - int(bs * 4) * 0.25) == 0.0) else 1)
-            stage_bytes["smooth"] += iters * U * 12 + M * ((4 * 12 + 12) if grids else (6 * 16 + 8 + 12)) + first_A * 24
-        else:
-            stage_bytes["area_normal"] += U * 12 + M * 12
-            stage_bytes["brush"] += U * 12 + M * 12 + first_A * 24
-        if grids:
-            # stitch + CCG normals: positions of the gathered leaves' grids read, normals written; leaf boxes read them again
-            stage_bytes["normals_bb"] += U * 12 + U * 12 + U * 12 + 24 * h.size
-        else:
-            stage_bytes["normals_bb"] += T * 12 + A * 12 + M * 12 + 24 * h.size
-        stage_bytes["bb_refit"] += 72 * anc
-    ses.stroke_end()
-    times = ses.stage_times()
-    ses.stage_timing(False)
-    return tot, stage_bytes, times
-
-
-def run_ours(args, rank, world):
-    from dune_sculpt_b200 import build as b
-    b.build_cuda()
-    b.build_host()
-    from dune_sculpt_b200 import capi
-    local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    mesh, diag, dabs = build_workload(args)
-    t0 = time.time()
-    dist_arg = None
-    if world > 1:
-        # NCCL id of the library's own communicator: made on rank 0, broadcast through torch.distributed
-        import torch
-        import torch.distributed as dist
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda:%d" % local_rank)
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        dist_arg = (world, rank, bytes(idt.cpu().numpy().tobytes()))
-    if args.config == "c5":
-        ses = capi.GridSession(mesh, device=local_rank, dist=dist_arg)
-    else:
-        ses = capi.SculptSession(mesh, device=local_rank, dist=dist_arg)  # fails loudly without a device / the .so
-    na = ses.node_arrays()
-    log("[bench] host PBVH build + device upload %.1fs, %d nodes (%d leaves)" %
-        (time.time() - t0, ses.totnode, int((na["flag"] & 1).sum())))
-    D, ctx = ses.D, ses.ctx
-    import ctypes as C
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-
-    dab_arr = (capi.DscDab * len(dabs))(*dabs)  # the stroke script as one C array
-
-    # every step starts from the same rest state: a device-to-device rollback to the checkpoint, timed as
-    # part of the step (without it the draw strokes pile up and later steps sweep a different surface)
-    ses.checkpoint()
-
-    def device_stroke():
-        ses._chk(D.dsc_state_restore(ctx))
-        ses._chk(D.dsc_stroke_begin(ctx, None))
-        ses._chk(D.dsc_dabs(ctx, dab_arr, len(dabs)))
-        ses._chk(D.dsc_stroke_end(ctx))
-
-    # ---- device-resident timing: `value`
-    for _ in range(args.warmup):
-        device_stroke()
-    ses.synchronize()
-    barrier()
-    log("[bench] rank %d: warm-up done (%.1fs since upload)" % (rank, time.time() - t0))
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    vd = 0
-    launches = 0
-    ses.timer_start()
-    for _ in range(args.steps):
-        device_stroke()
-        st = ses.stats()  # small D2H of the counters, once per stroke
-        vd += st["vertex_dabs"]
-        launches += st["kernel_launches"]
-    ms = ses.timer_stop()
-    clocks = sampler.stop()
-    barrier()
-    log("[bench] rank %d: timed strokes done, %.3f ms/step" % (rank, ms / args.steps))
-
-    # ---- end-to-end timing through the host API: `e2e`
-    H = ses.H
-    h2d = len(dabs) * C.sizeof(capi.DscDab)
-    d2h = mesh.totvert * 24 + ses.totnode * (48 + 4) + 8
-    for _ in range(1):
-        ses.rollback(); ses.stroke_begin(); ses.dabs(dab_arr, len(dabs)); ses.stroke_end()
-    ses.synchronize()
-    barrier()
-    vd_e = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ses.rollback()
-        ses.stroke_begin()
-        ses.dabs(dab_arr, len(dabs))  # host descriptors cross the ABI dab by dab inside the C loop
-        vd_e += ses.stats()["vertex_dabs"]
-        ses.stroke_end()  # flush + download co / no / boxes / flags into the host PBVH
-    ses.synchronize()
-    dt_e = time.perf_counter() - t0
-    barrier()
-    log("[bench] rank %d: end-to-end strokes done, %.3f ms/step" % (rank, 1e3 * dt_e / args.steps))
-
-    # ---- max over ranks
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([ms, dt_e], dtype=torch.float64, device="cuda:%d" % local_rank)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([float(vd), float(vd_e), float(launches)], dtype=torch.float64, device="cuda:%d" % local_rank)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        ms, dt_e = float(t[0]), float(t[1])
-        vd, vd_e, launches = int(s[0]), int(s[1]), int(s[2])
-
-    # ---- the sweep radius by radius (untimed for `value`: one more stroke, CUDA events around each radius group)
-    per = args.dabs_per_radius if args.config == "c3" else len(dabs)
-    sweep = []
-    ses._chk(D.dsc_state_restore(ctx))
-    ses._chk(D.dsc_stroke_begin(ctx, None))
-    vd_prev = 0
-    for g in range(len(dabs) // per):
-        grp = (capi.DscDab * per)(*dabs[g * per:(g + 1) * per])
-        ses.timer_start()
-        ses._chk(D.dsc_dabs(ctx, grp, per))
-        g_ms = ses.timer_stop()
-        vd_now = ses.stats()["vertex_dabs"]
-        sweep.append({"radius_pct_diag": round(100.0 * float(dabs[g * per].radius) / diag, 2), "dabs": per,
-                      "us_per_dab": round(1e3 * g_ms / per, 2), "vertex_dabs_per_dab": (vd_now - vd_prev) // per,
-                      "gvd_per_s": round((vd_now - vd_prev) / (g_ms * 1e-3) / 1e9, 2) if g_ms > 0 else None})
-        vd_prev = vd_now
-    ses._chk(D.dsc_stroke_end(ctx))
-    ses.synchronize()
-
-    log("[bench] rank %d: radius sweep done" % rank)
-    # ---- roofline of the dominant kernel (untimed analysis stroke, CUDA events per stage)
-    tot, stage_bytes, times = analysis_pass(ses, dabs, na, grids=args.config == "c5")
-    log("[bench] rank %d: analysis stroke done" % rank)
-    peak, peak_src = measured_peaks()
-    dom = max((k for k in stage_bytes), key=lambda k: times[k][0])
-    dom_ms, dom_launches = times[dom]
-    achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    total_bytes = sum(stage_bytes.values())
-    total_ms = ms / args.steps  # the timed strokes themselves: side-stream refit overlapped, no per-stage events
-    stages = {k: {"ms": round(times[k][0], 4), "launches": times[k][1], "alg_bytes": int(stage_bytes.get(k, 0)),
-                  "gbs": round(stage_bytes.get(k, 0) / (times[k][0] * 1e-3) / 1e9, 1) if times[k][0] > 0 else None}
-              for k in times}
-    # DRAM traffic of the dominant kernel: one `ncu --set full` capture (profiles/r1_traffic.json) gives measured
-    # bytes / algorithmic bytes for one launch; scaled to the average launch the `achieved` figure is quoted on
-    traffic, traffic_note = None, None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if dom == "normals_bb" and args.config == "c3":
-            traffic = int(stage_bytes[dom] / max(dom_launches, 1) * float(tr["traffic_over_algorithmic"]))
-            traffic_note = ("ncu dram__bytes_read+write of %s = %.3f x its algorithmic bytes on the captured launch (%s); "
-                            "scaled to the average launch" % (tr["kernel"], tr["traffic_over_algorithmic"], "profiles/r1_traffic.json"))
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-                "alg_bytes_per_launch": int(stage_bytes[dom] / max(dom_launches, 1)),
-                "whole_path": {"achieved": round(total_bytes / (total_ms * 1e-3) / 1e9, 1) if total_ms > 0 else None,
-                               "frac": round(total_bytes / (total_ms * 1e-3) / 1e9 / peak, 4) if total_ms > 0 else None,
-                               "frac_of_8TBs_nominal": round(total_bytes / (total_ms * 1e-3) / 1e9 / 8000.0, 4) if total_ms > 0 else None,
-                               "bytes_per_vertex_dab": round(total_bytes / max(tot["U"], 1), 2),
-                               "how": "algorithmic bytes of one stroke / device time of one timed stroke"},
-                "stages": stages, "radius_sweep": sweep}
-
-    if rank != 0:
-        ses.close()
-        return
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, OpenMP, bounded sample
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args, mesh, dabs)
-
-    ndabs = len(dabs) * args.steps
-    out = {
-        "metric": METRIC, "value": vd / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak" if world == 1 else "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh, len(dabs)),
-        "ms_per_dab": ms / ndabs, "vertex_dabs_per_step": vd // args.steps,
-        "e2e": {"value": vd_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * dt_e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-    }
-    if cpu:
-        out["cpu_baseline"] = cpu
-    emit(out)
-    ses.close()
-
-
-def cpu_baseline(args, mesh, dabs):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from dune_sculpt_b200 import build as b
-    b.build_oracle()
-    from oracle_py import GridOracle, Oracle
-    cores = os.cpu_count() or 1
-    t0 = time.time()
-    if args.config == "c5":
-        orc = GridOracle(mesh, threads=cores)
-        log("[bench] cpu_baseline: grids oracle build %.1fs" % (time.time() - t0))
-        sample = dabs[:args.c5_cpu_dabs]
-        orc.stroke_begin()
-        orc.dab(sample[0])
-        vd0 = orc.vertex_dabs()
-        t0 = time.perf_counter()
-        for d in sample:
-            orc.dab(d)
-        dt = time.perf_counter() - t0
-        vd = orc.vertex_dabs() - vd0
-        orc.close()
-        return {"value": vd / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "the first %d dabs of the same stroke (%.1f s), OpenMP over faces / edges / nodes" % (len(sample), dt),
-                "ms_per_dab": 1e3 * dt / len(sample)}
-    orc = Oracle(mesh, threads=cores)
-    log("[bench] cpu_baseline: oracle PBVH build %.1fs" % (time.time() - t0))
-    per = args.dabs_per_radius
-    nrad = len(dabs) // per
-    sample = [dabs[r * per + k] for r in range(nrad) for k in range(args.cpu_sample_per_radius)]
-    orc.stroke_begin()
-    orc.dab(sample[0])
-    vd0 = orc.vertex_dabs()
-    t0 = time.perf_counter()
-    for d in sample:
-        orc.dab(d)
-    dt = time.perf_counter() - t0
-    vd = orc.vertex_dabs() - vd0
-    orc.close()
-    return {"value": vd / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d dabs per radius x %d radii of the same sweep (%d dabs, %.1f s), OpenMP over hit nodes" %
-                      (args.cpu_sample_per_radius, nrad, len(sample), dt),
-            "ms_per_dab": 1e3 * dt / len(sample)}
+    desc = "%d dabs of each of the %d groups of the stroke per step (%d dabs), %d steps after %d warm-up steps" % (k, nrad, len(sample), args.steps, args.warmup)
+    emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic", "config": config_of(w, 1), "ms_per_dab": 1e3 * dt / (args.steps * len(sample)),
+          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 _REAL_STDOUT = None
@@ -517,38 +717,67 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"], help="the headline workload of the line (default c3)")
+    ap.add_argument("--side-configs", default=None, help="comma list of the other configs measured into `configs` (default: all at N=1, c5 at N>1; 'none')")
+    ap.add_argument("--side-steps", type=int, default=3)
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--dabs-per-radius", type=int, default=32)
-    ap.add_argument("--cpu-sample-per-radius", type=int, default=32,
-                    help="CPU legs: dabs of every radius of the sweep (32 = the whole stroke, ~ 13 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c3", choices=["c3", "c5"],
-                    help="c3 (default): the headline 16.7M-vertex draw sweep; c5: multires grids, draw stroke")
+    ap.add_argument("--no-verify-partition", dest="verify_partition", action="store_false")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of all its steps")
+    ap.add_argument("--c1-levels", type=int, default=8)
+    ap.add_argument("--c2-freq", type=int, default=316)
+    ap.add_argument("--c4-grid", type=int, default=2048)
+    ap.add_argument("--c4-dabs", type=int, default=50)
     ap.add_argument("--c5-base", type=int, default=25)
     ap.add_argument("--c5-level", type=int, default=7)
     ap.add_argument("--c5-dabs", type=int, default=100, help="draw dabs of the C5 stroke")
     ap.add_argument("--c5-smooth-dabs", type=int, default=100, help="smooth dabs ahead of them")
-    ap.add_argument("--c5-cpu-dabs", type=int, default=0, help="CPU legs of c5: the first N dabs of the stroke (0 = all of it, ~ 8 s)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    # the CPU arm's steps are bounded samples: cap them so the run ends within minutes
-    if args.c5_cpu_dabs <= 0:
-        args.c5_cpu_dabs = args.c5_dabs + args.c5_smooth_dabs
-    args.cpu_sample_per_radius = max(1, min(args.cpu_sample_per_radius, args.dabs_per_radius))
-    args.steps_ref = max(1, min(args.steps, 3))
-    args.warmup_ref = max(0, min(args.warmup, 1))
-
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    from dune_sculpt_b200 import build as b
+    b.build_cuda()
+    b.build_host()
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
-    run_ours(args, rank, world)
+    with_cpu = not args.no_cpu_baseline
+    res, clocks = measure(args.config, args, rank, world, local_rank, with_cpu)
+    if args.side_configs is None:
+        side = [c for c in ("c1", "c2", "c4", "c5") if c != args.config] if world == 1 else ([] if args.config == "c5" else ["c5"])
+    else:
+        side = [c for c in args.side_configs.split(",") if c and c != "none"]
+    sides = {}
+    for c in side:
+        try:
+            sides[c], _ = measure(c, args, rank, world, local_rank, with_cpu)
+        except Exception as e:  # a side config must not take the headline down with it
+            log("side config %s failed: %r" % (c, e))
+            sides[c] = {"error": repr(e)}
+    if rank == 0:
+        out = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"], "warmup": res["warmup"],
+               "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+               # one stroke on one mesh: the work is fixed as GPUs are added
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": res["config"],
+               "ms_per_dab": res["ms_per_dab"], "vertex_dabs_per_step": res["vertex_dabs_per_step"], "e2e": res["e2e"],
+               "gpu_launches": res["gpu_launches"], "clocks": clocks, "session_start_s": res["session_start_s"]}
+        for k in ("roofline", "cpu_baseline", "parity_fullsize", "parity_vs_1gpu"):
+            if k in res:
+                out[k] = res[k]
+        if sides:
+            out["configs"] = [dict(name=c, **v) for c, v in sides.items()]
+            if "c5" in sides:
+                out["c5"] = sides["c5"]
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

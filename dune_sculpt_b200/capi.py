@@ -43,7 +43,8 @@ class DscDab(C.Structure):
 
 class DscStrokeStats(C.Structure):
     _fields_ = [("vertex_dabs", C.c_int64), ("node_hits", C.c_int64), ("moved_verts", C.c_int64),
-                ("dabs", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("dabs", C.c_int64), ("kernel_launches", C.c_int64), ("area_verts", C.c_int64), ("area_inside", C.c_int64),
+                ("all_verts", C.c_int64), ("prims", C.c_int64), ("first_touch_verts", C.c_int64), ("refit_nodes", C.c_int64)]
 
 
 class BB(C.Structure):

@@ -35,6 +35,7 @@ struct DabGraph {
   cudaGraphExec_t exec = nullptr;
   int launches = 0;
   int stage_launches[DSC_NUM_STAGES] = {0};
+  std::vector<StageEvent> events; /* stage timing inside the replayed graph (dsc_stage_timing mode 2): event-record nodes */
 };
 
 struct DscContext {
@@ -134,7 +135,8 @@ struct DscContext {
   long long graph_launches = 0, ring_seq = 0;
 
   bool capture = false;
-  bool stage_timing = false;
+  bool capturing_now = false; /* between cudaStreamBeginCapture and EndCapture of get_graph */
+  int stage_timing = 0; /* 1: direct launches, an event pair around every kernel; 2: the same pairs as nodes of the replayed graphs */
   std::vector<StageEvent> events;
   float stage_ms[DSC_NUM_STAGES] = {0};
   int stage_launches[DSC_NUM_STAGES] = {0};
@@ -233,13 +235,16 @@ struct StageScope {
     if (ctx->stage_timing) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, st);
+      /* inside a capture a plain record is only a dependency marker; an external record becomes a node of the graph */
+      if (ctx->capturing_now) cudaEventRecordWithFlags(a, st, cudaEventRecordExternal);
+      else cudaEventRecord(a, st);
     }
   }
   ~StageScope()
   {
     if (ctx->stage_timing) {
-      cudaEventRecord(b, st);
+      if (ctx->capturing_now) cudaEventRecordWithFlags(b, st, cudaEventRecordExternal);
+      else cudaEventRecord(b, st);
       ctx->events.push_back({stage, a, b});
     }
   }
@@ -2260,7 +2265,7 @@ static int upload_per_vertex(DscContext *ctx, float *dst, const float *src)
 int dsc_set_mask(DscContext *ctx, const float *mask)
 {
   NEED_PBVH();
-  invalidate_graphs(ctx);
+  /* graphs are keyed by the presence of the layer (its device buffer never moves): nothing to invalidate */
   if (!mask) {
     ctx->m.mask = nullptr;
     return DSC_OK;
@@ -2298,7 +2303,6 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
   if (ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "stroke already open");
   int r = join_side(ctx);
   if (r) return r;
-  const float *old_automask = ctx->m.automask;
   if (automask) {
     if ((r = upload_per_vertex(ctx, ctx->d_automask, automask))) return r;
     ctx->m.automask = ctx->d_automask;
@@ -2306,7 +2310,6 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
   else {
     ctx->m.automask = nullptr;
   }
-  if (ctx->m.automask != old_automask) invalidate_graphs(ctx);
   CU(cudaMemsetAsync(ctx->m.leaf_state, 0, sizeof(unsigned) * (size_t)std::max(ctx->m.nleaf, 1), ctx->stream));
   CU(cudaMemsetAsync(ctx->m.st, 0, sizeof(DabState) * DSC_SLOTS, ctx->stream));
   CU(cudaMemsetAsync(ctx->m.tot, 0, sizeof(StrokeTotals), ctx->stream));
@@ -2547,7 +2550,10 @@ static int ring_commit(DscContext *ctx, long long seq_end)
 /* the launch sequence of `batch` dabs of one signature as an executable graph (built on first use) */
 static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r_graph)
 {
-  auto it = ctx->graphs.find(sig.key(batch));
+  /* the DevMesh a graph's kernels carry differs by the optional layers: one graph per combination */
+  const unsigned gkey = sig.key(batch) | (ctx->stage_timing == 2 ? 1u << 30 : 0u) | (ctx->m.mask ? 1u << 29 : 0u) |
+                        (ctx->m.automask ? 1u << 28 : 0u);
+  auto it = ctx->graphs.find(gkey);
   if (it != ctx->graphs.end()) {
     *r_graph = &it->second;
     return DSC_OK;
@@ -2558,7 +2564,9 @@ static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r
   const long long launches0 = ctx->launches;
   int stage0[DSC_NUM_STAGES];
   memcpy(stage0, ctx->stage_launches, sizeof(stage0));
+  const size_t ev0 = ctx->events.size();
   CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing_now = true;
   k_batch_begin<<<1, 1, 0, ctx->stream>>>(ctx->m, batch);
   r = DSC_OK;
   for (int j = 0; j < batch && r == DSC_OK; j++) r = enqueue_dab(ctx, sig, j, j & (DSC_SLOTS - 1), true);
@@ -2568,7 +2576,11 @@ static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r
       r = fail(ctx, DSC_ERR_CUDA, "joining the side stream into the captured batch failed");
   }
   cudaError_t e = cudaStreamEndCapture(ctx->stream, &g.graph);
+  ctx->capturing_now = false;
   ctx->side_busy = false;
+  /* the event pairs recorded while capturing belong to the graph: read after every replay */
+  g.events.assign(ctx->events.begin() + (long)ev0, ctx->events.end());
+  ctx->events.resize(ev0);
   if (r != DSC_OK) {
     if (e == cudaSuccess && g.graph) cudaGraphDestroy(g.graph);
     return r;
@@ -2584,7 +2596,7 @@ static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r
   /* capturing counted the launches once; they are counted per graph launch instead */
   ctx->launches = launches0;
   memcpy(ctx->stage_launches, stage0, sizeof(stage0));
-  *r_graph = &ctx->graphs.emplace(sig.key(batch), g).first->second;
+  *r_graph = &ctx->graphs.emplace(gkey, g).first->second;
   return DSC_OK;
 }
 
@@ -2633,7 +2645,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     if (dist && (ctx->stale_flags || !sig.do_normals || !sig.do_bounds))
       return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
     /* how many of the following dabs share the launch sequence */
-    const bool graphable = ctx->use_graphs && !(ctx->is_grids && ctx->grid_fused) && !ctx->stage_timing && !ctx->capture && (!dist || ctx->p2p) && !ctx->stale_flags &&
+    const bool graphable = ctx->use_graphs && !(ctx->is_grids && ctx->grid_fused) && ctx->stage_timing != 1 && !ctx->capture && (!dist || ctx->p2p) && !ctx->stale_flags &&
                            !ctx->any_slow_leaf && sig.do_normals && sig.do_bounds;
     int run = 1;
     const long long seq = ctx->ring_seq; /* ring position: runs across strokes; the state slot follows dab_index */
@@ -2683,6 +2695,14 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
       if ((r = get_graph(ctx, sig, batch, &g))) return r;
       if ((r = join_side(ctx))) return r; /* the graph's first dabs do not wait for an earlier refit themselves */
       CU(cudaGraphLaunch(g->exec, ctx->stream));
+      if (ctx->stage_timing == 2) {
+        /* kernel durations inside the replayed graph: the kernels still run back to back, only the read-out waits */
+        if ((r = sync_all(ctx))) return r;
+        for (auto &ev : g->events) {
+          float ms = 0.0f;
+          if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) ctx->stage_ms[ev.stage] += ms;
+        }
+      }
       ctx->launches += g->launches;
       for (int k = 0; k < DSC_NUM_STAGES; k++) ctx->stage_launches[k] += g->stage_launches[k];
       ctx->graph_launches++;
@@ -2803,6 +2823,12 @@ int dsc_stroke_stats(DscContext *ctx, DscStrokeStats *r)
   r->moved_verts = (int64_t)ctx->h_tot->moved_total;
   r->dabs = (int64_t)ctx->h_tot->dabs;
   r->kernel_launches = ctx->launches;
+  r->area_verts = (int64_t)ctx->h_tot->area_vd_total;
+  r->area_inside = (int64_t)ctx->h_tot->area_inside_total;
+  r->all_verts = (int64_t)ctx->h_tot->all_total;
+  r->prims = (int64_t)ctx->h_tot->prim_total;
+  r->first_touch_verts = (int64_t)ctx->h_tot->first_total;
+  r->refit_nodes = (int64_t)ctx->h_tot->refit_total;
   return DSC_OK;
 }
 
@@ -3320,7 +3346,7 @@ int dsc_stage_timing(DscContext *ctx, int enable)
     ctx->stage_ms[i] = 0.0f;
     ctx->stage_launches[i] = 0;
   }
-  ctx->stage_timing = enable != 0;
+  ctx->stage_timing = enable == 2 ? 2 : (enable != 0 ? 1 : 0);
   return DSC_OK;
 }
 

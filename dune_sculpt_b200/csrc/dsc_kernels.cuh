@@ -46,6 +46,12 @@ struct DabState {
 
 struct StrokeTotals {
   unsigned long long vd_total, hits_total, moved_total, dabs;
+  unsigned long long area_vd_total;     /* unique verts of the leaves the area pass walks (its U') */
+  unsigned long long area_inside_total; /* verts inside the sampling sphere (its M') */
+  unsigned long long all_total;         /* unique + shared verts of the gathered leaves (A of SURVEY.md 8d) */
+  unsigned long long prim_total;        /* their looptris / grids (T) */
+  unsigned long long first_total;       /* unique + shared verts of the leaves first touched in the stroke (undo snapshot) */
+  unsigned long long refit_total;       /* inner nodes the bottom-up refit rewrote */
   int search_count; /* leaves found by the last stand-alone search (search_list) */
   int flag_count;   /* leaves collected by k_collect_flagged (flag_list) */
   int flag_tiles;   /* their tiles (flag_tile_list) */
@@ -414,11 +420,15 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
       tl[k] = make_int4(t0 + k, r.x, r.y, bits);
     }
   }
-  unsigned long long vd = 0;
+  unsigned long long vd = 0, avd = 0, all = 0, prims = 0, first = 0;
+  if (ahit) avd = (unsigned long long)m.leaf_ucnt[l];
   if (hit) {
     m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((lst & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
     m.node_flag[l] = flag | set_flags;
     vd = (unsigned long long)m.leaf_ucnt[l];
+    all = vd + (unsigned long long)m.leaf_scnt[l];
+    prims = (unsigned long long)m.leaf_pcnt[l];
+    first = (lst & DSC_LEAF_TOUCHED) ? 0ull : all;
     if (tag_parity >= 0 && (ent_bits & DSC_ENT_BOUNDS)) {
       /* batch kernel: what k_tag_ancestors does on the side stream otherwise (the boxes are emptied later) */
       int *pending = m.pending + (size_t)tag_parity * m.totnode;
@@ -431,10 +441,22 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
       }
     }
   }
-  for (int o = 16; o > 0; o >>= 1) vd += __shfl_down_sync(0xffffffffu, vd, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    vd += __shfl_down_sync(0xffffffffu, vd, o);
+    all += __shfl_down_sync(0xffffffffu, all, o);
+    prims += __shfl_down_sync(0xffffffffu, prims, o);
+    first += __shfl_down_sync(0xffffffffu, first, o);
+  }
+  if (abal) {
+    for (int o = 16; o > 0; o >>= 1) avd += __shfl_down_sync(0xffffffffu, avd, o);
+    if (lane == 0) atomicAdd(&m.tot->area_vd_total, avd);
+  }
   if (lane == 0) {
     atomicAdd(&m.tot->vd_total, vd);
     atomicAdd(&m.tot->hits_total, (unsigned long long)__popc(bal));
+    atomicAdd(&m.tot->all_total, all);
+    atomicAdd(&m.tot->prim_total, prims);
+    if (first) atomicAdd(&m.tot->first_total, first);
   }
 }
 
@@ -547,6 +569,7 @@ __device__ __forceinline__ void dsc_refit_body(const DevMesh &m, int slot, int p
       for (int k = 0; k < 6; k++) __stcg(&m.bb[k * tn + p], box[k]);
       arrived[p] = 0;
       pending[p] = 0;
+      atomicAdd(&m.tot->refit_total, 1ull);
       t = tp;
     }
   }
@@ -868,6 +891,8 @@ __device__ __forceinline__ void dsc_brush_body(const DevMesh &m, const DabParams
   if (tid == 0) {
     s_moved = 0;
     dsc_brush_derive(st, d, D, cta == 0);
+    /* statistics: verts the area pass averaged (its M') */
+    if (cta == 0) m.tot->area_inside_total += (unsigned long long)(__ldcg(&st->acc[12]) + __ldcg(&st->acc[13]));
   }
   __syncthreads();
   constexpr int tool = TOOL;

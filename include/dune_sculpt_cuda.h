@@ -171,6 +171,13 @@ typedef struct DscStrokeStats {
   int64_t moved_verts;  /* sum over dabs of vertices the brush displaced */
   int64_t dabs;
   int64_t kernel_launches; /* kernels launched by this context since stroke begin */
+  int64_t area_verts;   /* sum over dabs of uniq_verts of the gathered leaves that reach the normal-sampling sphere */
+  int64_t area_inside;  /* sum over dabs of the vertices inside it (what the area normal / centre averages) */
+  /* the other terms of the algorithmic byte count, summed over dabs */
+  int64_t all_verts;         /* unique + shared verts of the gathered leaves (A) */
+  int64_t prims;             /* their looptris, or grids (T) */
+  int64_t first_touch_verts; /* A of the leaves first touched in the stroke (undo snapshot) */
+  int64_t refit_nodes;       /* inner nodes whose box the bottom-up refit rewrote */
 } DscStrokeStats;
 
 /* --- context ---------------------------------------------------------------------------- */
@@ -330,6 +337,9 @@ int dsc_timer_stop(DscContext *ctx, float *r_ms); /* synchronises */
 void *dsc_stream(DscContext *ctx);                /* cudaStream_t */
 /* per-stage device time of the dabs since the last reset; stage names via dsc_stage_name() */
 #define DSC_NUM_STAGES 8
+/* enable = 1: dabs are launched kernel by kernel with an event pair around each (a diagnostic path);
+ * enable = 2: the dabs run as they do untimed -- replayed CUDA graphs -- and the event pairs are nodes of those graphs,
+ * read after every replay: kernel durations of the path that is actually timed */
 int dsc_stage_timing(DscContext *ctx, int enable);
 int dsc_stage_times(DscContext *ctx, float r_ms[DSC_NUM_STAGES], int r_launches[DSC_NUM_STAGES]);
 const char *dsc_stage_name(int stage);

@@ -121,6 +121,9 @@ int or_grids_neighbors(const OrPbvh *p, int elem, int *r);
 int or_grids_max_neighbors(const OrPbvh *p);
 int or_grids_is_boundary(const OrPbvh *p, int elem); /* DAGGER SCULPT_vertex_is_boundary, subdiv_ccg.c:1949-2008 */
 void or_grids_average_all(OrPbvh *p);  /* KERNEL_subdiv_ccg_average_grids, subdiv_ccg.c:1170-1189 */
+/* threads > 1 only: accumulate vertex normals per vertex in the serial loop's order instead of with float atomics, so
+ * that the threaded run is bit-identical to the single-threaded restatement (bench.py's full-size parity legs) */
+void or_set_ordered_normals(int on);
 void or_grids_recalc_normals(OrPbvh *p); /* KERNEL_subdiv_ccg_recalc_normals, subdiv_ccg.c:782-790 */
 void or_grids_inner_normals(OrPbvh *p);  /* its first half alone: subdiv_ccg.c:670-740 on every grid (pin tests) */
 float *or_pbvh_mask(OrPbvh *p);

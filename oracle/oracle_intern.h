@@ -38,6 +38,9 @@ struct OrPbvh {
   int (*tri_v)[3];    /* mloop[tri].v resolved */
   int *tri_poly;
   unsigned char *vert_bitmap; /* one byte per vertex */
+  /* ordered threaded normals (or_set_ordered_normals): vertex -> incident looptri positions, ascending; position -> leaf */
+  int64_t *vt_off;
+  int *vt_pos, *pos_node;
   /* material / visibility inputs of the build and the vertex iterator (NULL: one material, nothing hidden) */
   short *poly_mat, *grid_mat;           /* MPoly.mat_nr, DMFlagMat.mat_nr */
   unsigned char *poly_flag, *grid_flag; /* MPoly.flag, DMFlagMat.flag (ME_SMOOTH = 1) */

@@ -549,6 +549,7 @@ void or_pbvh_free(OrPbvh *p)
   }
   free(p->nodes); free(p->prim_indices); free(p->co); free(p->no); free(p->mask);
   free(p->poly_start); free(p->poly_len); free(p->loop_v); free(p->tri_loop); free(p->tri_v);
+  free(p->vt_off); free(p->vt_pos); free(p->pos_node);
   free(p->poly_mat); free(p->grid_mat); free(p->poly_flag); free(p->grid_flag); free(p->vert_flag); free(p->grid_hidden);
   free(p->tri_poly); free(p->vert_bitmap); free(p->nb_off); free(p->nb_idx); free(p->boundary);
   free(p->face_start); free(p->face_num); free(p->grid_face); free(p->edge_off); free(p->edge_elems);
@@ -786,9 +787,71 @@ static void calc_poly_normal(const OrPbvh *p, int poly, float r_no[3])
  * One thread: the accumulation order is nodes in gather order, looptris in node order -- for one
  * vertex that is ascending position in prim_indices.  Threads > 1: float atomics as the
  * reference (pbvh.c:2970-2976), order not defined. */
+/* Threads > 1 with or_set_ordered_normals(1) (the full-size parity legs of bench.py): the accumulation runs per vertex
+ * instead of per looptri -- every dirty unique vert of a flagged node sums the poly normals of its incident looptris in
+ * ascending position in prim_indices, looptris of unflagged nodes left out (pbvh.c:2943) -- which is the order the
+ * single-threaded loop above produces, so the threaded oracle is bit-identical to the serial one. */
+int or_ordered_normals = 0;
+void or_set_ordered_normals(int on) { or_ordered_normals = on; }
+
+static void ensure_vert_tri_positions(OrPbvh *p)
+{
+  if (p->vt_off) return;
+  const int T = p->totprim, V = p->totvert;
+  p->vt_off = calloc((size_t)V + 2, sizeof(int64_t));
+  p->pos_node = malloc(sizeof(int) * (size_t)(T > 0 ? T : 1));
+  for (int n = 0; n < p->totnode; n++) {
+    const OrNode *node = &p->nodes[n];
+    if (!(node->flag & OR_PBVH_Leaf)) continue;
+    for (int i = 0; i < node->totprim; i++) p->pos_node[node->prim_offset + i] = n;
+  }
+  for (int pos = 0; pos < T; pos++) {
+    const int *vt = p->tri_v[p->prim_indices[pos]];
+    for (int j = 0; j < 3; j++) p->vt_off[vt[j] + 2]++;
+  }
+  for (int v = 0; v < V; v++) p->vt_off[v + 2] += p->vt_off[v + 1];
+  p->vt_pos = malloc(sizeof(int) * (size_t)(3 * (int64_t)T > 0 ? 3 * (int64_t)T : 1));
+  /* ascending position by construction; the corners of one looptri in the order the serial loop adds them (j = 2, 1, 0) */
+  for (int pos = 0; pos < T; pos++) {
+    const int *vt = p->tri_v[p->prim_indices[pos]];
+    for (int j = 3; j--;) p->vt_pos[p->vt_off[vt[j] + 1]++] = pos;
+  }
+}
+
 static void faces_update_normals(OrPbvh *p, const int *nodes, int totnode)
 {
   const int par = (or_threads > 1 && totnode > 1); /* pbvh.c:4953-4959 */
+  if (par && or_ordered_normals) {
+    ensure_vert_tri_positions(p);
+#pragma omp parallel for schedule(dynamic)
+    for (int n = 0; n < totnode; n++) {
+      OrNode *node = &p->nodes[nodes[n]];
+      if (!(node->flag & OR_PBVH_UpdateNormals)) continue;
+      for (int i = 0; i < node->uniq_verts; i++) {
+        const int v = node->vert_indices[i];
+        if (!p->vert_bitmap[v]) continue;
+        float acc[3] = {0.0f, 0.0f, 0.0f};
+        for (int64_t q = p->vt_off[v]; q < p->vt_off[v + 1]; q++) {
+          const int pos = p->vt_pos[q];
+          if (!(p->nodes[p->pos_node[pos]].flag & OR_PBVH_UpdateNormals)) continue;
+          float fn[3];
+          calc_poly_normal(p, p->tri_poly[p->prim_indices[pos]], fn);
+          acc[2] += fn[2]; acc[1] += fn[1]; acc[0] += fn[0];
+        }
+        normalize_v3(acc);
+        memcpy(p->no[v], acc, sizeof(acc));
+      }
+    }
+    /* flags and dirty bits drop only after every node has read its neighbours' flags */
+#pragma omp parallel for schedule(dynamic)
+    for (int n = 0; n < totnode; n++) {
+      OrNode *node = &p->nodes[nodes[n]];
+      if (!(node->flag & OR_PBVH_UpdateNormals)) continue;
+      for (int i = 0; i < node->uniq_verts; i++) p->vert_bitmap[node->vert_indices[i]] = 0;
+      node->flag &= ~(unsigned)OR_PBVH_UpdateNormals;
+    }
+    return;
+  }
 #pragma omp parallel for schedule(dynamic) if (par)
   for (int n = 0; n < totnode; n++) {
     OrNode *node = &p->nodes[nodes[n]];

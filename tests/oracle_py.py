@@ -59,6 +59,7 @@ def lib():
         L.or_update_bounds.argtypes = [C.c_void_p, C.c_int]
         L.or_recalc_all_normals.argtypes = [C.c_void_p]
         L.or_set_threads.argtypes = [C.c_int]
+        L.or_set_ordered_normals.argtypes = [C.c_int]
         L.or_stroke_begin.argtypes = [C.c_void_p, c_float_p]
         L.or_stroke_end.argtypes = [C.c_void_p]
         L.or_set_custom_curve.argtypes = [C.c_void_p, c_float_p]

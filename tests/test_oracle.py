@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from dune_sculpt_b200 import capi, meshgen, stroke
-from oracle_py import Oracle
+from oracle_py import Oracle, lib as oracle_lib
 
 
 def _meshes():
@@ -152,6 +152,29 @@ def test_single_thread_vs_openmp(tool):
     assert np.abs(res[0][1] - res[1][1]).max() <= 1e-5
     assert np.abs(res[0][2] - res[1][2]).max() <= tol
     assert np.array_equal(res[0][3], res[1][3])
+
+
+@pytest.mark.parametrize("mk", [lambda: meshgen.grid(129), lambda: meshgen.mixed_grid(60), lambda: meshgen.icosphere(20, noise=0.003)])
+def test_threaded_oracle_with_ordered_normals_is_bit_identical_to_the_serial_one(mk):
+    """or_set_ordered_normals: what bench.py's full-size parity legs run -- threads for speed, per-vertex sums in the serial
+    loop's order (ascending looptri position) for bits"""
+    m = mk()
+    dabs = stroke.c3_radius_sweep(m.bbox_diag(), dabs_per_radius=2)
+    res = []
+    for threads, ordered in ((1, 0), (4, 1)):
+        oracle_lib().or_set_ordered_normals(ordered)  # before the build: the initial normals are computed with it
+        o = Oracle(m, leaf_limit=200, threads=threads)
+        o.stroke_begin()
+        for d in dabs:
+            o.dab(d)
+        o.stroke_end()
+        na = o.node_arrays()
+        res.append((o.co(), o.no(), na["vb"], na["flag"], o.touched()))
+        o.L.or_set_ordered_normals(0)
+        o.set_threads(1)
+        o.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
 
 
 def test_golden_fixtures():
