@@ -3,8 +3,10 @@
 #include "dsc_kernels.cuh"
 #include "dsc_grids.cuh"
 
+#include <cupti.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <mutex>
 
 #include <algorithm>
 #include <cfloat>
@@ -131,6 +133,8 @@ struct DscContext {
   std::unordered_map<unsigned, DabGraph> graphs;
   bool use_graphs = true, use_pdl = false, use_batch_kernel = false;
   int batch_grid[4] = {0, 0, 0, 0}; /* resident CTAs of k_dab_batch<tool> */
+  int fused_grid[4] = {0, 0, 0, 0}; /* SMs x resident CTAs of k_dab_tile<tool> */
+  bool use_fused = false;           /* DSC_FUSE=1: boundary brush + fused interior brush / normals / boxes kernel */
   long long batch_launches = 0;
   long long graph_launches = 0, ring_seq = 0;
 
@@ -143,6 +147,7 @@ struct DscContext {
   long long launches = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int grid = 148 * 8;
+  int grid_bnd = 148 * 4;                        /* k_brush_boundary: a warp per tile */
   int grid_area = 148 * 8, grid_brush = 148 * 8; /* per-dab kernels: SMs x a multiple from DSC_GRID_AREA / DSC_GRID_BRUSH */
 };
 
@@ -232,7 +237,7 @@ struct StageScope {
   {
     ctx->launches++;
     ctx->stage_launches[stage]++;
-    if (ctx->stage_timing) {
+    if (ctx->stage_timing == 1 || ctx->stage_timing == 2) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
       /* inside a capture a plain record is only a dependency marker; an external record becomes a node of the graph */
@@ -242,7 +247,7 @@ struct StageScope {
   }
   ~StageScope()
   {
-    if (ctx->stage_timing) {
+    if (ctx->stage_timing == 1 || ctx->stage_timing == 2) {
       if (ctx->capturing_now) cudaEventRecordWithFlags(b, st, cudaEventRecordExternal);
       else cudaEventRecord(b, st);
       ctx->events.push_back({stage, a, b});
@@ -591,6 +596,103 @@ static void plan_halo(const DscMeshDesc *me, const DscPbvhDesc *pb, int world, c
   }
   std::sort(out.begin(), out.end());
   out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+/* ---- kernel durations of the replayed graphs: CUPTI activity records (dsc_stage_timing mode 3) ----
+ * Event pairs around a kernel measure launch latency with it (about 8 us per small kernel inside a graph), so the
+ * per-stage times of the timed path are taken from the hardware timestamps CUPTI records for every kernel node.
+ * libcupti is looked up at run time; when it cannot be loaded (or a profiler already owns the device) mode 3 is refused
+ * and the caller falls back to mode 2. */
+struct CuptiApi {
+  void *lib = nullptr;
+  CUptiResult (*Enable)(CUpti_ActivityKind) = nullptr;
+  CUptiResult (*Disable)(CUpti_ActivityKind) = nullptr;
+  CUptiResult (*Register)(CUpti_BuffersCallbackRequestFunc, CUpti_BuffersCallbackCompleteFunc) = nullptr;
+  CUptiResult (*FlushAll)(uint32_t) = nullptr;
+  CUptiResult (*Next)(uint8_t *, size_t, CUpti_Activity **) = nullptr;
+  bool registered = false;
+};
+static CuptiApi g_cupti;
+static std::mutex g_cupti_mu;
+static double g_cupti_ms[DSC_NUM_STAGES];
+static long long g_cupti_n[DSC_NUM_STAGES];
+
+static int stage_of_kernel(const char *name)
+{
+  if (!name) return ST_OTHER;
+  if (strstr(name, "k_gather")) return ST_GATHER;
+  if (strstr(name, "k_area")) return ST_AREA;
+  if (strstr(name, "k_brush")) return ST_BRUSH;
+  if (strstr(name, "k_smooth") || strstr(name, "k_snapshot")) return ST_SMOOTH;
+  if (strstr(name, "k_leaf_bb")) return ST_LEAFBB;
+  if (strstr(name, "k_normals") || strstr(name, "k_grid_") || strstr(name, "k_dab_tile") || strstr(name, "k_ghit")) return ST_NORMALS;
+  if (strstr(name, "k_tag_ancestors") || strstr(name, "k_refit") || strstr(name, "k_flush") || strstr(name, "k_reset_leaf_boxes")) return ST_FLUSH;
+  return ST_OTHER;
+}
+static void CUPTIAPI cupti_buffer_requested(uint8_t **buffer, size_t *size, size_t *max_records)
+{
+  *size = 8u << 20;
+  *buffer = (uint8_t *)aligned_alloc(8, *size);
+  *max_records = 0;
+}
+static void CUPTIAPI cupti_buffer_completed(CUcontext, uint32_t, uint8_t *buffer, size_t, size_t valid)
+{
+  CUpti_Activity *rec = nullptr;
+  std::lock_guard<std::mutex> lk(g_cupti_mu);
+  while (valid > 0 && g_cupti.Next(buffer, valid, &rec) == CUPTI_SUCCESS) {
+    if (rec->kind == CUPTI_ACTIVITY_KIND_CONCURRENT_KERNEL || rec->kind == CUPTI_ACTIVITY_KIND_KERNEL) {
+      const CUpti_ActivityKernel9 *k = (const CUpti_ActivityKernel9 *)rec;
+      const int st = stage_of_kernel(k->name);
+      g_cupti_ms[st] += 1e-6 * (double)(k->end - k->start);
+      g_cupti_n[st]++;
+    }
+  }
+  free(buffer);
+}
+static bool cupti_load()
+{
+  if (g_cupti.lib) return true;
+  const char *names[] = {"/usr/local/cuda/lib64/libcupti.so.12", "/usr/local/cuda/targets/x86_64-linux/lib/libcupti.so.12",
+                         "/usr/local/cuda/extras/CUPTI/lib64/libcupti.so.12", "libcupti.so.12", "libcupti.so"};
+  void *h = nullptr;
+  for (const char *n : names) {
+    if ((h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+  }
+  if (!h) return false;
+  g_cupti.Enable = (decltype(g_cupti.Enable))dlsym(h, "cuptiActivityEnable");
+  g_cupti.Disable = (decltype(g_cupti.Disable))dlsym(h, "cuptiActivityDisable");
+  g_cupti.Register = (decltype(g_cupti.Register))dlsym(h, "cuptiActivityRegisterCallbacks");
+  g_cupti.FlushAll = (decltype(g_cupti.FlushAll))dlsym(h, "cuptiActivityFlushAll");
+  g_cupti.Next = (decltype(g_cupti.Next))dlsym(h, "cuptiActivityGetNextRecord");
+  if (!g_cupti.Enable || !g_cupti.Disable || !g_cupti.Register || !g_cupti.FlushAll || !g_cupti.Next) {
+    dlclose(h);
+    return false;
+  }
+  g_cupti.lib = h;
+  return true;
+}
+static bool cupti_start()
+{
+  if (!cupti_load()) return false;
+  if (!g_cupti.registered) {
+    if (g_cupti.Register(cupti_buffer_requested, cupti_buffer_completed) != CUPTI_SUCCESS) return false;
+    g_cupti.registered = true;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_cupti_mu);
+    for (int i = 0; i < DSC_NUM_STAGES; i++) {
+      g_cupti_ms[i] = 0.0;
+      g_cupti_n[i] = 0;
+    }
+  }
+  return g_cupti.Enable(CUPTI_ACTIVITY_KIND_CONCURRENT_KERNEL) == CUPTI_SUCCESS;
+}
+static void cupti_stop()
+{
+  if (g_cupti.lib) {
+    g_cupti.FlushAll(1);
+    g_cupti.Disable(CUPTI_ACTIVITY_KIND_CONCURRENT_KERNEL);
+  }
 }
 
 extern "C" {
@@ -954,6 +1056,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   std::vector<int> leaf_ubeg(L), leaf_ucnt(L), leaf_scnt(L), leaf_pbeg(L), leaf_pcnt(L), leaf_tile0(L + 1, 0);
   std::vector<int2> tile_range;
   std::vector<int> tile_leaf;
+  std::vector<int> tile_ibnd; /* per tile: where its boundary run starts (a multiple of 32); meshes only */
   long long cur = 0;
   int expect_prim = 0;
   std::vector<int> grid_slot0;
@@ -991,8 +1094,20 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     leaf_tile0[L] = (int)tile_range.size();
   }
   else {
-    std::vector<int> ord;
+    /* Pass 1: tiles.  Every leaf's unique verts are bisected into tiles (membership only).
+     * Pass 2: a vertex is a BOUNDARY vertex when some other tile reads it -- it is a corner of a poly that has a
+     *         corner in another tile, or of a looptri held by another leaf (that leaf lists it as a shared vert).
+     * Pass 3: slots.  Inside a tile the interior verts come first, the boundary verts last (each part in rows); the
+     *         boundary part starts at a multiple of 32 (`ibnd`, a few interior verts may fall into it).  The dab then
+     *         displaces the boundary runs of the gathered tiles first (k_brush_boundary) and the interiors inside the
+     *         fused tile kernel, which finds every vertex it reads from another tile already displaced. */
+    std::vector<int> ord_all;
+    ord_all.reserve((size_t)V);
+    struct TileSpan { int lo, hi, leaf, base; };
+    std::vector<TileSpan> spans;
+    std::vector<int> tile_of_vert((size_t)V, -1);
     const float *hco = ctx->h_co.data();
+    std::vector<int> ord;
     for (int l = 0; l < L; l++) {
       const int n = leaves[l];
       cur = (cur + 31) & ~31ll;
@@ -1011,30 +1126,32 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         ctx->slot_of[v] = -2; /* claimed; the slot follows */
       }
       ord.assign(vi, vi + U);
-      leaf_tile0[l] = (int)tile_range.size();
+      leaf_tile0[l] = (int)spans.size();
       /* bisection of ord[lo, hi) into k tiles, slots from `base` */
       struct Job { int lo, hi, k, base; };
       std::vector<Job> jobs(1, Job{0, U, std::max(1, (U + DSC_TILE - 1) / DSC_TILE), (int)cur});
-      std::vector<int2> made;
+      std::vector<TileSpan> made;
+      const int g0 = (int)ord_all.size();
       while (!jobs.empty()) {
         const Job j = jobs.back();
         jobs.pop_back();
         const int cnt = j.hi - j.lo;
-        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (int i = j.lo; i < j.hi; i++) {
-          for (int k = 0; k < 3; k++) {
-            const float c = hco[(size_t)3 * ord[i] + k];
-            mn[k] = std::min(mn[k], c);
-            mx[k] = std::max(mx[k], c);
-          }
-        }
-        int ax[3] = {0, 1, 2};
-        std::sort(ax, ax + 3, [&](int a, int b) { return (mx[a] - mn[a]) > (mx[b] - mn[b]) || ((mx[a] - mn[a]) == (mx[b] - mn[b]) && a < b); });
         if (j.k > 1) {
+          float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+          for (int i = j.lo; i < j.hi; i++) {
+            for (int k = 0; k < 3; k++) {
+              const float c = hco[(size_t)3 * ord[i] + k];
+              mn[k] = std::min(mn[k], c);
+              mx[k] = std::max(mx[k], c);
+            }
+          }
+          int a = 0;
+          for (int k = 1; k < 3; k++) {
+            if ((mx[k] - mn[k]) > (mx[a] - mn[a])) a = k;
+          }
           const int kl = j.k / 2;
           long long nl = ((long long)cnt * kl + j.k - 1) / j.k;
           nl = std::min<long long>((nl + 31) & ~31ll, std::min<long long>((long long)kl * DSC_TILE, cnt));
-          const int a = ax[0];
           std::nth_element(ord.begin() + j.lo, ord.begin() + j.lo + nl, ord.begin() + j.hi, [&](int p, int q) {
             const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
             return cp < cq || (cp == cq && p < q);
@@ -1044,34 +1161,79 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
           jobs.push_back(Job{j.lo, j.lo + (int)nl, kl, j.base});
           continue;
         }
-        /* one tile: rows along the second-widest axis, ascending along the widest inside a row */
-        const int a = ax[0], b = ax[1];
-        const float ea = mx[a] - mn[a], eb2 = mx[b] - mn[b];
-        int rows = 1;
-        if (ea > 0.0f && eb2 > 0.0f) rows = std::max(1, std::min(cnt, (int)lrintf(sqrtf((float)cnt * eb2 / ea))));
-        auto row_of = [&](int v) {
-          if (rows <= 1) return 0;
-          const int rr = (int)((hco[(size_t)3 * v + b] - mn[b]) / eb2 * (float)rows);
-          return std::min(std::max(rr, 0), rows - 1);
-        };
-        std::sort(ord.begin() + j.lo, ord.begin() + j.hi, [&](int p, int q) {
-          const int rp = row_of(p), rq = row_of(q);
-          if (rp != rq) return rp < rq;
-          const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
-          return cp < cq || (cp == cq && p < q);
-        });
-        for (int i = j.lo; i < j.hi; i++) ctx->slot_of[ord[i]] = j.base + (i - j.lo);
-        made.push_back(make_int2(j.base, cnt));
+        made.push_back(TileSpan{g0 + j.lo, g0 + j.hi, l, j.base});
       }
-      std::sort(made.begin(), made.end(), [](const int2 &x, const int2 &y) { return x.x < y.x; });
-      for (const int2 &t : made) {
-        tile_range.push_back(t);
-        tile_leaf.push_back(l);
+      std::sort(made.begin(), made.end(), [](const TileSpan &x, const TileSpan &y) { return x.base < y.base; });
+      ord_all.insert(ord_all.end(), ord.begin(), ord.end());
+      for (const TileSpan &t : made) {
+        for (int i = t.lo; i < t.hi; i++) tile_of_vert[ord_all[i]] = (int)spans.size();
+        spans.push_back(t);
       }
       cur += U;
       if (cur > 0x7fffff00ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 slots");
     }
-    leaf_tile0[L] = (int)tile_range.size();
+    leaf_tile0[L] = (int)spans.size();
+    /* pass 2 */
+    std::vector<unsigned char> is_bnd((size_t)V, 0);
+    for (int l = 0; l < L; l++) {
+      for (int pos = leaf_pbeg[l]; pos < leaf_pbeg[l] + leaf_pcnt[l]; pos++) {
+        const int t = pb->prim_indices[pos];
+        if (t < 0 || t >= T) return fail(ctx, DSC_ERR_INVALID, "prim_indices[%d] out of range", pos);
+        const int p = ctx->h_tri_poly[t];
+        const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
+        int t0 = -2;
+        bool mixed = false;
+        for (int k = 0; k < len; k++) {
+          const int tv = tile_of_vert[ctx->h_loop_v[ls + k]];
+          if (t0 == -2) t0 = tv;
+          else if (tv != t0) mixed = true;
+        }
+        for (int k = 0; k < len; k++) {
+          const int v = ctx->h_loop_v[ls + k];
+          const int tv = tile_of_vert[v];
+          if (mixed || tv < 0 || spans[tv].leaf != l) is_bnd[v] = 1;
+        }
+      }
+    }
+    /* pass 3 */
+    tile_ibnd.assign(spans.size(), 0);
+    for (size_t ti = 0; ti < spans.size(); ti++) {
+      const TileSpan &sp = spans[ti];
+      const int cnt = sp.hi - sp.lo;
+      float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+      int ninterior = 0;
+      for (int i = sp.lo; i < sp.hi; i++) {
+        for (int k = 0; k < 3; k++) {
+          const float c = hco[(size_t)3 * ord_all[i] + k];
+          mn[k] = std::min(mn[k], c);
+          mx[k] = std::max(mx[k], c);
+        }
+        ninterior += is_bnd[ord_all[i]] ? 0 : 1;
+      }
+      int ax[3] = {0, 1, 2};
+      std::sort(ax, ax + 3, [&](int a, int b) { return (mx[a] - mn[a]) > (mx[b] - mn[b]) || ((mx[a] - mn[a]) == (mx[b] - mn[b]) && a < b); });
+      /* rows along the second-widest axis, ascending along the widest inside a row */
+      const int a = ax[0], b = ax[1];
+      const float ea = mx[a] - mn[a], eb2 = mx[b] - mn[b];
+      int rows = 1;
+      if (ea > 0.0f && eb2 > 0.0f) rows = std::max(1, std::min(cnt, (int)lrintf(sqrtf((float)cnt * eb2 / ea))));
+      auto row_of = [&](int v) {
+        if (rows <= 1) return 0;
+        const int rr = (int)((hco[(size_t)3 * v + b] - mn[b]) / eb2 * (float)rows);
+        return std::min(std::max(rr, 0), rows - 1);
+      };
+      std::sort(ord_all.begin() + sp.lo, ord_all.begin() + sp.hi, [&](int p, int q) {
+        if (is_bnd[p] != is_bnd[q]) return is_bnd[p] < is_bnd[q];
+        const int rp = row_of(p), rq = row_of(q);
+        if (rp != rq) return rp < rq;
+        const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
+        return cp < cq || (cp == cq && p < q);
+      });
+      for (int i = sp.lo; i < sp.hi; i++) ctx->slot_of[ord_all[i]] = sp.base + (i - sp.lo);
+      tile_range.push_back(make_int2(sp.base, cnt));
+      tile_leaf.push_back(sp.leaf);
+      tile_ibnd[ti] = ninterior & ~31;
+    }
   }
   const int NT = (int)tile_range.size();
   if (expect_prim != T) return fail(ctx, DSC_ERR_INVALID, "leaves hold %d looptris, mesh has %d", expect_prim, T);
@@ -1501,6 +1663,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         mx_v2 = std::max(mx_v2, t.v2w);
         mx_h = std::max(mx_h, t.ehalo);
       }
+      m.sm_stride = mx_nloc;
       m.sm_off_f = 12 * mx_nloc;
       m.sm_off_e = m.sm_off_f + 16 * (mx_ne + 1);
       m.sm_off_v2 = m.sm_off_e + 8 * ((mx_ne + 1) & ~1);
@@ -1516,9 +1679,13 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     }
 
     static_assert(sizeof(TileMeta) == 3 * sizeof(int4), "TileMeta is three int4");
+    /* tile_range.y = unique verts | start of the boundary run << 16; a leaf on the general path has no interior part (its
+     * whole tiles are displaced by the boundary kernel, its normals and box come from k_normals / k_leaf_bb) */
+    std::vector<int2> tile_range_dev(tile_range);
+    for (int t = 0; t < NT; t++) tile_range_dev[t].y |= (leaf_fast[tile_leaf[t]] ? tile_ibnd[t] : 0) << 16;
     if ((r = dev_upload_c(ctx, &m.stage_slots, stage)) || (r = dev_upload_c(ctx, &m.e_pv, e_pv)) ||
         (r = dev_upload_c(ctx, &m.e_halo_leaf, e_halo_leaf)) || (r = dev_upload_c(ctx, &m.tile_meta, tmeta)) ||
-        (r = dev_upload_c(ctx, &m.tile_range, tile_range)) || (r = dev_upload_c(ctx, &m.leaf_tile0, leaf_tile0)) ||
+        (r = dev_upload_c(ctx, &m.tile_range, tile_range_dev)) || (r = dev_upload_c(ctx, &m.leaf_tile0, leaf_tile0)) ||
         (r = dev_upload_c(ctx, &m.v2_goff, v2_goff)) || (r = dev_upload_c(ctx, &m.v2_idx, v2_idx)) ||
         (r = dev_upload_c(ctx, &m.leaf_fast, leaf_fast)))
       return r;
@@ -1685,6 +1852,21 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   int occ = 1;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_normals_tile, NT_THREADS, ctx->nb_smem));
   ctx->nb_grid = ctx->num_sms * std::max(occ, 1);
+  {
+    /* the fused dab kernel (interior brush + normals + boxes), one instantiation per tool */
+    const void *fn[4] = {(const void *)k_dab_tile<DSC_TOOL_DRAW>, (const void *)k_dab_tile<DSC_TOOL_INFLATE>,
+                         (const void *)k_dab_tile<DSC_TOOL_GRAB>, (const void *)k_dab_tile<DSC_TOOL_CLAY_STRIPS>};
+    for (int k = 0; k < 4; k++) {
+      CU(cudaFuncSetAttribute(fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
+      int o = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn[k], NT_THREADS, ctx->nb_smem));
+      ctx->fused_grid[k] = ctx->num_sms * std::max(o, 1);
+    }
+    /* opt-in: measured slower than the two passes (C3 sweep 24.6 vs 20.7 ms per stroke): both kernels are bound by
+     * instruction issue, not by HBM, so saving the second read of the positions buys nothing while the brush arithmetic
+     * runs at the tile kernel's occupancy */
+    ctx->use_fused = getenv("DSC_FUSE") != nullptr;
+  }
   {
     /* the persistent batch kernel, one instantiation per tool: every CTA must be resident */
     const void *fn[4] = {(const void *)k_dab_batch<DSC_TOOL_DRAW>, (const void *)k_dab_batch<DSC_TOOL_INFLATE>,
@@ -1885,24 +2067,28 @@ static int run_collect(DscContext *ctx, int flags)
   return DSC_OK;
 }
 /* normals and/or leaf boxes of the listed leaves (mode: NB_NORMALS | NB_BOUNDS) */
+/* the leaves that do not fit the shared-memory tile kernel (n-gons, oversized tiles): general gather kernels */
+static int run_slow_leaves(DscContext *ctx, LeafList ll, int mode)
+{
+  if (mode & NB_NORMALS) {
+    StageScope s(ctx, ST_NORMALS);
+    k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1, ll.mask);
+    LAUNCH_CHECK();
+  }
+  if (mode & NB_BOUNDS) {
+    StageScope s(ctx, ST_LEAFBB);
+    k_leaf_bb<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1);
+    LAUNCH_CHECK();
+  }
+  return DSC_OK;
+}
 static int run_normals_bounds(DscContext *ctx, LeafList ll, int mode, bool pdl = false)
 {
   {
     StageScope s(ctx, ST_NORMALS);
     CU(launch_k(k_normals_tile, ctx->nb_grid, NT_THREADS, ctx->nb_smem, ctx->stream, pdl, ctx->m, ll.tiles, ll.tile_count, mode, ll.mask));
   }
-  if (ctx->any_slow_leaf) {
-    if (mode & NB_NORMALS) {
-      StageScope s(ctx, ST_NORMALS);
-      k_normals<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1, ll.mask);
-      LAUNCH_CHECK();
-    }
-    if (mode & NB_BOUNDS) {
-      StageScope s(ctx, ST_LEAFBB);
-      k_leaf_bb<<<ctx->grid, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ll.list, ll.count, 1);
-      LAUNCH_CHECK();
-    }
-  }
+  if (ctx->any_slow_leaf) return run_slow_leaves(ctx, ll, mode);
   return DSC_OK;
 }
 static int run_clear(DscContext *ctx, LeafList ll, int clear_mask)
@@ -2405,7 +2591,9 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   cudaEvent_t ev_fork = capturing ? ctx->cap_fork : ctx->ev_fork, ev_bb = capturing ? ctx->cap_bb : ctx->ev_bb;
   cudaEvent_t ev_tag = capturing ? ctx->cap_tag : ctx->ev_tag;
   cudaEvent_t *ev_refit = capturing ? ctx->cap_refit : ctx->ev_refit;
-  const bool pdl = ctx->use_pdl && !ctx->stage_timing && !ctx->capture;
+  const bool pdl = ctx->use_pdl && ctx->stage_timing != 1 && ctx->stage_timing != 2 && !ctx->capture;
+  /* one pass over the positions for brush + normals + boxes: meshes on one GPU whose leaves carry no older flags */
+  const bool fused = ctx->use_fused && !ctx->is_grids && !dist && use_hits && tool != DSC_TOOL_SMOOTH;
   if (ctx->capture) CU(cudaMemsetAsync(ctx->d_capture, 0, sizeof(unsigned) * (size_t)ctx->nwords, st));
 
   /* 1. gather + undo membership + node marks.  It recycles the ring slot the refit of three dabs ago
@@ -2463,7 +2651,18 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
       CU(launch_k(k_area, ctx->grid_area, DSC_BLOCK, 0, st, pdl, m, j, slot));
     }
     if (dist && (r = dist_allreduce_dab(ctx, slot, sig.needs_area))) return r;
-    {
+    if (fused) {
+      /* the boundary runs of the gathered tiles first: what other tiles read is displaced before the fused kernel starts */
+      StageScope s(ctx, ST_BRUSH);
+      switch (tool) {
+        case DSC_TOOL_DRAW: k_brush_boundary<DSC_TOOL_DRAW><<<ctx->grid_bnd, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        case DSC_TOOL_INFLATE: k_brush_boundary<DSC_TOOL_INFLATE><<<ctx->grid_bnd, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        case DSC_TOOL_GRAB: k_brush_boundary<DSC_TOOL_GRAB><<<ctx->grid_bnd, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+        default: k_brush_boundary<DSC_TOOL_CLAY_STRIPS><<<ctx->grid_bnd, DSC_BLOCK, 0, st>>>(m, j, slot); break;
+      }
+      LAUNCH_CHECK();
+    }
+    else {
       StageScope s(ctx, ST_BRUSH);
       const bool bpdl = pdl && !dist;
       switch (tool) {
@@ -2490,6 +2689,21 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
     }
     if (ctx->is_grids) {
       if ((r = grids_after_brush(ctx, hits, j))) return r;
+    }
+    else if (fused) {
+      /* interior brush + normals + boxes in one pass over the gathered tiles */
+      {
+        StageScope s(ctx, ST_NORMALS);
+        const size_t sm = ctx->nb_smem;
+        switch (tool) {
+          case DSC_TOOL_DRAW: k_dab_tile<DSC_TOOL_DRAW><<<ctx->fused_grid[0], NT_THREADS, sm, st>>>(m, j, slot, mode); break;
+          case DSC_TOOL_INFLATE: k_dab_tile<DSC_TOOL_INFLATE><<<ctx->fused_grid[1], NT_THREADS, sm, st>>>(m, j, slot, mode); break;
+          case DSC_TOOL_GRAB: k_dab_tile<DSC_TOOL_GRAB><<<ctx->fused_grid[2], NT_THREADS, sm, st>>>(m, j, slot, mode); break;
+          default: k_dab_tile<DSC_TOOL_CLAY_STRIPS><<<ctx->fused_grid[3], NT_THREADS, sm, st>>>(m, j, slot, mode); break;
+        }
+        LAUNCH_CHECK();
+      }
+      if (ctx->any_slow_leaf && (r = run_slow_leaves(ctx, hits, mode))) return r;
     }
     else if (mode) {
       if ((r = run_normals_bounds(ctx, hits, mode, pdl && !dist && tool != DSC_TOOL_SMOOTH))) return r;
@@ -3346,6 +3560,15 @@ int dsc_stage_timing(DscContext *ctx, int enable)
     ctx->stage_ms[i] = 0.0f;
     ctx->stage_launches[i] = 0;
   }
+  if (ctx->stage_timing == 3) cupti_stop();
+  if (enable == 3) {
+    if (!cupti_start()) {
+      ctx->stage_timing = 0;
+      return fail(ctx, DSC_ERR_UNSUPPORTED, "CUPTI kernel tracing is not available (libcupti not found, or a profiler owns the device)");
+    }
+    ctx->stage_timing = 3;
+    return DSC_OK;
+  }
   ctx->stage_timing = enable == 2 ? 2 : (enable != 0 ? 1 : 0);
   return DSC_OK;
 }
@@ -3362,6 +3585,16 @@ int dsc_stage_times(DscContext *ctx, float r_ms[DSC_NUM_STAGES], int r_launches[
     cudaEventDestroy(ev.b);
   }
   ctx->events.clear();
+  if (ctx->stage_timing == 3) {
+    /* everything queued has run (sync_all above): pull the records */
+    g_cupti.FlushAll(1);
+    std::lock_guard<std::mutex> lk(g_cupti_mu);
+    for (int i = 0; i < DSC_NUM_STAGES; i++) {
+      if (r_ms) r_ms[i] = (float)g_cupti_ms[i];
+      if (r_launches) r_launches[i] = (int)g_cupti_n[i];
+    }
+    return DSC_OK;
+  }
   for (int i = 0; i < DSC_NUM_STAGES; i++) {
     if (r_ms) r_ms[i] = ctx->stage_ms[i];
     if (r_launches) r_launches[i] = ctx->stage_launches[i];

@@ -23,6 +23,7 @@
 #define DSC_ENT_FIRST 1       /* tile-list entry bits: first touch of the leaf in this stroke */
 #define DSC_ENT_NORMALS 2     /* the leaf updates its normals with this list */
 #define DSC_ENT_BOUNDS 4      /* ... its box */
+#define DSC_ENT_IBND_SHIFT 8  /* bits 8..18: where the tile's boundary run starts (unique verts other tiles read come last) */
 #define DSC_BLOCK 256
 #define DSC_LEAF_HIT 1u
 #define DSC_LEAF_FIRST 2u
@@ -90,7 +91,7 @@ struct DevMesh {
    * looptri position. */
   int ntile;
   const int *leaf_tile0;      /* [nleaf + 1] */
-  const int2 *tile_range;     /* {first slot, unique verts} */
+  const int2 *tile_range;     /* {first slot, unique verts | start of the boundary run << 16} */
   const int4 *tile_meta;      /* 3 per tile, see TileMeta */
   const int *stage_slots;     /* per tile: slots of the staged verts (counted in the leaf box first) */
   const ushort4 *e_pv;        /* local vertex indices of the entry's poly, w = 0xffff: triangle */
@@ -104,6 +105,8 @@ struct DevMesh {
   /* byte offsets of the tile kernel's shared-memory regions (sized for the largest tile of the mesh, so a region
    * never moves between tiles): positions at 0, then poly normals, poly entries, index words, other-leaf switches */
   int sm_off_f, sm_off_e, sm_off_v2, sm_off_h;
+  int sm_stride; /* floats between the x / y / z planes of the staged positions: the same for every tile (a launch constant,
+                    so the plane offsets fold into the shared-memory address of every load) */
   /* leaves */
   int nleaf;
   int max_chunks; /* ceil(max uniq_verts / DSC_CHUNK) */
@@ -417,7 +420,7 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
     int4 *tl = (pass == 0 ? m.tile_list : m.atile_list) + (size_t)slot * m.ntile + base + (incl - mine);
     for (int k = 0; k < mine; k++) {
       const int2 r = m.tile_range[t0 + k];
-      tl[k] = make_int4(t0 + k, r.x, r.y, bits);
+      tl[k] = make_int4(t0 + k, r.x, r.y & 0xffff, bits | ((r.y >> 16) << DSC_ENT_IBND_SHIFT));
     }
   }
   unsigned long long vd = 0, avd = 0, all = 0, prims = 0, first = 0;
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(1024) k_collect_flagged(DevMesh m, int flags)
     const int base = atomicAdd(&s_tiles, nt);
     for (int k = 0; k < nt; k++) {
       const int2 r = m.tile_range[t0 + k];
-      m.flag_tile_list[base + k] = make_int4(t0 + k, r.x, r.y, bits);
+      m.flag_tile_list[base + k] = make_int4(t0 + k, r.x, r.y & 0xffff, bits | ((r.y >> 16) << DSC_ENT_IBND_SHIFT));
     }
   }
   __syncthreads();
@@ -877,7 +880,80 @@ __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabPara
  * consecutive slots (float4 loads / stores of the SoA arrays).  First touch of a leaf in the stroke
  * snapshots co/no into orig_co/orig_no before the vertex is moved (row a9).  Displaced verts get
  * their vert_bitmap bit (pbvh.c:3729). */
+/* four consecutive slots from s0, positions already in X / Y / Z: snapshot on first touch, displacement; returns the
+ * moved nibble and the new positions (the caller stores them) */
 template<int TOOL>
+__device__ __forceinline__ unsigned dsc_brush_quad_core(const DevMesh &m, const DabParams &d, const BrushDerived &D, bool first, int s0,
+                                                        int nvalid, float radius_sq, bool need_no, float4 &X, float4 &Y, float4 &Z)
+{
+  constexpr int tool = TOOL;
+  constexpr bool use_orig = (tool == 5);
+  unsigned nib = 0;
+  float4 NX = make_float4(0, 0, 0, 0), NY = NX, NZ = NX;
+  float4 TX = X, TY = Y, TZ = Z;
+  if (first) {
+    NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0);
+    st4(m.ox, s0, X); st4(m.oy, s0, Y); st4(m.oz, s0, Z);
+    st4(m.onx, s0, NX); st4(m.ony, s0, NY); st4(m.onz, s0, NZ);
+  }
+  else if (use_orig) {
+    TX = ld4(m.ox, s0); TY = ld4(m.oy, s0); TZ = ld4(m.oz, s0);
+  }
+  if (tool == 18 && D.skip) return 0u;
+  float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+  const float txs[4] = {TX.x, TX.y, TX.z, TX.w}, tys[4] = {TY.x, TY.y, TY.z, TY.w}, tzs[4] = {TZ.x, TZ.y, TZ.z, TZ.w};
+  if (need_no && !first) {
+    /* only needed for verts inside; one cheap pre-test keeps the streaming case at 12 B/vert */
+    bool any = (tool == 18);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float dx = txs[j] - d.loc[0], dy = tys[j] - d.loc[1], dz = tzs[j] - d.loc[2];
+      any |= !((dx * dx + dy * dy + dz * dz) > radius_sq);
+    }
+    if (any) {
+      if (use_orig) { NX = ld4(m.onx, s0); NY = ld4(m.ony, s0); NZ = ld4(m.onz, s0); }
+      else { NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0); }
+    }
+  }
+  const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (j < nvalid && dsc_brush_vertex<TOOL>(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j], vys[j], vzs[j], radius_sq)) {
+      nib |= 1u << j;
+    }
+  }
+  if (nib) {
+    X = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    Y = make_float4(ys[0], ys[1], ys[2], ys[3]);
+    Z = make_float4(zs[0], zs[1], zs[2], zs[3]);
+  }
+  return nib;
+}
+/* the same straight on the global arrays */
+template<int TOOL>
+__device__ __forceinline__ unsigned dsc_brush_quad(const DevMesh &m, const DabParams &d, const BrushDerived &D, bool first, int s0, int nvalid,
+                                                   float radius_sq, bool need_no)
+{
+  if (nvalid <= 0) return 0u;
+  float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
+  const unsigned nib = dsc_brush_quad_core<TOOL>(m, d, D, first, s0, nvalid, radius_sq, need_no, X, Y, Z);
+  if (nib) {
+    st4(m.cx, s0, X);
+    st4(m.cy, s0, Y);
+    st4(m.cz, s0, Z);
+  }
+  return nib;
+}
+
+/* Draw / inflate / grab / clay strips over the unique verts of hit leaves (SURVEY.md 8a rows
+ * a11-a19), one instantiation per tool.  Each thread owns 4 consecutive slots (float4 loads / stores of the SoA
+ * arrays).  First touch of a leaf in the stroke snapshots co/no into orig_co/orig_no before the vertex is moved
+ * (row a9).  Displaced verts get their vert_bitmap bit (pbvh.c:3729).
+ * BOUNDARY = false: a CTA takes one whole tile at a time (the stand-alone brush pass: partitioned PBVHs, which
+ * exchange halo positions between the brush and the normals).
+ * BOUNDARY = true: a warp takes the boundary run of one tile at a time -- the unique verts other tiles read, which
+ * come last in the tile (slots [ibnd, count)); the interiors are displaced inside the fused tile kernel. */
+template<int TOOL, bool BOUNDARY>
 __device__ __forceinline__ void dsc_brush_body(const DevMesh &m, const DabParams &d, int slot, int cta, int ncta)
 {
   DabState *st = m.st + slot;
@@ -886,7 +962,8 @@ __device__ __forceinline__ void dsc_brush_body(const DevMesh &m, const DabParams
   __shared__ unsigned s_moved;
   const int tid = threadIdx.x, lane = tid & 31;
   const int total = __ldcg(&st->tile_count);
-  if (cta >= total && cta != 0) return; /* CTA 0 publishes the plane even when nothing was gathered */
+  const int first_unit = BOUNDARY ? cta * (DSC_BLOCK / 32) : cta;
+  if (first_unit >= total && cta != 0) return; /* CTA 0 publishes the plane even when nothing was gathered */
   __syncthreads(); /* D / s_moved of an earlier call */
   if (tid == 0) {
     s_moved = 0;
@@ -898,62 +975,37 @@ __device__ __forceinline__ void dsc_brush_body(const DevMesh &m, const DabParams
   constexpr int tool = TOOL;
   const float radius_sq = d.radius * d.radius;
   const bool need_no = (tool == 4) || (d.flags & 1);
-  constexpr bool use_orig = (tool == 5);
   unsigned moved_cnt = 0;
-  for (int u = cta; u < total; u += ncta) {
-    const int4 ent = __ldcg(&tl[u]);
-    const bool first = (ent.w & DSC_ENT_FIRST) != 0;
-    const int nvalid = ent.z - 4 * tid;
-    const int s0 = ent.y + 4 * tid;
-    unsigned nib = 0;
-    if (nvalid > 0) {
-      float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
-      float4 NX = make_float4(0, 0, 0, 0), NY = NX, NZ = NX;
-      float4 TX = X, TY = Y, TZ = Z;
-      if (first) {
-        NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0);
-        st4(m.ox, s0, X); st4(m.oy, s0, Y); st4(m.oz, s0, Z);
-        st4(m.onx, s0, NX); st4(m.ony, s0, NY); st4(m.onz, s0, NZ);
-      }
-      else if (use_orig) {
-        TX = ld4(m.ox, s0); TY = ld4(m.oy, s0); TZ = ld4(m.oz, s0);
-      }
-      if (!(tool == 18 && D.skip)) {
-        float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-        const float txs[4] = {TX.x, TX.y, TX.z, TX.w}, tys[4] = {TY.x, TY.y, TY.z, TY.w}, tzs[4] = {TZ.x, TZ.y, TZ.z, TZ.w};
-        if (need_no && !first) {
-          /* only needed for verts inside; one cheap pre-test keeps the streaming case at 12 B/vert */
-          bool any = (tool == 18);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const float dx = txs[j] - d.loc[0], dy = tys[j] - d.loc[1], dz = tzs[j] - d.loc[2];
-            any |= !((dx * dx + dy * dy + dz * dz) > radius_sq);
-          }
-          if (any) {
-            if (use_orig) { NX = ld4(m.onx, s0); NY = ld4(m.ony, s0); NZ = ld4(m.onz, s0); }
-            else { NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0); }
-          }
-        }
-        const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (j < nvalid && dsc_brush_vertex<TOOL>(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j],
-                                                   vys[j], vzs[j], radius_sq)) {
-            nib |= 1u << j;
-          }
-        }
-        if (nib) {
-          st4(m.cx, s0, make_float4(xs[0], xs[1], xs[2], xs[3]));
-          st4(m.cy, s0, make_float4(ys[0], ys[1], ys[2], ys[3]));
-          st4(m.cz, s0, make_float4(zs[0], zs[1], zs[2], zs[3]));
+  if (BOUNDARY) {
+    const int nw = DSC_BLOCK / 32;
+    for (int u = cta * nw + (tid >> 5); u < total; u += ncta * nw) { /* warp-uniform */
+      const int4 ent = __ldcg(&tl[u]);
+      const bool first = (ent.w & DSC_ENT_FIRST) != 0;
+      const int ibnd = (ent.w >> DSC_ENT_IBND_SHIFT) & 0x7ff;
+      for (int o = ibnd; o < ent.z; o += 128) {
+        const int s0 = ent.y + o + 4 * lane;
+        const unsigned nib = dsc_brush_quad<TOOL>(m, d, D, first, s0, ent.z - o - 4 * lane, radius_sq, need_no);
+        const unsigned w = dsc_pack_nibbles(nib, lane);
+        if (w && (lane & 7) == 0) {
+          atomicOr(&m.dirty[s0 >> 5], w); /* fire-and-forget RED: no round trip for the old word */
+          if (m.capture) atomicOr(&m.capture[s0 >> 5], w);
+          moved_cnt += __popc(w);
         }
       }
     }
-    const unsigned w = dsc_pack_nibbles(nib, lane);
-    if (w && (lane & 7) == 0) {
-      atomicOr(&m.dirty[s0 >> 5], w); /* fire-and-forget RED: no round trip for the old word */
-      if (m.capture) atomicOr(&m.capture[s0 >> 5], w);
-      moved_cnt += __popc(w);
+  }
+  else {
+    for (int u = cta; u < total; u += ncta) {
+      const int4 ent = __ldcg(&tl[u]);
+      const bool first = (ent.w & DSC_ENT_FIRST) != 0;
+      const int s0 = ent.y + 4 * tid;
+      const unsigned nib = dsc_brush_quad<TOOL>(m, d, D, first, s0, ent.z - 4 * tid, radius_sq, need_no);
+      const unsigned w = dsc_pack_nibbles(nib, lane);
+      if (w && (lane & 7) == 0) {
+        atomicOr(&m.dirty[s0 >> 5], w);
+        if (m.capture) atomicOr(&m.capture[s0 >> 5], w);
+        moved_cnt += __popc(w);
+      }
     }
   }
   if (moved_cnt) atomicAdd(&s_moved, moved_cnt);
@@ -965,7 +1017,13 @@ template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush(DevMesh 
   dsc_pdl_wait(); /* the area sums (or, without an area pass, the gather) */
   dsc_pdl_launch();
   const DabParams d = dsc_dab_entry(m, j).d;
-  dsc_brush_body<TOOL>(m, d, slot, blockIdx.x, gridDim.x);
+  dsc_brush_body<TOOL, false>(m, d, slot, blockIdx.x, gridDim.x);
+}
+/* the boundary runs of the gathered tiles, ahead of the fused tile kernel */
+template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush_boundary(DevMesh m, int j, int slot)
+{
+  const DabParams d = dsc_dab_entry(m, j).d;
+  dsc_brush_body<TOOL, true>(m, d, slot, blockIdx.x, gridDim.x);
 }
 
 /* snapshot only (smooth brush: first touch, before iteration 0) */
@@ -1373,6 +1431,8 @@ __device__ __forceinline__ void dsc_red_max(float *a, float v)
 #define NT_ACTIVE 1
 #define NT_ANYD 2
 #define NT_DO_B 4
+#define NT_DO_N 8
+#define NT_FIRST 16
 
 /* Producer / consumer form.  Warp 8 is the producer: for the NEXT tile it reads the descriptor, the
  * dirty words and the index-row offsets, publishes them in shared memory (double buffered), queues
@@ -1380,19 +1440,34 @@ __device__ __forceinline__ void dsc_red_max(float *a, float v)
  * while the 8 consumer warps compute the current tile, so no compute warp ever waits on a global
  * load.  Buffers are handed over with mbarriers: full[0] / empty[0] guard positions + entries +
  * staged verts (consumed by the box reduction and phase 2), full[1] / empty[1] the index words
- * (consumed by phase 3).  The consumers synchronise among themselves with a named barrier. */
+ * (consumed by phase 3).  The consumers synchronise among themselves with a named barrier.
+ *
+ * TOOL != 0 is the fused dab kernel: the tile's INTERIOR unique verts (slots [0, ibnd) of the tile: read by no other
+ * tile) are displaced by the brush right here, between the arrival of the positions in shared memory and the box /
+ * normal phases -- their new positions go to shared memory (phases 2-3 read them there) and to global memory, and
+ * their dirty bits live in shared memory only.  The boundary runs [ibnd, count) of all gathered tiles were displaced by
+ * k_brush_boundary before this kernel started, so every position this tile reads from another tile (staged verts) and
+ * the boundary part of its own bulk copy are post-brush already: same arithmetic, same bits as the two-pass form, one
+ * read of the positions less.  With a brush the dirty state of a tile is not known when its loads are queued: the poly
+ * entries, index words and other-leaf switches of every gathered tile are loaded. */
+template<int TOOL>
 __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const int4 *list, const int *count, int mode,
-                                                      const unsigned *upd, const int cta, const int ncta, const bool pdl)
+                                                      const unsigned *upd, const int cta, const int ncta, const bool pdl,
+                                                      const DabParams *dab = nullptr, DabState *dst = nullptr)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2], s_done;
   __shared__ __align__(16) int4 s_q[2][3];
-  __shared__ __align__(16) int4 s_ent[2]; /* {tile, first slot, unique verts, NT_* flags | dirty count << 8} */
+  __shared__ __align__(16) int4 s_ent[2]; /* {tile, first slot, unique verts | ibnd << 16, NT_* flags | dirty count << 8} */
   __shared__ float red[6][NT_CONSUMERS / 32];
   __shared__ unsigned sdirty[2][DSC_TILE / 32];
   __shared__ unsigned sgoff[2][DSC_TILE / 32 + 1];
   __shared__ unsigned s_upd[NT_UPD_WORDS];
+  __shared__ int s_dcount[2];
+  __shared__ BrushDerived s_D;
+  __shared__ unsigned s_moved;
   constexpr int NW = NT_CONSUMERS / 32;
+  constexpr bool BRUSH = TOOL != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tn = m.totnode;
   /* before the PDL wait: only what the gather (at least two launches back) and the upload wrote */
@@ -1414,7 +1489,12 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
     dsc_mbar_init(&s_full[1], 1);           /* TMA bytes only */
     dsc_mbar_init(&s_empty[0], NW);         /* one arrival per consumer warp */
     dsc_mbar_init(&s_empty[1], NW);
+    dsc_mbar_init(&s_done, NW);             /* a tile's poly normals / box partials have been read by every consumer warp */
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (BRUSH) {
+      s_moved = 0u;
+      dsc_brush_derive(dst, *dab, s_D, false); /* the plane / offset every vertex of the dab shares */
+    }
   }
   /* the producer's first descriptor: tile list entry, tile meta, index-row offsets (constant tables) */
   int4 ent = make_int4(0, 0, 0, 0), q = make_int4(0, 0, 0, 0);
@@ -1445,7 +1525,7 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
       const bool do_n = (mode & NB_NORMALS) && (ent.w & DSC_ENT_NORMALS);
       const bool do_b = (mode & NB_BOUNDS) && (ent.w & DSC_ENT_BOUNDS);
       const int ng = (U + 31) >> 5, G0 = ub >> 5;
-      const unsigned dw = (do_n && lane < ng) ? __ldcg(&m.dirty[G0 + lane]) : 0u;
+      const unsigned dw = ((do_n || BRUSH) && lane < ng) ? __ldcg(&m.dirty[G0 + lane]) : 0u;
       int dcount = __popc(dw);
       for (int o = 16; o > 0; o >>= 1) dcount += __shfl_xor_sync(0xffffffffu, dcount, o);
       const unsigned goff0 = __shfl_sync(0xffffffffu, go, 0);
@@ -1454,8 +1534,9 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
       const int X = __shfl_sync(0xffffffffu, q.x, 1), eb = __shfl_sync(0xffffffffu, q.y, 1);
       const int eown = __shfl_sync(0xffffffffu, q.z, 1), ehalo = __shfl_sync(0xffffffffu, q.w, 1);
       const int hb = __shfl_sync(0xffffffffu, q.x, 2), ntfast = __shfl_sync(0xffffffffu, q.w, 2);
-      const bool anyd = dcount > 0;
-      const bool active = (ntfast & (1 << 16)) && (anyd || do_b);
+      /* with a brush the interior verts may still become dirty: everything the normal phases need is loaded */
+      const bool anyd = BRUSH ? do_n : dcount > 0;
+      const bool active = (ntfast & (1 << 16)) && (BRUSH || anyd || do_b);
       /* positions / entries / staged verts / descriptor of tile k - 1 are released */
       dsc_mbar_wait(&s_empty[0], par_e0);
       par_e0 ^= 1u;
@@ -1464,12 +1545,16 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
       sgoff[set][lane] = go;
       if (lane == 0) {
         sgoff[set][ng] = glast;
-        s_ent[set] = make_int4(tile, ub, U, (active ? NT_ACTIVE : 0) | (anyd ? NT_ANYD : 0) | (do_b ? NT_DO_B : 0) | (dcount << 8));
+        s_dcount[set] = 0;
+        const int ibnd = BRUSH ? ((ent.w >> DSC_ENT_IBND_SHIFT) & 0x7ff) : 0;
+        s_ent[set] = make_int4(tile, ub, U | (ibnd << 16),
+                               (active ? NT_ACTIVE : 0) | (anyd ? NT_ANYD : 0) | (do_b ? NT_DO_B : 0) | (do_n ? NT_DO_N : 0) |
+                                   ((ent.w & DSC_ENT_FIRST) ? NT_FIRST : 0) | (dcount << 8));
       }
       const int ne = eown + ehalo;
       const int UA = (U + 3) & ~3;
-      const int nloc_a = dsc_tile_nloc_a(U, SB, X);
       const int v2w = anyd ? (int)(glast - goff0) : 0;
+      const int nloc_a = dsc_tile_nloc_a(U, SB, X);
       float *PX = reinterpret_cast<float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
       ushort4 *E = reinterpret_cast<ushort4 *>(smem_raw + m.sm_off_e);
       unsigned *V2 = reinterpret_cast<unsigned *>(smem_raw + m.sm_off_v2);
@@ -1544,6 +1629,13 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
 
   /* -------------------------------------------------------------------- consumer warps */
   unsigned par_f0 = 0u, par_f1 = 0u;
+  unsigned moved_cnt = 0u;
+  float radius_sq = 0.0f;
+  bool need_no = false;
+  if (BRUSH) {
+    radius_sq = dab->radius * dab->radius;
+    need_no = (TOOL == 4) || (dab->flags & 1);
+  }
   int k = 0;
   for (int h = cta; h < n; h += ncta, k++) {
     const int set = k & 1;
@@ -1557,37 +1649,72 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
       continue;
     }
     const int4 q0 = s_q[set][0], q1 = s_q[set][1], q2 = s_q[set][2];
-    const int ub = ent.y, U = ent.z, dcount = flags >> 8;
-    const bool anyd = (flags & NT_ANYD) != 0, do_b = (flags & NT_DO_B) != 0;
+    const int ub = ent.y, U = ent.z & 0xffff;
+    const bool do_b = (flags & NT_DO_B) != 0;
     const int SB = q0.w, X = q1.x, eown = q1.z, ne = q1.z + q1.w;
     const int ng = (U + 31) >> 5, G0 = ub >> 5;
     const int UA = (U + 3) & ~3;
-    const int nloc_a = dsc_tile_nloc_a(U, SB, X);
     const unsigned goff0 = sgoff[set][0];
-    const float *PX = reinterpret_cast<const float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
+    const int nloc_a = dsc_tile_nloc_a(U, SB, X);
+    float *PX = reinterpret_cast<float *>(smem_raw), *PY = PX + nloc_a, *PZ = PY + nloc_a;
     float4 *F = reinterpret_cast<float4 *>(smem_raw + m.sm_off_f); /* [ne + 1], entry ne = zero */
     const ushort4 *E = reinterpret_cast<const ushort4 *>(smem_raw + m.sm_off_e);
     const unsigned *V2 = reinterpret_cast<const unsigned *>(smem_raw + m.sm_off_v2);
     const unsigned char *H = smem_raw + m.sm_off_h;
-    if (do_b) {
-      /* box of the unique verts (four per thread) and of the box-counted staged verts, from shared memory */
-      float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
-      float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    bool anyd = (flags & NT_ANYD) != 0;
+    int dcount = flags >> 8;
+    /* the thread's four unique verts: brush (interior part), box */
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    if (BRUSH || do_b) {
       const int i0 = 4 * tid;
-      if (i0 + 3 < U) {
-        const float4 x4 = *reinterpret_cast<const float4 *>(PX + i0), y4 = *reinterpret_cast<const float4 *>(PY + i0),
-                     z4 = *reinterpret_cast<const float4 *>(PZ + i0);
-        mn[0] = fminf(fminf(x4.x, x4.y), fminf(x4.z, x4.w)); mx[0] = fmaxf(fmaxf(x4.x, x4.y), fmaxf(x4.z, x4.w));
-        mn[1] = fminf(fminf(y4.x, y4.y), fminf(y4.z, y4.w)); mx[1] = fmaxf(fmaxf(y4.x, y4.y), fmaxf(y4.z, y4.w));
-        mn[2] = fminf(fminf(z4.x, z4.y), fminf(z4.z, z4.w)); mx[2] = fmaxf(fmaxf(z4.x, z4.y), fmaxf(z4.z, z4.w));
-      }
-      else {
-        for (int i = i0; i < U; i++) {
-          mn[0] = fminf(mn[0], PX[i]); mx[0] = fmaxf(mx[0], PX[i]);
-          mn[1] = fminf(mn[1], PY[i]); mx[1] = fmaxf(mx[1], PY[i]);
-          mn[2] = fminf(mn[2], PZ[i]); mx[2] = fmaxf(mx[2], PZ[i]);
+      unsigned nib = 0u;
+      if (i0 < U) {
+        float4 x4 = *reinterpret_cast<const float4 *>(PX + i0), y4 = *reinterpret_cast<const float4 *>(PY + i0),
+               z4 = *reinterpret_cast<const float4 *>(PZ + i0);
+        if (BRUSH && i0 < (ent.z >> 16)) {
+          nib = dsc_brush_quad_core<TOOL == 0 ? 1 : TOOL>(m, *dab, s_D, (flags & NT_FIRST) != 0, ub + i0, 4, radius_sq, need_no, x4, y4, z4);
+          if (nib) {
+            *reinterpret_cast<float4 *>(PX + i0) = x4; *reinterpret_cast<float4 *>(PY + i0) = y4; *reinterpret_cast<float4 *>(PZ + i0) = z4;
+            st4(m.cx, ub + i0, x4); st4(m.cy, ub + i0, y4); st4(m.cz, ub + i0, z4);
+          }
+        }
+        if (do_b) {
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (i0 + j < U) {
+              mn[0] = fminf(mn[0], xs[j]); mx[0] = fmaxf(mx[0], xs[j]);
+              mn[1] = fminf(mn[1], ys[j]); mx[1] = fmaxf(mx[1], ys[j]);
+              mn[2] = fminf(mn[2], zs[j]); mx[2] = fmaxf(mx[2], zs[j]);
+            }
+          }
         }
       }
+      if (BRUSH) {
+        /* eight lanes own one dirty word: interior bits of this dab on top of the boundary bits the producer read */
+        const unsigned w = dsc_pack_nibbles(nib, lane);
+        int cnt = 0;
+        if ((lane & 7) == 0 && (i0 >> 5) < ng) {
+          const unsigned fin = sdirty[set][i0 >> 5] | w;
+          if (w) {
+            sdirty[set][i0 >> 5] = fin;
+            moved_cnt += __popc(w);
+            if (m.capture) atomicOr(&m.capture[G0 + (i0 >> 5)], w);
+            if (!(flags & NT_DO_N)) atomicOr(&m.dirty[G0 + (i0 >> 5)], w); /* no normal pass in this dab: the bits wait in the bitmap */
+          }
+          cnt = __popc(fin);
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+        if (lane == 0 && cnt) atomicAdd(&s_dcount[set], cnt);
+        asm volatile("bar.sync 1, 256;" ::: "memory"); /* displaced positions, dirty words and their count are in shared memory */
+        dcount = s_dcount[set];
+        anyd = (flags & NT_DO_N) && dcount > 0;
+      }
+    }
+    if (do_b) {
+      /* the box-counted staged verts, then the tile's share of the leaf box */
       for (int i = tid; i < SB; i += NT_CONSUMERS) {
         mn[0] = fminf(mn[0], PX[UA + i]); mx[0] = fmaxf(mx[0], PX[UA + i]);
         mn[1] = fminf(mn[1], PY[UA + i]); mx[1] = fmaxf(mx[1], PY[UA + i]);
@@ -1622,56 +1749,77 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
       /* the tile's share of the leaf box (the gather reset the box of every leaf it hit) */
       float v = red[lane][0];
       for (int w = 1; w < NW; w++) v = (lane < 3) ? fminf(v, red[lane][w]) : fmaxf(v, red[lane][w]);
-      float *dst = &m.bb[lane * tn + q2.y];
-      if (lane < 3) dsc_red_min(dst, v);
-      else dsc_red_max(dst, v);
+      float *dstp = &m.bb[lane * tn + q2.y];
+      if (lane < 3) dsc_red_min(dstp, v);
+      else dsc_red_max(dstp, v);
     }
-    if (anyd) {
-      /* phase 3: one warp per group of 32 verts */
+    if (BRUSH ? (flags & NT_ANYD) != 0 : anyd) {
+      /* phase 3: one warp per group of 32 verts.  (With a brush the index words were queued for every tile that may
+       * update normals: the hand-over runs even when nothing turned out dirty.) */
       dsc_mbar_wait(&s_full[1], par_f1);
       par_f1 ^= 1u;
-      for (int g = warp; g < ng; g += NW) {
-        const unsigned word = sdirty[set][g];
-        if (word == 0u) continue; /* warp-uniform */
-        if ((word >> lane) & 1u) {
-          const unsigned off = sgoff[set][g];
-          const int wd = (int)((sgoff[set][g + 1] - off) >> 5);
-          const unsigned *rp = V2 + (off - goff0) + lane;
-          float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-          if (wd == 3) {
-            const unsigned w0 = rp[0], w1 = rp[32], w2 = rp[64];
-            float4 f;
-            f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
-            f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
-            f = F[w1 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
-            f = F[w1 >> 16]; sx += f.x; sy += f.y; sz += f.z;
-            f = F[w2 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
-            f = F[w2 >> 16]; sx += f.x; sy += f.y; sz += f.z;
-          }
-          else {
-            for (int j = 0; j < wd; j++) {
-              const unsigned w0 = rp[j * 32];
+      if (anyd) {
+        for (int g = warp; g < ng; g += NW) {
+          const unsigned word = sdirty[set][g];
+          if (word == 0u) continue; /* warp-uniform */
+          if ((word >> lane) & 1u) {
+            const unsigned off = sgoff[set][g];
+            const int wd = (int)((sgoff[set][g + 1] - off) >> 5);
+            const unsigned *rp = V2 + (off - goff0) + lane;
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+            if (wd == 3) {
+              const unsigned w0 = rp[0], w1 = rp[32], w2 = rp[64];
               float4 f;
               f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
               f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+              f = F[w1 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+              f = F[w1 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+              f = F[w2 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+              f = F[w2 >> 16]; sx += f.x; sy += f.y; sz += f.z;
             }
+            else {
+              for (int j = 0; j < wd; j++) {
+                const unsigned w0 = rp[j * 32];
+                float4 f;
+                f = F[w0 & 0xffffu]; sx += f.x; sy += f.y; sz += f.z;
+                f = F[w0 >> 16]; sx += f.x; sy += f.y; sz += f.z;
+              }
+            }
+            dsc_normalize(sx, sy, sz);
+            const int sl = ub + g * 32 + lane;
+            m.nx[sl] = sx; m.ny[sl] = sy; m.nz[sl] = sz;
           }
-          dsc_normalize(sx, sy, sz);
-          const int s = ub + g * 32 + lane;
-          m.nx[s] = sx; m.ny[s] = sy; m.nz[s] = sz;
+          if (lane == 0) m.dirty[G0 + g] = 0u;
         }
-        if (lane == 0) m.dirty[G0 + g] = 0u;
       }
       __syncwarp();
       if (lane == 0) dsc_mbar_arrive(&s_empty[1]); /* index words: the producer may refill */
     }
     asm volatile("bar.sync 1, 256;" ::: "memory"); /* poly normals / box partials are free for the next tile */
   }
+  if (BRUSH) {
+    for (int o = 16; o > 0; o >>= 1) moved_cnt += __shfl_down_sync(0xffffffffu, moved_cnt, o);
+    if (lane == 0 && moved_cnt) atomicAdd(&s_moved, moved_cnt);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid == 0 && s_moved) atomicAdd(&m.tot->moved_total, (unsigned long long)s_moved);
+  }
 }
 __global__ void __launch_bounds__(NT_THREADS, 4) k_normals_tile(DevMesh m, const int4 *list, const int *count, int mode,
                                                                 const unsigned *upd)
 {
-  dsc_normals_tile_body(m, list, count, mode, upd, blockIdx.x, gridDim.x, true);
+  dsc_normals_tile_body<0>(m, list, count, mode, upd, blockIdx.x, gridDim.x, true);
+}
+/* the fused dab kernel: interior brush + normals + boxes of the gathered tiles of dab j (ring slot `slot`) */
+template<int TOOL>
+__global__ void __launch_bounds__(NT_THREADS, 4) k_dab_tile(DevMesh m, int j, int slot, int mode)
+{
+  __shared__ DabParams s_dab;
+  if (threadIdx.x < (int)(sizeof(DabParams) / 4)) {
+    reinterpret_cast<int *>(&s_dab)[threadIdx.x] = reinterpret_cast<const int *>(&dsc_dab_entry(m, j).d)[threadIdx.x];
+  }
+  __syncthreads();
+  dsc_normals_tile_body<TOOL>(m, m.tile_list + (size_t)slot * m.ntile, &m.st[slot].tile_count, mode, m.ghit + (size_t)slot * m.ghit_words,
+                              blockIdx.x, gridDim.x, false, &s_dab, m.st + slot);
 }
 
 /* ------------------------------------------------------------------ the whole dab path, persistent */
@@ -1729,10 +1877,10 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_dab_batch(DevMesh m, int batc
       const int nh = __ldcg(&m.st[slot].hit_count);
       for (int i = cta * NT_THREADS + tid; i < nh; i += ncta * NT_THREADS) dsc_reset_leaf_box(m, __ldcg(&hl[i]));
     }
-    dsc_brush_body<TOOL>(m, d, slot, cta, ncta);
+    dsc_brush_body<TOOL, false>(m, d, slot, cta, ncta);
     dsc_grid_sync(m.grid_bar, target, ncta);
     /* 4. + 5. normals and boxes, tile by tile */
-    dsc_normals_tile_body(m, m.tile_list + (size_t)slot * m.ntile, &m.st[slot].tile_count, mode,
+    dsc_normals_tile_body<0>(m, m.tile_list + (size_t)slot * m.ntile, &m.st[slot].tile_count, mode,
                           m.ghit + (size_t)slot * m.ghit_words, cta, ncta, false);
     dsc_grid_sync(m.grid_bar, target, ncta);
   }

@@ -339,7 +339,9 @@ void *dsc_stream(DscContext *ctx);                /* cudaStream_t */
 #define DSC_NUM_STAGES 8
 /* enable = 1: dabs are launched kernel by kernel with an event pair around each (a diagnostic path);
  * enable = 2: the dabs run as they do untimed -- replayed CUDA graphs -- and the event pairs are nodes of those graphs,
- * read after every replay: kernel durations of the path that is actually timed */
+ * read after every replay (each pair also measures the launch latency of its kernel node, about 8 us);
+ * enable = 3: the dabs run exactly as they do untimed and the durations are the hardware timestamps CUPTI records for
+ * every kernel (libcupti is looked up at run time; DSC_ERR_UNSUPPORTED when it cannot trace) */
 int dsc_stage_timing(DscContext *ctx, int enable);
 int dsc_stage_times(DscContext *ctx, float r_ms[DSC_NUM_STAGES], int r_launches[DSC_NUM_STAGES]);
 const char *dsc_stage_name(int stage);
