@@ -72,6 +72,7 @@ class PBVH(C.Structure):
         ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
         ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool), ("grids_pinned", C.c_bool),
         ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
+        ("dist_world", C.c_int), ("gather_whole", C.c_bool),
     ]
 
 
@@ -101,11 +102,12 @@ CUDA_SYMBOLS = [
     "dsc_timer_stop", "dsc_stream", "dsc_stage_timing", "dsc_stage_times", "dsc_stage_name",
     "dsc_dist_unique_id", "dsc_dist_init", "dsc_dist_partition", "dsc_dist_halo_plan", "dsc_dist_free",
     "dsc_dist_owned_range", "dsc_dist_grids_plan", "dsc_dist_uses_peer_memory", "dsc_dist_exchanges_skipped",
+    "dsc_dist_gather", "dsc_dist_dab_counts", "dsc_download_owned_mvert", "dsc_download_owned_ccg",
 ]
 HOST_SYMBOLS = [
     "BKE_mesh_poly_to_tri_count", "BKE_mesh_recalc_looptri", "BKE_pbvh_new", "BKE_pbvh_build_mesh", "BKE_pbvh_free",
     "DUNE_pbvh_mesh_sizes_set", "DUNE_pbvh_mask_layer_set", "DUNE_pbvh_vert_normals_set", "DUNE_pbvh_leaf_limit_set",
-    "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
+    "DUNE_pbvh_device_attach", "DUNE_pbvh_device_attach_dist", "DUNE_pbvh_device_gather", "DUNE_pbvh_device_detach", "DUNE_pbvh_device_sync_to_host", "DUNE_pbvh_device_error",
     "DUNE_pbvh_device_checkpoint", "DUNE_pbvh_device_rollback", "BKE_pbvh_build_grids", "BKE_pbvh_count_grid_quads", "BKE_pbvh_node_get_grids",
     "BKE_subdiv_ccg_key_top_level", "DUNE_subdiv_ccg_from_tables", "DUNE_subdiv_ccg_free", "DUNE_pbvh_device_attach_grids",
     "DUNE_pbvh_device_attach_grids_dist", "DUNE_multires_reshape_assign_final_coords",
@@ -184,6 +186,10 @@ def cuda_lib():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dsc_dist_uses_peer_memory.argtypes = [C.c_void_p]
         L.dsc_dist_exchanges_skipped.argtypes = [C.c_void_p, c_int_p]
+        L.dsc_dist_gather.argtypes = [C.c_void_p]
+        L.dsc_dist_dab_counts.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.dsc_download_owned_mvert.argtypes = [C.c_void_p, C.c_void_p, c_float_p]
+        L.dsc_download_owned_ccg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.dsc_dist_free.argtypes = [C.c_void_p]
         L.dsc_dist_free.restype = None
         _cuda = L
@@ -210,6 +216,7 @@ def host_lib():
         L.DUNE_pbvh_device_attach.argtypes = [C.POINTER(PBVH), C.c_int]
         L.DUNE_pbvh_device_detach.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_attach_dist.argtypes = [C.POINTER(PBVH), C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.DUNE_pbvh_device_gather.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_device_sync_to_host.argtypes = [C.POINTER(PBVH)]
         L.BKE_pbvh_build_grids.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.BKE_pbvh_build_grids.restype = None
@@ -549,6 +556,16 @@ class SculptSession:
         out = np.zeros((n.value, 36), dtype=np.uint8)
         self._chk(self.D.dsc_draw_download(self.ctx, int(node), out.ctypes.data, out.nbytes, C.byref(n)))
         return out
+
+    def gather(self):
+        """partitioned: every replica (device and host side) whole again -- collective, every rank calls it"""
+        self._chk(self.H.DUNE_pbvh_device_gather(self.pbvh))
+
+    def dist_dab_counts(self):
+        """partitioned: dabs this rank skipped / ran alone / exchanged"""
+        c = (C.c_longlong * 3)()
+        self._chk(self.D.dsc_dist_dab_counts(self.ctx, c))
+        return {"skipped": int(c[0]), "local": int(c[1]), "exchanged": int(c[2])}
 
     def checkpoint(self):
         """remember the resident mesh state (device-to-device)"""

@@ -19,6 +19,7 @@
 #include <vector>
 
 #define DSC_ABI_VERSION 1
+#define DSC_REGION_CHUNKS 16
 #define DSC_TILE_SMEM_BUDGET (96 * 1024) /* shared memory one tile may ask of k_normals_tile; heavier tiles take the general path */
 
 static thread_local std::string g_create_error;
@@ -112,6 +113,20 @@ struct DscContext {
   void *p2p_region = nullptr;
   void *p2p_peer_region[DSC_MAX_RANKS] = {nullptr};
   float *d_send_buf = nullptr, *d_recv_buf = nullptr;
+  /* which ranks a dab can reach (dist_dab_mask): conservative boxes of every rank's region -- DSC_REGION_CHUNKS runs of its
+   * leaves in traversal order plus the box of the halo elements it reads -- exact at stroke begin, grown by every dab that
+   * can move something inside them; all ranks keep the same copy (a pure function of the stroke-start boxes and the dabs) */
+  std::vector<float> regions;    /* [world][DSC_REGION_CHUNKS][6] */
+  std::vector<unsigned> leaf_reach; /* per leaf: bit per rank that gathering the leaf can affect -- its owner, the ranks that
+                                       read one of its elements, on grids the owners of every grid within two face hops (the
+                                       stitch and the normal pass reach one hop, a rank reads one hop beyond its own grids) */
+  std::vector<std::vector<int>> region_leaves; /* per rank: the leaves that can affect it, ascending */
+  int pending_skipped = 0;       /* grids: dabs this rank takes no part in whose all-coarse-vertex averaging is still to run */
+  bool last_dab_skipped = false;
+  bool subset_exchange = false;  /* peer-memory transport: dabs are exchanged among the ranks they reach only */
+  float *h_own = nullptr;        /* pinned staging of the owned slot runs (stroke-end sync of a partitioned PBVH) */
+  size_t h_own_floats = 0;
+  long long dist_skipped_dabs = 0, dist_local_dabs = 0, dist_exchanged_dabs = 0;
 
   int *d_slot_of = nullptr;
   float *d_mask = nullptr, *d_automask = nullptr, *d_curve = nullptr;
@@ -799,6 +814,7 @@ void dsc_ctx_destroy(DscContext *ctx)
   if (ctx->h_state) cudaFreeHost(ctx->h_state);
   if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
   if (ctx->h_list) cudaFreeHost(ctx->h_list);
+  if (ctx->h_own) cudaFreeHost(ctx->h_own);
   if (ctx->h_ray_out) cudaFreeHost(ctx->h_ray_out);
   if (ctx->h_ray_count) cudaFreeHost(ctx->h_ray_count);
   cudaEventDestroy(ctx->t0);
@@ -1951,6 +1967,42 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
           if (near) near_mask[l >> 5] |= 1u << (l & 31);
         }
         if ((r = dev_upload(ctx, &ctx->d_near_mask, near_mask))) return r;
+        /* which ranks gathering a leaf can affect: the owners of the grids of every face within two hops */
+        std::vector<std::vector<int>> fadj((size_t)F);
+        auto link_faces = [&](const std::vector<int> &fs) {
+          for (int a : fs) {
+            for (int b : fs) {
+              if (a != b) fadj[a].push_back(b);
+            }
+          }
+        };
+        std::vector<int> fs;
+        for (int e = 0; e < t.totedge; e++) {
+          fs.clear();
+          for (int k = t.edge_off[e]; k < t.edge_off[e + 1]; k++) fs.push_back(grid_face_h[t.edge_elems[(size_t)k * 2 * t.gs] / gs2h]);
+          link_faces(fs);
+        }
+        for (int v = 0; v < t.totcvert; v++) {
+          fs.clear();
+          for (int k = t.cvert_off[v]; k < t.cvert_off[v + 1]; k++) fs.push_back(grid_face_h[t.cvert_elems[k] / gs2h]);
+          link_faces(fs);
+        }
+        std::vector<unsigned> face_owner((size_t)F, 0u), hop1((size_t)F, 0u), hop2((size_t)F, 0u);
+        for (int f = 0; f < F; f++) {
+          for (int c = 0; c < t.face_num[f]; c++) face_owner[f] |= 1u << grid_owner[t.face_start[f] + c];
+        }
+        for (int f = 0; f < F; f++) {
+          hop1[f] = face_owner[f];
+          for (int b : fadj[f]) hop1[f] |= face_owner[b];
+        }
+        for (int f = 0; f < F; f++) {
+          hop2[f] = hop1[f];
+          for (int b : fadj[f]) hop2[f] |= hop1[b];
+        }
+        ctx->leaf_reach.assign((size_t)L, 0u);
+        for (int l = 0; l < L; l++) {
+          for (int k = 0; k < leaf_pcnt[l]; k++) ctx->leaf_reach[l] |= hop2[grid_face_h[pb->prim_indices[leaf_pbeg[l] + k]]];
+        }
       }
       sidx.resize(se.size());
       ridx.resize(re.size());
@@ -1993,6 +2045,16 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         if (l >= 0 && l < L) near_mask[l >> 5] |= 1u << (l & 31);
       }
       if ((r = dev_upload(ctx, &ctx->d_near_mask, near_mask))) return r;
+      /* which ranks gathering a leaf can affect: its owner and the ranks that read one of its vertices */
+      ctx->leaf_reach.assign((size_t)L, 0u);
+      for (int q = 0; q < ctx->world; q++) {
+        for (int l = ctx->leaf_range[q]; l < ctx->leaf_range[q + 1]; l++) ctx->leaf_reach[l] |= 1u << q;
+      }
+      for (const HaloTriple &t3 : tr) {
+        const int sl = ctx->slot_of[t3.vert];
+        const int l = (int)(std::upper_bound(leaf_ubeg.begin(), leaf_ubeg.end(), sl) - leaf_ubeg.begin()) - 1;
+        if (l >= 0 && l < L) ctx->leaf_reach[l] |= 1u << t3.reader;
+      }
     }
     ctx->send_off.assign(ctx->world + 1, 0);
     ctx->recv_off.assign(ctx->world + 1, 0);
@@ -2212,19 +2274,21 @@ static int dist_p2p_setup(DscContext *ctx)
     L.recv_off[q] = ctx->recv_off[q];
   }
   ctx->p2p = true;
+  /* dabs are exchanged among the ranks they reach only (DSC_DIST_ALL=1: among all ranks, the round-1 protocol) */
+  ctx->subset_exchange = getenv("DSC_DIST_ALL") == nullptr;
   return DSC_OK;
 }
 
 /* ---- multi-GPU steps of a dab ---- */
 /* one all-reduce pair per dab: the exact area sums and the bitmask of gathered leaves (disjoint per
  * rank, so sum == or) */
-static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
+static int dist_allreduce_dab(DscContext *ctx, int j, int slot, bool with_area)
 {
   if (ctx->p2p) {
     unsigned *gh = ctx->m.ghit + (size_t)slot * ctx->m.ghit_words;
-    k_p2p_reduce_push<<<dim3(1, ctx->world), 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
+    k_p2p_reduce_push<<<dim3(1, ctx->world), 256, 0, ctx->stream>>>(ctx->m, j, ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0);
     LAUNCH_CHECK();
-    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0, ctx->d_near_mask);
+    k_p2p_reduce_recv<<<1, 256, 0, ctx->stream>>>(ctx->m, j, ctx->link, ctx->m.st[slot].acc, gh, ctx->m.ghit_words, with_area ? 1 : 0, ctx->d_near_mask);
     LAUNCH_CHECK();
     ctx->launches += 2;
     return DSC_OK;
@@ -2240,7 +2304,7 @@ static int dist_allreduce_dab(DscContext *ctx, int slot, bool with_area)
   return DSC_OK;
 }
 /* one-ring halo: owners push the positions other ranks' leaves read */
-static int dist_halo_exchange(DscContext *ctx, bool normals = false, int cond = 1)
+static int dist_halo_exchange(DscContext *ctx, int j, bool normals = false, int cond = 1)
 {
   const int W = ctx->world;
   float *ax = normals ? ctx->m.nx : ctx->m.cx, *ay = normals ? ctx->m.ny : ctx->m.cy, *az = normals ? ctx->m.nz : ctx->m.cz;
@@ -2249,9 +2313,9 @@ static int dist_halo_exchange(DscContext *ctx, bool normals = false, int cond = 
     int most = 1;
     for (int q = 0; q < W; q++) most = std::max(most, std::max(ctx->send_off[q + 1] - ctx->send_off[q], ctx->recv_off[q + 1] - ctx->recv_off[q]));
     const int ctas = std::max(1, std::min((most + 1023) / 1024, std::max(1, ctx->num_sms / (2 * W))));
-    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_near_mask ? cond : 0, ctx->d_send_idx, ax, ay, az);
+    k_p2p_halo_push<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->m, j, ctx->link, ctx->d_near_mask ? cond : 0, ctx->d_send_idx, ax, ay, az);
     LAUNCH_CHECK();
-    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->link, ctx->d_near_mask ? cond : 0, ctx->d_recv_idx, ax, ay, az);
+    k_p2p_halo_recv<<<dim3(ctas, W), 256, 0, ctx->stream>>>(ctx->m, j, ctx->link, ctx->d_near_mask ? cond : 0, ctx->d_recv_idx, ax, ay, az);
     LAUNCH_CHECK();
     ctx->launches += 2;
     return DSC_OK;
@@ -2287,9 +2351,11 @@ static int dist_halo_exchange(DscContext *ctx, bool normals = false, int cond = 
   }
   return DSC_OK;
 }
-/* every rank broadcasts the runs it owns (vertex data, leaf boxes, leaf flags and stroke state), then
- * each replica flushes the whole tree: the BB-root reduction of SURVEY.md section 8e */
-static int dist_gather_all(DscContext *ctx)
+/* every rank broadcasts what it owns, then each replica flushes the whole tree: the BB-root reduction of SURVEY.md section 8e.
+ * Stroke end moves the leaf boxes, leaf flags and stroke state only (32 bytes per leaf); the vertex data stays with its
+ * owner -- a rank's host side takes its own runs (dsc_download_owned_*) -- unless a whole replica is asked for
+ * (dsc_dist_gather: tests, digests). */
+static int dist_gather_all(DscContext *ctx, bool vertex_data)
 {
   DevMesh &m = ctx->m;
   const int N = ctx->totnode;
@@ -2298,7 +2364,7 @@ static int dist_gather_all(DscContext *ctx)
   for (int q = 0; q < ctx->world; q++) {
     const int s0 = ctx->slot_range[q], sn = ctx->slot_range[q + 1] - s0;
     const int l0 = ctx->leaf_range[q], ln = ctx->leaf_range[q + 1] - l0;
-    if (sn > 0) {
+    if (sn > 0 && vertex_data) {
       for (int a = 0; a < 12; a++) NC(g_nccl.Broadcast(vert_arrays[a] + s0, vert_arrays[a] + s0, (size_t)sn, ncclFloat, q, ctx->comm, ctx->stream));
       /* grids: the stitch averages the mask layer too */
       if (ctx->is_grids && ctx->g.mask) NC(g_nccl.Broadcast(ctx->g.mask + s0, ctx->g.mask + s0, (size_t)sn, ncclFloat, q, ctx->comm, ctx->stream));
@@ -2352,7 +2418,7 @@ static int grids_recalc_normals(DscContext *ctx)
   return grids_average_all(ctx);
 }
 /* after the brush of a dab on grids: stitch, CCG normals of the gathered leaves' faces, leaf boxes */
-static int grids_after_brush(DscContext *ctx, LeafList hits, int j)
+static int grids_after_brush(DscContext *ctx, LeafList hits, int j, bool exch)
 {
   DevGrids &g = ctx->g;
   DevMesh &m = ctx->m;
@@ -2400,7 +2466,7 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j)
   if (ctx->grid_normals_flat) k_grid_normals_flat<<<ctx->num_sms * 8, 256, 0, st>>>(m, g, 0);
   else k_grid_normals<<<ctx->num_sms * 2, GN_BLOCK, ctx->gn_smem, st>>>(m, g, 0);
   LAUNCH_CHECK();
-  if (dist && (r = dist_halo_exchange(ctx, true))) return r; /* the new normals of the other ranks' halo elements */
+  if (exch && (r = dist_halo_exchange(ctx, j, true))) return r; /* the new normals of the other ranks' halo elements */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
   LAUNCH_CHECK();
   k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, 0, 0, seq, ctx->num_sms * 4);
@@ -2483,6 +2549,9 @@ int dsc_node_mark_update(DscContext *ctx, int node)
                            F_UpdateNormals | F_UpdateBB | F_UpdateOriginalBB | F_UpdateDrawBuffers | F_UpdateRedraw, 1);
 }
 
+static int dist_regions_refresh(DscContext *ctx);
+static int dist_flush_skipped(DscContext *ctx);
+
 int dsc_stroke_begin(DscContext *ctx, const float *automask)
 {
   NEED_PBVH();
@@ -2499,6 +2568,9 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
   CU(cudaMemsetAsync(ctx->m.leaf_state, 0, sizeof(unsigned) * (size_t)std::max(ctx->m.nleaf, 1), ctx->stream));
   CU(cudaMemsetAsync(ctx->m.st, 0, sizeof(DabState) * DSC_SLOTS, ctx->stream));
   CU(cudaMemsetAsync(ctx->m.tot, 0, sizeof(StrokeTotals), ctx->stream));
+  if (ctx->world > 1 && ctx->subset_exchange && (r = dist_regions_refresh(ctx))) return r;
+  ctx->pending_skipped = 0;
+  ctx->last_dab_skipped = false;
   ctx->launches = 0;
   ctx->dab_index = 0;
   ctx->last_slot = 0;
@@ -2510,15 +2582,16 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
 /* what decides the launch sequence of a dab (everything else is data in its ring entry) */
 struct DabSig {
   int tool, needs_area, do_normals, do_bounds, smooth_iters, smooth_tail;
+  int exch; /* partitioned PBVH: the dab is exchanged with other ranks */
   unsigned key(int batch) const
   {
     return (unsigned)tool | (unsigned)needs_area << 8 | (unsigned)do_normals << 9 | (unsigned)do_bounds << 10 |
-           (unsigned)smooth_iters << 11 | (unsigned)smooth_tail << 15 | (unsigned)batch << 16;
+           (unsigned)smooth_iters << 11 | (unsigned)smooth_tail << 15 | (unsigned)batch << 16 | (unsigned)exch << 27;
   }
   bool operator==(const DabSig &o) const { return key(0) == o.key(0); }
 };
 
-static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *sig)
+static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *sig, unsigned peers = 0u)
 {
   if (!dab) return fail(ctx, DSC_ERR_INVALID, "dab is NULL");
   const int tool = dab->tool;
@@ -2543,6 +2616,8 @@ static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *s
   sig->needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS;
   sig->smooth_iters = 0;
   sig->smooth_tail = 0;
+  e->peers = (int)peers;
+  sig->exch = (ctx->world > 1 && (peers & ~(1u << ctx->rank))) ? 1 : 0;
   const float rs = dab->radius * dab->radius_scale;
   float ar = sqrtf(dab->radius * dab->radius); /* radius of the normal-sampling sphere, same float steps as k_area */
   ar *= dab->normal_radius_factor;
@@ -2587,6 +2662,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   /* the stages below walk the hit list unless some leaf may still carry flags of an earlier dab */
   const bool use_hits = !ctx->stale_flags;
   const bool dist = ctx->world > 1;
+  const bool exch = dist && sig.exch; /* the dab reaches other ranks: reduce + halo exchanges among them */
   int r;
   cudaEvent_t ev_fork = capturing ? ctx->cap_fork : ctx->ev_fork, ev_bb = capturing ? ctx->cap_bb : ctx->ev_bb;
   cudaEvent_t ev_tag = capturing ? ctx->cap_tag : ctx->ev_tag;
@@ -2621,9 +2697,9 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
      * the smooth brush also reads neighbours that are in none of them (the next point along a coarse edge in the
      * sibling grid, one step inside another rank's grid): their owners' stitch may have moved them since the last
      * exchange, so the first iteration starts from a fresh halo */
-    if (dist && ctx->is_grids && (r = dist_halo_exchange(ctx, false, 2))) return r;
+    if (exch && ctx->is_grids && (r = dist_halo_exchange(ctx, j, false, 2))) return r;
     /* the bitmask of gathered leaves first: it tells every rank whether this dab's exchanges carry anything */
-    if (dist && (r = dist_allreduce_dab(ctx, slot, false))) return r;
+    if (exch && (r = dist_allreduce_dab(ctx, j, slot, false))) return r;
     {
       StageScope s(ctx, ST_SMOOTH);
       k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
@@ -2642,7 +2718,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
         k_smooth_b<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
         LAUNCH_CHECK();
       }
-      if (dist && (r = dist_halo_exchange(ctx))) return r; /* the next iteration reads the ring */
+      if (exch && (r = dist_halo_exchange(ctx, j))) return r; /* the next iteration reads the ring */
     }
   }
   else {
@@ -2650,7 +2726,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
       StageScope s(ctx, ST_AREA);
       CU(launch_k(k_area, ctx->grid_area, DSC_BLOCK, 0, st, pdl, m, j, slot));
     }
-    if (dist && (r = dist_allreduce_dab(ctx, slot, sig.needs_area))) return r;
+    if (exch && (r = dist_allreduce_dab(ctx, j, slot, sig.needs_area))) return r;
     if (fused) {
       /* the boundary runs of the gathered tiles first: what other tiles read is displaced before the fused kernel starts */
       StageScope s(ctx, ST_BRUSH);
@@ -2672,7 +2748,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
         default: CU(launch_k(k_brush<DSC_TOOL_CLAY_STRIPS>, ctx->grid_brush, DSC_BLOCK, 0, st, bpdl, m, j, slot)); break;
       }
     }
-    if (dist && (r = dist_halo_exchange(ctx))) return r;
+    if (exch && (r = dist_halo_exchange(ctx, j))) return r;
   }
   /* 4. normals, 5. bounds */
   if (use_hits) {
@@ -2688,7 +2764,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
       }
     }
     if (ctx->is_grids) {
-      if ((r = grids_after_brush(ctx, hits, j))) return r;
+      if ((r = grids_after_brush(ctx, hits, j, exch))) return r;
     }
     else if (fused) {
       /* interior brush + normals + boxes in one pass over the gathered tiles */
@@ -2844,6 +2920,130 @@ static int launch_batch_kernel(DscContext *ctx, const DabSig &sig, int count, in
   return DSC_OK;
 }
 
+/* ---- partitioned PBVH: the ranks a dab can reach ----
+ * A dab is exchanged among, and executed by, only the ranks whose region it can touch; the others skip it (on grids they
+ * still run the averaging of all coarse vertices that every dab does, subdiv_ccg.c:1303-1324) and run ahead.  The decision
+ * must come out the same on every rank without talking: it is a pure function of the region boxes all ranks hold at stroke
+ * begin and of the dabs so far.  A rank's boxes hold its leaves (shared verts included, as update_node_vb counts them) and
+ * the halo elements it reads; a dab that reaches a rank grows that rank's boxes by what it can move: a vertex moves at
+ * most `bound` and ends inside the brush's reach. */
+static int dist_regions_refresh(DscContext *ctx)
+{
+  const int W = ctx->world, NB = DSC_REGION_CHUNKS, N = ctx->totnode, L = ctx->m.nleaf;
+  ctx->regions.assign((size_t)W * NB * 6, 0.0f);
+  if ((int)ctx->leaf_reach.size() != L) {
+    ctx->regions.clear(); /* no reach table: every dab goes to every rank */
+    return DSC_OK;
+  }
+  if (ctx->region_leaves.empty()) {
+    ctx->region_leaves.resize((size_t)W);
+    for (int l = 0; l < L; l++) {
+      for (int q = 0; q < W; q++) {
+        if ((ctx->leaf_reach[l] >> q) & 1u) ctx->region_leaves[q].push_back(l);
+      }
+    }
+  }
+  int r = sync_all(ctx);
+  if (r) return r;
+  /* leaf boxes: every rank holds all of them (the stroke-end gather keeps them whole) */
+  std::vector<float> bb((size_t)6 * N);
+  CU(cudaMemcpy(bb.data(), ctx->m.bb, sizeof(float) * bb.size(), cudaMemcpyDeviceToHost));
+  for (int q = 0; q < W; q++) {
+    const std::vector<int> &ls = ctx->region_leaves[q];
+    const int n = (int)ls.size();
+    const int per = std::max(1, (n + NB - 1) / NB);
+    for (int c = 0; c < NB; c++) {
+      float *b = &ctx->regions[((size_t)q * NB + c) * 6];
+      for (int k = 0; k < 3; k++) {
+        b[k] = FLT_MAX;
+        b[3 + k] = -FLT_MAX;
+      }
+      for (int i = c * per; i < std::min(n, (c + 1) * per); i++) {
+        const int l = ls[i];
+        for (int k = 0; k < 3; k++) {
+          b[k] = std::min(b[k], bb[(size_t)k * N + l]);
+          b[3 + k] = std::max(b[3 + k], bb[(size_t)(3 + k) * N + l]);
+        }
+      }
+    }
+  }
+  return DSC_OK;
+}
+/* bit per rank the dab can reach; grows the reached ranks' boxes */
+static unsigned dist_dab_mask(DscContext *ctx, const DscDab *d)
+{
+  const int W = ctx->world, NB = DSC_REGION_CHUNKS;
+  if (W < 2) return 0u;
+  const unsigned all = (1u << W) - 1u;
+  if (!ctx->subset_exchange || ctx->regions.empty()) return all;
+  const float R = d->radius * std::max(d->radius_scale, 1.0f);
+  float smax = 0.0f, dl = 0.0f;
+  for (int k = 0; k < 3; k++) {
+    smax = std::max(smax, fabsf(d->scale[k]));
+    dl += d->grab_delta[k] * d->grab_delta[k];
+  }
+  dl = sqrtf(dl);
+  const float bs = fabsf(d->bstrength);
+  float reach = R, bound;
+  switch (d->tool) {
+    case DSC_TOOL_DRAW:
+    case DSC_TOOL_INFLATE: bound = d->radius * bs * std::max(smax, 1.0f); break;
+    case DSC_TOOL_GRAB: bound = dl * bs; break;
+    case DSC_TOOL_CLAY_STRIPS: reach = 4.0f * R; bound = 4.0f * R; break; /* brush-local cube, projection onto its plane */
+    default: bound = R; break;                                           /* smooth: towards the neighbour average */
+  }
+  bound = bound * 1.001f + 1e-6f * R;
+  reach = reach * 1.001f + bound;
+  unsigned mask = 0u;
+  for (int q = 0; q < W; q++) {
+    bool hit = false;
+    for (int c = 0; c < NB && !hit; c++) {
+      const float *b = &ctx->regions[((size_t)q * NB + c) * 6];
+      if (b[0] > b[3]) continue;
+      float dist = 0.0f;
+      for (int k = 0; k < 3; k++) {
+        const float c0 = d->location[k];
+        const float nearest = c0 < b[k] ? b[k] : (c0 > b[3 + k] ? b[3 + k] : c0);
+        dist += (c0 - nearest) * (c0 - nearest);
+      }
+      hit = dist <= reach * reach;
+    }
+    if (hit) mask |= 1u << q;
+  }
+  for (int q = 0; q < W; q++) {
+    if (!((mask >> q) & 1u)) continue;
+    for (int c = 0; c < NB; c++) {
+      float *b = &ctx->regions[((size_t)q * NB + c) * 6];
+      if (b[0] > b[3]) continue;
+      float lo[3], hi[3];
+      bool any = true;
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::max(b[k] - bound, d->location[k] - reach);
+        hi[k] = std::min(b[3 + k] + bound, d->location[k] + reach);
+        any = any && lo[k] <= hi[k];
+      }
+      if (!any) continue;
+      for (int k = 0; k < 3; k++) {
+        b[k] = std::min(b[k], lo[k]);
+        b[3 + k] = std::max(b[3 + k], hi[k]);
+      }
+    }
+  }
+  return mask;
+}
+/* grids: the dabs this rank skipped still averaged every coarse vertex (and every coarse edge with more than two faces) */
+static int dist_flush_skipped(DscContext *ctx)
+{
+  if (ctx->pending_skipped <= 0) return DSC_OK;
+  const int n = ctx->pending_skipped;
+  ctx->pending_skipped = 0;
+  if (!ctx->is_grids) return DSC_OK;
+  k_grid_skipped<<<ctx->num_sms, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->g, n);
+  LAUNCH_CHECK();
+  ctx->launches++;
+  return DSC_OK;
+}
+
 int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
 {
   NEED_PBVH();
@@ -2851,10 +3051,31 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
   if (!ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "dsc_stroke_begin first");
   int r;
   int i = 0;
+  /* partitioned: who takes part in which dab (sequential: the region boxes grow with the dabs) */
+  std::vector<unsigned> masks;
+  if (ctx->world > 1) {
+    masks.resize((size_t)count);
+    for (int k = 0; k < count; k++) masks[k] = dist_dab_mask(ctx, dabs + k);
+  }
+  auto mask_of = [&](int k) -> unsigned { return masks.empty() ? 0u : masks[k]; };
+  auto mine = [&](int k) -> bool { return masks.empty() || ((masks[k] >> ctx->rank) & 1u); };
   while (i < count) {
     DabEntry e;
     DabSig sig;
-    if ((r = make_entry(ctx, dabs + i, &e, &sig))) return r;
+    if (!mine(i)) {
+      /* out of this dab's reach: nothing of this rank can change, nothing it reads can change */
+      if ((r = make_entry(ctx, dabs + i, &e, &sig, mask_of(i)))) return r; /* the argument checks still apply */
+      ctx->pending_skipped++;
+      ctx->last_dab_skipped = true;
+      ctx->dist_skipped_dabs++;
+      i++;
+      continue;
+    }
+    if ((r = dist_flush_skipped(ctx))) return r;
+    ctx->last_dab_skipped = false;
+    if ((r = make_entry(ctx, dabs + i, &e, &sig, mask_of(i)))) return r;
+    if (sig.exch) ctx->dist_exchanged_dabs++;
+    else if (ctx->world > 1) ctx->dist_local_dabs++;
     const bool dist = ctx->world > 1;
     if (dist && (ctx->stale_flags || !sig.do_normals || !sig.do_bounds))
       return fail(ctx, DSC_ERR_UNSUPPORTED, "a partitioned PBVH updates normals and bounds with every dab");
@@ -2871,7 +3092,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
       while (run < 256 && i + run < count) {
         DabEntry e2;
         DabSig s2;
-        if (make_entry(ctx, dabs + i + run, &e2, &s2) != DSC_OK || !(s2 == sig)) break;
+        if (!mine(i + run) || make_entry(ctx, dabs + i + run, &e2, &s2, mask_of(i + run)) != DSC_OK || !(s2 == sig)) break;
         if ((r = ring_reserve(ctx, seq + run))) return r;
         ctx->h_ring[(seq + run) & (DSC_RING - 1)] = e2;
         run++;
@@ -2883,7 +3104,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
       while (run < 32 && i + run < count) {
         DabEntry e2;
         DabSig s2;
-        if (make_entry(ctx, dabs + i + run, &e2, &s2) != DSC_OK || !(s2 == sig)) break;
+        if (!mine(i + run) || make_entry(ctx, dabs + i + run, &e2, &s2, mask_of(i + run)) != DSC_OK || !(s2 == sig)) break;
         if ((r = ring_reserve(ctx, seq + run))) return r;
         ctx->h_ring[(seq + run) & (DSC_RING - 1)] = e2;
         run++;
@@ -2964,6 +3185,11 @@ static int read_list(DscContext *ctx, const int *d_list, const int *d_count, int
 
 int dsc_gather_readback(DscContext *ctx, int *r_nodes, int capacity, int *r_tot)
 {
+  if (ctx && ctx->have_pbvh && ctx->last_dab_skipped) {
+    /* the last dab was out of this rank's reach: it gathered none of its leaves */
+    if (r_tot) *r_tot = 0;
+    return sync_all(ctx);
+  }
   NEED_PBVH();
   const LeafList ll = hit_list(ctx, ctx->last_slot);
   return read_list(ctx, ll.list, ll.count, r_nodes, capacity, r_tot);
@@ -3084,7 +3310,8 @@ int dsc_stroke_end(DscContext *ctx)
   NEED_PBVH();
   if (!ctx->in_stroke) return fail(ctx, DSC_ERR_STATE, "no stroke open");
   int r;
-  if (ctx->world > 1 && (r = dist_gather_all(ctx))) return r;
+  if ((r = dist_flush_skipped(ctx))) return r;
+  if (ctx->world > 1 && (r = dist_gather_all(ctx, false))) return r;
   if (ctx->p2p) {
     int err = 0;
     CU(cudaMemcpyAsync(&err, ctx->link.flags + P2P_ERR, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -3104,6 +3331,110 @@ static int export3(DscContext *ctx, float *out, const float *ax, const float *ay
   LAUNCH_CHECK();
   CU(cudaMemcpyAsync(out, ctx->d_stage3, sizeof(float) * 3 * (size_t)ctx->totvert, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return DSC_OK;
+}
+
+/* every replica whole again: the owners' vertex data (positions, normals, undo snapshot, mask) travel over NCCL */
+int dsc_dist_gather(DscContext *ctx)
+{
+  NEED_PBVH();
+  if (ctx->world < 2) return DSC_OK;
+  int r = join_side(ctx);
+  if (r) return r;
+  if ((r = dist_flush_skipped(ctx))) return r;
+  if ((r = dist_gather_all(ctx, true))) return r;
+  return sync_all(ctx);
+}
+int dsc_dist_dab_counts(DscContext *ctx, long long r_counts[3])
+{
+  if (!ctx || !r_counts) return DSC_ERR_INVALID;
+  r_counts[0] = ctx->dist_skipped_dabs;
+  r_counts[1] = ctx->dist_local_dabs;
+  r_counts[2] = ctx->dist_exchanged_dabs;
+  return DSC_OK;
+}
+/* stroke-end sync of a partitioned PBVH: the runs this rank owns only.  Its slots are one contiguous run of every SoA
+ * array: six (seven) DMAs into pinned staging, then the host scatters them to vertex / element order. */
+static int download_owned_runs(DscContext *ctx, int narr, const float *const *arrs, int *r_s0, int *r_n)
+{
+  if (ctx->world < 2) return fail(ctx, DSC_ERR_STATE, "not a partitioned PBVH");
+  const int s0 = ctx->slot_range[ctx->rank], n = ctx->slot_range[ctx->rank + 1] - s0;
+  *r_s0 = s0;
+  *r_n = n;
+  if (ctx->vert_of_slot.empty()) {
+    ctx->vert_of_slot.assign((size_t)ctx->vpad, -1);
+    for (int v = 0; v < ctx->totvert; v++) ctx->vert_of_slot[ctx->slot_of[v]] = v;
+  }
+  if (n <= 0) return DSC_OK;
+  const size_t need = (size_t)narr * (size_t)n;
+  if (need > ctx->h_own_floats) {
+    if (ctx->h_own) cudaFreeHost(ctx->h_own);
+    ctx->h_own = nullptr;
+    CU(cudaMallocHost((void **)&ctx->h_own, sizeof(float) * need));
+    ctx->h_own_floats = need;
+  }
+  int r = join_side(ctx);
+  if (r) return r;
+  for (int a = 0; a < narr; a++) {
+    CU(cudaMemcpyAsync(ctx->h_own + (size_t)a * n, arrs[a] + s0, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSC_OK;
+}
+int dsc_download_owned_mvert(DscContext *ctx, void *r_mvert, float *r_no)
+{
+  NEED_PBVH();
+  if (ctx->is_grids || !r_mvert) return fail(ctx, DSC_ERR_INVALID, "mesh contexts only; r_mvert must not be NULL");
+  const float *arrs[6] = {ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny, ctx->m.nz};
+  int s0 = 0, n = 0;
+  int r = download_owned_runs(ctx, r_no ? 6 : 3, arrs, &s0, &n);
+  if (r) return r;
+  float *mv = (float *)r_mvert;
+  const float *h = ctx->h_own;
+  const int *vos = ctx->vert_of_slot.data();
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    const int v = vos[s0 + i];
+    if (v < 0) continue;
+    mv[(size_t)4 * v + 0] = h[i];
+    mv[(size_t)4 * v + 1] = h[(size_t)n + i];
+    mv[(size_t)4 * v + 2] = h[(size_t)2 * n + i];
+    if (r_no) {
+      r_no[(size_t)3 * v + 0] = h[(size_t)3 * n + i];
+      r_no[(size_t)3 * v + 1] = h[(size_t)4 * n + i];
+      r_no[(size_t)3 * v + 2] = h[(size_t)5 * n + i];
+    }
+  }
+  return DSC_OK;
+}
+int dsc_download_owned_ccg(DscContext *ctx, void *r_elems, int elem_floats, int mask_offset_floats, int normal_offset_floats)
+{
+  NEED_PBVH();
+  if (!ctx->is_grids || !r_elems || elem_floats < 3 || elem_floats > 16) return fail(ctx, DSC_ERR_INVALID, "grids contexts only; bad CCG element layout");
+  const float *arrs[7] = {ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny, ctx->m.nz, ctx->m.mask};
+  const bool with_mask = ctx->m.mask && mask_offset_floats >= 0;
+  int s0 = 0, n = 0;
+  int r = download_owned_runs(ctx, with_mask ? 7 : 6, arrs, &s0, &n);
+  if (r) return r;
+  float *out = (float *)r_elems;
+  const float *h = ctx->h_own;
+  const int *vos = ctx->vert_of_slot.data();
+  const int ef = elem_floats, mo = mask_offset_floats, no = normal_offset_floats;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    const int e = vos[s0 + i];
+    if (e < 0) continue;
+    float *rec = out + (size_t)ef * e;
+    rec[0] = h[i];
+    rec[1] = h[(size_t)n + i];
+    rec[2] = h[(size_t)2 * n + i];
+    if (no >= 0) {
+      rec[no] = h[(size_t)3 * n + i];
+      rec[no + 1] = h[(size_t)4 * n + i];
+      rec[no + 2] = h[(size_t)5 * n + i];
+    }
+    if (with_mask) rec[mo] = h[(size_t)6 * n + i];
+  }
   return DSC_OK;
 }
 

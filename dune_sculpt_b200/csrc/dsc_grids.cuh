@@ -500,6 +500,17 @@ __global__ void __launch_bounds__(128) k_grid_edges(DevMesh m, DevGrids g, int a
   dsc_grid_edges_body(m, g, all, dsc_grid_seq(m, j), blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(DSC_BLOCK) k_grid_cverts(DevMesh m, DevGrids g, int all) { dsc_grid_cverts_body(m, g, all, blockIdx.x, gridDim.x); }
+/* partitioned: `n` dabs in a row were out of this rank's reach.  Each of them still averaged every coarse vertex (and every
+ * coarse edge with more than two faces), whatever it touched (subdiv_ccg.c:1303-1324) -- a mean of equal floats is not
+ * always that float, so the passes are replayed, one after the other, group by group (the groups are disjoint and a thread
+ * keeps its groups across the repeats). */
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_skipped(DevMesh m, DevGrids g, int n)
+{
+  for (int k = 0; k < n; k++) {
+    if (g.has_odd_edges) dsc_grid_edges_body(m, g, 1, -1, blockIdx.x, gridDim.x);
+    dsc_grid_cverts_body(m, g, 1, blockIdx.x, gridDim.x);
+  }
+}
 /* coarse edges and coarse vertices in one launch: no element is in both a coarse-edge group and a corner group (the
  * edge pass leaves out the two end points of an edge, subdiv_ccg.c:1035), so the two passes -- and the pass over
  * untouched edges with more than two faces -- are independent.  The first `edge_ctas` CTAs take the edges. */

@@ -162,7 +162,7 @@ struct DabEntry {
   int set_flags;        /* node flags the gather sets on hit leaves */
   int ent_bits;         /* DSC_ENT_NORMALS | DSC_ENT_BOUNDS */
   int use_cos;          /* the area pass also samples the centre (clay strips) */
-  int pad;
+  int peers;            /* partitioned PBVH: bit per rank the dab can reach (the ranks that exchange it); 0 on one GPU */
 };
 
 __device__ __forceinline__ const DabEntry &dsc_dab_entry(const DevMesh &m, int j)
@@ -2223,17 +2223,19 @@ __global__ void k_halo_unpack(const float *__restrict__ buf, const int *__restri
  * A dab that gathers no leaf near a partition cut changes no halo element anywhere; every rank sees that in the
  * all-reduced bitmask of gathered leaves, and the halo exchanges of such a dab return at once on all ranks (`cond`). */
 #define DSC_MAX_RANKS 8
-#define P2P_DONE 16
-#define P2P_COUNT 32
-#define P2P_ROUND 49 /* exchanges completed so far: the kernels read their round here, so a dab's exchanges replay from a graph */
+#define P2P_DONE 16   /* [+ q]: the last round rank q delivered to me */
+#define P2P_COUNT 32  /* [+ q]: CTA counter of a push to rank q */
+#define P2P_ERR 48    /* a wait gave up (a peer never arrived): the host reports it at stroke end instead of hanging */
 #define P2P_RCOUNT 50 /* CTA counter of the receive kernel */
 #define P2P_NEAR 51    /* this dab gathered a leaf near a partition cut: its halo exchanges run */
-#define P2P_DIRTY 52   /* a dab near a cut has run since the last refresh of the smooth brush's halo */
 #define P2P_SKIPPED 53 /* exchanges skipped so far (statistics) */
-#define P2P_ERR 48 /* a wait gave up (a peer never arrived): the host reports it at stroke end instead of hanging */
+#define P2P_PROUND 56 /* [+ q]: exchanges completed with rank q so far.  Rounds are counted PER PAIR: a dab is exchanged only
+                         among the ranks it can reach (DabEntry.peers), so two ranks advance their common counter exactly on
+                         the dabs both take part in; the kernels read it here, so a dab's exchanges replay from a graph */
+#define P2P_PDIRTY 40 /* [+ q]: a dab near a cut has run with rank q since the smooth brush's halo was last refreshed from it */
 struct PeerLink {
   int world, rank;
-  int *flags;                      /* mine: [P2P_DONE + q] raised by rank q; [P2P_COUNT + q], [P2P_RCOUNT] local CTA counters; [P2P_ROUND]; [P2P_ERR] */
+  int *flags;                      /* mine, see P2P_* */
   int *peer_flags[DSC_MAX_RANKS];
   float *inbox;                    /* mine: halo inbox, the block from rank q at 3 * recv_off[q] */
   float *peer_inbox[DSC_MAX_RANKS];
@@ -2265,20 +2267,25 @@ __device__ __forceinline__ void dsc_flag_wait(const int *p, int round, int *err)
     }
   }
 }
-/* cond 0: always; 1: only when this dab is near a cut; 2: only when the halo is stale for the smooth brush */
-__device__ __forceinline__ bool dsc_p2p_skip(const PeerLink &L, int cond)
+/* the ranks dab j of the running batch is exchanged with (a bit per rank, this rank's own bit excluded) */
+__device__ __forceinline__ unsigned dsc_dab_peers(const DevMesh &m, const PeerLink &L, int j)
+{
+  return (unsigned)dsc_dab_entry(m, j).peers & ~(1u << L.rank);
+}
+/* cond 0: always; 1: only when this dab is near a cut; 2: only from peers whose halo is stale for the smooth brush */
+__device__ __forceinline__ bool dsc_p2p_skip(const PeerLink &L, int cond, int q)
 {
   if (cond == 1) return __ldcg(L.flags + P2P_NEAR) == 0;
-  if (cond == 2) return __ldcg(L.flags + P2P_DIRTY) == 0;
+  if (cond == 2) return __ldcg(L.flags + P2P_PDIRTY + q) == 0;
   return false;
 }
 /* grid (ctas_per_peer, world): blockIdx.y = peer */
-__global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, int cond, const int *__restrict__ idx, const float *__restrict__ ax,
-                                                       const float *__restrict__ ay, const float *__restrict__ az)
+__global__ void __launch_bounds__(256) k_p2p_halo_push(DevMesh m, int j, PeerLink L, int cond, const int *__restrict__ idx,
+                                                       const float *__restrict__ ax, const float *__restrict__ ay, const float *__restrict__ az)
 {
   const int q = blockIdx.y;
-  if (q == L.rank || dsc_p2p_skip(L, cond)) return;
-  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
+  if (!((dsc_dab_peers(m, L, j) >> q) & 1u) || dsc_p2p_skip(L, cond, q)) return;
+  const int round = __ldcg(L.flags + P2P_PROUND + q) + 1;
   const int n = L.send_off[q + 1] - L.send_off[q];
   const int *id = idx + L.send_off[q];
   float *dst = L.peer_inbox[q] + (size_t)(round & 1) * L.inbox_half + 3 * (size_t)L.peer_off[q];
@@ -2299,16 +2306,14 @@ __global__ void __launch_bounds__(256) k_p2p_halo_push(PeerLink L, int cond, con
     }
   }
 }
-__global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, int cond, const int *__restrict__ idx, float *__restrict__ ax,
+__global__ void __launch_bounds__(256) k_p2p_halo_recv(DevMesh m, int j, PeerLink L, int cond, const int *__restrict__ idx, float *__restrict__ ax,
                                                        float *__restrict__ ay, float *__restrict__ az)
 {
   const int q = blockIdx.y;
-  if (dsc_p2p_skip(L, cond)) {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) L.flags[P2P_SKIPPED] += 1;
-    return;
-  }
-  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
-  if (q != L.rank) {
+  const unsigned peers = dsc_dab_peers(m, L, j);
+  const bool live = ((peers >> q) & 1u) && !dsc_p2p_skip(L, cond, q);
+  if (live) {
+    const int round = __ldcg(L.flags + P2P_PROUND + q) + 1;
     if (threadIdx.x == 0) dsc_flag_wait(L.flags + P2P_DONE + q, round, L.flags + P2P_ERR);
     __syncthreads();
     const int n = L.recv_off[q + 1] - L.recv_off[q];
@@ -2321,24 +2326,34 @@ __global__ void __launch_bounds__(256) k_p2p_halo_recv(PeerLink L, int cond, con
       az[s] = __ldcg(&src[2 * n + i]);
     }
   }
-  /* the last CTA to leave closes the round (every CTA has read the counter by then) */
+  /* the last CTA to leave closes the rounds (every CTA has read the counters by then) */
   __syncthreads();
   if (threadIdx.x == 0) {
     const int total = (int)(gridDim.x * gridDim.y);
     if (atomicAdd(L.flags + P2P_RCOUNT, 1) + 1 == total) {
       L.flags[P2P_RCOUNT] = 0;
-      L.flags[P2P_ROUND] = round;
-      if (cond == 2) L.flags[P2P_DIRTY] = 0; /* every CTA read it when it started */
+      int skipped = 0;
+      for (int r = 0; r < L.world; r++) {
+        if (!((peers >> r) & 1u)) continue;
+        if (dsc_p2p_skip(L, cond, r)) {
+          skipped = 1;
+          continue;
+        }
+        L.flags[P2P_PROUND + r] += 1;
+        if (cond == 2) L.flags[P2P_PDIRTY + r] = 0;
+      }
+      if (skipped) L.flags[P2P_SKIPPED] += 1;
     }
   }
 }
-/* the per-dab all-reduce: the 16 exact area sums (int64) and the bitmask of gathered leaves.  grid (1, world) */
-__global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, const long long *__restrict__ acc, const unsigned *__restrict__ ghit,
-                                                         int words, int with_area)
+/* the per-dab reduce among the ranks the dab can reach: the 16 exact area sums (int64) and the bitmask of gathered
+ * leaves.  grid (1, world) */
+__global__ void __launch_bounds__(256) k_p2p_reduce_push(DevMesh m, int j, PeerLink L, const long long *__restrict__ acc,
+                                                         const unsigned *__restrict__ ghit, int words, int with_area)
 {
   const int q = blockIdx.y;
-  if (q == L.rank) return;
-  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
+  if (!((dsc_dab_peers(m, L, j) >> q) & 1u)) return;
+  const int round = __ldcg(L.flags + P2P_PROUND + q) + 1;
   long long *dst = L.peer_red[q] + (size_t)(round & 1) * L.red_half + (size_t)L.rank * L.red_stride;
   if (with_area && threadIdx.x < 16) dst[threadIdx.x] = acc[threadIdx.x];
   unsigned *dw = reinterpret_cast<unsigned *>(dst + 16);
@@ -2347,32 +2362,46 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_push(PeerLink L, const long 
   __syncthreads();
   if (threadIdx.x == 0) dsc_flag_raise(L.peer_flags[q] + P2P_DONE + L.rank, round);
 }
-__global__ void __launch_bounds__(256) k_p2p_reduce_recv(PeerLink L, long long *__restrict__ acc, unsigned *__restrict__ ghit, int words,
-                                                         int with_area, const unsigned *__restrict__ near_mask)
+__global__ void __launch_bounds__(256) k_p2p_reduce_recv(DevMesh m, int j, PeerLink L, long long *__restrict__ acc, unsigned *__restrict__ ghit,
+                                                         int words, int with_area, const unsigned *__restrict__ near_mask)
 {
-  const int round = __ldcg(L.flags + P2P_ROUND) + 1;
-  if (threadIdx.x < L.world && threadIdx.x != L.rank) dsc_flag_wait(L.flags + P2P_DONE + threadIdx.x, round, L.flags + P2P_ERR);
+  const unsigned peers = dsc_dab_peers(m, L, j);
+  if (threadIdx.x < L.world && ((peers >> threadIdx.x) & 1u)) {
+    dsc_flag_wait(L.flags + P2P_DONE + threadIdx.x, __ldcg(L.flags + P2P_PROUND + threadIdx.x) + 1, L.flags + P2P_ERR);
+  }
   __syncthreads();
-  const long long *red = L.red + (size_t)(round & 1) * L.red_half;
   int near = 0;
   if (with_area && threadIdx.x < 16) {
-    long long sum = 0;
-    for (int r = 0; r < L.world; r++) sum += r == L.rank ? acc[threadIdx.x] : __ldcg(&red[(size_t)r * L.red_stride + threadIdx.x]);
+    long long sum = acc[threadIdx.x];
+    for (int r = 0; r < L.world; r++) {
+      if ((peers >> r) & 1u) {
+        const long long *red = L.red + (size_t)((__ldcg(L.flags + P2P_PROUND + r) + 1) & 1) * L.red_half;
+        sum += __ldcg(&red[(size_t)r * L.red_stride + threadIdx.x]);
+      }
+    }
     acc[threadIdx.x] = sum;
   }
   for (int w = threadIdx.x; w < words; w += blockDim.x) {
     unsigned bits = ghit[w];
     for (int r = 0; r < L.world; r++) {
-      if (r != L.rank) bits |= __ldcg(reinterpret_cast<const unsigned *>(red + (size_t)r * L.red_stride + 16) + w);
+      if ((peers >> r) & 1u) {
+        const long long *red = L.red + (size_t)((__ldcg(L.flags + P2P_PROUND + r) + 1) & 1) * L.red_half;
+        bits |= __ldcg(reinterpret_cast<const unsigned *>(red + (size_t)r * L.red_stride + 16) + w);
+      }
     }
     ghit[w] = bits;
     if (near_mask && (bits & near_mask[w])) near = 1;
   }
   near = __syncthreads_or(near);
   if (threadIdx.x == 0) {
-    L.flags[P2P_ROUND] = round;
-    L.flags[P2P_NEAR] = near_mask ? near : 1;
-    if (near || !near_mask) L.flags[P2P_DIRTY] = 1;
+    const int is_near = near_mask ? near : 1;
+    L.flags[P2P_NEAR] = is_near;
+    for (int r = 0; r < L.world; r++) {
+      if ((peers >> r) & 1u) {
+        L.flags[P2P_PROUND + r] += 1;
+        if (is_near) L.flags[P2P_PDIRTY + r] = 1;
+      }
+    }
   }
 }
 

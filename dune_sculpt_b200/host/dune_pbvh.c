@@ -831,6 +831,7 @@ int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, i
     snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(NULL));
     return r;
   }
+  pbvh->dist_world = world > 1 ? world : 0;
   if (world > 1) {
     r = dsc_dist_init(ctx, world, rank, nccl_id);
     if (r != DSC_OK) {
@@ -1012,7 +1013,13 @@ static int sync_grids_to_host(PBVH *pbvh)
   for (int g = 1; g < G && contiguous; g++) {
     contiguous = (unsigned char *)pbvh->grids[g] == (unsigned char *)pbvh->grids[0] + (size_t)g * (size_t)area * (size_t)key->elem_size;
   }
-  if (contiguous) {
+  if (contiguous && pbvh->dist_world > 1 && !pbvh->gather_whole) {
+    /* partitioned: the grids this rank owns */
+    r = dsc_download_owned_ccg(pbvh->device, pbvh->grids[0], key->elem_size / (int)sizeof(float),
+                               key->has_mask ? key->mask_offset / (int)sizeof(float) : -1,
+                               key->has_normals ? key->normal_offset / (int)sizeof(float) : -1);
+  }
+  else if (contiguous) {
     if (!pbvh->grids_pinned && dsc_host_register(pbvh->device, pbvh->grids[0], E * (size_t)key->elem_size) == DSC_OK) pbvh->grids_pinned = true;
     r = dsc_download_ccg(pbvh->device, pbvh->grids[0], key->elem_size / (int)sizeof(float),
                          key->has_mask ? key->mask_offset / (int)sizeof(float) : -1,
@@ -1215,6 +1222,7 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
     snprintf(g_attach_error, sizeof(g_attach_error), "%s", dsc_last_error(NULL));
     return r;
   }
+  pbvh->dist_world = world > 1 ? world : 0;
   if (world > 1) {
     r = dsc_dist_init(ctx, world, rank, nccl_id);
     if (r != DSC_OK) {
@@ -1397,9 +1405,16 @@ int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
     pbvh->deformed = true;
     if (dsc_host_register(pbvh->device, dup, sizeof(MVert) * (size_t)V) == DSC_OK) pbvh->verts_pinned = true;
   }
-  /* whole MVert records and the normals array arrive by DMA; no host-side scatter */
-  int r = dsc_download_mvert(pbvh->device, pbvh->verts);
-  if (r == DSC_OK) r = dsc_download_no(pbvh->device, (float *)pbvh->vert_normals);
+  int r;
+  if (pbvh->dist_world > 1 && !pbvh->gather_whole) {
+    /* partitioned: the vertices this rank owns (their slots are one run of every device array) */
+    r = dsc_download_owned_mvert(pbvh->device, pbvh->verts, (float *)pbvh->vert_normals);
+  }
+  else {
+    /* whole MVert records and the normals array arrive by DMA; no host-side scatter */
+    r = dsc_download_mvert(pbvh->device, pbvh->verts);
+    if (r == DSC_OK) r = dsc_download_no(pbvh->device, (float *)pbvh->vert_normals);
+  }
   if (r != DSC_OK) return r;
   float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
   int *flag = malloc(sizeof(int) * (size_t)N);
@@ -1414,6 +1429,18 @@ int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
     pbvh->device_dirty = false;
   }
   free(bb); free(obb); free(flag);
+  return r;
+}
+
+int DUNE_pbvh_device_gather(PBVH *pbvh)
+{
+  if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
+  int r = dsc_dist_gather(pbvh->device);
+  if (r != DSC_OK) return r;
+  pbvh->gather_whole = true;
+  pbvh->device_dirty = true;
+  r = DUNE_pbvh_device_sync_to_host(pbvh);
+  pbvh->gather_whole = false;
   return r;
 }
 

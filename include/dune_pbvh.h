@@ -202,6 +202,10 @@ typedef struct PBVH {
   /* session tables (kernel/intern/paint.c:1685-1688 pmap, boundary info) */
   int *nb_offsets, *nb_indices;
   unsigned char *boundary;
+  /* partitioned over `dist_world` GPUs (one process each): stroke end brings back the runs this rank owns; the entries of
+   * the host arrays that other ranks own stay as they were until DUNE_pbvh_device_gather makes the replica whole */
+  int dist_world;
+  bool gather_whole; /* inside DUNE_pbvh_device_gather */
 } PBVH;
 
 typedef bool (*BKE_pbvh_SearchCallback)(PBVHNode *node, void *data);
@@ -297,6 +301,9 @@ int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device)
 int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *subdiv_ccg, int device, int world, int rank, const char *nccl_id);
 /* one rank of a PBVH partitioned across the GPUs of one box (see dsc_dist_init) */
 int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, const char *nccl_id);
+/* partitioned: the owners send their vertex data to every rank and the whole mesh comes back to this rank's host arrays
+ * (collective: every rank calls it) */
+int DUNE_pbvh_device_gather(PBVH *pbvh);
 void DUNE_pbvh_device_detach(PBVH *pbvh);
 /* bring host arrays (verts, normals, node boxes, flags) up to date with the device */
 int DUNE_pbvh_device_sync_to_host(PBVH *pbvh);

@@ -322,6 +322,17 @@ int dsc_dist_grids_plan(const DscGridsDesc *grids, const DscPbvhDesc *pbvh, int 
                         unsigned char *r_face_dom, unsigned char *r_edge_mine, unsigned char *r_cvert_mine, int **r_send_off,
                         int **r_send_elem, int **r_recv_off, int **r_recv_elem);
 void dsc_dist_free(void *p);
+/* How a partitioned stroke runs (peer-memory transport).  A dab is executed by, and exchanged among, only the ranks whose
+ * region it can reach -- decided identically on every rank from the region boxes all ranks hold at stroke begin and the dabs
+ * so far; the other ranks skip it and run ahead (on grids they replay the averaging of all coarse vertices every dab does).
+ * Stroke end moves leaf boxes, flags and stroke state only; the vertex data stays with its owner:
+ *   dsc_download_owned_mvert / _ccg  the runs this rank owns, scattered into the host arrays (the other entries untouched);
+ *   dsc_dist_gather                  every replica whole again (what the whole-array download calls then return);
+ *   dsc_dist_dab_counts              dabs this rank skipped / ran alone / exchanged since the context was made. */
+int dsc_dist_gather(DscContext *ctx);
+int dsc_dist_dab_counts(DscContext *ctx, long long r_counts[3]);
+int dsc_download_owned_mvert(DscContext *ctx, void *r_mvert /* [totvert] MVert */, float *r_no /* [totvert][3] or NULL */);
+int dsc_download_owned_ccg(DscContext *ctx, void *r_elems, int elem_floats, int mask_offset_floats, int normal_offset_floats);
 /* leaf nodes this rank owns: r_range[2] = first and one-past-last leaf in traversal order */
 int dsc_dist_owned_range(DscContext *ctx, int r_range[2]);
 /* 1 when the per-dab exchanges run as stores into the peers' HBM over NVLink (cudaIpc-mapped inboxes, flag

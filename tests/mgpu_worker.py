@@ -1,6 +1,7 @@
 """One rank of the multi-GPU parity check (launched by tests/test_gpu_multi.py, one process per GPU).
 Every rank holds the whole mesh, computes the leaves it owns, and after stroke end must hold exactly
 the state the single-process CPU oracle produces."""
+import ctypes as C
 import os
 import sys
 import time
@@ -22,6 +23,30 @@ def skipped(ses):
     return n.value
 
 
+def own_part_on_host(orc, ses, rank, what):
+    """after stroke end the HOST arrays of a rank hold the oracle's values for the vertices / elements it owns"""
+    rng, owner = ses.partition(ses.dist[0])
+    na = ses.node_arrays()
+    co_o, no_o = orc.co(), orc.no()
+    if hasattr(ses, "host_elements"):
+        co_h, no_h, _ = ses.host_elements()
+        gs2 = ses.mesh.grid_size ** 2
+        prim = ses.prim_indices()
+        mine = np.concatenate([prim[na["prim_offset"][n]:na["prim_offset"][n] + na["totprim"][n]] for n in np.nonzero(owner == rank)[0]] or
+                              [np.zeros(0, np.int32)])
+        idx = (mine[:, None].astype(np.int64) * gs2 + np.arange(gs2)[None, :]).reshape(-1)
+    else:
+        co_h = ses.mvert["co"] if not ses.pbvh.contents.deformed else np.ctypeslib.as_array(
+            C.cast(ses.pbvh.contents.verts, C.POINTER(C.c_float)), shape=(ses.mesh.totvert, 4))[:, :3]
+        no_h = np.ctypeslib.as_array(ses.pbvh.contents.vert_normals, shape=(ses.mesh.totvert * 3,)).reshape(-1, 3)
+        idx = np.concatenate([ses.node_vert_indices(int(n))[:na["uniq_verts"][n]] for n in np.nonzero(owner == rank)[0]] or
+                             [np.zeros(0, np.int32)])
+    bad = idx[(co_o[idx] != co_h[idx]).any(axis=1)]
+    assert bad.size == 0, "rank %d %s: host positions of the owned part differ at %d of %d (first %s, max %g)" % (
+        rank, what, bad.size, idx.size, bad[:6], np.abs(co_o[idx] - co_h[idx]).max())
+    assert np.array_equal(no_o[idx], no_h[idx]), "rank %d %s: host normals of the owned part differ" % (rank, what)
+
+
 def batched_stroke(orc, ses, dabs, rank, what):
     """a second stroke submitted as ONE dsc_dabs call: runs of one launch sequence replay as CUDA graphs, the
     peer-memory exchanges inside them (their round numbers live on the device)"""
@@ -34,6 +59,8 @@ def batched_stroke(orc, ses, dabs, rank, what):
     ses.stroke_begin(None)
     ses.dabs(arr, len(dabs))
     ses.stroke_end()
+    own_part_on_host(orc, ses, rank, what)
+    ses.gather()
     assert np.array_equal(orc.co(), ses.co()), "rank %d: batched %s stroke: positions differ" % (rank, what)
     assert np.array_equal(orc.no(), ses.no()), "rank %d: batched %s stroke: normals differ" % (rank, what)
     na = orc.node_arrays()
@@ -87,7 +114,9 @@ def main():
         hg = ses.hits()
         assert np.array_equal(mine, hg), "rank %d dab %d: own hit list differs (%d vs %d)" % (rank, i, mine.size, hg.size)
     orc.stroke_end()
-    ses.stroke_end()  # all-gathers the owned runs: every replica is whole again
+    ses.stroke_end()  # leaf boxes / flags / stroke state travel; the vertex data stays with its owner
+    own_part_on_host(orc, ses, rank, scenario)
+    ses.gather()      # every replica whole again
     vd = ses.stats()["vertex_dabs"]
     co_o, co_g = orc.co(), ses.co()
     assert np.array_equal(co_o, co_g), "rank %d: positions differ (max %g)" % (rank, np.abs(co_o - co_g).max())
@@ -100,7 +129,7 @@ def main():
     batched_stroke(orc, ses, dabs, rank, scenario)
     print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d skipped_exchanges %d" %
           (rank, world, scenario, rng[rank], rng[rank + 1], vd, orc.vertex_dabs(), ses.D.dsc_dist_uses_peer_memory(ses.ctx),
-           skipped(ses)), flush=True)
+           skipped(ses)), ses.dist_dab_counts(), flush=True)
     ses.close()
 
 
@@ -155,6 +184,8 @@ def multires(world, rank, nid, scenario):
         assert np.array_equal(mine, hg), "rank %d dab %d: own hit list differs (%d vs %d)" % (rank, i, mine.size, hg.size)
     orc.stroke_end()
     ses.stroke_end()
+    own_part_on_host(orc, ses, rank, scenario)
+    ses.gather()
     co_o, co_g = orc.co(), ses.co()
     bad = np.nonzero((co_o != co_g).any(axis=1))[0]
     gs2 = mr.grid_size ** 2
@@ -174,7 +205,7 @@ def multires(world, rank, nid, scenario):
     assert np.array_equal(orc.mask(), ses.mask()), "rank %d: mask layer differs after the batched stroke" % rank
     print("MGPU_OK rank %d/%d scenario %s own leaves [%d,%d) vertex_dabs %d of %d peer_memory %d skipped_exchanges %d" %
           (rank, world, scenario, rng[rank], rng[rank + 1], ses.stats()["vertex_dabs"], orc.vertex_dabs(),
-           ses.D.dsc_dist_uses_peer_memory(ses.ctx), skipped(ses)), flush=True)
+           ses.D.dsc_dist_uses_peer_memory(ses.ctx), skipped(ses)), ses.dist_dab_counts(), flush=True)
     ses.close()
 
 
