@@ -203,8 +203,9 @@ def C_float(x):
 def config_of(w, world):
     par = "single GPU"
     if world > 1:
-        par = ("PBVH partitioned spatially over %d GPUs (the same mesh: strong scaling); per dab the halo exchanges over NVLink peer "
-               "memory" % world)
+        par = ("PBVH partitioned spatially over %d GPUs (the same mesh and stroke: strong scaling); a dab runs on, and is exchanged over "
+               "NVLink peer memory among, only the ranks it can reach -- the others skip it and run ahead; stroke end brings every rank's "
+               "own runs back to its host" % world)
     return {"workload": w.desc, "parallelism": par, "verts": w.verts, "dabs_per_step": w.ndabs, "strokes_per_step": len(w.strokes),
             "brush": w.brush,
             "l2": ("inputs larger than L2 (resident arrays > 1 GB; every stroke sweeps them)" if w.verts > 4000000 else
@@ -635,6 +636,8 @@ def partition_digest(w, r, rank, local_rank):
     ses.stroke_begin(s["automask"])
     ses.dabs(r.arrs[0], len(r.arrs[0]))
     ses.stroke_end()
+    counts = ses.dist_dab_counts()
+    ses.gather()  # the owners' vertex data to every rank: whole replicas for the comparison
     co, no = ses.co(), ses.no()
     r.barrier()
     if rank == 0:
@@ -644,7 +647,8 @@ def partition_digest(w, r, rank, local_rank):
         one.dabs(r.arrs[0], len(r.arrs[0]))
         one.stroke_end()
         res = {"co_bit_equal": bool(np.array_equal(co, one.co())), "no_bit_equal": bool(np.array_equal(no, one.no())),
-               "sha1_co": hashlib.sha1(co.tobytes()).hexdigest()[:16]}
+               "sha1_co": hashlib.sha1(co.tobytes()).hexdigest()[:16],
+               "rank0_dabs": counts, "how": "rank 0's replica after one partitioned stroke + gather vs the same stroke on one GPU"}
         one.close()
     r.barrier()
     return res

@@ -2003,6 +2003,15 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         for (int l = 0; l < L; l++) {
           for (int k = 0; k < leaf_pcnt[l]; k++) ctx->leaf_reach[l] |= hop2[grid_face_h[pb->prim_indices[leaf_pbeg[l] + k]]];
         }
+        /* The skip of a dab's halo exchanges must come out the same on every rank, so "near a cut" has to be the same table
+         * everywhere: a leaf is near when gathering it can affect any OTHER rank (the halo_grid test above only knows this
+         * rank's halo -- with more than two ranks the tables differed and a rank could skip an exchange its peer ran). */
+        std::vector<unsigned> near_all((size_t)m.ghit_words, 0u);
+        for (int l = 0; l < L; l++) {
+          if (ctx->leaf_reach[l] & (ctx->leaf_reach[l] - 1u)) near_all[l >> 5] |= 1u << (l & 31);
+        }
+        CU(cudaMemcpyAsync(ctx->d_near_mask, near_all.data(), sizeof(unsigned) * near_all.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
       }
       sidx.resize(se.size());
       ridx.resize(re.size());

@@ -136,9 +136,15 @@ def main():
 def multires(world, rank, nid, scenario):
     """partitioned multires grids: smooth, draw, inflate, grab and clay strips dabs that straddle the partition cuts;
     after stroke end every replica must hold the oracle's elements, normals, mask layer and boxes, bit for bit"""
+    small_r = 0.04
     if scenario == "multires_open":
         mr, ll = meshgen.multires_plane(6, 4, noise=0.04, freq=9.0, with_mask=True), 3
         centres = [(-0.5 + 0.25 * i, 0.1 * i - 0.2, 0.0) for i in range(5)]
+    elif scenario == "multires_wide":
+        # many coarse faces, small dabs: most dabs reach one or two ranks only -- the others skip them and run ahead
+        mr, ll = meshgen.multires_plane(16, 3, noise=0.04, freq=9.0, with_mask=True), 4
+        centres = [(-0.7 + 0.35 * i, 0.3 * i - 0.6, 0.0) for i in range(5)]
+        small_r = 0.02
     else:
         mr, ll = meshgen.multires_cube(2, 4, noise=0.03, freq=13.0, with_mask=True), 5
         rng_ = np.random.default_rng(11)
@@ -147,19 +153,23 @@ def multires(world, rank, nid, scenario):
     dabs = []
     for i, c in enumerate(centres):
         c = np.asarray(c, dtype=np.float32)
-        n = tuple(c / max(np.linalg.norm(c), 1e-9)) if scenario != "multires_open" else (0.0, 0.0, 1.0)
+        n = tuple(c / max(np.linalg.norm(c), 1e-9)) if scenario == "multires" else (0.0, 0.0, 1.0)
         dabs.append(capi.make_dab(capi.TOOL_SMOOTH, c, diag * 0.22, bstrength=stroke._strength(capi.TOOL_SMOOTH, 0.6)))
         dabs.append(capi.make_dab(capi.TOOL_DRAW, c, diag * (0.12 + 0.05 * i), bstrength=stroke._strength(capi.TOOL_DRAW, 0.5),
                                   view_normal=n, flags=capi.DAB_FIRST_STEP if i == 0 else 0))
         dabs.append(capi.make_dab(capi.TOOL_INFLATE, c, diag * 0.3, bstrength=stroke._strength(capi.TOOL_INFLATE, 0.5), view_normal=n))
         dabs.append(capi.make_dab(capi.TOOL_CLAY_STRIPS, c, diag * 0.25, bstrength=stroke._strength(capi.TOOL_CLAY_STRIPS, 0.5),
                                   view_normal=n, grab_delta=(0.03, 0.01, 0.02)))
-    dabs.append(capi.make_dab(capi.TOOL_GRAB, np.asarray(centres[0], dtype=np.float32), diag * 0.3,
+    big = 0.3 if scenario != "multires_wide" else 0.08
+    if scenario == "multires_wide":
+        for d in dabs:
+            d.radius = d.radius * 0.3
+    dabs.append(capi.make_dab(capi.TOOL_GRAB, np.asarray(centres[0], dtype=np.float32), diag * big,
                               bstrength=stroke._strength(capi.TOOL_GRAB, 0.5), grab_delta=(0.02, -0.03, 0.04)))
     # small dabs: some of them gather no leaf near a partition cut, and their halo exchanges are skipped on every rank
     rs = np.random.default_rng(23)
-    for k in range(16):
-        if scenario == "multires_open":
+    for k in range(48 if scenario == "multires_wide" else 16):
+        if scenario != "multires":
             c = np.array([rs.uniform(-0.9, 0.9), rs.uniform(-0.9, 0.9), 0.0], dtype=np.float32)
             n = (0.0, 0.0, 1.0)
         else:
@@ -167,9 +177,9 @@ def multires(world, rank, nid, scenario):
             c = (c / np.linalg.norm(c)).astype(np.float32)
             n = tuple(c)
         if k % 2:
-            dabs.append(capi.make_dab(capi.TOOL_SMOOTH, c, diag * 0.04, bstrength=stroke._strength(capi.TOOL_SMOOTH, 0.6)))
+            dabs.append(capi.make_dab(capi.TOOL_SMOOTH, c, diag * small_r, bstrength=stroke._strength(capi.TOOL_SMOOTH, 0.6)))
         else:
-            dabs.append(capi.make_dab(capi.TOOL_DRAW, c, diag * 0.04, bstrength=stroke._strength(capi.TOOL_DRAW, 0.5), view_normal=n))
+            dabs.append(capi.make_dab(capi.TOOL_DRAW, c, diag * small_r, bstrength=stroke._strength(capi.TOOL_DRAW, 0.5), view_normal=n))
     orc = GridOracle(mr, leaf_limit=ll)
     ses = capi.GridSession(mr, leaf_limit=ll, device=rank, dist=(world, rank, nid))
     rng, owner = ses.partition(world)
