@@ -124,6 +124,11 @@ struct DscContext {
   int pending_skipped = 0;       /* grids: dabs this rank takes no part in whose all-coarse-vertex averaging is still to run */
   bool last_dab_skipped = false;
   bool subset_exchange = false;  /* peer-memory transport: dabs are exchanged among the ranks they reach only */
+  std::vector<int> own_grid_runs; /* partitioned grids: {first grid, count} of every run of consecutive owned grids */
+  int own_grid_count = 0;
+  int *d_own_grid_pos = nullptr;  /* [totgrid] rank of the grid among the owned ones, -1 */
+  float *d_own_pack = nullptr;    /* packed CCGElem records of the owned grids */
+  std::vector<void *> registered; /* host arrays this context page-locked and mapped (dsc_download_owned_*) */
   float *h_own = nullptr;        /* pinned staging of the owned slot runs (stroke-end sync of a partitioned PBVH) */
   size_t h_own_floats = 0;
   long long dist_skipped_dabs = 0, dist_local_dabs = 0, dist_exchanged_dabs = 0;
@@ -815,6 +820,7 @@ void dsc_ctx_destroy(DscContext *ctx)
   if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
   if (ctx->h_list) cudaFreeHost(ctx->h_list);
   if (ctx->h_own) cudaFreeHost(ctx->h_own);
+  for (void *p : ctx->registered) cudaHostUnregister(p);
   if (ctx->h_ray_out) cudaFreeHost(ctx->h_ray_out);
   if (ctx->h_ray_count) cudaFreeHost(ctx->h_ray_count);
   cudaEventDestroy(ctx->t0);
@@ -3390,10 +3396,100 @@ static int download_owned_runs(DscContext *ctx, int narr, const float *const *ar
   CU(cudaStreamSynchronize(ctx->stream));
   return DSC_OK;
 }
+/* The owned part straight into the host arrays: the arrays are page-locked and mapped, a kernel walks the vertices (grid
+ * elements) in THEIR order and stores the records of those this rank owns through the mapping -- consecutive owned
+ * vertices make full-width PCIe writes, every rank uses its own link, no host thread touches the data. */
+static void *mapped_host_ptr(DscContext *ctx, void *host, size_t bytes)
+{
+  void *dp = nullptr;
+  if (cudaHostGetDevicePointer(&dp, host, 0) == cudaSuccess && dp) return dp;
+  cudaGetLastError();
+  if (cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  ctx->registered.push_back(host);
+  if (cudaHostGetDevicePointer(&dp, host, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return dp;
+}
+__global__ void k_export_owned_mvert(float4 *__restrict__ mv, float *__restrict__ no, const float *__restrict__ cx, const float *__restrict__ cy,
+                                     const float *__restrict__ cz, const float *__restrict__ nx, const float *__restrict__ ny,
+                                     const float *__restrict__ nz, const int *__restrict__ slot_of, const unsigned *__restrict__ tail, int s0,
+                                     int s1, int totvert)
+{
+  /* a warp takes 32 consecutive vertices: when it owns them all, their normals leave as 24 aligned 16-byte stores (through
+   * shared memory) instead of 96 four-byte ones -- stores to mapped host memory cross PCIe one by one */
+  __shared__ float sn[8][96];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nround = (totvert + 31) & ~31;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nround; v += gridDim.x * blockDim.x) {
+    const int s = v < totvert ? slot_of[v] : -1;
+    const bool own = s >= s0 && s < s1;
+    float n3[3] = {0.0f, 0.0f, 0.0f};
+    if (own) {
+      mv[v] = make_float4(cx[s], cy[s], cz[s], __uint_as_float(tail ? tail[v] : 0u));
+      if (no) {
+        n3[0] = nx[s]; n3[1] = ny[s]; n3[2] = nz[s];
+      }
+    }
+    if (!no) continue;
+    if (__all_sync(0xffffffffu, own)) {
+      sn[warp][3 * lane] = n3[0]; sn[warp][3 * lane + 1] = n3[1]; sn[warp][3 * lane + 2] = n3[2];
+      __syncwarp();
+      if (lane < 24) reinterpret_cast<float4 *>(no + 3 * (size_t)(v - lane))[lane] = reinterpret_cast<const float4 *>(sn[warp])[lane];
+      __syncwarp();
+    }
+    else if (own) {
+      no[3 * (size_t)v + 0] = n3[0];
+      no[3 * (size_t)v + 1] = n3[1];
+      no[3 * (size_t)v + 2] = n3[2];
+    }
+  }
+}
+/* records of the owned grids, packed: grid g's records start at own_pos[g] * gs2 * ef floats */
+__global__ void k_export_owned_ccg(float *__restrict__ out, const float *__restrict__ cx, const float *__restrict__ cy, const float *__restrict__ cz,
+                                   const float *__restrict__ nx, const float *__restrict__ ny, const float *__restrict__ nz,
+                                   const float *__restrict__ mask, const int *__restrict__ slot_of, const int *__restrict__ own_pos, int gs2,
+                                   int totgrid, int ef, int mask_off, int no_off)
+{
+  for (int g = blockIdx.x; g < totgrid; g += gridDim.x) {
+    const int p = own_pos[g];
+    if (p < 0) continue;
+    const int sl0 = slot_of[(size_t)g * gs2]; /* a grid's elements are consecutive slots */
+    float *o = out + (size_t)p * gs2 * ef;
+    for (int t = threadIdx.x; t < gs2 * ef; t += blockDim.x) {
+      const int v = t / ef, k = t - v * ef;
+      const int s = sl0 + v;
+      float val = 0.0f;
+      if (k < 3) val = (k == 0 ? cx : (k == 1 ? cy : cz))[s];
+      else if (k == mask_off) val = mask ? mask[s] : 0.0f;
+      else if (no_off >= 0 && k >= no_off && k < no_off + 3) val = (k == no_off ? nx : (k == no_off + 1 ? ny : nz))[s];
+      o[t] = val;
+    }
+  }
+}
+
 int dsc_download_owned_mvert(DscContext *ctx, void *r_mvert, float *r_no)
 {
   NEED_PBVH();
   if (ctx->is_grids || !r_mvert) return fail(ctx, DSC_ERR_INVALID, "mesh contexts only; r_mvert must not be NULL");
+  if (ctx->world > 1 && !getenv("DSC_NO_MAPPED_SYNC")) {
+    void *dmv = mapped_host_ptr(ctx, r_mvert, sizeof(float) * 4 * (size_t)ctx->totvert);
+    void *dno = r_no ? mapped_host_ptr(ctx, r_no, sizeof(float) * 3 * (size_t)ctx->totvert) : nullptr;
+    if (dmv && (dno || !r_no)) {
+      int r = join_side(ctx);
+      if (r) return r;
+      k_export_owned_mvert<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>((float4 *)dmv, (float *)dno, ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny,
+                                                                     ctx->m.nz, ctx->d_slot_of, ctx->d_tail, ctx->slot_range[ctx->rank],
+                                                                     ctx->slot_range[ctx->rank + 1], ctx->totvert);
+      LAUNCH_CHECK();
+      CU(cudaStreamSynchronize(ctx->stream));
+      return DSC_OK;
+    }
+  }
   const float *arrs[6] = {ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny, ctx->m.nz};
   int s0 = 0, n = 0;
   int r = download_owned_runs(ctx, r_no ? 6 : 3, arrs, &s0, &n);
@@ -3420,6 +3516,51 @@ int dsc_download_owned_ccg(DscContext *ctx, void *r_elems, int elem_floats, int 
 {
   NEED_PBVH();
   if (!ctx->is_grids || !r_elems || elem_floats < 3 || elem_floats > 16) return fail(ctx, DSC_ERR_INVALID, "grids contexts only; bad CCG element layout");
+  if (ctx->world > 1 && !getenv("DSC_NO_MAPPED_SYNC")) {
+    /* whole CCGElem records of the owned grids are packed on the device in grid order; every run of consecutive owned grids
+     * is one DMA into the (page-locked) CCG storage -- a rank's grids are the grids of a patch of coarse faces, a few
+     * hundred runs of megabytes each */
+    const int gs2 = ctx->grid_size * ctx->grid_size;
+    if (ctx->own_grid_runs.empty()) {
+      std::vector<int> own;
+      const int s0 = ctx->slot_range[ctx->rank], s1 = ctx->slot_range[ctx->rank + 1];
+      for (int g = 0; g < ctx->totgrid; g++) {
+        const int sl = ctx->slot_of[(size_t)g * gs2];
+        if (sl >= s0 && sl < s1) own.push_back(g);
+      }
+      std::vector<int> pos((size_t)ctx->totgrid, -1);
+      for (size_t i = 0; i < own.size(); i++) pos[own[i]] = (int)i;
+      for (size_t i = 0; i < own.size();) {
+        size_t j = i + 1;
+        while (j < own.size() && own[j] == own[j - 1] + 1) j++;
+        ctx->own_grid_runs.push_back(own[i]);
+        ctx->own_grid_runs.push_back((int)(j - i));
+        i = j;
+      }
+      ctx->own_grid_count = (int)own.size();
+      int r0;
+      if ((r0 = dev_upload(ctx, &ctx->d_own_grid_pos, pos))) return r0;
+      if ((r0 = dev_alloc(ctx, &ctx->d_own_pack, (size_t)std::max(ctx->own_grid_count, 1) * gs2 * 16))) return r0;
+    }
+    if (elem_floats <= 16 && mapped_host_ptr(ctx, r_elems, sizeof(float) * (size_t)elem_floats * (size_t)ctx->totvert)) {
+      int r = join_side(ctx);
+      if (r) return r;
+      k_export_owned_ccg<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d_own_pack, ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny, ctx->m.nz,
+                                                                   ctx->m.mask, ctx->d_slot_of, ctx->d_own_grid_pos, gs2, ctx->totgrid, elem_floats,
+                                                                   mask_offset_floats, normal_offset_floats);
+      LAUNCH_CHECK();
+      const size_t grid_bytes = sizeof(float) * (size_t)elem_floats * gs2;
+      size_t at = 0;
+      for (size_t i = 0; i + 1 < ctx->own_grid_runs.size(); i += 2) {
+        const size_t bytes = grid_bytes * (size_t)ctx->own_grid_runs[i + 1];
+        CU(cudaMemcpyAsync((char *)r_elems + grid_bytes * (size_t)ctx->own_grid_runs[i], (const char *)ctx->d_own_pack + at, bytes,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        at += bytes;
+      }
+      CU(cudaStreamSynchronize(ctx->stream));
+      return DSC_OK;
+    }
+  }
   const float *arrs[7] = {ctx->m.cx, ctx->m.cy, ctx->m.cz, ctx->m.nx, ctx->m.ny, ctx->m.nz, ctx->m.mask};
   const bool with_mask = ctx->m.mask && mask_offset_floats >= 0;
   int s0 = 0, n = 0;
@@ -3505,7 +3646,15 @@ int dsc_host_register(DscContext *ctx, void *ptr, size_t bytes)
 {
   if (!ctx || !ptr) return DSC_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError(); /* the context page-locked it itself (dsc_download_owned_*): fine */
+    return DSC_OK;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, DSC_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+  }
   return DSC_OK;
 }
 int dsc_host_unregister(DscContext *ctx, void *ptr)
