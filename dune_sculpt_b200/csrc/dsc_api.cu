@@ -3422,7 +3422,7 @@ __global__ void k_export_owned_mvert(float4 *__restrict__ mv, float *__restrict_
 {
   /* a warp takes 32 consecutive vertices: when it owns them all, their normals leave as 24 aligned 16-byte stores (through
    * shared memory) instead of 96 four-byte ones -- stores to mapped host memory cross PCIe one by one */
-  __shared__ float sn[8][96];
+  __shared__ __align__(16) float sn[8][96];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nround = (totvert + 31) & ~31;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nround; v += gridDim.x * blockDim.x) {
