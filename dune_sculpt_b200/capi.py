@@ -26,6 +26,9 @@ CURVE_CUSTOM, CURVE_SMOOTH, CURVE_SPHERE, CURVE_ROOT, CURVE_SHARP, CURVE_LIN = 0
 CURVE_POW4, CURVE_INVSQUARE, CURVE_CONSTANT, CURVE_SMOOTHER = 6, 7, 8, 9
 DIR_AREA, DIR_VIEW, DIR_X, DIR_Y, DIR_Z = 0, 1, 2, 3, 4
 DAB_FRONTFACE, DAB_PLANE_TRIM, DAB_FIRST_STEP, DAB_NO_NORMALS, DAB_NO_BOUNDS = 1, 2, 4, 8, 16
+FALLOFF_SPHERE, FALLOFF_TUBE = 0, 1
+CLIP_X, CLIP_Y, CLIP_Z, LOCK_X, LOCK_Y, LOCK_Z = 1, 2, 4, 8, 16, 32
+ME_HIDE = 16
 PBVH_Leaf, PBVH_UpdateNormals, PBVH_UpdateBB, PBVH_UpdateOriginalBB = 1, 2, 4, 8
 PBVH_FullyHidden, PBVH_FullyMasked = 1 << 10, 1 << 11
 PBVH_UpdateDrawBuffers, PBVH_UpdateRedraw, PBVH_RebuildDrawBuffers = 1 << 4, 1 << 5, 1 << 9
@@ -38,6 +41,7 @@ class DscDab(C.Structure):
         ("bstrength", C.c_float), ("scale", C.c_float * 3), ("hardness", C.c_float),
         ("normal_radius_factor", C.c_float), ("plane_offset", C.c_float), ("plane_trim", C.c_float),
         ("tip_roundness", C.c_float), ("grab_delta", C.c_float * 3), ("radius_scale", C.c_float),
+        ("falloff_shape", C.c_int), ("clip_flags", C.c_int), ("clip_tolerance", C.c_float * 3), ("normal_weight", C.c_float),
     ]
 
 
@@ -119,7 +123,7 @@ HOST_SYMBOLS = [
     "BKE_pbvh_node_fully_masked_get", "BKE_pbvh_node_get_verts", "BKE_pbvh_node_num_verts", "BKE_pbvh_node_get_BB",
     "BKE_pbvh_node_get_original_BB", "BKE_pbvh_update_normals", "BKE_pbvh_update_bounds", "BKE_pbvh_vert_coords_alloc",
     "BKE_pbvh_vert_coords_apply", "BKE_pbvh_get_verts", "BKE_pbvh_get_vert_normals", "DUNE_sculpt_brush_strength",
-    "DUNE_sculpt_dab_defaults", "DUNE_sculpt_stroke_begin", "DUNE_sculpt_dab", "DUNE_sculpt_stroke_end",
+    "DUNE_sculpt_dab_defaults", "DUNE_sculpt_dab_symmetry", "DUNE_sculpt_stroke_begin", "DUNE_sculpt_dab", "DUNE_sculpt_stroke_end",
     "DUNE_sculpt_automask_boundary_edges", "DUNE_sculpt_automask_topology", "MEM_freeN",
 ]
 
@@ -271,6 +275,8 @@ def host_lib():
         L.DUNE_sculpt_brush_strength.restype = C.c_float
         L.DUNE_sculpt_dab_defaults.argtypes = [C.POINTER(DscDab), C.c_int]
         L.DUNE_sculpt_dab_defaults.restype = None
+        L.DUNE_sculpt_dab_symmetry.argtypes = [C.POINTER(DscDab), C.c_int, C.POINTER(DscDab)]
+        L.DUNE_sculpt_dab_symmetry.restype = C.c_int
         L.DUNE_sculpt_stroke_begin.argtypes = [C.POINTER(PBVH), c_float_p]
         L.DUNE_sculpt_dab.argtypes = [C.POINTER(PBVH), C.POINTER(DscDab)]
         L.DUNE_sculpt_stroke_end.argtypes = [C.POINTER(PBVH)]
@@ -331,13 +337,25 @@ def make_dab(tool, location, radius, **kw):
     d.location[:] = [float(x) for x in location]
     d.radius = float(radius)
     for k, v in kw.items():
-        if k in ("view_normal", "scale", "grab_delta"):
+        if k in ("view_normal", "scale", "grab_delta", "clip_tolerance"):
             getattr(d, k)[:] = [float(x) for x in v]
-        elif k in ("flags", "curve_preset", "sculpt_plane"):
+        elif k in ("flags", "curve_preset", "sculpt_plane", "falloff_shape", "clip_flags"):
             setattr(d, k, int(v))
         else:
             setattr(d, k, float(v))
     return d
+
+
+def dab_symmetry(d, symm):
+    """the symmetry passes of one dab (DUNE_sculpt_dab_symmetry): list of DscDab, the dab itself first"""
+    out = (DscDab * 8)()
+    n = host_lib().DUNE_sculpt_dab_symmetry(C.byref(d), int(symm), out)
+    res = []
+    for i in range(n):
+        c = DscDab()
+        C.memmove(C.byref(c), C.byref(out[i]), C.sizeof(DscDab))
+        res.append(c)
+    return res
 
 
 class SculptSession:

@@ -59,6 +59,7 @@ struct DscContext {
   std::vector<float> h_co, h_no, h_mask;
   std::vector<unsigned> h_tail;
   unsigned *d_tail = nullptr;
+  unsigned *d_hidden = nullptr;
   std::vector<int> h_poly_start, h_poly_len, h_loop_v, h_tri_vert, h_tri_poly, h_nb_off, h_nb_idx;
   std::vector<unsigned char> h_boundary;
   bool has_no = false, has_mask = false, has_nb = false;
@@ -71,6 +72,7 @@ struct DscContext {
   GridNb gnb = {}; /* smooth brush on grids: rim neighbour table in slot space */
   std::vector<int> h_rim_nb;
   std::vector<unsigned char> h_rim_bnd;
+  std::vector<unsigned char> h_elem_hidden; /* grids: DscGridsDesc.hidden */
   int rim_width = 0;
   size_t gn_smem = 0;
   /* draw-buffer fill (dsc_draw_*) */
@@ -1035,6 +1037,7 @@ int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *gr)
   ctx->h_grid_edge.assign(gr->grid_edge, gr->grid_edge + gr->totgrid);
   ctx->h_grid_cvert.assign(gr->grid_cvert, gr->grid_cvert + gr->totgrid);
   ctx->tottri = gr->totgrid; /* the PBVH's prims */
+  if (gr->hidden) ctx->h_elem_hidden.assign(gr->hidden, gr->hidden + (size_t)gr->totgrid * gr->grid_size * gr->grid_size);
   ctx->has_nb = gr->rim_neighbors != nullptr;
   if (ctx->has_nb) {
     if (gr->rim_width < 4) return fail(ctx, DSC_ERR_INVALID, "rim_width %d: a rim element has up to four neighbours or more", gr->rim_width);
@@ -1299,6 +1302,24 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   if ((r = dev_upload(ctx, &ctx->d_slot_of, ctx->slot_of))) return r;
   if ((r = dev_alloc(ctx, &ctx->d_stage3, (size_t)4 * V))) return r;
   if (!ctx->h_tail.empty() && (r = dev_upload(ctx, &ctx->d_tail, ctx->h_tail))) return r;
+  {
+    /* row a10: hidden verts (MVert.flag & ME_HIDE, the low byte of the tail word) / hidden grid elements, bit per slot */
+    std::vector<unsigned> hid((size_t)ctx->nwords, 0u);
+    bool any = false;
+    for (int v = 0; v < V; v++) {
+      const bool h = ctx->is_grids ? (!ctx->h_elem_hidden.empty() && ctx->h_elem_hidden[v]) : (!ctx->h_tail.empty() && (ctx->h_tail[v] & 16u));
+      if (h) {
+        const int sl = ctx->slot_of[v];
+        hid[(size_t)sl >> 5] |= 1u << (sl & 31);
+        any = true;
+      }
+    }
+    if (any) {
+      if ((r = dev_upload(ctx, &ctx->d_hidden, hid))) return r;
+      m.hidden = ctx->d_hidden;
+    }
+    std::vector<unsigned char>().swap(ctx->h_elem_hidden);
+  }
   if ((r = dev_alloc(ctx, &ctx->d_list, (size_t)std::max(V, L))) || (r = dev_zero(ctx, &ctx->d_count, 1))) return r;
 
   /* smooth adjacency in slot order */
@@ -2622,13 +2643,16 @@ static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *s
       return fail(ctx, DSC_ERR_UNSUPPORTED, "on grids every dab stitches, updates normals and bounds");
   }
   static_assert(sizeof(DabParams) == sizeof(DscDab), "DabParams mirrors DscDab");
-  static_assert(sizeof(DabEntry) == 128, "DabEntry is 128 bytes");
+  static_assert(sizeof(DabEntry) == 160, "DabEntry is 160 bytes");
   memset(e, 0, sizeof(*e));
   memcpy(&e->d, dab, sizeof(e->d));
   sig->tool = tool;
   sig->do_normals = !(dab->flags & DSC_DAB_NO_NORMALS);
   sig->do_bounds = !(dab->flags & DSC_DAB_NO_BOUNDS);
-  sig->needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS;
+  if (dab->falloff_shape != DSC_FALLOFF_SPHERE && dab->falloff_shape != DSC_FALLOFF_TUBE)
+    return fail(ctx, DSC_ERR_INVALID, "falloff_shape %d", dab->falloff_shape);
+  sig->needs_area = (tool == DSC_TOOL_DRAW && dab->sculpt_plane == DSC_DIR_AREA) || tool == DSC_TOOL_CLAY_STRIPS ||
+                    (tool == DSC_TOOL_GRAB && dab->normal_weight > 0.0f && dab->sculpt_plane == DSC_DIR_AREA);
   sig->smooth_iters = 0;
   sig->smooth_tail = 0;
   e->peers = (int)peers;

@@ -71,6 +71,7 @@ struct DevMesh {
   float *onx, *ony, *onz; /* undo snapshot: orig_no */
   float *tx, *ty, *tz;    /* Jacobi scratch (smooth) */
   const float *mask, *automask;
+  const unsigned *hidden; /* bit per slot: MVert.flag & ME_HIDE / grid_hidden -- the vertex iterator skips it (NULL: none) */
   unsigned *dirty;      /* PBVH.vert_bitmap, one bit per slot */
   unsigned *iter_moved; /* smooth: moved in this iteration */
   unsigned *capture;    /* debug: verts the current dab marked (NULL when capture is off) */
@@ -145,6 +146,9 @@ struct DabParams {
   int tool, curve_preset, flags, sculpt_plane;
   float loc[3], radius, view_n[3], bstrength, scale[3], hardness;
   float normal_radius_factor, plane_offset, plane_trim, tip_roundness, grab_delta[3], radius_scale;
+  int falloff_shape;      /* 1: tube (distance to the view line through the location) */
+  int clip_flags;         /* bits 0-2 locked axes, bits 3-5 mirror clipping */
+  float clip_tol[3], normal_weight;
 };
 
 /* One queued dab on the device: the descriptor plus what the host derives from it.  The per-dab
@@ -163,6 +167,7 @@ struct DabEntry {
   int ent_bits;         /* DSC_ENT_NORMALS | DSC_ENT_BOUNDS */
   int use_cos;          /* the area pass also samples the centre (clay strips) */
   int peers;            /* partitioned PBVH: bit per rank the dab can reach (the ranks that exchange it); 0 on one GPU */
+  int pad[2];
 };
 
 __device__ __forceinline__ const DabEntry &dsc_dab_entry(const DevMesh &m, int j)
@@ -270,6 +275,85 @@ __device__ __forceinline__ float dsc_strength_factor(const DevMesh &m, const Dab
   return avg;
 }
 
+/* row a11 brush test: squared distance to the brush location, or (tube) to the view line through it */
+__device__ __forceinline__ float dsc_test_distsq(const DabParams &d, float x, float y, float z)
+{
+  if (d.falloff_shape == 1) {
+    const float plane_d = -(d.view_n[0] * d.loc[0] + d.view_n[1] * d.loc[1] + d.view_n[2] * d.loc[2]);
+    const float side = (d.view_n[0] * x + d.view_n[1] * y + d.view_n[2] * z) + plane_d;
+    const float qx = (x + d.view_n[0] * (-side)) - d.loc[0];
+    const float qy = (y + d.view_n[1] * (-side)) - d.loc[1];
+    const float qz = (z + d.view_n[2] * (-side)) - d.loc[2];
+    return qx * qx + qy * qy + qz * qz;
+  }
+  const float dx = x - d.loc[0], dy = y - d.loc[1], dz = z - d.loc[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+/* row a11 clipping: locked axes keep their coordinate, a vertex within the tolerance of a clipping mirror plane stays on it */
+__device__ __forceinline__ void dsc_clip(const DabParams &d, float &x, float &y, float &z, float vx, float vy, float vz)
+{
+  if (!d.clip_flags) {
+    x = vx; y = vy; z = vz;
+    return;
+  }
+  if (!(d.clip_flags & 8)) x = ((d.clip_flags & 1) && fabsf(x) <= d.clip_tol[0]) ? 0.0f : vx;
+  if (!(d.clip_flags & 16)) y = ((d.clip_flags & 2) && fabsf(y) <= d.clip_tol[1]) ? 0.0f : vy;
+  if (!(d.clip_flags & 32)) z = ((d.clip_flags & 4) && fabsf(z) <= d.clip_tol[2]) ? 0.0f : vz;
+}
+/* the tube falloff's node test: squared distance from the line loc + t n to the box (0 when it crosses it, else the least
+ * distance to one of the 12 edges); same arithmetic as the host's and the oracle's */
+__device__ __forceinline__ float dsc_line_aabb_distsq(const float loc[3], const float n[3], const float bmin[3], const float bmax[3])
+{
+  float tmin = -3.402823466e+38f, tmax = 3.402823466e+38f;
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (n[k] != 0.0f) {
+      const float t1 = (bmin[k] - loc[k]) / n[k], t2 = (bmax[k] - loc[k]) / n[k];
+      const float lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
+      if (lo > tmin) tmin = lo;
+      if (hi < tmax) tmax = hi;
+    }
+    else if (loc[k] < bmin[k] || loc[k] > bmax[k]) {
+      inside = false;
+    }
+  }
+  if (inside && tmin <= tmax) return 0.0f;
+  const float a = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+  float best = 3.402823466e+38f;
+#pragma unroll
+  for (int axis = 0; axis < 3; axis++) {
+    const int u = (axis + 1) % 3, v = (axis + 2) % 3;
+    for (int c = 0; c < 4; c++) {
+      float p0[3], e[3] = {0.0f, 0.0f, 0.0f};
+      p0[axis] = bmin[axis];
+      p0[u] = (c & 1) ? bmax[u] : bmin[u];
+      p0[v] = (c & 2) ? bmax[v] : bmin[v];
+      e[axis] = bmax[axis] - bmin[axis];
+      const float w[3] = {p0[0] - loc[0], p0[1] - loc[1], p0[2] - loc[2]};
+      const float b = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+      const float cc = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+      const float dd = n[0] * w[0] + n[1] * w[1] + n[2] * w[2];
+      const float ee = e[0] * w[0] + e[1] * w[1] + e[2] * w[2];
+      const float denom = a * cc - b * b;
+      float sp = 0.0f;
+      if (denom > 1.0e-30f) {
+        sp = (b * dd - a * ee) / denom;
+        sp = sp < 0.0f ? 0.0f : (sp > 1.0f ? 1.0f : sp);
+      }
+      const float tp = (a > 0.0f) ? (dd + b * sp) / a : 0.0f;
+      float dist = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float df = (w[k] + e[k] * sp) - n[k] * tp;
+        dist += df * df;
+      }
+      if (dist < best) best = dist;
+    }
+  }
+  return best;
+}
+
 /* BKE_mesh_calc_poly_normal of the poly of looptri position `pos`
  * (kernel/intern/mesh_evaluate.c:39-86, lib/intern/math_geom.cc:31-69) */
 __device__ __forceinline__ void dsc_poly_normal(const DevMesh &m, unsigned pos, float &fx, float &fy, float &fz)
@@ -334,7 +418,7 @@ __device__ __forceinline__ void dsc_reset_leaf_box(const DevMesh &m, int leaf)
  * the reset of the next slot of the per-dab state ring. */
 __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, float cx, float cy, float cz, float radius_sq,
                                                 float area_radius_sq, int original, int ignore_ineffective, int mark,
-                                                int set_flags, int ent_bits, int bidx, int tag_parity)
+                                                int set_flags, int ent_bits, int bidx, int tag_parity, const float *tube_n = nullptr)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const int l = bidx * DSC_BLOCK + tid;
@@ -362,17 +446,20 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
     flag = __ldcg(&m.node_flag[l]);
     if (mark) lst = __ldcg(&m.leaf_state[l]);
     const float c[3] = {cx, cy, cz};
-    float t[3];
+    float t[3], lo[3], hi[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       const float bmin = __ldcg(&bbs[i * tn + l]), bmax = __ldcg(&bbs[(3 + i) * tn + l]);
+      lo[i] = bmin;
+      hi[i] = bmax;
       float nearest;
       if (bmin > c[i]) nearest = bmin;
       else if (bmax < c[i]) nearest = bmax;
       else nearest = c[i];
       t[i] = c[i] - nearest;
     }
-    const float dist = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    float dist = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    if (tube_n) dist = dsc_line_aabb_distsq(c, tube_n, lo, hi); /* tube falloff: the view line through the location */
     const bool skip = ignore_ineffective && (flag & (F_FullyHidden | F_FullyMasked));
     hit = !skip && (dist < radius_sq);
     ahit = hit && mark && (dist <= area_radius_sq);
@@ -475,8 +562,9 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather_dab(DevMesh m, int j, int 
   dsc_pdl_wait(); /* leaf boxes of the previous dab's tile kernel; ring_ctl of the batch head */
   dsc_pdl_launch();
   const DabEntry &e = dsc_dab_entry(m, j);
+  const float vn[3] = {e.d.view_n[0], e.d.view_n[1], e.d.view_n[2]};
   dsc_gather_body(m, slot, e.d.loc[0], e.d.loc[1], e.d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
-                  e.ent_bits, blockIdx.x, -1);
+                  e.ent_bits, blockIdx.x, -1, e.d.falloff_shape == 1 ? vn : nullptr);
 }
 
 /* leaves carrying any of `flags` (update_search_cb, pbvh.c:2891-2900) */
@@ -609,12 +697,19 @@ __device__ __forceinline__ unsigned dsc_pack_nibbles(unsigned nib, int lane)
   return w;
 }
 
+/* the hidden bits of the four slots from s0 (s0 is a multiple of 4) */
+__device__ __forceinline__ unsigned dsc_hidden4(const DevMesh &m, int s0)
+{
+  return m.hidden ? (__ldg(&m.hidden[s0 >> 5]) >> (s0 & 31)) & 0xfu : 0u;
+}
+
 /* ------------------------------------------------------------------- K3a area normal / centre */
 /* SURVEY.md 8a row a15.  Unique verts of hit leaves inside radius * normal_radius_factor; two
  * buckets by the sign of dot(view_normal, no); smoothstep weight; exact int64 sums.  Streams
  * float4 runs of the SoA position arrays; normals are only fetched for runs with a vert inside. */
 __device__ __forceinline__ void dsc_area_body(const DevMesh &m, const DabParams &d, int use_cos, int slot, int cta, int ncta)
 {
+  const bool use_orig = d.tool == 5; /* grab (normal weight): the stroke-start surface */
   DabState *st = m.st + slot;
   const int4 *alist = m.atile_list + (size_t)slot * m.ntile;
   __shared__ unsigned long long sacc[16];
@@ -634,22 +729,25 @@ __device__ __forceinline__ void dsc_area_body(const DevMesh &m, const DabParams 
     const int nvalid = ent.z - 4 * tid;
     if (nvalid <= 0) continue;
     const int s0 = ent.y + 4 * tid;
-    const float4 X = ld4(m.cx, s0), Y = ld4(m.cy, s0), Z = ld4(m.cz, s0);
+    /* a leaf the stroke has touched before this dab has its stroke-start state in the snapshot arrays */
+    const bool snap = use_orig && !(ent.w & DSC_ENT_FIRST);
+    const float4 X = ld4(snap ? m.ox : m.cx, s0), Y = ld4(snap ? m.oy : m.cy, s0), Z = ld4(snap ? m.oz : m.cz, s0);
     const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+    const unsigned hid = dsc_hidden4(m, s0);
     float dxs[4], dys[4], dzs[4], dsq[4];
     bool any = false;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       dxs[j] = xs[j] - d.loc[0]; dys[j] = ys[j] - d.loc[1]; dzs[j] = zs[j] - d.loc[2];
-      dsq[j] = dxs[j] * dxs[j] + dys[j] * dys[j] + dzs[j] * dzs[j];
-      any |= (j < nvalid) && !(dsq[j] > radius_sq);
+      dsq[j] = dsc_test_distsq(d, xs[j], ys[j], zs[j]);
+      any |= (j < nvalid) && !((hid >> j) & 1u) && !(dsq[j] > radius_sq);
     }
     if (!any) continue;
-    const float4 NX = ld4(m.nx, s0), NY = ld4(m.ny, s0), NZ = ld4(m.nz, s0);
+    const float4 NX = ld4(snap ? m.onx : m.nx, s0), NY = ld4(snap ? m.ony : m.ny, s0), NZ = ld4(snap ? m.onz : m.nz, s0);
     const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      if (j >= nvalid || dsq[j] > radius_sq) continue;
+      if (j >= nvalid || ((hid >> j) & 1u) || dsq[j] > radius_sq) continue;
       const float vx = vxs[j], vy = vys[j], vz = vzs[j];
       const bool flip = (d.view_n[0] * vx + d.view_n[1] * vy + d.view_n[2] * vz) <= 0.0f;
       const float q = 1.0f - (sqrtf(dsq[j]) / test_radius);
@@ -736,6 +834,7 @@ struct BrushDerived {
   float offset[3];
   /* clay strips */
   float origin[3], ax[3][3], sc[3], plane_no[3], plane_d, trim_sq, bstrength;
+  float grab[3]; /* grab: the drag, blended towards the sculpt normal when the brush has a normal weight */
   int flip, skip;
 };
 
@@ -798,6 +897,23 @@ __device__ void dsc_brush_derive(DabState *st, const DabParams &d, BrushDerived 
     /* what the host reads back as the plane: centre before the offset */
     ac[0] = area_co0[0]; ac[1] = area_co0[1]; ac[2] = area_co0[2];
   }
+  else if (d.tool == 5) {
+    D.grab[0] = d.grab_delta[0]; D.grab[1] = d.grab_delta[1]; D.grab[2] = d.grab_delta[2];
+    if (d.normal_weight > 0.0f) {
+      /* row a19, sculpt_project_v3_normal_align: the drag blended towards the sculpt normal, scaled to follow the cursor */
+      dsc_sculpt_normal(st, d, an);
+      const float len_signed = an[0] * D.grab[0] + an[1] * D.grab[1] + an[2] * D.grab[2];
+      const float fac = an[0] * d.view_n[0] + an[1] * d.view_n[1] + an[2] * d.view_n[2];
+      const float vax = an[0] - d.view_n[0] * fac, vay = an[1] - d.view_n[1] * fac, vaz = an[2] - d.view_n[2] * fac;
+      float lvs = fabsf(vax * an[0] + vay * an[1] + vaz * an[2]);
+      lvs = (lvs > 1.1920929e-07f) ? 1.0f / lvs : 1.0f;
+      const float w = (len_signed * d.normal_weight) * lvs;
+      for (int k = 0; k < 3; k++) {
+        D.grab[k] = D.grab[k] * (1.0f - d.normal_weight);
+        D.grab[k] = D.grab[k] + an[k] * w;
+      }
+    }
+  }
   if (publish) {
     for (int k = 0; k < 3; k++) {
       st->area_no[k] = an[k];
@@ -849,28 +965,27 @@ __device__ __forceinline__ bool dsc_brush_vertex(const DevMesh &m, const DabPara
     if ((d.flags & 2) && !((vx * vx + vy * vy + vz * vz) <= D.trim_sq)) return false;
     const float fade = D.bstrength * dsc_strength_factor(m, d, d.radius * dist, vnx, vny, vnz, s);
     const float px = vx * fade, py = vy * fade, pz = vz * fade;
-    x = x + px; y = y + py; z = z + pz;
+    dsc_clip(d, x, y, z, x + px, y + py, z + pz);
     return true;
   }
-  /* sphere test (row a11); grab tests and offsets the stroke-start coordinates (row a19) */
-  const float dx = tx - d.loc[0], dy = ty - d.loc[1], dz = tz - d.loc[2];
-  const float distsq = dx * dx + dy * dy + dz * dz;
+  /* sphere / tube test (row a11); grab tests and offsets the stroke-start coordinates (row a19) */
+  const float distsq = dsc_test_distsq(d, tx, ty, tz);
   if (distsq > radius_sq) return false;
   float fade = dsc_strength_factor(m, d, sqrtf(distsq), vnx, vny, vnz, s);
   if (tool == 1) {
     const float px = D.offset[0] * fade, py = D.offset[1] * fade, pz = D.offset[2] * fade;
-    x = x + px; y = y + py; z = z + pz;
+    dsc_clip(d, x, y, z, x + px, y + py, z + pz);
   }
   else if (tool == 4) {
     fade = d.bstrength * fade;
     const float sc = fade * d.radius;
     const float px = (vnx * sc) * d.scale[0], py = (vny * sc) * d.scale[1], pz = (vnz * sc) * d.scale[2];
-    x = x + px; y = y + py; z = z + pz;
+    dsc_clip(d, x, y, z, x + px, y + py, z + pz);
   }
   else {
     fade = d.bstrength * fade;
-    const float px = d.grab_delta[0] * fade, py = d.grab_delta[1] * fade, pz = d.grab_delta[2] * fade;
-    x = tx + px; y = ty + py; z = tz + pz;
+    const float px = D.grab[0] * fade, py = D.grab[1] * fade, pz = D.grab[2] * fade;
+    dsc_clip(d, x, y, z, tx + px, ty + py, tz + pz);
   }
   return true;
 }
@@ -902,14 +1017,12 @@ __device__ __forceinline__ unsigned dsc_brush_quad_core(const DevMesh &m, const 
   if (tool == 18 && D.skip) return 0u;
   float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
   const float txs[4] = {TX.x, TX.y, TX.z, TX.w}, tys[4] = {TY.x, TY.y, TY.z, TY.w}, tzs[4] = {TZ.x, TZ.y, TZ.z, TZ.w};
+  const unsigned hid = dsc_hidden4(m, s0);
   if (need_no && !first) {
     /* only needed for verts inside; one cheap pre-test keeps the streaming case at 12 B/vert */
     bool any = (tool == 18);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const float dx = txs[j] - d.loc[0], dy = tys[j] - d.loc[1], dz = tzs[j] - d.loc[2];
-      any |= !((dx * dx + dy * dy + dz * dz) > radius_sq);
-    }
+    for (int j = 0; j < 4; j++) any |= !(dsc_test_distsq(d, txs[j], tys[j], tzs[j]) > radius_sq);
     if (any) {
       if (use_orig) { NX = ld4(m.onx, s0); NY = ld4(m.ony, s0); NZ = ld4(m.onz, s0); }
       else { NX = ld4(m.nx, s0); NY = ld4(m.ny, s0); NZ = ld4(m.nz, s0); }
@@ -918,7 +1031,8 @@ __device__ __forceinline__ unsigned dsc_brush_quad_core(const DevMesh &m, const 
   const float vxs[4] = {NX.x, NX.y, NX.z, NX.w}, vys[4] = {NY.x, NY.y, NY.z, NY.w}, vzs[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    if (j < nvalid && dsc_brush_vertex<TOOL>(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j], vys[j], vzs[j], radius_sq)) {
+    if (j < nvalid && !((hid >> j) & 1u) &&
+        dsc_brush_vertex<TOOL>(m, d, D, s0 + j, xs[j], ys[j], zs[j], txs[j], tys[j], tzs[j], vxs[j], vys[j], vzs[j], radius_sq)) {
       nib |= 1u << j;
     }
   }
@@ -1090,10 +1204,9 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
       bool moved = false;
-      if (i < cnt) {
+      if (i < cnt && !(m.hidden && ((m.hidden[s >> 5] >> (s & 31)) & 1u))) {
         const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
-        const float dx = x - d.loc[0], dy = y - d.loc[1], dz = z - d.loc[2];
-        const float distsq = dx * dx + dy * dy + dz * dz;
+        const float distsq = dsc_test_distsq(d, x, y, z);
         if (!(distsq > radius_sq)) {
           float vnx = 0.0f, vny = 0.0f, vnz = 0.0f;
           if (d.flags & 1) { vnx = m.nx[s]; vny = m.ny[s]; vnz = m.nz[s]; }
@@ -1142,9 +1255,11 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
               rx = ax * f; ry = ay * f; rz = az * f;
             }
             const float vx = rx - x, vy = ry - y, vz = rz - z;
-            m.tx[s] = x + vx * fade;
-            m.ty[s] = y + vy * fade;
-            m.tz[s] = z + vz * fade;
+            float cx0 = x, cy0 = y, cz0 = z;
+            dsc_clip(d, cx0, cy0, cz0, x + vx * fade, y + vy * fade, z + vz * fade);
+            m.tx[s] = cx0;
+            m.ty[s] = cy0;
+            m.tz[s] = cz0;
           }
           moved = true;
         }
@@ -1194,9 +1309,11 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
           rx = ax * f; ry = ay * f; rz = az * f;
         }
         const float vx = rx - x, vy = ry - y, vz = rz - z;
-        m.tx[s] = x + vx * fade;
-        m.ty[s] = y + vy * fade;
-        m.tz[s] = z + vz * fade;
+        float cx0 = x, cy0 = y, cz0 = z;
+        dsc_clip(d, cx0, cy0, cz0, x + vx * fade, y + vy * fade, z + vz * fade);
+        m.tx[s] = cx0;
+        m.ty[s] = cy0;
+        m.tz[s] = cz0;
       }
       __syncthreads(); /* the list is reset for the next tile */
     }

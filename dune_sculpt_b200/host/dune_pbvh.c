@@ -955,7 +955,19 @@ int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, i
     gd.rim_neighbors = rim_nb;
     gd.rim_boundary = rim_bnd;
   }
+  /* grid_hidden (pbvh.c:2527): one BLI_bitmap per grid, NULL for a grid with nothing hidden */
+  unsigned char *elem_hidden = NULL;
+  if (pbvh->grid_hidden) {
+    for (int g = 0; g < G; g++) {
+      const BLI_bitmap *gh = pbvh->grid_hidden[g];
+      if (!gh) continue;
+      if (!elem_hidden) elem_hidden = calloc((size_t)G * (size_t)area, 1);
+      for (int i = 0; i < area; i++) elem_hidden[(size_t)g * area + i] = ((gh[i >> 5] >> (i & 31)) & 1u) ? 1 : 0;
+    }
+  }
+  gd.hidden = elem_hidden;
   r = dsc_grids_upload(ctx, &gd);
+  free(elem_hidden);
   free(rim_nb);
   free(rim_bnd);
   if (r == DSC_OK && (pbvh->want_draw_buffers & 1)) r = dsc_draw_enable(ctx);
@@ -1673,6 +1685,27 @@ void DUNE_sculpt_dab_defaults(DscDab *dab, int sculpt_tool)
   dab->radius = 1.0f;
   dab->radius_scale = 1.0f;
   dab->bstrength = DUNE_sculpt_brush_strength(sculpt_tool, 1.0f /* :20 */, 1.0f, false, false, 1.0f, 1.0f);
+}
+
+/* SCULPT_is_symmetry_iteration_valid + flip_v3_v3 (paint.h, sculpt.c do_symmetrical_brush_actions): the dab mirrored
+ * for every valid combination of the symmetry axes; r_dabs[0] is the dab itself.  Returns the count (1..8). */
+int DUNE_sculpt_dab_symmetry(const DscDab *dab, int symm, DscDab r_dabs[8])
+{
+  int n = 0;
+  for (int i = 0; i <= symm; i++) {
+    const bool valid = i == 0 || ((symm & i) && (symm != 5 || i != 3) && (symm != 6 || (i != 3 && i != 5)));
+    if (!valid) continue;
+    DscDab *o = &r_dabs[n++];
+    *o = *dab;
+    for (int k = 0; k < 3; k++) {
+      if (i & (1 << k)) {
+        o->location[k] = -o->location[k];
+        o->view_normal[k] = -o->view_normal[k];
+        o->grab_delta[k] = -o->grab_delta[k];
+      }
+    }
+  }
+  return n;
 }
 
 int DUNE_sculpt_stroke_begin(PBVH *pbvh, const float *automask)

@@ -355,6 +355,9 @@ float DUNE_sculpt_brush_strength(int sculpt_tool, float alpha, float pressure, b
                                  float overlap, float feather);
 /* Brush defaults (types/types_brush_defaults.h:9-91) into a dab descriptor */
 void DUNE_sculpt_dab_defaults(DscDab *dab, int sculpt_tool);
+/* the symmetry passes of one dab (Paint.symmetry_flags & PAINT_SYMM_AXIS_ALL, types_scene.h): r_dabs[0] is the dab
+ * itself, the others its mirror images in the valid axis combinations; returns how many */
+int DUNE_sculpt_dab_symmetry(const DscDab *dab, int symm, DscDab r_dabs[8]);
 int DUNE_sculpt_stroke_begin(PBVH *pbvh, const float *automask);
 int DUNE_sculpt_dab(PBVH *pbvh, const DscDab *dab);
 int DUNE_sculpt_stroke_end(PBVH *pbvh);

@@ -124,6 +124,9 @@ typedef struct DscGridsDesc {
   const int *rim_neighbors;    /* [totgrid][4 * grid_size - 4][rim_width] element indices, -1 = none */
   const unsigned char *rim_boundary; /* [totgrid][4 * grid_size - 4] element is a boundary element of the coarse mesh
                                         (subdiv_ccg.c:1972-2008), or NULL: none is */
+  /* [totgrid * grid_size^2] non-zero = the element is hidden (grid_hidden, pbvh.c:2527: a BLI_bitmap per grid) and
+   * the vertex iterator skips it; NULL: none is */
+  const unsigned char *hidden;
 } DscGridsDesc;
 
 /* The built PBVH, flattened.  Replaces PBVH.nodes / PBVHNode (kernel/intern/pbvh_intern.h:15-162).
@@ -162,7 +165,19 @@ typedef struct DscDab {
   float tip_roundness;
   float grab_delta[3];
   float radius_scale;
+  /* Brush.falloff_shape (types_brush_enums.h PAINT_FALLOFF_SHAPE_SPHERE / _TUBE): the tube tests and fades by the distance to
+   * the view line through the location (SCULPT_brush_test_circle_sq, sculpt.c:1560-1574) */
+  int falloff_shape;
+  /* StrokeCache.flag CLIP_X/Y/Z (1, 2, 4) and Sculpt.flags SCULPT_LOCK_X/Y/Z (8, 16, 32), already shifted down: bits 0..2
+   * clip the axis to 0 when the result is within clip_tolerance of it, bits 3..5 lock it (SCULPT_clip, sculpt.c:1484-1510) */
+  int clip_flags;
+  float clip_tolerance[3];
+  /* grab: Brush.normal_weight (sculpt_project_v3_normal_align on the drag, sculpt.c:3015-3018); 0 = plain drag */
+  float normal_weight;
 } DscDab;
+
+enum { DSC_FALLOFF_SPHERE = 0, DSC_FALLOFF_TUBE = 1 };
+enum { DSC_CLIP_X = 1, DSC_CLIP_Y = 2, DSC_CLIP_Z = 4, DSC_LOCK_X = 8, DSC_LOCK_Y = 16, DSC_LOCK_Z = 32 };
 
 /* Counters of the running stroke (device-side, read back on demand). */
 typedef struct DscStrokeStats {

@@ -81,7 +81,17 @@ typedef struct OrDab {
   float tip_roundness;
   float grab_delta[3];
   float radius_scale; /* gather radius multiplier, 1.0 normally */
+  int falloff_shape;  /* 0 sphere, 1 tube: distance to the view line through the location (types_brush_enums.h:600-603) */
+  int clip_flags;     /* bits 0-2: mirror clipping on the axis (CLIP_X << i); bits 3-5: axis locked (SCULPT_LOCK_X << i) */
+  float clip_tolerance[3];
+  float normal_weight; /* grab: blend of the drag towards the sculpt normal (types_brush.h:158) */
 } OrDab;
+/* DAGGER distance from the line loc + t n to a box, squared: the node test of the tube falloff (the view-line counterpart
+ * of the sphere callback, row a7).  0 when the line crosses the box, else the least distance to one of its 12 edges. */
+float or_line_aabb_distsq(const float loc[3], const float n[3], const float bmin[3], const float bmax[3]);
+struct OrPbvh;
+int or_gather_tube(struct OrPbvh *p, const float center[3], const float normal[3], float radius_sq, int original,
+                   int ignore_fully_ineffective, int *r_nodes);
 
 typedef struct OrPbvh OrPbvh;
 

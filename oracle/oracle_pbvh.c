@@ -687,6 +687,80 @@ static int search_sphere_cb(OrPbvh *p, OrNode *node, void *data_v)
   return (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) < data->radius_squared;
 }
 
+/* DAGGER tube falloff: the node passes when the view line through the brush location comes closer to its box than the
+ * radius (upstream: SCULPT_search_circle_cb over dist_squared_ray_to_aabb_v3).  Fixed here as: zero when the line
+ * crosses the box (slab test), else the least line-to-edge distance over the box's 12 edges. */
+float or_line_aabb_distsq(const float loc[3], const float n[3], const float bmin[3], const float bmax[3])
+{
+  float tmin = -FLT_MAX, tmax = FLT_MAX;
+  int inside = 1;
+  for (int k = 0; k < 3; k++) {
+    if (n[k] != 0.0f) {
+      const float t1 = (bmin[k] - loc[k]) / n[k], t2 = (bmax[k] - loc[k]) / n[k];
+      const float lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
+      if (lo > tmin) tmin = lo;
+      if (hi < tmax) tmax = hi;
+    }
+    else if (loc[k] < bmin[k] || loc[k] > bmax[k]) {
+      inside = 0;
+    }
+  }
+  if (inside && tmin <= tmax) return 0.0f;
+  const float a = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+  float best = FLT_MAX;
+  for (int axis = 0; axis < 3; axis++) {
+    const int u = (axis + 1) % 3, v = (axis + 2) % 3;
+    for (int c = 0; c < 4; c++) {
+      float p0[3], e[3] = {0.0f, 0.0f, 0.0f};
+      p0[axis] = bmin[axis];
+      p0[u] = (c & 1) ? bmax[u] : bmin[u];
+      p0[v] = (c & 2) ? bmax[v] : bmin[v];
+      e[axis] = bmax[axis] - bmin[axis];
+      const float w[3] = {p0[0] - loc[0], p0[1] - loc[1], p0[2] - loc[2]};
+      const float b = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+      const float cc = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+      const float dd = n[0] * w[0] + n[1] * w[1] + n[2] * w[2];
+      const float ee = e[0] * w[0] + e[1] * w[1] + e[2] * w[2];
+      const float denom = a * cc - b * b;
+      float sp = 0.0f;
+      if (denom > 1.0e-30f) {
+        sp = (b * dd - a * ee) / denom;
+        sp = sp < 0.0f ? 0.0f : (sp > 1.0f ? 1.0f : sp);
+      }
+      const float tp = (a > 0.0f) ? (dd + b * sp) / a : 0.0f;
+      float dist = 0.0f;
+      for (int k = 0; k < 3; k++) {
+        const float df = (w[k] + e[k] * sp) - n[k] * tp;
+        dist += df * df;
+      }
+      if (dist < best) best = dist;
+    }
+  }
+  return best;
+}
+typedef struct TubeData {
+  const float *center, *normal;
+  float radius_squared;
+  int original, ignore_fully_ineffective;
+} TubeData;
+static int search_tube_cb(OrPbvh *p, OrNode *node, void *data_v)
+{
+  (void)p;
+  const TubeData *data = data_v;
+  /* inner nodes never prune: the line distance is not exactly monotone in the box in floating point (the sphere test is),
+   * so a leaf passes on its own box alone */
+  if (!(node->flag & OR_PBVH_Leaf)) return 1;
+  if (data->ignore_fully_ineffective && (node->flag & (OR_PBVH_FullyHidden | OR_PBVH_FullyMasked))) return 0;
+  const OrBB *bb = data->original ? &node->orig_vb : &node->vb;
+  return or_line_aabb_distsq(data->center, data->normal, bb->bmin, bb->bmax) < data->radius_squared;
+}
+int or_gather_tube(OrPbvh *p, const float center[3], const float normal[3], float radius_sq, int original,
+                   int ignore_fully_ineffective, int *r_nodes)
+{
+  TubeData d = {center, normal, radius_sq, original, ignore_fully_ineffective};
+  return search_gather(p, search_tube_cb, &d, r_nodes);
+}
+
 int or_gather_sphere(OrPbvh *p, const float center[3], float radius_sq, int original,
                      int ignore_fully_ineffective, int *r_nodes)
 {

@@ -134,6 +134,44 @@ static float strength_factor(const OrPbvh *p, const OrDab *d, float len, const f
   return avg;
 }
 
+/* DAGGER row a10: the vertex iterator with PBVH_ITER_UNIQUE skips hidden vertices (MVert.flag & ME_HIDE) and hidden grid
+ * elements (grid_hidden), pbvh.c:4840-4897 + the iterator macro */
+static inline int vert_hidden(const OrPbvh *p, int v)
+{
+  if (p->vert_flag) return (p->vert_flag[v] & 16) != 0;
+  if (p->grid_hidden) return p->grid_hidden[v] != 0;
+  return 0;
+}
+
+/* DAGGER row a11 brush test: squared distance of co to the brush location (sphere) or to the view line through it (tube:
+ * co is projected onto the plane through the location whose normal is the view normal) */
+static inline float brush_test_distsq(const OrDab *d, const float co[3])
+{
+  if (d->falloff_shape == 1) {
+    const float plane_d = -dot_v3v3(d->view_normal, d->location);
+    const float side = dot_v3v3(d->view_normal, co) + plane_d;
+    float q[3];
+    for (int k = 0; k < 3; k++) {
+      const float proj = co[k] + d->view_normal[k] * (-side);
+      q[k] = proj - d->location[k];
+    }
+    return q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  }
+  const float dx = co[0] - d->location[0], dy = co[1] - d->location[1], dz = co[2] - d->location[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+
+/* DAGGER row a11 clipping: a locked axis keeps its coordinate; with mirror clipping a vertex within the tolerance of the
+ * mirror plane is held on it */
+static inline void sculpt_clip(const OrDab *d, float co[3], const float val[3])
+{
+  for (int i = 0; i < 3; i++) {
+    if (d->clip_flags & (8 << i)) continue; /* SCULPT_LOCK_X << i */
+    if ((d->clip_flags & (1 << i)) && (fabsf(co[i]) <= d->clip_tolerance[i])) co[i] = 0.0f; /* CLIP_X << i */
+    else co[i] = val[i];
+  }
+}
+
 void or_stroke_begin(OrPbvh *p, const float *automask)
 {
   free(p->automask);
@@ -178,6 +216,7 @@ typedef struct AreaAcc {
 static void calc_area_normal_and_center(OrPbvh *p, const OrDab *d, const int *nodes, int totnode,
                                         int use_nos, int use_cos, float r_no[3], float r_co[3])
 {
+  const int use_orig = (d->tool == OR_TOOL_GRAB); /* grab samples the stroke-start surface */
   AreaAcc sum;
   memset(&sum, 0, sizeof(sum));
   float test_radius = sqrtf(d->radius * d->radius);
@@ -193,13 +232,14 @@ static void calc_area_normal_and_center(OrPbvh *p, const OrDab *d, const int *no
     memset(&acc, 0, sizeof(acc));
     for (int i = 0; i < node->uniq_verts; i++) {
       const int v = node->vert_indices[i];
-      const float *co = p->co[v];
+      if (vert_hidden(p, v)) continue;
+      const float *co = use_orig ? p->orig_co[v] : p->co[v];
       const float dx = co[0] - d->location[0], dy = co[1] - d->location[1], dz = co[2] - d->location[2];
-      const float distsq = dx * dx + dy * dy + dz * dz;
+      const float distsq = brush_test_distsq(d, co);
       if (distsq > radius_sq) {
         continue;
       }
-      const float *no = p->no[v];
+      const float *no = use_orig ? p->orig_no[v] : p->no[v];
       const int flip = (dot_v3v3(d->view_normal, no) <= 0.0f);
       const float q = 1.0f - (sqrtf(distsq) / test_radius);
       const float f = clamp_f(3.0f * q * q - 2.0f * q * q * q, 0.0f, 1.0f);
@@ -303,44 +343,65 @@ static void do_simple_brush(OrPbvh *p, const OrDab *d, const int *nodes, int tot
       offset[k] = offset[k] * d->bstrength;
     }
   }
+  float grab_delta[3] = {d->grab_delta[0], d->grab_delta[1], d->grab_delta[2]};
+  if (d->tool == OR_TOOL_GRAB && d->normal_weight > 0.0f) {
+    /* DAGGER row a19 sculpt_project_v3_normal_align: the drag is blended towards the sculpt normal (the area normal of the
+     * stroke-start surface under the brush), scaled so that it still follows the cursor */
+    float sn[3];
+    sculpt_normal(p, d, nodes, totnode, sn);
+    memcpy(p->last_area_no, sn, sizeof(sn));
+    const float len_signed = dot_v3v3(sn, grab_delta);
+    const float fac = dot_v3v3(sn, d->view_normal);
+    float va[3];
+    for (int k = 0; k < 3; k++) va[k] = sn[k] - d->view_normal[k] * fac; /* project_plane_v3_v3v3 */
+    float len_view_scale = fabsf(dot_v3v3(va, sn));
+    len_view_scale = (len_view_scale > FLT_EPSILON) ? 1.0f / len_view_scale : 1.0f;
+    const float w = (len_signed * d->normal_weight) * len_view_scale;
+    for (int k = 0; k < 3; k++) {
+      grab_delta[k] = grab_delta[k] * (1.0f - d->normal_weight);
+      grab_delta[k] = grab_delta[k] + sn[k] * w;
+    }
+  }
   const int par = (or_threads > 1 && totnode > 1);
 #pragma omp parallel for schedule(dynamic) if (par)
   for (int n = 0; n < totnode; n++) {
     const OrNode *node = &p->nodes[nodes[n]];
     for (int i = 0; i < node->uniq_verts; i++) {
       const int v = node->vert_indices[i];
+      if (vert_hidden(p, v)) continue;
       const float *tco = (d->tool == OR_TOOL_GRAB) ? p->orig_co[v] : p->co[v];
       const float *tno = (d->tool == OR_TOOL_GRAB) ? p->orig_no[v] : p->no[v];
-      const float dx = tco[0] - d->location[0], dy = tco[1] - d->location[1], dz = tco[2] - d->location[2];
-      const float distsq = dx * dx + dy * dy + dz * dz;
+      const float distsq = brush_test_distsq(d, tco);
       if (distsq > radius_sq) {
         continue;
       }
       const float mask = p->mask ? p->mask[v] : 0.0f;
       float fade = strength_factor(p, d, sqrtf(distsq), tno, mask, v);
-      float proxy[3];
+      float proxy[3], val[3];
       if (d->tool == OR_TOOL_DRAW) {
         for (int k = 0; k < 3; k++) {
           proxy[k] = offset[k] * fade;
-          p->co[v][k] = p->co[v][k] + proxy[k];
+          val[k] = p->co[v][k] + proxy[k];
         }
       }
       else if (d->tool == OR_TOOL_INFLATE) {
         fade = d->bstrength * fade;
         const float s = fade * d->radius;
         for (int k = 0; k < 3; k++) {
-          const float val = p->no[v][k] * s;
-          proxy[k] = val * d->scale[k];
-          p->co[v][k] = p->co[v][k] + proxy[k];
+          const float nv = p->no[v][k] * s;
+          proxy[k] = nv * d->scale[k];
+          val[k] = p->co[v][k] + proxy[k];
         }
       }
       else { /* grab: co = orig_co + grab_delta * fade */
         fade = d->bstrength * fade;
         for (int k = 0; k < 3; k++) {
-          proxy[k] = d->grab_delta[k] * fade;
-          p->co[v][k] = p->orig_co[v][k] + proxy[k];
+          proxy[k] = grab_delta[k] * fade;
+          val[k] = p->orig_co[v][k] + proxy[k];
         }
       }
+      if (d->clip_flags) sculpt_clip(d, p->co[v], val);
+      else memcpy(p->co[v], val, sizeof(val));
       mark_moved(p, v, par);
     }
   }
@@ -411,6 +472,7 @@ static void do_clay_strips_brush(OrPbvh *p, const OrDab *d, const int *nodes, in
     const OrNode *node = &p->nodes[nodes[n]];
     for (int i = 0; i < node->uniq_verts; i++) {
       const int v = node->vert_indices[i];
+      if (vert_hidden(p, v)) continue;
       float *co = p->co[v];
       float rel[3] = {co[0] - origin[0], co[1] - origin[1], co[2] - origin[2]};
       float local[3];
@@ -451,10 +513,13 @@ static void do_clay_strips_brush(OrPbvh *p, const OrDab *d, const int *nodes, in
       }
       const float mask = p->mask ? p->mask[v] : 0.0f;
       const float fade = bstrength * strength_factor(p, d, d->radius * dist, p->no[v], mask, v);
+      float nv[3];
       for (int k = 0; k < 3; k++) {
         const float proxy = val[k] * fade;
-        co[k] = co[k] + proxy;
+        nv[k] = co[k] + proxy;
       }
+      if (d->clip_flags) sculpt_clip(d, co, nv);
+      else memcpy(co, nv, sizeof(nv));
       mark_moved(p, v, par);
     }
   }
@@ -525,9 +590,9 @@ static void do_smooth_brush(OrPbvh *p, const OrDab *d, const int *nodes, int tot
       const OrNode *node = &p->nodes[nodes[n]];
       for (int i = 0; i < node->uniq_verts; i++) {
         const int v = node->vert_indices[i];
+        if (vert_hidden(p, v)) continue;
         const float *co = p->co[v];
-        const float dx = co[0] - d->location[0], dy = co[1] - d->location[1], dz = co[2] - d->location[2];
-        const float distsq = dx * dx + dy * dy + dz * dz;
+        const float distsq = brush_test_distsq(d, co);
         if (distsq > radius_sq) {
           continue;
         }
@@ -535,10 +600,14 @@ static void do_smooth_brush(OrPbvh *p, const OrDab *d, const int *nodes, int tot
         const float fade = strength * strength_factor(p, d, sqrtf(distsq), p->no[v], mask, v);
         float avg[3];
         neighbor_average(p, (const float(*)[3])p->co, v, avg);
+        float nv[3];
         for (int k = 0; k < 3; k++) {
           const float val = avg[k] - co[k];
-          p->scratch[v][k] = co[k] + val * fade;
+          nv[k] = co[k] + val * fade;
         }
+        memcpy(p->scratch[v], co, sizeof(float[3]));
+        if (d->clip_flags) sculpt_clip(d, p->scratch[v], nv);
+        else memcpy(p->scratch[v], nv, sizeof(nv));
         p->iter_flag[v] = 1;
       }
     }
@@ -566,7 +635,8 @@ int or_dab(OrPbvh *p, const OrDab *d)
   p->dab_serial++;
   p->last_area_no[0] = p->last_area_no[1] = p->last_area_no[2] = 0.0f;
   memcpy(p->last_area_co, d->location, sizeof(float[3]));
-  p->last_tothit = or_gather_sphere(p, d->location, rs * rs, use_original, 1, p->last_hits);
+  if (d->falloff_shape == 1) p->last_tothit = or_gather_tube(p, d->location, d->view_normal, rs * rs, use_original, 1, p->last_hits);
+  else p->last_tothit = or_gather_sphere(p, d->location, rs * rs, use_original, 1, p->last_hits);
   const int *nodes = p->last_hits;
   const int totnode = p->last_tothit;
   for (int n = 0; n < totnode; n++) {

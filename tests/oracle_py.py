@@ -23,6 +23,7 @@ class OrDab(C.Structure):
         ("bstrength", C.c_float), ("scale", C.c_float * 3), ("hardness", C.c_float),
         ("normal_radius_factor", C.c_float), ("plane_offset", C.c_float), ("plane_trim", C.c_float),
         ("tip_roundness", C.c_float), ("grab_delta", C.c_float * 3), ("radius_scale", C.c_float),
+        ("falloff_shape", C.c_int), ("clip_flags", C.c_int), ("clip_tolerance", C.c_float * 3), ("normal_weight", C.c_float),
     ]
 
 

@@ -17,11 +17,11 @@ TOL_FRACTION = 1e-5  # of the bounding-box diagonal
 
 
 def run_parity(mesh, dabs, mask=None, automask=None, leaf_limit=0, exact=True, check_every=1, curve=None,
-               pre=None):
+               pre=None, vert_flag=None):
     diag = mesh.bbox_diag()
     tol = TOL_FRACTION * diag
-    orc = Oracle(mesh, mask=mask, leaf_limit=leaf_limit)
-    ses = capi.SculptSession(mesh, mask=mask, leaf_limit=leaf_limit, device=0)
+    orc = Oracle(mesh, mask=mask, leaf_limit=leaf_limit, vert_flag=vert_flag)
+    ses = capi.SculptSession(mesh, mask=mask, leaf_limit=leaf_limit, device=0, vert_flag=vert_flag)
     try:
         assert orc.totnode == ses.totnode
         if curve is not None:

@@ -38,7 +38,7 @@ def test_host_library_exports_every_declared_symbol():
 
 def test_dab_descriptor_layout():
     # DscDab is 4 ints + 20 floats, no padding: the kernels take it by value
-    assert C.sizeof(capi.DscDab) == 96
+    assert C.sizeof(capi.DscDab) == 120
     assert capi.DscDab.radius.offset == 28 and capi.DscDab.grab_delta.offset == 80 and capi.DscDab.radius_scale.offset == 92
 
 

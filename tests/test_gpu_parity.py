@@ -550,3 +550,112 @@ def test_raycast_matches_bke_pbvh_raycast(name):
     finally:
         ses.close()
         orc.close()
+
+
+# ---- rows a10 / a11 / a19: hidden verts, tube falloff, clipping and axis locks, grab normal weight ----------------
+
+def _hidden_flags(m, seed=5, frac=0.2):
+    rng = np.random.default_rng(seed)
+    vf = np.zeros(m.totvert, np.uint8)
+    vf[rng.random(m.totvert) < frac] = capi.ME_HIDE
+    # a fully hidden patch too, so whole leaves are flagged at build
+    co = m.co
+    vf[(co[:, 0] > 0.55) & (co[:, 1] > 0.55)] = capi.ME_HIDE
+    return vf
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_CLAY_STRIPS, capi.TOOL_SMOOTH, capi.TOOL_GRAB])
+def test_hidden_vertices_are_skipped_by_every_tool(tool):
+    m = meshgen.grid(97, height=0.05)
+    vf = _hidden_flags(m)
+    if tool == capi.TOOL_GRAB:
+        bs = stroke._strength(tool, 0.8)
+        dabs = [capi.make_dab(tool, (0.3, 0.3, 0.0), 0.45, bstrength=bs, grab_delta=np.array([0.1, -0.1, 0.3]) * (i + 1) / 6,
+                              flags=capi.DAB_FIRST_STEP if i == 0 else 0) for i in range(6)]
+    else:
+        dabs = _line_dabs(tool, (-0.6, -0.5, 0), (0.8, 0.7, 0), 0.3, 12)
+    before = m.co.copy()
+    res = run_parity(m, dabs, leaf_limit=300, vert_flag=vf)
+    hid = vf != 0
+    assert np.array_equal(res["co"][hid], before[hid]), "a hidden vertex moved"
+    assert res["moved"] > 0
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_SMOOTH, capi.TOOL_CLAY_STRIPS, capi.TOOL_GRAB])
+def test_tube_falloff_tests_the_view_line(tool):
+    # an icosphere seen along a tilted view: the tube reaches the far side too, the node test is the line-box distance
+    m = meshgen.icosphere(5)
+    vn = np.array([0.3, -0.2, 0.93], np.float32)
+    vn /= np.linalg.norm(vn)
+    kw = dict(view_normal=vn, falloff_shape=capi.FALLOFF_TUBE)
+    if tool == capi.TOOL_GRAB:
+        bs = stroke._strength(tool, 0.8)
+        dabs = [capi.make_dab(tool, (0.2, 0.1, 0.97), 0.3, bstrength=bs, grab_delta=np.array([0.1, 0.05, 0.2]) * (i + 1) / 5,
+                              flags=capi.DAB_FIRST_STEP if i == 0 else 0, **kw) for i in range(5)]
+    else:
+        dabs = _line_dabs(tool, (-0.3, -0.2, 0.93), (0.4, 0.3, 0.86), 0.25, 10, **kw)
+    res = run_parity(m, dabs, leaf_limit=400)
+    moved_far = (np.abs(res["co"] - m.co).max(axis=1) > 0) & (m.co @ vn < -0.5)
+    assert moved_far.any(), "the tube did not reach the far side of the sphere"
+
+
+def test_tube_falloff_with_hidden_and_mask_on_grid():
+    m = meshgen.grid(129, height=0.08)
+    vf = _hidden_flags(m, seed=9)
+    rng = np.random.default_rng(3)
+    mask = rng.random(m.totvert).astype(np.float32)
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.7, 0.1, 0.4), (0.7, -0.3, -0.4), 0.2, 14, falloff_shape=capi.FALLOFF_TUBE,
+                      view_normal=(0.0, 0.6, 0.8))
+    run_parity(m, dabs, mask=mask, leaf_limit=500, vert_flag=vf)
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_DRAW, capi.TOOL_INFLATE, capi.TOOL_SMOOTH, capi.TOOL_CLAY_STRIPS, capi.TOOL_GRAB])
+def test_mirror_clipping_and_axis_locks(tool):
+    m = meshgen.grid(97, height=0.05)
+    on_plane = np.abs(m.co[:, 0]) <= 0.011
+    assert on_plane.any()
+    kw = dict(clip_flags=capi.CLIP_X | capi.LOCK_Y, clip_tolerance=(0.011, 0.0, 0.0))
+    if tool == capi.TOOL_GRAB:
+        bs = stroke._strength(tool, 0.8)
+        dabs = [capi.make_dab(tool, (0.05, 0.1, 0.0), 0.4, bstrength=bs, grab_delta=np.array([0.2, 0.2, 0.3]) * (i + 1) / 5,
+                              flags=capi.DAB_FIRST_STEP if i == 0 else 0, **kw) for i in range(5)]
+    else:
+        dabs = _line_dabs(tool, (-0.3, -0.4, 0), (0.3, 0.5, 0), 0.3, 10, sculpt_plane=capi.DIR_X if tool == capi.TOOL_DRAW else capi.DIR_AREA, **kw)
+    res = run_parity(m, dabs, leaf_limit=300)
+    moved = np.abs(res["co"] - m.co).max(axis=1) > 0
+    assert moved.any()
+    assert np.array_equal(res["co"][:, 1], m.co[:, 1]), "a locked axis changed"
+    touched_on_plane = on_plane & moved
+    assert np.all(res["co"][touched_on_plane, 0] == 0.0), "a vertex inside the clip tolerance left the mirror plane"
+
+
+@pytest.mark.parametrize("weight,plane", [(0.35, capi.DIR_AREA), (1.0, capi.DIR_AREA), (0.5, capi.DIR_VIEW), (0.5, capi.DIR_Z)])
+def test_grab_normal_weight(weight, plane):
+    m = meshgen.icosphere(5)
+    bs = stroke._strength(capi.TOOL_GRAB, 0.9)
+    vn = np.array([0.2, 0.1, 0.97], np.float32)
+    vn /= np.linalg.norm(vn)
+    dabs = [capi.make_dab(capi.TOOL_GRAB, (0.3, 0.2, 0.93), 0.4, bstrength=bs, view_normal=vn, normal_weight=weight, sculpt_plane=plane,
+                          grab_delta=np.array([0.15, -0.05, 0.1]) * (i + 1) / 8, flags=capi.DAB_FIRST_STEP if i == 0 else 0)
+            for i in range(8)]
+    res = run_parity(m, dabs, leaf_limit=400)
+    plain = [capi.make_dab(capi.TOOL_GRAB, (0.3, 0.2, 0.93), 0.4, bstrength=bs, view_normal=vn, sculpt_plane=plane,
+                           grab_delta=np.array([0.15, -0.05, 0.1]) * (i + 1) / 8, flags=capi.DAB_FIRST_STEP if i == 0 else 0)
+             for i in range(8)]
+    ref = run_parity(m, plain, leaf_limit=400)
+    assert not np.array_equal(res["co"], ref["co"]), "the normal weight changed nothing"
+
+
+def test_symmetry_passes_through_the_dab_helper():
+    # X|Z symmetry: four passes per dab, each a mirror image (location, view normal, drag)
+    m = meshgen.icosphere(4)
+    base = _line_dabs(capi.TOOL_DRAW, (0.5, 0.1, 0.8), (0.6, 0.4, 0.65), 0.25, 4, view_normal=(0.4, 0.0, 0.9165))
+    dabs = []
+    for d in base:
+        dabs += capi.dab_symmetry(d, 1 | 4)
+    assert len(dabs) == 16
+    res = run_parity(m, dabs, leaf_limit=300)
+    # both halves were sculpted
+    moved = np.abs(res["co"] - m.co).max(axis=1) > 0
+    assert (moved & (m.co[:, 0] > 0.2) & (m.co[:, 2] > 0.2)).any() and (moved & (m.co[:, 0] < -0.2) & (m.co[:, 2] > 0.2)).any()
+    assert (moved & (m.co[:, 0] > 0.2) & (m.co[:, 2] < -0.2)).any() and (moved & (m.co[:, 0] < -0.2) & (m.co[:, 2] < -0.2)).any()

@@ -236,3 +236,92 @@ def test_raycast_closed_forms():
             assert orc.raycast(start, nrm, max_depth=1.5) is None
     finally:
         orc.close()
+
+
+# ---- rows a10 / a11 / a19 (dagger rows): closed forms of the hidden / tube / clip / normal-weight rules ----------
+
+def test_hidden_vertices_stay_and_do_not_count_in_the_area_normal():
+    m = meshgen.grid(65, height=0.0)
+    vf = np.zeros(m.totvert, np.uint8)
+    vf[::3] = capi.ME_HIDE
+    o = Oracle(m, leaf_limit=100, vert_flag=vf)
+    o.stroke_begin()
+    o.dab(capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.4, curve_preset=capi.CURVE_CONSTANT, sculpt_plane=capi.DIR_Z, bstrength=0.25))
+    inside = (m.co[:, 0] ** 2 + m.co[:, 1] ** 2) <= np.float32(0.4) ** 2
+    co = o.co()
+    vis = vf == 0
+    assert np.array_equal(co[~vis], m.co[~vis])
+    assert np.array_equal(co[inside & vis, 2], np.full((inside & vis).sum(), np.float32(0.4) * np.float32(0.25), np.float32))
+    assert np.array_equal(np.sort(o.moved()), np.nonzero(inside & vis)[0])
+    o.close()
+
+
+def test_tube_falloff_is_the_distance_to_the_view_line():
+    # two parallel sheets: the sphere brush moves the near one only, the tube both, by the same falloff of the XY distance
+    a = meshgen.grid(33, height=0.0)
+    co = np.concatenate([a.co, a.co + np.array([0, 0, -0.9], np.float32)])
+    m = meshgen.Mesh(np.ascontiguousarray(co, np.float32), np.concatenate([a.poly_start, a.poly_start + a.loop_v.size]).astype(np.int32),
+                     np.concatenate([a.poly_len, a.poly_len]).astype(np.int32), np.concatenate([a.loop_v, a.loop_v + a.totvert]).astype(np.int32))
+    kw = dict(curve_preset=capi.CURVE_LIN, sculpt_plane=capi.DIR_Z, bstrength=0.5, view_normal=(0, 0, 1))
+    o = Oracle(m, leaf_limit=100)
+    o.stroke_begin()
+    o.dab(capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.5, **kw))
+    dz = o.co()[:, 2] - m.co[:, 2]
+    assert dz[: a.totvert].max() > 0 and np.all(dz[a.totvert:] == 0)
+    o.close()
+    o = Oracle(m, leaf_limit=100)
+    o.stroke_begin()
+    o.dab(capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.5, falloff_shape=capi.FALLOFF_TUBE, **kw))
+    dz = o.co()[:, 2] - m.co[:, 2]
+    assert dz[: a.totvert].max() > 0
+    # within a few ulps: z of the far sheet is -0.9 + dz
+    assert np.allclose(dz[: a.totvert], dz[a.totvert:], atol=2e-7)
+    r = np.sqrt(m.co[: a.totvert, 0].astype(np.float64) ** 2 + m.co[: a.totvert, 1].astype(np.float64) ** 2)
+    want = np.where(r <= 0.5, 0.5 * 0.5 * (1.0 - r / 0.5), 0.0)
+    assert np.allclose(dz[: a.totvert], want, atol=1e-6)
+    o.close()
+
+
+def test_clip_holds_the_mirror_plane_and_lock_keeps_the_axis():
+    m = meshgen.grid(65, height=0.0)
+    o = Oracle(m, leaf_limit=100)
+    o.stroke_begin()
+    o.dab(capi.make_dab(capi.TOOL_DRAW, (0, 0, 0), 0.5, curve_preset=capi.CURVE_CONSTANT, sculpt_plane=capi.DIR_X, bstrength=0.25,
+                        clip_flags=capi.CLIP_X | capi.LOCK_Z, clip_tolerance=(0.02, 0, 0)))
+    co = o.co()
+    inside = (m.co[:, 0] ** 2 + m.co[:, 1] ** 2) < np.float32(0.5) ** 2  # on the rim the falloff is 0
+    near = np.abs(m.co[:, 0]) <= np.float32(0.02)
+    assert np.all(co[inside & near, 0] == 0.0)
+    assert np.array_equal(co[inside & ~near, 0], m.co[inside & ~near, 0] + np.float32(0.5) * np.float32(0.25))
+    assert np.array_equal(co[:, 2], m.co[:, 2]) and np.array_equal(co[:, 1], m.co[:, 1])
+    o.close()
+
+
+def test_grab_normal_weight_one_moves_along_the_normal_only():
+    # flat sheet, drag (dx, 0, dz), weight 1: the drag becomes n * dot(n, drag) * 1/|dot(n - view (n.view), n)| -- with the view
+    # along the normal the in-plane part of n vanishes and the scale falls back to 1: pure +Z motion of dz
+    m = meshgen.grid(65, height=0.0)
+    o = Oracle(m, leaf_limit=100)
+    o.stroke_begin()
+    o.dab(capi.make_dab(capi.TOOL_GRAB, (0, 0, 0), 0.4, curve_preset=capi.CURVE_CONSTANT, bstrength=1.0, grab_delta=(0.3, 0.0, 0.2),
+                        normal_weight=1.0, flags=capi.DAB_FIRST_STEP))
+    co = o.co()
+    inside = (m.co[:, 0] ** 2 + m.co[:, 1] ** 2) <= np.float32(0.4) ** 2
+    assert np.array_equal(co[inside, 0], m.co[inside, 0]) and np.array_equal(co[inside, 1], m.co[inside, 1])
+    assert np.allclose(co[inside, 2], 0.2, atol=1e-6)
+    assert np.array_equal(co[~inside], m.co[~inside])
+    o.close()
+
+
+def test_symmetry_helper_lists_the_valid_mirror_passes():
+    d = capi.make_dab(capi.TOOL_GRAB, (0.5, 0.25, -0.125), 0.3, view_normal=(0.6, 0.0, 0.8), grab_delta=(0.1, 0.2, 0.3))
+    for symm, want in [(0, [0]), (1, [0, 1]), (2, [0, 2]), (4, [0, 4]), (3, [0, 1, 2, 3]), (5, [0, 1, 4, 5]), (6, [0, 2, 4, 6]),
+                       (7, [0, 1, 2, 3, 4, 5, 6, 7])]:
+        out = capi.dab_symmetry(d, symm)
+        assert len(out) == len(want)
+        for o, i in zip(out, want):
+            sgn = np.array([-1.0 if i & (1 << k) else 1.0 for k in range(3)])
+            assert np.array_equal(np.array(o.location[:]), np.array(d.location[:]) * sgn)
+            assert np.array_equal(np.array(o.view_normal[:]), np.array(d.view_normal[:]) * sgn)
+            assert np.array_equal(np.array(o.grab_delta[:]), np.array(d.grab_delta[:]) * sgn)
+            assert o.radius == d.radius and o.tool == d.tool
