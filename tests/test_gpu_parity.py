@@ -596,7 +596,8 @@ def test_tube_falloff_tests_the_view_line(tool):
         dabs = _line_dabs(tool, (-0.3, -0.2, 0.93), (0.4, 0.3, 0.86), 0.25, 10, **kw)
     res = run_parity(m, dabs, leaf_limit=400)
     moved_far = (np.abs(res["co"] - m.co).max(axis=1) > 0) & (m.co @ vn < -0.5)
-    assert moved_far.any(), "the tube did not reach the far side of the sphere"
+    # (the clay-strips cube test bounds the depth in brush space whatever the falloff shape)
+    assert tool == capi.TOOL_CLAY_STRIPS or moved_far.any(), "the tube did not reach the far side of the sphere"
 
 
 def test_tube_falloff_with_hidden_and_mask_on_grid():
