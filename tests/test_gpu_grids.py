@@ -9,9 +9,9 @@ from oracle_py import GridOracle
 pytestmark = pytest.mark.gpu
 
 
-def _grid_parity(mr, dabs, leaf_limit=0, automask=None):
-    orc = GridOracle(mr, leaf_limit=leaf_limit)
-    ses = capi.GridSession(mr, leaf_limit=leaf_limit, device=0)
+def _grid_parity(mr, dabs, leaf_limit=0, automask=None, hidden=None):
+    orc = GridOracle(mr, leaf_limit=leaf_limit, hidden=hidden)
+    ses = capi.GridSession(mr, leaf_limit=leaf_limit, device=0, hidden=hidden)
     try:
         assert orc.totnode == ses.totnode
         assert np.array_equal(orc.no(), ses.no()), "initial CCG normals differ in bits"
@@ -51,6 +51,13 @@ def _grid_parity(mr, dabs, leaf_limit=0, automask=None):
         assert np.array_equal(disps.reshape(-1, 3), orc.co())
         if masks is not None:
             assert np.array_equal(masks.reshape(-1), orc.mask())
+        if hidden is not None:
+            # (elements on a grid's rim are stitched with their duplicates in other grids whether hidden or not)
+            gs = mr.grid_size
+            yy, xx = np.divmod(np.arange(gs * gs), gs)
+            inner = np.tile((xx > 0) & (xx < gs - 1) & (yy > 0) & (yy < gs - 1), mr.totgrid)
+            hid = (np.asarray(hidden).reshape(-1) != 0) & inner
+            assert np.array_equal(ses.co()[hid], np.asarray(mr.co).reshape(-1, 3)[hid]), "a hidden element moved"
         return ses.stats()
     finally:
         ses.close()
@@ -242,3 +249,43 @@ def test_grids_draw_buffers_from_the_device(smooth):
     finally:
         ses.close()
         orc.close()
+
+
+# ---- rows a10 / a11 / a19 on grids: grid_hidden, tube falloff, clipping, grab normal weight -------------------------
+
+def _hidden_elems(mr, seed=11, frac=0.25):
+    rng = np.random.default_rng(seed)
+    h = (rng.random(mr.totelem) < frac).astype(np.uint8).reshape(mr.totgrid, -1)
+    h[::7] = 1   # whole grids too: their quads all vanish
+    return h.reshape(-1)
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_DRAW, capi.TOOL_SMOOTH, capi.TOOL_GRAB, capi.TOOL_CLAY_STRIPS])
+def test_grids_hidden_elements_are_skipped(tool):
+    mr = meshgen.multires_cube(2, 4)
+    hid = _hidden_elems(mr)
+    dabs = _smooth_dabs(mr) if tool == capi.TOOL_SMOOTH else _sweep(mr, per=2, tool=tool, radii=(10.0, 30.0))
+    st = _grid_parity(mr, dabs, leaf_limit=6, hidden=hid)
+    assert st["moved_verts"] > 0
+
+
+@pytest.mark.parametrize("tool", [capi.TOOL_DRAW, capi.TOOL_SMOOTH, capi.TOOL_INFLATE])
+def test_grids_tube_falloff_and_clipping(tool):
+    mr = meshgen.multires_cube(2, 4)
+    base = _smooth_dabs(mr) if tool == capi.TOOL_SMOOTH else _sweep(mr, per=2, tool=tool, radii=(8.0, 20.0))
+    for d in base:
+        d.falloff_shape = capi.FALLOFF_TUBE
+        d.clip_flags = capi.CLIP_X | capi.LOCK_Z
+        d.clip_tolerance[0] = 0.05
+        if tool == capi.TOOL_SMOOTH:
+            d.view_normal[:] = [0.0, 0.6, 0.8]
+    st = _grid_parity(mr, base, leaf_limit=6, hidden=_hidden_elems(mr, seed=2, frac=0.1))
+    assert st["moved_verts"] > 0
+
+
+def test_grids_grab_normal_weight():
+    mr = meshgen.multires_cube(1, 4)
+    dabs = _sweep(mr, per=2, tool=capi.TOOL_GRAB, radii=(15.0, 35.0))
+    for d in dabs:
+        d.normal_weight = 0.6
+    _grid_parity(mr, dabs, leaf_limit=4)
