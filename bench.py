@@ -724,6 +724,11 @@ def main():
         os.dup2(2, 1)
     except OSError:
         _REAL_STDOUT = None
+    args = make_parser().parse_args()
+    run(args)
+
+
+def make_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -745,7 +750,10 @@ def main():
     ap.add_argument("--c5-level", type=int, default=7)
     ap.add_argument("--c5-dabs", type=int, default=100, help="draw dabs of the C5 stroke")
     ap.add_argument("--c5-smooth-dabs", type=int, default=100, help="smooth dabs ahead of them")
-    args = ap.parse_args()
+    return ap
+
+
+def run(args):
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

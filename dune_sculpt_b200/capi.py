@@ -76,7 +76,7 @@ class PBVH(C.Structure):
         ("device", C.c_void_p), ("device_dirty", C.c_bool), ("in_stroke", C.c_bool),
         ("normals_pinned", C.c_bool), ("verts_pinned", C.c_bool), ("grids_pinned", C.c_bool),
         ("nb_offsets", c_int_p), ("nb_indices", c_int_p), ("boundary", c_ubyte_p),
-        ("dist_world", C.c_int), ("gather_whole", C.c_bool),
+        ("dist_world", C.c_int), ("gather_whole", C.c_bool), ("synced_flag", C.c_void_p), ("host_vert_marks", C.c_bool),
     ]
 
 
@@ -96,7 +96,7 @@ class SculptSearchSphereData(C.Structure):
 # every symbol include/dune_sculpt_cuda.h declares (checked by tests/test_abi.py)
 CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
-    "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_stroke_begin", "dsc_dab",
+    "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_node_flags_apply", "dsc_vert_marks_or", "dsc_stroke_begin", "dsc_dab",
     "dsc_dabs", "dsc_state_save", "dsc_state_restore", "dsc_grids_upload", "dsc_download_mask",
     "dsc_raycast_enable", "dsc_raycast", "dsc_draw_enable", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
@@ -261,6 +261,11 @@ def host_lib():
         L.BKE_pbvh_update_bounds.restype = None
         L.BKE_pbvh_node_mark_update.argtypes = [C.POINTER(PBVHNode)]
         L.BKE_pbvh_node_mark_update.restype = None
+        L.BKE_pbvh_vert_mark_update.argtypes = [C.POINTER(PBVH), C.c_int]
+        L.BKE_pbvh_vert_mark_update.restype = None
+        for fn in ("BKE_pbvh_node_fully_hidden_set", "BKE_pbvh_node_fully_masked_set"):
+            getattr(L, fn).argtypes = [C.POINTER(PBVHNode), C.c_int]
+            getattr(L, fn).restype = None
         L.BKE_pbvh_vert_coords_alloc.argtypes = [C.POINTER(PBVH)]
         L.BKE_pbvh_vert_coords_alloc.restype = c_float_p
         L.BKE_pbvh_vert_coords_apply.argtypes = [C.POINTER(PBVH), c_float_p, C.c_int]
@@ -662,6 +667,31 @@ class SculptSession:
 
     def set_node_flag(self, node, flag, on=True):
         self._chk(self.D.dsc_node_flag_set(self.ctx, int(node), int(flag), int(on)))
+
+    # the reference's own node setters on the host PBVH: the change reaches the device with the next device call
+    def node_ptr(self, node):
+        return C.pointer(self.pbvh.contents.nodes[int(node)])
+
+    def bke_node_mark_update(self, node):
+        self.H.BKE_pbvh_node_mark_update(self.node_ptr(node))
+
+    def bke_vert_mark_update(self, vert):
+        self.H.BKE_pbvh_vert_mark_update(self.pbvh, int(vert))
+
+    def bke_node_fully_hidden_set(self, node, on=True):
+        self.H.BKE_pbvh_node_fully_hidden_set(self.node_ptr(node), int(on))
+
+    def bke_node_fully_masked_set(self, node, on=True):
+        self.H.BKE_pbvh_node_fully_masked_set(self.node_ptr(node), int(on))
+
+    def bke_update_normals(self):
+        self.H.BKE_pbvh_update_normals(self.pbvh, None)
+
+    def bke_update_bounds(self, flag):
+        self.H.BKE_pbvh_update_bounds(self.pbvh, int(flag))
+
+    def sync_to_host(self):
+        self._chk(self.H.DUNE_pbvh_device_sync_to_host(self.pbvh))
 
     def set_custom_curve(self, table):
         t = np.ascontiguousarray(table, dtype=np.float32)

@@ -2579,6 +2579,74 @@ int dsc_node_flag_set(DscContext *ctx, int node, int flag, int on)
   return DSC_OK;
 }
 
+__global__ void k_node_flags_apply(int *node_flag, const int *ops, int count)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int n = ops[3 * i];
+  node_flag[n] = (node_flag[n] | ops[3 * i + 1]) & ~ops[3 * i + 2];
+}
+__global__ void k_vert_marks_or(unsigned *dirty, const unsigned *bitmap, const int *slot_of, int totvert)
+{
+  const int nwords = (totvert + 31) >> 5;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+    unsigned bits = bitmap[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int v = (w << 5) + b;
+      if (v < totvert) {
+        const int s = slot_of[v];
+        atomicOr(&dirty[s >> 5], 1u << (s & 31));
+      }
+    }
+  }
+}
+
+int dsc_node_flags_apply(DscContext *ctx, int count, const int *nodes, const int *set_bits, const int *clear_bits)
+{
+  NEED_PBVH();
+  if (count <= 0) return DSC_OK;
+  if (!nodes || (!set_bits && !clear_bits)) return fail(ctx, DSC_ERR_INVALID, "node list is NULL");
+  std::vector<int> ops((size_t)3 * count);
+  int any_set = 0;
+  for (int i = 0; i < count; i++) {
+    if (nodes[i] < 0 || nodes[i] >= ctx->totnode) return fail(ctx, DSC_ERR_INVALID, "node %d out of range", nodes[i]);
+    ops[(size_t)3 * i] = ctx->dev_of_node[nodes[i]];
+    ops[(size_t)3 * i + 1] = set_bits ? set_bits[i] : 0;
+    ops[(size_t)3 * i + 2] = clear_bits ? clear_bits[i] : 0;
+    any_set |= ops[(size_t)3 * i + 1];
+  }
+  int r = join_side(ctx);
+  if (r) return r;
+  int *d_ops = nullptr;
+  CU(cudaMallocAsync((void **)&d_ops, sizeof(int) * ops.size(), ctx->stream));
+  /* pageable source: the copy is staged before the call returns, so `ops` may go out of scope */
+  CU(cudaMemcpyAsync(d_ops, ops.data(), sizeof(int) * ops.size(), cudaMemcpyHostToDevice, ctx->stream));
+  k_node_flags_apply<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->m.node_flag, d_ops, count);
+  LAUNCH_CHECK();
+  CU(cudaFreeAsync(d_ops, ctx->stream));
+  ctx->launches++;
+  /* leaves now carry flags no dab of the running stroke set: the per-dab stages walk the flags, not only their own hit list */
+  if (any_set & (F_UpdateNormals | F_UpdateBB)) ctx->stale_flags = true;
+  return DSC_OK;
+}
+
+int dsc_vert_marks_or(DscContext *ctx, const unsigned int *bitmap)
+{
+  NEED_PBVH();
+  if (!bitmap) return fail(ctx, DSC_ERR_INVALID, "bitmap is NULL");
+  const size_t nwords = ((size_t)ctx->totvert + 31) >> 5;
+  unsigned *d_bits = nullptr;
+  CU(cudaMallocAsync((void **)&d_bits, sizeof(unsigned) * nwords, ctx->stream));
+  CU(cudaMemcpyAsync(d_bits, bitmap, sizeof(unsigned) * nwords, cudaMemcpyHostToDevice, ctx->stream));
+  k_vert_marks_or<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->m.dirty, d_bits, ctx->d_slot_of, ctx->totvert);
+  LAUNCH_CHECK();
+  CU(cudaFreeAsync(d_bits, ctx->stream));
+  ctx->launches++;
+  return DSC_OK;
+}
+
 int dsc_node_mark_update(DscContext *ctx, int node)
 {
   return dsc_node_flag_set(ctx, node,

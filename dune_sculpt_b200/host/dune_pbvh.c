@@ -1013,12 +1013,16 @@ int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, i
 }
 
 /* device -> CCGElem storage (co, no, mask) and node boxes / flags */
+static int push_host_marks(PBVH *pbvh);
+static void flags_synced(PBVH *pbvh);
+
 static int sync_grids_to_host(PBVH *pbvh)
 {
   const CCGKey *key = &pbvh->gridkey;
   const int area = key->grid_area, G = pbvh->totgrid, N = pbvh->totnode;
   const size_t E = (size_t)G * (size_t)area;
   int r;
+  if ((r = push_host_marks(pbvh)) != DSC_OK) return r; /* so the flags that come back carry them */
   /* the grids of a SubdivCCG are one block (grids_storage, subdiv_ccg.c:116-122): whole CCGElem records are packed on
    * the device and land in it by DMA; grids allocated one by one take the layer-by-layer path */
   bool contiguous = G > 0 && key->elem_size % (int)sizeof(float) == 0;
@@ -1067,6 +1071,7 @@ static int sync_grids_to_host(PBVH *pbvh)
       memcpy(&pbvh->nodes[n].orig_vb, obb + 6 * (size_t)n, sizeof(float[6]));
       pbvh->nodes[n].flag = (unsigned)flag[n];
     }
+    flags_synced(pbvh);
     pbvh->device_dirty = false;
   }
   free(bb); free(obb); free(flag);
@@ -1128,6 +1133,7 @@ void BKE_pbvh_free(PBVH *pbvh)
   free(pbvh->nodes);
   free(pbvh->prim_indices);
   free(pbvh->vert_bitmap);
+  free(pbvh->synced_flag);
   free(pbvh->nb_offsets);
   free(pbvh->nb_indices);
   free(pbvh->boundary);
@@ -1380,6 +1386,8 @@ bool DUNE_pbvh_raycast_nearest(PBVH *pbvh, const float ray_start[3], const float
 int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask)
 {
   if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
+  const int pr = push_host_marks(pbvh);
+  if (pr != DSC_OK) return pr;
   return dsc_draw_update(pbvh->device, smooth ? 1 : 0, show_mask ? 1 : 0);
 }
 
@@ -1409,6 +1417,10 @@ int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
   if (!pbvh->device_dirty) return DSC_OK;
   if (pbvh->is_grids) return sync_grids_to_host(pbvh);
   const int V = pbvh->totvert, N = pbvh->totnode;
+  {
+    const int pr = push_host_marks(pbvh); /* so the flags that come back carry them */
+    if (pr != DSC_OK) return pr;
+  }
   if (!pbvh->deformed) {
     /* first write: take a private copy like BKE_pbvh_vert_coords_apply (pbvh.c:4714-4725) */
     MVert *dup = malloc(sizeof(MVert) * (size_t)V);
@@ -1438,6 +1450,7 @@ int DUNE_pbvh_device_sync_to_host(PBVH *pbvh)
       memcpy(&pbvh->nodes[n].orig_vb, obb + 6 * (size_t)n, sizeof(float[6]));
       pbvh->nodes[n].flag = (unsigned)flag[n];
     }
+    flags_synced(pbvh);
     pbvh->device_dirty = false;
   }
   free(bb); free(obb); free(flag);
@@ -1537,7 +1550,11 @@ void BKE_pbvh_node_mark_update(PBVHNode *node)
 {
   node->flag |= PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw;
 }
-void BKE_pbvh_vert_mark_update(PBVH *pbvh, int index) { pbvh->vert_bitmap[index >> 5] |= 1u << (index & 31); }
+void BKE_pbvh_vert_mark_update(PBVH *pbvh, int index)
+{
+  pbvh->vert_bitmap[index >> 5] |= 1u << (index & 31);
+  pbvh->host_vert_marks = true;
+}
 void BKE_pbvh_node_fully_hidden_set(PBVHNode *node, int fully_hidden)
 {
   if (fully_hidden) node->flag |= PBVH_FullyHidden;
@@ -1574,23 +1591,59 @@ void BKE_pbvh_node_get_original_BB(PBVHNode *node, float bb_min[3], float bb_max
 
 /* -------------------------------------------------------------------------------- updates */
 
-/* Host-side marks made since the last device call are pushed down first, then the device runs the
- * stage, then the host copies are refreshed lazily (device_dirty). */
-static void push_host_marks(PBVH *pbvh)
+/* Host-side marks made since the last push go down first, in one batch and whether or not the device already holds newer
+ * state: node flags changed through the BKE_pbvh_node_* setters (update / redraw / draw-buffer marks, FullyHidden,
+ * FullyMasked) as set / clear masks against the flags the device last saw, and the BKE_pbvh_vert_mark_update bitmap. */
+static void flags_synced(PBVH *pbvh)
 {
-  for (int n = 0; n < pbvh->totnode; n++) {
-    PBVHNode *node = &pbvh->nodes[n];
-    if ((node->flag & PBVH_Leaf) && (node->flag & (PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB))) {
-      dsc_node_flag_set(pbvh->device, n, (int)(node->flag & (PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB)), 1);
+  if (!pbvh->synced_flag) pbvh->synced_flag = malloc(sizeof(unsigned) * (size_t)pbvh->totnode);
+  for (int n = 0; n < pbvh->totnode; n++) pbvh->synced_flag[n] = pbvh->nodes[n].flag;
+}
+static int push_host_marks(PBVH *pbvh)
+{
+  if (!pbvh->device) return DSC_OK;
+  int r = DSC_OK;
+  if (!pbvh->synced_flag) {
+    flags_synced(pbvh); /* the device got the flags at attach */
+  }
+  else {
+    const unsigned forwarded = PBVH_UpdateNormals | PBVH_UpdateBB | PBVH_UpdateOriginalBB | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw |
+                               PBVH_RebuildDrawBuffers | PBVH_FullyHidden | PBVH_FullyMasked | PBVH_UpdateMask | PBVH_UpdateVisibility;
+    int count = 0, cap = 0;
+    int *nodes = NULL, *set = NULL, *clear = NULL;
+    for (int n = 0; n < pbvh->totnode; n++) {
+      const unsigned now = pbvh->nodes[n].flag, was = pbvh->synced_flag[n];
+      if (now == was) continue;
+      const unsigned s_ = now & ~was & forwarded, c_ = was & ~now & forwarded;
+      pbvh->synced_flag[n] = now;
+      if (!(s_ | c_)) continue;
+      if (count == cap) {
+        cap = cap ? 2 * cap : 64;
+        nodes = realloc(nodes, sizeof(int) * (size_t)cap);
+        set = realloc(set, sizeof(int) * (size_t)cap);
+        clear = realloc(clear, sizeof(int) * (size_t)cap);
+      }
+      nodes[count] = n; set[count] = (int)s_; clear[count] = (int)c_;
+      count++;
+    }
+    if (count) r = dsc_node_flags_apply(pbvh->device, count, nodes, set, clear);
+    free(nodes); free(set); free(clear);
+  }
+  if (r == DSC_OK && pbvh->host_vert_marks && !pbvh->is_grids) {
+    r = dsc_vert_marks_or(pbvh->device, pbvh->vert_bitmap);
+    if (r == DSC_OK) {
+      memset(pbvh->vert_bitmap, 0, sizeof(unsigned) * ((size_t)pbvh->totvert / 32 + 1)); /* the device's bitmap owns them now */
+      pbvh->host_vert_marks = false;
     }
   }
+  return r;
 }
 
 void BKE_pbvh_update_normals(PBVH *pbvh, struct SubdivCCG *subdiv_ccg)
 {
   (void)subdiv_ccg;
   if (!pbvh->device) return; /* no CPU fallback: without a device the PBVH is a plain container */
-  if (!pbvh->device_dirty) push_host_marks(pbvh);
+  push_host_marks(pbvh);
   dsc_update_normals(pbvh->device);
   pbvh->device_dirty = true;
 }
@@ -1598,7 +1651,7 @@ void BKE_pbvh_update_normals(PBVH *pbvh, struct SubdivCCG *subdiv_ccg)
 void BKE_pbvh_update_bounds(PBVH *pbvh, int flag)
 {
   if (!pbvh->nodes || !pbvh->device) return;
-  if (!pbvh->device_dirty) push_host_marks(pbvh);
+  push_host_marks(pbvh);
   dsc_update_bounds(pbvh->device, flag);
   pbvh->device_dirty = true;
 }
@@ -1711,13 +1764,17 @@ int DUNE_sculpt_dab_symmetry(const DscDab *dab, int symm, DscDab r_dabs[8])
 int DUNE_sculpt_stroke_begin(PBVH *pbvh, const float *automask)
 {
   if (!pbvh->device) return DSC_ERR_STATE;
-  int r = dsc_stroke_begin(pbvh->device, automask);
+  int r = push_host_marks(pbvh);
+  if (r != DSC_OK) return r;
+  r = dsc_stroke_begin(pbvh->device, automask);
   if (r == DSC_OK) pbvh->in_stroke = true;
   return r;
 }
 int DUNE_sculpt_dab(PBVH *pbvh, const DscDab *dab)
 {
   if (!pbvh->device) return DSC_ERR_STATE;
+  const int pr = push_host_marks(pbvh);
+  if (pr != DSC_OK) return pr;
   pbvh->device_dirty = true;
   return dsc_dab(pbvh->device, dab);
 }

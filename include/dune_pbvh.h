@@ -206,6 +206,10 @@ typedef struct PBVH {
    * the host arrays that other ranks own stay as they were until DUNE_pbvh_device_gather makes the replica whole */
   int dist_world;
   bool gather_whole; /* inside DUNE_pbvh_device_gather */
+  /* PBVHNode.flag as the device last saw it: what the BKE_pbvh_node_* setters changed since is pushed down in one batch before
+   * the next device call (they take a node, not the PBVH, so the change is found by comparing) */
+  unsigned int *synced_flag;
+  bool host_vert_marks; /* BKE_pbvh_vert_mark_update was called since the last push */
 } PBVH;
 
 typedef bool (*BKE_pbvh_SearchCallback)(PBVHNode *node, void *data);

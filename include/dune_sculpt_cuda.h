@@ -216,6 +216,14 @@ int dsc_set_custom_curve(DscContext *ctx, const float *table257); /* colortools.
 int dsc_set_mask(DscContext *ctx, const float *mask /* [totvert] or NULL */);
 /* PBVHNode.flag bits a host pass owns (FullyHidden / FullyMasked, pbvh.c:3678-3710) */
 int dsc_node_flag_set(DscContext *ctx, int node, int flag, int on);
+/* the host-side marks made since the last push, in one batch and in stream order (no host synchronisation): for each of the
+ * `count` listed nodes, set_bits are OR-ed into PBVHNode.flag and clear_bits removed.  What BKE_pbvh_node_mark_update,
+ * BKE_pbvh_node_mark_redraw, BKE_pbvh_node_fully_hidden_set / _masked_set (pbvh.c:3620-3710) change on a host PBVH whose
+ * truth lives on the device. */
+int dsc_node_flags_apply(DscContext *ctx, int count, const int *nodes, const int *set_bits, const int *clear_bits);
+/* BKE_pbvh_vert_mark_update (pbvh.c:3609-3613) marks made on the host: bitmap[totvert / 32 + 1], bit per vertex, OR-ed into the
+ * device's vertex bitmap (the verts whose normals the next normals update recomputes) */
+int dsc_vert_marks_or(DscContext *ctx, const unsigned int *bitmap);
 
 /* --- stroke: behind the stroke operator's per-dab sequence --------------- */
 int dsc_stroke_begin(DscContext *ctx, const float *automask /* [totvert] or NULL */);

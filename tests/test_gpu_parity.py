@@ -660,3 +660,59 @@ def test_symmetry_passes_through_the_dab_helper():
     moved = np.abs(res["co"] - m.co).max(axis=1) > 0
     assert (moved & (m.co[:, 0] > 0.2) & (m.co[:, 2] > 0.2)).any() and (moved & (m.co[:, 0] < -0.2) & (m.co[:, 2] > 0.2)).any()
     assert (moved & (m.co[:, 0] > 0.2) & (m.co[:, 2] < -0.2)).any() and (moved & (m.co[:, 0] < -0.2) & (m.co[:, 2] < -0.2)).any()
+
+
+def test_host_marks_made_while_the_device_is_ahead_reach_it():
+    """BKE_pbvh_node_fully_hidden_set / _mark_update / BKE_pbvh_vert_mark_update on the host PBVH between device calls, when the
+    device already holds newer state than the host: the marks are pushed with the next device call and survive the sync."""
+    from oracle_py import Oracle
+    m = meshgen.grid(97)
+    dabs = _line_dabs(capi.TOOL_DRAW, (-0.6, -0.3, 0.0), (0.6, 0.4, 0.0), 0.3, 8)
+    orc = Oracle(m, leaf_limit=200)
+    ses = capi.SculptSession(m, leaf_limit=200, device=0)
+    try:
+        leaves = np.nonzero(orc.node_arrays()["flag"] & 1)[0]
+        orc.stroke_begin(None)
+        ses.stroke_begin(None)
+        ses.capture(True)
+        for i, d in enumerate(dabs):
+            if i == 3:
+                assert ses.pbvh.contents.device_dirty
+                for k, n in enumerate(leaves[::3]):
+                    orc.set_node_flag(int(n), capi.PBVH_FullyMasked if k % 2 else capi.PBVH_FullyHidden, True)
+                    (ses.bke_node_fully_masked_set if k % 2 else ses.bke_node_fully_hidden_set)(int(n), True)
+            if i == 6:   # and taken back again
+                for k, n in enumerate(leaves[::6]):
+                    orc.set_node_flag(int(n), capi.PBVH_FullyHidden, False)
+                    ses.bke_node_fully_hidden_set(int(n), False)
+            orc.dab(d)
+            ses.dab(d)
+            assert np.array_equal(orc.hits(), ses.hits()), "dab %d: node-hit list" % i
+        orc.stroke_end()
+        ses.stroke_end()
+        assert np.array_equal(orc.co(), ses.co()) and np.array_equal(orc.no(), ses.no())
+        keep = capi.PBVH_FullyHidden | capi.PBVH_FullyMasked
+        assert np.array_equal(orc.node_arrays()["flag"] & keep, ses.node_arrays()["flag"] & keep)
+        # the advisor's case: a device call leaves the device ahead, then the host marks nodes and verts
+        ses.bke_update_bounds(capi.PBVH_UpdateBB)
+        assert ses.pbvh.contents.device_dirty
+        marked = [int(n) for n in leaves[1::5]]
+        for n in marked:
+            ses.bke_node_mark_update(n)
+            for v in ses.node_vert_indices(n)[:4]:
+                ses.bke_vert_mark_update(int(v))
+        ses.bke_update_normals()
+        ses.sync_to_host()
+        fl = ses.node_arrays()["flag"]
+        stay = capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB | capi.PBVH_UpdateDrawBuffers | capi.PBVH_UpdateRedraw
+        assert all((fl[n] & stay) == stay for n in marked), "marks made on the host were lost in the sync"
+        assert all(not (fl[n] & capi.PBVH_UpdateNormals) for n in marked), "the normals update did not see the marked nodes"
+        assert np.array_equal(ses.node_flags(), fl)
+        ses.bke_update_bounds(capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB)
+        ses.sync_to_host()
+        fl = ses.node_arrays()["flag"]
+        assert all(not (fl[n] & (capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB)) for n in marked)
+        assert np.array_equal(orc.no(), ses.no()), "recomputing the marked verts' normals from unchanged positions changed them"
+    finally:
+        ses.close()
+        orc.close()
