@@ -98,7 +98,7 @@ CUDA_SYMBOLS = [
     "dsc_ctx_create", "dsc_ctx_destroy", "dsc_last_error", "dsc_abi_version", "dsc_mesh_upload", "dsc_pbvh_upload",
     "dsc_recalc_normals", "dsc_set_custom_curve", "dsc_set_mask", "dsc_node_flag_set", "dsc_node_flags_apply", "dsc_vert_marks_or", "dsc_stroke_begin", "dsc_dab",
     "dsc_dabs", "dsc_state_save", "dsc_state_restore", "dsc_grids_upload", "dsc_download_mask",
-    "dsc_raycast_enable", "dsc_raycast", "dsc_draw_enable", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
+    "dsc_raycast_enable", "dsc_raycast", "dsc_draw_enable", "dsc_draw_leaf_shading", "dsc_draw_update", "dsc_draw_node_buffer", "dsc_draw_download",
     "dsc_gather_readback", "dsc_search_sphere", "dsc_last_area", "dsc_debug_capture", "dsc_last_moved",
     "dsc_stroke_stats", "dsc_stroke_end", "dsc_update_normals", "dsc_update_bounds", "dsc_node_mark_update",
     "dsc_download_co", "dsc_download_mvert", "dsc_download_ccg", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_download_node_bb",
@@ -241,7 +241,7 @@ def host_lib():
         L.DUNE_pbvh_device_attach_grids_dist.argtypes = [C.POINTER(PBVH), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.DUNE_pbvh_draw_buffers_enable.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_draw_buffers_enable.restype = None
-        L.DUNE_pbvh_update_draw_buffers.argtypes = [C.POINTER(PBVH), C.c_bool, C.c_bool]
+        L.DUNE_pbvh_update_draw_buffers.argtypes = [C.POINTER(PBVH), C.c_int, C.c_bool]
         L.DUNE_pbvh_raycast_enable.argtypes = [C.POINTER(PBVH)]
         L.DUNE_pbvh_raycast_enable.restype = None
         L.DUNE_pbvh_raycast_nearest.argtypes = [C.POINTER(PBVH), c_float_p, c_float_p, C.c_bool, C.c_float, c_float_p, c_int_p, c_int_p,
@@ -570,7 +570,7 @@ class SculptSession:
 
     def update_draw_buffers(self, smooth=True, show_mask=True):
         """pack the vertex buffers of the leaves flagged for a draw update, on the device"""
-        self._chk(self.H.DUNE_pbvh_update_draw_buffers(self.pbvh, bool(smooth), bool(show_mask)))
+        self._chk(self.H.DUNE_pbvh_update_draw_buffers(self.pbvh, int(smooth), bool(show_mask)))
 
     def draw_buffer(self, node):
         """the packed vertex buffer of a leaf, (verts, 36) bytes"""

@@ -83,7 +83,11 @@ struct DscContext {
   std::vector<int> vert_of_slot;
   const int4 *d_tri_slots = nullptr;
   unsigned *d_vbo = nullptr; /* [tottri * 3][9] packed vertex records, by looptri position; grids: [totgrid * draw_per_grid][9] */
-  int draw_per_grid = 0;
+  int draw_per_grid = 0; /* grids: records per grid of the uniform layout; -1 = the per-leaf layout (leaf_rec) */
+  std::vector<unsigned char> h_leaf_smooth; /* dsc_draw_leaf_shading: ME_SMOOTH per leaf */
+  std::vector<long long> h_leaf_rec;        /* grids, per-leaf layout: first record of each leaf (+ the total) */
+  unsigned char *d_leaf_smooth = nullptr;
+  long long *d_leaf_rec = nullptr;
   bool has_odd_edges = false; /* some coarse edge has more than two faces */
   bool grid_normals_flat = false; /* DSC_GRID_NORMALS_FLAT=1: the element-parallel normal pass (measured slower: 4 x the IEEE sqrt / div work) */
   bool grid_fused = false;    /* DSC_GRID_FUSED=1: the stages after the brush as one cooperative kernel instead of nine launches */
@@ -3995,10 +3999,32 @@ int dsc_draw_enable(DscContext *ctx)
   ctx->want_draw = true;
   return DSC_OK;
 }
+int dsc_draw_leaf_shading(DscContext *ctx, const unsigned char *node_smooth)
+{
+  NEED_PBVH();
+  if (!ctx->want_draw) return fail(ctx, DSC_ERR_STATE, "dsc_draw_enable first");
+  if (!node_smooth) return fail(ctx, DSC_ERR_INVALID, "node_smooth is NULL");
+  if (ctx->d_vbo) return fail(ctx, DSC_ERR_STATE, "the per-leaf shading comes before the first dsc_draw_update");
+  const int L = ctx->m.nleaf;
+  ctx->h_leaf_smooth.assign((size_t)std::max(L, 1), 0);
+  for (int l = 0; l < L; l++) ctx->h_leaf_smooth[l] = node_smooth[ctx->leaf_node[l]] ? 1 : 0;
+  int r;
+  if ((r = dev_upload(ctx, &ctx->d_leaf_smooth, ctx->h_leaf_smooth))) return r;
+  if (ctx->is_grids) {
+    const int gs = ctx->grid_size;
+    ctx->h_leaf_rec.assign((size_t)L + 1, 0);
+    for (int l = 0; l < L; l++)
+      ctx->h_leaf_rec[l + 1] = ctx->h_leaf_rec[l] + (long long)ctx->h_leaf_pcnt[l] * (ctx->h_leaf_smooth[l] ? gs * gs : (gs - 1) * (gs - 1) * 4);
+    if ((r = dev_upload(ctx, &ctx->d_leaf_rec, ctx->h_leaf_rec))) return r;
+  }
+  return DSC_OK;
+}
 int dsc_draw_update(DscContext *ctx, int smooth, int show_mask)
 {
   NEED_PBVH();
   if (!ctx->want_draw) return fail(ctx, DSC_ERR_STATE, "dsc_draw_enable first");
+  const bool per_leaf = smooth < 0;
+  if (per_leaf && ctx->h_leaf_smooth.empty()) return fail(ctx, DSC_ERR_STATE, "DSC_DRAW_SHADING_PER_LEAF needs dsc_draw_leaf_shading");
   int r = join_side(ctx);
   if (r) return r;
   const int flags = DSC_PBVH_UpdateDrawBuffers | DSC_PBVH_RebuildDrawBuffers;
@@ -4006,12 +4032,14 @@ int dsc_draw_update(DscContext *ctx, int smooth, int show_mask)
     /* gpu_pbvh_grid_buffers_update (gpu_buffers.c:548-725): gs^2 records per grid when smooth, 4 (gs - 1)^2 when flat; the
      * shading mode is a property of the mesh (grid_flag_mats) and fixes the layout at the first update */
     const int gs = ctx->grid_size;
-    const int per_grid = smooth ? gs * gs : (gs - 1) * (gs - 1) * 4;
+    const int per_grid = per_leaf ? -1 : (smooth ? gs * gs : (gs - 1) * (gs - 1) * 4);
     if (ctx->d_vbo && ctx->draw_per_grid != per_grid) return fail(ctx, DSC_ERR_STATE, "the shading mode of a grids context is fixed by its first dsc_draw_update");
-    if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, (size_t)std::max(ctx->totgrid, 1) * (size_t)per_grid * 9))) return r;
+    const size_t recs = per_leaf ? (size_t)ctx->h_leaf_rec.back() : (size_t)std::max(ctx->totgrid, 1) * (size_t)per_grid;
+    if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, std::max(recs, (size_t)1) * 9))) return r;
     ctx->draw_per_grid = per_grid;
     if ((r = run_collect(ctx, flags))) return r;
-    k_grid_draw_fill<<<ctx->num_sms * 4, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->g, ctx->m.flag_list, &ctx->m.tot->flag_count, smooth ? 1 : 0,
+    k_grid_draw_fill<<<ctx->num_sms * 4, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->g, ctx->m.flag_list, &ctx->m.tot->flag_count, smooth > 0 ? 1 : 0,
+                                                                       per_leaf ? ctx->d_leaf_smooth : nullptr, per_leaf ? ctx->d_leaf_rec : nullptr,
                                                                        (show_mask && ctx->g.mask) ? 1 : 0, ctx->d_vbo);
     LAUNCH_CHECK();
     ctx->launches++;
@@ -4020,7 +4048,8 @@ int dsc_draw_update(DscContext *ctx, int smooth, int show_mask)
   if (!ctx->d_vbo && (r = dev_zero(ctx, &ctx->d_vbo, (size_t)std::max(ctx->tottri, 1) * 3 * 9))) return r;
   if ((r = run_collect(ctx, flags))) return r;
   k_draw_fill<<<ctx->num_sms * 4, DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->d_tri_slots, ctx->m.flag_list, &ctx->m.tot->flag_count,
-                                                                smooth ? 1 : 0, (show_mask && ctx->m.mask) ? 1 : 0, ctx->d_vbo);
+                                                                smooth > 0 ? 1 : 0, per_leaf ? ctx->d_leaf_smooth : nullptr,
+                                                                (show_mask && ctx->m.mask) ? 1 : 0, ctx->d_vbo);
   LAUNCH_CHECK();
   ctx->launches++;
   return run_clear(ctx, flag_list(ctx), flags); /* pbvh.c:3276 */
@@ -4031,6 +4060,11 @@ int dsc_draw_node_buffer(DscContext *ctx, int node, void **r_device_ptr, int *r_
   if (!ctx->d_vbo) return fail(ctx, DSC_ERR_STATE, "dsc_draw_update first");
   if (node < 0 || node >= ctx->totnode || ctx->dev_of_node[node] >= ctx->m.nleaf) return fail(ctx, DSC_ERR_INVALID, "node %d is not a leaf", node);
   const int l = ctx->dev_of_node[node];
+  if (ctx->is_grids && ctx->draw_per_grid < 0) {
+    if (r_device_ptr) *r_device_ptr = ctx->d_vbo + (size_t)ctx->h_leaf_rec[l] * 9;
+    if (r_vert_len) *r_vert_len = (int)(ctx->h_leaf_rec[l + 1] - ctx->h_leaf_rec[l]);
+    return DSC_OK;
+  }
   const int per_prim = ctx->is_grids ? ctx->draw_per_grid : 3;
   if (r_device_ptr) *r_device_ptr = ctx->d_vbo + (size_t)ctx->h_leaf_pbeg[l] * per_prim * 9;
   if (r_vert_len) *r_vert_len = ctx->h_leaf_pcnt[l] * per_prim;

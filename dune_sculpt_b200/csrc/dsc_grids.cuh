@@ -423,20 +423,24 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_ghit_expand(DevMesh m, const unsi
  * four records per quad, corners (x, y), (x+1, y), (x+1, y+1), (x, y+1), the quad normal taken with the corners
  * reversed (gpu_buffers.c:664-666), the mean of the four masks, col = white.  A leaf's records start at
  * leaf_gbeg[leaf] * per_grid.  Byte-exact against the oracle on B200 (tests/test_gpu_grids.py). */
-__global__ void __launch_bounds__(DSC_BLOCK) k_grid_draw_fill(DevMesh m, DevGrids g, const int *list, const int *count, int smooth,
-                                                              int show_mask, unsigned *vbo)
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_draw_fill(DevMesh m, DevGrids g, const int *list, const int *count, int smooth_all,
+                                                              const unsigned char *leaf_smooth, const long long *leaf_rec, int show_mask,
+                                                              unsigned *vbo)
 {
   const int n = *count;
   const int gs = g.gs, gs1 = gs - 1, gs2 = g.gs2;
-  const int per_grid = smooth ? gs2 : gs1 * gs1 * 4;
   for (int h = blockIdx.x; h < n; h += gridDim.x) {
     const int l = list[h];
+    /* per leaf: ME_SMOOTH of the leaf's first grid (gpu_buffers.c:574); the leaf's records then start at leaf_rec[l] */
+    const int smooth = leaf_smooth ? (int)leaf_smooth[l] : smooth_all;
+    const int per_grid = smooth ? gs2 : gs1 * gs1 * 4;
     const int gb = g.leaf_gbeg[l], ge = g.leaf_gbeg[l + 1];
     const int units = smooth ? gs2 : gs1 * gs1;
+    const size_t base = leaf_rec ? (size_t)leaf_rec[l] : (size_t)gb * per_grid;
     for (int t = threadIdx.x; t < (ge - gb) * units; t += blockDim.x) {
       const int gi = t / units, u = t - gi * units;
       const int s0 = g.grid_slot0[g.leaf_grids[gb + gi]];
-      unsigned *rec = vbo + ((size_t)(gb + gi) * per_grid) * 9;
+      unsigned *rec = vbo + (base + (size_t)gi * per_grid) * 9;
       if (smooth) {
         const int s = s0 + u;
         rec += (size_t)u * 9;

@@ -2257,12 +2257,14 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_raycast(DevMesh m, const int4 *tr
  * and the mean mask of the looptri; smooth: the vertex normal and mask.  The buffer is indexed by looptri
  * position, so a leaf's VBO is one contiguous run. */
 __device__ __forceinline__ unsigned dsc_normal_short(float f) { return (unsigned)(unsigned short)(short)(int)(f * 32767.0f); }
-__global__ void __launch_bounds__(DSC_BLOCK) k_draw_fill(DevMesh m, const int4 *tri_slots, const int *list, const int *count, int smooth,
-                                                         int show_mask, unsigned *vbo)
+__global__ void __launch_bounds__(DSC_BLOCK) k_draw_fill(DevMesh m, const int4 *tri_slots, const int *list, const int *count, int smooth_all,
+                                                         const unsigned char *leaf_smooth, int show_mask, unsigned *vbo)
 {
   const int n = *count;
   for (int h = blockIdx.x; h < n; h += gridDim.x) {
     const int l = list[h];
+    /* per leaf: ME_SMOOTH of the poly of the leaf's first looptri (gpu_buffers.c:221-222) */
+    const int smooth = leaf_smooth ? (int)leaf_smooth[l] : smooth_all;
     const int pb = m.leaf_pbeg[l], pe = pb + m.leaf_pcnt[l];
     for (int pos = pb + threadIdx.x; pos < pe; pos += blockDim.x) {
       const int4 tv = tri_slots[pos];

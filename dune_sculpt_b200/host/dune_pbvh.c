@@ -815,6 +815,7 @@ void DUNE_subdiv_ccg_free(SubdivCCG *ccg)
 }
 
 /* the CCG's elements and adjacency as the flat tables of DscGridsDesc, the grids PBVH as DscPbvhDesc */
+static int push_leaf_shading(PBVH *pbvh, DscContext *ctx);
 int DUNE_pbvh_device_attach_grids(PBVH *pbvh, SubdivCCG *ccg, int device)
 {
   return DUNE_pbvh_device_attach_grids_dist(pbvh, ccg, device, 1, 0, NULL);
@@ -999,6 +1000,7 @@ int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, i
   pd.uniq_verts = uniq;
   pd.face_verts = face;
   if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
+  if (r == DSC_OK && (pbvh->want_draw_buffers & 1)) r = push_leaf_shading(pbvh, ctx);
   free(co); free(no); free(mask); free(face_start); free(face_num); free(edge_off); free(edge_elems); free(vert_off);
   free(vert_elems); free(bb); free(obb); free(child); free(flag); free(prim_off); free(totprim); free(uniq); free(face);
   if (r != DSC_OK) {
@@ -1013,6 +1015,24 @@ int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, i
 }
 
 /* device -> CCGElem storage (co, no, mask) and node boxes / flags */
+/* the shading of a leaf's draw buffer: ME_SMOOTH of the poly of its first looptri (gpu_buffers.c:221-222) or of its first grid
+ * (grid_flag_mats, gpu_buffers.c:574) */
+static int push_leaf_shading(PBVH *pbvh, DscContext *ctx)
+{
+  if (pbvh->is_grids ? !pbvh->grid_flag_mats : !pbvh->mpoly) return DSC_OK; /* no material flags: the caller names the shading */
+  unsigned char *sm = calloc((size_t)pbvh->totnode, 1);
+  for (int n = 0; n < pbvh->totnode; n++) {
+    const PBVHNode *node = &pbvh->nodes[n];
+    if (!(node->flag & PBVH_Leaf) || !node->totprim) continue;
+    const int prim = node->prim_indices[0];
+    sm[n] = pbvh->is_grids ? (pbvh->grid_flag_mats[prim].flag & ME_SMOOTH) != 0 :
+                             (pbvh->mpoly[pbvh->looptri[prim].poly].flag & ME_SMOOTH) != 0;
+  }
+  const int r = dsc_draw_leaf_shading(ctx, sm);
+  free(sm);
+  return r;
+}
+
 static int push_host_marks(PBVH *pbvh);
 static void flags_synced(PBVH *pbvh);
 
@@ -1334,6 +1354,7 @@ int DUNE_pbvh_device_attach_dist(PBVH *pbvh, int device, int world, int rank, co
   if (r == DSC_OK && (pbvh->want_draw_buffers & 1)) r = dsc_draw_enable(ctx);
   if (r == DSC_OK && (pbvh->want_draw_buffers & 2)) r = dsc_raycast_enable(ctx);
   if (r == DSC_OK) r = dsc_pbvh_upload(ctx, &pd);
+  if (r == DSC_OK && (pbvh->want_draw_buffers & 1)) r = push_leaf_shading(pbvh, ctx);
 
   free(tail); free(co); free(poly_start); free(poly_len); free(loop_v); free(tri_vert); free(tri_poly);
   free(bb); free(obb); free(child); free(flag); free(prim_off); free(totprim); free(uniq); free(face);
@@ -1383,12 +1404,12 @@ bool DUNE_pbvh_raycast_nearest(PBVH *pbvh, const float ray_start[3], const float
   return true;
 }
 
-int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask)
+int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, int shading, bool show_mask)
 {
   if (!pbvh || !pbvh->device) return DSC_ERR_STATE;
   const int pr = push_host_marks(pbvh);
   if (pr != DSC_OK) return pr;
-  return dsc_draw_update(pbvh->device, smooth ? 1 : 0, show_mask ? 1 : 0);
+  return dsc_draw_update(pbvh->device, shading, show_mask ? 1 : 0);
 }
 
 int DUNE_pbvh_node_draw_buffer(PBVH *pbvh, PBVHNode *node, void **r_device_ptr, int *r_vert_len)

@@ -288,7 +288,9 @@ void DUNE_pbvh_draw_buffers_enable(PBVH *pbvh);
 /* pbvh_update_draw_buffers (pbvh.c:3169-3285) on the device: pack the vertex buffers of the leaves flagged
  * PBVH_UpdateDrawBuffers / PBVH_RebuildDrawBuffers (gpu_buffers.c:174-305) and clear the flags; then the
  * device pointer and vertex count of a node's buffer for the GL copy */
-int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, bool smooth, bool show_mask);
+/* shading: DSC_DRAW_SHADING_PER_LEAF (-1) takes it per leaf from the material flags the PBVH was built with (ME_SMOOTH of the
+ * leaf's first poly / grid, what the reference does); 0 / 1 force flat / smooth on every leaf */
+int DUNE_pbvh_update_draw_buffers(PBVH *pbvh, int shading, bool show_mask);
 int DUNE_pbvh_node_draw_buffer(PBVH *pbvh, PBVHNode *node, void **r_device_ptr, int *r_vert_len);
 /* before the attach: keep the tables the device ray-cast needs (dsc_raycast_enable) */
 void DUNE_pbvh_raycast_enable(PBVH *pbvh);

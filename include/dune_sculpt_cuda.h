@@ -282,7 +282,7 @@ int dsc_upload_co(DscContext *ctx, const float *co /* [totvert][3] */); /* vert_
  *     on the pointer dsc_draw_node_buffer returns) instead of re-reading the node's triangles on the CPU.
  *     dsc_draw_enable comes between dsc_mesh_upload and dsc_pbvh_upload.  Grids (gpu_pbvh_grid_buffers_update,
  *     gpu_buffers.c:548-725): grid_size^2 records per grid when smooth, 4 (grid_size - 1)^2 when flat -- the shading
- *     mode of a grids context is fixed by its first dsc_draw_update.  Only flagged leaves are refilled, like the
+ *     mode (one for all leaves, or per leaf after dsc_draw_leaf_shading) of a grids context is fixed by its first dsc_draw_update.  Only flagged leaves are refilled, like the
  *     reference (an unflagged leaf keeps its last records even when a neighbour's stitch moved its rim). ---------- */
 int dsc_draw_enable(DscContext *ctx);
 
@@ -303,7 +303,12 @@ typedef struct DscRayHit {
 int dsc_raycast_enable(DscContext *ctx);
 int dsc_raycast(DscContext *ctx, const float ray_start[3], const float ray_normal[3], int original, float max_depth,
                 DscRayHit *r_hit);
-int dsc_draw_update(DscContext *ctx, int smooth /* ME_SMOOTH of the node's faces */, int show_mask);
+/* The reference picks the shading per leaf: ME_SMOOTH of the poly of the leaf's first looptri (gpu_buffers.c:221-222) or of the
+ * leaf's first grid (grid_flag_mats, gpu_buffers.c:574).  node_smooth[totnode] (leaves are read) hands those flags down, after
+ * dsc_pbvh_upload and before the first dsc_draw_update; on grids it also fixes the per-leaf record layout. */
+int dsc_draw_leaf_shading(DscContext *ctx, const unsigned char *node_smooth);
+enum { DSC_DRAW_SHADING_PER_LEAF = -1, DSC_DRAW_SHADING_FLAT = 0, DSC_DRAW_SHADING_SMOOTH = 1 };
+int dsc_draw_update(DscContext *ctx, int smooth /* DSC_DRAW_SHADING_*: every leaf flat / smooth, or per leaf */, int show_mask);
 int dsc_draw_node_buffer(DscContext *ctx, int node, void **r_device_ptr, int *r_vert_len);
 int dsc_draw_download(DscContext *ctx, int node, void *r_host, size_t capacity_bytes, int *r_vert_len);
 

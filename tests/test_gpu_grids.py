@@ -289,3 +289,32 @@ def test_grids_grab_normal_weight():
     for d in dabs:
         d.normal_weight = 0.6
     _grid_parity(mr, dabs, leaf_limit=4)
+
+
+def test_grids_draw_buffers_take_their_shading_per_leaf_from_grid_flag_mats():
+    """gpu_buffers.c:574: smooth or flat by ME_SMOOTH of the leaf's first grid; flat leaves hold 4 (gs - 1)^2 records per grid,
+    smooth ones gs^2, so the leaves' runs in the buffer have different lengths"""
+    mr = meshgen.multires_cube(2, 3, with_mask=True)
+    grid_flag = np.zeros(mr.totgrid, np.uint8)
+    grid_flag[mr.totgrid // 3:] = 1
+    grid_mat = np.zeros(mr.totgrid, np.int16)
+    orc = GridOracle(mr, leaf_limit=4, grid_mat=grid_mat, grid_flag=grid_flag)
+    ses = capi.GridSession(mr, leaf_limit=4, device=0, draw_buffers=True, grid_mat=grid_mat, grid_flag=grid_flag)
+    try:
+        na = orc.node_arrays()
+        prim = orc.prim_indices()
+        leaves = [int(n) for n in np.nonzero(na["flag"] & 1)[0]]
+        smooth_of = {n: bool(grid_flag[prim[na["prim_offset"][n]]] & 1) for n in leaves}
+        assert any(smooth_of.values()) and not all(smooth_of.values())
+        ses.update_draw_buffers(smooth=-1, show_mask=True)
+        lens = set()
+        for n in leaves:
+            ref = orc.draw_buffer(n, int(na["totprim"][n]), smooth=smooth_of[n])
+            got = ses.draw_buffer(n)
+            assert got.shape == ref.shape and np.array_equal(got, ref), n
+            lens.add(got.shape[0] // int(na["totprim"][n]))
+        gs = mr.grid_size
+        assert lens == {gs * gs, 4 * (gs - 1) * (gs - 1)}
+    finally:
+        ses.close()
+        orc.close()

@@ -716,3 +716,29 @@ def test_host_marks_made_while_the_device_is_ahead_reach_it():
     finally:
         ses.close()
         orc.close()
+
+
+def test_draw_buffers_take_their_shading_per_leaf_from_the_material_flags():
+    """gpu_buffers.c:221-222: a leaf's buffer is smooth or flat by ME_SMOOTH of the poly of its first looptri; the build splits
+    leaves by material / smooth flag (pbvh.c:411-466), so both kinds exist side by side"""
+    from oracle_py import Oracle
+    m = meshgen.grid(97)
+    cx = m.co[m.loop_v.reshape(-1, 4), 0].mean(axis=1)
+    poly_flag = (cx > 0.1).astype(np.uint8)          # ME_SMOOTH on one side
+    poly_mat = np.zeros(m.totpoly, np.int16)
+    mask = meshgen.low_freq_mask(m)
+    orc = Oracle(m, mask=mask, leaf_limit=200, poly_mat=poly_mat, poly_flag=poly_flag)
+    ses = capi.SculptSession(m, mask=mask, leaf_limit=200, device=0, draw_buffers=True, poly_mat=poly_mat, poly_flag=poly_flag)
+    try:
+        na = orc.node_arrays()
+        prim, tri_poly = orc.prim_indices(), orc.tri_poly()
+        leaves = [int(n) for n in np.nonzero(na["flag"] & 1)[0]]
+        smooth_of = {n: bool(poly_flag[tri_poly[prim[na["prim_offset"][n]]]] & 1) for n in leaves}
+        assert any(smooth_of.values()) and not all(smooth_of.values())
+        ses.update_draw_buffers(smooth=-1, show_mask=True)
+        for n in leaves:
+            ref = orc.draw_buffer(n, int(na["totprim"][n]), smooth=smooth_of[n], show_mask=True)
+            assert np.array_equal(ses.draw_buffer(n), ref), "leaf %d (%s)" % (n, "smooth" if smooth_of[n] else "flat")
+    finally:
+        ses.close()
+        orc.close()
