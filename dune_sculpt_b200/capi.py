@@ -314,7 +314,7 @@ class DscGridsDesc(C.Structure):
                 ("totface", C.c_int), ("face_start_grid", c_int_p), ("face_num_grids", c_int_p), ("totedge", C.c_int),
                 ("edge_offsets", c_int_p), ("edge_elems", c_int_p), ("totcvert", C.c_int), ("cvert_offsets", c_int_p),
                 ("cvert_elems", c_int_p), ("grid_edge", c_int_p), ("grid_cvert", c_int_p), ("rim_width", C.c_int),
-                ("rim_neighbors", c_int_p), ("rim_boundary", c_ubyte_p)]
+                ("rim_neighbors", c_int_p), ("rim_boundary", c_ubyte_p), ("hidden", c_ubyte_p)]
 
 
 class DscPbvhDesc(C.Structure):
