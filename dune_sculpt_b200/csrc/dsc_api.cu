@@ -2485,6 +2485,8 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j, bool exch)
     return DSC_OK;
   }
   const bool dist = ctx->world > 1;
+  /* how many leaves the dab gathered (on all ranks): none -> the reference's caller returns before the stitch */
+  const int *nhits = dist ? ctx->d_gcount : hits.count;
   if (dist) {
     /* the faces of the leaves ALL ranks gathered (the all-reduced bitmask), restricted to what this rank averages */
     CU(cudaMemsetAsync(ctx->d_gcount, 0, sizeof(int), st));
@@ -2500,7 +2502,7 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j, bool exch)
    * more faces run) and all coarse vertices */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
   LAUNCH_CHECK();
-  k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, ctx->has_odd_edges ? 1 : 0, 1, seq, ctx->num_sms * 4);
+  k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, ctx->has_odd_edges ? 1 : 0, 1, seq, ctx->num_sms * 4, nhits);
   LAUNCH_CHECK();
   /* BKE_pbvh_update_normals, PBVH_GRIDS branch (pbvh.c:4575-4583 -> subdiv_ccg.c:847-866) */
   if (ctx->grid_normals_flat) k_grid_normals_flat<<<ctx->num_sms * 8, 256, 0, st>>>(m, g, 0);
@@ -2509,7 +2511,7 @@ static int grids_after_brush(DscContext *ctx, LeafList hits, int j, bool exch)
   if (exch && (r = dist_halo_exchange(ctx, j, true))) return r; /* the new normals of the other ranks' halo elements */
   k_grid_inner<<<ctx->num_sms * 4, 128, 0, st>>>(m, g);
   LAUNCH_CHECK();
-  k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, 0, 0, seq, ctx->num_sms * 4);
+  k_grid_edges_cverts<<<ctx->num_sms * 5, 128, 0, st>>>(m, g, 0, 0, seq, ctx->num_sms * 4, nhits);
   LAUNCH_CHECK();
   /* BKE_pbvh_update_bounds: leaf boxes (the refit follows on the side stream) */
   k_grid_leaf_bb<<<ctx->num_sms * 4, DSC_BLOCK, 0, st>>>(m, hits.list, hits.count);
@@ -3087,6 +3089,8 @@ static unsigned dist_dab_mask(DscContext *ctx, const DscDab *d)
   if (W < 2) return 0u;
   const unsigned all = (1u << W) - 1u;
   if (!ctx->subset_exchange || ctx->regions.empty()) return all;
+  /* the tube reaches along the whole view line; a grab's drag blended towards the sculpt normal has no bound known up front */
+  if (d->falloff_shape != DSC_FALLOFF_SPHERE || (d->tool == DSC_TOOL_GRAB && d->normal_weight > 0.0f)) return all;
   const float R = d->radius * std::max(d->radius_scale, 1.0f);
   float smax = 0.0f, dl = 0.0f;
   for (int k = 0; k < 3; k++) {
@@ -3176,7 +3180,9 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     if (!mine(i)) {
       /* out of this dab's reach: nothing of this rank can change, nothing it reads can change */
       if ((r = make_entry(ctx, dabs + i, &e, &sig, mask_of(i)))) return r; /* the argument checks still apply */
-      ctx->pending_skipped++;
+      /* a dab no rank's region can reach gathers nothing anywhere: the reference then skips the stitch altogether
+       * (its caller returns on totnode == 0), so there is no all-coarse-vertex pass to replay */
+      if (mask_of(i)) ctx->pending_skipped++;
       ctx->last_dab_skipped = true;
       ctx->dist_skipped_dabs++;
       i++;

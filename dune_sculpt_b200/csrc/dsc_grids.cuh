@@ -518,8 +518,12 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_grid_skipped(DevMesh m, DevGrids 
 /* coarse edges and coarse vertices in one launch: no element is in both a coarse-edge group and a corner group (the
  * edge pass leaves out the two end points of an edge, subdiv_ccg.c:1035), so the two passes -- and the pass over
  * untouched edges with more than two faces -- are independent.  The first `edge_ctas` CTAs take the edges. */
-__global__ void __launch_bounds__(128) k_grid_edges_cverts(DevMesh m, DevGrids g, int odd_too, int all_cverts, int j, int edge_ctas)
+__global__ void __launch_bounds__(128) k_grid_edges_cverts(DevMesh m, DevGrids g, int odd_too, int all_cverts, int j, int edge_ctas,
+                                                           const int *nhits)
 {
+  /* a dab that gathered no leaf does not stitch at all (the stroke step returns on totnode == 0 before multires_stitch_grids):
+   * the passes over ALL odd edges / coarse vertices only run when something was hit -- the listed ones are empty then anyway */
+  if ((odd_too || all_cverts) && __ldcg(nhits) == 0) return;
   if ((int)blockIdx.x < edge_ctas) {
     const int seq = dsc_grid_seq(m, j);
     dsc_grid_edges_body(m, g, 0, seq, blockIdx.x, edge_ctas);
@@ -554,8 +558,10 @@ __global__ void __launch_bounds__(GN_BLOCK, 1) k_grid_dab(DevMesh m, DevGrids g,
   dsc_grid_inner_body(m, g, cta, ncta);
   dsc_grid_sync(m.grid_bar, target, ncta);
   dsc_grid_edges_body(m, g, 0, seq, cta, ncta);
-  if (g.has_odd_edges) dsc_grid_edges_body(m, g, 1, seq, cta, ncta);
-  dsc_grid_cverts_body(m, g, 1, cta, ncta); /* coarse vertices are not on any edge's list: same phase */
+  if (__ldcg(count) > 0) { /* nothing gathered: no stitch (the stroke step returns on totnode == 0) */
+    if (g.has_odd_edges) dsc_grid_edges_body(m, g, 1, seq, cta, ncta);
+    dsc_grid_cverts_body(m, g, 1, cta, ncta); /* coarse vertices are not on any edge's list: same phase */
+  }
   dsc_grid_sync(m.grid_bar, target, ncta);
   dsc_grid_normals_body(m, g, 0, gsm, cta, ncta);
   dsc_grid_sync(m.grid_bar, target, ncta);

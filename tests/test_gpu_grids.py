@@ -318,3 +318,17 @@ def test_grids_draw_buffers_take_their_shading_per_leaf_from_grid_flag_mats():
     finally:
         ses.close()
         orc.close()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_grids_dab_that_gathers_nothing_does_not_stitch(fused, monkeypatch):
+    """the stroke step returns before multires_stitch_grids when the gather is empty: no all-coarse-vertex averaging for that dab
+    (a mean of equal floats is not always that float, so running it anyway shows up in the bits)"""
+    if fused:
+        monkeypatch.setenv("DSC_GRID_FUSED", "1")
+    mr = meshgen.multires_cube(2, 4)
+    dabs = _sweep(mr, per=2, radii=(10.0, 25.0))
+    far = [capi.make_dab(capi.TOOL_DRAW, (9.0, 9.0, 9.0), 0.05, bstrength=0.3) for _ in range(3)]
+    dabs = [dabs[0], far[0], far[1], dabs[1], dabs[2], far[2], dabs[3]]
+    st = _grid_parity(mr, dabs, leaf_limit=6)
+    assert st["moved_verts"] > 0
