@@ -1,5 +1,7 @@
 """CUDA path vs CPU oracle on identical meshes and stroke scripts (the parity tests proper).
 Every test goes through the reference-named host API and the C ABI; nothing here touches torch."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -697,11 +699,16 @@ def test_host_marks_made_while_the_device_is_ahead_reach_it():
         ses.bke_update_bounds(capi.PBVH_UpdateBB)
         assert ses.pbvh.contents.device_dirty
         marked = [int(n) for n in leaves[1::5]]
+        orc.L.or_node_mark_update.argtypes = [C.c_void_p, C.c_int]
+        orc.L.or_vert_mark_update.argtypes = [C.c_void_p, C.c_int]
         for n in marked:
             ses.bke_node_mark_update(n)
+            orc.L.or_node_mark_update(orc.p, n)
             for v in ses.node_vert_indices(n)[:4]:
                 ses.bke_vert_mark_update(int(v))
+                orc.L.or_vert_mark_update(orc.p, int(v))
         ses.bke_update_normals()
+        orc.update_normals()
         ses.sync_to_host()
         fl = ses.node_arrays()["flag"]
         stay = capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB | capi.PBVH_UpdateDrawBuffers | capi.PBVH_UpdateRedraw
@@ -712,7 +719,8 @@ def test_host_marks_made_while_the_device_is_ahead_reach_it():
         ses.sync_to_host()
         fl = ses.node_arrays()["flag"]
         assert all(not (fl[n] & (capi.PBVH_UpdateBB | capi.PBVH_UpdateOriginalBB)) for n in marked)
-        assert np.array_equal(orc.no(), ses.no()), "recomputing the marked verts' normals from unchanged positions changed them"
+        # a marked vert gets the faces of the flagged leaves only (pbvh.c:3335-3375): whatever that gives, it is the same on both sides
+        assert np.array_equal(orc.no(), ses.no()), "normals of the verts marked on the host"
     finally:
         ses.close()
         orc.close()
