@@ -158,6 +158,12 @@ struct DscContext {
   cudaEvent_t ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
   std::unordered_map<unsigned, DabGraph> graphs;
   bool use_graphs = true, use_pdl = false, use_batch_kernel = false;
+  /* the inner nodes' boxes are refitted when somebody reads them (stroke end, a download), not after every dab: nothing on
+   * the device reads them (the gather and the ray-cast are flat over the leaves).  DSC_EAGER_REFIT=1: after every dab, on
+   * the side stream, as pbvh_flush_bb would */
+  bool lazy_refit = true, refit_pending = false;
+  float small_dab_frac = 0.0f, small_dab_radius = 0.0f; /* dabs up to this radius (fraction of the root box diagonal) take the persistent kernel */
+  int small_dab_grid = 1 << 30;                         /* ... on this many CTAs */
   int batch_grid[4] = {0, 0, 0, 0}; /* resident CTAs of k_dab_batch<tool> */
   int fused_grid[4] = {0, 0, 0, 0}; /* SMs x resident CTAs of k_dab_tile<tool> */
   bool use_fused = false;           /* DSC_FUSE=1: boundary brush + fused interior brush / normals / boxes kernel */
@@ -783,6 +789,9 @@ int dsc_ctx_create(int device, DscContext **r_ctx)
     /* measured slower than the graph replay (grid barriers cost more than the launch gaps they replace, and the
      * area / brush stages run at the tile kernel's lower occupancy): opt-in */
     ctx->use_batch_kernel = getenv("DSC_BATCH_KERNEL") != nullptr;
+    ctx->lazy_refit = getenv("DSC_EAGER_REFIT") == nullptr;
+    ctx->small_dab_frac = getenv("DSC_SMALL_DAB_FRAC") ? (float)atof(getenv("DSC_SMALL_DAB_FRAC")) : 1.0e9f;
+    if (getenv("DSC_BATCH_GRID")) ctx->small_dab_grid = std::max(1, atoi(getenv("DSC_BATCH_GRID")));
     ctx->use_pdl = getenv("DSC_PDL") != nullptr; /* measured: no gain on small dabs, a loss on large ones (early CTAs hold SM slots) */
   }
   for (int i = 0; ok && i < DSC_SLOTS; i++) ok = cudaEventCreateWithFlags(&ctx->ev_refit[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1076,6 +1085,15 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   std::sort(leaves.begin(), leaves.end(), [&](int a, int b) { return pb->prim_offset[a] < pb->prim_offset[b]; });
   const int L = (int)leaves.size();
   ctx->leaf_node = leaves;
+  {
+    /* the root box's diagonal scales the small-dab threshold */
+    double dd = 0.0;
+    for (int k = 0; k < 3; k++) {
+      const double e = (double)pb->node_bb[3 + k] - (double)pb->node_bb[k];
+      dd += e * e;
+    }
+    ctx->small_dab_radius = ctx->small_dab_frac >= 1.0e8f ? 3.0e38f : ctx->small_dab_frac * (float)sqrt(dd);
+  }
 
   /* slots: each leaf's unique verts are one 128-byte aligned run, cut into tiles of <= DSC_TILE
    * slots.  Inside a leaf the order is ours to choose (the host translates through slot_of), so the
@@ -2207,6 +2225,17 @@ static int run_flush_full(DscContext *ctx)
   LAUNCH_CHECK();
   return DSC_OK;
 }
+/* the deferred refit of the inner nodes: every inner box = the union of its children's, level by level -- the values
+ * pbvh_flush_bb (pbvh.c:3287-3317) leaves after each dab, because a box nobody refreshed already is that union */
+static int ensure_refit(DscContext *ctx)
+{
+  if (!ctx->refit_pending) return DSC_OK;
+  int r = join_side(ctx);
+  if (r) return r;
+  ctx->refit_pending = false;
+  ctx->launches++;
+  return run_flush_full(ctx);
+}
 /* flagged leaves -> normals / boxes -> whole-tree flush -> clear: every non-dab entry point */
 static int run_flagged(DscContext *ctx, int want)
 {
@@ -2693,10 +2722,11 @@ int dsc_stroke_begin(DscContext *ctx, const float *automask)
 struct DabSig {
   int tool, needs_area, do_normals, do_bounds, smooth_iters, smooth_tail;
   int exch; /* partitioned PBVH: the dab is exchanged with other ranks */
+  int small; /* a small dab: its whole path runs in the persistent kernel on a few CTAs (launch gaps dominate it otherwise) */
   unsigned key(int batch) const
   {
     return (unsigned)tool | (unsigned)needs_area << 8 | (unsigned)do_normals << 9 | (unsigned)do_bounds << 10 |
-           (unsigned)smooth_iters << 11 | (unsigned)smooth_tail << 15 | (unsigned)batch << 16 | (unsigned)exch << 27;
+           (unsigned)smooth_iters << 11 | (unsigned)smooth_tail << 15 | (unsigned)batch << 16 | (unsigned)small << 26 | (unsigned)exch << 27;
   }
   bool operator==(const DabSig &o) const { return key(0) == o.key(0); }
 };
@@ -2729,6 +2759,9 @@ static int make_entry(DscContext *ctx, const DscDab *dab, DabEntry *e, DabSig *s
                     (tool == DSC_TOOL_GRAB && dab->normal_weight > 0.0f && dab->sculpt_plane == DSC_DIR_AREA);
   sig->smooth_iters = 0;
   sig->smooth_tail = 0;
+  sig->small = (ctx->use_batch_kernel && ctx->world == 1 && tool != DSC_TOOL_SMOOTH &&
+                dab->radius * std::max(dab->radius_scale, 1.0f) <= ctx->small_dab_radius) ? 1 : 0;
+  e->gather_resets = (ctx->lazy_refit && ctx->world == 1 && sig->do_bounds && !ctx->stale_flags) ? 1 : 0;
   e->peers = (int)peers;
   sig->exch = (ctx->world > 1 && (peers & ~(1u << ctx->rank))) ? 1 : 0;
   const float rs = dab->radius * dab->radius_scale;
@@ -2787,12 +2820,13 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
 
   /* 1. gather + undo membership + node marks.  It recycles the ring slot the refit of three dabs ago
    * read (inside a captured batch the first three dabs follow a joined side stream). */
-  if (!capturing || j >= DSC_SLOTS - 1) CU(cudaStreamWaitEvent(st, ev_refit[(slot + 1) & (DSC_SLOTS - 1)], 0));
+  const bool eager = !ctx->lazy_refit && do_bounds && use_hits && !dist; /* tag + refit of this dab on the side stream */
+  if (eager && (!capturing || j >= DSC_SLOTS - 1)) CU(cudaStreamWaitEvent(st, ev_refit[(slot + 1) & (DSC_SLOTS - 1)], 0));
   {
     StageScope s(ctx, ST_GATHER);
     CU(launch_k(k_gather_dab, (m.nleaf + DSC_BLOCK - 1) / DSC_BLOCK, DSC_BLOCK, 0, st, pdl, m, j, slot));
   }
-  if (do_bounds && use_hits && !dist) {
+  if (eager) {
     /* side stream: tag the ancestors of the hit leaves for the bottom-up refit while the brush runs */
     CU(cudaEventRecord(ev_fork, st));
     CU(cudaStreamWaitEvent(ctx->stream2, ev_fork, 0));
@@ -2867,10 +2901,10 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
   if (use_hits) {
     const int mode = (do_normals ? NB_NORMALS : 0) | (do_bounds ? NB_BOUNDS : 0);
     if (do_bounds) {
-      if (!dist) {
+      if (eager) {
         CU(cudaStreamWaitEvent(st, ev_tag, 0));
       }
-      else {
+      else if (dist) {
         StageScope s(ctx, ST_OTHER);
         k_reset_leaf_boxes<<<ctx->num_sms, DSC_BLOCK, 0, st>>>(m, hits.list, hits.count, 0);
         LAUNCH_CHECK();
@@ -2897,7 +2931,7 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
     else if (mode) {
       if ((r = run_normals_bounds(ctx, hits, mode, pdl && !dist && tool != DSC_TOOL_SMOOTH))) return r;
     }
-    if (do_bounds && !dist) {
+    if (eager) {
       /* side stream: carry the refreshed leaf boxes up the tree; overlaps the next dab */
       CU(cudaEventRecord(ev_bb, st));
       CU(cudaStreamWaitEvent(ctx->stream2, ev_bb, 0));
@@ -3006,7 +3040,7 @@ static int get_graph(DscContext *ctx, const DabSig &sig, int batch, DabGraph **r
 /* `count` dabs of one launch sequence in one cooperative launch of the persistent batch kernel */
 static int launch_batch_kernel(DscContext *ctx, const DabSig &sig, int count, int slot0)
 {
-  void (*fn)(DevMesh, int, int, int) = nullptr;
+  void (*fn)(DevMesh, int, int, int, int) = nullptr;
   int k = 0;
   switch (sig.tool) {
     case DSC_TOOL_DRAW: fn = k_dab_batch<DSC_TOOL_DRAW>; k = 0; break;
@@ -3016,7 +3050,7 @@ static int launch_batch_kernel(DscContext *ctx, const DabSig &sig, int count, in
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)ctx->batch_grid[k], 1, 1);
+  cfg.gridDim = dim3((unsigned)std::min(ctx->batch_grid[k], ctx->small_dab_grid), 1, 1);
   cfg.blockDim = dim3(NT_THREADS, 1, 1);
   cfg.dynamicSmemBytes = ctx->nb_smem;
   cfg.stream = ctx->stream;
@@ -3027,7 +3061,7 @@ static int launch_batch_kernel(DscContext *ctx, const DabSig &sig, int count, in
   cfg.numAttrs = 1;
   k_batch_begin<<<1, 1, 0, ctx->stream>>>(ctx->m, count);
   LAUNCH_CHECK();
-  CU(cudaLaunchKernelEx(&cfg, fn, ctx->m, count, slot0, sig.needs_area));
+  CU(cudaLaunchKernelEx(&cfg, fn, ctx->m, count, slot0, sig.needs_area, ctx->lazy_refit ? 0 : 1));
   ctx->launches += 2;
   ctx->batch_launches++;
   return DSC_OK;
@@ -3204,7 +3238,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
     if ((r = ring_reserve(ctx, seq))) return r;
     ctx->h_ring[seq & (DSC_RING - 1)] = e;
     int batch = 1;
-    const bool batchable = graphable && ctx->use_batch_kernel && sig.tool != DSC_TOOL_SMOOTH && ctx->batch_grid[0] > 0;
+    const bool batchable = graphable && sig.small && ctx->batch_grid[0] > 0;
     if (batchable) {
       while (run < 256 && i + run < count) {
         DabEntry e2;
@@ -3266,6 +3300,7 @@ int dsc_dabs(DscContext *ctx, const DscDab *dabs, int count)
       ctx->launches++;
       if ((r = enqueue_dab(ctx, sig, 0, slot, false))) return r;
     }
+    if (ctx->lazy_refit && sig.do_bounds && !dist) ctx->refit_pending = true;
     /* flag bookkeeping of the sequence that just ran */
     if (!ctx->stale_flags) {
       if (!sig.do_normals || !sig.do_bounds) ctx->stale_flags = true;
@@ -3435,6 +3470,7 @@ int dsc_stroke_end(DscContext *ctx)
     CU(cudaStreamSynchronize(ctx->stream));
     if (err) return fail(ctx, DSC_ERR_NCCL, "a peer-memory exchange timed out: a rank did not queue the same exchanges");
   }
+  if ((r = ensure_refit(ctx))) return r;
   r = run_orig_flush(ctx);
   if (r) return r;
   ctx->in_stroke = false;
@@ -3803,8 +3839,9 @@ int dsc_download_node_bb(DscContext *ctx, float *r_bb, float *r_orig_bb)
   NEED_PBVH();
   const int N = ctx->totnode;
   std::vector<float> tmp((size_t)6 * N);
-  int r = sync_all(ctx);
+  int r = ensure_refit(ctx);
   if (r) return r;
+  if ((r = sync_all(ctx))) return r;
   for (int pass = 0; pass < 2; pass++) {
     float *out = pass ? r_orig_bb : r_bb;
     if (!out) continue;

@@ -167,7 +167,9 @@ struct DabEntry {
   int ent_bits;         /* DSC_ENT_NORMALS | DSC_ENT_BOUNDS */
   int use_cos;          /* the area pass also samples the centre (clay strips) */
   int peers;            /* partitioned PBVH: bit per rank the dab can reach (the ranks that exchange it); 0 on one GPU */
-  int pad[2];
+  int gather_resets;    /* the gather empties the boxes of the leaves it hits (the tile kernel accumulates into them); the inner
+                           nodes are refitted once, when somebody reads them (stroke end) */
+  int pad;
 };
 
 __device__ __forceinline__ const DabEntry &dsc_dab_entry(const DevMesh &m, int j)
@@ -513,6 +515,8 @@ __device__ __forceinline__ void dsc_gather_body(const DevMesh &m, int slot, floa
   unsigned long long vd = 0, avd = 0, all = 0, prims = 0, first = 0;
   if (ahit) avd = (unsigned long long)m.leaf_ucnt[l];
   if (hit) {
+    /* this thread is the only reader of the leaf's box in this launch; the next one is the tile kernel, which accumulates */
+    if (mark == 2) dsc_reset_leaf_box(m, l);
     m.leaf_state[l] = DSC_LEAF_HIT | DSC_LEAF_TOUCHED | ((lst & DSC_LEAF_TOUCHED) ? 0u : DSC_LEAF_FIRST);
     m.node_flag[l] = flag | set_flags;
     vd = (unsigned long long)m.leaf_ucnt[l];
@@ -563,8 +567,8 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_gather_dab(DevMesh m, int j, int 
   dsc_pdl_launch();
   const DabEntry &e = dsc_dab_entry(m, j);
   const float vn[3] = {e.d.view_n[0], e.d.view_n[1], e.d.view_n[2]};
-  dsc_gather_body(m, slot, e.d.loc[0], e.d.loc[1], e.d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
-                  e.ent_bits, blockIdx.x, -1, e.d.falloff_shape == 1 ? vn : nullptr);
+  dsc_gather_body(m, slot, e.d.loc[0], e.d.loc[1], e.d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, e.gather_resets ? 2 : 1,
+                  e.set_flags, e.ent_bits, blockIdx.x, -1, e.d.falloff_shape == 1 ? vn : nullptr);
 }
 
 /* leaves carrying any of `flags` (update_search_cb, pbvh.c:2891-2900) */
@@ -1964,7 +1968,7 @@ __device__ __forceinline__ void dsc_grid_sync(unsigned *bar, unsigned &target, u
  * CTA shape and shared memory are the tile kernel's; area and brush use its 8 compute warps.  Everything
  * a stage reads that an earlier stage of the same launch wrote goes through L2 (__ldcg / ld4). */
 template<int TOOL>
-__global__ void __launch_bounds__(NT_THREADS, 4) k_dab_batch(DevMesh m, int batch, int slot0, int needs_area)
+__global__ void __launch_bounds__(NT_THREADS, 4) k_dab_batch(DevMesh m, int batch, int slot0, int needs_area, int refit)
 {
   const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
   unsigned target = 0u;
@@ -1976,12 +1980,13 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_dab_batch(DevMesh m, int batc
     const int mode = ((e.ent_bits & DSC_ENT_NORMALS) ? NB_NORMALS : 0) | ((e.ent_bits & DSC_ENT_BOUNDS) ? NB_BOUNDS : 0);
     /* 1. gather + ancestor tags (first CTAs); the previous dab's refit rides along (last CTAs) */
     if (tid < DSC_BLOCK) {
+      const float vn[3] = {d.view_n[0], d.view_n[1], d.view_n[2]};
       for (int b = cta; b < gblocks; b += ncta) {
         dsc_gather_body(m, slot, d.loc[0], d.loc[1], d.loc[2], e.radius_sq, e.area_radius_sq, e.original, 1, 1, e.set_flags,
-                        e.ent_bits, b, j & 1);
+                        e.ent_bits, b, refit ? (j & 1) : -1, d.falloff_shape == 1 ? vn : nullptr);
       }
     }
-    if (j > 0) dsc_refit_body(m, (slot0 + j - 1) & (DSC_SLOTS - 1), (j - 1) & 1, (ncta - 1 - cta) * NT_THREADS + tid, ncta * NT_THREADS);
+    if (refit && j > 0) dsc_refit_body(m, (slot0 + j - 1) & (DSC_SLOTS - 1), (j - 1) & 1, (ncta - 1 - cta) * NT_THREADS + tid, ncta * NT_THREADS);
     dsc_grid_sync(m.grid_bar, target, ncta);
     /* 2. area normal / centre */
     if (needs_area) {
@@ -2001,7 +2006,7 @@ __global__ void __launch_bounds__(NT_THREADS, 4) k_dab_batch(DevMesh m, int batc
                           m.ghit + (size_t)slot * m.ghit_words, cta, ncta, false);
     dsc_grid_sync(m.grid_bar, target, ncta);
   }
-  dsc_refit_body(m, (slot0 + batch - 1) & (DSC_SLOTS - 1), (batch - 1) & 1, cta * NT_THREADS + tid, ncta * NT_THREADS);
+  if (refit) dsc_refit_body(m, (slot0 + batch - 1) & (DSC_SLOTS - 1), (batch - 1) & 1, cta * NT_THREADS + tid, ncta * NT_THREADS);
 }
 
 /* ------------------------------------------------------------------------------ K6 leaf BB */
@@ -2083,6 +2088,7 @@ __global__ void __launch_bounds__(1024) k_flush(DevMesh m)
     __threadfence_block();
     __syncthreads();
   }
+  if (threadIdx.x == 0) atomicAdd(&m.tot->refit_total, (unsigned long long)m.level_off[m.nlevel]); /* inner boxes rewritten */
 }
 
 /* drops leaf flags once their stage ran (pbvh.c:3007, 3295) */
