@@ -19,7 +19,7 @@ GCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # bit-parity with the CPU path: no FMA contraction; IEEE div/sqrt and denormals are nvcc defaults
-    "-fmad=false", "-Xcompiler", "-fPIC", "-shared",
+    "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared",
 ]
 
 

@@ -1065,8 +1065,29 @@ int dsc_grids_upload(DscContext *ctx, const DscGridsDesc *gr)
 
 static int dist_p2p_setup(DscContext *ctx);
 
+/* DSC_TIMING=1: where the session start goes, section by section, on stderr */
+struct UploadTimer {
+  bool on = getenv("DSC_TIMING") != nullptr;
+  double t0 = now();
+  static double now()
+  {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+  }
+  void mark(const char *what)
+  {
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "[dsc upload] %-24s %.3f s\n", what, t - t0);
+    t0 = t;
+  }
+};
+#define DSC_TMARK(what) upload_timer.mark(what)
+
 int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
 {
+  UploadTimer upload_timer;
   if (!ctx || !pb) return fail(ctx, DSC_ERR_INVALID, "NULL argument");
   if (!ctx->have_mesh) return fail(ctx, DSC_ERR_STATE, "dsc_mesh_upload must come first");
   if (ctx->have_pbvh) return fail(ctx, DSC_ERR_STATE, "a PBVH is already resident");
@@ -1095,6 +1116,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     ctx->small_dab_radius = ctx->small_dab_frac >= 1.0e8f ? 3.0e38f : ctx->small_dab_frac * (float)sqrt(dd);
   }
 
+  DSC_TMARK("start");
   /* slots: each leaf's unique verts are one 128-byte aligned run, cut into tiles of <= DSC_TILE
    * slots.  Inside a leaf the order is ours to choose (the host translates through slot_of), so the
    * verts are split by recursive coordinate bisection into spatially compact tiles and ordered in
@@ -1292,6 +1314,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   ctx->vpad = VP;
   ctx->nwords = VP / 32;
 
+  DSC_TMARK("slots+tiles");
   /* per-slot vertex data */
   auto to_slots = [&](const std::vector<float> &src, int comp, int stride) {
     std::vector<float> out((size_t)VP, 0.0f);
@@ -1344,6 +1367,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   }
   if ((r = dev_alloc(ctx, &ctx->d_list, (size_t)std::max(V, L))) || (r = dev_zero(ctx, &ctx->d_count, 1))) return r;
 
+  DSC_TMARK("vertex data upload");
   /* smooth adjacency in slot order */
   if (ctx->has_nb && ctx->is_grids) {
     /* the rim table, element indices -> slots; per-slot boundary flags only when the base mesh is open */
@@ -1491,6 +1515,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     CU(cudaStreamSynchronize(ctx->stream));
   }
   else
+  DSC_TMARK("smooth adjacency");
   /* looptris by position; vertex -> looptri CSR; per-tile local tables of the shared-memory normals kernel */
   {
     std::vector<int> tri_leaf((size_t)std::max(T, 1), 0);
@@ -1814,6 +1839,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     }
   }
 
+  DSC_TMARK("looptri + tile tables");
   /* leaves */
   {
     if ((r = dev_upload_c(ctx, &m.leaf_ubeg, leaf_ubeg)) || (r = dev_upload_c(ctx, &m.leaf_ucnt, leaf_ucnt)) ||
@@ -1837,6 +1863,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     CU(cudaStreamSynchronize(ctx->stream));
   }
 
+  DSC_TMARK("leaves");
   /* nodes in device numbering: leaves [0, L) in traversal order, then the inner nodes breadth-first */
   {
     std::vector<int> hflag(N), hchild(N);
@@ -1912,6 +1939,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   if ((r = dev_zero(ctx, &ctx->d_curve, 257))) return r;
   CU(cudaStreamSynchronize(ctx->stream));
 
+  DSC_TMARK("nodes");
   /* launch shape of the shared-memory normals kernel */
   CU(cudaFuncSetAttribute(k_normals_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->nb_smem));
   int occ = 1;
@@ -1944,6 +1972,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     }
   }
 
+  DSC_TMARK("launch shapes");
   /* multi-GPU: owned leaf run, hit-mask ring, halo index lists */
   m.own_lo = 0;
   m.own_hi = L;
@@ -2134,6 +2163,7 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     if ((r = dist_p2p_setup(ctx))) return r;
   }
 
+  DSC_TMARK("multi-GPU tables");
   /* the host staging copies are no longer needed */
   std::vector<int>().swap(ctx->h_rim_nb);
   std::vector<float>().swap(ctx->h_co);
