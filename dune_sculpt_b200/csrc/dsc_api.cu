@@ -1170,13 +1170,10 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
      *         boundary part starts at a multiple of 32 (`ibnd`, a few interior verts may fall into it).  The dab then
      *         displaces the boundary runs of the gathered tiles first (k_brush_boundary) and the interiors inside the
      *         fused tile kernel, which finds every vertex it reads from another tile already displaced. */
-    std::vector<int> ord_all;
-    ord_all.reserve((size_t)V);
     struct TileSpan { int lo, hi, leaf, base; };
-    std::vector<TileSpan> spans;
-    std::vector<int> tile_of_vert((size_t)V, -1);
     const float *hco = ctx->h_co.data();
-    std::vector<int> ord;
+    /* serial, cheap: the leaves' runs, the claim of every unique vertex, where each leaf's verts / tiles go */
+    std::vector<long long> ord0((size_t)L + 1, 0);
     for (int l = 0; l < L; l++) {
       const int n = leaves[l];
       cur = (cur + 31) & ~31ll;
@@ -1194,60 +1191,83 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         if (v < 0 || v >= V || ctx->slot_of[v] != -1) return fail(ctx, DSC_ERR_INVALID, "vertex %d is not unique in exactly one leaf", v);
         ctx->slot_of[v] = -2; /* claimed; the slot follows */
       }
-      ord.assign(vi, vi + U);
-      leaf_tile0[l] = (int)spans.size();
-      /* bisection of ord[lo, hi) into k tiles, slots from `base` */
-      struct Job { int lo, hi, k, base; };
-      std::vector<Job> jobs(1, Job{0, U, std::max(1, (U + DSC_TILE - 1) / DSC_TILE), (int)cur});
-      std::vector<TileSpan> made;
-      const int g0 = (int)ord_all.size();
-      while (!jobs.empty()) {
-        const Job j = jobs.back();
-        jobs.pop_back();
-        const int cnt = j.hi - j.lo;
-        if (j.k > 1) {
-          float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-          for (int i = j.lo; i < j.hi; i++) {
-            for (int k = 0; k < 3; k++) {
-              const float c = hco[(size_t)3 * ord[i] + k];
-              mn[k] = std::min(mn[k], c);
-              mx[k] = std::max(mx[k], c);
-            }
-          }
-          int a = 0;
-          for (int k = 1; k < 3; k++) {
-            if ((mx[k] - mn[k]) > (mx[a] - mn[a])) a = k;
-          }
-          const int kl = j.k / 2;
-          long long nl = ((long long)cnt * kl + j.k - 1) / j.k;
-          nl = std::min<long long>((nl + 31) & ~31ll, std::min<long long>((long long)kl * DSC_TILE, cnt));
-          std::nth_element(ord.begin() + j.lo, ord.begin() + j.lo + nl, ord.begin() + j.hi, [&](int p, int q) {
-            const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
-            return cp < cq || (cp == cq && p < q);
-          });
-          /* right half first on the stack so tiles come out in slot order */
-          jobs.push_back(Job{j.lo + (int)nl, j.hi, j.k - kl, j.base + (int)nl});
-          jobs.push_back(Job{j.lo, j.lo + (int)nl, kl, j.base});
-          continue;
-        }
-        made.push_back(TileSpan{g0 + j.lo, g0 + j.hi, l, j.base});
-      }
-      std::sort(made.begin(), made.end(), [](const TileSpan &x, const TileSpan &y) { return x.base < y.base; });
-      ord_all.insert(ord_all.end(), ord.begin(), ord.end());
-      for (const TileSpan &t : made) {
-        for (int i = t.lo; i < t.hi; i++) tile_of_vert[ord_all[i]] = (int)spans.size();
-        spans.push_back(t);
-      }
+      ord0[l + 1] = ord0[l] + U;
+      leaf_tile0[l + 1] = leaf_tile0[l] + std::max(1, (U + DSC_TILE - 1) / DSC_TILE); /* the bisection makes exactly that many */
       cur += U;
       if (cur > 0x7fffff00ll) return fail(ctx, DSC_ERR_UNSUPPORTED, "more than 2^31 slots");
     }
-    leaf_tile0[L] = (int)spans.size();
-    /* pass 2 */
+    std::vector<int> ord_all((size_t)ord0[L]);
+    std::vector<TileSpan> spans((size_t)leaf_tile0[L]);
+    std::vector<int> tile_of_vert((size_t)V, -1);
+    /* pass 1, leaf by leaf (independent): bisection of the leaf's unique verts into tiles */
+#pragma omp parallel
+    {
+      std::vector<int> ord;
+      std::vector<TileSpan> made;
+      struct Job { int lo, hi, k, base; };
+      std::vector<Job> jobs;
+#pragma omp for schedule(dynamic, 8)
+      for (int l = 0; l < L; l++) {
+        const int n = leaves[l];
+        const int *vi = pb->vert_indices + pb->vert_offset[n];
+        const int U = leaf_ucnt[l];
+        ord.assign(vi, vi + U);
+        /* bisection of ord[lo, hi) into k tiles, slots from `base` */
+        jobs.assign(1, Job{0, U, std::max(1, (U + DSC_TILE - 1) / DSC_TILE), leaf_ubeg[l]});
+        made.clear();
+        const int g0 = (int)ord0[l];
+        while (!jobs.empty()) {
+          const Job j = jobs.back();
+          jobs.pop_back();
+          const int cnt = j.hi - j.lo;
+          if (j.k > 1) {
+            float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (int i = j.lo; i < j.hi; i++) {
+              for (int k = 0; k < 3; k++) {
+                const float c = hco[(size_t)3 * ord[i] + k];
+                mn[k] = std::min(mn[k], c);
+                mx[k] = std::max(mx[k], c);
+              }
+            }
+            int a = 0;
+            for (int k = 1; k < 3; k++) {
+              if ((mx[k] - mn[k]) > (mx[a] - mn[a])) a = k;
+            }
+            const int kl = j.k / 2;
+            long long nl = ((long long)cnt * kl + j.k - 1) / j.k;
+            nl = std::min<long long>((nl + 31) & ~31ll, std::min<long long>((long long)kl * DSC_TILE, cnt));
+            std::nth_element(ord.begin() + j.lo, ord.begin() + j.lo + nl, ord.begin() + j.hi, [&](int p, int q) {
+              const float cp = hco[(size_t)3 * p + a], cq = hco[(size_t)3 * q + a];
+              return cp < cq || (cp == cq && p < q);
+            });
+            /* right half first on the stack so tiles come out in slot order */
+            jobs.push_back(Job{j.lo + (int)nl, j.hi, j.k - kl, j.base + (int)nl});
+            jobs.push_back(Job{j.lo, j.lo + (int)nl, kl, j.base});
+            continue;
+          }
+          made.push_back(TileSpan{g0 + j.lo, g0 + j.hi, l, j.base});
+        }
+        std::sort(made.begin(), made.end(), [](const TileSpan &x, const TileSpan &y) { return x.base < y.base; });
+        std::copy(ord.begin(), ord.end(), ord_all.begin() + g0);
+        for (size_t k = 0; k < made.size(); k++) {
+          const int ti = leaf_tile0[l] + (int)k;
+          for (int i = made[k].lo; i < made[k].hi; i++) tile_of_vert[ord_all[i]] = ti;
+          spans[(size_t)ti] = made[k];
+        }
+      }
+    }
+    /* pass 2 (a byte set to 1 from several threads is the same byte either way) */
     std::vector<unsigned char> is_bnd((size_t)V, 0);
+    int bad_prim = -1;
+#pragma omp parallel for schedule(dynamic, 8)
     for (int l = 0; l < L; l++) {
       for (int pos = leaf_pbeg[l]; pos < leaf_pbeg[l] + leaf_pcnt[l]; pos++) {
         const int t = pb->prim_indices[pos];
-        if (t < 0 || t >= T) return fail(ctx, DSC_ERR_INVALID, "prim_indices[%d] out of range", pos);
+        if (t < 0 || t >= T) {
+#pragma omp atomic write
+          bad_prim = pos;
+          continue;
+        }
         const int p = ctx->h_tri_poly[t];
         const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
         int t0 = -2;
@@ -1264,10 +1284,14 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         }
       }
     }
-    /* pass 3 */
+    if (bad_prim >= 0) return fail(ctx, DSC_ERR_INVALID, "prim_indices[%d] out of range", bad_prim);
+    /* pass 3, tile by tile (independent) */
     tile_ibnd.assign(spans.size(), 0);
-    for (size_t ti = 0; ti < spans.size(); ti++) {
-      const TileSpan &sp = spans[ti];
+    tile_range.assign(spans.size(), make_int2(0, 0));
+    tile_leaf.assign(spans.size(), 0);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long ti = 0; ti < (long long)spans.size(); ti++) {
+      const TileSpan &sp = spans[(size_t)ti];
       const int cnt = sp.hi - sp.lo;
       float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
       int ninterior = 0;
@@ -1299,9 +1323,9 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         return cp < cq || (cp == cq && p < q);
       });
       for (int i = sp.lo; i < sp.hi; i++) ctx->slot_of[ord_all[i]] = sp.base + (i - sp.lo);
-      tile_range.push_back(make_int2(sp.base, cnt));
-      tile_leaf.push_back(sp.leaf);
-      tile_ibnd[ti] = ninterior & ~31;
+      tile_range[(size_t)ti] = make_int2(sp.base, cnt);
+      tile_leaf[(size_t)ti] = sp.leaf;
+      tile_ibnd[(size_t)ti] = ninterior & ~31;
     }
   }
   const int NT = (int)tile_range.size();
@@ -1515,7 +1539,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
     CU(cudaStreamSynchronize(ctx->stream));
   }
   else
-  DSC_TMARK("smooth adjacency");
   /* looptris by position; vertex -> looptri CSR; per-tile local tables of the shared-memory normals kernel */
   {
     std::vector<int> tri_leaf((size_t)std::max(T, 1), 0);
