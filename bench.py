@@ -288,6 +288,14 @@ class Runner:
         log("%s rank %d: host PBVH build + device upload %.1fs, %d nodes (%d leaves)" % (w.name, rank, self.session_start_s, self.ses.totnode, self.nleaf))
         self.arrs = [(capi.DscDab * len(s["dabs"]))(*s["dabs"]) for s in w.strokes]
         self.mask_state = w.mask is not None
+        # the per-stroke layers (mask, automask factors) go up from page-locked memory, as a host application would keep them
+        seen = set()
+        self.pinned = []
+        for a in [w.mask] + [s["automask"] for s in w.strokes]:
+            if a is not None and id(a) not in seen:
+                seen.add(id(a))
+                if self.ses.D.dsc_host_register(self.ses.ctx, a.ctypes.data, a.nbytes) == 0:  # best effort: pageable works too
+                    self.pinned.append(a)
         self.ses.checkpoint()
 
     def barrier(self):
@@ -537,6 +545,9 @@ class Runner:
         return out
 
     def close(self):
+        for a in self.pinned:
+            self.ses.D.dsc_host_unregister(self.ses.ctx, a.ctypes.data)
+        self.pinned = []
         self.ses.close()
 
 

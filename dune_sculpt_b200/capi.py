@@ -178,6 +178,8 @@ def cuda_lib():
         for fn in ("dsc_download_co", "dsc_download_mvert", "dsc_host_register", "dsc_host_unregister", "dsc_download_no", "dsc_download_orig_co", "dsc_download_orig_no", "dsc_upload_co",
                    "dsc_set_custom_curve", "dsc_set_mask"):
             getattr(L, fn).argtypes = [C.c_void_p, c_float_p]
+        L.dsc_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.dsc_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         L.dsc_download_node_bb.argtypes = [C.c_void_p, c_float_p, c_float_p]
         L.dsc_download_node_flags.argtypes = [C.c_void_p, c_int_p]
         L.dsc_download_touched.argtypes = [C.c_void_p, c_ubyte_p]

@@ -2629,12 +2629,22 @@ int dsc_set_custom_curve(DscContext *ctx, const float *table257)
   return DSC_OK;
 }
 
+/* a per-vertex float layer (mask, automask factors) into slot order: one H2D copy in vertex order into the staging buffer,
+ * permuted on the device (the pad slots of dst stay zero from their allocation) */
+__global__ void k_scatter1(float *dst, const float *src, const int *slot_of, int totvert)
+{
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < totvert; v += gridDim.x * blockDim.x) dst[slot_of[v]] = src[v];
+}
 static int upload_per_vertex(DscContext *ctx, float *dst, const float *src)
 {
-  std::vector<float> tmp((size_t)ctx->vpad, 0.0f);
-  for (int v = 0; v < ctx->totvert; v++) tmp[ctx->slot_of[v]] = src[v];
-  CU(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = join_side(ctx);
+  if (r) return r;
+  /* stream order keeps the staging buffer safe: every earlier export / import through it was queued on this stream */
+  CU(cudaMemcpyAsync(ctx->d_stage3, src, sizeof(float) * (size_t)ctx->totvert, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream)); /* the caller's array is free again when the call returns (it may be page-locked) */
+  k_scatter1<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, ctx->d_stage3, ctx->d_slot_of, ctx->totvert);
+  LAUNCH_CHECK();
+  ctx->launches++;
   return DSC_OK;
 }
 
