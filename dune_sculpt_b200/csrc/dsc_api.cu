@@ -2910,17 +2910,13 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
     if (exch && ctx->is_grids && (r = dist_halo_exchange(ctx, j, false, 2))) return r;
     /* the bitmask of gathered leaves first: it tells every rank whether this dab's exchanges carry anything */
     if (exch && (r = dist_allreduce_dab(ctx, j, slot, false))) return r;
-    {
-      StageScope s(ctx, ST_SMOOTH);
-      k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
-      LAUNCH_CHECK();
-    }
+    /* (the undo snapshot of first-touched leaves rides in the first smoothing pass) */
     const int total = sig.smooth_iters + (sig.smooth_tail ? 1 : 0);
     for (int it = 0; it < total; it++) {
       {
         StageScope s(ctx, ST_SMOOTH);
-        if (ctx->is_grids) k_smooth_a<true><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0);
-        else k_smooth_a<false><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0);
+        if (ctx->is_grids) k_smooth_a<true><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0, it == 0 ? 1 : 0);
+        else k_smooth_a<false><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0, it == 0 ? 1 : 0);
         LAUNCH_CHECK();
       }
       {
