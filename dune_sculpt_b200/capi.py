@@ -766,7 +766,7 @@ class GridSession(SculptSession):
     BKE_pbvh_build_grids -> DUNE_pbvh_device_attach_grids; the dab / download methods are the mesh ones
     (a grid element is a vertex to them)"""
 
-    def __init__(self, mr, leaf_limit=0, device=0, dist=None, draw_buffers=False, grid_mat=None, grid_flag=None, hidden=None):
+    def __init__(self, mr, leaf_limit=0, device=0, dist=None, draw_buffers=False, grid_mat=None, grid_flag=None, hidden=None, raycast=False):
         """grid_mat / grid_flag = DMFlagMat per grid; hidden = [totelem] grid_hidden bit per element"""
         H = host_lib()
         self.H = H
@@ -821,6 +821,9 @@ class GridSession(SculptSession):
         self.ctx = None
         if draw_buffers:
             H.DUNE_pbvh_draw_buffers_enable(self.pbvh)
+        self.raycast_enabled = bool(raycast)
+        if raycast:
+            H.DUNE_pbvh_raycast_enable(self.pbvh)
         if device is not None:
             if dist is None:
                 self._chk(H.DUNE_pbvh_device_attach_grids(self.pbvh, self.ccg, int(device)))

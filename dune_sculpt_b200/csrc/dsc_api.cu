@@ -79,6 +79,8 @@ struct DscContext {
   bool want_draw = false, want_raycast = false;
   const int *d_slot_leaf = nullptr; /* [slots / 32] leaf owning the 32-slot group (ray-cast: undo-node lookup per vert) */
   RayLeafHit *d_ray_out = nullptr, *h_ray_out = nullptr; /* [nleaf] on the device, the first DSC_RAY_FIRST pinned */
+  GridRayHit *d_gray_out = nullptr;                       /* grids: the quads a ray touches */
+  int gray_capacity = 4096;
   int *d_ray_count = nullptr, *h_ray_count = nullptr;
   std::vector<int> vert_of_slot;
   const int4 *d_tri_slots = nullptr;
@@ -837,6 +839,7 @@ void dsc_ctx_destroy(DscContext *ctx)
   if (ctx->h_own) cudaFreeHost(ctx->h_own);
   for (void *p : ctx->registered) cudaHostUnregister(p);
   if (ctx->h_ray_out) cudaFreeHost(ctx->h_ray_out);
+  if (ctx->d_gray_out) cudaFree(ctx->d_gray_out);
   if (ctx->h_ray_count) cudaFreeHost(ctx->h_ray_count);
   cudaEventDestroy(ctx->t0);
   cudaEventDestroy(ctx->t1);
@@ -3966,11 +3969,128 @@ int dsc_raycast_enable(DscContext *ctx)
 {
   if (!ctx) return DSC_ERR_INVALID;
   if (ctx->have_pbvh) return fail(ctx, DSC_ERR_STATE, "dsc_raycast_enable comes before dsc_pbvh_upload");
-  if (ctx->is_grids) return fail(ctx, DSC_ERR_UNSUPPORTED, "the grids ray-cast (pbvh.c:4102-4200) is not on the device yet");
-  ctx->want_draw = true; /* the looptri corner table */
+  if (!ctx->is_grids) ctx->want_draw = true; /* the looptri corner table (grids: a quad's corners follow from its place) */
   ctx->want_raycast = true;
   return DSC_OK;
 }
+/* pbvh_grids_node_raycast (pbvh.c:4102-4200) under BKE_pbvh_raycast + the stroke operator's hit callback: the device lists
+ * the quads the ray touches, the host folds them in the reference's order */
+static int grids_raycast(DscContext *ctx, const RayParams &rp, const float ray_start[3], const float ray_normal[3], float max_depth,
+                         DscRayHit *r_hit)
+{
+  const int L = ctx->m.nleaf;
+  int r;
+  if (!ctx->d_ray_count && (r = dev_zero(ctx, &ctx->d_ray_count, 1))) return r;
+  std::vector<GridRayHit> hits;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (!ctx->d_gray_out) {
+      CU(cudaMalloc((void **)&ctx->d_gray_out, sizeof(GridRayHit) * (size_t)ctx->gray_capacity));
+    }
+    CU(cudaMemsetAsync(ctx->d_ray_count, 0, sizeof(int), ctx->stream));
+    k_grid_raycast<<<std::min(L, ctx->num_sms * 8), DSC_BLOCK, 0, ctx->stream>>>(ctx->m, ctx->g, rp, ctx->gray_capacity, ctx->d_ray_count,
+                                                                                    ctx->d_gray_out);
+    LAUNCH_CHECK();
+    ctx->launches += 1;
+    int nh = 0;
+    CU(cudaMemcpyAsync(&nh, ctx->d_ray_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nh > ctx->gray_capacity) {
+      /* a grazing ray touched more quads than the buffer holds: make room for all of them and ask again */
+      CU(cudaFree(ctx->d_gray_out));
+      ctx->d_gray_out = nullptr;
+      ctx->gray_capacity = nh + nh / 4 + 64;
+      continue;
+    }
+    hits.resize((size_t)std::max(nh, 0));
+    if (nh > 0) {
+      CU(cudaMemcpyAsync(hits.data(), ctx->d_gray_out, sizeof(GridRayHit) * (size_t)nh, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    break;
+  }
+  if (hits.empty()) return DSC_OK;
+  /* BKE_pbvh_search_callback_occluded (pbvh.c:2852-2889): leaves by entry distance, ties in traversal order; inside a leaf
+   * the quads in (grid, y, x) order */
+  std::sort(hits.begin(), hits.end(), [](const GridRayHit &a, const GridRayHit &b) {
+    if (a.tmin != b.tmin) return a.tmin < b.tmin;
+    if (a.leaf != b.leaf) return a.leaf < b.leaf;
+    return a.order < b.order;
+  });
+  float depth = max_depth, tmin = FLT_MAX;
+  const GridRayHit *win = nullptr;
+  size_t i = 0;
+  while (i < hits.size()) {
+    size_t e = i;
+    while (e < hits.size() && hits[e].leaf == hits[i].leaf) e++;
+    /* sculpt_raycast_cb: a leaf entered behind the best hit is not looked at */
+    if (hits[i].tmin < tmin) {
+      bool node_hit = false;
+      for (size_t k = i; k < e; k++) {
+        const GridRayHit &h = hits[k];
+        float d;
+        /* ray_face_intersection_quad (pbvh.c:3930-3949): the second triangle only when the first is not a nearer hit */
+        if (h.d1 >= 0.0f && h.d1 < depth) d = h.d1;
+        else if (h.d2 >= 0.0f && h.d2 < depth) d = h.d2;
+        else continue;
+        depth = d;
+        win = &h;
+        node_hit = true;
+      }
+      if (node_hit) tmin = depth;
+    }
+    i = e;
+  }
+  if (!win) return DSC_OK;
+  const GridRayHit &c = *win;
+  r_hit->hit = 1;
+  r_hit->depth = depth;
+  r_hit->face = c.grid; /* r_active_grid_index */
+  r_hit->node = ctx->leaf_node[c.leaf];
+  {
+    /* normal_quad_v3, lib/intern/math_geom.cc:51-69 */
+    float n1[3], n2[3], n[3];
+    for (int k = 0; k < 3; k++) {
+      n1[k] = c.co[0][k] - c.co[2][k];
+      n2[k] = c.co[1][k] - c.co[3][k];
+    }
+    n[0] = n1[1] * n2[2] - n1[2] * n2[1];
+    n[1] = n1[2] * n2[0] - n1[0] * n2[2];
+    n[2] = n1[0] * n2[1] - n1[1] * n2[0];
+    float d = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    if (d > 1.0e-35f) {
+      d = sqrtf(d);
+      const float f = 1.0f / d;
+      for (int k = 0; k < 3; k++) n[k] = n[k] * f;
+    }
+    else {
+      n[0] = n[1] = n[2] = 0.0f;
+    }
+    memcpy(r_hit->face_normal, n, sizeof(n));
+  }
+  {
+    /* the corner nearest to the hit point (pbvh.c:4170-4190): r_active_vertex_index as an element index */
+    const int gs = ctx->grid_size, gs1 = gs - 1;
+    const int y = c.quad / gs1, x = c.quad - y * gs1;
+    const int xy[4][2] = {{x, y}, {x + 1, y}, {x + 1, y + 1}, {x, y + 1}};
+    float location[3], nearest[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < 3; k++) location[k] = ray_start[k] + ray_normal[k] * depth;
+    int best = 0;
+    for (int j = 0; j < 4; j++) {
+      float da = 0.0f, db = 0.0f;
+      for (int k = 0; k < 3; k++) {
+        da += (location[k] - c.co[j][k]) * (location[k] - c.co[j][k]);
+        db += (location[k] - nearest[k]) * (location[k] - nearest[k]);
+      }
+      if (j == 0 || da < db) {
+        memcpy(nearest, c.co[j], sizeof(float[3]));
+        best = j;
+      }
+    }
+    r_hit->vertex = c.grid * gs * gs + xy[best][1] * gs + xy[best][0];
+  }
+  return DSC_OK;
+}
+
 int dsc_raycast(DscContext *ctx, const float ray_start[3], const float ray_normal[3], int original, float max_depth, DscRayHit *r_hit)
 {
   NEED_PBVH();
@@ -4000,6 +4120,7 @@ int dsc_raycast(DscContext *ctx, const float ray_start[3], const float ray_norma
   }
   rp.original = original ? 1 : 0;
   const int L = ctx->m.nleaf;
+  if (ctx->is_grids) return grids_raycast(ctx, rp, ray_start, ray_normal, max_depth, r_hit);
   if (!ctx->d_ray_out) {
     if ((r = dev_zero(ctx, &ctx->d_ray_out, (size_t)L))) return r;
     if ((r = dev_zero(ctx, &ctx->d_ray_count, 1))) return r;

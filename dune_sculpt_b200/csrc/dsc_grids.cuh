@@ -572,3 +572,59 @@ __global__ void __launch_bounds__(GN_BLOCK, 1) k_grid_dab(DevMesh m, DevGrids g,
   dsc_grid_sync(m.grid_bar, target, ncta);
   dsc_grid_leaf_bb_body(m, list, count, cta, ncta);
 }
+
+/* ---- ray-cast on grids: pbvh_grids_node_raycast (pbvh.c:4102-4200) ----
+ * One CTA per leaf the ray enters; every quad of the leaf's grids is tested as its two triangles (0, 1, 2) and (0, 2, 3)
+ * (ray_face_intersection_quad, pbvh.c:3930-3949).  The reference walks the quads in (grid, y, x) order with a running
+ * depth, and looks at the second triangle only when the first is not a nearer hit -- so which of a quad's two distances
+ * counts depends on the depth the walk arrives with.  The kernel therefore reports every quad the ray touches with BOTH
+ * distances and its place in the walk; the host folds them in the reference's order (a ray touches a handful of quads). */
+struct GridRayHit {
+  int leaf, grid, quad, order; /* quad = y * (gs - 1) + x; order = its place in the leaf's walk */
+  float tmin, d1, d2;          /* leaf entry distance; triangle distances, negative = no intersection */
+  int pad;
+  float co[4][3];
+};
+__global__ void __launch_bounds__(DSC_BLOCK) k_grid_raycast(DevMesh m, DevGrids g, RayParams r, int capacity, int *count, GridRayHit *out)
+{
+  const int gs = g.gs, gs1 = gs - 1, per = gs1 * gs1;
+  for (int l = blockIdx.x; l < m.nleaf; l += gridDim.x) {
+    float tmin;
+    if (!dsc_ray_leaf(m, r, l, tmin)) continue; /* CTA-uniform */
+    const bool use_orig = r.original && (m.leaf_state[l] & DSC_LEAF_TOUCHED);
+    const float *X = use_orig ? m.ox : m.cx, *Y = use_orig ? m.oy : m.cy, *Z = use_orig ? m.oz : m.cz;
+    const int gb = g.leaf_gbeg[l], total = (g.leaf_gbeg[l + 1] - gb) * per;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      const int gi = t / per, q = t - gi * per;
+      const int y = q / gs1, x = q - y * gs1;
+      const int grid = g.leaf_grids[gb + gi];
+      const int s0 = g.grid_slot0[grid];
+      const int sl[4] = {s0 + y * gs + x, s0 + y * gs + x + 1, s0 + (y + 1) * gs + x + 1, s0 + (y + 1) * gs + x};
+      if (m.hidden) {
+        /* paint_is_grid_face_hidden (paint.c:1234-1241): a quad with a hidden corner is not there */
+        bool hid = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) hid |= ((m.hidden[sl[k] >> 5] >> (sl[k] & 31)) & 1u) != 0u;
+        if (hid) continue;
+      }
+      float co[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        co[k][0] = X[sl[k]]; co[k][1] = Y[sl[k]]; co[k][2] = Z[sl[k]];
+      }
+      float d1 = -1.0f, d2 = -1.0f, lambda;
+      if (dsc_ray_tri(r, co[0], co[1], co[2], lambda)) d1 = lambda + 0.0f; /* >= 0 or -0 past the sign test: +0 canonical */
+      if (dsc_ray_tri(r, co[0], co[2], co[3], lambda)) d2 = lambda + 0.0f;
+      if (d1 < 0.0f && d2 < 0.0f) continue;
+      const int at = atomicAdd(count, 1);
+      if (at >= capacity) continue; /* counted: the host grows the buffer and asks again */
+      GridRayHit &h = out[at];
+      h.leaf = l; h.grid = grid; h.quad = q; h.order = t;
+      h.tmin = tmin; h.d1 = d1; h.d2 = d2; h.pad = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        h.co[k][0] = co[k][0]; h.co[k][1] = co[k][1]; h.co[k][2] = co[k][2];
+      }
+    }
+  }
+}

@@ -972,6 +972,7 @@ int DUNE_pbvh_device_attach_grids_dist(PBVH *pbvh, SubdivCCG *ccg, int device, i
   free(rim_nb);
   free(rim_bnd);
   if (r == DSC_OK && (pbvh->want_draw_buffers & 1)) r = dsc_draw_enable(ctx);
+  if (r == DSC_OK && (pbvh->want_draw_buffers & 2)) r = dsc_raycast_enable(ctx);
 
   float *bb = malloc(sizeof(float[6]) * (size_t)N), *obb = malloc(sizeof(float[6]) * (size_t)N);
   int *child = malloc(sizeof(int) * (size_t)N), *flag = malloc(sizeof(int) * (size_t)N), *prim_off = malloc(sizeof(int) * (size_t)N);

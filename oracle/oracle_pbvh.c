@@ -1165,7 +1165,8 @@ int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], i
     if (p->is_grids) {
       /* pbvh_grids_node_raycast (pbvh.c:4102-4200): the quads of the node's grids in grid, y, x order; a quad is its
        * two triangles (0, 1, 2) then (0, 2, 3), the second only looked at when the first is not a nearer hit
-       * (ray_face_intersection_quad, pbvh.c:3930-3949).  No hidden grid faces on this path.  r_face = the active grid. */
+       * (ray_face_intersection_quad, pbvh.c:3930-3949).  A quad with a hidden corner is skipped (paint_is_grid_face_hidden,
+       * paint.c:1234-1241).  r_face = the active grid. */
       const int gs = p->grid_size, gs2 = gs * gs;
       float (*src)[3] = use_orig ? p->orig_co : p->co;
       for (int gi = 0; gi < node->totprim; gi++) {
@@ -1173,6 +1174,7 @@ int or_raycast(OrPbvh *p, const float ray_start[3], const float ray_normal[3], i
         for (int y = 0; y < gs - 1; y++) {
           for (int x = 0; x < gs - 1; x++) {
             const int e[4] = {g * gs2 + y * gs + x, g * gs2 + y * gs + x + 1, g * gs2 + (y + 1) * gs + x + 1, g * gs2 + (y + 1) * gs + x};
+            if (p->grid_hidden && (p->grid_hidden[e[0]] || p->grid_hidden[e[1]] || p->grid_hidden[e[2]] || p->grid_hidden[e[3]])) continue;
             const float *co[4] = {src[e[0]], src[e[1]], src[e[2]], src[e[3]]};
             float depth_test;
             if (!((ray_tri_watertight(ray_start, &pc, co[0], co[1], co[2], &depth_test) && depth_test < depth) ||

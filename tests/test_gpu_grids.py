@@ -332,3 +332,93 @@ def test_grids_dab_that_gathers_nothing_does_not_stitch(fused, monkeypatch):
     dabs = [dabs[0], far[0], far[1], dabs[1], dabs[2], far[2], dabs[3]]
     st = _grid_parity(mr, dabs, leaf_limit=6)
     assert st["moved_verts"] > 0
+
+
+# ---- cursor pick on grids: pbvh_grids_node_raycast -------------------------------------------
+
+def _grid_rays(mr, rng, count):
+    co = np.asarray(mr.co, np.float32).reshape(-1, 3)
+    lo, hi = co.min(axis=0), co.max(axis=0)
+    ctr, ext = 0.5 * (lo + hi), float(np.linalg.norm(hi - lo))
+    gs = mr.grid_size
+    rays = []
+    for i in range(count):
+        kind = i % 5
+        if kind == 0:
+            target = lo + rng.random(3).astype(np.float32) * (hi - lo)
+        elif kind == 1:       # exactly at an element: the quads (and grids, and leaves) around it tie
+            target = co[rng.integers(mr.totelem)]
+        elif kind == 2:       # on a quad's edge or its diagonal: both triangles of a quad answer
+            g, y, x = rng.integers(mr.totgrid), rng.integers(gs - 1), rng.integers(gs - 1)
+            a = co[g * gs * gs + y * gs + x]
+            b = co[g * gs * gs + (y + 1) * gs + x + 1] if i % 2 else co[g * gs * gs + y * gs + x + 1]
+            target = (0.5 * (a + b)).astype(np.float32)
+        elif kind == 3:
+            target = co[rng.integers(mr.totelem)]
+        else:
+            target = ctr + (hi - lo) * 3.0 * np.sign(rng.normal(size=3)).astype(np.float32)  # a miss
+        if kind == 3:
+            d = np.zeros(3, np.float32)
+            d[rng.integers(3)] = 1.0 if rng.random() < 0.5 else -1.0
+        else:
+            d = rng.normal(size=3).astype(np.float32)
+            d /= np.float32(np.linalg.norm(d))
+        start = (np.asarray(target, np.float32) - d * np.float32(2.0 * ext)).astype(np.float32)
+        rays.append((start, d.astype(np.float32)))
+    return rays
+
+
+def _same_hit(ref, got, what):
+    assert (ref is None) == (got is None), (what, ref, got)
+    if ref is None:
+        return 0
+    assert np.float32(ref["depth"]).tobytes() == np.float32(got["depth"]).tobytes(), (what, ref, got)
+    assert ref["face"] == got["face"] and ref["vertex"] == got["vertex"] and ref["node"] == got["node"], (what, ref, got)
+    assert np.array_equal(ref["normal"].view(np.uint32), got["normal"].view(np.uint32)), what
+    return 1
+
+
+@pytest.mark.parametrize("hidden", [False, True])
+def test_grids_raycast_matches_pbvh_grids_node_raycast(hidden):
+    """depth, active grid, nearest element, quad normal and leaf of the nearest hit, bit-equal to BKE_pbvh_raycast over
+    pbvh_grids_node_raycast (pbvh.c:4102-4200): a quad is two triangles of which the second is only looked at when the first
+    is not a nearer hit, so the answer is a fold over the touched quads in (leaf by entry distance, grid, y, x) order --
+    the device lists the touched quads, the host folds.  Before a stroke (flat faces: rays through vertices, edges and
+    diagonals tie), mid-stroke with original / current coordinates (bumpy, non-planar quads), and after it."""
+    mr = meshgen.multires_cube(2, 4)
+    hid = _hidden_elems(mr, seed=4, frac=0.05) if hidden else None
+    orc = GridOracle(mr, leaf_limit=5, hidden=hid)
+    ses = capi.GridSession(mr, leaf_limit=5, device=0, hidden=hid, raycast=True)
+    try:
+        rng = np.random.default_rng(23)
+        rays = _grid_rays(mr, rng, 150)
+        hits = 0
+        for i, (s, d) in enumerate(rays):
+            hits += _same_hit(orc.raycast(s, d), ses.raycast(s, d), "ray %d" % i)
+        assert 60 < hits < len(rays)
+        s, d = rays[0]
+        full = orc.raycast(s, d)
+        if full is not None:
+            for md in (float(full["depth"]) * 0.5, float(full["depth"]), float(full["depth"]) * 1.5):
+                _same_hit(orc.raycast(s, d, max_depth=md), ses.raycast(s, d, max_depth=md), "max_depth %g" % md)
+        orc.stroke_begin(None)
+        ses.stroke_begin(None)
+        for dab in _sweep(mr, per=2, radii=(12.0, 30.0)) + _sweep(mr, per=1, tool=capi.TOOL_INFLATE, radii=(20.0,), seed=9):
+            dab.flags &= ~capi.DAB_FIRST_STEP
+            orc.dab(dab)
+            ses.dab(dab)
+        differ = 0
+        for i, (s, d) in enumerate(rays):
+            a = orc.raycast(s, d, original=True)
+            b = orc.raycast(s, d, original=False)
+            _same_hit(a, ses.raycast(s, d, original=True), "mid-stroke original ray %d" % i)
+            _same_hit(b, ses.raycast(s, d, original=False), "mid-stroke current ray %d" % i)
+            differ += (a is not None and b is not None and a["depth"] != b["depth"])
+        assert differ > 0
+        orc.stroke_end()
+        ses.stroke_end()
+        for i, (s, d) in enumerate(rays[:60]):
+            _same_hit(orc.raycast(s, d), ses.raycast(s, d), "after stroke ray %d" % i)
+    finally:
+        ses.close()
+        orc.close()
