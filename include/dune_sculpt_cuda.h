@@ -291,7 +291,9 @@ int dsc_draw_enable(DscContext *ctx);
  *     the mesh: depth, the looptri's MLoopTri.poly, the corner nearest to the hit point, the triangle normal and
  *     the leaf.  `original`: stroke-start boxes and, for leaves with an undo node, stroke-start coordinates.
  *     `max_depth`: the depth the caller's search starts from (the ray's length to the far clip); only nearer hits count.
- *     dsc_raycast_enable comes between dsc_mesh_upload and dsc_pbvh_upload.  Meshes only.  Synchronises. ---- */
+ *     dsc_raycast_enable comes between dsc_mesh_upload / dsc_grids_upload and dsc_pbvh_upload.  Synchronises.
+ *     Grids (pbvh_grids_node_raycast, pbvh.c:4102-4200): face = the active grid, vertex = the nearest corner of the hit
+ *     quad as an element index, the normal is the quad's; quads with a hidden corner are skipped. ---- */
 typedef struct DscRayHit {
   int hit;
   float depth;
