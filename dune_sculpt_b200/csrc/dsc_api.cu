@@ -1779,7 +1779,6 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
         mx_v2 = std::max(mx_v2, t.v2w);
         mx_h = std::max(mx_h, t.ehalo);
       }
-      m.sm_stride = mx_nloc;
       m.sm_off_f = 12 * mx_nloc;
       m.sm_off_e = m.sm_off_f + 16 * (mx_ne + 1);
       m.sm_off_v2 = m.sm_off_e + 8 * ((mx_ne + 1) & ~1);
@@ -2913,13 +2912,17 @@ static int enqueue_dab(DscContext *ctx, const DabSig &sig, int j, int slot, bool
     if (exch && ctx->is_grids && (r = dist_halo_exchange(ctx, j, false, 2))) return r;
     /* the bitmask of gathered leaves first: it tells every rank whether this dab's exchanges carry anything */
     if (exch && (r = dist_allreduce_dab(ctx, j, slot, false))) return r;
-    /* (the undo snapshot of first-touched leaves rides in the first smoothing pass) */
+    {
+      StageScope s(ctx, ST_SMOOTH);
+      k_snapshot<<<ctx->grid, DSC_BLOCK, 0, st>>>(m, slot);
+      LAUNCH_CHECK();
+    }
     const int total = sig.smooth_iters + (sig.smooth_tail ? 1 : 0);
     for (int it = 0; it < total; it++) {
       {
         StageScope s(ctx, ST_SMOOTH);
-        if (ctx->is_grids) k_smooth_a<true><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0, it == 0 ? 1 : 0);
-        else k_smooth_a<false><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0, it == 0 ? 1 : 0);
+        if (ctx->is_grids) k_smooth_a<true><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0);
+        else k_smooth_a<false><<<ctx->grid, DSC_BLOCK, 0, st>>>(m, ctx->gnb, j, slot, it == sig.smooth_iters ? 1 : 0);
         LAUNCH_CHECK();
       }
       {

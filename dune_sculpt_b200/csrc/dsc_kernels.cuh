@@ -106,8 +106,6 @@ struct DevMesh {
   /* byte offsets of the tile kernel's shared-memory regions (sized for the largest tile of the mesh, so a region
    * never moves between tiles): positions at 0, then poly normals, poly entries, index words, other-leaf switches */
   int sm_off_f, sm_off_e, sm_off_v2, sm_off_h;
-  int sm_stride; /* floats between the x / y / z planes of the staged positions: the same for every tile (a launch constant,
-                    so the plane offsets fold into the shared-memory address of every load) */
   /* leaves */
   int nleaf;
   int max_chunks; /* ceil(max uniq_verts / DSC_CHUNK) */
@@ -1144,6 +1142,23 @@ template<int TOOL> __global__ void __launch_bounds__(DSC_BLOCK) k_brush_boundary
   dsc_brush_body<TOOL, true>(m, d, slot, blockIdx.x, gridDim.x);
 }
 
+/* snapshot only (smooth brush: first touch, before iteration 0) */
+__global__ void __launch_bounds__(DSC_BLOCK) k_snapshot(DevMesh m, int slot)
+{
+  const DabState *st = m.st + slot;
+  const int4 *tl = m.tile_list + (size_t)slot * m.ntile;
+  const int tid = threadIdx.x;
+  const int total = st->tile_count;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    const int4 ent = tl[u];
+    if (!(ent.w & DSC_ENT_FIRST)) continue;
+    if (ent.z - 4 * tid <= 0) continue;
+    const int s0 = ent.y + 4 * tid;
+    st4(m.ox, s0, ld4(m.cx, s0)); st4(m.oy, s0, ld4(m.cy, s0)); st4(m.oz, s0, ld4(m.cz, s0));
+    st4(m.onx, s0, ld4(m.nx, s0)); st4(m.ony, s0, ld4(m.ny, s0)); st4(m.onz, s0, ld4(m.nz, s0));
+  }
+}
+
 /* ------------------------------------------------------------------------------- K4 smooth */
 /* One Jacobi iteration, part A: new position of every unique vert of a hit leaf inside the
  * sphere = co + (neighbour average - co) * fade, into the scratch arrays (SURVEY.md 8a row a20:
@@ -1158,8 +1173,7 @@ struct GridNb {
   const int *rim_nb;              /* [totgrid][4 gs - 4][rim_w] slots, -1 = none */
   const unsigned char *rim_bnd;   /* [totgrid][4 gs - 4] or NULL */
 };
-template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, GridNb gn, int j, int slot, int last_iteration,
-                                                                              int first_iteration)
+template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(DevMesh m, GridNb gn, int j, int slot, int last_iteration)
 {
   const DabEntry &ent_ = dsc_dab_entry(m, j);
   const DabParams d = ent_.d;
@@ -1192,12 +1206,6 @@ template<bool GRIDS> __global__ void __launch_bounds__(DSC_BLOCK) k_smooth_a(Dev
     for (int i = tid; i < cnt32; i += DSC_BLOCK) {
       const int s = beg + i;
       bool moved = false;
-      if (first_iteration && i < cnt && (ent.w & DSC_ENT_FIRST)) {
-        /* the undo snapshot of a leaf the stroke touches for the first time (every unique vert, hidden ones included):
-         * this pass only writes the scratch arrays, so the positions and normals it copies are still the stroke-start ones */
-        m.ox[s] = m.cx[s]; m.oy[s] = m.cy[s]; m.oz[s] = m.cz[s];
-        m.onx[s] = m.nx[s]; m.ony[s] = m.ny[s]; m.onz[s] = m.nz[s];
-      }
       if (i < cnt && !(m.hidden && ((m.hidden[s >> 5] >> (s & 31)) & 1u))) {
         const float x = m.cx[s], y = m.cy[s], z = m.cz[s];
         const float distsq = dsc_test_distsq(d, x, y, z);
@@ -1567,7 +1575,7 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
                                                       const DabParams *dab = nullptr, DabState *dst = nullptr)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2], s_done;
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
   __shared__ __align__(16) int4 s_q[2][3];
   __shared__ __align__(16) int4 s_ent[2]; /* {tile, first slot, unique verts | ibnd << 16, NT_* flags | dirty count << 8} */
   __shared__ float red[6][NT_CONSUMERS / 32];
@@ -1600,7 +1608,6 @@ __device__ __forceinline__ void dsc_normals_tile_body(const DevMesh &m, const in
     dsc_mbar_init(&s_full[1], 1);           /* TMA bytes only */
     dsc_mbar_init(&s_empty[0], NW);         /* one arrival per consumer warp */
     dsc_mbar_init(&s_empty[1], NW);
-    dsc_mbar_init(&s_done, NW);             /* a tile's poly normals / box partials have been read by every consumer warp */
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (BRUSH) {
       s_moved = 0u;
