@@ -1167,9 +1167,48 @@ void BKE_pbvh_free(PBVH *pbvh)
  * neighbour list of the sculpt neighbour iterator: per incident poly the previous and next corner
  * (kernel/intern/mesh.c:1566-1589), first occurrence kept.  An edge seen from one poly only makes
  * both its verts boundary verts. */
+/* the neighbours of v in iterator order into out[] (distinct, v itself left out), how often each was met into uses[];
+ * returns the count.  cap = 2 * (polys at v): enough for every corner's two neighbours */
+static int vert_neighbors(const PBVH *pbvh, const int *pm_off, const int *pm_idx, int v, int *out, int *uses)
+{
+  int n = 0;
+  for (int k = pm_off[v]; k < pm_off[v + 1]; k++) {
+    const MPoly *mp = &pbvh->mpoly[pm_idx[k]];
+    const MLoop *ml = &pbvh->mloop[mp->loopstart];
+    int corner = -1;
+    for (int j = 0; j < mp->totloop; j++) {
+      if ((int)ml[j].v == v) {
+        corner = j;
+        break;
+      }
+    }
+    if (corner < 0) continue;
+    const int adj[2] = {(int)ml[(corner + mp->totloop - 1) % mp->totloop].v, (int)ml[(corner + 1) % mp->totloop].v};
+    for (int j = 0; j < 2; j++) {
+      if (adj[j] == v) continue;
+      int at = -1;
+      for (int q = 0; q < n; q++) {
+        if (out[q] == adj[j]) {
+          at = q;
+          break;
+        }
+      }
+      if (at < 0) {
+        out[n] = adj[j];
+        uses[n++] = 1;
+      }
+      else {
+        uses[at]++;
+      }
+    }
+  }
+  return n;
+}
+
 static void build_neighbor_tables(PBVH *pbvh)
 {
   const int V = pbvh->totvert, P = pbvh->totpoly, Lp = pbvh->totloop;
+  /* vertex -> polys (kernel/intern/mesh_mapping.c:182-229): count, prefix, fill in poly order */
   int *pm_off = calloc((size_t)V + 1, sizeof(int));
   int *pm_idx = malloc(sizeof(int) * (size_t)(Lp ? Lp : 1));
   for (int p = 0; p < P; p++) {
@@ -1185,53 +1224,41 @@ static void build_neighbor_tables(PBVH *pbvh)
   }
   free(fill);
 
+  /* a vertex's list depends on nothing but its own polys: count in parallel, prefix, fill in parallel */
   pbvh->nb_offsets = malloc(sizeof(int) * ((size_t)V + 1));
-  pbvh->nb_indices = malloc(sizeof(int) * (size_t)(2 * Lp + 1));
   pbvh->boundary = calloc((size_t)V + 1, 1);
-  int *uses = malloc(sizeof(int) * (size_t)(2 * Lp + 1));
-  int n = 0;
+  int max_polys = 1;
   for (int v = 0; v < V; v++) {
-    const int first = n;
-    pbvh->nb_offsets[v] = n;
-    for (int k = pm_off[v]; k < pm_off[v + 1]; k++) {
-      const MPoly *mp = &pbvh->mpoly[pm_idx[k]];
-      const MLoop *ml = &pbvh->mloop[mp->loopstart];
-      int corner = -1;
-      for (int j = 0; j < mp->totloop; j++) {
-        if ((int)ml[j].v == v) {
-          corner = j;
-          break;
-        }
-      }
-      if (corner < 0) continue;
-      const int adj[2] = {(int)ml[(corner + mp->totloop - 1) % mp->totloop].v, (int)ml[(corner + 1) % mp->totloop].v};
-      for (int j = 0; j < 2; j++) {
-        if (adj[j] == v) continue;
-        int at = -1;
-        for (int q = first; q < n; q++) {
-          if (pbvh->nb_indices[q] == adj[j]) {
-            at = q;
-            break;
-          }
-        }
-        if (at < 0) {
-          pbvh->nb_indices[n] = adj[j];
-          uses[n++] = 1;
-        }
-        else {
-          uses[at]++;
-        }
-      }
-    }
-    for (int q = first; q < n; q++) {
-      if (uses[q] < 2) {
-        pbvh->boundary[v] = 1;
-        pbvh->boundary[pbvh->nb_indices[q]] = 1;
-      }
-    }
+    if (pm_off[v + 1] - pm_off[v] > max_polys) max_polys = pm_off[v + 1] - pm_off[v];
   }
-  pbvh->nb_offsets[V] = n;
-  free(uses);
+#pragma omp parallel
+  {
+    int *out = malloc(sizeof(int) * (size_t)(2 * max_polys)), *uses = malloc(sizeof(int) * (size_t)(2 * max_polys));
+#pragma omp for schedule(static)
+    for (int v = 0; v < V; v++) pbvh->nb_offsets[v + 1] = vert_neighbors(pbvh, pm_off, pm_idx, v, out, uses);
+    free(out);
+    free(uses);
+  }
+  pbvh->nb_offsets[0] = 0;
+  for (int v = 0; v < V; v++) pbvh->nb_offsets[v + 1] += pbvh->nb_offsets[v];
+  pbvh->nb_indices = malloc(sizeof(int) * ((size_t)pbvh->nb_offsets[V] + 1));
+#pragma omp parallel
+  {
+    int *uses = malloc(sizeof(int) * (size_t)(2 * max_polys));
+#pragma omp for schedule(static)
+    for (int v = 0; v < V; v++) {
+      int *out = pbvh->nb_indices + pbvh->nb_offsets[v];
+      const int n = vert_neighbors(pbvh, pm_off, pm_idx, v, out, uses);
+      /* an edge met once is a boundary edge: both ends are boundary verts (a byte set to 1 by several threads is 1) */
+      for (int q = 0; q < n; q++) {
+        if (uses[q] < 2) {
+          pbvh->boundary[v] = 1;
+          pbvh->boundary[out[q]] = 1;
+        }
+      }
+    }
+    free(uses);
+  }
   free(pm_off);
   free(pm_idx);
 }
