@@ -20,7 +20,6 @@
 
 #define DSC_ABI_VERSION 1
 #define DSC_REGION_CHUNKS 16
-#define DSC_TILE_SMEM_BUDGET (96 * 1024) /* shared memory one tile may ask of k_normals_tile; heavier tiles take the general path */
 
 static thread_local std::string g_create_error;
 
@@ -1544,232 +1543,36 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   else
   /* looptris by position; vertex -> looptri CSR; per-tile local tables of the shared-memory normals kernel */
   {
-    std::vector<int> tri_leaf((size_t)std::max(T, 1), 0);
-    std::vector<unsigned> deg((size_t)VP + 1, 0);
-    for (int l = 0; l < L; l++) {
-      for (int pos = leaf_pbeg[l]; pos < leaf_pbeg[l] + leaf_pcnt[l]; pos++) {
-        const int t = pb->prim_indices[pos];
-        if (t < 0 || t >= T) return fail(ctx, DSC_ERR_INVALID, "prim_indices[%d] out of range", pos);
-        tri_leaf[pos] = l;
-        for (int k = 0; k < 3; k++) deg[ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + k]]]++;
-      }
+    /* built on the host, leaf by leaf in parallel, appended in leaf order (dsc_tile_tables.h; checked against the serial
+     * construction without a GPU by tests/test_tile_tables.py) */
+    TileTablesIn tin;
+    tin.L = L; tin.VP = VP; tin.T = T; tin.NT = NT; tin.totpoly = ctx->totpoly;
+    tin.leaves = leaves.data();
+    tin.vert_indices = pb->vert_indices; tin.vert_offset = pb->vert_offset; tin.prim_indices = pb->prim_indices;
+    tin.slot_of = ctx->slot_of.data();
+    static_assert(sizeof(DscTileRange) == sizeof(int2), "DscTileRange is an int2");
+    tin.tile_range = reinterpret_cast<const DscTileRange *>(tile_range.data());
+    tin.leaf_tile0 = leaf_tile0.data();
+    tin.leaf_ucnt = leaf_ucnt.data(); tin.leaf_scnt = leaf_scnt.data(); tin.leaf_pbeg = leaf_pbeg.data(); tin.leaf_pcnt = leaf_pcnt.data();
+    tin.tri_vert = ctx->h_tri_vert.data(); tin.tri_poly = ctx->h_tri_poly.data(); tin.poly_start = ctx->h_poly_start.data();
+    tin.poly_len = ctx->h_poly_len.data(); tin.loop_v = ctx->h_loop_v.data();
+    TileTablesOut tt;
+    {
+      int where = -1;
+      const int tr = dsc_build_tile_tables(tin, tt, 0, &where);
+      if (tr == DSC_TT_BAD_PRIM) return fail(ctx, DSC_ERR_INVALID, "prim_indices[%d] out of range", where);
+      if (tr == DSC_TT_TOO_MANY_TILES) return fail(ctx, DSC_ERR_UNSUPPORTED, "leaf %d has too many tiles", where);
     }
-    std::vector<unsigned> vt_off((size_t)VP + 1, 0);
-    for (int s = 0; s < VP; s++) vt_off[s + 1] = vt_off[s] + deg[s];
-    std::vector<unsigned> vt_idx((size_t)std::max<unsigned>(vt_off[VP], 1u));
-    std::fill(deg.begin(), deg.end(), 0u);
-    for (int pos = 0; pos < T; pos++) {
-      const int t = pb->prim_indices[pos];
-      /* the reference adds the face normal for corner j = 2, 1, 0 (pbvh.c:2966); a vertex that is
-       * listed twice in one looptri gets it twice -- same here, order within a looptri is moot */
-      for (int k = 0; k < 3; k++) {
-        const int s = ctx->slot_of[ctx->h_tri_vert[(size_t)3 * t + k]];
-        vt_idx[vt_off[s] + deg[s]++] = (unsigned)pos;
-      }
-    }
-    std::vector<unsigned>().swap(deg);
-
-    /* ---- local tables, tile by tile ---- */
-    std::vector<int> leaf_sslots;          /* per leaf: slots of its shared verts (general path) */
-    std::vector<int> stage;                /* per tile: staged slots, box-counted ones first */
-    std::vector<unsigned short> e_pv;      /* 4 per entry */
-    std::vector<int> e_halo_leaf;          /* per other-leaf entry: that leaf */
-    std::vector<TileMeta> tmeta((size_t)std::max(NT, 1));
-    std::vector<unsigned> v2_goff((size_t)VP / 32 + 1, 0);
-    std::vector<unsigned> v2_idx;
-    v2_idx.reserve(vt_idx.size() / 2 + vt_idx.size() / 8);
-    std::vector<int> lstamp((size_t)VP, -1), lidx((size_t)VP, 0); /* slot -> local index in the current tile */
-    std::vector<int> sh_leaf((size_t)VP, -1), sh_done((size_t)VP, -1); /* slot is a shared vert of leaf / already box-counted */
-    std::vector<int> pstamp((size_t)std::max(ctx->totpoly, 1), -1), pentry((size_t)std::max(ctx->totpoly, 1), 0);
-    std::unordered_map<unsigned long long, int> halo;
-    std::vector<int> own_polys, halo_polys, halo_leaves, st_bb, st_x;
-    std::vector<unsigned> rows, raw, goff_local; /* entry ids of the current group, [row][lane]; bit 31 = other-leaf entry */
-    int next_group_to_fill = 0;
-    struct TileDims { int tile, nloc_a, ne, v2w, ehalo; };
-    std::vector<TileDims> tile_dims;
-    for (int l = 0; l < L; l++) {
-      const int n = leaves[l];
-      const int U_leaf = leaf_ucnt[l], S = leaf_scnt[l];
-      const int pbeg = leaf_pbeg[l], pend = pbeg + leaf_pcnt[l];
-      const int *vi = pb->vert_indices + pb->vert_offset[n];
-      leaf_sbeg[l] = (int)leaf_sslots.size();
-      for (int i = 0; i < S; i++) {
-        const int sl = ctx->slot_of[vi[U_leaf + i]];
-        leaf_sslots.push_back(sl);
-        sh_leaf[sl] = l;
-      }
-      bool ok = true;
-      const int t_lo = leaf_tile0[l], t_hi = leaf_tile0[l + 1];
-      for (int tg = t_lo; tg < t_hi; tg++) {
-        const int ub = tile_range[tg].x, U = tile_range[tg].y;
-        TileMeta &tm = tmeta[tg];
-        tm.ubeg = ub;
-        tm.ucnt = U;
-        tm.sbeg = (int)stage.size();
-        if ((e_pv.size() / 4) & 1) e_pv.insert(e_pv.end(), 4, (unsigned short)0); /* bulk copies start 16-byte aligned */
-        tm.ebeg = (int)(e_pv.size() / 4);
-        tm.hbeg = (int)e_halo_leaf.size();
-        tm.leaf = l;
-        tm.tile0 = t_lo;
-        for (int i = 0; i < U; i++) {
-          lstamp[ub + i] = tg;
-          lidx[ub + i] = i;
-        }
-        own_polys.clear();
-        halo_polys.clear();
-        halo_leaves.clear();
-        halo.clear();
-        const int G0 = ub / 32, ng = (U + 31) / 32;
-        for (; next_group_to_fill < G0; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
-        raw.clear();
-        goff_local.assign((size_t)ng, 0u);
-        for (int g = 0; g < ng; g++) {
-          const int i0 = g * 32, cntv = std::min(32, U - i0);
-          int width = 0;
-          for (int i = 0; i < cntv; i++) width = std::max(width, (int)(vt_off[ub + i0 + i + 1] - vt_off[ub + i0 + i]));
-          const int wpairs = (width + 1) / 2;
-          rows.assign((size_t)64 * std::max(wpairs, 1), 0xffffffffu);
-          for (int i = 0; i < cntv; i++) {
-            const int sl = ub + i0 + i;
-            int r2 = 0;
-            for (unsigned q = vt_off[sl]; q < vt_off[sl + 1]; q++, r2++) {
-              const int pos = (int)vt_idx[q];
-              const int p = ctx->h_tri_poly[pb->prim_indices[pos]];
-              unsigned e;
-              if (pos >= pbeg && pos < pend) {
-                if (pstamp[p] != tg) {
-                  pstamp[p] = tg;
-                  pentry[p] = (int)own_polys.size();
-                  own_polys.push_back(p);
-                }
-                e = (unsigned)pentry[p];
-              }
-              else {
-                const int ol = tri_leaf[pos];
-                const unsigned long long key = ((unsigned long long)(unsigned)p << 32) | (unsigned)ol;
-                auto it = halo.find(key);
-                if (it == halo.end()) {
-                  it = halo.emplace(key, (int)halo_polys.size()).first;
-                  halo_polys.push_back(p);
-                  halo_leaves.push_back(ol);
-                }
-                e = 0x80000000u | (unsigned)it->second;
-              }
-              rows[(size_t)r2 * 32 + i] = e;
-            }
-          }
-          goff_local[g] = (unsigned)(raw.size() / 2);
-          for (int w = 0; w < wpairs; w++) {
-            for (int i = 0; i < 32; i++) {
-              raw.push_back(rows[(size_t)(2 * w) * 32 + i]);
-              raw.push_back(rows[(size_t)(2 * w + 1) * 32 + i]);
-            }
-          }
-        }
-        next_group_to_fill = G0 + ng;
-        const int eown = (int)own_polys.size(), ehalo = (int)halo_polys.size(), ne = eown + ehalo;
-        tm.eown = eown;
-        tm.ehalo = ehalo;
-        if (ne >= 0xffff) ok = false;
-        /* pack the rows two entries to a word; other-leaf ids follow the own ones, padding -> the zero entry `ne` */
-        {
-          auto fix = [&](unsigned id) -> unsigned {
-            if (id == 0xffffffffu) return (unsigned)std::min(ne, 0xffff);
-            if (id & 0x80000000u) return (unsigned)std::min(eown + (int)(id & 0x7fffffffu), 0xfffe);
-            return (unsigned)std::min((int)id, 0xfffe);
-          };
-          const unsigned base = (unsigned)v2_idx.size();
-          for (size_t q = 0; q + 1 < raw.size(); q += 2) v2_idx.push_back(fix(raw[q]) | (fix(raw[q + 1]) << 16));
-          for (int g = 0; g < ng; g++) v2_goff[G0 + g] = base + goff_local[g];
-        }
-        /* staged verts: corners of the entries that are not unique verts of this tile */
-        st_bb.clear();
-        st_x.clear();
-        auto visit_poly = [&](int p) {
-          const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
-          if (len != 3 && len != 4) {
-            ok = false; /* n-gon: this leaf takes the general path */
-            return;
-          }
-          for (int k = 0; k < len; k++) {
-            const int sl = ctx->slot_of[ctx->h_loop_v[ls + k]];
-            if (lstamp[sl] == tg) continue;
-            lstamp[sl] = tg;
-            lidx[sl] = -1;
-            if (sh_leaf[sl] == l && sh_done[sl] != l) {
-              sh_done[sl] = l;
-              st_bb.push_back(sl);
-            }
-            else {
-              st_x.push_back(sl);
-            }
-          }
-        };
-        for (int p : own_polys) visit_poly(p);
-        for (int p : halo_polys) visit_poly(p);
-        if (tg == t_hi - 1) {
-          /* shared verts of the leaf that no tile reached through a poly of its unique verts */
-          for (int i = 0; i < S; i++) {
-            const int sl = leaf_sslots[(size_t)leaf_sbeg[l] + i];
-            if (sh_done[sl] != l) {
-              sh_done[sl] = l;
-              if (lstamp[sl] == tg && lidx[sl] == -1) {
-                /* staged here already as a plain corner: move it to the box-counted part */
-                st_x.erase(std::find(st_x.begin(), st_x.end(), sl));
-              }
-              lstamp[sl] = tg;
-              lidx[sl] = -1;
-              st_bb.push_back(sl);
-            }
-          }
-        }
-        std::sort(st_bb.begin(), st_bb.end());
-        std::sort(st_x.begin(), st_x.end());
-        int nloc = (U + 3) & ~3; /* staged verts follow the 16-byte padded unique run */
-        for (int sl : st_bb) {
-          lidx[sl] = nloc++;
-          stage.push_back(sl);
-        }
-        for (int sl : st_x) {
-          lidx[sl] = nloc++;
-          stage.push_back(sl);
-        }
-        tm.sbb = (int)st_bb.size();
-        tm.xcnt = (int)st_x.size();
-        if (nloc > 0xfffe) ok = false;
-        bool allquad = true;
-        auto emit = [&](int p) {
-          const int ls = ctx->h_poly_start[p], len = ctx->h_poly_len[p];
-          if (len != 4) allquad = false;
-          unsigned short loc[4] = {0, 0, 0, 0xffff};
-          if (len == 3 || len == 4) {
-            for (int k = 0; k < len; k++) loc[k] = (unsigned short)std::min(std::max(lidx[ctx->slot_of[ctx->h_loop_v[ls + k]]], 0), 0xfffe);
-          }
-          e_pv.insert(e_pv.end(), loc, loc + 4);
-        };
-        for (int p : own_polys) emit(p);
-        for (int p : halo_polys) emit(p);
-        e_halo_leaf.insert(e_halo_leaf.end(), halo_leaves.begin(), halo_leaves.end());
-        tm.ntfast = allquad ? 1 << 17 : 0;
-        const size_t bytes = dsc_tile_smem_bytes(dsc_tile_nloc_a(U, tm.sbb, tm.xcnt), ne, (int)(raw.size() / 2), ehalo);
-        if (bytes > DSC_TILE_SMEM_BUDGET) {
-          ok = false; /* a tile this heavy would push the regions past what an SM can hold: general path */
-        }
-        else {
-          tile_dims.push_back({tg, dsc_tile_nloc_a(U, tm.sbb, tm.xcnt), ne, (int)(raw.size() / 2), ehalo});
-        }
-      }
-      if (!ok) {
-        leaf_fast[l] = 0;
-        ctx->any_slow_leaf = true;
-        while (!tile_dims.empty() && tile_dims.back().tile >= t_lo) tile_dims.pop_back();
-      }
-      for (int tg = t_lo; tg < t_hi; tg++) tmeta[tg].ntfast |= (t_hi - t_lo) | (ok ? 1 << 16 : 0); /* bit 17: all entries are quads */
-      if (t_hi - t_lo > 0xffff) return fail(ctx, DSC_ERR_UNSUPPORTED, "leaf %d has too many tiles", l);
-    }
-    for (; next_group_to_fill <= VP / 32; next_group_to_fill++) v2_goff[next_group_to_fill] = (unsigned)v2_idx.size();
-    if (v2_idx.empty()) v2_idx.push_back(0u);
-    e_pv.insert(e_pv.end(), 8, (unsigned short)0); /* the last tile's bulk copy may read one entry past its own */
+    std::vector<int> &tri_leaf = tt.tri_leaf;
+    std::vector<unsigned> &vt_off = tt.vt_off, &vt_idx = tt.vt_idx;
+    std::vector<int> &leaf_sslots = tt.leaf_sslots, &stage = tt.stage, &e_halo_leaf = tt.e_halo_leaf;
+    std::vector<unsigned short> &e_pv = tt.e_pv;
+    std::vector<TileMeta> &tmeta = tt.tmeta;
+    std::vector<unsigned> &v2_goff = tt.v2_goff, &v2_idx = tt.v2_idx;
+    std::vector<TileDims> &tile_dims = tt.tile_dims;
+    leaf_sbeg = tt.leaf_sbeg;
+    leaf_fast = tt.leaf_fast;
+    if (tt.any_slow_leaf) ctx->any_slow_leaf = true;
     {
       /* every shared-memory region is sized for the largest fast tile, so it never moves between tiles */
       int mx_nloc = 4, mx_ne = 1, mx_v2 = 32, mx_h = 16;

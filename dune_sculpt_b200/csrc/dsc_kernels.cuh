@@ -1410,20 +1410,8 @@ __global__ void __launch_bounds__(DSC_BLOCK) k_normals(DevMesh m, const int *lis
 #define NT_BLOCK 256 /* compute threads of the tile kernel */
 #define NB_NORMALS 1
 #define NB_BOUNDS 2
-/* tile_meta: 3 x int4 per tile */
-struct TileMeta {
-  int ubeg, ucnt, sbeg, sbb;     /* unique slot run; staged verts: offset, how many count in the leaf box */
-  int xcnt, ebeg, eown, ehalo;   /* further staged verts; entries: offset (even), own-leaf, other-leaf */
-  int hbeg, leaf, tile0, ntfast; /* e_halo_leaf offset; leaf; its first tile; tile count | fast << 16 */
-};
-/* shared-memory regions of the tile kernel: positions SoA [3][nloc_a], poly normals float4 [ne + 1],
- * poly entries ushort4 [ne_a], index words [v2w], other-leaf entry switches [ehalo]; each region is
- * sized for the largest tile of the mesh (DevMesh.sm_off_*) */
-__host__ __device__ inline int dsc_tile_nloc_a(int ucnt, int sbb, int xcnt) { return (((ucnt + 3) & ~3) + sbb + xcnt + 3) & ~3; }
-__host__ __device__ inline size_t dsc_tile_smem_bytes(int nloc_a, int ne, int v2w, int ehalo)
-{
-  return 12 * (size_t)nloc_a + 16 * ((size_t)ne + 1) + 8 * (size_t)((ne + 1) & ~1) + 4 * (size_t)v2w + (((size_t)ehalo + 15) & ~(size_t)15);
-}
+/* TileMeta (3 x int4 per tile), dsc_tile_nloc_a, dsc_tile_smem_bytes and the host-side construction of the tile tables */
+#include "dsc_tile_tables.h"
 
 /* --- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier --- */
 __device__ __forceinline__ unsigned dsc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
