@@ -348,41 +348,71 @@ inline int dsc_build_tile_tables(const TileTablesIn &in, TileTablesOut &out, int
     for (int l = 0; l < L; l++) process_leaf(l, S_, outs[(size_t)l]);
   }
   mark("leaves (parallel)");
-  /* ---- the leaves' pieces appended in leaf order: the layout of the serial construction ---- */
-  int next_group_to_fill = 0;
+  /* ---- the leaves' pieces appended in leaf order: the layout of the serial construction ----
+   * where each leaf's pieces start follows from the sizes alone (serial, cheap); the copies and the offset fix-ups of a
+   * leaf touch only its own ranges (parallel) */
+  struct LeafBase { size_t sslots, stage, e_entries, halo, v2, dims; bool pad; };
+  std::vector<LeafBase> base((size_t)L + 1);
+  {
+    LeafBase c = {0, 0, 0, 0, 0, 0, false};
+    for (int l = 0; l < L; l++) {
+      const LeafOut &o = outs[(size_t)l];
+      if (o.too_many_tiles) {
+        if (r_where) *r_where = l;
+        return DSC_TT_TOO_MANY_TILES;
+      }
+      if (o.slow) out.any_slow_leaf = true;
+      c.pad = (c.e_entries & 1) != 0; /* the pad the leaf's first tile asks for: bulk copies start 16-byte aligned */
+      if (c.pad) c.e_entries++;
+      base[(size_t)l] = c;
+      c.sslots += o.leaf_sslots.size();
+      c.stage += o.stage.size();
+      c.e_entries += o.e_pv.size() / 4;
+      c.halo += o.e_halo_leaf.size();
+      c.v2 += o.v2_idx.size();
+      c.dims += o.tile_dims.size();
+    }
+    c.pad = false;
+    base[(size_t)L] = c;
+    out.leaf_sslots.assign(c.sslots, 0);
+    out.stage.assign(c.stage, 0);
+    out.e_pv.assign(c.e_entries * 4, (unsigned short)0); /* the pads stay zero */
+    out.e_halo_leaf.assign(c.halo, 0);
+    out.v2_idx.assign(c.v2, 0u);
+    out.tile_dims.assign(c.dims, TileDims());
+  }
+#pragma omp parallel for schedule(static) num_threads(nthreads)
   for (int l = 0; l < L; l++) {
     LeafOut &o = outs[(size_t)l];
-    if (o.too_many_tiles) {
-      if (r_where) *r_where = l;
-      return DSC_TT_TOO_MANY_TILES;
-    }
-    if (o.slow) out.any_slow_leaf = true;
-    out.leaf_sbeg[l] = (int)out.leaf_sslots.size();
-    out.leaf_sslots.insert(out.leaf_sslots.end(), o.leaf_sslots.begin(), o.leaf_sslots.end());
-    if ((out.e_pv.size() / 4) & 1) out.e_pv.insert(out.e_pv.end(), 4, (unsigned short)0); /* the pad the leaf's first tile asks for */
-    const int stage_base = (int)out.stage.size(), e_base = (int)(out.e_pv.size() / 4), h_base = (int)out.e_halo_leaf.size();
-    const unsigned v2_base = (unsigned)out.v2_idx.size();
+    const LeafBase &b = base[(size_t)l];
+    out.leaf_sbeg[l] = (int)b.sslots;
+    std::copy(o.leaf_sslots.begin(), o.leaf_sslots.end(), out.leaf_sslots.begin() + (long)b.sslots);
+    std::copy(o.stage.begin(), o.stage.end(), out.stage.begin() + (long)b.stage);
+    std::copy(o.e_pv.begin(), o.e_pv.end(), out.e_pv.begin() + (long)(b.e_entries * 4));
+    std::copy(o.e_halo_leaf.begin(), o.e_halo_leaf.end(), out.e_halo_leaf.begin() + (long)b.halo);
+    std::copy(o.v2_idx.begin(), o.v2_idx.end(), out.v2_idx.begin() + (long)b.v2);
+    std::copy(o.tile_dims.begin(), o.tile_dims.end(), out.tile_dims.begin() + (long)b.dims);
     const int t_lo = in.leaf_tile0[l], t_hi = in.leaf_tile0[l + 1];
     for (int tg = t_lo; tg < t_hi; tg++) {
       TileMeta &tm = out.tmeta[tg];
-      tm.sbeg += stage_base;
-      tm.ebeg += e_base;
-      tm.hbeg += h_base;
+      tm.sbeg += (int)b.stage;
+      tm.ebeg += (int)b.e_entries;
+      tm.hbeg += (int)b.halo;
       const int G0 = tm.ubeg / 32, ng = (tm.ucnt + 31) / 32;
-      for (; next_group_to_fill < G0; next_group_to_fill++) out.v2_goff[next_group_to_fill] = v2_base + o.tile_v2_begin[(size_t)(tg - t_lo)];
-      for (int g = 0; g < ng; g++) out.v2_goff[G0 + g] += v2_base;
-      next_group_to_fill = G0 + ng;
+      /* the groups of the pad slots between the previous tile (of this leaf or the one before) and this one point at
+       * this tile's first word; tile_meta's ubeg / ucnt were final after the leaf pass */
+      int g_prev = 0;
+      if (tg > 0) g_prev = out.tmeta[tg - 1].ubeg / 32 + (out.tmeta[tg - 1].ucnt + 31) / 32;
+      const unsigned first_word = (unsigned)b.v2 + o.tile_v2_begin[(size_t)(tg - t_lo)];
+      for (int g = g_prev; g < G0; g++) out.v2_goff[g] = first_word;
+      for (int g = 0; g < ng; g++) out.v2_goff[G0 + g] += (unsigned)b.v2;
     }
-    out.stage.insert(out.stage.end(), o.stage.begin(), o.stage.end());
-    out.e_pv.insert(out.e_pv.end(), o.e_pv.begin(), o.e_pv.end());
-    out.e_halo_leaf.insert(out.e_halo_leaf.end(), o.e_halo_leaf.begin(), o.e_halo_leaf.end());
-    out.v2_idx.insert(out.v2_idx.end(), o.v2_idx.begin(), o.v2_idx.end());
-    out.tile_dims.insert(out.tile_dims.end(), o.tile_dims.begin(), o.tile_dims.end());
     std::vector<int>().swap(o.leaf_sslots); /* release as we go */
     std::vector<int>().swap(o.stage);
     std::vector<unsigned short>().swap(o.e_pv);
     std::vector<unsigned>().swap(o.v2_idx);
   }
+  int next_group_to_fill = NT > 0 ? out.tmeta[(size_t)NT - 1].ubeg / 32 + (out.tmeta[(size_t)NT - 1].ucnt + 31) / 32 : 0;
   for (; next_group_to_fill <= VP / 32; next_group_to_fill++) out.v2_goff[next_group_to_fill] = (unsigned)out.v2_idx.size();
   if (out.v2_idx.empty()) out.v2_idx.push_back(0u);
   out.e_pv.insert(out.e_pv.end(), 8, (unsigned short)0); /* the last tile's bulk copy may read one entry past its own */
