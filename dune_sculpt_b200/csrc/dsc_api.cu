@@ -1344,7 +1344,11 @@ int dsc_pbvh_upload(DscContext *ctx, const DscPbvhDesc *pb)
   /* per-slot vertex data */
   auto to_slots = [&](const std::vector<float> &src, int comp, int stride) {
     std::vector<float> out((size_t)VP, 0.0f);
-    for (int v = 0; v < V; v++) out[ctx->slot_of[v]] = src[(size_t)stride * v + comp];
+    const int *so = ctx->slot_of.data();
+    const float *sp = src.data();
+    float *op = out.data();
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < V; v++) op[so[v]] = sp[(size_t)stride * v + comp]; /* slot_of is a permutation: no two writes meet */
     return out;
   };
   for (int k = 0; k < 3; k++) {

@@ -114,7 +114,9 @@ static void ensure_nodes(PBVH *pbvh, int totnode)
   pbvh->totnode = totnode;
 }
 
-static void leaf_collect_verts(PBVH *pbvh, PBVHNode *node, int node_index, int *stamp, int *local)
+/* `rank` = the leaf's place in build order (from 1), owner[v] = the lowest rank among the leaves that use v; stamp / local
+ * are the calling thread's own scratch (zeroed: rank 0 means "not seen") */
+static void leaf_collect_verts(PBVH *pbvh, PBVHNode *node, int rank, const int *owner, int *stamp, int *local)
 {
   /* pbvh.c:2149-2238: a vertex belongs ("unique") to the first leaf, in build order, that uses
    * it; later leaves list it after their unique verts.  Within a leaf, order = first use. */
@@ -125,10 +127,9 @@ static void leaf_collect_verts(PBVH *pbvh, PBVHNode *node, int node_index, int *
     const MLoopTri *lt = &pbvh->looptri[node->prim_indices[i]];
     for (int j = 0; j < 3; j++) {
       const int v = (int)pbvh->mloop[lt->tri[j]].v;
-      if (stamp[v] != node_index) {
-        stamp[v] = node_index;
-        if (!(pbvh->vert_bitmap[v >> 5] & (1u << (v & 31)))) {
-          pbvh->vert_bitmap[v >> 5] |= 1u << (v & 31);
+      if (stamp[v] != rank) {
+        stamp[v] = rank;
+        if (owner[v] == rank) {
           local[v] = (int)uniq++;
         }
         else {
@@ -344,7 +345,13 @@ static TmpNode *partition_rec(PBVH *pbvh, const PrimBox *pb, int offset, int cou
   return t;
 }
 
-static void number_rec(PBVH *pbvh, TmpNode *t, int index, int *stamp, int *local)
+/* the mesh leaves in build order (number_rec fills it; their vertex lists follow in a parallel pass) */
+typedef struct LeafOrder {
+  int *node;
+  int count, cap;
+} LeafOrder;
+
+static void number_rec(PBVH *pbvh, TmpNode *t, int index, LeafOrder *order)
 {
   if (!t->child[0]) {
     PBVHNode *node = &pbvh->nodes[index];
@@ -363,7 +370,11 @@ static void number_rec(PBVH *pbvh, TmpNode *t, int index, int *stamp, int *local
       node->flag |= PBVH_RebuildDrawBuffers | PBVH_UpdateDrawBuffers | PBVH_UpdateRedraw;
     }
     else {
-      leaf_collect_verts(pbvh, node, index, stamp, local);
+      if (order->count == order->cap) {
+        order->cap = order->cap ? 2 * order->cap : 1024;
+        order->node = realloc(order->node, sizeof(int) * (size_t)order->cap);
+      }
+      order->node[order->count++] = index;
     }
     free(t);
     return;
@@ -374,12 +385,12 @@ static void number_rec(PBVH *pbvh, TmpNode *t, int index, int *stamp, int *local
   node->children_offset = child;
   node->vb = t->vb;
   node->orig_vb = t->vb;
-  number_rec(pbvh, t->child[0], child, stamp, local);
-  number_rec(pbvh, t->child[1], child + 1, stamp, local);
+  number_rec(pbvh, t->child[0], child, order);
+  number_rec(pbvh, t->child[1], child + 1, order);
   free(t);
 }
 
-static void build_tree(PBVH *pbvh, const PrimBox *pb, int nprims, const BB *cb, int *stamp, int *local)
+static void build_tree(PBVH *pbvh, const PrimBox *pb, int nprims, const BB *cb)
 {
   TmpNode *root = NULL;
   struct timespec t0, t1, t2;
@@ -388,7 +399,46 @@ static void build_tree(PBVH *pbvh, const PrimBox *pb, int nprims, const BB *cb, 
 #pragma omp single
   root = partition_rec(pbvh, pb, 0, nprims, cb);
   clock_gettime(CLOCK_MONOTONIC, &t1);
-  number_rec(pbvh, root, 0, stamp, local);
+  /* pass 2a, serial and cheap: the nodes numbered in build_sub's order, the mesh leaves listed in that order */
+  LeafOrder order = {NULL, 0, 0};
+  number_rec(pbvh, root, 0, &order);
+  if (order.count) {
+    /* pass 2b: a vertex is unique in the FIRST leaf, in build order, that uses it (map_insert_vert + vert_bitmap,
+     * pbvh.c:2149-2171) = the lowest rank among its leaves: an order-free minimum, then every leaf collects its verts on
+     * its own (a thread's scratch pages are only touched where its leaves -- a contiguous, spatially coherent run -- reach) */
+    const int V = pbvh->totvert;
+    struct timespec ta, tb, tc; clock_gettime(CLOCK_MONOTONIC, &ta);
+    int *owner = malloc(sizeof(int) * (size_t)(V ? V : 1));
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < V; v++) owner[v] = 0x7fffffff;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < order.count; k++) {
+      const PBVHNode *node = &pbvh->nodes[order.node[k]];
+      const int rank = k + 1;
+      for (unsigned i = 0; i < node->totprim; i++) {
+        const MLoopTri *lt = &pbvh->looptri[node->prim_indices[i]];
+        for (int j = 0; j < 3; j++) {
+          int *o = &owner[pbvh->mloop[lt->tri[j]].v];
+          int cur = __atomic_load_n(o, __ATOMIC_RELAXED);
+          while (rank < cur && !__atomic_compare_exchange_n(o, &cur, rank, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+          }
+        }
+      }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &tb);
+#pragma omp parallel
+    {
+      int *stamp = calloc((size_t)(V ? V : 1), sizeof(int)), *local = calloc((size_t)(V ? V : 1), sizeof(int));
+#pragma omp for schedule(static)
+      for (int k = 0; k < order.count; k++) leaf_collect_verts(pbvh, &pbvh->nodes[order.node[k]], k + 1, owner, stamp, local);
+      free(stamp);
+      free(local);
+    }
+    free(owner);
+    clock_gettime(CLOCK_MONOTONIC, &tc);
+    if (getenv("DUNE_PBVH_TIMING")) fprintf(stderr, "owner %.3f collect %.3f\n", (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec), (tc.tv_sec - tb.tv_sec) + 1e-9 * (tc.tv_nsec - tb.tv_nsec));
+  }
+  free(order.node);
   clock_gettime(CLOCK_MONOTONIC, &t2);
   if (getenv("DUNE_PBVH_TIMING")) fprintf(stderr, "partition %.3f number %.3f\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), (t2.tv_sec - t1.tv_sec) + 1e-9 * (t2.tv_nsec - t1.tv_nsec));
 }
@@ -455,13 +505,7 @@ void BKE_pbvh_build_mesh(PBVH *pbvh, struct Mesh *mesh, const MPoly *mpoly, cons
   ensure_nodes(pbvh, 100);
   pbvh->totnode = 1;
 
-  int *stamp = malloc(sizeof(int) * (size_t)totvert);
-  int *local = malloc(sizeof(int) * (size_t)totvert);
-  for (int i = 0; i < totvert; i++) stamp[i] = -1;
-
-  build_tree(pbvh, pb, looptri_num, &cb, stamp, local);
-  free(stamp);
-  free(local);
+  build_tree(pbvh, pb, looptri_num, &cb);
   free(pb);
   memset(pbvh->vert_bitmap, 0, sizeof(unsigned) * ((size_t)totvert / 32 + 1)); /* pbvh.c:2512-2513 */
 }
@@ -534,7 +578,7 @@ void BKE_pbvh_build_grids(PBVH *pbvh, CCGElem **grids, int totgrid, CCGKey *key,
   pbvh->totnode = 0;
   ensure_nodes(pbvh, 100);
   pbvh->totnode = 1;
-  build_tree(pbvh, pb, totgrid, &cb, NULL, NULL);
+  build_tree(pbvh, pb, totgrid, &cb);
   free(pb);
 }
 
