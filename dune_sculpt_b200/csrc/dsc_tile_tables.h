@@ -90,35 +90,65 @@ inline int dsc_build_tile_tables(const TileTablesIn &in, TileTablesOut &out, int
     fprintf(stderr, "[dsc tile tables] %-22s %.3f s\n", what, t - t_mark);
     t_mark = t;
   };
-  /* ---- looptris by position; vertex -> looptri CSR ---- */
+  /* ---- looptris by position; vertex -> looptri CSR ----
+   * a slot's list holds the positions of its looptris in ascending order (the order a single-threaded
+   * pbvh_update_normals_accum_task_cb adds them): counted and filled in parallel with atomic cursors, then every list
+   * sorted -- the same table as a serial fill in position order */
+#ifdef _OPENMP
+  const int nthreads = threads > 0 ? threads : omp_get_max_threads();
+#else
+  const int nthreads = 1;
+  (void)threads;
+#endif
   out.tri_leaf.assign((size_t)std::max(T, 1), 0);
   std::vector<int> &tri_leaf = out.tri_leaf;
   std::vector<unsigned> deg((size_t)VP + 1, 0);
+  int bad_pos = -1;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
   for (int l = 0; l < L; l++) {
     for (int pos = in.leaf_pbeg[l]; pos < in.leaf_pbeg[l] + in.leaf_pcnt[l]; pos++) {
       const int t = in.prim_indices[pos];
       if (t < 0 || t >= T) {
-        if (r_where) *r_where = pos;
-        return DSC_TT_BAD_PRIM;
+#pragma omp atomic write
+        bad_pos = pos;
+        continue;
       }
       tri_leaf[pos] = l;
-      for (int k = 0; k < 3; k++) deg[in.slot_of[in.tri_vert[(size_t)3 * t + k]]]++;
+      for (int k = 0; k < 3; k++) {
+        unsigned *d = &deg[in.slot_of[in.tri_vert[(size_t)3 * t + k]]];
+#pragma omp atomic update
+        (*d)++;
+      }
     }
+  }
+  if (bad_pos >= 0) {
+    if (r_where) *r_where = bad_pos;
+    return DSC_TT_BAD_PRIM;
   }
   out.vt_off.assign((size_t)VP + 1, 0);
   std::vector<unsigned> &vt_off = out.vt_off;
   for (int s = 0; s < VP; s++) vt_off[s + 1] = vt_off[s] + deg[s];
   out.vt_idx.assign((size_t)std::max<unsigned>(vt_off[VP], 1u), 0u);
   std::vector<unsigned> &vt_idx = out.vt_idx;
-  std::fill(deg.begin(), deg.end(), 0u);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int s = 0; s <= VP; s++) deg[s] = 0u;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
   for (int pos = 0; pos < T; pos++) {
     const int t = in.prim_indices[pos];
     /* the reference adds the face normal for corner j = 2, 1, 0 (pbvh.c:2966); a vertex that is
      * listed twice in one looptri gets it twice -- same here, order within a looptri is moot */
     for (int k = 0; k < 3; k++) {
       const int s = in.slot_of[in.tri_vert[(size_t)3 * t + k]];
-      vt_idx[vt_off[s] + deg[s]++] = (unsigned)pos;
+      unsigned at;
+#pragma omp atomic capture
+      at = deg[s]++;
+      vt_idx[vt_off[s] + at] = (unsigned)pos;
     }
+  }
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int s = 0; s < VP; s++) {
+    const unsigned b = vt_off[s], e = vt_off[s + 1];
+    if (e - b > 1) std::sort(vt_idx.begin() + b, vt_idx.begin() + e);
   }
   std::vector<unsigned>().swap(deg);
 
@@ -335,12 +365,6 @@ inline int dsc_build_tile_tables(const TileTablesIn &in, TileTablesOut &out, int
       for (int tg = t_lo; tg < t_hi; tg++) out.tmeta[tg].ntfast |= (t_hi - t_lo) | (ok ? 1 << 16 : 0); /* bit 17: all entries are quads */
       if (t_hi - t_lo > 0xffff) o.too_many_tiles = true;
   };
-#ifdef _OPENMP
-  const int nthreads = threads > 0 ? threads : omp_get_max_threads();
-#else
-  const int nthreads = 1;
-  (void)threads;
-#endif
 #pragma omp parallel num_threads(nthreads)
   {
     Scratch S_(VP, in.totpoly);
