@@ -28,6 +28,7 @@ template<typename T> static uint64_t fnv_vec(uint64_t h, const std::vector<T> &v
  * more corners staged from other tiles).  r_hashes[12]: one per table + the flags.  Returns the builder's status. */
 extern "C" int tt_hashes(const DscMeshDesc *me, const DscPbvhDesc *pd, int tile, int scramble, int mode, uint64_t *r_hashes)
 {
+  if (tile <= 0 || tile > DSC_TILE || (tile & 31)) return -1; /* like the real layout: a 32-slot group belongs to one tile */
   const int V = me->totvert, T = me->tottri, N = pd->totnode;
   std::vector<int> leaves;
   for (int n = 0; n < N; n++) {

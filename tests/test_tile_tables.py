@@ -38,6 +38,8 @@ def _hashes(lib, me, pd, tile, scramble, mode):
 
 CASES = [
     ("grid", lambda: meshgen.grid(97), 200),
+    ("grid-tiny-leaves", lambda: meshgen.grid(33), 7),
+    ("ico-large-leaves", lambda: meshgen.icosphere(40, noise=0.02), 300),
     ("grid-default-leaves", lambda: meshgen.grid(257), 0),
     ("mixed", lambda: meshgen.mixed_grid(65), 150),      # tris, quads and n-gons: some leaves take the general path
     ("ico", lambda: meshgen.icosphere(20, noise=0.01), 111),
@@ -49,9 +51,9 @@ CASES = [
 def test_parallel_tile_tables_are_the_serial_ones(lib, name, mk, ll):
     ses = capi.SculptSession(mk(), leaf_limit=ll)
     me, pd, keep = ses.descs(with_neighbors=False)
-    for tile, scramble in ((1024, 0), (256, 0), (96, 1), (1024, 1)):
+    for tile, scramble in ((1024, 0), (256, 0), (96, 1), (1024, 1), (32, 0)):
         ref = _hashes(lib, me, pd, tile, scramble, 0)
-        for threads in (1, 3, 8):
+        for threads in (1, 3, 8, 16):
             got = _hashes(lib, me, pd, tile, scramble, threads)
             bad = [NAMES[i] for i in range(12) if ref[i] != got[i]]
             assert not bad, "%s tile %d scramble %d threads %d: %s differ" % (name, tile, scramble, threads, bad)
