@@ -764,6 +764,18 @@ def make_parser():
     return ap
 
 
+def share_host_threads(world):
+    """torchrun starts every rank with OMP_NUM_THREADS=1, which makes the host PBVH build and the upload's table passes serial:
+    give each rank its share of the cores instead (session start only; nothing on the timed path runs on host threads)"""
+    try:
+        import ctypes
+        n = max(1, (os.cpu_count() or 1) // max(world, 1))
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+        return n
+    except OSError:
+        return 0
+
+
 def run(args):
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)
@@ -781,6 +793,7 @@ def run(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
+        share_host_threads(world)
     with_cpu = not args.no_cpu_baseline
     res, clocks = measure(args.config, args, rank, world, local_rank, with_cpu)
     if args.side_configs is None:
